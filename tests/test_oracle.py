@@ -1,0 +1,117 @@
+"""CPU tests: the oracle against the golden vectors produced by the reference's own python
+(oracle/make_golden.py), and the oracle's two routes against each other."""
+import numpy as np
+import pytest
+
+from oracle import hiertcn_oracle as O
+from helpers import GOLDEN, load_hier_golden, small_case
+
+
+@pytest.mark.parametrize("name", ["hier_default_arch", "hier_downsample_3lvl"])
+def test_literal_oracle_matches_reference_graph(name):
+    z, x, y, m, w = load_hier_golden(name)
+    G = int(z["num_layer"])
+    out = O.forward_loss_metrics(x, y, m, z["state0"], w, G, "f64", literal=True)
+    np.testing.assert_allclose(out["pred"], z["pred_f64"], rtol=2e-6, atol=2e-6)   # fixture stored as f32
+    np.testing.assert_allclose(out["state"], z["state_f64"], rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(out["loss"], z["loss_f64"], rtol=1e-12)
+    np.testing.assert_allclose(out["loss_bt"], z["loss_bt_f64"], rtol=1e-10, atol=1e-12)
+    np.testing.assert_array_equal(out["ranks"], z["ranks_f64"])
+    got = np.asarray([out[k] for k in ("recall1", "recall5", "recall10", "mrr", "mrp")])
+    # loss.py:179 casts the rank comparison to tf.float32, so the reference's metric scalars carry
+    # fp32 rounding even in the fp64 run of the fixture generator
+    np.testing.assert_allclose(got, z["metrics_f64"], rtol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["hier_default_arch", "hier_downsample_3lvl"])
+def test_restructured_oracle_matches_reference_graph(name):
+    """gather instead of one-hot matmul, hoisted GRU, split in-projection == the literal graph."""
+    z, x, y, m, w = load_hier_golden(name)
+    G = int(z["num_layer"])
+    out = O.forward_loss_metrics(x, y, m, z["state0"], w, G, "f64", literal=False)
+    np.testing.assert_allclose(out["pred"], z["pred_f64"], rtol=2e-6, atol=2e-6)
+    np.testing.assert_allclose(out["state"], z["state_f64"], rtol=1e-11, atol=1e-12)
+    np.testing.assert_allclose(out["loss"], z["loss_f64"], rtol=1e-11)
+    np.testing.assert_array_equal(out["ranks"], z["ranks_f64"])
+
+
+@pytest.mark.parametrize("name", ["hier_default_arch", "hier_downsample_3lvl"])
+def test_f32_restructured_within_1e4(name):
+    """fp32 tier tolerance of the north star (1e-4 relative) holds for the fp32 oracle itself."""
+    z, x, y, m, w = load_hier_golden(name)
+    out = O.forward_loss_metrics(x, y, m, z["state0"], w, int(z["num_layer"]), "f32")
+    assert abs(out["loss"] - z["loss_f64"]) <= 1e-4 * abs(z["loss_f64"])
+    np.testing.assert_allclose(out["state"], z["state_f64"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(out["loss"], z["loss_f32"], rtol=1e-5)
+
+
+def test_bf16_tier_within_2e2():
+    z, x, y, m, w = load_hier_golden("hier_default_arch")
+    out = O.forward_loss_metrics(x, y, m, z["state0"], w, 2, "bf16")
+    assert abs(out["loss"] - z["loss_f64"]) <= 2e-2 * abs(z["loss_f64"])
+
+
+def test_embedding_gather_is_bit_exact_vs_onehot_matmul():
+    rng = np.random.default_rng(0)
+    E = rng.normal(size=(50, 128)).astype(np.float32)
+    ids = rng.integers(0, 50, size=(4, 9))
+    ids[0, :3] = 0
+    lit = O.dense(O.one_hot_signed(ids, 50), E)
+    np.testing.assert_array_equal(lit, O.emb_gather(ids, E))
+    assert (O.emb_gather(ids, E)[ids == 0] == 0).all()
+
+
+def test_loss_vectors():
+    z = np.load(GOLDEN + "/loss_vectors.npz")
+    for name in ("l2", "nce", "hinge_sigmoid", "hinge_logsigmoid", "hinge_linear", "bpr"):
+        got = O.calc_loss_sampled(z["pred"], z["y"], z["y_impression"], name, int(z["num_neg_sample"]),
+                                  float(z["nce_weight"]), float(z["hinge_delta"]))
+        np.testing.assert_allclose(got, z["loss_" + name], rtol=1e-10, atol=1e-12, err_msg=name)
+    for rm in ("l2", "inner_prod"):
+        np.testing.assert_allclose(O.calc_score(z["pred"], z["y_impression"], rm), z["score_" + rm], rtol=1e-12)
+
+
+def test_metric_fast_and_topk_vectors():
+    z = np.load(GOLDEN + "/loss_vectors.npz")
+    score, y_id = z["score"], z["y_id"]
+    mask_y = np.sign(y_id).astype(np.float64)
+    act = mask_y.sum(1)
+    uc = np.sign(act).sum()
+    act = act + 1e-6
+    got = O.calc_metric_fast(score, mask_y, act, uc, y_id)
+    np.testing.assert_allclose(np.asarray(got[:5]), z["metric_fast_scalars"], rtol=1e-6)
+    np.testing.assert_array_equal(got[6], z["metric_fast_ranks"])
+    np.testing.assert_allclose(got[5], z["metric_fast_ranks_float"], rtol=1e-6)
+    v, i = O.top_k(score, score.shape[-1])
+    np.testing.assert_array_equal(i, z["metric_topk_indices"])      # tie rule: lower index first
+    np.testing.assert_array_equal(v, z["metric_topk_values"])
+
+
+def test_causality_probe():
+    """customized_tcn_cell.py:163-180: a spike at t=5 must not leak to t<5."""
+    rng = np.random.default_rng(1)
+    w = {}
+    for lvl in range(3):
+        w[f"t/temporal_conv_net/tblock_{lvl}/conv1/kernel"] = rng.normal(size=(4, 8, 8)).astype(np.float32)
+        w[f"t/temporal_conv_net/tblock_{lvl}/conv1/bias"] = rng.normal(size=(8,)).astype(np.float32)
+    x = rng.normal(size=(2, 30, 8)).astype(np.float32)
+    x2 = x.copy()
+    x2[:, 5, :] += 1000.0
+    a = O.temporal_conv_net(x, w, "t", 3)
+    b = O.temporal_conv_net(x2, w, "t", 3)
+    np.testing.assert_array_equal(a[:, :5], b[:, :5])
+    assert np.abs(a[:, 5:] - b[:, 5:]).max() > 0
+
+
+def test_state_reset_and_row_independence():
+    x, y, m, s0, w = small_case(B=4, S=3, L=5, N=31, seed=3)
+    out = O.model_hier_restructured(x, y, m, s0, w, 2, "f32")
+    # permuting users permutes outputs
+    perm = np.array([2, 0, 3, 1])
+    out_p = O.model_hier_restructured([a[perm] for a in x], [a[perm] for a in y], [a[perm] for a in m],
+                                      s0[perm], w, 2, "f32")
+    np.testing.assert_allclose(out[0][perm], out_p[0], rtol=1e-5, atol=1e-6)
+    # mask 0 in the last slot zeroes the carried state
+    m2 = [a.copy() for a in m]
+    m2[-1][:] = 0
+    assert (O.model_hier_restructured(x, y, m2, s0, w, 2, "f32")[1] == 0).all()
