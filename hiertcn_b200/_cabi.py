@@ -1,0 +1,85 @@
+"""ctypes binding of libhtcn.so (include/htcn.h).  No torch types cross this boundary: callers pass
+raw device pointers (``tensor.data_ptr()``), sizes and a stream handle.
+
+There is no fallback: if the library is missing ``load()`` raises, and if a call fails the status is
+turned into ``HtcnError`` with the library's message."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libhtcn.so")
+
+HTCN_F32, HTCN_BF16 = 0, 1
+SCORE_CE, SCORE_RANK, SCORE_TOPK = 1, 2, 4
+LOSS_KINDS = {"nce": 0, "hinge_sigmoid": 1, "hinge_logsigmoid": 2, "hinge_linear": 3, "bpr": 4}
+MAX_TOPK = 128
+
+_p, _i, _u, _f = C.c_void_p, C.c_int32, C.c_uint32, C.c_float
+_pp = C.POINTER(C.c_void_p)        # host array of device pointers
+_ip = C.POINTER(C.c_int32)         # host int array
+
+# name -> argtypes; every function returns int32 status unless noted.  Keep in sync with include/htcn.h
+# (tests/test_cabi.py parses the header and compares).
+SIGNATURES = {
+    "htcn_gather_meanpool": [_p, _p, _i, _p, _p, _ip, _i, _i, _i, _p, _i, _p, _p],
+    "htcn_gru_sessions": [_p, _p, _p, _pp, _pp, _pp, _pp, _i, _p, _i, _i, _p, _p, _p, _p],
+    "htcn_tcn_forward": [_p, _i, _i, _p, _p, _pp, _pp, _i, _i, _ip, _i, _i, _i, _p, _p, _i, _p, _p],
+    "htcn_prepare_wout": [_p, _i, _p, _i, _p],
+    "htcn_score_ce_rank_topk": [_p, _i, _i, _p, _p, _i, _i, _p, _p, _i, _u, _i, _i, _p, _p, _p, _p, _p, _p],
+    "htcn_score_logits": [_p, _i, _i, _p, _i, _p, _i, _p, _p],
+    "htcn_target_logit": [_p, _i, _i, _p, _p, _i, _i, _p, _p, _p],
+    "htcn_score_finish": [_p, _p, _p, _i, _i, _p, _p, _p, _p, _p],
+    "htcn_topk_merge": [_p, _p, _i, _i, _i, _p, _p, _p],
+    "htcn_loss_metrics_reduce": [_p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p],
+    "htcn_sampled_rank_loss": [_p, _i, _i, _p, _p, _p, _i, _i, _f, _f, _p, _p],
+}
+PLAIN = {"htcn_abi_version": (C.c_int32, []), "htcn_last_error": (C.c_char_p, []),
+         "htcn_device_ok": (C.c_int32, [])}
+
+
+class HtcnError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load(path: str | None = None):
+    """dlopen libhtcn.so and declare every prototype.  Raises if the library is absent or a symbol is
+    missing -- the product path must fail loudly rather than fall back."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise HtcnError("libhtcn.so not found at %s -- build it with `python -m hiertcn_b200.build` "
+                        "(there is no CPU fallback)" % path)
+    lib = C.CDLL(path)
+    for name, (res, args) in PLAIN.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    for name, args in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = C.c_int32, args
+    _lib = lib
+    return lib
+
+
+def call(name: str, *args):
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise HtcnError("%s failed (%d): %s" % (name, rc, lib.htcn_last_error().decode()))
+
+
+def ptr_array(ptrs):
+    """host array of device pointers"""
+    arr = (C.c_void_p * len(ptrs))(*[C.c_void_p(int(p)) for p in ptrs])
+    return C.cast(arr, _pp), arr       # keep `arr` alive while the call runs
+
+
+def int_array(vals):
+    arr = (C.c_int32 * len(vals))(*[int(v) for v in vals])
+    return C.cast(arr, _ip), arr

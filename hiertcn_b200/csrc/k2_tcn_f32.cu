@@ -1,0 +1,222 @@
+// K2 (fp32 tier): in-projection + dilated causal conv residual stack as FFMA tile GEMMs.
+// One generic kernel evaluates one "level" for 128 consecutive flat rows x 128 output channels:
+//     out[r,:] = epi( sum_{tap<K} in[r - (K-1-tap)*d, :] @ W[tap]  + bias [+ sbias[slot(r), user(r), :]] )
+// with the shifted row taken as zero when it falls before the start of r's sequence -- the causal
+// left pad of customized_tcn_cell.py:46-49 -- and epi = relu(relu(.) + in[r,:]) for conv levels
+// (customized_tcn_cell.py:109-127: relu inside the conv, residual add, relu) or identity for the
+// in-projection (model_tcn.py:35, K = 1, no bias).  Levels are chained through an fp32 scratch in HBM
+// (L2-resident at these sizes); the bf16 tier (k2_tcn_bf16.cu) keeps them on chip instead.
+#include "common.cuh"
+
+namespace htcn {
+
+constexpr int kTM = 128;      // rows per CTA
+constexpr int kTK = 16;       // contraction chunk
+constexpr int kK2Threads = 256;
+
+struct LevelArgs {
+  const void* in;             // [R,128] f32 (or bf16 when in_bf16)
+  const float* w;             // [K,128,128]
+  const float* bias;          // [128] or NULL
+  const float* sbias;         // [S,B,128] or NULL
+  void* out;                  // [R or n_out,128]
+  const int* out_row;         // [R] or NULL
+  long long R;
+  int T, B, K, dil;
+  int conv_epilogue;          // 1: relu, +residual, relu; 0: linear
+  int in_bf16, out_bf16;
+};
+
+__device__ __forceinline__ float load_act(const void* base, bool bf16, long long idx) {
+  if (bf16) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[idx]);
+  return reinterpret_cast<const float*>(base)[idx];
+}
+
+__global__ void __launch_bounds__(kK2Threads)
+k2_level_f32(LevelArgs a, SlotTable slots) {
+  __shared__ __align__(16) float As[kTK][kTM];     // As[kk][row]
+  __shared__ __align__(16) float Bs[kTK][kDim];    // Bs[kk][col]
+  __shared__ int t_in_seq[kTM];                    // position of each tile row inside its sequence
+  const int tid = threadIdx.x;
+  const long long r0 = (long long)blockIdx.x * kTM;
+
+  if (tid < kTM) {
+    const long long r = r0 + tid;
+    int t = 0;
+    if (r < a.R) {
+      const int p = (int)(r % a.T);
+      int s = 0;
+      while (s + 1 < slots.n && slots.off[s + 1] <= p) ++s;
+      t = p - slots.off[s];
+    }
+    t_in_seq[tid] = t;
+  }
+  __syncthreads();
+
+  // thread tile: rows {ty*4..+3, 64+ty*4..+3} x cols {tx*4..+3, 64+tx*4..+3}
+  const int tx = tid & 15, ty = tid >> 4;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  const int lrow = tid & 127, lhalf = tid >> 7;   // loader mapping: row, 8-wide k half
+  for (int tap = 0; tap < a.K; ++tap) {
+    const int shift = (a.K - 1 - tap) * a.dil;
+    const long long src = r0 + lrow - shift;
+    const bool ok = (r0 + lrow < a.R) && (t_in_seq[lrow] - shift >= 0);
+    for (int c0 = 0; c0 < kDim; c0 += kTK) {
+      // A chunk: in[src][c0 + lhalf*8 .. +8] -> As[kk][lrow]
+      float v[8];
+      if (ok) {
+        if (a.in_bf16) {
+          const uint4 q = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.in) +
+                                                          src * kDim + c0 + lhalf * 8);
+          v[0] = bf16_lo(q.x); v[1] = bf16_hi(q.x); v[2] = bf16_lo(q.y); v[3] = bf16_hi(q.y);
+          v[4] = bf16_lo(q.z); v[5] = bf16_hi(q.z); v[6] = bf16_lo(q.w); v[7] = bf16_hi(q.w);
+        } else {
+          const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.in) + src * kDim + c0 + lhalf * 8);
+          const float4 q0 = p[0], q1 = p[1];
+          v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w; v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = 0.f;
+      }
+      // W chunk: w[tap][c0 + kk][0..127] -> Bs[kk][col]; 2048 floats = 256 threads x 2 float4
+      const float4* wp = reinterpret_cast<const float4*>(a.w + ((long long)tap * kDim + c0) * kDim);
+      const float4 w0 = __ldg(wp + tid), w1 = __ldg(wp + 256 + tid);
+      __syncthreads();           // previous chunk fully consumed
+#pragma unroll
+      for (int i = 0; i < 8; ++i) As[lhalf * 8 + i][lrow] = v[i];
+      reinterpret_cast<float4*>(&Bs[0][0])[tid] = w0;
+      reinterpret_cast<float4*>(&Bs[0][0])[256 + tid] = w1;
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < kTK; ++kk) {
+        const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+        const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][64 + ty * 4]);
+        const float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+        const float4 b1 = *reinterpret_cast<const float4*>(&Bs[kk][64 + tx * 4]);
+        const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      }
+    }
+  }
+
+  // ---- epilogue ------------------------------------------------------------------------------
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int lr = (i < 4) ? (ty * 4 + i) : (64 + ty * 4 + i - 4);
+    const long long r = r0 + lr;
+    if (r >= a.R) continue;
+    long long dst = r;
+    if (a.out_row) {
+      const int d = a.out_row[r];
+      if (d < 0) continue;
+      dst = d;
+    }
+    const float* sb = nullptr;
+    if (a.sbias) {
+      const int b = (int)(r / a.T), p = (int)(r % a.T);
+      int s = 0;
+      while (s + 1 < slots.n && slots.off[s + 1] <= p) ++s;
+      sb = a.sbias + ((long long)s * a.B + b) * kDim;
+    }
+#pragma unroll
+    for (int jh = 0; jh < 2; ++jh) {
+      const int c = jh * 64 + tx * 4;
+      float o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float v = acc[i][jh * 4 + j];
+        if (a.bias) v += __ldg(a.bias + c + j);
+        if (sb) v += __ldg(sb + c + j);
+        if (a.conv_epilogue) {
+          v = fmaxf(v, 0.f);
+          v = fmaxf(v + load_act(a.in, a.in_bf16, r * kDim + c + j), 0.f);
+        }
+        o[j] = v;
+      }
+      if (a.out_bf16) {
+        uint2 q = make_uint2(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]));
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(a.out) + dst * kDim + c) = q;
+      } else {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + dst * kDim + c) = make_float4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+}
+
+int32_t tcn_forward_f32(const void* xe, int xe_dtype, const float* w_in_x, const float* sbias,
+                        const float* const* conv_w, const float* const* conv_b, int n_levels, int K,
+                        const SlotTable& slots, int B, int T, const int* out_row, void* hout, int hout_dtype,
+                        float* scratch, cudaStream_t st) {
+  const long long R = (long long)B * T;
+  const int grid = ceil_div(R, kTM);
+  float* buf[2] = {scratch, scratch + R * kDim};
+  LevelArgs a{};
+  a.R = R; a.T = T; a.B = B;
+  // in-projection: K = 1, no bias, per-sequence bias = state half of the concat (model_hier.py:54-55)
+  a.in = xe; a.in_bf16 = (xe_dtype == HTCN_BF16);
+  a.w = w_in_x; a.bias = nullptr; a.sbias = sbias; a.K = 1; a.dil = 1; a.conv_epilogue = 0;
+  const bool last0 = (n_levels == 0);
+  a.out = last0 ? hout : (void*)buf[0];
+  a.out_row = last0 ? out_row : nullptr;
+  a.out_bf16 = last0 ? (hout_dtype == HTCN_BF16) : 0;
+  k2_level_f32<<<grid, kK2Threads, 0, st>>>(a, slots);
+  HTCN_LAUNCH_CHECK("k2_level_f32(in-proj)");
+  for (int l = 0; l < n_levels; ++l) {
+    const bool last = (l == n_levels - 1);
+    a.in = buf[l & 1]; a.in_bf16 = 0;
+    a.w = conv_w[l]; a.bias = conv_b[l]; a.sbias = nullptr; a.K = K; a.dil = 1 << l; a.conv_epilogue = 1;
+    a.out = last ? hout : (void*)buf[(l + 1) & 1];
+    a.out_row = last ? out_row : nullptr;
+    a.out_bf16 = last ? (hout_dtype == HTCN_BF16) : 0;
+    k2_level_f32<<<grid, kK2Threads, 0, st>>>(a, slots);
+    HTCN_LAUNCH_CHECK("k2_level_f32(conv)");
+  }
+  return HTCN_OK;
+}
+
+int32_t tcn_forward_bf16(const void* xe, int xe_dtype, const float* w_in_x, const float* sbias,
+                         const float* const* conv_w, const float* const* conv_b, int n_levels, int K,
+                         const SlotTable& slots, int B, int T, const int* out_row, void* hout, int hout_dtype,
+                         float* scratch, cudaStream_t st);
+
+}  // namespace htcn
+
+extern "C" int32_t htcn_tcn_forward(const void* xe, int32_t xe_dtype, int32_t precision, const float* w_in_x,
+                                    const float* sbias, const float* const* conv_w_host,
+                                    const float* const* conv_b_host, int32_t n_levels, int32_t kernel_size,
+                                    const int32_t* slot_off_host, int32_t B, int32_t T, int32_t S,
+                                    const int32_t* out_row, void* hout, int32_t hout_dtype, float* scratch,
+                                    void* stream) {
+  using namespace htcn;
+  HTCN_REQUIRE(xe && w_in_x && hout && slot_off_host, "tcn_forward: NULL pointer");
+  HTCN_REQUIRE(B > 0 && T > 0 && S > 0 && S <= HTCN_MAX_SLOTS, "tcn_forward: B=%d T=%d S=%d", B, T, S);
+  HTCN_REQUIRE(n_levels >= 0 && n_levels <= HTCN_MAX_LEVELS, "tcn_forward: n_levels=%d", n_levels);
+  HTCN_REQUIRE(kernel_size >= 1 && kernel_size <= 8, "tcn_forward: kernel_size=%d", kernel_size);
+  HTCN_REQUIRE((xe_dtype == HTCN_F32 || xe_dtype == HTCN_BF16) && (hout_dtype == HTCN_F32 || hout_dtype == HTCN_BF16),
+               "tcn_forward: bad dtype");
+  HTCN_REQUIRE(n_levels == 0 || (conv_w_host && conv_b_host), "tcn_forward: conv weights NULL");
+  SlotTable slots;
+  slots.n = S;
+  for (int i = 0; i <= S; ++i) slots.off[i] = slot_off_host[i];
+  HTCN_REQUIRE(slots.off[0] == 0 && slots.off[S] == T, "tcn_forward: slot_off does not span T");
+  if (precision == HTCN_F32) {
+    HTCN_REQUIRE(scratch || n_levels == 0, "tcn_forward: f32 tier needs scratch");
+    return tcn_forward_f32(xe, xe_dtype, w_in_x, sbias, conv_w_host, conv_b_host, n_levels, kernel_size, slots,
+                           B, T, out_row, hout, hout_dtype, scratch, as_stream(stream));
+  }
+  if (precision == HTCN_BF16)
+    return tcn_forward_bf16(xe, xe_dtype, w_in_x, sbias, conv_w_host, conv_b_host, n_levels, kernel_size, slots, B,
+                            T, out_row, hout, hout_dtype, scratch, as_stream(stream));
+  set_error("tcn_forward: precision %d", precision);
+  return HTCN_ERR_INVALID;
+}

@@ -1,0 +1,277 @@
+// K4 entry points (dispatch to the fp32 FFMA tier or the bf16 tcgen05 tier) and the small
+// finishing kernels: W_out layout preparation, partial merge (CE / rank), top-k merge, and the
+// masked two-level means of model.py:111-117 / loss.py:190-219.
+#include "common.cuh"
+
+namespace htcn {
+
+int32_t score_f32(const ScoreArgs& a, cudaStream_t st);
+int32_t target_logit_f32(const float* hout, const float* wt, const float* b_out, const int* y_id, int Q,
+                         int n_items, int n0, float* zy, cudaStream_t st);
+// bf16 tier (k4_score_bf16.cu)
+int32_t score_bf16(const ScoreArgs& a, cudaStream_t st);
+int32_t target_logit_bf16(const void* hout, const void* wt, const float* b_out, const int* y_id, int Q,
+                          int n_items, int n0, float* zy, cudaStream_t st);
+
+// ---- W_out [128, N] f32 -> W_out^T [N, 128] f32 | bf16 (32x32 smem transpose) ----------------
+template <bool kBf16>
+__global__ void prepare_wout_kernel(const float* __restrict__ w, int N, void* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int n = n0 + tx;
+    tile[i][tx] = (n < N) ? w[(long long)(c0 + i) * N + n] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int n = n0 + i;
+    if (n < N) {
+      const float v = tile[tx][i];
+      if (kBf16) reinterpret_cast<__nv_bfloat16*>(out)[(long long)n * kDim + c0 + tx] = __float2bfloat16_rn(v);
+      else reinterpret_cast<float*>(out)[(long long)n * kDim + c0 + tx] = v;
+    }
+  }
+}
+
+// ---- full logits for small catalogs (the tensor the reference materialises) ---------------------
+__global__ void score_logits_kernel(const void* __restrict__ hout, int h_bf16, int Q, const void* __restrict__ wt,
+                                    int w_bf16, const float* __restrict__ b_out, int n_items,
+                                    float* __restrict__ logits) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)Q * n_items) return;
+  const int q = (int)(i / n_items), j = (int)(i % n_items);
+  float acc = 0.f;
+  for (int k = 0; k < kDim; ++k) {
+    const float a = h_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(hout)[(long long)q * kDim + k])
+                           : reinterpret_cast<const float*>(hout)[(long long)q * kDim + k];
+    const float b = w_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(wt)[(long long)j * kDim + k])
+                           : reinterpret_cast<const float*>(wt)[(long long)j * kDim + k];
+    acc = fmaf(a, b, acc);
+  }
+  logits[i] = acc + b_out[j];
+}
+
+// ---- merge CE / rank partials -----------------------------------------------------------------
+__global__ void score_finish_kernel(const float* __restrict__ pm, const float* __restrict__ ps,
+                                    const int* __restrict__ pc, int n_part, int Q, const int* __restrict__ y_id,
+                                    const float* __restrict__ zy, float* __restrict__ loss_row,
+                                    float* __restrict__ rank_row) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= Q) return;
+  if (loss_row) {
+    float M = -INFINITY;
+    for (int p = 0; p < n_part; ++p) M = fmaxf(M, pm[(long long)p * Q + q]);
+    float s = 0.f;
+    for (int p = 0; p < n_part; ++p) s += ps[(long long)p * Q + q] * expf(pm[(long long)p * Q + q] - M);
+    const bool valid = !y_id || y_id[q] > 0;       // id 0: the label row is all zero -> loss 0
+    loss_row[q] = valid ? (M + logf(s)) - zy[q] : 0.f;
+  }
+  if (rank_row) {
+    int c = 0;
+    for (int p = 0; p < n_part; ++p) c += pc[(long long)p * Q + q];
+    rank_row[q] = (float)c;
+  }
+}
+
+// ---- top-k merge: one CTA per row, rank-by-counting over the n_part*k candidates ----------------
+// order: score desc, index asc (tf.nn.top_k); empty slots (idx < 0) sort last.
+__global__ void __launch_bounds__(128)
+topk_merge_kernel(const float* __restrict__ pv, const int* __restrict__ pi, int n_part, int Q, int k,
+                  float* __restrict__ ov, int* __restrict__ oi) {
+  extern __shared__ float sm[];
+  const int n = n_part * k;
+  float* v = sm;
+  int* id = reinterpret_cast<int*>(sm + n);
+  const int q = blockIdx.x;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int p = i / k, s = i % k;
+    const long long o = ((long long)p * Q + q) * k + s;
+    const int ii = pi[o];
+    id[i] = ii < 0 ? 0x7fffffff : ii;
+    v[i] = ii < 0 ? -INFINITY : pv[o];
+  }
+  for (int i = threadIdx.x; i < k; i += blockDim.x) {   // default fill (fewer than k candidates)
+    ov[(long long)q * k + i] = -INFINITY;
+    oi[(long long)q * k + i] = -1;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float vi = v[i];
+    const int ii = id[i];
+    if (ii == 0x7fffffff) continue;
+    int pos = 0;
+    for (int j = 0; j < n; ++j) {
+      const float vj = v[j];
+      const int ij = id[j];
+      pos += (vj > vi || (vj == vi && ij < ii)) ? 1 : 0;
+    }
+    if (pos < k) {
+      ov[(long long)q * k + pos] = vi;
+      oi[(long long)q * k + pos] = ii;
+    }
+  }
+}
+
+// ---- masked two-level means (single CTA, fixed summation order -> deterministic) ---------------
+__global__ void __launch_bounds__(1024)
+loss_metrics_reduce_kernel(const float* __restrict__ loss_row, const float* __restrict__ rank_row,
+                           const int* __restrict__ row_of, const int* __restrict__ y_id, int B, int T,
+                           int item_num, float* __restrict__ loss_bt, float* __restrict__ ranks,
+                           float* __restrict__ ranks_float, float* __restrict__ scalars) {
+  __shared__ float red[8][1024];
+  float part[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) part[i] = 0.f;
+  const float fN = (float)item_num;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    float s_loss = 0.f, s_r1 = 0.f, s_r5 = 0.f, s_r10 = 0.f, s_rr = 0.f, s_rf = 0.f, n = 0.f;
+    for (int t = 0; t < T; ++t) {
+      const long long i = (long long)b * T + t;
+      const int row = row_of ? row_of[i] : (int)i;
+      const bool m = y_id[i] > 0 && row >= 0;          // mask_y = sign(y_id)  (model.py:62)
+      float l = 0.f, rk = 0.f, rf = 0.f;
+      if (m) {
+        l = loss_row ? loss_row[row] : 0.f;
+        rk = rank_row ? rank_row[row] : 0.f;
+        rf = rk / fN;                                   // loss.py:190
+        s_loss += l;
+        s_rf += rf;
+        s_rr += 1.0f / (1.0f + rk);                     // loss.py:191
+        s_r1 += (rk <= 0.f) ? 1.f : 0.f;                // loss.py:194-196
+        s_r5 += (rk <= 4.f) ? 1.f : 0.f;
+        s_r10 += (rk <= 9.f) ? 1.f : 0.f;
+        n += 1.f;
+      }
+      if (loss_bt) loss_bt[i] = l;
+      if (ranks) ranks[i] = rk;
+      if (ranks_float) ranks_float[i] = rf;
+    }
+    const float act = n + 1e-6f;                        // model.py:114
+    part[0] += s_loss / act;                            // model.py:116
+    part[1] += s_r1 / act;
+    part[2] += s_r5 / act;
+    part[3] += s_r10 / act;
+    part[4] += s_rr / act;
+    part[5] += s_rf / act;
+    part[6] += (n > 0.f) ? 1.f : 0.f;                   // user_count (model.py:113)
+    part[7] += n;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[i][threadIdx.x] = part[i];
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) red[i][threadIdx.x] += red[i][threadIdx.x + s];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const float uc = red[6][0];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) scalars[i] = red[i][0] / uc;   // model.py:117, loss.py:215-219
+    scalars[6] = uc;
+    scalars[7] = red[7][0];
+  }
+}
+
+}  // namespace htcn
+
+using namespace htcn;
+
+extern "C" int32_t htcn_prepare_wout(const float* w_out, int32_t N, void* w_out_t, int32_t dtype, void* stream) {
+  HTCN_REQUIRE(w_out && w_out_t && N > 0, "prepare_wout: bad args");
+  dim3 grid(ceil_div(N, 32), kDim / 32), block(32, 8);
+  if (dtype == HTCN_BF16) prepare_wout_kernel<true><<<grid, block, 0, as_stream(stream)>>>(w_out, N, w_out_t);
+  else if (dtype == HTCN_F32) prepare_wout_kernel<false><<<grid, block, 0, as_stream(stream)>>>(w_out, N, w_out_t);
+  else HTCN_REQUIRE(false, "prepare_wout: dtype %d", dtype);
+  HTCN_LAUNCH_CHECK("prepare_wout");
+  return HTCN_OK;
+}
+
+extern "C" int32_t htcn_score_logits(const void* hout, int32_t hout_dtype, int32_t Q, const void* w_out_t,
+                                     int32_t w_dtype, const float* b_out, int32_t n_items, float* logits,
+                                     void* stream) {
+  HTCN_REQUIRE(hout && w_out_t && b_out && logits && Q > 0 && n_items > 0, "score_logits: bad args");
+  const long long n = (long long)Q * n_items;
+  score_logits_kernel<<<ceil_div(n, 256), 256, 0, as_stream(stream)>>>(hout, hout_dtype == HTCN_BF16, Q, w_out_t,
+                                                                      w_dtype == HTCN_BF16, b_out, n_items, logits);
+  HTCN_LAUNCH_CHECK("score_logits");
+  return HTCN_OK;
+}
+
+extern "C" int32_t htcn_target_logit(const void* hout, int32_t precision, int32_t Q, const void* w_out_t,
+                                     const float* b_out, int32_t n_items, int32_t n0, const int32_t* y_id,
+                                     float* target_logit, void* stream) {
+  HTCN_REQUIRE(hout && w_out_t && b_out && y_id && target_logit && Q > 0 && n_items > 0, "target_logit: bad args");
+  if (precision == HTCN_F32)
+    return target_logit_f32((const float*)hout, (const float*)w_out_t, b_out, y_id, Q, n_items, n0, target_logit,
+                            as_stream(stream));
+  if (precision == HTCN_BF16)
+    return target_logit_bf16(hout, w_out_t, b_out, y_id, Q, n_items, n0, target_logit, as_stream(stream));
+  HTCN_REQUIRE(false, "target_logit: precision %d", precision);
+}
+
+extern "C" int32_t htcn_score_ce_rank_topk(const void* hout, int32_t precision, int32_t Q, const void* w_out_t,
+                                           const float* b_out, int32_t n_items, int32_t n0, const int32_t* y_id,
+                                           float* target_logit, int32_t have_target, uint32_t flags, int32_t k,
+                                           int32_t n_split, float* part_max, float* part_sum, int32_t* part_cnt,
+                                           float* topk_val, int32_t* topk_idx, void* stream) {
+  HTCN_REQUIRE(hout && w_out_t && b_out && Q > 0 && n_items > 0 && n_split >= 1, "score: bad args");
+  HTCN_REQUIRE(flags != 0 && (flags & ~7u) == 0, "score: flags 0x%x", flags);
+  const bool need_t = flags & (HTCN_SCORE_CE | HTCN_SCORE_RANK);
+  HTCN_REQUIRE(!need_t || (y_id && target_logit), "score: CE/RANK need y_id and target_logit");
+  HTCN_REQUIRE(!(flags & HTCN_SCORE_CE) || (part_max && part_sum), "score: CE partial buffers NULL");
+  HTCN_REQUIRE(!(flags & HTCN_SCORE_RANK) || part_cnt, "score: RANK partial buffer NULL");
+  HTCN_REQUIRE(!(flags & HTCN_SCORE_TOPK) || (topk_val && topk_idx && k >= 1 && k <= HTCN_MAX_TOPK),
+               "score: TOPK buffers NULL or k=%d out of [1,%d]", k, HTCN_MAX_TOPK);
+  const int n_tiles = (n_items + 63) / 64;
+  HTCN_REQUIRE(n_split <= n_tiles, "score: n_split=%d exceeds the number of 64-item tiles (%d)", n_split, n_tiles);
+  cudaStream_t st = as_stream(stream);
+  if (need_t && !have_target) {
+    int32_t rc = htcn_target_logit(hout, precision, Q, w_out_t, b_out, n_items, n0, y_id, target_logit, stream);
+    if (rc) return rc;
+  }
+  ScoreArgs a{hout, w_out_t, b_out, y_id, target_logit, part_max, part_sum, part_cnt, topk_val, topk_idx,
+              Q, n_items, n0, k, n_split, flags};
+  if (precision == HTCN_F32) {
+    return score_f32(a, st);
+  }
+  if (precision == HTCN_BF16) return score_bf16(a, st);
+  HTCN_REQUIRE(false, "score: precision %d", precision);
+}
+
+extern "C" int32_t htcn_score_finish(const float* part_max, const float* part_sum, const int32_t* part_cnt,
+                                     int32_t n_part, int32_t Q, const int32_t* y_id, const float* target_logit,
+                                     float* loss_row, float* rank_row, void* stream) {
+  HTCN_REQUIRE(Q > 0 && n_part >= 1, "score_finish: bad sizes");
+  HTCN_REQUIRE(!loss_row || (part_max && part_sum && target_logit), "score_finish: CE inputs NULL");
+  HTCN_REQUIRE(!rank_row || part_cnt, "score_finish: rank input NULL");
+  score_finish_kernel<<<ceil_div(Q, 256), 256, 0, as_stream(stream)>>>(part_max, part_sum, part_cnt, n_part, Q,
+                                                                      y_id, target_logit, loss_row, rank_row);
+  HTCN_LAUNCH_CHECK("score_finish");
+  return HTCN_OK;
+}
+
+extern "C" int32_t htcn_topk_merge(const float* part_val, const int32_t* part_idx, int32_t n_part, int32_t Q,
+                                   int32_t k, float* out_val, int32_t* out_idx, void* stream) {
+  HTCN_REQUIRE(part_val && part_idx && out_val && out_idx && n_part >= 1 && Q > 0 && k >= 1, "topk_merge: bad args");
+  const size_t smem = (size_t)n_part * k * 8;
+  HTCN_REQUIRE(smem <= 200 * 1024, "topk_merge: n_part*k=%d candidates exceed shared memory", n_part * k);
+  HTCN_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  topk_merge_kernel<<<Q, 128, smem, as_stream(stream)>>>(part_val, part_idx, n_part, Q, k, out_val, out_idx);
+  HTCN_LAUNCH_CHECK("topk_merge");
+  return HTCN_OK;
+}
+
+extern "C" int32_t htcn_loss_metrics_reduce(const float* loss_row, const float* rank_row, const int32_t* row_of,
+                                            const int32_t* y_id, int32_t B, int32_t T, int32_t item_num,
+                                            float* loss_bt, float* ranks, float* ranks_float, float* scalars,
+                                            void* stream) {
+  HTCN_REQUIRE(y_id && scalars && B > 0 && T > 0 && item_num > 0, "loss_metrics_reduce: bad args");
+  loss_metrics_reduce_kernel<<<1, 1024, 0, as_stream(stream)>>>(loss_row, rank_row, row_of, y_id, B, T, item_num,
+                                                               loss_bt, ranks, ranks_float, scalars);
+  HTCN_LAUNCH_CHECK("loss_metrics_reduce");
+  return HTCN_OK;
+}

@@ -1,0 +1,96 @@
+// Sampled ranking losses of reference loss.py:22-71 (nce / hinge_sigmoid / hinge_logsigmoid /
+// hinge_linear / bpr).  pred [Q,128] is l2-normalised (tf.nn.l2_normalize: x * rsqrt(max(sum x^2, 1e-12)))
+// and scored by inner product against the positive row and k negative rows of `table`.
+// One warp per query row: 1 + k gathered 512 B rows (K1-style 128-bit loads), warp-shuffle dots.
+#include "common.cuh"
+
+namespace htcn {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float log_sigmoid(float x) {   // stable log(sigmoid(x))
+  return fminf(x, 0.f) - log1pf(expf(-fabsf(x)));
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+template <bool kBf16>
+__global__ void __launch_bounds__(256)
+sampled_loss_kernel(const void* __restrict__ pred, int Q, const float4* __restrict__ table,
+                    const int* __restrict__ pos_id, const int* __restrict__ neg_id, int k, int kind,
+                    float delta, float nce_weight, float* __restrict__ loss_row) {
+  const int lane = threadIdx.x & 31;
+  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (q >= Q) return;
+  const int pos = pos_id[q];
+  if (pos <= 0) {
+    if (lane == 0) loss_row[q] = 0.f;
+    return;
+  }
+  float4 p;
+  if (kBf16) {
+    const uint2 u = reinterpret_cast<const uint2*>(pred)[(long long)q * 32 + lane];
+    p = make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
+  } else {
+    p = reinterpret_cast<const float4*>(pred)[(long long)q * 32 + lane];
+  }
+  const float ss = warp_sum(p.x * p.x + p.y * p.y + p.z * p.z + p.w * p.w);
+  const float inv = rsqrtf(fmaxf(ss, 1e-12f));
+  p.x *= inv; p.y *= inv; p.z *= inv; p.w *= inv;
+  const float4 yp = ldg_nc_f4(table + (long long)pos * 32 + lane);
+  const float inner = warp_sum(p.x * yp.x + p.y * yp.y + p.z * yp.z + p.w * yp.w);
+  float acc = 0.f;
+  for (int j0 = 0; j0 < k; j0 += 4) {
+    float4 v[4];
+    int id[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      id[i] = (j0 + i < k) ? __ldg(neg_id + (long long)q * k + j0 + i) : -1;
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (id[i] > 0) v[i] = ldg_nc_f4(table + (long long)id[i] * 32 + lane);   // id 0 -> zero row
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (id[i] < 0) continue;
+      const float s = warp_sum(p.x * v[i].x + p.y * v[i].y + p.z * v[i].z + p.w * v[i].w);
+      switch (kind) {
+        case HTCN_LOSS_NCE: acc += log_sigmoid(-s); break;                                           // :29
+        case HTCN_LOSS_HINGE_SIGMOID: acc += fmaxf(sigmoidf_(s) - sigmoidf_(inner) + delta, 0.f); break;     // :37-40
+        case HTCN_LOSS_HINGE_LOGSIGMOID: acc += fmaxf(log_sigmoid(s) - log_sigmoid(inner) + delta, 0.f); break;  // :47-50
+        case HTCN_LOSS_HINGE_LINEAR: acc += fmaxf(s - inner + delta, 0.f); break;                    // :57-60
+        case HTCN_LOSS_BPR: acc += log_sigmoid(sigmoidf_(inner) - sigmoidf_(s)); break;              // :65-70
+      }
+    }
+  }
+  if (lane == 0) {
+    float out;
+    if (kind == HTCN_LOSS_NCE) out = -log_sigmoid(inner) - acc / (float)k * nce_weight;             // :31
+    else if (kind == HTCN_LOSS_BPR) out = -acc / (float)k;
+    else out = acc / (float)k;
+    loss_row[q] = out;
+  }
+}
+
+}  // namespace htcn
+
+extern "C" int32_t htcn_sampled_rank_loss(const void* pred, int32_t precision, int32_t Q, const float* table,
+                                          const int32_t* pos_id, const int32_t* neg_id, int32_t k,
+                                          int32_t loss_kind, float hinge_delta, float nce_weight,
+                                          float* loss_row, void* stream) {
+  using namespace htcn;
+  HTCN_REQUIRE(pred && table && pos_id && neg_id && loss_row && Q > 0 && k > 0, "sampled_rank_loss: bad args");
+  HTCN_REQUIRE(loss_kind >= HTCN_LOSS_NCE && loss_kind <= HTCN_LOSS_BPR, "sampled_rank_loss: kind %d", loss_kind);
+  const int grid = ceil_div(Q, 8);
+  if (precision == HTCN_BF16)
+    sampled_loss_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(pred, Q, (const float4*)table, pos_id, neg_id, k,
+                                                                  loss_kind, hinge_delta, nce_weight, loss_row);
+  else if (precision == HTCN_F32)
+    sampled_loss_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(pred, Q, (const float4*)table, pos_id, neg_id, k,
+                                                                   loss_kind, hinge_delta, nce_weight, loss_row);
+  else
+    HTCN_REQUIRE(false, "sampled_rank_loss: precision %d", precision);
+  HTCN_LAUNCH_CHECK("sampled_loss_kernel");
+  return HTCN_OK;
+}

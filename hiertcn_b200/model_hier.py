@@ -1,0 +1,365 @@
+"""Host-side mirror of the reference's model surface for the hot path.
+
+    reference                                   here
+    ---------------------------------------     -------------------------------------------------
+    model_hier(args,x,y,mask,state,...)          model_hier(...)  -> (CatalogScores, state)
+      (model_hier.py:21-94)                      HierTCN.build / forward / loss / step
+    model_tcn(args,x,...) (model_tcn.py:13-44)   model_tcn(...)
+    sess.run([loss,state,ranks_float,...])       HierTCN.step(x_list,y_list,mask_list,state)
+      (run_hier_xing.py:145-149,301-302)
+
+PyTorch is used for device memory, streams and pinned staging only; all arithmetic is done by the
+sm_100a kernels behind the C ABI (hiertcn_b200/_cabi.py -> libhtcn.so).  There is no CPU path: without
+the library or without a CUDA device every entry point raises.
+
+Execution order (the GRU input is the teacher-forced mean of the session's true items,
+so the S-step recurrence is hoisted out of the session loop):
+
+    K1 gather+meanpool -> K3 GRU over sessions (+ state half of the in-projection)
+       -> K2 in-projection + causal conv stack -> K4 catalog scoring with fused CE / rank / top-k
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from . import _cabi as cabi
+from .data_loader import pack_batch
+from .weights import hier_weight_shapes, init_weights
+
+D = 128
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise cabi.HtcnError("hiertcn_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return torch
+
+
+class CatalogScores:
+    """Lazy stand-in for the reference's ``pred_all [B,T,N]`` (model_hier.py:76-79).  The logits are
+    never written to HBM; losses / ranks / top-k are produced by streaming reductions on demand.
+    ``materialize()`` builds the dense tensor for small catalogs (tests, debugging)."""
+
+    def __init__(self, model, hout, Q, row_of, y_rows, y_id, B, T):
+        self.model, self.hout, self.Q = model, hout, Q
+        self.row_of, self.y_rows, self.y_id, self.B, self.T = row_of, y_rows, y_id, B, T
+        self._cache = {}
+
+    @property
+    def shape(self):
+        return (self.B, self.T, self.model.N)
+
+    def materialize(self):
+        """[B,T,N] fp32 numpy; masked positions are zero rows like ``pred *= mask_y`` (model.py:105)."""
+        torch = _torch()
+        m = self.model
+        out = np.zeros((self.B * self.T, m.N), dtype=np.float32)
+        if self.Q:
+            lg = torch.empty((self.Q, m.N), dtype=torch.float32, device=m.device)
+            cabi.call("htcn_score_logits", self.hout.data_ptr(), m.act_dtype, self.Q, m.wt.data_ptr(), m.act_dtype,
+                      m.b_out.data_ptr(), m.N, lg.data_ptr(), m.stream_ptr())
+            rows = self.row_of.cpu().numpy()
+            out[rows >= 0] = lg.cpu().numpy()[rows[rows >= 0]]
+        return out.reshape(self.B, self.T, m.N)
+
+
+class HierTCN:
+    """HierTCN forward + catalog scoring on one B200.
+
+    args: namespace with the reference's hyper-parameter names (hiertcn_b200.args.make_args()).
+    weights: dict keyed by the TF variable names of SURVEY.md A.6 (hiertcn_b200.weights); random init if None.
+    """
+
+    def __init__(self, args, weights=None, device=None, precision=None, seed=1234):
+        self.args = args
+        self.precision = precision or getattr(args, "precision", "bf16")
+        if self.precision not in ("f32", "bf16"):
+            raise ValueError("precision must be 'f32' or 'bf16'")
+        if args.model_type != "hier" or args.model_low_type != "tcn":
+            raise NotImplementedError("only model_type='hier' with model_low_type='tcn' is the hot path")
+        if list(args.tcn_channel) != [128] * len(args.tcn_channel) or args.hidden_dim != 128:
+            raise NotImplementedError("the sm_100a kernels are built for C = H = 128 (reference defaults)")
+        if getattr(args, "emb_dim", 128) > 128:
+            raise NotImplementedError("emb_dim > 128")
+        for flag in ("has_batchnorm", "has_layernorm", "has_gap", "has_impression", "l2_normalize"):
+            if getattr(args, flag, False):
+                raise NotImplementedError("%s is outside the hot path (SURVEY.md A.8)" % flag)
+        if float(args.dropout) != 0.0:
+            raise NotImplementedError("dropout > 0 (reference default 0.0, args.py:64)")
+        self.N = int(args.item_num)
+        self.G = int(args.num_layer)
+        self.K = int(args.kernel_size)
+        self.n_levels = len(args.tcn_channel)
+        self.host_weights = weights
+        self.seed = seed
+        self.device = device
+        self.built = False
+        self._ws = {}
+
+    # ------------------------------------------------------------------ build
+    def build(self):
+        torch = _torch()
+        cabi.load()
+        if self.device is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        if not cabi.load().htcn_device_ok():
+            raise cabi.HtcnError("current CUDA device is not compute capability 10.x (B200)")
+        a = self.args
+        w = self.host_weights
+        if w is None:
+            w = init_weights(hier_weight_shapes(self.N, a.hidden_dim, self.G, tuple(a.tcn_channel), self.K,
+                                                getattr(a, "emb_dim", 128)), seed=self.seed)
+        from .weights import fold_weightnorm
+        w = fold_weightnorm(w)
+        ed = w["hier/emb/kernel"].shape[1]
+        dev = self.device
+
+        def up(x):
+            return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(dev)
+
+        E = np.zeros((self.N, D), np.float32)           # emb_dim < 128 is zero-padded (same math)
+        E[:, :ed] = w["hier/emb/kernel"]
+        be = np.zeros(D, np.float32)
+        be[:ed] = w["hier/emb/bias"]
+        w_in = w["hier/tcn/emb/kernel"]                 # [ed + G*H, 128]
+        w_in_x = np.zeros((D, 128), np.float32)
+        w_in_x[:ed] = w_in[:ed]
+        self.E, self.b_emb = up(E), up(be)
+        self.w_in_x, self.w_in_state = up(w_in_x), up(w_in[ed:])
+        self.conv_w = [up(w[f"hier/tcn/temporal_conv_net/tblock_{l}/conv1/kernel"]) for l in range(self.n_levels)]
+        self.conv_b = [up(w[f"hier/tcn/temporal_conv_net/tblock_{l}/conv1/bias"]) for l in range(self.n_levels)]
+        self.gru = []
+        for g in range(self.G):
+            p = f"hier/multi_rnn_cell/cell_{g}/gru_cell"
+            gw, cw = w[p + "/gates/kernel"], w[p + "/candidate/kernel"]
+            if g == 0 and ed < D:                       # pad the input rows of layer 0
+                pad = np.zeros((D - ed, gw.shape[1]), np.float32)
+                gw = np.concatenate([gw[:ed], pad, gw[ed:]], 0)
+                pad = np.zeros((D - ed, cw.shape[1]), np.float32)
+                cw = np.concatenate([cw[:ed], pad, cw[ed:]], 0)
+            self.gru.append((up(gw), up(w[p + "/gates/bias"]), up(cw), up(w[p + "/candidate/bias"])))
+        self.b_out = up(w["hier/tcn/dense/bias"])
+        w_out = up(w["hier/tcn/dense/kernel"])          # [128, N] TF layout
+        self.act_dtype = cabi.HTCN_BF16 if self.precision == "bf16" else cabi.HTCN_F32
+        tdt = torch.bfloat16 if self.precision == "bf16" else torch.float32
+        self.act_torch_dtype = tdt
+        self.wt = torch.empty((self.N, D), dtype=tdt, device=dev)          # W_out^T, K-major rows
+        cabi.call("htcn_prepare_wout", w_out.data_ptr(), self.N, self.wt.data_ptr(), self.act_dtype, self.stream_ptr())
+        self.wt_f32 = self.wt if self.precision == "f32" else None
+        torch.cuda.synchronize(dev)
+        del w_out
+        self._conv_w_pp = cabi.ptr_array([t.data_ptr() for t in self.conv_w])
+        self._conv_b_pp = cabi.ptr_array([t.data_ptr() for t in self.conv_b])
+        self._gru_pp = [cabi.ptr_array([l[i].data_ptr() for l in self.gru]) for i in range(4)]
+        self.built = True
+        return self
+
+    def stream_ptr(self):
+        return _torch().cuda.current_stream(self.device).cuda_stream
+
+    def _buf(self, name, shape, dtype):
+        torch = _torch()
+        t = self._ws.get(name)
+        n = int(np.prod(shape))
+        if t is None or t.dtype != dtype or t.numel() < n:
+            t = torch.empty(max(n, 1), dtype=dtype, device=self.device)
+            self._ws[name] = t
+        return t[:n].view(*shape) if n else t[:0]
+
+    # ------------------------------------------------------------------ host -> device staging
+    def stage(self, x_list, y_list, mask_list, state=None):
+        """Pack the reference batch layout (data_loader.dequeue) and copy it to the device.
+        Returns a dict of device tensors + host metadata; H2D bytes are in ['h2d_bytes']."""
+        torch = _torch()
+        pk = pack_batch(x_list, y_list, mask_list)
+        B, T = pk["x_id"].shape
+        S = len(x_list)
+        valid = pk["y_id"].reshape(-1) > 0
+        row_of = np.where(valid, np.cumsum(valid) - 1, -1).astype(np.int32)
+        Q = int(valid.sum())
+        y_rows = np.ascontiguousarray(pk["y_id"].reshape(-1)[valid])
+        if state is None:
+            state = np.zeros((B, self.G * 128), np.float32)
+        host = dict(x_id=pk["x_id"], y_id=pk["y_id"], mask=pk["mask"], row_of=row_of, y_rows=y_rows,
+                    state=np.ascontiguousarray(state, dtype=np.float32))
+        dev, nbytes = {}, 0
+        for k, v in host.items():
+            t = torch.from_numpy(v)
+            if v.size:
+                t = t.pin_memory()
+            dev[k] = t.to(self.device, non_blocking=True)
+            nbytes += v.nbytes
+        dev.update(B=B, T=T, S=S, Q=Q, slot_off=pk["slot_off"], h2d_bytes=nbytes)
+        return dev
+
+    # ------------------------------------------------------------------ forward (K1 -> K3 -> K2)
+    def forward(self, x_list=None, y_list=None, mask_list=None, state=None, staged=None):
+        """Hierarchical forward up to the user embeddings.  Returns (CatalogScores, state_out [B,G*H] device)."""
+        if not self.built:
+            self.build()
+        torch = _torch()
+        d = staged if staged is not None else self.stage(x_list, y_list, mask_list, state)
+        B, T, S, Q = d["B"], d["T"], d["S"], d["Q"]
+        st = self.stream_ptr()
+        f32 = torch.float32
+        slot_p, slot_keep = cabi.int_array(d["slot_off"])
+        xe = self._buf("xe", (B * T, D), self.act_torch_dtype)
+        yp = self._buf("yp", (S, B, D), f32)
+        cabi.call("htcn_gather_meanpool", self.E.data_ptr(), self.b_emb.data_ptr(), self.N, d["x_id"].data_ptr(),
+                  d["y_id"].data_ptr(), slot_p, B, T, S, xe.data_ptr(), self.act_dtype, yp.data_ptr(), st)
+        sbias = self._buf("sbias", (S, B, D), f32)
+        state_out = torch.empty((B, self.G * 128), dtype=f32, device=self.device)
+        cabi.call("htcn_gru_sessions", yp.data_ptr(), d["mask"].data_ptr(), d["state"].data_ptr(),
+                  self._gru_pp[0][0], self._gru_pp[1][0], self._gru_pp[2][0], self._gru_pp[3][0], self.G,
+                  self.w_in_state.data_ptr(), B, S, None, sbias.data_ptr(), state_out.data_ptr(), st)
+        hout = self._buf("hout", (max(Q, 1), D), self.act_torch_dtype)
+        k2_precision = self._k2_precision()
+        scratch = self._buf("k2_scratch", (2 * B * T, D), f32) if k2_precision == cabi.HTCN_F32 else None
+        cabi.call("htcn_tcn_forward", xe.data_ptr(), self.act_dtype, k2_precision, self.w_in_x.data_ptr(),
+                  sbias.data_ptr(), self._conv_w_pp[0], self._conv_b_pp[0], self.n_levels, self.K, slot_p, B, T, S,
+                  d["row_of"].data_ptr(), hout.data_ptr(), self.act_dtype,
+                  scratch.data_ptr() if scratch is not None else None, st)
+        del slot_keep
+        scores = CatalogScores(self, hout, Q, d["row_of"], d["y_rows"], d["y_id"], B, T)
+        return scores, state_out
+
+    def _k2_precision(self):
+        # the bf16 (tcgen05) conv stack is selected when the library provides it; until then the bf16 tier
+        # runs the fp32 FFMA conv stack on bf16 inputs/outputs (more accurate, slower)
+        return cabi.HTCN_BF16 if (self.precision == "bf16" and getattr(self, "k2_tcgen05", False)) else cabi.HTCN_F32
+
+    # ------------------------------------------------------------------ loss / metrics / top-k (K4)
+    def n_split_for(self, Q, n_items):
+        tiles_q = max(1, math.ceil(Q / 128))
+        want = math.ceil(2 * 148 / tiles_q)
+        return int(max(1, min(want, 32, max(1, n_items // 256))))
+
+    def score(self, scores: CatalogScores, ce=True, rank=True, topk=0):
+        """One streaming sweep over the catalog.  Returns dict of device tensors:
+        loss_row [Q], rank_row [Q] and, with topk, topk_val / topk_idx [Q,k]."""
+        torch = _torch()
+        Q = scores.Q
+        key = (ce, rank, topk)
+        if key in scores._cache:
+            return scores._cache[key]
+        out = {}
+        if Q == 0:
+            scores._cache[key] = out
+            return out
+        st = self.stream_ptr()
+        f32, i32 = torch.float32, torch.int32
+        flags = (cabi.SCORE_CE if ce else 0) | (cabi.SCORE_RANK if rank else 0) | (cabi.SCORE_TOPK if topk else 0)
+        ns = self.n_split_for(Q, self.N)
+        zy = self._buf("zy", (Q,), f32)
+        pm = self._buf("pm", (ns, Q), f32) if ce else None
+        ps = self._buf("ps", (ns, Q), f32) if ce else None
+        pc = self._buf("pc", (ns, Q), i32) if rank else None
+        tv = self._buf("tv", (ns, Q, topk), f32) if topk else None
+        ti = self._buf("ti", (ns, Q, topk), i32) if topk else None
+        P = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
+        cabi.call("htcn_score_ce_rank_topk", scores.hout.data_ptr(), self.act_dtype, Q, self.wt.data_ptr(),
+                  self.b_out.data_ptr(), self.N, 0, scores.y_rows.data_ptr(), zy.data_ptr(), 0, flags, topk, ns,
+                  P(pm), P(ps), P(pc), P(tv), P(ti), st)
+        if ce or rank:
+            loss_row = self._buf("loss_row", (Q,), f32) if ce else None
+            rank_row = self._buf("rank_row", (Q,), f32) if rank else None
+            cabi.call("htcn_score_finish", P(pm), P(ps), P(pc), ns, Q, scores.y_rows.data_ptr(), zy.data_ptr(),
+                      P(loss_row), P(rank_row), st)
+            out.update(loss_row=loss_row, rank_row=rank_row, target_logit=zy)
+        if topk:
+            ov = torch.empty((Q, topk), dtype=f32, device=self.device)
+            oi = torch.empty((Q, topk), dtype=i32, device=self.device)
+            cabi.call("htcn_topk_merge", tv.data_ptr(), ti.data_ptr(), ns, Q, topk, ov.data_ptr(), oi.data_ptr(), st)
+            out.update(topk_val=ov, topk_idx=oi)
+        scores._cache[key] = out
+        return out
+
+    def loss(self, scores: CatalogScores, metrics=True, per_position=False):
+        """Softmax-CE loss with the reference's two-level masked mean (model.py:105-117) and, with
+        ``metrics``, calc_metric_fast (loss.py:163-221).  Returns dict of device tensors:
+        scalars[8] = {loss, recall@1, recall@5, recall@10, mrr, mrp, user_count, n_valid} (+ [B,T] maps)."""
+        torch = _torch()
+        r = self.score(scores, ce=True, rank=metrics)
+        B, T = scores.B, scores.T
+        f32 = torch.float32
+        scalars = torch.empty(8, dtype=f32, device=self.device)
+        maps = {}
+        if per_position:
+            for n in ("loss_bt", "ranks", "ranks_float"):
+                maps[n] = torch.empty((B, T), dtype=f32, device=self.device)
+        P = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
+        cabi.call("htcn_loss_metrics_reduce", P(r.get("loss_row")), P(r.get("rank_row")), scores.row_of.data_ptr(),
+                  scores.y_id.data_ptr(), B, T, self.N, P(maps.get("loss_bt")), P(maps.get("ranks")),
+                  P(maps.get("ranks_float")), scalars.data_ptr(), self.stream_ptr())
+        return dict(scalars=scalars, **maps)
+
+    def sampled_loss(self, scores: CatalogScores, neg_ids, kind=None):
+        """Sampled ranking loss (reference loss.py:22-71) of the user embeddings against the rows of the
+        output table W_out^T: positive = the true next item, negatives = ``neg_ids [Q,k]`` (host or device)."""
+        torch = _torch()
+        a = self.args
+        kind = kind or a.loss
+        if kind not in cabi.LOSS_KINDS:
+            raise ValueError("sampled loss kind %r" % kind)
+        if self.wt_f32 is None:                  # gather table is fp32 in both tiers
+            self.wt_f32 = self.wt.float().contiguous()
+        neg = neg_ids if hasattr(neg_ids, "data_ptr") else torch.from_numpy(np.ascontiguousarray(neg_ids, np.int32)).to(self.device)
+        Q, k = neg.shape
+        assert Q == scores.Q
+        out = torch.empty(Q, dtype=torch.float32, device=self.device)
+        cabi.call("htcn_sampled_rank_loss", scores.hout.data_ptr(), self.act_dtype, Q, self.wt_f32.data_ptr(),
+                  scores.y_rows.data_ptr(), neg.data_ptr(), k, cabi.LOSS_KINDS[kind], float(a.hinge_delta),
+                  float(a.nce_weight), out.data_ptr(), self.stream_ptr())
+        return out
+
+    # ------------------------------------------------------------------ the reference's sess.run
+    def step(self, x_list, y_list, mask_list, state=None, metrics=True, per_position=False, topk=0):
+        """Host in, host out -- the call ``sess.run([loss, state, ranks_float, ...], feed_dict)`` of
+        run_hier_xing.py:145-149 maps to.  Includes the H2D of the batch and the D2H of the results."""
+        scores, state_out = self.forward(x_list, y_list, mask_list, state)
+        r = self.loss(scores, metrics=metrics, per_position=per_position)
+        out = {}
+        sc = r["scalars"].cpu().numpy()
+        out.update(loss=sc[0], recall1=sc[1], recall5=sc[2], recall10=sc[3], mrr=sc[4], mrp=sc[5],
+                   user_count=sc[6], n_valid=sc[7], state=state_out.cpu().numpy())
+        for n in ("loss_bt", "ranks", "ranks_float"):
+            if n in r:
+                out[n] = r[n].cpu().numpy()
+        if topk:
+            t = self.score(scores, ce=False, rank=False, topk=topk)
+            out["topk_val"] = t["topk_val"].cpu().numpy() if t else np.zeros((0, topk), np.float32)
+            out["topk_idx"] = t["topk_idx"].cpu().numpy() if t else np.zeros((0, topk), np.int32)
+            out["row_of"] = scores.row_of.cpu().numpy()
+        return out
+
+
+# ---------------------------------------------------------------------- functional surface
+_MODELS = {}
+
+
+def _model_for(args, weights, precision):
+    key = (id(weights), precision, int(args.item_num))
+    m = _MODELS.get(key)
+    if m is None:
+        m = HierTCN(args, weights, precision=precision).build()
+        _MODELS.clear()
+        _MODELS[key] = m
+    return m
+
+
+def model_hier(args, x, y, mask, state, x_gap=None, x_impression=None, name="hier", reuse=None, training=True,
+               weights=None, precision=None):
+    """Signature of reference model_hier.py:21: x, y are S-lists of id arrays [B, L_s] (the reference feeds
+    one-hot tensors built from these ids, model.py:59-61), mask an S-list of [B,1], state [B, G*H].
+    Returns (pred_all, state): pred_all is a lazy ``CatalogScores`` (call .materialize() for the dense
+    [B,T,N] tensor at small N); state is a numpy array."""
+    if x_gap is not None or x_impression is not None:
+        raise NotImplementedError("has_gap / has_impression are unreachable in the XING runner (SURVEY A.8 #12)")
+    if name != "hier":
+        raise NotImplementedError("variable scope other than 'hier'")
+    m = _model_for(args, weights, precision or getattr(args, "precision", "bf16"))
+    scores, state_out = m.forward(x, y, mask, state)
+    return scores, state_out.cpu().numpy()

@@ -1,0 +1,203 @@
+/*
+ * htcn.h -- C ABI of the B200-native HierTCN hot path (libhtcn.so, sm_100a).
+ *
+ * The reference (JiaxuanYou/HierTCN, TensorFlow 1.6) has NO plugin / operator / FFI interface: its
+ * only seams are Python call signatures and the feed_dict/fetch contract.  This
+ * header therefore DEFINES the boundary: one entry point per op group of the reference graph, each
+ * citing the reference code it replaces.  hiertcn_b200/_cabi.py binds it with ctypes; INTEGRATION.md
+ * shows the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative htcn_status; htcn_last_error() gives the
+ *     thread-local message.  No exceptions cross the boundary.
+ *   - the CALLER owns every buffer.  All data pointers are DEVICE pointers unless a name ends in
+ *     _host.  Nothing is allocated inside; nothing is retained after return.
+ *   - every call only ENQUEUES work on `stream` (a cudaStream_t passed as void*; NULL = default
+ *     stream) and is asynchronous with respect to the host.
+ *   - row-major, channels-last.  D (embedding width) = C (TCN channels) = H (GRU units) = 128, the
+ *     value the reference hard-codes (model_hier.py:50,85; model_tcn.py:35; args.py:51,56).
+ *   - ids are int32, 0 = null item (model.py:59-61).
+ *   - there is NO CPU fallback: on a machine without an sm_100 device every compute entry point
+ *     returns HTCN_ERR_CUDA.
+ */
+#ifndef HTCN_H_
+#define HTCN_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HTCN_ABI_VERSION 1
+#define HTCN_DIM 128          /* D = C = H */
+#define HTCN_MAX_SLOTS 64     /* S (args.max_session_num, default 10) */
+#define HTCN_MAX_LEVELS 8     /* TCN levels (len(args.tcn_channel)) */
+#define HTCN_MAX_GRU_LAYERS 4 /* args.num_layer */
+#define HTCN_MAX_TOPK 128
+
+typedef enum {
+  HTCN_OK = 0,
+  HTCN_ERR_INVALID = -1,      /* bad argument (null pointer, unsupported size)        */
+  HTCN_ERR_CUDA = -2,         /* CUDA runtime/driver error, message has the details   */
+  HTCN_ERR_UNSUPPORTED = -3   /* valid request this build does not implement          */
+} htcn_status;
+
+typedef enum { HTCN_F32 = 0, HTCN_BF16 = 1 } htcn_dtype;
+
+/* flags of htcn_score_ce_rank_topk */
+#define HTCN_SCORE_CE   1u    /* softmax cross-entropy partials            (loss.py:20-21)   */
+#define HTCN_SCORE_RANK 2u    /* strict-greater rank count                 (loss.py:179)     */
+#define HTCN_SCORE_TOPK 4u    /* per-row top-k (score desc, index asc)     (loss.py:120)     */
+
+/* loss kinds of htcn_sampled_rank_loss (reference loss.py:22-71) */
+typedef enum {
+  HTCN_LOSS_NCE = 0, HTCN_LOSS_HINGE_SIGMOID = 1, HTCN_LOSS_HINGE_LOGSIGMOID = 2,
+  HTCN_LOSS_HINGE_LINEAR = 3, HTCN_LOSS_BPR = 4
+} htcn_sampled_loss;
+
+int32_t htcn_abi_version(void);
+const char* htcn_last_error(void);
+/* 1 if the current device is compute capability 10.x, 0 otherwise (never errors) */
+int32_t htcn_device_ok(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * K1  embedding gather + session mean-pool.
+ * Replaces: tf.one_hot(id,N)*sign(id) (model.py:59-61) followed by dense(...,'emb') -- a
+ * [B*L,N]x[N,128] GEMM on a materialised one-hot (model_hier.py:50 -> customized_dense_layer.py:155-172)
+ * -- and the mean-pool + dense-with-bias of the true items (model_hier.py:83-85).
+ *   xe[b,p,:]  = E[x_id[b,p],:]  (id 0 -> zeros; bit-exact copy; optionally rounded to bf16)
+ *   yp[s,b,:]  = (sum_{p in slot s, y>0} E[y_id[b,p],:]) / n_{b,s} + emb_bias      (NaN if n == 0, like 0/0 in TF)
+ * x_id,y_id [B,T] int32; slot_off_host [S+1] int32 HOST array (slot s = columns slot_off[s]..slot_off[s+1]).
+ * xe may be NULL (skip the x gather) and yp may be NULL (skip the pool).
+ * ------------------------------------------------------------------------------------------- */
+int32_t htcn_gather_meanpool(const float* emb_table, const float* emb_bias, int32_t item_num,
+                             const int32_t* x_id, const int32_t* y_id, const int32_t* slot_off_host,
+                             int32_t B, int32_t T, int32_t S,
+                             void* xe, int32_t xe_dtype, float* yp, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K3  GRU over sessions (+ hoisted state half of the TCN in-projection).
+ * Replaces: S Python-unrolled calls of rnn.MultiRNNCell([GRUCell(H)]*G, state_is_tuple=False)
+ * (model_hier.py:30-37,91; formula customed_gru_cell.py:309-337, stacking :1050-1073, linear
+ * :1187-1197), the reset state *= mask[i] (model_hier.py:93) and the state columns of
+ * tile+concat+dense (model_hier.py:54-55 + model_tcn.py:35).
+ *   for s in 0..S-1:  state_pre[s] = state;  sbias[s] = state @ w_in_state;
+ *                     state = mask[s] * GRU_stack(yp[s], state)
+ * yp [S,B,128]; mask [S,B]; state_in [B,G*128]; gate_w[g] [(in+128),256] (r first, then u),
+ * gate_b[g] [256], cand_w[g] [(in+128),128], cand_b[g] [128]  (in = 128 for every layer);
+ * w_in_state [G*128,128] = rows D.. of hier/tcn/emb/kernel.
+ * Outputs: state_pre [S,B,G*128] (may be NULL), sbias [S,B,128] (may be NULL), state_out [B,G*128].
+ * ------------------------------------------------------------------------------------------- */
+int32_t htcn_gru_sessions(const float* yp, const float* mask, const float* state_in,
+                          const float* const* gate_w_host, const float* const* gate_b_host,
+                          const float* const* cand_w_host, const float* const* cand_b_host,
+                          int32_t num_layer, const float* w_in_state,
+                          int32_t B, int32_t S,
+                          float* state_pre, float* sbias, float* state_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K2  low-level TCN: in-projection + dilated causal conv residual stack.
+ * Replaces: model_tcn's dense(x,128,use_bias=False,'emb') (model_tcn.py:35) and
+ * TemporalConvNet -> TemporalBlock -> CausalConv1D (customized_tcn_cell.py:46-49,109-127,147-161;
+ * customized_convolution_layer.py:171-198): per level l, d = 2^l,
+ *   a = relu(b_l + sum_k h[t-(K-1-k)d] W_l[k]);  h' = relu(a + h)         (one conv per block)
+ * Rows are the flat [B*T] positions; a sequence is one (b, slot) run of slot_off[s+1]-slot_off[s]
+ * positions (for the single-level model_tcn: S = 1, T = L).
+ *   h0[b,p,:] = xe[b,p,:] @ w_in_x + sbias[slot(p), b, :]      (sbias may be NULL: plain model_tcn)
+ * xe [B,T,128] of xe_dtype (f32 | bf16); w_in_x [128,128] f32 (rows 0..D-1 of hier/tcn/emb/kernel);
+ * conv_w_host[l] -> [K,128,128] f32, conv_b_host[l] -> [128] f32 (HOST arrays of DEVICE pointers);
+ * slot_off_host [S+1] HOST array.
+ * precision: HTCN_F32 = FFMA tier (1e-4); HTCN_BF16 = tcgen05 tier (2e-2; operands rounded to bf16,
+ *   fp32 accumulate, level activations kept on chip).
+ * out_row [B*T] int32 or NULL: destination row of each position in hout (-1 = drop the row);
+ *   used to compact away padded positions before catalog scoring.
+ * hout [n_out_rows,128] of hout_dtype.  scratch: 2*B*T*128 floats (used by the f32 tier only, may be
+ *   NULL for the bf16 tier).
+ * ------------------------------------------------------------------------------------------- */
+int32_t htcn_tcn_forward(const void* xe, int32_t xe_dtype, int32_t precision,
+                         const float* w_in_x, const float* sbias,
+                         const float* const* conv_w_host, const float* const* conv_b_host,
+                         int32_t n_levels, int32_t kernel_size, const int32_t* slot_off_host,
+                         int32_t B, int32_t T, int32_t S,
+                         const int32_t* out_row, void* hout, int32_t hout_dtype, float* scratch,
+                         void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * weight preparation for K4 (one-time, at load): w_out [128,N] f32 (the TF layout of
+ * hier/tcn/dense/kernel, model_tcn.py:41) -> w_out_t [N,128] in f32 or bf16 (K-major rows).
+ * ------------------------------------------------------------------------------------------- */
+int32_t htcn_prepare_wout(const float* w_out, int32_t N, void* w_out_t, int32_t dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K4  full-catalog scoring with fused CE / rank / top-k epilogues.  Logits never reach HBM.
+ * Replaces: dense(pred, units=output_dim) (model_tcn.py:41) -> [B,T,N] logits,
+ * softmax_cross_entropy_with_logits (loss.py:20-21), calc_metric_fast's strict-greater rank
+ * (loss.py:179) and tf.nn.top_k ordering (loss.py:120).
+ *   z[q,j] = hout[q,:] . w_out_t[n0+j,:] + b_out[n0+j],   j in [0, n_items)   (one catalog shard)
+ * hout [Q,128] (f32 or bf16 per `precision`), w_out_t [n_items,128] same dtype, b_out [n_items] f32.
+ * y_id [Q] int32 GLOBAL target ids (needed for CE/RANK; may be NULL for TOPK only).
+ * target_logit [Q] f32: z[q, y_id[q]] -- INPUT when have_target != 0 (computed by the shard that
+ *   owns the id and exchanged by the caller), else computed here (requires the shard to own every id).
+ * n_split: number of catalog splits processed by separate CTAs (>=1); partial results per split:
+ *   part_max [n_split,Q], part_sum [n_split,Q]   sum_j exp(z - part_max)        (CE)
+ *   part_cnt [n_split,Q] int32                   #{j: z > target_logit}         (RANK)
+ *   topk_val [n_split,Q,k] f32, topk_idx [n_split,Q,k] int32 (global ids, unsorted; -1 = empty)  (TOPK)
+ * Merge them with htcn_score_finish / htcn_topk_merge (or exchange them across ranks first).
+ * ------------------------------------------------------------------------------------------- */
+int32_t htcn_score_ce_rank_topk(const void* hout, int32_t precision, int32_t Q,
+                                const void* w_out_t, const float* b_out, int32_t n_items, int32_t n0,
+                                const int32_t* y_id, float* target_logit, int32_t have_target,
+                                uint32_t flags, int32_t k, int32_t n_split,
+                                float* part_max, float* part_sum, int32_t* part_cnt,
+                                float* topk_val, int32_t* topk_idx, void* stream);
+
+/* full logits (small catalogs / debugging only -- this is the [B,T,N] tensor the reference materialises,
+ * model_hier.py:76-79): logits[q, j] = hout[q,:] . w_out_t[j,:] + b_out[j], fp32 fmaf chain over k in
+ * both tiers (bf16 operands are widened).  logits [Q, n_items] f32. */
+int32_t htcn_score_logits(const void* hout, int32_t hout_dtype, int32_t Q, const void* w_out_t,
+                          int32_t w_dtype, const float* b_out, int32_t n_items, float* logits, void* stream);
+
+/* target logits only: target_logit[q] = hout[q,:] . w_out_t[y_id[q]-n0,:] + b_out[y_id[q]-n0] when the
+ * shard [n0, n0+n_items) owns y_id[q], else the entry is left untouched (pre-fill with 0 and
+ * all-reduce-sum across shards).  Same arithmetic as the sweep of htcn_score_ce_rank_topk. */
+int32_t htcn_target_logit(const void* hout, int32_t precision, int32_t Q,
+                          const void* w_out_t, const float* b_out, int32_t n_items, int32_t n0,
+                          const int32_t* y_id, float* target_logit, void* stream);
+
+/* merge CE / rank partials of n_part (= splits x shards) parts:
+ *   loss_row[q] = log sum_j exp(z_j) - target_logit[q]   (0 where y_id == 0);  rank_row[q] = sum cnt */
+int32_t htcn_score_finish(const float* part_max, const float* part_sum, const int32_t* part_cnt,
+                          int32_t n_part, int32_t Q, const int32_t* y_id, const float* target_logit,
+                          float* loss_row, float* rank_row, void* stream);
+
+/* k-way merge of per-part top-k lists -> [Q,k] sorted by (score desc, index asc) [TF top_k order] */
+int32_t htcn_topk_merge(const float* part_val, const int32_t* part_idx, int32_t n_part, int32_t Q,
+                        int32_t k, float* out_val, int32_t* out_idx, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * masked two-level means of model.py:111-117 and loss.py:190-219.
+ * loss_row / rank_row [n_rows] are indexed through row_of [B*T] int32 (NULL = identity; -1 = padded
+ * position).  y_id [B,T].  Outputs: loss_bt, ranks, ranks_float [B,T] (masked, 0 at padding; any may be
+ * NULL) and scalars[8] = {loss, recall@1, recall@5, recall@10, mrr, mrp, user_count, n_valid}.
+ * Deterministic (fixed summation order).
+ * ------------------------------------------------------------------------------------------- */
+int32_t htcn_loss_metrics_reduce(const float* loss_row, const float* rank_row, const int32_t* row_of,
+                                 const int32_t* y_id, int32_t B, int32_t T, int32_t item_num,
+                                 float* loss_bt, float* ranks, float* ranks_float, float* scalars,
+                                 void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * sampled ranking losses (reference loss.py:22-71): pred [Q,128] is l2-normalised, scored by inner
+ * product against the positive row table[pos_id[q]] and k negatives table[neg_id[q,j]].
+ * table [N,128] f32.  loss_row [Q] (0 where pos_id == 0).
+ * ------------------------------------------------------------------------------------------- */
+int32_t htcn_sampled_rank_loss(const void* pred, int32_t precision, int32_t Q, const float* table,
+                               const int32_t* pos_id, const int32_t* neg_id, int32_t k,
+                               int32_t loss_kind, float hinge_delta, float nce_weight,
+                               float* loss_row, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HTCN_H_ */

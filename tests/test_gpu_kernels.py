@@ -1,0 +1,320 @@
+"""GPU parity tests, kernel by kernel, through the C ABI (ctypes -> libhtcn.so), against the CPU oracle
+on the same seeded inputs.  Bars (north star): gathers bit-exact; fp32 tier within 1e-4 relative;
+bf16 tier within 2e-2; ranks / top-k sets exact up to fp near-ties, which the oracle quantifies."""
+import numpy as np
+import pytest
+
+from helpers import small_case
+from oracle import hiertcn_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from hiertcn_b200 import _cabi as cabi
+    cabi.load()
+    assert cabi.load().htcn_device_ok() == 1, "not an sm_100 device"
+    return cabi
+
+
+def dev(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+def P(t):
+    return t.data_ptr() if t is not None else None
+
+
+def pack(x, y, m):
+    from hiertcn_b200.data_loader import pack_batch
+    return pack_batch(x, y, m)
+
+
+# ------------------------------------------------------------------------------------------ K1
+@pytest.mark.parametrize("lengths,B,S,L,N", [("ragged", 37, 4, 9, 1000), ("dense", 16, 10, 20, 20778),
+                                             ("ragged", 1, 1, 1, 5)])
+def test_k1_gather_bit_exact_and_meanpool(lib, lengths, B, S, L, N):
+    x, y, m, s0, w = small_case(B=B, S=S, L=L, N=N, seed=1, lengths=lengths)
+    pk = pack(x, y, m)
+    pk["x_id"][0, 0] = 0
+    T = pk["x_id"].shape[1]
+    E, be = w["hier/emb/kernel"], w["hier/emb/bias"]
+    Ed, bed = dev(E), dev(be)
+    xid, yid = dev(pk["x_id"]), dev(pk["y_id"])
+    slot_p, keep = lib.int_array(pk["slot_off"])
+    xe = torch.empty((B, T, 128), dtype=torch.float32, device="cuda")
+    yp = torch.empty((S, B, 128), dtype=torch.float32, device="cuda")
+    lib.call("htcn_gather_meanpool", P(Ed), P(bed), N, P(xid), P(yid), slot_p, B, T, S, P(xe), lib.HTCN_F32, P(yp), None)
+    ref = O.emb_gather(pk["x_id"], E)
+    assert np.array_equal(xe.cpu().numpy().view(np.uint32), ref.view(np.uint32)), "fp32 gather must be bit-exact"
+    # bf16 output: the same rows rounded to nearest-even
+    xeb = torch.empty((B, T, 128), dtype=torch.bfloat16, device="cuda")
+    lib.call("htcn_gather_meanpool", P(Ed), P(bed), N, P(xid), P(yid), slot_p, B, T, S, P(xeb), lib.HTCN_BF16, None, None)
+    assert np.array_equal(xeb.float().cpu().numpy(), O.bf16_round(ref))
+    # mean-pool: sequential accumulation == oracle's, bit for bit
+    ref_yp = np.stack([O.meanpool_emb(yy.astype(np.int64), E, be) for yy in y])
+    got = yp.cpu().numpy()
+    assert np.array_equal(got.view(np.uint32), ref_yp.view(np.uint32))
+
+
+def test_k1_null_and_out_of_range_ids(lib):
+    N, B, T = 50, 2, 6
+    rng = np.random.default_rng(0)
+    E = rng.normal(size=(N, 128)).astype(np.float32)
+    ids = np.array([[0, 1, 49, 50, -3, 7], [0, 0, 0, 0, 0, 0]], np.int32)
+    xe = torch.full((B, T, 128), 7.0, dtype=torch.float32, device="cuda")
+    slot_p, keep = lib.int_array([0, T])
+    lib.call("htcn_gather_meanpool", P(dev(E)), None, N, P(dev(ids)), None, slot_p, B, T, 1, P(xe), lib.HTCN_F32, None, None)
+    got = xe.cpu().numpy()
+    assert (got[0, 0] == 0).all() and (got[0, 3] == 0).all() and (got[0, 4] == 0).all() and (got[1] == 0).all()
+    assert np.array_equal(got[0, 1], E[1]) and np.array_equal(got[0, 2], E[49])
+
+
+# ------------------------------------------------------------------------------------------ K3
+@pytest.mark.parametrize("B,S", [(5, 3), (70, 10), (32, 1)])
+def test_k3_gru_sessions(lib, B, S):
+    x, y, m, s0, w = small_case(B=B, S=S, L=6, N=211, seed=2)
+    state_pre, state_out, yps = O.gru_over_sessions(y, m, s0, w, 2, "f32")
+    w_in = w["hier/tcn/emb/kernel"]
+    sb_ref = np.stack([state_pre[s] @ w_in[128:] for s in range(S)])
+    gru = []
+    for g in range(2):
+        p = f"hier/multi_rnn_cell/cell_{g}/gru_cell"
+        gru.append([dev(w[p + "/gates/kernel"]), dev(w[p + "/gates/bias"]), dev(w[p + "/candidate/kernel"]),
+                    dev(w[p + "/candidate/bias"])])
+    pps = [lib.ptr_array([l[i].data_ptr() for l in gru]) for i in range(4)]
+    mask = dev(np.stack([mm.reshape(-1) for mm in m]).astype(np.float32))
+    yp, st_in, wis = dev(yps.astype(np.float32)), dev(s0), dev(w_in[128:])
+    spre = torch.empty((S, B, 256), dtype=torch.float32, device="cuda")
+    sbias = torch.empty((S, B, 128), dtype=torch.float32, device="cuda")
+    sout = torch.empty((B, 256), dtype=torch.float32, device="cuda")
+    lib.call("htcn_gru_sessions", P(yp), P(mask), P(st_in), pps[0][0], pps[1][0], pps[2][0], pps[3][0], 2, P(wis),
+             B, S, P(spre), P(sbias), P(sout), None)
+    np.testing.assert_allclose(spre.cpu().numpy(), state_pre, rtol=1e-4, atol=2e-6)
+    np.testing.assert_allclose(sout.cpu().numpy(), state_out, rtol=1e-4, atol=2e-6)
+    np.testing.assert_allclose(sbias.cpu().numpy(), sb_ref, rtol=1e-4, atol=2e-5)
+    # reset: where mask == 0 the carried state is exactly zero
+    last = np.asarray(m[-1]).reshape(-1) == 0
+    assert (sout.cpu().numpy()[last] == 0).all()
+
+
+# ------------------------------------------------------------------------------------------ K2
+def run_k2(lib, xe_t, xe_dtype, w, sbias, slot_off, B, T, S, K, n_levels, out_row=None, n_out=None,
+           hout_dtype=None, precision=None):
+    conv_w = [dev(w[f"hier/tcn/temporal_conv_net/tblock_{l}/conv1/kernel"]) for l in range(n_levels)]
+    conv_b = [dev(w[f"hier/tcn/temporal_conv_net/tblock_{l}/conv1/bias"]) for l in range(n_levels)]
+    wpp, bpp = lib.ptr_array([t.data_ptr() for t in conv_w]), lib.ptr_array([t.data_ptr() for t in conv_b])
+    w_in_x = dev(w["hier/tcn/emb/kernel"][:128])
+    hout_dtype = lib.HTCN_F32 if hout_dtype is None else hout_dtype
+    precision = lib.HTCN_F32 if precision is None else precision
+    n_out = B * T if n_out is None else n_out
+    hout = torch.zeros((n_out, 128), dtype=torch.float32 if hout_dtype == lib.HTCN_F32 else torch.bfloat16, device="cuda")
+    scratch = torch.empty((2 * B * T, 128), dtype=torch.float32, device="cuda")
+    slot_p, keep = lib.int_array(slot_off)
+    lib.call("htcn_tcn_forward", P(xe_t), xe_dtype, precision, P(w_in_x), P(sbias), wpp[0], bpp[0], n_levels, K, slot_p,
+             B, T, S, P(out_row), P(hout), hout_dtype, P(scratch), None)
+    return hout
+
+
+@pytest.mark.parametrize("B,S,L,K,levels", [(7, 3, 9, 5, 2), (3, 1, 300, 5, 4), (40, 10, 20, 5, 2), (4, 2, 1, 3, 3)])
+def test_k2_tcn_f32(lib, B, S, L, K, levels):
+    x, y, m, s0, w = small_case(B=B, S=S, L=L, N=301, seed=3, tcn_channel=(128,) * levels, kernel_size=K,
+                                lengths="ragged" if L < 100 else "dense")
+    pk = pack(x, y, m)
+    T = pk["x_id"].shape[1]
+    state_pre, _, _ = O.gru_over_sessions(y, m, s0, w, 2, "f32")
+    houts, sbs = O.tcn_hidden_restructured(x, state_pre, w, "f32")
+    ref = np.concatenate(houts, 1)                                  # [B,T,128]
+    xe = O.emb_gather(pk["x_id"], w["hier/emb/kernel"])
+    sbias = dev(np.stack(sbs).astype(np.float32))
+    got = run_k2(lib, dev(xe), lib.HTCN_F32, w, sbias, pk["slot_off"], B, T, S, K, levels).cpu().numpy().reshape(B, T, 128)
+    np.testing.assert_allclose(got, ref, rtol=1e-4, atol=1e-4)
+    # compaction: only rows with a valid target are written, in order
+    valid = pk["y_id"].reshape(-1) > 0
+    row_of = np.where(valid, np.cumsum(valid) - 1, -1).astype(np.int32)
+    gotc = run_k2(lib, dev(xe), lib.HTCN_F32, w, sbias, pk["slot_off"], B, T, S, K, levels, out_row=dev(row_of),
+                  n_out=int(valid.sum())).cpu().numpy()
+    np.testing.assert_array_equal(gotc, got.reshape(-1, 128)[valid])
+
+
+def test_k2_causality(lib):
+    """customized_tcn_cell.py:163-180 probe: a spike at t=5 must not reach t<5, nor other sequences."""
+    B, L, levels, K = 3, 40, 3, 5
+    x, y, m, s0, w = small_case(B=B, S=1, L=L, N=50, seed=4, tcn_channel=(128,) * levels, kernel_size=K, lengths="dense")
+    rng = np.random.default_rng(0)
+    xe = rng.normal(size=(B, L, 128)).astype(np.float32)
+    xe2 = xe.copy()
+    xe2[1, 5] += 1000.0
+    a = run_k2(lib, dev(xe), lib.HTCN_F32, w, None, [0, L], B, L, 1, K, levels).cpu().numpy().reshape(B, L, 128)
+    b = run_k2(lib, dev(xe2), lib.HTCN_F32, w, None, [0, L], B, L, 1, K, levels).cpu().numpy().reshape(B, L, 128)
+    assert np.array_equal(a[1, :5], b[1, :5]) and np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2])
+    assert np.abs(a[1, 5:] - b[1, 5:]).max() > 0
+
+
+# ------------------------------------------------------------------------------------------ K4
+def run_score(lib, hout, wt, b_out, y_rows, flags, k=0, n_split=1, n0=0, precision=None, zy_in=None):
+    precision = lib.HTCN_F32 if precision is None else precision
+    Q, n_items = hout.shape[0], wt.shape[0]
+    f32, i32 = torch.float32, torch.int32
+    zy = torch.zeros(Q, dtype=f32, device="cuda") if zy_in is None else zy_in
+    pm = torch.empty((n_split, Q), dtype=f32, device="cuda")
+    ps = torch.empty((n_split, Q), dtype=f32, device="cuda")
+    pc = torch.empty((n_split, Q), dtype=i32, device="cuda")
+    tv = torch.empty((n_split, Q, max(k, 1)), dtype=f32, device="cuda")
+    ti = torch.empty((n_split, Q, max(k, 1)), dtype=i32, device="cuda")
+    lib.call("htcn_score_ce_rank_topk", P(hout), precision, Q, P(wt), P(b_out), n_items, n0, P(y_rows), P(zy),
+             0 if zy_in is None else 1, flags, k, n_split, P(pm), P(ps), P(pc), P(tv), P(ti), None)
+    return zy, pm, ps, pc, tv, ti
+
+
+@pytest.mark.parametrize("Q,N,n_split", [(200, 1000, 1), (130, 20778, 7), (5, 77, 1), (257, 4099, 3)])
+def test_k4_f32_ce_rank_topk(lib, Q, N, n_split):
+    rng = np.random.default_rng(Q + N)
+    hout = rng.normal(size=(Q, 128)).astype(np.float32)
+    w_out = (rng.normal(size=(128, N)) * 0.3).astype(np.float32)
+    b_out = (rng.normal(size=N) * 0.2).astype(np.float32)
+    y = rng.integers(1, N, size=Q).astype(np.int32)
+    k = min(100, N)
+    wt = torch.empty((N, 128), dtype=torch.float32, device="cuda")
+    lib.call("htcn_prepare_wout", P(dev(w_out)), N, P(wt), lib.HTCN_F32, None)
+    assert np.array_equal(wt.cpu().numpy(), w_out.T)
+    hd, bd, yd = dev(hout), dev(b_out), dev(y)
+    flags = lib.SCORE_CE | lib.SCORE_RANK | lib.SCORE_TOPK
+    zy, pm, ps, pc, tv, ti = run_score(lib, hd, wt, bd, yd, flags, k, n_split)
+    loss_row = torch.empty(Q, dtype=torch.float32, device="cuda")
+    rank_row = torch.empty(Q, dtype=torch.float32, device="cuda")
+    lib.call("htcn_score_finish", P(pm), P(ps), P(pc), n_split, Q, P(yd), P(zy), P(loss_row), P(rank_row), None)
+    ov = torch.empty((Q, k), dtype=torch.float32, device="cuda")
+    oi = torch.empty((Q, k), dtype=torch.int32, device="cuda")
+    lib.call("htcn_topk_merge", P(tv), P(ti), n_split, Q, k, P(ov), P(oi), None)
+    # the full logits through the ABI == what the sweep saw
+    lg = torch.empty((Q, N), dtype=torch.float32, device="cuda")
+    lib.call("htcn_score_logits", P(hd), lib.HTCN_F32, Q, P(wt), lib.HTCN_F32, P(bd), N, P(lg), None)
+    z_gpu = lg.cpu().numpy()
+    z64 = hout.astype(np.float64) @ w_out.astype(np.float64) + b_out
+    np.testing.assert_allclose(z_gpu, z64, rtol=1e-4, atol=1e-4)
+    # target logit is bit-identical to the swept logit (self-consistent strict-greater rank)
+    zy_h = zy.cpu().numpy()
+    assert np.array_equal(zy_h, z_gpu[np.arange(Q), y])
+    # CE
+    ref_loss = O.softmax_cross_entropy_with_logits(y, z64)
+    np.testing.assert_allclose(loss_row.cpu().numpy(), ref_loss, rtol=1e-4, atol=1e-5)
+    # rank: exact w.r.t. the GPU's own logits; within the oracle's near-tie ambiguity w.r.t. fp64
+    rank_self = (z_gpu > zy_h[:, None]).sum(1)
+    np.testing.assert_array_equal(rank_row.cpu().numpy(), rank_self)
+    rank64 = (z64 > z64[np.arange(Q), y][:, None]).sum(1)
+    amb = O.rank_ambiguity(z64, y, 1e-5)
+    assert (np.abs(rank_self - rank64) <= amb).all()
+    # top-k: exact (values and order incl. tie rule) w.r.t. the GPU's own logits
+    v_ref, i_ref = O.top_k(z_gpu, k)
+    np.testing.assert_array_equal(oi.cpu().numpy(), i_ref)
+    np.testing.assert_array_equal(ov.cpu().numpy(), v_ref)
+
+
+def test_k4_topk_ties_prefer_lower_index(lib):
+    Q, N, k = 3, 300, 10
+    hout = np.zeros((Q, 128), np.float32)
+    hout[:, 0] = 1.0
+    w_out = np.zeros((128, N), np.float32)
+    w_out[0] = np.round(np.random.default_rng(0).normal(size=N) * 2) / 2     # many exact ties
+    b_out = np.zeros(N, np.float32)
+    wt = torch.empty((N, 128), dtype=torch.float32, device="cuda")
+    lib.call("htcn_prepare_wout", P(dev(w_out)), N, P(wt), lib.HTCN_F32, None)
+    for n_split in (1, 4):
+        _, _, _, _, tv, ti = run_score(lib, dev(hout), wt, dev(b_out), None, lib.SCORE_TOPK, k, n_split)
+        ov = torch.empty((Q, k), dtype=torch.float32, device="cuda")
+        oi = torch.empty((Q, k), dtype=torch.int32, device="cuda")
+        lib.call("htcn_topk_merge", P(tv), P(ti), n_split, Q, k, P(ov), P(oi), None)
+        v_ref, i_ref = O.top_k(np.tile(w_out[0], (Q, 1)), k)
+        np.testing.assert_array_equal(oi.cpu().numpy(), i_ref)
+
+
+def test_k4_sharded_catalog_equals_single(lib):
+    """catalog split into 3 shards (n0 offsets, exchanged target logits) == one shard."""
+    rng = np.random.default_rng(5)
+    Q, N, k = 150, 3000, 50
+    hout = rng.normal(size=(Q, 128)).astype(np.float32)
+    w_out = (rng.normal(size=(128, N)) * 0.3).astype(np.float32)
+    b_out = (rng.normal(size=N) * 0.2).astype(np.float32)
+    y = rng.integers(1, N, size=Q).astype(np.int32)
+    wt = torch.empty((N, 128), dtype=torch.float32, device="cuda")
+    lib.call("htcn_prepare_wout", P(dev(w_out)), N, P(wt), lib.HTCN_F32, None)
+    hd, bd, yd = dev(hout), dev(b_out), dev(y)
+    flags = lib.SCORE_CE | lib.SCORE_RANK | lib.SCORE_TOPK
+    zy1, pm1, ps1, pc1, tv1, ti1 = run_score(lib, hd, wt, bd, yd, flags, k, 1)
+    bounds = [0, 1000, 2100, N]
+    zy = torch.zeros(Q, dtype=torch.float32, device="cuda")
+    for s in range(3):   # step 1: every shard fills the target logits it owns (all-reduce-sum in the multi-GPU path)
+        lib.call("htcn_target_logit", P(hd), lib.HTCN_F32, Q, P(wt[bounds[s]:bounds[s + 1]]), P(bd[bounds[s]:bounds[s + 1]]),
+                 bounds[s + 1] - bounds[s], bounds[s], P(yd), P(zy), None)
+    assert np.array_equal(zy.cpu().numpy(), zy1.cpu().numpy())
+    parts = [run_score(lib, hd, wt[bounds[s]:bounds[s + 1]].contiguous(), bd[bounds[s]:bounds[s + 1]].contiguous(), yd,
+                       flags, k, 1, n0=bounds[s], zy_in=zy) for s in range(3)]
+    pm = torch.cat([p[1] for p in parts]); ps = torch.cat([p[2] for p in parts]); pc = torch.cat([p[3] for p in parts])
+    tv = torch.cat([p[4] for p in parts]); ti = torch.cat([p[5] for p in parts])
+    outs = []
+    for (n_part, a, b, c, d, e) in ((3, pm, ps, pc, tv, ti), (1, pm1, ps1, pc1, tv1, ti1)):
+        loss_row = torch.empty(Q, dtype=torch.float32, device="cuda")
+        rank_row = torch.empty(Q, dtype=torch.float32, device="cuda")
+        lib.call("htcn_score_finish", P(a), P(b), P(c), n_part, Q, P(yd), P(zy), P(loss_row), P(rank_row), None)
+        ov = torch.empty((Q, k), dtype=torch.float32, device="cuda")
+        oi = torch.empty((Q, k), dtype=torch.int32, device="cuda")
+        lib.call("htcn_topk_merge", P(d), P(e), n_part, Q, k, P(ov), P(oi), None)
+        outs.append((loss_row.cpu().numpy(), rank_row.cpu().numpy(), ov.cpu().numpy(), oi.cpu().numpy()))
+    np.testing.assert_allclose(outs[0][0], outs[1][0], rtol=1e-5, atol=1e-6)
+    np.testing.assert_array_equal(outs[0][1], outs[1][1])
+    np.testing.assert_array_equal(outs[0][3], outs[1][3])
+    np.testing.assert_array_equal(outs[0][2], outs[1][2])
+
+
+# ------------------------------------------------------------------------------------------ reductions / sampled loss
+def test_loss_metrics_reduce(lib):
+    rng = np.random.default_rng(9)
+    B, T, N = 9, 13, 500
+    y = rng.integers(0, N, size=(B, T)).astype(np.int32)
+    y[rng.random((B, T)) < 0.4] = 0
+    y[3] = 0                                   # a user with no valid position
+    valid = y.reshape(-1) > 0
+    row_of = np.where(valid, np.cumsum(valid) - 1, -1).astype(np.int32)
+    Q = int(valid.sum())
+    loss_row = rng.random(Q).astype(np.float32) * 5
+    rank_row = rng.integers(0, 30, size=Q).astype(np.float32)
+    out = [torch.empty((B, T), dtype=torch.float32, device="cuda") for _ in range(3)]
+    sc = torch.empty(8, dtype=torch.float32, device="cuda")
+    lib.call("htcn_loss_metrics_reduce", P(dev(loss_row)), P(dev(rank_row)), P(dev(row_of)), P(dev(y)), B, T, N,
+             P(out[0]), P(out[1]), P(out[2]), P(sc), None)
+    loss_bt = np.zeros(B * T, np.float32); loss_bt[valid] = loss_row
+    ranks = np.zeros(B * T, np.float32); ranks[valid] = rank_row
+    mask = valid.reshape(B, T).astype(np.float32)
+    act = mask.sum(1); uc = np.sign(act).sum(); act = act + np.float32(1e-6)
+    um = lambda a: (a.reshape(B, T).sum(1) / act).sum() / uc  # noqa: E731
+    rk = ranks.reshape(B, T)
+    ref = [um(loss_bt), um((rk <= 0) * mask), um((rk <= 4) * mask), um((rk <= 9) * mask), um(mask / (1 + rk)),
+           um(rk / N * mask), uc, valid.sum()]
+    np.testing.assert_allclose(sc.cpu().numpy(), np.asarray(ref, np.float32), rtol=2e-6)
+    np.testing.assert_array_equal(out[0].cpu().numpy().reshape(-1), loss_bt)
+    np.testing.assert_array_equal(out[1].cpu().numpy().reshape(-1), ranks)
+
+
+@pytest.mark.parametrize("kind", ["nce", "hinge_sigmoid", "hinge_logsigmoid", "hinge_linear", "bpr"])
+def test_sampled_rank_loss(lib, kind):
+    rng = np.random.default_rng(3)
+    Q, N, k = 77, 900, 20
+    pred = rng.normal(size=(Q, 128)).astype(np.float32)
+    table = rng.normal(size=(N, 128)).astype(np.float32)
+    pos = rng.integers(1, N, size=Q).astype(np.int32)
+    pos[5] = 0
+    neg = rng.integers(1, N, size=(Q, k)).astype(np.int32)
+    out = torch.empty(Q, dtype=torch.float32, device="cuda")
+    lib.call("htcn_sampled_rank_loss", P(dev(pred)), lib.HTCN_F32, Q, P(dev(table)), P(dev(pos)), P(dev(neg)), k,
+             lib.LOSS_KINDS[kind], 0.1, 1.0, P(out), None)
+    ref = O.calc_loss_sampled(pred[None].astype(np.float64), table[pos][None].astype(np.float64),
+                              table[neg][None].astype(np.float64), kind, k, 1.0, 0.1)[0]
+    ref[pos == 0] = 0
+    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=1e-4, atol=1e-5)

@@ -1,0 +1,107 @@
+"""GPU parity of the whole hot path through the Python surface (HierTCN.step == the reference's
+sess.run fetch list) against the golden fixtures and the CPU oracle."""
+import numpy as np
+import pytest
+
+from helpers import load_hier_golden, small_case
+from oracle import hiertcn_oracle as O
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+def make_model(w, N, precision, levels=2, K=5):
+    from hiertcn_b200.args import make_args
+    from hiertcn_b200.model_hier import HierTCN
+    a = make_args(["--item_num", str(N), "--tcn_channel", ",".join(["128"] * levels), "--kernel_size", str(K)])
+    return HierTCN(a, w, precision=precision).build()
+
+
+def check_against(out, ref, tol, ranks_exact):
+    assert abs(out["loss"] - ref["loss"]) <= tol * abs(ref["loss"]), (out["loss"], ref["loss"])
+    np.testing.assert_allclose(out["state"], ref["state"], rtol=max(tol, 1e-4), atol=max(tol, 1e-4) * 0.1)
+    np.testing.assert_allclose(out["loss_bt"], ref["loss_bt"], rtol=tol, atol=tol)
+    if ranks_exact:
+        np.testing.assert_array_equal(out["ranks"], ref["ranks"])
+    for k_out, k_ref in (("recall1", "recall1"), ("recall5", "recall5"), ("recall10", "recall10"), ("mrr", "mrr"), ("mrp", "mrp")):
+        assert abs(out[k_out] - ref[k_ref]) <= max(tol, 1e-5) * max(1.0, abs(ref[k_ref])) if ranks_exact else True
+
+
+def test_step_f32_matches_golden_reference_run():
+    """fixture produced by running the reference's own model_hier/loss python (oracle/make_golden.py)"""
+    z, x, y, m, w = load_hier_golden("hier_default_arch")
+    model = make_model(w, int(z["N"]), "f32")
+    out = model.step(x, y, m, z["state0"], per_position=True)
+    assert abs(out["loss"] - z["loss_f64"]) <= 1e-4 * abs(z["loss_f64"])
+    np.testing.assert_allclose(out["state"], z["state_f64"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(out["loss_bt"], z["loss_bt_f64"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_array_equal(out["ranks"], z["ranks_f64"])      # N=61, well separated logits
+    got = np.asarray([out[k] for k in ("recall1", "recall5", "recall10", "mrr", "mrp")])
+    np.testing.assert_allclose(got, z["metrics_f64"], rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("B,S,L,N,lengths", [(64, 10, 20, 20778, "ragged"), (9, 4, 20, 997, "dense"), (3, 2, 1, 40, "dense")])
+def test_step_f32_matches_oracle(B, S, L, N, lengths):
+    x, y, m, s0, w = small_case(B=B, S=S, L=L, N=N, seed=B, lengths=lengths)
+    ref = O.forward_loss_metrics(x, y, m, s0, w, 2, "f64")
+    model = make_model(w, N, "f32")
+    out = model.step(x, y, m, s0, per_position=True, topk=min(100, N))
+    assert abs(out["loss"] - ref["loss"]) <= 1e-4 * abs(ref["loss"])
+    np.testing.assert_allclose(out["state"], ref["state"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(out["loss_bt"], ref["loss_bt"], rtol=1e-4, atol=2e-5)
+    y_id = np.concatenate([np.asarray(v) for v in y], 1).astype(np.int64)
+    amb = O.rank_ambiguity(ref["pred"], y_id, 2e-5) * (y_id > 0)
+    assert (np.abs(out["ranks"] - ref["ranks"]) <= amb).all()
+    assert np.mean(out["ranks"] == ref["ranks"]) > 0.98
+    assert abs(out["mrr"] - ref["mrr"]) < 2e-3 and abs(out["mrp"] - ref["mrp"]) < 1e-4
+    # top-k sets of the valid rows vs the oracle's logits: identical wherever the k-th gap is not a near-tie
+    valid = y_id.reshape(-1) > 0
+    zv = ref["pred"].reshape(-1, N)[valid]
+    k = out["topk_idx"].shape[1]
+    v_ref, i_ref = O.top_k(zv, k)
+    same = np.array([set(a) == set(b) for a, b in zip(out["topk_idx"], i_ref)])
+    srt = -np.sort(-zv, axis=1)
+    gap = (srt[:, k - 1] - srt[:, k]) if N > k else np.ones(len(zv))
+    assert same[gap > 1e-4].all()
+    np.testing.assert_allclose(out["topk_val"], v_ref, rtol=1e-4, atol=1e-4)
+
+
+def test_materialized_logits_match_reference_pred():
+    z, x, y, m, w = load_hier_golden("hier_default_arch")
+    from hiertcn_b200.args import make_args
+    from hiertcn_b200.model_hier import model_hier
+    a = make_args(["--item_num", str(int(z["N"]))])
+    pred, state = model_hier(a, x, y, m, z["state0"], weights=w, precision="f32")
+    np.testing.assert_allclose(pred.materialize(), z["pred_f64"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(state, z["state_f64"], rtol=1e-4, atol=1e-5)
+
+
+def test_state_carry_across_batches_and_user_independence():
+    x, y, m, s0, w = small_case(B=8, S=3, L=6, N=101, seed=21)
+    model = make_model(w, 101, "f32")
+    o1 = model.step(x, y, m, s0, per_position=True)
+    perm = np.random.default_rng(0).permutation(8)
+    o2 = model.step([a[perm] for a in x], [a[perm] for a in y], [a[perm] for a in m], s0[perm], per_position=True)
+    np.testing.assert_array_equal(o1["loss_bt"][perm], o2["loss_bt"])       # rows are independent users
+    np.testing.assert_array_equal(o1["state"][perm], o2["state"])
+    o3 = model.step(x, y, m, o1["state"])                                     # carried state feeds the next batch
+    ref = O.forward_loss_metrics(x, y, m, o1["state"], w, 2, "f64")
+    assert abs(o3["loss"] - ref["loss"]) <= 1e-4 * abs(ref["loss"])
+
+
+def test_bf16_tier_within_2e2():
+    x, y, m, s0, w = small_case(B=40, S=5, L=12, N=5000, seed=33)
+    ref = O.forward_loss_metrics(x, y, m, s0, w, 2, "f64")
+    model = make_model(w, 5000, "bf16")
+    out = model.step(x, y, m, s0, per_position=True, topk=100)
+    assert abs(out["loss"] - ref["loss"]) <= 2e-2 * abs(ref["loss"])
+    np.testing.assert_allclose(out["loss_bt"], ref["loss_bt"], rtol=2e-2, atol=2e-2)
+    np.testing.assert_allclose(out["state"], ref["state"], rtol=1e-4, atol=1e-5)     # GRU stays fp32
+    assert abs(out["mrr"] - ref["mrr"]) < 2e-2 and abs(out["mrp"] - ref["mrp"]) < 2e-3
+    # top-k sets vs the bf16-emulating oracle: high overlap (operands rounded identically, order differs)
+    refb = O.forward_loss_metrics(x, y, m, s0, w, 2, "bf16")
+    y_id = np.concatenate([np.asarray(v) for v in y], 1).astype(np.int64)
+    zv = refb["pred"].reshape(-1, 5000)[y_id.reshape(-1) > 0]
+    _, i_ref = O.top_k(zv, 100)
+    overlap = np.mean([len(set(a) & set(b)) / 100.0 for a, b in zip(out["topk_idx"], i_ref)])
+    assert overlap > 0.97, overlap

@@ -1,0 +1,74 @@
+"""CPU tests of the host-side mirror: args surface, batch layout, queue loader, weight contract."""
+import numpy as np
+
+from hiertcn_b200.args import make_args
+from hiertcn_b200.data_loader import (Dataloader_hier_model_xing, make_synthetic_interactions, pack_batch,
+                                      synthetic_batch)
+from hiertcn_b200.weights import fold_weightnorm, hier_weight_shapes, init_weights, load_npz, save_npz
+
+
+def test_args_defaults_match_reference():
+    a = make_args()
+    # reference args.py defaults (file:line in hiertcn_b200/args.py)
+    assert (a.batch_size, a.item_num, a.output_dim, a.hidden_dim, a.num_layer) == (32, 20778, 20778, 128, 2)
+    assert a.tcn_channel == [128, 128] and a.kernel_size == 5 and a.strides == 1 and a.dropout == 0.0
+    assert (a.max_activity_len, a.max_session_num, a.num_neg_sample, a.hinge_delta) == (20, 10, 20, 0.1)
+    assert a.loss == "cross_entropy" and a.learning_rate == 1e-2 and not a.has_batchnorm
+    b = make_args(["--tcn_channel", "128,128,128,128", "--batch_size", "4096", "--item_num", "1000000"])
+    assert b.tcn_channel == [128] * 4 and b.batch_size == 4096 and b.output_dim == 1000000
+    assert make_args(["--model_type", "tcn"]).tcn_channel == [128, 128, 128, 128, 256, 256]   # args.py:310-311
+
+
+def test_synthetic_batch_layout():
+    x, y, m = synthetic_batch(6, S=4, L=7, item_num=50, seed=3, lengths="ragged")
+    assert len(x) == len(y) == len(m) == 4
+    for xs, ys, ms in zip(x, y, m):
+        assert xs.shape == ys.shape and ms.shape == (6, 1) and xs.dtype == np.float64
+        assert (xs[:, 0] == 0).all()                               # null id first (data_loader.py:246-261)
+        assert (xs[:, 1:] == ys[:, :-1]).all()                      # x is y shifted right by one
+        n = (ys > 0).sum(1)
+        assert (n >= 1).all() and n.max() == ys.shape[1]            # L_s = per-slot max
+        for b in range(6):                                          # zero right-padding only
+            assert (ys[b, :n[b]] > 0).all() and (ys[b, n[b]:] == 0).all()
+        assert ys.max() < 50
+    pk = pack_batch(x, y, m)
+    assert pk["x_id"].dtype == np.int32 and pk["x_id"].shape == pk["y_id"].shape
+    assert pk["slot_off"][0] == 0 and pk["slot_off"][-1] == pk["x_id"].shape[1] and pk["mask"].shape == (4, 6)
+
+
+def test_queue_loader_semantics():
+    table, data = make_synthetic_interactions(60, 80, seed=1)
+    a = make_args(["--batch_size", "4", "--max_session_num", "3", "--max_activity_len", "5"])
+    ld = Dataloader_hier_model_xing(a, "train", data=(table, data))
+    seen_reset = False
+    for _ in range(6):
+        x, y, m, info = ld.get_batch()
+        assert len(x) == 3 and all(v.shape[0] == 4 for v in x)
+        for xs, ys, ms, inf in zip(x, y, m, info):
+            assert xs.shape[1] <= 5 and inf.shape == ys.shape + (5,)
+            assert (xs[:, 1:] == ys[:, :-1]).all()
+            assert ((ys > 0).sum(1) >= 1).all()
+            assert (inf[..., 1] == ys).all()                        # info carries the item id of each y
+            seen_reset |= bool((ms == 0).any())
+            # sessions of one slot never mix users: user_id constant over the valid positions
+            for b in range(4):
+                u = inf[b, ys[b] > 0, 0]
+                assert (u == u[0]).all()
+    assert seen_reset
+
+
+def test_weight_contract_names_and_roundtrip(tmp_path):
+    s = hier_weight_shapes(20778)
+    assert sum(int(np.prod(v)) for v in s.values()) == 5750698       # SURVEY.md A.6 / BASELINE.md
+    assert s["hier/tcn/emb/kernel"] == (384, 128) and s["hier/tcn/dense/kernel"] == (128, 20778)
+    w = init_weights(hier_weight_shapes(30), seed=1)
+    assert (w["hier/multi_rnn_cell/cell_0/gru_cell/gates/bias"] == 1).all()
+    assert (w["hier/emb/bias"] == 0).all()
+    save_npz(tmp_path / "w.npz", w)
+    w2 = load_npz(tmp_path / "w.npz")
+    assert list(w2) == list(w) and all((w2[k] == w[k]).all() for k in w)
+    # weight-norm folds into the kernel
+    w3 = dict(w)
+    w3["hier/tcn/dense/g"] = np.full(30, 2.0, np.float32)
+    f = fold_weightnorm(w3)
+    np.testing.assert_allclose(np.sqrt((f["hier/tcn/dense/kernel"] ** 2).sum(0)), 2.0, rtol=1e-5)
