@@ -1,17 +1,421 @@
-// placeholder until the tcgen05 tier lands (next commit): loud failure, never a fallback
+// K4 (bf16 tier): full-catalog scoring on the 5th-gen tensor cores.
+//
+//   Z[q, j] = Hout[q, :] . W_out^T[j, :] + b[j]        Hout [Q,128] bf16, W_out^T [N,128] bf16, fp32 accumulate
+//
+// One CTA owns a 128-row query tile (A, 32 KB, loaded once by TMA, stays resident) and sweeps its
+// catalog split in tiles of BN items streamed by TMA through a 2-stage shared-memory ring (128-byte
+// swizzle, K-major).  One elected thread issues tcgen05.mma (M=128, N=BN, K=16 x 8 k-steps) into a
+// double-buffered TMEM accumulator (2 x BN fp32 columns); the epilogue warps drain buffer i with
+// tcgen05.ld while the tensor core fills buffer i+1.  Logits never leave the SM: the epilogue keeps, per
+// row, sum_j exp(z_j - z_y) (softmax-CE, loss.py:20-21), #{j: z_j > z_y} (rank, loss.py:179) and / or a
+// k-entry heap (top-k, loss.py:120) -- "TMEM lane = row", so every row statistic is a per-thread scalar.
+//
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..9 = epilogue (a warp may only touch TMEM lanes 32*(warp%4)..+31; the two warps sharing a lane
+// quarter split the tile's columns in halves).  Top-k mode uses 4 epilogue warps (one heap per row).
+//
+// Softmax reference point: the target logit z_y (computed up front by k4_target_bf16 with the SAME
+// tcgen05.mma arithmetic, so z_y compares equal to itself in the sweep).  CE loss = log sum_j exp(z_j - z_y):
+// no running max, no rescaling.  Terms far below z_y flush to zero harmlessly (the j = y term is 1).
 #include "common.cuh"
+#include "sm100.cuh"
+
 namespace htcn {
-int32_t score_bf16(const ScoreArgs&, cudaStream_t) {
-  set_error("score: bf16 tier not built");
-  return HTCN_ERR_UNSUPPORTED;
+using namespace sm100;
+
+constexpr int kBM = 128;
+constexpr int kChunkBytesA = kBM * 128;          // one 64-column (128 B) chunk of the A tile
+constexpr int kThreadsBf16 = 320;
+constexpr float kLog2e = 1.4426950408889634f;
+
+enum : unsigned { kModeDump = 8u };              // internal: write raw logits (test hook)
+
+template <int BN>
+struct alignas(1024) ScoreSmem {
+  uint8_t a[2][kChunkBytesA];                     // K chunks 0..63 / 64..127
+  uint8_t b[2][2][BN * 128];                      // [stage][chunk]
+  float bias[8][128];                             // per epilogue warp
+  float comb_sum[kBM];                            // column-half 1 -> half 0 hand-off at the end of the sweep
+  int comb_cnt[kBM];
+  uint64_t a_full, b_full[2], b_empty[2], t_full[2], t_empty[2];
+  uint32_t tmem_base;
+};
+
+template <int BN, unsigned kFlags>
+__global__ void __launch_bounds__(kThreadsBf16, 1)
+k4_score_bf16(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, ScoreArgs a,
+              float* __restrict__ dump) {
+  constexpr bool kCE = kFlags & HTCN_SCORE_CE, kRank = kFlags & HTCN_SCORE_RANK, kTopk = kFlags & HTCN_SCORE_TOPK;
+  constexpr bool kDump = kFlags & kModeDump;
+  constexpr int kEpiWarps = kTopk ? 4 : 8;
+  constexpr int kColsPerWarp = BN / (kEpiWarps / 4);
+  constexpr uint32_t kTmemCols = 2 * BN;
+  extern __shared__ uint8_t smem_raw[];
+  auto& sm = *reinterpret_cast<ScoreSmem<BN>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* heap_v = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(&sm) + sizeof(ScoreSmem<BN>));
+  int* heap_i = reinterpret_cast<int*>(heap_v + a.k * kBM);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * kBM;
+  const int split = blockIdx.y;
+  const int n_tiles_all = (a.n_items + BN - 1) / BN;
+  const int t_begin = (int)((long long)n_tiles_all * split / a.n_split);
+  const int t_end = (int)((long long)n_tiles_all * (split + 1) / a.n_split);
+  const int n_tiles = t_end - t_begin;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+    mbar_init(&sm.a_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&sm.b_full[s], 1);
+      mbar_init(&sm.b_empty[s], 1);
+      mbar_init(&sm.t_full[s], 1);
+      mbar_init(&sm.t_empty[s], kEpiWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<kTmemCols>(&sm.tmem_base);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = sm.tmem_base;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&sm.a_full, 2 * kChunkBytesA);
+      tma_load_2d(sm.a[0], &tmap_a, 0, q0, &sm.a_full);
+      tma_load_2d(sm.a[1], &tmap_a, 64, q0, &sm.a_full);
+      for (int i = 0; i < n_tiles; ++i) {
+        const int s = i & 1;
+        mbar_wait(&sm.b_empty[s], ((i >> 1) & 1) ^ 1);         // slot free (first pass succeeds immediately)
+        mbar_arrive_expect_tx(&sm.b_full[s], 2 * BN * 128);
+        const int j0 = (t_begin + i) * BN;                      // rows beyond n_items are zero-filled by TMA
+        tma_load_2d(sm.b[s][0], &tmap_b, 0, j0, &sm.b_full[s]);
+        tma_load_2d(sm.b[s][1], &tmap_b, 64, j0, &sm.b_full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kBM, BN);
+      mbar_wait(&sm.a_full, 0);
+      for (int i = 0; i < n_tiles; ++i) {
+        const int s = i & 1, buf = i & 1;
+        mbar_wait(&sm.t_empty[buf], ((i >> 1) & 1) ^ 1);        // epilogue drained this accumulator
+        mbar_wait(&sm.b_full[s], (i >> 1) & 1);                 // TMA landed
+        tc_fence_after_sync();
+        const uint32_t d = tmem + buf * BN;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {                           // K = 128 = 8 x 16
+          const uint64_t da = make_desc_k_sw128(smem_u32(sm.a[k >> 2]) + (k & 3) * 32);
+          const uint64_t db = make_desc_k_sw128(smem_u32(sm.b[s][k >> 2]) + (k & 3) * 32);
+          umma_bf16(d, da, db, idesc, k > 0);
+        }
+        umma_commit(&sm.b_empty[s]);                            // smem slot reusable once these MMAs retire
+        umma_commit(&sm.t_full[buf]);                           // accumulator ready
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int ew = warp - 2;                                    // 0..7
+    const bool active = ew < kEpiWarps;
+    if (active) {
+      const int quarter = warp & 3;                             // TMEM lane quarter this warp may access
+      const int half = ew >> 2;                                 // column half (0 when kEpiWarps == 4)
+      const int row = quarter * 32 + lane;
+      const bool row_ok = q0 + row < a.Q;
+      const int col0 = half * kColsPerWarp;
+      float* bias_s = sm.bias[ew];
+      float zy = 0.f, zyl = 0.f, thr = -INFINITY;
+      float sum4[4] = {0.f, 0.f, 0.f, 0.f};                     // 4 independent partial sums (ILP + accuracy)
+      int cnt = 0;
+      if ((kCE || kRank) && row_ok) {
+        zy = a.zy[q0 + row];
+        zyl = zy * kLog2e;
+      }
+      RowHeap heap{heap_v + row, heap_i + row, kBM, a.k};
+      if (kTopk) heap.init();
+
+      for (int i = 0; i < n_tiles; ++i) {
+        const int buf = i & 1;
+        const int j0 = (t_begin + i) * BN;
+        // stage this warp's bias slice (kColsPerWarp floats) -- warp-private, no cross-warp sync
+        __syncwarp();
+#pragma unroll
+        for (int c = lane; c < kColsPerWarp; c += 32) {
+          const int j = j0 + col0 + c;
+          bias_s[c] = (j < a.n_items) ? __ldg(a.b_out + j) : 0.f;
+        }
+        __syncwarp();
+        mbar_wait(&sm.t_full[buf], (i >> 1) & 1);
+        tc_fence_after_sync();
+        const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + buf * BN + col0;
+        const int lim = a.n_items - j0 - col0;                  // columns of this warp's slice that exist
+#pragma unroll 1
+        for (int c = 0; c < kColsPerWarp; c += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c, r);
+          tmem_ld_wait();
+          if (c + 32 <= lim) {                                  // full chunk: branch-free
+#pragma unroll
+            for (int u4 = 0; u4 < 8; ++u4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c + u4 * 4);
+              const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+              for (int v = 0; v < 4; ++v) {
+                const int u = u4 * 4 + v;
+                const float z = __uint_as_float(r[u]) + bb[v];
+                if (kDump) {
+                  if (row_ok) dump[(long long)(q0 + row) * a.n_items + j0 + col0 + c + u] = z;
+                }
+                if (kCE) sum4[v] += ex2_approx(fmaf(z, kLog2e, -zyl));
+                if (kRank) cnt += (z > zy) ? 1 : 0;
+                if (kTopk) {
+                  if (z > thr) thr = heap.replace_root(z, a.n0 + j0 + col0 + c + u);
+                }
+              }
+            }
+          } else if (c < lim) {                                 // ragged last tile of the catalog
+#pragma unroll 1
+            for (int u = 0; u < 32; ++u) {
+              float z = 0.f;
+#pragma unroll
+              for (int w = 0; w < 32; ++w)
+                if (w == u) z = __uint_as_float(r[w]);
+              if (c + u < lim) {
+                z += bias_s[c + u];
+                if (kDump) {
+                  if (row_ok) dump[(long long)(q0 + row) * a.n_items + j0 + col0 + c + u] = z;
+                }
+                if (kCE) sum4[0] += ex2_approx(fmaf(z, kLog2e, -zyl));
+                if (kRank) cnt += (z > zy) ? 1 : 0;
+                if (kTopk) {
+                  if (z > thr) thr = heap.replace_root(z, a.n0 + j0 + col0 + c + u);
+                }
+              }
+            }
+          }
+        }
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.t_empty[buf]);
+      }
+      float sum = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
+      if (kEpiWarps == 8) {                                     // fold column half 1 into half 0
+        if (half == 1) {
+          sm.comb_sum[row] = sum;
+          sm.comb_cnt[row] = cnt;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (half == 0) {
+          sum += sm.comb_sum[row];
+          cnt += sm.comb_cnt[row];
+        }
+      }
+      if (row_ok && half == 0) {
+        const long long o = (long long)split * a.Q + q0 + row;
+        if (kCE) {
+          a.part_max[o] = zy;              // reference point of this partial sum
+          a.part_sum[o] = sum;
+        }
+        if (kRank) a.part_cnt[o] = cnt;
+        if (kTopk) {
+          for (int s = 0; s < a.k; ++s) {
+            const int id = heap.i(s);
+            a.topk_val[o * a.k + s] = heap.v(s);
+            a.topk_idx[o * a.k + s] = (id == 0x7fffffff) ? -1 : id;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc<kTmemCols>(tmem);
+  }
 }
-int32_t target_logit_bf16(const void*, const void*, const float*, const int*, int, int, int, float*, cudaStream_t) {
-  set_error("target_logit: bf16 tier not built");
-  return HTCN_ERR_UNSUPPORTED;
+
+// ---- target logits with the sweep's arithmetic ---------------------------------------------------
+// Per 128-row tile: A = the query rows, B = the 128 gathered target rows W_out^T[y_q]; one M=128,N=128
+// tcgen05 product; thread r keeps the diagonal D[r][r].  Operands are written to shared memory by the
+// threads themselves in the 128-byte-swizzled K-major layout the UMMA descriptor expects.
+struct alignas(1024) TargetSmem {
+  uint8_t a[2][kChunkBytesA];
+  uint8_t b[2][kChunkBytesA];
+  uint64_t done;
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void store_row_sw128(uint8_t (*dst)[kChunkBytesA], int r, const uint4* src /*16 x 16 B or null*/) {
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    const uint4 v = src ? __ldg(src + c) : make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4*>(&dst[c >> 3][r * 128 + (((c & 7) ^ (r & 7)) << 4)]) = v;
+  }
 }
-int32_t tcn_forward_bf16(const void*, int, const float*, const float*, const float* const*, const float* const*, int,
-                         int, const SlotTable&, int, int, const int*, void*, int, float*, cudaStream_t) {
-  set_error("tcn_forward: bf16 tier not built");
-  return HTCN_ERR_UNSUPPORTED;
+
+__global__ void __launch_bounds__(128, 1)
+k4_target_bf16(const __nv_bfloat16* __restrict__ hout, const __nv_bfloat16* __restrict__ wt,
+               const float* __restrict__ b_out, const int* __restrict__ y_id, int Q, int n_items, int n0,
+               float* __restrict__ zy) {
+  extern __shared__ uint8_t smem_raw[];
+  auto& sm = *reinterpret_cast<TargetSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int r = threadIdx.x, warp = r >> 5, lane = r & 31;
+  const int q = blockIdx.x * kBM + r;
+  int y = -1;
+  if (q < Q) {
+    y = y_id[q] - n0;
+    if (y < 0 || y >= n_items) y = -1;
+  }
+  store_row_sw128(sm.a, r, q < Q ? reinterpret_cast<const uint4*>(hout + (long long)q * kDim) : nullptr);
+  store_row_sw128(sm.b, r, y >= 0 ? reinterpret_cast<const uint4*>(wt + (long long)y * kDim) : nullptr);
+  fence_proxy_async_smem();                    // make the generic-proxy stores visible to the tensor core
+  if (r == 0) {
+    mbar_init(&sm.done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<128>(&sm.tmem_base);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = sm.tmem_base;
+  if (r == 0) {
+    constexpr uint32_t idesc = make_idesc_bf16(kBM, 128);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const uint64_t da = make_desc_k_sw128(smem_u32(sm.a[k >> 2]) + (k & 3) * 32);
+      const uint64_t db = make_desc_k_sw128(smem_u32(sm.b[k >> 2]) + (k & 3) * 32);
+      umma_bf16(tmem, da, db, idesc, k > 0);
+    }
+    umma_commit(&sm.done);
+  }
+  mbar_wait(&sm.done, 0);
+  tc_fence_after_sync();
+  uint32_t v[32];
+  tmem_ld_32x32(tmem + ((uint32_t)(warp * 32) << 16) + warp * 32, v);   // this warp's 32x32 diagonal block
+  tmem_ld_wait();
+  float d = 0.f;
+#pragma unroll
+  for (int u = 0; u < 32; ++u)
+    if (u == lane) d = __uint_as_float(v[u]);
+  if (y >= 0) zy[q] = d + __ldg(b_out + y);
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after_sync();
+    tmem_dealloc<128>(tmem);
+  }
 }
+
+// ---- host side ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int32_t make_tmap_bf16_rows(CUtensorMap* out, const void* base, uint64_t rows, uint32_t box_rows) {
+  static EncodeTiledFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+      set_error("cuTensorMapEncodeTiled not available from the driver (%d)", (int)e);
+      return HTCN_ERR_CUDA;
+    }
+    encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) {
+    set_error("tensor map base %p is not 16-byte aligned", base);
+    return HTCN_ERR_INVALID;
+  }
+  const cuuint64_t dims[2] = {(cuuint64_t)kDim, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)kDim * 2};         // bytes between rows
+  const cuuint32_t box[2] = {64, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) rows=%llu box_rows=%u", (int)r, (unsigned long long)rows, box_rows);
+    return HTCN_ERR_CUDA;
+  }
+  return HTCN_OK;
+}
+
+template <int BN, unsigned kFlags>
+static int32_t launch_score(const ScoreArgs& a, float* dump, cudaStream_t st) {
+  CUtensorMap ta, tb;
+  int32_t rc = make_tmap_bf16_rows(&ta, a.hout, (uint64_t)a.Q, kBM);
+  if (rc) return rc;
+  rc = make_tmap_bf16_rows(&tb, a.wt, (uint64_t)a.n_items, BN);
+  if (rc) return rc;
+  const size_t smem = sizeof(ScoreSmem<BN>) + 1024 + ((kFlags & HTCN_SCORE_TOPK) ? (size_t)a.k * kBM * 8 : 0);
+  if (smem > 227 * 1024) {
+    set_error("score(bf16): k=%d needs %zu B of shared memory (max 232448); use k <= 112", a.k, smem);
+    return HTCN_ERR_UNSUPPORTED;
+  }
+  auto kern = k4_score_bf16<BN, kFlags>;
+  HTCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(ceil_div(a.Q, kBM), a.n_split);
+  kern<<<grid, kThreadsBf16, smem, st>>>(ta, tb, a, dump);
+  HTCN_LAUNCH_CHECK("k4_score_bf16");
+  return HTCN_OK;
+}
+
+int32_t score_bf16(const ScoreArgs& a, cudaStream_t st) {
+  const int n_tiles = (a.n_items + 255) / 256;
+  if (a.n_split > n_tiles && !(a.flags & HTCN_SCORE_TOPK)) {
+    set_error("score(bf16): n_split=%d exceeds the number of 256-item tiles (%d)", a.n_split, n_tiles);
+    return HTCN_ERR_INVALID;
+  }
+  if (a.flags & HTCN_SCORE_TOPK) {
+    const int n_tiles128 = (a.n_items + 127) / 128;
+    if (a.n_split > n_tiles128) {
+      set_error("score(bf16): n_split=%d exceeds the number of 128-item tiles (%d)", a.n_split, n_tiles128);
+      return HTCN_ERR_INVALID;
+    }
+    if (a.flags != HTCN_SCORE_TOPK) {
+      set_error("score(bf16): TOPK cannot be combined with CE/RANK in one sweep (run two calls)");
+      return HTCN_ERR_UNSUPPORTED;
+    }
+    return launch_score<128, HTCN_SCORE_TOPK>(a, nullptr, st);
+  }
+  switch (a.flags) {
+    case HTCN_SCORE_CE: return launch_score<256, HTCN_SCORE_CE>(a, nullptr, st);
+    case HTCN_SCORE_RANK: return launch_score<256, HTCN_SCORE_RANK>(a, nullptr, st);
+    case HTCN_SCORE_CE | HTCN_SCORE_RANK: return launch_score<256, HTCN_SCORE_CE | HTCN_SCORE_RANK>(a, nullptr, st);
+  }
+  set_error("score(bf16): flags 0x%x", a.flags);
+  return HTCN_ERR_INVALID;
+}
+
+int32_t target_logit_bf16(const void* hout, const void* wt, const float* b_out, const int* y_id, int Q, int n_items,
+                          int n0, float* zy, cudaStream_t st) {
+  const size_t smem = sizeof(TargetSmem) + 1024;
+  HTCN_CUDA(cudaFuncSetAttribute(k4_target_bf16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k4_target_bf16<<<ceil_div(Q, kBM), 128, smem, st>>>((const __nv_bfloat16*)hout, (const __nv_bfloat16*)wt, b_out, y_id, Q,
+                                                     n_items, n0, zy);
+  HTCN_LAUNCH_CHECK("k4_target_bf16");
+  return HTCN_OK;
+}
+
+int32_t dump_logits_bf16(const void* hout, int Q, const void* wt, const float* b_out, int n_items, float* logits,
+                         cudaStream_t st) {
+  ScoreArgs a{};
+  a.hout = hout; a.wt = wt; a.b_out = b_out; a.Q = Q; a.n_items = n_items; a.n_split = 1; a.flags = kModeDump;
+  return launch_score<256, kModeDump>(a, logits, st);
+}
+
 }  // namespace htcn
+
+// test hook (not part of include/htcn.h): the exact logits the tcgen05 sweep sees, for parity tests
+extern "C" int32_t htcn_debug_logits_bf16(const void* hout, int32_t Q, const void* w_out_t, const float* b_out,
+                                          int32_t n_items, float* logits, void* stream) {
+  using namespace htcn;
+  HTCN_REQUIRE(hout && w_out_t && b_out && logits && Q > 0 && n_items > 0, "debug_logits_bf16: bad args");
+  return dump_logits_bf16(hout, Q, w_out_t, b_out, n_items, logits, as_stream(stream));
+}

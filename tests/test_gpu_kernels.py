@@ -70,7 +70,8 @@ def test_k1_null_and_out_of_range_ids(lib):
     ids = np.array([[0, 1, 49, 50, -3, 7], [0, 0, 0, 0, 0, 0]], np.int32)
     xe = torch.full((B, T, 128), 7.0, dtype=torch.float32, device="cuda")
     slot_p, keep = lib.int_array([0, T])
-    lib.call("htcn_gather_meanpool", P(dev(E)), None, N, P(dev(ids)), None, slot_p, B, T, 1, P(xe), lib.HTCN_F32, None, None)
+    Ed, idd = dev(E), dev(ids)          # keep the device tensors alive across the async launch
+    lib.call("htcn_gather_meanpool", P(Ed), None, N, P(idd), None, slot_p, B, T, 1, P(xe), lib.HTCN_F32, None, None)
     got = xe.cpu().numpy()
     assert (got[0, 0] == 0).all() and (got[0, 3] == 0).all() and (got[0, 4] == 0).all() and (got[1] == 0).all()
     assert np.array_equal(got[0, 1], E[1]) and np.array_equal(got[0, 2], E[49])
@@ -182,7 +183,8 @@ def test_k4_f32_ce_rank_topk(lib, Q, N, n_split):
     y = rng.integers(1, N, size=Q).astype(np.int32)
     k = min(100, N)
     wt = torch.empty((N, 128), dtype=torch.float32, device="cuda")
-    lib.call("htcn_prepare_wout", P(dev(w_out)), N, P(wt), lib.HTCN_F32, None)
+    w_out_d = dev(w_out)
+    lib.call("htcn_prepare_wout", P(w_out_d), N, P(wt), lib.HTCN_F32, None)
     assert np.array_equal(wt.cpu().numpy(), w_out.T)
     hd, bd, yd = dev(hout), dev(b_out), dev(y)
     flags = lib.SCORE_CE | lib.SCORE_RANK | lib.SCORE_TOPK
@@ -225,9 +227,11 @@ def test_k4_topk_ties_prefer_lower_index(lib):
     w_out[0] = np.round(np.random.default_rng(0).normal(size=N) * 2) / 2     # many exact ties
     b_out = np.zeros(N, np.float32)
     wt = torch.empty((N, 128), dtype=torch.float32, device="cuda")
-    lib.call("htcn_prepare_wout", P(dev(w_out)), N, P(wt), lib.HTCN_F32, None)
+    w_out_d = dev(w_out)
+    lib.call("htcn_prepare_wout", P(w_out_d), N, P(wt), lib.HTCN_F32, None)
     for n_split in (1, 4):
-        _, _, _, _, tv, ti = run_score(lib, dev(hout), wt, dev(b_out), None, lib.SCORE_TOPK, k, n_split)
+        hd, bd = dev(hout), dev(b_out)
+        _, _, _, _, tv, ti = run_score(lib, hd, wt, bd, None, lib.SCORE_TOPK, k, n_split)
         ov = torch.empty((Q, k), dtype=torch.float32, device="cuda")
         oi = torch.empty((Q, k), dtype=torch.int32, device="cuda")
         lib.call("htcn_topk_merge", P(tv), P(ti), n_split, Q, k, P(ov), P(oi), None)
@@ -244,7 +248,8 @@ def test_k4_sharded_catalog_equals_single(lib):
     b_out = (rng.normal(size=N) * 0.2).astype(np.float32)
     y = rng.integers(1, N, size=Q).astype(np.int32)
     wt = torch.empty((N, 128), dtype=torch.float32, device="cuda")
-    lib.call("htcn_prepare_wout", P(dev(w_out)), N, P(wt), lib.HTCN_F32, None)
+    w_out_d = dev(w_out)
+    lib.call("htcn_prepare_wout", P(w_out_d), N, P(wt), lib.HTCN_F32, None)
     hd, bd, yd = dev(hout), dev(b_out), dev(y)
     flags = lib.SCORE_CE | lib.SCORE_RANK | lib.SCORE_TOPK
     zy1, pm1, ps1, pc1, tv1, ti1 = run_score(lib, hd, wt, bd, yd, flags, k, 1)
@@ -287,7 +292,8 @@ def test_loss_metrics_reduce(lib):
     rank_row = rng.integers(0, 30, size=Q).astype(np.float32)
     out = [torch.empty((B, T), dtype=torch.float32, device="cuda") for _ in range(3)]
     sc = torch.empty(8, dtype=torch.float32, device="cuda")
-    lib.call("htcn_loss_metrics_reduce", P(dev(loss_row)), P(dev(rank_row)), P(dev(row_of)), P(dev(y)), B, T, N,
+    lr_d, rr_d, ro_d, y_d = dev(loss_row), dev(rank_row), dev(row_of), dev(y)
+    lib.call("htcn_loss_metrics_reduce", P(lr_d), P(rr_d), P(ro_d), P(y_d), B, T, N,
              P(out[0]), P(out[1]), P(out[2]), P(sc), None)
     loss_bt = np.zeros(B * T, np.float32); loss_bt[valid] = loss_row
     ranks = np.zeros(B * T, np.float32); ranks[valid] = rank_row
@@ -312,9 +318,68 @@ def test_sampled_rank_loss(lib, kind):
     pos[5] = 0
     neg = rng.integers(1, N, size=(Q, k)).astype(np.int32)
     out = torch.empty(Q, dtype=torch.float32, device="cuda")
-    lib.call("htcn_sampled_rank_loss", P(dev(pred)), lib.HTCN_F32, Q, P(dev(table)), P(dev(pos)), P(dev(neg)), k,
+    pred_d, table_d, pos_d, neg_d = dev(pred), dev(table), dev(pos), dev(neg)
+    lib.call("htcn_sampled_rank_loss", P(pred_d), lib.HTCN_F32, Q, P(table_d), P(pos_d), P(neg_d), k,
              lib.LOSS_KINDS[kind], 0.1, 1.0, P(out), None)
     ref = O.calc_loss_sampled(pred[None].astype(np.float64), table[pos][None].astype(np.float64),
                               table[neg][None].astype(np.float64), kind, k, 1.0, 0.1)[0]
     ref[pos == 0] = 0
     np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=1e-4, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------ K4 bf16 (tcgen05)
+def debug_logits_bf16(lib, hd, wt, bd):
+    import ctypes as C
+    L = lib.load()
+    fn = L.htcn_debug_logits_bf16
+    fn.restype = C.c_int32
+    fn.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    Q, N = hd.shape[0], wt.shape[0]
+    out = torch.full((Q, N), float("nan"), dtype=torch.float32, device="cuda")
+    rc = fn(P(hd), Q, P(wt), P(bd), N, P(out), None)
+    assert rc == 0, L.htcn_last_error()
+    torch.cuda.synchronize()
+    return out
+
+
+@pytest.mark.parametrize("Q,N,n_split", [(128, 256, 1), (200, 1000, 1), (130, 20778, 7), (5, 77, 1), (300, 4099, 3)])
+def test_k4_bf16_tcgen05(lib, Q, N, n_split):
+    rng = np.random.default_rng(Q + N)
+    hout = O.bf16_round(rng.normal(size=(Q, 128)).astype(np.float32))
+    w_out = (rng.normal(size=(128, N)) * 0.3).astype(np.float32)
+    b_out = (rng.normal(size=N) * 0.2).astype(np.float32)
+    y = rng.integers(1, N, size=Q).astype(np.int32)
+    k = min(100, N)
+    w_out_d = dev(w_out)
+    wt = torch.empty((N, 128), dtype=torch.bfloat16, device="cuda")
+    lib.call("htcn_prepare_wout", P(w_out_d), N, P(wt), lib.HTCN_BF16, None)
+    assert np.array_equal(wt.float().cpu().numpy(), O.bf16_round(w_out.T))
+    hd, bd, yd = dev(hout).to(torch.bfloat16), dev(b_out), dev(y)
+    # 1. the logits the tensor-core sweep sees == bf16 operands, fp32 accumulate
+    z_gpu = debug_logits_bf16(lib, hd, wt, bd).cpu().numpy()
+    z64 = hout.astype(np.float64) @ O.bf16_round(w_out).astype(np.float64) + b_out
+    np.testing.assert_allclose(z_gpu, z64, rtol=2e-5, atol=2e-5)
+    # 2. CE + rank in one sweep, target logit through the same tcgen05 arithmetic
+    zy, pm, ps, pc, _, _ = run_score(lib, hd, wt, bd, yd, lib.SCORE_CE | lib.SCORE_RANK, 0, n_split, precision=lib.HTCN_BF16)
+    zy_h = zy.cpu().numpy()
+    assert np.array_equal(zy_h, z_gpu[np.arange(Q), y]), "target logit must be bit-identical to the swept logit"
+    loss_row = torch.empty(Q, dtype=torch.float32, device="cuda")
+    rank_row = torch.empty(Q, dtype=torch.float32, device="cuda")
+    lib.call("htcn_score_finish", P(pm), P(ps), P(pc), n_split, Q, P(yd), P(zy), P(loss_row), P(rank_row), None)
+    ref_loss = O.softmax_cross_entropy_with_logits(y, z_gpu.astype(np.float64))
+    np.testing.assert_allclose(loss_row.cpu().numpy(), ref_loss, rtol=1e-4, atol=1e-5)
+    np.testing.assert_array_equal(rank_row.cpu().numpy(), (z_gpu > zy_h[:, None]).sum(1))
+    # rank-only and CE-only specialisations agree with the fused one
+    _, _, _, pc2, _, _ = run_score(lib, hd, wt, bd, yd, lib.SCORE_RANK, 0, n_split, precision=lib.HTCN_BF16, zy_in=zy)
+    assert torch.equal(pc2.sum(0), pc.sum(0))
+    _, pm3, ps3, _, _, _ = run_score(lib, hd, wt, bd, yd, lib.SCORE_CE, 0, n_split, precision=lib.HTCN_BF16, zy_in=zy)
+    assert torch.equal(ps3, ps)
+    # 3. top-k (separate sweep, 128-item tiles)
+    ns_topk = min(n_split, max(1, N // 128))
+    _, _, _, _, tv, ti = run_score(lib, hd, wt, bd, None, lib.SCORE_TOPK, k, ns_topk, precision=lib.HTCN_BF16)
+    ov = torch.empty((Q, k), dtype=torch.float32, device="cuda")
+    oi = torch.empty((Q, k), dtype=torch.int32, device="cuda")
+    lib.call("htcn_topk_merge", P(tv), P(ti), ns_topk, Q, k, P(ov), P(oi), None)
+    v_ref, i_ref = O.top_k(z_gpu, k)
+    np.testing.assert_array_equal(oi.cpu().numpy(), i_ref)
+    np.testing.assert_array_equal(ov.cpu().numpy(), v_ref)
