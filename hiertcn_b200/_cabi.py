@@ -67,9 +67,25 @@ def load(path: str | None = None):
     return lib
 
 
+# kernels launched per successful call (bench.py's gpu_launches claim); htcn_tcn_forward launches
+# n_levels + 1 (counted by the caller through note_launches)
+LAUNCHES_PER_CALL = {"htcn_gather_meanpool": 2, "htcn_gru_sessions": 1, "htcn_tcn_forward": 0,
+                     "htcn_prepare_wout": 1, "htcn_score_ce_rank_topk": 2, "htcn_score_logits": 1,
+                     "htcn_target_logit": 1, "htcn_score_finish": 1, "htcn_topk_merge": 1,
+                     "htcn_loss_metrics_reduce": 1, "htcn_sampled_rank_loss": 1}
+launch_count = 0
+
+
+def note_launches(n: int):
+    global launch_count
+    launch_count += n
+
+
 def call(name: str, *args):
+    global launch_count
     lib = load()
     rc = getattr(lib, name)(*args)
+    launch_count += LAUNCHES_PER_CALL.get(name, 0)
     if rc != 0:
         raise HtcnError("%s failed (%d): %s" % (name, rc, lib.htcn_last_error().decode()))
 

@@ -222,6 +222,7 @@ class HierTCN:
                   sbias.data_ptr(), self._conv_w_pp[0], self._conv_b_pp[0], self.n_levels, self.K, slot_p, B, T, S,
                   d["row_of"].data_ptr(), hout.data_ptr(), self.act_dtype,
                   scratch.data_ptr() if scratch is not None else None, st)
+        cabi.note_launches(self.n_levels + 1)
         del slot_keep
         scores = CatalogScores(self, hout, Q, d["row_of"], d["y_rows"], d["y_id"], B, T)
         return scores, state_out
@@ -260,9 +261,21 @@ class HierTCN:
         tv = self._buf("tv", (ns, Q, topk), f32) if topk else None
         ti = self._buf("ti", (ns, Q, topk), i32) if topk else None
         P = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
+        need_t = ce or rank
+        if need_t:      # target logits first (own launch so the sweep can be timed on its own)
+            cabi.call("htcn_target_logit", scores.hout.data_ptr(), self.act_dtype, Q, self.wt.data_ptr(),
+                      self.b_out.data_ptr(), self.N, 0, scores.y_rows.data_ptr(), zy.data_ptr(), st)
+        ev = getattr(self, "sweep_events", None)
+        if ev is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(torch.cuda.current_stream(self.device))
         cabi.call("htcn_score_ce_rank_topk", scores.hout.data_ptr(), self.act_dtype, Q, self.wt.data_ptr(),
-                  self.b_out.data_ptr(), self.N, 0, scores.y_rows.data_ptr(), zy.data_ptr(), 0, flags, topk, ns,
-                  P(pm), P(ps), P(pc), P(tv), P(ti), st)
+                  self.b_out.data_ptr(), self.N, 0, scores.y_rows.data_ptr() if need_t else None, zy.data_ptr(), 1,
+                  flags, topk, ns, P(pm), P(ps), P(pc), P(tv), P(ti), st)
+        cabi.note_launches(-1)          # have_target=1: the sweep call launched one kernel, not two
+        if ev is not None:
+            e1.record(torch.cuda.current_stream(self.device))
+            ev.append((e0, e1, 2.0 * Q * 128 * self.N))
         if ce or rank:
             loss_row = self._buf("loss_row", (Q,), f32) if ce else None
             rank_row = self._buf("rank_row", (Q,), f32) if rank else None

@@ -115,3 +115,15 @@ def test_state_reset_and_row_independence():
     m2 = [a.copy() for a in m]
     m2[-1][:] = 0
     assert (O.model_hier_restructured(x, y, m2, s0, w, 2, "f32")[1] == 0).all()
+
+
+@pytest.mark.parametrize("literal", [True, False])
+def test_torch_cpu_port_matches_golden(literal):
+    """the CPU-baseline port that bench.py times is held to the same golden vectors"""
+    from oracle.torch_cpu import CpuHierTCN
+    z, x, y, m, w = load_hier_golden("hier_default_arch")
+    out = CpuHierTCN(w).step(x, y, m, z["state0"], literal=literal, chunk=16)
+    assert abs(out["loss"] - z["loss_f64"]) <= 1e-4 * abs(z["loss_f64"])
+    np.testing.assert_allclose(out["state"], z["state_f64"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(out["loss_bt"], z["loss_bt_f64"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_array_equal(out["ranks"], z["ranks_f64"])
