@@ -10,9 +10,9 @@
 // row, sum_j exp(z_j - z_y) (softmax-CE, loss.py:20-21), #{j: z_j > z_y} (rank, loss.py:179) and / or a
 // k-entry heap (top-k, loss.py:120) -- "TMEM lane = row", so every row statistic is a per-thread scalar.
 //
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2..9 = epilogue (a warp may only touch TMEM lanes 32*(warp%4)..+31; the two warps sharing a lane
-// quarter split the tile's columns in halves).  Top-k mode uses 4 epilogue warps (one heap per row).
+// Warp roles (576 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..17 = epilogue (a warp may only touch TMEM lanes 32*(warp%4)..+31; the four warps sharing a lane
+// quarter split the tile's columns in 4 slices of 64).  Top-k mode uses 4 epilogue warps (one heap per row).
 //
 // Softmax reference point: the target logit z_y (computed up front by k4_target_bf16 with the SAME
 // tcgen05.mma arithmetic, so z_y compares equal to itself in the sweep).  CE loss = log sum_j exp(z_j - z_y):
@@ -25,7 +25,7 @@ using namespace sm100;
 
 constexpr int kBM = 128;
 constexpr int kChunkBytesA = kBM * 128;          // one 64-column (128 B) chunk of the A tile
-constexpr int kThreadsBf16 = 320;
+constexpr int kSlicesScore = 4;                  // CE/RANK sweep: 4 column slices x 4 lane quarters = 16 epilogue warps
 constexpr float kLog2e = 1.4426950408889634f;
 
 enum : unsigned { kModeDump = 8u };              // internal: write raw logits (test hook)
@@ -34,21 +34,26 @@ template <int BN>
 struct alignas(1024) ScoreSmem {
   uint8_t a[2][kChunkBytesA];                     // K chunks 0..63 / 64..127
   uint8_t b[2][2][BN * 128];                      // [stage][chunk]
-  float bias[8][128];                             // per epilogue warp
-  float comb_sum[kBM];                            // column-half 1 -> half 0 hand-off at the end of the sweep
-  int comb_cnt[kBM];
+  float bias[16][128];                            // per epilogue warp
+  float comb_sum[3][kBM];                         // column slices 1..3 -> slice 0 hand-off at the end of the sweep
+  int comb_cnt[3][kBM];
   uint64_t a_full, b_full[2], b_empty[2], t_full[2], t_empty[2];
   uint32_t tmem_base;
 };
 
+template <unsigned kFlags>
+constexpr int score_threads() { return 64 + 32 * 4 * ((kFlags & HTCN_SCORE_TOPK) ? 1 : kSlicesScore); }
+
 template <int BN, unsigned kFlags>
-__global__ void __launch_bounds__(kThreadsBf16, 1)
+__global__ void __launch_bounds__(score_threads<kFlags>(), 1)
 k4_score_bf16(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, ScoreArgs a,
               float* __restrict__ dump) {
   constexpr bool kCE = kFlags & HTCN_SCORE_CE, kRank = kFlags & HTCN_SCORE_RANK, kTopk = kFlags & HTCN_SCORE_TOPK;
   constexpr bool kDump = kFlags & kModeDump;
-  constexpr int kEpiWarps = kTopk ? 4 : 8;
-  constexpr int kColsPerWarp = BN / (kEpiWarps / 4);
+  constexpr int kSlices = kTopk ? 1 : kSlicesScore;           // column slices per tile (one heap per row in top-k mode)
+  constexpr int kEpiWarps = 4 * kSlices;
+  constexpr int kColsPerWarp = BN / kSlices;
+  constexpr int kBiasPerLane = kColsPerWarp / 32;
   constexpr uint32_t kTmemCols = 2 * BN;
   extern __shared__ uint8_t smem_raw[];
   auto& sm = *reinterpret_cast<ScoreSmem<BN>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -123,13 +128,15 @@ k4_score_bf16(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
     const bool active = ew < kEpiWarps;
     if (active) {
       const int quarter = warp & 3;                             // TMEM lane quarter this warp may access
-      const int half = ew >> 2;                                 // column half (0 when kEpiWarps == 4)
+      const int half = ew >> 2;                                 // column slice of this warp (0 when kSlices == 1)
       const int row = quarter * 32 + lane;
       const bool row_ok = q0 + row < a.Q;
       const int col0 = half * kColsPerWarp;
       float* bias_s = sm.bias[ew];
+      const uint32_t bias_sa = smem_u32(bias_s);
       float zy = 0.f, zyl = 0.f, thr = -INFINITY;
       float sum4[4] = {0.f, 0.f, 0.f, 0.f};                     // 4 independent partial sums (ILP + accuracy)
+      float cf[4] = {0.f, 0.f, 0.f, 0.f};                       // per-tile rank counts as floats (FSET.BF + FADD)
       int cnt = 0;
       if ((kCE || kRank) && row_ok) {
         zy = a.zy[q0 + row];
@@ -138,80 +145,106 @@ k4_score_bf16(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
       RowHeap heap{heap_v + row, heap_i + row, kBM, a.k};
       if (kTopk) heap.init();
 
-      for (int i = 0; i < n_tiles; ++i) {
-        const int buf = i & 1;
-        const int j0 = (t_begin + i) * BN;
-        // stage this warp's bias slice (kColsPerWarp floats) -- warp-private, no cross-warp sync
-        __syncwarp();
+      // one 32-column chunk held in registers; `c` = column offset inside this warp's slice
+      auto process = [&](const uint32_t (&r)[32], int c, int lim, int jbase) {
+        if (c + 32 <= lim) {                                    // full chunk: branch-free
 #pragma unroll
-        for (int c = lane; c < kColsPerWarp; c += 32) {
-          const int j = j0 + col0 + c;
-          bias_s[c] = (j < a.n_items) ? __ldg(a.b_out + j) : 0.f;
-        }
-        __syncwarp();
-        mbar_wait(&sm.t_full[buf], (i >> 1) & 1);
-        tc_fence_after_sync();
-        const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + buf * BN + col0;
-        const int lim = a.n_items - j0 - col0;                  // columns of this warp's slice that exist
-#pragma unroll 1
-        for (int c = 0; c < kColsPerWarp; c += 32) {
-          uint32_t r[32];
-          tmem_ld_32x32(taddr + c, r);
-          tmem_ld_wait();
-          if (c + 32 <= lim) {                                  // full chunk: branch-free
+          for (int u4 = 0; u4 < 8; ++u4) {
+            const float4 b4 = lds_f4(bias_sa + (c + u4 * 4) * 4);
+            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+            float z[4];
 #pragma unroll
-            for (int u4 = 0; u4 < 8; ++u4) {
-              const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c + u4 * 4);
-              const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-              for (int v = 0; v < 4; ++v) {
-                const int u = u4 * 4 + v;
-                const float z = __uint_as_float(r[u]) + bb[v];
-                if (kDump) {
-                  if (row_ok) dump[(long long)(q0 + row) * a.n_items + j0 + col0 + c + u] = z;
-                }
-                if (kCE) sum4[v] += ex2_approx(fmaf(z, kLog2e, -zyl));
-                if (kRank) cnt += (z > zy) ? 1 : 0;
-                if (kTopk) {
-                  if (z > thr) thr = heap.replace_root(z, a.n0 + j0 + col0 + c + u);
-                }
+            for (int v = 0; v < 4; ++v) {
+              z[v] = __uint_as_float(r[u4 * 4 + v]) + bb[v];
+              if (kDump) {
+                if (row_ok) dump[(long long)(q0 + row) * a.n_items + jbase + c + u4 * 4 + v] = z[v];
+              }
+              if (kCE) sum4[v] += ex2_approx(fmaf(z[v], kLog2e, -zyl));
+              if (kTopk) {
+                if (z[v] > thr) thr = heap.replace_root(z[v], a.n0 + jbase + c + u4 * 4 + v);
               }
             }
-          } else if (c < lim) {                                 // ragged last tile of the catalog
-#pragma unroll 1
-            for (int u = 0; u < 32; ++u) {
-              float z = 0.f;
+            if (kRank) {
 #pragma unroll
-              for (int w = 0; w < 32; ++w)
-                if (w == u) z = __uint_as_float(r[w]);
-              if (c + u < lim) {
-                z += bias_s[c + u];
-                if (kDump) {
-                  if (row_ok) dump[(long long)(q0 + row) * a.n_items + j0 + col0 + c + u] = z;
-                }
-                if (kCE) sum4[0] += ex2_approx(fmaf(z, kLog2e, -zyl));
-                if (kRank) cnt += (z > zy) ? 1 : 0;
-                if (kTopk) {
-                  if (z > thr) thr = heap.replace_root(z, a.n0 + j0 + col0 + c + u);
-                }
+              for (int v = 0; v < 4; ++v) cf[v] += set_gt_f(z[v], zy);
+            }
+          }
+        } else if (c < lim) {                                   // ragged last tile of the catalog
+#pragma unroll 1
+          for (int u = 0; u < 32; ++u) {
+            float z = 0.f;
+#pragma unroll
+            for (int w = 0; w < 32; ++w)
+              if (w == u) z = __uint_as_float(r[w]);
+            if (c + u < lim) {
+              z += bias_s[c + u];
+              if (kDump) {
+                if (row_ok) dump[(long long)(q0 + row) * a.n_items + jbase + c + u] = z;
+              }
+              if (kCE) sum4[0] += ex2_approx(fmaf(z, kLog2e, -zyl));
+              if (kRank) cf[0] += set_gt_f(z, zy);
+              if (kTopk) {
+                if (z > thr) thr = heap.replace_root(z, a.n0 + jbase + c + u);
               }
             }
           }
         }
-        tc_fence_before_sync();
+      };
+
+      // bias slice of tile i+1 is fetched into registers while tile i is consumed (hides the L2 latency)
+      float bnext[kBiasPerLane];
+      auto fetch_bias = [&](int i) {
+#pragma unroll
+        for (int u = 0; u < kBiasPerLane; ++u) {
+          const int j = (t_begin + i) * BN + col0 + u * 32 + lane;
+          bnext[u] = (i < n_tiles && j < a.n_items) ? __ldg(a.b_out + j) : 0.f;
+        }
+      };
+      fetch_bias(0);
+      for (int i = 0; i < n_tiles; ++i) {
+        const int buf = i & 1;
+        const int j0 = (t_begin + i) * BN;
+        __syncwarp();                                           // previous tile's readers are done with bias_s
+#pragma unroll
+        for (int u = 0; u < kBiasPerLane; ++u) bias_s[u * 32 + lane] = bnext[u];
         __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.t_empty[buf]);
+        fetch_bias(i + 1);
+        mbar_wait(&sm.t_full[buf], (i >> 1) & 1);
+        tc_fence_after_sync();
+        const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + buf * BN + col0;
+        const int lim = a.n_items - j0 - col0;                  // columns of this warp's slice that exist
+        const int jbase = j0 + col0;
+#pragma unroll
+        for (int c = 0; c < kColsPerWarp; c += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c, r);
+          tmem_ld_wait(r);
+          if (c + 32 == kColsPerWarp) {
+            // every TMEM read of this accumulator has retired: hand it back before the last chunk's math
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.t_empty[buf]);
+          }
+          process(r, c, lim, jbase);
+        }
+        if (kRank) {                                            // flush the float counters (exact: <= 128 per tile)
+          cnt += (int)((cf[0] + cf[1]) + (cf[2] + cf[3]));
+          cf[0] = cf[1] = cf[2] = cf[3] = 0.f;
+        }
       }
       float sum = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
-      if (kEpiWarps == 8) {                                     // fold column half 1 into half 0
-        if (half == 1) {
-          sm.comb_sum[row] = sum;
-          sm.comb_cnt[row] = cnt;
+      if (kSlices > 1) {                                        // fold column slices 1.. into slice 0
+        if (half > 0) {
+          sm.comb_sum[half - 1][row] = sum;
+          sm.comb_cnt[half - 1][row] = cnt;
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
         if (half == 0) {
-          sum += sm.comb_sum[row];
-          cnt += sm.comb_cnt[row];
+#pragma unroll
+          for (int h = 0; h < kSlices - 1; ++h) {
+            sum += sm.comb_sum[h][row];
+            cnt += sm.comb_cnt[h][row];
+          }
         }
       }
       if (row_ok && half == 0) {
@@ -361,7 +394,7 @@ static int32_t launch_score(const ScoreArgs& a, float* dump, cudaStream_t st) {
   auto kern = k4_score_bf16<BN, kFlags>;
   HTCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(ceil_div(a.Q, kBM), a.n_split);
-  kern<<<grid, kThreadsBf16, smem, st>>>(ta, tb, a, dump);
+  kern<<<grid, score_threads<kFlags>(), smem, st>>>(ta, tb, a, dump);
   HTCN_LAUNCH_CHECK("k4_score_bf16");
   return HTCN_OK;
 }
