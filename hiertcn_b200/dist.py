@@ -1,0 +1,181 @@
+"""Multi-GPU plumbing for the hot path: one process per GPU, torch.distributed (NCCL on the box, gloo in
+the CPU tests).  The reference has no distributed code at all; this is the B200-native
+addition the north star asks for.
+
+Two shardings:
+
+* users (data-parallel): rows of the batch are independent users (reference data_loader.py:153-156), so each
+  rank runs the whole forward + scoring on its own users with a replicated catalog; the only exchange is the
+  all-reduce of the loss / metric partial sums (``allreduce_scalars``).
+* catalog (config 4, 8M items): rank r owns rows [n0_r, n1_r) of W_out^T.  ``ShardedCatalogScorer.score``:
+    1. all-gather the query rows (user embeddings Hout, 256 B/row in bf16) and their target ids,
+    2. every rank fills the target logits of the ids it owns; all-reduce(SUM) completes the vector,
+    3. local sweep over the shard -> per-row partials (max, sumexp, count) and a local top-k,
+    4. all-to-all: each rank receives, for ITS OWN rows, the partials of every shard,
+    5. merge: log-sum-exp across shards, rank = sum of counts, k-way top-k merge (score desc, global index asc).
+
+The arithmetic of steps 2, 3 and 5 is delegated to an ``ops`` object: ``CudaScoreOps`` (the sm_100a kernels
+through the C ABI) in production; the gloo tests inject a numpy implementation to exercise the choreography
+on CPU.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_bounds(n_items: int, world: int, align: int = 256):
+    """Row ranges of the catalog shards: contiguous, multiples of ``align`` items (whole MMA tiles) except the last."""
+    per = -(-n_items // world)
+    per = -(-per // align) * align
+    b = [min(r * per, n_items) for r in range(world + 1)]
+    b[-1] = n_items
+    return b
+
+
+def allreduce_scalars(scalars, dist, world):
+    """Global loss/metrics from per-rank ``scalars[8]`` = {loss, r@1, r@5, r@10, mrr, mrp, user_count, n_valid}:
+    the per-rank values are means over that rank's users (model.py:116-117), so weight by user_count."""
+    if world == 1:
+        return scalars
+    t = scalars.clone()
+    t[:6] *= scalars[6]
+    dist.all_reduce(t)
+    t[:6] /= t[6]
+    return t
+
+
+class ShardedCatalogScorer:
+    """Catalog-sharded scoring with CE / rank / top-k merged across ranks (see module docstring)."""
+
+    def __init__(self, ops, dist, rank: int, world: int, n_items: int, n_split: int = 1):
+        self.ops, self.dist, self.rank, self.world = ops, dist, rank, world
+        self.bounds = shard_bounds(n_items, world)
+        self.n0, self.n1 = self.bounds[rank], self.bounds[rank + 1]
+        self.n_split = n_split
+
+    def score(self, hout, y_id, k: int = 0, ce: bool = True, rank_metric: bool = True):
+        """hout [Q_local,128], y_id [Q_local] (global ids; may be None when only top-k is wanted).
+        Every rank must pass the same Q_local.  Returns dict(loss_row, rank_row, topk_val, topk_idx) for the
+        LOCAL rows."""
+        o, d, W = self.ops, self.dist, self.world
+        Ql = hout.shape[0]
+        need_t = (ce or rank_metric) and y_id is not None
+        # 1. every shard must see every query row
+        h_all = o.all_gather_rows(d, hout, W)                       # [W*Ql, 128]
+        y_all = o.all_gather_rows(d, y_id, W) if need_t else None
+        Q = W * Ql
+        # 2. target logits: owner fills, all-reduce completes
+        zy = None
+        if need_t:
+            zy = o.zeros_f32(Q)
+            o.target_logit(h_all, y_all, self.n0, self.n1, zy)
+            d.all_reduce(zy)
+        # 3. local sweep
+        part = o.sweep(h_all, y_all, zy, self.n0, self.n1, k, self.n_split, ce and need_t, rank_metric and need_t)
+        # 4. all-to-all of the partials: [n_split, W, Ql, ...] -> every rank gets its own rows from every shard
+        out = {}
+        if need_t:
+            merged = {}
+            for name in ("pm", "ps", "pc"):
+                if part.get(name) is not None:
+                    merged[name] = o.all_to_all_rows(d, part[name], W, Ql)      # [W*n_split, Ql]
+            zy_local = o.slice_rows(zy, self.rank * Ql, Ql)
+            # 5. merge
+            out.update(o.finish(merged.get("pm"), merged.get("ps"), merged.get("pc"), y_id, zy_local))
+        if k:
+            tv = o.all_to_all_rows(d, part["tv"], W, Ql)                         # [W*n_split, Ql, k]
+            ti = o.all_to_all_rows(d, part["ti"], W, Ql)
+            out.update(o.topk_merge(tv, ti, k))
+        return out
+
+
+class CudaScoreOps:
+    """The production ``ops``: device tensors + libhtcn kernels (through the C ABI)."""
+
+    def __init__(self, model):
+        import torch
+        from . import _cabi as cabi
+        self.torch, self.cabi, self.m = torch, cabi, model
+
+    # ---- collectives on device tensors
+    def all_gather_rows(self, dist, t, world):
+        out = self.torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t.contiguous())
+        return out
+
+    def all_to_all_rows(self, dist, part, world, Ql):
+        """part [n_split, world*Ql, ...] -> [world*n_split, Ql, ...] holding this rank's rows from every shard"""
+        ns = part.shape[0]
+        tail = tuple(part.shape[2:])
+        send = part.reshape((ns, world, Ql) + tail).transpose(0, 1).contiguous()     # [world, ns, Ql, ...]
+        recv = self.torch.empty_like(send)
+        dist.all_to_all_single(recv, send)
+        return recv.reshape((world * ns, Ql) + tail)
+
+    def zeros_f32(self, n):
+        return self.torch.zeros(n, dtype=self.torch.float32, device=self.m.device)
+
+    def slice_rows(self, t, start, n):
+        return t[start:start + n].contiguous()
+
+    # ---- kernels
+    def target_logit(self, h_all, y_all, n0, n1, zy):
+        m = self.m
+        self.cabi.call("htcn_target_logit", h_all.data_ptr(), m.act_dtype, h_all.shape[0], m.wt.data_ptr(),
+                       m.b_out.data_ptr(), n1 - n0, n0, y_all.data_ptr(), zy.data_ptr(), m.stream_ptr())
+
+    def sweep(self, h_all, y_all, zy, n0, n1, k, n_split, ce, rank):
+        torch, cabi, m = self.torch, self.cabi, self.m
+        Q = h_all.shape[0]
+        f32, i32 = torch.float32, torch.int32
+        P = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
+        out = dict(pm=None, ps=None, pc=None, tv=None, ti=None)
+        flags = (cabi.SCORE_CE if ce else 0) | (cabi.SCORE_RANK if rank else 0)
+        if flags:
+            out["pm"] = torch.empty((n_split, Q), dtype=f32, device=m.device) if ce else None
+            out["ps"] = torch.empty((n_split, Q), dtype=f32, device=m.device) if ce else None
+            out["pc"] = torch.empty((n_split, Q), dtype=i32, device=m.device) if rank else None
+            cabi.call("htcn_score_ce_rank_topk", h_all.data_ptr(), m.act_dtype, Q, m.wt.data_ptr(), m.b_out.data_ptr(),
+                      n1 - n0, n0, y_all.data_ptr(), zy.data_ptr(), 1, flags, 0, n_split, P(out["pm"]), P(out["ps"]),
+                      P(out["pc"]), None, None, m.stream_ptr())
+        if k:
+            out["tv"] = torch.empty((n_split, Q, k), dtype=f32, device=m.device)
+            out["ti"] = torch.empty((n_split, Q, k), dtype=i32, device=m.device)
+            cabi.call("htcn_score_ce_rank_topk", h_all.data_ptr(), m.act_dtype, Q, m.wt.data_ptr(), m.b_out.data_ptr(),
+                      n1 - n0, n0, None, None, 1, cabi.SCORE_TOPK, k, n_split, None, None, None, P(out["tv"]),
+                      P(out["ti"]), m.stream_ptr())
+        return out
+
+    def finish(self, pm, ps, pc, y_id, zy_local):
+        torch, cabi, m = self.torch, self.cabi, self.m
+        Ql = zy_local.shape[0]
+        n_part = (pm if pm is not None else pc).shape[0]
+        P = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
+        loss_row = torch.empty(Ql, dtype=torch.float32, device=m.device) if pm is not None else None
+        rank_row = torch.empty(Ql, dtype=torch.float32, device=m.device) if pc is not None else None
+        cabi.call("htcn_score_finish", P(pm), P(ps), P(pc), n_part, Ql, y_id.data_ptr(), zy_local.data_ptr(),
+                  P(loss_row), P(rank_row), m.stream_ptr())
+        return dict(loss_row=loss_row, rank_row=rank_row)
+
+    def topk_merge(self, tv, ti, k):
+        torch, cabi, m = self.torch, self.cabi, self.m
+        n_part, Ql = tv.shape[0], tv.shape[1]
+        ov = torch.empty((Ql, k), dtype=torch.float32, device=m.device)
+        oi = torch.empty((Ql, k), dtype=torch.int32, device=m.device)
+        cabi.call("htcn_topk_merge", tv.data_ptr(), ti.data_ptr(), n_part, Ql, k, ov.data_ptr(), oi.data_ptr(),
+                  m.stream_ptr())
+        return dict(topk_val=ov, topk_idx=oi)
+
+
+def make_sharded_model(args, weights, rank, world, precision="bf16"):
+    """HierTCN whose W_out^T / b_out hold only this rank's catalog shard (rows [n0, n1))."""
+    from .model_hier import HierTCN
+    n_items = int(args.item_num)
+    b = shard_bounds(n_items, world)
+    n0, n1 = b[rank], b[rank + 1]
+    w = dict(weights)
+    w["hier/tcn/dense/kernel"] = np.ascontiguousarray(weights["hier/tcn/dense/kernel"][:, n0:n1])
+    w["hier/tcn/dense/bias"] = np.ascontiguousarray(weights["hier/tcn/dense/bias"][n0:n1])
+    m = HierTCN(args, w, precision=precision)
+    m.out_rows = n1 - n0
+    return m.build(), n0, n1

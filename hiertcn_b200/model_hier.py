@@ -146,8 +146,9 @@ class HierTCN:
         self.act_dtype = cabi.HTCN_BF16 if self.precision == "bf16" else cabi.HTCN_F32
         tdt = torch.bfloat16 if self.precision == "bf16" else torch.float32
         self.act_torch_dtype = tdt
-        self.wt = torch.empty((self.N, D), dtype=tdt, device=dev)          # W_out^T, K-major rows
-        cabi.call("htcn_prepare_wout", w_out.data_ptr(), self.N, self.wt.data_ptr(), self.act_dtype, self.stream_ptr())
+        self.n_out = int(w_out.shape[1])               # == N, or this rank's catalog shard (hiertcn_b200.dist)
+        self.wt = torch.empty((self.n_out, D), dtype=tdt, device=dev)      # W_out^T, K-major rows
+        cabi.call("htcn_prepare_wout", w_out.data_ptr(), self.n_out, self.wt.data_ptr(), self.act_dtype, self.stream_ptr())
         self.wt_f32 = self.wt if self.precision == "f32" else None
         torch.cuda.synchronize(dev)
         del w_out
