@@ -163,6 +163,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--batch", type=int, default=0, help="override users per GPU (debugging)")
+    ap.add_argument("--n-split", type=int, default=0, help="override the catalog split count of the K4 sweep")
     opt = ap.parse_args()
     wl = dict(WORKLOADS[opt.workload])
     if opt.batch:
@@ -188,6 +189,7 @@ def main():
     w = make_weights(wl)
     a = make_args(["--item_num", str(wl["N"]), "--batch_size", str(wl["B"]), "--emb_dim", str(wl["emb_dim"])])
     model = HierTCN(a, w, precision=opt.precision).build()
+    model.force_n_split = opt.n_split
     x, y, m, s0 = make_inputs(wl, seed=1 + rank)
     B, T = wl["B"], wl["S"] * wl["L"]
 

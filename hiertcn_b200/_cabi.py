@@ -15,6 +15,7 @@ HTCN_F32, HTCN_BF16 = 0, 1
 SCORE_CE, SCORE_RANK, SCORE_TOPK = 1, 2, 4
 LOSS_KINDS = {"nce": 0, "hinge_sigmoid": 1, "hinge_logsigmoid": 2, "hinge_linear": 3, "bpr": 4}
 MAX_TOPK = 128
+WT_PITCH_BF16 = 144
 
 _p, _i, _u, _f = C.c_void_p, C.c_int32, C.c_uint32, C.c_float
 _pp = C.POINTER(C.c_void_p)        # host array of device pointers
@@ -26,7 +27,7 @@ SIGNATURES = {
     "htcn_gather_meanpool": [_p, _p, _i, _p, _p, _ip, _i, _i, _i, _p, _i, _p, _p],
     "htcn_gru_sessions": [_p, _p, _p, _pp, _pp, _pp, _pp, _i, _p, _i, _i, _p, _p, _p, _p],
     "htcn_tcn_forward": [_p, _i, _i, _p, _p, _pp, _pp, _i, _i, _ip, _i, _i, _i, _p, _p, _i, _p, _p],
-    "htcn_prepare_wout": [_p, _i, _p, _i, _p],
+    "htcn_prepare_wout": [_p, _p, _i, _p, _i, _p],
     "htcn_score_ce_rank_topk": [_p, _i, _i, _p, _p, _i, _i, _p, _p, _i, _u, _i, _i, _p, _p, _p, _p, _p, _p],
     "htcn_score_logits": [_p, _i, _i, _p, _i, _p, _i, _p, _p],
     "htcn_target_logit": [_p, _i, _i, _p, _p, _i, _i, _p, _p, _p],

@@ -12,6 +12,9 @@
 namespace htcn {
 
 constexpr int kDim = HTCN_DIM;  // D = C = H = 128
+// bf16 tier: W_out^T rows are stored augmented, [128 weights | b_hi | b_lo | 14 zeros], so that the tensor core
+// adds the bias (htcn_prepare_wout writes this layout; the fp32 tier keeps plain 128-float rows + b_out)
+constexpr int kWtPitchBf16 = HTCN_WT_PITCH_BF16;
 
 // thread-local error message (htcn_last_error)
 void set_error(const char* fmt, ...);

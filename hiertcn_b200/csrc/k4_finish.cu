@@ -13,12 +13,26 @@ int32_t score_bf16(const ScoreArgs& a, cudaStream_t st);
 int32_t target_logit_bf16(const void* hout, const void* wt, const float* b_out, const int* y_id, int Q,
                           int n_items, int n0, float* zy, cudaStream_t st);
 
-// ---- W_out [128, N] f32 -> W_out^T [N, 128] f32 | bf16 (32x32 smem transpose) ----------------
+// ---- W_out [128, N] f32 -> W_out^T [N, 128] f32 | [N, 144] bf16 augmented (32x32 smem transpose) ----
 template <bool kBf16>
-__global__ void prepare_wout_kernel(const float* __restrict__ w, int N, void* __restrict__ out) {
+__global__ void prepare_wout_kernel(const float* __restrict__ w, const float* __restrict__ b, int N,
+                                    void* __restrict__ out) {
   __shared__ float tile[32][33];
-  const int n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  constexpr int pitch = kBf16 ? kWtPitchBf16 : kDim;
+  const int n0 = blockIdx.x * 32;
   const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
+  if (blockIdx.y == kDim / 32) {                  // bf16 only: the bias columns 128..143 of 32 items
+    if (ty == 0 && n0 + tx < N) {
+      __nv_bfloat16* row = reinterpret_cast<__nv_bfloat16*>(out) + (long long)(n0 + tx) * pitch + kDim;
+      const float bv = b[n0 + tx];
+      const __nv_bfloat16 hi = __float2bfloat16_rn(bv);
+      row[0] = hi;
+      row[1] = __float2bfloat16_rn(bv - __bfloat162float(hi));
+      for (int i = 2; i < pitch - kDim; ++i) row[i] = __float2bfloat16_rn(0.f);
+    }
+    return;
+  }
+  const int c0 = blockIdx.y * 32;
   for (int i = ty; i < 32; i += 8) {
     const int n = n0 + tx;
     tile[i][tx] = (n < N) ? w[(long long)(c0 + i) * N + n] : 0.f;
@@ -28,8 +42,8 @@ __global__ void prepare_wout_kernel(const float* __restrict__ w, int N, void* __
     const int n = n0 + i;
     if (n < N) {
       const float v = tile[tx][i];
-      if (kBf16) reinterpret_cast<__nv_bfloat16*>(out)[(long long)n * kDim + c0 + tx] = __float2bfloat16_rn(v);
-      else reinterpret_cast<float*>(out)[(long long)n * kDim + c0 + tx] = v;
+      if (kBf16) reinterpret_cast<__nv_bfloat16*>(out)[(long long)n * pitch + c0 + tx] = __float2bfloat16_rn(v);
+      else reinterpret_cast<float*>(out)[(long long)n * pitch + c0 + tx] = v;
     }
   }
 }
@@ -41,15 +55,17 @@ __global__ void score_logits_kernel(const void* __restrict__ hout, int h_bf16, i
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)Q * n_items) return;
   const int q = (int)(i / n_items), j = (int)(i % n_items);
+  const __nv_bfloat16* wb = reinterpret_cast<const __nv_bfloat16*>(wt) + (long long)j * kWtPitchBf16;
   float acc = 0.f;
   for (int k = 0; k < kDim; ++k) {
     const float a = h_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(hout)[(long long)q * kDim + k])
                            : reinterpret_cast<const float*>(hout)[(long long)q * kDim + k];
-    const float b = w_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(wt)[(long long)j * kDim + k])
-                           : reinterpret_cast<const float*>(wt)[(long long)j * kDim + k];
+    const float b = w_bf16 ? __bfloat162float(wb[k]) : reinterpret_cast<const float*>(wt)[(long long)j * kDim + k];
     acc = fmaf(a, b, acc);
   }
-  logits[i] = acc + b_out[j];
+  // bf16 tier: the bias is the (hi, lo) pair stored in the augmented columns, as the tensor-core sweep sees it
+  const float bias = w_bf16 ? (__bfloat162float(wb[kDim]) + __bfloat162float(wb[kDim + 1])) : b_out[j];
+  logits[i] = acc + bias;
 }
 
 // ---- merge CE / rank partials -----------------------------------------------------------------
@@ -180,12 +196,20 @@ loss_metrics_reduce_kernel(const float* __restrict__ loss_row, const float* __re
 
 using namespace htcn;
 
-extern "C" int32_t htcn_prepare_wout(const float* w_out, int32_t N, void* w_out_t, int32_t dtype, void* stream) {
+extern "C" int32_t htcn_prepare_wout(const float* w_out, const float* b_out, int32_t N, void* w_out_t, int32_t dtype,
+                                     void* stream) {
   HTCN_REQUIRE(w_out && w_out_t && N > 0, "prepare_wout: bad args");
-  dim3 grid(ceil_div(N, 32), kDim / 32), block(32, 8);
-  if (dtype == HTCN_BF16) prepare_wout_kernel<true><<<grid, block, 0, as_stream(stream)>>>(w_out, N, w_out_t);
-  else if (dtype == HTCN_F32) prepare_wout_kernel<false><<<grid, block, 0, as_stream(stream)>>>(w_out, N, w_out_t);
-  else HTCN_REQUIRE(false, "prepare_wout: dtype %d", dtype);
+  dim3 block(32, 8);
+  if (dtype == HTCN_BF16) {
+    HTCN_REQUIRE(b_out, "prepare_wout: the bf16 layout folds the bias in, b_out is required");
+    dim3 grid(ceil_div(N, 32), kDim / 32 + 1);
+    prepare_wout_kernel<true><<<grid, block, 0, as_stream(stream)>>>(w_out, b_out, N, w_out_t);
+  } else if (dtype == HTCN_F32) {
+    dim3 grid(ceil_div(N, 32), kDim / 32);
+    prepare_wout_kernel<false><<<grid, block, 0, as_stream(stream)>>>(w_out, b_out, N, w_out_t);
+  } else {
+    HTCN_REQUIRE(false, "prepare_wout: dtype %d", dtype);
+  }
   HTCN_LAUNCH_CHECK("prepare_wout");
   return HTCN_OK;
 }
@@ -193,7 +217,8 @@ extern "C" int32_t htcn_prepare_wout(const float* w_out, int32_t N, void* w_out_
 extern "C" int32_t htcn_score_logits(const void* hout, int32_t hout_dtype, int32_t Q, const void* w_out_t,
                                      int32_t w_dtype, const float* b_out, int32_t n_items, float* logits,
                                      void* stream) {
-  HTCN_REQUIRE(hout && w_out_t && b_out && logits && Q > 0 && n_items > 0, "score_logits: bad args");
+  HTCN_REQUIRE(hout && w_out_t && logits && Q > 0 && n_items > 0, "score_logits: bad args");
+  HTCN_REQUIRE(b_out || w_dtype == HTCN_BF16, "score_logits: b_out is NULL");
   const long long n = (long long)Q * n_items;
   score_logits_kernel<<<ceil_div(n, 256), 256, 0, as_stream(stream)>>>(hout, hout_dtype == HTCN_BF16, Q, w_out_t,
                                                                       w_dtype == HTCN_BF16, b_out, n_items, logits);
@@ -204,7 +229,8 @@ extern "C" int32_t htcn_score_logits(const void* hout, int32_t hout_dtype, int32
 extern "C" int32_t htcn_target_logit(const void* hout, int32_t precision, int32_t Q, const void* w_out_t,
                                      const float* b_out, int32_t n_items, int32_t n0, const int32_t* y_id,
                                      float* target_logit, void* stream) {
-  HTCN_REQUIRE(hout && w_out_t && b_out && y_id && target_logit && Q > 0 && n_items > 0, "target_logit: bad args");
+  HTCN_REQUIRE(hout && w_out_t && y_id && target_logit && Q > 0 && n_items > 0, "target_logit: bad args");
+  HTCN_REQUIRE(b_out || precision == HTCN_BF16, "target_logit: b_out is NULL");
   if (precision == HTCN_F32)
     return target_logit_f32((const float*)hout, (const float*)w_out_t, b_out, y_id, Q, n_items, n0, target_logit,
                             as_stream(stream));
@@ -218,7 +244,8 @@ extern "C" int32_t htcn_score_ce_rank_topk(const void* hout, int32_t precision, 
                                            float* target_logit, int32_t have_target, uint32_t flags, int32_t k,
                                            int32_t n_split, float* part_max, float* part_sum, int32_t* part_cnt,
                                            float* topk_val, int32_t* topk_idx, void* stream) {
-  HTCN_REQUIRE(hout && w_out_t && b_out && Q > 0 && n_items > 0 && n_split >= 1, "score: bad args");
+  HTCN_REQUIRE(hout && w_out_t && Q > 0 && n_items > 0 && n_split >= 1, "score: bad args");
+  HTCN_REQUIRE(b_out || precision == HTCN_BF16, "score: b_out is NULL");
   HTCN_REQUIRE(flags != 0 && (flags & ~7u) == 0, "score: flags 0x%x", flags);
   const bool need_t = flags & (HTCN_SCORE_CE | HTCN_SCORE_RANK);
   HTCN_REQUIRE(!need_t || (y_id && target_logit), "score: CE/RANK need y_id and target_logit");

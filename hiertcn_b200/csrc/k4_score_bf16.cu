@@ -1,14 +1,20 @@
 // K4 (bf16 tier): full-catalog scoring on the 5th-gen tensor cores.
 //
-//   Z[q, j] = Hout[q, :] . W_out^T[j, :] + b[j]        Hout [Q,128] bf16, W_out^T [N,128] bf16, fp32 accumulate
+//   Z[q, j] = Hout[q, :] . W_out^T[j, :] + b[j]        Hout [Q,128] bf16, fp32 accumulate in TMEM
+//
+// W_out^T is stored AUGMENTED: [N, 144] bf16 rows = 128 weights | b_hi | b_lo | 14 zeros (htcn_prepare_wout), and
+// the A operand gets a constant 16-wide K chunk [1, 1, 0, ...]: the bias is added by the tensor core
+// (a 9th K=16 MMA per tile) instead of by the epilogue, which is the bottleneck.  b_hi + b_lo (two bf16) carry the
+// fp32 bias to 2^-17 relative.
 //
 // One CTA owns a 128-row query tile (A, 32 KB, loaded once by TMA, stays resident) and sweeps its
-// catalog split in tiles of BN items streamed by TMA through a 2-stage shared-memory ring (128-byte
-// swizzle, K-major).  One elected thread issues tcgen05.mma (M=128, N=BN, K=16 x 8 k-steps) into a
-// double-buffered TMEM accumulator (2 x BN fp32 columns); the epilogue warps drain buffer i with
-// tcgen05.ld while the tensor core fills buffer i+1.  Logits never leave the SM: the epilogue keeps, per
-// row, sum_j exp(z_j - z_y) (softmax-CE, loss.py:20-21), #{j: z_j > z_y} (rank, loss.py:179) and / or a
-// k-entry heap (top-k, loss.py:120) -- "TMEM lane = row", so every row statistic is a per-thread scalar.
+// catalog split in tiles of BN items streamed by TMA through a 2-stage shared-memory ring (K-major; the two
+// 64-column weight chunks use the 128-byte swizzle, the 16-column bias chunk the 32-byte swizzle).
+// One elected thread issues tcgen05.mma (M=128, N=BN, K=16) x 9 into a double-buffered TMEM accumulator
+// (2 x BN fp32 columns); the epilogue warps drain buffer i with tcgen05.ld while the tensor core fills
+// buffer i+1.  Logits never leave the SM: the epilogue keeps, per row, sum_j exp(z_j - z_y) (softmax-CE,
+// loss.py:20-21), #{j: z_j > z_y} (rank, loss.py:179) and / or a k-entry heap (top-k, loss.py:120) --
+// "TMEM lane = row", so every row statistic is a per-thread scalar.
 //
 // Warp roles (576 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
 // warps 2..17 = epilogue (a warp may only touch TMEM lanes 32*(warp%4)..+31; the four warps sharing a lane
@@ -32,29 +38,51 @@ enum : unsigned { kModeDump = 8u };              // internal: write raw logits (
 
 template <int BN>
 struct alignas(1024) ScoreSmem {
-  uint8_t a[2][kChunkBytesA];                     // K chunks 0..63 / 64..127
+  uint8_t a[2][kChunkBytesA];                     // K chunks 0..63 / 64..127 (128B swizzle)
+  uint8_t a_bias[kBM * 32];                       // K chunk 128..143 = [1,1,0,...] per row (32B swizzle), constant
   uint8_t b[2][2][BN * 128];                      // [stage][chunk]
-  float bias[16][128];                            // per epilogue warp
+  uint8_t b_bias[2][BN * 32];                     // [stage] K chunk 128..143 = [b_hi, b_lo, 0...] per item
   float comb_sum[3][kBM];                         // column slices 1..3 -> slice 0 hand-off at the end of the sweep
   int comb_cnt[3][kBM];
   uint64_t a_full, b_full[2], b_empty[2], t_full[2], t_empty[2];
   uint32_t tmem_base;
 };
 
+// constant A chunk: row r = bf16 [1, 1, 0 x14]; 32-byte swizzle: 16-byte chunk index ^= (r >> 2) & 1
+__device__ __forceinline__ void write_a_bias_row(uint8_t* a_bias, int r) {
+  const int sw = (r >> 2) & 1;
+  *reinterpret_cast<uint4*>(a_bias + r * 32 + ((0 ^ sw) << 4)) = make_uint4(0x3F803F80u, 0u, 0u, 0u);
+  *reinterpret_cast<uint4*>(a_bias + r * 32 + ((1 ^ sw) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+}
+
+// the 9 MMAs of one tile: 8 x (K=16) over the two 128B-swizzled weight chunks + 1 over the bias chunk
+template <int BN>
+__device__ __forceinline__ void issue_tile_mmas(uint32_t d, const uint8_t (*a)[kChunkBytesA], const uint8_t* a_bias,
+                                                const uint8_t* b0, const uint8_t* b1, const uint8_t* b_bias) {
+  constexpr uint32_t idesc = make_idesc_bf16(kBM, BN);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const uint64_t da = make_desc_k_sw128(smem_u32(a[k >> 2]) + (k & 3) * 32);
+    const uint64_t db = make_desc_k_sw128(smem_u32((k >> 2) ? b1 : b0) + (k & 3) * 32);
+    umma_bf16(d, da, db, idesc, k > 0);
+  }
+  umma_bf16(d, make_desc_k_sw32(smem_u32(a_bias)), make_desc_k_sw32(smem_u32(b_bias)), idesc, true);
+}
+
 template <unsigned kFlags>
 constexpr int score_threads() { return 64 + 32 * 4 * ((kFlags & HTCN_SCORE_TOPK) ? 1 : kSlicesScore); }
 
 template <int BN, unsigned kFlags>
 __global__ void __launch_bounds__(score_threads<kFlags>(), 1)
-k4_score_bf16(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, ScoreArgs a,
-              float* __restrict__ dump) {
+k4_score_bf16(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+              const __grid_constant__ CUtensorMap tmap_bb, ScoreArgs a, float* __restrict__ dump) {
   constexpr bool kCE = kFlags & HTCN_SCORE_CE, kRank = kFlags & HTCN_SCORE_RANK, kTopk = kFlags & HTCN_SCORE_TOPK;
   constexpr bool kDump = kFlags & kModeDump;
   constexpr int kSlices = kTopk ? 1 : kSlicesScore;           // column slices per tile (one heap per row in top-k mode)
   constexpr int kEpiWarps = 4 * kSlices;
   constexpr int kColsPerWarp = BN / kSlices;
-  constexpr int kBiasPerLane = kColsPerWarp / 32;
   constexpr uint32_t kTmemCols = 2 * BN;
+  constexpr uint32_t kStageBytes = 2 * BN * 128 + BN * 32;
   extern __shared__ uint8_t smem_raw[];
   auto& sm = *reinterpret_cast<ScoreSmem<BN>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* heap_v = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(&sm) + sizeof(ScoreSmem<BN>));
@@ -71,6 +99,7 @@ k4_score_bf16(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
+    prefetch_tmap(&tmap_bb);
     mbar_init(&sm.a_full, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&sm.b_full[s], 1);
@@ -80,6 +109,8 @@ k4_score_bf16(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
     }
     fence_barrier_init();
   }
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + kBM) write_a_bias_row(sm.a_bias, threadIdx.x - 64);
+  fence_proxy_async_smem();                                     // generic-proxy smem writes -> tensor core
   if (warp == 1) tmem_alloc<kTmemCols>(&sm.tmem_base);
   tc_fence_before_sync();
   __syncthreads();
@@ -94,37 +125,31 @@ k4_score_bf16(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
       tma_load_2d(sm.a[1], &tmap_a, 64, q0, &sm.a_full);
       for (int i = 0; i < n_tiles; ++i) {
         const int s = i & 1;
-        mbar_wait(&sm.b_empty[s], ((i >> 1) & 1) ^ 1);         // slot free (first pass succeeds immediately)
-        mbar_arrive_expect_tx(&sm.b_full[s], 2 * BN * 128);
+        mbar_wait_relaxed(&sm.b_empty[s], ((i >> 1) & 1) ^ 1);  // slot free (first pass succeeds immediately)
+        mbar_arrive_expect_tx(&sm.b_full[s], kStageBytes);
         const int j0 = (t_begin + i) * BN;                      // rows beyond n_items are zero-filled by TMA
         tma_load_2d(sm.b[s][0], &tmap_b, 0, j0, &sm.b_full[s]);
         tma_load_2d(sm.b[s][1], &tmap_b, 64, j0, &sm.b_full[s]);
+        tma_load_2d(sm.b_bias[s], &tmap_bb, 128, j0, &sm.b_full[s]);
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(kBM, BN);
       mbar_wait(&sm.a_full, 0);
       for (int i = 0; i < n_tiles; ++i) {
         const int s = i & 1, buf = i & 1;
-        mbar_wait(&sm.t_empty[buf], ((i >> 1) & 1) ^ 1);        // epilogue drained this accumulator
+        mbar_wait_relaxed(&sm.t_empty[buf], ((i >> 1) & 1) ^ 1);  // epilogue drained this accumulator
         mbar_wait(&sm.b_full[s], (i >> 1) & 1);                 // TMA landed
         tc_fence_after_sync();
-        const uint32_t d = tmem + buf * BN;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {                           // K = 128 = 8 x 16
-          const uint64_t da = make_desc_k_sw128(smem_u32(sm.a[k >> 2]) + (k & 3) * 32);
-          const uint64_t db = make_desc_k_sw128(smem_u32(sm.b[s][k >> 2]) + (k & 3) * 32);
-          umma_bf16(d, da, db, idesc, k > 0);
-        }
+        issue_tile_mmas<BN>(tmem + buf * BN, sm.a, sm.a_bias, sm.b[s][0], sm.b[s][1], sm.b_bias[s]);
         umma_commit(&sm.b_empty[s]);                            // smem slot reusable once these MMAs retire
         umma_commit(&sm.t_full[buf]);                           // accumulator ready
       }
     }
   } else {
     // ===================== epilogue =====================
-    const int ew = warp - 2;                                    // 0..7
+    const int ew = warp - 2;
     const bool active = ew < kEpiWarps;
     if (active) {
       const int quarter = warp & 3;                             // TMEM lane quarter this warp may access
@@ -132,8 +157,6 @@ k4_score_bf16(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
       const int row = quarter * 32 + lane;
       const bool row_ok = q0 + row < a.Q;
       const int col0 = half * kColsPerWarp;
-      float* bias_s = sm.bias[ew];
-      const uint32_t bias_sa = smem_u32(bias_s);
       float zy = 0.f, zyl = 0.f, thr = -INFINITY;
       float sum4[4] = {0.f, 0.f, 0.f, 0.f};                     // 4 independent partial sums (ILP + accuracy)
       float cf[4] = {0.f, 0.f, 0.f, 0.f};                       // per-tile rank counts as floats (FSET.BF + FADD)
@@ -149,24 +172,15 @@ k4_score_bf16(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
       auto process = [&](const uint32_t (&r)[32], int c, int lim, int jbase) {
         if (c + 32 <= lim) {                                    // full chunk: branch-free
 #pragma unroll
-          for (int u4 = 0; u4 < 8; ++u4) {
-            const float4 b4 = lds_f4(bias_sa + (c + u4 * 4) * 4);
-            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-            float z[4];
-#pragma unroll
-            for (int v = 0; v < 4; ++v) {
-              z[v] = __uint_as_float(r[u4 * 4 + v]) + bb[v];
-              if (kDump) {
-                if (row_ok) dump[(long long)(q0 + row) * a.n_items + jbase + c + u4 * 4 + v] = z[v];
-              }
-              if (kCE) sum4[v] += ex2_approx(fmaf(z[v], kLog2e, -zyl));
-              if (kTopk) {
-                if (z[v] > thr) thr = heap.replace_root(z[v], a.n0 + jbase + c + u4 * 4 + v);
-              }
+          for (int u = 0; u < 32; ++u) {
+            const float z = __uint_as_float(r[u]);
+            if (kDump) {
+              if (row_ok) dump[(long long)(q0 + row) * a.n_items + jbase + c + u] = z;
             }
-            if (kRank) {
-#pragma unroll
-              for (int v = 0; v < 4; ++v) cf[v] += set_gt_f(z[v], zy);
+            if (kCE) sum4[u & 3] += ex2_approx(fmaf(z, kLog2e, -zyl));
+            if (kRank) cf[u & 3] += set_gt_f(z, zy);
+            if (kTopk) {
+              if (z > thr) thr = heap.replace_root(z, a.n0 + jbase + c + u);
             }
           }
         } else if (c < lim) {                                   // ragged last tile of the catalog
@@ -177,7 +191,6 @@ k4_score_bf16(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
             for (int w = 0; w < 32; ++w)
               if (w == u) z = __uint_as_float(r[w]);
             if (c + u < lim) {
-              z += bias_s[c + u];
               if (kDump) {
                 if (row_ok) dump[(long long)(q0 + row) * a.n_items + jbase + c + u] = z;
               }
@@ -191,24 +204,9 @@ k4_score_bf16(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
         }
       };
 
-      // bias slice of tile i+1 is fetched into registers while tile i is consumed (hides the L2 latency)
-      float bnext[kBiasPerLane];
-      auto fetch_bias = [&](int i) {
-#pragma unroll
-        for (int u = 0; u < kBiasPerLane; ++u) {
-          const int j = (t_begin + i) * BN + col0 + u * 32 + lane;
-          bnext[u] = (i < n_tiles && j < a.n_items) ? __ldg(a.b_out + j) : 0.f;
-        }
-      };
-      fetch_bias(0);
       for (int i = 0; i < n_tiles; ++i) {
         const int buf = i & 1;
         const int j0 = (t_begin + i) * BN;
-        __syncwarp();                                           // previous tile's readers are done with bias_s
-#pragma unroll
-        for (int u = 0; u < kBiasPerLane; ++u) bias_s[u * 32 + lane] = bnext[u];
-        __syncwarp();
-        fetch_bias(i + 1);
         mbar_wait(&sm.t_full[buf], (i >> 1) & 1);
         tc_fence_after_sync();
         const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + buf * BN + col0;
@@ -273,17 +271,20 @@ k4_score_bf16(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
 }
 
 // ---- target logits with the sweep's arithmetic ---------------------------------------------------
-// Per 128-row tile: A = the query rows, B = the 128 gathered target rows W_out^T[y_q]; one M=128,N=128
-// tcgen05 product; thread r keeps the diagonal D[r][r].  Operands are written to shared memory by the
-// threads themselves in the 128-byte-swizzled K-major layout the UMMA descriptor expects.
+// Per 128-row tile: A = the query rows, B = the 128 gathered (augmented) target rows W_out^T[y_q]; the same 9
+// tcgen05.mma of shape M=128,N=128; thread r keeps the diagonal D[r][r].  Operands are written to shared memory
+// by the threads themselves in the swizzled K-major layouts the UMMA descriptors expect.
 struct alignas(1024) TargetSmem {
   uint8_t a[2][kChunkBytesA];
   uint8_t b[2][kChunkBytesA];
+  uint8_t a_bias[kBM * 32];
+  uint8_t b_bias[kBM * 32];
   uint64_t done;
   uint32_t tmem_base;
 };
 
-__device__ __forceinline__ void store_row_sw128(uint8_t (*dst)[kChunkBytesA], int r, const uint4* src /*16 x 16 B or null*/) {
+// 16 x 16 B chunks of one 256 B row -> two 128B-swizzled [128 x 128 B] buffers (chunk index ^= row % 8)
+__device__ __forceinline__ void store_row_sw128(uint8_t (*dst)[kChunkBytesA], int r, const uint4* src /*or null*/) {
 #pragma unroll
   for (int c = 0; c < 16; ++c) {
     const uint4 v = src ? __ldg(src + c) : make_uint4(0, 0, 0, 0);
@@ -292,9 +293,8 @@ __device__ __forceinline__ void store_row_sw128(uint8_t (*dst)[kChunkBytesA], in
 }
 
 __global__ void __launch_bounds__(128, 1)
-k4_target_bf16(const __nv_bfloat16* __restrict__ hout, const __nv_bfloat16* __restrict__ wt,
-               const float* __restrict__ b_out, const int* __restrict__ y_id, int Q, int n_items, int n0,
-               float* __restrict__ zy) {
+k4_target_bf16(const __nv_bfloat16* __restrict__ hout, const __nv_bfloat16* __restrict__ wt /*[n,144]*/,
+               const int* __restrict__ y_id, int Q, int n_items, int n0, float* __restrict__ zy) {
   extern __shared__ uint8_t smem_raw[];
   auto& sm = *reinterpret_cast<TargetSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int r = threadIdx.x, warp = r >> 5, lane = r & 31;
@@ -304,8 +304,15 @@ k4_target_bf16(const __nv_bfloat16* __restrict__ hout, const __nv_bfloat16* __re
     y = y_id[q] - n0;
     if (y < 0 || y >= n_items) y = -1;
   }
+  const uint4* wrow = y >= 0 ? reinterpret_cast<const uint4*>(wt + (long long)y * kWtPitchBf16) : nullptr;
   store_row_sw128(sm.a, r, q < Q ? reinterpret_cast<const uint4*>(hout + (long long)q * kDim) : nullptr);
-  store_row_sw128(sm.b, r, y >= 0 ? reinterpret_cast<const uint4*>(wt + (long long)y * kDim) : nullptr);
+  store_row_sw128(sm.b, r, wrow);
+  write_a_bias_row(sm.a_bias, r);
+  {
+    const int sw = (r >> 2) & 1;                                // chunks 16,17 of the augmented row: [b_hi, b_lo, 0...]
+    *reinterpret_cast<uint4*>(sm.b_bias + r * 32 + ((0 ^ sw) << 4)) = wrow ? __ldg(wrow + 16) : make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4*>(sm.b_bias + r * 32 + ((1 ^ sw) << 4)) = wrow ? __ldg(wrow + 17) : make_uint4(0, 0, 0, 0);
+  }
   fence_proxy_async_smem();                    // make the generic-proxy stores visible to the tensor core
   if (r == 0) {
     mbar_init(&sm.done, 1);
@@ -317,25 +324,19 @@ k4_target_bf16(const __nv_bfloat16* __restrict__ hout, const __nv_bfloat16* __re
   tc_fence_after_sync();
   const uint32_t tmem = sm.tmem_base;
   if (r == 0) {
-    constexpr uint32_t idesc = make_idesc_bf16(kBM, 128);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const uint64_t da = make_desc_k_sw128(smem_u32(sm.a[k >> 2]) + (k & 3) * 32);
-      const uint64_t db = make_desc_k_sw128(smem_u32(sm.b[k >> 2]) + (k & 3) * 32);
-      umma_bf16(tmem, da, db, idesc, k > 0);
-    }
+    issue_tile_mmas<128>(tmem, sm.a, sm.a_bias, sm.b[0], sm.b[1], sm.b_bias);
     umma_commit(&sm.done);
   }
   mbar_wait(&sm.done, 0);
   tc_fence_after_sync();
   uint32_t v[32];
   tmem_ld_32x32(tmem + ((uint32_t)(warp * 32) << 16) + warp * 32, v);   // this warp's 32x32 diagonal block
-  tmem_ld_wait();
+  tmem_ld_wait(v);
   float d = 0.f;
 #pragma unroll
   for (int u = 0; u < 32; ++u)
     if (u == lane) d = __uint_as_float(v[u]);
-  if (y >= 0) zy[q] = d + __ldg(b_out + y);
+  if (y >= 0) zy[q] = d;
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 0) {
@@ -349,7 +350,10 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int32_t make_tmap_bf16_rows(CUtensorMap* out, const void* base, uint64_t rows, uint32_t box_rows) {
+// 2-D bf16 row-major [rows, cols] tensor with `pitch_elems` elements per row; box = box_cols x box_rows;
+// swizzle_bytes in {32, 128} must equal box_cols * 2.
+int32_t make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint32_t cols, uint32_t pitch_elems,
+                       uint32_t box_cols, uint32_t box_rows, int swizzle_bytes) {
   static EncodeTiledFn encode = nullptr;
   if (!encode) {
     void* fn = nullptr;
@@ -365,15 +369,16 @@ int32_t make_tmap_bf16_rows(CUtensorMap* out, const void* base, uint64_t rows, u
     set_error("tensor map base %p is not 16-byte aligned", base);
     return HTCN_ERR_INVALID;
   }
-  const cuuint64_t dims[2] = {(cuuint64_t)kDim, (cuuint64_t)rows};
-  const cuuint64_t strides[1] = {(cuuint64_t)kDim * 2};         // bytes between rows
-  const cuuint32_t box[2] = {64, box_rows};
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)pitch_elems * 2};  // bytes between rows
+  const cuuint32_t box[2] = {box_cols, box_rows};
   const cuuint32_t estr[2] = {1, 1};
   CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                      CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed (%d) rows=%llu box_rows=%u", (int)r, (unsigned long long)rows, box_rows);
+    set_error("cuTensorMapEncodeTiled failed (%d) rows=%llu box=%ux%u", (int)r, (unsigned long long)rows, box_cols, box_rows);
     return HTCN_ERR_CUDA;
   }
   return HTCN_OK;
@@ -381,10 +386,12 @@ int32_t make_tmap_bf16_rows(CUtensorMap* out, const void* base, uint64_t rows, u
 
 template <int BN, unsigned kFlags>
 static int32_t launch_score(const ScoreArgs& a, float* dump, cudaStream_t st) {
-  CUtensorMap ta, tb;
-  int32_t rc = make_tmap_bf16_rows(&ta, a.hout, (uint64_t)a.Q, kBM);
+  CUtensorMap ta, tb, tbb;
+  int32_t rc = make_tmap_bf16(&ta, a.hout, (uint64_t)a.Q, kDim, kDim, 64, kBM, 128);
   if (rc) return rc;
-  rc = make_tmap_bf16_rows(&tb, a.wt, (uint64_t)a.n_items, BN);
+  rc = make_tmap_bf16(&tb, a.wt, (uint64_t)a.n_items, kWtPitchBf16, kWtPitchBf16, 64, BN, 128);
+  if (rc) return rc;
+  rc = make_tmap_bf16(&tbb, a.wt, (uint64_t)a.n_items, kWtPitchBf16, kWtPitchBf16, 16, BN, 32);
   if (rc) return rc;
   const size_t smem = sizeof(ScoreSmem<BN>) + 1024 + ((kFlags & HTCN_SCORE_TOPK) ? (size_t)a.k * kBM * 8 : 0);
   if (smem > 227 * 1024) {
@@ -394,7 +401,7 @@ static int32_t launch_score(const ScoreArgs& a, float* dump, cudaStream_t st) {
   auto kern = k4_score_bf16<BN, kFlags>;
   HTCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(ceil_div(a.Q, kBM), a.n_split);
-  kern<<<grid, score_threads<kFlags>(), smem, st>>>(ta, tb, a, dump);
+  kern<<<grid, score_threads<kFlags>(), smem, st>>>(ta, tb, tbb, a, dump);
   HTCN_LAUNCH_CHECK("k4_score_bf16");
   return HTCN_OK;
 }
@@ -428,18 +435,18 @@ int32_t score_bf16(const ScoreArgs& a, cudaStream_t st) {
 
 int32_t target_logit_bf16(const void* hout, const void* wt, const float* b_out, const int* y_id, int Q, int n_items,
                           int n0, float* zy, cudaStream_t st) {
+  (void)b_out;                                   // the bias lives in the augmented columns of wt
   const size_t smem = sizeof(TargetSmem) + 1024;
   HTCN_CUDA(cudaFuncSetAttribute(k4_target_bf16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k4_target_bf16<<<ceil_div(Q, kBM), 128, smem, st>>>((const __nv_bfloat16*)hout, (const __nv_bfloat16*)wt, b_out, y_id, Q,
+  k4_target_bf16<<<ceil_div(Q, kBM), 128, smem, st>>>((const __nv_bfloat16*)hout, (const __nv_bfloat16*)wt, y_id, Q,
                                                      n_items, n0, zy);
   HTCN_LAUNCH_CHECK("k4_target_bf16");
   return HTCN_OK;
 }
 
-int32_t dump_logits_bf16(const void* hout, int Q, const void* wt, const float* b_out, int n_items, float* logits,
-                         cudaStream_t st) {
+int32_t dump_logits_bf16(const void* hout, int Q, const void* wt, int n_items, float* logits, cudaStream_t st) {
   ScoreArgs a{};
-  a.hout = hout; a.wt = wt; a.b_out = b_out; a.Q = Q; a.n_items = n_items; a.n_split = 1; a.flags = kModeDump;
+  a.hout = hout; a.wt = wt; a.Q = Q; a.n_items = n_items; a.n_split = 1; a.flags = kModeDump;
   return launch_score<256, kModeDump>(a, logits, st);
 }
 
@@ -449,6 +456,7 @@ int32_t dump_logits_bf16(const void* hout, int Q, const void* wt, const float* b
 extern "C" int32_t htcn_debug_logits_bf16(const void* hout, int32_t Q, const void* w_out_t, const float* b_out,
                                           int32_t n_items, float* logits, void* stream) {
   using namespace htcn;
-  HTCN_REQUIRE(hout && w_out_t && b_out && logits && Q > 0 && n_items > 0, "debug_logits_bf16: bad args");
-  return dump_logits_bf16(hout, Q, w_out_t, b_out, n_items, logits, as_stream(stream));
+  (void)b_out;
+  HTCN_REQUIRE(hout && w_out_t && logits && Q > 0 && n_items > 0, "debug_logits_bf16: bad args");
+  return dump_logits_bf16(hout, Q, w_out_t, n_items, logits, as_stream(stream));
 }

@@ -56,6 +56,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Same, for the producer / MMA-issuer threads that run far ahead of the epilogue: back off with nanosleep so
+// the spinning warp does not steal issue slots (and power) from the epilogue warps sharing its SM sub-partition.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(200);
+    if (clock64() - t0 > 4000000000LL) {
+      printf("htcn: mbarrier wait timed out (block %d,%d thread %d bar %u parity %u)\n", blockIdx.x, blockIdx.y,
+             threadIdx.x, smem_u32(bar), parity);
+      __trap();
+    }
+  }
+}
+
 // ---- TMA ----------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
@@ -95,6 +110,17 @@ __device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t smem_addr) {
   d |= (uint64_t)(1024 >> 4) << 32;
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)2 << 61;
+  return d;
+}
+// Same for a 16-column (32 B per row) K-major operand with the 32-byte swizzle (16-byte chunk index ^= (row>>2)&1),
+// 8-row groups 256 B apart, layout = 6 (SWIZZLE_32B).  One K=16 MMA consumes the whole row.
+__device__ __forceinline__ uint64_t make_desc_k_sw32(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(256 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)6 << 61;
   return d;
 }
 // Instruction descriptor for kind::f16: bf16 x bf16 -> fp32, both operands K-major.
@@ -169,7 +195,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }  // namespace sm100
 
 // ---- host: tensor maps ---------------------------------------------------------------------------------
-// 2-D bf16 row-major [rows, 128] tensor, box = 64 columns (128 B) x box_rows, 128-byte swizzle.
-int32_t make_tmap_bf16_rows(CUtensorMap* out, const void* base, uint64_t rows, uint32_t box_rows);
+int32_t make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint32_t cols, uint32_t pitch_elems,
+                       uint32_t box_cols, uint32_t box_rows, int swizzle_bytes);
 
 }  // namespace htcn

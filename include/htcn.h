@@ -35,6 +35,7 @@ extern "C" {
 #define HTCN_MAX_LEVELS 8     /* TCN levels (len(args.tcn_channel)) */
 #define HTCN_MAX_GRU_LAYERS 4 /* args.num_layer */
 #define HTCN_MAX_TOPK 128
+#define HTCN_WT_PITCH_BF16 144 /* bf16 elements per W_out^T row in the bf16 tier (see htcn_prepare_wout) */
 
 typedef enum {
   HTCN_OK = 0,
@@ -124,10 +125,15 @@ int32_t htcn_tcn_forward(const void* xe, int32_t xe_dtype, int32_t precision,
                          void* stream);
 
 /* ---------------------------------------------------------------------------------------------
- * weight preparation for K4 (one-time, at load): w_out [128,N] f32 (the TF layout of
- * hier/tcn/dense/kernel, model_tcn.py:41) -> w_out_t [N,128] in f32 or bf16 (K-major rows).
+ * weight preparation for K4 (one-time, at load): w_out [128,N] f32 + b_out [N] f32 (the TF layout of
+ * hier/tcn/dense/{kernel,bias}, model_tcn.py:41) -> w_out_t, K-major rows:
+ *   HTCN_F32 : [N,128] f32 (b_out is not used; pass it to the scoring calls)
+ *   HTCN_BF16: [N,HTCN_WT_PITCH_BF16] bf16 = 128 weights | bf16(b) | bf16(b - bf16(b)) | 14 zeros -- the bias is
+ *              folded into the GEMM as a 9th K=16 step (b_hi + b_lo carry it to 2^-17 relative), so the bf16
+ *              scoring kernels never read b_out.
  * ------------------------------------------------------------------------------------------- */
-int32_t htcn_prepare_wout(const float* w_out, int32_t N, void* w_out_t, int32_t dtype, void* stream);
+int32_t htcn_prepare_wout(const float* w_out, const float* b_out, int32_t N, void* w_out_t, int32_t dtype,
+                          void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K4  full-catalog scoring with fused CE / rank / top-k epilogues.  Logits never reach HBM.
@@ -135,7 +141,8 @@ int32_t htcn_prepare_wout(const float* w_out, int32_t N, void* w_out_t, int32_t 
  * softmax_cross_entropy_with_logits (loss.py:20-21), calc_metric_fast's strict-greater rank
  * (loss.py:179) and tf.nn.top_k ordering (loss.py:120).
  *   z[q,j] = hout[q,:] . w_out_t[n0+j,:] + b_out[n0+j],   j in [0, n_items)   (one catalog shard)
- * hout [Q,128] (f32 or bf16 per `precision`), w_out_t [n_items,128] same dtype, b_out [n_items] f32.
+ * hout [Q,128] (f32 or bf16 per `precision`), w_out_t = the shard's rows of htcn_prepare_wout's output in the
+ * same dtype ([n_items,128] f32 or [n_items,144] bf16), b_out [n_items] f32 (read by the f32 tier only).
  * y_id [Q] int32 GLOBAL target ids (needed for CE/RANK; may be NULL for TOPK only).
  * target_logit [Q] f32: z[q, y_id[q]] -- INPUT when have_target != 0 (computed by the shard that
  *   owns the id and exchanged by the caller), else computed here (requires the shard to own every id).

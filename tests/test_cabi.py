@@ -48,7 +48,7 @@ def test_argument_validation_returns_error_not_crash(built):
     from hiertcn_b200 import _cabi as cabi
     cabi.load(built)
     with pytest.raises(cabi.HtcnError, match="bad"):
-        cabi.call("htcn_prepare_wout", None, 0, None, 0, None)
+        cabi.call("htcn_prepare_wout", None, None, 0, None, 0, None)
     with pytest.raises(cabi.HtcnError):
         cabi.call("htcn_topk_merge", None, None, 1, 1, 1, None, None, None)
 

@@ -184,7 +184,7 @@ def test_k4_f32_ce_rank_topk(lib, Q, N, n_split):
     k = min(100, N)
     wt = torch.empty((N, 128), dtype=torch.float32, device="cuda")
     w_out_d = dev(w_out)
-    lib.call("htcn_prepare_wout", P(w_out_d), N, P(wt), lib.HTCN_F32, None)
+    lib.call("htcn_prepare_wout", P(w_out_d), None, N, P(wt), lib.HTCN_F32, None)
     assert np.array_equal(wt.cpu().numpy(), w_out.T)
     hd, bd, yd = dev(hout), dev(b_out), dev(y)
     flags = lib.SCORE_CE | lib.SCORE_RANK | lib.SCORE_TOPK
@@ -228,7 +228,7 @@ def test_k4_topk_ties_prefer_lower_index(lib):
     b_out = np.zeros(N, np.float32)
     wt = torch.empty((N, 128), dtype=torch.float32, device="cuda")
     w_out_d = dev(w_out)
-    lib.call("htcn_prepare_wout", P(w_out_d), N, P(wt), lib.HTCN_F32, None)
+    lib.call("htcn_prepare_wout", P(w_out_d), None, N, P(wt), lib.HTCN_F32, None)
     for n_split in (1, 4):
         hd, bd = dev(hout), dev(b_out)
         _, _, _, _, tv, ti = run_score(lib, hd, wt, bd, None, lib.SCORE_TOPK, k, n_split)
@@ -249,7 +249,7 @@ def test_k4_sharded_catalog_equals_single(lib):
     y = rng.integers(1, N, size=Q).astype(np.int32)
     wt = torch.empty((N, 128), dtype=torch.float32, device="cuda")
     w_out_d = dev(w_out)
-    lib.call("htcn_prepare_wout", P(w_out_d), N, P(wt), lib.HTCN_F32, None)
+    lib.call("htcn_prepare_wout", P(w_out_d), None, N, P(wt), lib.HTCN_F32, None)
     hd, bd, yd = dev(hout), dev(b_out), dev(y)
     flags = lib.SCORE_CE | lib.SCORE_RANK | lib.SCORE_TOPK
     zy1, pm1, ps1, pc1, tv1, ti1 = run_score(lib, hd, wt, bd, yd, flags, k, 1)
@@ -351,10 +351,14 @@ def test_k4_bf16_tcgen05(lib, Q, N, n_split):
     y = rng.integers(1, N, size=Q).astype(np.int32)
     k = min(100, N)
     w_out_d = dev(w_out)
-    wt = torch.empty((N, 128), dtype=torch.bfloat16, device="cuda")
-    lib.call("htcn_prepare_wout", P(w_out_d), N, P(wt), lib.HTCN_BF16, None)
-    assert np.array_equal(wt.float().cpu().numpy(), O.bf16_round(w_out.T))
+    wt = torch.empty((N, lib.WT_PITCH_BF16), dtype=torch.bfloat16, device="cuda")
     hd, bd, yd = dev(hout).to(torch.bfloat16), dev(b_out), dev(y)
+    lib.call("htcn_prepare_wout", P(w_out_d), P(bd), N, P(wt), lib.HTCN_BF16, None)
+    wt_h = wt.float().cpu().numpy()
+    assert np.array_equal(wt_h[:, :128], O.bf16_round(w_out.T))
+    b_hi = O.bf16_round(b_out)                                   # bias folded into the GEMM as (hi, lo) bf16 columns
+    assert np.array_equal(wt_h[:, 128], b_hi) and np.array_equal(wt_h[:, 129], O.bf16_round(b_out - b_hi))
+    assert (wt_h[:, 130:] == 0).all()
     # 1. the logits the tensor-core sweep sees == bf16 operands, fp32 accumulate
     z_gpu = debug_logits_bf16(lib, hd, wt, bd).cpu().numpy()
     z64 = hout.astype(np.float64) @ O.bf16_round(w_out).astype(np.float64) + b_out
