@@ -1,0 +1,149 @@
+"""Parity at BASELINE.json's full sizes (configs[1]: 4096 users x 200 positions x 1M items, bf16 tier) through
+size-independent properties -- the CPU oracle cannot finish this size:
+  * split invariance: 1 vs 4 vs 7 catalog splits give identical ranks and the same loss,
+  * shard invariance: 3 catalog shards (n0 offsets, exchanged target logits) == one shard,
+  * spot check of sampled rows against fully materialised logits (fp32 fmaf chain through the ABI),
+  * top-k lists are sorted, start at the row maximum and contain the target iff rank < k,
+  * user permutation equivariance and determinism (bit-identical reruns)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+N, B = 1_000_000, 4096
+
+
+@pytest.fixture(scope="module")
+def big():
+    from hiertcn_b200.args import make_args
+    from hiertcn_b200.data_loader import ItemSampler, synthetic_batch
+    from hiertcn_b200.model_hier import HierTCN
+    from hiertcn_b200.weights import hier_weight_shapes, init_weights
+    w = init_weights(hier_weight_shapes(N, emb_dim=100), seed=1234, kernel_scale=3.0, bias_noise=0.3)
+    a = make_args(["--item_num", str(N), "--emb_dim", "100", "--batch_size", str(B)])
+    model = HierTCN(a, w, precision="bf16").build()
+    x, y, m = synthetic_batch(B, 10, 20, N, seed=5, lengths="ragged", sampler=ItemSampler(N, "zipf"))
+    s0 = np.random.default_rng(1).normal(0, 0.5, size=(B, 256)).astype(np.float32)
+    scores, state = model.forward(x, y, m, s0)
+    torch.cuda.synchronize()
+    return model, scores, state, (x, y, m, s0)
+
+
+def run_score(model, scores, n_split, flags_ce=True, flags_rank=True):
+    model.force_n_split = n_split
+    scores._cache.clear()
+    r = model.score(scores, ce=flags_ce, rank=flags_rank)
+    out = {k: v.clone() for k, v in r.items()}
+    model.force_n_split = 0
+    return out
+
+
+def test_cfg2_split_invariance_and_determinism(big):
+    model, scores, _, _ = big
+    r1 = run_score(model, scores, 1)
+    r4 = run_score(model, scores, 4)
+    r7 = run_score(model, scores, 7)
+    r4b = run_score(model, scores, 4)
+    assert torch.equal(r1["rank_row"], r4["rank_row"]) and torch.equal(r1["rank_row"], r7["rank_row"])
+    assert torch.equal(r4["loss_row"], r4b["loss_row"]), "same launch twice must be bit-identical"
+    torch.testing.assert_close(r1["loss_row"], r4["loss_row"], rtol=2e-6, atol=2e-6)
+    torch.testing.assert_close(r1["loss_row"], r7["loss_row"], rtol=2e-6, atol=2e-6)
+    loss = r4["loss_row"]
+    assert torch.isfinite(loss).all() and (loss > -1e-4).all()          # log sum_j exp(z_j - z_y) >= 0
+    assert (r4["rank_row"] >= 0).all() and (r4["rank_row"] < N).all()
+
+
+def test_cfg2_spot_check_against_materialised_logits(big):
+    from hiertcn_b200 import _cabi as cabi
+    model, scores, _, _ = big
+    r = run_score(model, scores, 4)
+    Q = scores.Q
+    idx = torch.from_numpy(np.random.default_rng(0).choice(Q, 48, replace=False)).cuda()
+    h = scores.hout[idx].contiguous()
+    lg = torch.empty((48, N), dtype=torch.float32, device="cuda")
+    cabi.call("htcn_score_logits", h.data_ptr(), cabi.HTCN_BF16, 48, model.wt.data_ptr(), cabi.HTCN_BF16, None, N,
+              lg.data_ptr(), None)
+    z = lg.double()
+    y = scores.y_rows[idx].long()
+    zy = z.gather(1, y[:, None])
+    loss_ref = (torch.logsumexp(z, 1) - zy[:, 0]).float()
+    torch.testing.assert_close(r["loss_row"][idx], loss_ref, rtol=2e-3, atol=2e-3)      # bf16 tier bar is 2e-2
+    rank_ref = (z > zy).sum(1).float()
+    near = ((z - zy).abs() <= 2e-5 * zy.abs().clamp(min=1.0)).sum(1).float() - 1          # fp near-ties of the target
+    assert ((r["rank_row"][idx] - rank_ref).abs() <= near).all()
+    torch.testing.assert_close(r["target_logit"][idx], zy[:, 0].float(), rtol=2e-5, atol=2e-5)
+
+
+def test_cfg2_topk_properties_and_shard_invariance(big):
+    from hiertcn_b200 import _cabi as cabi
+    model, scores, _, _ = big
+    k, Qs = 100, 384
+    h = scores.hout[:Qs].contiguous()
+    y = scores.y_rows[:Qs].contiguous()
+    f32, i32 = torch.float32, torch.int32
+
+    def sweep(n0, n1, zy, have, flags, ns):
+        pm = torch.empty((ns, Qs), dtype=f32, device="cuda"); ps = torch.empty_like(pm)
+        pc = torch.empty((ns, Qs), dtype=i32, device="cuda")
+        tv = torch.empty((ns, Qs, k), dtype=f32, device="cuda"); ti = torch.empty((ns, Qs, k), dtype=i32, device="cuda")
+        cabi.call("htcn_score_ce_rank_topk", h.data_ptr(), cabi.HTCN_BF16, Qs, model.wt[n0:n1].data_ptr(), None,
+                  n1 - n0, n0, y.data_ptr(), zy.data_ptr(), have, flags, k, ns, pm.data_ptr(), ps.data_ptr(),
+                  pc.data_ptr(), tv.data_ptr(), ti.data_ptr(), None)
+        return pm, ps, pc, tv, ti
+
+    def finish(parts, zy):
+        pm = torch.cat([p[0] for p in parts]); ps = torch.cat([p[1] for p in parts]); pc = torch.cat([p[2] for p in parts])
+        lr = torch.empty(Qs, dtype=f32, device="cuda"); rr = torch.empty(Qs, dtype=f32, device="cuda")
+        cabi.call("htcn_score_finish", pm.data_ptr(), ps.data_ptr(), pc.data_ptr(), pm.shape[0], Qs, y.data_ptr(),
+                  zy.data_ptr(), lr.data_ptr(), rr.data_ptr(), None)
+        return lr, rr
+
+    def merge(parts):
+        tv = torch.cat([p[3] for p in parts]); ti = torch.cat([p[4] for p in parts])
+        ov = torch.empty((Qs, k), dtype=f32, device="cuda"); oi = torch.empty((Qs, k), dtype=i32, device="cuda")
+        cabi.call("htcn_topk_merge", tv.data_ptr(), ti.data_ptr(), tv.shape[0], Qs, k, ov.data_ptr(), oi.data_ptr(), None)
+        return ov, oi
+
+    zy1 = torch.zeros(Qs, dtype=f32, device="cuda")
+    one_ce = [sweep(0, N, zy1, 0, cabi.SCORE_CE | cabi.SCORE_RANK, 2)]
+    one_tk = [sweep(0, N, zy1, 1, cabi.SCORE_TOPK, 3)]
+    lr1, rr1 = finish(one_ce, zy1)
+    ov1, oi1 = merge(one_tk)
+    bounds = [0, 333_312, 700_160, N]
+    zy3 = torch.zeros(Qs, dtype=f32, device="cuda")
+    for s in range(3):
+        cabi.call("htcn_target_logit", h.data_ptr(), cabi.HTCN_BF16, Qs, model.wt[bounds[s]:bounds[s + 1]].data_ptr(), None,
+                  bounds[s + 1] - bounds[s], bounds[s], y.data_ptr(), zy3.data_ptr(), None)
+    assert torch.equal(zy1, zy3)
+    sh_ce = [sweep(bounds[s], bounds[s + 1], zy3, 1, cabi.SCORE_CE | cabi.SCORE_RANK, 1) for s in range(3)]
+    sh_tk = [sweep(bounds[s], bounds[s + 1], zy3, 1, cabi.SCORE_TOPK, 2) for s in range(3)]
+    lr3, rr3 = finish(sh_ce, zy3)
+    ov3, oi3 = merge(sh_tk)
+    assert torch.equal(rr1, rr3) and torch.equal(oi1, oi3) and torch.equal(ov1, ov3)
+    torch.testing.assert_close(lr1, lr3, rtol=2e-6, atol=2e-6)
+    # top-k properties
+    assert (ov1[:, :-1] >= ov1[:, 1:]).all(), "descending"
+    tie = ov1[:, :-1] == ov1[:, 1:]
+    assert (oi1[:, :-1][tie] < oi1[:, 1:][tie]).all(), "ties -> lower index first"
+    assert (oi1 >= 0).all() and (oi1 < N).all()
+    for r in range(Qs):
+        assert len(set(oi1[r].tolist())) == k
+    in_topk = (oi1 == y[:, None]).any(1)
+    assert torch.equal(in_topk, rr1 < k), "target is in the top-k list iff its rank < k"
+    pos = (oi1 == y[:, None]).float().argmax(1)
+    assert torch.equal(pos[in_topk].float(), rr1[in_topk]) or (ov1[in_topk].gather(1, pos[in_topk][:, None])[:, 0] == zy1[in_topk]).all()
+
+
+def test_cfg2_user_permutation_equivariance(big):
+    model, scores, state, (x, y, m, s0) = big
+    r = model.loss(scores, metrics=True, per_position=True)
+    base_loss = r["loss_bt"].clone(); base_rank = r["ranks"].clone(); base_sc = r["scalars"].clone()
+    perm = np.random.default_rng(3).permutation(B)
+    sc2, state2 = model.forward([a[perm] for a in x], [a[perm] for a in y], [a[perm] for a in m], s0[perm])
+    r2 = model.loss(sc2, metrics=True, per_position=True)
+    p = torch.from_numpy(perm).cuda()
+    assert torch.equal(state[p], state2)
+    assert torch.equal(base_rank[p], r2["ranks"])
+    torch.testing.assert_close(base_loss[p], r2["loss_bt"], rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(base_sc, r2["scalars"], rtol=1e-4, atol=1e-6)
