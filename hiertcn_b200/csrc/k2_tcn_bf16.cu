@@ -1,9 +1,324 @@
-// placeholder until the tcgen05 conv stack lands: loud failure, never a fallback
+// K2 (bf16 tier): in-projection + dilated causal conv residual stack as a tcgen05 implicit GEMM, all levels
+// fused on chip.  Replaces model_tcn.py:35 + customized_tcn_cell.py:46-49,109-127,147-161 (see k2_tcn_f32.cu for
+// the op-level description; the arithmetic here is bf16 operands, fp32 accumulate, activations rounded to bf16
+// between levels -- the roundings oracle/hiertcn_oracle.py's "bf16" mode mirrors).
+//
+// Work unit = one 128-row tile (MMA M = 128).  The rows of a tile are positions of one or more sequences laid
+// out WITH their causal zero padding as physical rows:
+//   short sequences (L + P <= 128, P = (K-1)*d_max): floor(128/(L+P)) sequences per tile, each preceded by P
+//     zero rows -- the left pad of customized_tcn_cell.py:46-48 -- which also isolates neighbours;
+//   long sequences (config 3, L = 256): one sequence chunk per tile with the receptive-field halo
+//     RF-1 = (K-1)(2^n - 1) rows recomputed in front of the 128-(RF-1) new output positions.
+// The activation tile lives in shared memory in the NO-SWIZZLE K-major UMMA layout with 8-row core matrices made
+// contiguous (SBO = 128 B): row r / 16-byte channel chunk c sits at c*ROWS*16 + r*16, i.e. rows are uniformly
+// 16 B apart, so conv tap k of a level with dilation d is the SAME buffer addressed through a descriptor whose
+// start address is moved back by (K-1-k)*d rows.  No im2col, no per-tap copies: 5 taps = 5 descriptors.
+// Weights (bf16 [tap][cout][cin], 32 KB per tap, L2-resident) stream through a 2-stage TMA ring (128B swizzle).
+// Per layer: K x 8 tcgen05.mma (M=128, N=128, K=16) into one 128-column TMEM accumulator, then the 4 epilogue
+// warps (TMEM lane = row) apply bias / relu / residual / relu, round to bf16 and write the next layer's operand
+// in place (zero rows stay zero).  Two CTAs fit per SM (110 KB smem, 128 TMEM columns each) so one CTA's
+// epilogue overlaps the other's MMAs.
 #include "common.cuh"
+#include "sm100.cuh"
+
 namespace htcn {
-int32_t tcn_forward_bf16(const void*, int, const float*, const float*, const float* const*, const float* const*, int,
-                         int, const SlotTable&, int, int, const int*, void*, int, float*, cudaStream_t) {
-  set_error("tcn_forward: the bf16 (tcgen05) conv stack is not built; use precision HTCN_F32");
-  return HTCN_ERR_UNSUPPORTED;
+using namespace sm100;
+
+constexpr int kTR = 128;                 // rows per tile
+constexpr int kMaxSpare = 32;            // supports (K-1)*d_max <= 32 rows of negative shift
+constexpr int kRows = kTR + kMaxSpare;   // rows of the activation buffer (spare rows in front)
+constexpr int kActBytes = 16 * kRows * 16;          // 16 channel chunks x rows x 16 B = 40 KB
+constexpr int kWStageBytes = 2 * 128 * 128;         // one tap: [128 cout][128 cin] bf16, two 64-col swizzled chunks
+constexpr int kWStages = 2;                         // 2 x 32 KB: with the 40 KB tile two CTAs fit one SM
+constexpr int kK2Threads = 192;          // warps 0-3 epilogue/loader, warp 4 TMA producer, warp 5 MMA issuer
+
+struct K2Slot {          // per session slot: tiling of its B sequences
+  int off, L;            // first column in [B,T], length
+  int tile0;             // first global tile index of this slot
+  int seq_per_tile;      // > 0: short mode;  0: long mode
+  int tiles_per_seq;     // long mode
+};
+struct K2Geom {
+  int n_slots, n_tiles, B, T, K, n_levels;
+  int P;                 // zero rows in front of each short sequence = max shift of the deepest level
+  int rf1;               // receptive field - 1 (long mode halo)
+  K2Slot slot[HTCN_MAX_SLOTS];
+};
+
+struct alignas(1024) K2Smem {
+  uint8_t w[kWStages][kWStageBytes];     // 64 KB
+  uint8_t act[kActBytes];                // 40 KB
+  float bias[HTCN_MAX_LEVELS][kDim];
+  uint64_t w_full[kWStages], w_empty[kWStages], acc_ready, act_ready;
+  uint32_t tmem_base;
+};
+
+// no-swizzle K-major descriptor: core matrix = 8 rows x 16 B contiguous (SBO = 128 B), the two 16-byte K chunks of
+// one K=16 step are LBO = kRows*16 B apart
+__device__ __forceinline__ uint64_t make_desc_act(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((kRows * 16) >> 4) << 16;     // leading byte offset (K direction)
+  d |= (uint64_t)(128 >> 4) << 32;              // stride byte offset (8-row groups)
+  d |= (uint64_t)1 << 46;
+  return d;                                     // layout type 0 = no swizzle
 }
+
+__device__ __forceinline__ void tile_geometry(const K2Geom& g, int tile, int r, const int* out_row, int& src,
+                                              int& dst, int& sb) {
+  int s = 0;
+  while (s + 1 < g.n_slots && g.slot[s + 1].tile0 <= tile) ++s;
+  const K2Slot& sl = g.slot[s];
+  const int lt = tile - sl.tile0;
+  int b, t;
+  bool is_out;
+  if (sl.seq_per_tile > 0) {
+    const int stride = sl.L + g.P;
+    const int seg = r / stride;
+    t = r % stride - g.P;
+    b = lt * sl.seq_per_tile + seg;
+    is_out = seg < sl.seq_per_tile;
+  } else {
+    const int step = kTR - g.rf1;
+    b = lt / sl.tiles_per_seq;
+    const int t0 = (lt % sl.tiles_per_seq) * step;
+    t = t0 - g.rf1 + r;
+    is_out = t >= t0;
+  }
+  const bool data = b < g.B && t >= 0 && t < sl.L;
+  src = data ? b * g.T + sl.off + t : -1;
+  sb = s * g.B + (b < g.B ? b : 0);
+  dst = -1;
+  if (data && is_out) dst = out_row ? out_row[src] : src;
+}
+
+__global__ void __launch_bounds__(kK2Threads, 2)
+k2_tcn_bf16(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfloat16* __restrict__ xe,
+            const float* __restrict__ sbias, const float* __restrict__ bias_all /*[n_levels][128]*/,
+            const int* __restrict__ out_row, __nv_bfloat16* __restrict__ hout) {
+  extern __shared__ uint8_t smem_raw[];
+  auto& sm = *reinterpret_cast<K2Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_layers = g.n_levels + 1;                       // layer 0 = in-projection
+  const int my_tiles = (g.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (tid == 0) {
+    prefetch_tmap(&tmap_w);
+    for (int s = 0; s < kWStages; ++s) {
+      mbar_init(&sm.w_full[s], 1);
+      mbar_init(&sm.w_empty[s], 1);
+    }
+    mbar_init(&sm.acc_ready, 1);
+    mbar_init(&sm.act_ready, kTR);
+    fence_barrier_init();
+  }
+  for (int i = tid; i < g.n_levels * kDim; i += kK2Threads) sm.bias[i / kDim][i % kDim] = bias_all[i];
+  for (int i = tid; i < kActBytes / 16; i += kK2Threads) reinterpret_cast<uint4*>(sm.act)[i] = make_uint4(0, 0, 0, 0);
+  if (warp == 5) tmem_alloc<128>(&sm.tmem_base);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = sm.tmem_base;
+
+  if (warp == 4) {
+    // ===================== weight producer: [W_in, L0 taps, L1 taps, ...] per tile, 2-stage ring =====================
+    if (lane == 0) {
+      const int per_tile = 1 + g.n_levels * g.K;
+      long long n = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        for (int j = 0; j < per_tile; ++j, ++n) {
+          const int s = (int)(n % kWStages);
+          mbar_wait_relaxed(&sm.w_empty[s], (uint32_t)(((n / kWStages) & 1) ^ 1));
+          mbar_arrive_expect_tx(&sm.w_full[s], kWStageBytes);
+          tma_load_2d(sm.w[s], &tmap_w, 0, j * 128, &sm.w_full[s]);
+          tma_load_2d(sm.w[s] + kWStageBytes / 2, &tmap_w, 64, j * 128, &sm.w_full[s]);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kTR, 128);
+      const uint32_t act0 = smem_u32(sm.act);
+      long long n = 0, n_act = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        for (int layer = 0; layer < n_layers; ++layer, ++n_act) {
+          mbar_wait(&sm.act_ready, (uint32_t)(n_act & 1));       // operand tile written + fenced by the epilogue warps
+          tc_fence_after_sync();
+          const int taps = layer == 0 ? 1 : g.K;
+          const int dil = layer == 0 ? 1 : (1 << (layer - 1));
+          for (int tap = 0; tap < taps; ++tap, ++n) {
+            const int s = (int)(n % kWStages);
+            mbar_wait(&sm.w_full[s], (uint32_t)((n / kWStages) & 1));
+            tc_fence_after_sync();
+            const int shift = (taps - 1 - tap) * dil;            // rows back in time (customized_tcn_cell.py:46-49)
+            const uint32_t a_base = act0 + (uint32_t)(kMaxSpare - shift) * 16;
+            const uint32_t w_base = smem_u32(sm.w[s]);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const uint64_t da = make_desc_act(a_base + (uint32_t)(2 * k) * (kRows * 16));
+              const uint64_t db = make_desc_k_sw128(w_base + (k >> 2) * (kWStageBytes / 2) + (k & 3) * 32);
+              umma_bf16(tmem, da, db, idesc, (tap | k) != 0);
+            }
+            umma_commit(&sm.w_empty[s]);
+          }
+          umma_commit(&sm.acc_ready);
+        }
+      }
+    }
+  } else {
+    // ===================== loader + epilogue: thread = tile row =====================
+    const int r = tid;                                          // 0..127, TMEM lane r (warp w owns lanes 32w..32w+31)
+    uint8_t* my_act = sm.act + (kMaxSpare + r) * 16;            // + c * kRows * 16 for channel chunk c
+    long long n_acc = 0;
+    for (int it = 0; it < my_tiles; ++it) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      int src, dst, sb;
+      tile_geometry(g, tile, r, out_row, src, dst, sb);
+      // ---- stage the input rows (bf16 Xe) into the operand layout; zero rows stay zero
+      {
+        const uint4* p = src >= 0 ? reinterpret_cast<const uint4*>(xe + (long long)src * kDim) : nullptr;
+#pragma unroll
+        for (int c = 0; c < 16; ++c)
+          *reinterpret_cast<uint4*>(my_act + c * (kRows * 16)) = p ? __ldg(p + c) : make_uint4(0, 0, 0, 0);
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&sm.act_ready);
+      for (int layer = 0; layer < n_layers; ++layer, ++n_acc) {
+        mbar_wait(&sm.acc_ready, (uint32_t)(n_acc & 1));
+        tc_fence_after_sync();
+        const bool last = layer == n_layers - 1;
+        const float* bias_l = layer > 0 ? sm.bias[layer - 1] : nullptr;
+        const float* sb_row = (layer == 0 && sbias && src >= 0) ? sbias + (long long)sb * kDim : nullptr;
+#pragma unroll 1
+        for (int cc = 0; cc < 4; ++cc) {                         // 4 x 32 channels
+          uint32_t v[32];
+          tmem_ld_32x32(tmem + ((uint32_t)(warp * 32) << 16) + cc * 32, v);
+          tmem_ld_wait(v);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {                          // 4 x 8 channels = one 16-byte chunk each
+            const int c = cc * 4 + q;
+            uint4* slot = reinterpret_cast<uint4*>(my_act + c * (kRows * 16));
+            float o[8];
+            if (layer == 0) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(v[q * 8 + e]);
+              if (sb_row) {
+                const float4 s0 = __ldg(reinterpret_cast<const float4*>(sb_row + c * 8));
+                const float4 s1 = __ldg(reinterpret_cast<const float4*>(sb_row + c * 8 + 4));
+                o[0] += s0.x; o[1] += s0.y; o[2] += s0.z; o[3] += s0.w;
+                o[4] += s1.x; o[5] += s1.y; o[6] += s1.z; o[7] += s1.w;
+              }
+            } else {
+              const uint4 res = *slot;                           // this row's input to the level (bf16 x 8)
+              const float rs[8] = {bf16_lo(res.x), bf16_hi(res.x), bf16_lo(res.y), bf16_hi(res.y),
+                                   bf16_lo(res.z), bf16_hi(res.z), bf16_lo(res.w), bf16_hi(res.w)};
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float a = fmaxf(__uint_as_float(v[q * 8 + e]) + bias_l[c * 8 + e], 0.f);   // relu(conv + b)
+                o[e] = fmaxf(a + rs[e], 0.f);                                                    // relu(a + residual)
+              }
+            }
+            uint4 packed = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
+                                      pack_bf16x2(o[6], o[7]));
+            if (src < 0) packed = make_uint4(0, 0, 0, 0);        // causal pad rows stay zero at every level
+            if (!last) *slot = packed;
+            else if (dst >= 0) reinterpret_cast<uint4*>(hout + (long long)dst * kDim)[c] = packed;
+          }
+        }
+        tc_fence_before_sync();
+        if (!last) {
+          fence_proxy_async_smem();
+          mbar_arrive(&sm.act_ready);
+        }
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after_sync();
+    tmem_dealloc<128>(tmem);
+  }
+}
+
+// weights f32 [tap][cin][cout] (TF layout, customized_convolution_layer.py:137) -> bf16 [tap][cout][cin]
+__global__ void k2_prepare_weights(const float* __restrict__ w_in_x, const float* const* __restrict__ conv_w_dev,
+                                   int n_levels, int K, __nv_bfloat16* __restrict__ out) {
+  const int j = blockIdx.x;                       // weight tile: 0 = in-projection, 1 + l*K + tap
+  const float* src = j == 0 ? w_in_x : conv_w_dev[(j - 1) / K] + (long long)((j - 1) % K) * kDim * kDim;
+  for (int i = threadIdx.x; i < kDim * kDim; i += blockDim.x) {
+    const int cout = i / kDim, cin = i % kDim;
+    out[(long long)j * kDim * kDim + i] = __float2bfloat16_rn(src[cin * kDim + cout]);
+  }
+}
+
+int32_t tcn_forward_bf16(const void* xe, int xe_dtype, const float* w_in_x, const float* sbias,
+                         const float* const* conv_w, const float* const* conv_b, int n_levels, int K,
+                         const SlotTable& slots, int B, int T, const int* out_row, void* hout, int hout_dtype,
+                         float* scratch, cudaStream_t st) {
+  if (xe_dtype != HTCN_BF16 || hout_dtype != HTCN_BF16) {
+    set_error("tcn_forward(bf16): xe and hout must be bf16");
+    return HTCN_ERR_INVALID;
+  }
+  if (!scratch) {
+    set_error("tcn_forward(bf16): scratch is required (%d bytes for the bf16 weight tiles)",
+              (1 + n_levels * K) * kDim * kDim * 2 + HTCN_MAX_LEVELS * (kDim * 4 + 8));
+    return HTCN_ERR_INVALID;
+  }
+  const int P = n_levels > 0 ? (K - 1) * (1 << (n_levels - 1)) : 0;
+  if (P > kMaxSpare) {
+    set_error("tcn_forward(bf16): (K-1)*2^(levels-1) = %d rows of causal shift exceed the fused kernel's %d; use HTCN_F32",
+              P, kMaxSpare);
+    return HTCN_ERR_UNSUPPORTED;
+  }
+  K2Geom g{};
+  g.n_slots = slots.n; g.B = B; g.T = T; g.K = K; g.n_levels = n_levels; g.P = P;
+  g.rf1 = (K - 1) * ((1 << n_levels) - 1);
+  if (g.rf1 >= kTR - 8) {
+    set_error("tcn_forward(bf16): receptive field %d does not leave room in a 128-row tile", g.rf1 + 1);
+    return HTCN_ERR_UNSUPPORTED;
+  }
+  int tiles = 0;
+  for (int s = 0; s < slots.n; ++s) {
+    K2Slot& sl = g.slot[s];
+    sl.off = slots.off[s];
+    sl.L = slots.off[s + 1] - slots.off[s];
+    sl.tile0 = tiles;
+    if (sl.L + P <= kTR) {
+      sl.seq_per_tile = kTR / (sl.L + P);
+      sl.tiles_per_seq = 0;
+      tiles += (B + sl.seq_per_tile - 1) / sl.seq_per_tile;
+    } else {
+      sl.seq_per_tile = 0;
+      sl.tiles_per_seq = (sl.L + (kTR - g.rf1) - 1) / (kTR - g.rf1);
+      tiles += B * sl.tiles_per_seq;
+    }
+  }
+  g.n_tiles = tiles;
+  // scratch layout: [bf16 weight tiles][device array of conv_w pointers][biases]
+  uint8_t* sc = reinterpret_cast<uint8_t*>(scratch);
+  __nv_bfloat16* w_bf16 = reinterpret_cast<__nv_bfloat16*>(sc);
+  const size_t w_bytes = (size_t)(1 + n_levels * K) * kDim * kDim * 2;
+  const float** ptrs_dev = reinterpret_cast<const float**>(sc + w_bytes);
+  float* bias_dev = reinterpret_cast<float*>(sc + w_bytes + HTCN_MAX_LEVELS * 8);
+  if (n_levels > 0) {
+    HTCN_CUDA(cudaMemcpyAsync(ptrs_dev, conv_w, sizeof(float*) * n_levels, cudaMemcpyHostToDevice, st));
+    for (int l = 0; l < n_levels; ++l)
+      HTCN_CUDA(cudaMemcpyAsync(bias_dev + l * kDim, conv_b[l], kDim * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  k2_prepare_weights<<<1 + n_levels * K, 256, 0, st>>>(w_in_x, ptrs_dev, n_levels, K, w_bf16);
+  HTCN_LAUNCH_CHECK("k2_prepare_weights");
+  CUtensorMap tw;
+  int32_t rc = make_tmap_bf16(&tw, w_bf16, (uint64_t)(1 + n_levels * K) * kDim, kDim, kDim, 64, 128, 128);
+  if (rc) return rc;
+  const size_t smem = sizeof(K2Smem) + 1024;
+  HTCN_CUDA(cudaFuncSetAttribute(k2_tcn_bf16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = tiles < 2 * 148 ? tiles : 2 * 148;
+  k2_tcn_bf16<<<grid, kK2Threads, smem, st>>>(tw, g, (const __nv_bfloat16*)xe, sbias, bias_dev, out_row,
+                                              (__nv_bfloat16*)hout);
+  HTCN_LAUNCH_CHECK("k2_tcn_bf16");
+  return HTCN_OK;
+}
+
 }  // namespace htcn

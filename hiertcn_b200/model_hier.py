@@ -220,7 +220,10 @@ class HierTCN:
                   self.w_in_state.data_ptr(), B, S, None, sbias.data_ptr(), state_out.data_ptr(), st)
         hout = self._buf("hout", (max(Q, 1), D), self.act_torch_dtype)
         k2_precision = self._k2_precision()
-        scratch = self._buf("k2_scratch", (2 * B * T, D), f32) if k2_precision == cabi.HTCN_F32 else None
+        if k2_precision == cabi.HTCN_F32:
+            scratch = self._buf("k2_scratch", (2 * B * T, D), f32)
+        else:       # bf16 weight tiles + pointer table + biases of the fused tcgen05 conv stack
+            scratch = self._buf("k2_scratch_bf16", ((1 + self.n_levels * self.K) * 8192 + 4096,), f32)
         cabi.call("htcn_tcn_forward", xe.data_ptr(), self.act_dtype, k2_precision, self.w_in_x.data_ptr(),
                   sbias.data_ptr(), self._conv_w_pp[0], self._conv_b_pp[0], self.n_levels, self.K, slot_p, B, T, S,
                   d["row_of"].data_ptr(), hout.data_ptr(), self.act_dtype,
@@ -231,9 +234,9 @@ class HierTCN:
         return scores, state_out
 
     def _k2_precision(self):
-        # the bf16 (tcgen05) conv stack is selected when the library provides it; until then the bf16 tier
-        # runs the fp32 FFMA conv stack on bf16 inputs/outputs (more accurate, slower)
-        return cabi.HTCN_BF16 if (self.precision == "bf16" and getattr(self, "k2_tcgen05", False)) else cabi.HTCN_F32
+        # bf16 tier: fused tcgen05 conv stack (k2_tcn_bf16.cu); set self.k2_tcgen05 = False to run the fp32 FFMA
+        # conv stack on bf16 inputs/outputs instead (more accurate, slower)
+        return cabi.HTCN_BF16 if (self.precision == "bf16" and getattr(self, "k2_tcgen05", True)) else cabi.HTCN_F32
 
     # ------------------------------------------------------------------ loss / metrics / top-k (K4)
     def n_split_for(self, Q, n_items):

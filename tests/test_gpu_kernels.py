@@ -387,3 +387,61 @@ def test_k4_bf16_tcgen05(lib, Q, N, n_split):
     v_ref, i_ref = O.top_k(z_gpu, k)
     np.testing.assert_array_equal(oi.cpu().numpy(), i_ref)
     np.testing.assert_array_equal(ov.cpu().numpy(), v_ref)
+
+
+# ------------------------------------------------------------------------------------------ K2 bf16 (tcgen05, fused levels)
+def run_k2_bf16(lib, xe_bf16, w, sbias, slot_off, B, T, S, K, n_levels, out_row=None, n_out=None):
+    conv_w = [dev(w[f"hier/tcn/temporal_conv_net/tblock_{l}/conv1/kernel"]) for l in range(n_levels)]
+    conv_b = [dev(w[f"hier/tcn/temporal_conv_net/tblock_{l}/conv1/bias"]) for l in range(n_levels)]
+    wpp, bpp = lib.ptr_array([t.data_ptr() for t in conv_w]), lib.ptr_array([t.data_ptr() for t in conv_b])
+    w_in_x = dev(w["hier/tcn/emb/kernel"][:128])
+    n_out = B * T if n_out is None else n_out
+    hout = torch.zeros((n_out, 128), dtype=torch.bfloat16, device="cuda")
+    scratch = torch.empty(((1 + n_levels * K) * 8192 + 4096,), dtype=torch.float32, device="cuda")
+    slot_p, keep = lib.int_array(slot_off)
+    lib.call("htcn_tcn_forward", P(xe_bf16), lib.HTCN_BF16, lib.HTCN_BF16, P(w_in_x), P(sbias), wpp[0], bpp[0], n_levels, K,
+             slot_p, B, T, S, P(out_row), P(hout), lib.HTCN_BF16, P(scratch), None)
+    torch.cuda.synchronize()
+    return hout
+
+
+@pytest.mark.parametrize("B,S,L,K,levels", [(7, 3, 9, 5, 2), (3, 1, 300, 5, 4), (150, 10, 20, 5, 2), (4, 2, 1, 3, 3), (5, 1, 200, 5, 2)])
+def test_k2_tcn_bf16_tcgen05(lib, B, S, L, K, levels):
+    x, y, m, s0, w = small_case(B=B, S=S, L=L, N=301, seed=3, tcn_channel=(128,) * levels, kernel_size=K,
+                                lengths="ragged" if L < 100 else "dense", kernel_scale=1.0)
+    pk = pack(x, y, m)
+    T = pk["x_id"].shape[1]
+    state_pre, _, _ = O.gru_over_sessions(y, m, s0, w, 2, "f32")
+    houts, sbs = O.tcn_hidden_restructured(x, state_pre, w, "bf16")
+    ref = O.bf16_round(np.concatenate(houts, 1))
+    ref32 = np.concatenate(O.tcn_hidden_restructured(x, state_pre, w, "f64")[0], 1)
+    xe = dev(O.emb_gather(pk["x_id"], w["hier/emb/kernel"])).to(torch.bfloat16)
+    sbias = dev(np.stack(sbs).astype(np.float32))
+    got = run_k2_bf16(lib, xe, w, sbias, pk["slot_off"], B, T, S, K, levels).float().cpu().numpy().reshape(B, T, 128)
+    scale = np.abs(ref32).max()
+    # vs the bf16-emulating oracle: same roundings, different accumulation order -> a few bf16 ulps
+    assert np.abs(got - ref).max() <= 2e-2 * scale, (np.abs(got - ref).max(), scale)
+    assert np.abs(got - ref).mean() <= 2e-3 * scale
+    # vs exact arithmetic: the 2e-2 tier bar
+    assert np.abs(got - ref32).max() <= 2e-2 * scale + 2e-2
+    # compaction
+    valid = pk["y_id"].reshape(-1) > 0
+    row_of = np.where(valid, np.cumsum(valid) - 1, -1).astype(np.int32)
+    ro = dev(row_of)
+    gotc = run_k2_bf16(lib, xe, w, sbias, pk["slot_off"], B, T, S, K, levels, out_row=ro, n_out=int(valid.sum())).float().cpu().numpy()
+    np.testing.assert_array_equal(gotc, got.reshape(-1, 128)[valid])
+
+
+def test_k2_bf16_causality_and_isolation(lib):
+    B, L, levels, K = 6, 20, 2, 5
+    x, y, m, s0, w = small_case(B=B, S=1, L=L, N=50, seed=4, tcn_channel=(128,) * levels, kernel_size=K, lengths="dense")
+    rng = np.random.default_rng(0)
+    xe = rng.normal(size=(B, L, 128)).astype(np.float32)
+    xe2 = xe.copy()
+    xe2[2, 5] += 100.0
+    a = run_k2_bf16(lib, dev(xe).to(torch.bfloat16), w, None, [0, L], B, L, 1, K, levels).float().cpu().numpy().reshape(B, L, 128)
+    b = run_k2_bf16(lib, dev(xe2).to(torch.bfloat16), w, None, [0, L], B, L, 1, K, levels).float().cpu().numpy().reshape(B, L, 128)
+    assert np.array_equal(a[2, :5], b[2, :5]), "no leak into the past"
+    for other in (0, 1, 3, 4, 5):
+        assert np.array_equal(a[other], b[other]), "no leak into neighbouring sequences of the same tile"
+    assert np.abs(a[2, 5:] - b[2, 5:]).max() > 0
