@@ -23,6 +23,8 @@
 // Softmax reference point: the target logit z_y (computed up front by k4_target_bf16 with the SAME
 // tcgen05.mma arithmetic, so z_y compares equal to itself in the sweep).  CE loss = log sum_j exp(z_j - z_y):
 // no running max, no rescaling.  Terms far below z_y flush to zero harmlessly (the j = y term is 1).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "sm100.cuh"
 
@@ -35,6 +37,21 @@ constexpr int kSlicesScore = 4;                  // CE/RANK sweep: 4 column slic
 constexpr float kLog2e = 1.4426950408889634f;
 
 enum : unsigned { kModeDump = 8u };              // internal: write raw logits (test hook)
+
+// internal kFlags bits: 1 of every 8 / 4 exponentials of the CE sum runs on the FMA pipe instead of the MUFU pipe
+enum : unsigned { kModePoly8 = 16u, kModePoly4 = 32u };
+
+// 2^t on the FMA/ALU pipes: round-to-nearest split t = n + f, f in [-0.5, 0.5]; 2^f by a degree-3 polynomial with
+// p(0) = 1 (max relative error 1.0e-4 -- bf16-tier only); 2^n by adding n to the exponent field.
+__device__ __forceinline__ float ex2_poly(float t) {
+  t = fmaxf(t, -125.0f);
+  const float r = t + 12582912.0f;               // 1.5 * 2^23: n = round(t) lands in the low mantissa bits
+  const float f = t - (r - 12582912.0f);
+  float p = fmaf(f, 0.05500892922282219f, 0.24221095442771912f);
+  p = fmaf(p, f, 0.6932829022407532f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(r) << 23));
+}
 
 template <int BN>
 struct alignas(1024) ScoreSmem {
@@ -78,6 +95,7 @@ k4_score_bf16(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
               const __grid_constant__ CUtensorMap tmap_bb, ScoreArgs a, float* __restrict__ dump) {
   constexpr bool kCE = kFlags & HTCN_SCORE_CE, kRank = kFlags & HTCN_SCORE_RANK, kTopk = kFlags & HTCN_SCORE_TOPK;
   constexpr bool kDump = kFlags & kModeDump;
+  constexpr int kPolyEvery = (kFlags & kModePoly4) ? 4 : (kFlags & kModePoly8) ? 8 : 0x40000000;
   constexpr int kSlices = kTopk ? 1 : kSlicesScore;           // column slices per tile (one heap per row in top-k mode)
   constexpr int kEpiWarps = 4 * kSlices;
   constexpr int kColsPerWarp = BN / kSlices;
@@ -177,7 +195,12 @@ k4_score_bf16(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
             if (kDump) {
               if (row_ok) dump[(long long)(q0 + row) * a.n_items + jbase + c + u] = z;
             }
-            if (kCE) sum4[u & 3] += ex2_approx(fmaf(z, kLog2e, -zyl));
+            if (kCE) {
+              // the MUFU pipe (16 ex2/clk/SM) bounds this loop: every kPolyEvery-th exponential is evaluated on the
+              // FMA pipe instead (degree-3 polynomial, 1e-4 relative, exact at t = 0)
+              const float t = fmaf(z, kLog2e, -zyl);
+              sum4[u & 3] += ((u % kPolyEvery) == kPolyEvery - 1) ? ex2_poly(t) : ex2_approx(t);
+            }
             if (kRank) cf[u & 3] += set_gt_f(z, zy);
             if (kTopk) {
               if (z > thr) thr = heap.replace_root(z, a.n0 + jbase + c + u);
@@ -427,7 +450,14 @@ int32_t score_bf16(const ScoreArgs& a, cudaStream_t st) {
   switch (a.flags) {
     case HTCN_SCORE_CE: return launch_score<256, HTCN_SCORE_CE>(a, nullptr, st);
     case HTCN_SCORE_RANK: return launch_score<256, HTCN_SCORE_RANK>(a, nullptr, st);
-    case HTCN_SCORE_CE | HTCN_SCORE_RANK: return launch_score<256, HTCN_SCORE_CE | HTCN_SCORE_RANK>(a, nullptr, st);
+    case HTCN_SCORE_CE | HTCN_SCORE_RANK: {
+      // 1 of every 8 exponentials runs on the FMA pipe (1e-4 relative polynomial): measured 821 -> 843 TFLOP/s on the
+      // cfg2 sweep (MUFU-bound and power-capped); 1 of 4 is slower (778).  HTCN_POLY_EVERY=0 turns it off.
+      static const int poly = [] { const char* e = getenv("HTCN_POLY_EVERY"); return e ? atoi(e) : 8; }();
+      if (poly == 8) return launch_score<256, HTCN_SCORE_CE | HTCN_SCORE_RANK | kModePoly8>(a, nullptr, st);
+      if (poly == 4) return launch_score<256, HTCN_SCORE_CE | HTCN_SCORE_RANK | kModePoly4>(a, nullptr, st);
+      return launch_score<256, HTCN_SCORE_CE | HTCN_SCORE_RANK>(a, nullptr, st);
+    }
   }
   set_error("score(bf16): flags 0x%x", a.flags);
   return HTCN_ERR_INVALID;
