@@ -1,0 +1,76 @@
+"""Multi-GPU (NCCL) test of catalog-sharded scoring: world = 2 ranks, each owning half of the catalog
+(hiertcn_b200.dist.ShardedCatalogScorer + CudaScoreOps) must reproduce single-GPU scoring of the whole catalog --
+loss rows, ranks and top-k lists.  Skipped on boxes with fewer than 2 GPUs (run: gpurun --gpus 2 -- pytest ...)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, precision, ret):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from hiertcn_b200.args import make_args
+        from hiertcn_b200.dist import CudaScoreOps, ShardedCatalogScorer, make_sharded_model
+        from hiertcn_b200.model_hier import HierTCN
+        from hiertcn_b200.weights import hier_weight_shapes, init_weights
+        N, Ql, k = 50_000, 300, 100
+        w = init_weights(hier_weight_shapes(N), seed=3, kernel_scale=2.0, bias_noise=0.2)
+        a = make_args(["--item_num", str(N)])
+        rng = np.random.default_rng(0)
+        h_all = (rng.normal(size=(world * Ql, 128))).astype(np.float32)
+        y_all = rng.integers(1, N, size=world * Ql).astype(np.int32)
+        dt = torch.bfloat16 if precision == "bf16" else torch.float32
+        h = torch.from_numpy(h_all[rank * Ql:(rank + 1) * Ql]).cuda().to(dt)
+        y = torch.from_numpy(y_all[rank * Ql:(rank + 1) * Ql]).cuda()
+        # sharded: this rank holds rows [n0, n1) of W_out^T
+        m_sh, n0, n1 = make_sharded_model(a, w, rank, world, precision)
+        sc = ShardedCatalogScorer(CudaScoreOps(m_sh), dist, rank, world, N, n_split=3)
+        out = sc.score(h, y, k=k)
+        # single GPU, whole catalog
+        m_full = HierTCN(a, w, precision=precision).build()
+        ops = CudaScoreOps(m_full)
+        zy = torch.zeros(Ql, dtype=torch.float32, device="cuda")
+        ops.target_logit(h, y, 0, N, zy)
+        part = ops.sweep(h, y, zy, 0, N, k, 2, True, True)
+        ref = ops.finish(part["pm"], part["ps"], part["pc"], y, zy)
+        ref.update(ops.topk_merge(part["tv"], part["ti"], k))
+        torch.cuda.synchronize()
+        ok = (torch.equal(out["rank_row"], ref["rank_row"]) and torch.equal(out["topk_idx"], ref["topk_idx"])
+              and torch.equal(out["topk_val"], ref["topk_val"])
+              and torch.allclose(out["loss_row"], ref["loss_row"], rtol=2e-6, atol=2e-6))
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("precision", ["bf16", "f32"])
+def test_sharded_catalog_scoring_nccl(precision):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, precision, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    assert all(ret.get(r) for r in range(2)), dict(ret)
