@@ -33,11 +33,13 @@ SIGNATURES = {
     "htcn_target_logit": [_p, _i, _i, _p, _p, _i, _i, _p, _p, _p],
     "htcn_score_finish": [_p, _p, _p, _i, _i, _p, _p, _p, _p, _p],
     "htcn_topk_merge": [_p, _p, _i, _i, _i, _p, _p, _p],
+    "htcn_score_topk": [_p, _i, _i, _p, _p, _i, _i, _i, _i, _p, C.c_int64, _p, _p, _p, _p],
     "htcn_loss_metrics_reduce": [_p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p],
     "htcn_sampled_rank_loss": [_p, _i, _i, _p, _p, _p, _i, _i, _f, _f, _p, _p],
 }
 PLAIN = {"htcn_abi_version": (C.c_int32, []), "htcn_last_error": (C.c_char_p, []),
-         "htcn_device_ok": (C.c_int32, [])}
+         "htcn_device_ok": (C.c_int32, []),
+         "htcn_topk_workspace_bytes": (C.c_int64, [_i, _i, _i, _i, _i])}
 
 
 class HtcnError(RuntimeError):
@@ -72,7 +74,7 @@ def load(path: str | None = None):
 # n_levels + 1 (counted by the caller through note_launches)
 LAUNCHES_PER_CALL = {"htcn_gather_meanpool": 2, "htcn_gru_sessions": 1, "htcn_tcn_forward": 0,
                      "htcn_prepare_wout": 1, "htcn_score_ce_rank_topk": 2, "htcn_score_logits": 1,
-                     "htcn_target_logit": 1, "htcn_score_finish": 1, "htcn_topk_merge": 1,
+                     "htcn_target_logit": 1, "htcn_score_finish": 1, "htcn_topk_merge": 1, "htcn_score_topk": 5,
                      "htcn_loss_metrics_reduce": 1, "htcn_sampled_rank_loss": 1}
 launch_count = 0
 

@@ -12,6 +12,16 @@ int32_t target_logit_f32(const float* hout, const float* wt, const float* b_out,
 int32_t score_bf16(const ScoreArgs& a, cudaStream_t st);
 int32_t target_logit_bf16(const void* hout, const void* wt, const float* b_out, const int* y_id, int Q,
                           int n_items, int n0, float* zy, cudaStream_t st);
+long long topk_workspace_bytes_bf16(int Q, int n_items, int k, int n_split);
+int32_t score_topk_bf16(const void* hout, int Q, const void* wt, int n_items, int n0, int k, int n_split, void* workspace,
+                        long long workspace_bytes, float* out_val, int* out_idx, int* overflow_rows, cudaStream_t st);
+
+// the two-pass method needs >= k finite column groups of 256 items per row to produce a threshold
+static bool topk_two_pass_ok(int precision, int n_items, int k) { return precision == HTCN_BF16 && n_items >= 1024 * k; }
+static int topk_heap_splits(int precision, int n_items, int n_split) {
+  const int tiles = precision == HTCN_BF16 ? (n_items + 127) / 128 : (n_items + 63) / 64;
+  return n_split < 1 ? 1 : (n_split > tiles ? tiles : n_split);
+}
 
 // ---- W_out [128, N] f32 -> W_out^T [N, 128] f32 | [N, 144] bf16 augmented (32x32 smem transpose) ----
 template <bool kBf16>
@@ -273,6 +283,35 @@ extern "C" int32_t htcn_score_ce_rank_topk(const void* hout, int32_t precision, 
   }
   if (precision == HTCN_BF16) return score_bf16(a, st);
   HTCN_REQUIRE(false, "score: precision %d", precision);
+}
+
+extern "C" int64_t htcn_topk_workspace_bytes(int32_t precision, int32_t Q, int32_t n_items, int32_t k, int32_t n_split) {
+  if (topk_two_pass_ok(precision, n_items, k)) return topk_workspace_bytes_bf16(Q, n_items, k, n_split);
+  return (int64_t)topk_heap_splits(precision, n_items, n_split) * Q * k * 8 + 256;
+}
+
+extern "C" int32_t htcn_score_topk(const void* hout, int32_t precision, int32_t Q, const void* w_out_t, const float* b_out,
+                                   int32_t n_items, int32_t n0, int32_t k, int32_t n_split, void* workspace,
+                                   int64_t workspace_bytes, float* out_val, int32_t* out_idx, int32_t* overflow_rows,
+                                   void* stream) {
+  HTCN_REQUIRE(hout && w_out_t && workspace && out_val && out_idx && Q > 0 && n_items > 0, "score_topk: bad args");
+  HTCN_REQUIRE(k >= 1 && k <= HTCN_MAX_TOPK, "score_topk: k=%d out of [1,%d]", k, HTCN_MAX_TOPK);
+  HTCN_REQUIRE(precision == HTCN_F32 || precision == HTCN_BF16, "score_topk: precision %d", precision);
+  HTCN_REQUIRE(workspace_bytes >= htcn_topk_workspace_bytes(precision, Q, n_items, k, n_split),
+               "score_topk: workspace too small (%lld bytes)", (long long)workspace_bytes);
+  cudaStream_t st = as_stream(stream);
+  if (topk_two_pass_ok(precision, n_items, k))
+    return score_topk_bf16(hout, Q, w_out_t, n_items, n0, k, n_split, workspace, workspace_bytes, out_val, out_idx,
+                           overflow_rows, st);
+  // heap sweep into [ns, Q, k] partial lists, then merge
+  const int ns = topk_heap_splits(precision, n_items, n_split);
+  float* tv = reinterpret_cast<float*>(workspace);
+  int32_t* ti = reinterpret_cast<int32_t*>(tv + (size_t)ns * Q * k);
+  if (overflow_rows) HTCN_CUDA(cudaMemsetAsync(overflow_rows, 0, 4, st));
+  int32_t rc = htcn_score_ce_rank_topk(hout, precision, Q, w_out_t, b_out, n_items, n0, nullptr, nullptr, 1,
+                                       HTCN_SCORE_TOPK, k, ns, nullptr, nullptr, nullptr, tv, ti, stream);
+  if (rc) return rc;
+  return htcn_topk_merge(tv, ti, ns, Q, k, out_val, out_idx, stream);
 }
 
 extern "C" int32_t htcn_score_finish(const float* part_max, const float* part_sum, const int32_t* part_cnt,

@@ -40,6 +40,21 @@ enum : unsigned { kModeDump = 8u };              // internal: write raw logits (
 
 // internal kFlags bits: 1 of every 8 / 4 exponentials of the CE sum runs on the FMA pipe instead of the MUFU pipe
 enum : unsigned { kModePoly8 = 16u, kModePoly4 = 32u };
+// internal kFlags bits of the two-pass top-k (htcn_score_topk): pass 1 = per-row maxima of column groups,
+// pass 2 = append every logit >= the row threshold to the row's candidate list
+enum : unsigned { kModeGroupMax = 64u, kModeFilter = 128u };
+constexpr int kGroupTiles = 4;                   // a column group = this warp's 64-column slice of 4 consecutive tiles
+
+struct TopkAux {
+  float* gmax;          // [Q][ng_total]   pass 1 out (pre-filled with -inf)
+  int ng_per_split;     // group slots per split (multiple of 4 slices)
+  int ng_total;
+  const float* thr;     // [Q]             pass 2 in: lower bound of the k-th best score of the row
+  int* cand_cnt;        // [Q]             pass 2 out
+  float* cand_val;      // [Q][cap]
+  int* cand_idx;        // [Q][cap]
+  int cap;
+};
 
 // 2^t on the FMA/ALU pipes: round-to-nearest split t = n + f, f in [-0.5, 0.5]; 2^f by a degree-3 polynomial with
 // p(0) = 1 (max relative error 1.0e-4 -- bf16-tier only); 2^n by adding n to the exponent field.
@@ -92,9 +107,10 @@ constexpr int score_threads() { return 64 + 32 * 4 * ((kFlags & HTCN_SCORE_TOPK)
 template <int BN, unsigned kFlags>
 __global__ void __launch_bounds__(score_threads<kFlags>(), 1)
 k4_score_bf16(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-              const __grid_constant__ CUtensorMap tmap_bb, ScoreArgs a, float* __restrict__ dump) {
+              const __grid_constant__ CUtensorMap tmap_bb, ScoreArgs a, float* __restrict__ dump, TopkAux aux) {
   constexpr bool kCE = kFlags & HTCN_SCORE_CE, kRank = kFlags & HTCN_SCORE_RANK, kTopk = kFlags & HTCN_SCORE_TOPK;
   constexpr bool kDump = kFlags & kModeDump;
+  constexpr bool kGMax = kFlags & kModeGroupMax, kFilter = kFlags & kModeFilter;
   constexpr int kPolyEvery = (kFlags & kModePoly4) ? 4 : (kFlags & kModePoly8) ? 8 : 0x40000000;
   constexpr int kSlices = kTopk ? 1 : kSlicesScore;           // column slices per tile (one heap per row in top-k mode)
   constexpr int kEpiWarps = 4 * kSlices;
@@ -185,10 +201,38 @@ k4_score_bf16(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
       }
       RowHeap heap{heap_v + row, heap_i + row, kBM, a.k};
       if (kTopk) heap.init();
+      float gm = -INFINITY;                                     // running maximum of the current column group (pass 1)
+      float row_thr = INFINITY;                                 // candidate threshold of this row (pass 2)
+      if (kFilter && row_ok) row_thr = aux.thr[q0 + row];
+      auto append = [&](float z, int j) {                       // rare path of pass 2
+        const int pos = atomicAdd(aux.cand_cnt + q0 + row, 1);
+        if (pos < aux.cap) {
+          aux.cand_val[(long long)(q0 + row) * aux.cap + pos] = z;
+          aux.cand_idx[(long long)(q0 + row) * aux.cap + pos] = j;
+        } else {
+          row_thr = INFINITY;      // the list overflowed (mass ties): the row is redone by the heap path, stop appending
+        }
+      };
 
       // one 32-column chunk held in registers; `c` = column offset inside this warp's slice
       auto process = [&](const uint32_t (&r)[32], int c, int lim, int jbase) {
-        if (c + 32 <= lim) {                                    // full chunk: branch-free
+        if ((kGMax || kFilter) && c + 32 <= lim) {              // two-pass top-k: one FMNMX per logit
+          float m0 = __uint_as_float(r[0]), m1 = __uint_as_float(r[1]), m2 = __uint_as_float(r[2]), m3 = __uint_as_float(r[3]);
+#pragma unroll
+          for (int u = 4; u < 32; u += 4) {
+            m0 = fmaxf(m0, __uint_as_float(r[u]));
+            m1 = fmaxf(m1, __uint_as_float(r[u + 1]));
+            m2 = fmaxf(m2, __uint_as_float(r[u + 2]));
+            m3 = fmaxf(m3, __uint_as_float(r[u + 3]));
+          }
+          const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+          if (kGMax) gm = fmaxf(gm, m);
+          if (kFilter && m >= row_thr) {                        // some logit of this chunk is a candidate (rare)
+#pragma unroll
+            for (int u = 0; u < 32; ++u)
+              if (__uint_as_float(r[u]) >= row_thr) append(__uint_as_float(r[u]), a.n0 + jbase + c + u);
+          }
+        } else if (c + 32 <= lim) {                             // full chunk: branch-free
 #pragma unroll
           for (int u = 0; u < 32; ++u) {
             const float z = __uint_as_float(r[u]);
@@ -222,6 +266,8 @@ k4_score_bf16(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
               if (kTopk) {
                 if (z > thr) thr = heap.replace_root(z, a.n0 + jbase + c + u);
               }
+              if (kGMax) gm = fmaxf(gm, z);
+              if (kFilter && z >= row_thr) append(z, a.n0 + jbase + c + u);
             }
           }
         }
@@ -251,6 +297,11 @@ k4_score_bf16(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
         if (kRank) {                                            // flush the float counters (exact: <= 128 per tile)
           cnt += (int)((cf[0] + cf[1]) + (cf[2] + cf[3]));
           cf[0] = cf[1] = cf[2] = cf[3] = 0.f;
+        }
+        if (kGMax && ((i % kGroupTiles) == kGroupTiles - 1 || i == n_tiles - 1)) {
+          if (row_ok)
+            aux.gmax[(long long)(q0 + row) * aux.ng_total + split * aux.ng_per_split + (i / kGroupTiles) * kSlices + half] = gm;
+          gm = -INFINITY;
         }
       }
       float sum = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
@@ -408,7 +459,7 @@ int32_t make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint32
 }
 
 template <int BN, unsigned kFlags>
-static int32_t launch_score(const ScoreArgs& a, float* dump, cudaStream_t st) {
+static int32_t launch_score(const ScoreArgs& a, float* dump, cudaStream_t st, const TopkAux& aux = TopkAux{}) {
   CUtensorMap ta, tb, tbb;
   int32_t rc = make_tmap_bf16(&ta, a.hout, (uint64_t)a.Q, kDim, kDim, 64, kBM, 128);
   if (rc) return rc;
@@ -424,7 +475,7 @@ static int32_t launch_score(const ScoreArgs& a, float* dump, cudaStream_t st) {
   auto kern = k4_score_bf16<BN, kFlags>;
   HTCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(ceil_div(a.Q, kBM), a.n_split);
-  kern<<<grid, score_threads<kFlags>(), smem, st>>>(ta, tb, tbb, a, dump);
+  kern<<<grid, score_threads<kFlags>(), smem, st>>>(ta, tb, tbb, a, dump, aux);
   HTCN_LAUNCH_CHECK("k4_score_bf16");
   return HTCN_OK;
 }
@@ -471,6 +522,157 @@ int32_t target_logit_bf16(const void* hout, const void* wt, const float* b_out, 
   k4_target_bf16<<<ceil_div(Q, kBM), 128, smem, st>>>((const __nv_bfloat16*)hout, (const __nv_bfloat16*)wt, y_id, Q,
                                                      n_items, n0, zy);
   HTCN_LAUNCH_CHECK("k4_target_bf16");
+  return HTCN_OK;
+}
+
+// ---- two-pass top-k ---------------------------------------------------------------------------------------
+// The k-th largest of the per-group maxima is a lower bound T of the row's k-th best score (k distinct items reach
+// it), and only ~k items are >= T, so a second sweep that appends those items to a per-row list followed by an exact
+// selection yields the exact top-k (tf.nn.top_k order) with epilogues of ONE compare per logit in both sweeps.
+__device__ __forceinline__ uint32_t float_key(float f) {       // order-preserving float -> uint
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// T[q] = k-th largest of gmax[q][0..n) by a 4-round byte radix select; -inf when fewer than k finite groups exist
+__global__ void __launch_bounds__(256)
+topk_threshold_kernel(const float* __restrict__ gmax, int n, int k, float* __restrict__ thr) {
+  __shared__ int hist[256];
+  __shared__ uint32_t s_prefix;
+  __shared__ int s_k;
+  const float* row = gmax + (long long)blockIdx.x * n;
+  uint32_t prefix = 0;
+  int kk = k;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    hist[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t hi_mask = shift == 24 ? 0u : (0xFFFFFFFFu << (shift + 8));
+    for (int i = threadIdx.x; i < n; i += 256) {
+      const uint32_t key = float_key(row[i]);
+      if ((key & hi_mask) == prefix) atomicAdd(&hist[(key >> shift) & 255], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int acc = 0, b = 255;
+      for (; b > 0; --b) {
+        if (acc + hist[b] >= kk) break;
+        acc += hist[b];
+      }
+      s_prefix = prefix | ((uint32_t)b << shift);
+      s_k = kk - acc;
+    }
+    __syncthreads();
+    prefix = s_prefix;
+    kk = s_k;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const uint32_t u = (prefix & 0x80000000u) ? (prefix & 0x7FFFFFFFu) : ~prefix;
+    float t = __uint_as_float(u);
+    if (n < k || !(t > -INFINITY)) t = -INFINITY;
+    thr[blockIdx.x] = t;
+  }
+}
+
+// exact top-k of each row's candidate list, (score desc, index asc); rows whose list overflowed are counted
+__global__ void __launch_bounds__(128)
+topk_select_kernel(const float* __restrict__ cv, const int* __restrict__ ci, const int* __restrict__ cnt, int cap, int k,
+                   float* __restrict__ ov, int* __restrict__ oi, int* __restrict__ overflow_rows) {
+  extern __shared__ float sm_sel[];
+  float* v = sm_sel;
+  int* id = reinterpret_cast<int*>(sm_sel + cap);
+  const int q = blockIdx.x;
+  const int total = cnt[q];
+  const int n = total < cap ? total : cap;
+  if (threadIdx.x == 0 && total > cap) atomicAdd(overflow_rows, 1);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    v[i] = cv[(long long)q * cap + i];
+    id[i] = ci[(long long)q * cap + i];
+  }
+  for (int i = threadIdx.x; i < k; i += blockDim.x) {
+    ov[(long long)q * k + i] = -INFINITY;
+    oi[(long long)q * k + i] = -1;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float vi = v[i];
+    const int ii = id[i];
+    int pos = 0;
+    for (int j = 0; j < n; ++j) pos += (v[j] > vi || (v[j] == vi && id[j] < ii)) ? 1 : 0;
+    if (pos < k) {
+      ov[(long long)q * k + pos] = vi;
+      oi[(long long)q * k + pos] = ii;
+    }
+  }
+}
+
+__global__ void fill_f32_kernel(float* p, long long n, float v) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+
+static inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+struct TopkPlan {
+  int n_split, ng_per_split, ng_total, cap;
+  size_t off_gmax, off_thr, off_cnt, off_cv, off_ci, bytes;
+};
+
+static TopkPlan topk_plan(int Q, int n_items, int k, int n_split) {
+  TopkPlan p{};
+  const int n_tiles = (n_items + 255) / 256;
+  p.n_split = n_split < 1 ? 1 : (n_split > n_tiles ? n_tiles : n_split);
+  const int max_tiles_split = (n_tiles + p.n_split - 1) / p.n_split + 1;
+  p.ng_per_split = ((max_tiles_split + kGroupTiles - 1) / kGroupTiles) * kSlicesScore;
+  p.ng_total = p.ng_per_split * p.n_split;
+  p.cap = 4 * k < 256 ? 256 : 4 * k;
+  size_t o = 0;
+  p.off_gmax = o; o += align256((size_t)Q * p.ng_total * 4);
+  p.off_thr = o; o += align256((size_t)Q * 4);
+  p.off_cnt = o; o += align256((size_t)Q * 4 + 4);          // + the overflow counter
+  p.off_cv = o; o += align256((size_t)Q * p.cap * 4);
+  p.off_ci = o; o += align256((size_t)Q * p.cap * 4);
+  p.bytes = o;
+  return p;
+}
+
+long long topk_workspace_bytes_bf16(int Q, int n_items, int k, int n_split) { return (long long)topk_plan(Q, n_items, k, n_split).bytes; }
+
+int32_t score_topk_bf16(const void* hout, int Q, const void* wt, int n_items, int n0, int k, int n_split, void* workspace,
+                        long long workspace_bytes, float* out_val, int* out_idx, int* overflow_rows, cudaStream_t st) {
+  const TopkPlan p = topk_plan(Q, n_items, k, n_split);
+  if ((long long)p.bytes > workspace_bytes) {
+    set_error("score_topk: workspace too small (%lld < %zu bytes)", workspace_bytes, p.bytes);
+    return HTCN_ERR_INVALID;
+  }
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  TopkAux aux{};
+  aux.gmax = reinterpret_cast<float*>(ws + p.off_gmax);
+  aux.ng_per_split = p.ng_per_split;
+  aux.ng_total = p.ng_total;
+  float* thr = reinterpret_cast<float*>(ws + p.off_thr);
+  aux.thr = thr;
+  aux.cand_cnt = reinterpret_cast<int*>(ws + p.off_cnt);
+  aux.cand_val = reinterpret_cast<float*>(ws + p.off_cv);
+  aux.cand_idx = reinterpret_cast<int*>(ws + p.off_ci);
+  aux.cap = p.cap;
+  int* ovf = aux.cand_cnt + Q;
+  fill_f32_kernel<<<592, 256, 0, st>>>(aux.gmax, (long long)Q * p.ng_total, -INFINITY);
+  HTCN_CUDA(cudaMemsetAsync(aux.cand_cnt, 0, (size_t)Q * 4 + 4, st));
+  ScoreArgs a{};
+  a.hout = hout; a.wt = wt; a.Q = Q; a.n_items = n_items; a.n0 = n0; a.n_split = p.n_split; a.k = 0;
+  a.flags = kModeGroupMax;
+  int32_t rc = launch_score<256, kModeGroupMax>(a, nullptr, st, aux);
+  if (rc) return rc;
+  topk_threshold_kernel<<<Q, 256, 0, st>>>(aux.gmax, p.ng_total, k, thr);
+  HTCN_LAUNCH_CHECK("topk_threshold_kernel");
+  a.flags = kModeFilter;
+  rc = launch_score<256, kModeFilter>(a, nullptr, st, aux);
+  if (rc) return rc;
+  const size_t smem = (size_t)p.cap * 8;
+  HTCN_CUDA(cudaFuncSetAttribute(topk_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  topk_select_kernel<<<Q, 128, smem, st>>>(aux.cand_val, aux.cand_idx, aux.cand_cnt, p.cap, k, out_val, out_idx, ovf);
+  HTCN_LAUNCH_CHECK("topk_select_kernel");
+  if (overflow_rows) HTCN_CUDA(cudaMemcpyAsync(overflow_rows, ovf, 4, cudaMemcpyDeviceToDevice, st));
   return HTCN_OK;
 }
 

@@ -263,14 +263,13 @@ class HierTCN:
             return out
         st = self.stream_ptr()
         f32, i32 = torch.float32, torch.int32
-        flags = (cabi.SCORE_CE if ce else 0) | (cabi.SCORE_RANK if rank else 0) | (cabi.SCORE_TOPK if topk else 0)
+        flags = (cabi.SCORE_CE if ce else 0) | (cabi.SCORE_RANK if rank else 0)
         ns = self.n_split_for(Q, self.N)
         zy = self._buf("zy", (Q,), f32)
         pm = self._buf("pm", (ns, Q), f32) if ce else None
         ps = self._buf("ps", (ns, Q), f32) if ce else None
         pc = self._buf("pc", (ns, Q), i32) if rank else None
-        tv = self._buf("tv", (ns, Q, topk), f32) if topk else None
-        ti = self._buf("ti", (ns, Q, topk), i32) if topk else None
+        tv = ti = None
         P = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
         need_t = ce or rank
         if need_t:      # target logits first (own launch so the sweep can be timed on its own)
@@ -280,10 +279,11 @@ class HierTCN:
         if ev is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(torch.cuda.current_stream(self.device))
-        cabi.call("htcn_score_ce_rank_topk", scores.hout.data_ptr(), self.act_dtype, Q, self.wt.data_ptr(),
-                  self.b_out.data_ptr(), self.N, 0, scores.y_rows.data_ptr() if need_t else None, zy.data_ptr(), 1,
-                  flags, topk, ns, P(pm), P(ps), P(pc), P(tv), P(ti), st)
-        cabi.note_launches(-1)          # have_target=1: the sweep call launched one kernel, not two
+        if flags:
+            cabi.call("htcn_score_ce_rank_topk", scores.hout.data_ptr(), self.act_dtype, Q, self.wt.data_ptr(),
+                      self.b_out.data_ptr(), self.N, 0, scores.y_rows.data_ptr(), zy.data_ptr(), 1,
+                      flags, 0, ns, P(pm), P(ps), P(pc), None, None, st)
+            cabi.note_launches(-1)      # have_target=1: the sweep call launched one kernel, not two
         if ev is not None:
             e1.record(torch.cuda.current_stream(self.device))
             ev.append((e0, e1, 2.0 * Q * 128 * self.N))
@@ -294,12 +294,33 @@ class HierTCN:
                       P(loss_row), P(rank_row), st)
             out.update(loss_row=loss_row, rank_row=rank_row, target_logit=zy)
         if topk:
-            ov = torch.empty((Q, topk), dtype=f32, device=self.device)
-            oi = torch.empty((Q, topk), dtype=i32, device=self.device)
-            cabi.call("htcn_topk_merge", tv.data_ptr(), ti.data_ptr(), ns, Q, topk, ov.data_ptr(), oi.data_ptr(), st)
-            out.update(topk_val=ov, topk_idx=oi)
+            out.update(self.topk(scores.hout, Q, topk))
         scores._cache[key] = out
         return out
+
+    def topk(self, hout, Q, k, n0=0):
+        """Exact top-k of every row of ``hout`` over this model's catalog (shard).  Returns dict(topk_val, topk_idx)
+        [Q,k] device tensors in tf.nn.top_k order.  Uses the two-pass tensor-core method on large bf16 catalogs and
+        redoes the call with the heap sweep if a candidate list overflowed."""
+        torch = _torch()
+        f32, i32 = torch.float32, torch.int32
+        tiles_q = max(1, math.ceil(Q / 128))
+        ns = int(max(1, min(math.ceil(2 * 148 / tiles_q), 32, max(1, self.n_out // 256))))
+        nbytes = int(cabi.load().htcn_topk_workspace_bytes(self.act_dtype, Q, self.n_out, k, ns))
+        ws = self._buf("topk_ws", (nbytes,), torch.uint8)
+        ov = torch.empty((Q, k), dtype=f32, device=self.device)
+        oi = torch.empty((Q, k), dtype=i32, device=self.device)
+        ovf = torch.zeros(1, dtype=i32, device=self.device)
+        cabi.call("htcn_score_topk", hout.data_ptr(), self.act_dtype, Q, self.wt.data_ptr(), self.b_out.data_ptr(), self.n_out,
+                  n0, k, ns, ws.data_ptr(), nbytes, ov.data_ptr(), oi.data_ptr(), ovf.data_ptr(), self.stream_ptr())
+        if int(ovf.item()):                                   # pathological ties: exact heap path
+            tv = torch.empty((ns, Q, k), dtype=f32, device=self.device)
+            ti = torch.empty((ns, Q, k), dtype=i32, device=self.device)
+            cabi.call("htcn_score_ce_rank_topk", hout.data_ptr(), self.act_dtype, Q, self.wt.data_ptr(), self.b_out.data_ptr(),
+                      self.n_out, n0, None, None, 1, cabi.SCORE_TOPK, k, ns, None, None, None, tv.data_ptr(), ti.data_ptr(),
+                      self.stream_ptr())
+            cabi.call("htcn_topk_merge", tv.data_ptr(), ti.data_ptr(), ns, Q, k, ov.data_ptr(), oi.data_ptr(), self.stream_ptr())
+        return dict(topk_val=ov, topk_idx=oi)
 
     def loss(self, scores: CatalogScores, metrics=True, per_position=False):
         """Softmax-CE loss with the reference's two-level masked mean (model.py:105-117) and, with

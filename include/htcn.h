@@ -178,6 +178,24 @@ int32_t htcn_score_finish(const float* part_max, const float* part_sum, const in
                           int32_t n_part, int32_t Q, const int32_t* y_id, const float* target_logit,
                           float* loss_row, float* rank_row, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Exact per-row top-k over one catalog shard in one call (config 4): out_val / out_idx [Q,k] sorted by
+ * (score desc, GLOBAL index asc) = tf.nn.top_k order (loss.py:120); idx -1 / val -inf pad rows with < k items.
+ *   bf16 tier, large shards: two tensor-core sweeps with one compare per logit each -- (1) per-row maxima of
+ *     column groups, whose k-th largest is a lower bound T of the row's k-th best score; (2) every logit >= T is
+ *     appended to the row's candidate list (~k entries) -- then an exact selection.  If a candidate list
+ *     overflows (pathological ties), *overflow_rows (device int, may be NULL) counts the affected rows and the
+ *     caller should redo them with htcn_score_ce_rank_topk(HTCN_SCORE_TOPK), the heap path, which is always exact.
+ *   f32 tier / small shards: the heap sweep + htcn_topk_merge, internally.
+ * workspace: htcn_topk_workspace_bytes(...) bytes of device memory, caller-owned.  Merge shards with
+ * htcn_topk_merge(n_part = number of shards).
+ * ------------------------------------------------------------------------------------------- */
+int64_t htcn_topk_workspace_bytes(int32_t precision, int32_t Q, int32_t n_items, int32_t k, int32_t n_split);
+int32_t htcn_score_topk(const void* hout, int32_t precision, int32_t Q, const void* w_out_t, const float* b_out,
+                        int32_t n_items, int32_t n0, int32_t k, int32_t n_split, void* workspace,
+                        int64_t workspace_bytes, float* out_val, int32_t* out_idx, int32_t* overflow_rows,
+                        void* stream);
+
 /* k-way merge of per-part top-k lists -> [Q,k] sorted by (score desc, index asc) [TF top_k order] */
 int32_t htcn_topk_merge(const float* part_val, const int32_t* part_idx, int32_t n_part, int32_t Q,
                         int32_t k, float* out_val, int32_t* out_idx, void* stream);

@@ -18,7 +18,7 @@ def header_functions():
     src = open(os.path.join(ROOT, "include", "htcn.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     out = {}
-    for m in re.finditer(r"(?:int32_t|const char\*)\s+(htcn_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
+    for m in re.finditer(r"(?:int32_t|int64_t|const char\*)\s+(htcn_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
         args = m.group(2).strip()
         out[m.group(1)] = 0 if args in ("void", "") else len([a for a in args.split(",") if a.strip()])
     return out
