@@ -4,8 +4,9 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
 A "step" is one pass of the hot path over one batch of synthetic XING-shaped input:
-K1 gather+meanpool -> K3 GRU over sessions -> K2 causal conv stack -> K4 full-catalog scoring with fused
-softmax-CE + rank metrics -> masked two-level means (the fetch list of run_hier_xing.py:145-149).
+K1 gather+meanpool -> K3 GRU over sessions -> K2 causal conv stack -> sampled ranking loss (k=20 negatives,
+hinge_logsigmoid, loss.py:42-50) -> K4 full-catalog scoring with fused softmax-CE + rank metrics -> masked
+two-level means (the fetch list of run_hier_xing.py:145-149).
 Workload at every N: BASELINE.json configs[1] -- batch 4096 users x 10 sessions x 20 positions (dense),
 ~1M items, emb 100-d (zero-padded to 128), bf16 tier; users shard data-parallel over ranks (weak scaling),
 the catalog is replicated, the only collective is the all-reduce of the loss/metric partial sums.
@@ -218,10 +219,14 @@ def main():
 
     # ---------------- device-resident arm (`value`) ----------------
     staged = model.stage(x, y, m, s0)
+    neg_host = np.random.default_rng(11 + rank).integers(1, wl["N"], size=(int(staged["Q"]), 20), dtype=np.int32)
+    neg_dev = torch.from_numpy(neg_host).cuda()
     torch.cuda.synchronize()
+    sampled = {}
 
     def dev_step():
         scores, state_out = model.forward(staged=staged)
+        sampled["scalars"] = model.sampled_loss_mean(scores, neg_dev)
         r = model.loss(scores, metrics=True)
         return reduce_scalars(r["scalars"])
 
@@ -266,21 +271,21 @@ def main():
 
     # ---------------- end-to-end arm (`e2e`): host numpy in, host results out ----------------
     for _ in range(2):
-        out = model.step(x, y, m, s0)
+        out = model.step(x, y, m, s0, neg_ids=neg_host)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     e2e_steps = max(2, min(opt.steps, 5))
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        out = model.step(x, y, m, s0)
+        out = model.step(x, y, m, s0, neg_ids=neg_host)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     t_e = torch.tensor([dt], device="cuda")
     if world > 1:
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
     e2e_value = world * B / (float(t_e.item()) / e2e_steps)
-    h2d = staged["h2d_bytes"]
+    h2d = staged["h2d_bytes"] + neg_host.nbytes
     d2h = 8 * 4 + B * 256 * 4
 
     if rank != 0:
@@ -304,7 +309,7 @@ def main():
                        "parallelism": "dp%d over users, catalog replicated" % world,
                        "l2": "inputs larger than L2: catalog %.0f MB + activations %.0f MB per step vs 126 MB L2"
                              % (wl["N"] * 256 / 1e6, B * T * 256 * 3 / 1e6)},
-            "loss": float(scalars[0]), "mrr": float(scalars[4]),
+            "loss": float(scalars[0]), "mrr": float(scalars[4]), "sampled_loss": float(sampled["scalars"][0].item()),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "api": "HierTCN.step(x_list, y_list, mask_list, state) numpy in / numpy out"},
             "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks}

@@ -184,11 +184,16 @@ class HierTCN:
         row_of = np.where(valid, np.cumsum(valid) - 1, -1).astype(np.int32)
         Q = int(valid.sum())
         y_rows = np.ascontiguousarray(pk["y_id"].reshape(-1)[valid])
-        if state is None:
-            state = np.zeros((B, self.G * 128), np.float32)
-        host = dict(x_id=pk["x_id"], y_id=pk["y_id"], mask=pk["mask"], row_of=row_of, y_rows=y_rows,
-                    state=np.ascontiguousarray(state, dtype=np.float32))
+        host = dict(x_id=pk["x_id"], y_id=pk["y_id"], mask=pk["mask"], row_of=row_of, y_rows=y_rows)
         dev, nbytes = {}, 0
+        if hasattr(state, "data_ptr"):
+            # device-resident carried state: the previous step's state_out stays in HBM instead of
+            # round-tripping through host numpy every batch like the reference does (run_hier_xing.py:291,301)
+            dev["state"] = state.to(device=self.device, dtype=torch.float32).contiguous()
+        else:
+            if state is None:
+                state = np.zeros((B, self.G * 128), np.float32)
+            host["state"] = np.ascontiguousarray(state, dtype=np.float32)
         for k, v in host.items():
             t = torch.from_numpy(v)
             if v.size:
@@ -341,12 +346,22 @@ class HierTCN:
                   P(maps.get("ranks_float")), scalars.data_ptr(), self.stream_ptr())
         return dict(scalars=scalars, **maps)
 
+    def sampled_loss_mean(self, scores: CatalogScores, neg_ids, kind=None):
+        """Sampled ranking loss reduced with the reference's two-level masked mean (model.py:111-117).
+        Returns a device tensor scalars[8] whose element 0 is the loss."""
+        torch = _torch()
+        rows = self.sampled_loss(scores, neg_ids, kind)
+        scalars = torch.empty(8, dtype=torch.float32, device=self.device)
+        cabi.call("htcn_loss_metrics_reduce", rows.data_ptr(), None, scores.row_of.data_ptr(), scores.y_id.data_ptr(),
+                  scores.B, scores.T, self.N, None, None, None, scalars.data_ptr(), self.stream_ptr())
+        return scalars
+
     def sampled_loss(self, scores: CatalogScores, neg_ids, kind=None):
         """Sampled ranking loss (reference loss.py:22-71) of the user embeddings against the rows of the
         output table W_out^T: positive = the true next item, negatives = ``neg_ids [Q,k]`` (host or device)."""
         torch = _torch()
         a = self.args
-        kind = kind or a.loss
+        kind = kind or (a.loss if a.loss in cabi.LOSS_KINDS else "hinge_logsigmoid")
         if kind not in cabi.LOSS_KINDS:
             raise ValueError("sampled loss kind %r" % kind)
         if self.wt_f32 is None:                  # gather table is fp32 in both tiers
@@ -361,18 +376,23 @@ class HierTCN:
         return out
 
     # ------------------------------------------------------------------ the reference's sess.run
-    def step(self, x_list, y_list, mask_list, state=None, metrics=True, per_position=False, topk=0):
+    def step(self, x_list, y_list, mask_list, state=None, metrics=True, per_position=False, topk=0,
+             state_on_device=False, neg_ids=None):
         """Host in, host out -- the call ``sess.run([loss, state, ranks_float, ...], feed_dict)`` of
-        run_hier_xing.py:145-149 maps to.  Includes the H2D of the batch and the D2H of the results."""
+        run_hier_xing.py:145-149 maps to.  Includes the H2D of the batch and the D2H of the results.
+        ``state`` may be a numpy array (reference behaviour) or the device tensor returned by a previous step with
+        ``state_on_device=True`` (then the carried state never leaves HBM)."""
         scores, state_out = self.forward(x_list, y_list, mask_list, state)
         r = self.loss(scores, metrics=metrics, per_position=per_position)
         out = {}
         sc = r["scalars"].cpu().numpy()
         out.update(loss=sc[0], recall1=sc[1], recall5=sc[2], recall10=sc[3], mrr=sc[4], mrp=sc[5],
-                   user_count=sc[6], n_valid=sc[7], state=state_out.cpu().numpy())
+                   user_count=sc[6], n_valid=sc[7], state=state_out if state_on_device else state_out.cpu().numpy())
         for n in ("loss_bt", "ranks", "ranks_float"):
             if n in r:
                 out[n] = r[n].cpu().numpy()
+        if neg_ids is not None:                     # sampled ranking loss of reference loss.py:22-71 on the same forward
+            out["sampled_loss"] = float(self.sampled_loss_mean(scores, neg_ids)[0].item())
         if topk:
             t = self.score(scores, ce=False, rank=False, topk=topk)
             out["topk_val"] = t["topk_val"].cpu().numpy() if t else np.zeros((0, topk), np.float32)

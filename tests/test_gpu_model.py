@@ -85,6 +85,10 @@ def test_state_carry_across_batches_and_user_independence():
     np.testing.assert_array_equal(o1["loss_bt"][perm], o2["loss_bt"])       # rows are independent users
     np.testing.assert_array_equal(o1["state"][perm], o2["state"])
     o3 = model.step(x, y, m, o1["state"])                                     # carried state feeds the next batch
+    o1d = model.step(x, y, m, s0, state_on_device=True)                       # ... or stays on the device
+    assert o1d["state"].is_cuda and np.array_equal(o1d["state"].cpu().numpy(), o1["state"])
+    o3d = model.step(x, y, m, o1d["state"])
+    assert o3d["loss"] == o3["loss"]
     ref = O.forward_loss_metrics(x, y, m, o1["state"], w, 2, "f64")
     assert abs(o3["loss"] - ref["loss"]) <= 1e-4 * abs(ref["loss"])
 
