@@ -52,6 +52,16 @@ def load_peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
 
 
+def load_traffic(opt, wl):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture (only valid for the default
+    cfg2 / bf16 configuration it was taken on); None otherwise"""
+    p = os.path.join(ROOT, "profiles", "r1_k4_traffic.json")
+    if opt.workload != "cfg2" or opt.batch or opt.precision != "bf16" or opt.n_split or not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    return d["dram_bytes_read"] + d["dram_bytes_write"]
+
+
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -299,7 +309,7 @@ def main():
     roofline = {"kernel": "k4_score_bf16<256,CE|RANK>" if opt.precision == "bf16" else "k4_score_f32",
                 "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "peak_source": peaks["src"] + " (sustained cuBLAS bf16: the kernel is timed inside a long step)",
-                "traffic": None, "ms_per_launch": sweep_ms, "share_of_step": sweep_ms / ms_per_step,
+                "traffic": load_traffic(opt, wl), "ms_per_launch": sweep_ms, "share_of_step": sweep_ms / ms_per_step,
                 "flops_per_launch": sweep[0][1]}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": opt.steps, "warmup": warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
