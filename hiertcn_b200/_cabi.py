@@ -16,6 +16,7 @@ SCORE_CE, SCORE_RANK, SCORE_TOPK = 1, 2, 4
 LOSS_KINDS = {"nce": 0, "hinge_sigmoid": 1, "hinge_logsigmoid": 2, "hinge_linear": 3, "bpr": 4}
 MAX_TOPK = 128
 WT_PITCH_BF16 = 144
+GRU_SCRATCH_BYTES = 14 * 128 * 128 * 2 + 64 + 768 * 4
 
 _p, _i, _u, _f = C.c_void_p, C.c_int32, C.c_uint32, C.c_float
 _pp = C.POINTER(C.c_void_p)        # host array of device pointers
@@ -25,7 +26,7 @@ _ip = C.POINTER(C.c_int32)         # host int array
 # (tests/test_cabi.py parses the header and compares).
 SIGNATURES = {
     "htcn_gather_meanpool": [_p, _p, _i, _p, _p, _ip, _i, _i, _i, _p, _i, _p, _p],
-    "htcn_gru_sessions": [_p, _p, _p, _pp, _pp, _pp, _pp, _i, _p, _i, _i, _p, _p, _p, _p],
+    "htcn_gru_sessions": [_p, _p, _p, _pp, _pp, _pp, _pp, _i, _p, _i, _i, _i, _p, _p, _p, _p, _p],
     "htcn_tcn_forward": [_p, _i, _i, _p, _p, _pp, _pp, _i, _i, _ip, _i, _i, _i, _p, _p, _i, _p, _p],
     "htcn_prepare_wout": [_p, _p, _i, _p, _i, _p],
     "htcn_score_ce_rank_topk": [_p, _i, _i, _p, _p, _i, _i, _p, _p, _i, _u, _i, _i, _p, _p, _p, _p, _p, _p],
@@ -34,7 +35,7 @@ SIGNATURES = {
     "htcn_score_finish": [_p, _p, _p, _i, _i, _p, _p, _p, _p, _p],
     "htcn_topk_merge": [_p, _p, _i, _i, _i, _p, _p, _p],
     "htcn_score_topk": [_p, _i, _i, _p, _p, _i, _i, _i, _i, _p, C.c_int64, _p, _p, _p, _p],
-    "htcn_loss_metrics_reduce": [_p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p],
+    "htcn_loss_metrics_reduce": [_p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p],
     "htcn_sampled_rank_loss": [_p, _i, _i, _p, _p, _p, _i, _i, _f, _f, _p, _p],
 }
 PLAIN = {"htcn_abi_version": (C.c_int32, []), "htcn_last_error": (C.c_char_p, []),
@@ -75,7 +76,7 @@ def load(path: str | None = None):
 LAUNCHES_PER_CALL = {"htcn_gather_meanpool": 2, "htcn_gru_sessions": 1, "htcn_tcn_forward": 0,
                      "htcn_prepare_wout": 1, "htcn_score_ce_rank_topk": 2, "htcn_score_logits": 1,
                      "htcn_target_logit": 1, "htcn_score_finish": 1, "htcn_topk_merge": 1, "htcn_score_topk": 5,
-                     "htcn_loss_metrics_reduce": 1, "htcn_sampled_rank_loss": 1}
+                     "htcn_loss_metrics_reduce": 2, "htcn_sampled_rank_loss": 1}
 launch_count = 0
 
 

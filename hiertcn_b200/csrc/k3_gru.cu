@@ -144,12 +144,18 @@ k3_gru_sessions(const float* __restrict__ yp, const float* __restrict__ mask, co
   }
 }
 
+int32_t gru_sessions_bf16(const float* yp, const float* mask, const float* state_in, const float* const* gate_w,
+                          const float* const* gate_b, const float* const* cand_w, const float* const* cand_b,
+                          const float* w_in_state, int B, int S, float* state_pre, float* sbias, float* state_out,
+                          float* scratch, cudaStream_t st);
+
 }  // namespace htcn
 
 extern "C" int32_t htcn_gru_sessions(const float* yp, const float* mask, const float* state_in,
                                      const float* const* gate_w_host, const float* const* gate_b_host,
                                      const float* const* cand_w_host, const float* const* cand_b_host,
                                      int32_t num_layer, const float* w_in_state, int32_t B, int32_t S,
+                                     int32_t precision, float* scratch,
                                      float* state_pre, float* sbias, float* state_out, void* stream) {
   using namespace htcn;
   HTCN_REQUIRE(yp && mask && state_in && state_out && gate_w_host && gate_b_host && cand_w_host && cand_b_host,
@@ -165,6 +171,13 @@ extern "C" int32_t htcn_gru_sessions(const float* yp, const float* mask, const f
     W.cand_w[g] = cand_w_host[g];
     W.cand_b[g] = cand_b_host[g];
     HTCN_REQUIRE(W.gate_w[g] && W.gate_b[g] && W.cand_w[g] && W.cand_b[g], "gru_sessions: layer %d weights NULL", g);
+  }
+  HTCN_REQUIRE(precision == HTCN_F32 || precision == HTCN_BF16, "gru_sessions: precision %d", precision);
+  if (precision == HTCN_BF16) {
+    HTCN_REQUIRE(num_layer == 2, "gru_sessions(bf16): the tensor-core kernel is built for num_layer == 2 (got %d)", num_layer);
+    HTCN_REQUIRE(scratch, "gru_sessions(bf16): scratch (HTCN_GRU_SCRATCH_BYTES) is required");
+    return gru_sessions_bf16(yp, mask, state_in, W.gate_w, W.gate_b, W.cand_w, W.cand_b, w_in_state, B, S, state_pre, sbias,
+                             state_out, scratch, as_stream(stream));
   }
   const size_t smem = sizeof(float) * (size_t)(3 + num_layer) * kUB * kDim;
   HTCN_CUDA(cudaFuncSetAttribute(k3_gru_sessions, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

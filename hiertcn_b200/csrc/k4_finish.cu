@@ -139,57 +139,74 @@ topk_merge_kernel(const float* __restrict__ pv, const int* __restrict__ pi, int 
   }
 }
 
-// ---- masked two-level means (single CTA, fixed summation order -> deterministic) ---------------
-// One warp per user: lanes stride over the T positions (coalesced), fixed-shape shuffle tree per user, each warp
-// accumulates its users in order, then a fixed block tree.  ~13 MB through one SM at cfg2 = ~0.15 ms.
+// ---- masked two-level means (fixed summation order -> deterministic) -----------------------------
+// Phase 1: one warp per user, lanes stride over the T positions (coalesced), fixed-shape shuffle tree ->
+// user_part[b][8] = {loss, r@1, r@5, r@10, rr, rank_float}/(n_b + 1e-6), [n_b > 0], n_b.
+// Phase 2: one CTA sums the users in a fixed order.
 __device__ __forceinline__ float warp_sum_f(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
 
+__global__ void __launch_bounds__(256)
+loss_metrics_user_kernel(const float* __restrict__ loss_row, const float* __restrict__ rank_row,
+                         const int* __restrict__ row_of, const int* __restrict__ y_id, int B, int T, int item_num,
+                         float* __restrict__ loss_bt, float* __restrict__ ranks, float* __restrict__ ranks_float,
+                         float* __restrict__ user_part) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const float fN = (float)item_num;
+  float s[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};     // loss, r@1, r@5, r@10, rr, rank_float, n
+  for (int t = lane; t < T; t += 32) {
+    const long long i = (long long)b * T + t;
+    const int row = row_of ? row_of[i] : (int)i;
+    const bool m = y_id[i] > 0 && row >= 0;              // mask_y = sign(y_id)  (model.py:62)
+    float l = 0.f, rk = 0.f, rf = 0.f;
+    if (m) {
+      l = loss_row ? loss_row[row] : 0.f;
+      rk = rank_row ? rank_row[row] : 0.f;
+      rf = rk / fN;                                       // loss.py:190
+      s[0] += l;
+      s[1] += (rk <= 0.f) ? 1.f : 0.f;                    // loss.py:194-196
+      s[2] += (rk <= 4.f) ? 1.f : 0.f;
+      s[3] += (rk <= 9.f) ? 1.f : 0.f;
+      s[4] += 1.0f / (1.0f + rk);                         // loss.py:191
+      s[5] += rf;
+      s[6] += 1.f;
+    }
+    if (loss_bt) loss_bt[i] = l;
+    if (ranks) ranks[i] = rk;
+    if (ranks_float) ranks_float[i] = rf;
+  }
+#pragma unroll
+  for (int i = 0; i < 7; ++i) s[i] = warp_sum_f(s[i]);
+  if (lane == 0) {
+    const float act = s[6] + 1e-6f;                       // model.py:114
+    float* o = user_part + (long long)b * 8;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) o[i] = s[i] / act;        // model.py:116, loss.py:208-213
+    o[6] = (s[6] > 0.f) ? 1.f : 0.f;                      // user_count (model.py:113)
+    o[7] = s[6];
+  }
+}
+
 __global__ void __launch_bounds__(1024)
-loss_metrics_reduce_kernel(const float* __restrict__ loss_row, const float* __restrict__ rank_row,
-                           const int* __restrict__ row_of, const int* __restrict__ y_id, int B, int T,
-                           int item_num, float* __restrict__ loss_bt, float* __restrict__ ranks,
-                           float* __restrict__ ranks_float, float* __restrict__ scalars) {
+loss_metrics_final_kernel(const float* __restrict__ user_part, int B, float* __restrict__ scalars) {
   __shared__ float red[8][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float part[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) part[i] = 0.f;
-  const float fN = (float)item_num;
-  for (int b = warp; b < B; b += 32) {
-    float s[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // loss, r@1, r@5, r@10, rr, rank_float, n
-    for (int t = lane; t < T; t += 32) {
-      const long long i = (long long)b * T + t;
-      const int row = row_of ? row_of[i] : (int)i;
-      const bool m = y_id[i] > 0 && row >= 0;          // mask_y = sign(y_id)  (model.py:62)
-      float l = 0.f, rk = 0.f, rf = 0.f;
-      if (m) {
-        l = loss_row ? loss_row[row] : 0.f;
-        rk = rank_row ? rank_row[row] : 0.f;
-        rf = rk / fN;                                   // loss.py:190
-        s[0] += l;
-        s[1] += (rk <= 0.f) ? 1.f : 0.f;                // loss.py:194-196
-        s[2] += (rk <= 4.f) ? 1.f : 0.f;
-        s[3] += (rk <= 9.f) ? 1.f : 0.f;
-        s[4] += 1.0f / (1.0f + rk);                     // loss.py:191
-        s[5] += rf;
-        s[6] += 1.f;
-      }
-      if (loss_bt) loss_bt[i] = l;
-      if (ranks) ranks[i] = rk;
-      if (ranks_float) ranks_float[i] = rf;
-    }
-#pragma unroll
-    for (int i = 0; i < 7; ++i) s[i] = warp_sum_f(s[i]);
-    const float act = s[6] + 1e-6f;                     // model.py:114
-#pragma unroll
-    for (int i = 0; i < 6; ++i) part[i] += s[i] / act;  // model.py:116, loss.py:208-213
-    part[6] += (s[6] > 0.f) ? 1.f : 0.f;                // user_count (model.py:113)
-    part[7] += s[6];
+  for (int b = threadIdx.x; b < B; b += 1024) {
+    const float4 a = reinterpret_cast<const float4*>(user_part)[(long long)b * 2];
+    const float4 c = reinterpret_cast<const float4*>(user_part)[(long long)b * 2 + 1];
+    part[0] += a.x; part[1] += a.y; part[2] += a.z; part[3] += a.w;
+    part[4] += c.x; part[5] += c.y; part[6] += c.z; part[7] += c.w;
   }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) part[i] = warp_sum_f(part[i]);
   if (lane == 0) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) red[i][warp] = part[i];
@@ -339,11 +356,13 @@ extern "C" int32_t htcn_topk_merge(const float* part_val, const int32_t* part_id
 
 extern "C" int32_t htcn_loss_metrics_reduce(const float* loss_row, const float* rank_row, const int32_t* row_of,
                                             const int32_t* y_id, int32_t B, int32_t T, int32_t item_num,
-                                            float* loss_bt, float* ranks, float* ranks_float, float* scalars,
-                                            void* stream) {
-  HTCN_REQUIRE(y_id && scalars && B > 0 && T > 0 && item_num > 0, "loss_metrics_reduce: bad args");
-  loss_metrics_reduce_kernel<<<1, 1024, 0, as_stream(stream)>>>(loss_row, rank_row, row_of, y_id, B, T, item_num,
-                                                               loss_bt, ranks, ranks_float, scalars);
-  HTCN_LAUNCH_CHECK("loss_metrics_reduce");
+                                            float* loss_bt, float* ranks, float* ranks_float, float* user_part,
+                                            float* scalars, void* stream) {
+  HTCN_REQUIRE(y_id && scalars && user_part && B > 0 && T > 0 && item_num > 0, "loss_metrics_reduce: bad args");
+  loss_metrics_user_kernel<<<ceil_div(B, 8), 256, 0, as_stream(stream)>>>(loss_row, rank_row, row_of, y_id, B, T, item_num,
+                                                                        loss_bt, ranks, ranks_float, user_part);
+  HTCN_LAUNCH_CHECK("loss_metrics_user_kernel");
+  loss_metrics_final_kernel<<<1, 1024, 0, as_stream(stream)>>>(user_part, B, scalars);
+  HTCN_LAUNCH_CHECK("loss_metrics_final_kernel");
   return HTCN_OK;
 }

@@ -220,9 +220,14 @@ class HierTCN:
                   d["y_id"].data_ptr(), slot_p, B, T, S, xe.data_ptr(), self.act_dtype, yp.data_ptr(), st)
         sbias = self._buf("sbias", (S, B, D), f32)
         state_out = torch.empty((B, self.G * 128), dtype=f32, device=self.device)
+        # bf16 tier: tensor-core GRU (bf16 operands, fp32 state) when the stack has 2 layers; set self.k3_tcgen05 = False
+        # to keep the fp32 FFMA recurrence
+        k3_bf16 = self.precision == "bf16" and self.G == 2 and getattr(self, "k3_tcgen05", True)
+        k3_scratch = self._buf("k3_scratch", (cabi.GRU_SCRATCH_BYTES // 4 + 64,), f32) if k3_bf16 else None
         cabi.call("htcn_gru_sessions", yp.data_ptr(), d["mask"].data_ptr(), d["state"].data_ptr(),
                   self._gru_pp[0][0], self._gru_pp[1][0], self._gru_pp[2][0], self._gru_pp[3][0], self.G,
-                  self.w_in_state.data_ptr(), B, S, None, sbias.data_ptr(), state_out.data_ptr(), st)
+                  self.w_in_state.data_ptr(), B, S, cabi.HTCN_BF16 if k3_bf16 else cabi.HTCN_F32,
+                  k3_scratch.data_ptr() if k3_bf16 else None, None, sbias.data_ptr(), state_out.data_ptr(), st)
         hout = self._buf("hout", (max(Q, 1), D), self.act_torch_dtype)
         k2_precision = self._k2_precision()
         if k2_precision == cabi.HTCN_F32:
@@ -343,7 +348,8 @@ class HierTCN:
         P = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
         cabi.call("htcn_loss_metrics_reduce", P(r.get("loss_row")), P(r.get("rank_row")), scores.row_of.data_ptr(),
                   scores.y_id.data_ptr(), B, T, self.N, P(maps.get("loss_bt")), P(maps.get("ranks")),
-                  P(maps.get("ranks_float")), scalars.data_ptr(), self.stream_ptr())
+                  P(maps.get("ranks_float")), self._buf("user_part", (B, 8), f32).data_ptr(), scalars.data_ptr(),
+                  self.stream_ptr())
         return dict(scalars=scalars, **maps)
 
     def sampled_loss_mean(self, scores: CatalogScores, neg_ids, kind=None):
@@ -353,7 +359,8 @@ class HierTCN:
         rows = self.sampled_loss(scores, neg_ids, kind)
         scalars = torch.empty(8, dtype=torch.float32, device=self.device)
         cabi.call("htcn_loss_metrics_reduce", rows.data_ptr(), None, scores.row_of.data_ptr(), scores.y_id.data_ptr(),
-                  scores.B, scores.T, self.N, None, None, None, scalars.data_ptr(), self.stream_ptr())
+                  scores.B, scores.T, self.N, None, None, None,
+                  self._buf("user_part", (scores.B, 8), torch.float32).data_ptr(), scalars.data_ptr(), self.stream_ptr())
         return scalars
 
     def sampled_loss(self, scores: CatalogScores, neg_ids, kind=None):

@@ -89,12 +89,16 @@ int32_t htcn_gather_meanpool(const float* emb_table, const float* emb_bias, int3
  * gate_b[g] [256], cand_w[g] [(in+128),128], cand_b[g] [128]  (in = 128 for every layer);
  * w_in_state [G*128,128] = rows D.. of hier/tcn/emb/kernel.
  * Outputs: state_pre [S,B,G*128] (may be NULL), sbias [S,B,128] (may be NULL), state_out [B,G*128].
+ * precision: HTCN_F32 = fp32 FFMA (1e-4 tier, any num_layer <= 4);
+ *            HTCN_BF16 = tcgen05 tensor cores, bf16 operands / fp32 accumulate and fp32 state (num_layer == 2 only);
+ *                        needs scratch >= HTCN_GRU_SCRATCH_BYTES device bytes (bf16 weight tiles), else may be NULL.
  * ------------------------------------------------------------------------------------------- */
+#define HTCN_GRU_SCRATCH_BYTES (14 * 128 * 128 * 2 + 64 + 768 * 4)
 int32_t htcn_gru_sessions(const float* yp, const float* mask, const float* state_in,
                           const float* const* gate_w_host, const float* const* gate_b_host,
                           const float* const* cand_w_host, const float* const* cand_b_host,
                           int32_t num_layer, const float* w_in_state,
-                          int32_t B, int32_t S,
+                          int32_t B, int32_t S, int32_t precision, float* scratch,
                           float* state_pre, float* sbias, float* state_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
@@ -204,13 +208,14 @@ int32_t htcn_topk_merge(const float* part_val, const int32_t* part_idx, int32_t 
  * masked two-level means of model.py:111-117 and loss.py:190-219.
  * loss_row / rank_row [n_rows] are indexed through row_of [B*T] int32 (NULL = identity; -1 = padded
  * position).  y_id [B,T].  Outputs: loss_bt, ranks, ranks_float [B,T] (masked, 0 at padding; any may be
- * NULL) and scalars[8] = {loss, recall@1, recall@5, recall@10, mrr, mrp, user_count, n_valid}.
+ * NULL), user_part [B,8] (per-user means, also scratch for the second phase) and
+ * scalars[8] = {loss, recall@1, recall@5, recall@10, mrr, mrp, user_count, n_valid}.
  * Deterministic (fixed summation order).
  * ------------------------------------------------------------------------------------------- */
 int32_t htcn_loss_metrics_reduce(const float* loss_row, const float* rank_row, const int32_t* row_of,
                                  const int32_t* y_id, int32_t B, int32_t T, int32_t item_num,
-                                 float* loss_bt, float* ranks, float* ranks_float, float* scalars,
-                                 void* stream);
+                                 float* loss_bt, float* ranks, float* ranks_float, float* user_part,
+                                 float* scalars, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * sampled ranking losses (reference loss.py:22-71): pred [Q,128] is l2-normalised, scored by inner

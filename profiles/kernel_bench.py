@@ -94,14 +94,17 @@ def main():
     sbias = torch.empty((S, B, 128), dtype=f32, device="cuda")
     state_out = torch.empty((B, 256), dtype=f32, device="cuda")
     g = model._gru_pp
-    k3 = lambda: cabi.call("htcn_gru_sessions", yp.data_ptr(), d["mask"].data_ptr(), d["state"].data_ptr(), g[0][0], g[1][0],  # noqa: E731
-                           g[2][0], g[3][0], 2, model.w_in_state.data_ptr(), B, S, None, sbias.data_ptr(), state_out.data_ptr(), st)
+    k3s = torch.empty(cabi.GRU_SCRATCH_BYTES // 4 + 64, dtype=f32, device="cuda")
+    k3 = lambda prec: cabi.call("htcn_gru_sessions", yp.data_ptr(), d["mask"].data_ptr(), d["state"].data_ptr(), g[0][0], g[1][0],  # noqa: E731
+                                g[2][0], g[3][0], 2, model.w_in_state.data_ptr(), B, S, prec, k3s.data_ptr(), None, sbias.data_ptr(),
+                                state_out.data_ptr(), st)
     if want("k3"):
-        ms = timed(k3)
-        line(out, "K3 GRU over sessions (fp32)", ms, "hbm", B * S * (128 + 2 * 256) * 4, "hbm_gbs",
-             "cfg2 shape; algorithmic bytes only (Yp in, state/sbias out); in practice latency/L2-bound: %.2f TFLOP/s fp32"
-             % (B * 3.93e6 / (ms * 1e-3) / 1e12))
-    k3()
+        for nm, prec in (("fp32 FFMA", cabi.HTCN_F32), ("bf16 tcgen05", cabi.HTCN_BF16)):
+            ms = timed(lambda: k3(prec))
+            line(out, "K3 GRU over sessions (%s)" % nm, ms, "hbm", B * S * (128 + 2 * 256) * 4, "hbm_gbs",
+                 "cfg2 shape; algorithmic bytes only (Yp in, state/sbias out); in practice latency/L2-bound: %.2f TFLOP/s"
+                 % (B * (3.93e6 + 10 * 2 * 256 * 128) / (ms * 1e-3) / 1e12))
+    k3(cabi.HTCN_BF16)
 
     # ---- K2
     if want("k2"):

@@ -96,7 +96,18 @@ def test_k3_gru_sessions(lib, B, S):
     sbias = torch.empty((S, B, 128), dtype=torch.float32, device="cuda")
     sout = torch.empty((B, 256), dtype=torch.float32, device="cuda")
     lib.call("htcn_gru_sessions", P(yp), P(mask), P(st_in), pps[0][0], pps[1][0], pps[2][0], pps[3][0], 2, P(wis),
-             B, S, P(spre), P(sbias), P(sout), None)
+             B, S, lib.HTCN_F32, None, P(spre), P(sbias), P(sout), None)
+    # bf16 tier: tcgen05 GRU (bf16 operands, fp32 accumulate + fp32 state)
+    spre_b, sbias_b, sout_b = torch.empty_like(spre), torch.empty_like(sbias), torch.empty_like(sout)
+    scratch = torch.empty(lib.GRU_SCRATCH_BYTES // 4 + 64, dtype=torch.float32, device="cuda")
+    lib.call("htcn_gru_sessions", P(yp), P(mask), P(st_in), pps[0][0], pps[1][0], pps[2][0], pps[3][0], 2, P(wis),
+             B, S, lib.HTCN_BF16, P(scratch), P(spre_b), P(sbias_b), P(sout_b), None)
+    torch.cuda.synchronize()
+    for got, ref in ((spre_b, state_pre), (sout_b, state_out), (sbias_b, sb_ref)):
+        err = np.abs(got.cpu().numpy() - ref)
+        assert err.max() <= 2e-2 * max(1.0, np.abs(ref).max()), err.max()
+        assert err.mean() <= 2e-3
+    assert (sout_b.cpu().numpy()[np.asarray(m[-1]).reshape(-1) == 0] == 0).all()
     np.testing.assert_allclose(spre.cpu().numpy(), state_pre, rtol=1e-4, atol=2e-6)
     np.testing.assert_allclose(sout.cpu().numpy(), state_out, rtol=1e-4, atol=2e-6)
     np.testing.assert_allclose(sbias.cpu().numpy(), sb_ref, rtol=1e-4, atol=2e-5)
@@ -293,8 +304,9 @@ def test_loss_metrics_reduce(lib):
     out = [torch.empty((B, T), dtype=torch.float32, device="cuda") for _ in range(3)]
     sc = torch.empty(8, dtype=torch.float32, device="cuda")
     lr_d, rr_d, ro_d, y_d = dev(loss_row), dev(rank_row), dev(row_of), dev(y)
+    up = torch.empty((B, 8), dtype=torch.float32, device="cuda")
     lib.call("htcn_loss_metrics_reduce", P(lr_d), P(rr_d), P(ro_d), P(y_d), B, T, N,
-             P(out[0]), P(out[1]), P(out[2]), P(sc), None)
+             P(out[0]), P(out[1]), P(out[2]), P(up), P(sc), None)
     loss_bt = np.zeros(B * T, np.float32); loss_bt[valid] = loss_row
     ranks = np.zeros(B * T, np.float32); ranks[valid] = rank_row
     mask = valid.reshape(B, T).astype(np.float32)

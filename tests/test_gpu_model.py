@@ -100,7 +100,11 @@ def test_bf16_tier_within_2e2():
     out = model.step(x, y, m, s0, per_position=True, topk=100)
     assert abs(out["loss"] - ref["loss"]) <= 2e-2 * abs(ref["loss"])
     np.testing.assert_allclose(out["loss_bt"], ref["loss_bt"], rtol=2e-2, atol=2e-2)
-    np.testing.assert_allclose(out["state"], ref["state"], rtol=1e-4, atol=1e-5)     # GRU stays fp32
+    np.testing.assert_allclose(out["state"], ref["state"], rtol=2e-2, atol=2e-2)     # tensor-core GRU: bf16 operands, fp32 state
+    model.k3_tcgen05 = False                                                          # the fp32 recurrence is still selectable
+    out32 = model.step(x, y, m, s0)
+    np.testing.assert_allclose(out32["state"], ref["state"], rtol=1e-4, atol=1e-5)
+    model.k3_tcgen05 = True
     assert abs(out["mrr"] - ref["mrr"]) < 2e-2 and abs(out["mrp"] - ref["mrp"]) < 2e-3
     # top-k sets vs the bf16-emulating oracle: high overlap (operands rounded identically, order differs)
     refb = O.forward_loss_metrics(x, y, m, s0, w, 2, "bf16")
