@@ -16,7 +16,10 @@ SCORE_CE, SCORE_RANK, SCORE_TOPK = 1, 2, 4
 LOSS_KINDS = {"nce": 0, "hinge_sigmoid": 1, "hinge_logsigmoid": 2, "hinge_linear": 3, "bpr": 4}
 MAX_TOPK = 128
 WT_PITCH_BF16 = 144
-GRU_SCRATCH_BYTES = 14 * 128 * 128 * 2 + 64 + 768 * 4
+
+
+def gru_scratch_bytes(B):
+    return 14 * 128 * 128 * 2 + 4096 + ((B + 127) // 128) * 128 * 1024
 
 _p, _i, _u, _f = C.c_void_p, C.c_int32, C.c_uint32, C.c_float
 _pp = C.POINTER(C.c_void_p)        # host array of device pointers

@@ -175,7 +175,7 @@ extern "C" int32_t htcn_gru_sessions(const float* yp, const float* mask, const f
   HTCN_REQUIRE(precision == HTCN_F32 || precision == HTCN_BF16, "gru_sessions: precision %d", precision);
   if (precision == HTCN_BF16) {
     HTCN_REQUIRE(num_layer == 2, "gru_sessions(bf16): the tensor-core kernel is built for num_layer == 2 (got %d)", num_layer);
-    HTCN_REQUIRE(scratch, "gru_sessions(bf16): scratch (HTCN_GRU_SCRATCH_BYTES) is required");
+    HTCN_REQUIRE(scratch, "gru_sessions(bf16): scratch (HTCN_GRU_SCRATCH_BYTES(B)) is required");
     return gru_sessions_bf16(yp, mask, state_in, W.gate_w, W.gate_b, W.cand_w, W.cand_b, w_in_state, B, S, state_pre, sbias,
                              state_out, scratch, as_stream(stream));
   }

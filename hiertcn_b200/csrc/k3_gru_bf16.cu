@@ -2,9 +2,11 @@
 // steps; the recurrence never leaves the SM pair of buffers it needs:
 //   * the GEMM operand [in | hidden] (128 x 256 bf16, no-swizzle K-major, 64 KB) lives in shared memory and is
 //     rewritten in place by the epilogue warps between the five GEMM phases of a step,
-//   * the fp32 state is kept in the caller's state_out buffer (L2-resident, each thread re-reads only its own row),
-//   * accumulators live in TMEM: gates -> columns 0..255, candidate -> 256..383, state half of the TCN
-//     in-projection (sbias) -> 384..511, so the update gate's pre-activation is still there when h' is formed.
+//   * the fp32 recurrent state lives in TENSOR MEMORY: columns 256..383 = h0, 384..511 = h1 of the 128 users
+//     (TMEM lane = user), read with tcgen05.ld and updated with tcgen05.st -- nothing of the recurrence touches
+//     HBM/L2 except the step's input Yp[s] and the emitted sbias / state_pre rows,
+//   * accumulators share TMEM columns 0..255: gates -> 0..255 (r | u); the candidate and the sbias product reuse
+//     0..127 once r has been consumed, so the update gate's pre-activation is still there when h' is formed.
 // Weights (bf16, [n][k] tiles of 32 KB, 14 per step, L2-resident) stream through a 3-stage TMA ring -- 192 KB per
 // layer do not fit next to the operand, see DESIGN.md for the cluster variant that would make them resident.
 //
@@ -68,11 +70,41 @@ __device__ __forceinline__ void put_half(uint8_t* act_row, int half, const float
   }
 }
 
+constexpr uint32_t kColH = 256;                   // TMEM columns of the fp32 state: [h0 128 | h1 128]
+
+// this thread's 32 state values (layer l, columns cc*32..+31) <-> TMEM
+__device__ __forceinline__ void ld_state(uint32_t t_lane, int l, int cc, float (&h)[32]) {
+  uint32_t v[32];
+  tmem_ld_32x32(t_lane + kColH + l * 128 + cc * 32, v);
+  tmem_ld_wait(v);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) h[i] = __uint_as_float(v[i]);
+}
+__device__ __forceinline__ void st_state(uint32_t t_lane, int l, int cc, const float (&h)[32]) {
+  uint32_t v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(h[i]);
+  tmem_st_32x32(t_lane + kColH + l * 128 + cc * 32, v);
+}
+// operand half <- bf16(state layer l)
+__device__ __forceinline__ void put_half_state(uint8_t* act_row, int half, uint32_t t_lane, int l) {
+#pragma unroll 1
+  for (int cc = 0; cc < 4; ++cc) {
+    float h[32];
+    ld_state(t_lane, l, cc, h);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float v[8] = {h[q * 8], h[q * 8 + 1], h[q * 8 + 2], h[q * 8 + 3], h[q * 8 + 4], h[q * 8 + 5], h[q * 8 + 6], h[q * 8 + 7]};
+      put_chunk(act_row, half * 16 + cc * 4 + q, v);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kGThreads, 1)
 k3_gru_bf16(const __grid_constant__ CUtensorMap tmap_w, const float* __restrict__ yp, const float* __restrict__ mask,
             const float* __restrict__ state_in, const float* __restrict__ bias_all /* [bg0 256][bc0 128][bg1 256][bc1 128] */,
             int B, int S, int do_sbias, float* __restrict__ state_pre, float* __restrict__ sbias,
-            float* __restrict__ state /* = state_out, also the fp32 working copy */) {
+            float* __restrict__ state_out) {
   extern __shared__ uint8_t smem_raw[];
   auto& sm = *reinterpret_cast<K3Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -144,8 +176,8 @@ k3_gru_bf16(const __grid_constant__ CUtensorMap tmap_w, const float* __restrict_
       for (int s = 0; s < S; ++s) {
         if (do_sbias) {
           wait_operand();
-          tile_mma(384, 0, true);
-          tile_mma(384, 1, false);
+          tile_mma(0, 0, true);
+          tile_mma(0, 1, false);
           umma_commit(&sm.acc_ready);
         }
         for (int l = 0; l < 2; ++l) {
@@ -156,8 +188,8 @@ k3_gru_bf16(const __grid_constant__ CUtensorMap tmap_w, const float* __restrict_
           tile_mma(128, 1, false);
           umma_commit(&sm.acc_ready);
           wait_operand();                                   // candidate: N = 128
-          tile_mma(256, 0, true);
-          tile_mma(256, 1, false);
+          tile_mma(0, 0, true);                             // reuses the r columns, consumed by E_g
+          tile_mma(0, 1, false);
           umma_commit(&sm.acc_ready);
         }
       }
@@ -168,10 +200,10 @@ k3_gru_bf16(const __grid_constant__ CUtensorMap tmap_w, const float* __restrict_
     const int b = blockIdx.x * kGM + r;
     const bool ok = b < B;
     uint8_t* act_row = sm.act + r * 16;
-    float* st_row = state + (long long)(ok ? b : 0) * 256;        // fp32 working state [h0 | h1] of this user
     const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
     long long n_acc = 0;
     auto operand_ready = [&]() {
+      tc_fence_before_sync();
       fence_proxy_async_smem();
       mbar_arrive(&sm.act_ready);
     };
@@ -180,27 +212,43 @@ k3_gru_bf16(const __grid_constant__ CUtensorMap tmap_w, const float* __restrict_
       tc_fence_after_sync();
       ++n_acc;
     };
-    // prologue: working state <- state_in
-    if (ok) {
-      for (int c = 0; c < 64; ++c)
-        reinterpret_cast<float4*>(st_row)[c] = __ldg(reinterpret_cast<const float4*>(state_in + (long long)b * 256) + c);
-    }
+    // prologue: TMEM state <- state_in (rows beyond B hold zeros)
+    for (int l = 0; l < 2; ++l)
+      for (int cc = 0; cc < 4; ++cc) {
+        float h[32];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 a = ok ? __ldg(reinterpret_cast<const float4*>(state_in + (long long)b * 256 + l * 128 + cc * 32) + i)
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+          h[i * 4] = a.x; h[i * 4 + 1] = a.y; h[i * 4 + 2] = a.z; h[i * 4 + 3] = a.w;
+        }
+        st_state(t_lane, l, cc, h);
+      }
+    tmem_st_wait();
     for (int s = 0; s < S; ++s) {
       const float m = ok ? __ldg(mask + (long long)s * B + b) : 0.f;
       const float* x = ok ? yp + ((long long)s * B + b) * kDim : nullptr;
-      if (ok && state_pre) {
-        for (int c = 0; c < 64; ++c)
-          reinterpret_cast<float4*>(state_pre + ((long long)s * B + b) * 256)[c] = reinterpret_cast<const float4*>(st_row)[c];
+      if (state_pre) {
+        for (int l = 0; l < 2; ++l)
+          for (int cc = 0; cc < 4; ++cc) {
+            float h[32];
+            ld_state(t_lane, l, cc, h);
+            if (ok) {
+              float4* o = reinterpret_cast<float4*>(state_pre + ((long long)s * B + b) * 256 + l * 128 + cc * 32);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) o[i] = make_float4(h[i * 4], h[i * 4 + 1], h[i * 4 + 2], h[i * 4 + 3]);
+            }
+          }
       }
       if (do_sbias) {
-        put_half(act_row, 0, ok ? st_row : nullptr);
-        put_half(act_row, 1, ok ? st_row + 128 : nullptr);
+        put_half_state(act_row, 0, t_lane, 0);
+        put_half_state(act_row, 1, t_lane, 1);
         operand_ready();
         wait_acc();                                          // ---- E_sb: sbias[s] out, operand <- [x | h0]
 #pragma unroll 1
         for (int cc = 0; cc < 4; ++cc) {
           uint32_t v[32];
-          tmem_ld_32x32(t_lane + 384 + cc * 32, v);
+          tmem_ld_32x32(t_lane + cc * 32, v);
           tmem_ld_wait(v);
           if (ok) {
             float4* o = reinterpret_cast<float4*>(sbias + ((long long)s * B + b) * kDim + cc * 32);
@@ -210,41 +258,41 @@ k3_gru_bf16(const __grid_constant__ CUtensorMap tmap_w, const float* __restrict_
                                  __uint_as_float(v[q * 4 + 3]));
           }
         }
-        tc_fence_before_sync();
       }
       put_half(act_row, 0, x);
-      put_half(act_row, 1, ok ? st_row : nullptr);
+      put_half_state(act_row, 1, t_lane, 0);
       operand_ready();
       for (int l = 0; l < 2; ++l) {
-        float* h = st_row + l * 128;                           // fp32 state of this layer (start of the step)
         wait_acc();                                            // ---- E_g: operand hidden half <- r * h
 #pragma unroll 1
         for (int cc = 0; cc < 4; ++cc) {
           uint32_t v[32];
+          float h[32];
           tmem_ld_32x32(t_lane + cc * 32, v);                  // r pre-activations, columns cc*32..+31
           tmem_ld_wait(v);
+          ld_state(t_lane, l, cc, h);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             float o[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               const int col = cc * 32 + q * 8 + e;
-              const float rr = sigmoid_fast(__uint_as_float(v[q * 8 + e]) + sm.bg[l][col]);
-              o[e] = ok ? rr * h[col] : 0.f;
+              o[e] = sigmoid_fast(__uint_as_float(v[q * 8 + e]) + sm.bg[l][col]) * h[q * 8 + e];
             }
             put_chunk(act_row, 16 + cc * 4 + q, o);
           }
         }
-        tc_fence_before_sync();
         operand_ready();
         wait_acc();                                            // ---- E_c: h' = u*h + (1-u)*c
 #pragma unroll 1
         for (int cc = 0; cc < 4; ++cc) {
           uint32_t vc[32], vu[32];
-          tmem_ld_32x32(t_lane + 256 + cc * 32, vc);           // candidate pre-activations
+          float h[32];
+          tmem_ld_32x32(t_lane + cc * 32, vc);                 // candidate pre-activations (columns 0..127, reused)
           tmem_ld_32x32(t_lane + 128 + cc * 32, vu);           // update-gate pre-activations (still in TMEM)
           tmem_ld_wait(vc);
           tmem_ld_wait(vu);
+          ld_state(t_lane, l, cc, h);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             float o[8];
@@ -253,21 +301,31 @@ k3_gru_bf16(const __grid_constant__ CUtensorMap tmap_w, const float* __restrict_
               const int col = cc * 32 + q * 8 + e;
               const float c = tanh_fast(__uint_as_float(vc[q * 8 + e]) + sm.bc[l][col]);
               const float u = sigmoid_fast(__uint_as_float(vu[q * 8 + e]) + sm.bg[l][128 + col]);
-              const float hn = ok ? fmaf(u, h[col] - c, c) : 0.f;      // u*h + (1-u)*c
-              o[e] = hn;                                               // UNMASKED: the input of the layer above
-              if (ok) h[col] = m * hn;                                 // state *= mask (model_hier.py:93)
+              o[e] = fmaf(u, h[q * 8 + e] - c, c);             // u*h + (1-u)*c, UNMASKED: the input of the layer above
+              h[q * 8 + e] = m * o[e];                         // state *= mask (model_hier.py:93)
             }
-            if (l == 0) put_chunk(act_row, cc * 4 + q, o);             // layer 1 input half
+            if (l == 0) put_chunk(act_row, cc * 4 + q, o);     // layer 1 input half
           }
+          st_state(t_lane, l, cc, h);
         }
-        tc_fence_before_sync();
+        tmem_st_wait();
         if (l == 0) {
-          put_half(act_row, 1, ok ? st_row + 128 : nullptr);           // [h0' | h1]
+          put_half_state(act_row, 1, t_lane, 1);               // [h0' | h1]
           operand_ready();
         }
       }
       // after layer 1: the next phase (sbias of step s+1 or [x | h0] of step s+1) is staged at the top of the loop
     }
+    for (int l = 0; l < 2; ++l)
+      for (int cc = 0; cc < 4; ++cc) {
+        float h[32];
+        ld_state(t_lane, l, cc, h);
+        if (ok) {
+          float4* o = reinterpret_cast<float4*>(state_out + (long long)b * 256 + l * 128 + cc * 32);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = make_float4(h[i * 4], h[i * 4 + 1], h[i * 4 + 2], h[i * 4 + 3]);
+        }
+      }
   }
   tc_fence_before_sync();
   __syncthreads();

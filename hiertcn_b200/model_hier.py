@@ -223,7 +223,7 @@ class HierTCN:
         # bf16 tier: tensor-core GRU (bf16 operands, fp32 state) when the stack has 2 layers; set self.k3_tcgen05 = False
         # to keep the fp32 FFMA recurrence
         k3_bf16 = self.precision == "bf16" and self.G == 2 and getattr(self, "k3_tcgen05", True)
-        k3_scratch = self._buf("k3_scratch", (cabi.GRU_SCRATCH_BYTES // 4 + 64,), f32) if k3_bf16 else None
+        k3_scratch = self._buf("k3_scratch", (cabi.gru_scratch_bytes(B) // 4,), f32) if k3_bf16 else None
         cabi.call("htcn_gru_sessions", yp.data_ptr(), d["mask"].data_ptr(), d["state"].data_ptr(),
                   self._gru_pp[0][0], self._gru_pp[1][0], self._gru_pp[2][0], self._gru_pp[3][0], self.G,
                   self.w_in_state.data_ptr(), B, S, cabi.HTCN_BF16 if k3_bf16 else cabi.HTCN_F32,

@@ -91,9 +91,9 @@ int32_t htcn_gather_meanpool(const float* emb_table, const float* emb_bias, int3
  * Outputs: state_pre [S,B,G*128] (may be NULL), sbias [S,B,128] (may be NULL), state_out [B,G*128].
  * precision: HTCN_F32 = fp32 FFMA (1e-4 tier, any num_layer <= 4);
  *            HTCN_BF16 = tcgen05 tensor cores, bf16 operands / fp32 accumulate and fp32 state (num_layer == 2 only);
- *                        needs scratch >= HTCN_GRU_SCRATCH_BYTES device bytes (bf16 weight tiles), else may be NULL.
+ *                        needs scratch >= HTCN_GRU_SCRATCH_BYTES(B) device bytes (bf16 weight tiles + working state), else may be NULL.
  * ------------------------------------------------------------------------------------------- */
-#define HTCN_GRU_SCRATCH_BYTES (14 * 128 * 128 * 2 + 64 + 768 * 4)
+#define HTCN_GRU_SCRATCH_BYTES(B) (14 * 128 * 128 * 2 + 4096 + (((B) + 127) / 128) * 128 * 1024)
 int32_t htcn_gru_sessions(const float* yp, const float* mask, const float* state_in,
                           const float* const* gate_w_host, const float* const* gate_b_host,
                           const float* const* cand_w_host, const float* const* cand_b_host,

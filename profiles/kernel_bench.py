@@ -94,7 +94,7 @@ def main():
     sbias = torch.empty((S, B, 128), dtype=f32, device="cuda")
     state_out = torch.empty((B, 256), dtype=f32, device="cuda")
     g = model._gru_pp
-    k3s = torch.empty(cabi.GRU_SCRATCH_BYTES // 4 + 64, dtype=f32, device="cuda")
+    k3s = torch.empty(cabi.gru_scratch_bytes(B) // 4, dtype=f32, device="cuda")
     k3 = lambda prec: cabi.call("htcn_gru_sessions", yp.data_ptr(), d["mask"].data_ptr(), d["state"].data_ptr(), g[0][0], g[1][0],  # noqa: E731
                                 g[2][0], g[3][0], 2, model.w_in_state.data_ptr(), B, S, prec, k3s.data_ptr(), None, sbias.data_ptr(),
                                 state_out.data_ptr(), st)

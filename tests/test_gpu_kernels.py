@@ -99,7 +99,7 @@ def test_k3_gru_sessions(lib, B, S):
              B, S, lib.HTCN_F32, None, P(spre), P(sbias), P(sout), None)
     # bf16 tier: tcgen05 GRU (bf16 operands, fp32 accumulate + fp32 state)
     spre_b, sbias_b, sout_b = torch.empty_like(spre), torch.empty_like(sbias), torch.empty_like(sout)
-    scratch = torch.empty(lib.GRU_SCRATCH_BYTES // 4 + 64, dtype=torch.float32, device="cuda")
+    scratch = torch.empty(lib.gru_scratch_bytes(B) // 4, dtype=torch.float32, device="cuda")
     lib.call("htcn_gru_sessions", P(yp), P(mask), P(st_in), pps[0][0], pps[1][0], pps[2][0], pps[3][0], 2, P(wis),
              B, S, lib.HTCN_BF16, P(scratch), P(spre_b), P(sbias_b), P(sout_b), None)
     torch.cuda.synchronize()
