@@ -139,11 +139,23 @@ class CudaScoreOps:
                       n1 - n0, n0, y_all.data_ptr(), zy.data_ptr(), 1, flags, 0, n_split, P(out["pm"]), P(out["ps"]),
                       P(out["pc"]), None, None, m.stream_ptr())
         if k:
-            out["tv"] = torch.empty((n_split, Q, k), dtype=f32, device=m.device)
-            out["ti"] = torch.empty((n_split, Q, k), dtype=i32, device=m.device)
-            cabi.call("htcn_score_ce_rank_topk", h_all.data_ptr(), m.act_dtype, Q, m.wt.data_ptr(), m.b_out.data_ptr(),
-                      n1 - n0, n0, None, None, 1, cabi.SCORE_TOPK, k, n_split, None, None, None, P(out["tv"]),
-                      P(out["ti"]), m.stream_ptr())
+            # exact local top-k of the shard in one call (two tensor-core sweeps on large bf16 shards, heap sweep
+            # otherwise); one sorted list per row = one "part" for the cross-shard merge
+            nb = int(cabi.load().htcn_topk_workspace_bytes(m.act_dtype, Q, n1 - n0, k, n_split))
+            ws = torch.empty(nb, dtype=torch.uint8, device=m.device)
+            out["tv"] = torch.empty((1, Q, k), dtype=f32, device=m.device)
+            out["ti"] = torch.empty((1, Q, k), dtype=i32, device=m.device)
+            ovf = torch.zeros(1, dtype=i32, device=m.device)
+            cabi.call("htcn_score_topk", h_all.data_ptr(), m.act_dtype, Q, m.wt.data_ptr(), m.b_out.data_ptr(), n1 - n0, n0, k,
+                      n_split, ws.data_ptr(), nb, out["tv"].data_ptr(), out["ti"].data_ptr(), ovf.data_ptr(), m.stream_ptr())
+            if int(ovf.item()):              # mass ties overflowed a candidate list: redo with the always-exact heap sweep
+                tv = torch.empty((n_split, Q, k), dtype=f32, device=m.device)
+                ti = torch.empty((n_split, Q, k), dtype=i32, device=m.device)
+                cabi.call("htcn_score_ce_rank_topk", h_all.data_ptr(), m.act_dtype, Q, m.wt.data_ptr(), m.b_out.data_ptr(),
+                          n1 - n0, n0, None, None, 1, cabi.SCORE_TOPK, k, n_split, None, None, None, tv.data_ptr(),
+                          ti.data_ptr(), m.stream_ptr())
+                cabi.call("htcn_topk_merge", tv.data_ptr(), ti.data_ptr(), n_split, Q, k, out["tv"].data_ptr(),
+                          out["ti"].data_ptr(), m.stream_ptr())
         return out
 
     def finish(self, pm, ps, pc, y_id, zy_local):
