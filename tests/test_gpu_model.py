@@ -113,3 +113,32 @@ def test_bf16_tier_within_2e2():
     _, i_ref = O.top_k(zv, 100)
     overlap = np.mean([len(set(a) & set(b)) / 100.0 for a, b in zip(out["topk_idx"], i_ref)])
     assert overlap > 0.97, overlap
+
+
+def test_evaluate_hier_loop_matches_oracle_batch_by_batch():
+    """queue loader (reference enqueue/dequeue semantics) -> evaluate_hier with device-resident carried state ==
+    the oracle fed the same batches with the state carried on the host (run_hier_xing.py:83-207)"""
+    from hiertcn_b200.args import make_args
+    from hiertcn_b200.data_loader import Dataloader_hier_model_xing, make_synthetic_interactions
+    from hiertcn_b200.model_hier import HierTCN
+    from hiertcn_b200.run_hier import evaluate_hier
+    from hiertcn_b200.weights import hier_weight_shapes, init_weights
+    N = 300
+    table, data = make_synthetic_interactions(120, N, seed=4)
+    a = make_args(["--item_num", str(N), "--batch_size", "6", "--max_session_num", "4", "--max_activity_len", "8"])
+    w = init_weights(hier_weight_shapes(N), seed=8, kernel_scale=2.0, bias_noise=0.1)
+    model = HierTCN(a, w, precision="f32").build()
+    res = evaluate_hier(model, Dataloader_hier_model_xing(a, "train", data=(table, data)), max_batches=4)
+    ld = Dataloader_hier_model_xing(a, "train", data=(table, data))
+    state = np.zeros((6, 256), np.float32)
+    acc = dict(loss=0.0, mrr=0.0, mrp=0.0, recall10=0.0)
+    for _ in range(4):
+        x, y, m, _ = ld.get_batch()
+        ref = O.forward_loss_metrics(x, y, m, state, w, 2, "f64")
+        state = ref["state"]
+        for k in acc:
+            acc[k] += float(ref[k])
+    assert res["batches"] == 4
+    for k in acc:
+        assert abs(res[k] - acc[k] / 4) <= 1e-4 * max(1.0, abs(acc[k] / 4)), (k, res[k], acc[k] / 4)
+    assert len(res["rank_by_position"]) >= 4 and 0.0 <= res["user_rank_mean"] <= 1.0
