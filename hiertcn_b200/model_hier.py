@@ -25,7 +25,6 @@ import math
 import numpy as np
 
 from . import _cabi as cabi
-from .data_loader import pack_batch
 from .weights import hier_weight_shapes, init_weights
 
 D = 128
@@ -173,34 +172,84 @@ class HierTCN:
         return t[:n].view(*shape) if n else t[:0]
 
     # ------------------------------------------------------------------ host -> device staging
-    def stage(self, x_list, y_list, mask_list, state=None):
-        """Pack the reference batch layout (data_loader.dequeue) and copy it to the device.
+    def _pinned(self, slot, name, shape, dtype):
+        """reusable pinned host staging tensor (grow-only) of staging set ``slot``; returns (torch tensor, numpy view)"""
+        torch = _torch()
+        key = (slot, name)
+        n = int(np.prod(shape))
+        t = self._pin.get(key)
+        if t is None or t.dtype != dtype or t.numel() < n:
+            t = torch.empty(max(n, 1), dtype=dtype).pin_memory()
+            self._pin[key] = t
+        v = t[:n].view(*shape) if n else t[:0]
+        return v, v.numpy()
+
+    def stage(self, x_list, y_list, mask_list, state=None, neg_ids=None):
+        """Pack the reference batch layout (data_loader.dequeue) straight into pinned staging buffers and copy it to
+        the device (asynchronously, on the current stream).  Two staging sets alternate, each guarded by an event,
+        so the host can prepare batch i+1 while the copies of batch i are still in flight.
         Returns a dict of device tensors + host metadata; H2D bytes are in ['h2d_bytes']."""
         torch = _torch()
-        pk = pack_batch(x_list, y_list, mask_list)
-        B, T = pk["x_id"].shape
+        if not self.built:
+            self.build()
+        if not hasattr(self, "_pin"):
+            self._pin, self._pin_ev, self._pin_next = {}, [None, None], 0
+        slot = self._pin_next
+        self._pin_next ^= 1
+        if self._pin_ev[slot] is not None:
+            self._pin_ev[slot].synchronize()                    # the previous copies out of this set have completed
         S = len(x_list)
-        valid = pk["y_id"].reshape(-1) > 0
-        row_of = np.where(valid, np.cumsum(valid) - 1, -1).astype(np.int32)
-        Q = int(valid.sum())
-        y_rows = np.ascontiguousarray(pk["y_id"].reshape(-1)[valid])
-        host = dict(x_id=pk["x_id"], y_id=pk["y_id"], mask=pk["mask"], row_of=row_of, y_rows=y_rows)
+        lens = [int(np.shape(x)[1]) for x in x_list]
+        B = int(np.shape(x_list[0])[0])
+        T = int(sum(lens))
+        slot_off = np.zeros(S + 1, dtype=np.int32)
+        slot_off[1:] = np.cumsum(lens)
+        i32, f32 = torch.int32, torch.float32
+        tx, nx = self._pinned(slot, "x_id", (B, T), i32)
+        ty, ny = self._pinned(slot, "y_id", (B, T), i32)
+        tm, nm = self._pinned(slot, "mask", (S, B), f32)
+        for s in range(S):                                      # cast + concat in one pass, no temporaries
+            nx[:, slot_off[s]:slot_off[s + 1]] = x_list[s]
+            ny[:, slot_off[s]:slot_off[s + 1]] = y_list[s]
+            nm[s] = np.asarray(mask_list[s]).reshape(-1)
+        valid = ny.reshape(-1) > 0
+        tr, nr = self._pinned(slot, "row_of", (B * T,), i32)
+        np.cumsum(valid, dtype=np.int32, out=nr)
+        Q = int(nr[-1]) if nr.size else 0
+        nr -= 1
+        nr[~valid] = -1
+        tq, nq = self._pinned(slot, "y_rows", (Q,), i32)
+        if Q:
+            nq[:] = ny.reshape(-1)[valid]
+        host = dict(x_id=tx, y_id=ty, mask=tm, row_of=tr, y_rows=tq)
         dev, nbytes = {}, 0
         if hasattr(state, "data_ptr"):
             # device-resident carried state (SURVEY 8f-1): the previous step's state_out stays in HBM instead of
             # round-tripping through host numpy every batch like the reference does (run_hier_xing.py:291,301)
-            dev["state"] = state.to(device=self.device, dtype=torch.float32).contiguous()
+            dev["state"] = state.to(device=self.device, dtype=f32).contiguous()
         else:
-            if state is None:
-                state = np.zeros((B, self.G * 128), np.float32)
-            host["state"] = np.ascontiguousarray(state, dtype=np.float32)
-        for k, v in host.items():
-            t = torch.from_numpy(v)
-            if v.size:
-                t = t.pin_memory()
-            dev[k] = t.to(self.device, non_blocking=True)
-            nbytes += v.nbytes
-        dev.update(B=B, T=T, S=S, Q=Q, slot_off=pk["slot_off"], h2d_bytes=nbytes)
+            ts, ns_ = self._pinned(slot, "state", (B, self.G * 128), f32)
+            ns_[:] = 0.0 if state is None else state
+            host["state"] = ts
+        if neg_ids is not None and not hasattr(neg_ids, "data_ptr"):
+            tn, nn = self._pinned(slot, "neg_ids", tuple(np.shape(neg_ids)), i32)
+            nn[:] = neg_ids
+            host["neg_ids"] = tn
+        # H2D on a dedicated copy stream: the copies of batch i+1 overlap the kernels of batch i
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        compute = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self._copy_stream):
+            for k, t in host.items():
+                dev[k] = t.to(self.device, non_blocking=True)
+                nbytes += t.numel() * t.element_size()
+        ev = torch.cuda.Event()
+        ev.record(self._copy_stream)
+        compute.wait_event(ev)
+        for k in host:
+            dev[k].record_stream(compute)
+        self._pin_ev[slot] = ev
+        dev.update(B=B, T=T, S=S, Q=Q, slot_off=slot_off, h2d_bytes=nbytes)
         return dev
 
     # ------------------------------------------------------------------ forward (K1 -> K3 -> K2)
@@ -238,7 +287,10 @@ class HierTCN:
                   sbias.data_ptr(), self._conv_w_pp[0], self._conv_b_pp[0], self.n_levels, self.K, slot_p, B, T, S,
                   d["row_of"].data_ptr(), hout.data_ptr(), self.act_dtype,
                   scratch.data_ptr() if scratch is not None else None, st)
-        cabi.note_launches(self.n_levels + 1)
+        # fp32: one launch per level + the in-projection; bf16: weight-tile preparation + the fused stack
+        cabi.note_launches(2 if k2_precision == cabi.HTCN_BF16 else self.n_levels + 1)
+        if k3_bf16:
+            cabi.note_launches(1)                   # k3_prepare_weights (htcn_gru_sessions counts one launch)
         del slot_keep
         scores = CatalogScores(self, hout, Q, d["row_of"], d["y_rows"], d["y_id"], B, T)
         return scores, state_out
@@ -383,28 +435,75 @@ class HierTCN:
         return out
 
     # ------------------------------------------------------------------ the reference's sess.run
+    def step_async(self, x_list, y_list, mask_list, state=None, metrics=True, per_position=False, topk=0,
+                   state_on_device=False, neg_ids=None):
+        """Enqueue one step (H2D on the copy stream, kernels and the D2H of the results on the compute stream) and
+        return a ``PendingStep``; ``.result()`` waits for it and returns the host dict of ``step``.  Submitting step
+        i+1 before collecting step i hides the host-side batch packing and the PCIe copies behind the kernels."""
+        torch = _torch()
+        staged = self.stage(x_list, y_list, mask_list, state, neg_ids)
+        scores, state_out = self.forward(staged=staged)
+        if "neg_ids" in staged:
+            neg_ids = staged["neg_ids"]
+        r = self.loss(scores, metrics=metrics, per_position=per_position)
+        dev = {"scalars": r["scalars"]}
+        if not state_on_device:
+            dev["state"] = state_out
+        for n in ("loss_bt", "ranks", "ranks_float"):
+            if n in r:
+                dev[n] = r[n]
+        if neg_ids is not None:                     # sampled ranking loss of reference loss.py:22-71 on the same forward
+            dev["sampled"] = self.sampled_loss_mean(scores, neg_ids)
+        if topk:
+            t = self.score(scores, ce=False, rank=False, topk=topk)
+            if t:
+                dev["topk_val"], dev["topk_idx"] = t["topk_val"], t["topk_idx"]
+            dev["row_of"] = scores.row_of
+        if not hasattr(self, "_res_next"):
+            self._res_next = 0
+        slot = 2 + self._res_next                   # result staging sets 2..4 (0/1 are the input sets)
+        self._res_next = (self._res_next + 1) % 3
+        host = {}
+        for k, t in dev.items():
+            pt, _ = self._pinned(slot, "res_" + k, tuple(t.shape), t.dtype)
+            pt.copy_(t, non_blocking=True)
+            host[k] = pt
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        return PendingStep(ev, host, state_out if state_on_device else None, topk)
+
     def step(self, x_list, y_list, mask_list, state=None, metrics=True, per_position=False, topk=0,
              state_on_device=False, neg_ids=None):
         """Host in, host out -- the call ``sess.run([loss, state, ranks_float, ...], feed_dict)`` of
         run_hier_xing.py:145-149 maps to.  Includes the H2D of the batch and the D2H of the results.
         ``state`` may be a numpy array (reference behaviour) or the device tensor returned by a previous step with
         ``state_on_device=True`` (then the carried state never leaves HBM)."""
-        scores, state_out = self.forward(x_list, y_list, mask_list, state)
-        r = self.loss(scores, metrics=metrics, per_position=per_position)
-        out = {}
-        sc = r["scalars"].cpu().numpy()
-        out.update(loss=sc[0], recall1=sc[1], recall5=sc[2], recall10=sc[3], mrr=sc[4], mrp=sc[5],
-                   user_count=sc[6], n_valid=sc[7], state=state_out if state_on_device else state_out.cpu().numpy())
-        for n in ("loss_bt", "ranks", "ranks_float"):
-            if n in r:
-                out[n] = r[n].cpu().numpy()
-        if neg_ids is not None:                     # sampled ranking loss of reference loss.py:22-71 on the same forward
-            out["sampled_loss"] = float(self.sampled_loss_mean(scores, neg_ids)[0].item())
-        if topk:
-            t = self.score(scores, ce=False, rank=False, topk=topk)
-            out["topk_val"] = t["topk_val"].cpu().numpy() if t else np.zeros((0, topk), np.float32)
-            out["topk_idx"] = t["topk_idx"].cpu().numpy() if t else np.zeros((0, topk), np.int32)
-            out["row_of"] = scores.row_of.cpu().numpy()
+        return self.step_async(x_list, y_list, mask_list, state, metrics, per_position, topk, state_on_device,
+                               neg_ids).result()
+
+
+class PendingStep:
+    """Handle of an enqueued step; ``result()`` blocks on its completion event and copies the results out of the
+    pinned staging buffers (which are reused three steps later)."""
+
+    def __init__(self, event, host, state_dev, topk):
+        self.event, self.host, self.state_dev, self.topk = event, host, state_dev, topk
+
+    def result(self):
+        self.event.synchronize()
+        h = {k: v.numpy() for k, v in self.host.items()}
+        sc = h["scalars"]
+        out = dict(loss=sc[0], recall1=sc[1], recall5=sc[2], recall10=sc[3], mrr=sc[4], mrp=sc[5],
+                   user_count=sc[6], n_valid=sc[7])
+        out["state"] = self.state_dev if self.state_dev is not None else h["state"].copy()
+        for n in ("loss_bt", "ranks", "ranks_float", "row_of"):
+            if n in h:
+                out[n] = h[n].copy()
+        if "sampled" in h:
+            out["sampled_loss"] = float(h["sampled"][0])
+        if self.topk:
+            out["topk_val"] = h["topk_val"].copy() if "topk_val" in h else np.zeros((0, self.topk), np.float32)
+            out["topk_idx"] = h["topk_idx"].copy() if "topk_idx" in h else np.zeros((0, self.topk), np.int32)
         return out
 
 
