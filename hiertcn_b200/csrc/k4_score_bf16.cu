@@ -344,6 +344,202 @@ k4_score_bf16(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
   }
 }
 
+// ---- the same sweep with cta_group::2 ---------------------------------------------------------------------------
+// A cluster of 2 CTAs owns 256 query rows.  Each CTA keeps its own 128-row A tile and accumulators (its own TMEM),
+// but the pair SHARES every B tile: CTA r loads items [j0 + 128 r, +128) and the leader's single M=256 tcgen05.mma
+// reads both halves, halving the L2->smem traffic and the B-operand shared-memory reads per logit.  Barriers: TMA
+// bytes of both CTAs are credited to the leader's b_full; tcgen05.commit multicasts to b_empty / t_full of both CTAs;
+// the epilogue warps of both CTAs release the accumulator on the leader's t_empty (remote mbarrier arrive).
+// CE / RANK (and the logits dump of the tests) only; top-k modes use the 1-CTA kernel.
+constexpr int kStages2 = 3;
+struct alignas(1024) ScoreSmem2 {
+  uint8_t a[2][kChunkBytesA];
+  uint8_t a_bias[kBM * 32];
+  uint8_t b[kStages2][2][128 * 128];             // [stage][chunk], this CTA's 128 of the tile's 256 items
+  uint8_t b_bias[kStages2][128 * 32];
+  float comb_sum[3][kBM];
+  int comb_cnt[3][kBM];
+  uint64_t a_full, b_full[kStages2], b_empty[kStages2], t_full[2], t_empty[2];
+  uint32_t tmem_base;
+};
+
+template <unsigned kFlags>
+__global__ void __launch_bounds__(64 + 32 * 4 * kSlicesScore, 1)
+k4_score_bf16_cg2(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                  const __grid_constant__ CUtensorMap tmap_bb, ScoreArgs a, float* __restrict__ dump) {
+  constexpr bool kCE = kFlags & HTCN_SCORE_CE, kRank = kFlags & HTCN_SCORE_RANK, kDump = kFlags & kModeDump;
+  constexpr int kPolyEvery = (kFlags & kModePoly4) ? 4 : (kFlags & kModePoly8) ? 8 : 0x40000000;
+  constexpr int BN = 256, kSlices = kSlicesScore, kEpiWarps = 4 * kSlices, kColsPerWarp = BN / kSlices;
+  constexpr uint32_t kHalfStageBytes = 2 * 128 * 128 + 128 * 32;
+  extern __shared__ uint8_t smem_raw[];
+  auto& sm = *reinterpret_cast<ScoreSmem2*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();                      // 0 = leader of the pair
+  const int q0 = blockIdx.x * kBM;
+  const int split = blockIdx.y;
+  const int n_tiles_all = (a.n_items + BN - 1) / BN;
+  const int t_begin = (int)((long long)n_tiles_all * split / a.n_split);
+  const int t_end = (int)((long long)n_tiles_all * (split + 1) / a.n_split);
+  const int n_tiles = t_end - t_begin;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+    prefetch_tmap(&tmap_bb);
+    mbar_init(&sm.a_full, 1);
+    for (int s = 0; s < kStages2; ++s) {
+      mbar_init(&sm.b_full[s], 1);
+      mbar_init(&sm.b_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&sm.t_full[s], 1);
+      mbar_init(&sm.t_empty[s], 2 * kEpiWarps);                 // the epilogue warps of BOTH CTAs
+    }
+    fence_barrier_init();
+  }
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + kBM) write_a_bias_row(sm.a_bias, threadIdx.x - 64);
+  fence_proxy_async_smem();
+  if (warp == 1) tmem_alloc_cg2<512>(&sm.tmem_base);
+  tc_fence_before_sync();
+  cluster_sync_all();                                           // barriers of both CTAs are initialised
+  tc_fence_after_sync();
+  const uint32_t tmem = sm.tmem_base;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs; bytes land on the leader's barriers) =====================
+    if (lane == 0) {
+      if (rank == 0) mbar_arrive_expect_tx(&sm.a_full, 2 * 2 * kChunkBytesA);
+      tma_load_2d_cg2(sm.a[0], &tmap_a, 0, q0, &sm.a_full);
+      tma_load_2d_cg2(sm.a[1], &tmap_a, 64, q0, &sm.a_full);
+      for (int i = 0; i < n_tiles; ++i) {
+        const int s = i % kStages2;
+        mbar_wait_relaxed(&sm.b_empty[s], (uint32_t)(((i / kStages2) & 1) ^ 1));
+        if (rank == 0) mbar_arrive_expect_tx(&sm.b_full[s], 2 * kHalfStageBytes);
+        const int j0 = (t_begin + i) * BN + (int)rank * 128;    // this CTA's half of the tile
+        tma_load_2d_cg2(sm.b[s][0], &tmap_b, 0, j0, &sm.b_full[s]);
+        tma_load_2d_cg2(sm.b[s][1], &tmap_b, 64, j0, &sm.b_full[s]);
+        tma_load_2d_cg2(sm.b_bias[s], &tmap_bb, 128, j0, &sm.b_full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader only) =====================
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * kBM, BN);
+      mbar_wait(&sm.a_full, 0);
+      for (int i = 0; i < n_tiles; ++i) {
+        const int s = i % kStages2, buf = i & 1;
+        mbar_wait(&sm.t_empty[buf], ((i >> 1) & 1) ^ 1);        // tight: the pair's hand-shake latency is on the critical path
+        mbar_wait(&sm.b_full[s], (uint32_t)((i / kStages2) & 1));
+        tc_fence_after_sync();
+        const uint32_t d = tmem + buf * BN;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint64_t da = make_desc_k_sw128(smem_u32(sm.a[k >> 2]) + (k & 3) * 32);
+          const uint64_t db = make_desc_k_sw128(smem_u32(sm.b[s][k >> 2]) + (k & 3) * 32);
+          umma_bf16_cg2(d, da, db, idesc, k > 0);
+        }
+        umma_bf16_cg2(d, make_desc_k_sw32(smem_u32(sm.a_bias)), make_desc_k_sw32(smem_u32(sm.b_bias[s])), idesc, true);
+        umma_commit_cg2(&sm.b_empty[s], 0b11);
+        umma_commit_cg2(&sm.t_full[buf], 0b11);
+      }
+    }
+  } else {
+    // ===================== epilogue (identical row bookkeeping to the 1-CTA kernel) =====================
+    const int ew = warp - 2;
+    const int quarter = warp & 3, half = ew >> 2;
+    const int row = quarter * 32 + lane;
+    const bool row_ok = q0 + row < a.Q;
+    const int col0 = half * kColsPerWarp;
+    float zy = 0.f, zyl = 0.f;
+    float sum4[4] = {0.f, 0.f, 0.f, 0.f}, cf[4] = {0.f, 0.f, 0.f, 0.f};
+    int cnt = 0;
+    if ((kCE || kRank) && row_ok) {
+      zy = a.zy[q0 + row];
+      zyl = zy * kLog2e;
+    }
+    for (int i = 0; i < n_tiles; ++i) {
+      const int buf = i & 1;
+      const int j0 = (t_begin + i) * BN;
+      mbar_wait(&sm.t_full[buf], (i >> 1) & 1);
+      tc_fence_after_sync();
+      const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + buf * BN + col0;
+      const int lim = a.n_items - j0 - col0;
+      const int jbase = j0 + col0;
+#pragma unroll
+      for (int c = 0; c < kColsPerWarp; c += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + c, r);
+        tmem_ld_wait(r);
+        if (c + 32 == kColsPerWarp) {
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(&sm.t_empty[buf], 0);   // the leader's barrier
+        }
+        if (c + 32 <= lim) {
+#pragma unroll
+          for (int u = 0; u < 32; ++u) {
+            const float z = __uint_as_float(r[u]);
+            if (kDump) {
+              if (row_ok) dump[(long long)(q0 + row) * a.n_items + jbase + c + u] = z;
+            }
+            if (kCE) {
+              const float t = fmaf(z, kLog2e, -zyl);
+              sum4[u & 3] += ((u % kPolyEvery) == kPolyEvery - 1) ? ex2_poly(t) : ex2_approx(t);
+            }
+            if (kRank) cf[u & 3] += set_gt_f(z, zy);
+          }
+        } else if (c < lim) {
+#pragma unroll 1
+          for (int u = 0; u < 32; ++u) {
+            float z = 0.f;
+#pragma unroll
+            for (int w = 0; w < 32; ++w)
+              if (w == u) z = __uint_as_float(r[w]);
+            if (c + u < lim) {
+              if (kDump) {
+                if (row_ok) dump[(long long)(q0 + row) * a.n_items + jbase + c + u] = z;
+              }
+              if (kCE) sum4[0] += ex2_approx(fmaf(z, kLog2e, -zyl));
+              if (kRank) cf[0] += set_gt_f(z, zy);
+            }
+          }
+        }
+      }
+      if (kRank) {
+        cnt += (int)((cf[0] + cf[1]) + (cf[2] + cf[3]));
+        cf[0] = cf[1] = cf[2] = cf[3] = 0.f;
+      }
+    }
+    float sum = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
+    if (half > 0) {
+      sm.comb_sum[half - 1][row] = sum;
+      sm.comb_cnt[half - 1][row] = cnt;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+    if (half == 0) {
+#pragma unroll
+      for (int h = 0; h < kSlices - 1; ++h) {
+        sum += sm.comb_sum[h][row];
+        cnt += sm.comb_cnt[h][row];
+      }
+      if (row_ok) {
+        const long long o = (long long)split * a.Q + q0 + row;
+        if (kCE) {
+          a.part_max[o] = zy;
+          a.part_sum[o] = sum;
+        }
+        if (kRank) a.part_cnt[o] = cnt;
+      }
+    }
+  }
+  tc_fence_before_sync();
+  cluster_sync_all();                                           // nobody exits while the peer may still signal it
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc_cg2<512>(tmem);
+  }
+}
+
 // ---- target logits with the sweep's arithmetic ---------------------------------------------------
 // Per 128-row tile: A = the query rows, B = the 128 gathered (augmented) target rows W_out^T[y_q]; the same 9
 // tcgen05.mma of shape M=128,N=128; thread r keeps the diagonal D[r][r].  Operands are written to shared memory
@@ -480,6 +676,41 @@ static int32_t launch_score(const ScoreArgs& a, float* dump, cudaStream_t st, co
   return HTCN_OK;
 }
 
+template <unsigned kFlags>
+static int32_t launch_score_cg2(const ScoreArgs& a, float* dump, cudaStream_t st) {
+  CUtensorMap ta, tb, tbb;
+  int32_t rc = make_tmap_bf16(&ta, a.hout, (uint64_t)a.Q, kDim, kDim, 64, kBM, 128);
+  if (rc) return rc;
+  rc = make_tmap_bf16(&tb, a.wt, (uint64_t)a.n_items, kWtPitchBf16, kWtPitchBf16, 64, 128, 128);     // half tiles
+  if (rc) return rc;
+  rc = make_tmap_bf16(&tbb, a.wt, (uint64_t)a.n_items, kWtPitchBf16, kWtPitchBf16, 16, 128, 32);
+  if (rc) return rc;
+  const size_t smem = sizeof(ScoreSmem2) + 1024;
+  auto kern = k4_score_bf16_cg2<kFlags>;
+  HTCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(2 * ((ceil_div(a.Q, kBM) + 1) / 2)), (unsigned)a.n_split, 1);   // whole CTA pairs
+  cfg.blockDim = dim3(64 + 32 * 4 * kSlicesScore, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  HTCN_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tbb, a, dump));
+  return HTCN_OK;
+}
+
+static int cta_group_env() {
+  // CTA pairs sharing the B operand: +4.4% on the power-capped cfg2 sweep (837 -> 874 TFLOP/s); HTCN_K4_CTA_GROUP=1
+  // selects the single-CTA kernel
+  static const int cg = [] { const char* e = getenv("HTCN_K4_CTA_GROUP"); return e ? atoi(e) : 2; }();
+  return cg;
+}
+
 int32_t score_bf16(const ScoreArgs& a, cudaStream_t st) {
   const int n_tiles = (a.n_items + 255) / 256;
   if (a.n_split > n_tiles && !(a.flags & HTCN_SCORE_TOPK)) {
@@ -497,6 +728,16 @@ int32_t score_bf16(const ScoreArgs& a, cudaStream_t st) {
       return HTCN_ERR_UNSUPPORTED;
     }
     return launch_score<128, HTCN_SCORE_TOPK>(a, nullptr, st);
+  }
+  if (cta_group_env() == 2) {
+    static const int poly = [] { const char* e = getenv("HTCN_POLY_EVERY"); return e ? atoi(e) : 8; }();
+    switch (a.flags) {
+      case HTCN_SCORE_CE: return launch_score_cg2<HTCN_SCORE_CE>(a, nullptr, st);
+      case HTCN_SCORE_RANK: return launch_score_cg2<HTCN_SCORE_RANK>(a, nullptr, st);
+      case HTCN_SCORE_CE | HTCN_SCORE_RANK:
+        if (poly == 8) return launch_score_cg2<HTCN_SCORE_CE | HTCN_SCORE_RANK | kModePoly8>(a, nullptr, st);
+        return launch_score_cg2<HTCN_SCORE_CE | HTCN_SCORE_RANK>(a, nullptr, st);
+    }
   }
   switch (a.flags) {
     case HTCN_SCORE_CE: return launch_score<256, HTCN_SCORE_CE>(a, nullptr, st);
@@ -679,6 +920,7 @@ int32_t score_topk_bf16(const void* hout, int Q, const void* wt, int n_items, in
 int32_t dump_logits_bf16(const void* hout, int Q, const void* wt, int n_items, float* logits, cudaStream_t st) {
   ScoreArgs a{};
   a.hout = hout; a.wt = wt; a.Q = Q; a.n_items = n_items; a.n_split = 1; a.flags = kModeDump;
+  if (cta_group_env() == 2) return launch_score_cg2<kModeDump>(a, logits, st);
   return launch_score<256, kModeDump>(a, logits, st);
 }
 
