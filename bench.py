@@ -328,12 +328,12 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "api": "HierTCN.step_async(x_list, y_list, mask_list, state).result(): numpy in / numpy out, pipelined 2 deep"},
             "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks}
-    if not opt.no_cpu_baseline:
+    if world > 1:
+        dist.destroy_process_group()
+    if not opt.no_cpu_baseline and world == 1:          # the CPU baseline is reported at N=1 only
         base, _, _, _ = cpu_baseline(wl, w, seconds_target=12.0)
         line["cpu_baseline"] = base
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
