@@ -73,7 +73,63 @@ sampled_loss_kernel(const void* __restrict__ pred, int Q, const float4* __restri
   }
 }
 
+// calc_score (reference loss.py:76-105): score of k candidate rows per query, 'l2' = -||p - y'||^2 or 'inner_prod' = <p, y'>
+// (pred is NOT normalised here, exactly like the reference).  One warp per query.
+template <bool kBf16>
+__global__ void __launch_bounds__(256)
+calc_score_kernel(const void* __restrict__ pred, int Q, const float4* __restrict__ table, const int* __restrict__ cand_id,
+                  int k, int mode, float* __restrict__ score) {
+  const int lane = threadIdx.x & 31;
+  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (q >= Q) return;
+  float4 p;
+  if (kBf16) {
+    const uint2 u = reinterpret_cast<const uint2*>(pred)[(long long)q * 32 + lane];
+    p = make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
+  } else {
+    p = reinterpret_cast<const float4*>(pred)[(long long)q * 32 + lane];
+  }
+  for (int j0 = 0; j0 < k; j0 += 4) {
+    float4 v[4];
+    int id[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      id[i] = (j0 + i < k) ? __ldg(cand_id + (long long)q * k + j0 + i) : -1;
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (id[i] > 0) v[i] = ldg_nc_f4(table + (long long)id[i] * 32 + lane);   // id 0 -> zero row
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (id[i] < 0) continue;
+      float t;
+      if (mode == 0) {
+        const float dx = p.x - v[i].x, dy = p.y - v[i].y, dz = p.z - v[i].z, dw = p.w - v[i].w;
+        t = -warp_sum(dx * dx + dy * dy + dz * dz + dw * dw);                  // loss.py:94
+      } else {
+        t = warp_sum(p.x * v[i].x + p.y * v[i].y + p.z * v[i].z + p.w * v[i].w);   // loss.py:96-97
+      }
+      if (lane == 0) score[(long long)q * k + j0 + i] = t;
+    }
+  }
+}
+
 }  // namespace htcn
+
+extern "C" int32_t htcn_calc_score(const void* pred, int32_t precision, int32_t Q, const float* table,
+                                   const int32_t* cand_id, int32_t k, int32_t rank_metric, float* score, void* stream) {
+  using namespace htcn;
+  HTCN_REQUIRE(pred && table && cand_id && score && Q > 0 && k > 0, "calc_score: bad args");
+  HTCN_REQUIRE(rank_metric == 0 || rank_metric == 1, "calc_score: rank_metric %d (0 = l2, 1 = inner_prod)", rank_metric);
+  const int grid = ceil_div(Q, 8);
+  if (precision == HTCN_BF16)
+    calc_score_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(pred, Q, (const float4*)table, cand_id, k, rank_metric, score);
+  else if (precision == HTCN_F32)
+    calc_score_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(pred, Q, (const float4*)table, cand_id, k, rank_metric, score);
+  else
+    HTCN_REQUIRE(false, "calc_score: precision %d", precision);
+  HTCN_LAUNCH_CHECK("calc_score_kernel");
+  return HTCN_OK;
+}
 
 extern "C" int32_t htcn_sampled_rank_loss(const void* pred, int32_t precision, int32_t Q, const float* table,
                                           const int32_t* pos_id, const int32_t* neg_id, int32_t k,

@@ -227,6 +227,12 @@ int32_t htcn_sampled_rank_loss(const void* pred, int32_t precision, int32_t Q, c
                                int32_t loss_kind, float hinge_delta, float nce_weight,
                                float* loss_row, void* stream);
 
+/* calc_score (reference loss.py:76-105): score[q,j] of k candidate rows table[cand_id[q,j]] for every query;
+ * rank_metric 0 = 'l2' (-||pred - y'||^2), 1 = 'inner_prod' (<pred, y'>); pred is not normalised (as in the
+ * reference).  cand_id [Q,k] int32 (0 -> zero row), score [Q,k] f32. */
+int32_t htcn_calc_score(const void* pred, int32_t precision, int32_t Q, const float* table,
+                        const int32_t* cand_id, int32_t k, int32_t rank_metric, float* score, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -142,3 +142,29 @@ def test_evaluate_hier_loop_matches_oracle_batch_by_batch():
     for k in acc:
         assert abs(res[k] - acc[k] / 4) <= 1e-4 * max(1.0, abs(acc[k] / 4)), (k, res[k], acc[k] / 4)
     assert len(res["rank_by_position"]) >= 4 and 0.0 <= res["user_rank_mean"] <= 1.0
+
+
+def test_loss_module_surface():
+    """hiertcn_b200.loss mirrors reference loss.py on the lazy scores handle"""
+    from hiertcn_b200 import loss as L
+    x, y, m, s0, w = small_case(B=6, S=3, L=7, N=211, seed=9)
+    ref = O.forward_loss_metrics(x, y, m, s0, w, 2, "f64")
+    model = make_model(w, 211, "f32")
+    scores, _ = model.forward(x, y, m, s0)
+    np.testing.assert_allclose(L.calc_loss(scores).cpu().numpy(), ref["loss_bt"], rtol=1e-4, atol=2e-5)
+    rec1, rec5, rec10, mrr, mrp, ranks_float, ranks = L.calc_metric_fast(scores)
+    np.testing.assert_array_equal(ranks.cpu().numpy(), ref["ranks"])
+    assert abs(float(mrr) - ref["mrr"]) < 1e-5 and abs(float(rec10) - ref["recall10"]) < 1e-6
+    # calc_score against the oracle on the user embeddings the kernels produced
+    rng = np.random.default_rng(0)
+    cand = rng.integers(1, 211, size=(scores.Q, 5)).astype(np.int32)
+    hout = scores.hout.float().cpu().numpy()
+    table = w["hier/tcn/dense/kernel"].T
+    for mode in ("l2", "inner_prod"):
+        got = L.calc_score(scores, cand, mode).cpu().numpy()
+        want = O.calc_score(hout[None].astype(np.float64), table[cand][None].astype(np.float64), mode)[0]
+        np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-4)
+    v, i = L.top_k(scores, 10)
+    z = (hout.astype(np.float64) @ w["hier/tcn/dense/kernel"].astype(np.float64) + w["hier/tcn/dense/bias"])
+    _, i_ref = O.top_k(z, 10)
+    assert np.mean(i.cpu().numpy() == i_ref) > 0.99
