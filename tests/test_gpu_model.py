@@ -168,3 +168,27 @@ def test_loss_module_surface():
     z = (hout.astype(np.float64) @ w["hier/tcn/dense/kernel"].astype(np.float64) + w["hier/tcn/dense/bias"])
     _, i_ref = O.top_k(z, 10)
     assert np.mean(i.cpu().numpy() == i_ref) > 0.99
+
+
+@pytest.mark.parametrize("seed", list(range(8)))
+def test_randomised_shapes_both_tiers(seed):
+    """random batch geometry / catalog size / conv stack: fp32 tier within 1e-4, bf16 tier within 2e-2 of the fp64 oracle"""
+    rng = np.random.default_rng(1000 + seed)
+    B, S, L = int(rng.integers(1, 70)), int(rng.integers(1, 12)), int(rng.integers(1, 22))
+    N = int(rng.choice([2, 17, 129, 257, 1000, 3001]))
+    levels, K = int(rng.integers(1, 4)), int(rng.integers(2, 6))
+    x, y, m, s0, w = small_case(B=B, S=S, L=L, N=N, seed=seed, tcn_channel=(128,) * levels, kernel_size=K,
+                                lengths="ragged" if seed % 2 else "dense", kernel_scale=1.5)
+    ref = O.forward_loss_metrics(x, y, m, s0, w, 2, "f64")
+    y_id = np.concatenate([np.asarray(v) for v in y], 1).astype(np.int64)
+    for precision, tol in (("f32", 1e-4), ("bf16", 2e-2)):
+        model = make_model(w, N, precision, levels=levels, K=K)
+        out = model.step(x, y, m, s0, per_position=True, topk=min(5, N))
+        assert abs(out["loss"] - ref["loss"]) <= tol * max(abs(ref["loss"]), 1e-3), (precision, out["loss"], ref["loss"])
+        np.testing.assert_allclose(out["loss_bt"], ref["loss_bt"], rtol=tol, atol=tol)
+        np.testing.assert_allclose(out["state"], ref["state"], rtol=max(tol, 1e-4), atol=max(tol, 1e-5))
+        if precision == "f32":
+            amb = O.rank_ambiguity(ref["pred"], y_id, 2e-5) * (y_id > 0)
+            assert (np.abs(out["ranks"] - ref["ranks"]) <= amb).all()
+        assert out["n_valid"] == (y_id > 0).sum() and out["user_count"] == ((y_id > 0).sum(1) > 0).sum()
+        assert out["topk_idx"].shape == (int((y_id > 0).sum()), min(5, N))
