@@ -1,0 +1,107 @@
+"""Single-level TCN (reference model_tcn.py:13-44 as called from model.py:71-73 with the one-hot item sequence;
+BASELINE config 3: low-level TCN only, long sequences, dilations 1-2-4-8).
+
+    x ids [B,L] -> 'tcn/emb' (one-hot x [N,128] kernel == a row gather, no bias) -> TemporalConvNet -> dense to N logits
+
+on the same kernels as the hierarchical path: K1 gathers the rows of ``tcn/emb/kernel`` (id 0 -> zeros), K2 runs the
+conv stack (its in-projection is fed the identity, because here the 'emb' dense IS the gather), K4 scores the
+catalog.  Only 128-channel levels are supported by the sm_100a kernels (the reference's default single-level stack
+ends with two 256-channel levels, args.py:310-311 -- config 3 uses [128]*4).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _cabi as cabi
+from .model_hier import CatalogScores, HierTCN, _torch
+from .weights import fold_weightnorm
+
+D = 128
+
+
+class TCN(HierTCN):
+    """model_tcn on one B200: ``forward(x_ids [B,L], y_ids [B,L]) -> CatalogScores`` (losses / ranks / top-k through the
+    inherited ``loss`` / ``score`` / ``topk``)."""
+
+    def __init__(self, args, weights, device=None, precision=None, scope="tcn"):
+        self.args = args
+        self.precision = precision or getattr(args, "precision", "bf16")
+        if list(args.tcn_channel) != [128] * len(args.tcn_channel):
+            raise NotImplementedError("the sm_100a conv kernels are built for 128-channel levels")
+        self.N = int(args.item_num)
+        self.K = int(args.kernel_size)
+        self.n_levels = len(args.tcn_channel)
+        self.G = 0
+        self.host_weights, self.scope, self.device = weights, scope, device
+        self.built = False
+        self._ws = {}
+
+    def build(self):
+        torch = _torch()
+        cabi.load()
+        if self.device is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        if not cabi.load().htcn_device_ok():
+            raise cabi.HtcnError("current CUDA device is not compute capability 10.x (B200)")
+        w = fold_weightnorm(self.host_weights)
+        sc = self.scope
+        up = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(self.device)  # noqa: E731
+        self.E = up(w[sc + "/emb/kernel"])                      # [N,128]: the in-projection applied to a one-hot
+        self.b_emb = up(np.zeros(D, np.float32))
+        self.w_in_x = up(np.eye(D, dtype=np.float32))
+        self.conv_w = [up(w[f"{sc}/temporal_conv_net/tblock_{l}/conv1/kernel"]) for l in range(self.n_levels)]
+        self.conv_b = [up(w[f"{sc}/temporal_conv_net/tblock_{l}/conv1/bias"]) for l in range(self.n_levels)]
+        self.b_out = up(w[sc + "/dense/bias"])
+        w_out = up(w[sc + "/dense/kernel"])
+        self.act_dtype = cabi.HTCN_BF16 if self.precision == "bf16" else cabi.HTCN_F32
+        self.act_torch_dtype = torch.bfloat16 if self.precision == "bf16" else torch.float32
+        self.n_out = int(w_out.shape[1])
+        pitch = cabi.WT_PITCH_BF16 if self.precision == "bf16" else D
+        self.wt = torch.empty((self.n_out, pitch), dtype=self.act_torch_dtype, device=self.device)
+        cabi.call("htcn_prepare_wout", w_out.data_ptr(), self.b_out.data_ptr(), self.n_out, self.wt.data_ptr(),
+                  self.act_dtype, self.stream_ptr())
+        self.wt_f32 = self.wt if self.precision == "f32" else None
+        torch.cuda.synchronize(self.device)
+        self._conv_w_pp = cabi.ptr_array([t.data_ptr() for t in self.conv_w])
+        self._conv_b_pp = cabi.ptr_array([t.data_ptr() for t in self.conv_b])
+        self.built = True
+        return self
+
+    def forward(self, x_ids, y_ids=None):
+        """x_ids [B,L] item ids (0 = padding), y_ids [B,L] next-item targets (0 = not scored; default: every position
+        is scored against id 0, i.e. only hidden states / top-k are meaningful)."""
+        if not self.built:
+            self.build()
+        torch = _torch()
+        x = np.ascontiguousarray(np.asarray(x_ids), dtype=np.int32)
+        B, L = x.shape
+        y = np.ascontiguousarray(np.asarray(y_ids), dtype=np.int32) if y_ids is not None else np.ones_like(x)
+        valid = y.reshape(-1) > 0
+        row_of = np.where(valid, np.cumsum(valid) - 1, -1).astype(np.int32)
+        Q = int(valid.sum())
+        dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(self.device)  # noqa: E731
+        x_d, y_d, row_d, yrows_d = dev(x), dev(y), dev(row_of), dev(y.reshape(-1)[valid])
+        st = self.stream_ptr()
+        slot_p, keep = cabi.int_array([0, L])
+        xe = self._buf("xe", (B * L, D), self.act_torch_dtype)
+        cabi.call("htcn_gather_meanpool", self.E.data_ptr(), None, self.N, x_d.data_ptr(), None, slot_p, B, L, 1,
+                  xe.data_ptr(), self.act_dtype, None, st)
+        hout = self._buf("hout", (max(Q, 1), D), self.act_torch_dtype)
+        prec = self._k2_precision()
+        if prec == cabi.HTCN_F32:
+            scratch = self._buf("k2_scratch", (2 * B * L, D), torch.float32)
+        else:
+            scratch = self._buf("k2_scratch_bf16", ((1 + self.n_levels * self.K) * 8192 + 4096,), torch.float32)
+        cabi.call("htcn_tcn_forward", xe.data_ptr(), self.act_dtype, prec, self.w_in_x.data_ptr(), None,
+                  self._conv_w_pp[0], self._conv_b_pp[0], self.n_levels, self.K, slot_p, B, L, 1, row_d.data_ptr(),
+                  hout.data_ptr(), self.act_dtype, scratch.data_ptr(), st)
+        return CatalogScores(self, hout, Q, row_d, yrows_d, y_d, B, L)
+
+
+def model_tcn(args, x, x_gap=None, x_impression=None, name="tcn", reuse=None, training=True, mask=None, weights=None,
+              precision=None, y=None):
+    """Signature of reference model_tcn.py:13.  ``x`` are item ids [B,L] (the reference is fed their one-hot,
+    model.py:56,73).  Returns the lazy ``CatalogScores`` standing for ``pred [B,L,N]``."""
+    if x_gap is not None or x_impression is not None:
+        raise NotImplementedError("has_gap / has_impression are outside the hot path")
+    return TCN(args, weights, precision=precision or getattr(args, "precision", "bf16"), scope=name).build().forward(x, y)

@@ -192,3 +192,34 @@ def test_randomised_shapes_both_tiers(seed):
             assert (np.abs(out["ranks"] - ref["ranks"]) <= amb).all()
         assert out["n_valid"] == (y_id > 0).sum() and out["user_count"] == ((y_id > 0).sum(1) > 0).sum()
         assert out["topk_idx"].shape == (int((y_id > 0).sum()), min(5, N))
+
+
+@pytest.mark.parametrize("B,L,levels,precision", [(5, 40, 2, "f32"), (3, 300, 4, "f32"), (6, 300, 4, "bf16"), (9, 17, 3, "bf16")])
+def test_single_level_model_tcn(B, L, levels, precision):
+    """reference model_tcn.py (single-level TCN on the one-hot item sequence, BASELINE config 3 shape)"""
+    from hiertcn_b200.args import make_args
+    from hiertcn_b200.model_tcn import TCN
+    from hiertcn_b200.weights import init_weights, tcn_weight_shapes
+    N, K = 257, 5
+    w = init_weights(tcn_weight_shapes(N, (128,) * levels, K, output_dim=N), seed=3, kernel_scale=1.5, bias_noise=0.1)
+    rng = np.random.default_rng(B + L)
+    x = rng.integers(1, N, size=(B, L))
+    x[:, 0] = 0
+    n = rng.integers(1, L + 1, size=B)
+    y = np.where(np.arange(L)[None, :] < n[:, None], rng.integers(1, N, size=(B, L)), 0)
+    a = make_args(["--item_num", str(N), "--tcn_channel", ",".join(["128"] * levels), "--kernel_size", str(K)])
+    model = TCN(a, w, precision=precision).build()
+    scores = model.forward(x, y)
+    pred64 = O.model_tcn(O.one_hot_signed(x, N, np.float64), {k: v.astype(np.float64) for k, v in w.items()}, "tcn", "f64")
+    loss, loss_bt, mask_y, act, uc, pred_m = O.hier_loss(pred64, y)
+    met = O.calc_metric_fast(pred_m, mask_y, act, uc, y)
+    tol = 1e-4 if precision == "f32" else 2e-2
+    if precision == "f32":
+        np.testing.assert_allclose(scores.materialize(), pred_m, rtol=1e-4, atol=2e-4)
+    r = model.loss(scores, metrics=True, per_position=True)
+    sc = r["scalars"].cpu().numpy()
+    assert abs(sc[0] - loss) <= tol * abs(loss)
+    np.testing.assert_allclose(r["loss_bt"].cpu().numpy(), loss_bt, rtol=tol, atol=tol)
+    if precision == "f32":
+        amb = O.rank_ambiguity(pred_m, y, 2e-5) * (y > 0)
+        assert (np.abs(r["ranks"].cpu().numpy() - met[6]) <= amb).all()
