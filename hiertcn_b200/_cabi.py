@@ -19,7 +19,7 @@ WT_PITCH_BF16 = 144
 
 
 def gru_scratch_bytes(B):
-    return 14 * 128 * 128 * 2 + 4096 + ((B + 127) // 128) * 128 * 1024
+    return 14 * 128 * 128 * 2 + 4096          # HTCN_GRU_SCRATCH_BYTES: independent of B (the fp32 state lives in TMEM)
 
 _p, _i, _u, _f = C.c_void_p, C.c_int32, C.c_uint32, C.c_float
 _pp = C.POINTER(C.c_void_p)        # host array of device pointers

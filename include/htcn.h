@@ -91,9 +91,9 @@ int32_t htcn_gather_meanpool(const float* emb_table, const float* emb_bias, int3
  * Outputs: state_pre [S,B,G*128] (may be NULL), sbias [S,B,128] (may be NULL), state_out [B,G*128].
  * precision: HTCN_F32 = fp32 FFMA (1e-4 tier, any num_layer <= 4);
  *            HTCN_BF16 = tcgen05 tensor cores, bf16 operands / fp32 accumulate and fp32 state (num_layer == 2 only);
- *                        needs scratch >= HTCN_GRU_SCRATCH_BYTES(B) device bytes (bf16 weight tiles + working state), else may be NULL.
+ *                        needs scratch >= HTCN_GRU_SCRATCH_BYTES(B) device bytes (bf16 weight tiles), else may be NULL.
  * ------------------------------------------------------------------------------------------- */
-#define HTCN_GRU_SCRATCH_BYTES(B) (14 * 128 * 128 * 2 + 4096 + (((B) + 127) / 128) * 128 * 1024)
+#define HTCN_GRU_SCRATCH_BYTES(B) (14 * 128 * 128 * 2 + 4096)   /* independent of B: the fp32 state lives in TMEM */
 int32_t htcn_gru_sessions(const float* yp, const float* mask, const float* state_in,
                           const float* const* gate_w_host, const float* const* gate_b_host,
                           const float* const* cand_w_host, const float* const* cand_b_host,
@@ -117,9 +117,11 @@ int32_t htcn_gru_sessions(const float* yp, const float* mask, const float* state
  *   fp32 accumulate, level activations kept on chip).
  * out_row [B*T] int32 or NULL: destination row of each position in hout (-1 = drop the row);
  *   used to compact away padded positions before catalog scoring.
- * hout [n_out_rows,128] of hout_dtype.  scratch: 2*B*T*128 floats (used by the f32 tier only, may be
- *   NULL for the bf16 tier).
+ * hout [n_out_rows,128] of hout_dtype.  scratch (device, caller-owned): f32 tier 2*B*T*128 floats (level
+ *   ping-pong); bf16 tier HTCN_TCN_SCRATCH_BYTES(n_levels, kernel_size) bytes (bf16 weight tiles).
+ * The bf16 tier requires xe and hout in bf16 and (K-1)*2^(n_levels-1) <= 32 rows of causal shift.
  * ------------------------------------------------------------------------------------------- */
+#define HTCN_TCN_SCRATCH_BYTES(n_levels, K) ((1 + (n_levels) * (K)) * 128 * 128 * 2 + 8 * 8 + 8 * 512 + 256)
 int32_t htcn_tcn_forward(const void* xe, int32_t xe_dtype, int32_t precision,
                          const float* w_in_x, const float* sbias,
                          const float* const* conv_w_host, const float* const* conv_b_host,
