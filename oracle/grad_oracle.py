@@ -1,0 +1,121 @@
+"""Gradient / optimiser oracle for the training step (TEST INFRASTRUCTURE ONLY -- see oracle/__init__.py).
+
+The reference trains with ``tf.train.AdamOptimizer(lr).minimize(loss)`` (model.py:134-141) on the loss of
+model.py:105-117; TensorFlow's autodiff is not restated anywhere in the reference sources, so the gradient
+oracle is torch autograd (float64, CPU) over a restatement of the forward whose VALUE is pinned: ``loss_fp64``
+below must agree with oracle/hiertcn_oracle.forward_loss_metrics (checked against the golden vectors that the
+reference's own python produced, tests/test_oracle.py), in the literal form (one-hot x table matmuls, state
+concat, S unrolled cell calls -- model.py:59-61, model_hier.py:39-94) and in the restructured form the kernels
+follow.  Gradients of the two forms agree to fp64 round-off, and both are checked against central finite
+differences in tests/test_oracle.py.  Parity status: values pinned, TF's Adam formula restated from its
+published definition -- "parity unpinned" for the optimiser.
+
+The carried user state enters through a placeholder (model.py:44, run_hier_xing.py:291), so no gradient flows
+into ``state`` -- backpropagation through time is truncated at the batch boundary.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+PARAM_ORDER = ("hier/emb/kernel", "hier/emb/bias", "hier/tcn/emb/kernel", "hier/tcn/dense/kernel", "hier/tcn/dense/bias")
+
+
+def _params(w, dtype=torch.float64):
+    return {k: torch.tensor(np.asarray(v), dtype=dtype, requires_grad=True) for k, v in w.items()}
+
+
+def _gru(p, x, state, G, H):
+    """customed_gru_cell.py:309-337 (cell), :1050-1073 (stacking, state_is_tuple=False)"""
+    new, cur = [], x
+    for g in range(G):
+        pre = f"hier/multi_rnn_cell/cell_{g}/gru_cell/"
+        h = state[:, g * H:(g + 1) * H]
+        v = torch.sigmoid(torch.cat([cur, h], 1) @ p[pre + "gates/kernel"] + p[pre + "gates/bias"])
+        r, u = v[:, :H], v[:, H:]
+        c = torch.tanh(torch.cat([cur, r * h], 1) @ p[pre + "candidate/kernel"] + p[pre + "candidate/bias"])
+        cur = u * h + (1 - u) * c
+        new.append(cur)
+    return torch.cat(new, 1)
+
+
+def _tcn(p, h, n_levels, K):
+    """customized_tcn_cell.py:46-49,109-127,157-161: one conv per block, relu inside and after the residual"""
+    for lvl in range(n_levels):
+        pre = f"hier/tcn/temporal_conv_net/tblock_{lvl}/conv1/"
+        d = 2 ** lvl
+        xp = F.pad(h.transpose(1, 2), ((K - 1) * d, 0))
+        a = F.conv1d(xp, p[pre + "kernel"].permute(2, 1, 0), p[pre + "bias"], dilation=d).transpose(1, 2)
+        h = torch.relu(torch.relu(a) + h)
+    return h
+
+
+def loss_fp64(p, x_list, y_list, mask_list, state, num_layer=2, literal=False):
+    """Scalar training loss (model.py:105-117) as a torch expression of the parameter dict ``p``."""
+    dt = p["hier/emb/kernel"].dtype
+    E, be = p["hier/emb/kernel"], p["hier/emb/bias"]
+    N, H = E.shape[0], 128
+    n_levels = sum(1 for k in p if k.endswith("conv1/kernel"))
+    K = p["hier/tcn/temporal_conv_net/tblock_0/conv1/kernel"].shape[0]
+    state = torch.tensor(np.asarray(state), dtype=dt)
+    houts = []
+    for s in range(len(x_list)):
+        x = torch.from_numpy(np.asarray(x_list[s]).astype(np.int64))
+        y = torch.from_numpy(np.asarray(y_list[s]).astype(np.int64))
+        if literal:
+            ohx = F.one_hot(x, N).to(dt) * torch.sign(x).unsqueeze(-1).to(dt)
+            ohy = F.one_hot(y, N).to(dt) * torch.sign(y).unsqueeze(-1).to(dt)
+            xe = ohx @ E                                                        # model_hier.py:50
+            cnt = torch.sign(ohy.abs().sum(2)).sum(1, keepdim=True)
+            ys = (ohy.sum(1) / cnt) @ E + be                                    # model_hier.py:83-85
+        else:
+            xe = E[x] * (x > 0).unsqueeze(-1)
+            ys = (E[y] * (y > 0).unsqueeze(-1)).sum(1) / (y > 0).sum(1, keepdim=True) + be
+        feat = state.unsqueeze(1).expand(-1, xe.shape[1], -1)
+        h0 = torch.cat([xe, feat], -1) @ p["hier/tcn/emb/kernel"]               # model_hier.py:54-55, model_tcn.py:35
+        houts.append(_tcn(p, h0, n_levels, K))
+        state = _gru(p, ys, state, num_layer, H) * torch.tensor(np.asarray(mask_list[s]), dtype=dt).reshape(-1, 1)
+    hout = torch.cat(houts, 1)
+    y_id = torch.from_numpy(np.concatenate([np.asarray(v) for v in y_list], 1).astype(np.int64))
+    mask = (y_id > 0).to(dt)
+    z = (hout @ p["hier/tcn/dense/kernel"] + p["hier/tcn/dense/bias"]) * mask.unsqueeze(-1)     # model.py:105
+    lse = torch.logsumexp(z, -1)
+    zy = z.gather(2, y_id.unsqueeze(-1)).squeeze(-1)
+    loss_bt = (lse - zy) * mask                                                  # loss.py:20-21, model.py:110
+    act = mask.sum(1)
+    uc = torch.sign(act).sum()
+    return ((loss_bt.sum(1) / (act + 1e-6)).sum() / uc), state                   # model.py:111-117
+
+
+def loss_and_grads(w, x_list, y_list, mask_list, state, num_layer=2, literal=False):
+    """-> (loss float, dict name -> fp64 numpy gradient, new state)"""
+    p = _params(w)
+    loss, st = loss_fp64(p, x_list, y_list, mask_list, state, num_layer, literal)
+    loss.backward()
+    g = {k: (v.grad.numpy() if v.grad is not None else np.zeros(v.shape)) for k, v in p.items()}
+    return float(loss.detach()), g, st.detach().numpy()
+
+
+def adam_tf(w, g, m, v, t, lr=1e-2, beta1=0.9, beta2=0.999, eps=1e-8):
+    """One step of TF-1.x AdamOptimizer: epsilon outside the bias-corrected root.
+    ``t`` is the 1-based step number.  Updates the dicts in place (numpy, any float dtype)."""
+    lr_t = lr * np.sqrt(1.0 - beta2 ** t) / (1.0 - beta1 ** t)
+    for k in w:
+        m[k] = beta1 * m[k] + (1 - beta1) * g[k]
+        v[k] = beta2 * v[k] + (1 - beta2) * g[k] * g[k]
+        w[k] = w[k] - lr_t * m[k] / (np.sqrt(v[k]) + eps)
+
+
+def train_steps(w, batches, state0, lr=1e-2, num_layer=2):
+    """Run len(batches) Adam steps in fp64 carrying the user state like run_hier_xing.py:291,301.
+    Returns (list of losses, final weights fp64, final state)."""
+    w = {k: np.asarray(a, np.float64).copy() for k, a in w.items()}
+    m = {k: np.zeros_like(a) for k, a in w.items()}
+    v = {k: np.zeros_like(a) for k, a in w.items()}
+    state, losses = np.asarray(state0, np.float64), []
+    for t, (x, y, mk) in enumerate(batches, 1):
+        loss, g, state = loss_and_grads(w, x, y, mk, state, num_layer)
+        losses.append(loss)
+        adam_tf(w, g, m, v, t, lr)
+    return losses, w, state
