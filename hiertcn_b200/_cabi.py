@@ -41,10 +41,21 @@ SIGNATURES = {
     "htcn_loss_metrics_reduce": [_p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p],
     "htcn_sampled_rank_loss": [_p, _i, _i, _p, _p, _p, _i, _i, _f, _f, _p, _p],
     "htcn_calc_score": [_p, _i, _i, _p, _p, _i, _i, _p, _p],
+    # training step
+    "htcn_loss_row_weights": [_p, _p, _i, _i, _p, _p],
+    "htcn_score_ce_backward": [_p, _i, _i, _p, _p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p],
+    "htcn_tcn_forward_train": [_p, _p, _p, _pp, _pp, _i, _i, _ip, _i, _i, _i, _p, _p, _p, _p, _p],
+    "htcn_tcn_backward": [_p, _p, _p, _p, _pp, _i, _i, _ip, _i, _i, _i, _p, _p, _p, _pp, _pp, _p, _p, _p, _p],
+    "htcn_gru_sessions_train": [_p, _p, _p, _pp, _pp, _pp, _pp, _i, _p, _i, _i, _p, _p, _p, _p, _p],
+    "htcn_gru_backward": [_p, _p, _p, _p, _pp, _pp, _i, _p, _i, _i, _p, _p, _pp, _pp, _pp, _pp, _p, _p, _p],
+    "htcn_gather_backward": [_p, _p, _p, _p, _ip, _i, _i, _i, _i, _p, _p, _p],
+    "htcn_adam_step": [_p, _p, _p, _p, C.c_int64, _f, _f, _f, _f, _p, _i, _p],
+    "htcn_refresh_wout": [_p, _p, _i, _p, _i, _p],
 }
 PLAIN = {"htcn_abi_version": (C.c_int32, []), "htcn_last_error": (C.c_char_p, []),
          "htcn_device_ok": (C.c_int32, []),
-         "htcn_topk_workspace_bytes": (C.c_int64, [_i, _i, _i, _i, _i])}
+         "htcn_topk_workspace_bytes": (C.c_int64, [_i, _i, _i, _i, _i]),
+         "htcn_gru_backward_scratch_floats": (C.c_int64, [_i, _i, _i])}
 
 
 class HtcnError(RuntimeError):
@@ -80,7 +91,10 @@ def load(path: str | None = None):
 LAUNCHES_PER_CALL = {"htcn_gather_meanpool": 2, "htcn_gru_sessions": 1, "htcn_tcn_forward": 0,
                      "htcn_prepare_wout": 1, "htcn_score_ce_rank_topk": 2, "htcn_score_logits": 1,
                      "htcn_target_logit": 1, "htcn_score_finish": 1, "htcn_topk_merge": 1, "htcn_score_topk": 5,
-                     "htcn_loss_metrics_reduce": 2, "htcn_sampled_rank_loss": 1, "htcn_calc_score": 1}
+                     "htcn_loss_metrics_reduce": 2, "htcn_sampled_rank_loss": 1, "htcn_calc_score": 1,
+                     # training step (the per-call counts of the multi-launch entry points are added by the caller)
+                     "htcn_loss_row_weights": 1, "htcn_score_ce_backward": 1, "htcn_gru_sessions_train": 1,
+                     "htcn_gather_backward": 2, "htcn_adam_step": 1, "htcn_refresh_wout": 1}
 launch_count = 0
 
 

@@ -1,0 +1,148 @@
+// K2 training path (fp32): the conv stack forward with every level's activations saved, and its backward.
+//
+// forward (customized_tcn_cell.py:109-127, one conv per block):   p = conv_l(h_l) + b_l,  a_l = relu(p),
+//                                                                 h_{l+1} = relu(a_l + h_l)
+// backward, given dL/dh_{l+1}:   ds = dL/dh_{l+1} * [h_{l+1} > 0]        (TF ReluGrad: gradient where output > 0)
+//                                dp = ds * [a_l > 0]
+//                                dW_l[tap] += h_l[shifted by the tap]^T dp,   db_l += colsum(dp)
+//                                dL/dh_l = ds + sum_tap dp[shifted the other way] W_l[tap]^T   (transposed convolution)
+// and for the in-projection h_0 = Xe W_in[:128] + sbias[slot, user]  (model_hier.py:54-55, model_tcn.py:35):
+//                                dW_in_x += Xe^T dh_0,  dsbias[s,b] = sum_{t in slot s} dh_0[b,t],  dXe = dh_0 W_in_x^T
+#include "train.cuh"
+
+namespace htcn {
+
+namespace {
+
+__global__ void relu_bwd_kernel(long long n4, float4* __restrict__ dcur, const float4* __restrict__ h_next,
+                                const float4* __restrict__ a_l, float4* __restrict__ dp) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 d = dcur[i];
+  const float4 h = h_next[i], a = a_l[i];
+  d.x = h.x > 0.f ? d.x : 0.f; d.y = h.y > 0.f ? d.y : 0.f; d.z = h.z > 0.f ? d.z : 0.f; d.w = h.w > 0.f ? d.w : 0.f;
+  dcur[i] = d;
+  float4 p;
+  p.x = a.x > 0.f ? d.x : 0.f; p.y = a.y > 0.f ? d.y : 0.f; p.z = a.z > 0.f ? d.z : 0.f; p.w = a.w > 0.f ? d.w : 0.f;
+  dp[i] = p;
+}
+
+// dsbias[s, b, c] = sum_{t in slot s} dh0[b, t, c]
+__global__ void slot_sum_kernel(const float* __restrict__ dh0, int B, int T, SlotTable slots, float* __restrict__ dsbias) {
+  const int c = threadIdx.x;                   // 128 threads
+  const int b = blockIdx.x, s = blockIdx.y;
+  float acc = 0.f;
+  for (int t = slots.off[s]; t < slots.off[s + 1]; ++t) acc += dh0[((long long)b * T + t) * kDim + c];
+  dsbias[((long long)s * B + b) * kDim + c] = acc;
+}
+
+// dst[row_of[r], :] = src[r, :]  (gather = 1)   or   dst[r, :] = row_of[r] >= 0 ? src[row_of[r], :] : 0   (gather = 0)
+__global__ void rows_compact_kernel(long long R, const int* __restrict__ row_of, const float4* __restrict__ src,
+                                    float4* __restrict__ dst, int gather) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one float4
+  if (i >= R * 32) return;
+  const long long r = i >> 5;
+  const int c = (int)(i & 31);
+  const int q = row_of[r];
+  if (gather) {
+    if (q >= 0) dst[(long long)q * 32 + c] = src[i];
+  } else {
+    dst[i] = q >= 0 ? src[(long long)q * 32 + c] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+}  // namespace
+}  // namespace htcn
+
+extern "C" int32_t htcn_tcn_forward_train(const float* xe, const float* w_in_x, const float* sbias,
+                                          const float* const* conv_w_host, const float* const* conv_b_host,
+                                          int32_t n_levels, int32_t kernel_size, const int32_t* slot_off_host, int32_t B,
+                                          int32_t T, int32_t S, const int32_t* out_row, float* h_save, float* a_save,
+                                          float* hout, void* stream) {
+  using namespace htcn;
+  HTCN_REQUIRE(xe && w_in_x && h_save && hout && slot_off_host && out_row, "tcn_forward_train: NULL pointer");
+  HTCN_REQUIRE(B > 0 && T > 0 && S > 0 && S <= HTCN_MAX_SLOTS, "tcn_forward_train: B=%d T=%d S=%d", B, T, S);
+  HTCN_REQUIRE(n_levels >= 0 && n_levels <= HTCN_MAX_LEVELS && kernel_size >= 1 && kernel_size <= 8,
+               "tcn_forward_train: n_levels=%d kernel_size=%d", n_levels, kernel_size);
+  HTCN_REQUIRE(n_levels == 0 || (conv_w_host && conv_b_host && a_save), "tcn_forward_train: conv weights / a_save NULL");
+  SlotTable slots;
+  slots.n = S;
+  for (int i = 0; i <= S; ++i) slots.off[i] = slot_off_host[i];
+  HTCN_REQUIRE(slots.off[0] == 0 && slots.off[S] == T, "tcn_forward_train: slot_off does not span T");
+  cudaStream_t st = as_stream(stream);
+  const long long R = (long long)B * T;
+  LevelArgs a{};
+  a.R = R; a.T = T; a.B = B;
+  a.in = xe; a.w = w_in_x; a.sbias = sbias; a.K = 1; a.dil = 1; a.conv_epilogue = 0; a.out = h_save;
+  int32_t rc = k2_level_launch(a, slots, st);
+  if (rc) return rc;
+  for (int l = 0; l < n_levels; ++l) {
+    a.in = h_save + (long long)l * R * kDim;
+    a.w = conv_w_host[l]; a.bias = conv_b_host[l]; a.sbias = nullptr; a.K = kernel_size; a.dil = 1 << l;
+    a.conv_epilogue = 1;
+    a.out = h_save + (long long)(l + 1) * R * kDim;
+    a.aux = a_save + (long long)l * R * kDim;
+    rc = k2_level_launch(a, slots, st);
+    if (rc) return rc;
+  }
+  rows_compact_kernel<<<ceil_div(R * 32, 256), 256, 0, st>>>(
+      R, out_row, reinterpret_cast<const float4*>(h_save + (long long)n_levels * R * kDim),
+      reinterpret_cast<float4*>(hout), 1);
+  HTCN_LAUNCH_CHECK("rows_compact_kernel");
+  return HTCN_OK;
+}
+
+extern "C" int32_t htcn_tcn_backward(const float* d_hout, const int32_t* out_row, const float* xe, const float* w_in_x,
+                                     const float* const* conv_w_host, int32_t n_levels, int32_t kernel_size,
+                                     const int32_t* slot_off_host, int32_t B, int32_t T, int32_t S, const float* h_save,
+                                     const float* a_save, float* scratch, float* const* d_conv_w_host,
+                                     float* const* d_conv_b_host, float* d_w_in_x, float* d_sbias, float* d_xe,
+                                     void* stream) {
+  using namespace htcn;
+  HTCN_REQUIRE(d_hout && out_row && xe && w_in_x && h_save && scratch && d_w_in_x && d_sbias && d_xe && slot_off_host,
+               "tcn_backward: NULL pointer");
+  HTCN_REQUIRE(B > 0 && T > 0 && S > 0 && S <= HTCN_MAX_SLOTS, "tcn_backward: B=%d T=%d S=%d", B, T, S);
+  HTCN_REQUIRE(n_levels >= 0 && n_levels <= HTCN_MAX_LEVELS && kernel_size >= 1 && kernel_size <= 8,
+               "tcn_backward: n_levels=%d kernel_size=%d", n_levels, kernel_size);
+  HTCN_REQUIRE(n_levels == 0 || (conv_w_host && a_save && d_conv_w_host && d_conv_b_host), "tcn_backward: conv pointers NULL");
+  SlotTable slots;
+  slots.n = S;
+  for (int i = 0; i <= S; ++i) slots.off[i] = slot_off_host[i];
+  HTCN_REQUIRE(slots.off[0] == 0 && slots.off[S] == T, "tcn_backward: slot_off does not span T");
+  cudaStream_t st = as_stream(stream);
+  const long long R = (long long)B * T;
+  float* dcur = scratch;                    // [R,128] gradient flowing down the stack
+  float* dp = scratch + R * kDim;           // [R,128] gradient at the conv pre-activation
+  const int eb = ceil_div(R * 32, 256);
+  rows_compact_kernel<<<eb, 256, 0, st>>>(R, out_row, reinterpret_cast<const float4*>(d_hout),
+                                          reinterpret_cast<float4*>(dcur), 0);
+  HTCN_LAUNCH_CHECK("rows_compact_kernel(scatter)");
+  int32_t rc;
+  for (int l = n_levels - 1; l >= 0; --l) {
+    const float* h_l = h_save + (long long)l * R * kDim;
+    const float* h_n = h_save + (long long)(l + 1) * R * kDim;
+    const float* a_l = a_save + (long long)l * R * kDim;
+    relu_bwd_kernel<<<eb, 256, 0, st>>>(R * 32, reinterpret_cast<float4*>(dcur), reinterpret_cast<const float4*>(h_n),
+                                        reinterpret_cast<const float4*>(a_l), reinterpret_cast<float4*>(dp));
+    HTCN_LAUNCH_CHECK("relu_bwd_kernel");
+    const int dil = 1 << l;
+    for (int tap = 0; tap < kernel_size; ++tap) {
+      rc = sgemm_tn_atomic(R, h_l, kDim, dp, kDim, d_conv_w_host[l] + (long long)tap * kDim * kDim, kDim,
+                           (kernel_size - 1 - tap) * dil, T, &slots, st);
+      if (rc) return rc;
+    }
+    rc = colsum_atomic(R, dp, kDim, kDim, d_conv_b_host[l], st);
+    if (rc) return rc;
+    LevelArgs a{};
+    a.R = R; a.T = T; a.B = B;
+    a.in = dp; a.w = conv_w_host[l]; a.K = kernel_size; a.dil = dil; a.conv_epilogue = 2; a.resid = dcur; a.out = dcur;
+    a.anti = 1; a.w_nt = 1;
+    rc = k2_level_launch(a, slots, st);
+    if (rc) return rc;
+  }
+  rc = sgemm_tn_atomic(R, xe, kDim, dcur, kDim, d_w_in_x, kDim, 0, T, nullptr, st);
+  if (rc) return rc;
+  slot_sum_kernel<<<dim3(B, S), kDim, 0, st>>>(dcur, B, T, slots, d_sbias);
+  HTCN_LAUNCH_CHECK("slot_sum_kernel");
+  return sgemm(true, R, kDim, kDim, dcur, kDim, w_in_x, kDim, d_xe, kDim, false, st);
+}

@@ -6,7 +6,7 @@
 // (customized_tcn_cell.py:109-127: relu inside the conv, residual add, relu) or identity for the
 // in-projection (model_tcn.py:35, K = 1, no bias).  Levels are chained through an fp32 scratch in HBM
 // (L2-resident at these sizes); the bf16 tier (k2_tcn_bf16.cu) keeps them on chip instead.
-#include "common.cuh"
+#include "train.cuh"
 
 namespace htcn {
 
@@ -14,18 +14,6 @@ constexpr int kTM = 128;      // rows per CTA
 constexpr int kTK = 16;       // contraction chunk
 constexpr int kK2Threads = 256;
 
-struct LevelArgs {
-  const void* in;             // [R,128] f32 (or bf16 when in_bf16)
-  const float* w;             // [K,128,128]
-  const float* bias;          // [128] or NULL
-  const float* sbias;         // [S,B,128] or NULL
-  void* out;                  // [R or n_out,128]
-  const int* out_row;         // [R] or NULL
-  long long R;
-  int T, B, K, dil;
-  int conv_epilogue;          // 1: relu, +residual, relu; 0: linear
-  int in_bf16, out_bf16;
-};
 
 __device__ __forceinline__ float load_act(const void* base, bool bf16, long long idx) {
   if (bf16) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[idx]);
@@ -37,19 +25,22 @@ k2_level_f32(LevelArgs a, SlotTable slots) {
   __shared__ __align__(16) float As[kTK][kTM];     // As[kk][row]
   __shared__ __align__(16) float Bs[kTK][kDim];    // Bs[kk][col]
   __shared__ int t_in_seq[kTM];                    // position of each tile row inside its sequence
+  __shared__ int t_left[kTM];                      // rows remaining after it in the sequence (anti-causal taps)
   const int tid = threadIdx.x;
   const long long r0 = (long long)blockIdx.x * kTM;
 
   if (tid < kTM) {
     const long long r = r0 + tid;
-    int t = 0;
+    int t = 0, left = 0;
     if (r < a.R) {
       const int p = (int)(r % a.T);
       int s = 0;
       while (s + 1 < slots.n && slots.off[s + 1] <= p) ++s;
       t = p - slots.off[s];
+      left = slots.off[s + 1] - 1 - p;
     }
     t_in_seq[tid] = t;
+    t_left[tid] = left;
   }
   __syncthreads();
 
@@ -64,8 +55,8 @@ k2_level_f32(LevelArgs a, SlotTable slots) {
   const int lrow = tid & 127, lhalf = tid >> 7;   // loader mapping: row, 8-wide k half
   for (int tap = 0; tap < a.K; ++tap) {
     const int shift = (a.K - 1 - tap) * a.dil;
-    const long long src = r0 + lrow - shift;
-    const bool ok = (r0 + lrow < a.R) && (t_in_seq[lrow] - shift >= 0);
+    const long long src = a.anti ? (r0 + lrow + shift) : (r0 + lrow - shift);
+    const bool ok = (r0 + lrow < a.R) && (a.anti ? (shift <= t_left[lrow]) : (t_in_seq[lrow] - shift >= 0));
     for (int c0 = 0; c0 < kDim; c0 += kTK) {
       // A chunk: in[src][c0 + lhalf*8 .. +8] -> As[kk][lrow]
       float v[8];
@@ -85,13 +76,22 @@ k2_level_f32(LevelArgs a, SlotTable slots) {
         for (int i = 0; i < 8; ++i) v[i] = 0.f;
       }
       // W chunk: w[tap][c0 + kk][0..127] -> Bs[kk][col]; 2048 floats = 256 threads x 2 float4
-      const float4* wp = reinterpret_cast<const float4*>(a.w + ((long long)tap * kDim + c0) * kDim);
-      const float4 w0 = __ldg(wp + tid), w1 = __ldg(wp + 256 + tid);
+      // (transposed use: Bs[kk][col] = w[tap][col][c0 + kk], each thread 8 consecutive kk of one col)
+      const float4* wp0 = a.w_nt
+          ? reinterpret_cast<const float4*>(a.w + ((long long)tap * kDim + lrow) * kDim + c0 + lhalf * 8)
+          : reinterpret_cast<const float4*>(a.w + ((long long)tap * kDim + c0) * kDim) + tid;
+      const float4 w0 = __ldg(wp0), w1 = __ldg(wp0 + (a.w_nt ? 1 : 256));
       __syncthreads();           // previous chunk fully consumed
 #pragma unroll
       for (int i = 0; i < 8; ++i) As[lhalf * 8 + i][lrow] = v[i];
-      reinterpret_cast<float4*>(&Bs[0][0])[tid] = w0;
-      reinterpret_cast<float4*>(&Bs[0][0])[256 + tid] = w1;
+      if (a.w_nt) {
+        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) Bs[lhalf * 8 + i][lrow] = wv[i];
+      } else {
+        reinterpret_cast<float4*>(&Bs[0][0])[tid] = w0;
+        reinterpret_cast<float4*>(&Bs[0][0])[256 + tid] = w1;
+      }
       __syncthreads();
 #pragma unroll
       for (int kk = 0; kk < kTK; ++kk) {
@@ -131,18 +131,23 @@ k2_level_f32(LevelArgs a, SlotTable slots) {
 #pragma unroll
     for (int jh = 0; jh < 2; ++jh) {
       const int c = jh * 64 + tx * 4;
-      float o[4];
+      float o[4], ax[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         float v = acc[i][jh * 4 + j];
         if (a.bias) v += __ldg(a.bias + c + j);
         if (sb) v += __ldg(sb + c + j);
-        if (a.conv_epilogue) {
+        if (a.conv_epilogue == 1) {
           v = fmaxf(v, 0.f);
+          ax[j] = v;
           v = fmaxf(v + load_act(a.in, a.in_bf16, r * kDim + c + j), 0.f);
+        } else if (a.conv_epilogue == 2) {
+          v += a.resid[r * kDim + c + j];
         }
         o[j] = v;
       }
+      if (a.aux && a.conv_epilogue == 1)
+        *reinterpret_cast<float4*>(a.aux + r * kDim + c) = make_float4(ax[0], ax[1], ax[2], ax[3]);
       if (a.out_bf16) {
         uint2 q = make_uint2(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]));
         *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(a.out) + dst * kDim + c) = q;
@@ -151,6 +156,12 @@ k2_level_f32(LevelArgs a, SlotTable slots) {
       }
     }
   }
+}
+
+int32_t k2_level_launch(const LevelArgs& a, const SlotTable& slots, cudaStream_t st) {
+  k2_level_f32<<<ceil_div(a.R, kTM), kK2Threads, 0, st>>>(a, slots);
+  HTCN_LAUNCH_CHECK("k2_level_f32");
+  return HTCN_OK;
 }
 
 int32_t tcn_forward_f32(const void* xe, int xe_dtype, const float* w_in_x, const float* sbias,

@@ -48,7 +48,8 @@ __device__ __forceinline__ void dot_block(float (&acc)[NU], const float* __restr
 __global__ void __launch_bounds__(kGruThreads, 1)
 k3_gru_sessions(const float* __restrict__ yp, const float* __restrict__ mask, const float* __restrict__ state_in,
                 GruWeights W, const float* __restrict__ w_in_state, int B, int S,
-                float* __restrict__ state_pre, float* __restrict__ sbias, float* __restrict__ state_out) {
+                float* __restrict__ state_pre, float* __restrict__ sbias, float* __restrict__ state_out,
+                float* __restrict__ gates_save /* [S][G][3][B][128] = r, u, c of every cell call, or NULL */) {
   extern __shared__ float smem[];
   const int G = W.num_layer;
   float* xin = smem;                         // [kUB][128]   layer-0 input of this step
@@ -102,12 +103,21 @@ k3_gru_sessions(const float* __restrict__ yp, const float* __restrict__ mask, co
         dot_block<kUB>(acc, inp, 0, W.gate_w[g], 2 * kDim, tid);
         dot_block<kUB>(acc, hg, 0, W.gate_w[g] + (long long)kDim * 2 * kDim, 2 * kDim, tid);
         const float bias = __ldg(W.gate_b[g] + tid);
+        float* gsave = gates_save ? gates_save + ((long long)(s * G + g) * 3 + (tid < kDim ? 0 : 1)) * B * kDim : nullptr;
         if (tid < kDim) {
 #pragma unroll
-          for (int u = 0; u < kUB; ++u) rh[u * kDim + tid] = sigmoid_f(acc[u] + bias) * hg[u * kDim + tid];
+          for (int u = 0; u < kUB; ++u) {
+            const float r = sigmoid_f(acc[u] + bias);
+            rh[u * kDim + tid] = r * hg[u * kDim + tid];
+            if (gsave && b0 + u < B) gsave[(long long)(b0 + u) * kDim + tid] = r;
+          }
         } else {
 #pragma unroll
-          for (int u = 0; u < kUB; ++u) ug[u * kDim + tid - kDim] = sigmoid_f(acc[u] + bias);
+          for (int u = 0; u < kUB; ++u) {
+            const float z = sigmoid_f(acc[u] + bias);
+            ug[u * kDim + tid - kDim] = z;
+            if (gsave && b0 + u < B) gsave[(long long)(b0 + u) * kDim + tid - kDim] = z;
+          }
         }
       }
       __syncthreads();
@@ -126,6 +136,8 @@ k3_gru_sessions(const float* __restrict__ yp, const float* __restrict__ mask, co
           const float c = tanhf(acc[u] + bias);
           const float uu = ug[i];
           hg[i] = uu * hg[i] + (1.0f - uu) * c;
+          if (gates_save && b0 + u0 + u < B)
+            gates_save[((long long)(s * G + g) * 3 + 2) * B * kDim + (long long)(b0 + u0 + u) * kDim + col] = c;
         }
       }
       __syncthreads();
@@ -151,12 +163,12 @@ int32_t gru_sessions_bf16(const float* yp, const float* mask, const float* state
 
 }  // namespace htcn
 
-extern "C" int32_t htcn_gru_sessions(const float* yp, const float* mask, const float* state_in,
-                                     const float* const* gate_w_host, const float* const* gate_b_host,
-                                     const float* const* cand_w_host, const float* const* cand_b_host,
-                                     int32_t num_layer, const float* w_in_state, int32_t B, int32_t S,
-                                     int32_t precision, float* scratch,
-                                     float* state_pre, float* sbias, float* state_out, void* stream) {
+static int32_t gru_sessions_impl(const float* yp, const float* mask, const float* state_in,
+                                 const float* const* gate_w_host, const float* const* gate_b_host,
+                                 const float* const* cand_w_host, const float* const* cand_b_host,
+                                 int32_t num_layer, const float* w_in_state, int32_t B, int32_t S,
+                                 int32_t precision, float* scratch,
+                                 float* state_pre, float* sbias, float* state_out, float* gates_save, void* stream) {
   using namespace htcn;
   HTCN_REQUIRE(yp && mask && state_in && state_out && gate_w_host && gate_b_host && cand_w_host && cand_b_host,
                "gru_sessions: NULL pointer");
@@ -182,7 +194,31 @@ extern "C" int32_t htcn_gru_sessions(const float* yp, const float* mask, const f
   const size_t smem = sizeof(float) * (size_t)(3 + num_layer) * kUB * kDim;
   HTCN_CUDA(cudaFuncSetAttribute(k3_gru_sessions, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k3_gru_sessions<<<ceil_div(B, kUB), kGruThreads, smem, as_stream(stream)>>>(
-      yp, mask, state_in, W, w_in_state, B, S, state_pre, sbias, state_out);
+      yp, mask, state_in, W, w_in_state, B, S, state_pre, sbias, state_out, gates_save);
   HTCN_LAUNCH_CHECK("k3_gru_sessions");
   return HTCN_OK;
+}
+
+extern "C" int32_t htcn_gru_sessions(const float* yp, const float* mask, const float* state_in,
+                                     const float* const* gate_w_host, const float* const* gate_b_host,
+                                     const float* const* cand_w_host, const float* const* cand_b_host,
+                                     int32_t num_layer, const float* w_in_state, int32_t B, int32_t S,
+                                     int32_t precision, float* scratch,
+                                     float* state_pre, float* sbias, float* state_out, void* stream) {
+  return gru_sessions_impl(yp, mask, state_in, gate_w_host, gate_b_host, cand_w_host, cand_b_host, num_layer, w_in_state,
+                           B, S, precision, scratch, state_pre, sbias, state_out, nullptr, stream);
+}
+
+// fp32 forward that also saves the gate activations (r, u, c of every cell call) and the pre-step states for
+// htcn_gru_backward
+extern "C" int32_t htcn_gru_sessions_train(const float* yp, const float* mask, const float* state_in,
+                                           const float* const* gate_w_host, const float* const* gate_b_host,
+                                           const float* const* cand_w_host, const float* const* cand_b_host,
+                                           int32_t num_layer, const float* w_in_state, int32_t B, int32_t S,
+                                           float* state_pre, float* sbias, float* state_out, float* gates_save,
+                                           void* stream) {
+  using namespace htcn;
+  HTCN_REQUIRE(state_pre && gates_save, "gru_sessions_train: state_pre and gates_save are required");
+  return gru_sessions_impl(yp, mask, state_in, gate_w_host, gate_b_host, cand_w_host, cand_b_host, num_layer, w_in_state,
+                           B, S, HTCN_F32, nullptr, state_pre, sbias, state_out, gates_save, stream);
 }

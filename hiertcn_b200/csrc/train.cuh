@@ -1,0 +1,44 @@
+// Internal building blocks of the training step (backward + Adam), fp32 on the FMA pipe.
+// The reference trains with tf.train.AdamOptimizer(lr).minimize(loss) (model.py:134-141); TensorFlow's autodiff
+// produces dense gradients for every variable (the one-hot matmuls make even the embedding gradients dense).
+#pragma once
+
+#include "common.cuh"
+
+namespace htcn {
+
+// one level of the fp32 conv stack (k2_tcn_f32.cu), also used transposed / anti-causal by the backward
+struct LevelArgs {
+  const void* in;             // [R,128] f32 (or bf16 when in_bf16)
+  const float* w;             // [K,128,128]
+  const float* bias;          // [128] or NULL
+  const float* sbias;         // [S,B,128] or NULL
+  void* out;                  // [R or n_out,128]
+  const int* out_row;         // [R] or NULL
+  long long R;
+  int T, B, K, dil;
+  int conv_epilogue;          // 1: relu, +residual, relu; 0: linear; 2: + resid[r,:] (backward: data gradient)
+  int in_bf16, out_bf16;
+  float* aux;                 // [R,128] relu(conv + bias) before the residual add, saved for the backward, or NULL
+  const float* resid;         // [R,128] added in epilogue 2 (may alias out)
+  int anti;                   // 1: taps read r + shift, zero beyond the END of r's sequence (transposed convolution)
+  int w_nt;                   // 1: every W[tap] is applied transposed
+};
+int32_t k2_level_launch(const LevelArgs& a, const SlotTable& slots, cudaStream_t st);
+
+// C[M,N] (+)= A[M,K] * op(B).  trans_b = 0: B is [K,N] with leading dimension ldb; trans_b = 1: B is [N,K].
+// N % 128 == 0, K % 16 == 0, all leading dimensions multiples of 4 floats, 16-byte aligned bases.
+int32_t sgemm(bool trans_b, long long M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
+              int ldc, bool accumulate, cudaStream_t st);
+
+// Split-K "TN" product with atomic accumulation, the weight-gradient form:
+//     C[c, f] += sum_{r < R} A[src(r), c] * D[r, f]        c, f in [0,128)
+// src(r) = r - shift, taken as a zero row when r's position inside its sequence is < shift (the causal left pad of
+// customized_tcn_cell.py:46-49); shift = 0 (and slots == nullptr) for plain products.
+int32_t sgemm_tn_atomic(long long R, const float* A, int lda, const float* D, int ldd, float* C, int ldc, int shift,
+                        int T, const SlotTable* slots, cudaStream_t st);
+
+// out[f] += sum_r D[r, f]  (f < cols, cols <= 256)
+int32_t colsum_atomic(long long R, const float* D, int ldd, int cols, float* out, cudaStream_t st);
+
+}  // namespace htcn

@@ -1,0 +1,253 @@
+"""Training step of the hot path: forward with saved activations, backward, TF-flavoured Adam -- the B200 replacement of
+``sess.run([train_op, loss, state, ...])`` (reference run_hier_xing.py:301-302; train_op =
+``tf.train.AdamOptimizer(lr).minimize(loss)``, model.py:134-141; lr schedule run_hier_xing.py:265-269).
+
+All arithmetic is in libhtcn.so (include/htcn.h, "Training step"); torch provides device memory, streams and the NCCL
+all-reduce of the gradients for data-parallel training.  fp32 like the reference.
+
+Every parameter, gradient and Adam moment lives in ONE flat fp32 buffer each, so the optimiser is a single launch and the
+data-parallel exchange a single all-reduce.  The output table is kept as W_out^T [N,128] (what the scoring kernels read);
+``state_dict()`` transposes it back to the TF variable layout.  Like TensorFlow's gradients through the one-hot matmuls,
+the embedding / output-table gradients are dense, and Adam's moment decay touches every row every step.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from . import _cabi as cabi
+from .model_hier import D, HierTCN, _torch
+
+
+class HierTCNTrainer:
+    """``Trainer(model).train_step(x_list, y_list, mask_list, state)`` == one ``sess.run([train_op, loss, state])``.
+
+    model: a built fp32-tier ``HierTCN``; its parameter tensors are re-homed into the flat buffer (the model keeps
+    working for evaluation and sees every update).  ``dist``: a torch.distributed module with an initialised process
+    group for data-parallel training over users (gradients and the user count are all-reduced), or None."""
+
+    def __init__(self, model: HierTCN, learning_rate=None, beta1=0.9, beta2=0.999, eps=1e-8, dist=None, world=1):
+        torch = _torch()
+        if not model.built:
+            model.build()
+        if model.precision != "f32":
+            raise NotImplementedError("training runs in the fp32 tier (the reference's precision); build the model with "
+                                      "precision='f32'")
+        if model.n_out != model.N:
+            raise NotImplementedError("training with a catalog-sharded output table")
+        self.m, self.dist, self.world = model, dist, int(world)
+        self.lr = float(model.args.learning_rate if learning_rate is None else learning_rate)
+        self.beta1, self.beta2, self.eps = float(beta1), float(beta2), float(eps)
+        self.t = 0
+        m = model
+        N, G, L, K = m.N, m.G, m.n_levels, m.K
+        spec = [("E", (N, D)), ("wt", (N, D)), ("b_out", (N,)), ("b_emb", (D,)), ("w_in_x", (D, D)),
+                ("w_in_state", (G * D, D))]
+        for l in range(L):
+            spec += [(f"conv_w{l}", (K, D, D)), (f"conv_b{l}", (D,))]
+        for g in range(G):
+            spec += [(f"gate_w{g}", (2 * D, 2 * D)), (f"gate_b{g}", (2 * D,)), (f"cand_w{g}", (2 * D, D)), (f"cand_b{g}", (D,))]
+        self.spec, self.offsets, off = spec, {}, 0
+        for name, shape in spec:
+            self.offsets[name] = off
+            off += -(-int(np.prod(shape)) // 4) * 4                 # 16-byte aligned segments
+        self.n_flat = off
+        f32 = torch.float32
+        self.params = torch.zeros(off, dtype=f32, device=m.device)
+        self.grads = torch.zeros(off, dtype=f32, device=m.device)
+        self.adam_m = torch.zeros(off, dtype=f32, device=m.device)
+        self.adam_v = torch.zeros(off, dtype=f32, device=m.device)
+        cur = {"E": m.E, "wt": m.wt, "b_out": m.b_out, "b_emb": m.b_emb, "w_in_x": m.w_in_x, "w_in_state": m.w_in_state}
+        for l in range(L):
+            cur[f"conv_w{l}"], cur[f"conv_b{l}"] = m.conv_w[l], m.conv_b[l]
+        for g in range(G):
+            cur[f"gate_w{g}"], cur[f"gate_b{g}"], cur[f"cand_w{g}"], cur[f"cand_b{g}"] = m.gru[g]
+        self.p, self.g = {}, {}
+        for name, shape in spec:
+            self.p[name] = self._view(self.params, name, shape)
+            self.g[name] = self._view(self.grads, name, shape)
+            self.p[name].copy_(cur[name].reshape(shape))
+        # re-home the model's tensors (views of the flat buffer: updates are visible to forward / evaluation)
+        m.E, m.wt, m.b_out, m.b_emb = self.p["E"], self.p["wt"], self.p["b_out"], self.p["b_emb"]
+        m.wt_f32 = m.wt
+        m.w_in_x, m.w_in_state = self.p["w_in_x"], self.p["w_in_state"]
+        m.conv_w = [self.p[f"conv_w{l}"] for l in range(L)]
+        m.conv_b = [self.p[f"conv_b{l}"] for l in range(L)]
+        m.gru = [tuple(self.p[f"{n}{g}"] for n in ("gate_w", "gate_b", "cand_w", "cand_b")) for g in range(G)]
+        m._conv_w_pp = cabi.ptr_array([t.data_ptr() for t in m.conv_w])
+        m._conv_b_pp = cabi.ptr_array([t.data_ptr() for t in m.conv_b])
+        m._gru_pp = [cabi.ptr_array([l[i].data_ptr() for l in m.gru]) for i in range(4)]
+        self._d_conv_w = cabi.ptr_array([self.g[f"conv_w{l}"].data_ptr() for l in range(L)])
+        self._d_conv_b = cabi.ptr_array([self.g[f"conv_b{l}"].data_ptr() for l in range(L)])
+        self._d_gru = [cabi.ptr_array([self.g[f"{n}{g}"].data_ptr() for g in range(G)])
+                       for n in ("gate_w", "gate_b", "cand_w", "cand_b")]
+        torch.cuda.synchronize(m.device)
+
+    def _view(self, flat, name, shape):
+        o = self.offsets[name]
+        return flat[o:o + int(np.prod(shape))].view(*shape)
+
+    # ------------------------------------------------------------------ forward + backward
+    def forward_backward(self, x_list=None, y_list=None, mask_list=None, state=None, staged=None, metrics=False):
+        """Accumulates the gradients of sum_b(sum_t loss/(n_b+1e-6)) into ``self.grads`` (the 1/user_count is applied by
+        the optimiser).  Returns dict(scalars [8] device: loss, ..., user_count, n_valid; state [B,G*H] device)."""
+        torch = _torch()
+        m = self.m
+        d = staged if staged is not None else m.stage(x_list, y_list, mask_list, state)
+        B, T, S, Q = d["B"], d["T"], d["S"], d["Q"]
+        G, L, K, N = m.G, m.n_levels, m.K, m.N
+        R = B * T
+        st = m.stream_ptr()
+        f32 = torch.float32
+        P = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
+        slot_p, slot_keep = cabi.int_array(d["slot_off"])
+        buf = m._buf
+        # ---- forward, keeping what the backward needs
+        xe = buf("tr_xe", (R, D), f32)
+        yp = buf("tr_yp", (S, B, D), f32)
+        cabi.call("htcn_gather_meanpool", m.E.data_ptr(), m.b_emb.data_ptr(), N, d["x_id"].data_ptr(), d["y_id"].data_ptr(),
+                  slot_p, B, T, S, xe.data_ptr(), cabi.HTCN_F32, yp.data_ptr(), st)
+        state_pre = buf("tr_state_pre", (S, B, G * D), f32)
+        sbias = buf("tr_sbias", (S, B, D), f32)
+        gates = buf("tr_gates", (S, G, 3, B, D), f32)
+        state_out = torch.empty((B, G * D), dtype=f32, device=m.device)
+        cabi.call("htcn_gru_sessions_train", yp.data_ptr(), d["mask"].data_ptr(), d["state"].data_ptr(), m._gru_pp[0][0],
+                  m._gru_pp[1][0], m._gru_pp[2][0], m._gru_pp[3][0], G, m.w_in_state.data_ptr(), B, S,
+                  state_pre.data_ptr(), sbias.data_ptr(), state_out.data_ptr(), gates.data_ptr(), st)
+        h_save = buf("tr_h_save", (L + 1, R, D), f32)
+        a_save = buf("tr_a_save", (max(L, 1), R, D), f32)
+        hout = buf("tr_hout", (max(Q, 1), D), f32)
+        cabi.call("htcn_tcn_forward_train", xe.data_ptr(), m.w_in_x.data_ptr(), sbias.data_ptr(), m._conv_w_pp[0],
+                  m._conv_b_pp[0], L, K, slot_p, B, T, S, d["row_of"].data_ptr(), h_save.data_ptr(), a_save.data_ptr(),
+                  hout.data_ptr(), st)
+        cabi.note_launches(L + 2)
+        scalars = torch.zeros(8, dtype=f32, device=m.device)
+        if Q == 0:
+            return dict(scalars=scalars, state=state_out)
+        # ---- loss (one streaming sweep: log-sum-exp per row, optionally the rank metrics)
+        ns = m.n_split_for(Q, N)
+        zy = buf("zy", (Q,), f32)
+        pm, ps = buf("pm", (ns, Q), f32), buf("ps", (ns, Q), f32)
+        pc = buf("pc", (ns, Q), torch.int32) if metrics else None
+        cabi.call("htcn_target_logit", hout.data_ptr(), cabi.HTCN_F32, Q, m.wt.data_ptr(), m.b_out.data_ptr(), N, 0,
+                  d["y_rows"].data_ptr(), zy.data_ptr(), st)
+        cabi.call("htcn_score_ce_rank_topk", hout.data_ptr(), cabi.HTCN_F32, Q, m.wt.data_ptr(), m.b_out.data_ptr(), N, 0,
+                  d["y_rows"].data_ptr(), zy.data_ptr(), 1, cabi.SCORE_CE | (cabi.SCORE_RANK if metrics else 0), 0, ns,
+                  pm.data_ptr(), ps.data_ptr(), P(pc), None, None, st)
+        cabi.note_launches(-1)
+        loss_row = buf("loss_row", (Q,), f32)
+        rank_row = buf("rank_row", (Q,), f32) if metrics else None
+        cabi.call("htcn_score_finish", pm.data_ptr(), ps.data_ptr(), P(pc), ns, Q, d["y_rows"].data_ptr(), zy.data_ptr(),
+                  loss_row.data_ptr(), P(rank_row), st)
+        cabi.call("htcn_loss_metrics_reduce", loss_row.data_ptr(), P(rank_row), d["row_of"].data_ptr(), d["y_id"].data_ptr(),
+                  B, T, N, None, None, None, buf("user_part", (B, 8), f32).data_ptr(), scalars.data_ptr(), st)
+        # ---- backward
+        g_row = buf("tr_g_row", (Q,), f32)
+        cabi.call("htcn_loss_row_weights", d["y_id"].data_ptr(), d["row_of"].data_ptr(), B, T, g_row.data_ptr(), st)
+        d_hout = buf("tr_d_hout", (Q, D), f32)
+        cabi.call("htcn_score_ce_backward", hout.data_ptr(), cabi.HTCN_F32, Q, m.wt.data_ptr(), m.b_out.data_ptr(), N, 0,
+                  d["y_rows"].data_ptr(), loss_row.data_ptr(), zy.data_ptr(), g_row.data_ptr(), d_hout.data_ptr(),
+                  self.g["wt"].data_ptr(), self.g["b_out"].data_ptr(), st)
+        d_sbias = buf("tr_d_sbias", (S, B, D), f32)
+        d_xe = buf("tr_d_xe", (R, D), f32)
+        k2_scratch = buf("tr_k2_scratch", (2, R, D), f32)
+        cabi.call("htcn_tcn_backward", d_hout.data_ptr(), d["row_of"].data_ptr(), xe.data_ptr(), m.w_in_x.data_ptr(),
+                  m._conv_w_pp[0], L, K, slot_p, B, T, S, h_save.data_ptr(), a_save.data_ptr(), k2_scratch.data_ptr(),
+                  self._d_conv_w[0], self._d_conv_b[0], self.g["w_in_x"].data_ptr(), d_sbias.data_ptr(), d_xe.data_ptr(), st)
+        cabi.note_launches(1 + L * (K + 3) + 3)
+        d_yp = buf("tr_d_yp", (S, B, D), f32)
+        n_scr = int(cabi.load().htcn_gru_backward_scratch_floats(B, S, G))
+        k3_scratch = buf("tr_k3_scratch", (n_scr,), f32)
+        cabi.call("htcn_gru_backward", yp.data_ptr(), d["mask"].data_ptr(), state_pre.data_ptr(), gates.data_ptr(),
+                  m._gru_pp[0][0], m._gru_pp[2][0], G, m.w_in_state.data_ptr(), B, S, d_sbias.data_ptr(),
+                  k3_scratch.data_ptr(), self._d_gru[0][0], self._d_gru[1][0], self._d_gru[2][0], self._d_gru[3][0],
+                  self.g["w_in_state"].data_ptr(), d_yp.data_ptr(), st)
+        cabi.note_launches(G * (S + 1) + 4 * S * G + 9 * G)
+        cabi.call("htcn_gather_backward", d_xe.data_ptr(), d_yp.data_ptr(), d["x_id"].data_ptr(), d["y_id"].data_ptr(),
+                  slot_p, B, T, S, N, self.g["E"].data_ptr(), self.g["b_emb"].data_ptr(), st)
+        del slot_keep
+        return dict(scalars=scalars, state=state_out)
+
+    # ------------------------------------------------------------------ optimiser
+    def lr_t(self, lr=None):
+        lr = self.lr if lr is None else float(lr)
+        return lr * math.sqrt(1.0 - self.beta2 ** self.t) / (1.0 - self.beta1 ** self.t)
+
+    def apply_gradients(self, scalars, lr=None):
+        """All-reduce (data parallel) and apply one Adam step; clears the gradient buffer."""
+        if self.world > 1:
+            self.dist.all_reduce(self.grads)
+            from .dist import allreduce_scalars
+            scalars = allreduce_scalars(scalars, self.dist, self.world)
+        self.t += 1
+        cabi.call("htcn_adam_step", self.params.data_ptr(), self.grads.data_ptr(), self.adam_m.data_ptr(),
+                  self.adam_v.data_ptr(), self.n_flat, self.lr_t(lr), self.beta1, self.beta2, self.eps,
+                  scalars[6:7].data_ptr(), 1, self.m.stream_ptr())
+        return scalars
+
+    def train_step(self, x_list, y_list, mask_list, state=None, lr=None, metrics=False, state_on_device=False):
+        """One optimisation step on one batch.  Returns dict(loss, user_count, n_valid, state [+ metrics]); ``state`` is
+        the carried user state for the next batch (numpy, or the device tensor with ``state_on_device``)."""
+        r = self.forward_backward(x_list, y_list, mask_list, state, metrics=metrics)
+        sc = self.apply_gradients(r["scalars"], lr).cpu().numpy()
+        out = dict(loss=float(sc[0]), user_count=float(sc[6]), n_valid=float(sc[7]))
+        if metrics:
+            out.update(recall1=float(sc[1]), recall5=float(sc[2]), recall10=float(sc[3]), mrr=float(sc[4]), mrp=float(sc[5]))
+        out["state"] = r["state"] if state_on_device else r["state"].cpu().numpy()
+        return out
+
+    # ------------------------------------------------------------------ inspection / checkpoint
+    def named_gradients(self, user_count, clear=True):
+        """Gradients of the reference loss (model.py:117) keyed by TF variable name, as fp64 numpy; call after
+        ``forward_backward`` with user_count = its scalars[6]."""
+        g = {k: (v.detach().cpu().numpy().astype(np.float64) / float(user_count)) for k, v in self.g.items()}
+        if clear:
+            self.grads.zero_()
+        return self._to_tf_names(g)
+
+    def state_dict(self):
+        """Current weights keyed by the TF variable names of SURVEY.md A.6 (numpy fp32)."""
+        return {k: v.astype(np.float32) for k, v in self._to_tf_names({k: v.detach().cpu().numpy() for k, v in self.p.items()}).items()}
+
+    def _to_tf_names(self, t):
+        m = self.m
+        w = {"hier/emb/kernel": t["E"], "hier/emb/bias": t["b_emb"],
+             "hier/tcn/emb/kernel": np.concatenate([t["w_in_x"], t["w_in_state"]], 0),
+             "hier/tcn/dense/kernel": np.ascontiguousarray(t["wt"].T), "hier/tcn/dense/bias": t["b_out"]}
+        for l in range(m.n_levels):
+            w[f"hier/tcn/temporal_conv_net/tblock_{l}/conv1/kernel"] = t[f"conv_w{l}"]
+            w[f"hier/tcn/temporal_conv_net/tblock_{l}/conv1/bias"] = t[f"conv_b{l}"]
+        for g in range(m.G):
+            p = f"hier/multi_rnn_cell/cell_{g}/gru_cell"
+            w[p + "/gates/kernel"], w[p + "/gates/bias"] = t[f"gate_w{g}"], t[f"gate_b{g}"]
+            w[p + "/candidate/kernel"], w[p + "/candidate/bias"] = t[f"cand_w{g}"], t[f"cand_b{g}"]
+        return w
+
+
+def lr_for_epoch(base_lr, epoch, lr_schedule=True):
+    """run_hier_xing.py:265-269: the learning rate is divided by 5 when epoch 60 starts and again at epoch 120."""
+    if not lr_schedule:
+        return base_lr
+    return base_lr / (5.0 if epoch >= 60 else 1.0) / (5.0 if epoch >= 120 else 1.0)
+
+
+def run_hier(trainer: HierTCNTrainer, loader_train, epochs, epoch_batches_train, lr_schedule=True, start_epoch=0,
+             on_epoch_end=None, verbose=False):
+    """The training half of reference run_hier_xing.py:257-307: ``epoch_batches_train`` steps per epoch, the user state
+    carried across batches (on the device here), the step-wise lr schedule.  Returns the per-epoch mean training loss."""
+    state, hist = None, []
+    for epoch in range(start_epoch, epochs):
+        lr = lr_for_epoch(trainer.lr, epoch, lr_schedule)
+        tot = 0.0
+        for _ in range(epoch_batches_train):
+            x_list, y_list, mask_list, _info = loader_train.get_batch()
+            out = trainer.train_step(x_list, y_list, mask_list, state, lr=lr, state_on_device=True)
+            state = out["state"]
+            tot += out["loss"]
+        hist.append(tot / max(1, epoch_batches_train))
+        if verbose:
+            print("epoch %d lr %.5f training loss %.5f" % (epoch, lr, hist[-1]))
+        if on_epoch_end is not None:
+            on_epoch_end(epoch, trainer)
+    return hist

@@ -235,6 +235,84 @@ int32_t htcn_sampled_rank_loss(const void* pred, int32_t precision, int32_t Q, c
 int32_t htcn_calc_score(const void* pred, int32_t precision, int32_t Q, const float* table,
                         const int32_t* cand_id, int32_t k, int32_t rank_metric, float* score, void* stream);
 
+/* =============================================================================================
+ * Training step: replaces tf.train.AdamOptimizer(lr).minimize(loss) of model.py:134-141,
+ * i.e. TensorFlow's autodiff of the graph of model.py:54-117 + the Adam update, run by
+ * sess.run([train_op, loss, state, ...]) in run_hier_xing.py:301-302.  fp32 throughout (the reference's
+ * precision); every gradient buffer is ACCUMULATED into (+=) unless stated, so the caller zeroes them once
+ * per step (htcn_adam_step can do it while it reads them).  Gradients are those of
+ *     sum_b ( sum_t loss[b,t] / (n_b + 1e-6) )            (model.py:110-116)
+ * and the 1/user_count of model.py:117 is applied by htcn_adam_step (grad_div), so that data-parallel ranks
+ * can all-reduce(SUM) gradients and user_count first.  The carried state is a placeholder in the reference
+ * (model.py:44): no gradient flows into state_in.
+ * ============================================================================================= */
+
+/* g_row[row_of[b,t]] = 1 / (n_b + 1e-6) for every scored position; y_id [B,T], row_of [B*T], g_row [Q]. */
+int32_t htcn_loss_row_weights(const int32_t* y_id, const int32_t* row_of, int32_t B, int32_t T, float* g_row,
+                              void* stream);
+
+/* Backward of dense(pred, N) + softmax_cross_entropy_with_logits (model_tcn.py:41, loss.py:20-21) without
+ * materialising [Q,N]: recomputes the logits tile by tile from hout [Q,128] (f32 or bf16) and the fp32 table
+ * w_out_t [n_items,128] / b_out, using lse_row = loss_row + target_logit from the forward sweep.
+ * d_hout [Q,128] is overwritten; d_w_out_t [n_items,128] and d_b_out [n_items] are accumulated. */
+int32_t htcn_score_ce_backward(const void* hout, int32_t hout_dtype, int32_t Q, const float* w_out_t,
+                               const float* b_out, int32_t n_items, int32_t n0, const int32_t* y_id,
+                               const float* loss_row, const float* target_logit, const float* g_row,
+                               float* d_hout, float* d_w_out_t, float* d_b_out, void* stream);
+
+/* K2 forward that keeps what the backward needs: h_save [(n_levels+1), B*T, 128] (the in-projection output and
+ * every level's output) and a_save [n_levels, B*T, 128] (relu(conv+bias) before the residual add);
+ * hout [Q,128] f32 = rows of the last level compacted through out_row [B*T] (-1 = not scored). */
+int32_t htcn_tcn_forward_train(const float* xe, const float* w_in_x, const float* sbias,
+                               const float* const* conv_w_host, const float* const* conv_b_host, int32_t n_levels,
+                               int32_t kernel_size, const int32_t* slot_off_host, int32_t B, int32_t T, int32_t S,
+                               const int32_t* out_row, float* h_save, float* a_save, float* hout, void* stream);
+
+/* Backward of the conv stack + in-projection (customized_tcn_cell.py:109-127, model_tcn.py:35).
+ * scratch: 2*B*T*128 floats.  d_conv_w[l] [K,128,128], d_conv_b[l] [128], d_w_in_x [128,128] accumulated;
+ * d_sbias [S,B,128] and d_xe [B*T,128] overwritten. */
+int32_t htcn_tcn_backward(const float* d_hout, const int32_t* out_row, const float* xe, const float* w_in_x,
+                          const float* const* conv_w_host, int32_t n_levels, int32_t kernel_size,
+                          const int32_t* slot_off_host, int32_t B, int32_t T, int32_t S, const float* h_save,
+                          const float* a_save, float* scratch, float* const* d_conv_w_host,
+                          float* const* d_conv_b_host, float* d_w_in_x, float* d_sbias, float* d_xe, void* stream);
+
+/* K3 fp32 forward that also saves state_pre [S,B,G*128] and gates_save [S,G,3,B,128] (r, u, c of every cell). */
+int32_t htcn_gru_sessions_train(const float* yp, const float* mask, const float* state_in,
+                                const float* const* gate_w_host, const float* const* gate_b_host,
+                                const float* const* cand_w_host, const float* const* cand_b_host, int32_t num_layer,
+                                const float* w_in_state, int32_t B, int32_t S, float* state_pre, float* sbias,
+                                float* state_out, float* gates_save, void* stream);
+
+/* Back-propagation through the S session steps (model_hier.py:30-37,91,93), truncated at the batch boundary.
+ * d_sbias [S,B,128] comes from htcn_tcn_backward.  scratch: htcn_gru_backward_scratch_floats(B,S,G) floats.
+ * Weight / bias gradients and d_w_in_state [G*128,128] are accumulated; d_yp [S,B,128] is overwritten.
+ * Requires G*128 == 256. */
+int64_t htcn_gru_backward_scratch_floats(int32_t B, int32_t S, int32_t num_layer);
+int32_t htcn_gru_backward(const float* yp, const float* mask, const float* state_pre, const float* gates_save,
+                          const float* const* gate_w_host, const float* const* cand_w_host, int32_t num_layer,
+                          const float* w_in_state, int32_t B, int32_t S, const float* d_sbias, float* scratch,
+                          float* const* d_gate_w_host, float* const* d_gate_b_host, float* const* d_cand_w_host,
+                          float* const* d_cand_b_host, float* d_w_in_state, float* d_yp, void* stream);
+
+/* Backward of K1 (model.py:59-61, model_hier.py:50,83-85): d_emb[x] += d_xe[b,t]; d_emb[y] += d_yp[s,b] / n_{b,s};
+ * d_emb_bias += sum_{s,b} d_yp[s,b].  d_emb [item_num,128] is the DENSE gradient TensorFlow produces. */
+int32_t htcn_gather_backward(const float* d_xe, const float* d_yp, const int32_t* x_id, const int32_t* y_id,
+                             const int32_t* slot_off_host, int32_t B, int32_t T, int32_t S, int32_t item_num,
+                             float* d_emb, float* d_emb_bias, void* stream);
+
+/* tf.train.AdamOptimizer update over a flat parameter buffer of n floats (n % 4 == 0):
+ *     g' = grad / *grad_div (grad_div: device scalar, e.g. the global user_count; NULL = 1)
+ *     m = b1 m + (1-b1) g';  v = b2 v + (1-b2) g'^2;  param -= lr_t m / (sqrt(v) + eps)
+ * with lr_t = lr sqrt(1 - b2^t) / (1 - b1^t) computed by the caller (t = 1-based step).  zero_grad != 0 clears
+ * grad for the next step. */
+int32_t htcn_adam_step(float* param, float* grad, float* m, float* v, int64_t n, float lr_t, float beta1, float beta2,
+                       float eps, const float* grad_div, int32_t zero_grad, void* stream);
+
+/* After an update of the fp32 master W_out^T [N,128] / b_out: rebuild the bf16 scoring layout [N,144]. */
+int32_t htcn_refresh_wout(const float* w_out_t_f32, const float* b_out, int32_t N, void* w_out_t, int32_t dtype,
+                          void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,196 @@
+"""GPU parity of the training step (backward kernels + Adam, include/htcn.h "Training step") against the autograd /
+TF-Adam oracle (oracle/grad_oracle.py), through the C ABI and the Python trainer."""
+import numpy as np
+import pytest
+
+from helpers import load_hier_golden, small_case
+from oracle import grad_oracle as GO
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def make_trainer(w, N, lr=1e-2, levels=2, K=5):
+    from hiertcn_b200.args import make_args
+    from hiertcn_b200.model_hier import HierTCN
+    from hiertcn_b200.train import HierTCNTrainer
+    a = make_args(["--item_num", str(N), "--tcn_channel", ",".join(["128"] * levels), "--kernel_size", str(K)])
+    return HierTCNTrainer(HierTCN(a, w, precision="f32").build(), learning_rate=lr)
+
+
+def assert_grads_close(got, ref, tol=2e-4):
+    for k in ref:
+        scale = np.abs(ref[k]).max()
+        err = np.abs(got[k] - ref[k]).max()
+        assert err <= tol * scale + 1e-9, (k, err, scale)
+
+
+@pytest.mark.parametrize("Q,N", [(200, 300), (128, 128), (1, 1000), (333, 20778)])
+def test_score_ce_backward_matches_numpy(Q, N):
+    from hiertcn_b200 import _cabi as cabi
+    rng = np.random.default_rng(Q + N)
+    h = rng.normal(0, 1, (Q, 128)).astype(np.float32)
+    wt = rng.normal(0, 0.2, (N, 128)).astype(np.float32)
+    b = rng.normal(0, 0.5, N).astype(np.float32)
+    y = rng.integers(1, N, Q).astype(np.int32)
+    g = rng.uniform(0.1, 1.0, Q).astype(np.float32)
+    z = h.astype(np.float64) @ wt.astype(np.float64).T + b
+    mx = z.max(1, keepdims=True)
+    lse = (mx + np.log(np.exp(z - mx).sum(1, keepdims=True)))[:, 0]
+    zy = z[np.arange(Q), y]
+    p = np.exp(z - lse[:, None])
+    p[np.arange(Q), y] -= 1.0
+    p *= g[:, None]
+    ref_dh, ref_dw, ref_db = p @ wt, p.T @ h, p.sum(0)
+    h_d, wt_d, b_d, y_d, g_d = dev(h), dev(wt), dev(b), dev(y), dev(g)
+    loss_d, zy_d = dev((lse - zy).astype(np.float32)), dev(zy.astype(np.float32))
+    dh = torch.full((Q, 128), 7.0, device="cuda")             # overwritten
+    dw = torch.ones((N, 128), device="cuda")                  # accumulated into
+    db = torch.ones(N, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    cabi.call("htcn_score_ce_backward", h_d.data_ptr(), cabi.HTCN_F32, Q, wt_d.data_ptr(), b_d.data_ptr(), N, 0,
+              y_d.data_ptr(), loss_d.data_ptr(), zy_d.data_ptr(), g_d.data_ptr(), dh.data_ptr(), dw.data_ptr(), db.data_ptr(), st)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(dh.cpu().numpy(), ref_dh, rtol=0, atol=2e-5 * np.abs(ref_dh).max() + 1e-7)
+    np.testing.assert_allclose(dw.cpu().numpy() - 1.0, ref_dw, rtol=0, atol=2e-5 * np.abs(ref_dw).max() + 2e-6)
+    np.testing.assert_allclose(db.cpu().numpy() - 1.0, ref_db, rtol=0, atol=2e-5 * np.abs(ref_db).max() + 2e-6)
+
+
+def test_adam_step_matches_tf_formula():
+    from hiertcn_b200 import _cabi as cabi
+    rng = np.random.default_rng(0)
+    n = 4096 + 8
+    w = {"a": rng.normal(0, 1, n)}
+    m = {"a": np.zeros(n)}
+    v = {"a": np.zeros(n)}
+    p_d = dev(w["a"].astype(np.float32))
+    m_d, v_d = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    div = dev(np.asarray([4.0], np.float32))
+    st = torch.cuda.current_stream().cuda_stream
+    for t in range(1, 6):
+        g = rng.normal(0, 1, n) * (rng.random(n) < 0.7)       # some exactly-zero gradients
+        g_d = dev((g * 4.0).astype(np.float32))
+        GO.adam_tf(w, {"a": g}, m, v, t, lr=0.01)
+        lr_t = 0.01 * np.sqrt(1 - 0.999 ** t) / (1 - 0.9 ** t)
+        cabi.call("htcn_adam_step", p_d.data_ptr(), g_d.data_ptr(), m_d.data_ptr(), v_d.data_ptr(), n, float(lr_t), 0.9, 0.999,
+                  1e-8, div.data_ptr(), 1, st)
+        assert float(g_d.abs().max()) == 0.0                  # zero_grad
+    np.testing.assert_allclose(p_d.cpu().numpy(), w["a"], rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(m_d.cpu().numpy(), m["a"], rtol=2e-5, atol=1e-7)
+    np.testing.assert_allclose(v_d.cpu().numpy(), v["a"], rtol=2e-5, atol=1e-7)
+
+
+def test_refresh_wout_equals_prepare_wout():
+    from hiertcn_b200 import _cabi as cabi
+    rng = np.random.default_rng(1)
+    N = 1000
+    w_out = rng.normal(0, 0.3, (128, N)).astype(np.float32)
+    b = rng.normal(0, 1, N).astype(np.float32)
+    st = torch.cuda.current_stream().cuda_stream
+    a = torch.zeros((N, 144), dtype=torch.bfloat16, device="cuda")
+    c = torch.ones((N, 144), dtype=torch.bfloat16, device="cuda")
+    w_d, b_d, wt_d = dev(w_out), dev(b), dev(np.ascontiguousarray(w_out.T))
+    cabi.call("htcn_prepare_wout", w_d.data_ptr(), b_d.data_ptr(), N, a.data_ptr(), cabi.HTCN_BF16, st)
+    cabi.call("htcn_refresh_wout", wt_d.data_ptr(), b_d.data_ptr(), N, c.data_ptr(), cabi.HTCN_BF16, st)
+    torch.cuda.synchronize()
+    assert torch.equal(a.view(torch.int16), c.view(torch.int16))
+
+
+@pytest.mark.parametrize("case", [dict(B=5, S=3, L=7, N=97, seed=0), dict(B=9, S=4, L=20, N=997, seed=1, lengths="dense"),
+                                  dict(B=3, S=2, L=1, N=40, seed=2, lengths="dense"),
+                                  dict(B=33, S=10, L=20, N=3001, seed=3, mask_keep=0.8)])
+def test_gradients_match_autograd_oracle(case):
+    x, y, m, s0, w = small_case(**case)
+    N = case["N"]
+    ref_loss, ref_g, ref_state = GO.loss_and_grads(w, x, y, m, s0)
+    tr = make_trainer(w, N)
+    r = tr.forward_backward(x, y, m, s0)
+    sc = r["scalars"].cpu().numpy()
+    assert abs(sc[0] - ref_loss) <= 1e-4 * abs(ref_loss)
+    np.testing.assert_allclose(r["state"].cpu().numpy(), ref_state, rtol=1e-4, atol=1e-5)
+    got = tr.named_gradients(sc[6])
+    assert set(got) == set(ref_g)
+    assert_grads_close(got, ref_g)
+    assert np.all(got["hier/emb/kernel"][0] == 0)           # the null id owns no row gradient
+    assert float(tr.grads.abs().max()) == 0.0                # cleared
+
+
+def test_gradients_on_reference_golden_inputs():
+    """inputs / weights of the fixture made by the reference's own python (forward value pinned there)"""
+    z, x, y, m, w = load_hier_golden("hier_default_arch")
+    ref_loss, ref_g, _ = GO.loss_and_grads(w, x, y, m, z["state0"], int(z["num_layer"]), literal=True)
+    np.testing.assert_allclose(ref_loss, z["loss_f64"], rtol=1e-11)
+    tr = make_trainer(w, int(z["N"]))
+    r = tr.forward_backward(x, y, m, z["state0"])
+    sc = r["scalars"].cpu().numpy()
+    assert abs(sc[0] - z["loss_f64"]) <= 1e-4 * abs(z["loss_f64"])
+    assert_grads_close(tr.named_gradients(sc[6]), ref_g)
+
+
+def test_three_level_k3_stack_gradients():
+    x, y, m, s0, w = small_case(B=6, S=3, L=9, N=211, seed=4, tcn_channel=(128, 128, 128), kernel_size=3)
+    _, ref_g, _ = GO.loss_and_grads(w, x, y, m, s0)
+    tr = make_trainer(w, 211, levels=3, K=3)
+    r = tr.forward_backward(x, y, m, s0)
+    assert_grads_close(tr.named_gradients(r["scalars"].cpu().numpy()[6]), ref_g)
+
+
+def test_train_steps_follow_tf_adam_oracle():
+    from hiertcn_b200.data_loader import synthetic_batch
+    x0, y0, m0, s0, w = small_case(B=8, S=3, L=6, N=151, seed=6, kernel_scale=1.0)
+    batches = [(x0, y0, m0)]
+    for i in range(3):
+        batches.append(synthetic_batch(8, 3, 6, 151, seed=20 + i, lengths="ragged", id_dist="uniform", mask_keep=0.7))
+    ref_losses, ref_w, ref_state = GO.train_steps(w, batches, s0, lr=1e-2)
+    tr = make_trainer(w, 151, lr=1e-2)
+    state, losses = s0, []
+    for xb, yb, mb in batches:
+        out = tr.train_step(xb, yb, mb, state)
+        state = out["state"]
+        losses.append(out["loss"])
+    np.testing.assert_allclose(losses, ref_losses, rtol=2e-3)
+    assert losses[-1] < losses[0] or ref_losses[-1] >= ref_losses[0]
+    got = tr.state_dict()
+    # Adam normalises every coordinate to ~lr per step, so a gradient that is ~0 can flip sign between fp32 and fp64:
+    # compare in units of the total possible movement (steps * lr)
+    budget = len(batches) * 1e-2
+    for k in ref_w:
+        diff = np.abs(got[k] - ref_w[k])
+        assert np.mean(diff) <= 0.02 * budget, (k, float(np.mean(diff)))
+        assert np.mean(diff > 0.25 * budget) < 0.01, k
+    np.testing.assert_allclose(state, ref_state, rtol=0, atol=5e-3)
+
+
+def test_model_sees_updates_and_eval_matches_oracle_after_training():
+    """the trainer re-homes the model's tensors: evaluation through HierTCN.step uses the updated weights"""
+    from oracle import hiertcn_oracle as O
+    x, y, m, s0, w = small_case(B=6, S=3, L=6, N=131, seed=8, kernel_scale=1.0)
+    tr = make_trainer(w, 131)
+    before = tr.m.step(x, y, m, s0)["loss"]
+    for _ in range(5):
+        tr.train_step(x, y, m, s0)
+    after = tr.m.step(x, y, m, s0)
+    assert after["loss"] < before
+    ref = O.forward_loss_metrics(x, y, m, s0, tr.state_dict(), 2, "f64")
+    assert abs(after["loss"] - ref["loss"]) <= 1e-4 * abs(ref["loss"])
+
+
+def test_run_hier_training_loop_and_lr_schedule():
+    from hiertcn_b200.data_loader import Dataloader_hier_model_xing, make_synthetic_interactions
+    from hiertcn_b200.train import lr_for_epoch, run_hier
+    assert lr_for_epoch(1e-2, 0) == 1e-2 and abs(lr_for_epoch(1e-2, 60) - 2e-3) < 1e-12
+    assert abs(lr_for_epoch(1e-2, 120) - 4e-4) < 1e-12 and lr_for_epoch(1e-2, 200, lr_schedule=False) == 1e-2
+    from hiertcn_b200.args import make_args
+    from hiertcn_b200.model_hier import HierTCN
+    from hiertcn_b200.train import HierTCNTrainer
+    N = 257
+    a = make_args(["--item_num", str(N), "--batch_size", "16", "--max_session_num", "4", "--max_activity_len", "8"])
+    data = make_synthetic_interactions(64, N, seed=3)
+    loader = Dataloader_hier_model_xing(a, "train", data=data)
+    tr = HierTCNTrainer(HierTCN(a, None, precision="f32").build(), learning_rate=1e-2)
+    hist = run_hier(tr, loader, epochs=3, epoch_batches_train=6)
+    assert len(hist) == 3 and hist[-1] < hist[0]
