@@ -74,3 +74,58 @@ def test_sharded_catalog_scoring_nccl(precision):
         p.join(300)
         assert p.exitcode == 0
     assert all(ret.get(r) for r in range(2)), dict(ret)
+
+
+def _train_worker(rank, world, port, ret):
+    """data-parallel training: each rank owns half of the users; after 3 Adam steps every rank must hold the weights a
+    single process gets from the whole batch (gradients and the user count are all-reduced, hiertcn_b200.train)."""
+    import sys
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        from helpers import small_case
+        from hiertcn_b200.args import make_args
+        from hiertcn_b200.data_loader import synthetic_batch
+        from hiertcn_b200.model_hier import HierTCN
+        from hiertcn_b200.train import HierTCNTrainer
+        N, B = 503, 12
+        _, _, _, s0, w = small_case(B=B, S=3, L=6, N=N, seed=11, kernel_scale=1.0)
+        a = make_args(["--item_num", str(N)])
+        batches = [synthetic_batch(B, 3, 6, N, seed=40 + i, lengths="ragged", id_dist="uniform", mask_keep=0.7) for i in range(3)]
+        lo, hi = rank * B // world, (rank + 1) * B // world
+        tr = HierTCNTrainer(HierTCN(a, w, precision="f32").build(), learning_rate=1e-2, dist=dist, world=world)
+        ref = HierTCNTrainer(HierTCN(a, w, precision="f32").build(), learning_rate=1e-2)
+        st_dp, st_ref, ok = s0[lo:hi], s0, True
+        for x, y, m in batches:
+            o = tr.train_step([v[lo:hi] for v in x], [v[lo:hi] for v in y], [v[lo:hi] for v in m], st_dp)
+            r = ref.train_step(x, y, m, st_ref)
+            st_dp, st_ref = o["state"], r["state"]
+            ok &= abs(o["loss"] - r["loss"]) <= 1e-5 * abs(r["loss"]) and o["user_count"] == r["user_count"]
+            ok &= bool(np.allclose(st_dp, st_ref[lo:hi], rtol=1e-4, atol=1e-5))
+        wd, wr = tr.state_dict(), ref.state_dict()
+        budget = 3 * 1e-2
+        for k in wr:      # atomics reorder fp32 sums, and Adam turns a sign flip of a ~0 gradient into an lr-sized move
+            d = np.abs(wd[k] - wr[k])
+            ok &= float(np.mean(d)) <= 0.01 * budget and float(np.mean(d > 0.25 * budget)) < 0.005
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_data_parallel_training_nccl():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    port = _free_port()
+    procs = [ctx.Process(target=_train_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    assert all(ret.get(r) for r in range(2)), dict(ret)
