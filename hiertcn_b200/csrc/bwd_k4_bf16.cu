@@ -1,0 +1,346 @@
+// K4 backward on the tensor cores (bf16 operands, fp32 accumulation): the gradient of the full-catalog softmax
+// cross-entropy without materialising the [Q, N] logits or their gradient, as two passes of ONE kernel shaped like a
+// flash-attention forward:
+//
+//     S = X Y^T        (tcgen05, 128 x 64 per iteration, K = 128, accumulator in TMEM, double-buffered)
+//     P = f(S)         (epilogue warps: TMEM -> registers -> exp / one-hot / scale -> bf16 -> 128B-swizzled smem)
+//     O += P V^T       (tcgen05, 128 x 128, K = 64; the accumulator O stays in TMEM for the whole sweep)
+//
+//   pass A (dHout): X = Hout rows (128 per CTA, stationary), Y = W_out^T rows (items, streamed), V = W_out [128, N];
+//                   P[q, j] = exp(z - lse_q) - [j == y_q];  dHout[q] = g_q * O[q]
+//   pass B (dW^T):  X = W_out^T rows (128 items per CTA, stationary), Y = Hout rows (queries, streamed),
+//                   V = Hout^T [128, Q];  P[j, q] = g_q (exp(z - lse_q) - [j == y_q]);  dW^T[j] += O[j];
+//                   db[j] += sum_q P[j, q]
+//
+// with z = S + b and lse_q = loss_q + z_{q, y_q} from the forward sweep.  "TMEM lane = stationary row": every epilogue
+// thread owns one row of S, so P is written to shared memory as the K-major A operand of the second product with plain
+// 16-byte stores, and db is a thread-local sum.  Replaces TensorFlow's dense [B,T,N] softmax gradient + two GEMMs on it
+// (model_tcn.py:41, loss.py:20-21, model.py:134-141).
+#include "common.cuh"
+#include "sm100.cuh"
+
+namespace htcn {
+using namespace sm100;
+
+namespace {
+constexpr int kBM = 128;          // stationary rows (TMEM lanes)
+constexpr int kBN = 64;           // streamed rows per iteration
+constexpr int kStages = 3;
+constexpr int kEpiWarps = 8;      // 2 column halves x 4 TMEM lane quarters
+constexpr int kThreads = 64 + 32 * kEpiWarps;
+constexpr uint32_t kTmemCols = 256;    // S[2] at columns 0 / 64, O at columns 128..255
+constexpr float kLog2e = 1.4426950408889634f;
+
+struct alignas(1024) BwdSmem {
+  uint8_t x[2][kBM * 128];             // stationary operand: K chunks 0..63 / 64..127
+  uint8_t y[kStages][2][kBN * 128];    // streamed operand of S = X Y^T
+  uint8_t v[kStages][kBM * 128];       // streamed operand of O += P V^T: [128 dims][64 streamed indices]
+  uint8_t p[2][kBM * 128];             // P tile [128 lanes][64 streamed indices]
+  float colA[2][kBN];
+  float colB[2][kBN];
+  int colI[2][kBN];
+  uint64_t x_full, full[kStages], empty[kStages], s_full[2], s_free[2], p_full[2], p_free[2], o_full;
+  uint32_t tmem_base;
+};
+
+struct BwdArgs {
+  const float* b_out;       // [n_items]
+  const int* y_id;          // [Q] global target ids
+  const float* loss_row;    // [Q]
+  const float* zy;          // [Q]
+  const float* g_row;       // [Q]
+  float* out;               // pass A: d_hout [Q,128]; pass B: d_wt [n_items,128]   (atomic accumulation)
+  float* d_b;               // pass B: [n_items] or NULL
+  int Q, n_items, n0;
+  int n_stream;             // rows of the streamed operand (pass A: n_items, pass B: Q)
+  int n_split;
+};
+
+template <bool kPassB>
+__global__ void __launch_bounds__(kThreads, 1)
+k4_ce_backward_bf16(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_y,
+                    const __grid_constant__ CUtensorMap tmap_v, BwdArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  auto& sm = *reinterpret_cast<BwdSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * kBM;                                   // first stationary row
+  const int tiles_all = (a.n_stream + kBN - 1) / kBN;
+  const int t_begin = (int)((long long)tiles_all * blockIdx.y / a.n_split);
+  const int t_end = (int)((long long)tiles_all * (blockIdx.y + 1) / a.n_split);
+  const int n_iter = t_end - t_begin;
+  if (n_iter <= 0) return;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmap_x);
+    prefetch_tmap(&tmap_y);
+    prefetch_tmap(&tmap_v);
+    mbar_init(&sm.x_full, 1);
+    mbar_init(&sm.o_full, 1);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&sm.full[s], 1);
+      mbar_init(&sm.empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&sm.s_full[s], 1);
+      mbar_init(&sm.s_free[s], kEpiWarps);
+      mbar_init(&sm.p_full[s], kEpiWarps);
+      mbar_init(&sm.p_free[s], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<kTmemCols>(&sm.tmem_base);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = sm.tmem_base;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&sm.x_full, 2 * kBM * 128);
+      tma_load_2d(sm.x[0], &tmap_x, 0, m0, &sm.x_full);
+      tma_load_2d(sm.x[1], &tmap_x, 64, m0, &sm.x_full);
+      for (int i = 0; i < n_iter; ++i) {
+        const int s = i % kStages;
+        mbar_wait_relaxed(&sm.empty[s], ((i / kStages) & 1) ^ 1);
+        mbar_arrive_expect_tx(&sm.full[s], 2 * kBN * 128 + kBM * 128);
+        const int j0 = (t_begin + i) * kBN;                          // rows / columns beyond the tensor are zero-filled
+        tma_load_2d(sm.y[s][0], &tmap_y, 0, j0, &sm.full[s]);
+        tma_load_2d(sm.y[s][1], &tmap_y, 64, j0, &sm.full[s]);
+        tma_load_2d(sm.v[s], &tmap_v, j0, 0, &sm.full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(kBM, kBN);
+      constexpr uint32_t idesc_o = make_idesc_bf16(kBM, kBM);
+      auto issue_s = [&](int i) {                                    // S[i & 1] = X Y_i^T
+        const int s = i % kStages, buf = i & 1;
+        mbar_wait_relaxed(&sm.s_free[buf], ((i >> 1) & 1) ^ 1);      // epilogue drained this accumulator
+        mbar_wait(&sm.full[s], (i / kStages) & 1);
+        tc_fence_after_sync();
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_bf16(tmem + buf * kBN, make_desc_k_sw128(smem_u32(sm.x[k >> 2]) + (k & 3) * 32),
+                    make_desc_k_sw128(smem_u32(sm.y[s][k >> 2]) + (k & 3) * 32), idesc_s, k > 0);
+        umma_commit(&sm.s_full[buf]);
+      };
+      mbar_wait(&sm.x_full, 0);
+      issue_s(0);
+      for (int i = 0; i < n_iter; ++i) {
+        if (i + 1 < n_iter) issue_s(i + 1);                          // the tensor core works on S(i+1) during epilogue(i)
+        const int s = i % kStages, pb = i & 1;
+        mbar_wait_relaxed(&sm.p_full[pb], (i >> 1) & 1);             // P(i) is in shared memory
+        tc_fence_after_sync();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem + 128, make_desc_k_sw128(smem_u32(sm.p[pb]) + k * 32),
+                    make_desc_k_sw128(smem_u32(sm.v[s]) + k * 32), idesc_o, (i > 0) || (k > 0));
+        umma_commit(&sm.empty[s]);                                   // Y_i and V_i consumed
+        umma_commit(&sm.p_free[pb]);
+      }
+      umma_commit(&sm.o_full);
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int ew = warp - 2;
+    const int quarter = warp & 3;                                    // TMEM lane quarter this warp may access
+    const int half = ew >> 2;                                        // 32-column half of the 64-wide S tile
+    const int row = quarter * 32 + lane;                             // stationary row = TMEM lane
+    const int et = ew * 32 + lane;                                   // 0..255
+    const int mrow = m0 + row;
+    // per-lane constants
+    float laneL = 0.f;            // pass A: lse_q * log2e          pass B: b_j * log2e
+    int laneI = -1;               // pass A: y_q                    pass B: global item id
+    float lane_g = 0.f;           // pass A: g_q
+    if (!kPassB) {
+      if (mrow < a.Q) {
+        laneL = (a.loss_row[mrow] + a.zy[mrow]) * kLog2e;
+        laneI = a.y_id[mrow];
+        lane_g = a.g_row[mrow];
+      }
+    } else if (mrow < a.n_items) {
+      laneL = a.b_out[mrow] * kLog2e;
+      laneI = a.n0 + mrow;
+    }
+    float db_acc = 0.f;
+
+    for (int i = 0; i < n_iter; ++i) {
+      const int buf = i & 1;
+      const int j0 = (t_begin + i) * kBN;
+      if (et < kBN) {                                                // stage the per-column vectors of this tile
+        const int j = j0 + et;
+        if (!kPassB) {
+          sm.colA[buf][et] = (j < a.n_items) ? a.b_out[j] * kLog2e : -INFINITY;
+        } else {
+          const bool ok = j < a.Q;
+          sm.colA[buf][et] = ok ? (a.loss_row[j] + a.zy[j]) * kLog2e : INFINITY;
+          sm.colB[buf][et] = ok ? a.g_row[j] : 0.f;
+          sm.colI[buf][et] = ok ? a.y_id[j] : -2;
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+      mbar_wait(&sm.s_full[buf], (i >> 1) & 1);
+      tc_fence_after_sync();
+      uint32_t r[32];
+      tmem_ld_32x32(tmem + ((uint32_t)(quarter * 32) << 16) + buf * kBN + half * 32, r);
+      tmem_ld_wait(r);
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.s_free[buf]);                   // S(i) is in registers
+      uint32_t pk[16];
+      const int tgt = kPassB ? 0 : laneI - (a.n0 + j0 + half * 32);   // pass A: tile-local column of this row's target
+#pragma unroll
+      for (int u = 0; u < 32; u += 4) {                               // 4 columns per 128-bit read of the column vectors
+        const float4 cA = *reinterpret_cast<const float4*>(&sm.colA[buf][half * 32 + u]);
+        float4 cB = make_float4(0.f, 0.f, 0.f, 0.f);
+        int4 cI = make_int4(0, 0, 0, 0);
+        if (kPassB) {
+          cB = *reinterpret_cast<const float4*>(&sm.colB[buf][half * 32 + u]);
+          cI = *reinterpret_cast<const int4*>(&sm.colI[buf][half * 32 + u]);
+        }
+        const float av[4] = {cA.x, cA.y, cA.z, cA.w};
+        const float bv[4] = {cB.x, cB.y, cB.z, cB.w};
+        const int iv[4] = {cI.x, cI.y, cI.z, cI.w};
+        float pv[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float z = __uint_as_float(r[u + e]);
+          if (!kPassB) {
+            pv[e] = ex2_approx(fmaf(z, kLog2e, av[e] - laneL)) - ((u + e == tgt) ? 1.f : 0.f);
+          } else {
+            pv[e] = bv[e] * (ex2_approx(fmaf(z, kLog2e, laneL - av[e])) - ((iv[e] == laneI) ? 1.f : 0.f));
+            db_acc += pv[e];
+          }
+        }
+        pk[u >> 1] = pack_bf16x2(pv[0], pv[1]);
+        pk[(u >> 1) + 1] = pack_bf16x2(pv[2], pv[3]);
+      }
+      mbar_wait(&sm.p_free[buf], ((i >> 1) & 1) ^ 1);                // the product that read P(i-2) has retired
+      uint8_t* prow = sm.p[buf] + row * 128;
+#pragma unroll
+      for (int c16 = 0; c16 < 4; ++c16) {                            // 16-byte chunk index ^= row % 8 (128B swizzle)
+        const int chunk = (half * 4 + c16) ^ (row & 7);
+        *reinterpret_cast<uint4*>(prow + (chunk << 4)) = make_uint4(pk[c16 * 4], pk[c16 * 4 + 1], pk[c16 * 4 + 2], pk[c16 * 4 + 3]);
+      }
+      fence_proxy_async_smem();                                      // generic-proxy writes -> tensor core reads
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.p_full[buf]);
+    }
+
+    // ---- O -> global ---------------------------------------------------------------------------------------------
+    mbar_wait(&sm.o_full, 0);
+    tc_fence_after_sync();
+    const bool row_ok = kPassB ? (mrow < a.n_items) : (mrow < a.Q);
+    const float scale = kPassB ? 1.f : lane_g;
+#pragma unroll
+    for (int c = 0; c < 64; c += 32) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem + ((uint32_t)(quarter * 32) << 16) + 128 + half * 64 + c, r);
+      tmem_ld_wait(r);
+      if (row_ok) {
+        float* dst = a.out + (long long)mrow * kDim + half * 64 + c;
+#pragma unroll
+        for (int u = 0; u < 32; u += 4)
+          atomicAdd(reinterpret_cast<float4*>(dst + u),
+                    make_float4(__uint_as_float(r[u]) * scale, __uint_as_float(r[u + 1]) * scale,
+                                __uint_as_float(r[u + 2]) * scale, __uint_as_float(r[u + 3]) * scale));
+      }
+    }
+    if (kPassB && a.d_b && row_ok) atomicAdd(a.d_b + mrow, db_acc);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc<kTmemCols>(tmem);
+  }
+}
+
+// src [R,128] f32 -> rows [R,128] bf16 (optional) and its transpose [128, r_pad] bf16 (optional), 32x32 smem tiles
+__global__ void cast_transpose_bf16_kernel(const float* __restrict__ src, long long R, __nv_bfloat16* __restrict__ rows,
+                                           __nv_bfloat16* __restrict__ tr, long long r_pad) {
+  __shared__ float tile[32][33];
+  const long long r0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;       // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const long long r = r0 + i;
+    const float v = (r < R) ? src[r * kDim + c0 + tx] : 0.f;
+    tile[i][tx] = v;
+    if (rows && r < R) rows[r * kDim + c0 + tx] = __float2bfloat16_rn(v);
+  }
+  __syncthreads();
+  if (tr) {
+    for (int i = ty; i < 32; i += 8) {
+      const long long r = r0 + tx;
+      if (r < r_pad) tr[(long long)(c0 + i) * r_pad + r] = __float2bfloat16_rn(tile[tx][i]);
+    }
+  }
+}
+
+template <bool kPassB>
+int32_t launch_bwd(const void* x, uint64_t x_rows, uint32_t x_pitch, const void* y, uint64_t y_rows, uint32_t y_pitch,
+                   const void* v, uint64_t v_cols, uint64_t v_pitch, BwdArgs a, cudaStream_t st) {
+  CUtensorMap tx, ty, tv;
+  int32_t rc = make_tmap_bf16(&tx, x, x_rows, kDim, x_pitch, 64, kBM, 128);
+  if (rc) return rc;
+  rc = make_tmap_bf16(&ty, y, y_rows, kDim, y_pitch, 64, kBN, 128);
+  if (rc) return rc;
+  rc = make_tmap_bf16(&tv, v, kDim, (uint32_t)v_cols, (uint32_t)v_pitch, 64, kBM, 128);
+  if (rc) return rc;
+  const int m_tiles = ceil_div((long long)x_rows, kBM);
+  const int s_tiles = ceil_div(a.n_stream, kBN);
+  int ns = ceil_div(4 * 148, m_tiles);                  // about four waves of CTAs
+  if (ns > s_tiles) ns = s_tiles;
+  if (ns > 65535) ns = 65535;
+  if (ns < 1) ns = 1;
+  a.n_split = ns;
+  const size_t smem = sizeof(BwdSmem) + 1024;
+  auto kern = k4_ce_backward_bf16<kPassB>;
+  HTCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<dim3(m_tiles, ns), kThreads, smem, st>>>(tx, ty, tv, a);
+  HTCN_LAUNCH_CHECK("k4_ce_backward_bf16");
+  return HTCN_OK;
+}
+
+}  // namespace
+}  // namespace htcn
+
+using namespace htcn;
+
+extern "C" int32_t htcn_cast_transpose_bf16(const float* src, int64_t R, void* dst_rows, void* dst_t, int64_t r_pad,
+                                            void* stream) {
+  HTCN_REQUIRE(src && R > 0 && (dst_rows || dst_t), "cast_transpose_bf16: bad args");
+  HTCN_REQUIRE(!dst_t || (r_pad >= R && r_pad % 8 == 0), "cast_transpose_bf16: r_pad=%lld must be >= R and a multiple of 8",
+               (long long)r_pad);
+  const long long span = dst_t ? r_pad : R;
+  cast_transpose_bf16_kernel<<<dim3(ceil_div(span, 32), kDim / 32), dim3(32, 8), 0, as_stream(stream)>>>(
+      src, R, reinterpret_cast<__nv_bfloat16*>(dst_rows), reinterpret_cast<__nv_bfloat16*>(dst_t), r_pad);
+  HTCN_LAUNCH_CHECK("cast_transpose_bf16_kernel");
+  return HTCN_OK;
+}
+
+extern "C" int32_t htcn_score_ce_backward_bf16(const void* hout, const void* hout_t, int64_t q_pad, int32_t Q,
+                                               const void* w_out_t, const void* w_out, int64_t n_pad,
+                                               const float* b_out, int32_t n_items, int32_t n0, const int32_t* y_id,
+                                               const float* loss_row, const float* target_logit, const float* g_row,
+                                               float* d_hout, float* d_w_out_t, float* d_b_out, void* stream) {
+  HTCN_REQUIRE(hout && hout_t && w_out_t && w_out && b_out && y_id && loss_row && target_logit && g_row && d_hout && d_w_out_t,
+               "score_ce_backward_bf16: NULL pointer");
+  HTCN_REQUIRE(Q >= 0 && n_items > 0 && q_pad >= Q && q_pad % 8 == 0 && n_pad >= n_items && n_pad % 8 == 0,
+               "score_ce_backward_bf16: Q=%d q_pad=%lld n_items=%d n_pad=%lld", Q, (long long)q_pad, n_items, (long long)n_pad);
+  if (Q == 0) return HTCN_OK;
+  cudaStream_t st = as_stream(stream);
+  HTCN_CUDA(cudaMemsetAsync(d_hout, 0, sizeof(float) * (size_t)Q * kDim, st));
+  BwdArgs a{b_out, y_id, loss_row, target_logit, g_row, d_hout, nullptr, Q, n_items, n0, n_items, 1};
+  int32_t rc = launch_bwd<false>(hout, (uint64_t)Q, kDim, w_out_t, (uint64_t)n_items, kWtPitchBf16, w_out, (uint64_t)n_items,
+                                 (uint64_t)n_pad, a, st);
+  if (rc) return rc;
+  a.out = d_w_out_t;
+  a.d_b = d_b_out;
+  a.n_stream = Q;
+  return launch_bwd<true>(w_out_t, (uint64_t)n_items, kWtPitchBf16, hout, (uint64_t)Q, kDim, hout_t, (uint64_t)Q,
+                          (uint64_t)q_pad, a, st);
+}

@@ -141,6 +141,7 @@ class HierTCN:
                 cw = np.concatenate([cw[:ed], pad, cw[ed:]], 0)
             self.gru.append((up(gw), up(w[p + "/gates/bias"]), up(cw), up(w[p + "/candidate/bias"])))
         self.b_out = up(w["hier/tcn/dense/bias"])
+        self._w_out_host = w["hier/tcn/dense/kernel"]   # fp32 master of the output table (hiertcn_b200.train, bf16 tier)
         w_out = up(w["hier/tcn/dense/kernel"])          # [128, N] TF layout
         self.act_dtype = cabi.HTCN_BF16 if self.precision == "bf16" else cabi.HTCN_F32
         tdt = torch.bfloat16 if self.precision == "bf16" else torch.float32

@@ -23,17 +23,17 @@ from .model_hier import D, HierTCN, _torch
 class HierTCNTrainer:
     """``Trainer(model).train_step(x_list, y_list, mask_list, state)`` == one ``sess.run([train_op, loss, state])``.
 
-    model: a built fp32-tier ``HierTCN``; its parameter tensors are re-homed into the flat buffer (the model keeps
-    working for evaluation and sees every update).  ``dist``: a torch.distributed module with an initialised process
+    model: a built ``HierTCN``; its parameter tensors are re-homed into the flat buffer (the model keeps working for
+    evaluation and sees every update).  Parameters, gradients, Adam and the K1/K2/K3 forward+backward are fp32 in both
+    tiers; with ``precision='bf16'`` the catalog products (the loss sweep and its backward, > 95% of the FLOPs) run on the
+    tensor cores with bf16 operands derived from the fp32 masters after every update.  ``dist``: a torch.distributed module with an initialised process
     group for data-parallel training over users (gradients and the user count are all-reduced), or None."""
 
     def __init__(self, model: HierTCN, learning_rate=None, beta1=0.9, beta2=0.999, eps=1e-8, dist=None, world=1):
         torch = _torch()
         if not model.built:
             model.build()
-        if model.precision != "f32":
-            raise NotImplementedError("training runs in the fp32 tier (the reference's precision); build the model with "
-                                      "precision='f32'")
+        self.bf16 = model.precision == "bf16"
         if model.n_out != model.N:
             raise NotImplementedError("training with a catalog-sharded output table")
         self.m, self.dist, self.world = model, dist, int(world)
@@ -58,7 +58,9 @@ class HierTCNTrainer:
         self.grads = torch.zeros(off, dtype=f32, device=m.device)
         self.adam_m = torch.zeros(off, dtype=f32, device=m.device)
         self.adam_v = torch.zeros(off, dtype=f32, device=m.device)
-        cur = {"E": m.E, "wt": m.wt, "b_out": m.b_out, "b_emb": m.b_emb, "w_in_x": m.w_in_x, "w_in_state": m.w_in_state}
+        wt_master = m.wt if not self.bf16 else torch.from_numpy(
+            np.ascontiguousarray(np.asarray(m._w_out_host, dtype=np.float32).T)).to(m.device)
+        cur = {"E": m.E, "wt": wt_master, "b_out": m.b_out, "b_emb": m.b_emb, "w_in_x": m.w_in_x, "w_in_state": m.w_in_state}
         for l in range(L):
             cur[f"conv_w{l}"], cur[f"conv_b{l}"] = m.conv_w[l], m.conv_b[l]
         for g in range(G):
@@ -69,8 +71,14 @@ class HierTCNTrainer:
             self.g[name] = self._view(self.grads, name, shape)
             self.p[name].copy_(cur[name].reshape(shape))
         # re-home the model's tensors (views of the flat buffer: updates are visible to forward / evaluation)
-        m.E, m.wt, m.b_out, m.b_emb = self.p["E"], self.p["wt"], self.p["b_out"], self.p["b_emb"]
-        m.wt_f32 = m.wt
+        m.E, m.b_out, m.b_emb = self.p["E"], self.p["b_out"], self.p["b_emb"]
+        m.wt_f32 = self.p["wt"]
+        if not self.bf16:
+            m.wt = self.p["wt"]
+        else:       # m.wt stays the derived bf16 scoring layout [N,144]; plus the TF-layout copy the backward streams
+            self.n_pad = -(-N // 8) * 8
+            self.w_out_bf16 = torch.zeros((D, self.n_pad), dtype=torch.bfloat16, device=m.device)
+            self._refresh_bf16_tables()
         m.w_in_x, m.w_in_state = self.p["w_in_x"], self.p["w_in_state"]
         m.conv_w = [self.p[f"conv_w{l}"] for l in range(L)]
         m.conv_b = [self.p[f"conv_b{l}"] for l in range(L)]
@@ -83,6 +91,13 @@ class HierTCNTrainer:
         self._d_gru = [cabi.ptr_array([self.g[f"{n}{g}"].data_ptr() for g in range(G)])
                        for n in ("gate_w", "gate_b", "cand_w", "cand_b")]
         torch.cuda.synchronize(m.device)
+
+    def _refresh_bf16_tables(self):
+        m = self.m
+        st = m.stream_ptr()
+        cabi.call("htcn_refresh_wout", self.p["wt"].data_ptr(), self.p["b_out"].data_ptr(), m.N, m.wt.data_ptr(),
+                  cabi.HTCN_BF16, st)
+        cabi.call("htcn_cast_transpose_bf16", self.p["wt"].data_ptr(), m.N, None, self.w_out_bf16.data_ptr(), self.n_pad, st)
 
     def _view(self, flat, name, shape):
         o = self.offsets[name]
@@ -130,9 +145,16 @@ class HierTCNTrainer:
         zy = buf("zy", (Q,), f32)
         pm, ps = buf("pm", (ns, Q), f32), buf("ps", (ns, Q), f32)
         pc = buf("pc", (ns, Q), torch.int32) if metrics else None
-        cabi.call("htcn_target_logit", hout.data_ptr(), cabi.HTCN_F32, Q, m.wt.data_ptr(), m.b_out.data_ptr(), N, 0,
+        hq, prec = hout, cabi.HTCN_F32
+        if self.bf16:     # bf16 copies of the user embeddings: rows for the sweeps, the transpose for dW^T = P^T Hout
+            q_pad = -(-Q // 8) * 8
+            hq = buf("tr_hout_bf16", (Q, D), torch.bfloat16)
+            hq_t = buf("tr_hout_t_bf16", (D, q_pad), torch.bfloat16)
+            cabi.call("htcn_cast_transpose_bf16", hout.data_ptr(), Q, hq.data_ptr(), hq_t.data_ptr(), q_pad, st)
+            prec = cabi.HTCN_BF16
+        cabi.call("htcn_target_logit", hq.data_ptr(), prec, Q, m.wt.data_ptr(), m.b_out.data_ptr(), N, 0,
                   d["y_rows"].data_ptr(), zy.data_ptr(), st)
-        cabi.call("htcn_score_ce_rank_topk", hout.data_ptr(), cabi.HTCN_F32, Q, m.wt.data_ptr(), m.b_out.data_ptr(), N, 0,
+        cabi.call("htcn_score_ce_rank_topk", hq.data_ptr(), prec, Q, m.wt.data_ptr(), m.b_out.data_ptr(), N, 0,
                   d["y_rows"].data_ptr(), zy.data_ptr(), 1, cabi.SCORE_CE | (cabi.SCORE_RANK if metrics else 0), 0, ns,
                   pm.data_ptr(), ps.data_ptr(), P(pc), None, None, st)
         cabi.note_launches(-1)
@@ -146,9 +168,15 @@ class HierTCNTrainer:
         g_row = buf("tr_g_row", (Q,), f32)
         cabi.call("htcn_loss_row_weights", d["y_id"].data_ptr(), d["row_of"].data_ptr(), B, T, g_row.data_ptr(), st)
         d_hout = buf("tr_d_hout", (Q, D), f32)
-        cabi.call("htcn_score_ce_backward", hout.data_ptr(), cabi.HTCN_F32, Q, m.wt.data_ptr(), m.b_out.data_ptr(), N, 0,
-                  d["y_rows"].data_ptr(), loss_row.data_ptr(), zy.data_ptr(), g_row.data_ptr(), d_hout.data_ptr(),
-                  self.g["wt"].data_ptr(), self.g["b_out"].data_ptr(), st)
+        if self.bf16:
+            cabi.call("htcn_score_ce_backward_bf16", hq.data_ptr(), hq_t.data_ptr(), q_pad, Q, m.wt.data_ptr(),
+                      self.w_out_bf16.data_ptr(), self.n_pad, m.b_out.data_ptr(), N, 0, d["y_rows"].data_ptr(),
+                      loss_row.data_ptr(), zy.data_ptr(), g_row.data_ptr(), d_hout.data_ptr(), self.g["wt"].data_ptr(),
+                      self.g["b_out"].data_ptr(), st)
+        else:
+            cabi.call("htcn_score_ce_backward", hout.data_ptr(), cabi.HTCN_F32, Q, m.wt.data_ptr(), m.b_out.data_ptr(), N, 0,
+                      d["y_rows"].data_ptr(), loss_row.data_ptr(), zy.data_ptr(), g_row.data_ptr(), d_hout.data_ptr(),
+                      self.g["wt"].data_ptr(), self.g["b_out"].data_ptr(), st)
         d_sbias = buf("tr_d_sbias", (S, B, D), f32)
         d_xe = buf("tr_d_xe", (R, D), f32)
         k2_scratch = buf("tr_k2_scratch", (2, R, D), f32)
@@ -184,6 +212,8 @@ class HierTCNTrainer:
         cabi.call("htcn_adam_step", self.params.data_ptr(), self.grads.data_ptr(), self.adam_m.data_ptr(),
                   self.adam_v.data_ptr(), self.n_flat, self.lr_t(lr), self.beta1, self.beta2, self.eps,
                   scalars[6:7].data_ptr(), 1, self.m.stream_ptr())
+        if self.bf16:
+            self._refresh_bf16_tables()
         return scalars
 
     def train_step(self, x_list, y_list, mask_list, state=None, lr=None, metrics=False, state_on_device=False):

@@ -260,6 +260,21 @@ int32_t htcn_score_ce_backward(const void* hout, int32_t hout_dtype, int32_t Q, 
                                const float* loss_row, const float* target_logit, const float* g_row,
                                float* d_hout, float* d_w_out_t, float* d_b_out, void* stream);
 
+/* The same backward on the tensor cores (bf16 operands, fp32 accumulation and outputs): two tcgen05 passes, each
+ * recomputing its logits tile in TMEM, turning it into dL/dZ in the epilogue and feeding it straight back to the tensor
+ * core as the operand of the second product.  Operands (all bf16, built with htcn_cast_transpose_bf16 /
+ * htcn_refresh_wout):  hout [Q,128], hout_t [128,q_pad] (its transpose), w_out_t [n_items,144] (scoring layout),
+ * w_out [128,n_pad] (TF layout).  q_pad, n_pad: row pitches, multiples of 8.  Outputs as htcn_score_ce_backward. */
+int32_t htcn_score_ce_backward_bf16(const void* hout, const void* hout_t, int64_t q_pad, int32_t Q,
+                                    const void* w_out_t, const void* w_out, int64_t n_pad, const float* b_out,
+                                    int32_t n_items, int32_t n0, const int32_t* y_id, const float* loss_row,
+                                    const float* target_logit, const float* g_row, float* d_hout, float* d_w_out_t,
+                                    float* d_b_out, void* stream);
+
+/* src [R,128] f32 -> dst_rows [R,128] bf16 (or NULL) and dst_t [128,r_pad] bf16 = its transpose (or NULL; columns
+ * R..r_pad-1 are zero).  r_pad % 8 == 0. */
+int32_t htcn_cast_transpose_bf16(const float* src, int64_t R, void* dst_rows, void* dst_t, int64_t r_pad, void* stream);
+
 /* K2 forward that keeps what the backward needs: h_save [(n_levels+1), B*T, 128] (the in-projection output and
  * every level's output) and a_save [n_levels, B*T, 128] (relu(conv+bias) before the residual add);
  * hout [Q,128] f32 = rows of the last level compacted through out_row [B*T] (-1 = not scored). */

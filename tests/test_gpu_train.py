@@ -14,12 +14,12 @@ def dev(a):
     return torch.from_numpy(np.ascontiguousarray(a)).cuda()
 
 
-def make_trainer(w, N, lr=1e-2, levels=2, K=5):
+def make_trainer(w, N, lr=1e-2, levels=2, K=5, precision="f32"):
     from hiertcn_b200.args import make_args
     from hiertcn_b200.model_hier import HierTCN
     from hiertcn_b200.train import HierTCNTrainer
     a = make_args(["--item_num", str(N), "--tcn_channel", ",".join(["128"] * levels), "--kernel_size", str(K)])
-    return HierTCNTrainer(HierTCN(a, w, precision="f32").build(), learning_rate=lr)
+    return HierTCNTrainer(HierTCN(a, w, precision=precision).build(), learning_rate=lr)
 
 
 def assert_grads_close(got, ref, tol=2e-4):
@@ -194,3 +194,86 @@ def test_run_hier_training_loop_and_lr_schedule():
     tr = HierTCNTrainer(HierTCN(a, None, precision="f32").build(), learning_rate=1e-2)
     hist = run_hier(tr, loader, epochs=3, epoch_batches_train=6)
     assert len(hist) == 3 and hist[-1] < hist[0]
+
+
+# ------------------------------------------------------------------------------------------------ bf16 tensor-core tier
+def bf16r(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(torch.bfloat16).float().numpy()
+
+
+@pytest.mark.parametrize("Q,N", [(200, 300), (128, 64), (1, 1000), (333, 20778), (1500, 257)])
+def test_score_ce_backward_bf16_matches_numpy(Q, N):
+    """tcgen05 backward vs fp64 numpy on the SAME bf16-rounded operands; dL/dZ itself is rounded to bf16 on its way back
+    into the tensor core, hence the bf16-tier tolerance (north star: 2e-2 relative)."""
+    from hiertcn_b200 import _cabi as cabi
+    rng = np.random.default_rng(Q * 7 + N)
+    h = bf16r(rng.normal(0, 1, (Q, 128)))
+    wt = bf16r(rng.normal(0, 0.2, (N, 128)))
+    b = rng.normal(0, 0.5, N).astype(np.float32)
+    y = rng.integers(1, N, Q).astype(np.int32)
+    g = rng.uniform(0.1, 1.0, Q).astype(np.float32)
+    z = h.astype(np.float64) @ wt.astype(np.float64).T + b
+    mx = z.max(1, keepdims=True)
+    lse = (mx + np.log(np.exp(z - mx).sum(1, keepdims=True)))[:, 0]
+    zy = z[np.arange(Q), y]
+    p = np.exp(z - lse[:, None])
+    p[np.arange(Q), y] -= 1.0
+    p *= g[:, None]
+    ref_dh, ref_dw, ref_db = p @ wt, p.T @ h, p.sum(0)
+    st = torch.cuda.current_stream().cuda_stream
+    q_pad, n_pad = -(-Q // 8) * 8, -(-N // 8) * 8
+    h_d, wt_d, b_d = dev(h), dev(wt), dev(b)
+    hq = torch.empty((Q, 128), dtype=torch.bfloat16, device="cuda")
+    hq_t = torch.empty((128, q_pad), dtype=torch.bfloat16, device="cuda")
+    w_aug = torch.empty((N, 144), dtype=torch.bfloat16, device="cuda")
+    w_tf = torch.empty((128, n_pad), dtype=torch.bfloat16, device="cuda")
+    cabi.call("htcn_cast_transpose_bf16", h_d.data_ptr(), Q, hq.data_ptr(), hq_t.data_ptr(), q_pad, st)
+    cabi.call("htcn_cast_transpose_bf16", wt_d.data_ptr(), N, None, w_tf.data_ptr(), n_pad, st)
+    cabi.call("htcn_refresh_wout", wt_d.data_ptr(), b_d.data_ptr(), N, w_aug.data_ptr(), cabi.HTCN_BF16, st)
+    torch.cuda.synchronize()
+    assert torch.equal(hq.float().cpu(), torch.from_numpy(h)) and torch.equal(hq_t[:, :Q].float().cpu(), torch.from_numpy(h.T))
+    assert float(hq_t[:, Q:].abs().sum()) == 0.0
+    y_d, g_d = dev(y), dev(g)
+    loss_d, zy_d = dev((lse - zy).astype(np.float32)), dev(zy.astype(np.float32))
+    dh = torch.full((Q, 128), 7.0, device="cuda")
+    dw = torch.ones((N, 128), device="cuda")
+    db = torch.ones(N, device="cuda")
+    cabi.call("htcn_score_ce_backward_bf16", hq.data_ptr(), hq_t.data_ptr(), q_pad, Q, w_aug.data_ptr(), w_tf.data_ptr(), n_pad,
+              b_d.data_ptr(), N, 0, y_d.data_ptr(), loss_d.data_ptr(), zy_d.data_ptr(), g_d.data_ptr(), dh.data_ptr(),
+              dw.data_ptr(), db.data_ptr(), st)
+    torch.cuda.synchronize()
+    for got, ref in ((dh.cpu().numpy(), ref_dh), (dw.cpu().numpy() - 1.0, ref_dw), (db.cpu().numpy() - 1.0, ref_db)):
+        assert np.abs(got - ref).max() <= 1e-2 * np.abs(ref).max() + 1e-6, (np.abs(got - ref).max(), np.abs(ref).max())
+        assert np.linalg.norm(got - ref) <= 5e-3 * np.linalg.norm(ref) + 1e-6
+
+
+@pytest.mark.parametrize("case", [dict(B=5, S=3, L=7, N=97, seed=0), dict(B=33, S=10, L=20, N=3001, seed=3, mask_keep=0.8)])
+def test_gradients_bf16_tier(case):
+    x, y, m, s0, w = small_case(**case)
+    ref_loss, ref_g, ref_state = GO.loss_and_grads(w, x, y, m, s0)
+    tr = make_trainer(w, case["N"], precision="bf16")
+    r = tr.forward_backward(x, y, m, s0)
+    sc = r["scalars"].cpu().numpy()
+    assert abs(sc[0] - ref_loss) <= 2e-2 * abs(ref_loss)
+    got = tr.named_gradients(sc[6])
+    for k in ref_g:
+        assert np.linalg.norm(got[k] - ref_g[k]) <= 2e-2 * np.linalg.norm(ref_g[k]) + 1e-9, k
+        assert np.abs(got[k] - ref_g[k]).max() <= 4e-2 * np.abs(ref_g[k]).max() + 1e-9, k
+
+
+def test_train_steps_bf16_tier_track_oracle():
+    from hiertcn_b200.data_loader import synthetic_batch
+    x0, y0, m0, s0, w = small_case(B=8, S=3, L=6, N=151, seed=6, kernel_scale=1.0)
+    batches = [(x0, y0, m0)] + [synthetic_batch(8, 3, 6, 151, seed=20 + i, lengths="ragged", id_dist="uniform", mask_keep=0.7)
+                                for i in range(3)]
+    ref_losses, _, _ = GO.train_steps(w, batches, s0, lr=1e-2)
+    tr = make_trainer(w, 151, lr=1e-2, precision="bf16")
+    state, losses = s0, []
+    for xb, yb, mb in batches:
+        out = tr.train_step(xb, yb, mb, state)
+        state = out["state"]
+        losses.append(out["loss"])
+    np.testing.assert_allclose(losses, ref_losses, rtol=2e-2)
+    # evaluation through the bf16 model sees the refreshed tables
+    ev = tr.m.step(x0, y0, m0, s0)
+    assert np.isfinite(ev["loss"]) and ev["loss"] < losses[0]
