@@ -36,19 +36,21 @@ struct alignas(1024) BwdSmem {
   uint8_t y[kStages][2][kBN * 128];    // streamed operand of S = X Y^T
   uint8_t v[kStages][kBM * 128];       // streamed operand of O += P V^T: [128 dims][64 streamed indices]
   uint8_t p[2][kBM * 128];             // P tile [128 lanes][64 streamed indices]
-  float colA[2][kBN];
-  float colB[2][kBN];
-  int colI[2][kBN];
+  float colA[kStages][kBN];            // per streamed index, bulk-copied with the tiles (BwdArgs::bL / lseL / gq / yq)
+  float colB[kStages][kBN];
+  int colI[kStages][kBN];
   uint64_t x_full, full[kStages], empty[kStages], s_full[2], s_free[2], p_full[2], p_free[2], o_full;
   uint32_t tmem_base;
 };
 
 struct BwdArgs {
-  const float* b_out;       // [n_items]
-  const int* y_id;          // [Q] global target ids
-  const float* loss_row;    // [Q]
-  const float* zy;          // [Q]
-  const float* g_row;       // [Q]
+  // per-index vectors prepared by k4_bwd_prep_kernel, padded to whole 64-index tiles:
+  //   bL [ceil64(n_items)] = b_out * log2e (-inf padding);  lseL [ceil64(Q)] = (loss_row + zy) * log2e (+inf padding);
+  //   gq [ceil64(Q)] = g_row (0 padding);  yq [ceil64(Q)] = y_id (-2 padding)
+  const float* bL;
+  const float* lseL;
+  const float* gq;
+  const int* yq;
   float* out;               // pass A: d_hout [Q,128]; pass B: d_wt [n_items,128]   (atomic accumulation)
   float* d_b;               // pass B: [n_items] or NULL
   int Q, n_items, n0;
@@ -103,11 +105,18 @@ k4_ce_backward_bf16(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       for (int i = 0; i < n_iter; ++i) {
         const int s = i % kStages;
         mbar_wait_relaxed(&sm.empty[s], ((i / kStages) & 1) ^ 1);
-        mbar_arrive_expect_tx(&sm.full[s], 2 * kBN * 128 + kBM * 128);
+        mbar_arrive_expect_tx(&sm.full[s], 2 * kBN * 128 + kBM * 128 + (kPassB ? 3 : 1) * kBN * 4);
         const int j0 = (t_begin + i) * kBN;                          // rows / columns beyond the tensor are zero-filled
         tma_load_2d(sm.y[s][0], &tmap_y, 0, j0, &sm.full[s]);
         tma_load_2d(sm.y[s][1], &tmap_y, 64, j0, &sm.full[s]);
         tma_load_2d(sm.v[s], &tmap_v, j0, 0, &sm.full[s]);
+        if (!kPassB) {
+          bulk_load_1d(sm.colA[s], a.bL + j0, kBN * 4, &sm.full[s]);
+        } else {
+          bulk_load_1d(sm.colA[s], a.lseL + j0, kBN * 4, &sm.full[s]);
+          bulk_load_1d(sm.colB[s], a.gq + j0, kBN * 4, &sm.full[s]);
+          bulk_load_1d(sm.colI[s], a.yq + j0, kBN * 4, &sm.full[s]);
+        }
       }
     }
   } else if (warp == 1) {
@@ -148,7 +157,6 @@ k4_ce_backward_bf16(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     const int quarter = warp & 3;                                    // TMEM lane quarter this warp may access
     const int half = ew >> 2;                                        // 32-column half of the 64-wide S tile
     const int row = quarter * 32 + lane;                             // stationary row = TMEM lane
-    const int et = ew * 32 + lane;                                   // 0..255
     const int mrow = m0 + row;
     // per-lane constants
     float laneL = 0.f;            // pass A: lse_q * log2e          pass B: b_j * log2e
@@ -156,31 +164,20 @@ k4_ce_backward_bf16(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     float lane_g = 0.f;           // pass A: g_q
     if (!kPassB) {
       if (mrow < a.Q) {
-        laneL = (a.loss_row[mrow] + a.zy[mrow]) * kLog2e;
-        laneI = a.y_id[mrow];
-        lane_g = a.g_row[mrow];
+        laneL = a.lseL[mrow];
+        laneI = a.yq[mrow];
+        lane_g = a.gq[mrow];
       }
     } else if (mrow < a.n_items) {
-      laneL = a.b_out[mrow] * kLog2e;
+      laneL = a.bL[mrow];
       laneI = a.n0 + mrow;
     }
     float db_acc = 0.f;
 
     for (int i = 0; i < n_iter; ++i) {
-      const int buf = i & 1;
+      const int buf = i & 1, st = i % kStages;
       const int j0 = (t_begin + i) * kBN;
-      if (et < kBN) {                                                // stage the per-column vectors of this tile
-        const int j = j0 + et;
-        if (!kPassB) {
-          sm.colA[buf][et] = (j < a.n_items) ? a.b_out[j] * kLog2e : -INFINITY;
-        } else {
-          const bool ok = j < a.Q;
-          sm.colA[buf][et] = ok ? (a.loss_row[j] + a.zy[j]) * kLog2e : INFINITY;
-          sm.colB[buf][et] = ok ? a.g_row[j] : 0.f;
-          sm.colI[buf][et] = ok ? a.y_id[j] : -2;
-        }
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+      mbar_wait(&sm.full[st], (i / kStages) & 1);                    // the column vectors of this tile have landed
       mbar_wait(&sm.s_full[buf], (i >> 1) & 1);
       tc_fence_after_sync();
       uint32_t r[32];
@@ -193,12 +190,12 @@ k4_ce_backward_bf16(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       const int tgt = kPassB ? 0 : laneI - (a.n0 + j0 + half * 32);   // pass A: tile-local column of this row's target
 #pragma unroll
       for (int u = 0; u < 32; u += 4) {                               // 4 columns per 128-bit read of the column vectors
-        const float4 cA = *reinterpret_cast<const float4*>(&sm.colA[buf][half * 32 + u]);
+        const float4 cA = *reinterpret_cast<const float4*>(&sm.colA[st][half * 32 + u]);
         float4 cB = make_float4(0.f, 0.f, 0.f, 0.f);
         int4 cI = make_int4(0, 0, 0, 0);
         if (kPassB) {
-          cB = *reinterpret_cast<const float4*>(&sm.colB[buf][half * 32 + u]);
-          cI = *reinterpret_cast<const int4*>(&sm.colI[buf][half * 32 + u]);
+          cB = *reinterpret_cast<const float4*>(&sm.colB[st][half * 32 + u]);
+          cI = *reinterpret_cast<const int4*>(&sm.colI[st][half * 32 + u]);
         }
         const float av[4] = {cA.x, cA.y, cA.z, cA.w};
         const float bv[4] = {cB.x, cB.y, cB.z, cB.w};
@@ -255,6 +252,20 @@ k4_ce_backward_bf16(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   if (warp == 1) {
     tc_fence_after_sync();
     tmem_dealloc<kTmemCols>(tmem);
+  }
+}
+
+__global__ void k4_bwd_prep_kernel(const float* __restrict__ b_out, int n_items, int n64, const float* __restrict__ loss_row,
+                                   const float* __restrict__ zy, const float* __restrict__ g_row,
+                                   const int* __restrict__ y_id, int Q, int q64, float* __restrict__ bL,
+                                   float* __restrict__ lseL, float* __restrict__ gq, int* __restrict__ yq) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n64) bL[i] = (i < n_items) ? b_out[i] * kLog2e : -INFINITY;
+  if (i < q64) {
+    const bool ok = i < Q;
+    lseL[i] = ok ? (loss_row[i] + zy[i]) * kLog2e : INFINITY;
+    gq[i] = ok ? g_row[i] : 0.f;
+    yq[i] = ok ? y_id[i] : -2;
   }
 }
 
@@ -326,15 +337,25 @@ extern "C" int32_t htcn_score_ce_backward_bf16(const void* hout, const void* hou
                                                const void* w_out_t, const void* w_out, int64_t n_pad,
                                                const float* b_out, int32_t n_items, int32_t n0, const int32_t* y_id,
                                                const float* loss_row, const float* target_logit, const float* g_row,
-                                               float* d_hout, float* d_w_out_t, float* d_b_out, void* stream) {
-  HTCN_REQUIRE(hout && hout_t && w_out_t && w_out && b_out && y_id && loss_row && target_logit && g_row && d_hout && d_w_out_t,
+                                               float* workspace, float* d_hout, float* d_w_out_t, float* d_b_out,
+                                               void* stream) {
+  HTCN_REQUIRE(hout && hout_t && w_out_t && w_out && b_out && y_id && loss_row && target_logit && g_row && workspace &&
+                   d_hout && d_w_out_t,
                "score_ce_backward_bf16: NULL pointer");
   HTCN_REQUIRE(Q >= 0 && n_items > 0 && q_pad >= Q && q_pad % 8 == 0 && n_pad >= n_items && n_pad % 8 == 0,
                "score_ce_backward_bf16: Q=%d q_pad=%lld n_items=%d n_pad=%lld", Q, (long long)q_pad, n_items, (long long)n_pad);
   if (Q == 0) return HTCN_OK;
   cudaStream_t st = as_stream(stream);
   HTCN_CUDA(cudaMemsetAsync(d_hout, 0, sizeof(float) * (size_t)Q * kDim, st));
-  BwdArgs a{b_out, y_id, loss_row, target_logit, g_row, d_hout, nullptr, Q, n_items, n0, n_items, 1};
+  const int q64 = ceil_div(Q, kBN) * kBN, n64 = ceil_div(n_items, kBN) * kBN;
+  float* bL = workspace;                 // HTCN_CE_BWD_BF16_WS_FLOATS(Q, n_items)
+  float* lseL = bL + n64;
+  float* gq = lseL + q64;
+  int* yq = reinterpret_cast<int*>(gq + q64);
+  k4_bwd_prep_kernel<<<ceil_div(q64 > n64 ? q64 : n64, 256), 256, 0, st>>>(b_out, n_items, n64, loss_row, target_logit, g_row,
+                                                                          y_id, Q, q64, bL, lseL, gq, yq);
+  HTCN_LAUNCH_CHECK("k4_bwd_prep_kernel");
+  BwdArgs a{bL, lseL, gq, yq, d_hout, nullptr, Q, n_items, n0, n_items, 1};
   int32_t rc = launch_bwd<false>(hout, (uint64_t)Q, kDim, w_out_t, (uint64_t)n_items, kWtPitchBf16, w_out, (uint64_t)n_items,
                                  (uint64_t)n_pad, a, st);
   if (rc) return rc;

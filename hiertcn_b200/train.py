@@ -171,8 +171,9 @@ class HierTCNTrainer:
         if self.bf16:
             cabi.call("htcn_score_ce_backward_bf16", hq.data_ptr(), hq_t.data_ptr(), q_pad, Q, m.wt.data_ptr(),
                       self.w_out_bf16.data_ptr(), self.n_pad, m.b_out.data_ptr(), N, 0, d["y_rows"].data_ptr(),
-                      loss_row.data_ptr(), zy.data_ptr(), g_row.data_ptr(), d_hout.data_ptr(), self.g["wt"].data_ptr(),
-                      self.g["b_out"].data_ptr(), st)
+                      loss_row.data_ptr(), zy.data_ptr(), g_row.data_ptr(),
+                      buf("tr_k4_ws", (cabi.ce_bwd_bf16_ws_floats(Q, N),), f32).data_ptr(), d_hout.data_ptr(),
+                      self.g["wt"].data_ptr(), self.g["b_out"].data_ptr(), st)
         else:
             cabi.call("htcn_score_ce_backward", hout.data_ptr(), cabi.HTCN_F32, Q, m.wt.data_ptr(), m.b_out.data_ptr(), N, 0,
                       d["y_rows"].data_ptr(), loss_row.data_ptr(), zy.data_ptr(), g_row.data_ptr(), d_hout.data_ptr(),

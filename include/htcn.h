@@ -264,12 +264,14 @@ int32_t htcn_score_ce_backward(const void* hout, int32_t hout_dtype, int32_t Q, 
  * recomputing its logits tile in TMEM, turning it into dL/dZ in the epilogue and feeding it straight back to the tensor
  * core as the operand of the second product.  Operands (all bf16, built with htcn_cast_transpose_bf16 /
  * htcn_refresh_wout):  hout [Q,128], hout_t [128,q_pad] (its transpose), w_out_t [n_items,144] (scoring layout),
- * w_out [128,n_pad] (TF layout).  q_pad, n_pad: row pitches, multiples of 8.  Outputs as htcn_score_ce_backward. */
+ * w_out [128,n_pad] (TF layout).  q_pad, n_pad: row pitches, multiples of 8.  workspace:
+ * HTCN_CE_BWD_BF16_WS_FLOATS(Q, n_items) floats.  Outputs as htcn_score_ce_backward. */
+#define HTCN_CE_BWD_BF16_WS_FLOATS(Q, N) (3 * ((((int64_t)(Q)) + 63) / 64 * 64) + ((((int64_t)(N)) + 63) / 64 * 64))
 int32_t htcn_score_ce_backward_bf16(const void* hout, const void* hout_t, int64_t q_pad, int32_t Q,
                                     const void* w_out_t, const void* w_out, int64_t n_pad, const float* b_out,
                                     int32_t n_items, int32_t n0, const int32_t* y_id, const float* loss_row,
-                                    const float* target_logit, const float* g_row, float* d_hout, float* d_w_out_t,
-                                    float* d_b_out, void* stream);
+                                    const float* target_logit, const float* g_row, float* workspace, float* d_hout,
+                                    float* d_w_out_t, float* d_b_out, void* stream);
 
 /* src [R,128] f32 -> dst_rows [R,128] bf16 (or NULL) and dst_t [128,r_pad] bf16 = its transpose (or NULL; columns
  * R..r_pad-1 are zero).  r_pad % 8 == 0. */

@@ -239,8 +239,9 @@ def test_score_ce_backward_bf16_matches_numpy(Q, N):
     dw = torch.ones((N, 128), device="cuda")
     db = torch.ones(N, device="cuda")
     cabi.call("htcn_score_ce_backward_bf16", hq.data_ptr(), hq_t.data_ptr(), q_pad, Q, w_aug.data_ptr(), w_tf.data_ptr(), n_pad,
-              b_d.data_ptr(), N, 0, y_d.data_ptr(), loss_d.data_ptr(), zy_d.data_ptr(), g_d.data_ptr(), dh.data_ptr(),
-              dw.data_ptr(), db.data_ptr(), st)
+              b_d.data_ptr(), N, 0, y_d.data_ptr(), loss_d.data_ptr(), zy_d.data_ptr(), g_d.data_ptr(),
+              torch.empty(cabi.ce_bwd_bf16_ws_floats(Q, N), device="cuda").data_ptr(), dh.data_ptr(), dw.data_ptr(),
+              db.data_ptr(), st)
     torch.cuda.synchronize()
     for got, ref in ((dh.cpu().numpy(), ref_dh), (dw.cpu().numpy() - 1.0, ref_dw), (db.cpu().numpy() - 1.0, ref_db)):
         assert np.abs(got - ref).max() <= 1e-2 * np.abs(ref).max() + 1e-6, (np.abs(got - ref).max(), np.abs(ref).max())
