@@ -25,8 +25,9 @@ using namespace sm100;
 namespace {
 constexpr int kBM = 128;          // stationary rows (TMEM lanes)
 constexpr int kBN = 64;           // streamed rows per iteration
-constexpr int kStages = 3;
-constexpr int kEpiWarps = 8;      // 2 column halves x 4 TMEM lane quarters
+constexpr int kStages = 4;       // 2 tiles in use + 2 in flight: a 64-index tile is only ~0.3 us of math, TMA latency is ~1 us
+constexpr int kEpiWarps = 16;     // 4 column groups of 16 x 4 TMEM lane quarters (enough warps to hide the TMEM / MUFU latency)
+constexpr int kColsPerWarp = kBN / (kEpiWarps / 4);
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr uint32_t kTmemCols = 256;    // S[2] at columns 0 / 64, O at columns 128..255
 constexpr float kLog2e = 1.4426950408889634f;
@@ -104,7 +105,7 @@ k4_ce_backward_bf16(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       tma_load_2d(sm.x[1], &tmap_x, 64, m0, &sm.x_full);
       for (int i = 0; i < n_iter; ++i) {
         const int s = i % kStages;
-        mbar_wait_relaxed(&sm.empty[s], ((i / kStages) & 1) ^ 1);
+        mbar_wait(&sm.empty[s], ((i / kStages) & 1) ^ 1);
         mbar_arrive_expect_tx(&sm.full[s], 2 * kBN * 128 + kBM * 128 + (kPassB ? 3 : 1) * kBN * 4);
         const int j0 = (t_begin + i) * kBN;                          // rows / columns beyond the tensor are zero-filled
         tma_load_2d(sm.y[s][0], &tmap_y, 0, j0, &sm.full[s]);
@@ -126,7 +127,7 @@ k4_ce_backward_bf16(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       constexpr uint32_t idesc_o = make_idesc_bf16(kBM, kBM);
       auto issue_s = [&](int i) {                                    // S[i & 1] = X Y_i^T
         const int s = i % kStages, buf = i & 1;
-        mbar_wait_relaxed(&sm.s_free[buf], ((i >> 1) & 1) ^ 1);      // epilogue drained this accumulator
+        mbar_wait(&sm.s_free[buf], ((i >> 1) & 1) ^ 1);              // epilogue drained this accumulator
         mbar_wait(&sm.full[s], (i / kStages) & 1);
         tc_fence_after_sync();
 #pragma unroll
@@ -140,7 +141,7 @@ k4_ce_backward_bf16(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       for (int i = 0; i < n_iter; ++i) {
         if (i + 1 < n_iter) issue_s(i + 1);                          // the tensor core works on S(i+1) during epilogue(i)
         const int s = i % kStages, pb = i & 1;
-        mbar_wait_relaxed(&sm.p_full[pb], (i >> 1) & 1);             // P(i) is in shared memory
+        mbar_wait(&sm.p_full[pb], (i >> 1) & 1);                     // P(i) is in shared memory (critical path: spin)
         tc_fence_after_sync();
 #pragma unroll
         for (int k = 0; k < 4; ++k)
@@ -155,7 +156,7 @@ k4_ce_backward_bf16(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     // ===================== epilogue =====================
     const int ew = warp - 2;
     const int quarter = warp & 3;                                    // TMEM lane quarter this warp may access
-    const int half = ew >> 2;                                        // 32-column half of the 64-wide S tile
+    const int cg = ew >> 2;                                          // 16-column group of the 64-wide S tile
     const int row = quarter * 32 + lane;                             // stationary row = TMEM lane
     const int mrow = m0 + row;
     // per-lane constants
@@ -180,22 +181,22 @@ k4_ce_backward_bf16(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       mbar_wait(&sm.full[st], (i / kStages) & 1);                    // the column vectors of this tile have landed
       mbar_wait(&sm.s_full[buf], (i >> 1) & 1);
       tc_fence_after_sync();
-      uint32_t r[32];
-      tmem_ld_32x32(tmem + ((uint32_t)(quarter * 32) << 16) + buf * kBN + half * 32, r);
+      uint32_t r[kColsPerWarp];
+      tmem_ld_32x16(tmem + ((uint32_t)(quarter * 32) << 16) + buf * kBN + cg * kColsPerWarp, r);
       tmem_ld_wait(r);
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.s_free[buf]);                   // S(i) is in registers
-      uint32_t pk[16];
-      const int tgt = kPassB ? 0 : laneI - (a.n0 + j0 + half * 32);   // pass A: tile-local column of this row's target
+      uint32_t pk[kColsPerWarp / 2];
+      const int tgt = kPassB ? 0 : laneI - (a.n0 + j0 + cg * kColsPerWarp);   // pass A: tile-local column of this row's target
 #pragma unroll
-      for (int u = 0; u < 32; u += 4) {                               // 4 columns per 128-bit read of the column vectors
-        const float4 cA = *reinterpret_cast<const float4*>(&sm.colA[st][half * 32 + u]);
+      for (int u = 0; u < kColsPerWarp; u += 4) {                     // 4 columns per 128-bit read of the column vectors
+        const float4 cA = *reinterpret_cast<const float4*>(&sm.colA[st][cg * kColsPerWarp + u]);
         float4 cB = make_float4(0.f, 0.f, 0.f, 0.f);
         int4 cI = make_int4(0, 0, 0, 0);
         if (kPassB) {
-          cB = *reinterpret_cast<const float4*>(&sm.colB[st][half * 32 + u]);
-          cI = *reinterpret_cast<const int4*>(&sm.colI[st][half * 32 + u]);
+          cB = *reinterpret_cast<const float4*>(&sm.colB[st][cg * kColsPerWarp + u]);
+          cI = *reinterpret_cast<const int4*>(&sm.colI[st][cg * kColsPerWarp + u]);
         }
         const float av[4] = {cA.x, cA.y, cA.z, cA.w};
         const float bv[4] = {cB.x, cB.y, cB.z, cB.w};
@@ -217,8 +218,8 @@ k4_ce_backward_bf16(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       mbar_wait(&sm.p_free[buf], ((i >> 1) & 1) ^ 1);                // the product that read P(i-2) has retired
       uint8_t* prow = sm.p[buf] + row * 128;
 #pragma unroll
-      for (int c16 = 0; c16 < 4; ++c16) {                            // 16-byte chunk index ^= row % 8 (128B swizzle)
-        const int chunk = (half * 4 + c16) ^ (row & 7);
+      for (int c16 = 0; c16 < kColsPerWarp / 8; ++c16) {             // 16-byte chunk index ^= row % 8 (128B swizzle)
+        const int chunk = (cg * (kColsPerWarp / 8) + c16) ^ (row & 7);
         *reinterpret_cast<uint4*>(prow + (chunk << 4)) = make_uint4(pk[c16 * 4], pk[c16 * 4 + 1], pk[c16 * 4 + 2], pk[c16 * 4 + 3]);
       }
       fence_proxy_async_smem();                                      // generic-proxy writes -> tensor core reads
@@ -231,13 +232,12 @@ k4_ce_backward_bf16(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     tc_fence_after_sync();
     const bool row_ok = kPassB ? (mrow < a.n_items) : (mrow < a.Q);
     const float scale = kPassB ? 1.f : lane_g;
-#pragma unroll
-    for (int c = 0; c < 64; c += 32) {
-      uint32_t r[32];
-      tmem_ld_32x32(tmem + ((uint32_t)(quarter * 32) << 16) + 128 + half * 64 + c, r);
+    {
+      uint32_t r[32];                                                // 128 output columns / 4 column groups
+      tmem_ld_32x32(tmem + ((uint32_t)(quarter * 32) << 16) + 128 + cg * 32, r);
       tmem_ld_wait(r);
       if (row_ok) {
-        float* dst = a.out + (long long)mrow * kDim + half * 64 + c;
+        float* dst = a.out + (long long)mrow * kDim + cg * 32;
 #pragma unroll
         for (int u = 0; u < 32; u += 4)
           atomicAdd(reinterpret_cast<float4*>(dst + u),
