@@ -38,6 +38,10 @@ WORKLOADS = {
     # BASELINE.json configs[0]: the reference's own CPU-runnable case (parity-test size)
     "cfg1": dict(B=64, S=10, L=20, N=20778, emb_dim=128, lengths="dense",
                  desc="HierTCN fwd + full-catalog CE+rank scoring, XING shape, 20778 items, batch 64 users"),
+    # BASELINE.json configs[4]: training step (fwd + bwd + Adam), data-parallel over users with an NCCL gradient
+    # all-reduce, GLOBAL batch 4096 (strong scaling), full-softmax CE at the reference's catalog size
+    "cfg5": dict(B=4096, S=10, L=20, N=20778, emb_dim=128, lengths="dense", train=True,
+                 desc="HierTCN training step (fwd+bwd+Adam, full-softmax CE), XING shape, 20778 items, global batch 4096 users"),
 }
 METRIC = "user-seqs/sec HierTCN fwd+full-catalog scoring"
 UNIT = "user-seq/s"
@@ -164,6 +168,102 @@ def run_reference(opt, wl):
     print(json.dumps(line))
 
 
+def run_training(opt, wl):
+    """BASELINE config 5: one optimisation step = forward with saved activations + backward + all-reduce + Adam
+    (hiertcn_b200.train).  Strong scaling: the global batch is split over the ranks."""
+    import torch
+    import torch.distributed as dist
+    from hiertcn_b200 import _cabi as cabi
+    from hiertcn_b200.args import make_args
+    from hiertcn_b200.model_hier import HierTCN
+    from hiertcn_b200.train import HierTCNTrainer
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    warmup = max(opt.warmup, 3)
+    peaks = load_peaks()
+    Bg = wl["B"]
+    B = Bg // world
+    w = make_weights(wl)
+    a = make_args(["--item_num", str(wl["N"]), "--batch_size", str(B)])
+    tr = HierTCNTrainer(HierTCN(a, w, precision=opt.precision).build(), dist=dist if world > 1 else None, world=world)
+    x, y, m, s0 = make_inputs(wl, seed=1 + rank, B=B)
+    staged = tr.m.stage(x, y, m, s0)
+    sampler = ClockSampler(local)
+    if rank == 0 and not os.environ.get("HTCN_BENCH_NO_SAMPLER"):
+        sampler.start()
+        time.sleep(0.5)
+
+    def dev_step():
+        r = tr.forward_backward(staged=staged)
+        return tr.apply_gradients(r["scalars"])
+
+    for _ in range(warmup):
+        sc = dev_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    l0 = cabi.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    t_wall0 = time.time()
+    e0.record()
+    for _ in range(opt.steps):
+        sc = dev_step()
+    e1.record()
+    torch.cuda.synchronize()
+    t_wall1 = time.time()
+    launches = cabi.launch_count - l0
+    if world > 1:
+        dist.barrier()
+    t_ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t_ms.item()) / opt.steps
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    loss_dev = float(sc.cpu().numpy()[0])
+    # end to end: numpy batch in (H2D inside), loss + carried state out (D2H inside)
+    state = s0
+    for _ in range(2):
+        state = tr.train_step(x, y, m, state)["state"]
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e2e_steps = max(2, min(opt.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        out = tr.train_step(x, y, m, state)
+        state = out["state"]
+    dt = time.perf_counter() - t0
+    t_e = torch.tensor([dt], device="cuda")
+    if world > 1:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    Q = int(staged["Q"])
+    flops = 3 * 2.0 * Q * 128 * wl["N"] * world          # catalog products: logits, dHout, dW_out^T (recompute not counted)
+    line = {"metric": "user-seqs/sec HierTCN training step (fwd+bwd+Adam)", "value": Bg / (ms_per_step * 1e-3), "unit": UNIT,
+            "n_gpus": world, "steps": opt.steps, "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": opt.precision, "data": "synthetic",
+            "config": {"workload": wl["desc"], "users_per_gpu": B, "items": wl["N"], "scored_rows_per_gpu": Q,
+                       "parallelism": "dp%d over users, one all-reduce of the flat gradient buffer (%d floats)" % (world, tr.n_flat),
+                       "l2": "saved activations %.0f MB per step vs 126 MB L2" % (B * 200 * 512 * 5 / 1e6)},
+            "loss": loss_dev, "loss_after_e2e_steps": out["loss"],
+            "e2e": {"value": Bg / (float(t_e.item()) / e2e_steps), "unit": UNIT, "h2d_bytes_per_step": int(staged["h2d_bytes"]),
+                    "d2h_bytes_per_step": 8 * 4 + B * 256 * 4, "steps": e2e_steps,
+                    "api": "HierTCNTrainer.train_step(x_list, y_list, mask_list, state): numpy in / loss + state out"},
+            "gpu_launches": int(launches),
+            "roofline": {"kernel": "whole step, catalog products only", "bound": "tensor", "achieved": flops / (ms_per_step * 1e-3) / 1e12 / world,
+                         "peak": peaks["tf_sust"], "unit": "TFLOP/s", "frac": flops / (ms_per_step * 1e-3) / 1e12 / world / peaks["tf_sust"],
+                         "peak_source": peaks["src"], "traffic": None},
+            "clocks": clocks}
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -181,6 +281,8 @@ def main():
         wl["B"] = opt.batch
     if opt.impl == "reference":
         return run_reference(opt, wl)
+    if wl.get("train"):
+        return run_training(opt, wl)
 
     import torch
     import torch.distributed as dist
