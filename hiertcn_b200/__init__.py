@@ -9,6 +9,7 @@ Host-side mirror of the reference surface (numpy / torch plumbing only; all arit
     model_tcn.TCN             single-level TCN, model_tcn(...)                                  (reference model_tcn.py)
     loss                      calc_loss / calc_score / calc_metric_fast / top_k                 (reference loss.py)
     run_hier.evaluate_hier    evaluation loop with device-resident carried state                (reference run_hier_xing.py)
+    train.HierTCNTrainer      training step: forward + backward + TF-flavoured Adam, run_hier loop (model.py:134-141)
     dist                      data-parallel scalar all-reduce, catalog-sharded scoring (NCCL)
     _cabi                     ctypes binding of include/htcn.h
 

@@ -4,7 +4,7 @@ here; the reference round-trips it through host numpy, run_hier_xing.py:241,291,
 MRR / recall@{1,5,10} per batch and report their means, plus the per-position and per-user rank analyses
 (run_hier_xing.py:11-31, 59-79) computed from the ``ranks_float`` map the scoring kernel emits.
 
-Training (``run_hier``: backward + Adam, run_hier_xing.py:210-350) is not part of this round's hot path.
+The training half of the same function (backward + Adam, run_hier_xing.py:257-307) is hiertcn_b200.train.run_hier.
 """
 from __future__ import annotations
 
