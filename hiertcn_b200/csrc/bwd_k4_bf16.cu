@@ -3,7 +3,7 @@
 // flash-attention forward:
 //
 //     S = X Y^T        (tcgen05, 128 x 64 per iteration, K = 128, accumulator in TMEM, double-buffered)
-//     P = f(S)         (epilogue warps: TMEM -> registers -> exp / one-hot / scale -> bf16 -> 128B-swizzled smem)
+//     P = f(S)         (epilogue warps: TMEM -> registers -> exp / one-hot / scale -> bf16 pairs -> TMEM)
 //     O += P V^T       (tcgen05, 128 x 128, K = 64; the accumulator O stays in TMEM for the whole sweep)
 //
 //   pass A (dHout): X = Hout rows (128 per CTA, stationary), Y = W_out^T rows (items, streamed), V = W_out [128, N];
@@ -13,8 +13,8 @@
 //                   db[j] += sum_q P[j, q]
 //
 // with z = S + b and lse_q = loss_q + z_{q, y_q} from the forward sweep.  "TMEM lane = stationary row": every epilogue
-// thread owns one row of S, so P is written to shared memory as the K-major A operand of the second product with plain
-// 16-byte stores, and db is a thread-local sum.  Replaces TensorFlow's dense [B,T,N] softmax gradient + two GEMMs on it
+// thread owns one row of S, so P goes back to tensor memory as the A operand of the second product with one tcgen05.st
+// per thread, and db is a thread-local sum.  Replaces TensorFlow's dense [B,T,N] softmax gradient + two GEMMs on it
 // (model_tcn.py:41, loss.py:20-21, model.py:134-141).
 #include "common.cuh"
 #include "sm100.cuh"
@@ -25,18 +25,22 @@ using namespace sm100;
 namespace {
 constexpr int kBM = 128;          // stationary rows (TMEM lanes)
 constexpr int kBN = 64;           // streamed rows per iteration
-constexpr int kStages = 4;       // 2 tiles in use + 2 in flight: a 64-index tile is only ~0.3 us of math, TMA latency is ~1 us
+constexpr int kStages = 5;        // 3 tiles in use (V of tile i, Y of i+1, i+2) + 2 in flight: a 64-index tile is ~0.3 us of
+                                  // math, TMA latency ~1 us
 constexpr int kEpiWarps = 16;     // 4 column groups of 16 x 4 TMEM lane quarters (enough warps to hide the TMEM / MUFU latency)
 constexpr int kColsPerWarp = kBN / (kEpiWarps / 4);
 constexpr int kThreads = 64 + 32 * kEpiWarps;
-constexpr uint32_t kTmemCols = 256;    // S[2] at columns 0 / 64, O at columns 128..255
+constexpr uint32_t kTmemCols = 512;    // S[2] at columns 0 / 64, O at 128..255, P[2] (bf16 pairs) at 256 / 288
+constexpr uint32_t kTmemO = 128, kTmemP = 256;
+// P is a TMEM-resident A operand of the second product (tcgen05.mma with A from tensor memory, two bf16 per 32-bit
+// column): no P stores to shared memory, no fence.proxy.async, and the product reads only V from shared memory.
+
 constexpr float kLog2e = 1.4426950408889634f;
 
 struct alignas(1024) BwdSmem {
   uint8_t x[2][kBM * 128];             // stationary operand: K chunks 0..63 / 64..127
   uint8_t y[kStages][2][kBN * 128];    // streamed operand of S = X Y^T
   uint8_t v[kStages][kBM * 128];       // streamed operand of O += P V^T: [128 dims][64 streamed indices]
-  uint8_t p[2][kBM * 128];             // P tile [128 lanes][64 streamed indices]
   float colA[kStages][kBN];            // per streamed index, bulk-copied with the tiles (BwdArgs::bL / lseL / gq / yq)
   float colB[kStages][kBN];
   int colI[kStages][kBN];
@@ -138,15 +142,19 @@ k4_ce_backward_bf16(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       };
       mbar_wait(&sm.x_full, 0);
       issue_s(0);
+      if (n_iter > 1) issue_s(1);
       for (int i = 0; i < n_iter; ++i) {
-        if (i + 1 < n_iter) issue_s(i + 1);                          // the tensor core works on S(i+1) during epilogue(i)
+        // S(i+2) reuses the accumulator of S(i): it is issued as soon as the epilogue has pulled S(i) into registers
+        // (which the epilogue does one tile ahead), i.e. BEFORE waiting for P(i)
+        if (i + 2 < n_iter) issue_s(i + 2);
         const int s = i % kStages, pb = i & 1;
         mbar_wait(&sm.p_full[pb], (i >> 1) & 1);                     // P(i) is in shared memory (critical path: spin)
         tc_fence_after_sync();
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem + 128, make_desc_k_sw128(smem_u32(sm.p[pb]) + k * 32),
-                    make_desc_k_sw128(smem_u32(sm.v[s]) + k * 32), idesc_o, (i > 0) || (k > 0));
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t dv = make_desc_k_sw128(smem_u32(sm.v[s]) + k * 32);
+          umma_bf16_ts(tmem + kTmemO, tmem + kTmemP + pb * (kBN / 2) + k * 8, dv, idesc_o, (i > 0) || (k > 0));
+        }
         umma_commit(&sm.empty[s]);                                   // Y_i and V_i consumed
         umma_commit(&sm.p_free[pb]);
       }
@@ -175,18 +183,27 @@ k4_ce_backward_bf16(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     }
     float db_acc = 0.f;
 
+    // Software pipeline: the TMEM read of S(i+1) is issued BEFORE the math of S(i).  All epilogue warps are released by
+    // the same barrier, so without this every tile is a TMEM-read phase (32 KB at 64 B/clk) followed by a MUFU phase.
+    const uint32_t s_lane = tmem + ((uint32_t)(quarter * 32) << 16) + cg * kColsPerWarp;
+    uint32_t r[kColsPerWarp], rn[kColsPerWarp];
+    mbar_wait(&sm.s_full[0], 0);
+    tc_fence_after_sync();
+    tmem_ld_32x16(s_lane, r);
+    tmem_ld_wait(r);
+    tc_fence_before_sync();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sm.s_free[0]);
     for (int i = 0; i < n_iter; ++i) {
       const int buf = i & 1, st = i % kStages;
       const int j0 = (t_begin + i) * kBN;
+      const bool more = i + 1 < n_iter;
+      if (more) {
+        mbar_wait(&sm.s_full[buf ^ 1], ((i + 1) >> 1) & 1);
+        tc_fence_after_sync();
+        tmem_ld_32x16(s_lane + (buf ^ 1) * kBN, rn);                 // in flight during the math below
+      }
       mbar_wait(&sm.full[st], (i / kStages) & 1);                    // the column vectors of this tile have landed
-      mbar_wait(&sm.s_full[buf], (i >> 1) & 1);
-      tc_fence_after_sync();
-      uint32_t r[kColsPerWarp];
-      tmem_ld_32x16(tmem + ((uint32_t)(quarter * 32) << 16) + buf * kBN + cg * kColsPerWarp, r);
-      tmem_ld_wait(r);
-      tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.s_free[buf]);                   // S(i) is in registers
       uint32_t pk[kColsPerWarp / 2];
       const int tgt = kPassB ? 0 : laneI - (a.n0 + j0 + cg * kColsPerWarp);   // pass A: tile-local column of this row's target
 #pragma unroll
@@ -216,15 +233,20 @@ k4_ce_backward_bf16(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         pk[(u >> 1) + 1] = pack_bf16x2(pv[2], pv[3]);
       }
       mbar_wait(&sm.p_free[buf], ((i >> 1) & 1) ^ 1);                // the product that read P(i-2) has retired
-      uint8_t* prow = sm.p[buf] + row * 128;
-#pragma unroll
-      for (int c16 = 0; c16 < kColsPerWarp / 8; ++c16) {             // 16-byte chunk index ^= row % 8 (128B swizzle)
-        const int chunk = (cg * (kColsPerWarp / 8) + c16) ^ (row & 7);
-        *reinterpret_cast<uint4*>(prow + (chunk << 4)) = make_uint4(pk[c16 * 4], pk[c16 * 4 + 1], pk[c16 * 4 + 2], pk[c16 * 4 + 3]);
-      }
-      fence_proxy_async_smem();                                      // generic-proxy writes -> tensor core reads
+      tc_fence_after_sync();
+      tmem_st_32x8(tmem + ((uint32_t)(quarter * 32) << 16) + kTmemP + buf * (kBN / 2) + cg * (kColsPerWarp / 2), pk);
+      tmem_st_wait();
+      tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.p_full[buf]);
+      if (more) {
+        tmem_ld_wait(rn);
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.s_free[buf ^ 1]);             // S(i+1) is in registers
+#pragma unroll
+        for (int u = 0; u < kColsPerWarp; ++u) r[u] = rn[u];
+      }
     }
 
     // ---- O -> global ---------------------------------------------------------------------------------------------
@@ -234,7 +256,7 @@ k4_ce_backward_bf16(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     const float scale = kPassB ? 1.f : lane_g;
     {
       uint32_t r[32];                                                // 128 output columns / 4 column groups
-      tmem_ld_32x32(tmem + ((uint32_t)(quarter * 32) << 16) + 128 + cg * 32, r);
+      tmem_ld_32x32(tmem + ((uint32_t)(quarter * 32) << 16) + kTmemO + cg * 32, r);
       tmem_ld_wait(r);
       if (row_ok) {
         float* dst = a.out + (long long)mrow * kDim + cg * 32;
