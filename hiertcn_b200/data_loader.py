@@ -206,3 +206,20 @@ class Dataloader_hier_model_xing:
     def get_batch(self):
         self.done = self.enqueue_loop()
         return self.dequeue()
+
+    # cursor of the loader (not saved by the reference, run_hier_xing.py:317-321: a resumed run restarts the epoch)
+    def state_dict(self):
+        return dict(index=[int(i) for i in self.index], index_pointer=int(self.index_pointer),
+                    rng=self._rng.bit_generator.state,
+                    data=[[[int(v) for v in s] for s in q] for q in self.data],
+                    info=[[np.asarray(s).tolist() for s in q] for q in self.info],
+                    mask=[[int(v) for v in q] for q in self.mask], queue_len=[float(v) for v in self.queue_len])
+
+    def load_state_dict(self, d):
+        self.index = np.asarray(d["index"], dtype=np.int64)
+        self.index_pointer = int(d["index_pointer"])
+        self._rng.bit_generator.state = d["rng"]
+        self.data = [deque(np.asarray(s, dtype=np.int64) for s in q) for q in d["data"]]
+        self.info = [deque(np.asarray(s, dtype=np.float64).reshape(-1, 5) for s in q) for q in d["info"]]
+        self.mask = [deque(int(v) for v in q) for q in d["mask"]]
+        self.queue_len = np.asarray(d["queue_len"], dtype=np.float64)

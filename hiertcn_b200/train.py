@@ -241,6 +241,61 @@ class HierTCNTrainer:
         """Current weights keyed by the TF variable names of SURVEY.md A.6 (numpy fp32)."""
         return {k: v.astype(np.float32) for k, v in self._to_tf_names({k: v.detach().cpu().numpy() for k, v in self.p.items()}).items()}
 
+    # checkpoint: the variables under their TF names plus what the reference's tf.train.Saver leaves out and a resumed run
+    # needs to continue the same trajectory (SURVEY.md 5: Adam slots ARE in the Saver; the carried user state, the loader
+    # cursor and the decayed learning rate are not)
+    def save_checkpoint(self, path, state=None, loader=None, epoch=0):
+        import json
+        torch = _torch()
+        torch.cuda.synchronize(self.m.device)
+        out = {"w|" + k.replace("/", "|"): v for k, v in self.state_dict().items()}
+        for tag, flat in (("Adam", self.adam_m), ("Adam_1", self.adam_v)):       # TF slot names
+            views = {n: self._view(flat, n, sh).detach().cpu().numpy() for n, sh in self.spec}
+            for k, v in self._to_tf_names(views).items():
+                out[tag + "|" + k.replace("/", "|")] = v
+        out["meta"] = np.frombuffer(json.dumps(dict(step=self.t, lr=self.lr, beta1=self.beta1, beta2=self.beta2, eps=self.eps,
+                                                    epoch=int(epoch), precision=self.m.precision)).encode(), dtype=np.uint8)
+        if state is not None:
+            out["carried_state"] = state.detach().cpu().numpy() if hasattr(state, "detach") else np.asarray(state, np.float32)
+        if loader is not None and hasattr(loader, "state_dict"):
+            out["loader"] = np.frombuffer(json.dumps(loader.state_dict()).encode(), dtype=np.uint8)
+        np.savez(path, **out)
+
+    def load_checkpoint(self, path, loader=None):
+        """Restores weights, Adam slots, step counter and lr; returns dict(epoch, state) (state = carried user state or None)."""
+        import json
+        torch = _torch()
+        z = np.load(path)
+        meta = json.loads(bytes(z["meta"]).decode())
+
+        def scatter(prefix, flat):
+            t = {k[len(prefix):].replace("|", "/"): z[k] for k in z.files if k.startswith(prefix)}
+            m = self.m
+            named = {"E": t["hier/emb/kernel"], "b_emb": t["hier/emb/bias"], "w_in_x": t["hier/tcn/emb/kernel"][:D],
+                     "w_in_state": t["hier/tcn/emb/kernel"][D:], "wt": np.ascontiguousarray(t["hier/tcn/dense/kernel"].T),
+                     "b_out": t["hier/tcn/dense/bias"]}
+            for l in range(m.n_levels):
+                named[f"conv_w{l}"] = t[f"hier/tcn/temporal_conv_net/tblock_{l}/conv1/kernel"]
+                named[f"conv_b{l}"] = t[f"hier/tcn/temporal_conv_net/tblock_{l}/conv1/bias"]
+            for g in range(m.G):
+                p = f"hier/multi_rnn_cell/cell_{g}/gru_cell"
+                named[f"gate_w{g}"], named[f"gate_b{g}"] = t[p + "/gates/kernel"], t[p + "/gates/bias"]
+                named[f"cand_w{g}"], named[f"cand_b{g}"] = t[p + "/candidate/kernel"], t[p + "/candidate/bias"]
+            for n, sh in self.spec:
+                self._view(flat, n, sh).copy_(torch.from_numpy(np.ascontiguousarray(named[n], dtype=np.float32)).reshape(sh))
+
+        scatter("w|", self.params)
+        scatter("Adam|", self.adam_m)
+        scatter("Adam_1|", self.adam_v)
+        self.grads.zero_()
+        self.t, self.lr = int(meta["step"]), float(meta["lr"])
+        if self.bf16:
+            self._refresh_bf16_tables()
+        if loader is not None and "loader" in z.files and hasattr(loader, "load_state_dict"):
+            loader.load_state_dict(json.loads(bytes(z["loader"]).decode()))
+        torch.cuda.synchronize(self.m.device)
+        return dict(epoch=int(meta["epoch"]), state=z["carried_state"] if "carried_state" in z.files else None)
+
     def _to_tf_names(self, t):
         m = self.m
         w = {"hier/emb/kernel": t["E"], "hier/emb/bias": t["b_emb"],

@@ -278,3 +278,34 @@ def test_train_steps_bf16_tier_track_oracle():
     # evaluation through the bf16 model sees the refreshed tables
     ev = tr.m.step(x0, y0, m0, s0)
     assert np.isfinite(ev["loss"]) and ev["loss"] < losses[0]
+
+
+@pytest.mark.parametrize("precision", ["f32", "bf16"])
+def test_checkpoint_resume_continues_the_same_trajectory(tmp_path, precision):
+    """weights under TF variable names + Adam slots + step + carried state: resuming == never stopping"""
+    from hiertcn_b200.data_loader import synthetic_batch
+    _, _, _, s0, w = small_case(B=6, S=3, L=5, N=113, seed=9, kernel_scale=1.0)
+    batches = [synthetic_batch(6, 3, 5, 113, seed=60 + i, lengths="ragged", id_dist="uniform", mask_keep=0.7) for i in range(5)]
+    a_tr = make_trainer(w, 113, precision=precision)
+    state = s0
+    for xb, yb, mb in batches[:3]:
+        state = a_tr.train_step(xb, yb, mb, state)["state"]
+    ck = str(tmp_path / "ck.npz")
+    a_tr.save_checkpoint(ck, state=state, epoch=7)
+    rest_a = []
+    for xb, yb, mb in batches[3:]:
+        o = a_tr.train_step(xb, yb, mb, state)
+        state = o["state"]
+        rest_a.append(o["loss"])
+    b_tr = make_trainer(w, 113, precision=precision)          # fresh process stand-in: initial weights, then restore
+    meta = b_tr.load_checkpoint(ck)
+    assert meta["epoch"] == 7 and b_tr.t == 3
+    st_b, rest_b = meta["state"], []
+    for xb, yb, mb in batches[3:]:
+        o = b_tr.train_step(xb, yb, mb, st_b)
+        st_b = o["state"]
+        rest_b.append(o["loss"])
+    np.testing.assert_allclose(rest_b, rest_a, rtol=1e-5 if precision == "f32" else 1e-3)
+    z = np.load(ck)
+    assert "w|hier|tcn|dense|kernel" in z.files and z["w|hier|tcn|dense|kernel"].shape == (128, 113)
+    assert "Adam|hier|emb|kernel" in z.files and "Adam_1|hier|multi_rnn_cell|cell_1|gru_cell|gates|kernel" in z.files

@@ -72,3 +72,20 @@ def test_weight_contract_names_and_roundtrip(tmp_path):
     w3["hier/tcn/dense/g"] = np.full(30, 2.0, np.float32)
     f = fold_weightnorm(w3)
     np.testing.assert_allclose(np.sqrt((f["hier/tcn/dense/kernel"] ** 2).sum(0)), 2.0, rtol=1e-5)
+
+
+def test_loader_state_dict_resumes_the_same_batches():
+    import json
+    table, data = make_synthetic_interactions(40, 101, seed=5)
+    a = make_args(["--batch_size", "4", "--max_session_num", "3", "--max_activity_len", "5", "--shuffle"])
+    ld = Dataloader_hier_model_xing(a, "train", data=(table, data))
+    for _ in range(3):
+        ld.get_batch()
+    snap = json.loads(json.dumps(ld.state_dict()))           # survives a JSON round trip (checkpoint format)
+    want = [ld.get_batch() for _ in range(4)]
+    ld2 = Dataloader_hier_model_xing(a, "train", data=(table, data))
+    ld2.load_state_dict(snap)
+    got = [ld2.get_batch() for _ in range(4)]
+    for (x1, y1, m1, i1), (x2, y2, m2, i2) in zip(want, got):
+        for u, v in zip(x1 + y1 + m1 + i1, x2 + y2 + m2 + i2):
+            np.testing.assert_array_equal(u, v)
