@@ -53,11 +53,13 @@ SIGNATURES = {
     "htcn_gather_backward": [_p, _p, _p, _p, _ip, _i, _i, _i, _i, _p, _p, _p],
     "htcn_adam_step": [_p, _p, _p, _p, C.c_int64, _f, _f, _f, _f, _p, _i, _p],
     "htcn_refresh_wout": [_p, _p, _i, _p, _i, _p],
+    "htcn_assemble_batch": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p],
 }
 PLAIN = {"htcn_abi_version": (C.c_int32, []), "htcn_last_error": (C.c_char_p, []),
          "htcn_device_ok": (C.c_int32, []),
          "htcn_topk_workspace_bytes": (C.c_int64, [_i, _i, _i, _i, _i]),
-         "htcn_gru_backward_scratch_floats": (C.c_int64, [_i, _i, _i])}
+         "htcn_gru_backward_scratch_floats": (C.c_int64, [_i, _i, _i]),
+         "htcn_batcher_scratch_ints": (C.c_int64, [_i, _i])}
 
 
 class HtcnError(RuntimeError):
@@ -97,7 +99,7 @@ LAUNCHES_PER_CALL = {"htcn_gather_meanpool": 2, "htcn_gru_sessions": 1, "htcn_tc
                      # training step (the per-call counts of the multi-launch entry points are added by the caller)
                      "htcn_loss_row_weights": 1, "htcn_score_ce_backward": 1, "htcn_gru_sessions_train": 1,
                      "htcn_gather_backward": 2, "htcn_adam_step": 1, "htcn_refresh_wout": 1,
-                     "htcn_score_ce_backward_bf16": 3, "htcn_cast_transpose_bf16": 1}
+                     "htcn_score_ce_backward_bf16": 3, "htcn_cast_transpose_bf16": 1, "htcn_assemble_batch": 4}
 launch_count = 0
 
 

@@ -436,13 +436,14 @@ class HierTCN:
         return out
 
     # ------------------------------------------------------------------ the reference's sess.run
-    def step_async(self, x_list, y_list, mask_list, state=None, metrics=True, per_position=False, topk=0,
-                   state_on_device=False, neg_ids=None):
+    def step_async(self, x_list=None, y_list=None, mask_list=None, state=None, metrics=True, per_position=False, topk=0,
+                   state_on_device=False, neg_ids=None, staged=None):
         """Enqueue one step (H2D on the copy stream, kernels and the D2H of the results on the compute stream) and
         return a ``PendingStep``; ``.result()`` waits for it and returns the host dict of ``step``.  Submitting step
         i+1 before collecting step i hides the host-side batch packing and the PCIe copies behind the kernels."""
         torch = _torch()
-        staged = self.stage(x_list, y_list, mask_list, state, neg_ids)
+        if staged is None:         # host batch; a DeviceBatcher (hiertcn_b200.device_batcher) hands in `staged` directly
+            staged = self.stage(x_list, y_list, mask_list, state, neg_ids)
         scores, state_out = self.forward(staged=staged)
         if "neg_ids" in staged:
             neg_ids = staged["neg_ids"]
@@ -473,14 +474,14 @@ class HierTCN:
         ev.record(torch.cuda.current_stream(self.device))
         return PendingStep(ev, host, state_out if state_on_device else None, topk)
 
-    def step(self, x_list, y_list, mask_list, state=None, metrics=True, per_position=False, topk=0,
-             state_on_device=False, neg_ids=None):
+    def step(self, x_list=None, y_list=None, mask_list=None, state=None, metrics=True, per_position=False, topk=0,
+             state_on_device=False, neg_ids=None, staged=None):
         """Host in, host out -- the call ``sess.run([loss, state, ranks_float, ...], feed_dict)`` of
         run_hier_xing.py:145-149 maps to.  Includes the H2D of the batch and the D2H of the results.
         ``state`` may be a numpy array (reference behaviour) or the device tensor returned by a previous step with
         ``state_on_device=True`` (then the carried state never leaves HBM)."""
         return self.step_async(x_list, y_list, mask_list, state, metrics, per_position, topk, state_on_device,
-                               neg_ids).result()
+                               neg_ids, staged).result()
 
 
 class PendingStep:

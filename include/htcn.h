@@ -330,6 +330,22 @@ int32_t htcn_adam_step(float* param, float* grad, float* m, float* v, int64_t n,
 int32_t htcn_refresh_wout(const float* w_out_t_f32, const float* b_out, int32_t N, void* w_out_t, int32_t dtype,
                           void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Device-side batch assembly.  Replaces the host loop of data_loader.py:233-272 (dequeue: pad the
+ * sessions at the head of every slot's queue, x = y shifted by one, reset mask) for an interaction log resident in HBM:
+ *   items [n_events] int32 (item ids, sessions contiguous), sess_off [n_sessions+1] int32,
+ *   sched_sess [B, sched_pitch] int32 / sched_last [B, sched_pitch] uint8: for every user slot the session ids in
+ *   dequeue order and whether a session is its user's last (the queue discipline of data_loader.py:170-231, replayed
+ *   once on the host).  The batch takes sessions first_session .. first_session+S-1 of every slot.
+ * Outputs: x_id, y_id [B, S*L] (every slot padded to L = max_activity_len), mask [S,B], and the compaction of the scored
+ * positions: row_of [B*S*L] (-1 = padding), y_rows [<= B*S*L], n_valid[1] (= Q).  scratch: htcn_batcher_scratch_ints ints.
+ * ------------------------------------------------------------------------------------------- */
+int64_t htcn_batcher_scratch_ints(int32_t B, int32_t T);
+int32_t htcn_assemble_batch(const int32_t* items, const int32_t* sess_off, const int32_t* sched_sess,
+                            const uint8_t* sched_last, int32_t sched_pitch, int32_t first_session, int32_t B, int32_t S,
+                            int32_t L, int32_t* x_id, int32_t* y_id, float* mask, int32_t* row_of, int32_t* y_rows,
+                            int32_t* n_valid, int32_t* scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

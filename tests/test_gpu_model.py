@@ -223,3 +223,41 @@ def test_single_level_model_tcn(B, L, levels, precision):
     if precision == "f32":
         amb = O.rank_ambiguity(pred_m, y, 2e-5) * (y > 0)
         assert (np.abs(r["ranks"].cpu().numpy() - met[6]) <= amb).all()
+
+
+@pytest.mark.parametrize("precision", ["f32", "bf16"])
+def test_device_batcher_equals_host_loader(precision):
+    """batches assembled in HBM (htcn_assemble_batch, fixed slot width) == the queue loader's host batches: same loss,
+    metrics, carried state, and the same per-position ranks on the positions both layouts hold"""
+    from hiertcn_b200.args import make_args
+    from hiertcn_b200.data_loader import Dataloader_hier_model_xing, make_synthetic_interactions
+    from hiertcn_b200.device_batcher import DeviceBatcher
+    from hiertcn_b200.model_hier import HierTCN
+    from hiertcn_b200.run_hier import evaluate_hier
+    N = 997
+    a = make_args(["--item_num", str(N), "--batch_size", "12", "--max_session_num", "4", "--max_activity_len", "9"])
+    data = make_synthetic_interactions(80, N, seed=4)
+    model = HierTCN(a, None, precision=precision).build()
+    host = Dataloader_hier_model_xing(a, "train", data=data)
+    devb = DeviceBatcher(a, data, passes=1)
+    assert devb.n_batches >= 3
+    st_h = st_d = None
+    for k in range(3):
+        x, y, m, _ = host.get_batch()
+        oh = model.step(x, y, m, st_h, per_position=True, state_on_device=True)
+        st_h = oh["state"]
+        staged = devb.next(st_d)
+        od = model.step(staged=staged, per_position=True, state_on_device=True)
+        st_d = od["state"]
+        for key in ("loss", "recall1", "recall5", "recall10", "mrr", "mrp", "user_count", "n_valid"):
+            assert abs(oh[key] - od[key]) <= 1e-5 * max(1.0, abs(oh[key])), (k, key, oh[key], od[key])
+        assert torch.allclose(st_h, st_d, rtol=1e-5, atol=1e-6)
+        # host layout: slot s has width L_s = batch max; device layout: width 9 -> compare slot by slot
+        off, L = 0, 9
+        for s in range(4):
+            w = y[s].shape[1]
+            np.testing.assert_array_equal(oh["ranks"][:, off:off + w], od["ranks"][:, s * L:s * L + w])
+            assert (od["ranks"][:, s * L + w:(s + 1) * L] == 0).all()
+            off += w
+    res = evaluate_hier(model, DeviceBatcher(a, data, passes=1), max_batches=2)
+    assert res["batches"] == 2 and np.isfinite(res["loss"])

@@ -89,3 +89,31 @@ def test_loader_state_dict_resumes_the_same_batches():
     for (x1, y1, m1, i1), (x2, y2, m2, i2) in zip(want, got):
         for u, v in zip(x1 + y1 + m1 + i1, x2 + y2 + m2 + i2):
             np.testing.assert_array_equal(u, v)
+
+
+def test_device_batcher_schedule_replays_the_loader_queues():
+    """hiertcn_b200.device_batcher.build_schedule (host half of the GPU batcher) vs the queue loader, batch by batch"""
+    from hiertcn_b200.device_batcher import build_schedule
+    table, data = make_synthetic_interactions(60, 211, seed=8)
+    for shuffle in (False, True):
+        a = make_args(["--batch_size", "5", "--max_session_num", "3", "--max_activity_len", "6"] + (["--shuffle"] if shuffle else []))
+        ld = Dataloader_hier_model_xing(a, "train", data=(table, data))
+        n_train = int(table.shape[0] * 0.8)
+        items, sess_off, sched, flag, lens = build_schedule(table[:n_train], data, 5, shuffle, getattr(a, "seed", 0), passes=2)
+        B, S, L = 5, 3, 6
+        for k in range(int(lens.min()) // S):
+            x, y, m, _ = ld.get_batch()
+            for s in range(S):
+                for b in range(B):
+                    sid = sched[b, k * S + s]
+                    seq = items[sess_off[sid]:sess_off[sid + 1]][:L]
+                    n = len(seq)
+                    yy = np.zeros(L, np.int64)
+                    xx = np.zeros(L, np.int64)
+                    yy[:n] = seq
+                    xx[1:min(n + 1, L)] = seq[:L - 1][:n]
+                    w = y[s].shape[1]
+                    np.testing.assert_array_equal(y[s][b], yy[:w])
+                    np.testing.assert_array_equal(x[s][b], xx[:w])
+                    assert (yy[w:] == 0).all()
+                    assert m[s][b, 0] == 1 - flag[b, k * S + s]
