@@ -100,6 +100,61 @@ __global__ void score_finish_kernel(const float* __restrict__ pm, const float* _
   }
 }
 
+// ---- exact redo of CE rows whose tensor-core partial sum overflowed ---------------------------------------------------
+// The bf16 sweep keeps sum_j 2^((z_j - z_y) log2e) with the TARGET logit as reference point (no running max): a row whose
+// best logit exceeds its target logit by more than ~88 overflows fp32 and comes out of score_finish as +inf / NaN.  Such
+// rows (softmax probability of the target < e^-88) are redone here with an online-max log-sum-exp over the whole
+// catalog, one CTA per row, same bf16 operands; rows with a finite loss are skipped (one load each).
+__global__ void __launch_bounds__(256)
+ce_repair_bf16_kernel(const __nv_bfloat16* __restrict__ hout, int Q, const __nv_bfloat16* __restrict__ wt, int n_items,
+                      const float* __restrict__ zy, float* __restrict__ loss_row, int* __restrict__ repaired) {
+  __shared__ float h[kDim];
+  __shared__ float red_m[8], red_s[8];
+  for (int q = blockIdx.x; q < Q; q += gridDim.x) {
+    const float cur = loss_row[q];
+    if (isfinite(cur)) continue;                                  // block-uniform
+    __syncthreads();
+    if (threadIdx.x < kDim) h[threadIdx.x] = __bfloat162float(hout[(long long)q * kDim + threadIdx.x]);
+    __syncthreads();
+    float m = -INFINITY, sum = 0.f;
+    for (int j = threadIdx.x; j < n_items; j += blockDim.x) {
+      const uint4* row = reinterpret_cast<const uint4*>(wt + (long long)j * kWtPitchBf16);
+      float z = 0.f;
+#pragma unroll 4
+      for (int c = 0; c < kDim / 8; ++c) {
+        const uint4 w = __ldg(row + c);
+        const float* hh = h + c * 8;
+        z = fmaf(hh[0], bf16_lo(w.x), z); z = fmaf(hh[1], bf16_hi(w.x), z);
+        z = fmaf(hh[2], bf16_lo(w.y), z); z = fmaf(hh[3], bf16_hi(w.y), z);
+        z = fmaf(hh[4], bf16_lo(w.z), z); z = fmaf(hh[5], bf16_hi(w.z), z);
+        z = fmaf(hh[6], bf16_lo(w.w), z); z = fmaf(hh[7], bf16_hi(w.w), z);
+      }
+      const uint32_t bb = *reinterpret_cast<const uint32_t*>(wt + (long long)j * kWtPitchBf16 + kDim);   // b_hi | b_lo
+      z += bf16_lo(bb) + bf16_hi(bb);
+      const float mn = fmaxf(m, z);
+      sum = sum * __expf(m - mn) + __expf(z - mn);
+      m = mn;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, sum, o);
+      const float mn = fmaxf(m, m2);
+      sum = (mn == -INFINITY) ? 0.f : sum * __expf(m - mn) + s2 * __expf(m2 - mn);
+      m = mn;
+    }
+    if ((threadIdx.x & 31) == 0) { red_m[threadIdx.x >> 5] = m; red_s[threadIdx.x >> 5] = sum; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float M = -INFINITY;
+      for (int w = 0; w < 8; ++w) M = fmaxf(M, red_m[w]);
+      float S = 0.f;
+      for (int w = 0; w < 8; ++w) S += (red_m[w] == -INFINITY) ? 0.f : red_s[w] * expf(red_m[w] - M);
+      loss_row[q] = (M + logf(S)) - zy[q];
+      if (repaired) atomicAdd(repaired, 1);
+    }
+  }
+}
+
 // ---- top-k merge: one CTA per row, rank-by-counting over the n_part*k candidates ----------------
 // order: score desc, index asc (tf.nn.top_k); empty slots (idx < 0) sort last.
 __global__ void __launch_bounds__(128)
@@ -340,6 +395,20 @@ extern "C" int32_t htcn_score_finish(const float* part_max, const float* part_su
   score_finish_kernel<<<ceil_div(Q, 256), 256, 0, as_stream(stream)>>>(part_max, part_sum, part_cnt, n_part, Q,
                                                                       y_id, target_logit, loss_row, rank_row);
   HTCN_LAUNCH_CHECK("score_finish");
+  return HTCN_OK;
+}
+
+extern "C" int32_t htcn_score_ce_repair(const void* hout, int32_t precision, int32_t Q, const void* w_out_t,
+                                        int32_t n_items, const float* target_logit, float* loss_row, int32_t* repaired,
+                                        void* stream) {
+  HTCN_REQUIRE(hout && w_out_t && target_logit && loss_row && Q > 0 && n_items > 0, "score_ce_repair: bad args");
+  if (precision == HTCN_F32) return HTCN_OK;           // the fp32 sweep keeps a running max: nothing to repair
+  HTCN_REQUIRE(precision == HTCN_BF16, "score_ce_repair: precision %d", precision);
+  const int grid = Q < 148 * 8 ? Q : 148 * 8;
+  ce_repair_bf16_kernel<<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(hout), Q,
+                                                            reinterpret_cast<const __nv_bfloat16*>(w_out_t), n_items,
+                                                            target_logit, loss_row, repaired);
+  HTCN_LAUNCH_CHECK("ce_repair_bf16_kernel");
   return HTCN_OK;
 }
 

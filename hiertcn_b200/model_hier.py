@@ -355,6 +355,10 @@ class HierTCN:
             rank_row = self._buf("rank_row", (Q,), f32) if rank else None
             cabi.call("htcn_score_finish", P(pm), P(ps), P(pc), ns, Q, scores.y_rows.data_ptr(), zy.data_ptr(),
                       P(loss_row), P(rank_row), st)
+            if ce and self.precision == "bf16" and self.n_out == self.N:
+                # rows whose target is > 88 nats below the best logit overflow the target-referenced partial sum: redo them
+                cabi.call("htcn_score_ce_repair", scores.hout.data_ptr(), self.act_dtype, Q, self.wt.data_ptr(), self.N,
+                          zy.data_ptr(), loss_row.data_ptr(), None, st)
             out.update(loss_row=loss_row, rank_row=rank_row, target_logit=zy)
         if topk:
             out.update(self.topk(scores.hout, Q, topk))

@@ -162,6 +162,9 @@ class HierTCNTrainer:
         rank_row = buf("rank_row", (Q,), f32) if metrics else None
         cabi.call("htcn_score_finish", pm.data_ptr(), ps.data_ptr(), P(pc), ns, Q, d["y_rows"].data_ptr(), zy.data_ptr(),
                   loss_row.data_ptr(), P(rank_row), st)
+        if self.bf16:
+            cabi.call("htcn_score_ce_repair", hq.data_ptr(), prec, Q, m.wt.data_ptr(), N, zy.data_ptr(), loss_row.data_ptr(),
+                      None, st)
         cabi.call("htcn_loss_metrics_reduce", loss_row.data_ptr(), P(rank_row), d["row_of"].data_ptr(), d["y_id"].data_ptr(),
                   B, T, N, None, None, None, buf("user_part", (B, 8), f32).data_ptr(), scalars.data_ptr(), st)
         # ---- backward

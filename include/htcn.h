@@ -202,6 +202,14 @@ int32_t htcn_score_topk(const void* hout, int32_t precision, int32_t Q, const vo
                         int64_t workspace_bytes, float* out_val, int32_t* out_idx, int32_t* overflow_rows,
                         void* stream);
 
+/* Exact redo of the cross-entropy rows whose bf16-tier partial sum overflowed: the tensor-core sweep sums
+ * 2^((z_j - z_y) log2e) with the target logit as reference point, which exceeds fp32 when some logit beats the target by
+ * more than ~88 (target probability < e^-88); such rows leave htcn_score_finish as +inf.  This call recomputes them with
+ * an online-max log-sum-exp over the whole (unsharded) catalog on the same bf16 operands and overwrites loss_row; finite
+ * rows cost one load.  repaired (device int, may be NULL) is incremented per redone row.  No-op in the fp32 tier. */
+int32_t htcn_score_ce_repair(const void* hout, int32_t precision, int32_t Q, const void* w_out_t, int32_t n_items,
+                             const float* target_logit, float* loss_row, int32_t* repaired, void* stream);
+
 /* k-way merge of per-part top-k lists -> [Q,k] sorted by (score desc, index asc) [TF top_k order] */
 int32_t htcn_topk_merge(const float* part_val, const int32_t* part_idx, int32_t n_part, int32_t Q,
                         int32_t k, float* out_val, int32_t* out_idx, void* stream);

@@ -401,6 +401,37 @@ def test_k4_bf16_tcgen05(lib, Q, N, n_split):
     np.testing.assert_array_equal(ov.cpu().numpy(), v_ref)
 
 
+def test_k4_bf16_ce_overflow_rows_are_repaired(lib):
+    """a target more than ~88 nats below the best logit overflows the target-referenced partial sum of the tensor-core
+    sweep (+inf out of score_finish); htcn_score_ce_repair redoes exactly those rows with a running-max log-sum-exp"""
+    rng = np.random.default_rng(3)
+    Q, N = 150, 3000
+    hout = O.bf16_round(rng.normal(size=(Q, 128)).astype(np.float32))
+    w_out = (rng.normal(size=(128, N)) * 0.3).astype(np.float32)
+    b_out = (rng.normal(size=N) * 0.2).astype(np.float32)
+    y = rng.integers(1, N, size=Q).astype(np.int32)
+    bad = np.arange(0, Q, 7)
+    hout[bad] *= 12.0                                                 # logit spread of these rows ~ +-120
+    hout = O.bf16_round(hout)
+    wt = torch.empty((N, lib.WT_PITCH_BF16), dtype=torch.bfloat16, device="cuda")
+    hd, bd, yd, w_out_d = dev(hout).to(torch.bfloat16), dev(b_out), dev(y), dev(w_out)
+    lib.call("htcn_prepare_wout", P(w_out_d), P(bd), N, P(wt), lib.HTCN_BF16, None)
+    z_gpu = debug_logits_bf16(lib, hd, wt, bd).cpu().numpy().astype(np.float64)
+    ref = O.softmax_cross_entropy_with_logits(y, z_gpu)
+    zy, pm, ps, pc, _, _ = run_score(lib, hd, wt, bd, yd, lib.SCORE_CE | lib.SCORE_RANK, 0, 3, precision=lib.HTCN_BF16)
+    loss_row = torch.empty(Q, dtype=torch.float32, device="cuda")
+    lib.call("htcn_score_finish", P(pm), P(ps), P(pc), 3, Q, P(yd), P(zy), P(loss_row), None, None)
+    before = loss_row.cpu().numpy()
+    overflowed = ~np.isfinite(before)
+    assert overflowed.any() and set(np.flatnonzero(overflowed)) <= set(bad)      # the case does exercise the overflow
+    cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+    lib.call("htcn_score_ce_repair", P(hd), lib.HTCN_BF16, Q, P(wt), N, P(zy), P(loss_row), P(cnt), None)
+    after = loss_row.cpu().numpy()
+    assert int(cnt.item()) == int(overflowed.sum())
+    np.testing.assert_array_equal(after[~overflowed], before[~overflowed])       # finite rows untouched
+    np.testing.assert_allclose(after, ref, rtol=1e-4, atol=1e-4)
+
+
 # ------------------------------------------------------------------------------------------ K2 bf16 (tcgen05, fused levels)
 def run_k2_bf16(lib, xe_bf16, w, sbias, slot_off, B, T, S, K, n_levels, out_row=None, n_out=None):
     conv_w = [dev(w[f"hier/tcn/temporal_conv_net/tblock_{l}/conv1/kernel"]) for l in range(n_levels)]
