@@ -2,13 +2,13 @@
 // cross-entropy without materialising the [Q, N] logits or their gradient, as two passes of ONE kernel shaped like a
 // flash-attention forward:
 //
-//     S = X Y^T        (tcgen05, 128 x 64 per iteration, K = 128, accumulator in TMEM, double-buffered)
-//     P = f(S)         (epilogue warps: TMEM -> registers -> exp / one-hot / scale -> bf16 pairs -> TMEM)
-//     O += P V^T       (tcgen05, 128 x 128, K = 64; the accumulator O stays in TMEM for the whole sweep)
+//     S = X Y^T        (tcgen05, 2 x (128 x 64) per iteration, K = 128, accumulators in TMEM, double-buffered)
+//     P = f(S)         (epilogue warps: TMEM -> registers -> exp / one-hot / scale -> bf16 pairs -> TMEM, over S)
+//     O += P V^T       (tcgen05 with A from TMEM, 2 x (128 x 128), K = 64; O stays in TMEM for the whole sweep)
 //
-//   pass A (dHout): X = Hout rows (128 per CTA, stationary), Y = W_out^T rows (items, streamed), V = W_out [128, N];
+//   pass A (dHout): X = Hout rows (256 per CTA, stationary), Y = W_out^T rows (items, streamed), V = W_out [128, N];
 //                   P[q, j] = exp(z - lse_q) - [j == y_q];  dHout[q] = g_q * O[q]
-//   pass B (dW^T):  X = W_out^T rows (128 items per CTA, stationary), Y = Hout rows (queries, streamed),
+//   pass B (dW^T):  X = W_out^T rows (256 items per CTA, stationary), Y = Hout rows (queries, streamed),
 //                   V = Hout^T [128, Q];  P[j, q] = g_q (exp(z - lse_q) - [j == y_q]);  dW^T[j] += O[j];
 //                   db[j] += sum_q P[j, q]
 //
@@ -23,28 +23,31 @@ namespace htcn {
 using namespace sm100;
 
 namespace {
-constexpr int kBM = 128;          // stationary rows (TMEM lanes)
+constexpr int kBM = 128;          // TMEM lanes = rows of one stationary half
+constexpr int kHalves = 2;        // a CTA keeps 2 x 128 stationary rows, so every streamed tile (32 KB out of L2) is used
+                                  // twice: at one half per CTA the kernel ran into the L2 bandwidth ceiling (~43 B/clk/SM)
 constexpr int kBN = 64;           // streamed rows per iteration
-constexpr int kStages = 5;        // 3 tiles in use (V of tile i, Y of i+1, i+2) + 2 in flight: a 64-index tile is ~0.3 us of
-                                  // math, TMA latency ~1 us
-constexpr int kEpiWarps = 16;     // 4 column groups of 16 x 4 TMEM lane quarters (enough warps to hide the TMEM / MUFU latency)
-constexpr int kColsPerWarp = kBN / (kEpiWarps / 4);
+constexpr int kStages = 4;
+constexpr int kEpiWarps = 16;     // (half, 32-column group) x 4 TMEM lane quarters
+constexpr int kColsPerWarp = 32;
 constexpr int kThreads = 64 + 32 * kEpiWarps;
-constexpr uint32_t kTmemCols = 512;    // S[2] at columns 0 / 64, O at 128..255, P[2] (bf16 pairs) at 256 / 288
-constexpr uint32_t kTmemO = 128, kTmemP = 256;
+// TMEM map (512 columns): S[half][buf] = 64 fp32 columns at (half*2 + buf)*64; O[half] = 128 columns at 256 + half*128.
 // P is a TMEM-resident A operand of the second product (tcgen05.mma with A from tensor memory, two bf16 per 32-bit
-// column): no P stores to shared memory, no fence.proxy.async, and the product reads only V from shared memory.
-
+// column) and ALIASES S: the epilogue warp that has read columns [32 cg, 32 cg + 32) of S(half, buf) writes its 16 packed
+// columns back to [32 cg, 32 cg + 16).  The tensor pipe executes in issue order, so S(i+2) -- issued after the product that
+// consumes P(i) -- cannot overwrite P(i) early, and no "accumulator free" barriers are needed.
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kTmemO = 256;
 constexpr float kLog2e = 1.4426950408889634f;
 
 struct alignas(1024) BwdSmem {
-  uint8_t x[2][kBM * 128];             // stationary operand: K chunks 0..63 / 64..127
+  uint8_t x[kHalves][2][kBM * 128];    // stationary operand: [half][K chunk 0..63 / 64..127]
   uint8_t y[kStages][2][kBN * 128];    // streamed operand of S = X Y^T
   uint8_t v[kStages][kBM * 128];       // streamed operand of O += P V^T: [128 dims][64 streamed indices]
   float colA[kStages][kBN];            // per streamed index, bulk-copied with the tiles (BwdArgs::bL / lseL / gq / yq)
   float colB[kStages][kBN];
   int colI[kStages][kBN];
-  uint64_t x_full, full[kStages], empty[kStages], s_full[2], s_free[2], p_full[2], p_free[2], o_full;
+  uint64_t x_full, full[kStages], empty[kStages], s_full[2], p_full[2], o_full;
   uint32_t tmem_base;
 };
 
@@ -70,7 +73,7 @@ k4_ce_backward_bf16(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   extern __shared__ uint8_t smem_raw[];
   auto& sm = *reinterpret_cast<BwdSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * kBM;                                   // first stationary row
+  const int m0 = blockIdx.x * (kHalves * kBM);                       // first stationary row
   const int tiles_all = (a.n_stream + kBN - 1) / kBN;
   const int t_begin = (int)((long long)tiles_all * blockIdx.y / a.n_split);
   const int t_end = (int)((long long)tiles_all * (blockIdx.y + 1) / a.n_split);
@@ -89,9 +92,7 @@ k4_ce_backward_bf16(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&sm.s_full[s], 1);
-      mbar_init(&sm.s_free[s], kEpiWarps);
       mbar_init(&sm.p_full[s], kEpiWarps);
-      mbar_init(&sm.p_free[s], 1);
     }
     fence_barrier_init();
   }
@@ -104,9 +105,11 @@ k4_ce_backward_bf16(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      mbar_arrive_expect_tx(&sm.x_full, 2 * kBM * 128);
-      tma_load_2d(sm.x[0], &tmap_x, 0, m0, &sm.x_full);
-      tma_load_2d(sm.x[1], &tmap_x, 64, m0, &sm.x_full);
+      mbar_arrive_expect_tx(&sm.x_full, kHalves * 2 * kBM * 128);
+      for (int h = 0; h < kHalves; ++h) {
+        tma_load_2d(sm.x[h][0], &tmap_x, 0, m0 + h * kBM, &sm.x_full);
+        tma_load_2d(sm.x[h][1], &tmap_x, 64, m0 + h * kBM, &sm.x_full);
+      }
       for (int i = 0; i < n_iter; ++i) {
         const int s = i % kStages;
         mbar_wait(&sm.empty[s], ((i / kStages) & 1) ^ 1);
@@ -129,34 +132,33 @@ k4_ce_backward_bf16(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(kBM, kBN);
       constexpr uint32_t idesc_o = make_idesc_bf16(kBM, kBM);
-      auto issue_s = [&](int i) {                                    // S[i & 1] = X Y_i^T
+      auto issue_s = [&](int i) {                                    // S[h][i & 1] = X_h Y_i^T for both halves
         const int s = i % kStages, buf = i & 1;
-        mbar_wait(&sm.s_free[buf], ((i >> 1) & 1) ^ 1);              // epilogue drained this accumulator
         mbar_wait(&sm.full[s], (i / kStages) & 1);
         tc_fence_after_sync();
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          umma_bf16(tmem + buf * kBN, make_desc_k_sw128(smem_u32(sm.x[k >> 2]) + (k & 3) * 32),
-                    make_desc_k_sw128(smem_u32(sm.y[s][k >> 2]) + (k & 3) * 32), idesc_s, k > 0);
+        for (int h = 0; h < kHalves; ++h)
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            umma_bf16(tmem + (h * 2 + buf) * kBN, make_desc_k_sw128(smem_u32(sm.x[h][k >> 2]) + (k & 3) * 32),
+                      make_desc_k_sw128(smem_u32(sm.y[s][k >> 2]) + (k & 3) * 32), idesc_s, k > 0);
         umma_commit(&sm.s_full[buf]);
       };
       mbar_wait(&sm.x_full, 0);
       issue_s(0);
       if (n_iter > 1) issue_s(1);
       for (int i = 0; i < n_iter; ++i) {
-        // S(i+2) reuses the accumulator of S(i): it is issued as soon as the epilogue has pulled S(i) into registers
-        // (which the epilogue does one tile ahead), i.e. BEFORE waiting for P(i)
-        if (i + 2 < n_iter) issue_s(i + 2);
         const int s = i % kStages, pb = i & 1;
-        mbar_wait(&sm.p_full[pb], (i >> 1) & 1);                     // P(i) is in shared memory (critical path: spin)
+        mbar_wait(&sm.p_full[pb], (i >> 1) & 1);                     // P(i) of both halves is in tensor memory
         tc_fence_after_sync();
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t dv = make_desc_k_sw128(smem_u32(sm.v[s]) + k * 32);
-          umma_bf16_ts(tmem + kTmemO, tmem + kTmemP + pb * (kBN / 2) + k * 8, dv, idesc_o, (i > 0) || (k > 0));
-        }
+        for (int h = 0; h < kHalves; ++h)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)                                // K steps 0,1: column group 0's P; 2,3: group 1's
+            umma_bf16_ts(tmem + kTmemO + h * kBM, tmem + (h * 2 + pb) * kBN + (k >> 1) * 32 + (k & 1) * 8,
+                         make_desc_k_sw128(smem_u32(sm.v[s]) + k * 32), idesc_o, (i > 0) || (k > 0));
         umma_commit(&sm.empty[s]);                                   // Y_i and V_i consumed
-        umma_commit(&sm.p_free[pb]);
+        if (i + 2 < n_iter) issue_s(i + 2);                          // overwrites S/P(i): ordered behind the product above
       }
       umma_commit(&sm.o_full);
     }
@@ -164,9 +166,10 @@ k4_ce_backward_bf16(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     // ===================== epilogue =====================
     const int ew = warp - 2;
     const int quarter = warp & 3;                                    // TMEM lane quarter this warp may access
-    const int cg = ew >> 2;                                          // 16-column group of the 64-wide S tile
-    const int row = quarter * 32 + lane;                             // stationary row = TMEM lane
-    const int mrow = m0 + row;
+    const int half = ew >> 3;                                        // stationary half
+    const int cg = (ew >> 2) & 1;                                    // 32-column group of the 64-wide S tile
+    const int row = quarter * 32 + lane;                             // TMEM lane
+    const int mrow = m0 + half * kBM + row;                          // stationary row
     // per-lane constants
     float laneL = 0.f;            // pass A: lse_q * log2e          pass B: b_j * log2e
     int laneI = -1;               // pass A: y_q                    pass B: global item id
@@ -182,28 +185,18 @@ k4_ce_backward_bf16(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       laneI = a.n0 + mrow;
     }
     float db_acc = 0.f;
+    const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
 
-    // Software pipeline: the TMEM read of S(i+1) is issued BEFORE the math of S(i).  All epilogue warps are released by
-    // the same barrier, so without this every tile is a TMEM-read phase (32 KB at 64 B/clk) followed by a MUFU phase.
-    const uint32_t s_lane = tmem + ((uint32_t)(quarter * 32) << 16) + cg * kColsPerWarp;
-    uint32_t r[kColsPerWarp], rn[kColsPerWarp];
-    mbar_wait(&sm.s_full[0], 0);
-    tc_fence_after_sync();
-    tmem_ld_32x16(s_lane, r);
-    tmem_ld_wait(r);
-    tc_fence_before_sync();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&sm.s_free[0]);
     for (int i = 0; i < n_iter; ++i) {
       const int buf = i & 1, st = i % kStages;
       const int j0 = (t_begin + i) * kBN;
-      const bool more = i + 1 < n_iter;
-      if (more) {
-        mbar_wait(&sm.s_full[buf ^ 1], ((i + 1) >> 1) & 1);
-        tc_fence_after_sync();
-        tmem_ld_32x16(s_lane + (buf ^ 1) * kBN, rn);                 // in flight during the math below
-      }
+      const uint32_t sp = lane_base + (half * 2 + buf) * kBN + cg * kColsPerWarp;    // this warp's S columns = its P columns
       mbar_wait(&sm.full[st], (i / kStages) & 1);                    // the column vectors of this tile have landed
+      mbar_wait(&sm.s_full[buf], (i >> 1) & 1);
+      tc_fence_after_sync();
+      uint32_t r[kColsPerWarp];
+      tmem_ld_32x32(sp, r);
+      tmem_ld_wait(r);
       uint32_t pk[kColsPerWarp / 2];
       const int tgt = kPassB ? 0 : laneI - (a.n0 + j0 + cg * kColsPerWarp);   // pass A: tile-local column of this row's target
 #pragma unroll
@@ -232,21 +225,11 @@ k4_ce_backward_bf16(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         pk[u >> 1] = pack_bf16x2(pv[0], pv[1]);
         pk[(u >> 1) + 1] = pack_bf16x2(pv[2], pv[3]);
       }
-      mbar_wait(&sm.p_free[buf], ((i >> 1) & 1) ^ 1);                // the product that read P(i-2) has retired
-      tc_fence_after_sync();
-      tmem_st_32x8(tmem + ((uint32_t)(quarter * 32) << 16) + kTmemP + buf * (kBN / 2) + cg * (kColsPerWarp / 2), pk);
+      tmem_st_32x16(sp, pk);                                         // P over the first half of the columns just read
       tmem_st_wait();
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.p_full[buf]);
-      if (more) {
-        tmem_ld_wait(rn);
-        tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.s_free[buf ^ 1]);             // S(i+1) is in registers
-#pragma unroll
-        for (int u = 0; u < kColsPerWarp; ++u) r[u] = rn[u];
-      }
     }
 
     // ---- O -> global ---------------------------------------------------------------------------------------------
@@ -254,12 +237,13 @@ k4_ce_backward_bf16(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     tc_fence_after_sync();
     const bool row_ok = kPassB ? (mrow < a.n_items) : (mrow < a.Q);
     const float scale = kPassB ? 1.f : lane_g;
-    {
-      uint32_t r[32];                                                // 128 output columns / 4 column groups
-      tmem_ld_32x32(tmem + ((uint32_t)(quarter * 32) << 16) + kTmemO + cg * 32, r);
+#pragma unroll
+    for (int c = 0; c < 64; c += 32) {                               // 128 output columns / 2 column groups
+      uint32_t r[32];
+      tmem_ld_32x32(lane_base + kTmemO + half * kBM + cg * 64 + c, r);
       tmem_ld_wait(r);
       if (row_ok) {
-        float* dst = a.out + (long long)mrow * kDim + cg * 32;
+        float* dst = a.out + (long long)mrow * kDim + cg * 64 + c;
 #pragma unroll
         for (int u = 0; u < 32; u += 4)
           atomicAdd(reinterpret_cast<float4*>(dst + u),
@@ -323,7 +307,7 @@ int32_t launch_bwd(const void* x, uint64_t x_rows, uint32_t x_pitch, const void*
   if (rc) return rc;
   rc = make_tmap_bf16(&tv, v, kDim, (uint32_t)v_cols, (uint32_t)v_pitch, 64, kBM, 128);
   if (rc) return rc;
-  const int m_tiles = ceil_div((long long)x_rows, kBM);
+  const int m_tiles = ceil_div((long long)x_rows, kHalves * kBM);
   const int s_tiles = ceil_div(a.n_stream, kBN);
   int ns = ceil_div(4 * 148, m_tiles);                  // about four waves of CTAs
   if (ns > s_tiles) ns = s_tiles;
