@@ -19,6 +19,8 @@
 #include "common.cuh"
 #include "sm100.cuh"
 
+#include <cstddef>
+
 namespace htcn {
 using namespace sm100;
 
@@ -100,7 +102,7 @@ k4_ce_backward_bf16(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  const uint32_t tmem = sm.tmem_base;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, sm.tmem_base, 0);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -129,9 +131,12 @@ k4_ce_backward_bf16(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // The whole warp runs this (warp-uniform waits and descriptor arithmetic); one elected lane issues.
+    {
+      const bool leader = elect_one();
       constexpr uint32_t idesc_s = make_idesc_bf16(kBM, kBN);
       constexpr uint32_t idesc_o = make_idesc_bf16(kBM, kBM);
+      const uint32_t x_addr = smem_u32(sm.x[0][0]), y_addr = smem_u32(sm.y[0][0]), v_addr = smem_u32(sm.v[0]);
       auto issue_s = [&](int i) {                                    // S[h][i & 1] = X_h Y_i^T for both halves
         const int s = i % kStages, buf = i & 1;
         mbar_wait(&sm.full[s], (i / kStages) & 1);
@@ -139,10 +144,12 @@ k4_ce_backward_bf16(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
 #pragma unroll
         for (int h = 0; h < kHalves; ++h)
 #pragma unroll
-          for (int k = 0; k < 8; ++k)
-            umma_bf16(tmem + (h * 2 + buf) * kBN, make_desc_k_sw128(smem_u32(sm.x[h][k >> 2]) + (k & 3) * 32),
-                      make_desc_k_sw128(smem_u32(sm.y[s][k >> 2]) + (k & 3) * 32), idesc_s, k > 0);
-        umma_commit(&sm.s_full[buf]);
+          for (int k = 0; k < 8; ++k) {
+            const uint64_t da = make_desc_k_sw128(x_addr + (h * 2 + (k >> 2)) * (kBM * 128) + (k & 3) * 32);
+            const uint64_t db = make_desc_k_sw128(y_addr + (s * 2 + (k >> 2)) * (kBN * 128) + (k & 3) * 32);
+            if (leader) umma_bf16(tmem + (h * 2 + buf) * kBN, da, db, idesc_s, k > 0);
+          }
+        if (leader) umma_commit(&sm.s_full[buf]);
       };
       mbar_wait(&sm.x_full, 0);
       issue_s(0);
@@ -154,13 +161,16 @@ k4_ce_backward_bf16(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
 #pragma unroll
         for (int h = 0; h < kHalves; ++h)
 #pragma unroll
-          for (int k = 0; k < 4; ++k)                                // K steps 0,1: column group 0's P; 2,3: group 1's
-            umma_bf16_ts(tmem + kTmemO + h * kBM, tmem + (h * 2 + pb) * kBN + (k >> 1) * 32 + (k & 1) * 8,
-                         make_desc_k_sw128(smem_u32(sm.v[s]) + k * 32), idesc_o, (i > 0) || (k > 0));
-        umma_commit(&sm.empty[s]);                                   // Y_i and V_i consumed
+          for (int k = 0; k < 4; ++k) {                              // K steps 0,1: column group 0's P; 2,3: group 1's
+            const uint64_t dv = make_desc_k_sw128(v_addr + s * (kBM * 128) + k * 32);
+            if (leader)
+              umma_bf16_ts(tmem + kTmemO + h * kBM, tmem + (h * 2 + pb) * kBN + (k >> 1) * 32 + (k & 1) * 8, dv, idesc_o,
+                           (i > 0) || (k > 0));
+          }
+        if (leader) umma_commit(&sm.empty[s]);                       // Y_i and V_i consumed
         if (i + 2 < n_iter) issue_s(i + 2);                          // overwrites S/P(i): ordered behind the product above
       }
-      umma_commit(&sm.o_full);
+      if (leader) umma_commit(&sm.o_full);
     }
   } else {
     // ===================== epilogue =====================
@@ -186,6 +196,10 @@ k4_ce_backward_bf16(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     }
     float db_acc = 0.f;
     const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
+    // colA / colB / colI are consecutive [kStages][kBN] arrays: shared-window address of this warp's first column
+    const uint32_t col_base = smem_u32(&sm.colA[0][0]) + cg * kColsPerWarp * 4;
+    static_assert(offsetof(BwdSmem, colB) == offsetof(BwdSmem, colA) + kStages * kBN * 4 &&
+                  offsetof(BwdSmem, colI) == offsetof(BwdSmem, colB) + kStages * kBN * 4, "column vectors must be contiguous");
 
     for (int i = 0; i < n_iter; ++i) {
       const int buf = i & 1, st = i % kStages;
@@ -201,16 +215,16 @@ k4_ce_backward_bf16(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       const int tgt = kPassB ? 0 : laneI - (a.n0 + j0 + cg * kColsPerWarp);   // pass A: tile-local column of this row's target
 #pragma unroll
       for (int u = 0; u < kColsPerWarp; u += 4) {                     // 4 columns per 128-bit read of the column vectors
-        const float4 cA = *reinterpret_cast<const float4*>(&sm.colA[st][cg * kColsPerWarp + u]);
-        float4 cB = make_float4(0.f, 0.f, 0.f, 0.f);
-        int4 cI = make_int4(0, 0, 0, 0);
+        // explicit ld.shared: through the generic `sm` reference these compile to LD.E (generic loads, 20% of the stalls)
+        const float4 cA = lds_f4(col_base + (st * kBN + u) * 4);
+        float4 cB = make_float4(0.f, 0.f, 0.f, 0.f), cI = cB;
         if (kPassB) {
-          cB = *reinterpret_cast<const float4*>(&sm.colB[st][cg * kColsPerWarp + u]);
-          cI = *reinterpret_cast<const int4*>(&sm.colI[st][cg * kColsPerWarp + u]);
+          cB = lds_f4(col_base + ((kStages + st) * kBN + u) * 4);
+          cI = lds_f4(col_base + ((2 * kStages + st) * kBN + u) * 4);
         }
         const float av[4] = {cA.x, cA.y, cA.z, cA.w};
         const float bv[4] = {cB.x, cB.y, cB.z, cB.w};
-        const int iv[4] = {cI.x, cI.y, cI.z, cI.w};
+        const int iv[4] = {__float_as_int(cI.x), __float_as_int(cI.y), __float_as_int(cI.z), __float_as_int(cI.w)};
         float pv[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {

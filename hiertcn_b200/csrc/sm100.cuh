@@ -71,6 +71,19 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
   }
 }
 
+// One lane of a converged warp (elect.sync).  Issue tcgen05.mma / TMA from `if (elect_one())` inside WARP-UNIFORM control
+// flow: under an `if (lane == 0)` branch the compiler treats every operand as divergent and wraps each instruction that
+// takes uniform-register operands in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall (~100 clk per MMA, measured).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- TMA ----------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
