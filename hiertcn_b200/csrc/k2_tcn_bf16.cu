@@ -118,7 +118,7 @@ k2_tcn_bf16(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfl
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  const uint32_t tmem = sm.tmem_base;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, sm.tmem_base, 0);
 
   if (warp == 4) {
     // ===================== weight producer: [W_in, L0 taps, L1 taps, ...] per tile, 2-stage ring =====================
@@ -137,7 +137,10 @@ k2_tcn_bf16(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfl
     }
   } else if (warp == 5) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // the whole warp runs the (warp-uniform) waits and descriptor arithmetic, one elected lane issues: under an
+    // `if (lane == 0)` branch every tcgen05.mma is wrapped in an ELECT / R2UR.BROADCAST waterfall (~100 clk per MMA)
+    {
+      const bool leader = elect_one();
       constexpr uint32_t idesc = make_idesc_bf16(kTR, 128);
       const uint32_t act0 = smem_u32(sm.act);
       long long n = 0, n_act = 0;
@@ -158,11 +161,11 @@ k2_tcn_bf16(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfl
             for (int k = 0; k < 8; ++k) {
               const uint64_t da = make_desc_act(a_base + (uint32_t)(2 * k) * (kRows * 16));
               const uint64_t db = make_desc_k_sw128(w_base + (k >> 2) * (kWStageBytes / 2) + (k & 3) * 32);
-              umma_bf16(tmem, da, db, idesc, (tap | k) != 0);
+              if (leader) umma_bf16(tmem, da, db, idesc, (tap | k) != 0);
             }
-            umma_commit(&sm.w_empty[s]);
+            if (leader) umma_commit(&sm.w_empty[s]);
           }
-          umma_commit(&sm.acc_ready);
+          if (leader) umma_commit(&sm.acc_ready);
         }
       }
     }

@@ -130,7 +130,7 @@ k3_gru_bf16(const __grid_constant__ CUtensorMap tmap_w, const float* __restrict_
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  const uint32_t tmem = sm.tmem_base;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, sm.tmem_base, 0);
 
   if (warp == 4) {
     // ===================== weight producer =====================
@@ -149,7 +149,10 @@ k3_gru_bf16(const __grid_constant__ CUtensorMap tmap_w, const float* __restrict_
     }
   } else if (warp == 5) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // the whole warp runs the (warp-uniform) waits and descriptor arithmetic, one elected lane issues: under an
+    // `if (lane == 0)` branch every tcgen05.mma is wrapped in an ELECT / R2UR.BROADCAST waterfall (~100 clk per MMA)
+    {
+      const bool leader = elect_one();
       constexpr uint32_t idesc = make_idesc_bf16(kGM, 128);
       const uint32_t act0 = smem_u32(sm.act);
       long long n = 0, n_act = 0;
@@ -163,9 +166,9 @@ k3_gru_bf16(const __grid_constant__ CUtensorMap tmap_w, const float* __restrict_
         for (int k = 0; k < 8; ++k) {
           const uint64_t da = make_desc_gru_act(act0 + (uint32_t)(k_half * 16 + 2 * k) * (kGM * 16));
           const uint64_t db = make_desc_k_sw128(w_base + (k >> 2) * (kGTileBytes / 2) + (k & 3) * 32);
-          umma_bf16(tmem + d_col, da, db, idesc, !(first && k == 0));
+          if (leader) umma_bf16(tmem + d_col, da, db, idesc, !(first && k == 0));
         }
-        umma_commit(&sm.w_empty[st]);
+        if (leader) umma_commit(&sm.w_empty[st]);
         ++n;
       };
       auto wait_operand = [&]() {
@@ -178,7 +181,7 @@ k3_gru_bf16(const __grid_constant__ CUtensorMap tmap_w, const float* __restrict_
           wait_operand();
           tile_mma(0, 0, true);
           tile_mma(0, 1, false);
-          umma_commit(&sm.acc_ready);
+          if (leader) umma_commit(&sm.acc_ready);
         }
         for (int l = 0; l < 2; ++l) {
           wait_operand();                                   // gates: N = 256 as two column halves
@@ -186,11 +189,11 @@ k3_gru_bf16(const __grid_constant__ CUtensorMap tmap_w, const float* __restrict_
           tile_mma(0, 1, false);
           tile_mma(128, 0, true);
           tile_mma(128, 1, false);
-          umma_commit(&sm.acc_ready);
+          if (leader) umma_commit(&sm.acc_ready);
           wait_operand();                                   // candidate: N = 128
           tile_mma(0, 0, true);                             // reuses the r columns, consumed by E_g
           tile_mma(0, 1, false);
-          umma_commit(&sm.acc_ready);
+          if (leader) umma_commit(&sm.acc_ready);
         }
       }
     }

@@ -88,17 +88,19 @@ __device__ __forceinline__ void write_a_bias_row(uint8_t* a_bias, int r) {
 }
 
 // the 9 MMAs of one tile: 8 x (K=16) over the two 128B-swizzled weight chunks + 1 over the bias chunk
+// Called by the WHOLE MMA warp (warp-uniform descriptor arithmetic); the elected lane issues.
 template <int BN>
-__device__ __forceinline__ void issue_tile_mmas(uint32_t d, const uint8_t (*a)[kChunkBytesA], const uint8_t* a_bias,
+__device__ __forceinline__ void issue_tile_mmas(bool leader, uint32_t d, const uint8_t (*a)[kChunkBytesA], const uint8_t* a_bias,
                                                 const uint8_t* b0, const uint8_t* b1, const uint8_t* b_bias) {
   constexpr uint32_t idesc = make_idesc_bf16(kBM, BN);
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const uint64_t da = make_desc_k_sw128(smem_u32(a[k >> 2]) + (k & 3) * 32);
     const uint64_t db = make_desc_k_sw128(smem_u32((k >> 2) ? b1 : b0) + (k & 3) * 32);
-    umma_bf16(d, da, db, idesc, k > 0);
+    if (leader) umma_bf16(d, da, db, idesc, k > 0);
   }
-  umma_bf16(d, make_desc_k_sw32(smem_u32(a_bias)), make_desc_k_sw32(smem_u32(b_bias)), idesc, true);
+  const uint64_t dab = make_desc_k_sw32(smem_u32(a_bias)), dbb = make_desc_k_sw32(smem_u32(b_bias));
+  if (leader) umma_bf16(d, dab, dbb, idesc, true);
 }
 
 template <unsigned kFlags>
@@ -149,7 +151,7 @@ k4_score_bf16(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  const uint32_t tmem = sm.tmem_base;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, sm.tmem_base, 0);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -169,16 +171,21 @@ k4_score_bf16(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // warp-uniform control flow, one elected lane issues (an `if (lane == 0)` branch costs an ELECT / R2UR.BROADCAST
+    // waterfall, ~100 clk, per tcgen05.mma)
+    {
+      const bool leader = elect_one();
       mbar_wait(&sm.a_full, 0);
       for (int i = 0; i < n_tiles; ++i) {
         const int s = i & 1, buf = i & 1;
         mbar_wait_relaxed(&sm.t_empty[buf], ((i >> 1) & 1) ^ 1);  // epilogue drained this accumulator
         mbar_wait(&sm.b_full[s], (i >> 1) & 1);                 // TMA landed
         tc_fence_after_sync();
-        issue_tile_mmas<BN>(tmem + buf * BN, sm.a, sm.a_bias, sm.b[s][0], sm.b[s][1], sm.b_bias[s]);
-        umma_commit(&sm.b_empty[s]);                            // smem slot reusable once these MMAs retire
-        umma_commit(&sm.t_full[buf]);                           // accumulator ready
+        issue_tile_mmas<BN>(leader, tmem + buf * BN, sm.a, sm.a_bias, sm.b[s][0], sm.b[s][1], sm.b_bias[s]);
+        if (leader) {
+          umma_commit(&sm.b_empty[s]);                          // smem slot reusable once these MMAs retire
+          umma_commit(&sm.t_full[buf]);                         // accumulator ready
+        }
       }
     }
   } else {
@@ -403,7 +410,7 @@ k4_score_bf16_cg2(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   tc_fence_before_sync();
   cluster_sync_all();                                           // barriers of both CTAs are initialised
   tc_fence_after_sync();
-  const uint32_t tmem = sm.tmem_base;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, sm.tmem_base, 0);
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs; bytes land on the leader's barriers) =====================
@@ -423,7 +430,8 @@ k4_score_bf16_cg2(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader only) =====================
-    if (lane == 0 && rank == 0) {
+    if (rank == 0) {                                            // warp-uniform; one elected lane issues
+      const bool leader = elect_one();
       constexpr uint32_t idesc = make_idesc_bf16(2 * kBM, BN);
       mbar_wait(&sm.a_full, 0);
       for (int i = 0; i < n_tiles; ++i) {
@@ -436,11 +444,14 @@ k4_score_bf16_cg2(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         for (int k = 0; k < 8; ++k) {
           const uint64_t da = make_desc_k_sw128(smem_u32(sm.a[k >> 2]) + (k & 3) * 32);
           const uint64_t db = make_desc_k_sw128(smem_u32(sm.b[s][k >> 2]) + (k & 3) * 32);
-          umma_bf16_cg2(d, da, db, idesc, k > 0);
+          if (leader) umma_bf16_cg2(d, da, db, idesc, k > 0);
         }
-        umma_bf16_cg2(d, make_desc_k_sw32(smem_u32(sm.a_bias)), make_desc_k_sw32(smem_u32(sm.b_bias[s])), idesc, true);
-        umma_commit_cg2(&sm.b_empty[s], 0b11);
-        umma_commit_cg2(&sm.t_full[buf], 0b11);
+        const uint64_t dab = make_desc_k_sw32(smem_u32(sm.a_bias)), dbb = make_desc_k_sw32(smem_u32(sm.b_bias[s]));
+        if (leader) {
+          umma_bf16_cg2(d, dab, dbb, idesc, true);
+          umma_commit_cg2(&sm.b_empty[s], 0b11);
+          umma_commit_cg2(&sm.t_full[buf], 0b11);
+        }
       }
     }
   } else {
@@ -592,10 +603,11 @@ k4_target_bf16(const __nv_bfloat16* __restrict__ hout, const __nv_bfloat16* __re
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  const uint32_t tmem = sm.tmem_base;
-  if (r == 0) {
-    issue_tile_mmas<128>(tmem, sm.a, sm.a_bias, sm.b[0], sm.b[1], sm.b_bias);
-    umma_commit(&sm.done);
+  const uint32_t tmem = __shfl_sync(0xffffffffu, sm.tmem_base, 0);
+  if (warp == 0) {
+    const bool leader = elect_one();
+    issue_tile_mmas<128>(leader, tmem, sm.a, sm.a_bias, sm.b[0], sm.b[1], sm.b_bias);
+    if (leader) umma_commit(&sm.done);
   }
   mbar_wait(&sm.done, 0);
   tc_fence_after_sync();
