@@ -110,9 +110,19 @@ ce_repair_bf16_kernel(const __nv_bfloat16* __restrict__ hout, int Q, const __nv_
                       const float* __restrict__ zy, float* __restrict__ loss_row, int* __restrict__ repaired) {
   __shared__ float h[kDim];
   __shared__ float red_m[8], red_s[8];
-  for (int q = blockIdx.x; q < Q; q += gridDim.x) {
-    const float cur = loss_row[q];
-    if (isfinite(cur)) continue;                                  // block-uniform
+  __shared__ int bad_rows[256];
+  __shared__ int n_bad;
+  for (int base = blockIdx.x * 256; base < Q; base += gridDim.x * 256) {       // 256 rows checked per pass, one per thread
+    const int qc = base + threadIdx.x;
+    const bool bad = qc < Q && !isfinite(loss_row[qc]);
+    if (!__syncthreads_or(bad)) continue;                         // the common case: nothing to redo in this chunk
+    if (threadIdx.x == 0) n_bad = 0;
+    __syncthreads();
+    if (bad) bad_rows[atomicAdd(&n_bad, 1)] = qc;
+    __syncthreads();
+    const int nb = n_bad;
+    for (int bi = 0; bi < nb; ++bi) {
+    const int q = bad_rows[bi];
     __syncthreads();
     if (threadIdx.x < kDim) h[threadIdx.x] = __bfloat162float(hout[(long long)q * kDim + threadIdx.x]);
     __syncthreads();
@@ -151,6 +161,7 @@ ce_repair_bf16_kernel(const __nv_bfloat16* __restrict__ hout, int Q, const __nv_
       for (int w = 0; w < 8; ++w) S += (red_m[w] == -INFINITY) ? 0.f : red_s[w] * expf(red_m[w] - M);
       loss_row[q] = (M + logf(S)) - zy[q];
       if (repaired) atomicAdd(repaired, 1);
+    }
     }
   }
 }
@@ -404,7 +415,8 @@ extern "C" int32_t htcn_score_ce_repair(const void* hout, int32_t precision, int
   HTCN_REQUIRE(hout && w_out_t && target_logit && loss_row && Q > 0 && n_items > 0, "score_ce_repair: bad args");
   if (precision == HTCN_F32) return HTCN_OK;           // the fp32 sweep keeps a running max: nothing to repair
   HTCN_REQUIRE(precision == HTCN_BF16, "score_ce_repair: precision %d", precision);
-  const int grid = Q < 148 * 8 ? Q : 148 * 8;
+  const int chunks = ceil_div(Q, 256);
+  const int grid = chunks < 148 * 8 ? chunks : 148 * 8;
   ce_repair_bf16_kernel<<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(hout), Q,
                                                             reinterpret_cast<const __nv_bfloat16*>(w_out_t), n_items,
                                                             target_logit, loss_row, repaired);
