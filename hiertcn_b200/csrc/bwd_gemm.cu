@@ -112,8 +112,9 @@ int32_t sgemm(bool trans_b, long long M, int N, int K, const float* A, int lda, 
 
 // ---- C[c,f] += sum_r A[src(r), c] * D[r, f]  (split over row chunks, atomic accumulation) -----------------------
 __global__ void __launch_bounds__(kThreads)
-sgemm_tn_atomic_kernel(long long R, int chunk, const float* __restrict__ A, int lda, const float* __restrict__ D,
-                       int ldd, float* __restrict__ C, int ldc, int shift, int T, SlotTable slots) {
+sgemm_tn_atomic_kernel(long long R, int chunk, const void* __restrict__ A, int lda, int a_bf16,
+                       const float* __restrict__ D, int ldd, float* __restrict__ C, int ldc, int shift, int T,
+                       SlotTable slots) {
   __shared__ __align__(16) float As[kS][kT];     // As[rr][c]
   __shared__ __align__(16) float Ds[kS][kT];     // Ds[rr][f]
   const int tid = threadIdx.x;
@@ -144,7 +145,14 @@ sgemm_tn_atomic_kernel(long long R, int chunk, const float* __restrict__ A, int 
           while (s + 1 < slots.n && slots.off[s + 1] <= p) ++s;
           ok = (p - slots.off[s] - shift >= 0);
         }
-        if (ok) a[h] = *reinterpret_cast<const float4*>(A + (r - shift) * lda + col);
+        if (ok) {
+          if (a_bf16) {
+            const uint2 q = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(A) + (r - shift) * lda + col);
+            a[h] = make_float4(bf16_lo(q.x), bf16_hi(q.x), bf16_lo(q.y), bf16_hi(q.y));
+          } else {
+            a[h] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(A) + (r - shift) * lda + col);
+          }
+        }
       }
     }
     __syncthreads();
@@ -169,8 +177,8 @@ sgemm_tn_atomic_kernel(long long R, int chunk, const float* __restrict__ A, int 
   }
 }
 
-int32_t sgemm_tn_atomic(long long R, const float* A, int lda, const float* D, int ldd, float* C, int ldc, int shift,
-                        int T, const SlotTable* slots, cudaStream_t st) {
+int32_t sgemm_tn_atomic(long long R, const void* A, int lda, const float* D, int ldd, float* C, int ldc, int shift,
+                        int T, const SlotTable* slots, cudaStream_t st, bool a_bf16) {
   HTCN_REQUIRE(R > 0 && lda % 4 == 0 && ldd % 4 == 0 && ldc % 4 == 0, "sgemm_tn_atomic: R=%lld", R);
   HTCN_REQUIRE(shift == 0 || (slots && T > 0), "sgemm_tn_atomic: a shifted product needs the slot table");
   long long chunk = (R + 295) / 296;                  // about two waves of CTAs
@@ -178,8 +186,8 @@ int32_t sgemm_tn_atomic(long long R, const float* A, int lda, const float* D, in
   if (chunk < 128) chunk = 128;
   if (chunk > 8192) chunk = 8192;
   SlotTable none{};
-  sgemm_tn_atomic_kernel<<<ceil_div(R, chunk), kThreads, 0, st>>>(R, (int)chunk, A, lda, D, ldd, C, ldc, shift, T,
-                                                                  slots ? *slots : none);
+  sgemm_tn_atomic_kernel<<<ceil_div(R, chunk), kThreads, 0, st>>>(R, (int)chunk, A, lda, a_bf16 ? 1 : 0, D, ldd, C, ldc,
+                                                                  shift, T, slots ? *slots : none);
   HTCN_LAUNCH_CHECK("sgemm_tn_atomic_kernel");
   return HTCN_OK;
 }

@@ -14,12 +14,21 @@ namespace htcn {
 
 namespace {
 
-__global__ void relu_bwd_kernel(long long n4, float4* __restrict__ dcur, const float4* __restrict__ h_next,
-                                const float4* __restrict__ a_l, float4* __restrict__ dp) {
+template <bool kBf16>
+__global__ void relu_bwd_kernel(long long n4, float4* __restrict__ dcur, const void* __restrict__ h_next,
+                                const void* __restrict__ a_l, float4* __restrict__ dp) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   float4 d = dcur[i];
-  const float4 h = h_next[i], a = a_l[i];
+  float4 h, a;
+  if (kBf16) {
+    const uint2 hq = reinterpret_cast<const uint2*>(h_next)[i], aq = reinterpret_cast<const uint2*>(a_l)[i];
+    h = make_float4(bf16_lo(hq.x), bf16_hi(hq.x), bf16_lo(hq.y), bf16_hi(hq.y));
+    a = make_float4(bf16_lo(aq.x), bf16_hi(aq.x), bf16_lo(aq.y), bf16_hi(aq.y));
+  } else {
+    h = reinterpret_cast<const float4*>(h_next)[i];
+    a = reinterpret_cast<const float4*>(a_l)[i];
+  }
   d.x = h.x > 0.f ? d.x : 0.f; d.y = h.y > 0.f ? d.y : 0.f; d.z = h.z > 0.f ? d.z : 0.f; d.w = h.w > 0.f ? d.w : 0.f;
   dcur[i] = d;
   float4 p;
@@ -92,15 +101,35 @@ extern "C" int32_t htcn_tcn_forward_train(const float* xe, const float* w_in_x, 
   return HTCN_OK;
 }
 
-extern "C" int32_t htcn_tcn_backward(const float* d_hout, const int32_t* out_row, const float* xe, const float* w_in_x,
-                                     const float* const* conv_w_host, int32_t n_levels, int32_t kernel_size,
-                                     const int32_t* slot_off_host, int32_t B, int32_t T, int32_t S, const float* h_save,
-                                     const float* a_save, float* scratch, float* const* d_conv_w_host,
-                                     float* const* d_conv_b_host, float* d_w_in_x, float* d_sbias, float* d_xe,
-                                     void* stream) {
+extern "C" int32_t htcn_tcn_forward_train_bf16(const void* xe, const float* w_in_x, const float* sbias,
+                                               const float* const* conv_w_host, const float* const* conv_b_host,
+                                               int32_t n_levels, int32_t kernel_size, const int32_t* slot_off_host,
+                                               int32_t B, int32_t T, int32_t S, const int32_t* out_row, void* h_save,
+                                               void* a_save, void* hout, float* scratch, void* stream) {
+  using namespace htcn;
+  HTCN_REQUIRE(xe && w_in_x && h_save && hout && slot_off_host && out_row && scratch, "tcn_forward_train_bf16: NULL pointer");
+  HTCN_REQUIRE(B > 0 && T > 0 && S > 0 && S <= HTCN_MAX_SLOTS, "tcn_forward_train_bf16: B=%d T=%d S=%d", B, T, S);
+  HTCN_REQUIRE(n_levels >= 0 && n_levels <= HTCN_MAX_LEVELS && kernel_size >= 1 && kernel_size <= 8,
+               "tcn_forward_train_bf16: n_levels=%d kernel_size=%d", n_levels, kernel_size);
+  HTCN_REQUIRE(n_levels == 0 || (conv_w_host && conv_b_host && a_save), "tcn_forward_train_bf16: conv weights / a_save NULL");
+  SlotTable slots;
+  slots.n = S;
+  for (int i = 0; i <= S; ++i) slots.off[i] = slot_off_host[i];
+  HTCN_REQUIRE(slots.off[0] == 0 && slots.off[S] == T, "tcn_forward_train_bf16: slot_off does not span T");
+  return tcn_forward_bf16(xe, HTCN_BF16, w_in_x, sbias, conv_w_host, conv_b_host, n_levels, kernel_size, slots, B, T, out_row,
+                          hout, HTCN_BF16, scratch, as_stream(stream), h_save, a_save);
+}
+
+extern "C" int32_t htcn_tcn_backward(const float* d_hout, const int32_t* out_row, const void* xe, int32_t save_dtype,
+                                     const float* w_in_x, const float* const* conv_w_host, int32_t n_levels,
+                                     int32_t kernel_size, const int32_t* slot_off_host, int32_t B, int32_t T, int32_t S,
+                                     const void* h_save, const void* a_save, float* scratch,
+                                     float* const* d_conv_w_host, float* const* d_conv_b_host, float* d_w_in_x,
+                                     float* d_sbias, float* d_xe, void* stream) {
   using namespace htcn;
   HTCN_REQUIRE(d_hout && out_row && xe && w_in_x && h_save && scratch && d_w_in_x && d_sbias && d_xe && slot_off_host,
                "tcn_backward: NULL pointer");
+  HTCN_REQUIRE(save_dtype == HTCN_F32 || save_dtype == HTCN_BF16, "tcn_backward: save_dtype %d", save_dtype);
   HTCN_REQUIRE(B > 0 && T > 0 && S > 0 && S <= HTCN_MAX_SLOTS, "tcn_backward: B=%d T=%d S=%d", B, T, S);
   HTCN_REQUIRE(n_levels >= 0 && n_levels <= HTCN_MAX_LEVELS && kernel_size >= 1 && kernel_size <= 8,
                "tcn_backward: n_levels=%d kernel_size=%d", n_levels, kernel_size);
@@ -110,6 +139,8 @@ extern "C" int32_t htcn_tcn_backward(const float* d_hout, const int32_t* out_row
   for (int i = 0; i <= S; ++i) slots.off[i] = slot_off_host[i];
   HTCN_REQUIRE(slots.off[0] == 0 && slots.off[S] == T, "tcn_backward: slot_off does not span T");
   cudaStream_t st = as_stream(stream);
+  const bool bf = save_dtype == HTCN_BF16;
+  const size_t esz = bf ? 2 : 4;
   const long long R = (long long)B * T;
   float* dcur = scratch;                    // [R,128] gradient flowing down the stack
   float* dp = scratch + R * kDim;           // [R,128] gradient at the conv pre-activation
@@ -119,16 +150,18 @@ extern "C" int32_t htcn_tcn_backward(const float* d_hout, const int32_t* out_row
   HTCN_LAUNCH_CHECK("rows_compact_kernel(scatter)");
   int32_t rc;
   for (int l = n_levels - 1; l >= 0; --l) {
-    const float* h_l = h_save + (long long)l * R * kDim;
-    const float* h_n = h_save + (long long)(l + 1) * R * kDim;
-    const float* a_l = a_save + (long long)l * R * kDim;
-    relu_bwd_kernel<<<eb, 256, 0, st>>>(R * 32, reinterpret_cast<float4*>(dcur), reinterpret_cast<const float4*>(h_n),
-                                        reinterpret_cast<const float4*>(a_l), reinterpret_cast<float4*>(dp));
+    const uint8_t* h_l = reinterpret_cast<const uint8_t*>(h_save) + (size_t)l * R * kDim * esz;
+    const uint8_t* h_n = reinterpret_cast<const uint8_t*>(h_save) + (size_t)(l + 1) * R * kDim * esz;
+    const uint8_t* a_l = reinterpret_cast<const uint8_t*>(a_save) + (size_t)l * R * kDim * esz;
+    if (bf)
+      relu_bwd_kernel<true><<<eb, 256, 0, st>>>(R * 32, reinterpret_cast<float4*>(dcur), h_n, a_l, reinterpret_cast<float4*>(dp));
+    else
+      relu_bwd_kernel<false><<<eb, 256, 0, st>>>(R * 32, reinterpret_cast<float4*>(dcur), h_n, a_l, reinterpret_cast<float4*>(dp));
     HTCN_LAUNCH_CHECK("relu_bwd_kernel");
     const int dil = 1 << l;
     for (int tap = 0; tap < kernel_size; ++tap) {
       rc = sgemm_tn_atomic(R, h_l, kDim, dp, kDim, d_conv_w_host[l] + (long long)tap * kDim * kDim, kDim,
-                           (kernel_size - 1 - tap) * dil, T, &slots, st);
+                           (kernel_size - 1 - tap) * dil, T, &slots, st, bf);
       if (rc) return rc;
     }
     rc = colsum_atomic(R, dp, kDim, kDim, d_conv_b_host[l], st);
@@ -140,7 +173,7 @@ extern "C" int32_t htcn_tcn_backward(const float* d_hout, const int32_t* out_row
     rc = k2_level_launch(a, slots, st);
     if (rc) return rc;
   }
-  rc = sgemm_tn_atomic(R, xe, kDim, dcur, kDim, d_w_in_x, kDim, 0, T, nullptr, st);
+  rc = sgemm_tn_atomic(R, xe, kDim, dcur, kDim, d_w_in_x, kDim, 0, T, nullptr, st, bf);
   if (rc) return rc;
   slot_sum_kernel<<<dim3(B, S), kDim, 0, st>>>(dcur, B, T, slots, d_sbias);
   HTCN_LAUNCH_CHECK("slot_sum_kernel");

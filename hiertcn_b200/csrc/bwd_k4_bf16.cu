@@ -290,15 +290,17 @@ __global__ void k4_bwd_prep_kernel(const float* __restrict__ b_out, int n_items,
 }
 
 // src [R,128] f32 -> rows [R,128] bf16 (optional) and its transpose [128, r_pad] bf16 (optional), 32x32 smem tiles
-__global__ void cast_transpose_bf16_kernel(const float* __restrict__ src, long long R, __nv_bfloat16* __restrict__ rows,
-                                           __nv_bfloat16* __restrict__ tr, long long r_pad) {
+__global__ void cast_transpose_bf16_kernel(const void* __restrict__ src, int src_bf16, long long R,
+                                           __nv_bfloat16* __restrict__ rows, __nv_bfloat16* __restrict__ tr, long long r_pad) {
   __shared__ float tile[32][33];
   const long long r0 = (long long)blockIdx.x * 32;
   const int c0 = blockIdx.y * 32;
   const int tx = threadIdx.x, ty = threadIdx.y;       // 32 x 8
   for (int i = ty; i < 32; i += 8) {
     const long long r = r0 + i;
-    const float v = (r < R) ? src[r * kDim + c0 + tx] : 0.f;
+    const float v = (r >= R) ? 0.f
+                    : src_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src)[r * kDim + c0 + tx])
+                               : reinterpret_cast<const float*>(src)[r * kDim + c0 + tx];
     tile[i][tx] = v;
     if (rows && r < R) rows[r * kDim + c0 + tx] = __float2bfloat16_rn(v);
   }
@@ -341,14 +343,15 @@ int32_t launch_bwd(const void* x, uint64_t x_rows, uint32_t x_pitch, const void*
 
 using namespace htcn;
 
-extern "C" int32_t htcn_cast_transpose_bf16(const float* src, int64_t R, void* dst_rows, void* dst_t, int64_t r_pad,
-                                            void* stream) {
+extern "C" int32_t htcn_cast_transpose_bf16(const void* src, int32_t src_dtype, int64_t R, void* dst_rows, void* dst_t,
+                                            int64_t r_pad, void* stream) {
   HTCN_REQUIRE(src && R > 0 && (dst_rows || dst_t), "cast_transpose_bf16: bad args");
+  HTCN_REQUIRE(src_dtype == HTCN_F32 || src_dtype == HTCN_BF16, "cast_transpose_bf16: src_dtype %d", src_dtype);
   HTCN_REQUIRE(!dst_t || (r_pad >= R && r_pad % 8 == 0), "cast_transpose_bf16: r_pad=%lld must be >= R and a multiple of 8",
                (long long)r_pad);
   const long long span = dst_t ? r_pad : R;
   cast_transpose_bf16_kernel<<<dim3(ceil_div(span, 32), kDim / 32), dim3(32, 8), 0, as_stream(stream)>>>(
-      src, R, reinterpret_cast<__nv_bfloat16*>(dst_rows), reinterpret_cast<__nv_bfloat16*>(dst_t), r_pad);
+      src, src_dtype == HTCN_BF16, R, reinterpret_cast<__nv_bfloat16*>(dst_rows), reinterpret_cast<__nv_bfloat16*>(dst_t), r_pad);
   HTCN_LAUNCH_CHECK("cast_transpose_bf16_kernel");
   return HTCN_OK;
 }

@@ -65,7 +65,7 @@ __device__ __forceinline__ uint64_t make_desc_act(uint32_t smem_addr) {
 }
 
 __device__ __forceinline__ void tile_geometry(const K2Geom& g, int tile, int r, const int* out_row, int& src,
-                                              int& dst, int& sb) {
+                                              int& dst, int& sb, bool& own) {
   int s = 0;
   while (s + 1 < g.n_slots && g.slot[s + 1].tile0 <= tile) ++s;
   const K2Slot& sl = g.slot[s];
@@ -89,13 +89,16 @@ __device__ __forceinline__ void tile_geometry(const K2Geom& g, int tile, int r, 
   src = data ? b * g.T + sl.off + t : -1;
   sb = s * g.B + (b < g.B ? b : 0);
   dst = -1;
-  if (data && is_out) dst = out_row ? out_row[src] : src;
+  own = data && is_out;            // this tile produces the row's final values at every level (halo rows are recomputed)
+  if (own) dst = out_row ? out_row[src] : src;
 }
 
 __global__ void __launch_bounds__(kK2Threads, 2)
 k2_tcn_bf16(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfloat16* __restrict__ xe,
             const float* __restrict__ sbias, const float* __restrict__ bias_all /*[n_levels][128]*/,
-            const int* __restrict__ out_row, __nv_bfloat16* __restrict__ hout) {
+            const int* __restrict__ out_row, __nv_bfloat16* __restrict__ hout,
+            __nv_bfloat16* __restrict__ h_save /* [(n_levels+1)][B*T][128] every layer's output, or NULL */,
+            __nv_bfloat16* __restrict__ a_save /* [n_levels][B*T][128] relu(conv + b) before the residual, or NULL */) {
   extern __shared__ uint8_t smem_raw[];
   auto& sm = *reinterpret_cast<K2Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -177,7 +180,9 @@ k2_tcn_bf16(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfl
     for (int it = 0; it < my_tiles; ++it) {
       const int tile = blockIdx.x + it * gridDim.x;
       int src, dst, sb;
-      tile_geometry(g, tile, r, out_row, src, dst, sb);
+      bool own;
+      tile_geometry(g, tile, r, out_row, src, dst, sb, own);
+      const long long RT = (long long)g.B * g.T;
       // ---- stage the input rows (bf16 Xe) into the operand layout; zero rows stay zero
       {
         const uint4* p = src >= 0 ? reinterpret_cast<const uint4*>(xe + (long long)src * kDim) : nullptr;
@@ -202,7 +207,7 @@ k2_tcn_bf16(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfl
           for (int q = 0; q < 4; ++q) {                          // 4 x 8 channels = one 16-byte chunk each
             const int c = cc * 4 + q;
             uint4* slot = reinterpret_cast<uint4*>(my_act + c * (kRows * 16));
-            float o[8];
+            float o[8], av[8];
             if (layer == 0) {
 #pragma unroll
               for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(v[q * 8 + e]);
@@ -219,12 +224,18 @@ k2_tcn_bf16(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfl
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
                 const float a = fmaxf(__uint_as_float(v[q * 8 + e]) + bias_l[c * 8 + e], 0.f);   // relu(conv + b)
+                av[e] = a;
                 o[e] = fmaxf(a + rs[e], 0.f);                                                    // relu(a + residual)
               }
+              if (a_save && own)
+                reinterpret_cast<uint4*>(a_save + ((long long)(layer - 1) * RT + src) * kDim)[c] =
+                    make_uint4(pack_bf16x2(av[0], av[1]), pack_bf16x2(av[2], av[3]), pack_bf16x2(av[4], av[5]),
+                               pack_bf16x2(av[6], av[7]));
             }
             uint4 packed = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
                                       pack_bf16x2(o[6], o[7]));
             if (src < 0) packed = make_uint4(0, 0, 0, 0);        // causal pad rows stay zero at every level
+            if (h_save && own) reinterpret_cast<uint4*>(h_save + ((long long)layer * RT + src) * kDim)[c] = packed;
             if (!last) *slot = packed;
             else if (dst >= 0) reinterpret_cast<uint4*>(hout + (long long)dst * kDim)[c] = packed;
           }
@@ -259,7 +270,7 @@ __global__ void k2_prepare_weights(const float* __restrict__ w_in_x, const float
 int32_t tcn_forward_bf16(const void* xe, int xe_dtype, const float* w_in_x, const float* sbias,
                          const float* const* conv_w, const float* const* conv_b, int n_levels, int K,
                          const SlotTable& slots, int B, int T, const int* out_row, void* hout, int hout_dtype,
-                         float* scratch, cudaStream_t st) {
+                         float* scratch, cudaStream_t st, void* h_save, void* a_save) {
   if (xe_dtype != HTCN_BF16 || hout_dtype != HTCN_BF16) {
     set_error("tcn_forward(bf16): xe and hout must be bf16");
     return HTCN_ERR_INVALID;
@@ -319,7 +330,7 @@ int32_t tcn_forward_bf16(const void* xe, int xe_dtype, const float* w_in_x, cons
   HTCN_CUDA(cudaFuncSetAttribute(k2_tcn_bf16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = tiles < 2 * 148 ? tiles : 2 * 148;
   k2_tcn_bf16<<<grid, kK2Threads, smem, st>>>(tw, g, (const __nv_bfloat16*)xe, sbias, bias_dev, out_row,
-                                              (__nv_bfloat16*)hout);
+                                              (__nv_bfloat16*)hout, (__nv_bfloat16*)h_save, (__nv_bfloat16*)a_save);
   HTCN_LAUNCH_CHECK("k2_tcn_bf16");
   return HTCN_OK;
 }

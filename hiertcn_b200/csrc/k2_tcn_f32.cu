@@ -195,10 +195,7 @@ int32_t tcn_forward_f32(const void* xe, int xe_dtype, const float* w_in_x, const
   return HTCN_OK;
 }
 
-int32_t tcn_forward_bf16(const void* xe, int xe_dtype, const float* w_in_x, const float* sbias,
-                         const float* const* conv_w, const float* const* conv_b, int n_levels, int K,
-                         const SlotTable& slots, int B, int T, const int* out_row, void* hout, int hout_dtype,
-                         float* scratch, cudaStream_t st);
+
 
 }  // namespace htcn
 

@@ -26,6 +26,13 @@ struct LevelArgs {
 };
 int32_t k2_level_launch(const LevelArgs& a, const SlotTable& slots, cudaStream_t st);
 
+// fused tcgen05 conv stack (k2_tcn_bf16.cu); h_save / a_save (bf16, optional) keep every layer's output and every
+// level's pre-residual activation for the backward
+int32_t tcn_forward_bf16(const void* xe, int xe_dtype, const float* w_in_x, const float* sbias,
+                         const float* const* conv_w, const float* const* conv_b, int n_levels, int K,
+                         const SlotTable& slots, int B, int T, const int* out_row, void* hout, int hout_dtype,
+                         float* scratch, cudaStream_t st, void* h_save = nullptr, void* a_save = nullptr);
+
 // C[M,N] (+)= A[M,K] * op(B).  trans_b = 0: B is [K,N] with leading dimension ldb; trans_b = 1: B is [N,K].
 // N % 128 == 0, K % 16 == 0, all leading dimensions multiples of 4 floats, 16-byte aligned bases.
 int32_t sgemm(bool trans_b, long long M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
@@ -35,8 +42,9 @@ int32_t sgemm(bool trans_b, long long M, int N, int K, const float* A, int lda, 
 //     C[c, f] += sum_{r < R} A[src(r), c] * D[r, f]        c, f in [0,128)
 // src(r) = r - shift, taken as a zero row when r's position inside its sequence is < shift (the causal left pad of
 // customized_tcn_cell.py:46-49); shift = 0 (and slots == nullptr) for plain products.
-int32_t sgemm_tn_atomic(long long R, const float* A, int lda, const float* D, int ldd, float* C, int ldc, int shift,
-                        int T, const SlotTable* slots, cudaStream_t st);
+// A is fp32, or bf16 when a_bf16 (then lda counts bf16 elements).
+int32_t sgemm_tn_atomic(long long R, const void* A, int lda, const float* D, int ldd, float* C, int ldc, int shift,
+                        int T, const SlotTable* slots, cudaStream_t st, bool a_bf16 = false);
 
 // out[f] += sum_r D[r, f]  (f < cols, cols <= 256)
 int32_t colsum_atomic(long long R, const float* D, int ldd, int cols, float* out, cudaStream_t st);

@@ -97,7 +97,8 @@ class HierTCNTrainer:
         st = m.stream_ptr()
         cabi.call("htcn_refresh_wout", self.p["wt"].data_ptr(), self.p["b_out"].data_ptr(), m.N, m.wt.data_ptr(),
                   cabi.HTCN_BF16, st)
-        cabi.call("htcn_cast_transpose_bf16", self.p["wt"].data_ptr(), m.N, None, self.w_out_bf16.data_ptr(), self.n_pad, st)
+        cabi.call("htcn_cast_transpose_bf16", self.p["wt"].data_ptr(), cabi.HTCN_F32, m.N, None, self.w_out_bf16.data_ptr(),
+                  self.n_pad, st)
 
     def _view(self, flat, name, shape):
         o = self.offsets[name]
@@ -119,10 +120,15 @@ class HierTCNTrainer:
         slot_p, slot_keep = cabi.int_array(d["slot_off"])
         buf = m._buf
         # ---- forward, keeping what the backward needs
-        xe = buf("tr_xe", (R, D), f32)
+        # bf16 tier: the conv stack runs on the tensor cores too (fused tcgen05 kernel, activations saved in bf16) when
+        # its causal reach fits the kernel's tile; otherwise, and in the fp32 tier, the fp32 level kernels
+        fused = (self.bf16 and getattr(self, "k2_tcgen05", True) and (K - 1) * (1 << max(L - 1, 0)) <= 32
+                 and (K - 1) * ((1 << L) - 1) < 120)
+        sdt, sdt_c = (torch.bfloat16, cabi.HTCN_BF16) if fused else (f32, cabi.HTCN_F32)
+        xe = buf("tr_xe_bf16" if fused else "tr_xe", (R, D), sdt)
         yp = buf("tr_yp", (S, B, D), f32)
         cabi.call("htcn_gather_meanpool", m.E.data_ptr(), m.b_emb.data_ptr(), N, d["x_id"].data_ptr(), d["y_id"].data_ptr(),
-                  slot_p, B, T, S, xe.data_ptr(), cabi.HTCN_F32, yp.data_ptr(), st)
+                  slot_p, B, T, S, xe.data_ptr(), sdt_c, yp.data_ptr(), st)
         state_pre = buf("tr_state_pre", (S, B, G * D), f32)
         sbias = buf("tr_sbias", (S, B, D), f32)
         gates = buf("tr_gates", (S, G, 3, B, D), f32)
@@ -130,13 +136,20 @@ class HierTCNTrainer:
         cabi.call("htcn_gru_sessions_train", yp.data_ptr(), d["mask"].data_ptr(), d["state"].data_ptr(), m._gru_pp[0][0],
                   m._gru_pp[1][0], m._gru_pp[2][0], m._gru_pp[3][0], G, m.w_in_state.data_ptr(), B, S,
                   state_pre.data_ptr(), sbias.data_ptr(), state_out.data_ptr(), gates.data_ptr(), st)
-        h_save = buf("tr_h_save", (L + 1, R, D), f32)
-        a_save = buf("tr_a_save", (max(L, 1), R, D), f32)
-        hout = buf("tr_hout", (max(Q, 1), D), f32)
-        cabi.call("htcn_tcn_forward_train", xe.data_ptr(), m.w_in_x.data_ptr(), sbias.data_ptr(), m._conv_w_pp[0],
-                  m._conv_b_pp[0], L, K, slot_p, B, T, S, d["row_of"].data_ptr(), h_save.data_ptr(), a_save.data_ptr(),
-                  hout.data_ptr(), st)
-        cabi.note_launches(L + 2)
+        h_save = buf("tr_h_save_bf16" if fused else "tr_h_save", (L + 1, R, D), sdt)
+        a_save = buf("tr_a_save_bf16" if fused else "tr_a_save", (max(L, 1), R, D), sdt)
+        hout = buf("tr_hout_bf16" if fused else "tr_hout", (max(Q, 1), D), sdt)
+        if fused:
+            k2f_scratch = buf("k2_scratch_bf16", ((1 + L * K) * 8192 + 4096,), f32)
+            cabi.call("htcn_tcn_forward_train_bf16", xe.data_ptr(), m.w_in_x.data_ptr(), sbias.data_ptr(), m._conv_w_pp[0],
+                      m._conv_b_pp[0], L, K, slot_p, B, T, S, d["row_of"].data_ptr(), h_save.data_ptr(), a_save.data_ptr(),
+                      hout.data_ptr(), k2f_scratch.data_ptr(), st)
+            cabi.note_launches(2)
+        else:
+            cabi.call("htcn_tcn_forward_train", xe.data_ptr(), m.w_in_x.data_ptr(), sbias.data_ptr(), m._conv_w_pp[0],
+                      m._conv_b_pp[0], L, K, slot_p, B, T, S, d["row_of"].data_ptr(), h_save.data_ptr(), a_save.data_ptr(),
+                      hout.data_ptr(), st)
+            cabi.note_launches(L + 2)
         scalars = torch.zeros(8, dtype=f32, device=m.device)
         if Q == 0:
             return dict(scalars=scalars, state=state_out)
@@ -146,11 +159,14 @@ class HierTCNTrainer:
         pm, ps = buf("pm", (ns, Q), f32), buf("ps", (ns, Q), f32)
         pc = buf("pc", (ns, Q), torch.int32) if metrics else None
         hq, prec = hout, cabi.HTCN_F32
-        if self.bf16:     # bf16 copies of the user embeddings: rows for the sweeps, the transpose for dW^T = P^T Hout
+        if self.bf16:     # bf16 user embeddings: rows for the sweeps, the transpose for dW^T = P^T Hout
             q_pad = -(-Q // 8) * 8
-            hq = buf("tr_hout_bf16", (Q, D), torch.bfloat16)
             hq_t = buf("tr_hout_t_bf16", (D, q_pad), torch.bfloat16)
-            cabi.call("htcn_cast_transpose_bf16", hout.data_ptr(), Q, hq.data_ptr(), hq_t.data_ptr(), q_pad, st)
+            if fused:
+                cabi.call("htcn_cast_transpose_bf16", hout.data_ptr(), cabi.HTCN_BF16, Q, None, hq_t.data_ptr(), q_pad, st)
+            else:
+                hq = buf("tr_hout_bf16", (Q, D), torch.bfloat16)
+                cabi.call("htcn_cast_transpose_bf16", hout.data_ptr(), cabi.HTCN_F32, Q, hq.data_ptr(), hq_t.data_ptr(), q_pad, st)
             prec = cabi.HTCN_BF16
         cabi.call("htcn_target_logit", hq.data_ptr(), prec, Q, m.wt.data_ptr(), m.b_out.data_ptr(), N, 0,
                   d["y_rows"].data_ptr(), zy.data_ptr(), st)
@@ -184,7 +200,7 @@ class HierTCNTrainer:
         d_sbias = buf("tr_d_sbias", (S, B, D), f32)
         d_xe = buf("tr_d_xe", (R, D), f32)
         k2_scratch = buf("tr_k2_scratch", (2, R, D), f32)
-        cabi.call("htcn_tcn_backward", d_hout.data_ptr(), d["row_of"].data_ptr(), xe.data_ptr(), m.w_in_x.data_ptr(),
+        cabi.call("htcn_tcn_backward", d_hout.data_ptr(), d["row_of"].data_ptr(), xe.data_ptr(), sdt_c, m.w_in_x.data_ptr(),
                   m._conv_w_pp[0], L, K, slot_p, B, T, S, h_save.data_ptr(), a_save.data_ptr(), k2_scratch.data_ptr(),
                   self._d_conv_w[0], self._d_conv_b[0], self.g["w_in_x"].data_ptr(), d_sbias.data_ptr(), d_xe.data_ptr(), st)
         cabi.note_launches(1 + L * (K + 3) + 3)

@@ -281,9 +281,10 @@ int32_t htcn_score_ce_backward_bf16(const void* hout, const void* hout_t, int64_
                                     const float* target_logit, const float* g_row, float* workspace, float* d_hout,
                                     float* d_w_out_t, float* d_b_out, void* stream);
 
-/* src [R,128] f32 -> dst_rows [R,128] bf16 (or NULL) and dst_t [128,r_pad] bf16 = its transpose (or NULL; columns
- * R..r_pad-1 are zero).  r_pad % 8 == 0. */
-int32_t htcn_cast_transpose_bf16(const float* src, int64_t R, void* dst_rows, void* dst_t, int64_t r_pad, void* stream);
+/* src [R,128] (f32 or bf16) -> dst_rows [R,128] bf16 (or NULL) and dst_t [128,r_pad] bf16 = its transpose (or NULL;
+ * columns R..r_pad-1 are zero).  r_pad % 8 == 0. */
+int32_t htcn_cast_transpose_bf16(const void* src, int32_t src_dtype, int64_t R, void* dst_rows, void* dst_t,
+                                 int64_t r_pad, void* stream);
 
 /* K2 forward that keeps what the backward needs: h_save [(n_levels+1), B*T, 128] (the in-projection output and
  * every level's output) and a_save [n_levels, B*T, 128] (relu(conv+bias) before the residual add);
@@ -293,13 +294,23 @@ int32_t htcn_tcn_forward_train(const float* xe, const float* w_in_x, const float
                                int32_t kernel_size, const int32_t* slot_off_host, int32_t B, int32_t T, int32_t S,
                                const int32_t* out_row, float* h_save, float* a_save, float* hout, void* stream);
 
+/* The same on the tensor cores: the fused tcgen05 conv stack (htcn_tcn_forward, HTCN_BF16) with every layer's output
+ * (h_save [(n_levels+1), B*T, 128]) and every level's pre-residual activation (a_save [n_levels, B*T, 128]) written out
+ * in bf16.  xe [B*T,128] bf16, hout [Q,128] bf16; scratch as htcn_tcn_forward's bf16 tier (HTCN_TCN_SCRATCH_BYTES). */
+int32_t htcn_tcn_forward_train_bf16(const void* xe, const float* w_in_x, const float* sbias,
+                                    const float* const* conv_w_host, const float* const* conv_b_host, int32_t n_levels,
+                                    int32_t kernel_size, const int32_t* slot_off_host, int32_t B, int32_t T, int32_t S,
+                                    const int32_t* out_row, void* h_save, void* a_save, void* hout, float* scratch,
+                                    void* stream);
+
 /* Backward of the conv stack + in-projection (customized_tcn_cell.py:109-127, model_tcn.py:35).
- * scratch: 2*B*T*128 floats.  d_conv_w[l] [K,128,128], d_conv_b[l] [128], d_w_in_x [128,128] accumulated;
- * d_sbias [S,B,128] and d_xe [B*T,128] overwritten. */
-int32_t htcn_tcn_backward(const float* d_hout, const int32_t* out_row, const float* xe, const float* w_in_x,
-                          const float* const* conv_w_host, int32_t n_levels, int32_t kernel_size,
-                          const int32_t* slot_off_host, int32_t B, int32_t T, int32_t S, const float* h_save,
-                          const float* a_save, float* scratch, float* const* d_conv_w_host,
+ * xe, h_save, a_save are of save_dtype (HTCN_F32 from htcn_tcn_forward_train, HTCN_BF16 from ..._train_bf16); the
+ * gradients are fp32.  scratch: 2*B*T*128 floats.  d_conv_w[l] [K,128,128], d_conv_b[l] [128], d_w_in_x [128,128]
+ * accumulated; d_sbias [S,B,128] and d_xe [B*T,128] overwritten. */
+int32_t htcn_tcn_backward(const float* d_hout, const int32_t* out_row, const void* xe, int32_t save_dtype,
+                          const float* w_in_x, const float* const* conv_w_host, int32_t n_levels, int32_t kernel_size,
+                          const int32_t* slot_off_host, int32_t B, int32_t T, int32_t S, const void* h_save,
+                          const void* a_save, float* scratch, float* const* d_conv_w_host,
                           float* const* d_conv_b_host, float* d_w_in_x, float* d_sbias, float* d_xe, void* stream);
 
 /* K3 fp32 forward that also saves state_pre [S,B,G*128] and gates_save [S,G,3,B,128] (r, u, c of every cell). */

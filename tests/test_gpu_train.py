@@ -227,12 +227,14 @@ def test_score_ce_backward_bf16_matches_numpy(Q, N):
     hq_t = torch.empty((128, q_pad), dtype=torch.bfloat16, device="cuda")
     w_aug = torch.empty((N, 144), dtype=torch.bfloat16, device="cuda")
     w_tf = torch.empty((128, n_pad), dtype=torch.bfloat16, device="cuda")
-    cabi.call("htcn_cast_transpose_bf16", h_d.data_ptr(), Q, hq.data_ptr(), hq_t.data_ptr(), q_pad, st)
-    cabi.call("htcn_cast_transpose_bf16", wt_d.data_ptr(), N, None, w_tf.data_ptr(), n_pad, st)
+    cabi.call("htcn_cast_transpose_bf16", h_d.data_ptr(), cabi.HTCN_F32, Q, hq.data_ptr(), hq_t.data_ptr(), q_pad, st)
+    cabi.call("htcn_cast_transpose_bf16", wt_d.data_ptr(), cabi.HTCN_F32, N, None, w_tf.data_ptr(), n_pad, st)
+    hq_t2 = torch.empty((128, q_pad), dtype=torch.bfloat16, device="cuda")          # bf16 source -> same transpose
+    cabi.call("htcn_cast_transpose_bf16", hq.data_ptr(), cabi.HTCN_BF16, Q, None, hq_t2.data_ptr(), q_pad, st)
     cabi.call("htcn_refresh_wout", wt_d.data_ptr(), b_d.data_ptr(), N, w_aug.data_ptr(), cabi.HTCN_BF16, st)
     torch.cuda.synchronize()
     assert torch.equal(hq.float().cpu(), torch.from_numpy(h)) and torch.equal(hq_t[:, :Q].float().cpu(), torch.from_numpy(h.T))
-    assert float(hq_t[:, Q:].abs().sum()) == 0.0
+    assert float(hq_t[:, Q:].abs().sum()) == 0.0 and torch.equal(hq_t.view(torch.int16), hq_t2.view(torch.int16))
     y_d, g_d = dev(y), dev(g)
     loss_d, zy_d = dev((lse - zy).astype(np.float32)), dev(zy.astype(np.float32))
     dh = torch.full((Q, 128), 7.0, device="cuda")
@@ -248,11 +250,15 @@ def test_score_ce_backward_bf16_matches_numpy(Q, N):
         assert np.linalg.norm(got - ref) <= 5e-3 * np.linalg.norm(ref) + 1e-6
 
 
+@pytest.mark.parametrize("fused_conv", [True, False])
 @pytest.mark.parametrize("case", [dict(B=5, S=3, L=7, N=97, seed=0), dict(B=33, S=10, L=20, N=3001, seed=3, mask_keep=0.8)])
-def test_gradients_bf16_tier(case):
+def test_gradients_bf16_tier(case, fused_conv):
+    """catalog products on the tensor cores; the conv stack either on the tensor cores too (fused kernel, bf16 saved
+    activations) or on the fp32 level kernels"""
     x, y, m, s0, w = small_case(**case)
     ref_loss, ref_g, ref_state = GO.loss_and_grads(w, x, y, m, s0)
     tr = make_trainer(w, case["N"], precision="bf16")
+    tr.k2_tcgen05 = fused_conv
     r = tr.forward_backward(x, y, m, s0)
     sc = r["scalars"].cpu().numpy()
     assert abs(sc[0] - ref_loss) <= 2e-2 * abs(ref_loss)
