@@ -263,9 +263,14 @@ def test_gradients_bf16_tier(case, fused_conv):
     sc = r["scalars"].cpu().numpy()
     assert abs(sc[0] - ref_loss) <= 2e-2 * abs(ref_loss)
     got = tr.named_gradients(sc[6])
+    # fused conv forward: bf16 activations flip the ReLU gates of ~0.2% of the near-zero pre-activations, i.e. a
+    # sqrt(0.002) ~ 4% relative error of every gradient below the conv stack w.r.t. exact arithmetic (unbiased noise)
+    tol = 8e-2 if fused_conv else 2e-2
     for k in ref_g:
-        assert np.linalg.norm(got[k] - ref_g[k]) <= 2e-2 * np.linalg.norm(ref_g[k]) + 1e-9, k
-        assert np.abs(got[k] - ref_g[k]).max() <= 4e-2 * np.abs(ref_g[k]).max() + 1e-9, k
+        g, r = got[k].ravel(), ref_g[k].ravel()
+        assert np.linalg.norm(g - r) <= tol * np.linalg.norm(r) + 1e-9, k
+        assert np.abs(g - r).max() <= 2 * tol * np.abs(r).max() + 1e-9, k
+        assert g @ r >= 0.995 * np.linalg.norm(g) * np.linalg.norm(r), k
 
 
 def test_train_steps_bf16_tier_track_oracle():
@@ -315,3 +320,45 @@ def test_checkpoint_resume_continues_the_same_trajectory(tmp_path, precision):
     z = np.load(ck)
     assert "w|hier|tcn|dense|kernel" in z.files and z["w|hier|tcn|dense|kernel"].shape == (128, 113)
     assert "Adam|hier|emb|kernel" in z.files and "Adam_1|hier|multi_rnn_cell|cell_1|gru_cell|gates|kernel" in z.files
+
+
+@pytest.mark.parametrize("B,S,L,K,levels", [(7, 3, 9, 5, 2), (40, 10, 20, 5, 2), (3, 1, 300, 5, 3), (4, 2, 1, 3, 3)])
+def test_fused_conv_forward_saves_match_fp32_levels(B, S, L, K, levels):
+    """htcn_tcn_forward_train_bf16 (fused tcgen05 stack, bf16 saves) vs htcn_tcn_forward_train (fp32 level kernels):
+    every layer's output, every pre-residual activation and the compacted user embeddings, to bf16 accuracy"""
+    from hiertcn_b200 import _cabi as cabi
+    rng = np.random.default_rng(B * 100 + L)
+    T, R = S * L, B * S * L
+    xe = rng.normal(0, 1, (R, 128)).astype(np.float32)
+    xe_b = torch.from_numpy(xe).cuda().to(torch.bfloat16)
+    xe_f = xe_b.float()                                       # both paths see the same (bf16-representable) inputs
+    w_in = dev((rng.normal(0, 1, (128, 128)) / np.sqrt(128)).astype(np.float32))
+    sb = dev(rng.normal(0, 0.5, (S, B, 128)).astype(np.float32))
+    cw = [dev((rng.normal(0, 1, (K, 128, 128)) / np.sqrt(128 * K) * 1.5).astype(np.float32)) for _ in range(levels)]
+    cb = [dev(rng.normal(0, 0.1, 128).astype(np.float32)) for _ in range(levels)]
+    valid = rng.random(R) < 0.8
+    row_of = np.where(valid, np.cumsum(valid) - 1, -1).astype(np.int32)
+    Q = int(valid.sum())
+    row_d = dev(row_of)
+    slot_p, keep = cabi.int_array(np.arange(S + 1) * L)
+    wp, wk = cabi.ptr_array([t.data_ptr() for t in cw])
+    bp, bk = cabi.ptr_array([t.data_ptr() for t in cb])
+    st = torch.cuda.current_stream().cuda_stream
+    h32 = torch.zeros((levels + 1, R, 128), device="cuda")
+    a32 = torch.zeros((levels, R, 128), device="cuda")
+    o32 = torch.zeros((Q, 128), device="cuda")
+    cabi.call("htcn_tcn_forward_train", xe_f.data_ptr(), w_in.data_ptr(), sb.data_ptr(), wp, bp, levels, K, slot_p, B, T, S,
+              row_d.data_ptr(), h32.data_ptr(), a32.data_ptr(), o32.data_ptr(), st)
+    h16 = torch.full((levels + 1, R, 128), float("nan"), dtype=torch.bfloat16, device="cuda")
+    a16 = torch.full((levels, R, 128), float("nan"), dtype=torch.bfloat16, device="cuda")
+    o16 = torch.full((Q, 128), float("nan"), dtype=torch.bfloat16, device="cuda")
+    scratch = torch.empty((1 + levels * K) * 8192 + 4096, device="cuda")
+    cabi.call("htcn_tcn_forward_train_bf16", xe_b.data_ptr(), w_in.data_ptr(), sb.data_ptr(), wp, bp, levels, K, slot_p, B,
+              T, S, row_d.data_ptr(), h16.data_ptr(), a16.data_ptr(), o16.data_ptr(), scratch.data_ptr(), st)
+    torch.cuda.synchronize()
+    for name, got, ref in (("h", h16, h32), ("a", a16, a32), ("hout", o16, o32)):
+        g, r = got.float().cpu().numpy(), ref.cpu().numpy()
+        assert np.isfinite(g).all(), name + ": rows not written"
+        err = np.abs(g - r)
+        assert err.max() <= 3e-2 * np.abs(r).max() + 1e-3, (name, float(err.max()), float(np.abs(r).max()))
+        assert np.linalg.norm(g - r) <= 1e-2 * np.linalg.norm(r), (name, float(np.linalg.norm(g - r) / np.linalg.norm(r)))
