@@ -25,7 +25,9 @@ constexpr int kGM = 128;                          // users per CTA
 constexpr int kGActBytes = 32 * kGM * 16;         // 32 x 16-byte K chunks (K = 256) x 128 rows = 64 KB
 constexpr int kGTileBytes = 2 * 128 * 128;        // one weight tile [128 n][128 k] bf16 = 32 KB
 constexpr int kGStages = 3;
-constexpr int kGThreads = 192;                    // warps 0-3 epilogue (thread = user), 4 = TMA producer, 5 = MMA issuer
+constexpr int kGEpiWarps = 16;                    // 4 TMEM lane quarters x 4 column groups of 32: a thread owns 32 columns of one user
+constexpr int kGThreads = 32 * (kGEpiWarps + 2);  // warps 0-15 epilogue, 16 = TMA producer, 17 = MMA issuer
+constexpr int kGProducerWarp = kGEpiWarps, kGMmaWarp = kGEpiWarps + 1;
 constexpr int kTilesSb = 2, kTilesGates = 4, kTilesCand = 2;
 
 struct alignas(1024) K3Smem {
@@ -57,10 +59,10 @@ __device__ __forceinline__ void put_chunk(uint8_t* act_row, int chunk, const flo
   *reinterpret_cast<uint4*>(act_row + chunk * (kGM * 16)) =
       make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
 }
-// operand half (0 = input, 1 = hidden) <- bf16(src[0..127]) (src may be NULL -> zeros)
-__device__ __forceinline__ void put_half(uint8_t* act_row, int half, const float* src) {
-#pragma unroll 4
-  for (int c = 0; c < 16; ++c) {
+// operand half (0 = input, 1 = hidden), columns cg*32..+31 <- bf16(src[..]) (src may be NULL -> zeros)
+__device__ __forceinline__ void put_half(uint8_t* act_row, int half, const float* src, int cg) {
+#pragma unroll
+  for (int c = cg * 4; c < cg * 4 + 4; ++c) {
     float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (src) {
       const float4 a = *reinterpret_cast<const float4*>(src + c * 8), b = *reinterpret_cast<const float4*>(src + c * 8 + 4);
@@ -86,10 +88,9 @@ __device__ __forceinline__ void st_state(uint32_t t_lane, int l, int cc, const f
   for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(h[i]);
   tmem_st_32x32(t_lane + kColH + l * 128 + cc * 32, v);
 }
-// operand half <- bf16(state layer l)
-__device__ __forceinline__ void put_half_state(uint8_t* act_row, int half, uint32_t t_lane, int l) {
-#pragma unroll 1
-  for (int cc = 0; cc < 4; ++cc) {
+// operand half, columns cc*32..+31 <- bf16(state layer l)
+__device__ __forceinline__ void put_half_state(uint8_t* act_row, int half, uint32_t t_lane, int l, int cc) {
+  {
     float h[32];
     ld_state(t_lane, l, cc, h);
 #pragma unroll
@@ -118,7 +119,7 @@ k3_gru_bf16(const __grid_constant__ CUtensorMap tmap_w, const float* __restrict_
       mbar_init(&sm.w_empty[s], 1);
     }
     mbar_init(&sm.acc_ready, 1);
-    mbar_init(&sm.act_ready, kGM);
+    mbar_init(&sm.act_ready, 32 * kGEpiWarps);
     fence_barrier_init();
   }
   for (int i = tid; i < 768; i += kGThreads) {
@@ -126,13 +127,13 @@ k3_gru_bf16(const __grid_constant__ CUtensorMap tmap_w, const float* __restrict_
     if (j < 256) sm.bg[l][j] = bias_all[i];
     else sm.bc[l][j - 256] = bias_all[i];
   }
-  if (warp == 5) tmem_alloc<512>(&sm.tmem_base);
+  if (warp == kGMmaWarp) tmem_alloc<512>(&sm.tmem_base);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = __shfl_sync(0xffffffffu, sm.tmem_base, 0);
 
-  if (warp == 4) {
+  if (warp == kGProducerWarp) {
     // ===================== weight producer =====================
     if (lane == 0) {
       long long n = 0;
@@ -147,7 +148,7 @@ k3_gru_bf16(const __grid_constant__ CUtensorMap tmap_w, const float* __restrict_
       }
       (void)tiles_per_step;
     }
-  } else if (warp == 5) {
+  } else if (warp == kGMmaWarp) {
     // ===================== MMA issuer =====================
     // the whole warp runs the (warp-uniform) waits and descriptor arithmetic, one elected lane issues: under an
     // `if (lane == 0)` branch every tcgen05.mma is wrapped in an ELECT / R2UR.BROADCAST waterfall (~100 clk per MMA)
@@ -198,12 +199,13 @@ k3_gru_bf16(const __grid_constant__ CUtensorMap tmap_w, const float* __restrict_
       }
     }
   } else {
-    // ===================== epilogue: thread = user row =====================
-    const int r = tid;
+    // ===================== epilogue: thread = 32 columns (cc) of one user row =====================
+    const int quarter = warp & 3, cc = warp >> 2;
+    const int r = quarter * 32 + lane;
     const int b = blockIdx.x * kGM + r;
     const bool ok = b < B;
     uint8_t* act_row = sm.act + r * 16;
-    const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t t_lane = tmem + ((uint32_t)(quarter * 32) << 16);
     long long n_acc = 0;
     auto operand_ready = [&]() {
       tc_fence_before_sync();
@@ -216,8 +218,7 @@ k3_gru_bf16(const __grid_constant__ CUtensorMap tmap_w, const float* __restrict_
       ++n_acc;
     };
     // prologue: TMEM state <- state_in (rows beyond B hold zeros)
-    for (int l = 0; l < 2; ++l)
-      for (int cc = 0; cc < 4; ++cc) {
+    for (int l = 0; l < 2; ++l) {
         float h[32];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -232,8 +233,7 @@ k3_gru_bf16(const __grid_constant__ CUtensorMap tmap_w, const float* __restrict_
       const float m = ok ? __ldg(mask + (long long)s * B + b) : 0.f;
       const float* x = ok ? yp + ((long long)s * B + b) * kDim : nullptr;
       if (state_pre) {
-        for (int l = 0; l < 2; ++l)
-          for (int cc = 0; cc < 4; ++cc) {
+        for (int l = 0; l < 2; ++l) {
             float h[32];
             ld_state(t_lane, l, cc, h);
             if (ok) {
@@ -244,12 +244,11 @@ k3_gru_bf16(const __grid_constant__ CUtensorMap tmap_w, const float* __restrict_
           }
       }
       if (do_sbias) {
-        put_half_state(act_row, 0, t_lane, 0);
-        put_half_state(act_row, 1, t_lane, 1);
+        put_half_state(act_row, 0, t_lane, 0, cc);
+        put_half_state(act_row, 1, t_lane, 1, cc);
         operand_ready();
         wait_acc();                                          // ---- E_sb: sbias[s] out, operand <- [x | h0]
-#pragma unroll 1
-        for (int cc = 0; cc < 4; ++cc) {
+        {
           uint32_t v[32];
           tmem_ld_32x32(t_lane + cc * 32, v);
           tmem_ld_wait(v);
@@ -262,13 +261,12 @@ k3_gru_bf16(const __grid_constant__ CUtensorMap tmap_w, const float* __restrict_
           }
         }
       }
-      put_half(act_row, 0, x);
-      put_half_state(act_row, 1, t_lane, 0);
+      put_half(act_row, 0, x, cc);
+      put_half_state(act_row, 1, t_lane, 0, cc);
       operand_ready();
       for (int l = 0; l < 2; ++l) {
         wait_acc();                                            // ---- E_g: operand hidden half <- r * h
-#pragma unroll 1
-        for (int cc = 0; cc < 4; ++cc) {
+        {
           uint32_t v[32];
           float h[32];
           tmem_ld_32x32(t_lane + cc * 32, v);                  // r pre-activations, columns cc*32..+31
@@ -287,8 +285,7 @@ k3_gru_bf16(const __grid_constant__ CUtensorMap tmap_w, const float* __restrict_
         }
         operand_ready();
         wait_acc();                                            // ---- E_c: h' = u*h + (1-u)*c
-#pragma unroll 1
-        for (int cc = 0; cc < 4; ++cc) {
+        {
           uint32_t vc[32], vu[32];
           float h[32];
           tmem_ld_32x32(t_lane + cc * 32, vc);                 // candidate pre-activations (columns 0..127, reused)
@@ -313,14 +310,13 @@ k3_gru_bf16(const __grid_constant__ CUtensorMap tmap_w, const float* __restrict_
         }
         tmem_st_wait();
         if (l == 0) {
-          put_half_state(act_row, 1, t_lane, 1);               // [h0' | h1]
+          put_half_state(act_row, 1, t_lane, 1, cc);           // [h0' | h1]
           operand_ready();
         }
       }
       // after layer 1: the next phase (sbias of step s+1 or [x | h0] of step s+1) is staged at the top of the loop
     }
-    for (int l = 0; l < 2; ++l)
-      for (int cc = 0; cc < 4; ++cc) {
+    for (int l = 0; l < 2; ++l) {
         float h[32];
         ld_state(t_lane, l, cc, h);
         if (ok) {
@@ -332,7 +328,7 @@ k3_gru_bf16(const __grid_constant__ CUtensorMap tmap_w, const float* __restrict_
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == kGMmaWarp) {
     tc_fence_after_sync();
     tmem_dealloc<512>(tmem);
   }
