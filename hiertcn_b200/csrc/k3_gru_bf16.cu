@@ -15,6 +15,8 @@
 //   P_g0 : [r|u] = sigmoid([x | h0] Wg0 + bg0)          E: operand hidden half <- r * h0
 //   P_c0 : c = tanh([x | r*h0] Wc0 + bc0)               E: h0' = u*h0 + (1-u)*c ; state <- m*h0' ; operand <- [h0' | h1]
 //   P_g1 / P_c1 : the same for layer 1 with input h0'   E: state <- m*h1' ; operand <- [m*h0' | m*h1']
+#include <cstdlib>
+
 #include "common.cuh"
 #include "sm100.cuh"
 
@@ -352,10 +354,21 @@ __global__ void k3_prepare_weights(const float* __restrict__ w_in_state, const f
   }
 }
 
+int32_t gru_sessions_bf16_cluster(const float* yp, const float* mask, const float* state_in, const float* const* gate_w,
+                                  const float* const* gate_b, const float* const* cand_w, const float* const* cand_b,
+                                  const float* w_in_state, int B, int S, float* state_pre, float* sbias, float* state_out,
+                                  float* scratch, cudaStream_t st);
+
 int32_t gru_sessions_bf16(const float* yp, const float* mask, const float* state_in, const float* const* gate_w,
                           const float* const* gate_b, const float* const* cand_w, const float* const* cand_b,
                           const float* w_in_state, int B, int S, float* state_pre, float* sbias, float* state_out,
                           float* scratch, cudaStream_t st) {
+  // default: the 4-CTA cluster kernel with shared-memory-resident weights (k3_gru_cluster.cu); HTCN_K3_CLUSTER=0 selects
+  // this file's single-CTA kernel that streams the weights from L2
+  const char* cl = getenv("HTCN_K3_CLUSTER");
+  if (!cl || atoi(cl) != 0)
+    return gru_sessions_bf16_cluster(yp, mask, state_in, gate_w, gate_b, cand_w, cand_b, w_in_state, B, S, state_pre, sbias,
+                                     state_out, scratch, st);
   // scratch layout: [14 bf16 weight tiles][4 device pointers][768 bias floats]
   uint8_t* sc = reinterpret_cast<uint8_t*>(scratch);
   __nv_bfloat16* w_bf16 = reinterpret_cast<__nv_bfloat16*>(sc);

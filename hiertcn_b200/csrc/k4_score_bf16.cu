@@ -68,6 +68,52 @@ __device__ __forceinline__ float ex2_poly(float t) {
   return __int_as_float(__float_as_int(p) + (__float_as_int(r) << 23));
 }
 
+// ---- packed (f32x2) CE + rank epilogue ------------------------------------------------------------------------
+// FFMA2 / FADD2 process two logits per issue slot: t = z*log2e - zy*log2e, the two running sums.  Per logit that is
+// 3.5 issue slots (FFMA2/2, MUFU.EX2, FADD2/2, FSET.BF, FADD2/2) instead of 5, which leaves room to move more of the
+// exponentials off the MUFU pipe (16/clk/SM, the bound of this loop): kPolyPairs of the 16 logit pairs of a 32-column
+// chunk evaluate 2^t on the FMA pipe, again two lanes per instruction.
+enum : unsigned { kModePacked = 256u, kPolyPairsShift = 9u, kPolyDeg2 = 8192u };   // kFlags bits 9..12 = kPolyPairs
+constexpr unsigned packed_flags(int poly_pairs, bool deg2 = false) {
+  return kModePacked | ((unsigned)poly_pairs << kPolyPairsShift) | (deg2 ? kPolyDeg2 : 0u);
+}
+
+template <bool kDeg2>
+__device__ __forceinline__ float2 ex2_poly2(float2 t) {
+  t.x = fmaxf(t.x, -125.0f);
+  t.y = fmaxf(t.y, -125.0f);
+  const float2 r = fadd2(t, make_float2(12582912.0f, 12582912.0f));
+  const float2 n = fadd2(r, make_float2(-12582912.0f, -12582912.0f));
+  const float2 f = ffma2(n, make_float2(-1.0f, -1.0f), t);
+  float2 p;
+  if (kDeg2) {                                     // max relative error 2.0e-3, mean -2.4e-4
+    p = ffma2(f, make_float2(0.23986403f, 0.23986403f), make_float2(0.70294179f, 0.70294179f));
+  } else {                                         // max relative error 1.0e-4
+    p = ffma2(f, make_float2(0.05500892922282219f, 0.05500892922282219f), make_float2(0.24221095442771912f, 0.24221095442771912f));
+    p = ffma2(p, f, make_float2(0.6932829022407532f, 0.6932829022407532f));
+  }
+  p = ffma2(p, f, make_float2(1.0f, 1.0f));
+  return make_float2(__int_as_float(__float_as_int(p.x) + (__float_as_int(r.x) << 23)),
+                     __int_as_float(__float_as_int(p.y) + (__float_as_int(r.y) << 23)));
+}
+
+// one full 32-column chunk of a row: sum2 += 2^((z - zy) log2e), cf2 += [z > zy]
+template <bool kCE, bool kRank, int kPolyPairs, bool kDeg2>
+__device__ __forceinline__ void ce_rank_chunk_packed(const uint32_t (&r)[32], float zy, float nzyl, float2 (&sum2)[2],
+                                                     float2 (&cf2)[2]) {
+#pragma unroll
+  for (int p = 0; p < 16; ++p) {
+    const float2 z = make_float2(__uint_as_float(r[2 * p]), __uint_as_float(r[2 * p + 1]));
+    if (kCE) {
+      const float2 t = ffma2(z, make_float2(kLog2e, kLog2e), make_float2(nzyl, nzyl));
+      const bool poly = ((p + 1) * kPolyPairs) / 16 != (p * kPolyPairs) / 16;
+      const float2 e = poly ? ex2_poly2<kDeg2>(t) : make_float2(ex2_approx(t.x), ex2_approx(t.y));
+      sum2[p & 1] = fadd2(sum2[p & 1], e);
+    }
+    if (kRank) cf2[p & 1] = fadd2(cf2[p & 1], make_float2(set_gt_f(z.x, zy), set_gt_f(z.y, zy)));
+  }
+}
+
 template <int BN>
 struct alignas(1024) ScoreSmem {
   uint8_t a[2][kChunkBytesA];                     // K chunks 0..63 / 64..127 (128B swizzle)
@@ -376,6 +422,8 @@ k4_score_bf16_cg2(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                   const __grid_constant__ CUtensorMap tmap_bb, ScoreArgs a, float* __restrict__ dump) {
   constexpr bool kCE = kFlags & HTCN_SCORE_CE, kRank = kFlags & HTCN_SCORE_RANK, kDump = kFlags & kModeDump;
   constexpr int kPolyEvery = (kFlags & kModePoly4) ? 4 : (kFlags & kModePoly8) ? 8 : 0x40000000;
+  constexpr bool kPacked = (kFlags & kModePacked) && !kDump;
+  constexpr int kPolyPairs = (kFlags >> kPolyPairsShift) & 15;
   constexpr int BN = 256, kSlices = kSlicesScore, kEpiWarps = 4 * kSlices, kColsPerWarp = BN / kSlices;
   constexpr uint32_t kHalfStageBytes = 2 * 128 * 128 + 128 * 32;
   extern __shared__ uint8_t smem_raw[];
@@ -463,6 +511,7 @@ k4_score_bf16_cg2(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const int col0 = half * kColsPerWarp;
     float zy = 0.f, zyl = 0.f;
     float sum4[4] = {0.f, 0.f, 0.f, 0.f}, cf[4] = {0.f, 0.f, 0.f, 0.f};
+    float2 sum2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, cf2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
     int cnt = 0;
     if ((kCE || kRank) && row_ok) {
       zy = a.zy[q0 + row];
@@ -486,7 +535,9 @@ k4_score_bf16_cg2(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(&sm.t_empty[buf], 0);   // the leader's barrier
         }
-        if (c + 32 <= lim) {
+        if (kPacked && c + 32 <= lim) {
+          ce_rank_chunk_packed<kCE, kRank, kPolyPairs, (kFlags & kPolyDeg2) != 0>(r, zy, -zyl, sum2, cf2);
+        } else if (c + 32 <= lim) {
 #pragma unroll
           for (int u = 0; u < 32; ++u) {
             const float z = __uint_as_float(r[u]);
@@ -519,9 +570,14 @@ k4_score_bf16_cg2(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       if (kRank) {
         cnt += (int)((cf[0] + cf[1]) + (cf[2] + cf[3]));
         cf[0] = cf[1] = cf[2] = cf[3] = 0.f;
+        if (kPacked) {
+          cnt += (int)((cf2[0].x + cf2[0].y) + (cf2[1].x + cf2[1].y));
+          cf2[0] = cf2[1] = make_float2(0.f, 0.f);
+        }
       }
     }
     float sum = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
+    if (kPacked) sum += (sum2[0].x + sum2[0].y) + (sum2[1].x + sum2[1].y);
     if (half > 0) {
       sm.comb_sum[half - 1][row] = sum;
       sm.comb_cnt[half - 1][row] = cnt;
@@ -746,9 +802,27 @@ int32_t score_bf16(const ScoreArgs& a, cudaStream_t st) {
     switch (a.flags) {
       case HTCN_SCORE_CE: return launch_score_cg2<HTCN_SCORE_CE>(a, nullptr, st);
       case HTCN_SCORE_RANK: return launch_score_cg2<HTCN_SCORE_RANK>(a, nullptr, st);
-      case HTCN_SCORE_CE | HTCN_SCORE_RANK:
-        if (poly == 8) return launch_score_cg2<HTCN_SCORE_CE | HTCN_SCORE_RANK | kModePoly8>(a, nullptr, st);
-        return launch_score_cg2<HTCN_SCORE_CE | HTCN_SCORE_RANK>(a, nullptr, st);
+      case HTCN_SCORE_CE | HTCN_SCORE_RANK: {
+        // HTCN_K4_EPI = number of polynomial pairs (of 16) of the packed epilogue, +100 for the degree-2 polynomial;
+        // -1 = the scalar epilogue
+        const char* epi_env = getenv("HTCN_K4_EPI");   // read per call: the sweep script switches variants in-process
+        const int epi = epi_env ? atoi(epi_env) : 104;
+        constexpr unsigned kCR = HTCN_SCORE_CE | HTCN_SCORE_RANK;
+        switch (epi) {
+          case 0: return launch_score_cg2<kCR | packed_flags(0)>(a, nullptr, st);
+          case 2: return launch_score_cg2<kCR | packed_flags(2)>(a, nullptr, st);
+          case 3: return launch_score_cg2<kCR | packed_flags(3)>(a, nullptr, st);
+          case 4: return launch_score_cg2<kCR | packed_flags(4)>(a, nullptr, st);
+          case 5: return launch_score_cg2<kCR | packed_flags(5)>(a, nullptr, st);
+          case 6: return launch_score_cg2<kCR | packed_flags(6)>(a, nullptr, st);
+          case 104: return launch_score_cg2<kCR | packed_flags(4, true)>(a, nullptr, st);
+          case 105: return launch_score_cg2<kCR | packed_flags(5, true)>(a, nullptr, st);
+          case 106: return launch_score_cg2<kCR | packed_flags(6, true)>(a, nullptr, st);
+          default: break;
+        }
+        if (poly == 8) return launch_score_cg2<kCR | kModePoly8>(a, nullptr, st);
+        return launch_score_cg2<kCR>(a, nullptr, st);
+      }
     }
   }
   switch (a.flags) {

@@ -318,6 +318,28 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// packed fp32 pairs (FFMA2 / FADD2, sm_100+): one issue slot for two lanes of an epilogue's per-logit arithmetic
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{ .reg .b64 a, b, c, d;\n\t"
+      "mov.b64 a, {%2, %3}; mov.b64 b, {%4, %5}; mov.b64 c, {%6, %7};\n\t"
+      "fma.rn.f32x2 d, a, b, c;\n\t"
+      "mov.b64 {%0, %1}, d; }"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  float2 d;
+  asm("{ .reg .b64 a, b, d;\n\t"
+      "mov.b64 a, {%2, %3}; mov.b64 b, {%4, %5};\n\t"
+      "add.rn.f32x2 d, a, b;\n\t"
+      "mov.b64 {%0, %1}, d; }"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+
 }  // namespace sm100
 
 // ---- host: tensor maps ---------------------------------------------------------------------------------

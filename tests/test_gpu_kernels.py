@@ -116,6 +116,42 @@ def test_k3_gru_sessions(lib, B, S):
     assert (sout.cpu().numpy()[last] == 0).all()
 
 
+@pytest.mark.parametrize("B,S,with_sbias", [(300, 4, True), (129, 2, False)])
+def test_k3_cluster_variants_agree(lib, B, S, with_sbias, monkeypatch):
+    """The three bf16 GRU kernels -- weights streamed from L2 (HTCN_K3_CLUSTER=0), 4-CTA cluster with resident weights
+    and plain DSMEM stores (=1) or st.async (=2, default) -- run the same arithmetic: equal results, and within the bf16
+    bar of the oracle (customed_gru_cell.py:309-337)."""
+    x, y, m, s0, w = small_case(B=B, S=S, L=4, N=97, seed=5)
+    state_pre, state_out, yps = O.gru_over_sessions(y, m, s0, w, 2, "f32")
+    w_in = w["hier/tcn/emb/kernel"]
+    gru = []
+    for g in range(2):
+        p = f"hier/multi_rnn_cell/cell_{g}/gru_cell"
+        gru.append([dev(w[p + "/gates/kernel"]), dev(w[p + "/gates/bias"]), dev(w[p + "/candidate/kernel"]),
+                    dev(w[p + "/candidate/bias"])])
+    pps = [lib.ptr_array([l[i].data_ptr() for l in gru]) for i in range(4)]
+    mask = dev(np.stack([mm.reshape(-1) for mm in m]).astype(np.float32))
+    yp, st_in, wis = dev(yps.astype(np.float32)), dev(s0), dev(w_in[128:])
+    scratch = torch.empty(lib.gru_scratch_bytes(B) // 4, dtype=torch.float32, device="cuda")
+    res = {}
+    for mode in ("0", "1", "2"):
+        monkeypatch.setenv("HTCN_K3_CLUSTER", mode)
+        spre = torch.full((S, B, 256), 7.0, dtype=torch.float32, device="cuda")
+        sbias = torch.full((S, B, 128), 7.0, dtype=torch.float32, device="cuda")
+        sout = torch.full((B, 256), 7.0, dtype=torch.float32, device="cuda")
+        lib.call("htcn_gru_sessions", P(yp), P(mask), P(st_in), pps[0][0], pps[1][0], pps[2][0], pps[3][0], 2,
+                 P(wis) if with_sbias else None, B, S, lib.HTCN_BF16, P(scratch), P(spre), P(sbias) if with_sbias else None,
+                 P(sout), None)
+        torch.cuda.synchronize()
+        res[mode] = (spre.cpu().numpy(), sout.cpu().numpy(), sbias.cpu().numpy())
+    for mode in ("1", "2"):
+        for a, b in zip(res[mode][:2 + with_sbias], res["0"]):
+            np.testing.assert_allclose(a, b, rtol=0, atol=1e-5)
+    for got, ref in ((res["2"][0], state_pre), (res["2"][1], state_out)):
+        err = np.abs(got - ref)
+        assert err.max() <= 2e-2 * max(1.0, np.abs(ref).max()), err.max()
+
+
 # ------------------------------------------------------------------------------------------ K2
 def run_k2(lib, xe_t, xe_dtype, w, sbias, slot_off, B, T, S, K, n_levels, out_row=None, n_out=None,
            hout_dtype=None, precision=None):
