@@ -59,7 +59,7 @@ struct TopkAux {
 // 2^t on the FMA/ALU pipes: round-to-nearest split t = n + f, f in [-0.5, 0.5]; 2^f by a degree-3 polynomial with
 // p(0) = 1 (max relative error 1.0e-4 -- bf16-tier only); 2^n by adding n to the exponent field.
 __device__ __forceinline__ float ex2_poly(float t) {
-  t = fmaxf(t, -125.0f);
+  t = fminf(fmaxf(t, -125.0f), 128.0f);          // the exponent-field add below wraps outside [-126, 128)
   const float r = t + 12582912.0f;               // 1.5 * 2^23: n = round(t) lands in the low mantissa bits
   const float f = t - (r - 12582912.0f);
   float p = fmaf(f, 0.05500892922282219f, 0.24221095442771912f);
@@ -80,8 +80,9 @@ constexpr unsigned packed_flags(int poly_pairs, bool deg2 = false) {
 
 template <bool kDeg2>
 __device__ __forceinline__ float2 ex2_poly2(float2 t) {
-  t.x = fmaxf(t.x, -125.0f);
-  t.y = fmaxf(t.y, -125.0f);
+  // 2^n is formed by adding n to the exponent field, which WRAPS outside [-126, 128).  Instead of clamping every value
+  // (two FMNMX each), the caller tracks max |t| over the polynomial lanes (one FMNMX3 per pair) and declares the row's
+  // partial sum overflowed when it reaches kPolyRange: htcn_score_ce_repair then redoes the row exactly.
   const float2 r = fadd2(t, make_float2(12582912.0f, 12582912.0f));
   const float2 n = fadd2(r, make_float2(-12582912.0f, -12582912.0f));
   const float2 f = ffma2(n, make_float2(-1.0f, -1.0f), t);
@@ -98,15 +99,17 @@ __device__ __forceinline__ float2 ex2_poly2(float2 t) {
 }
 
 // one full 32-column chunk of a row: sum2 += 2^((z - zy) log2e), cf2 += [z > zy]
+constexpr float kPolyRange = 125.0f;             // |t| the exponent-field arithmetic of ex2_poly2 handles
 template <bool kCE, bool kRank, int kPolyPairs, bool kDeg2>
 __device__ __forceinline__ void ce_rank_chunk_packed(const uint32_t (&r)[32], float zy, float nzyl, float2 (&sum2)[2],
-                                                     float2 (&cf2)[2]) {
+                                                     float2 (&cf2)[2], float& amax) {
 #pragma unroll
   for (int p = 0; p < 16; ++p) {
     const float2 z = make_float2(__uint_as_float(r[2 * p]), __uint_as_float(r[2 * p + 1]));
     if (kCE) {
       const float2 t = ffma2(z, make_float2(kLog2e, kLog2e), make_float2(nzyl, nzyl));
       const bool poly = ((p + 1) * kPolyPairs) / 16 != (p * kPolyPairs) / 16;
+      if (poly) amax = fmaxf(fmaxf(amax, fabsf(t.x)), fabsf(t.y));     // one FMNMX3
       const float2 e = poly ? ex2_poly2<kDeg2>(t) : make_float2(ex2_approx(t.x), ex2_approx(t.y));
       sum2[p & 1] = fadd2(sum2[p & 1], e);
     }
@@ -512,6 +515,7 @@ k4_score_bf16_cg2(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     float zy = 0.f, zyl = 0.f;
     float sum4[4] = {0.f, 0.f, 0.f, 0.f}, cf[4] = {0.f, 0.f, 0.f, 0.f};
     float2 sum2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, cf2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+    float amax = 0.f;                                            // max |t| seen by the polynomial lanes
     int cnt = 0;
     if ((kCE || kRank) && row_ok) {
       zy = a.zy[q0 + row];
@@ -523,6 +527,27 @@ k4_score_bf16_cg2(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       mbar_wait(&sm.t_full[buf], (i >> 1) & 1);
       tc_fence_after_sync();
       const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + buf * BN + col0;
+      if (kPacked && j0 + BN <= a.n_items) {
+        // every tile but the last of the catalog: no column bounds, rank counts stay in the float accumulators
+        // (16 increments per lane and tile: exact far beyond the flush interval below)
+#pragma unroll
+        for (int c = 0; c < kColsPerWarp; c += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c, r);
+          tmem_ld_wait(r);
+          if (c + 32 == kColsPerWarp) {
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(&sm.t_empty[buf], 0);   // the leader's barrier
+          }
+          ce_rank_chunk_packed<kCE, kRank, kPolyPairs, (kFlags & kPolyDeg2) != 0>(r, zy, -zyl, sum2, cf2, amax);
+        }
+        if (kRank && (i & 4095) == 4095) {
+          cnt += (int)((cf2[0].x + cf2[0].y) + (cf2[1].x + cf2[1].y));
+          cf2[0] = cf2[1] = make_float2(0.f, 0.f);
+        }
+        continue;
+      }
       const int lim = a.n_items - j0 - col0;
       const int jbase = j0 + col0;
 #pragma unroll
@@ -536,7 +561,7 @@ k4_score_bf16_cg2(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           if (lane == 0) mbar_arrive_cluster(&sm.t_empty[buf], 0);   // the leader's barrier
         }
         if (kPacked && c + 32 <= lim) {
-          ce_rank_chunk_packed<kCE, kRank, kPolyPairs, (kFlags & kPolyDeg2) != 0>(r, zy, -zyl, sum2, cf2);
+          ce_rank_chunk_packed<kCE, kRank, kPolyPairs, (kFlags & kPolyDeg2) != 0>(r, zy, -zyl, sum2, cf2, amax);
         } else if (c + 32 <= lim) {
 #pragma unroll
           for (int u = 0; u < 32; ++u) {
@@ -578,6 +603,8 @@ k4_score_bf16_cg2(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
     float sum = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
     if (kPacked) sum += (sum2[0].x + sum2[0].y) + (sum2[1].x + sum2[1].y);
+    if (kPacked && !(amax < kPolyRange)) sum = INFINITY;         // a polynomial lane left its range: the row is redone exactly
+    if (kPacked && kRank) cnt += (int)((cf2[0].x + cf2[0].y) + (cf2[1].x + cf2[1].y));   // counts of the fast-path tiles
     if (half > 0) {
       sm.comb_sum[half - 1][row] = sum;
       sm.comb_cnt[half - 1][row] = cnt;
@@ -806,7 +833,7 @@ int32_t score_bf16(const ScoreArgs& a, cudaStream_t st) {
         // HTCN_K4_EPI = number of polynomial pairs (of 16) of the packed epilogue, +100 for the degree-2 polynomial;
         // -1 = the scalar epilogue
         const char* epi_env = getenv("HTCN_K4_EPI");   // read per call: the sweep script switches variants in-process
-        const int epi = epi_env ? atoi(epi_env) : 104;
+        const int epi = epi_env ? atoi(epi_env) : 4;
         constexpr unsigned kCR = HTCN_SCORE_CE | HTCN_SCORE_RANK;
         switch (epi) {
           case 0: return launch_score_cg2<kCR | packed_flags(0)>(a, nullptr, st);
