@@ -363,8 +363,8 @@ int32_t gru_sessions_bf16(const float* yp, const float* mask, const float* state
                           const float* const* gate_b, const float* const* cand_w, const float* const* cand_b,
                           const float* w_in_state, int B, int S, float* state_pre, float* sbias, float* state_out,
                           float* scratch, cudaStream_t st) {
-  // default: the 4-CTA cluster kernel with shared-memory-resident weights (k3_gru_cluster.cu); HTCN_K3_CLUSTER=0 selects
-  // this file's single-CTA kernel that streams the weights from L2
+  // default: the 4-CTA cluster kernel with shared-memory-resident weights (k3_gru_cluster.cu; HTCN_K3_CLUSTER=1 / 2 pick
+  // its DSMEM publication scheme); HTCN_K3_CLUSTER=0 selects this file's single-CTA kernel that streams the weights from L2
   const char* cl = getenv("HTCN_K3_CLUSTER");
   if (!cl || atoi(cl) != 0)
     return gru_sessions_bf16_cluster(yp, mask, state_in, gate_w, gate_b, cand_w, cand_b, w_in_state, B, S, state_pre, sbias,

@@ -6,10 +6,12 @@
 // 128 SMs work on a batch of 4096 users instead of 32, and each of the five dependent GEMM phases of a step is an
 // N = 64 / N = 32 product (16 tcgen05.mma) instead of N = 256 / 128.
 //
-// Every CTA keeps a full copy of the GEMM operand [in | hidden] (128 users x 256 bf16, no-swizzle K-major, 64 KB).
+// Every CTA keeps a full copy of the GEMM operand, three 128-column slots [x | h0 | h1] (128 users x 384 bf16, no-swizzle
+// K-major, 96 KB); a product reads two adjacent slots: [x | h0] for layer 0, [h0 | h1] for layer 1 and for sbias, so the
+// sbias product rides in the same phase as the gates of layer 0 and a step is FOUR dependent phases.
 // After a phase, an epilogue thread holds 8 columns of one user (r*h, or h'): it writes that ONE 16-byte K chunk into the
-// operand buffers of all 4 CTAs through distributed shared memory (st.shared::cluster), so the h' slices are exchanged
-// without touching L2.  The fp32 recurrent state slice (8 + 8 values per thread) lives in registers.
+// operand buffers of all 4 CTAs through distributed shared memory (st.async / st.shared::cluster), so the h' slices are
+// exchanged without touching L2.  The fp32 recurrent state slice (8 + 8 values per thread) lives in registers.
 //
 // Synchronisation per phase (two mbarriers per CTA, no cluster-wide barrier.cluster on the critical path):
 //   act_ready : 4 CTAs x 16 epilogue warps arrive remotely (fence.proxy.async by every writer, then one
@@ -18,10 +20,10 @@
 //               completes, this CTA's accumulator is ready AND all four operand buffers are free to be rewritten.
 //
 // Step s (customed_gru_cell.py:309-337 per layer, :1050-1073 stacking; model_hier.py:54-55,91,93):
-//   P_sb : sbias[s] = [h0 | h1] @ W_in[D:]                         (state BEFORE the session)
-//   P_g0 : [r|u] = sigmoid([x | h0] Wg0 + bg0)          E: operand hidden half <- r * h0
-//   P_c0 : c = tanh([x | r*h0] Wc0 + bc0)               E: h0' = u*h0 + (1-u)*c ; state <- m*h0' ; operand <- [h0' | h1]
-//   P_g1 / P_c1 : the same for layer 1 with input h0'   E: state <- m*h1'
+//   P1 : [r|u] = sigmoid([x | h0] Wg0 + bg0),  sbias[s] = [h0 | h1] @ W_in[D:]      E: h0 slot <- r * h0
+//   P2 : c = tanh([x | r*h0] Wc0 + bc0)        E: h0' = u*h0 + (1-u)*c ; state <- m*h0' ; h0 slot <- h0'
+//   P3 : [r|u] = sigmoid([h0' | h1] Wg1 + bg1)                                       E: h1 slot <- r * h1
+//   P4 : c = tanh([h0' | r*h1] Wc1 + bc1)      E: state <- m*h1' ; slots <- [x_{s+1} | m*h0' | m*h1']
 #include <cstdlib>
 
 #include "common.cuh"
@@ -34,7 +36,8 @@ namespace k3c {
 constexpr int kM = 128;                           // users per cluster
 constexpr int kCl = 4;                            // CTAs per cluster
 constexpr int kSlice = 128 / kCl;                 // hidden columns per CTA
-constexpr int kActBytes = 32 * kM * 16;           // 32 x 16-byte K chunks (K = 256) x 128 rows = 64 KB
+constexpr int kSlotX = 0, kSlotH0 = 16, kSlotH1 = 32;   // operand slots (first 16-byte K chunk): [x | h0 | h1], 128 columns each
+constexpr int kActBytes = 48 * kM * 16;           // 48 x 16-byte K chunks x 128 rows = 96 KB; a product reads 32 consecutive chunks
 constexpr int kEpiWarps = 16;                     // 4 TMEM lane quarters x 4 groups of 8 columns
 constexpr int kThreads = 32 * (kEpiWarps + 1);    // warps 0-15 epilogue, 16 = weight load + MMA issuer
 constexpr int kMmaWarp = kEpiWarps;
@@ -46,7 +49,7 @@ constexpr uint32_t kColG = 0, kColC = 64, kColSb = 96, kTmemCols = 128;
 
 struct alignas(1024) Smem {
   uint8_t w[kBlobBytes];                          // 112 KB, resident
-  uint8_t act[kActBytes];                         // 64 KB
+  uint8_t act[kActBytes];                         // 96 KB
   float bg[2][256];
   float bc[2][128];
   uint64_t w_full, acc_ready, act_ready;
@@ -175,28 +178,40 @@ k3_gru_bf16_cluster(const uint8_t* __restrict__ w_blob /* [4][kBlobBytes] */, co
     mbar_wait(&sm.w_full, 0);
     const uint32_t act0 = smem_u32(sm.act), w0 = smem_u32(sm.w);
     uint32_t n_act = 0;
-    // one phase: D[128 x n_rows] = operand[128 x 256] * W[n_rows x 256]^T
-    auto phase = [&](uint32_t d_col, int row_off, int n_rows, uint32_t idesc) {
+    auto begin_phase = [&]() {
       mbar_wait_cluster(&sm.act_ready, n_act & 1);
       ++n_act;
       if (kAsync) fence_proxy_async_all();                       // st.async data (generic proxy) -> UMMA operand reads (async proxy)
       tc_fence_after_sync();
+    };
+    // D[128 x n_rows] = operand chunks [a_chunk, a_chunk + 32) (K = 256) * W[n_rows x 256]^T
+    auto product = [&](uint32_t d_col, int a_chunk, int row_off, int n_rows, uint32_t idesc) {
       const uint32_t wb = w0 + (uint32_t)row_off * 512;           // matrices are stored one after the other: 512 B per row
 #pragma unroll
       for (int k = 0; k < 16; ++k) {
-        const uint64_t da = make_desc_nosw(act0 + (uint32_t)(2 * k) * (kM * 16), kM * 16);
+        const uint64_t da = make_desc_nosw(act0 + (uint32_t)(a_chunk + 2 * k) * (kM * 16), kM * 16);
         const uint64_t db = make_desc_nosw(wb + (uint32_t)(2 * k) * (uint32_t)(n_rows * 16), (uint32_t)(n_rows * 16));
         if (leader) umma_bf16(tmem + d_col, da, db, idesc, k > 0);
       }
+    };
+    auto end_phase = [&]() {
       if (leader) umma_commit_multicast(&sm.acc_ready, (uint16_t)((1u << kCl) - 1));
     };
     constexpr uint32_t idesc64 = make_idesc_bf16(kM, 64), idesc32 = make_idesc_bf16(kM, 32);
     for (int s = 0; s < S; ++s) {
-      if (do_sbias) phase(kColSb, kOffSb, 32, idesc32);
-      phase(kColG, kOffG0, 64, idesc64);
-      phase(kColC, kOffC0, 32, idesc32);
-      phase(kColG, kOffG1, 64, idesc64);
-      phase(kColC, kOffC1, 32, idesc32);
+      begin_phase();                                              // P1: operand [x | h0 | h1]
+      product(kColG, kSlotX, kOffG0, 64, idesc64);                //   gates of layer 0 from [x | h0]
+      if (do_sbias) product(kColSb, kSlotH0, kOffSb, 32, idesc32);//   sbias[s] from [h0 | h1], same phase
+      end_phase();
+      begin_phase();                                              // P2: [x | r*h0]
+      product(kColC, kSlotX, kOffC0, 32, idesc32);
+      end_phase();
+      begin_phase();                                              // P3: [h0' | h1]
+      product(kColG, kSlotH0, kOffG1, 64, idesc64);
+      end_phase();
+      begin_phase();                                              // P4: [h0' | r*h1]
+      product(kColC, kSlotH0, kOffC1, 32, idesc32);
+      end_phase();
     }
   } else {
     // ===================== epilogue: thread = 8 hidden columns of one user =====================
@@ -205,7 +220,7 @@ k3_gru_bf16_cluster(const uint8_t* __restrict__ w_blob /* [4][kBlobBytes] */, co
     const int b = tile * kM + r;
     const bool ok = b < B;
     const int col = (int)crank * kSlice + sub * 8;                // first of this thread's 8 hidden columns
-    const int chunk = col >> 3;                                   // its 16-byte K chunk inside an operand half
+    const int chunk = col >> 3;                                   // its 16-byte K chunk inside an operand slot
     const uint32_t t_lane = tmem + ((uint32_t)(quarter * 32) << 16);
     uint8_t* act_row = sm.act + r * 16;
     uint32_t act_remote[kCl], bar_remote[kCl];
@@ -214,24 +229,35 @@ k3_gru_bf16_cluster(const uint8_t* __restrict__ w_blob /* [4][kBlobBytes] */, co
       act_remote[d] = mapa_u32(smem_u32(act_row), (uint32_t)d);
       bar_remote[d] = mapa_u32(smem_u32(&sm.act_ready), (uint32_t)d);
     }
-    // this thread's chunk of operand half `half` in all 4 CTAs <- bf16(v)
-    auto put_all = [&](int half, const float (&v)[8]) {
+    // this thread's chunk of operand slot `slot0` (kSlotH0 / kSlotH1) in all 4 CTAs <- bf16(v)
+    auto put_all = [&](int slot0, const float (&v)[8]) {
       const uint4 p = pack8(v);
-      const uint32_t off = (uint32_t)(half * 16 + chunk) * (kM * 16);
+      const uint32_t off = (uint32_t)(slot0 + chunk) * (kM * 16);
 #pragma unroll
       for (int d = 0; d < kCl; ++d) {
         if (kAsync) st_async_v4(act_remote[d] + off, p, bar_remote[d]);
         else st_cluster_v4(act_remote[d] + off, p);
       }
     };
-    // `halves` = operand halves every thread of the cluster wrote with put_all in this phase (32 KB each per CTA buffer)
-    auto signal = [&](int halves) {
+    // the x slot is written locally: every CTA stages the full input of its 128 users (this thread: 32 columns)
+    auto put_x = [&](int s) {
+      const float4* x = reinterpret_cast<const float4*>(yp + ((long long)s * B + b) * kDim + sub * 32);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 q0 = ok ? __ldg(x + 2 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 q1 = ok ? __ldg(x + 2 * i + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float v[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+        *reinterpret_cast<uint4*>(act_row + (kSlotX + sub * 4 + i) * (kM * 16)) = pack8(v);
+      }
+    };
+    // `slots` = operand slots every thread of the cluster wrote with put_all in this phase (32 KB each per CTA buffer)
+    auto signal = [&](int slots) {
       fence_proxy_async_all();                                    // generic-proxy writes (local + remote) -> async proxy
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) {
         if (kAsync) {
-          if (warp == 0) mbar_arrive_expect_tx(&sm.act_ready, (uint32_t)halves * (kM * 128 * 2));
+          if (warp == 0) mbar_arrive_expect_tx(&sm.act_ready, (uint32_t)slots * (kM * 128 * 2));
           else mbar_arrive(&sm.act_ready);
         } else {
           fence_acq_rel_cluster();
@@ -253,12 +279,12 @@ k3_gru_bf16_cluster(const uint8_t* __restrict__ w_blob /* [4][kBlobBytes] */, co
       const float4 a1 = ok ? __ldg(reinterpret_cast<const float4*>(state_in + (long long)b * 256 + l * 128 + col) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
       h[l][0] = a0.x; h[l][1] = a0.y; h[l][2] = a0.z; h[l][3] = a0.w; h[l][4] = a1.x; h[l][5] = a1.y; h[l][6] = a1.z; h[l][7] = a1.w;
     }
+    put_x(0);                                                     // operand of the first phase: [x_0 | h0 | h1]
+    put_all(kSlotH0, h[0]);
+    put_all(kSlotH1, h[1]);
+    signal(2);
     for (int s = 0; s < S; ++s) {
       const float m = ok ? __ldg(mask + (long long)s * B + b) : 0.f;
-      const float* x = yp + ((long long)s * B + b) * kDim + sub * 32;   // this thread stages 32 input columns locally
-      float4 xv[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) xv[i] = ok ? __ldg(reinterpret_cast<const float4*>(x) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
       if (state_pre && ok) {
 #pragma unroll
         for (int l = 0; l < 2; ++l) {
@@ -267,31 +293,9 @@ k3_gru_bf16_cluster(const uint8_t* __restrict__ w_blob /* [4][kBlobBytes] */, co
           o[1] = make_float4(h[l][4], h[l][5], h[l][6], h[l][7]);
         }
       }
-      if (do_sbias) {
-        put_all(0, h[0]);                                         // buffers are free: E_c of layer 1 waited for every CTA's P_c1
-        put_all(1, h[1]);
-        signal(2);
-        wait_acc();                                               // ---- E_sb: sbias[s] out
-        uint32_t v[8];
-        tmem_ld_32x8(t_lane + kColSb + sub * 8, v);
-        tmem_ld_wait8(v);
-        if (ok) {
-          float4* o = reinterpret_cast<float4*>(sbias + ((long long)s * B + b) * kDim + col);
-          o[0] = make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
-          o[1] = make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
-        }
-      }
-      // operand <- [x | h0]: the input half is written locally (every CTA stages the full x of its 128 users)
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float v[8] = {xv[2 * i].x, xv[2 * i].y, xv[2 * i].z, xv[2 * i].w, xv[2 * i + 1].x, xv[2 * i + 1].y, xv[2 * i + 1].z, xv[2 * i + 1].w};
-        *reinterpret_cast<uint4*>(act_row + (sub * 4 + i) * (kM * 16)) = pack8(v);
-      }
-      put_all(1, h[0]);
-      signal(1);
 #pragma unroll
       for (int l = 0; l < 2; ++l) {
-        wait_acc();                                               // ---- E_g: operand hidden half <- r * h
+        wait_acc();                                               // ---- E_g: hidden slot of layer l <- r * h
         uint32_t vr[8], vu[8];
         tmem_ld_32x8(t_lane + kColG + sub * 8, vr);
         tmem_ld_32x8(t_lane + kColG + 32 + sub * 8, vu);
@@ -303,8 +307,18 @@ k3_gru_bf16_cluster(const uint8_t* __restrict__ w_blob /* [4][kBlobBytes] */, co
           rh[e] = sigmoid_fast(__uint_as_float(vr[e]) + sm.bg[l][col + e]) * h[l][e];
           u[e] = sigmoid_fast(__uint_as_float(vu[e]) + sm.bg[l][128 + col + e]);
         }
-        put_all(1, rh);
+        put_all(l == 0 ? kSlotH0 : kSlotH1, rh);
         signal(1);
+        if (l == 0 && do_sbias) {                                 // sbias[s] rode along with the gates of layer 0
+          uint32_t v[8];
+          tmem_ld_32x8(t_lane + kColSb + sub * 8, v);
+          tmem_ld_wait8(v);
+          if (ok) {
+            float4* o = reinterpret_cast<float4*>(sbias + ((long long)s * B + b) * kDim + col);
+            o[0] = make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
+            o[1] = make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
+          }
+        }
         wait_acc();                                               // ---- E_c: h' = u*h + (1-u)*c
         uint32_t vc[8];
         tmem_ld_32x8(t_lane + kColC + sub * 8, vc);
@@ -317,12 +331,16 @@ k3_gru_bf16_cluster(const uint8_t* __restrict__ w_blob /* [4][kBlobBytes] */, co
           h[l][e] = m * o[e];                                     // state *= mask (model_hier.py:93)
         }
         if (l == 0) {
-          put_all(0, o);                                          // [h0' | h1]
-          put_all(1, h[1]);
+          put_all(kSlotH0, o);                                    // layer 1 reads [h0' | h1]; the h1 slot still holds h1
+          signal(1);
+        } else if (s + 1 < S) {
+          put_x(s + 1);                                           // next step: [x_{s+1} | m*h0' | m*h1']
+          put_all(kSlotH0, h[0]);
+          put_all(kSlotH1, h[1]);
           signal(2);
         }
       }
-      // the accumulator wait of P_c1 (count 4: every CTA's MMAs) doubles as "operand buffers free" for the next step
+      // every accumulator wait has count 4 (all CTAs' MMAs of the phase): it doubles as "operand buffers free"
     }
     if (ok) {
 #pragma unroll
@@ -351,12 +369,16 @@ __global__ void k3_prepare_weights_cluster(const float* __restrict__ w_in_state,
   const float* src = mat == 0 ? w_in_state : w_dev[mat - 1];
   const int ld = (mat == 1 || mat == 3) ? 256 : 128;
   __nv_bfloat16* dst = out + (size_t)c * (kBlobBytes / 2) + (size_t)row_off * 256;
-  for (int i = threadIdx.x; i < n_rows * 256; i += blockDim.x) {
-    const int k = i / n_rows, n = i % n_rows;                    // consecutive threads read consecutive output columns
-    const int ocol = n_rows == 64 ? ((n >> 5) * 128 + c * kSlice + (n & 31)) : (c * kSlice + n);   // gates: r rows, then u rows
-    const float v = src ? src[(long long)k * ld + ocol] : 0.f;
-    dst[((size_t)(k >> 3) * n_rows + n) * 8 + (k & 7)] = __float2bfloat16_rn(v);
-  }
+  // one thread = one 16-byte K chunk of one row: 8 coalesced reads (a warp covers 32 consecutive output columns), one
+  // 16-byte write; blockIdx.y picks 4 of the 32 K chunks
+  const int i = threadIdx.x;
+  if (i >= 4 * n_rows) return;
+  const int kc = blockIdx.y * 4 + i / n_rows, n = i % n_rows;
+  const int ocol = n_rows == 64 ? ((n >> 5) * 128 + c * kSlice + (n & 31)) : (c * kSlice + n);   // gates: r rows, then u rows
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) v[e] = src ? src[(long long)(kc * 8 + e) * ld + ocol] : 0.f;
+  *reinterpret_cast<uint4*>(dst + ((size_t)kc * n_rows + n) * 8) = pack8(v);
 }
 
 int32_t gru_sessions_bf16_cluster(const float* yp, const float* mask, const float* state_in, const float* const* gate_w,
@@ -376,12 +398,13 @@ int32_t gru_sessions_bf16_cluster(const float* yp, const float* mask, const floa
     HTCN_CUDA(cudaMemcpyAsync(bias_dev + l * 384, gate_b[l], 256 * 4, cudaMemcpyDeviceToDevice, st));
     HTCN_CUDA(cudaMemcpyAsync(bias_dev + l * 384 + 256, cand_b[l], 128 * 4, cudaMemcpyDeviceToDevice, st));
   }
-  k3_prepare_weights_cluster<<<kCl * 5, 256, 0, st>>>(w_in_state, ptrs_dev, reinterpret_cast<__nv_bfloat16*>(sc));
+  k3_prepare_weights_cluster<<<dim3(kCl * 5, 8), 256, 0, st>>>(w_in_state, ptrs_dev, reinterpret_cast<__nv_bfloat16*>(sc));
   HTCN_LAUNCH_CHECK("k3_prepare_weights_cluster");
   const size_t smem = sizeof(Smem) + 1024;
-  // HTCN_K3_CLUSTER=1: plain DSMEM stores + cluster-scope fence; default (2): st.async with transaction bytes
+  // default (1): plain DSMEM stores published by one cluster-scope fence per warp and phase (146 us at B=4096, S=10);
+  // HTCN_K3_CLUSTER=2: st.async with transaction bytes (154 us)
   const char* env = getenv("HTCN_K3_CLUSTER");
-  auto kern = (env && atoi(env) == 1) ? k3_gru_bf16_cluster<false> : k3_gru_bf16_cluster<true>;
+  auto kern = (env && atoi(env) == 2) ? k3_gru_bf16_cluster<true> : k3_gru_bf16_cluster<false>;
   HTCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<kCl * ceil_div(B, kM), kThreads, smem, st>>>(sc, yp, mask, state_in, bias_dev, B, S, sbias != nullptr, state_pre, sbias,
                                                      state_out);
