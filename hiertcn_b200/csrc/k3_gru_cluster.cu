@@ -239,16 +239,23 @@ k3_gru_bf16_cluster(const uint8_t* __restrict__ w_blob /* [4][kBlobBytes] */, co
         else st_cluster_v4(act_remote[d] + off, p);
       }
     };
-    // the x slot is written locally: every CTA stages the full input of its 128 users (this thread: 32 columns)
-    auto put_x = [&](int s) {
+    // the x slot is written locally: every CTA stages the full input of its 128 users (this thread: 32 columns).  The
+    // rows of step s+1 are fetched (and packed to bf16: 16 registers) at the top of step s, a whole step before their use:
+    // loading them where they are stored put ~1 us of HBM latency on the critical path of every step (ncu: long_scoreboard)
+    uint4 xp[4];
+    auto fetch_x = [&](int s) {
       const float4* x = reinterpret_cast<const float4*>(yp + ((long long)s * B + b) * kDim + sub * 32);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float4 q0 = ok ? __ldg(x + 2 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
         const float4 q1 = ok ? __ldg(x + 2 * i + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
         const float v[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-        *reinterpret_cast<uint4*>(act_row + (kSlotX + sub * 4 + i) * (kM * 16)) = pack8(v);
+        xp[i] = pack8(v);
       }
+    };
+    auto put_x = [&]() {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(act_row + (kSlotX + sub * 4 + i) * (kM * 16)) = xp[i];
     };
     // `slots` = operand slots every thread of the cluster wrote with put_all in this phase (32 KB each per CTA buffer)
     auto signal = [&](int slots) {
@@ -279,12 +286,14 @@ k3_gru_bf16_cluster(const uint8_t* __restrict__ w_blob /* [4][kBlobBytes] */, co
       const float4 a1 = ok ? __ldg(reinterpret_cast<const float4*>(state_in + (long long)b * 256 + l * 128 + col) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
       h[l][0] = a0.x; h[l][1] = a0.y; h[l][2] = a0.z; h[l][3] = a0.w; h[l][4] = a1.x; h[l][5] = a1.y; h[l][6] = a1.z; h[l][7] = a1.w;
     }
-    put_x(0);                                                     // operand of the first phase: [x_0 | h0 | h1]
+    fetch_x(0);
+    put_x();                                                      // operand of the first phase: [x_0 | h0 | h1]
     put_all(kSlotH0, h[0]);
     put_all(kSlotH1, h[1]);
     signal(2);
     for (int s = 0; s < S; ++s) {
       const float m = ok ? __ldg(mask + (long long)s * B + b) : 0.f;
+      if (s + 1 < S) fetch_x(s + 1);
       if (state_pre && ok) {
 #pragma unroll
         for (int l = 0; l < 2; ++l) {
@@ -334,7 +343,7 @@ k3_gru_bf16_cluster(const uint8_t* __restrict__ w_blob /* [4][kBlobBytes] */, co
           put_all(kSlotH0, o);                                    // layer 1 reads [h0' | h1]; the h1 slot still holds h1
           signal(1);
         } else if (s + 1 < S) {
-          put_x(s + 1);                                           // next step: [x_{s+1} | m*h0' | m*h1']
+          put_x();                                                // next step: [x_{s+1} | m*h0' | m*h1']
           put_all(kSlotH0, h[0]);
           put_all(kSlotH1, h[1]);
           signal(2);
