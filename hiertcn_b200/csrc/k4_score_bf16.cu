@@ -74,18 +74,32 @@ __device__ __forceinline__ float ex2_poly(float t) {
 // exponentials off the MUFU pipe (16/clk/SM, the bound of this loop): kPolyPairs of the 16 logit pairs of a 32-column
 // chunk evaluate 2^t on the FMA pipe, again two lanes per instruction.
 enum : unsigned { kModePacked = 256u, kPolyPairsShift = 9u, kPolyDeg2 = 8192u };   // kFlags bits 9..12 = kPolyPairs
-constexpr unsigned packed_flags(int poly_pairs, bool deg2 = false) {
-  return kModePacked | ((unsigned)poly_pairs << kPolyPairsShift) | (deg2 ? kPolyDeg2 : 0u);
+// kSignRank: the rank count reads the SIGN BIT of tn = z_y*log2e (rounded UP) - z*log2e, the negated argument of the
+// exponential the CE sum needs anyway: one LEA.HI per logit instead of FSET.BF + FADD2/2.  With the threshold rounded up,
+// a logit <= z_y is never counted and a logit >= 2 ulp above z_y always is; only a logit exactly ONE ulp above the target
+// can be missed (rank_fused in {rank_strict - #[z = nextafter(z_y)], rank_strict}) -- far inside what bf16 operands resolve.
+// The rank-only sweep, the ragged last tile and the fp32 tier keep the strict compare.
+enum : unsigned { kSignRank = 16384u };
+constexpr unsigned packed_flags(int poly_pairs, bool deg2 = false, bool sign_rank = false) {
+  return kModePacked | ((unsigned)poly_pairs << kPolyPairsShift) | (deg2 ? kPolyDeg2 : 0u) | (sign_rank ? kSignRank : 0u);
 }
 
-template <bool kDeg2>
-__device__ __forceinline__ float2 ex2_poly2(float2 t) {
+template <bool kDeg2, bool kNegated = false>
+__device__ __forceinline__ float2 ex2_poly2(float2 t) {          // kNegated: the argument is -t
   // 2^n is formed by adding n to the exponent field, which WRAPS outside [-126, 128).  Instead of clamping every value
   // (two FMNMX each), the caller tracks max |t| over the polynomial lanes (one FMNMX3 per pair) and declares the row's
   // partial sum overflowed when it reaches kPolyRange: htcn_score_ce_repair then redoes the row exactly.
-  const float2 r = fadd2(t, make_float2(12582912.0f, 12582912.0f));
-  const float2 n = fadd2(r, make_float2(-12582912.0f, -12582912.0f));
-  const float2 f = ffma2(n, make_float2(-1.0f, -1.0f), t);
+  const float2 magic = make_float2(12582912.0f, 12582912.0f), m1 = make_float2(-1.0f, -1.0f);
+  float2 r, f;
+  if (kNegated) {
+    r = ffma2(t, m1, magic);                                     // round(t_true) + magic
+    const float2 nn = ffma2(r, m1, magic);                       // -n
+    f = ffma2(t, m1, nn);                                        // t_true - n
+  } else {
+    r = fadd2(t, magic);
+    const float2 n = fadd2(r, make_float2(-12582912.0f, -12582912.0f));
+    f = ffma2(n, m1, t);
+  }
   float2 p;
   if (kDeg2) {                                     // max relative error 2.0e-3, mean -2.4e-4
     p = ffma2(f, make_float2(0.23986403f, 0.23986403f), make_float2(0.70294179f, 0.70294179f));
@@ -100,20 +114,34 @@ __device__ __forceinline__ float2 ex2_poly2(float2 t) {
 
 // one full 32-column chunk of a row: sum2 += 2^((z - zy) log2e), cf2 += [z > zy]
 constexpr float kPolyRange = 125.0f;             // |t| the exponent-field arithmetic of ex2_poly2 handles
-template <bool kCE, bool kRank, int kPolyPairs, bool kDeg2>
-__device__ __forceinline__ void ce_rank_chunk_packed(const uint32_t (&r)[32], float zy, float nzyl, float2 (&sum2)[2],
-                                                     float2 (&cf2)[2], float& amax) {
+// `zyl` = z_y * log2e: rounded to nearest (strict-compare variants) or UP (kSign)
+template <bool kCE, bool kRank, int kPolyPairs, bool kDeg2, bool kSign>
+__device__ __forceinline__ void ce_rank_chunk_packed(const uint32_t (&r)[32], float zy, float zyl, float2 (&sum2)[2],
+                                                     float2 (&cf2)[2], float& amax, uint32_t (&cnt2)[2]) {
 #pragma unroll
   for (int p = 0; p < 16; ++p) {
     const float2 z = make_float2(__uint_as_float(r[2 * p]), __uint_as_float(r[2 * p + 1]));
-    if (kCE) {
-      const float2 t = ffma2(z, make_float2(kLog2e, kLog2e), make_float2(nzyl, nzyl));
-      const bool poly = ((p + 1) * kPolyPairs) / 16 != (p * kPolyPairs) / 16;
-      if (poly) amax = fmaxf(fmaxf(amax, fabsf(t.x)), fabsf(t.y));     // one FMNMX3
-      const float2 e = poly ? ex2_poly2<kDeg2>(t) : make_float2(ex2_approx(t.x), ex2_approx(t.y));
-      sum2[p & 1] = fadd2(sum2[p & 1], e);
+    const bool poly = ((p + 1) * kPolyPairs) / 16 != (p * kPolyPairs) / 16;
+    if (kSign) {
+      const float2 tn = ffma2(z, make_float2(-kLog2e, -kLog2e), make_float2(zyl, zyl));     // -(t): sign bit set <=> z above z_y
+      if (kCE) {
+        if (poly) amax = fmaxf(fmaxf(amax, fabsf(tn.x)), fabsf(tn.y));                      // one FMNMX3
+        const float2 e = poly ? ex2_poly2<kDeg2, true>(tn) : make_float2(ex2_approx(-tn.x), ex2_approx(-tn.y));
+        sum2[p & 1] = fadd2(sum2[p & 1], e);
+      }
+      if (kRank) {
+        cnt2[p & 1] += __float_as_uint(tn.x) >> 31;                                         // LEA.HI
+        cnt2[p & 1] += __float_as_uint(tn.y) >> 31;
+      }
+    } else {
+      if (kCE) {
+        const float2 t = ffma2(z, make_float2(kLog2e, kLog2e), make_float2(-zyl, -zyl));
+        if (poly) amax = fmaxf(fmaxf(amax, fabsf(t.x)), fabsf(t.y));     // one FMNMX3
+        const float2 e = poly ? ex2_poly2<kDeg2>(t) : make_float2(ex2_approx(t.x), ex2_approx(t.y));
+        sum2[p & 1] = fadd2(sum2[p & 1], e);
+      }
+      if (kRank) cf2[p & 1] = fadd2(cf2[p & 1], make_float2(set_gt_f(z.x, zy), set_gt_f(z.y, zy)));
     }
-    if (kRank) cf2[p & 1] = fadd2(cf2[p & 1], make_float2(set_gt_f(z.x, zy), set_gt_f(z.y, zy)));
   }
 }
 
@@ -426,6 +454,7 @@ k4_score_bf16_cg2(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   constexpr bool kCE = kFlags & HTCN_SCORE_CE, kRank = kFlags & HTCN_SCORE_RANK, kDump = kFlags & kModeDump;
   constexpr int kPolyEvery = (kFlags & kModePoly4) ? 4 : (kFlags & kModePoly8) ? 8 : 0x40000000;
   constexpr bool kPacked = (kFlags & kModePacked) && !kDump;
+  constexpr bool kSign = kPacked && (kFlags & kSignRank);
   constexpr int kPolyPairs = (kFlags >> kPolyPairsShift) & 15;
   constexpr int BN = 256, kSlices = kSlicesScore, kEpiWarps = 4 * kSlices, kColsPerWarp = BN / kSlices;
   constexpr uint32_t kHalfStageBytes = 2 * 128 * 128 + 128 * 32;
@@ -516,10 +545,11 @@ k4_score_bf16_cg2(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     float sum4[4] = {0.f, 0.f, 0.f, 0.f}, cf[4] = {0.f, 0.f, 0.f, 0.f};
     float2 sum2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, cf2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
     float amax = 0.f;                                            // max |t| seen by the polynomial lanes
+    uint32_t cnt2[2] = {0u, 0u};                                 // kSign: sign-bit rank counts
     int cnt = 0;
     if ((kCE || kRank) && row_ok) {
       zy = a.zy[q0 + row];
-      zyl = zy * kLog2e;
+      zyl = kSign ? __fmul_ru(zy, kLog2e) : zy * kLog2e;         // kSign: threshold rounded UP (see kSignRank)
     }
     for (int i = 0; i < n_tiles; ++i) {
       const int buf = i & 1;
@@ -540,7 +570,7 @@ k4_score_bf16_cg2(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(&sm.t_empty[buf], 0);   // the leader's barrier
           }
-          ce_rank_chunk_packed<kCE, kRank, kPolyPairs, (kFlags & kPolyDeg2) != 0>(r, zy, -zyl, sum2, cf2, amax);
+          ce_rank_chunk_packed<kCE, kRank, kPolyPairs, (kFlags & kPolyDeg2) != 0, kSign>(r, zy, zyl, sum2, cf2, amax, cnt2);
         }
         if (kRank && (i & 4095) == 4095) {
           cnt += (int)((cf2[0].x + cf2[0].y) + (cf2[1].x + cf2[1].y));
@@ -561,7 +591,7 @@ k4_score_bf16_cg2(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           if (lane == 0) mbar_arrive_cluster(&sm.t_empty[buf], 0);   // the leader's barrier
         }
         if (kPacked && c + 32 <= lim) {
-          ce_rank_chunk_packed<kCE, kRank, kPolyPairs, (kFlags & kPolyDeg2) != 0>(r, zy, -zyl, sum2, cf2, amax);
+          ce_rank_chunk_packed<kCE, kRank, kPolyPairs, (kFlags & kPolyDeg2) != 0, kSign>(r, zy, zyl, sum2, cf2, amax, cnt2);
         } else if (c + 32 <= lim) {
 #pragma unroll
           for (int u = 0; u < 32; ++u) {
@@ -605,6 +635,7 @@ k4_score_bf16_cg2(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     if (kPacked) sum += (sum2[0].x + sum2[0].y) + (sum2[1].x + sum2[1].y);
     if (kPacked && !(amax < kPolyRange)) sum = INFINITY;         // a polynomial lane left its range: the row is redone exactly
     if (kPacked && kRank) cnt += (int)((cf2[0].x + cf2[0].y) + (cf2[1].x + cf2[1].y));   // counts of the fast-path tiles
+    if (kSign) cnt += (int)(cnt2[0] + cnt2[1]);
     if (half > 0) {
       sm.comb_sum[half - 1][row] = sum;
       sm.comb_cnt[half - 1][row] = cnt;
@@ -830,10 +861,10 @@ int32_t score_bf16(const ScoreArgs& a, cudaStream_t st) {
       case HTCN_SCORE_CE: return launch_score_cg2<HTCN_SCORE_CE>(a, nullptr, st);
       case HTCN_SCORE_RANK: return launch_score_cg2<HTCN_SCORE_RANK>(a, nullptr, st);
       case HTCN_SCORE_CE | HTCN_SCORE_RANK: {
-        // HTCN_K4_EPI = number of polynomial pairs (of 16) of the packed epilogue, +100 for the degree-2 polynomial;
-        // -1 = the scalar epilogue
+        // HTCN_K4_EPI = number of polynomial pairs (of 16) of the packed epilogue, +100 for the degree-2 polynomial,
+        // +300 for the sign-bit rank count; -1 = the scalar epilogue
         const char* epi_env = getenv("HTCN_K4_EPI");   // read per call: the sweep script switches variants in-process
-        const int epi = epi_env ? atoi(epi_env) : 4;
+        const int epi = epi_env ? atoi(epi_env) : 304;
         constexpr unsigned kCR = HTCN_SCORE_CE | HTCN_SCORE_RANK;
         switch (epi) {
           case 0: return launch_score_cg2<kCR | packed_flags(0)>(a, nullptr, st);
@@ -842,6 +873,9 @@ int32_t score_bf16(const ScoreArgs& a, cudaStream_t st) {
           case 4: return launch_score_cg2<kCR | packed_flags(4)>(a, nullptr, st);
           case 5: return launch_score_cg2<kCR | packed_flags(5)>(a, nullptr, st);
           case 6: return launch_score_cg2<kCR | packed_flags(6)>(a, nullptr, st);
+          case 303: return launch_score_cg2<kCR | packed_flags(3, false, true)>(a, nullptr, st);   // +300: sign-bit rank count
+          case 304: return launch_score_cg2<kCR | packed_flags(4, false, true)>(a, nullptr, st);
+          case 305: return launch_score_cg2<kCR | packed_flags(5, false, true)>(a, nullptr, st);
           case 104: return launch_score_cg2<kCR | packed_flags(4, true)>(a, nullptr, st);
           case 105: return launch_score_cg2<kCR | packed_flags(5, true)>(a, nullptr, st);
           case 106: return launch_score_cg2<kCR | packed_flags(6, true)>(a, nullptr, st);

@@ -390,10 +390,11 @@ def debug_logits_bf16(lib, hd, wt, bd):
     return out
 
 
-# epilogue variants of the fused CE+rank sweep (HTCN_K4_EPI): the default (= "4") is the packed f32x2 epilogue with 1/4 of
-# the exponentials on the FMA pipe (degree-3 polynomial, 1e-4 per term); "104" = the same with a degree-2 polynomial
-# (2e-3 per term, still a tenth of the bf16 tier's 2e-2 bar); "-1" = the scalar epilogue.  Ranks are exact in all of them.
-@pytest.mark.parametrize("epi,tol", [(None, 1e-4), ("104", 1e-3), ("-1", 1e-4)])
+# epilogue variants of the fused CE+rank sweep (HTCN_K4_EPI): the default (= "304") is the packed f32x2 epilogue with 1/4 of
+# the exponentials on the FMA pipe (degree-3 polynomial, 1e-4 per term) and the sign-bit rank count; "4" = the same with
+# the strict FSET compare; "104" = degree-2 polynomial (2e-3 per term, a tenth of the bf16 tier's 2e-2 bar); "-1" = the
+# scalar epilogue.
+@pytest.mark.parametrize("epi,tol", [(None, 1e-4), ("4", 1e-4), ("304", 1e-4), ("104", 1e-3), ("-1", 1e-4)])
 @pytest.mark.parametrize("Q,N,n_split", [(128, 256, 1), (200, 1000, 1), (130, 20778, 7), (5, 77, 1), (300, 4099, 3)])
 def test_k4_bf16_tcgen05(lib, Q, N, n_split, epi, tol, monkeypatch):
     if epi is not None:
@@ -428,10 +429,22 @@ def test_k4_bf16_tcgen05(lib, Q, N, n_split, epi, tol, monkeypatch):
     lib.call("htcn_score_finish", P(pm), P(ps), P(pc), n_split, Q, P(yd), P(zy), P(loss_row), P(rank_row), None)
     ref_loss = O.softmax_cross_entropy_with_logits(y, z_gpu.astype(np.float64))
     np.testing.assert_allclose(loss_row.cpu().numpy(), ref_loss, rtol=tol, atol=tol / 10)
-    np.testing.assert_array_equal(rank_row.cpu().numpy(), (z_gpu > zy_h[:, None]).sum(1))
+    # strict count of the swept logits; the sign-bit rank count of the packed epilogue (default, "304") may miss a logit
+    # that is exactly ONE ulp above the target and nothing else (k4_score_bf16.cu: kSignRank)
+    strict = (z_gpu > zy_h[:, None]).sum(1)
+    one_ulp = (z_gpu == np.nextafter(zy_h, np.float32(np.inf))[:, None]).sum(1)
+    got_rank = rank_row.cpu().numpy()
+    if epi in ("4", "104", "-1"):
+        np.testing.assert_array_equal(got_rank, strict)
+    else:
+        assert ((got_rank <= strict) & (got_rank >= strict - one_ulp)).all(), (got_rank - strict)
     # rank-only and CE-only specialisations agree with the fused one
     _, _, _, pc2, _, _ = run_score(lib, hd, wt, bd, yd, lib.SCORE_RANK, 0, n_split, precision=lib.HTCN_BF16, zy_in=zy)
-    assert torch.equal(pc2.sum(0), pc.sum(0))
+    if epi in ("4", "104", "-1"):
+        assert torch.equal(pc2.sum(0), pc.sum(0))
+    else:
+        d = (pc2.sum(0) - pc.sum(0)).cpu().numpy()
+        assert ((d >= 0) & (d <= one_ulp)).all()
     _, pm3, ps3, _, _, _ = run_score(lib, hd, wt, bd, yd, lib.SCORE_CE, 0, n_split, precision=lib.HTCN_BF16, zy_in=zy)
     torch.testing.assert_close(ps3, ps, rtol=2.5 * tol, atol=0)  # the fused variant evaluates part of the exps by polynomial
     # 3. top-k (separate sweep, 128-item tiles)
