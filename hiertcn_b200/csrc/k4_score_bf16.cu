@@ -113,6 +113,9 @@ __device__ __forceinline__ float2 ex2_poly2(float2 t) {          // kNegated: th
 }
 
 // one full 32-column chunk of a row: sum2 += 2^((z - zy) log2e), cf2 += [z > zy]
+__device__ __forceinline__ void add_sign_bit(uint32_t& acc, float x) {      // acc += (x < 0 or x == -0)
+  asm("{ .reg .u32 t;\n\tshr.u32 t, %1, 31;\n\tadd.u32 %0, %0, t; }" : "+r"(acc) : "r"(__float_as_uint(x)));
+}
 constexpr float kPolyRange = 125.0f;             // |t| the exponent-field arithmetic of ex2_poly2 handles
 // `zyl` = z_y * log2e: rounded to nearest (strict-compare variants) or UP (kSign)
 template <bool kCE, bool kRank, int kPolyPairs, bool kDeg2, bool kSign>
@@ -129,9 +132,9 @@ __device__ __forceinline__ void ce_rank_chunk_packed(const uint32_t (&r)[32], fl
         const float2 e = poly ? ex2_poly2<kDeg2, true>(tn) : make_float2(ex2_approx(-tn.x), ex2_approx(-tn.y));
         sum2[p & 1] = fadd2(sum2[p & 1], e);
       }
-      if (kRank) {
-        cnt2[p & 1] += __float_as_uint(tn.x) >> 31;                                         // LEA.HI
-        cnt2[p & 1] += __float_as_uint(tn.y) >> 31;
+      if (kRank) {                                               // one LEA.HI each; the asm keeps the compiler from
+        add_sign_bit(cnt2[p & 1], tn.x);                         // re-associating the chain into SHF + LEA + IADD3 trees
+        add_sign_bit(cnt2[(p & 1) ^ 1], tn.y);
       }
     } else {
       if (kCE) {
