@@ -28,6 +28,9 @@ import time
 
 import numpy as np
 
+# stdout carries exactly ONE JSON line: NCCL's own debug output (e.g. "NCCL version ..." under NCCL_DEBUG=VERSION) goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
