@@ -861,8 +861,12 @@ int32_t score_bf16(const ScoreArgs& a, cudaStream_t st) {
   if (cta_group_env() == 2) {
     static const int poly = [] { const char* e = getenv("HTCN_POLY_EVERY"); return e ? atoi(e) : 8; }();
     switch (a.flags) {
-      case HTCN_SCORE_CE: return launch_score_cg2<HTCN_SCORE_CE>(a, nullptr, st);
-      case HTCN_SCORE_RANK: return launch_score_cg2<HTCN_SCORE_RANK>(a, nullptr, st);
+      case HTCN_SCORE_CE: {                                       // training forward: packed epilogue unless HTCN_K4_EPI=-1
+        const char* e = getenv("HTCN_K4_EPI");
+        if (e && atoi(e) < 0) return launch_score_cg2<HTCN_SCORE_CE>(a, nullptr, st);
+        return launch_score_cg2<HTCN_SCORE_CE | packed_flags(4)>(a, nullptr, st);
+      }
+      case HTCN_SCORE_RANK: return launch_score_cg2<HTCN_SCORE_RANK>(a, nullptr, st);   // strict compare, 0.99 of the MMA peak
       case HTCN_SCORE_CE | HTCN_SCORE_RANK: {
         // HTCN_K4_EPI = number of polynomial pairs (of 16) of the packed epilogue, +100 for the degree-2 polynomial,
         // +300 for the sign-bit rank count; -1 = the scalar epilogue
