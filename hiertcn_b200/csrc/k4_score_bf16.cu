@@ -80,6 +80,9 @@ enum : unsigned { kModePacked = 256u, kPolyPairsShift = 9u, kPolyDeg2 = 8192u };
 // can be missed (rank_fused in {rank_strict - #[z = nextafter(z_y)], rank_strict}) -- far inside what bf16 operands resolve.
 // The rank-only sweep, the ragged last tile and the fp32 tier keep the strict compare.
 enum : unsigned { kSignRank = 16384u };
+enum : unsigned { kTwoSlices = 32768u };          // A/B variant: 8 epilogue warps (2 column slices of 128) instead of 16
+template <unsigned kFlags>
+constexpr int cg2_slices() { return (kFlags & kTwoSlices) ? 2 : kSlicesScore; }
 constexpr unsigned packed_flags(int poly_pairs, bool deg2 = false, bool sign_rank = false) {
   return kModePacked | ((unsigned)poly_pairs << kPolyPairsShift) | (deg2 ? kPolyDeg2 : 0u) | (sign_rank ? kSignRank : 0u);
 }
@@ -451,7 +454,7 @@ struct alignas(1024) ScoreSmem2 {
 };
 
 template <unsigned kFlags>
-__global__ void __launch_bounds__(64 + 32 * 4 * kSlicesScore, 1)
+__global__ void __launch_bounds__(64 + 32 * 4 * cg2_slices<kFlags>(), 1)
 k4_score_bf16_cg2(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const __grid_constant__ CUtensorMap tmap_bb, ScoreArgs a, float* __restrict__ dump) {
   constexpr bool kCE = kFlags & HTCN_SCORE_CE, kRank = kFlags & HTCN_SCORE_RANK, kDump = kFlags & kModeDump;
@@ -459,7 +462,7 @@ k4_score_bf16_cg2(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   constexpr bool kPacked = (kFlags & kModePacked) && !kDump;
   constexpr bool kSign = kPacked && (kFlags & kSignRank);
   constexpr int kPolyPairs = (kFlags >> kPolyPairsShift) & 15;
-  constexpr int BN = 256, kSlices = kSlicesScore, kEpiWarps = 4 * kSlices, kColsPerWarp = BN / kSlices;
+  constexpr int BN = 256, kSlices = cg2_slices<kFlags>(), kEpiWarps = 4 * kSlices, kColsPerWarp = BN / kSlices;
   constexpr uint32_t kHalfStageBytes = 2 * 128 * 128 + 128 * 32;
   extern __shared__ uint8_t smem_raw[];
   auto& sm = *reinterpret_cast<ScoreSmem2*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -819,7 +822,7 @@ static int32_t launch_score_cg2(const ScoreArgs& a, float* dump, cudaStream_t st
   HTCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(2 * ((ceil_div(a.Q, kBM) + 1) / 2)), (unsigned)a.n_split, 1);   // whole CTA pairs
-  cfg.blockDim = dim3(64 + 32 * 4 * kSlicesScore, 1, 1);
+  cfg.blockDim = dim3(64 + 32 * 4 * cg2_slices<kFlags>(), 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -882,6 +885,7 @@ int32_t score_bf16(const ScoreArgs& a, cudaStream_t st) {
           case 6: return launch_score_cg2<kCR | packed_flags(6)>(a, nullptr, st);
           case 303: return launch_score_cg2<kCR | packed_flags(3, false, true)>(a, nullptr, st);   // +300: sign-bit rank count
           case 304: return launch_score_cg2<kCR | packed_flags(4, false, true)>(a, nullptr, st);
+          case 1304: return launch_score_cg2<kCR | packed_flags(4, false, true) | kTwoSlices>(a, nullptr, st);   // 8 epilogue warps
           case 305: return launch_score_cg2<kCR | packed_flags(5, false, true)>(a, nullptr, st);
           case 104: return launch_score_cg2<kCR | packed_flags(4, true)>(a, nullptr, st);
           case 105: return launch_score_cg2<kCR | packed_flags(5, true)>(a, nullptr, st);
