@@ -18,6 +18,8 @@
 // warps (TMEM lane = row) apply bias / relu / residual / relu, round to bf16 and write the next layer's operand
 // in place (zero rows stay zero).  Two CTAs fit per SM (110 KB smem, 128 TMEM columns each) so one CTA's
 // epilogue overlaps the other's MMAs.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "sm100.cuh"
 
@@ -93,6 +95,11 @@ __device__ __forceinline__ void tile_geometry(const K2Geom& g, int tile, int r, 
   if (own) dst = out_row ? out_row[src] : src;
 }
 
+// kPair: the CTAs run as clusters of 2 that walk the SAME weight sequence in lock step; each CTA fetches one of the two
+// 64-column chunks of a weight tile and TMA-multicasts it into both CTAs' rings, so every weight byte crosses L2 -> SM once
+// per CTA pair instead of once per CTA (the kernel sat at the L2 read ceiling: 352 KB of weights per 128-row tile).
+// A ring stage is refilled only when BOTH CTAs' MMAs have released it (tcgen05.commit multicast onto both w_empty barriers).
+template <bool kPair>
 __global__ void __launch_bounds__(kK2Threads, 2)
 k2_tcn_bf16(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfloat16* __restrict__ xe,
             const float* __restrict__ sbias, const float* __restrict__ bias_all /*[n_levels][128]*/,
@@ -103,13 +110,16 @@ k2_tcn_bf16(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfl
   auto& sm = *reinterpret_cast<K2Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_layers = g.n_levels + 1;                       // layer 0 = in-projection
-  const int my_tiles = (g.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  // kPair: both CTAs of a pair run the tile count of its first CTA; a tile index >= n_tiles is a dummy tile (all rows zero)
+  const int first_cta = kPair ? ((int)blockIdx.x & ~1) : (int)blockIdx.x;
+  const int my_tiles = (g.n_tiles - first_cta + (int)gridDim.x - 1) / (int)gridDim.x;
+  const uint32_t crank = kPair ? cluster_ctarank() : 0u;
 
   if (tid == 0) {
     prefetch_tmap(&tmap_w);
     for (int s = 0; s < kWStages; ++s) {
       mbar_init(&sm.w_full[s], 1);
-      mbar_init(&sm.w_empty[s], 1);
+      mbar_init(&sm.w_empty[s], kPair ? 2 : 1);
     }
     mbar_init(&sm.acc_ready, 1);
     mbar_init(&sm.act_ready, kTR);
@@ -119,7 +129,8 @@ k2_tcn_bf16(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfl
   for (int i = tid; i < kActBytes / 16; i += kK2Threads) reinterpret_cast<uint4*>(sm.act)[i] = make_uint4(0, 0, 0, 0);
   if (warp == 5) tmem_alloc<128>(&sm.tmem_base);
   tc_fence_before_sync();
-  __syncthreads();
+  if (kPair) cluster_sync_all();                  // the peer's barriers are initialised before any multicast lands on them
+  else __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = __shfl_sync(0xffffffffu, sm.tmem_base, 0);
 
@@ -133,8 +144,12 @@ k2_tcn_bf16(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfl
           const int s = (int)(n % kWStages);
           mbar_wait_relaxed(&sm.w_empty[s], (uint32_t)(((n / kWStages) & 1) ^ 1));
           mbar_arrive_expect_tx(&sm.w_full[s], kWStageBytes);
-          tma_load_2d(sm.w[s], &tmap_w, 0, j * 128, &sm.w_full[s]);
-          tma_load_2d(sm.w[s] + kWStageBytes / 2, &tmap_w, 64, j * 128, &sm.w_full[s]);
+          if (kPair) {                                           // this CTA's chunk, into both rings
+            tma_load_2d_multicast(sm.w[s] + crank * (kWStageBytes / 2), &tmap_w, 64 * (int)crank, j * 128, &sm.w_full[s], 0b11);
+          } else {
+            tma_load_2d(sm.w[s], &tmap_w, 0, j * 128, &sm.w_full[s]);
+            tma_load_2d(sm.w[s] + kWStageBytes / 2, &tmap_w, 64, j * 128, &sm.w_full[s]);
+          }
         }
       }
     }
@@ -166,7 +181,10 @@ k2_tcn_bf16(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfl
               const uint64_t db = make_desc_k_sw128(w_base + (k >> 2) * (kWStageBytes / 2) + (k & 3) * 32);
               if (leader) umma_bf16(tmem, da, db, idesc, (tap | k) != 0);
             }
-            if (leader) umma_commit(&sm.w_empty[s]);
+            if (leader) {
+              if (kPair) umma_commit_mc(&sm.w_empty[s], 0b11);
+              else umma_commit(&sm.w_empty[s]);
+            }
           }
           if (leader) umma_commit(&sm.acc_ready);
         }
@@ -249,7 +267,8 @@ k2_tcn_bf16(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfl
     }
   }
   tc_fence_before_sync();
-  __syncthreads();
+  if (kPair) cluster_sync_all();                  // nobody exits while the peer may still multicast into its ring
+  else __syncthreads();
   if (warp == 5) {
     tc_fence_after_sync();
     tmem_dealloc<128>(tmem);
@@ -327,10 +346,35 @@ int32_t tcn_forward_bf16(const void* xe, int xe_dtype, const float* w_in_x, cons
   int32_t rc = make_tmap_bf16(&tw, w_bf16, (uint64_t)(1 + n_levels * K) * kDim, kDim, kDim, 64, 128, 128);
   if (rc) return rc;
   const size_t smem = sizeof(K2Smem) + 1024;
-  HTCN_CUDA(cudaFuncSetAttribute(k2_tcn_bf16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // HTCN_K2_MULTICAST=1: CTA pairs with multicast weights.  Measured: 0.727 vs 0.719 ms (hier), 1.49 vs 1.55 ms (cfg3) --
+  // halving the L2 -> SM weight traffic buys nothing, the kernel is bound by the latency of its 2-deep weight ring and of
+  // the dependent layer chain, not by L2 bandwidth; independent CTAs stay the default.
+  const char* mc = getenv("HTCN_K2_MULTICAST");
+  if (mc && atoi(mc) != 0 && tiles >= 2) {
+    auto kern = k2_tcn_bf16<true>;
+    HTCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg{};
+    const int grid = tiles < 2 * 148 ? ((tiles + 1) & ~1) : 2 * 148;
+    cfg.gridDim = dim3((unsigned)grid, 1, 1);
+    cfg.blockDim = dim3(kK2Threads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    HTCN_CUDA(cudaLaunchKernelEx(&cfg, kern, tw, g, (const __nv_bfloat16*)xe, sbias, (const float*)bias_dev, out_row,
+                                 (__nv_bfloat16*)hout, (__nv_bfloat16*)h_save, (__nv_bfloat16*)a_save));
+    return HTCN_OK;
+  }
+  auto kern = k2_tcn_bf16<false>;
+  HTCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = tiles < 2 * 148 ? tiles : 2 * 148;
-  k2_tcn_bf16<<<grid, kK2Threads, smem, st>>>(tw, g, (const __nv_bfloat16*)xe, sbias, bias_dev, out_row,
-                                              (__nv_bfloat16*)hout, (__nv_bfloat16*)h_save, (__nv_bfloat16*)a_save);
+  kern<<<grid, kK2Threads, smem, st>>>(tw, g, (const __nv_bfloat16*)xe, sbias, bias_dev, out_row,
+                                       (__nv_bfloat16*)hout, (__nv_bfloat16*)h_save, (__nv_bfloat16*)a_save);
   HTCN_LAUNCH_CHECK("k2_tcn_bf16");
   return HTCN_OK;
 }

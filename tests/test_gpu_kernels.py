@@ -570,6 +570,14 @@ def test_k2_tcn_bf16_tcgen05(lib, B, S, L, K, levels):
     ro = dev(row_of)
     gotc = run_k2_bf16(lib, xe, w, sbias, pk["slot_off"], B, T, S, K, levels, out_row=ro, n_out=int(valid.sum())).float().cpu().numpy()
     np.testing.assert_array_equal(gotc, got.reshape(-1, 128)[valid])
+    # CTA pairs with TMA-multicast weights (HTCN_K2_MULTICAST=1; odd tile counts run a dummy tile): bit-identical
+    import os
+    os.environ["HTCN_K2_MULTICAST"] = "1"
+    try:
+        got_mc = run_k2_bf16(lib, xe, w, sbias, pk["slot_off"], B, T, S, K, levels).float().cpu().numpy().reshape(B, T, 128)
+    finally:
+        del os.environ["HTCN_K2_MULTICAST"]
+    np.testing.assert_array_equal(got_mc, got)
 
 
 def test_k2_bf16_causality_and_isolation(lib):
