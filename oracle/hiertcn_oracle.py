@@ -384,6 +384,22 @@ def rank_ambiguity(score, y_id, rel_eps):
     return (np.abs(score - target) <= tol).sum(-1) - 1
 
 
+def rank_sign_bit(z32, zy32):
+    """Bit-level restatement of the rank count of the bf16 tier's fused CE+rank sweep (k4_score_bf16.cu: kSignRank), the
+    device-side form of `rank = #{j: Z[j] > Z[y]}` (loss.py:179): a logit is counted when the SIGN BIT of
+        tn = fma_rn(z, -c, T),   c = fl32(log2 e),   T = fl32_round_up(z_y * c)
+    is set.  fma rounds the exact value T - z*c once, and rounding never changes the sign of a non-zero value, so the
+    sign bit is set iff T - z*c < 0 exactly.  z32 [Q,N] float32 logits, zy32 [Q] float32 target logits."""
+    c = np.float64(np.float32(1.4426950408889634))
+    z = np.asarray(z32, np.float32).astype(np.float64)
+    zy = np.asarray(zy32, np.float32).astype(np.float64)
+    p = zy * c                                                    # exact: 24 x 24 significant bits fit in a double
+    t = p.astype(np.float32)
+    t = np.where(t.astype(np.float64) < p, np.nextafter(t, np.float32(np.inf)), t).astype(np.float64)   # round up
+    e = t[..., None] - z * c     # exact where it matters (|e| <= |t|, Sterbenz); elsewhere the double rounding keeps the sign
+    return (e < 0).sum(-1)
+
+
 # --------------------------------------------------------------------------------------
 # sampled ranking losses + calc_score (loss.py:22-71, 76-105)
 # --------------------------------------------------------------------------------------

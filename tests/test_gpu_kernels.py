@@ -438,6 +438,11 @@ def test_k4_bf16_tcgen05(lib, Q, N, n_split, epi, tol, monkeypatch):
         np.testing.assert_array_equal(got_rank, strict)
     else:
         assert ((got_rank <= strict) & (got_rank >= strict - one_ulp)).all(), (got_rank - strict)
+        # ... and bit-exact against the oracle's restatement of that count (full 256-item tiles; the ragged last tile of the
+        # catalog uses the strict compare)
+        n_full = (N // 256) * 256
+        want = O.rank_sign_bit(z_gpu[:, :n_full], zy_h) + (z_gpu[:, n_full:] > zy_h[:, None]).sum(1)
+        np.testing.assert_array_equal(got_rank, want)
     # rank-only and CE-only specialisations agree with the fused one
     _, _, _, pc2, _, _ = run_score(lib, hd, wt, bd, yd, lib.SCORE_RANK, 0, n_split, precision=lib.HTCN_BF16, zy_in=zy)
     if epi in ("4", "104", "-1"):

@@ -127,3 +127,31 @@ def test_torch_cpu_port_matches_golden(literal):
     np.testing.assert_allclose(out["state"], z["state_f64"], rtol=1e-4, atol=1e-5)
     np.testing.assert_allclose(out["loss_bt"], z["loss_bt_f64"], rtol=1e-4, atol=1e-5)
     np.testing.assert_array_equal(out["ranks"], z["ranks_f64"])
+
+
+def test_sign_bit_rank_is_strict_rank_up_to_one_ulp():
+    """the rank count of the fused bf16 sweep (oracle restatement `rank_sign_bit` of k4_score_bf16.cu: kSignRank) against
+    the strict compare of loss.py:179: never counts a logit <= the target, always counts a logit >= 2 ulp above it; only
+    a logit exactly one ulp above the target may be missed"""
+    rng = np.random.default_rng(0)
+    zy = np.concatenate([rng.normal(size=4000) * 10.0 ** rng.integers(-3, 3, size=4000),
+                         np.float32([1.0, -1.0, 0.75, 1.386, 1.387, -1.386, 2.0 ** -20, -(2.0 ** 20), 0.0])]).astype(np.float32)
+    up = lambda a, k: a if k == 0 else up(np.nextafter(a, np.float32(np.inf)), k - 1)       # noqa: E731
+    dn = lambda a, k: a if k == 0 else dn(np.nextafter(a, np.float32(-np.inf)), k - 1)      # noqa: E731
+    # adversarial columns: the target itself, 1..3 ulp below, 1..3 ulp above
+    cols = np.stack([zy, dn(zy, 1), dn(zy, 2), dn(zy, 3), up(zy, 1), up(zy, 2), up(zy, 3)], 1).astype(np.float32)
+    for j in range(4):                                                 # <= target: never counted
+        assert (O.rank_sign_bit(cols[:, j:j + 1], zy) == 0).all(), j
+    for j in (5, 6):                                                   # >= 2 ulp above: always counted
+        assert (O.rank_sign_bit(cols[:, j:j + 1], zy) == 1).all(), j
+    one = O.rank_sign_bit(cols[:, 4:5], zy)                            # exactly 1 ulp above: either
+    assert set(np.unique(one)) <= {0, 1} and 0 < one.mean() <= 1.0
+    # random logits: strict - #[z == nextafter(z_y)] <= rank <= strict
+    z = (rng.normal(size=(64, 5000)) * 3).astype(np.float32)
+    y = rng.integers(0, 5000, size=64)
+    zyr = z[np.arange(64), y]
+    z[:, :8] = np.stack([up(zyr, k) for k in range(4)] + [dn(zyr, k) for k in range(4)], 1)   # ties and near-ties in every row
+    strict = (z > zyr[:, None]).sum(1)
+    one_ulp = (z == np.nextafter(zyr, np.float32(np.inf))[:, None]).sum(1)
+    got = O.rank_sign_bit(z, zyr)
+    assert ((got <= strict) & (got >= strict - one_ulp)).all()
