@@ -32,7 +32,9 @@ constexpr int kRows = kTR + kMaxSpare;   // rows of the activation buffer (spare
 constexpr int kActBytes = 16 * kRows * 16;          // 16 channel chunks x rows x 16 B = 40 KB
 constexpr int kWStageBytes = 2 * 128 * 128;         // one tap: [128 cout][128 cin] bf16, two 64-col swizzled chunks
 constexpr int kWStages = 2;                         // 2 x 32 KB: with the 40 KB tile two CTAs fit one SM
-constexpr int kK2Threads = 192;          // warps 0-3 epilogue/loader, warp 4 TMA producer, warp 5 MMA issuer
+constexpr int kK2EpiWarps = 8;           // 4 TMEM lane quarters x 2 channel halves: a thread owns 64 channels of one tile row
+constexpr int kK2Threads = 32 * (kK2EpiWarps + 2);   // warps 0-7 epilogue/loader, warp 8 TMA producer, warp 9 MMA issuer
+constexpr int kK2ProducerWarp = kK2EpiWarps, kK2MmaWarp = kK2EpiWarps + 1;
 
 struct K2Slot {          // per session slot: tiling of its B sequences
   int off, L;            // first column in [B,T], length
@@ -122,19 +124,19 @@ k2_tcn_bf16(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfl
       mbar_init(&sm.w_empty[s], kPair ? 2 : 1);
     }
     mbar_init(&sm.acc_ready, 1);
-    mbar_init(&sm.act_ready, kTR);
+    mbar_init(&sm.act_ready, 32 * kK2EpiWarps);
     fence_barrier_init();
   }
   for (int i = tid; i < g.n_levels * kDim; i += kK2Threads) sm.bias[i / kDim][i % kDim] = bias_all[i];
   for (int i = tid; i < kActBytes / 16; i += kK2Threads) reinterpret_cast<uint4*>(sm.act)[i] = make_uint4(0, 0, 0, 0);
-  if (warp == 5) tmem_alloc<128>(&sm.tmem_base);
+  if (warp == kK2MmaWarp) tmem_alloc<128>(&sm.tmem_base);
   tc_fence_before_sync();
   if (kPair) cluster_sync_all();                  // the peer's barriers are initialised before any multicast lands on them
   else __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = __shfl_sync(0xffffffffu, sm.tmem_base, 0);
 
-  if (warp == 4) {
+  if (warp == kK2ProducerWarp) {
     // ===================== weight producer: [W_in, L0 taps, L1 taps, ...] per tile, 2-stage ring =====================
     if (lane == 0) {
       const int per_tile = 1 + g.n_levels * g.K;
@@ -153,7 +155,7 @@ k2_tcn_bf16(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfl
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kK2MmaWarp) {
     // ===================== MMA issuer =====================
     // the whole warp runs the (warp-uniform) waits and descriptor arithmetic, one elected lane issues: under an
     // `if (lane == 0)` branch every tcgen05.mma is wrapped in an ELECT / R2UR.BROADCAST waterfall (~100 clk per MMA)
@@ -191,8 +193,11 @@ k2_tcn_bf16(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfl
       }
     }
   } else {
-    // ===================== loader + epilogue: thread = tile row =====================
-    const int r = tid;                                          // 0..127, TMEM lane r (warp w owns lanes 32w..32w+31)
+    // ===================== loader + epilogue: thread = 64 channels (half ch) of one tile row =====================
+    // (with 4 epilogue warps -- one per scheduler -- the dependent FADD/FMNMX chains of the epilogue issued at ~4.5 clk per
+    // instruction and the MMA warp spent 2/3 of its time waiting for act_ready: ncu source view, profiles/r1_k2_ncu.txt)
+    const int r = tid & 127;                                    // TMEM lane r (warp w may touch lanes 32(w%4)..+31)
+    const int ch = tid >> 7;                                    // channel half: 64*ch .. 64*ch+63
     uint8_t* my_act = sm.act + (kMaxSpare + r) * 16;            // + c * kRows * 16 for channel chunk c
     long long n_acc = 0;
     for (int it = 0; it < my_tiles; ++it) {
@@ -205,7 +210,7 @@ k2_tcn_bf16(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfl
       {
         const uint4* p = src >= 0 ? reinterpret_cast<const uint4*>(xe + (long long)src * kDim) : nullptr;
 #pragma unroll
-        for (int c = 0; c < 16; ++c)
+        for (int c = ch * 8; c < ch * 8 + 8; ++c)
           *reinterpret_cast<uint4*>(my_act + c * (kRows * 16)) = p ? __ldg(p + c) : make_uint4(0, 0, 0, 0);
       }
       fence_proxy_async_smem();
@@ -217,9 +222,16 @@ k2_tcn_bf16(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfl
         const float* bias_l = layer > 0 ? sm.bias[layer - 1] : nullptr;
         const float* sb_row = (layer == 0 && sbias && src >= 0) ? sbias + (long long)sb * kDim : nullptr;
 #pragma unroll 1
-        for (int cc = 0; cc < 4; ++cc) {                         // 4 x 32 channels
+        for (int cc = ch * 2; cc < ch * 2 + 2; ++cc) {           // 2 x 32 channels
+          // the per-(slot, user) bias of the in-projection: all 8 loads of this 32-channel group in flight BEFORE the TMEM
+          // read (inside the q loop each 16-byte group exposed a full L2 latency: 22 % of the epilogue warps' samples)
+          float4 sbv[8];
+          if (sb_row) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) sbv[i] = __ldg(reinterpret_cast<const float4*>(sb_row + cc * 32) + i);
+          }
           uint32_t v[32];
-          tmem_ld_32x32(tmem + ((uint32_t)(warp * 32) << 16) + cc * 32, v);
+          tmem_ld_32x32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + cc * 32, v);
           tmem_ld_wait(v);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {                          // 4 x 8 channels = one 16-byte chunk each
@@ -230,8 +242,7 @@ k2_tcn_bf16(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfl
 #pragma unroll
               for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(v[q * 8 + e]);
               if (sb_row) {
-                const float4 s0 = __ldg(reinterpret_cast<const float4*>(sb_row + c * 8));
-                const float4 s1 = __ldg(reinterpret_cast<const float4*>(sb_row + c * 8 + 4));
+                const float4 s0 = sbv[2 * q], s1 = sbv[2 * q + 1];
                 o[0] += s0.x; o[1] += s0.y; o[2] += s0.z; o[3] += s0.w;
                 o[4] += s1.x; o[5] += s1.y; o[6] += s1.z; o[7] += s1.w;
               }
@@ -269,7 +280,7 @@ k2_tcn_bf16(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfl
   tc_fence_before_sync();
   if (kPair) cluster_sync_all();                  // nobody exits while the peer may still multicast into its ring
   else __syncthreads();
-  if (warp == 5) {
+  if (warp == kK2MmaWarp) {
     tc_fence_after_sync();
     tmem_dealloc<128>(tmem);
   }
