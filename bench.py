@@ -28,7 +28,10 @@ import time
 
 import numpy as np
 
-# stdout carries exactly ONE JSON line: NCCL's own debug output (e.g. "NCCL version ..." under NCCL_DEBUG=VERSION) goes to stderr
+# stdout carries exactly ONE JSON line.  NCCL prints "NCCL version ..." to stdout under NCCL_DEBUG=VERSION and honours
+# NCCL_DEBUG_FILE only above that level, so VERSION is raised to WARN (same line, now into the file = stderr).
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
