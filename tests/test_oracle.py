@@ -155,3 +155,38 @@ def test_sign_bit_rank_is_strict_rank_up_to_one_ulp():
     one_ulp = (z == np.nextafter(zyr, np.float32(np.inf))[:, None]).sum(1)
     got = O.rank_sign_bit(z, zyr)
     assert ((got <= strict) & (got >= strict - one_ulp)).all()
+
+
+def test_k4_exp2_polynomials_meet_their_stated_error():
+    """the FMA-pipe exponentials of the bf16 catalog sweep (k4_score_bf16.cu: ex2_poly2): coefficients are read from the
+    CUDA source, evaluated in float32 exactly like the kernel (round-to-nearest split, Horner, p(0) = 1) and compared
+    with 2^t: degree 3 within 1.1e-4 relative (the default), degree 2 within 2.0e-3 (HTCN_K4_EPI=104)."""
+    import os
+    import re
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "hiertcn_b200", "csrc",
+                            "k4_score_bf16.cu")).read()
+    body = src[src.index("__device__ __forceinline__ float2 ex2_poly2"):]
+    body = body[:body.index("return make_float2")]
+    deg2 = [np.float32(x) for x in re.findall(r"make_float2\((0\.\d+)f,", body[body.index("if (kDeg2)"):body.index("} else {", body.index("if (kDeg2)"))])]
+    deg3 = [np.float32(x) for x in re.findall(r"make_float2\((0\.\d+)f,", body[body.index("} else {", body.index("if (kDeg2)")):])]
+    assert len(deg2) == 2 and len(deg3) == 3, (deg2, deg3)
+    t = np.linspace(-60.0, 60.0, 400001).astype(np.float32)
+    magic = np.float32(12582912.0)
+    r = (t + magic).astype(np.float32)
+    n = (r - magic).astype(np.float32)
+    f = (t - n).astype(np.float32)
+    assert np.abs(f).max() <= 0.5
+
+    def horner(cs):
+        p = np.float32(cs[0]) * f + np.float32(cs[1])
+        for c in cs[2:]:
+            p = (p * f + np.float32(c)).astype(np.float32)
+        return ((p * f).astype(np.float32) + np.float32(1.0)).astype(np.float32)
+
+    exact = np.exp2(f.astype(np.float64))
+    e3 = np.abs(horner(deg3).astype(np.float64) / exact - 1).max()
+    e2 = np.abs(horner(deg2).astype(np.float64) / exact - 1).max()
+    assert e3 <= 1.1e-4 and e2 <= 2.0e-3, (e3, e2)
+    # 2^n by exponent-field addition is exact for |t| < 125 (the range the kernel's max|t| guard enforces)
+    scaled = (horner(deg3).view(np.int32) + (r.view(np.int32) << 23)).view(np.float32)
+    assert np.abs(scaled.astype(np.float64) / np.exp2(t.astype(np.float64)) - 1).max() <= 1.1e-4
