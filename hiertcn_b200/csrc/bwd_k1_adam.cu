@@ -58,7 +58,14 @@ __global__ void adam_kernel(long long n4, float4* __restrict__ p, float4* __rest
                             const float* __restrict__ grad_div, int zero_grad) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
-  const float sc = grad_div ? 1.0f / *grad_div : 1.0f;
+  // a batch without a single scored user (user_count == 0) has no loss: the reference's 0/0 would turn every weight
+  // and both moments into NaN for good -- skip the update (the step counter of the caller still advances)
+  const float div = grad_div ? *grad_div : 1.0f;
+  if (!(div > 0.f)) {
+    if (zero_grad) g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+  const float sc = 1.0f / div;
   float4 gg = g[i], mm = m[i], vv = v[i], pp = p[i];
 #define HTCN_ADAM1(c)                                 \
   {                                                   \

@@ -105,16 +105,26 @@ __global__ void score_finish_kernel(const float* __restrict__ pm, const float* _
 // best logit exceeds its target logit by more than ~88 overflows fp32 and comes out of score_finish as +inf / NaN.  Such
 // rows (softmax probability of the target < e^-88) are redone here with an online-max log-sum-exp over the whole
 // catalog, one CTA per row, same bf16 operands; rows with a finite loss are skipped (one load each).
+// Shard mode (loss_row == NULL; catalog-sharded scoring, hiertcn_b200/dist.py): a row is bad when one of THIS shard's
+// n_split partial sums is non-finite; its exact (max, sum exp(z - max)) over the shard replaces the shard's partials
+// (split 0 gets the pair, the other splits the neutral element (-inf, 0)), so that the cross-shard log-sum-exp merge of
+// htcn_score_finish -- which accepts any reference point per part -- comes out finite.
 __global__ void __launch_bounds__(256)
 ce_repair_bf16_kernel(const __nv_bfloat16* __restrict__ hout, int Q, const __nv_bfloat16* __restrict__ wt, int n_items,
-                      const float* __restrict__ zy, float* __restrict__ loss_row, int* __restrict__ repaired) {
+                      const float* __restrict__ zy, float* __restrict__ loss_row, float* __restrict__ part_max,
+                      float* __restrict__ part_sum, int n_split, int* __restrict__ repaired) {
   __shared__ float h[kDim];
   __shared__ float red_m[8], red_s[8];
   __shared__ int bad_rows[256];
   __shared__ int n_bad;
   for (int base = blockIdx.x * 256; base < Q; base += gridDim.x * 256) {       // 256 rows checked per pass, one per thread
     const int qc = base + threadIdx.x;
-    const bool bad = qc < Q && !isfinite(loss_row[qc]);
+    bool bad = false;
+    if (qc < Q) {
+      if (loss_row) bad = !isfinite(loss_row[qc]);
+      else
+        for (int p = 0; p < n_split; ++p) bad |= !isfinite(part_sum[(long long)p * Q + qc]);
+    }
     if (!__syncthreads_or(bad)) continue;                         // the common case: nothing to redo in this chunk
     if (threadIdx.x == 0) n_bad = 0;
     __syncthreads();
@@ -159,7 +169,16 @@ ce_repair_bf16_kernel(const __nv_bfloat16* __restrict__ hout, int Q, const __nv_
       for (int w = 0; w < 8; ++w) M = fmaxf(M, red_m[w]);
       float S = 0.f;
       for (int w = 0; w < 8; ++w) S += (red_m[w] == -INFINITY) ? 0.f : red_s[w] * expf(red_m[w] - M);
-      loss_row[q] = (M + logf(S)) - zy[q];
+      if (loss_row) {
+        loss_row[q] = (M + logf(S)) - zy[q];
+      } else {
+        part_max[q] = M;
+        part_sum[q] = S;
+        for (int p = 1; p < n_split; ++p) {
+          part_max[(long long)p * Q + q] = -INFINITY;
+          part_sum[(long long)p * Q + q] = 0.f;
+        }
+      }
       if (repaired) atomicAdd(repaired, 1);
     }
     }
@@ -419,8 +438,24 @@ extern "C" int32_t htcn_score_ce_repair(const void* hout, int32_t precision, int
   const int grid = chunks < 148 * 8 ? chunks : 148 * 8;
   ce_repair_bf16_kernel<<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(hout), Q,
                                                             reinterpret_cast<const __nv_bfloat16*>(w_out_t), n_items,
-                                                            target_logit, loss_row, repaired);
+                                                            target_logit, loss_row, nullptr, nullptr, 0, repaired);
   HTCN_LAUNCH_CHECK("ce_repair_bf16_kernel");
+  return HTCN_OK;
+}
+
+extern "C" int32_t htcn_score_ce_repair_shard(const void* hout, int32_t precision, int32_t Q, const void* w_out_t,
+                                              int32_t n_items, float* part_max, float* part_sum, int32_t n_split,
+                                              int32_t* repaired, void* stream) {
+  HTCN_REQUIRE(hout && w_out_t && part_max && part_sum && Q > 0 && n_items > 0 && n_split >= 1,
+               "score_ce_repair_shard: bad args");
+  if (precision == HTCN_F32) return HTCN_OK;           // the fp32 sweep keeps a running max per split
+  HTCN_REQUIRE(precision == HTCN_BF16, "score_ce_repair_shard: precision %d", precision);
+  const int chunks = ceil_div(Q, 256);
+  const int grid = chunks < 148 * 8 ? chunks : 148 * 8;
+  ce_repair_bf16_kernel<<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(hout), Q,
+                                                            reinterpret_cast<const __nv_bfloat16*>(w_out_t), n_items,
+                                                            nullptr, nullptr, part_max, part_sum, n_split, repaired);
+  HTCN_LAUNCH_CHECK("ce_repair_bf16_kernel(shard)");
   return HTCN_OK;
 }
 

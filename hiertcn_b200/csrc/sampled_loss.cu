@@ -20,7 +20,7 @@ template <bool kBf16>
 __global__ void __launch_bounds__(256)
 sampled_loss_kernel(const void* __restrict__ pred, int Q, const float4* __restrict__ table,
                     const int* __restrict__ pos_id, const int* __restrict__ neg_id, int k, int kind,
-                    float delta, float nce_weight, float* __restrict__ loss_row) {
+                    float delta, float nce_weight, int nce_div, float* __restrict__ loss_row) {
   const int lane = threadIdx.x & 31;
   const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (q >= Q) return;
@@ -66,7 +66,7 @@ sampled_loss_kernel(const void* __restrict__ pred, int Q, const float4* __restri
   }
   if (lane == 0) {
     float out;
-    if (kind == HTCN_LOSS_NCE) out = -log_sigmoid(inner) - acc / (float)k * nce_weight;             // :31
+    if (kind == HTCN_LOSS_NCE) out = -log_sigmoid(inner) - acc / (float)nce_div * nce_weight;       // :31 (args.num_neg_sample)
     else if (kind == HTCN_LOSS_BPR) out = -acc / (float)k;
     else out = acc / (float)k;
     loss_row[q] = out;
@@ -134,17 +134,18 @@ extern "C" int32_t htcn_calc_score(const void* pred, int32_t precision, int32_t 
 extern "C" int32_t htcn_sampled_rank_loss(const void* pred, int32_t precision, int32_t Q, const float* table,
                                           const int32_t* pos_id, const int32_t* neg_id, int32_t k,
                                           int32_t loss_kind, float hinge_delta, float nce_weight,
-                                          float* loss_row, void* stream) {
+                                          int32_t num_neg_sample, float* loss_row, void* stream) {
   using namespace htcn;
   HTCN_REQUIRE(pred && table && pos_id && neg_id && loss_row && Q > 0 && k > 0, "sampled_rank_loss: bad args");
   HTCN_REQUIRE(loss_kind >= HTCN_LOSS_NCE && loss_kind <= HTCN_LOSS_BPR, "sampled_rank_loss: kind %d", loss_kind);
+  const int nce_div = num_neg_sample > 0 ? num_neg_sample : k;
   const int grid = ceil_div(Q, 8);
   if (precision == HTCN_BF16)
     sampled_loss_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(pred, Q, (const float4*)table, pos_id, neg_id, k,
-                                                                  loss_kind, hinge_delta, nce_weight, loss_row);
+                                                                  loss_kind, hinge_delta, nce_weight, nce_div, loss_row);
   else if (precision == HTCN_F32)
     sampled_loss_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(pred, Q, (const float4*)table, pos_id, neg_id, k,
-                                                                   loss_kind, hinge_delta, nce_weight, loss_row);
+                                                                   loss_kind, hinge_delta, nce_weight, nce_div, loss_row);
   else
     HTCN_REQUIRE(false, "sampled_rank_loss: precision %d", precision);
   HTCN_LAUNCH_CHECK("sampled_loss_kernel");

@@ -38,7 +38,9 @@ def allreduce_scalars(scalars, dist, world):
     if world == 1:
         return scalars
     t = scalars.clone()
-    t[:6] *= scalars[6]
+    # a rank whose batch holds no scored user reports 0/0 = NaN means with user_count 0: it must contribute nothing
+    # (NaN * 0 would poison the global means)
+    t[:6] = (scalars[:6] * scalars[6]).where(scalars[6] > 0, scalars.new_zeros(()))
     dist.all_reduce(t)
     t[:6] /= t[6]
     return t
@@ -52,6 +54,11 @@ class ShardedCatalogScorer:
         self.bounds = shard_bounds(n_items, world)
         self.n0, self.n1 = self.bounds[rank], self.bounds[rank + 1]
         self.n_split = n_split
+        self.phases = None          # set to [] to have every phase boundary recorded (ops.mark -> CUDA events; bench.py)
+
+    def _mark(self, name):
+        if self.phases is not None and hasattr(self.ops, "mark"):
+            self.phases.append((name, self.ops.mark()))
 
     def score(self, hout, y_id, k: int = 0, ce: bool = True, rank_metric: bool = True):
         """hout [Q_local,128], y_id [Q_local] (global ids; may be None when only top-k is wanted).
@@ -60,32 +67,54 @@ class ShardedCatalogScorer:
         o, d, W = self.ops, self.dist, self.world
         Ql = hout.shape[0]
         need_t = (ce or rank_metric) and y_id is not None
+        self._mark("start")
         # 1. every shard must see every query row
         h_all = o.all_gather_rows(d, hout, W)                       # [W*Ql, 128]
         y_all = o.all_gather_rows(d, y_id, W) if need_t else None
+        self._mark("allgather_queries")
         Q = W * Ql
         # 2. target logits: owner fills, all-reduce completes
         zy = None
         if need_t:
             zy = o.zeros_f32(Q)
             o.target_logit(h_all, y_all, self.n0, self.n1, zy)
+            self._mark("target_logit")
             d.all_reduce(zy)
-        # 3. local sweep
+            self._mark("allreduce_target")
+        # 3. local sweep (+ exact redo of the rows whose target-referenced partial sum left fp32 range in THIS shard:
+        #    the dominant logit of a row may live in another shard than its target)
         part = o.sweep(h_all, y_all, zy, self.n0, self.n1, k, self.n_split, ce and need_t, rank_metric and need_t)
+        if ce and need_t and hasattr(o, "repair_parts"):
+            o.repair_parts(h_all, self.n0, self.n1, part["pm"], part["ps"])
+        self._mark("sweep")
         # 4. all-to-all of the partials: [n_split, W, Ql, ...] -> every rank gets its own rows from every shard
         out = {}
+        merged = {}
         if need_t:
-            merged = {}
             for name in ("pm", "ps", "pc"):
                 if part.get(name) is not None:
                     merged[name] = o.all_to_all_rows(d, part[name], W, Ql)      # [W*n_split, Ql]
-            zy_local = o.slice_rows(zy, self.rank * Ql, Ql)
-            # 5. merge
-            out.update(o.finish(merged.get("pm"), merged.get("ps"), merged.get("pc"), y_id, zy_local))
         if k:
             tv = o.all_to_all_rows(d, part["tv"], W, Ql)                         # [W*n_split, Ql, k]
             ti = o.all_to_all_rows(d, part["ti"], W, Ql)
+        self._mark("alltoall_partials")
+        # 5. merge
+        if need_t:
+            zy_local = o.slice_rows(zy, self.rank * Ql, Ql)
+            out.update(o.finish(merged.get("pm"), merged.get("ps"), merged.get("pc"), y_id, zy_local))
+            out["target_logit"] = zy_local
+        if k:
             out.update(o.topk_merge(tv, ti, k))
+        self._mark("merge")
+        return out
+
+    def phase_ms(self):
+        """device milliseconds of every phase recorded since ``phases`` was last reset (call after a synchronize)"""
+        out = {}
+        ph = self.phases or []
+        for (_, e0), (name, e1) in zip(ph[:-1], ph[1:]):
+            if name != "start":
+                out[name] = out.get(name, 0.0) + e0.elapsed_time(e1)
         return out
 
 
@@ -114,6 +143,18 @@ class CudaScoreOps:
 
     def zeros_f32(self, n):
         return self.torch.zeros(n, dtype=self.torch.float32, device=self.m.device)
+
+    def mark(self):
+        """CUDA event on the compute stream (torch's collectives make the compute stream wait for them, so the span
+        between two marks covers the collectives enqueued in between)"""
+        e = self.torch.cuda.Event(enable_timing=True)
+        e.record(self.torch.cuda.current_stream(self.m.device))
+        return e
+
+    def repair_parts(self, h_all, n0, n1, pm, ps):
+        m = self.m
+        self.cabi.call("htcn_score_ce_repair_shard", h_all.data_ptr(), m.act_dtype, h_all.shape[0], m.wt.data_ptr(),
+                       n1 - n0, pm.data_ptr(), ps.data_ptr(), pm.shape[0], None, m.stream_ptr())
 
     def slice_rows(self, t, start, n):
         return t[start:start + n].contiguous()

@@ -46,6 +46,15 @@ class CatalogScores:
         self.model, self.hout, self.Q = model, hout, Q
         self.row_of, self.y_rows, self.y_id, self.B, self.T = row_of, y_rows, y_id, B, T
         self._cache = {}
+        self.generation = model.generation
+
+    def check_fresh(self):
+        """``hout`` / ``row_of`` and the cached loss rows are views of the model's reusable workspaces: a later
+        ``forward`` / ``step`` / training step on the same model overwrites them.  Using a stale handle raises instead of
+        returning the other batch's numbers."""
+        if self.generation != self.model.generation:
+            raise cabi.HtcnError("stale CatalogScores: the model ran another forward since this handle was created "
+                                 "(its workspaces were reused); score / materialize it before the next forward")
 
     @property
     def shape(self):
@@ -54,6 +63,7 @@ class CatalogScores:
     def materialize(self):
         """[B,T,N] fp32 numpy; masked positions are zero rows like ``pred *= mask_y`` (model.py:105)."""
         torch = _torch()
+        self.check_fresh()
         m = self.model
         out = np.zeros((self.B * self.T, m.N), dtype=np.float32)
         if self.Q:
@@ -96,7 +106,14 @@ class HierTCN:
         self.seed = seed
         self.device = device
         self.built = False
+        self._init_runtime_state()
+
+    def _init_runtime_state(self):
+        """workspaces, pinned staging sets (two input sets + three result sets, see ``stage`` / ``step_async``) and the
+        generation counter that invalidates ``CatalogScores`` handles whose workspaces were reused"""
         self._ws = {}
+        self._pin, self._pin_ev, self._pin_next, self._res_next = {}, [None, None], 0, 0
+        self.generation = 0
 
     # ------------------------------------------------------------------ build
     def build(self):
@@ -193,8 +210,6 @@ class HierTCN:
         torch = _torch()
         if not self.built:
             self.build()
-        if not hasattr(self, "_pin"):
-            self._pin, self._pin_ev, self._pin_next = {}, [None, None], 0
         slot = self._pin_next
         self._pin_next ^= 1
         if self._pin_ev[slot] is not None:
@@ -260,6 +275,7 @@ class HierTCN:
             self.build()
         torch = _torch()
         d = staged if staged is not None else self.stage(x_list, y_list, mask_list, state)
+        self.generation += 1            # handles of earlier forwards now point at overwritten workspaces
         B, T, S, Q = d["B"], d["T"], d["S"], d["Q"]
         st = self.stream_ptr()
         f32 = torch.float32
@@ -316,6 +332,11 @@ class HierTCN:
         """One streaming sweep over the catalog.  Returns dict of device tensors:
         loss_row [Q], rank_row [Q] and, with topk, topk_val / topk_idx [Q,k]."""
         torch = _torch()
+        scores.check_fresh()
+        if self.n_out != self.N:
+            raise cabi.HtcnError("this model holds a catalog shard (%d of %d output rows): score it through "
+                                 "hiertcn_b200.dist.ShardedCatalogScorer (or HierTCN.topk with the shard offset)"
+                                 % (self.n_out, self.N))
         Q = scores.Q
         key = (ce, rank, topk)
         if key in scores._cache:
@@ -424,6 +445,9 @@ class HierTCN:
         """Sampled ranking loss (reference loss.py:22-71) of the user embeddings against the rows of the
         output table W_out^T: positive = the true next item, negatives = ``neg_ids [Q,k]`` (host or device)."""
         torch = _torch()
+        scores.check_fresh()
+        if self.n_out != self.N:
+            raise cabi.HtcnError("sampled_loss gathers rows of the whole output table; this model holds a catalog shard")
         a = self.args
         kind = kind or (a.loss if a.loss in cabi.LOSS_KINDS else "hinge_logsigmoid")
         if kind not in cabi.LOSS_KINDS:
@@ -436,7 +460,7 @@ class HierTCN:
         out = torch.empty(Q, dtype=torch.float32, device=self.device)
         cabi.call("htcn_sampled_rank_loss", scores.hout.data_ptr(), self.act_dtype, Q, self.wt_f32.data_ptr(),
                   scores.y_rows.data_ptr(), neg.data_ptr(), k, cabi.LOSS_KINDS[kind], float(a.hinge_delta),
-                  float(a.nce_weight), out.data_ptr(), self.stream_ptr())
+                  float(a.nce_weight), int(a.num_neg_sample), out.data_ptr(), self.stream_ptr())
         return out
 
     # ------------------------------------------------------------------ the reference's sess.run
@@ -465,8 +489,6 @@ class HierTCN:
             if t:
                 dev["topk_val"], dev["topk_idx"] = t["topk_val"], t["topk_idx"]
             dev["row_of"] = scores.row_of
-        if not hasattr(self, "_res_next"):
-            self._res_next = 0
         slot = 2 + self._res_next                   # result staging sets 2..4 (0/1 are the input sets)
         self._res_next = (self._res_next + 1) % 3
         host = {}
@@ -517,26 +539,43 @@ class PendingStep:
 _MODELS = {}
 
 
+def _weights_fingerprint(weights):
+    """cheap content key of a weight dict: names, shapes and a strided sample of every tensor (a full sha256 of a 1M-item
+    table costs a second per call); catches a dict mutated in place or replaced by another one at a recycled id()"""
+    if weights is None:
+        return None
+    h = []
+    for k in sorted(weights):
+        a = np.asarray(weights[k])
+        flat = a.reshape(-1)
+        step = max(1, flat.size // 61)
+        h.append((k, a.shape, flat[::step][:64].astype(np.float64).tobytes()))
+    return hash(tuple(h))
+
+
 def _model_for(args, weights, precision):
-    key = (id(weights), precision, int(args.item_num))
-    m = _MODELS.get(key)
-    if m is None:
+    key = (id(weights), _weights_fingerprint(weights), precision, int(args.item_num), tuple(args.tcn_channel),
+           int(args.num_layer), int(args.kernel_size))
+    hit = _MODELS.get(key)
+    if hit is None:
         m = HierTCN(args, weights, precision=precision).build()
         _MODELS.clear()
-        _MODELS[key] = m
-    return m
+        _MODELS[key] = (m, weights)          # the strong reference keeps id(weights) from being recycled
+        return m
+    return hit[0]
 
 
 def model_hier(args, x, y, mask, state, x_gap=None, x_impression=None, name="hier", reuse=None, training=True,
-               weights=None, precision=None):
+               weights=None, precision=None, model=None):
     """Signature of reference model_hier.py:21: x, y are S-lists of id arrays [B, L_s] (the reference feeds
     one-hot tensors built from these ids, model.py:59-61), mask an S-list of [B,1], state [B, G*H].
     Returns (pred_all, state): pred_all is a lazy ``CatalogScores`` (call .materialize() for the dense
-    [B,T,N] tensor at small N); state is a numpy array."""
+    [B,T,N] tensor at small N); state is a numpy array.  ``model``: an explicit built ``HierTCN`` to run on (otherwise
+    one is built from ``weights`` and cached).  The returned handle is valid until the next forward on that model."""
     if x_gap is not None or x_impression is not None:
         raise NotImplementedError("has_gap / has_impression are unreachable in the XING runner (SURVEY A.8 #12)")
     if name != "hier":
         raise NotImplementedError("variable scope other than 'hier'")
-    m = _model_for(args, weights, precision or getattr(args, "precision", "bf16"))
+    m = model if model is not None else _model_for(args, weights, precision or getattr(args, "precision", "bf16"))
     scores, state_out = m.forward(x, y, mask, state)
     return scores, state_out.cpu().numpy()

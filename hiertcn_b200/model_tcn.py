@@ -34,7 +34,7 @@ class TCN(HierTCN):
         self.G = 0
         self.host_weights, self.scope, self.device = weights, scope, device
         self.built = False
-        self._ws = {}
+        self._init_runtime_state()
 
     def build(self):
         torch = _torch()
@@ -73,6 +73,7 @@ class TCN(HierTCN):
         if not self.built:
             self.build()
         torch = _torch()
+        self.generation += 1
         x = np.ascontiguousarray(np.asarray(x_ids), dtype=np.int32)
         B, L = x.shape
         y = np.ascontiguousarray(np.asarray(y_ids), dtype=np.int32) if y_ids is not None else np.ones_like(x)

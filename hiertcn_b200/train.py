@@ -111,6 +111,7 @@ class HierTCNTrainer:
         torch = _torch()
         m = self.m
         d = staged if staged is not None else m.stage(x_list, y_list, mask_list, state)
+        m.generation += 1               # the loss workspaces are shared with HierTCN.score: older handles are stale
         B, T, S, Q = d["B"], d["T"], d["S"], d["Q"]
         G, L, K, N = m.G, m.n_levels, m.K, m.N
         R = B * T
@@ -292,16 +293,27 @@ class HierTCNTrainer:
         def scatter(prefix, flat):
             t = {k[len(prefix):].replace("|", "/"): z[k] for k in z.files if k.startswith(prefix)}
             m = self.m
-            named = {"E": t["hier/emb/kernel"], "b_emb": t["hier/emb/bias"], "w_in_x": t["hier/tcn/emb/kernel"][:D],
-                     "w_in_state": t["hier/tcn/emb/kernel"][D:], "wt": np.ascontiguousarray(t["hier/tcn/dense/kernel"].T),
-                     "b_out": t["hier/tcn/dense/bias"]}
+            ed = t["hier/emb/kernel"].shape[1]          # TF shapes carry emb_dim; the device layout is padded to 128
+
+            def pad_cols(a):
+                return np.pad(a, [(0, 0)] * (a.ndim - 1) + [(0, D - ed)])
+
+            def pad_rows(a):                             # [ed + rest, C] -> [128 + rest, C]
+                return np.concatenate([a[:ed], np.zeros((D - ed, a.shape[1]), a.dtype), a[ed:]], 0)
+
+            named = {"E": pad_cols(t["hier/emb/kernel"]), "b_emb": pad_cols(t["hier/emb/bias"]),
+                     "w_in_x": pad_rows(t["hier/tcn/emb/kernel"])[:D], "w_in_state": t["hier/tcn/emb/kernel"][ed:],
+                     "wt": np.ascontiguousarray(t["hier/tcn/dense/kernel"].T), "b_out": t["hier/tcn/dense/bias"]}
             for l in range(m.n_levels):
                 named[f"conv_w{l}"] = t[f"hier/tcn/temporal_conv_net/tblock_{l}/conv1/kernel"]
                 named[f"conv_b{l}"] = t[f"hier/tcn/temporal_conv_net/tblock_{l}/conv1/bias"]
             for g in range(m.G):
                 p = f"hier/multi_rnn_cell/cell_{g}/gru_cell"
-                named[f"gate_w{g}"], named[f"gate_b{g}"] = t[p + "/gates/kernel"], t[p + "/gates/bias"]
-                named[f"cand_w{g}"], named[f"cand_b{g}"] = t[p + "/candidate/kernel"], t[p + "/candidate/bias"]
+                gw, cw = t[p + "/gates/kernel"], t[p + "/candidate/kernel"]
+                if g == 0:
+                    gw, cw = pad_rows(gw), pad_rows(cw)
+                named[f"gate_w{g}"], named[f"gate_b{g}"] = gw, t[p + "/gates/bias"]
+                named[f"cand_w{g}"], named[f"cand_b{g}"] = cw, t[p + "/candidate/bias"]
             for n, sh in self.spec:
                 self._view(flat, n, sh).copy_(torch.from_numpy(np.ascontiguousarray(named[n], dtype=np.float32)).reshape(sh))
 
@@ -319,16 +331,21 @@ class HierTCNTrainer:
 
     def _to_tf_names(self, t):
         m = self.m
-        w = {"hier/emb/kernel": t["E"], "hier/emb/bias": t["b_emb"],
-             "hier/tcn/emb/kernel": np.concatenate([t["w_in_x"], t["w_in_state"]], 0),
+        ed = int(getattr(m.args, "emb_dim", D))    # emb_dim < 128 is zero-padded on the device: emit the TF shapes
+        cut = lambda a: np.concatenate([a[:ed], a[D:]], 0)  # noqa: E731  drop the padded input rows
+        w = {"hier/emb/kernel": t["E"][:, :ed], "hier/emb/bias": t["b_emb"][:ed],
+             "hier/tcn/emb/kernel": np.concatenate([t["w_in_x"][:ed], t["w_in_state"]], 0),
              "hier/tcn/dense/kernel": np.ascontiguousarray(t["wt"].T), "hier/tcn/dense/bias": t["b_out"]}
         for l in range(m.n_levels):
             w[f"hier/tcn/temporal_conv_net/tblock_{l}/conv1/kernel"] = t[f"conv_w{l}"]
             w[f"hier/tcn/temporal_conv_net/tblock_{l}/conv1/bias"] = t[f"conv_b{l}"]
         for g in range(m.G):
             p = f"hier/multi_rnn_cell/cell_{g}/gru_cell"
-            w[p + "/gates/kernel"], w[p + "/gates/bias"] = t[f"gate_w{g}"], t[f"gate_b{g}"]
-            w[p + "/candidate/kernel"], w[p + "/candidate/bias"] = t[f"cand_w{g}"], t[f"cand_b{g}"]
+            gw, cw = t[f"gate_w{g}"], t[f"cand_w{g}"]
+            if g == 0 and ed < D:
+                gw, cw = cut(gw), cut(cw)
+            w[p + "/gates/kernel"], w[p + "/gates/bias"] = gw, t[f"gate_b{g}"]
+            w[p + "/candidate/kernel"], w[p + "/candidate/bias"] = cw, t[f"cand_b{g}"]
         return w
 
 

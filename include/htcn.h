@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define HTCN_ABI_VERSION 1
+#define HTCN_ABI_VERSION 2
 #define HTCN_DIM 128          /* D = C = H */
 #define HTCN_MAX_SLOTS 64     /* S (args.max_session_num, default 10) */
 #define HTCN_MAX_LEVELS 8     /* TCN levels (len(args.tcn_channel)) */
@@ -210,6 +210,13 @@ int32_t htcn_score_topk(const void* hout, int32_t precision, int32_t Q, const vo
 int32_t htcn_score_ce_repair(const void* hout, int32_t precision, int32_t Q, const void* w_out_t, int32_t n_items,
                              const float* target_logit, float* loss_row, int32_t* repaired, void* stream);
 
+/* The same repair for ONE SHARD of a sharded catalog, applied to the shard's partials BEFORE they are exchanged: a row
+ * with a non-finite part_sum in any of the shard's n_split splits gets its exact (max_j z_j, sum_j exp(z_j - max)) over
+ * the shard's n_items rows written to split 0 and the neutral element (-inf, 0) to the other splits; htcn_score_finish
+ * merges parts with arbitrary reference points, so the cross-shard loss comes out finite.  No-op in the fp32 tier. */
+int32_t htcn_score_ce_repair_shard(const void* hout, int32_t precision, int32_t Q, const void* w_out_t, int32_t n_items,
+                                   float* part_max, float* part_sum, int32_t n_split, int32_t* repaired, void* stream);
+
 /* k-way merge of per-part top-k lists -> [Q,k] sorted by (score desc, index asc) [TF top_k order] */
 int32_t htcn_topk_merge(const float* part_val, const int32_t* part_idx, int32_t n_part, int32_t Q,
                         int32_t k, float* out_val, int32_t* out_idx, void* stream);
@@ -230,12 +237,14 @@ int32_t htcn_loss_metrics_reduce(const float* loss_row, const float* rank_row, c
 /* ---------------------------------------------------------------------------------------------
  * sampled ranking losses (reference loss.py:22-71): pred [Q,128] is l2-normalised, scored by inner
  * product against the positive row table[pos_id[q]] and k negatives table[neg_id[q,j]].
- * table [N,128] f32.  loss_row [Q] (0 where pos_id == 0).
+ * table [N,128] f32.  loss_row [Q] (0 where pos_id == 0).  The hinge / bpr kinds average over the k
+ * negatives supplied (reduce_mean, loss.py:40,50,60,70); nce divides the negative term by
+ * num_neg_sample = args.num_neg_sample (loss.py:31), which may differ from k (<= 0: use k).
  * ------------------------------------------------------------------------------------------- */
 int32_t htcn_sampled_rank_loss(const void* pred, int32_t precision, int32_t Q, const float* table,
                                const int32_t* pos_id, const int32_t* neg_id, int32_t k,
                                int32_t loss_kind, float hinge_delta, float nce_weight,
-                               float* loss_row, void* stream);
+                               int32_t num_neg_sample, float* loss_row, void* stream);
 
 /* calc_score (reference loss.py:76-105): score[q,j] of k candidate rows table[cand_id[q,j]] for every query;
  * rank_metric 0 = 'l2' (-||pred - y'||^2), 1 = 'inner_prod' (<pred, y'>); pred is not normalised (as in the

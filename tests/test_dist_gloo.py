@@ -128,6 +128,11 @@ def _worker(rank, world, port, ret):
         g = allreduce_scalars(s, dist, world)
         exp_loss = sum((1.0 + r) * (3.0 + r) for r in range(world)) / sum(3.0 + r for r in range(world))
         ok = ok and abs(float(g[0]) - exp_loss) < 1e-6 and float(g[6]) == sum(3.0 + r for r in range(world))
+        # a rank whose batch holds no scored user reports NaN means (0/0) with user_count 0: it must not poison the result
+        nan = float("nan")
+        s0 = torch.tensor([nan] * 6 + [0.0, 0.0]) if rank == 0 else torch.tensor([2.0, .1, .2, .3, .4, .5, 4.0, 9.0])
+        g0 = allreduce_scalars(s0, dist, world)
+        ok = ok and bool(torch.isfinite(g0).all()) and abs(float(g0[0]) - 2.0) < 1e-6 and float(g0[6]) == 4.0 * (world - 1)
         ret[rank] = bool(ok)
     finally:
         dist.destroy_process_group()

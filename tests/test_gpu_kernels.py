@@ -367,10 +367,11 @@ def test_sampled_rank_loss(lib, kind):
     neg = rng.integers(1, N, size=(Q, k)).astype(np.int32)
     out = torch.empty(Q, dtype=torch.float32, device="cuda")
     pred_d, table_d, pos_d, neg_d = dev(pred), dev(table), dev(pos), dev(neg)
+    nns = 25                                   # args.num_neg_sample != k: only nce reads it (loss.py:31)
     lib.call("htcn_sampled_rank_loss", P(pred_d), lib.HTCN_F32, Q, P(table_d), P(pos_d), P(neg_d), k,
-             lib.LOSS_KINDS[kind], 0.1, 1.0, P(out), None)
+             lib.LOSS_KINDS[kind], 0.1, 0.7, nns, P(out), None)
     ref = O.calc_loss_sampled(pred[None].astype(np.float64), table[pos][None].astype(np.float64),
-                              table[neg][None].astype(np.float64), kind, k, 1.0, 0.1)[0]
+                              table[neg][None].astype(np.float64), kind, nns, 0.7, 0.1)[0]
     ref[pos == 0] = 0
     np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=1e-4, atol=1e-5)
 
@@ -390,10 +391,10 @@ def debug_logits_bf16(lib, hd, wt, bd):
     return out
 
 
-# epilogue variants of the fused CE+rank sweep (HTCN_K4_EPI): the default (= "304") is the packed f32x2 epilogue with 1/4 of
-# the exponentials on the FMA pipe (degree-3 polynomial, 1e-4 per term) and the sign-bit rank count; "4" = the same with
-# the strict FSET compare; "104" = degree-2 polynomial (2e-3 per term, a tenth of the bf16 tier's 2e-2 bar); "-1" = the
-# scalar epilogue.
+# epilogue variants of the fused CE+rank sweep (HTCN_K4_EPI): the default (= "4") is the packed f32x2 epilogue with 1/4 of
+# the exponentials on the FMA pipe (degree-3 polynomial, 1e-4 per term) and the STRICT FSET compare (rank == #{z > z_y} on
+# the swept logits, bit for bit); "304" = the opt-in sign-bit rank count (3.7% faster, may miss a logit one ulp above the
+# target); "104" = degree-2 polynomial (2e-3 per term, a tenth of the bf16 tier's 2e-2 bar); "-1" = the scalar epilogue.
 @pytest.mark.parametrize("epi,tol", [(None, 1e-4), ("4", 1e-4), ("304", 1e-4), ("104", 1e-3), ("-1", 1e-4)])
 @pytest.mark.parametrize("Q,N,n_split", [(128, 256, 1), (200, 1000, 1), (130, 20778, 7), (5, 77, 1), (300, 4099, 3)])
 def test_k4_bf16_tcgen05(lib, Q, N, n_split, epi, tol, monkeypatch):
@@ -429,12 +430,12 @@ def test_k4_bf16_tcgen05(lib, Q, N, n_split, epi, tol, monkeypatch):
     lib.call("htcn_score_finish", P(pm), P(ps), P(pc), n_split, Q, P(yd), P(zy), P(loss_row), P(rank_row), None)
     ref_loss = O.softmax_cross_entropy_with_logits(y, z_gpu.astype(np.float64))
     np.testing.assert_allclose(loss_row.cpu().numpy(), ref_loss, rtol=tol, atol=tol / 10)
-    # strict count of the swept logits; the sign-bit rank count of the packed epilogue (default, "304") may miss a logit
+    # strict count of the swept logits; the sign-bit rank count of the packed epilogue (opt-in, "304") may miss a logit
     # that is exactly ONE ulp above the target and nothing else (k4_score_bf16.cu: kSignRank)
     strict = (z_gpu > zy_h[:, None]).sum(1)
     one_ulp = (z_gpu == np.nextafter(zy_h, np.float32(np.inf))[:, None]).sum(1)
     got_rank = rank_row.cpu().numpy()
-    if epi in ("4", "104", "-1"):
+    if epi in (None, "4", "104", "-1"):
         np.testing.assert_array_equal(got_rank, strict)
     else:
         assert ((got_rank <= strict) & (got_rank >= strict - one_ulp)).all(), (got_rank - strict)
@@ -445,7 +446,7 @@ def test_k4_bf16_tcgen05(lib, Q, N, n_split, epi, tol, monkeypatch):
         np.testing.assert_array_equal(got_rank, want)
     # rank-only and CE-only specialisations agree with the fused one
     _, _, _, pc2, _, _ = run_score(lib, hd, wt, bd, yd, lib.SCORE_RANK, 0, n_split, precision=lib.HTCN_BF16, zy_in=zy)
-    if epi in ("4", "104", "-1"):
+    if epi in (None, "4", "104", "-1"):
         assert torch.equal(pc2.sum(0), pc.sum(0))
     else:
         d = (pc2.sum(0) - pc.sum(0)).cpu().numpy()
@@ -492,6 +493,56 @@ def test_k4_bf16_ce_overflow_rows_are_repaired(lib):
     assert int(cnt.item()) == int(overflowed.sum())
     np.testing.assert_array_equal(after[~overflowed], before[~overflowed])       # finite rows untouched
     np.testing.assert_allclose(after, ref, rtol=1e-4, atol=1e-4)
+
+
+def test_k4_bf16_sharded_ce_dominant_logit_in_another_shard(lib):
+    """catalog-sharded CE (hiertcn_b200/dist.py): the target lives in shard A, one logit ~100 nats above it in shard B.
+    Shard B's target-referenced partial sum overflows (+inf); htcn_score_ce_repair_shard rewrites that shard's partials as
+    an exact (max, sum exp) pair before the exchange, and the cross-shard merge of htcn_score_finish comes out finite and
+    equal to the unsharded log-sum-exp."""
+    rng = np.random.default_rng(5)
+    Q, N, ns = 140, 2048, 2
+    bounds = [0, 1024, N]
+    hout = O.bf16_round(rng.normal(size=(Q, 128)).astype(np.float32) * 0.3)
+    hout[:, 0] = 1.0
+    w_out = O.bf16_round((rng.normal(size=(128, N)) * 0.3).astype(np.float32))
+    w_out[0, :] = 0.0
+    b_out = np.zeros(N, np.float32)
+    b_out[1500] = 100.0                                                   # every row: z[1500] ~ 100 + noise, in shard B
+    y = rng.integers(1, 1024, size=Q).astype(np.int32)                    # every target in shard A
+    wt = torch.empty((N, lib.WT_PITCH_BF16), dtype=torch.bfloat16, device="cuda")
+    hd, bd, yd, w_out_d = dev(hout).to(torch.bfloat16), dev(b_out), dev(y), dev(w_out)
+    lib.call("htcn_prepare_wout", P(w_out_d), P(bd), N, P(wt), lib.HTCN_BF16, None)
+    z_gpu = debug_logits_bf16(lib, hd, wt, bd).cpu().numpy().astype(np.float64)
+    ref = O.softmax_cross_entropy_with_logits(y, z_gpu)
+    zy = torch.zeros(Q, dtype=torch.float32, device="cuda")
+    for s in range(2):
+        lib.call("htcn_target_logit", P(hd), lib.HTCN_BF16, Q, P(wt[bounds[s]:bounds[s + 1]]), None, bounds[s + 1] - bounds[s],
+                 bounds[s], P(yd), P(zy), None)
+    parts, fixed = [], []
+    for s in range(2):
+        wsh = wt[bounds[s]:bounds[s + 1]]
+        _, pm, ps, pc, _, _ = run_score(lib, hd, wsh, bd, yd, lib.SCORE_CE | lib.SCORE_RANK, 0, ns, n0=bounds[s],
+                                        precision=lib.HTCN_BF16, zy_in=zy)
+        parts.append((pm.clone(), ps.clone(), pc))
+        cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+        lib.call("htcn_score_ce_repair_shard", P(hd), lib.HTCN_BF16, Q, P(wsh), bounds[s + 1] - bounds[s], P(pm), P(ps), ns,
+                 P(cnt), None)
+        fixed.append((pm, ps, pc, int(cnt.item())))
+    assert fixed[0][3] == 0 and fixed[1][3] == Q                          # only shard B needed the redo, for every row
+    assert torch.equal(fixed[0][0], parts[0][0]) and torch.equal(fixed[0][1], parts[0][1])
+
+    def merged(ps_list):
+        pm = torch.cat([p[0] for p in ps_list]); ps = torch.cat([p[1] for p in ps_list]); pc = torch.cat([p[2] for p in ps_list])
+        lr = torch.empty(Q, dtype=torch.float32, device="cuda"); rr = torch.empty(Q, dtype=torch.float32, device="cuda")
+        lib.call("htcn_score_finish", P(pm), P(ps), P(pc), pm.shape[0], Q, P(yd), P(zy), P(lr), P(rr), None)
+        return lr.cpu().numpy(), rr.cpu().numpy()
+
+    raw, _ = merged(parts)
+    assert not np.isfinite(raw).any()                                     # without the repair the batch mean is poisoned
+    got, rk = merged(fixed)
+    np.testing.assert_allclose(got, ref, rtol=1e-4, atol=1e-4)
+    np.testing.assert_array_equal(rk, (z_gpu > z_gpu[np.arange(Q), y][:, None]).sum(1))
 
 
 @pytest.mark.parametrize("spike", [100.0, -100.0])

@@ -261,3 +261,30 @@ def test_device_batcher_equals_host_loader(precision):
             off += w
     res = evaluate_hier(model, DeviceBatcher(a, data, passes=1), max_batches=2)
     assert res["batches"] == 2 and np.isfinite(res["loss"])
+    # a FRESH model whose first call is the staged path (no host batch ever staged through it): the pinned result sets
+    # must exist without stage() having run
+    fresh = HierTCN(a, None, precision=precision).build()
+    res2 = evaluate_hier(fresh, DeviceBatcher(a, data, passes=1), max_batches=2)
+    assert res2["batches"] == 2 and abs(res2["loss"] - res["loss"]) <= 1e-6 * abs(res["loss"])
+
+
+def test_stale_scores_handle_raises_and_shard_model_refuses_full_scoring():
+    from hiertcn_b200 import _cabi as cabi
+    from hiertcn_b200.args import make_args
+    from hiertcn_b200.dist import make_sharded_model
+    from hiertcn_b200.model_hier import HierTCN
+    x, y, m, s0, w = small_case(B=4, S=2, L=5, N=600, seed=2)
+    a = make_args(["--item_num", "600"])
+    model = HierTCN(a, w, precision="f32").build()
+    sc1, _ = model.forward(x, y, m, s0)
+    l1 = float(model.loss(sc1)["scalars"][0].item())
+    sc2, _ = model.forward([v[::-1].copy() for v in x], [v[::-1].copy() for v in y], [v[::-1].copy() for v in m], s0[::-1].copy())
+    with pytest.raises(cabi.HtcnError, match="stale"):
+        model.loss(sc1)                                  # its hout workspace now holds the second batch
+    with pytest.raises(cabi.HtcnError, match="stale"):
+        sc1.materialize()
+    assert abs(float(model.loss(sc2)["scalars"][0].item()) - l1) <= 1e-5 * abs(l1)      # user order does not matter
+    shard, n0, n1 = make_sharded_model(a, w, 1, 2, "f32")
+    sc3, _ = shard.forward(x, y, m, s0)
+    with pytest.raises(cabi.HtcnError, match="shard"):
+        shard.loss(sc3)
