@@ -28,7 +28,7 @@ _ip = C.POINTER(C.c_int32)         # host int array
 # name -> argtypes; every function returns int32 status unless noted.  Keep in sync with include/htcn.h
 # (tests/test_cabi.py parses the header and compares).
 SIGNATURES = {
-    "htcn_gather_meanpool": [_p, _p, _i, _p, _p, _ip, _i, _i, _i, _p, _i, _p, _p],
+    "htcn_gather_meanpool": [_p, _i, _p, _i, _p, _p, _ip, _i, _i, _i, _p, _i, _p, _p],
     "htcn_gru_sessions": [_p, _p, _p, _pp, _pp, _pp, _pp, _i, _p, _i, _i, _i, _p, _p, _p, _p, _p],
     "htcn_tcn_forward": [_p, _i, _i, _p, _p, _pp, _pp, _i, _i, _ip, _i, _i, _i, _p, _p, _i, _p, _p],
     "htcn_prepare_wout": [_p, _p, _i, _p, _i, _p],
@@ -40,6 +40,7 @@ SIGNATURES = {
     "htcn_score_ce_repair": [_p, _i, _i, _p, _i, _p, _p, _p, _p],
     "htcn_score_ce_repair_shard": [_p, _i, _i, _p, _i, _p, _p, _i, _p, _p],
     "htcn_score_topk": [_p, _i, _i, _p, _p, _i, _i, _i, _i, _p, C.c_int64, _p, _p, _p, _p],
+    "htcn_score_ce_rank_topk_fused": [_p, _i, _i, _p, _p, _i, _i, _p, _p, _i, _i, _p, C.c_int64, _p, _p, _p, _p, _p, _p, _p],
     "htcn_loss_metrics_reduce": [_p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p],
     "htcn_sampled_rank_loss": [_p, _i, _i, _p, _p, _p, _i, _i, _f, _f, _i, _p, _p],
     "htcn_calc_score": [_p, _i, _i, _p, _p, _i, _i, _p, _p],
@@ -98,7 +99,7 @@ def load(path: str | None = None):
 LAUNCHES_PER_CALL = {"htcn_gather_meanpool": 2, "htcn_gru_sessions": 1, "htcn_tcn_forward": 0,
                      "htcn_prepare_wout": 1, "htcn_score_ce_rank_topk": 2, "htcn_score_logits": 1,
                      "htcn_target_logit": 1, "htcn_score_finish": 1, "htcn_topk_merge": 1, "htcn_score_topk": 5, "htcn_score_ce_repair": 1,
-                     "htcn_score_ce_repair_shard": 1,
+                     "htcn_score_ce_repair_shard": 1, "htcn_score_ce_rank_topk_fused": 6,
                      "htcn_loss_metrics_reduce": 2, "htcn_sampled_rank_loss": 1, "htcn_calc_score": 1,
                      # training step (the per-call counts of the multi-launch entry points are added by the caller)
                      "htcn_loss_row_weights": 1, "htcn_score_ce_backward": 1, "htcn_gru_sessions_train": 1,

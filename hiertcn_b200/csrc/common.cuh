@@ -140,4 +140,38 @@ struct RowHeap {
   }
 };
 
+// ---- (score desc, index asc) = tf.nn.top_k order (loss.py:120) as ONE descending 64-bit key ---------------------------
+// high word: order-preserving image of the score; low word: ~index.  Key 0 = empty slot (sorts last).
+__device__ __forceinline__ unsigned long long topk_key(float v, int idx) {
+  if (v == 0.f) v = 0.f;                                     // -0.0 and +0.0 compare equal: one key for both
+  const uint32_t u = __float_as_uint(v);
+  const uint32_t ord = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  return ((unsigned long long)ord << 32) | (uint32_t)(~idx);
+}
+__device__ __forceinline__ float topk_key_val(unsigned long long key) {
+  const uint32_t ord = (uint32_t)(key >> 32);
+  return __uint_as_float((ord & 0x80000000u) ? (ord & 0x7FFFFFFFu) : ~ord);
+}
+__device__ __forceinline__ int topk_key_idx(unsigned long long key) { return (int)(~(uint32_t)key); }
+
+// block-wide bitonic sort of n_pad (power of two) keys in shared memory, DESCENDING; every thread of the CTA calls it
+// (ends with a __syncthreads)
+__device__ __forceinline__ void bitonic_sort_desc(unsigned long long* keys, int n_pad) {
+  for (int size = 2; size <= n_pad; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = threadIdx.x; t < (n_pad >> 1); t += blockDim.x) {
+        const int lo = 2 * t - (t & (stride - 1));           // lower element of the pair
+        const int hi = lo + stride;
+        const bool desc = (lo & size) == 0;
+        const unsigned long long a = keys[lo], b = keys[hi];
+        if ((a < b) == desc) {
+          keys[lo] = b;
+          keys[hi] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
 }  // namespace htcn

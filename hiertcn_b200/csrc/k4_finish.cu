@@ -14,7 +14,8 @@ int32_t target_logit_bf16(const void* hout, const void* wt, const float* b_out, 
                           int n_items, int n0, float* zy, cudaStream_t st);
 long long topk_workspace_bytes_bf16(int Q, int n_items, int k, int n_split);
 int32_t score_topk_bf16(const void* hout, int Q, const void* wt, int n_items, int n0, int k, int n_split, void* workspace,
-                        long long workspace_bytes, float* out_val, int* out_idx, int* overflow_rows, cudaStream_t st);
+                        long long workspace_bytes, float* out_val, int* out_idx, int* overflow_rows, cudaStream_t st,
+                        const ScoreArgs* ce = nullptr);
 
 // the two-pass method needs >= k finite column groups of 256 items per row to produce a threshold
 static bool topk_two_pass_ok(int precision, int n_items, int k) { return precision == HTCN_BF16 && n_items >= 1024 * k; }
@@ -182,6 +183,37 @@ ce_repair_bf16_kernel(const __nv_bfloat16* __restrict__ hout, int Q, const __nv_
       if (repaired) atomicAdd(repaired, 1);
     }
     }
+  }
+}
+
+// ---- top-k merge, sort network: one CTA per row, bitonic sort of 64-bit keys in shared memory ---------------------------
+// key = order-preserving image of the score in the high word, ~index in the low word: DESCENDING key order is
+// (score desc, index asc) = tf.nn.top_k order (loss.py:120).  Empty slots (idx < 0) carry key 0 and sort last.
+// n_pad = next power of two >= n_part*k; O(n log^2 n) compare-exchanges instead of the O(n^2) counting kernel below
+// (9 shards x 100: 28 k vs 810 k per row), and the lists are read and written once, coalesced.
+__global__ void __launch_bounds__(256)
+topk_merge_sort_kernel(const float* __restrict__ pv, const int* __restrict__ pi, int n_part, int Q, int k, int n_pad,
+                       float* __restrict__ ov, int* __restrict__ oi) {
+  extern __shared__ unsigned long long keys[];
+  const int n = n_part * k;
+  const int q = blockIdx.x;
+  for (int i = threadIdx.x; i < n_pad; i += blockDim.x) {
+    unsigned long long key = 0ull;
+    if (i < n) {
+      const int p = i / k, s = i % k;
+      const long long o = ((long long)p * Q + q) * k + s;
+      const int ii = pi[o];
+      if (ii >= 0) key = topk_key(pv[o], ii);
+    }
+    keys[i] = key;
+  }
+  __syncthreads();
+  bitonic_sort_desc(keys, n_pad);
+  for (int i = threadIdx.x; i < k; i += blockDim.x) {
+    const unsigned long long key = i < n_pad ? keys[i] : 0ull;
+    const bool empty = key == 0ull;
+    ov[(long long)q * k + i] = empty ? -INFINITY : topk_key_val(key);
+    oi[(long long)q * k + i] = empty ? -1 : topk_key_idx(key);
   }
 }
 
@@ -416,6 +448,32 @@ extern "C" int32_t htcn_score_topk(const void* hout, int32_t precision, int32_t 
   return htcn_topk_merge(tv, ti, ns, Q, k, out_val, out_idx, stream);
 }
 
+extern "C" int32_t htcn_score_ce_rank_topk_fused(const void* hout, int32_t precision, int32_t Q, const void* w_out_t,
+                                                 const float* b_out, int32_t n_items, int32_t n0, const int32_t* y_id,
+                                                 const float* target_logit, int32_t k, int32_t n_split, void* workspace,
+                                                 int64_t workspace_bytes, float* part_max, float* part_sum,
+                                                 int32_t* part_cnt, float* out_val, int32_t* out_idx,
+                                                 int32_t* overflow_rows, void* stream) {
+  HTCN_REQUIRE(hout && w_out_t && y_id && target_logit && part_max && part_sum && part_cnt && out_val && out_idx && workspace,
+               "score_fused: NULL pointer");
+  HTCN_REQUIRE(Q > 0 && n_items > 0 && n_split >= 1 && k >= 1 && k <= HTCN_MAX_TOPK, "score_fused: Q=%d n_items=%d k=%d", Q,
+               n_items, k);
+  if (topk_two_pass_ok(precision, n_items, k)) {
+    HTCN_REQUIRE(workspace_bytes >= topk_workspace_bytes_bf16(Q, n_items, k, n_split), "score_fused: workspace too small");
+    ScoreArgs a{hout, w_out_t, b_out, y_id, target_logit, part_max, part_sum, part_cnt, nullptr, nullptr,
+                Q, n_items, n0, 0, n_split, HTCN_SCORE_CE | HTCN_SCORE_RANK};
+    return score_topk_bf16(hout, Q, w_out_t, n_items, n0, k, n_split, workspace, workspace_bytes, out_val, out_idx,
+                           overflow_rows, as_stream(stream), &a);
+  }
+  // fp32 tier / small shards: the loss sweep and the heap top-k as separate sweeps
+  int32_t rc = htcn_score_ce_rank_topk(hout, precision, Q, w_out_t, b_out, n_items, n0, y_id, const_cast<float*>(target_logit),
+                                       1, HTCN_SCORE_CE | HTCN_SCORE_RANK, 0, n_split, part_max, part_sum, part_cnt, nullptr,
+                                       nullptr, stream);
+  if (rc) return rc;
+  return htcn_score_topk(hout, precision, Q, w_out_t, b_out, n_items, n0, k, n_split, workspace, workspace_bytes, out_val,
+                         out_idx, overflow_rows, stream);
+}
+
 extern "C" int32_t htcn_score_finish(const float* part_max, const float* part_sum, const int32_t* part_cnt,
                                      int32_t n_part, int32_t Q, const int32_t* y_id, const float* target_logit,
                                      float* loss_row, float* rank_row, void* stream) {
@@ -462,6 +520,19 @@ extern "C" int32_t htcn_score_ce_repair_shard(const void* hout, int32_t precisio
 extern "C" int32_t htcn_topk_merge(const float* part_val, const int32_t* part_idx, int32_t n_part, int32_t Q,
                                    int32_t k, float* out_val, int32_t* out_idx, void* stream) {
   HTCN_REQUIRE(part_val && part_idx && out_val && out_idx && n_part >= 1 && Q > 0 && k >= 1, "topk_merge: bad args");
+  {
+    int n_pad = 2;
+    while (n_pad < n_part * k) n_pad <<= 1;
+    if (n_pad <= 16384) {                                  // 128 KB of keys: the sort network
+      const size_t smem_sort = (size_t)n_pad * 8;
+      HTCN_CUDA(cudaFuncSetAttribute(topk_merge_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sort));
+      const int threads = n_pad / 2 < 256 ? (n_pad / 2 < 32 ? 32 : n_pad / 2) : 256;
+      topk_merge_sort_kernel<<<Q, threads, smem_sort, as_stream(stream)>>>(part_val, part_idx, n_part, Q, k, n_pad, out_val,
+                                                                        out_idx);
+      HTCN_LAUNCH_CHECK("topk_merge_sort");
+      return HTCN_OK;
+    }
+  }
   const size_t smem = (size_t)n_part * k * 8;
   HTCN_REQUIRE(smem <= 200 * 1024, "topk_merge: n_part*k=%d candidates exceed shared memory", n_part * k);
   HTCN_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -121,12 +121,15 @@ __device__ __forceinline__ void add_sign_bit(uint32_t& acc, float x) {      // a
 }
 constexpr float kPolyRange = 125.0f;             // |t| the exponent-field arithmetic of ex2_poly2 handles
 // `zyl` = z_y * log2e: rounded to nearest (strict-compare variants) or UP (kSign)
-template <bool kCE, bool kRank, int kPolyPairs, bool kDeg2, bool kSign>
+// kGMax: also keep the running maximum of the logits (pass 1 of the two-pass top-k fused into the loss sweep): one FMNMX3
+// per logit pair.
+template <bool kCE, bool kRank, int kPolyPairs, bool kDeg2, bool kSign, bool kGMax = false>
 __device__ __forceinline__ void ce_rank_chunk_packed(const uint32_t (&r)[32], float zy, float zyl, float2 (&sum2)[2],
-                                                     float2 (&cf2)[2], float& amax, uint32_t (&cnt2)[2]) {
+                                                     float2 (&cf2)[2], float& amax, uint32_t (&cnt2)[2], float (&gm2)[2]) {
 #pragma unroll
   for (int p = 0; p < 16; ++p) {
     const float2 z = make_float2(__uint_as_float(r[2 * p]), __uint_as_float(r[2 * p + 1]));
+    if (kGMax) gm2[p & 1] = fmaxf(fmaxf(gm2[p & 1], z.x), z.y);                              // one FMNMX3
     const bool poly = ((p + 1) * kPolyPairs) / 16 != (p * kPolyPairs) / 16;
     if (kSign) {
       const float2 tn = ffma2(z, make_float2(-kLog2e, -kLog2e), make_float2(zyl, zyl));     // -(t): sign bit set <=> z above z_y
@@ -306,7 +309,7 @@ k4_score_bf16(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
 
       // one 32-column chunk held in registers; `c` = column offset inside this warp's slice
       auto process = [&](const uint32_t (&r)[32], int c, int lim, int jbase) {
-        if ((kGMax || kFilter) && c + 32 <= lim) {              // two-pass top-k: one FMNMX per logit
+        if ((kGMax || kFilter) && !(kCE || kRank || kTopk || kDump) && c + 32 <= lim) {   // two-pass top-k: one FMNMX per logit
           float m0 = __uint_as_float(r[0]), m1 = __uint_as_float(r[1]), m2 = __uint_as_float(r[2]), m3 = __uint_as_float(r[3]);
 #pragma unroll
           for (int u = 4; u < 32; u += 4) {
@@ -336,6 +339,7 @@ k4_score_bf16(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
               sum4[u & 3] += ((u % kPolyEvery) == kPolyEvery - 1) ? ex2_poly(t) : ex2_approx(t);
             }
             if (kRank) cf[u & 3] += set_gt_f(z, zy);
+            if (kGMax) gm = fmaxf(gm, z);                       // pass 1 fused into the loss sweep
             if (kTopk) {
               if (z > thr) thr = heap.replace_root(z, a.n0 + jbase + c + u);
             }
@@ -456,8 +460,11 @@ struct alignas(1024) ScoreSmem2 {
 template <unsigned kFlags>
 __global__ void __launch_bounds__(64 + 32 * 4 * cg2_slices<kFlags>(), 1)
 k4_score_bf16_cg2(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                  const __grid_constant__ CUtensorMap tmap_bb, ScoreArgs a, float* __restrict__ dump) {
+                  const __grid_constant__ CUtensorMap tmap_bb, ScoreArgs a, float* __restrict__ dump, TopkAux aux) {
   constexpr bool kCE = kFlags & HTCN_SCORE_CE, kRank = kFlags & HTCN_SCORE_RANK, kDump = kFlags & kModeDump;
+  // two-pass top-k (htcn_score_topk): pass 1 = per-row maxima of column groups -- on its own, or FUSED into the CE / rank
+  // sweep (htcn_score_ce_rank_topk_fused: loss + rank + top-k in two sweeps instead of three); pass 2 = candidate filter
+  constexpr bool kGMax = kFlags & kModeGroupMax, kFilter = kFlags & kModeFilter;
   constexpr int kPolyEvery = (kFlags & kModePoly4) ? 4 : (kFlags & kModePoly8) ? 8 : 0x40000000;
   constexpr bool kPacked = (kFlags & kModePacked) && !kDump;
   constexpr bool kSign = kPacked && (kFlags & kSignRank);
@@ -557,6 +564,26 @@ k4_score_bf16_cg2(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       zy = a.zy[q0 + row];
       zyl = kSign ? __fmul_ru(zy, kLog2e) : zy * kLog2e;         // kSign: threshold rounded UP (see kSignRank)
     }
+    float gm2[2] = {-INFINITY, -INFINITY};                       // running maxima of the current column group (pass 1)
+    float row_thr = INFINITY;                                    // candidate threshold of this row (pass 2)
+    if (kFilter && row_ok) row_thr = aux.thr[q0 + row];
+    auto append = [&](float z, int j) {                          // rare path of pass 2
+      const int pos = atomicAdd(aux.cand_cnt + q0 + row, 1);
+      if (pos < aux.cap) {
+        aux.cand_val[(long long)(q0 + row) * aux.cap + pos] = z;
+        aux.cand_idx[(long long)(q0 + row) * aux.cap + pos] = j;
+      } else {
+        row_thr = INFINITY;        // the list overflowed (mass ties): the row is redone by the heap path, stop appending
+      }
+    };
+    auto flush_group = [&](int i) {                              // a column group = this warp's slice of kGroupTiles tiles
+      if (kGMax && ((i % kGroupTiles) == kGroupTiles - 1 || i == n_tiles - 1)) {
+        if (row_ok)
+          aux.gmax[(long long)(q0 + row) * aux.ng_total + split * aux.ng_per_split + (i / kGroupTiles) * kSlices + half] =
+              fmaxf(gm2[0], gm2[1]);
+        gm2[0] = gm2[1] = -INFINITY;
+      }
+    };
     for (int i = 0; i < n_tiles; ++i) {
       const int buf = i & 1;
       const int j0 = (t_begin + i) * BN;
@@ -576,12 +603,13 @@ k4_score_bf16_cg2(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(&sm.t_empty[buf], 0);   // the leader's barrier
           }
-          ce_rank_chunk_packed<kCE, kRank, kPolyPairs, (kFlags & kPolyDeg2) != 0, kSign>(r, zy, zyl, sum2, cf2, amax, cnt2);
+          ce_rank_chunk_packed<kCE, kRank, kPolyPairs, (kFlags & kPolyDeg2) != 0, kSign, kGMax>(r, zy, zyl, sum2, cf2, amax, cnt2, gm2);
         }
         if (kRank && (i & 4095) == 4095) {
           cnt += (int)((cf2[0].x + cf2[0].y) + (cf2[1].x + cf2[1].y));
           cf2[0] = cf2[1] = make_float2(0.f, 0.f);
         }
+        flush_group(i);
         continue;
       }
       const int lim = a.n_items - j0 - col0;
@@ -597,7 +625,24 @@ k4_score_bf16_cg2(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           if (lane == 0) mbar_arrive_cluster(&sm.t_empty[buf], 0);   // the leader's barrier
         }
         if (kPacked && c + 32 <= lim) {
-          ce_rank_chunk_packed<kCE, kRank, kPolyPairs, (kFlags & kPolyDeg2) != 0, kSign>(r, zy, zyl, sum2, cf2, amax, cnt2);
+          ce_rank_chunk_packed<kCE, kRank, kPolyPairs, (kFlags & kPolyDeg2) != 0, kSign, kGMax>(r, zy, zyl, sum2, cf2, amax, cnt2, gm2);
+        } else if ((kGMax || kFilter) && !(kCE || kRank || kDump) && c + 32 <= lim) {
+          // stand-alone passes of the two-pass top-k: one FMNMX per logit
+          float m0 = __uint_as_float(r[0]), m1 = __uint_as_float(r[1]), m2 = __uint_as_float(r[2]), m3 = __uint_as_float(r[3]);
+#pragma unroll
+          for (int u = 4; u < 32; u += 4) {
+            m0 = fmaxf(m0, __uint_as_float(r[u]));
+            m1 = fmaxf(m1, __uint_as_float(r[u + 1]));
+            m2 = fmaxf(m2, __uint_as_float(r[u + 2]));
+            m3 = fmaxf(m3, __uint_as_float(r[u + 3]));
+          }
+          const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+          if (kGMax) gm2[0] = fmaxf(gm2[0], m);
+          if (kFilter && m >= row_thr) {                         // some logit of this chunk is a candidate (rare)
+#pragma unroll
+            for (int u = 0; u < 32; ++u)
+              if (__uint_as_float(r[u]) >= row_thr) append(__uint_as_float(r[u]), a.n0 + jbase + c + u);
+          }
         } else if (c + 32 <= lim) {
 #pragma unroll
           for (int u = 0; u < 32; ++u) {
@@ -610,6 +655,7 @@ k4_score_bf16_cg2(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
               sum4[u & 3] += ((u % kPolyEvery) == kPolyEvery - 1) ? ex2_poly(t) : ex2_approx(t);
             }
             if (kRank) cf[u & 3] += set_gt_f(z, zy);
+            if (kGMax) gm2[u & 1] = fmaxf(gm2[u & 1], z);
           }
         } else if (c < lim) {
 #pragma unroll 1
@@ -624,10 +670,13 @@ k4_score_bf16_cg2(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
               }
               if (kCE) sum4[0] += ex2_approx(fmaf(z, kLog2e, -zyl));
               if (kRank) cf[0] += set_gt_f(z, zy);
+              if (kGMax) gm2[0] = fmaxf(gm2[0], z);
+              if (kFilter && z >= row_thr) append(z, a.n0 + jbase + c + u);
             }
           }
         }
       }
+      flush_group(i);
       if (kRank) {
         cnt += (int)((cf[0] + cf[1]) + (cf[2] + cf[3]));
         cf[0] = cf[1] = cf[2] = cf[3] = 0.f;
@@ -809,7 +858,7 @@ static int32_t launch_score(const ScoreArgs& a, float* dump, cudaStream_t st, co
 }
 
 template <unsigned kFlags>
-static int32_t launch_score_cg2(const ScoreArgs& a, float* dump, cudaStream_t st) {
+static int32_t launch_score_cg2(const ScoreArgs& a, float* dump, cudaStream_t st, const TopkAux& aux = TopkAux{}) {
   CUtensorMap ta, tb, tbb;
   int32_t rc = make_tmap_bf16(&ta, a.hout, (uint64_t)a.Q, kDim, kDim, 64, kBM, 128);
   if (rc) return rc;
@@ -832,15 +881,15 @@ static int32_t launch_score_cg2(const ScoreArgs& a, float* dump, cudaStream_t st
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  HTCN_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tbb, a, dump));
+  HTCN_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tbb, a, dump, aux));
   return HTCN_OK;
 }
 
 static int cta_group_env() {
   // CTA pairs sharing the B operand: +4.4% on the power-capped cfg2 sweep (837 -> 874 TFLOP/s); HTCN_K4_CTA_GROUP=1
   // selects the single-CTA kernel
-  static const int cg = [] { const char* e = getenv("HTCN_K4_CTA_GROUP"); return e ? atoi(e) : 2; }();
-  return cg;
+  const char* e = getenv("HTCN_K4_CTA_GROUP");      // read per call: the tests switch variants in-process
+  return e ? atoi(e) : 2;
 }
 
 int32_t score_bf16(const ScoreArgs& a, cudaStream_t st) {
@@ -975,35 +1024,24 @@ topk_threshold_kernel(const float* __restrict__ gmax, int n, int k, float* __res
   }
 }
 
-// exact top-k of each row's candidate list, (score desc, index asc); rows whose list overflowed are counted
-__global__ void __launch_bounds__(128)
-topk_select_kernel(const float* __restrict__ cv, const int* __restrict__ ci, const int* __restrict__ cnt, int cap, int k,
-                   float* __restrict__ ov, int* __restrict__ oi, int* __restrict__ overflow_rows) {
-  extern __shared__ float sm_sel[];
-  float* v = sm_sel;
-  int* id = reinterpret_cast<int*>(sm_sel + cap);
+// exact top-k of each row's candidate list, (score desc, index asc); rows whose list overflowed are counted.
+// Bitonic sort of the (<= cap, padded to a power of two) candidates as 64-bit keys in shared memory.
+__global__ void __launch_bounds__(256)
+topk_select_kernel(const float* __restrict__ cv, const int* __restrict__ ci, const int* __restrict__ cnt, int cap, int n_pad,
+                   int k, float* __restrict__ ov, int* __restrict__ oi, int* __restrict__ overflow_rows) {
+  extern __shared__ unsigned long long sel_keys[];
   const int q = blockIdx.x;
   const int total = cnt[q];
   const int n = total < cap ? total : cap;
   if (threadIdx.x == 0 && total > cap) atomicAdd(overflow_rows, 1);
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    v[i] = cv[(long long)q * cap + i];
-    id[i] = ci[(long long)q * cap + i];
-  }
-  for (int i = threadIdx.x; i < k; i += blockDim.x) {
-    ov[(long long)q * k + i] = -INFINITY;
-    oi[(long long)q * k + i] = -1;
-  }
+  for (int i = threadIdx.x; i < n_pad; i += blockDim.x)
+    sel_keys[i] = i < n ? topk_key(cv[(long long)q * cap + i], ci[(long long)q * cap + i]) : 0ull;
   __syncthreads();
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const float vi = v[i];
-    const int ii = id[i];
-    int pos = 0;
-    for (int j = 0; j < n; ++j) pos += (v[j] > vi || (v[j] == vi && id[j] < ii)) ? 1 : 0;
-    if (pos < k) {
-      ov[(long long)q * k + pos] = vi;
-      oi[(long long)q * k + pos] = ii;
-    }
+  bitonic_sort_desc(sel_keys, n_pad);
+  for (int i = threadIdx.x; i < k; i += blockDim.x) {
+    const unsigned long long key = i < n_pad ? sel_keys[i] : 0ull;
+    ov[(long long)q * k + i] = key ? topk_key_val(key) : -INFINITY;
+    oi[(long long)q * k + i] = key ? topk_key_idx(key) : -1;
   }
 }
 
@@ -1038,13 +1076,21 @@ static TopkPlan topk_plan(int Q, int n_items, int k, int n_split) {
 
 long long topk_workspace_bytes_bf16(int Q, int n_items, int k, int n_split) { return (long long)topk_plan(Q, n_items, k, n_split).bytes; }
 
+// `ce`: when non-NULL, pass 1 is FUSED into the CE + rank sweep described by *ce (its Q / n_items / n0 / hout / wt must be
+// those of this call; ce->n_split is overridden by the plan's): loss + rank + top-k cost two catalog sweeps, not three.
 int32_t score_topk_bf16(const void* hout, int Q, const void* wt, int n_items, int n0, int k, int n_split, void* workspace,
-                        long long workspace_bytes, float* out_val, int* out_idx, int* overflow_rows, cudaStream_t st) {
+                        long long workspace_bytes, float* out_val, int* out_idx, int* overflow_rows, cudaStream_t st,
+                        const ScoreArgs* ce) {
   const TopkPlan p = topk_plan(Q, n_items, k, n_split);
   if ((long long)p.bytes > workspace_bytes) {
     set_error("score_topk: workspace too small (%lld < %zu bytes)", workspace_bytes, p.bytes);
     return HTCN_ERR_INVALID;
   }
+  if (ce && p.n_split != n_split) {
+    set_error("score_fused: n_split=%d exceeds the number of 256-item tiles of the shard", n_split);
+    return HTCN_ERR_INVALID;
+  }
+  const bool cg2 = cta_group_env() == 2;
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   TopkAux aux{};
   aux.gmax = reinterpret_cast<float*>(ws + p.off_gmax);
@@ -1062,16 +1108,27 @@ int32_t score_topk_bf16(const void* hout, int Q, const void* wt, int n_items, in
   ScoreArgs a{};
   a.hout = hout; a.wt = wt; a.Q = Q; a.n_items = n_items; a.n0 = n0; a.n_split = p.n_split; a.k = 0;
   a.flags = kModeGroupMax;
-  int32_t rc = launch_score<256, kModeGroupMax>(a, nullptr, st, aux);
+  int32_t rc;
+  if (ce) {                      // fused: the loss sweep also records the group maxima (one FMNMX3 per logit pair more)
+    ScoreArgs f = *ce;
+    f.n_split = p.n_split;
+    constexpr unsigned kCRG = HTCN_SCORE_CE | HTCN_SCORE_RANK | kModeGroupMax;
+    rc = cg2 ? launch_score_cg2<kCRG | packed_flags(4)>(f, nullptr, st, aux)
+             : launch_score<256, kCRG>(f, nullptr, st, aux);
+  } else {
+    rc = cg2 ? launch_score_cg2<kModeGroupMax>(a, nullptr, st, aux) : launch_score<256, kModeGroupMax>(a, nullptr, st, aux);
+  }
   if (rc) return rc;
   topk_threshold_kernel<<<Q, 256, 0, st>>>(aux.gmax, p.ng_total, k, thr);
   HTCN_LAUNCH_CHECK("topk_threshold_kernel");
   a.flags = kModeFilter;
-  rc = launch_score<256, kModeFilter>(a, nullptr, st, aux);
+  rc = cg2 ? launch_score_cg2<kModeFilter>(a, nullptr, st, aux) : launch_score<256, kModeFilter>(a, nullptr, st, aux);
   if (rc) return rc;
-  const size_t smem = (size_t)p.cap * 8;
+  int n_pad = 2;
+  while (n_pad < p.cap) n_pad <<= 1;
+  const size_t smem = (size_t)n_pad * 8;
   HTCN_CUDA(cudaFuncSetAttribute(topk_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  topk_select_kernel<<<Q, 128, smem, st>>>(aux.cand_val, aux.cand_idx, aux.cand_cnt, p.cap, k, out_val, out_idx, ovf);
+  topk_select_kernel<<<Q, 256, smem, st>>>(aux.cand_val, aux.cand_idx, aux.cand_cnt, p.cap, n_pad, k, out_val, out_idx, ovf);
   HTCN_LAUNCH_CHECK("topk_select_kernel");
   if (overflow_rows) HTCN_CUDA(cudaMemcpyAsync(overflow_rows, ovf, 4, cudaMemcpyDeviceToDevice, st));
   return HTCN_OK;

@@ -69,8 +69,10 @@ class ShardedCatalogScorer:
         need_t = (ce or rank_metric) and y_id is not None
         self._mark("start")
         # 1. every shard must see every query row
-        h_all = o.all_gather_rows(d, hout, W)                       # [W*Ql, 128]
-        y_all = o.all_gather_rows(d, y_id, W) if need_t else None
+        gather = (lambda t: t) if W == 1 else (lambda t: o.all_gather_rows(d, t, W))      # world 1: one shard, no exchange
+        exchange = (lambda t: t) if W == 1 else (lambda t: o.all_to_all_rows(d, t, W, Ql))
+        h_all = gather(hout)                                        # [W*Ql, 128]
+        y_all = gather(y_id) if need_t else None
         self._mark("allgather_queries")
         Q = W * Ql
         # 2. target logits: owner fills, all-reduce completes
@@ -79,7 +81,8 @@ class ShardedCatalogScorer:
             zy = o.zeros_f32(Q)
             o.target_logit(h_all, y_all, self.n0, self.n1, zy)
             self._mark("target_logit")
-            d.all_reduce(zy)
+            if W > 1:
+                d.all_reduce(zy)
             self._mark("allreduce_target")
         # 3. local sweep (+ exact redo of the rows whose target-referenced partial sum left fp32 range in THIS shard:
         #    the dominant logit of a row may live in another shard than its target)
@@ -93,10 +96,10 @@ class ShardedCatalogScorer:
         if need_t:
             for name in ("pm", "ps", "pc"):
                 if part.get(name) is not None:
-                    merged[name] = o.all_to_all_rows(d, part[name], W, Ql)      # [W*n_split, Ql]
+                    merged[name] = exchange(part[name])                          # [W*n_split, Ql]
         if k:
-            tv = o.all_to_all_rows(d, part["tv"], W, Ql)                         # [W*n_split, Ql, k]
-            ti = o.all_to_all_rows(d, part["ti"], W, Ql)
+            tv = exchange(part["tv"])                                            # [W*n_split, Ql, k]
+            ti = exchange(part["ti"])
         self._mark("alltoall_partials")
         # 5. merge
         if need_t:
@@ -163,7 +166,8 @@ class CudaScoreOps:
     def target_logit(self, h_all, y_all, n0, n1, zy):
         m = self.m
         self.cabi.call("htcn_target_logit", h_all.data_ptr(), m.act_dtype, h_all.shape[0], m.wt.data_ptr(),
-                       m.b_out.data_ptr(), n1 - n0, n0, y_all.data_ptr(), zy.data_ptr(), m.stream_ptr())
+                       m.b_out.data_ptr() if m.b_out is not None else None, n1 - n0, n0, y_all.data_ptr(), zy.data_ptr(),
+                       m.stream_ptr())
 
     def sweep(self, h_all, y_all, zy, n0, n1, k, n_split, ce, rank):
         torch, cabi, m = self.torch, self.cabi, self.m
@@ -172,11 +176,27 @@ class CudaScoreOps:
         P = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
         out = dict(pm=None, ps=None, pc=None, tv=None, ti=None)
         flags = (cabi.SCORE_CE if ce else 0) | (cabi.SCORE_RANK if rank else 0)
+        fused = bool(k) and ce and rank and getattr(self, "fuse_topk", True)
         if flags:
             out["pm"] = torch.empty((n_split, Q), dtype=f32, device=m.device) if ce else None
             out["ps"] = torch.empty((n_split, Q), dtype=f32, device=m.device) if ce else None
             out["pc"] = torch.empty((n_split, Q), dtype=i32, device=m.device) if rank else None
-            cabi.call("htcn_score_ce_rank_topk", h_all.data_ptr(), m.act_dtype, Q, m.wt.data_ptr(), m.b_out.data_ptr(),
+        if fused:
+            # loss + rank + top-k in two sweeps of the shard: the CE / rank sweep records the group maxima pass 1 of the
+            # two-pass top-k would need a sweep of its own for
+            nb = int(cabi.load().htcn_topk_workspace_bytes(m.act_dtype, Q, n1 - n0, k, n_split))
+            ws = torch.empty(nb, dtype=torch.uint8, device=m.device)
+            out["tv"] = torch.empty((1, Q, k), dtype=f32, device=m.device)
+            out["ti"] = torch.empty((1, Q, k), dtype=i32, device=m.device)
+            ovf = torch.zeros(1, dtype=i32, device=m.device)
+            cabi.call("htcn_score_ce_rank_topk_fused", h_all.data_ptr(), m.act_dtype, Q, m.wt.data_ptr(), P(m.b_out), n1 - n0,
+                      n0, y_all.data_ptr(), zy.data_ptr(), k, n_split, ws.data_ptr(), nb, P(out["pm"]), P(out["ps"]),
+                      P(out["pc"]), out["tv"].data_ptr(), out["ti"].data_ptr(), ovf.data_ptr(), m.stream_ptr())
+            if int(ovf.item()):              # mass ties overflowed a candidate list: the always-exact heap sweep
+                self._heap_topk(h_all, n0, n1, k, n_split, out)
+            return out
+        if flags:
+            cabi.call("htcn_score_ce_rank_topk", h_all.data_ptr(), m.act_dtype, Q, m.wt.data_ptr(), P(m.b_out),
                       n1 - n0, n0, y_all.data_ptr(), zy.data_ptr(), 1, flags, 0, n_split, P(out["pm"]), P(out["ps"]),
                       P(out["pc"]), None, None, m.stream_ptr())
         if k:
@@ -187,16 +207,23 @@ class CudaScoreOps:
             out["tv"] = torch.empty((1, Q, k), dtype=f32, device=m.device)
             out["ti"] = torch.empty((1, Q, k), dtype=i32, device=m.device)
             ovf = torch.zeros(1, dtype=i32, device=m.device)
-            cabi.call("htcn_score_topk", h_all.data_ptr(), m.act_dtype, Q, m.wt.data_ptr(), m.b_out.data_ptr(), n1 - n0, n0, k,
+            cabi.call("htcn_score_topk", h_all.data_ptr(), m.act_dtype, Q, m.wt.data_ptr(), P(m.b_out), n1 - n0, n0, k,
                       n_split, ws.data_ptr(), nb, out["tv"].data_ptr(), out["ti"].data_ptr(), ovf.data_ptr(), m.stream_ptr())
-            if int(ovf.item()):              # mass ties overflowed a candidate list: redo with the always-exact heap sweep
-                tv = torch.empty((n_split, Q, k), dtype=f32, device=m.device)
-                ti = torch.empty((n_split, Q, k), dtype=i32, device=m.device)
-                cabi.call("htcn_score_ce_rank_topk", h_all.data_ptr(), m.act_dtype, Q, m.wt.data_ptr(), m.b_out.data_ptr(),
-                          n1 - n0, n0, None, None, 1, cabi.SCORE_TOPK, k, n_split, None, None, None, tv.data_ptr(),
-                          ti.data_ptr(), m.stream_ptr())
-                cabi.call("htcn_topk_merge", tv.data_ptr(), ti.data_ptr(), n_split, Q, k, out["tv"].data_ptr(),
-                          out["ti"].data_ptr(), m.stream_ptr())
+            if int(ovf.item()):
+                self._heap_topk(h_all, n0, n1, k, n_split, out)
+        return out
+
+    def _heap_topk(self, h_all, n0, n1, k, n_split, out):
+        """one k-entry heap per row in shared memory: slower, but exact whatever the ties"""
+        torch, cabi, m = self.torch, self.cabi, self.m
+        Q = h_all.shape[0]
+        tv = torch.empty((n_split, Q, k), dtype=torch.float32, device=m.device)
+        ti = torch.empty((n_split, Q, k), dtype=torch.int32, device=m.device)
+        cabi.call("htcn_score_ce_rank_topk", h_all.data_ptr(), m.act_dtype, Q, m.wt.data_ptr(),
+                  m.b_out.data_ptr() if m.b_out is not None else None, n1 - n0, n0, None, None, 1, cabi.SCORE_TOPK, k, n_split,
+                  None, None, None, tv.data_ptr(), ti.data_ptr(), m.stream_ptr())
+        cabi.call("htcn_topk_merge", tv.data_ptr(), ti.data_ptr(), n_split, Q, k, out["tv"].data_ptr(), out["ti"].data_ptr(),
+                  m.stream_ptr())
         return out
 
     def finish(self, pm, ps, pc, y_id, zy_local):
@@ -218,6 +245,30 @@ class CudaScoreOps:
         cabi.call("htcn_topk_merge", tv.data_ptr(), ti.data_ptr(), n_part, Ql, k, ov.data_ptr(), oi.data_ptr(),
                   m.stream_ptr())
         return dict(topk_val=ov, topk_idx=oi)
+
+
+class CatalogTable:
+    """A catalog (shard) resident in HBM for scoring-only use -- BASELINE config 4: user embeddings in, CE / rank / top-k
+    out, no encoder.  Holds W_out^T in the scoring layout of ``htcn_prepare_wout`` ([n,144] bf16 with the bias folded in,
+    or [n,128] f32 + b_out) and exposes what ``CudaScoreOps`` reads from a model."""
+
+    def __init__(self, wt, b_out=None, precision="bf16", n_items=None):
+        from . import _cabi as cabi
+        import torch
+        cabi.load()
+        self.wt, self.b_out, self.precision = wt, b_out, precision
+        self.act_dtype = cabi.HTCN_BF16 if precision == "bf16" else cabi.HTCN_F32
+        self.device = wt.device
+        self.n_out = int(wt.shape[0])
+        self.N = int(n_items if n_items is not None else self.n_out)
+        self._torch = torch
+
+    def stream_ptr(self):
+        return self._torch.cuda.current_stream(self.device).cuda_stream
+
+    def rows(self, n0, n1):
+        """view of rows [n0, n1) as its own table (a shard of a replicated catalog shares the memory)"""
+        return CatalogTable(self.wt[n0:n1], None if self.b_out is None else self.b_out[n0:n1], self.precision, self.N)
 
 
 def make_sharded_model(args, weights, rank, world, precision="bf16"):

@@ -85,7 +85,7 @@ class TCN(HierTCN):
         st = self.stream_ptr()
         slot_p, keep = cabi.int_array([0, L])
         xe = self._buf("xe", (B * L, D), self.act_torch_dtype)
-        cabi.call("htcn_gather_meanpool", self.E.data_ptr(), None, self.N, x_d.data_ptr(), None, slot_p, B, L, 1,
+        cabi.call("htcn_gather_meanpool", self.E.data_ptr(), D, None, self.N, x_d.data_ptr(), None, slot_p, B, L, 1,
                   xe.data_ptr(), self.act_dtype, None, st)
         hout = self._buf("hout", (max(Q, 1), D), self.act_torch_dtype)
         prec = self._k2_precision()

@@ -44,12 +44,12 @@ def evaluate_hier(model, loader, max_batches=None, results_path=None, verbose=Fa
         if hasattr(loader, "next"):                              # DeviceBatcher: the batch is assembled in HBM
             staged = loader.next(state)
             t1 = time.time()
-            out = model.step(staged=staged, per_position=True, state_on_device=True)
+            out = model.step(staged=staged, per_position=("ranks_float",), state_on_device=True)
             y_list = [staged["y_id"].cpu().numpy()]
         else:
             x_list, y_list, mask_list, _ = loader.get_batch()
             t1 = time.time()
-            out = model.step(x_list, y_list, mask_list, state, per_position=True, state_on_device=True)
+            out = model.step(x_list, y_list, mask_list, state, per_position=("ranks_float",), state_on_device=True)
         state = out["state"]                                     # stays in HBM between batches
         t2 = time.time()
         t_load += t1 - t0

@@ -60,6 +60,10 @@ class HierTCNTrainer:
         self.adam_v = torch.zeros(off, dtype=f32, device=m.device)
         wt_master = m.wt if not self.bf16 else torch.from_numpy(
             np.ascontiguousarray(np.asarray(m._w_out_host, dtype=np.float32).T)).to(m.device)
+        if m.emb_pitch != D:            # training keeps the table at the full 128-float pitch (dense dE, one flat buffer)
+            E_full = torch.zeros((N, D), dtype=f32, device=m.device)
+            E_full[:, :m.emb_pitch] = m.E
+            m.E, m.emb_pitch = E_full, D
         cur = {"E": m.E, "wt": wt_master, "b_out": m.b_out, "b_emb": m.b_emb, "w_in_x": m.w_in_x, "w_in_state": m.w_in_state}
         for l in range(L):
             cur[f"conv_w{l}"], cur[f"conv_b{l}"] = m.conv_w[l], m.conv_b[l]
@@ -130,7 +134,7 @@ class HierTCNTrainer:
         sdt, sdt_c = (torch.bfloat16, cabi.HTCN_BF16) if fused else (f32, cabi.HTCN_F32)
         xe = buf("tr_xe_bf16" if fused else "tr_xe", (R, D), sdt)
         yp = buf("tr_yp", (S, B, D), f32)
-        cabi.call("htcn_gather_meanpool", m.E.data_ptr(), m.b_emb.data_ptr(), N, d["x_id"].data_ptr(), d["y_id"].data_ptr(),
+        cabi.call("htcn_gather_meanpool", m.E.data_ptr(), D, m.b_emb.data_ptr(), N, d["x_id"].data_ptr(), d["y_id"].data_ptr(),
                   slot_p, B, T, S, xe.data_ptr(), sdt_c, yp.data_ptr(), st)
         state_pre = buf("tr_state_pre", (S, B, G * D), f32)
         sbias = buf("tr_sbias", (S, B, D), f32)
@@ -228,9 +232,17 @@ class HierTCNTrainer:
     def apply_gradients(self, scalars, lr=None):
         """All-reduce (data parallel) and apply one Adam step; clears the gradient buffer."""
         if self.world > 1:
+            ev = getattr(self, "allreduce_events", None)    # bench.py: [] -> (start, end) CUDA events of every exchange
+            if ev is not None:
+                torch = _torch()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(torch.cuda.current_stream(self.m.device))
             self.dist.all_reduce(self.grads)
             from .dist import allreduce_scalars
             scalars = allreduce_scalars(scalars, self.dist, self.world)
+            if ev is not None:
+                e1.record(torch.cuda.current_stream(self.m.device))
+                ev.append((e0, e1))
         self.t += 1
         cabi.call("htcn_adam_step", self.params.data_ptr(), self.grads.data_ptr(), self.adam_m.data_ptr(),
                   self.adam_v.data_ptr(), self.n_flat, self.lr_t(lr), self.beta1, self.beta2, self.eps,

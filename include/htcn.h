@@ -70,9 +70,12 @@ int32_t htcn_device_ok(void);
  *   xe[b,p,:]  = E[x_id[b,p],:]  (id 0 -> zeros; bit-exact copy; optionally rounded to bf16)
  *   yp[s,b,:]  = (sum_{p in slot s, y>0} E[y_id[b,p],:]) / n_{b,s} + emb_bias      (NaN if n == 0, like 0/0 in TF)
  * x_id,y_id [B,T] int32; slot_off_host [S+1] int32 HOST array (slot s = columns slot_off[s]..slot_off[s+1]).
+ * emb_table [item_num, emb_pitch] f32: emb_pitch floats per row (multiple of 4, <= 128; 128 = the reference's width).
+ *   A narrower embedding (BASELINE config 2: 100-d) is stored packed -- 400 B rows -- and the output rows are zero
+ *   from column emb_pitch on.  emb_bias [128] (zero beyond the embedding width).
  * xe may be NULL (skip the x gather) and yp may be NULL (skip the pool).
  * ------------------------------------------------------------------------------------------- */
-int32_t htcn_gather_meanpool(const float* emb_table, const float* emb_bias, int32_t item_num,
+int32_t htcn_gather_meanpool(const float* emb_table, int32_t emb_pitch, const float* emb_bias, int32_t item_num,
                              const int32_t* x_id, const int32_t* y_id, const int32_t* slot_off_host,
                              int32_t B, int32_t T, int32_t S,
                              void* xe, int32_t xe_dtype, float* yp, void* stream);
@@ -201,6 +204,19 @@ int32_t htcn_score_topk(const void* hout, int32_t precision, int32_t Q, const vo
                         int32_t n_items, int32_t n0, int32_t k, int32_t n_split, void* workspace,
                         int64_t workspace_bytes, float* out_val, int32_t* out_idx, int32_t* overflow_rows,
                         void* stream);
+
+/* Loss + rank + top-k of one catalog shard in TWO sweeps (instead of the three of htcn_score_ce_rank_topk(CE|RANK) +
+ * htcn_score_topk): the CE / rank sweep also records the per-row maxima of its column groups (one 3-input max per logit
+ * pair on top of the loss epilogue), i.e. pass 1 of the two-pass top-k; the second sweep appends the candidates, then
+ * the exact selection.  Arguments as in htcn_score_ce_rank_topk (have_target = 1: target_logit is an input) and
+ * htcn_score_topk; workspace = htcn_topk_workspace_bytes(...).  Partials go to part_max / part_sum / part_cnt
+ * [n_split, Q] (merge with htcn_score_finish), the sorted list to out_val / out_idx [Q, k].
+ * fp32 tier and shards too small for the two-pass method run the separate sweeps internally. */
+int32_t htcn_score_ce_rank_topk_fused(const void* hout, int32_t precision, int32_t Q, const void* w_out_t,
+                                      const float* b_out, int32_t n_items, int32_t n0, const int32_t* y_id,
+                                      const float* target_logit, int32_t k, int32_t n_split, void* workspace,
+                                      int64_t workspace_bytes, float* part_max, float* part_sum, int32_t* part_cnt,
+                                      float* out_val, int32_t* out_idx, int32_t* overflow_rows, void* stream);
 
 /* Exact redo of the cross-entropy rows whose bf16-tier partial sum overflowed: the tensor-core sweep sums
  * 2^((z_j - z_y) log2e) with the target logit as reference point, which exceeds fp32 when some logit beats the target by

@@ -83,11 +83,11 @@ def main():
     yp = torch.empty((S, B, 128), dtype=f32, device="cuda")
     if want("k1"):
         for name, buf, dt, e in (("K1 gather+meanpool (fp32 out)", xe32, cabi.HTCN_F32, 4), ("K1 gather+meanpool (bf16 out)", xe, cabi.HTCN_BF16, 2)):
-            ms = timed(lambda: cabi.call("htcn_gather_meanpool", model.E.data_ptr(), model.b_emb.data_ptr(), N, d["x_id"].data_ptr(),
+            ms = timed(lambda: cabi.call("htcn_gather_meanpool", model.E.data_ptr(), model.emb_pitch, model.b_emb.data_ptr(), N, d["x_id"].data_ptr(),
                                          d["y_id"].data_ptr(), slot_p, B, T, S, buf.data_ptr(), dt, yp.data_ptr(), st))
             work = B * (2 * T * 512 + 2 * T * 4 + T * 128 * e + S * 512)       # rows read (x,y) + ids + outputs
             line(out, name, ms, "hbm", work, "hbm_gbs", "cfg2 shape, uniform ids, 1M x 128 fp32 table; two launches (gather, meanpool)")
-    cabi.call("htcn_gather_meanpool", model.E.data_ptr(), model.b_emb.data_ptr(), N, d["x_id"].data_ptr(), d["y_id"].data_ptr(),
+    cabi.call("htcn_gather_meanpool", model.E.data_ptr(), model.emb_pitch, model.b_emb.data_ptr(), N, d["x_id"].data_ptr(), d["y_id"].data_ptr(),
               slot_p, B, T, S, xe.data_ptr(), cabi.HTCN_BF16, yp.data_ptr(), st)
 
     # ---- K3

@@ -50,17 +50,44 @@ def test_k1_gather_bit_exact_and_meanpool(lib, lengths, B, S, L, N):
     slot_p, keep = lib.int_array(pk["slot_off"])
     xe = torch.empty((B, T, 128), dtype=torch.float32, device="cuda")
     yp = torch.empty((S, B, 128), dtype=torch.float32, device="cuda")
-    lib.call("htcn_gather_meanpool", P(Ed), P(bed), N, P(xid), P(yid), slot_p, B, T, S, P(xe), lib.HTCN_F32, P(yp), None)
+    lib.call("htcn_gather_meanpool", P(Ed), 128, P(bed), N, P(xid), P(yid), slot_p, B, T, S, P(xe), lib.HTCN_F32, P(yp), None)
     ref = O.emb_gather(pk["x_id"], E)
     assert np.array_equal(xe.cpu().numpy().view(np.uint32), ref.view(np.uint32)), "fp32 gather must be bit-exact"
     # bf16 output: the same rows rounded to nearest-even
     xeb = torch.empty((B, T, 128), dtype=torch.bfloat16, device="cuda")
-    lib.call("htcn_gather_meanpool", P(Ed), P(bed), N, P(xid), P(yid), slot_p, B, T, S, P(xeb), lib.HTCN_BF16, None, None)
+    lib.call("htcn_gather_meanpool", P(Ed), 128, P(bed), N, P(xid), P(yid), slot_p, B, T, S, P(xeb), lib.HTCN_BF16, None, None)
     assert np.array_equal(xeb.float().cpu().numpy(), O.bf16_round(ref))
     # mean-pool: sequential accumulation == oracle's, bit for bit
     ref_yp = np.stack([O.meanpool_emb(yy.astype(np.int64), E, be) for yy in y])
     got = yp.cpu().numpy()
     assert np.array_equal(got.view(np.uint32), ref_yp.view(np.uint32))
+
+
+@pytest.mark.parametrize("ed", [100, 64, 4])
+def test_k1_packed_table_equals_zero_padded(lib, ed):
+    """emb_dim < 128 (BASELINE config 2: 100-d): the table is stored with emb_pitch = emb_dim floats per row; gather and
+    mean-pool must equal -- bit for bit -- what the zero-padded 128-wide table gives"""
+    B, S, L, N = 9, 3, 7, 333
+    x, y, m, s0, _ = small_case(B=B, S=S, L=L, N=N, seed=4)
+    pk = pack(x, y, m)
+    T = pk["x_id"].shape[1]
+    rng = np.random.default_rng(ed)
+    E = rng.normal(size=(N, ed)).astype(np.float32)
+    be = np.zeros(128, np.float32)
+    be[:ed] = rng.normal(size=ed)
+    Epad = np.zeros((N, 128), np.float32)
+    Epad[:, :ed] = E
+    xid, yid, bed = dev(pk["x_id"]), dev(pk["y_id"]), dev(be)
+    slot_p, keep = lib.int_array(pk["slot_off"])
+    outs = []
+    for tab, pitch in ((dev(E), ed), (dev(Epad), 128)):
+        xe = torch.empty((B, T, 128), dtype=torch.float32, device="cuda")
+        yp = torch.empty((S, B, 128), dtype=torch.float32, device="cuda")
+        lib.call("htcn_gather_meanpool", P(tab), pitch, P(bed), N, P(xid), P(yid), slot_p, B, T, S, P(xe), lib.HTCN_F32, P(yp), None)
+        outs.append((xe.cpu().numpy(), yp.cpu().numpy()))
+    assert np.array_equal(outs[0][0].view(np.uint32), outs[1][0].view(np.uint32))
+    assert np.array_equal(outs[0][1].view(np.uint32), outs[1][1].view(np.uint32))
+    assert np.array_equal(outs[0][0], O.emb_gather(pk["x_id"], Epad))
 
 
 def test_k1_null_and_out_of_range_ids(lib):
@@ -71,7 +98,7 @@ def test_k1_null_and_out_of_range_ids(lib):
     xe = torch.full((B, T, 128), 7.0, dtype=torch.float32, device="cuda")
     slot_p, keep = lib.int_array([0, T])
     Ed, idd = dev(E), dev(ids)          # keep the device tensors alive across the async launch
-    lib.call("htcn_gather_meanpool", P(Ed), None, N, P(idd), None, slot_p, B, T, 1, P(xe), lib.HTCN_F32, None, None)
+    lib.call("htcn_gather_meanpool", P(Ed), 128, None, N, P(idd), None, slot_p, B, T, 1, P(xe), lib.HTCN_F32, None, None)
     got = xe.cpu().numpy()
     assert (got[0, 0] == 0).all() and (got[0, 3] == 0).all() and (got[0, 4] == 0).all() and (got[1] == 0).all()
     assert np.array_equal(got[0, 1], E[1]) and np.array_equal(got[0, 2], E[49])
@@ -674,6 +701,72 @@ def test_score_topk_two_pass_exact(lib, Q, N, k, n_split):
     v_ref, i_ref = O.top_k(z_gpu, k)
     np.testing.assert_array_equal(oi.cpu().numpy(), i_ref + n0)
     np.testing.assert_array_equal(ov.cpu().numpy(), v_ref)
+
+
+@pytest.mark.parametrize("cta_group", ["2", "1"])
+@pytest.mark.parametrize("Q,N,k,n_split", [(200, 120_000, 100, 3), (130, 300_001, 50, 5), (257, 20_000, 100, 2)])
+def test_score_fused_loss_rank_topk_equals_separate_sweeps(lib, Q, N, k, n_split, cta_group, monkeypatch):
+    """htcn_score_ce_rank_topk_fused (the CE / rank sweep also records the group maxima of the two-pass top-k): partials
+    bit-identical to the plain CE | RANK sweep, top-k list identical to the oracle's order on the swept logits"""
+    monkeypatch.setenv("HTCN_K4_CTA_GROUP", cta_group)
+    if cta_group == "1" and N != 120_000:
+        pytest.skip("single-CTA variant: one shape is enough")
+    rng = np.random.default_rng(N + 1)
+    hout = O.bf16_round(rng.normal(size=(Q, 128)).astype(np.float32))
+    w_out = (rng.normal(size=(128, N)) * 0.3).astype(np.float32)
+    b_out = (rng.normal(size=N) * 0.2).astype(np.float32)
+    y = rng.integers(1, N, size=Q).astype(np.int32)
+    w_out_d, bd, yd = dev(w_out), dev(b_out), dev(y)
+    wt = torch.empty((N, lib.WT_PITCH_BF16), dtype=torch.bfloat16, device="cuda")
+    lib.call("htcn_prepare_wout", P(w_out_d), P(bd), N, P(wt), lib.HTCN_BF16, None)
+    hd = dev(hout).to(torch.bfloat16)
+    z_gpu = debug_logits_bf16(lib, hd, wt, bd).cpu().numpy()
+    n0 = 3_000_000
+    y_glob = dev(y + n0)
+    zy = torch.zeros(Q, dtype=torch.float32, device="cuda")
+    lib.call("htcn_target_logit", P(hd), lib.HTCN_BF16, Q, P(wt), None, N, n0, P(y_glob), P(zy), None)
+    _, pm0, ps0, pc0, _, _ = run_score(lib, hd, wt, bd, y_glob, lib.SCORE_CE | lib.SCORE_RANK, 0, n_split, n0=n0,
+                                       precision=lib.HTCN_BF16, zy_in=zy)
+    nbytes = int(lib.load().htcn_topk_workspace_bytes(lib.HTCN_BF16, Q, N, k, n_split))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    pm = torch.empty((n_split, Q), dtype=torch.float32, device="cuda"); ps = torch.empty_like(pm)
+    pc = torch.empty((n_split, Q), dtype=torch.int32, device="cuda")
+    ov = torch.empty((Q, k), dtype=torch.float32, device="cuda")
+    oi = torch.empty((Q, k), dtype=torch.int32, device="cuda")
+    ovf = torch.full((1,), -1, dtype=torch.int32, device="cuda")
+    lib.call("htcn_score_ce_rank_topk_fused", P(hd), lib.HTCN_BF16, Q, P(wt), P(bd), N, n0, P(y_glob), P(zy), k, n_split,
+             P(ws), nbytes, P(pm), P(ps), P(pc), P(ov), P(oi), P(ovf), None)
+    assert int(ovf.item()) == 0
+    assert torch.equal(pc, pc0) and torch.equal(pm, pm0) and torch.equal(ps, ps0)
+    np.testing.assert_array_equal(pc.sum(0).cpu().numpy(), (z_gpu > zy.cpu().numpy()[:, None]).sum(1))
+    v_ref, i_ref = O.top_k(z_gpu, k)
+    np.testing.assert_array_equal(oi.cpu().numpy(), i_ref + n0)
+    np.testing.assert_array_equal(ov.cpu().numpy(), v_ref)
+
+
+@pytest.mark.parametrize("n_part,k,Q", [(9, 100, 70), (1, 100, 5), (3, 7, 33), (32, 128, 4)])
+def test_topk_merge_sort_network(lib, n_part, k, Q):
+    """htcn_topk_merge (bitonic sort of 64-bit (score, ~index) keys): (score desc, index asc), duplicates of a score across
+    parts ordered by index, empty slots (idx -1) last, -0.0 == +0.0"""
+    rng = np.random.default_rng(n_part * 1000 + k)
+    v = rng.integers(-6, 6, size=(n_part, Q, k)).astype(np.float32) * 0.5       # many ties
+    v[rng.random(v.shape) < 0.05] = -0.0
+    idx = np.stack([rng.permutation(n_part * k * 3)[:n_part * k].reshape(n_part, k) for _ in range(Q)], 1).astype(np.int32)
+    empty = rng.random(idx.shape) < 0.1
+    idx[empty] = -1
+    ov = torch.empty((Q, k), dtype=torch.float32, device="cuda")
+    oi = torch.empty((Q, k), dtype=torch.int32, device="cuda")
+    vd, idd = dev(v), dev(idx)
+    lib.call("htcn_topk_merge", P(vd), P(idd), n_part, Q, k, P(ov), P(oi), None)
+    got_v, got_i = ov.cpu().numpy(), oi.cpu().numpy()
+    for q in range(Q):
+        vv, ii = v[:, q].reshape(-1).astype(np.float64), idx[:, q].reshape(-1).astype(np.int64)
+        keep = ii >= 0
+        order = np.lexsort((ii[keep], -vv[keep]))[:k]
+        n = len(order)
+        np.testing.assert_array_equal(got_i[q, :n], ii[keep][order])
+        np.testing.assert_array_equal(got_v[q, :n], vv[keep][order])
+        assert (got_i[q, n:] == -1).all() and np.isneginf(got_v[q, n:]).all()
 
 
 def test_score_topk_overflow_is_reported_and_model_falls_back(lib):
