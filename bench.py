@@ -15,6 +15,16 @@ Prints ONE JSON line (rank 0).  `value` = device-resident throughput; `e2e` = th
 numpy buffers (H2D of the batch + D2H of loss/metrics/state inside the timed region).
 `--impl reference` times the CPU port of the reference graph (oracle/torch_cpu.py; TensorFlow 1.6 cannot be
 installed here) on the host cores, on a bounded sample of the same workload.
+
+Extra legs on the same JSON line (every N; the headline `value` stays configs[1], weak scaling):
+  `strong`  -- configs[1] with a GLOBAL batch of 4096 users split over the ranks (strong scaling of the forward path)
+  `sharded` -- BASELINE configs[3]: CE + rank + top-100 of 4096 queries over 8M items, the catalog sharded N ways
+               (hiertcn_b200.dist.ShardedCatalogScorer), device time per phase / collective, and `sharded_parity`:
+               ranks, top-k indices and values of the sharded path == the replicated single-GPU path, bit for bit, on a
+               1M-item catalog (loss rows to 2e-6)
+  `train`   -- BASELINE configs[4]: training step (fwd + bwd + all-reduce + Adam), global batch 4096 (strong scaling),
+               with the device time of the gradient all-reduce
+  `kernels` -- per-kernel device times of the step (K1 gather, K3 GRU, K2 conv stack, sampled loss) with their rooflines
 """
 from __future__ import annotations
 
@@ -158,6 +168,24 @@ def cpu_baseline(wl, w, seconds_target=15.0, steps=1, warmup=0):
                        "(gather + streamed catalog), %.1f s/step" % (users, wl["B"], wl["N"], dt)), dt, users, out
 
 
+def cpu_literal_cfg1(steps=2):
+    """BASELINE.md's LITERAL CPU form at configs[0] (B=64, N=20 778): one-hot x table matmuls and a materialised
+    [B,T,N] logits tensor, the op sequence of the TF graph (oracle/torch_cpu.py, literal=True), on all host cores."""
+    import torch
+    from oracle.torch_cpu import CpuHierTCN          # CPU baseline leg only
+    wl = WORKLOADS["cfg1"]
+    torch.set_num_threads(os.cpu_count() or 1)
+    model = CpuHierTCN(make_weights(wl))
+    x, y, m, s0 = make_inputs(wl, seed=98)
+    model.step(x, y, m, s0, literal=True)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        model.step(x, y, m, s0, literal=True)
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": wl["B"] / dt, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+            "sample": "configs[0] whole: %d users, %d items, literal one-hot/[B,T,N] form, %.2f s/step" % (wl["B"], wl["N"], dt)}
+
+
 def run_reference(opt, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -175,20 +203,31 @@ def run_reference(opt, wl):
 
 
 def run_training(opt, wl):
-    """BASELINE config 5: one optimisation step = forward with saved activations + backward + all-reduce + Adam
-    (hiertcn_b200.train).  Strong scaling: the global batch is split over the ranks."""
+    """`--workload cfg5`: the training step as the headline line"""
     import torch
     import torch.distributed as dist
-    from hiertcn_b200 import _cabi as cabi
-    from hiertcn_b200.args import make_args
-    from hiertcn_b200.model_hier import HierTCN
-    from hiertcn_b200.train import HierTCNTrainer
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    line = train_leg(opt, wl, rank, world, local, sample_clocks=True)
+    if world > 1:
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line))
+
+
+def train_leg(opt, wl, rank, world, local, sample_clocks=False):
+    """BASELINE config 5: one optimisation step = forward with saved activations + backward + all-reduce + Adam
+    (hiertcn_b200.train).  Strong scaling: the global batch is split over the ranks.  Returns the JSON object (rank 0)."""
+    import torch
+    import torch.distributed as dist
+    from hiertcn_b200 import _cabi as cabi
+    from hiertcn_b200.args import make_args
+    from hiertcn_b200.model_hier import HierTCN
+    from hiertcn_b200.train import HierTCNTrainer
     warmup = max(opt.warmup, 3)
     peaks = load_peaks()
     Bg = wl["B"]
@@ -196,10 +235,35 @@ def run_training(opt, wl):
     w = make_weights(wl)
     a = make_args(["--item_num", str(wl["N"]), "--batch_size", str(B)])
     tr = HierTCNTrainer(HierTCN(a, w, precision=opt.precision).build(), dist=dist if world > 1 else None, world=world)
-    x, y, m, s0 = make_inputs(wl, seed=1 + rank, B=B)
+    # every rank generates the same global batch and takes its slice of the users
+    xg, yg, mg, sg = make_inputs(wl, seed=1, B=Bg)
+    lo, hi = rank * B, (rank + 1) * B
+    x, y, m, s0 = [v[lo:hi] for v in xg], [v[lo:hi] for v in yg], [v[lo:hi] for v in mg], sg[lo:hi]
     staged = tr.m.stage(x, y, m, s0)
+    # in-run parity of the data-parallel exchange: the all-reduced gradient of the rank slices == the gradient one
+    # process computes on the whole batch (rank 0 runs it), and every rank holds the same parameters afterwards
+    dp_parity = None
+    if world > 1:
+        r = tr.forward_backward(staged=staged)
+        g_dp = tr.grads.clone()
+        sc_dp = r["scalars"].clone()
+        sc_dp[:6] *= sc_dp[6]
+        tr.grads.zero_()
+        dist.all_reduce(g_dp)
+        dist.all_reduce(sc_dp)
+        if rank == 0:
+            ref = HierTCNTrainer(HierTCN(a, w, precision=opt.precision).build())
+            rr = ref.forward_backward(xg, yg, mg, sg)
+            err = float((g_dp - ref.grads).norm() / ref.grads.norm())
+            loss_dp, loss_ref = float(sc_dp[0] / sc_dp[6]), float(rr["scalars"][0])
+            dp_parity = {"grad_rel_err": err, "loss_dp": loss_dp, "loss_single": loss_ref,
+                         "ok": bool(err <= 1e-4 and abs(loss_dp - loss_ref) <= 1e-5 * abs(loss_ref)
+                                    and float(sc_dp[6]) == float(rr["scalars"][6]))}
+            del ref, rr
+        del g_dp
+        torch.cuda.empty_cache()
     sampler = ClockSampler(local)
-    if rank == 0 and not os.environ.get("HTCN_BENCH_NO_SAMPLER"):
+    if rank == 0 and sample_clocks and not os.environ.get("HTCN_BENCH_NO_SAMPLER"):
         sampler.start()
         time.sleep(0.5)
 
@@ -212,6 +276,7 @@ def run_training(opt, wl):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    tr.allreduce_events = []
     l0 = cabi.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
@@ -229,8 +294,22 @@ def run_training(opt, wl):
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms_per_step = float(t_ms.item()) / opt.steps
-    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 and sample_clocks else None
+    ar = [a0.elapsed_time(a1) for a0, a1 in tr.allreduce_events]
+    tr.allreduce_events = None
+    t_ar = torch.tensor([float(np.mean(ar)) if ar else 0.0], device="cuda")
+    if world > 1:
+        dist.all_reduce(t_ar, op=dist.ReduceOp.MAX)
+    allreduce_ms = float(t_ar.item())
     loss_dev = float(sc.cpu().numpy()[0])
+    if world > 1:       # the replicas must hold bit-identical parameters after the timed steps
+        cs = torch.stack([tr.params.double().sum(), tr.params.double().abs().sum()])
+        cmax, cmin = cs.clone(), cs.clone()
+        dist.all_reduce(cmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cmin, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            dp_parity["replicas_identical"] = bool(torch.equal(cmax, cmin))
+            dp_parity["ok"] = dp_parity["ok"] and dp_parity["replicas_identical"]
     # end to end: numpy batch in (H2D inside), loss + carried state out (D2H inside)
     state = s0
     for _ in range(2):
@@ -247,9 +326,8 @@ def run_training(opt, wl):
     t_e = torch.tensor([dt], device="cuda")
     if world > 1:
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-        dist.destroy_process_group()
     if rank != 0:
-        return
+        return None
     Q = int(staged["Q"])
     flops = 3 * 2.0 * Q * 128 * wl["N"] * world          # catalog products: logits, dHout, dW_out^T (recompute not counted)
     line = {"metric": "user-seqs/sec HierTCN training step (fwd+bwd+Adam)", "value": Bg / (ms_per_step * 1e-3), "unit": UNIT,
@@ -263,11 +341,176 @@ def run_training(opt, wl):
                     "d2h_bytes_per_step": 8 * 4 + B * 256 * 4, "steps": e2e_steps,
                     "api": "HierTCNTrainer.train_step(x_list, y_list, mask_list, state): numpy in / loss + state out"},
             "gpu_launches": int(launches),
+            "dp_parity": dp_parity,
+            "allreduce": {"ms_per_step": allreduce_ms, "share_of_step": allreduce_ms / ms_per_step, "bytes": int(tr.n_flat) * 4,
+                          "overlap": "none: one NCCL all-reduce of the flat gradient buffer between backward and Adam "
+                                     "(device time between two events on the compute stream, max over ranks)"},
             "roofline": {"kernel": "whole step, catalog products only", "bound": "tensor", "achieved": flops / (ms_per_step * 1e-3) / 1e12 / world,
                          "peak": peaks["tf_sust"], "unit": "TFLOP/s", "frac": flops / (ms_per_step * 1e-3) / 1e12 / world / peaks["tf_sust"],
                          "peak_source": peaks["src"], "traffic": None},
             "clocks": clocks}
-    print(json.dumps(line))
+    return line
+
+
+def sharded_leg(opt, rank, world, local, items=8 * 1024 * 1024, queries=4096, k=100, parity_items=1_000_000):
+    """BASELINE configs[3]: CE + rank + top-k of `queries` query rows over `items` items, the catalog sharded over the
+    ranks (rank r owns rows [n0_r, n1_r) of W_out^T in the bf16 scoring layout).  Device time per phase / collective (max
+    over ranks), and an in-run parity check of the sharded path against the replicated single-GPU path on a catalog of
+    `parity_items` items: ranks, top-k indices and values bit for bit, loss rows to 2e-6."""
+    import torch
+    import torch.distributed as dist
+    from hiertcn_b200 import _cabi as cabi
+    from hiertcn_b200.dist import CatalogTable, CudaScoreOps, ShardedCatalogScorer, shard_bounds
+    dev = torch.device("cuda", local)
+    cabi.load()
+
+    def table(n_rows, seed):
+        g = torch.Generator(device=dev).manual_seed(seed)
+        wt = torch.empty((n_rows, cabi.WT_PITCH_BF16), dtype=torch.bfloat16, device=dev)
+        step = 1 << 20                                   # prepare in slices: the fp32 TF-layout source is 4x the table
+        for r0 in range(0, n_rows, step):
+            n = min(step, n_rows - r0)
+            w = torch.randn((128, n), device=dev, generator=g) * 0.3
+            b = torch.randn(n, device=dev, generator=g) * 0.2
+            cabi.call("htcn_prepare_wout", w.data_ptr(), b.data_ptr(), n, wt[r0:r0 + n].data_ptr(), cabi.HTCN_BF16,
+                      torch.cuda.current_stream(dev).cuda_stream)
+            torch.cuda.synchronize(dev)
+        return wt
+
+    def n_split_for(Q):
+        return int(max(1, min(max(-(-2 * 148 // max(1, -(-Q // 128))), 4), 32)))
+
+    Ql = queries // world
+    # ---- parity: the same 1M-item table on every rank; sharded N ways vs scored whole on this rank
+    full = CatalogTable(table(parity_items, 4242), None, "bf16", parity_items)
+    gq = torch.Generator(device=dev).manual_seed(900 + rank)
+    Qp = min(Ql, 512)
+    hp = torch.randn((Qp, 128), device=dev, generator=gq).to(torch.bfloat16)
+    yp = torch.randint(1, parity_items, (Qp,), device=dev, generator=gq, dtype=torch.int32)
+    b = shard_bounds(parity_items, world)
+    sc = ShardedCatalogScorer(CudaScoreOps(full.rows(b[rank], b[rank + 1])), dist, rank, world, parity_items, n_split=3)
+    got = sc.score(hp, yp, k=k)
+    ops = CudaScoreOps(full)
+    zy = torch.zeros(Qp, dtype=torch.float32, device=dev)
+    ops.target_logit(hp, yp, 0, parity_items, zy)
+    part = ops.sweep(hp, yp, zy, 0, parity_items, k, 4, True, True)
+    ref = ops.finish(part["pm"], part["ps"], part["pc"], yp, zy)
+    ref.update(ops.topk_merge(part["tv"], part["ti"], k))
+    torch.cuda.synchronize(dev)
+    checks = dict(rank=torch.equal(got["rank_row"], ref["rank_row"]), topk_idx=torch.equal(got["topk_idx"], ref["topk_idx"]),
+                  topk_val=torch.equal(got["topk_val"], ref["topk_val"]),
+                  loss=bool(torch.allclose(got["loss_row"], ref["loss_row"], rtol=2e-6, atol=2e-6)))
+    ok = torch.tensor([int(all(checks.values()))] + [int(v) for v in checks.values()], device=dev)
+    if world > 1:
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    del full, ops, part, ref, got, sc
+    torch.cuda.empty_cache()
+    # ---- timing: 8M items, this rank's shard only
+    b = shard_bounds(items, world)
+    n0, n1 = b[rank], b[rank + 1]
+    shard = CatalogTable(table(n1 - n0, 100 + rank), None, "bf16", items)
+    h = torch.randn((Ql, 128), device=dev, generator=gq).to(torch.bfloat16)
+    y = torch.randint(1, items, (Ql,), device=dev, generator=gq, dtype=torch.int32)
+    ns = n_split_for(queries)
+    sc = ShardedCatalogScorer(CudaScoreOps(shard), dist, rank, world, items, n_split=ns)
+    for _ in range(3):
+        out = sc.score(h, y, k=k)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    steps = max(3, opt.steps)
+    sc.phases = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = sc.score(h, y, k=k)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    phases = sc.phase_ms()
+    names = ["allgather_queries", "target_logit", "allreduce_target", "sweep", "alltoall_partials", "merge"]
+    t = torch.tensor([e0.elapsed_time(e1) / steps] + [phases.get(n, 0.0) / steps for n in names], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    v, i = out["topk_val"], out["topk_idx"]
+    sane = bool((v[:, :-1] >= v[:, 1:]).all() and (i >= 0).all() and (i < items).all() and torch.isfinite(out["loss_row"]).all())
+    if rank != 0:
+        return None
+    ms = float(t[0].item())
+    ph = {n: float(t[1 + j].item()) for j, n in enumerate(names)}
+    coll = {n: ph[n] for n in ("allgather_queries", "allreduce_target", "alltoall_partials")}
+    return {"workload": "CE + rank + top-%d of %d queries over %d items, catalog sharded %d ways (bf16 tier)" % (k, queries, items, world),
+            "ms_per_call": ms, "queries_per_s": queries / (ms * 1e-3), "n_split": ns,
+            "useful_tflops_per_gpu": 2.0 * queries * 128 * (items / world) / (ms * 1e-3) / 1e12,
+            "phase_ms": ph, "collective_ms": sum(coll.values()), "limiting_collective": max(coll, key=coll.get) if world > 1 else None,
+            "sorted_in_range_finite": sane, "sharded_parity": bool(ok[0].item()),
+            "parity_checks": {n: bool(ok[1 + j].item()) for j, n in enumerate(checks)},
+            "parity_config": "%d queries per rank x %d items: sharded %d ways vs whole catalog on one GPU" % (Qp, parity_items, world)}
+
+
+def kernels_leg(model, staged, neg_dev, peaks, wl):
+    """Device time of every kernel group of one step on its own (CUDA events on the launching stream, inputs of the whole
+    batch = far larger than L2), with the roofline each is held against (SURVEY 8d algorithmic bytes / FLOPs)."""
+    import torch
+    from hiertcn_b200 import _cabi as cabi
+    B, T, S, Q = staged["B"], staged["T"], staged["S"], staged["Q"]
+    st = model.stream_ptr()
+    f32 = torch.float32
+    slot_p, keep = cabi.int_array(staged["slot_off"])
+    xe = model._buf("xe", (B * T, 128), model.act_torch_dtype)
+    yp = model._buf("yp", (S, B, 128), f32)
+    sbias = model._buf("sbias", (S, B, 128), f32)
+    state_out = torch.empty((B, 256), dtype=f32, device=model.device)
+    hout = model._buf("hout", (max(Q, 1), 128), model.act_torch_dtype)
+    k3s = model._buf("k3_scratch", (cabi.gru_scratch_bytes(B) // 4,), f32)
+    k2s = model._buf("k2_scratch_bf16", ((1 + model.n_levels * model.K) * 8192 + 4096,), f32)
+    g = model._gru_pp
+    e = 2 if model.precision == "bf16" else 4
+
+    def k1():
+        cabi.call("htcn_gather_meanpool", model.E.data_ptr(), model.emb_pitch, model.b_emb.data_ptr(), model.N, staged["x_id"].data_ptr(),
+                  staged["y_id"].data_ptr(), slot_p, B, T, S, xe.data_ptr(), model.act_dtype, yp.data_ptr(), st)
+
+    def k3():
+        cabi.call("htcn_gru_sessions", yp.data_ptr(), staged["mask"].data_ptr(), staged["state"].data_ptr(), g[0][0], g[1][0], g[2][0],
+                  g[3][0], 2, model.w_in_state.data_ptr(), B, S, model.act_dtype, k3s.data_ptr(), None, sbias.data_ptr(),
+                  state_out.data_ptr(), st)
+
+    def k2():
+        cabi.call("htcn_tcn_forward", xe.data_ptr(), model.act_dtype, model._k2_precision(), model.w_in_x.data_ptr(), sbias.data_ptr(),
+                  model._conv_w_pp[0], model._conv_b_pp[0], model.n_levels, model.K, slot_p, B, T, S, staged["row_of"].data_ptr(),
+                  hout.data_ptr(), model.act_dtype, k2s.data_ptr(), st)
+
+    out = {}
+    scores, _ = model.forward(staged=staged)
+
+    def sl():
+        model.sampled_loss(scores, neg_dev)
+
+    row_b = model.emb_pitch * 4                              # bytes of one gathered table row (packed: emb_dim floats)
+    works = {
+        "k1_gather_meanpool": (k1, "hbm", B * (2 * T * row_b + 2 * T * 4 + T * 128 * e + S * 512),
+                               "rows read for x and y (%d B each, packed emb_dim) + ids + Xe/Yp written" % row_b),
+        "k3_gru_sessions": (k3, "hbm", B * S * (128 + 2 * 256) * 4, "Yp in, state_pre/sbias out; latency-bound in practice"),
+        "k2_tcn_forward": (k2, "tensor", Q * (model.n_levels * 2.0 * model.K * 128 * 128 + 2.0 * 128 * 128), "useful FLOPs of the scored positions"),
+        "sampled_rank_loss": (sl, "hbm", Q * (21 * 512 + 128 * e + 21 * 4 + 4), "21 gathered fp32 rows of W_out^T per position + the query row"),
+    }
+    for name, (fn, bound, work, note) in works.items():
+        for _ in range(2):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(model.device)
+        e0.record(torch.cuda.current_stream(model.device))
+        for _ in range(3):
+            fn()
+        e1.record(torch.cuda.current_stream(model.device))
+        torch.cuda.synchronize(model.device)
+        ms = e0.elapsed_time(e1) / 3
+        peak = peaks["hbm"] if bound == "hbm" else peaks["tf_burst"]
+        ach = work / (ms * 1e-3) / (1e9 if bound == "hbm" else 1e12)
+        out[name] = {"ms": ms, "bound": bound, "achieved": ach, "peak": peak, "unit": "GB/s" if bound == "hbm" else "TFLOP/s",
+                     "frac": ach / peak, "work": note}
+    del keep
+    return out
 
 
 def main():
@@ -279,6 +522,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-legs", action="store_true", help="skip the strong / sharded / train / kernels legs")
     ap.add_argument("--batch", type=int, default=0, help="override users per GPU (debugging)")
     ap.add_argument("--n-split", type=int, default=0, help="override the catalog split count of the K4 sweep")
     opt = ap.parse_args()
@@ -388,8 +632,11 @@ def main():
     scalars = sc.cpu().numpy()
 
     # ---------------- end-to-end arm (`e2e`): host numpy in, host results out ----------------
+    # the fetch list of run_hier_xing.py:145-149: loss, state, the metric means and the per-position ranks_float map
+    # (mask_y = sign(y_id) is host data already)
+    fetch = ("ranks_float",)
     for _ in range(2):
-        out = model.step(x, y, m, s0, neg_ids=neg_host)
+        out = model.step(x, y, m, s0, neg_ids=neg_host, per_position=fetch)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -397,7 +644,7 @@ def main():
     t0 = time.perf_counter()
     pend = None
     for _ in range(e2e_steps):                  # depth-2 software pipeline: pack + H2D of step i+1 overlap step i
-        nxt = model.step_async(x, y, m, s0, neg_ids=neg_host)
+        nxt = model.step_async(x, y, m, s0, neg_ids=neg_host, per_position=fetch)
         if pend is not None:
             out = pend.result()
         pend = nxt
@@ -409,7 +656,56 @@ def main():
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
     e2e_value = world * B / (float(t_e.item()) / e2e_steps)
     h2d = staged["h2d_bytes"] + neg_host.nbytes
-    d2h = 8 * 4 + B * 256 * 4
+    d2h = 8 * 4 + B * 256 * 4 + B * T * 4 + 8 * 4          # scalars, state, ranks_float [B,T], sampled-loss scalars
+    assert out["ranks_float"].shape == (B, T)
+
+    # ---------------- extra legs (see module docstring) ----------------
+    legs = {}
+    if not opt.no_legs:
+        kern = kernels_leg(model, staged, neg_dev, peaks, wl) if rank == 0 else None
+        # strong scaling of configs[1]: the global batch of wl["B"] users split over the ranks
+        if world > 1 and wl["B"] % world == 0:
+            Bs = wl["B"] // world
+            xs, ys, ms_, ss = make_inputs(wl, seed=50 + rank, B=Bs)
+            staged_s = model.stage(xs, ys, ms_, ss)
+            neg_s = neg_dev[:int(staged_s["Q"])]
+
+            def strong_step():
+                scores, _ = model.forward(staged=staged_s)
+                model.sampled_loss_mean(scores, neg_s)
+                return reduce_scalars(model.loss(scores, metrics=True)["scalars"])
+
+            for _ in range(3):
+                strong_step()
+            drain()
+            torch.cuda.synchronize()
+            dist.barrier()
+            s0e, s1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0e.record()
+            for _ in range(opt.steps):
+                strong_step()
+            drain()
+            s1e.record()
+            torch.cuda.synchronize()
+            ts = torch.tensor([s0e.elapsed_time(s1e) / opt.steps], device="cuda")
+            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+            legs["strong"] = {"workload": "configs[1], global batch %d users split over %d GPUs" % (wl["B"], world),
+                              "users_per_gpu": Bs, "ms_per_step": float(ts.item()), "value": wl["B"] / (float(ts.item()) * 1e-3),
+                              "unit": UNIT, "scaling": "strong"}
+            del staged_s
+        else:
+            legs["strong"] = {"workload": "configs[1], global batch %d users on 1 GPU" % wl["B"], "users_per_gpu": wl["B"],
+                              "ms_per_step": ms_per_step, "value": value, "unit": UNIT, "scaling": "strong"}
+        if kern is not None:
+            legs["kernels"] = kern
+        sh = sharded_leg(opt, rank, world, local)
+        if sh is not None:
+            legs["sharded"] = sh
+        torch.cuda.empty_cache()
+        tl = train_leg(opt, dict(WORKLOADS["cfg5"]), rank, world, local)
+        if tl is not None:
+            legs["train"] = {k: tl[k] for k in ("metric", "value", "unit", "ms_per_step", "scaling", "config", "loss", "e2e",
+                                                "gpu_launches", "allreduce", "dp_parity", "roofline")}
 
     if rank != 0:
         if world > 1:
@@ -436,10 +732,12 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "api": "HierTCN.step_async(x_list, y_list, mask_list, state).result(): numpy in / numpy out, pipelined 2 deep"},
             "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks}
+    line.update(legs)
     if world > 1:
         dist.destroy_process_group()
     if not opt.no_cpu_baseline and world == 1:          # the CPU baseline is reported at N=1 only
         base, _, _, _ = cpu_baseline(wl, w, seconds_target=12.0)
+        base["literal_cfg1"] = cpu_literal_cfg1()
         line["cpu_baseline"] = base
     print(json.dumps(line))
 

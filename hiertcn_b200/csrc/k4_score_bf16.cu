@@ -1113,8 +1113,9 @@ int32_t score_topk_bf16(const void* hout, int Q, const void* wt, int n_items, in
     ScoreArgs f = *ce;
     f.n_split = p.n_split;
     constexpr unsigned kCRG = HTCN_SCORE_CE | HTCN_SCORE_RANK | kModeGroupMax;
+    // same epilogue variants as the plain CE | RANK sweep of score_bf16 (its defaults), so the partials are bit-identical
     rc = cg2 ? launch_score_cg2<kCRG | packed_flags(4)>(f, nullptr, st, aux)
-             : launch_score<256, kCRG>(f, nullptr, st, aux);
+             : launch_score<256, kCRG | kModePoly8>(f, nullptr, st, aux);
   } else {
     rc = cg2 ? launch_score_cg2<kModeGroupMax>(a, nullptr, st, aux) : launch_score<256, kModeGroupMax>(a, nullptr, st, aux);
   }

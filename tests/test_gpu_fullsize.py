@@ -3,6 +3,9 @@ size-independent properties -- the CPU oracle cannot finish this size:
   * split invariance: 1 vs 4 vs 7 catalog splits give identical ranks and the same loss,
   * shard invariance: 3 catalog shards (n0 offsets, exchanged target logits) == one shard,
   * spot check of sampled rows against fully materialised logits (fp32 fmaf chain through the ABI),
+  * CPU ORACLE at this size on a sample: 32 of the 4096 users through oracle.model_hier_restructured (users are
+    independent rows, so a slice costs seconds) vs the user embeddings K1 -> K3 -> K2 produced for the whole batch;
+    48 sampled rows' CE / rank / top-100 recomputed in numpy float64 over the whole 1M-item catalog,
   * top-k lists are sorted, start at the row maximum and contain the target iff rank < k,
   * user permutation equivariance and determinism (bit-identical reruns)."""
 import numpy as np
@@ -27,6 +30,7 @@ def big():
     s0 = np.random.default_rng(1).normal(0, 0.5, size=(B, 256)).astype(np.float32)
     scores, state = model.forward(x, y, m, s0)
     torch.cuda.synchronize()
+    model.test_weights = w
     return model, scores, state, (x, y, m, s0)
 
 
@@ -147,3 +151,80 @@ def test_cfg2_user_permutation_equivariance(big):
     assert torch.equal(base_rank[p], r2["ranks"])
     torch.testing.assert_close(base_loss[p], r2["loss_bt"], rtol=1e-6, atol=1e-6)
     torch.testing.assert_close(base_sc, r2["scalars"], rtol=1e-4, atol=1e-6)
+
+
+def test_cfg2_sampled_users_against_cpu_oracle(big):
+    """K1 -> K3 -> K2 at B = 4096 (32 GRU clusters, 6400 conv tiles) vs the numpy oracle on 32 sampled users
+    (reference model_hier.py:39-94 in the restructured order, proved equal to the literal one by tests/test_oracle.py)"""
+    from oracle import hiertcn_oracle as O
+    model, scores, state, (x, y, m, s0) = big
+    if scores.generation != model.generation:          # an earlier test ran another forward on the shared model
+        scores, state = model.forward(x, y, m, s0)
+    w = model.test_weights
+    idx = np.sort(np.random.default_rng(7).choice(B, 32, replace=False))
+    xs, ys, ms = [a[idx] for a in x], [a[idx] for a in y], [a[idx] for a in m]
+    T = scores.T
+    rows = scores.row_of.cpu().numpy().reshape(B, T)[idx]
+    valid = rows >= 0
+    y_id = np.concatenate(ys, 1)
+    assert np.array_equal(valid, y_id > 0)
+    got = scores.hout.float().cpu().numpy()[rows[valid]]
+    got_state = state.cpu().numpy()[idx]
+    h64, st64 = O.model_hier_restructured(xs, ys, ms, s0[idx], w, 2, "f64", return_hidden=True)
+    hb, _ = O.model_hier_restructured(xs, ys, ms, s0[idx], w, 2, "bf16", return_hidden=True)
+    ref, refb = h64[valid], hb[valid]
+    scale = np.abs(ref).max()
+    fro = lambda a, b: np.linalg.norm(a - b) / np.linalg.norm(b)  # noqa: E731
+    # bf16 tier bar (north star): 2e-2
+    assert np.abs(got - ref).max() <= 2e-2 * scale, (np.abs(got - ref).max(), scale)
+    assert fro(got, ref) <= 1e-2, fro(got, ref)
+    # against the oracle that rounds its operands to bf16 at the same places the error is that of the summation order,
+    # the bf16 GRU operands and one bf16 ulp of the stored result
+    assert fro(got, refb) <= 1e-2, fro(got, refb)
+    np.testing.assert_allclose(got_state, st64, rtol=2e-2, atol=2e-2)
+
+
+def test_cfg2_sampled_rows_ce_rank_topk_against_numpy_f64(big):
+    """K4 at the benchmark size vs numpy float64 on the same bf16-rounded operands: 48 sampled rows of the 819 200 scored
+    positions, the whole 1M-item catalog (chunked).  CE (loss.py:20-21), strict rank (loss.py:179), top-100 (loss.py:120)."""
+    from oracle import hiertcn_oracle as O
+    model, scores, state, (x, y, m, s0) = big
+    if scores.generation != model.generation:
+        scores, state = model.forward(x, y, m, s0)
+    w = model.test_weights
+    r = run_score(model, scores, 4)
+    Q, k = scores.Q, 100
+    idx = np.sort(np.random.default_rng(11).choice(Q, 48, replace=False))
+    idx_d = torch.from_numpy(idx).cuda()
+    hq = scores.hout[idx_d].contiguous()
+    yq = scores.y_rows[idx_d].cpu().numpy().astype(np.int64)
+    tk = model.topk(hq, 48, k)
+    h = hq.float().cpu().numpy().astype(np.float64)                 # bf16 values, exact
+    W, bias = w["hier/tcn/dense/kernel"], w["hier/tcn/dense/bias"]
+    b_hi = O.bf16_round(bias)
+    b_eff = b_hi.astype(np.float64) + O.bf16_round(bias - b_hi).astype(np.float64)     # the [b_hi, b_lo] pair of the table
+    z = np.empty((48, N), np.float64)
+    for c0 in range(0, N, 1 << 16):
+        c1 = min(N, c0 + (1 << 16))
+        z[:, c0:c1] = h @ O.bf16_round(W[:, c0:c1]).astype(np.float64) + b_eff[c0:c1]
+    zy = z[np.arange(48), yq]
+    mx = z.max(1)
+    loss_ref = mx + np.log(np.exp(z - mx[:, None]).sum(1)) - zy
+    np.testing.assert_allclose(r["target_logit"][idx_d].cpu().numpy(), zy, rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(r["loss_row"][idx_d].cpu().numpy(), loss_ref, rtol=2e-3, atol=2e-3)    # bf16 tier bar: 2e-2
+    rank_ref = (z > zy[:, None]).sum(1)
+    amb = O.rank_ambiguity(z, yq, 3e-5)                 # columns an fp32-accumulated logit may order differently
+    got_rank = r["rank_row"][idx_d].cpu().numpy()
+    assert (np.abs(got_rank - rank_ref) <= amb).all(), (got_rank, rank_ref, amb)
+    # top-100: (score desc, index asc); identical index sets wherever the k-th gap is not an fp32 near-tie
+    order = np.argsort(-z, axis=1, kind="stable")[:, :k + 1]
+    v_sorted = np.take_along_axis(z, order, 1)
+    got_i, got_v = tk["topk_idx"].cpu().numpy(), tk["topk_val"].cpu().numpy()
+    np.testing.assert_allclose(got_v, v_sorted[:, :k], rtol=1e-4, atol=1e-4)
+    gap = v_sorted[:, k - 1] - v_sorted[:, k]
+    for q in range(48):
+        if gap[q] > 1e-4:
+            assert set(got_i[q].tolist()) == set(order[q, :k].tolist()), q
+        clear = np.abs(np.diff(v_sorted[q, :k + 1])) > 1e-4              # clear[j]: positions j and j+1 are well separated
+        pos_ok = np.concatenate([clear[:1], clear[:-1] & clear[1:]])      # both neighbours of a position are
+        assert (got_i[q] == order[q, :k])[pos_ok].all(), q

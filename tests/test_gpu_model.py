@@ -17,16 +17,6 @@ def make_model(w, N, precision, levels=2, K=5):
     return HierTCN(a, w, precision=precision).build()
 
 
-def check_against(out, ref, tol, ranks_exact):
-    assert abs(out["loss"] - ref["loss"]) <= tol * abs(ref["loss"]), (out["loss"], ref["loss"])
-    np.testing.assert_allclose(out["state"], ref["state"], rtol=max(tol, 1e-4), atol=max(tol, 1e-4) * 0.1)
-    np.testing.assert_allclose(out["loss_bt"], ref["loss_bt"], rtol=tol, atol=tol)
-    if ranks_exact:
-        np.testing.assert_array_equal(out["ranks"], ref["ranks"])
-    for k_out, k_ref in (("recall1", "recall1"), ("recall5", "recall5"), ("recall10", "recall10"), ("mrr", "mrr"), ("mrp", "mrp")):
-        assert abs(out[k_out] - ref[k_ref]) <= max(tol, 1e-5) * max(1.0, abs(ref[k_ref])) if ranks_exact else True
-
-
 def test_step_f32_matches_golden_reference_run():
     """fixture produced by running the reference's own model_hier/loss python (oracle/make_golden.py)"""
     z, x, y, m, w = load_hier_golden("hier_default_arch")
@@ -113,6 +103,28 @@ def test_bf16_tier_within_2e2():
     _, i_ref = O.top_k(zv, 100)
     overlap = np.mean([len(set(a) & set(b)) / 100.0 for a, b in zip(out["topk_idx"], i_ref)])
     assert overlap > 0.97, overlap
+
+
+def test_step_bf16_exact_baseline_config1():
+    """BASELINE.json configs[0] exactly (batch 64, 10 sessions x 20 positions, 20 778 items) in the bf16 tier, end to end
+    against the fp64 oracle at the north star's 2e-2 bar"""
+    B, S, L, N = 64, 10, 20, 20778
+    x, y, m, s0, w = small_case(B=B, S=S, L=L, N=N, seed=64, lengths="dense")
+    ref = O.forward_loss_metrics(x, y, m, s0, w, 2, "f64")
+    model = make_model(w, N, "bf16")
+    out = model.step(x, y, m, s0, per_position=True)
+    assert abs(out["loss"] - ref["loss"]) <= 2e-2 * abs(ref["loss"])
+    np.testing.assert_allclose(out["loss_bt"], ref["loss_bt"], rtol=2e-2, atol=2e-2)
+    np.testing.assert_allclose(out["state"], ref["state"], rtol=2e-2, atol=2e-2)
+    assert abs(out["mrr"] - ref["mrr"]) < 2e-2 and abs(out["mrp"] - ref["mrp"]) < 2e-3
+    for kk in ("recall1", "recall5", "recall10"):
+        assert abs(out[kk] - ref[kk]) < 2e-2
+    # ranks: integer counts on bf16-rounded operands; against the fp64 logits they may differ by the number of columns
+    # within the bf16 tier's logit error of the target
+    y_id = np.concatenate([np.asarray(v) for v in y], 1).astype(np.int64)
+    amb = O.rank_ambiguity(ref["pred"], y_id, 2e-2) * (y_id > 0)
+    assert np.mean(np.abs(out["ranks"] - ref["ranks"]) <= amb) > 0.99
+    assert np.abs(out["ranks_float"] - ref["ranks_float"]).max() < 2e-2
 
 
 def test_evaluate_hier_loop_matches_oracle_batch_by_batch():
