@@ -181,7 +181,9 @@ def test_cfg2_sampled_users_against_cpu_oracle(big):
     # against the oracle that rounds its operands to bf16 at the same places the error is that of the summation order,
     # the bf16 GRU operands and one bf16 ulp of the stored result
     assert fro(got, refb) <= 1e-2, fro(got, refb)
-    np.testing.assert_allclose(got_state, st64, rtol=2e-2, atol=2e-2)
+    # carried state after 10 recurrent steps on bf16 operands (fp32 state, |h| <= 1): 2e-2 in norm, 5e-2 worst element
+    assert fro(got_state, st64) <= 2e-2, fro(got_state, st64)
+    assert np.abs(got_state - st64).max() <= 5e-2
 
 
 def test_cfg2_sampled_rows_ce_rank_topk_against_numpy_f64(big):
