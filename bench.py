@@ -465,7 +465,7 @@ def kernels_leg(model, staged, neg_dev, peaks, wl):
     state_out = torch.empty((B, 256), dtype=f32, device=model.device)
     hout = model._buf("hout", (max(Q, 1), 128), model.act_torch_dtype)
     k3s = model._buf("k3_scratch", (cabi.gru_scratch_bytes(B) // 4,), f32)
-    k2s = model._buf("k2_scratch_bf16", ((1 + model.n_levels * model.K) * 8192 + 4096,), f32)
+    k2s = model._buf("k2_scratch_bf16", (cabi.tcn_scratch_floats(model.n_levels, model.K),), f32)
     g = model._gru_pp
     e = 2 if model.precision == "bf16" else 4
 
@@ -480,7 +480,7 @@ def kernels_leg(model, staged, neg_dev, peaks, wl):
 
     def k2():
         cabi.call("htcn_tcn_forward", xe.data_ptr(), model.act_dtype, model._k2_precision(), model.w_in_x.data_ptr(), sbias.data_ptr(),
-                  model._conv_w_pp[0], model._conv_b_pp[0], model.n_levels, model.K, slot_p, B, T, S, staged["row_of"].data_ptr(),
+                  model._conv_w_pp[0], model._conv_b_pp[0], None, None, model.n_levels, model.K, slot_p, B, T, S, staged["row_of"].data_ptr(),
                   hout.data_ptr(), model.act_dtype, k2s.data_ptr(), st)
 
     out = {}

@@ -18,6 +18,11 @@ MAX_TOPK = 128
 WT_PITCH_BF16 = 144
 
 
+def tcn_scratch_floats(n_levels, K):
+    """HTCN_TCN_SCRATCH_BYTES / 4: bf16 weight tiles (K taps + a possible down-sample kernel per level) + tables"""
+    return ((1 + n_levels * (K + 1)) * 128 * 128 * 2 + 640 + 2 * 8 * 512 + 256 + 3) // 4
+
+
 def gru_scratch_bytes(B):
     return 14 * 128 * 128 * 2 + 4096          # HTCN_GRU_SCRATCH_BYTES: independent of B (the fp32 state lives in TMEM)
 
@@ -30,7 +35,7 @@ _ip = C.POINTER(C.c_int32)         # host int array
 SIGNATURES = {
     "htcn_gather_meanpool": [_p, _i, _p, _i, _p, _p, _ip, _i, _i, _i, _p, _i, _p, _p],
     "htcn_gru_sessions": [_p, _p, _p, _pp, _pp, _pp, _pp, _i, _p, _i, _i, _i, _p, _p, _p, _p, _p],
-    "htcn_tcn_forward": [_p, _i, _i, _p, _p, _pp, _pp, _i, _i, _ip, _i, _i, _i, _p, _p, _i, _p, _p],
+    "htcn_tcn_forward": [_p, _i, _i, _p, _p, _pp, _pp, _pp, _pp, _i, _i, _ip, _i, _i, _i, _p, _p, _i, _p, _p],
     "htcn_prepare_wout": [_p, _p, _i, _p, _i, _p],
     "htcn_score_ce_rank_topk": [_p, _i, _i, _p, _p, _i, _i, _p, _p, _i, _u, _i, _i, _p, _p, _p, _p, _p, _p],
     "htcn_score_logits": [_p, _i, _i, _p, _i, _p, _i, _p, _p],
@@ -49,9 +54,9 @@ SIGNATURES = {
     "htcn_score_ce_backward": [_p, _i, _i, _p, _p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p],
     "htcn_score_ce_backward_bf16": [_p, _p, C.c_int64, _i, _p, _p, C.c_int64, _p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p],
     "htcn_cast_transpose_bf16": [_p, _i, C.c_int64, _p, _p, C.c_int64, _p],
-    "htcn_tcn_forward_train_bf16": [_p, _p, _p, _pp, _pp, _i, _i, _ip, _i, _i, _i, _p, _p, _p, _p, _p, _p],
-    "htcn_tcn_forward_train": [_p, _p, _p, _pp, _pp, _i, _i, _ip, _i, _i, _i, _p, _p, _p, _p, _p],
-    "htcn_tcn_backward": [_p, _p, _p, _i, _p, _pp, _i, _i, _ip, _i, _i, _i, _p, _p, _p, _pp, _pp, _p, _p, _p, _p],
+    "htcn_tcn_forward_train_bf16": [_p, _p, _p, _pp, _pp, _pp, _pp, _i, _i, _ip, _i, _i, _i, _p, _p, _p, _p, _p, _p],
+    "htcn_tcn_forward_train": [_p, _p, _p, _pp, _pp, _pp, _pp, _i, _i, _ip, _i, _i, _i, _p, _p, _p, _p, _p],
+    "htcn_tcn_backward": [_p, _p, _p, _i, _p, _pp, _pp, _i, _i, _ip, _i, _i, _i, _p, _p, _p, _pp, _pp, _pp, _pp, _p, _p, _p, _p],
     "htcn_gru_sessions_train": [_p, _p, _p, _pp, _pp, _pp, _pp, _i, _p, _i, _i, _p, _p, _p, _p, _p],
     "htcn_gru_backward": [_p, _p, _p, _p, _pp, _pp, _i, _p, _i, _i, _p, _p, _pp, _pp, _pp, _pp, _p, _p, _p],
     "htcn_gather_backward": [_p, _p, _p, _p, _ip, _i, _i, _i, _i, _p, _p, _p],

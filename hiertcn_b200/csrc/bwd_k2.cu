@@ -6,6 +6,8 @@
 //                                dp = ds * [a_l > 0]
 //                                dW_l[tap] += h_l[shifted by the tap]^T dp,   db_l += colsum(dp)
 //                                dL/dh_l = ds + sum_tap dp[shifted the other way] W_l[tap]^T   (transposed convolution)
+// a level with the 1x1 down-sample residual (h_{l+1} = relu(a_l + h_l Wds + bds), customized_tcn_cell.py:102-106,123-124):
+//                                dWds += h_l^T ds,  dbds += colsum(ds),  dL/dh_l = ds Wds^T + (transposed convolution)
 // and for the in-projection h_0 = Xe W_in[:128] + sbias[slot, user]  (model_hier.py:54-55, model_tcn.py:35):
 //                                dW_in_x += Xe^T dh_0,  dsbias[s,b] = sum_{t in slot s} dh_0[b,t],  dXe = dh_0 W_in_x^T
 #include "train.cuh"
@@ -65,6 +67,7 @@ __global__ void rows_compact_kernel(long long R, const int* __restrict__ row_of,
 
 extern "C" int32_t htcn_tcn_forward_train(const float* xe, const float* w_in_x, const float* sbias,
                                           const float* const* conv_w_host, const float* const* conv_b_host,
+                                          const float* const* ds_w_host, const float* const* ds_b_host,
                                           int32_t n_levels, int32_t kernel_size, const int32_t* slot_off_host, int32_t B,
                                           int32_t T, int32_t S, const int32_t* out_row, float* h_save, float* a_save,
                                           float* hout, void* stream) {
@@ -87,8 +90,19 @@ extern "C" int32_t htcn_tcn_forward_train(const float* xe, const float* w_in_x, 
   if (rc) return rc;
   for (int l = 0; l < n_levels; ++l) {
     a.in = h_save + (long long)l * R * kDim;
-    a.w = conv_w_host[l]; a.bias = conv_b_host[l]; a.sbias = nullptr; a.K = kernel_size; a.dil = 1 << l;
-    a.conv_epilogue = 1;
+    a.sbias = nullptr;
+    const bool ds = ds_w_host && ds_w_host[l];
+    if (ds) {
+      // res = h_l Wds + bds, parked in a_save[l]: the conv launch below reads resid[r,c] and then writes aux[r,c] from the
+      // same thread, so the two may share the buffer
+      a.w = ds_w_host[l]; a.bias = ds_b_host ? ds_b_host[l] : nullptr; a.K = 1; a.dil = 1; a.conv_epilogue = 0;
+      a.out = a_save + (long long)l * R * kDim; a.aux = nullptr;
+      rc = k2_level_launch(a, slots, st);
+      if (rc) return rc;
+    }
+    a.w = conv_w_host[l]; a.bias = conv_b_host[l]; a.K = kernel_size; a.dil = 1 << l;
+    a.conv_epilogue = ds ? 3 : 1;
+    a.resid = ds ? a_save + (long long)l * R * kDim : nullptr;
     a.out = h_save + (long long)(l + 1) * R * kDim;
     a.aux = a_save + (long long)l * R * kDim;
     rc = k2_level_launch(a, slots, st);
@@ -103,6 +117,7 @@ extern "C" int32_t htcn_tcn_forward_train(const float* xe, const float* w_in_x, 
 
 extern "C" int32_t htcn_tcn_forward_train_bf16(const void* xe, const float* w_in_x, const float* sbias,
                                                const float* const* conv_w_host, const float* const* conv_b_host,
+                                               const float* const* ds_w_host, const float* const* ds_b_host,
                                                int32_t n_levels, int32_t kernel_size, const int32_t* slot_off_host,
                                                int32_t B, int32_t T, int32_t S, const int32_t* out_row, void* h_save,
                                                void* a_save, void* hout, float* scratch, void* stream) {
@@ -116,15 +131,17 @@ extern "C" int32_t htcn_tcn_forward_train_bf16(const void* xe, const float* w_in
   slots.n = S;
   for (int i = 0; i <= S; ++i) slots.off[i] = slot_off_host[i];
   HTCN_REQUIRE(slots.off[0] == 0 && slots.off[S] == T, "tcn_forward_train_bf16: slot_off does not span T");
-  return tcn_forward_bf16(xe, HTCN_BF16, w_in_x, sbias, conv_w_host, conv_b_host, n_levels, kernel_size, slots, B, T, out_row,
+  return tcn_forward_bf16(xe, HTCN_BF16, w_in_x, sbias, conv_w_host, conv_b_host, ds_w_host, ds_b_host, n_levels, kernel_size, slots, B, T, out_row,
                           hout, HTCN_BF16, scratch, as_stream(stream), h_save, a_save);
 }
 
 extern "C" int32_t htcn_tcn_backward(const float* d_hout, const int32_t* out_row, const void* xe, int32_t save_dtype,
-                                     const float* w_in_x, const float* const* conv_w_host, int32_t n_levels,
+                                     const float* w_in_x, const float* const* conv_w_host,
+                                     const float* const* ds_w_host, int32_t n_levels,
                                      int32_t kernel_size, const int32_t* slot_off_host, int32_t B, int32_t T, int32_t S,
                                      const void* h_save, const void* a_save, float* scratch,
-                                     float* const* d_conv_w_host, float* const* d_conv_b_host, float* d_w_in_x,
+                                     float* const* d_conv_w_host, float* const* d_conv_b_host,
+                                     float* const* d_ds_w_host, float* const* d_ds_b_host, float* d_w_in_x,
                                      float* d_sbias, float* d_xe, void* stream) {
   using namespace htcn;
   HTCN_REQUIRE(d_hout && out_row && xe && w_in_x && h_save && scratch && d_w_in_x && d_sbias && d_xe && slot_off_host,
@@ -166,9 +183,21 @@ extern "C" int32_t htcn_tcn_backward(const float* d_hout, const int32_t* out_row
     }
     rc = colsum_atomic(R, dp, kDim, kDim, d_conv_b_host[l], st);
     if (rc) return rc;
+    const float* resid = dcur;                  // identity residual: dL/dh_l = ds + ...
+    if (ds_w_host && ds_w_host[l]) {            // down-sample residual: dWds += h_l^T ds, dbds += colsum(ds), ds Wds^T + ...
+      HTCN_REQUIRE(d_ds_w_host && d_ds_w_host[l] && d_ds_b_host && d_ds_b_host[l], "tcn_backward: down-sample gradient pointers NULL");
+      rc = sgemm_tn_atomic(R, h_l, kDim, dcur, kDim, d_ds_w_host[l], kDim, 0, T, nullptr, st, bf);
+      if (rc) return rc;
+      rc = colsum_atomic(R, dcur, kDim, kDim, d_ds_b_host[l], st);
+      if (rc) return rc;
+      float* dres = scratch + 2 * R * kDim;     // third scratch plane
+      rc = sgemm(true, R, kDim, kDim, dcur, kDim, ds_w_host[l], kDim, dres, kDim, false, st);
+      if (rc) return rc;
+      resid = dres;
+    }
     LevelArgs a{};
     a.R = R; a.T = T; a.B = B;
-    a.in = dp; a.w = conv_w_host[l]; a.K = kernel_size; a.dil = dil; a.conv_epilogue = 2; a.resid = dcur; a.out = dcur;
+    a.in = dp; a.w = conv_w_host[l]; a.K = kernel_size; a.dil = dil; a.conv_epilogue = 2; a.resid = resid; a.out = dcur;
     a.anti = 1; a.w_nt = 1;
     rc = k2_level_launch(a, slots, st);
     if (rc) return rc;

@@ -44,6 +44,8 @@ struct K2Slot {          // per session slot: tiling of its B sequences
 };
 struct K2Geom {
   int n_slots, n_tiles, B, T, K, n_levels;
+  unsigned ds_mask;      // bit l: level l has a 1x1 down-sample residual (customized_tcn_cell.py:102-106): one more weight
+                         // tile after the level's taps, accumulated into TMEM columns 128..255
   int P;                 // zero rows in front of each short sequence = max shift of the deepest level
   int rf1;               // receptive field - 1 (long mode halo)
   K2Slot slot[HTCN_MAX_SLOTS];
@@ -105,6 +107,7 @@ template <bool kPair>
 __global__ void __launch_bounds__(kK2Threads, 2)
 k2_tcn_bf16(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfloat16* __restrict__ xe,
             const float* __restrict__ sbias, const float* __restrict__ bias_all /*[n_levels][128]*/,
+            const float* __restrict__ ds_bias_all /*[n_levels][128], read only for the levels of g.ds_mask*/,
             const int* __restrict__ out_row, __nv_bfloat16* __restrict__ hout,
             __nv_bfloat16* __restrict__ h_save /* [(n_levels+1)][B*T][128] every layer's output, or NULL */,
             __nv_bfloat16* __restrict__ a_save /* [n_levels][B*T][128] relu(conv + b) before the residual, or NULL */) {
@@ -129,7 +132,10 @@ k2_tcn_bf16(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfl
   }
   for (int i = tid; i < g.n_levels * kDim; i += kK2Threads) sm.bias[i / kDim][i % kDim] = bias_all[i];
   for (int i = tid; i < kActBytes / 16; i += kK2Threads) reinterpret_cast<uint4*>(sm.act)[i] = make_uint4(0, 0, 0, 0);
-  if (warp == kK2MmaWarp) tmem_alloc<128>(&sm.tmem_base);
+  if (warp == kK2MmaWarp) {
+    if (g.ds_mask) tmem_alloc<256>(&sm.tmem_base);            // second accumulator: the down-sample residual
+    else tmem_alloc<128>(&sm.tmem_base);
+  }
   tc_fence_before_sync();
   if (kPair) cluster_sync_all();                  // the peer's barriers are initialised before any multicast lands on them
   else __syncthreads();
@@ -139,7 +145,7 @@ k2_tcn_bf16(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfl
   if (warp == kK2ProducerWarp) {
     // ===================== weight producer: [W_in, L0 taps, L1 taps, ...] per tile, 2-stage ring =====================
     if (lane == 0) {
-      const int per_tile = 1 + g.n_levels * g.K;
+      const int per_tile = 1 + g.n_levels * g.K + __popc(g.ds_mask);
       long long n = 0;
       for (int it = 0; it < my_tiles; ++it) {
         for (int j = 0; j < per_tile; ++j, ++n) {
@@ -188,6 +194,24 @@ k2_tcn_bf16(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfl
               else umma_commit(&sm.w_empty[s]);
             }
           }
+          if (layer > 0 && ((g.ds_mask >> (layer - 1)) & 1u)) {  // res = in @ W_ds: unshifted rows, second accumulator
+            const int s = (int)(n % kWStages);
+            mbar_wait(&sm.w_full[s], (uint32_t)((n / kWStages) & 1));
+            tc_fence_after_sync();
+            const uint32_t a_base = act0 + (uint32_t)kMaxSpare * 16;
+            const uint32_t w_base = smem_u32(sm.w[s]);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const uint64_t da = make_desc_act(a_base + (uint32_t)(2 * k) * (kRows * 16));
+              const uint64_t db = make_desc_k_sw128(w_base + (k >> 2) * (kWStageBytes / 2) + (k & 3) * 32);
+              if (leader) umma_bf16(tmem + 128, da, db, idesc, k != 0);
+            }
+            if (leader) {
+              if (kPair) umma_commit_mc(&sm.w_empty[s], 0b11);
+              else umma_commit(&sm.w_empty[s]);
+            }
+            ++n;
+          }
           if (leader) umma_commit(&sm.acc_ready);
         }
       }
@@ -220,6 +244,8 @@ k2_tcn_bf16(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfl
         tc_fence_after_sync();
         const bool last = layer == n_layers - 1;
         const float* bias_l = layer > 0 ? sm.bias[layer - 1] : nullptr;
+        const bool ds = layer > 0 && ((g.ds_mask >> (layer - 1)) & 1u);
+        const float* ds_bias_l = ds ? ds_bias_all + (layer - 1) * kDim : nullptr;
         const float* sb_row = (layer == 0 && sbias && src >= 0) ? sbias + (long long)sb * kDim : nullptr;
 #pragma unroll 1
         for (int cc = ch * 2; cc < ch * 2 + 2; ++cc) {           // 2 x 32 channels
@@ -247,9 +273,22 @@ k2_tcn_bf16(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfl
                 o[4] += s1.x; o[5] += s1.y; o[6] += s1.z; o[7] += s1.w;
               }
             } else {
-              const uint4 res = *slot;                           // this row's input to the level (bf16 x 8)
-              const float rs[8] = {bf16_lo(res.x), bf16_hi(res.x), bf16_lo(res.y), bf16_hi(res.y),
-                                   bf16_lo(res.z), bf16_hi(res.z), bf16_lo(res.w), bf16_hi(res.w)};
+              float rs[8];
+              if (ds) {                                          // residual = in @ W_ds + b_ds from the second accumulator
+                uint32_t v2[8];
+                tmem_ld_32x8(tmem + ((uint32_t)((warp & 3) * 32) << 16) + 128 + c * 8, v2);
+                tmem_ld_wait(v2);
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(ds_bias_l + c * 8));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(ds_bias_l + c * 8) + 1);
+                rs[0] = __uint_as_float(v2[0]) + b0.x; rs[1] = __uint_as_float(v2[1]) + b0.y;
+                rs[2] = __uint_as_float(v2[2]) + b0.z; rs[3] = __uint_as_float(v2[3]) + b0.w;
+                rs[4] = __uint_as_float(v2[4]) + b1.x; rs[5] = __uint_as_float(v2[5]) + b1.y;
+                rs[6] = __uint_as_float(v2[6]) + b1.z; rs[7] = __uint_as_float(v2[7]) + b1.w;
+              } else {
+                const uint4 res = *slot;                         // this row's input to the level (bf16 x 8)
+                rs[0] = bf16_lo(res.x); rs[1] = bf16_hi(res.x); rs[2] = bf16_lo(res.y); rs[3] = bf16_hi(res.y);
+                rs[4] = bf16_lo(res.z); rs[5] = bf16_hi(res.z); rs[6] = bf16_lo(res.w); rs[7] = bf16_hi(res.w);
+              }
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
                 const float a = fmaxf(__uint_as_float(v[q * 8 + e]) + bias_l[c * 8 + e], 0.f);   // relu(conv + b)
@@ -282,15 +321,20 @@ k2_tcn_bf16(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfl
   else __syncthreads();
   if (warp == kK2MmaWarp) {
     tc_fence_after_sync();
-    tmem_dealloc<128>(tmem);
+    if (g.ds_mask) tmem_dealloc<256>(tmem);
+    else tmem_dealloc<128>(tmem);
   }
 }
 
 // weights f32 [tap][cin][cout] (TF layout, customized_convolution_layer.py:137) -> bf16 [tap][cout][cin]
-__global__ void k2_prepare_weights(const float* __restrict__ w_in_x, const float* const* __restrict__ conv_w_dev,
-                                   int n_levels, int K, __nv_bfloat16* __restrict__ out) {
-  const int j = blockIdx.x;                       // weight tile: 0 = in-projection, 1 + l*K + tap
-  const float* src = j == 0 ? w_in_x : conv_w_dev[(j - 1) / K] + (long long)((j - 1) % K) * kDim * kDim;
+// tile_src[j]: the [128 cin][128 cout] fp32 source of weight tile j, in the order the kernel consumes them:
+// in-projection, then per level its K taps and, if it has one, the down-sample Dense kernel
+constexpr int kK2MaxWeightTiles = 1 + HTCN_MAX_LEVELS * 9;
+constexpr int kK2PtrTableBytes = 640;            // >= kK2MaxWeightTiles pointers, keeps the bias arrays 16-byte aligned
+static_assert(kK2MaxWeightTiles * 8 <= kK2PtrTableBytes, "pointer table");
+__global__ void k2_prepare_weights(const float* const* __restrict__ tile_src, __nv_bfloat16* __restrict__ out) {
+  const int j = blockIdx.x;
+  const float* src = tile_src[j];
   for (int i = threadIdx.x; i < kDim * kDim; i += blockDim.x) {
     const int cout = i / kDim, cin = i % kDim;
     out[(long long)j * kDim * kDim + i] = __float2bfloat16_rn(src[cin * kDim + cout]);
@@ -298,7 +342,8 @@ __global__ void k2_prepare_weights(const float* __restrict__ w_in_x, const float
 }
 
 int32_t tcn_forward_bf16(const void* xe, int xe_dtype, const float* w_in_x, const float* sbias,
-                         const float* const* conv_w, const float* const* conv_b, int n_levels, int K,
+                         const float* const* conv_w, const float* const* conv_b, const float* const* ds_w,
+                         const float* const* ds_b, int n_levels, int K,
                          const SlotTable& slots, int B, int T, const int* out_row, void* hout, int hout_dtype,
                          float* scratch, cudaStream_t st, void* h_save, void* a_save) {
   if (xe_dtype != HTCN_BF16 || hout_dtype != HTCN_BF16) {
@@ -307,7 +352,7 @@ int32_t tcn_forward_bf16(const void* xe, int xe_dtype, const float* w_in_x, cons
   }
   if (!scratch) {
     set_error("tcn_forward(bf16): scratch is required (%d bytes for the bf16 weight tiles)",
-              (1 + n_levels * K) * kDim * kDim * 2 + HTCN_MAX_LEVELS * (kDim * 4 + 8));
+              (int)HTCN_TCN_SCRATCH_BYTES(n_levels, K));
     return HTCN_ERR_INVALID;
   }
   const int P = n_levels > 0 ? (K - 1) * (1 << (n_levels - 1)) : 0;
@@ -340,21 +385,37 @@ int32_t tcn_forward_bf16(const void* xe, int xe_dtype, const float* w_in_x, cons
     }
   }
   g.n_tiles = tiles;
-  // scratch layout: [bf16 weight tiles][device array of conv_w pointers][biases]
+  // scratch layout: [bf16 weight tiles (HTCN_TCN_SCRATCH_BYTES reserves K+1 per level)][tile source pointers][conv biases]
+  // [down-sample biases]
+  const float* tile_src[kK2MaxWeightTiles];
+  int n_wt = 0;
+  tile_src[n_wt++] = w_in_x;
+  for (int l = 0; l < n_levels; ++l) {
+    for (int tap = 0; tap < K; ++tap) tile_src[n_wt++] = conv_w[l] + (long long)tap * kDim * kDim;
+    if (ds_w && ds_w[l]) {
+      g.ds_mask |= 1u << l;
+      tile_src[n_wt++] = ds_w[l];
+    }
+  }
   uint8_t* sc = reinterpret_cast<uint8_t*>(scratch);
   __nv_bfloat16* w_bf16 = reinterpret_cast<__nv_bfloat16*>(sc);
-  const size_t w_bytes = (size_t)(1 + n_levels * K) * kDim * kDim * 2;
+  const size_t w_bytes = (size_t)(1 + n_levels * (K + 1)) * kDim * kDim * 2;
   const float** ptrs_dev = reinterpret_cast<const float**>(sc + w_bytes);
-  float* bias_dev = reinterpret_cast<float*>(sc + w_bytes + HTCN_MAX_LEVELS * 8);
-  if (n_levels > 0) {
-    HTCN_CUDA(cudaMemcpyAsync(ptrs_dev, conv_w, sizeof(float*) * n_levels, cudaMemcpyHostToDevice, st));
-    for (int l = 0; l < n_levels; ++l)
-      HTCN_CUDA(cudaMemcpyAsync(bias_dev + l * kDim, conv_b[l], kDim * 4, cudaMemcpyDeviceToDevice, st));
+  float* bias_dev = reinterpret_cast<float*>(sc + w_bytes + kK2PtrTableBytes);
+  float* ds_bias_dev = bias_dev + HTCN_MAX_LEVELS * kDim;
+  // (pageable host source: the runtime stages the copy before returning, the stack array may die afterwards)
+  HTCN_CUDA(cudaMemcpyAsync(ptrs_dev, tile_src, sizeof(float*) * n_wt, cudaMemcpyHostToDevice, st));
+  for (int l = 0; l < n_levels; ++l) {
+    HTCN_CUDA(cudaMemcpyAsync(bias_dev + l * kDim, conv_b[l], kDim * 4, cudaMemcpyDeviceToDevice, st));
+    if ((g.ds_mask >> l) & 1u) {
+      if (ds_b && ds_b[l]) HTCN_CUDA(cudaMemcpyAsync(ds_bias_dev + l * kDim, ds_b[l], kDim * 4, cudaMemcpyDeviceToDevice, st));
+      else HTCN_CUDA(cudaMemsetAsync(ds_bias_dev + l * kDim, 0, kDim * 4, st));
+    }
   }
-  k2_prepare_weights<<<1 + n_levels * K, 256, 0, st>>>(w_in_x, ptrs_dev, n_levels, K, w_bf16);
+  k2_prepare_weights<<<n_wt, 256, 0, st>>>(ptrs_dev, w_bf16);
   HTCN_LAUNCH_CHECK("k2_prepare_weights");
   CUtensorMap tw;
-  int32_t rc = make_tmap_bf16(&tw, w_bf16, (uint64_t)(1 + n_levels * K) * kDim, kDim, kDim, 64, 128, 128);
+  int32_t rc = make_tmap_bf16(&tw, w_bf16, (uint64_t)n_wt * kDim, kDim, kDim, 64, 128, 128);
   if (rc) return rc;
   const size_t smem = sizeof(K2Smem) + 1024;
   // HTCN_K2_MULTICAST=1: CTA pairs with multicast weights.  Measured: 0.727 vs 0.719 ms (hier), 1.49 vs 1.55 ms (cfg3) --
@@ -377,14 +438,15 @@ int32_t tcn_forward_bf16(const void* xe, int xe_dtype, const float* w_in_x, cons
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    HTCN_CUDA(cudaLaunchKernelEx(&cfg, kern, tw, g, (const __nv_bfloat16*)xe, sbias, (const float*)bias_dev, out_row,
+    HTCN_CUDA(cudaLaunchKernelEx(&cfg, kern, tw, g, (const __nv_bfloat16*)xe, sbias, (const float*)bias_dev,
+                                 (const float*)ds_bias_dev, out_row,
                                  (__nv_bfloat16*)hout, (__nv_bfloat16*)h_save, (__nv_bfloat16*)a_save));
     return HTCN_OK;
   }
   auto kern = k2_tcn_bf16<false>;
   HTCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = tiles < 2 * 148 ? tiles : 2 * 148;
-  kern<<<grid, kK2Threads, smem, st>>>(tw, g, (const __nv_bfloat16*)xe, sbias, bias_dev, out_row,
+  kern<<<grid, kK2Threads, smem, st>>>(tw, g, (const __nv_bfloat16*)xe, sbias, bias_dev, ds_bias_dev, out_row,
                                        (__nv_bfloat16*)hout, (__nv_bfloat16*)h_save, (__nv_bfloat16*)a_save);
   HTCN_LAUNCH_CHECK("k2_tcn_bf16");
   return HTCN_OK;

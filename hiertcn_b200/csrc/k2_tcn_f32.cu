@@ -2,9 +2,10 @@
 // One generic kernel evaluates one "level" for 128 consecutive flat rows x 128 output channels:
 //     out[r,:] = epi( sum_{tap<K} in[r - (K-1-tap)*d, :] @ W[tap]  + bias [+ sbias[slot(r), user(r), :]] )
 // with the shifted row taken as zero when it falls before the start of r's sequence -- the causal
-// left pad of customized_tcn_cell.py:46-49 -- and epi = relu(relu(.) + in[r,:]) for conv levels
-// (customized_tcn_cell.py:109-127: relu inside the conv, residual add, relu) or identity for the
-// in-projection (model_tcn.py:35, K = 1, no bias).  Levels are chained through an fp32 scratch in HBM
+// left pad of customized_tcn_cell.py:46-49 -- and epi = relu(relu(.) + res[r,:]) for conv levels
+// (customized_tcn_cell.py:109-127: relu inside the conv, residual add, relu; res = in, or the 1x1 down-sample
+// Dense(in) of :102-106,123-124 computed by a K = 1 launch of this kernel when the level changes the width) or
+// identity for the in-projection (model_tcn.py:35, K = 1, no bias).  Levels are chained through an fp32 scratch in HBM
 // (L2-resident at these sizes); the bf16 tier (k2_tcn_bf16.cu) keeps them on chip instead.
 #include "train.cuh"
 
@@ -137,16 +138,17 @@ k2_level_f32(LevelArgs a, SlotTable slots) {
         float v = acc[i][jh * 4 + j];
         if (a.bias) v += __ldg(a.bias + c + j);
         if (sb) v += __ldg(sb + c + j);
-        if (a.conv_epilogue == 1) {
+        if (a.conv_epilogue == 1 || a.conv_epilogue == 3) {
           v = fmaxf(v, 0.f);
           ax[j] = v;
-          v = fmaxf(v + load_act(a.in, a.in_bf16, r * kDim + c + j), 0.f);
+          const float res = a.conv_epilogue == 1 ? load_act(a.in, a.in_bf16, r * kDim + c + j) : a.resid[r * kDim + c + j];
+          v = fmaxf(v + res, 0.f);
         } else if (a.conv_epilogue == 2) {
           v += a.resid[r * kDim + c + j];
         }
         o[j] = v;
       }
-      if (a.aux && a.conv_epilogue == 1)
+      if (a.aux && (a.conv_epilogue == 1 || a.conv_epilogue == 3))
         *reinterpret_cast<float4*>(a.aux + r * kDim + c) = make_float4(ax[0], ax[1], ax[2], ax[3]);
       if (a.out_bf16) {
         uint2 q = make_uint2(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]));
@@ -165,12 +167,14 @@ int32_t k2_level_launch(const LevelArgs& a, const SlotTable& slots, cudaStream_t
 }
 
 int32_t tcn_forward_f32(const void* xe, int xe_dtype, const float* w_in_x, const float* sbias,
-                        const float* const* conv_w, const float* const* conv_b, int n_levels, int K,
+                        const float* const* conv_w, const float* const* conv_b, const float* const* ds_w,
+                        const float* const* ds_b, int n_levels, int K,
                         const SlotTable& slots, int B, int T, const int* out_row, void* hout, int hout_dtype,
                         float* scratch, cudaStream_t st) {
   const long long R = (long long)B * T;
   const int grid = ceil_div(R, kTM);
   float* buf[2] = {scratch, scratch + R * kDim};
+  float* res_buf = scratch + 2 * R * kDim;        // down-sample residual of the current level (only with ds_w)
   LevelArgs a{};
   a.R = R; a.T = T; a.B = B;
   // in-projection: K = 1, no bias, per-sequence bias = state half of the concat (model_hier.py:54-55)
@@ -184,8 +188,16 @@ int32_t tcn_forward_f32(const void* xe, int xe_dtype, const float* w_in_x, const
   HTCN_LAUNCH_CHECK("k2_level_f32(in-proj)");
   for (int l = 0; l < n_levels; ++l) {
     const bool last = (l == n_levels - 1);
-    a.in = buf[l & 1]; a.in_bf16 = 0;
-    a.w = conv_w[l]; a.bias = conv_b[l]; a.sbias = nullptr; a.K = K; a.dil = 1 << l; a.conv_epilogue = 1;
+    const bool ds = ds_w && ds_w[l];
+    a.in = buf[l & 1]; a.in_bf16 = 0; a.sbias = nullptr;
+    if (ds) {                                     // res = in @ W_ds + b_ds (customized_tcn_cell.py:102-106,123-124)
+      a.w = ds_w[l]; a.bias = ds_b ? ds_b[l] : nullptr; a.K = 1; a.dil = 1; a.conv_epilogue = 0;
+      a.out = res_buf; a.out_row = nullptr; a.out_bf16 = 0;
+      k2_level_f32<<<grid, kK2Threads, 0, st>>>(a, slots);
+      HTCN_LAUNCH_CHECK("k2_level_f32(down-sample)");
+    }
+    a.w = conv_w[l]; a.bias = conv_b[l]; a.K = K; a.dil = 1 << l; a.conv_epilogue = ds ? 3 : 1;
+    a.resid = ds ? res_buf : nullptr;
     a.out = last ? hout : (void*)buf[(l + 1) & 1];
     a.out_row = last ? out_row : nullptr;
     a.out_bf16 = last ? (hout_dtype == HTCN_BF16) : 0;
@@ -201,7 +213,8 @@ int32_t tcn_forward_f32(const void* xe, int xe_dtype, const float* w_in_x, const
 
 extern "C" int32_t htcn_tcn_forward(const void* xe, int32_t xe_dtype, int32_t precision, const float* w_in_x,
                                     const float* sbias, const float* const* conv_w_host,
-                                    const float* const* conv_b_host, int32_t n_levels, int32_t kernel_size,
+                                    const float* const* conv_b_host, const float* const* ds_w_host,
+                                    const float* const* ds_b_host, int32_t n_levels, int32_t kernel_size,
                                     const int32_t* slot_off_host, int32_t B, int32_t T, int32_t S,
                                     const int32_t* out_row, void* hout, int32_t hout_dtype, float* scratch,
                                     void* stream) {
@@ -219,11 +232,11 @@ extern "C" int32_t htcn_tcn_forward(const void* xe, int32_t xe_dtype, int32_t pr
   HTCN_REQUIRE(slots.off[0] == 0 && slots.off[S] == T, "tcn_forward: slot_off does not span T");
   if (precision == HTCN_F32) {
     HTCN_REQUIRE(scratch || n_levels == 0, "tcn_forward: f32 tier needs scratch");
-    return tcn_forward_f32(xe, xe_dtype, w_in_x, sbias, conv_w_host, conv_b_host, n_levels, kernel_size, slots,
+    return tcn_forward_f32(xe, xe_dtype, w_in_x, sbias, conv_w_host, conv_b_host, ds_w_host, ds_b_host, n_levels, kernel_size, slots,
                            B, T, out_row, hout, hout_dtype, scratch, as_stream(stream));
   }
   if (precision == HTCN_BF16)
-    return tcn_forward_bf16(xe, xe_dtype, w_in_x, sbias, conv_w_host, conv_b_host, n_levels, kernel_size, slots, B,
+    return tcn_forward_bf16(xe, xe_dtype, w_in_x, sbias, conv_w_host, conv_b_host, ds_w_host, ds_b_host, n_levels, kernel_size, slots, B,
                             T, out_row, hout, hout_dtype, scratch, as_stream(stream));
   set_error("tcn_forward: precision %d", precision);
   return HTCN_ERR_INVALID;

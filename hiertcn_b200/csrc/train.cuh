@@ -17,10 +17,11 @@ struct LevelArgs {
   const int* out_row;         // [R] or NULL
   long long R;
   int T, B, K, dil;
-  int conv_epilogue;          // 1: relu, +residual, relu; 0: linear; 2: + resid[r,:] (backward: data gradient)
+  int conv_epilogue;          // 1: relu, + in[r,:] (identity residual), relu; 0: linear; 2: + resid[r,:] (backward: data
+                              // gradient); 3: relu, + resid[r,:], relu (down-sample residual, customized_tcn_cell.py:102-106,123-124)
   int in_bf16, out_bf16;
   float* aux;                 // [R,128] relu(conv + bias) before the residual add, saved for the backward, or NULL
-  const float* resid;         // [R,128] added in epilogue 2 (may alias out)
+  const float* resid;         // [R,128] added in epilogues 2 and 3 (may alias out in 2)
   int anti;                   // 1: taps read r + shift, zero beyond the END of r's sequence (transposed convolution)
   int w_nt;                   // 1: every W[tap] is applied transposed
 };
@@ -28,8 +29,11 @@ int32_t k2_level_launch(const LevelArgs& a, const SlotTable& slots, cudaStream_t
 
 // fused tcgen05 conv stack (k2_tcn_bf16.cu); h_save / a_save (bf16, optional) keep every layer's output and every
 // level's pre-residual activation for the backward
+// ds_w / ds_b: per level, the 1x1 down-sample residual Dense of customized_tcn_cell.py:102-106 (entry NULL = identity
+// residual; the arrays themselves may be NULL)
 int32_t tcn_forward_bf16(const void* xe, int xe_dtype, const float* w_in_x, const float* sbias,
-                         const float* const* conv_w, const float* const* conv_b, int n_levels, int K,
+                         const float* const* conv_w, const float* const* conv_b, const float* const* ds_w,
+                         const float* const* ds_b, int n_levels, int K,
                          const SlotTable& slots, int B, int T, const int* out_row, void* hout, int hout_dtype,
                          float* scratch, cudaStream_t st, void* h_save = nullptr, void* a_save = nullptr);
 

@@ -89,10 +89,11 @@ class HierTCN:
             raise ValueError("precision must be 'f32' or 'bf16'")
         if args.model_type != "hier" or args.model_low_type != "tcn":
             raise NotImplementedError("only model_type='hier' with model_low_type='tcn' is the hot path")
-        if list(args.tcn_channel) != [128] * len(args.tcn_channel) or args.hidden_dim != 128:
-            raise NotImplementedError("the sm_100a kernels are built for C = H = 128 (reference defaults)")
-        if getattr(args, "emb_dim", 128) > 128:
-            raise NotImplementedError("emb_dim > 128")
+        # widths below 128 run zero-padded to 128 (hiertcn_b200.weights.to_device_layout); levels that change the width get
+        # the 1x1 down-sample residual of customized_tcn_cell.py:102-106
+        if max(list(args.tcn_channel) + [int(args.hidden_dim), int(getattr(args, "emb_dim", 128))]) > 128:
+            raise NotImplementedError("widths above 128 (tcn_channel / hidden_dim / emb_dim): the sm_100a kernels run "
+                                      "128-wide blocks")
         for flag in ("has_batchnorm", "has_layernorm", "has_gap", "has_impression", "l2_normalize"):
             if getattr(args, flag, False):
                 raise NotImplementedError("%s is outside the hot path (SURVEY.md A.8)" % flag)
@@ -128,9 +129,14 @@ class HierTCN:
         if w is None:
             w = init_weights(hier_weight_shapes(self.N, a.hidden_dim, self.G, tuple(a.tcn_channel), self.K,
                                                 getattr(a, "emb_dim", 128)), seed=self.seed)
-        from .weights import fold_weightnorm
+        from .weights import fold_weightnorm, to_device_layout
         w = fold_weightnorm(w)
-        ed = w["hier/emb/kernel"].shape[1]
+        lay, meta = to_device_layout(w, "hier")          # every width zero-padded to 128
+        self.layout_meta = meta
+        if meta["G"] != self.G or meta["K"] != self.K or len(meta["channels"]) != self.n_levels:
+            raise ValueError("weights do not match args: num_layer %d/%d kernel_size %d/%d levels %d/%d"
+                             % (meta["G"], self.G, meta["K"], self.K, len(meta["channels"]), self.n_levels))
+        ed = meta["ed"]
         dev = self.device
 
         def up(x):
@@ -139,30 +145,16 @@ class HierTCN:
         # emb_dim < 128: the table is stored PACKED (emb_pitch floats per row, e.g. 100 -> 400 B rows) and K1 zero-fills
         # the output rows beyond it (same math as a zero-padded table, 22% fewer gathered bytes at config 2's 100-d)
         self.emb_pitch = min(D, -(-ed // 4) * 4)
-        E = np.zeros((self.N, self.emb_pitch), np.float32)
-        E[:, :ed] = w["hier/emb/kernel"]
-        be = np.zeros(D, np.float32)
-        be[:ed] = w["hier/emb/bias"]
-        w_in = w["hier/tcn/emb/kernel"]                 # [ed + G*H, 128]
-        w_in_x = np.zeros((D, 128), np.float32)
-        w_in_x[:ed] = w_in[:ed]
-        self.E, self.b_emb = up(E), up(be)
-        self.w_in_x, self.w_in_state = up(w_in_x), up(w_in[ed:])
-        self.conv_w = [up(w[f"hier/tcn/temporal_conv_net/tblock_{l}/conv1/kernel"]) for l in range(self.n_levels)]
-        self.conv_b = [up(w[f"hier/tcn/temporal_conv_net/tblock_{l}/conv1/bias"]) for l in range(self.n_levels)]
-        self.gru = []
-        for g in range(self.G):
-            p = f"hier/multi_rnn_cell/cell_{g}/gru_cell"
-            gw, cw = w[p + "/gates/kernel"], w[p + "/candidate/kernel"]
-            if g == 0 and ed < D:                       # pad the input rows of layer 0
-                pad = np.zeros((D - ed, gw.shape[1]), np.float32)
-                gw = np.concatenate([gw[:ed], pad, gw[ed:]], 0)
-                pad = np.zeros((D - ed, cw.shape[1]), np.float32)
-                cw = np.concatenate([cw[:ed], pad, cw[ed:]], 0)
-            self.gru.append((up(gw), up(w[p + "/gates/bias"]), up(cw), up(w[p + "/candidate/bias"])))
-        self.b_out = up(w["hier/tcn/dense/bias"])
-        self._w_out_host = w["hier/tcn/dense/kernel"]   # fp32 master of the output table (hiertcn_b200.train, bf16 tier)
-        w_out = up(w["hier/tcn/dense/kernel"])          # [128, N] TF layout
+        self.E, self.b_emb = up(lay["E"][:, :self.emb_pitch]), up(lay["b_emb"])
+        self.w_in_x, self.w_in_state = up(lay["w_in_x"]), up(lay["w_in_state"])
+        self.conv_w = [up(lay[f"conv_w{l}"]) for l in range(self.n_levels)]
+        self.conv_b = [up(lay[f"conv_b{l}"]) for l in range(self.n_levels)]
+        self.ds_w = [up(lay[f"ds_w{l}"]) if meta["ds"][l] else None for l in range(self.n_levels)]
+        self.ds_b = [up(lay[f"ds_b{l}"]) if meta["ds"][l] else None for l in range(self.n_levels)]
+        self.gru = [tuple(up(lay[f"{n}{g}"]) for n in ("gate_w", "gate_b", "cand_w", "cand_b")) for g in range(self.G)]
+        self.b_out = up(lay["b_out"])
+        self._w_out_host = lay["w_out"]                 # fp32 master of the output table (hiertcn_b200.train, bf16 tier)
+        w_out = up(lay["w_out"])                        # [128, N] TF layout (rows beyond the last level's width are zero)
         self.act_dtype = cabi.HTCN_BF16 if self.precision == "bf16" else cabi.HTCN_F32
         tdt = torch.bfloat16 if self.precision == "bf16" else torch.float32
         self.act_torch_dtype = tdt
@@ -174,11 +166,19 @@ class HierTCN:
         self.wt_f32 = self.wt if self.precision == "f32" else None
         torch.cuda.synchronize(dev)
         del w_out
-        self._conv_w_pp = cabi.ptr_array([t.data_ptr() for t in self.conv_w])
-        self._conv_b_pp = cabi.ptr_array([t.data_ptr() for t in self.conv_b])
-        self._gru_pp = [cabi.ptr_array([l[i].data_ptr() for l in self.gru]) for i in range(4)]
+        self.refresh_pointer_tables()
         self.built = True
         return self
+
+    def refresh_pointer_tables(self):
+        """host arrays of device pointers the C ABI takes (rebuilt when the trainer re-homes the parameters)"""
+        self._conv_w_pp = cabi.ptr_array([t.data_ptr() for t in self.conv_w])
+        self._conv_b_pp = cabi.ptr_array([t.data_ptr() for t in self.conv_b])
+        self.has_ds = any(t is not None for t in self.ds_w)
+        self._ds_w_pp = cabi.ptr_array([t.data_ptr() if t is not None else 0 for t in self.ds_w]) if self.has_ds else (None, None)
+        self._ds_b_pp = cabi.ptr_array([t.data_ptr() if t is not None else 0 for t in self.ds_b]) if self.has_ds else (None, None)
+        if self.G:
+            self._gru_pp = [cabi.ptr_array([l[i].data_ptr() for l in self.gru]) for i in range(4)]
 
     def stream_ptr(self):
         return _torch().cuda.current_stream(self.device).cuda_stream
@@ -248,7 +248,11 @@ class HierTCN:
             dev["state"] = state.to(device=self.device, dtype=f32).contiguous()
         else:
             ts, ns_ = self._pinned(slot, "state", (B, self.G * 128), f32)
-            ns_[:] = 0.0 if state is None else state
+            if state is None:
+                ns_[:] = 0.0
+            else:
+                from .weights import pad_state
+                ns_[:] = pad_state(state, self.layout_meta)       # hidden_dim < 128: zero-padded units
             host["state"] = ts
         if neg_ids is not None and not hasattr(neg_ids, "data_ptr"):
             tn, nn = self._pinned(slot, "neg_ids", tuple(np.shape(neg_ids)), i32)
@@ -300,15 +304,16 @@ class HierTCN:
         hout = self._buf("hout", (max(Q, 1), D), self.act_torch_dtype)
         k2_precision = self._k2_precision()
         if k2_precision == cabi.HTCN_F32:
-            scratch = self._buf("k2_scratch", (2 * B * T, D), f32)
+            scratch = self._buf("k2_scratch", ((3 if self.has_ds else 2) * B * T, D), f32)
         else:       # bf16 weight tiles + pointer table + biases of the fused tcgen05 conv stack
-            scratch = self._buf("k2_scratch_bf16", ((1 + self.n_levels * self.K) * 8192 + 4096,), f32)
+            scratch = self._buf("k2_scratch_bf16", (cabi.tcn_scratch_floats(self.n_levels, self.K),), f32)
         cabi.call("htcn_tcn_forward", xe.data_ptr(), self.act_dtype, k2_precision, self.w_in_x.data_ptr(),
-                  sbias.data_ptr(), self._conv_w_pp[0], self._conv_b_pp[0], self.n_levels, self.K, slot_p, B, T, S,
+                  sbias.data_ptr(), self._conv_w_pp[0], self._conv_b_pp[0], self._ds_w_pp[0], self._ds_b_pp[0],
+                  self.n_levels, self.K, slot_p, B, T, S,
                   d["row_of"].data_ptr(), hout.data_ptr(), self.act_dtype,
                   scratch.data_ptr() if scratch is not None else None, st)
         # fp32: one launch per level + the in-projection; bf16: weight-tile preparation + the fused stack
-        cabi.note_launches(2 if k2_precision == cabi.HTCN_BF16 else self.n_levels + 1)
+        cabi.note_launches(2 if k2_precision == cabi.HTCN_BF16 else self.n_levels + 1 + sum(t is not None for t in self.ds_w))
         if k3_bf16:
             cabi.note_launches(1)                   # k3_prepare_weights (htcn_gru_sessions counts one launch)
         del slot_keep
@@ -522,7 +527,7 @@ class HierTCN:
             host[k] = pt
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.device))
-        return PendingStep(ev, host, state_out if state_on_device else None, topk)
+        return PendingStep(ev, host, state_out if state_on_device else None, topk, self.layout_meta)
 
     def step(self, x_list=None, y_list=None, mask_list=None, state=None, metrics=True, per_position=False, topk=0,
              state_on_device=False, neg_ids=None, staged=None):
@@ -538,8 +543,8 @@ class PendingStep:
     """Handle of an enqueued step; ``result()`` blocks on its completion event and copies the results out of the
     pinned staging buffers (which are reused three steps later)."""
 
-    def __init__(self, event, host, state_dev, topk):
-        self.event, self.host, self.state_dev, self.topk = event, host, state_dev, topk
+    def __init__(self, event, host, state_dev, topk, layout_meta=None):
+        self.event, self.host, self.state_dev, self.topk, self.layout_meta = event, host, state_dev, topk, layout_meta
 
     def result(self):
         self.event.synchronize()
@@ -547,7 +552,12 @@ class PendingStep:
         sc = h["scalars"]
         out = dict(loss=sc[0], recall1=sc[1], recall5=sc[2], recall10=sc[3], mrr=sc[4], mrp=sc[5],
                    user_count=sc[6], n_valid=sc[7])
-        out["state"] = self.state_dev if self.state_dev is not None else h["state"].copy()
+        if self.state_dev is not None:
+            out["state"] = self.state_dev              # device layout [B, G*128] (opaque; feed it back as ``state``)
+        else:
+            from .weights import unpad_state
+            st = h["state"].copy()
+            out["state"] = unpad_state(st, self.layout_meta) if self.layout_meta is not None else st
         for n in ("loss_bt", "ranks", "ranks_float", "row_of"):
             if n in h:
                 out[n] = h[n].copy()
@@ -602,4 +612,5 @@ def model_hier(args, x, y, mask, state, x_gap=None, x_impression=None, name="hie
         raise NotImplementedError("variable scope other than 'hier'")
     m = model if model is not None else _model_for(args, weights, precision or getattr(args, "precision", "bf16"))
     scores, state_out = m.forward(x, y, mask, state)
-    return scores, state_out.cpu().numpy()
+    from .weights import unpad_state
+    return scores, unpad_state(state_out.cpu().numpy(), m.layout_meta)

@@ -5,8 +5,9 @@ BASELINE config 3: low-level TCN only, long sequences, dilations 1-2-4-8).
 
 on the same kernels as the hierarchical path: K1 gathers the rows of ``tcn/emb/kernel`` (id 0 -> zeros), K2 runs the
 conv stack (its in-projection is fed the identity, because here the 'emb' dense IS the gather), K4 scores the
-catalog.  Only 128-channel levels are supported by the sm_100a kernels (the reference's default single-level stack
-ends with two 256-channel levels, args.py:310-311 -- config 3 uses [128]*4).
+catalog.  Levels up to 128 channels (narrower ones run zero-padded, width changes get the 1x1 down-sample residual of
+customized_tcn_cell.py:102-106); the reference's default single-level stack ends with two 256-channel levels
+(args.py:310-311), which the 128-wide kernels do not run -- config 3 uses [128]*4.
 """
 from __future__ import annotations
 
@@ -26,8 +27,8 @@ class TCN(HierTCN):
     def __init__(self, args, weights, device=None, precision=None, scope="tcn"):
         self.args = args
         self.precision = precision or getattr(args, "precision", "bf16")
-        if list(args.tcn_channel) != [128] * len(args.tcn_channel):
-            raise NotImplementedError("the sm_100a conv kernels are built for 128-channel levels")
+        if max(args.tcn_channel) > 128:
+            raise NotImplementedError("tcn_channel above 128: the sm_100a kernels run 128-wide blocks")
         self.N = int(args.item_num)
         self.K = int(args.kernel_size)
         self.n_levels = len(args.tcn_channel)
@@ -43,16 +44,19 @@ class TCN(HierTCN):
             self.device = torch.device("cuda", torch.cuda.current_device())
         if not cabi.load().htcn_device_ok():
             raise cabi.HtcnError("current CUDA device is not compute capability 10.x (B200)")
-        w = fold_weightnorm(self.host_weights)
-        sc = self.scope
+        from .weights import to_device_layout
+        lay, meta = to_device_layout(fold_weightnorm(self.host_weights), self.scope)
+        self.layout_meta = meta
         up = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(self.device)  # noqa: E731
-        self.E = up(w[sc + "/emb/kernel"])                      # [N,128]: the in-projection applied to a one-hot
-        self.b_emb = up(np.zeros(D, np.float32))
-        self.w_in_x = up(np.eye(D, dtype=np.float32))
-        self.conv_w = [up(w[f"{sc}/temporal_conv_net/tblock_{l}/conv1/kernel"]) for l in range(self.n_levels)]
-        self.conv_b = [up(w[f"{sc}/temporal_conv_net/tblock_{l}/conv1/bias"]) for l in range(self.n_levels)]
-        self.b_out = up(w[sc + "/dense/bias"])
-        w_out = up(w[sc + "/dense/kernel"])
+        self.E = up(lay["E"])                                   # [N,128]: the in-projection applied to a one-hot
+        self.emb_pitch = D
+        self.b_emb, self.w_in_x = up(lay["b_emb"]), up(lay["w_in_x"])
+        self.conv_w = [up(lay[f"conv_w{l}"]) for l in range(self.n_levels)]
+        self.conv_b = [up(lay[f"conv_b{l}"]) for l in range(self.n_levels)]
+        self.ds_w = [up(lay[f"ds_w{l}"]) if meta["ds"][l] else None for l in range(self.n_levels)]
+        self.ds_b = [up(lay[f"ds_b{l}"]) if meta["ds"][l] else None for l in range(self.n_levels)]
+        self.b_out = up(lay["b_out"])
+        w_out = up(lay["w_out"])
         self.act_dtype = cabi.HTCN_BF16 if self.precision == "bf16" else cabi.HTCN_F32
         self.act_torch_dtype = torch.bfloat16 if self.precision == "bf16" else torch.float32
         self.n_out = int(w_out.shape[1])
@@ -62,8 +66,7 @@ class TCN(HierTCN):
                   self.act_dtype, self.stream_ptr())
         self.wt_f32 = self.wt if self.precision == "f32" else None
         torch.cuda.synchronize(self.device)
-        self._conv_w_pp = cabi.ptr_array([t.data_ptr() for t in self.conv_w])
-        self._conv_b_pp = cabi.ptr_array([t.data_ptr() for t in self.conv_b])
+        self.refresh_pointer_tables()
         self.built = True
         return self
 
@@ -90,11 +93,11 @@ class TCN(HierTCN):
         hout = self._buf("hout", (max(Q, 1), D), self.act_torch_dtype)
         prec = self._k2_precision()
         if prec == cabi.HTCN_F32:
-            scratch = self._buf("k2_scratch", (2 * B * L, D), torch.float32)
+            scratch = self._buf("k2_scratch", ((3 if self.has_ds else 2) * B * L, D), torch.float32)
         else:
-            scratch = self._buf("k2_scratch_bf16", ((1 + self.n_levels * self.K) * 8192 + 4096,), torch.float32)
+            scratch = self._buf("k2_scratch_bf16", (cabi.tcn_scratch_floats(self.n_levels, self.K),), torch.float32)
         cabi.call("htcn_tcn_forward", xe.data_ptr(), self.act_dtype, prec, self.w_in_x.data_ptr(), None,
-                  self._conv_w_pp[0], self._conv_b_pp[0], self.n_levels, self.K, slot_p, B, L, 1, row_d.data_ptr(),
+                  self._conv_w_pp[0], self._conv_b_pp[0], self._ds_w_pp[0], self._ds_b_pp[0], self.n_levels, self.K, slot_p, B, L, 1, row_d.data_ptr(),
                   hout.data_ptr(), self.act_dtype, scratch.data_ptr(), st)
         return CatalogScores(self, hout, Q, row_d, yrows_d, y_d, B, L)
 

@@ -46,6 +46,8 @@ class HierTCNTrainer:
                 ("w_in_state", (G * D, D))]
         for l in range(L):
             spec += [(f"conv_w{l}", (K, D, D)), (f"conv_b{l}", (D,))]
+            if m.ds_w[l] is not None:           # 1x1 down-sample residual of a level that changes the width
+                spec += [(f"ds_w{l}", (D, D)), (f"ds_b{l}", (D,))]
         for g in range(G):
             spec += [(f"gate_w{g}", (2 * D, 2 * D)), (f"gate_b{g}", (2 * D,)), (f"cand_w{g}", (2 * D, D)), (f"cand_b{g}", (D,))]
         self.spec, self.offsets, off = spec, {}, 0
@@ -67,6 +69,8 @@ class HierTCNTrainer:
         cur = {"E": m.E, "wt": wt_master, "b_out": m.b_out, "b_emb": m.b_emb, "w_in_x": m.w_in_x, "w_in_state": m.w_in_state}
         for l in range(L):
             cur[f"conv_w{l}"], cur[f"conv_b{l}"] = m.conv_w[l], m.conv_b[l]
+            if m.ds_w[l] is not None:
+                cur[f"ds_w{l}"], cur[f"ds_b{l}"] = m.ds_w[l], m.ds_b[l]
         for g in range(G):
             cur[f"gate_w{g}"], cur[f"gate_b{g}"], cur[f"cand_w{g}"], cur[f"cand_b{g}"] = m.gru[g]
         self.p, self.g = {}, {}
@@ -86,12 +90,15 @@ class HierTCNTrainer:
         m.w_in_x, m.w_in_state = self.p["w_in_x"], self.p["w_in_state"]
         m.conv_w = [self.p[f"conv_w{l}"] for l in range(L)]
         m.conv_b = [self.p[f"conv_b{l}"] for l in range(L)]
+        m.ds_w = [self.p.get(f"ds_w{l}") for l in range(L)]
+        m.ds_b = [self.p.get(f"ds_b{l}") for l in range(L)]
         m.gru = [tuple(self.p[f"{n}{g}"] for n in ("gate_w", "gate_b", "cand_w", "cand_b")) for g in range(G)]
-        m._conv_w_pp = cabi.ptr_array([t.data_ptr() for t in m.conv_w])
-        m._conv_b_pp = cabi.ptr_array([t.data_ptr() for t in m.conv_b])
-        m._gru_pp = [cabi.ptr_array([l[i].data_ptr() for l in m.gru]) for i in range(4)]
+        m.refresh_pointer_tables()
         self._d_conv_w = cabi.ptr_array([self.g[f"conv_w{l}"].data_ptr() for l in range(L)])
         self._d_conv_b = cabi.ptr_array([self.g[f"conv_b{l}"].data_ptr() for l in range(L)])
+        null = (None, None)
+        self._d_ds_w = cabi.ptr_array([self.g[f"ds_w{l}"].data_ptr() if f"ds_w{l}" in self.g else 0 for l in range(L)]) if m.has_ds else null
+        self._d_ds_b = cabi.ptr_array([self.g[f"ds_b{l}"].data_ptr() if f"ds_b{l}" in self.g else 0 for l in range(L)]) if m.has_ds else null
         self._d_gru = [cabi.ptr_array([self.g[f"{n}{g}"].data_ptr() for g in range(G)])
                        for n in ("gate_w", "gate_b", "cand_w", "cand_b")]
         torch.cuda.synchronize(m.device)
@@ -147,14 +154,14 @@ class HierTCNTrainer:
         a_save = buf("tr_a_save_bf16" if fused else "tr_a_save", (max(L, 1), R, D), sdt)
         hout = buf("tr_hout_bf16" if fused else "tr_hout", (max(Q, 1), D), sdt)
         if fused:
-            k2f_scratch = buf("k2_scratch_bf16", ((1 + L * K) * 8192 + 4096,), f32)
+            k2f_scratch = buf("k2_scratch_bf16", (cabi.tcn_scratch_floats(L, K),), f32)
             cabi.call("htcn_tcn_forward_train_bf16", xe.data_ptr(), m.w_in_x.data_ptr(), sbias.data_ptr(), m._conv_w_pp[0],
-                      m._conv_b_pp[0], L, K, slot_p, B, T, S, d["row_of"].data_ptr(), h_save.data_ptr(), a_save.data_ptr(),
+                      m._conv_b_pp[0], m._ds_w_pp[0], m._ds_b_pp[0], L, K, slot_p, B, T, S, d["row_of"].data_ptr(), h_save.data_ptr(), a_save.data_ptr(),
                       hout.data_ptr(), k2f_scratch.data_ptr(), st)
             cabi.note_launches(2)
         else:
             cabi.call("htcn_tcn_forward_train", xe.data_ptr(), m.w_in_x.data_ptr(), sbias.data_ptr(), m._conv_w_pp[0],
-                      m._conv_b_pp[0], L, K, slot_p, B, T, S, d["row_of"].data_ptr(), h_save.data_ptr(), a_save.data_ptr(),
+                      m._conv_b_pp[0], m._ds_w_pp[0], m._ds_b_pp[0], L, K, slot_p, B, T, S, d["row_of"].data_ptr(), h_save.data_ptr(), a_save.data_ptr(),
                       hout.data_ptr(), st)
             cabi.note_launches(L + 2)
         scalars = torch.zeros(8, dtype=f32, device=m.device)
@@ -206,10 +213,11 @@ class HierTCNTrainer:
                       self.g["wt"].data_ptr(), self.g["b_out"].data_ptr(), st)
         d_sbias = buf("tr_d_sbias", (S, B, D), f32)
         d_xe = buf("tr_d_xe", (R, D), f32)
-        k2_scratch = buf("tr_k2_scratch", (2, R, D), f32)
+        k2_scratch = buf("tr_k2_scratch", (3 if m.has_ds else 2, R, D), f32)
         cabi.call("htcn_tcn_backward", d_hout.data_ptr(), d["row_of"].data_ptr(), xe.data_ptr(), sdt_c, m.w_in_x.data_ptr(),
-                  m._conv_w_pp[0], L, K, slot_p, B, T, S, h_save.data_ptr(), a_save.data_ptr(), k2_scratch.data_ptr(),
-                  self._d_conv_w[0], self._d_conv_b[0], self.g["w_in_x"].data_ptr(), d_sbias.data_ptr(), d_xe.data_ptr(), st)
+                  m._conv_w_pp[0], m._ds_w_pp[0], L, K, slot_p, B, T, S, h_save.data_ptr(), a_save.data_ptr(),
+                  k2_scratch.data_ptr(), self._d_conv_w[0], self._d_conv_b[0], self._d_ds_w[0], self._d_ds_b[0],
+                  self.g["w_in_x"].data_ptr(), d_sbias.data_ptr(), d_xe.data_ptr(), st)
         cabi.note_launches(1 + L * (K + 3) + 3)
         d_yp = buf("tr_d_yp", (S, B, D), f32)
         n_scr = int(cabi.load().htcn_gru_backward_scratch_floats(B, S, G))
@@ -259,7 +267,11 @@ class HierTCNTrainer:
         out = dict(loss=float(sc[0]), user_count=float(sc[6]), n_valid=float(sc[7]))
         if metrics:
             out.update(recall1=float(sc[1]), recall5=float(sc[2]), recall10=float(sc[3]), mrr=float(sc[4]), mrp=float(sc[5]))
-        out["state"] = r["state"] if state_on_device else r["state"].cpu().numpy()
+        if state_on_device:
+            out["state"] = r["state"]
+        else:
+            from .weights import unpad_state
+            out["state"] = unpad_state(r["state"].cpu().numpy(), self.m.layout_meta)
         return out
 
     # ------------------------------------------------------------------ inspection / checkpoint
@@ -290,7 +302,11 @@ class HierTCNTrainer:
         out["meta"] = np.frombuffer(json.dumps(dict(step=self.t, lr=self.lr, beta1=self.beta1, beta2=self.beta2, eps=self.eps,
                                                     epoch=int(epoch), precision=self.m.precision)).encode(), dtype=np.uint8)
         if state is not None:
-            out["carried_state"] = state.detach().cpu().numpy() if hasattr(state, "detach") else np.asarray(state, np.float32)
+            if hasattr(state, "detach"):        # device tensor = the padded device layout [B, G*128]: store [B, G*H]
+                from .weights import unpad_state
+                out["carried_state"] = unpad_state(state.detach().cpu().numpy(), self.m.layout_meta)
+            else:
+                out["carried_state"] = np.asarray(state, np.float32)
         if loader is not None and hasattr(loader, "state_dict"):
             out["loader"] = np.frombuffer(json.dumps(loader.state_dict()).encode(), dtype=np.uint8)
         np.savez(path, **out)
@@ -303,29 +319,10 @@ class HierTCNTrainer:
         meta = json.loads(bytes(z["meta"]).decode())
 
         def scatter(prefix, flat):
+            from .weights import to_device_layout
             t = {k[len(prefix):].replace("|", "/"): z[k] for k in z.files if k.startswith(prefix)}
-            m = self.m
-            ed = t["hier/emb/kernel"].shape[1]          # TF shapes carry emb_dim; the device layout is padded to 128
-
-            def pad_cols(a):
-                return np.pad(a, [(0, 0)] * (a.ndim - 1) + [(0, D - ed)])
-
-            def pad_rows(a):                             # [ed + rest, C] -> [128 + rest, C]
-                return np.concatenate([a[:ed], np.zeros((D - ed, a.shape[1]), a.dtype), a[ed:]], 0)
-
-            named = {"E": pad_cols(t["hier/emb/kernel"]), "b_emb": pad_cols(t["hier/emb/bias"]),
-                     "w_in_x": pad_rows(t["hier/tcn/emb/kernel"])[:D], "w_in_state": t["hier/tcn/emb/kernel"][ed:],
-                     "wt": np.ascontiguousarray(t["hier/tcn/dense/kernel"].T), "b_out": t["hier/tcn/dense/bias"]}
-            for l in range(m.n_levels):
-                named[f"conv_w{l}"] = t[f"hier/tcn/temporal_conv_net/tblock_{l}/conv1/kernel"]
-                named[f"conv_b{l}"] = t[f"hier/tcn/temporal_conv_net/tblock_{l}/conv1/bias"]
-            for g in range(m.G):
-                p = f"hier/multi_rnn_cell/cell_{g}/gru_cell"
-                gw, cw = t[p + "/gates/kernel"], t[p + "/candidate/kernel"]
-                if g == 0:
-                    gw, cw = pad_rows(gw), pad_rows(cw)
-                named[f"gate_w{g}"], named[f"gate_b{g}"] = gw, t[p + "/gates/bias"]
-                named[f"cand_w{g}"], named[f"cand_b{g}"] = cw, t[p + "/candidate/bias"]
+            named, _ = to_device_layout(t, "hier")       # TF shapes -> the 128-padded device layout
+            named["wt"] = np.ascontiguousarray(named.pop("w_out").T)
             for n, sh in self.spec:
                 self._view(flat, n, sh).copy_(torch.from_numpy(np.ascontiguousarray(named[n], dtype=np.float32)).reshape(sh))
 
@@ -342,23 +339,9 @@ class HierTCNTrainer:
         return dict(epoch=int(meta["epoch"]), state=z["carried_state"] if "carried_state" in z.files else None)
 
     def _to_tf_names(self, t):
-        m = self.m
-        ed = int(getattr(m.args, "emb_dim", D))    # emb_dim < 128 is zero-padded on the device: emit the TF shapes
-        cut = lambda a: np.concatenate([a[:ed], a[D:]], 0)  # noqa: E731  drop the padded input rows
-        w = {"hier/emb/kernel": t["E"][:, :ed], "hier/emb/bias": t["b_emb"][:ed],
-             "hier/tcn/emb/kernel": np.concatenate([t["w_in_x"][:ed], t["w_in_state"]], 0),
-             "hier/tcn/dense/kernel": np.ascontiguousarray(t["wt"].T), "hier/tcn/dense/bias": t["b_out"]}
-        for l in range(m.n_levels):
-            w[f"hier/tcn/temporal_conv_net/tblock_{l}/conv1/kernel"] = t[f"conv_w{l}"]
-            w[f"hier/tcn/temporal_conv_net/tblock_{l}/conv1/bias"] = t[f"conv_b{l}"]
-        for g in range(m.G):
-            p = f"hier/multi_rnn_cell/cell_{g}/gru_cell"
-            gw, cw = t[f"gate_w{g}"], t[f"cand_w{g}"]
-            if g == 0 and ed < D:
-                gw, cw = cut(gw), cut(cw)
-            w[p + "/gates/kernel"], w[p + "/gates/bias"] = gw, t[f"gate_b{g}"]
-            w[p + "/candidate/kernel"], w[p + "/candidate/bias"] = cw, t[f"cand_b{g}"]
-        return w
+        """flat-buffer views (device layout, every width padded to 128) -> the TF names / shapes of SURVEY A.6"""
+        from .weights import from_device_layout
+        return from_device_layout(t, self.m.layout_meta)
 
 
 def lr_for_epoch(base_lr, epoch, lr_schedule=True):

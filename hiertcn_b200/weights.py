@@ -123,3 +123,154 @@ def fold_weightnorm(w):
                 v = g * v / np.sqrt((v * v).sum(0, keepdims=True))
         out[k] = v.astype(np.float32)
     return out
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# Device layout.  The sm_100a kernels are built for 128-wide blocks (MMA tiles, 512-byte rows): every width of the model
+# -- embedding (model_hier.py:50), GRU units (args.py:51), TCN channels (args.py:56) -- is run ZERO-PADDED to 128.
+# A padded channel has zero weights and zero bias in front of a relu, so it stays exactly zero through every level; a
+# padded GRU unit has zero weights and zero gate biases, so r = u = 1/2, c = 0 and h' = h/2 = 0 from a zero state; nothing
+# reads a padded value through a non-zero weight.  Results equal the unpadded model's (the extra terms are exact zeros),
+# and the gradients of the padded entries are exactly zero, so training never moves them.
+# --------------------------------------------------------------------------------------------------------------------
+PAD = 128
+
+
+def _pad2(a, rows, cols):
+    out = np.zeros((rows, cols), np.float32)
+    out[:a.shape[0], :a.shape[1]] = a
+    return out
+
+
+def _pad1(a, n):
+    out = np.zeros(n, np.float32)
+    out[:a.shape[0]] = a
+    return out
+
+
+def layout_meta(w, scope="hier"):
+    """shapes the TF-named dict ``w`` implies: emb_dim, hidden_dim, num_layer, channels, kernel_size, per-level
+    down-sample flags.  ``scope`` 'hier' = model_hier (GRU + conditioned TCN), otherwise a plain model_tcn scope."""
+    tcn = scope + "/tcn" if scope == "hier" else scope
+    m = {"scope": scope, "tcn": tcn}
+    chans, ds, l = [], [], 0
+    while f"{tcn}/temporal_conv_net/tblock_{l}/conv1/kernel" in w:
+        k = w[f"{tcn}/temporal_conv_net/tblock_{l}/conv1/kernel"]
+        m["K"] = int(k.shape[0])
+        chans.append(int(k.shape[2]))
+        ds.append(f"{tcn}/temporal_conv_net/tblock_{l}/dense/kernel" in w)
+        l += 1
+    m["channels"], m["ds"] = chans, ds
+    m.setdefault("K", 1)
+    if scope == "hier":
+        m["ed"] = int(w["hier/emb/kernel"].shape[1])
+        G = 0
+        while f"hier/multi_rnn_cell/cell_{G}/gru_cell/gates/kernel" in w:
+            G += 1
+        m["G"] = G
+        m["H"] = int(w["hier/multi_rnn_cell/cell_0/gru_cell/candidate/kernel"].shape[1]) if G else PAD
+    else:
+        m["ed"], m["G"], m["H"] = PAD, 0, PAD
+    for name, v in (("emb_dim", m["ed"]), ("hidden_dim", m["H"])) + tuple(("tcn_channel", c) for c in chans):
+        if v > PAD:
+            raise NotImplementedError("%s = %d: widths above 128 are not built (the kernels run 128-wide blocks)" % (name, v))
+    return m
+
+
+def to_device_layout(w, scope="hier"):
+    """TF-named weights -> dict of the arrays the kernels read, every width zero-padded to 128:
+    E [N,128], b_emb [128], w_in_x [128,128], w_in_state [G*128,128], conv_w{l} [K,128,128], conv_b{l} [128],
+    ds_w{l} [128,128] / ds_b{l} [128] (levels that change the width, customized_tcn_cell.py:102-106),
+    gate_w{g} [256,256] (rows [x | h], columns [r | u]), gate_b{g} [256], cand_w{g} [256,128], cand_b{g} [128],
+    w_out [128,N] (TF layout), b_out [N].  Returns (dict, meta)."""
+    m = layout_meta(w, scope)
+    tcn, ed, H, G = m["tcn"], m["ed"], m["H"], m["G"]
+    d = OrderedDict()
+    if scope == "hier":
+        d["E"] = _pad2(w["hier/emb/kernel"], w["hier/emb/kernel"].shape[0], PAD)
+        d["b_emb"] = _pad1(w["hier/emb/bias"], PAD)
+        w_in = w[tcn + "/emb/kernel"]                                   # [ed + G*H, 128]
+        d["w_in_x"] = _pad2(w_in[:ed], PAD, PAD)
+        ws = np.zeros((max(G, 1) * PAD, PAD), np.float32)
+        for g in range(G):
+            ws[g * PAD:g * PAD + H] = w_in[ed + g * H:ed + (g + 1) * H]
+        d["w_in_state"] = ws
+    else:
+        d["E"] = np.ascontiguousarray(w[tcn + "/emb/kernel"], np.float32)    # the 'emb' dense applied to a one-hot = a gather
+        d["b_emb"] = np.zeros(PAD, np.float32)
+        d["w_in_x"] = np.eye(PAD, dtype=np.float32)
+    for l, c in enumerate(m["channels"]):
+        p = f"{tcn}/temporal_conv_net/tblock_{l}"
+        k = w[p + "/conv1/kernel"]
+        kw = np.zeros((k.shape[0], PAD, PAD), np.float32)
+        kw[:, :k.shape[1], :k.shape[2]] = k
+        d[f"conv_w{l}"], d[f"conv_b{l}"] = kw, _pad1(w[p + "/conv1/bias"], PAD)
+        if m["ds"][l]:
+            d[f"ds_w{l}"], d[f"ds_b{l}"] = _pad2(w[p + "/dense/kernel"], PAD, PAD), _pad1(w[p + "/dense/bias"], PAD)
+    for g in range(G):
+        p = f"hier/multi_rnn_cell/cell_{g}/gru_cell"
+        inp = ed if g == 0 else H
+        gw, gb, cw, cb = w[p + "/gates/kernel"], w[p + "/gates/bias"], w[p + "/candidate/kernel"], w[p + "/candidate/bias"]
+        GW, CW, GB = np.zeros((2 * PAD, 2 * PAD), np.float32), np.zeros((2 * PAD, PAD), np.float32), np.zeros(2 * PAD, np.float32)
+        for r0, r1, dst in ((0, inp, 0), (inp, inp + H, PAD)):          # rows: input block, hidden block
+            GW[dst:dst + r1 - r0, :H] = gw[r0:r1, :H]                   # r gate columns
+            GW[dst:dst + r1 - r0, PAD:PAD + H] = gw[r0:r1, H:]          # u gate columns
+            CW[dst:dst + r1 - r0, :H] = cw[r0:r1]
+        GB[:H], GB[PAD:PAD + H] = gb[:H], gb[H:]
+        d[f"gate_w{g}"], d[f"gate_b{g}"], d[f"cand_w{g}"], d[f"cand_b{g}"] = GW, GB, CW, _pad1(cb, PAD)
+    if tcn + "/dense/kernel" in w:
+        wo = w[tcn + "/dense/kernel"]
+        d["w_out"] = _pad2(wo, PAD, wo.shape[1])
+        d["b_out"] = np.ascontiguousarray(w[tcn + "/dense/bias"], np.float32)
+    return d, m
+
+
+def from_device_layout(d, m):
+    """inverse of ``to_device_layout``: slices the padding off and restores the TF names / shapes.  ``d`` may hold the
+    output table as ``w_out`` [128,N] or as ``wt`` [N,128] (its transpose, what the scoring kernels read)."""
+    tcn, ed, H, G = m["tcn"], m["ed"], m["H"], m["G"]
+    w = OrderedDict()
+    if m["scope"] == "hier":
+        w["hier/emb/kernel"] = d["E"][:, :ed]
+        w["hier/emb/bias"] = d["b_emb"][:ed]
+        w[tcn + "/emb/kernel"] = np.concatenate([d["w_in_x"][:ed]] + [d["w_in_state"][g * PAD:g * PAD + H] for g in range(G)], 0)
+    else:
+        w[tcn + "/emb/kernel"] = d["E"]
+    cin = PAD
+    for l, c in enumerate(m["channels"]):
+        p = f"{tcn}/temporal_conv_net/tblock_{l}"
+        w[p + "/conv1/kernel"], w[p + "/conv1/bias"] = d[f"conv_w{l}"][:, :cin, :c], d[f"conv_b{l}"][:c]
+        if m["ds"][l]:
+            w[p + "/dense/kernel"], w[p + "/dense/bias"] = d[f"ds_w{l}"][:cin, :c], d[f"ds_b{l}"][:c]
+        cin = c
+    if "w_out" in d or "wt" in d:
+        wo = d["w_out"] if "w_out" in d else np.ascontiguousarray(d["wt"].T)
+        w[tcn + "/dense/kernel"], w[tcn + "/dense/bias"] = wo[:cin], d["b_out"]
+    for g in range(G):
+        p = f"hier/multi_rnn_cell/cell_{g}/gru_cell"
+        inp = ed if g == 0 else H
+        GW, GB, CW, CB = d[f"gate_w{g}"], d[f"gate_b{g}"], d[f"cand_w{g}"], d[f"cand_b{g}"]
+        rows = np.r_[0:inp, PAD:PAD + H]
+        w[p + "/gates/kernel"] = np.concatenate([GW[rows][:, :H], GW[rows][:, PAD:PAD + H]], 1)
+        w[p + "/gates/bias"] = np.concatenate([GB[:H], GB[PAD:PAD + H]])
+        w[p + "/candidate/kernel"], w[p + "/candidate/bias"] = CW[rows][:, :H], CB[:H]
+    return OrderedDict((k, np.ascontiguousarray(v, dtype=v.dtype)) for k, v in w.items())
+
+
+def pad_state(state, m):
+    """carried user state [B, G*H] -> device layout [B, G*128]"""
+    state = np.asarray(state, np.float32)
+    H, G = m["H"], m["G"]
+    if H == PAD:
+        return state
+    out = np.zeros((state.shape[0], G * PAD), np.float32)
+    for g in range(G):
+        out[:, g * PAD:g * PAD + H] = state[:, g * H:(g + 1) * H]
+    return out
+
+
+def unpad_state(state, m):
+    H, G = m["H"], m["G"]
+    if H == PAD:
+        return state
+    return np.concatenate([state[:, g * PAD:g * PAD + H] for g in range(G)], 1)

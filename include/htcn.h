@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define HTCN_ABI_VERSION 2
+#define HTCN_ABI_VERSION 3
 #define HTCN_DIM 128          /* D = C = H */
 #define HTCN_MAX_SLOTS 64     /* S (args.max_session_num, default 10) */
 #define HTCN_MAX_LEVELS 8     /* TCN levels (len(args.tcn_channel)) */
@@ -109,7 +109,11 @@ int32_t htcn_gru_sessions(const float* yp, const float* mask, const float* state
  * Replaces: model_tcn's dense(x,128,use_bias=False,'emb') (model_tcn.py:35) and
  * TemporalConvNet -> TemporalBlock -> CausalConv1D (customized_tcn_cell.py:46-49,109-127,147-161;
  * customized_convolution_layer.py:171-198): per level l, d = 2^l,
- *   a = relu(b_l + sum_k h[t-(K-1-k)d] W_l[k]);  h' = relu(a + h)         (one conv per block)
+ *   a = relu(b_l + sum_k h[t-(K-1-k)d] W_l[k]);  h' = relu(a + res)       (one conv per block)
+ *   res = h, or h @ Wds_l + bds_l for a level that changes the width (the 1x1 Dense of customized_tcn_cell.py:102-106,
+ *   123-124): ds_w_host[l] -> [128,128] f32, ds_b_host[l] -> [128] f32, entry NULL = identity residual; both arrays may
+ *   be NULL.  Widths below 128 (and emb / hidden sizes below 128) are run zero-padded to 128 by the host
+ *   (hiertcn_b200.weights.to_device_layout): padded channels stay exactly zero through every level.
  * Rows are the flat [B*T] positions; a sequence is one (b, slot) run of slot_off[s+1]-slot_off[s]
  * positions (for the single-level model_tcn: S = 1, T = L).
  *   h0[b,p,:] = xe[b,p,:] @ w_in_x + sbias[slot(p), b, :]      (sbias may be NULL: plain model_tcn)
@@ -121,13 +125,15 @@ int32_t htcn_gru_sessions(const float* yp, const float* mask, const float* state
  * out_row [B*T] int32 or NULL: destination row of each position in hout (-1 = drop the row);
  *   used to compact away padded positions before catalog scoring.
  * hout [n_out_rows,128] of hout_dtype.  scratch (device, caller-owned): f32 tier 2*B*T*128 floats (level
- *   ping-pong); bf16 tier HTCN_TCN_SCRATCH_BYTES(n_levels, kernel_size) bytes (bf16 weight tiles).
+ *   ping-pong; 3*B*T*128 when a level has a down-sample residual); bf16 tier HTCN_TCN_SCRATCH_BYTES(n_levels,
+ *   kernel_size) bytes (bf16 weight tiles).
  * The bf16 tier requires xe and hout in bf16 and (K-1)*2^(n_levels-1) <= 32 rows of causal shift.
  * ------------------------------------------------------------------------------------------- */
-#define HTCN_TCN_SCRATCH_BYTES(n_levels, K) ((1 + (n_levels) * (K)) * 128 * 128 * 2 + 8 * 8 + 8 * 512 + 256)
+#define HTCN_TCN_SCRATCH_BYTES(n_levels, K) ((1 + (n_levels) * ((K) + 1)) * 128 * 128 * 2 + 640 + 2 * 8 * 512 + 256)
 int32_t htcn_tcn_forward(const void* xe, int32_t xe_dtype, int32_t precision,
                          const float* w_in_x, const float* sbias,
                          const float* const* conv_w_host, const float* const* conv_b_host,
+                         const float* const* ds_w_host, const float* const* ds_b_host,
                          int32_t n_levels, int32_t kernel_size, const int32_t* slot_off_host,
                          int32_t B, int32_t T, int32_t S,
                          const int32_t* out_row, void* hout, int32_t hout_dtype, float* scratch,
@@ -315,7 +321,8 @@ int32_t htcn_cast_transpose_bf16(const void* src, int32_t src_dtype, int64_t R, 
  * every level's output) and a_save [n_levels, B*T, 128] (relu(conv+bias) before the residual add);
  * hout [Q,128] f32 = rows of the last level compacted through out_row [B*T] (-1 = not scored). */
 int32_t htcn_tcn_forward_train(const float* xe, const float* w_in_x, const float* sbias,
-                               const float* const* conv_w_host, const float* const* conv_b_host, int32_t n_levels,
+                               const float* const* conv_w_host, const float* const* conv_b_host,
+                               const float* const* ds_w_host, const float* const* ds_b_host, int32_t n_levels,
                                int32_t kernel_size, const int32_t* slot_off_host, int32_t B, int32_t T, int32_t S,
                                const int32_t* out_row, float* h_save, float* a_save, float* hout, void* stream);
 
@@ -323,20 +330,24 @@ int32_t htcn_tcn_forward_train(const float* xe, const float* w_in_x, const float
  * (h_save [(n_levels+1), B*T, 128]) and every level's pre-residual activation (a_save [n_levels, B*T, 128]) written out
  * in bf16.  xe [B*T,128] bf16, hout [Q,128] bf16; scratch as htcn_tcn_forward's bf16 tier (HTCN_TCN_SCRATCH_BYTES). */
 int32_t htcn_tcn_forward_train_bf16(const void* xe, const float* w_in_x, const float* sbias,
-                                    const float* const* conv_w_host, const float* const* conv_b_host, int32_t n_levels,
+                                    const float* const* conv_w_host, const float* const* conv_b_host,
+                                    const float* const* ds_w_host, const float* const* ds_b_host, int32_t n_levels,
                                     int32_t kernel_size, const int32_t* slot_off_host, int32_t B, int32_t T, int32_t S,
                                     const int32_t* out_row, void* h_save, void* a_save, void* hout, float* scratch,
                                     void* stream);
 
 /* Backward of the conv stack + in-projection (customized_tcn_cell.py:109-127, model_tcn.py:35).
  * xe, h_save, a_save are of save_dtype (HTCN_F32 from htcn_tcn_forward_train, HTCN_BF16 from ..._train_bf16); the
- * gradients are fp32.  scratch: 2*B*T*128 floats.  d_conv_w[l] [K,128,128], d_conv_b[l] [128], d_w_in_x [128,128]
+ * gradients are fp32.  scratch: 2*B*T*128 floats (3*B*T*128 with a down-sample level).  d_conv_w[l] [K,128,128],
+ * d_conv_b[l] [128], d_ds_w[l] [128,128], d_ds_b[l] [128] (levels with ds_w_host[l] != NULL), d_w_in_x [128,128]
  * accumulated; d_sbias [S,B,128] and d_xe [B*T,128] overwritten. */
 int32_t htcn_tcn_backward(const float* d_hout, const int32_t* out_row, const void* xe, int32_t save_dtype,
-                          const float* w_in_x, const float* const* conv_w_host, int32_t n_levels, int32_t kernel_size,
+                          const float* w_in_x, const float* const* conv_w_host, const float* const* ds_w_host,
+                          int32_t n_levels, int32_t kernel_size,
                           const int32_t* slot_off_host, int32_t B, int32_t T, int32_t S, const void* h_save,
                           const void* a_save, float* scratch, float* const* d_conv_w_host,
-                          float* const* d_conv_b_host, float* d_w_in_x, float* d_sbias, float* d_xe, void* stream);
+                          float* const* d_conv_b_host, float* const* d_ds_w_host, float* const* d_ds_b_host,
+                          float* d_w_in_x, float* d_sbias, float* d_xe, void* stream);
 
 /* K3 fp32 forward that also saves state_pre [S,B,G*128] and gates_save [S,G,3,B,128] (r, u, c of every cell). */
 int32_t htcn_gru_sessions_train(const float* yp, const float* mask, const float* state_in,

@@ -47,7 +47,9 @@ def _tcn(p, h, n_levels, K):
         d = 2 ** lvl
         xp = F.pad(h.transpose(1, 2), ((K - 1) * d, 0))
         a = F.conv1d(xp, p[pre + "kernel"].permute(2, 1, 0), p[pre + "bias"], dilation=d).transpose(1, 2)
-        h = torch.relu(torch.relu(a) + h)
+        ds = f"hier/tcn/temporal_conv_net/tblock_{lvl}/dense/"
+        res = h @ p[ds + "kernel"] + p[ds + "bias"] if (ds + "kernel") in p else h      # customized_tcn_cell.py:102-106,123-124
+        h = torch.relu(torch.relu(a) + res)
     return h
 
 
@@ -55,7 +57,7 @@ def loss_fp64(p, x_list, y_list, mask_list, state, num_layer=2, literal=False):
     """Scalar training loss (model.py:105-117) as a torch expression of the parameter dict ``p``."""
     dt = p["hier/emb/kernel"].dtype
     E, be = p["hier/emb/kernel"], p["hier/emb/bias"]
-    N, H = E.shape[0], 128
+    N, H = E.shape[0], p["hier/multi_rnn_cell/cell_0/gru_cell/candidate/kernel"].shape[1]
     n_levels = sum(1 for k in p if k.endswith("conv1/kernel"))
     K = p["hier/tcn/temporal_conv_net/tblock_0/conv1/kernel"].shape[0]
     state = torch.tensor(np.asarray(state), dtype=dt)

@@ -109,9 +109,9 @@ def main():
     # ---- K2
     if want("k2"):
         hout = torch.empty((B * T, 128), dtype=bf16, device="cuda")
-        sc = torch.empty(((1 + 2 * 5) * 8192 + 4096,), dtype=f32, device="cuda")
+        sc = torch.empty((cabi.tcn_scratch_floats(2, 5),), dtype=f32, device="cuda")
         ms = timed(lambda: cabi.call("htcn_tcn_forward", xe.data_ptr(), cabi.HTCN_BF16, cabi.HTCN_BF16, model.w_in_x.data_ptr(),
-                                     sbias.data_ptr(), model._conv_w_pp[0], model._conv_b_pp[0], 2, 5, slot_p, B, T, S, None,
+                                     sbias.data_ptr(), model._conv_w_pp[0], model._conv_b_pp[0], None, None, 2, 5, slot_p, B, T, S, None,
                                      hout.data_ptr(), cabi.HTCN_BF16, sc.data_ptr(), st))
         line(out, "K2 conv stack bf16 tcgen05 (hier, 2 levels)", ms, "tensor", B * (65.54e6 + 2 * T * 128 * 128), "bf16_tflops", "cfg2 shape: 40960 sequences x 20")
         # cfg3: 4096 sequences x 256, 4 levels, dilations 1-2-4-8
@@ -120,7 +120,7 @@ def main():
         B3, L3 = 4096, 256
         xe3 = torch.randn((B3 * L3, 128), device="cuda").to(bf16)
         h3 = torch.empty((B3 * L3, 128), dtype=bf16, device="cuda")
-        sc3 = torch.empty(((1 + 4 * 5) * 8192 + 4096,), dtype=f32, device="cuda")
+        sc3 = torch.empty((cabi.tcn_scratch_floats(4, 5),), dtype=f32, device="cuda")
         sp3, k3keep = cabi.int_array([0, L3])
         ms = timed(lambda: cabi.call("htcn_tcn_forward", xe3.data_ptr(), cabi.HTCN_BF16, cabi.HTCN_BF16, m3.w_in_x.data_ptr(), None,
                                      m3._conv_w_pp[0], m3._conv_b_pp[0], 4, 5, sp3, B3, L3, 1, None, h3.data_ptr(), cabi.HTCN_BF16,

@@ -180,20 +180,35 @@ def test_k3_cluster_variants_agree(lib, B, S, with_sbias, monkeypatch):
 
 
 # ------------------------------------------------------------------------------------------ K2
+def k2_weights(lib, w, n_levels):
+    """device-layout conv stack of a TF-named dict (widths zero-padded to 128, down-sample kernels where the width changes)"""
+    from hiertcn_b200.weights import to_device_layout
+    lay, meta = to_device_layout(w)
+    assert len(meta["channels"]) == n_levels
+    t = dict(conv_w=[dev(lay[f"conv_w{l}"]) for l in range(n_levels)], conv_b=[dev(lay[f"conv_b{l}"]) for l in range(n_levels)],
+             ds_w=[dev(lay[f"ds_w{l}"]) if meta["ds"][l] else None for l in range(n_levels)],
+             ds_b=[dev(lay[f"ds_b{l}"]) if meta["ds"][l] else None for l in range(n_levels)], w_in_x=dev(lay["w_in_x"]))
+    t["wpp"] = lib.ptr_array([x.data_ptr() for x in t["conv_w"]])
+    t["bpp"] = lib.ptr_array([x.data_ptr() for x in t["conv_b"]])
+    has_ds = any(meta["ds"])
+    t["dwpp"] = lib.ptr_array([x.data_ptr() if x is not None else 0 for x in t["ds_w"]]) if has_ds else (None, None)
+    t["dbpp"] = lib.ptr_array([x.data_ptr() if x is not None else 0 for x in t["ds_b"]]) if has_ds else (None, None)
+    t["has_ds"] = has_ds
+    return t
+
+
 def run_k2(lib, xe_t, xe_dtype, w, sbias, slot_off, B, T, S, K, n_levels, out_row=None, n_out=None,
            hout_dtype=None, precision=None):
-    conv_w = [dev(w[f"hier/tcn/temporal_conv_net/tblock_{l}/conv1/kernel"]) for l in range(n_levels)]
-    conv_b = [dev(w[f"hier/tcn/temporal_conv_net/tblock_{l}/conv1/bias"]) for l in range(n_levels)]
-    wpp, bpp = lib.ptr_array([t.data_ptr() for t in conv_w]), lib.ptr_array([t.data_ptr() for t in conv_b])
-    w_in_x = dev(w["hier/tcn/emb/kernel"][:128])
+    t = k2_weights(lib, w, n_levels)
     hout_dtype = lib.HTCN_F32 if hout_dtype is None else hout_dtype
     precision = lib.HTCN_F32 if precision is None else precision
     n_out = B * T if n_out is None else n_out
     hout = torch.zeros((n_out, 128), dtype=torch.float32 if hout_dtype == lib.HTCN_F32 else torch.bfloat16, device="cuda")
-    scratch = torch.empty((2 * B * T, 128), dtype=torch.float32, device="cuda")
+    scratch = torch.empty(((3 if t["has_ds"] else 2) * B * T, 128), dtype=torch.float32, device="cuda")
     slot_p, keep = lib.int_array(slot_off)
-    lib.call("htcn_tcn_forward", P(xe_t), xe_dtype, precision, P(w_in_x), P(sbias), wpp[0], bpp[0], n_levels, K, slot_p,
-             B, T, S, P(out_row), P(hout), hout_dtype, P(scratch), None)
+    lib.call("htcn_tcn_forward", P(xe_t), xe_dtype, precision, P(t["w_in_x"]), P(sbias), t["wpp"][0], t["bpp"][0],
+             t["dwpp"][0], t["dbpp"][0], n_levels, K, slot_p, B, T, S, P(out_row), P(hout), hout_dtype, P(scratch), None)
+    torch.cuda.synchronize()
     return hout
 
 
@@ -614,18 +629,45 @@ def test_k4_bf16_single_overflowing_logit_in_a_polynomial_lane(lib, epi, spike, 
 
 # ------------------------------------------------------------------------------------------ K2 bf16 (tcgen05, fused levels)
 def run_k2_bf16(lib, xe_bf16, w, sbias, slot_off, B, T, S, K, n_levels, out_row=None, n_out=None):
-    conv_w = [dev(w[f"hier/tcn/temporal_conv_net/tblock_{l}/conv1/kernel"]) for l in range(n_levels)]
-    conv_b = [dev(w[f"hier/tcn/temporal_conv_net/tblock_{l}/conv1/bias"]) for l in range(n_levels)]
-    wpp, bpp = lib.ptr_array([t.data_ptr() for t in conv_w]), lib.ptr_array([t.data_ptr() for t in conv_b])
-    w_in_x = dev(w["hier/tcn/emb/kernel"][:128])
+    t = k2_weights(lib, w, n_levels)
     n_out = B * T if n_out is None else n_out
     hout = torch.zeros((n_out, 128), dtype=torch.bfloat16, device="cuda")
-    scratch = torch.empty(((1 + n_levels * K) * 8192 + 4096,), dtype=torch.float32, device="cuda")
+    scratch = torch.empty((lib.tcn_scratch_floats(n_levels, K),), dtype=torch.float32, device="cuda")
     slot_p, keep = lib.int_array(slot_off)
-    lib.call("htcn_tcn_forward", P(xe_bf16), lib.HTCN_BF16, lib.HTCN_BF16, P(w_in_x), P(sbias), wpp[0], bpp[0], n_levels, K,
-             slot_p, B, T, S, P(out_row), P(hout), lib.HTCN_BF16, P(scratch), None)
+    lib.call("htcn_tcn_forward", P(xe_bf16), lib.HTCN_BF16, lib.HTCN_BF16, P(t["w_in_x"]), P(sbias), t["wpp"][0], t["bpp"][0],
+             t["dwpp"][0], t["dbpp"][0], n_levels, K, slot_p, B, T, S, P(out_row), P(hout), lib.HTCN_BF16, P(scratch), None)
     torch.cuda.synchronize()
     return hout
+
+
+@pytest.mark.parametrize("channels,K", [((32, 32, 48), 3), ((64, 128, 96), 5), ((128, 40), 5)])
+@pytest.mark.parametrize("tier", ["f32", "bf16"])
+def test_k2_downsample_residual_and_narrow_levels(lib, channels, K, tier):
+    """levels narrower than 128 (zero-padded) and width changes with the 1x1 down-sample residual Dense
+    (customized_tcn_cell.py:102-106,123-126), both tiers, against the oracle on the UNPADDED weights"""
+    B, S, L, levels = 9, 3, 11, len(channels)
+    x, y, m, s0, w = small_case(B=B, S=S, L=L, N=211, seed=17, tcn_channel=channels, kernel_size=K)
+    for l in range(levels):                       # non-zero down-sample biases
+        k = f"hier/tcn/temporal_conv_net/tblock_{l}/dense/bias"
+        if k in w:
+            w[k] = np.random.default_rng(l).normal(0, 0.2, size=w[k].shape).astype(np.float32)
+    pk = pack(x, y, m)
+    T = pk["x_id"].shape[1]
+    state_pre, _, _ = O.gru_over_sessions(y, m, s0, w, 2, "f32")
+    houts, sbs = O.tcn_hidden_restructured(x, state_pre, w, "f64" if tier == "f32" else "bf16")
+    ref = np.concatenate(houts, 1)                                  # [B,T,C_last]
+    C = channels[-1]
+    xe = O.emb_gather(pk["x_id"], w["hier/emb/kernel"])
+    sbias = dev(np.stack(sbs).astype(np.float32))
+    if tier == "f32":
+        got = run_k2(lib, dev(xe), lib.HTCN_F32, w, sbias, pk["slot_off"], B, T, S, K, levels).cpu().numpy().reshape(B, T, 128)
+        np.testing.assert_allclose(got[..., :C], ref, rtol=1e-4, atol=1e-4)
+    else:
+        got = run_k2_bf16(lib, dev(xe).to(torch.bfloat16), w, sbias, pk["slot_off"], B, T, S, K, levels).float().cpu().numpy().reshape(B, T, 128)
+        err = np.abs(got[..., :C] - ref)
+        assert err.max() <= 2e-2 * max(1.0, np.abs(ref).max()), err.max()
+        assert np.linalg.norm(got[..., :C] - ref) <= 1e-2 * np.linalg.norm(ref)
+    assert (got[..., C:] == 0).all(), "padded channels must stay exactly zero"
 
 
 @pytest.mark.parametrize("B,S,L,K,levels", [(7, 3, 9, 5, 2), (3, 1, 300, 5, 4), (150, 10, 20, 5, 2), (4, 2, 1, 3, 3), (5, 1, 200, 5, 2)])

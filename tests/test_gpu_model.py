@@ -56,6 +56,34 @@ def test_step_f32_matches_oracle(B, S, L, N, lengths):
     np.testing.assert_allclose(out["topk_val"], v_ref, rtol=1e-4, atol=1e-4)
 
 
+@pytest.mark.parametrize("precision,tol", [("f32", 1e-4), ("bf16", 2e-2)])
+def test_step_matches_golden_downsample_narrow_widths(precision, tol):
+    """fixture produced by the reference's own python with tcn_channel = [32, 32, 48], hidden_dim = 16, kernel_size = 3:
+    two levels use the 1x1 down-sample residual (customized_tcn_cell.py:102-106,123-126); every width runs zero-padded"""
+    from hiertcn_b200.args import make_args
+    from hiertcn_b200.model_hier import HierTCN
+    z, x, y, m, w = load_hier_golden("hier_downsample_3lvl")
+    N = int(z["N"])
+    a = make_args(["--item_num", str(N), "--tcn_channel", "32,32,48", "--kernel_size", "3", "--hidden_dim", "16"])
+    model = HierTCN(a, w, precision=precision).build()
+    out = model.step(x, y, m, z["state0"], per_position=True)
+    assert out["state"].shape == z["state_f64"].shape
+    assert abs(out["loss"] - z["loss_f64"]) <= tol * abs(z["loss_f64"])
+    np.testing.assert_allclose(out["state"], z["state_f64"], rtol=max(tol, 1e-4), atol=max(tol, 1e-5))
+    np.testing.assert_allclose(out["loss_bt"], z["loss_bt_f64"], rtol=tol, atol=max(tol, 1e-5))
+    if precision == "f32":
+        np.testing.assert_array_equal(out["ranks"], z["ranks_f64"])
+        got = np.asarray([out[k] for k in ("recall1", "recall5", "recall10", "mrr", "mrp")])
+        np.testing.assert_allclose(got, z["metrics_f64"], rtol=1e-4, atol=1e-6)
+        pred = model.forward(x, y, m, z["state0"])[0].materialize()
+        np.testing.assert_allclose(pred, z["pred_f64"], rtol=1e-4, atol=1e-4)
+    else:
+        assert abs(out["mrr"] - z["metrics_f64"][3]) < 5e-2
+    # the carried state round-trips through the host in the TF shape [B, G*H]
+    out2 = model.step(x, y, m, out["state"])
+    assert np.isfinite(out2["loss"])
+
+
 def test_materialized_logits_match_reference_pred():
     z, x, y, m, w = load_hier_golden("hier_default_arch")
     from hiertcn_b200.args import make_args

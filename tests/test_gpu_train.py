@@ -22,6 +22,18 @@ def make_trainer(w, N, lr=1e-2, levels=2, K=5, precision="f32"):
     return HierTCNTrainer(HierTCN(a, w, precision=precision).build(), learning_rate=lr)
 
 
+def make_trainer_for(w, N, lr=1e-2, precision="f32"):
+    """trainer for a weight dict of any (<= 128) widths: args are read off the shapes"""
+    from hiertcn_b200.args import make_args
+    from hiertcn_b200.model_hier import HierTCN
+    from hiertcn_b200.train import HierTCNTrainer
+    from hiertcn_b200.weights import layout_meta
+    m = layout_meta(w)
+    a = make_args(["--item_num", str(N), "--tcn_channel", ",".join(str(c) for c in m["channels"]), "--kernel_size", str(m["K"]),
+                   "--hidden_dim", str(m["H"]), "--num_layer", str(m["G"]), "--emb_dim", str(m["ed"])])
+    return HierTCNTrainer(HierTCN(a, w, precision=precision).build(), learning_rate=lr)
+
+
 def assert_grads_close(got, ref, tol=2e-4):
     for k in ref:
         scale = np.abs(ref[k]).max()
@@ -362,3 +374,45 @@ def test_fused_conv_forward_saves_match_fp32_levels(B, S, L, K, levels):
         err = np.abs(g - r)
         assert err.max() <= 3e-2 * np.abs(r).max() + 1e-3, (name, float(err.max()), float(np.abs(r).max()))
         assert np.linalg.norm(g - r) <= 1e-2 * np.linalg.norm(r), (name, float(np.linalg.norm(g - r) / np.linalg.norm(r)))
+
+
+@pytest.mark.parametrize("precision,tol", [("f32", 2e-4), ("bf16", 3e-2)])
+def test_gradients_downsample_levels_and_narrow_widths(precision, tol):
+    """the reference-generated fixture with tcn_channel = [32, 32, 48], hidden_dim = 16, kernel_size = 3: two levels change the
+    width (1x1 down-sample residual, customized_tcn_cell.py:102-106,123-126) and every width runs zero-padded to 128"""
+    z, x, y, m, w = load_hier_golden("hier_downsample_3lvl")
+    N = int(z["N"])
+    ref_loss, ref_g, ref_state = GO.loss_and_grads(w, x, y, m, z["state0"])
+    assert abs(ref_loss - float(z["loss_f64"])) <= 1e-9 * abs(ref_loss)      # the autograd restatement reproduces the fixture
+    tr = make_trainer_for(w, N, precision=precision)
+    r = tr.forward_backward(x, y, m, z["state0"])
+    sc = r["scalars"].cpu().numpy()
+    assert abs(sc[0] - ref_loss) <= max(tol, 1e-4) * abs(ref_loss)
+    got = tr.named_gradients(sc[6])
+    assert set(got) == set(ref_g)
+    for k in ref_g:
+        assert got[k].shape == ref_g[k].shape, k
+        if precision == "f32":
+            assert np.abs(got[k] - ref_g[k]).max() <= tol * np.abs(ref_g[k]).max() + 1e-9, k
+        else:
+            assert np.linalg.norm(got[k] - ref_g[k]) <= tol * np.linalg.norm(ref_g[k]) + 1e-9, k
+    # the padded entries of every parameter have exactly zero gradient (training never moves them)
+    from hiertcn_b200.weights import from_device_layout, to_device_layout
+    tr.forward_backward(x, y, m, z["state0"])
+    flat = {k: v.detach().cpu().numpy() for k, v in tr.g.items()}
+    inner, _ = to_device_layout(from_device_layout(flat, tr.m.layout_meta))       # padding zeroed
+    inner["wt"] = np.ascontiguousarray(inner.pop("w_out").T)
+    for k in flat:
+        assert np.array_equal(flat[k], inner[k]), k
+    tr.grads.zero_()
+    # ... and one Adam step keeps the trajectory of the fp64 oracle
+    if precision == "f32":
+        ref_losses, ref_w, _ = GO.train_steps(w, [(x, y, m)], z["state0"], lr=1e-2)
+        out = tr.train_step(x, y, m, z["state0"])
+        assert abs(out["loss"] - ref_losses[0]) <= 1e-4 * abs(ref_losses[0])
+        assert out["state"].shape == z["state0"].shape
+        sd = tr.state_dict()
+        for k in ref_w:
+            assert sd[k].shape == ref_w[k].shape
+            diff = np.abs(sd[k] - ref_w[k])        # the first Adam step moves every coordinate by ~lr * sign(g)
+            assert np.mean(diff) <= 0.02 * 1e-2 and np.mean(diff > 0.25 * 1e-2) < 0.01, k

@@ -117,3 +117,27 @@ def test_device_batcher_schedule_replays_the_loader_queues():
                     np.testing.assert_array_equal(x[s][b], xx[:w])
                     assert (yy[w:] == 0).all()
                     assert m[s][b, 0] == 1 - flag[b, k * S + s]
+
+
+def test_device_layout_padding_is_exact_and_round_trips():
+    """hiertcn_b200.weights.to_device_layout zero-pads every width to 128: (1) it round-trips the TF names / shapes, and
+    (2) the oracle evaluated on the PADDED model (as a 128-wide TF-named dict) reproduces the unpadded model exactly -- the
+    padded channels / GRU units stay zero, so the kernels' 128-wide blocks compute the reference's function"""
+    from helpers import load_hier_golden
+    from hiertcn_b200.weights import from_device_layout, pad_state, to_device_layout, unpad_state
+    from oracle import hiertcn_oracle as O
+    for name in ("hier_default_arch", "hier_downsample_3lvl"):
+        z, x, y, m, w = load_hier_golden(name)
+        lay, meta = to_device_layout(w)
+        back = from_device_layout(lay, meta)
+        assert set(back) == set(w)
+        for k in w:
+            assert back[k].shape == w[k].shape and np.array_equal(back[k], w[k]), k
+    assert meta["channels"] == [32, 32, 48] and meta["ds"] == [True, False, True] and meta["H"] == 16
+    wide = from_device_layout(lay, dict(meta, ed=128, H=128, channels=[128] * 3))      # the padded model, TF-named
+    ref = O.forward_loss_metrics(x, y, m, z["state0"], w, 2, "f64")
+    pad = O.forward_loss_metrics(x, y, m, pad_state(z["state0"], meta), wide, 2, "f64")
+    assert pad["loss"] == ref["loss"]
+    assert np.array_equal(pad["pred"], ref["pred"]) and np.array_equal(unpad_state(pad["state"], meta), ref["state"])
+    full = pad["state"].reshape(len(ref["state"]), 2, 128)
+    assert (full[:, :, 16:] == 0).all(), "padded GRU units must stay exactly zero"
