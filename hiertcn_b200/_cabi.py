@@ -46,6 +46,10 @@ SIGNATURES = {
     "htcn_score_ce_repair_shard": [_p, _i, _i, _p, _i, _p, _p, _i, _p, _p],
     "htcn_score_topk": [_p, _i, _i, _p, _p, _i, _i, _i, _i, _p, C.c_int64, _p, _p, _p, _p],
     "htcn_score_ce_rank_topk_fused": [_p, _i, _i, _p, _p, _i, _i, _p, _p, _i, _i, _p, C.c_int64, _p, _p, _p, _p, _p, _p, _p],
+    "htcn_catalog_gram": [_p, _i, _p, _i, _p, _p, _p],
+    "htcn_logit_rownorm": [_p, _i, _i, _p, _f, _p, _p],
+    "htcn_score_ce_rank_l2norm": [_p, _i, _i, _p, _p, _i, _i, _p, _p, _p, _i, _p, _p, _p, _p, _p],
+    "htcn_scale_rows": [_p, _p, C.c_int64, _i, _p],
     "htcn_loss_metrics_reduce": [_p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p],
     "htcn_sampled_rank_loss": [_p, _i, _i, _p, _p, _p, _i, _i, _f, _f, _i, _p, _p],
     "htcn_calc_score": [_p, _i, _i, _p, _p, _i, _i, _p, _p],
@@ -68,7 +72,8 @@ PLAIN = {"htcn_abi_version": (C.c_int32, []), "htcn_last_error": (C.c_char_p, []
          "htcn_device_ok": (C.c_int32, []),
          "htcn_topk_workspace_bytes": (C.c_int64, [_i, _i, _i, _i, _i]),
          "htcn_gru_backward_scratch_floats": (C.c_int64, [_i, _i, _i]),
-         "htcn_batcher_scratch_ints": (C.c_int64, [_i, _i])}
+         "htcn_batcher_scratch_ints": (C.c_int64, [_i, _i]),
+         "htcn_catalog_gram_scratch_floats": (C.c_int64, [])}
 
 
 class HtcnError(RuntimeError):
@@ -105,7 +110,11 @@ LAUNCHES_PER_CALL = {"htcn_gather_meanpool": 2, "htcn_gru_sessions": 1, "htcn_tc
                      "htcn_prepare_wout": 1, "htcn_score_ce_rank_topk": 2, "htcn_score_logits": 1,
                      "htcn_target_logit": 1, "htcn_score_finish": 1, "htcn_topk_merge": 1, "htcn_score_topk": 5, "htcn_score_ce_repair": 1,
                      "htcn_score_ce_repair_shard": 1, "htcn_score_ce_rank_topk_fused": 6,
-                     "htcn_loss_metrics_reduce": 2, "htcn_sampled_rank_loss": 1, "htcn_calc_score": 1,
+                     "htcn_catalog_gram": [_p, _i, _p, _i, _p, _p, _p],
+    "htcn_logit_rownorm": [_p, _i, _i, _p, _f, _p, _p],
+    "htcn_score_ce_rank_l2norm": [_p, _i, _i, _p, _p, _i, _i, _p, _p, _p, _i, _p, _p, _p, _p, _p],
+    "htcn_scale_rows": [_p, _p, C.c_int64, _i, _p],
+    "htcn_loss_metrics_reduce": 2, "htcn_sampled_rank_loss": 1, "htcn_calc_score": 1,
                      # training step (the per-call counts of the multi-launch entry points are added by the caller)
                      "htcn_loss_row_weights": 1, "htcn_score_ce_backward": 1, "htcn_gru_sessions_train": 1,
                      "htcn_gather_backward": 2, "htcn_adam_step": 1, "htcn_refresh_wout": 1,

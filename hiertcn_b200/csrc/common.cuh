@@ -36,6 +36,8 @@ struct ScoreArgs {
   float* topk_val; int* topk_idx;                    // [n_split,Q,k]
   int Q, n_items, n0, k, n_split;
   unsigned flags;
+  const float* row_scale;    // [Q] or NULL: the CE sum runs on row_scale[q] * z (l2-normalised head, model_tcn.py:42-43);
+                             // part_max then holds the SCALED reference point; ranks always compare the raw logits
 };
 
 #define HTCN_REQUIRE(cond, ...)            \

@@ -81,6 +81,9 @@ enum : unsigned { kModePacked = 256u, kPolyPairsShift = 9u, kPolyDeg2 = 8192u };
 // The rank-only sweep, the ragged last tile and the fp32 tier keep the strict compare.
 enum : unsigned { kSignRank = 16384u };
 enum : unsigned { kTwoSlices = 32768u };          // A/B variant: 8 epilogue warps (2 column slices of 128) instead of 16
+// kRowScale: the exponent multiplier is row_scale[q] * log2e instead of the constant log2e (l2-normalised head,
+// model_tcn.py:42-43); a compile-time variant so the default sweep keeps its immediate operands
+enum : unsigned { kRowScale = 65536u };
 template <unsigned kFlags>
 constexpr int cg2_slices() { return (kFlags & kTwoSlices) ? 2 : kSlicesScore; }
 constexpr unsigned packed_flags(int poly_pairs, bool deg2 = false, bool sign_rank = false) {
@@ -125,14 +128,15 @@ constexpr float kPolyRange = 125.0f;             // |t| the exponent-field arith
 // per logit pair.
 template <bool kCE, bool kRank, int kPolyPairs, bool kDeg2, bool kSign, bool kGMax = false>
 __device__ __forceinline__ void ce_rank_chunk_packed(const uint32_t (&r)[32], float zy, float zyl, float2 (&sum2)[2],
-                                                     float2 (&cf2)[2], float& amax, uint32_t (&cnt2)[2], float (&gm2)[2]) {
+                                                     float2 (&cf2)[2], float& amax, uint32_t (&cnt2)[2], float (&gm2)[2],
+                                                     const float cl = kLog2e /* exponent multiplier (kRowScale: per row) */) {
 #pragma unroll
   for (int p = 0; p < 16; ++p) {
     const float2 z = make_float2(__uint_as_float(r[2 * p]), __uint_as_float(r[2 * p + 1]));
     if (kGMax) gm2[p & 1] = fmaxf(fmaxf(gm2[p & 1], z.x), z.y);                              // one FMNMX3
     const bool poly = ((p + 1) * kPolyPairs) / 16 != (p * kPolyPairs) / 16;
     if (kSign) {
-      const float2 tn = ffma2(z, make_float2(-kLog2e, -kLog2e), make_float2(zyl, zyl));     // -(t): sign bit set <=> z above z_y
+      const float2 tn = ffma2(z, make_float2(-cl, -cl), make_float2(zyl, zyl));     // -(t): sign bit set <=> z above z_y
       if (kCE) {
         if (poly) amax = fmaxf(fmaxf(amax, fabsf(tn.x)), fabsf(tn.y));                      // one FMNMX3
         const float2 e = poly ? ex2_poly2<kDeg2, true>(tn) : make_float2(ex2_approx(-tn.x), ex2_approx(-tn.y));
@@ -144,7 +148,7 @@ __device__ __forceinline__ void ce_rank_chunk_packed(const uint32_t (&r)[32], fl
       }
     } else {
       if (kCE) {
-        const float2 t = ffma2(z, make_float2(kLog2e, kLog2e), make_float2(-zyl, -zyl));
+        const float2 t = ffma2(z, make_float2(cl, cl), make_float2(-zyl, -zyl));
         if (poly) amax = fmaxf(fmaxf(amax, fabsf(t.x)), fabsf(t.y));     // one FMNMX3
         const float2 e = poly ? ex2_poly2<kDeg2>(t) : make_float2(ex2_approx(t.x), ex2_approx(t.y));
         sum2[p & 1] = fadd2(sum2[p & 1], e);
@@ -288,9 +292,11 @@ k4_score_bf16(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
       float sum4[4] = {0.f, 0.f, 0.f, 0.f};                     // 4 independent partial sums (ILP + accuracy)
       float cf[4] = {0.f, 0.f, 0.f, 0.f};                       // per-tile rank counts as floats (FSET.BF + FADD)
       int cnt = 0;
+      float cl = kLog2e;                                        // exponent multiplier
       if ((kCE || kRank) && row_ok) {
         zy = a.zy[q0 + row];
-        zyl = zy * kLog2e;
+        if (kFlags & kRowScale) cl = a.row_scale[q0 + row] * kLog2e;
+        zyl = zy * cl;
       }
       RowHeap heap{heap_v + row, heap_i + row, kBM, a.k};
       if (kTopk) heap.init();
@@ -335,7 +341,7 @@ k4_score_bf16(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
             if (kCE) {
               // the MUFU pipe (16 ex2/clk/SM) bounds this loop: every kPolyEvery-th exponential is evaluated on the
               // FMA pipe instead (degree-3 polynomial, 1e-4 relative, exact at t = 0)
-              const float t = fmaf(z, kLog2e, -zyl);
+              const float t = fmaf(z, cl, -zyl);
               sum4[u & 3] += ((u % kPolyEvery) == kPolyEvery - 1) ? ex2_poly(t) : ex2_approx(t);
             }
             if (kRank) cf[u & 3] += set_gt_f(z, zy);
@@ -355,7 +361,7 @@ k4_score_bf16(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
               if (kDump) {
                 if (row_ok) dump[(long long)(q0 + row) * a.n_items + jbase + c + u] = z;
               }
-              if (kCE) sum4[0] += ex2_approx(fmaf(z, kLog2e, -zyl));
+              if (kCE) sum4[0] += ex2_approx(fmaf(z, cl, -zyl));
               if (kRank) cf[0] += set_gt_f(z, zy);
               if (kTopk) {
                 if (z > thr) thr = heap.replace_root(z, a.n0 + jbase + c + u);
@@ -416,7 +422,7 @@ k4_score_bf16(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
       if (row_ok && half == 0) {
         const long long o = (long long)split * a.Q + q0 + row;
         if (kCE) {
-          a.part_max[o] = zy;              // reference point of this partial sum
+          a.part_max[o] = (kFlags & kRowScale) ? zy * a.row_scale[q0 + row] : zy;      // reference point of this partial sum
           a.part_sum[o] = sum;
         }
         if (kRank) a.part_cnt[o] = cnt;
@@ -560,9 +566,11 @@ k4_score_bf16_cg2(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     float amax = 0.f;                                            // max |t| seen by the polynomial lanes
     uint32_t cnt2[2] = {0u, 0u};                                 // kSign: sign-bit rank counts
     int cnt = 0;
+    float cl = kLog2e;                                           // exponent multiplier
     if ((kCE || kRank) && row_ok) {
       zy = a.zy[q0 + row];
-      zyl = kSign ? __fmul_ru(zy, kLog2e) : zy * kLog2e;         // kSign: threshold rounded UP (see kSignRank)
+      if (kFlags & kRowScale) cl = a.row_scale[q0 + row] * kLog2e;
+      zyl = kSign ? __fmul_ru(zy, cl) : zy * cl;                 // kSign: threshold rounded UP (see kSignRank)
     }
     float gm2[2] = {-INFINITY, -INFINITY};                       // running maxima of the current column group (pass 1)
     float row_thr = INFINITY;                                    // candidate threshold of this row (pass 2)
@@ -603,7 +611,10 @@ k4_score_bf16_cg2(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(&sm.t_empty[buf], 0);   // the leader's barrier
           }
-          ce_rank_chunk_packed<kCE, kRank, kPolyPairs, (kFlags & kPolyDeg2) != 0, kSign, kGMax>(r, zy, zyl, sum2, cf2, amax, cnt2, gm2);
+          if (kFlags & kRowScale)
+            ce_rank_chunk_packed<kCE, kRank, kPolyPairs, (kFlags & kPolyDeg2) != 0, kSign, kGMax>(r, zy, zyl, sum2, cf2, amax, cnt2, gm2, cl);
+          else
+            ce_rank_chunk_packed<kCE, kRank, kPolyPairs, (kFlags & kPolyDeg2) != 0, kSign, kGMax>(r, zy, zyl, sum2, cf2, amax, cnt2, gm2);
         }
         if (kRank && (i & 4095) == 4095) {
           cnt += (int)((cf2[0].x + cf2[0].y) + (cf2[1].x + cf2[1].y));
@@ -625,7 +636,10 @@ k4_score_bf16_cg2(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           if (lane == 0) mbar_arrive_cluster(&sm.t_empty[buf], 0);   // the leader's barrier
         }
         if (kPacked && c + 32 <= lim) {
-          ce_rank_chunk_packed<kCE, kRank, kPolyPairs, (kFlags & kPolyDeg2) != 0, kSign, kGMax>(r, zy, zyl, sum2, cf2, amax, cnt2, gm2);
+          if (kFlags & kRowScale)
+            ce_rank_chunk_packed<kCE, kRank, kPolyPairs, (kFlags & kPolyDeg2) != 0, kSign, kGMax>(r, zy, zyl, sum2, cf2, amax, cnt2, gm2, cl);
+          else
+            ce_rank_chunk_packed<kCE, kRank, kPolyPairs, (kFlags & kPolyDeg2) != 0, kSign, kGMax>(r, zy, zyl, sum2, cf2, amax, cnt2, gm2);
         } else if ((kGMax || kFilter) && !(kCE || kRank || kDump) && c + 32 <= lim) {
           // stand-alone passes of the two-pass top-k: one FMNMX per logit
           float m0 = __uint_as_float(r[0]), m1 = __uint_as_float(r[1]), m2 = __uint_as_float(r[2]), m3 = __uint_as_float(r[3]);
@@ -651,7 +665,7 @@ k4_score_bf16_cg2(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
               if (row_ok) dump[(long long)(q0 + row) * a.n_items + jbase + c + u] = z;
             }
             if (kCE) {
-              const float t = fmaf(z, kLog2e, -zyl);
+              const float t = fmaf(z, cl, -zyl);
               sum4[u & 3] += ((u % kPolyEvery) == kPolyEvery - 1) ? ex2_poly(t) : ex2_approx(t);
             }
             if (kRank) cf[u & 3] += set_gt_f(z, zy);
@@ -668,7 +682,7 @@ k4_score_bf16_cg2(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
               if (kDump) {
                 if (row_ok) dump[(long long)(q0 + row) * a.n_items + jbase + c + u] = z;
               }
-              if (kCE) sum4[0] += ex2_approx(fmaf(z, kLog2e, -zyl));
+              if (kCE) sum4[0] += ex2_approx(fmaf(z, cl, -zyl));
               if (kRank) cf[0] += set_gt_f(z, zy);
               if (kGMax) gm2[0] = fmaxf(gm2[0], z);
               if (kFilter && z >= row_thr) append(z, a.n0 + jbase + c + u);
@@ -705,7 +719,7 @@ k4_score_bf16_cg2(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       if (row_ok) {
         const long long o = (long long)split * a.Q + q0 + row;
         if (kCE) {
-          a.part_max[o] = zy;
+          a.part_max[o] = (kFlags & kRowScale) ? zy * a.row_scale[q0 + row] : zy;
           a.part_sum[o] = sum;
         }
         if (kRank) a.part_cnt[o] = cnt;
@@ -909,6 +923,15 @@ int32_t score_bf16(const ScoreArgs& a, cudaStream_t st) {
       return HTCN_ERR_UNSUPPORTED;
     }
     return launch_score<128, HTCN_SCORE_TOPK>(a, nullptr, st);
+  }
+  if (a.row_scale) {                 // l2-normalised head: per-row exponent multiplier (CE | RANK only)
+    if (a.flags != (HTCN_SCORE_CE | HTCN_SCORE_RANK)) {
+      set_error("score(bf16): row_scale needs flags = CE | RANK");
+      return HTCN_ERR_UNSUPPORTED;
+    }
+    constexpr unsigned kCRS = HTCN_SCORE_CE | HTCN_SCORE_RANK | kRowScale;
+    if (cta_group_env() == 2) return launch_score_cg2<kCRS | packed_flags(4)>(a, nullptr, st);
+    return launch_score<256, kCRS | kModePoly8>(a, nullptr, st);
   }
   if (cta_group_env() == 2) {
     static const int poly = [] { const char* e = getenv("HTCN_POLY_EVERY"); return e ? atoi(e) : 8; }();

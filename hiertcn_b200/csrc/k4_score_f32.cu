@@ -49,6 +49,7 @@ k4_score_f32(ScoreArgs a) {
   const bool row_thread = tid < kQM;
   const bool row_ok = row_thread && (q0 + tid < a.Q);
   float zy = 0.f, run_m = -INFINITY, run_s = 0.f, thr = -INFINITY;
+  const float rs = (row_ok && a.row_scale) ? a.row_scale[q0 + tid] : 1.f;
   int cnt = 0;
   RowHeap heap{heap_v + tid, heap_i + tid, kQM, a.k};
   if (row_ok && (a.flags & (HTCN_SCORE_CE | HTCN_SCORE_RANK))) zy = a.zy[q0 + tid];
@@ -103,12 +104,13 @@ k4_score_f32(ScoreArgs a) {
       const int r = tid;
       for (int c = 0; c < lim; ++c) {
         const float z = Zs[r * kQN + (c ^ (r & 31))] + bias_s[c];
-        if (a.flags & HTCN_SCORE_CE) {        // online softmax partial (max, sum exp(z - max))
-          if (z > run_m) {
-            run_s = run_s * expf(run_m - z) + 1.0f;
-            run_m = z;
+        if (a.flags & HTCN_SCORE_CE) {        // online softmax partial (max, sum exp(z - max)) of the (scaled) logits
+          const float zs = a.row_scale ? z * rs : z;
+          if (zs > run_m) {
+            run_s = run_s * expf(run_m - zs) + 1.0f;
+            run_m = zs;
           } else {
-            run_s += expf(z - run_m);
+            run_s += expf(zs - run_m);
           }
         }
         if (a.flags & HTCN_SCORE_RANK) cnt += (z > zy) ? 1 : 0;

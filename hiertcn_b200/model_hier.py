@@ -70,6 +70,8 @@ class CatalogScores:
             lg = torch.empty((self.Q, m.N), dtype=torch.float32, device=m.device)
             cabi.call("htcn_score_logits", self.hout.data_ptr(), m.act_dtype, self.Q, m.wt.data_ptr(), m.act_dtype,
                       m.b_out.data_ptr(), m.N, lg.data_ptr(), m.stream_ptr())
+            if m.l2_normalize:          # model_tcn.py:42-43
+                cabi.call("htcn_scale_rows", lg.data_ptr(), m.row_scale(self).data_ptr(), self.Q, m.N, m.stream_ptr())
             rows = self.row_of.cpu().numpy()
             out[rows >= 0] = lg.cpu().numpy()[rows[rows >= 0]]
         return out.reshape(self.B, self.T, m.N)
@@ -94,9 +96,12 @@ class HierTCN:
         if max(list(args.tcn_channel) + [int(args.hidden_dim), int(getattr(args, "emb_dim", 128))]) > 128:
             raise NotImplementedError("widths above 128 (tcn_channel / hidden_dim / emb_dim): the sm_100a kernels run "
                                       "128-wide blocks")
-        for flag in ("has_batchnorm", "has_layernorm", "has_gap", "has_impression", "l2_normalize"):
+        for flag in ("has_batchnorm", "has_layernorm", "has_impression"):
             if getattr(args, flag, False):
                 raise NotImplementedError("%s is outside the hot path (SURVEY.md A.8)" % flag)
+        if getattr(args, "has_gap", False) and getattr(args, "train_gap", False):
+            raise NotImplementedError("train_gap (learned gap bandwidth, model_hier.py:42-45); the fixed-bandwidth decay is built")
+        self.l2_normalize = bool(getattr(args, "l2_normalize", False))     # model_tcn.py:42-43
         if float(args.dropout) != 0.0:
             raise NotImplementedError("dropout > 0 (reference default 0.0, args.py:64)")
         self.N = int(args.item_num)
@@ -205,10 +210,15 @@ class HierTCN:
         v = t[:n].view(*shape) if n else t[:0]
         return v, v.numpy()
 
-    def stage(self, x_list, y_list, mask_list, state=None, neg_ids=None):
+    def stage(self, x_list, y_list, mask_list, state=None, neg_ids=None, mask_warmstart=None, x_gap=None):
         """Pack the reference batch layout (data_loader.dequeue) straight into pinned staging buffers and copy it to
         the device (asynchronously, on the current stream).  Two staging sets alternate, each guarded by an event,
         so the host can prepare batch i+1 while the copies of batch i are still in flight.
+        ``mask_warmstart [B,T]`` (0/1): multiplied into mask_y like model.py:102-103 -- masked positions are not scored
+        and do not count in the per-user means (they still feed the GRU's mean-pool, as in the reference).
+        ``x_gap``: S-list of [B,1] time gaps; with ``args.has_gap`` the carried state is decayed by
+        exp(-gap / args.gap_bandwidth) before every slot (model_hier.py:40-47).  The decay of slot s+1 is folded into the
+        reset mask of slot s (both multiply the state between two GRU steps) and that of slot 0 into the incoming state.
         Returns a dict of device tensors + host metadata; H2D bytes are in ['h2d_bytes']."""
         torch = _torch()
         if not self.built:
@@ -231,7 +241,21 @@ class HierTCN:
             nx[:, slot_off[s]:slot_off[s + 1]] = x_list[s]
             ny[:, slot_off[s]:slot_off[s + 1]] = y_list[s]
             nm[s] = np.asarray(mask_list[s]).reshape(-1)
+        decay0 = None
+        if x_gap is not None and getattr(self.args, "has_gap", False):
+            bw = np.float32(self.args.gap_bandwidth)
+            dec = [np.exp(-np.asarray(g, np.float32).reshape(-1) / bw) for g in x_gap]
+            decay0 = dec[0]
+            for s in range(S - 1):
+                nm[s] *= dec[s + 1]
         valid = ny.reshape(-1) > 0
+        host_extra = {}
+        if mask_warmstart is not None:
+            warm = np.asarray(mask_warmstart).reshape(-1) > 0
+            valid &= warm
+            tl, nl = self._pinned(slot, "y_loss", (B, T), i32)       # y_id with the warm-start mask applied: the loss side
+            nl[:] = ny * warm.reshape(B, T)
+            host_extra["y_loss"] = tl
         tr, nr = self._pinned(slot, "row_of", (B * T,), i32)
         np.cumsum(valid, dtype=np.int32, out=nr)
         Q = int(nr[-1]) if nr.size else 0
@@ -240,12 +264,16 @@ class HierTCN:
         tq, nq = self._pinned(slot, "y_rows", (Q,), i32)
         if Q:
             nq[:] = ny.reshape(-1)[valid]
-        host = dict(x_id=tx, y_id=ty, mask=tm, row_of=tr, y_rows=tq)
+        host = dict(x_id=tx, y_id=ty, mask=tm, row_of=tr, y_rows=tq, **host_extra)
         dev, nbytes = {}, 0
         if hasattr(state, "data_ptr"):
             # device-resident carried state: the previous step's state_out stays in HBM instead of
             # round-tripping through host numpy every batch like the reference does (run_hier_xing.py:291,301)
             dev["state"] = state.to(device=self.device, dtype=f32).contiguous()
+            if decay0 is not None:
+                dev["state"] = dev["state"].clone()
+                d0 = torch.from_numpy(np.ascontiguousarray(decay0)).to(self.device)
+                cabi.call("htcn_scale_rows", dev["state"].data_ptr(), d0.data_ptr(), B, self.G * 128, self.stream_ptr())
         else:
             ts, ns_ = self._pinned(slot, "state", (B, self.G * 128), f32)
             if state is None:
@@ -253,6 +281,8 @@ class HierTCN:
             else:
                 from .weights import pad_state
                 ns_[:] = pad_state(state, self.layout_meta)       # hidden_dim < 128: zero-padded units
+                if decay0 is not None:
+                    ns_ *= decay0[:, None]
             host["state"] = ts
         if neg_ids is not None and not hasattr(neg_ids, "data_ptr"):
             tn, nn = self._pinned(slot, "neg_ids", tuple(np.shape(neg_ids)), i32)
@@ -276,12 +306,12 @@ class HierTCN:
         return dev
 
     # ------------------------------------------------------------------ forward (K1 -> K3 -> K2)
-    def forward(self, x_list=None, y_list=None, mask_list=None, state=None, staged=None):
+    def forward(self, x_list=None, y_list=None, mask_list=None, state=None, staged=None, mask_warmstart=None, x_gap=None):
         """Hierarchical forward up to the user embeddings.  Returns (CatalogScores, state_out [B,G*H] device)."""
         if not self.built:
             self.build()
         torch = _torch()
-        d = staged if staged is not None else self.stage(x_list, y_list, mask_list, state)
+        d = staged if staged is not None else self.stage(x_list, y_list, mask_list, state, None, mask_warmstart, x_gap)
         self.generation += 1            # handles of earlier forwards now point at overwritten workspaces
         B, T, S, Q = d["B"], d["T"], d["S"], d["Q"]
         st = self.stream_ptr()
@@ -317,7 +347,7 @@ class HierTCN:
         if k3_bf16:
             cabi.note_launches(1)                   # k3_prepare_weights (htcn_gru_sessions counts one launch)
         del slot_keep
-        scores = CatalogScores(self, hout, Q, d["row_of"], d["y_rows"], d["y_id"], B, T)
+        scores = CatalogScores(self, hout, Q, d["row_of"], d["y_rows"], d.get("y_loss", d["y_id"]), B, T)
         return scores, state_out
 
     def _k2_precision(self):
@@ -371,8 +401,20 @@ class HierTCN:
         if ev is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(torch.cuda.current_stream(self.device))
-        fused = bool(topk) and ce and rank      # loss + rank + top-k: two catalog sweeps instead of three
-        if fused:
+        fused = bool(topk) and ce and rank and not self.l2_normalize    # loss + rank + top-k: two catalog sweeps instead of three
+        zy_fin = zy
+        if self.l2_normalize and flags:
+            # l2-normalised head (model_tcn.py:42-43): CE on row_scale * z with row_scale = 1/||z|| from the catalog's Gram
+            # matrix; ranks are invariant under the positive scale
+            rs = self.row_scale(scores)
+            pm = pm if pm is not None else self._buf("pm", (ns, Q), f32)
+            ps = ps if ps is not None else self._buf("ps", (ns, Q), f32)
+            pc = pc if pc is not None else self._buf("pc", (ns, Q), i32)
+            zy_fin = self._buf("zy_scaled", (Q,), f32)
+            cabi.call("htcn_score_ce_rank_l2norm", scores.hout.data_ptr(), self.act_dtype, Q, self.wt.data_ptr(),
+                      self.b_out.data_ptr(), self.N, 0, scores.y_rows.data_ptr(), zy.data_ptr(), rs.data_ptr(), ns,
+                      pm.data_ptr(), ps.data_ptr(), pc.data_ptr(), zy_fin.data_ptr(), st)
+        elif fused:
             nbytes = int(cabi.load().htcn_topk_workspace_bytes(self.act_dtype, Q, self.N, topk, ns))
             ws = self._buf("topk_ws", (nbytes,), torch.uint8)
             ov = torch.empty((Q, topk), dtype=f32, device=self.device)
@@ -394,19 +436,45 @@ class HierTCN:
         if ce or rank:
             loss_row = self._buf("loss_row", (Q,), f32) if ce else None
             rank_row = self._buf("rank_row", (Q,), f32) if rank else None
-            cabi.call("htcn_score_finish", P(pm), P(ps), P(pc), ns, Q, scores.y_rows.data_ptr(), zy.data_ptr(),
-                      P(loss_row), P(rank_row), st)
-            if ce and self.precision == "bf16" and self.n_out == self.N:
+            cabi.call("htcn_score_finish", P(pm) if ce else None, P(ps) if ce else None, P(pc) if rank else None, ns, Q,
+                      scores.y_rows.data_ptr(), zy_fin.data_ptr(), P(loss_row), P(rank_row), st)
+            if ce and self.precision == "bf16" and self.n_out == self.N and not self.l2_normalize:
                 # rows whose target is > 88 nats below the best logit overflow the target-referenced partial sum: redo them
                 cabi.call("htcn_score_ce_repair", scores.hout.data_ptr(), self.act_dtype, Q, self.wt.data_ptr(), self.N,
                           zy.data_ptr(), loss_row.data_ptr(), None, st)
-            out.update(loss_row=loss_row, rank_row=rank_row, target_logit=zy)
+            out.update(loss_row=loss_row, rank_row=rank_row, target_logit=zy_fin)
         if fused and int(self._topk_overflow.item()):          # pathological ties overflowed a candidate list
             out.update(self.topk(scores.hout, Q, topk))
         elif topk and not fused:
             out.update(self.topk(scores.hout, Q, topk))
+            if self.l2_normalize:       # same order, normalised values
+                cabi.call("htcn_scale_rows", out["topk_val"].data_ptr(), self.row_scale(scores).data_ptr(), Q, topk, st)
         scores._cache[key] = out
         return out
+
+    def row_scale(self, scores: CatalogScores):
+        """[Q] 1 / max(||z_q||, 1e-6) of every scored row's logits over the whole catalog (tf.nn.l2_normalize, epsilon 1e-12
+        on the squared norm) from the quadratic form h^T G h + 2 h.c + s; the catalog's Gram data (G, c, s) is built once
+        per set of output weights (``invalidate_gram`` after an update)."""
+        torch = _torch()
+        if "row_scale" in scores._cache:
+            return scores._cache["row_scale"]
+        f32 = torch.float32
+        if getattr(self, "_gram", None) is None:
+            n_scr = int(cabi.load().htcn_catalog_gram_scratch_floats())
+            scr = torch.empty(n_scr, dtype=f32, device=self.device)
+            self._gram = torch.empty(D * D + D + 4, dtype=f32, device=self.device)
+            cabi.call("htcn_catalog_gram", self.wt.data_ptr(), self.act_dtype, self.b_out.data_ptr(), self.n_out,
+                      scr.data_ptr(), self._gram.data_ptr(), self.stream_ptr())
+        rs = torch.empty(max(scores.Q, 1), dtype=f32, device=self.device)
+        if scores.Q:
+            cabi.call("htcn_logit_rownorm", scores.hout.data_ptr(), self.act_dtype, scores.Q, self._gram.data_ptr(), 1e-12,
+                      rs.data_ptr(), self.stream_ptr())
+        scores._cache["row_scale"] = rs
+        return rs
+
+    def invalidate_gram(self):
+        self._gram = None
 
     def topk(self, hout, Q, k, n0=0):
         """Exact top-k of every row of ``hout`` over this model's catalog (shard).  Returns dict(topk_val, topk_idx)
@@ -490,13 +558,13 @@ class HierTCN:
 
     # ------------------------------------------------------------------ the reference's sess.run
     def step_async(self, x_list=None, y_list=None, mask_list=None, state=None, metrics=True, per_position=False, topk=0,
-                   state_on_device=False, neg_ids=None, staged=None):
+                   state_on_device=False, neg_ids=None, staged=None, mask_warmstart=None, x_gap=None):
         """Enqueue one step (H2D on the copy stream, kernels and the D2H of the results on the compute stream) and
         return a ``PendingStep``; ``.result()`` waits for it and returns the host dict of ``step``.  Submitting step
         i+1 before collecting step i hides the host-side batch packing and the PCIe copies behind the kernels."""
         torch = _torch()
         if staged is None:         # host batch; a DeviceBatcher (hiertcn_b200.device_batcher) hands in `staged` directly
-            staged = self.stage(x_list, y_list, mask_list, state, neg_ids)
+            staged = self.stage(x_list, y_list, mask_list, state, neg_ids, mask_warmstart, x_gap)
         scores, state_out = self.forward(staged=staged)
         if "neg_ids" in staged:
             neg_ids = staged["neg_ids"]
@@ -530,13 +598,13 @@ class HierTCN:
         return PendingStep(ev, host, state_out if state_on_device else None, topk, self.layout_meta)
 
     def step(self, x_list=None, y_list=None, mask_list=None, state=None, metrics=True, per_position=False, topk=0,
-             state_on_device=False, neg_ids=None, staged=None):
+             state_on_device=False, neg_ids=None, staged=None, mask_warmstart=None, x_gap=None):
         """Host in, host out -- the call ``sess.run([loss, state, ranks_float, ...], feed_dict)`` of
         run_hier_xing.py:145-149 maps to.  Includes the H2D of the batch and the D2H of the results.
         ``state`` may be a numpy array (reference behaviour) or the device tensor returned by a previous step with
         ``state_on_device=True`` (then the carried state never leaves HBM)."""
         return self.step_async(x_list, y_list, mask_list, state, metrics, per_position, topk, state_on_device,
-                               neg_ids, staged).result()
+                               neg_ids, staged, mask_warmstart, x_gap).result()
 
 
 class PendingStep:
@@ -606,11 +674,11 @@ def model_hier(args, x, y, mask, state, x_gap=None, x_impression=None, name="hie
     Returns (pred_all, state): pred_all is a lazy ``CatalogScores`` (call .materialize() for the dense
     [B,T,N] tensor at small N); state is a numpy array.  ``model``: an explicit built ``HierTCN`` to run on (otherwise
     one is built from ``weights`` and cached).  The returned handle is valid until the next forward on that model."""
-    if x_gap is not None or x_impression is not None:
-        raise NotImplementedError("has_gap / has_impression are unreachable in the XING runner (SURVEY A.8 #12)")
+    if x_impression is not None:
+        raise NotImplementedError("has_impression is unreachable in the XING runner (SURVEY A.8 #12)")
     if name != "hier":
         raise NotImplementedError("variable scope other than 'hier'")
     m = model if model is not None else _model_for(args, weights, precision or getattr(args, "precision", "bf16"))
-    scores, state_out = m.forward(x, y, mask, state)
+    scores, state_out = m.forward(x, y, mask, state, x_gap=x_gap)
     from .weights import unpad_state
     return scores, unpad_state(state_out.cpu().numpy(), m.layout_meta)

@@ -36,6 +36,8 @@ class HierTCNTrainer:
         self.bf16 = model.precision == "bf16"
         if model.n_out != model.N:
             raise NotImplementedError("training with a catalog-sharded output table")
+        if model.l2_normalize:
+            raise NotImplementedError("training through the l2-normalised head (model_tcn.py:42-43): evaluation only")
         self.m, self.dist, self.world = model, dist, int(world)
         self.lr = float(model.args.learning_rate if learning_rate is None else learning_rate)
         self.beta1, self.beta2, self.eps = float(beta1), float(beta2), float(eps)
@@ -116,12 +118,14 @@ class HierTCNTrainer:
         return flat[o:o + int(np.prod(shape))].view(*shape)
 
     # ------------------------------------------------------------------ forward + backward
-    def forward_backward(self, x_list=None, y_list=None, mask_list=None, state=None, staged=None, metrics=False):
+    def forward_backward(self, x_list=None, y_list=None, mask_list=None, state=None, staged=None, metrics=False,
+                         mask_warmstart=None, x_gap=None):
         """Accumulates the gradients of sum_b(sum_t loss/(n_b+1e-6)) into ``self.grads`` (the 1/user_count is applied by
         the optimiser).  Returns dict(scalars [8] device: loss, ..., user_count, n_valid; state [B,G*H] device)."""
         torch = _torch()
         m = self.m
-        d = staged if staged is not None else m.stage(x_list, y_list, mask_list, state)
+        d = staged if staged is not None else m.stage(x_list, y_list, mask_list, state, None, mask_warmstart, x_gap)
+        y_loss = d.get("y_loss", d["y_id"])     # mask_y of model.py:62,102-103: targets with the warm-start mask applied
         m.generation += 1               # the loss workspaces are shared with HierTCN.score: older handles are stale
         B, T, S, Q = d["B"], d["T"], d["S"], d["Q"]
         G, L, K, N = m.G, m.n_levels, m.K, m.N
@@ -195,11 +199,11 @@ class HierTCNTrainer:
         if self.bf16:
             cabi.call("htcn_score_ce_repair", hq.data_ptr(), prec, Q, m.wt.data_ptr(), N, zy.data_ptr(), loss_row.data_ptr(),
                       None, st)
-        cabi.call("htcn_loss_metrics_reduce", loss_row.data_ptr(), P(rank_row), d["row_of"].data_ptr(), d["y_id"].data_ptr(),
+        cabi.call("htcn_loss_metrics_reduce", loss_row.data_ptr(), P(rank_row), d["row_of"].data_ptr(), y_loss.data_ptr(),
                   B, T, N, None, None, None, buf("user_part", (B, 8), f32).data_ptr(), scalars.data_ptr(), st)
         # ---- backward
         g_row = buf("tr_g_row", (Q,), f32)
-        cabi.call("htcn_loss_row_weights", d["y_id"].data_ptr(), d["row_of"].data_ptr(), B, T, g_row.data_ptr(), st)
+        cabi.call("htcn_loss_row_weights", y_loss.data_ptr(), d["row_of"].data_ptr(), B, T, g_row.data_ptr(), st)
         d_hout = buf("tr_d_hout", (Q, D), f32)
         if self.bf16:
             cabi.call("htcn_score_ce_backward_bf16", hq.data_ptr(), hq_t.data_ptr(), q_pad, Q, m.wt.data_ptr(),
@@ -259,10 +263,11 @@ class HierTCNTrainer:
             self._refresh_bf16_tables()
         return scalars
 
-    def train_step(self, x_list, y_list, mask_list, state=None, lr=None, metrics=False, state_on_device=False):
+    def train_step(self, x_list, y_list, mask_list, state=None, lr=None, metrics=False, state_on_device=False,
+                   mask_warmstart=None, x_gap=None):
         """One optimisation step on one batch.  Returns dict(loss, user_count, n_valid, state [+ metrics]); ``state`` is
         the carried user state for the next batch (numpy, or the device tensor with ``state_on_device``)."""
-        r = self.forward_backward(x_list, y_list, mask_list, state, metrics=metrics)
+        r = self.forward_backward(x_list, y_list, mask_list, state, metrics=metrics, mask_warmstart=mask_warmstart, x_gap=x_gap)
         sc = self.apply_gradients(r["scalars"], lr).cpu().numpy()
         out = dict(loss=float(sc[0]), user_count=float(sc[6]), n_valid=float(sc[7]))
         if metrics:

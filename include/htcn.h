@@ -239,6 +239,32 @@ int32_t htcn_score_ce_repair(const void* hout, int32_t precision, int32_t Q, con
 int32_t htcn_score_ce_repair_shard(const void* hout, int32_t precision, int32_t Q, const void* w_out_t, int32_t n_items,
                                    float* part_max, float* part_sum, int32_t n_split, int32_t* repaired, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * l2-normalised scoring head (reference model_tcn.py:42-43: pred = tf.nn.l2_normalize(pred, dim=-1) over the N logits of
+ * a position), without materialising the logits: the squared norm of a logits row is the quadratic form
+ *     sum_j (h . w_j + b_j)^2 = h^T G h + 2 h . c + s,   G = sum_j w_j w_j^T,  c = sum_j b_j w_j,  s = sum_j b_j^2.
+ *   htcn_catalog_gram: gram [128*128 + 128 + 4] f32 = G | c | s of the table w_out_t (layout of htcn_prepare_wout for
+ *     `precision`; b_out read by the f32 tier); scratch: htcn_catalog_gram_scratch_floats() floats.  Deterministic.
+ *     Sharded catalogs: sum the shards' gram arrays (all-reduce) before use.
+ *   htcn_logit_rownorm: row_scale[q] = rsqrt(max(||z_q||^2, eps)) (eps = 1e-12 = tf.nn.l2_normalize's epsilon).
+ *   htcn_score_ce_rank_l2norm: the CE | RANK sweep of htcn_score_ce_rank_topk on the normalised logits
+ *     row_scale[q] * z[q, :] (the per-row scale multiplies the exponent; ranks compare raw logits -- the order is
+ *     invariant).  target_logit [Q] (raw, input); target_scaled [Q] = row_scale * target_logit (output): pass it to
+ *     htcn_score_finish as the target logit.  The partial sums cannot overflow (|scaled logit| <= 1): no repair pass.
+ *   htcn_scale_rows: x[r, :] *= row_scale[r]  (x [R, C] f32; e.g. top-k values of the normalised head, or the carried
+ *     state times a gap decay, model_hier.py:40-47).
+ * ------------------------------------------------------------------------------------------- */
+int64_t htcn_catalog_gram_scratch_floats(void);
+int32_t htcn_catalog_gram(const void* w_out_t, int32_t precision, const float* b_out, int32_t n_items, float* scratch,
+                          float* gram, void* stream);
+int32_t htcn_logit_rownorm(const void* hout, int32_t precision, int32_t Q, const float* gram, float eps, float* row_scale,
+                           void* stream);
+int32_t htcn_score_ce_rank_l2norm(const void* hout, int32_t precision, int32_t Q, const void* w_out_t, const float* b_out,
+                                  int32_t n_items, int32_t n0, const int32_t* y_id, const float* target_logit,
+                                  const float* row_scale, int32_t n_split, float* part_max, float* part_sum,
+                                  int32_t* part_cnt, float* target_scaled, void* stream);
+int32_t htcn_scale_rows(float* x, const float* row_scale, int64_t R, int32_t C, void* stream);
+
 /* k-way merge of per-part top-k lists -> [Q,k] sorted by (score desc, index asc) [TF top_k order] */
 int32_t htcn_topk_merge(const float* part_val, const int32_t* part_idx, int32_t n_part, int32_t Q,
                         int32_t k, float* out_val, int32_t* out_idx, void* stream);

@@ -214,7 +214,8 @@ def _cast_weights(w, precision):
     return {k: np.asarray(v).astype(dt) for k, v in w.items()}
 
 
-def model_hier_literal(x_ids, y_ids, masks, state, w, num_layer=2, precision="f32"):
+def model_hier_literal(x_ids, y_ids, masks, state, w, num_layer=2, precision="f32", x_gap=None, gap_bandwidth=168.0,
+                       l2_norm=False):
     """Literal mirror of model.py:59-61 + model_hier.py:39-94 (feasible for small N only).
 
     x_ids / y_ids: S-lists of int arrays [B, L_s]; masks: S-list of [B,1]; state [B, G*H].
@@ -227,12 +228,15 @@ def model_hier_literal(x_ids, y_ids, masks, state, w, num_layer=2, precision="f3
     N = w["hier/emb/kernel"].shape[0]
     preds = []
     for s in range(len(x_ids)):
+        if x_gap is not None:                                                 # model_hier.py:40-47 (train_gap off)
+            state = state * np.exp(-np.asarray(x_gap[s]).astype(dt) / dt(gap_bandwidth))
         x = one_hot_signed(x_ids[s], N, dt)                                   # model.py:59
         y = one_hot_signed(y_ids[s], N, dt)                                   # model.py:60
         x_slice = dense(x, w["hier/emb/kernel"])                              # model_hier.py:50
         feat = np.tile(state[:, None, :], (1, x_slice.shape[1], 1))           # :54
         x_slice = np.concatenate([x_slice, feat], -1)                         # :55
-        preds.append(model_tcn(x_slice, w, "hier/tcn", precision))            # :63
+        p = model_tcn(x_slice, w, "hier/tcn", precision)                     # :63
+        preds.append(l2_normalize(p) if l2_norm else p)                      # model_tcn.py:42-43
         cnt = np.sign(np.abs(y).sum(2)).sum(1, keepdims=True)                 # :83
         with np.errstate(invalid="ignore", divide="ignore"):
             y_slice = y.sum(1) / cnt                                          # :84
@@ -242,7 +246,7 @@ def model_hier_literal(x_ids, y_ids, masks, state, w, num_layer=2, precision="f3
     return np.concatenate(preds, 1), state                                   # :76-79,94
 
 
-def gru_over_sessions(y_ids, masks, state0, w, num_layer=2, precision="f32"):
+def gru_over_sessions(y_ids, masks, state0, w, num_layer=2, precision="f32", x_gap=None, gap_bandwidth=168.0):
     """Hoisted recurrence: returns (state_pre [S,B,GH] = state seen by session s's TCN,
     state_out [B,GH], Yp [S,B,D]).  Valid because the GRU input is teacher-forced
     (model_hier.py:83-91) and the TCN output never feeds it."""
@@ -252,6 +256,8 @@ def gru_over_sessions(y_ids, masks, state0, w, num_layer=2, precision="f32"):
     pre, yps = [], []
     wc = _cast_weights({k: v for k, v in w.items() if "multi_rnn_cell" in k}, precision)
     for s in range(len(y_ids)):
+        if x_gap is not None:                                                 # model_hier.py:40-47: decay before the slot
+            state = state * np.exp(-np.asarray(x_gap[s]).astype(dt) / dt(gap_bandwidth))
         pre.append(state)
         yp = meanpool_emb(y_ids[s], E, be)
         yps.append(yp)
@@ -290,15 +296,16 @@ def score_catalog(hout, w, precision="f32"):
 
 
 def model_hier_restructured(x_ids, y_ids, masks, state, w, num_layer=2, precision="f32",
-                            return_hidden=False):
+                            return_hidden=False, x_gap=None, gap_bandwidth=168.0, l2_norm=False):
     """Restructured route; same outputs as model_hier_literal (up to fp summation order)."""
     state_pre, state_out, _ = gru_over_sessions(y_ids, masks, state, w, num_layer,
-                                                "f64" if precision == "f64" else "f32")
+                                                "f64" if precision == "f64" else "f32", x_gap, gap_bandwidth)
     houts, _ = tcn_hidden_restructured(x_ids, state_pre, w, precision)
     hout = np.concatenate(houts, 1)
     if return_hidden:
         return hout, state_out
-    return score_catalog(hout, w, precision), state_out
+    z = score_catalog(hout, w, precision)
+    return (l2_normalize(z) if l2_norm else z), state_out
 
 
 # --------------------------------------------------------------------------------------
@@ -321,12 +328,14 @@ def softmax_cross_entropy_with_logits(labels_onehot_or_ids, logits):
     return np.where(ids > 0, lse - zy, 0.0).astype(z.dtype)
 
 
-def hier_loss(pred_all, y_id):
+def hier_loss(pred_all, y_id, mask_warmstart=None):
     """model.py:62,105-117: mask logits, CE, mask loss, per-user mean (+1e-6), mean over users with
     >=1 valid position.  Returns (loss scalar, loss_bt [B,T] masked, mask_y, activity_count(+1e-6), user_count)."""
     y_id = np.asarray(y_id).astype(np.int64)
     dt = pred_all.dtype
     mask_y = np.sign(y_id).astype(dt)                                         # model.py:62
+    if mask_warmstart is not None:
+        mask_y = mask_y * np.asarray(mask_warmstart).astype(dt)               # model.py:102-103
     pred = pred_all * mask_y[..., None]                                       # :105
     loss_bt = softmax_cross_entropy_with_logits(y_id, pred) * mask_y          # :108,111
     activity_count = mask_y.sum(1)                                            # :112
@@ -454,11 +463,15 @@ def calc_score(pred, y_impression, rank_metric="l2"):
 # --------------------------------------------------------------------------------------
 
 
-def forward_loss_metrics(x_ids, y_ids, masks, state, w, num_layer=2, precision="f32", literal=False):
+def forward_loss_metrics(x_ids, y_ids, masks, state, w, num_layer=2, precision="f32", literal=False, x_gap=None,
+                         gap_bandwidth=168.0, l2_norm=False, mask_warmstart=None):
     fwd = model_hier_literal if literal else model_hier_restructured
-    pred_all, state_out = fwd(x_ids, y_ids, masks, state, w, num_layer, precision)
+    pred_all, state_out = fwd(x_ids, y_ids, masks, state, w, num_layer, precision, x_gap=x_gap,
+                              gap_bandwidth=gap_bandwidth, l2_norm=l2_norm)
     y_id = np.concatenate([np.asarray(y) for y in y_ids], 1).astype(np.int64)   # run_hier_xing.py:278
-    loss, loss_bt, mask_y, act, ucount, pred_masked = hier_loss(pred_all, y_id)
+    loss, loss_bt, mask_y, act, ucount, pred_masked = hier_loss(pred_all, y_id, mask_warmstart)
+    # calc_metric_fast reads the target score through the one-hot label tensor y (loss.py:179), which the warm-start mask
+    # does not touch: a position masked only by mask_warmstart compares its zeroed scores with 0 and is then masked out
     rec1, rec5, rec10, mrr, mrp, ranks_float, ranks = calc_metric_fast(pred_masked, mask_y, act, ucount, y_id)
     return dict(loss=loss, loss_bt=loss_bt, state=state_out, recall1=rec1, recall5=rec5, recall10=rec10,
                 mrr=mrr, mrp=mrp, ranks_float=ranks_float, ranks=ranks, mask_y=mask_y, pred=pred_masked)

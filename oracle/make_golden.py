@@ -54,20 +54,26 @@ def _set_args(a, **kw):
 
 
 def hier_case(tf, a, ref_loss, ref_hier, *, name, N, B, S, Lmax, hidden_dim, num_layer, tcn_channel,
-              kernel_size, seed, store_weights, kernel_scale=2.0):
+              kernel_size, seed, store_weights, kernel_scale=2.0, has_gap=False, l2_normalize=False, warm_start=False):
+    """``has_gap``: the gap decay of model_hier.py:40-47 (train_gap off) with random gaps; ``l2_normalize``: the normalised
+    head of model_tcn.py:42-43; ``warm_start``: a random mask_warmstart multiplied into mask_y (model.py:102-103)."""
     sys.path.insert(0, ROOT)
     from hiertcn_b200.data_loader import synthetic_batch
     from hiertcn_b200.weights import hier_weight_shapes, init_weights, weights_sha256
 
     _set_args(a, item_num=N, output_dim=N, hidden_dim=hidden_dim, num_layer=num_layer,
               tcn_channel=list(tcn_channel), kernel_size=kernel_size, dropout=0.0, loss="cross_entropy",
-              model_type="hier", model_low_type="tcn")
+              model_type="hier", model_low_type="tcn", has_gap=has_gap, train_gap=False, gap_bandwidth=168.0,
+              l2_normalize=l2_normalize, warm_start=warm_start)
     shapes = hier_weight_shapes(N, hidden_dim, num_layer, tcn_channel, kernel_size)
     w = init_weights(shapes, seed=seed, kernel_scale=kernel_scale, bias_noise=0.1)
     x_list, y_list, mask_list = synthetic_batch(B, S, Lmax, N, seed=seed + 1, lengths="ragged",
                                                 id_dist="uniform", mask_keep=0.6)
     rng = np.random.default_rng(seed + 2)
     state0 = rng.normal(0, 0.5, size=(B, hidden_dim * num_layer)).astype(np.float32)
+    x_gap = [rng.exponential(120.0, size=(B, 1)).astype(np.float32) for _ in range(S)] if has_gap else None
+    T_all = sum(x.shape[1] for x in x_list)
+    mask_warm = (rng.random((B, T_all)) < 0.7).astype(np.float32) if warm_start else None
 
     # ---- run the reference graph code eagerly (float64 so the fixture is a precise target) ----
     res = {}
@@ -80,11 +86,14 @@ def hier_case(tf, a, ref_loss, ref_hier, *, name, N, B, S, Lmax, hidden_dim, num
         xs = [tf.one_hot(t, depth=N, dtype=dt) * tf.cast(tf.expand_dims(tf.sign(t), axis=-1), dtype=dt) for t in x_ids]
         ys = [tf.one_hot(t, depth=N, dtype=dt) * tf.cast(tf.expand_dims(tf.sign(t), axis=-1), dtype=dt) for t in y_ids]
         masks = [m.astype(dt) for m in mask_list]
-        pred, state = ref_hier.model_hier(a, xs, ys, masks, state0.astype(dt), training=np.asarray(False))
+        gaps = [g.astype(dt) for g in x_gap] if has_gap else None
+        pred, state = ref_hier.model_hier(a, xs, ys, masks, state0.astype(dt), x_gap=gaps, training=np.asarray(False))
         y_id = np.concatenate(y_ids, 1)
         y = tf.one_hot(y_id, depth=N, dtype=dt) * tf.cast(tf.expand_dims(tf.sign(y_id), axis=-1), dtype=dt)
         # model.py:62,105-117 (restated -- model.py itself cannot be imported)
         mask_y = tf.cast(tf.sign(y_id), dtype=dt)
+        if warm_start:
+            mask_y = mask_y * mask_warm.astype(dt)               # model.py:102-103
         pred = pred * tf.expand_dims(mask_y, -1)
         loss_bt = ref_loss.calc_loss(pred, y)                    # reference loss.py:20-21
         loss_bt = loss_bt * mask_y
@@ -116,6 +125,11 @@ def hier_case(tf, a, ref_loss, ref_hier, *, name, N, B, S, Lmax, hidden_dim, num
                metrics_f64=np.asarray([r64[k] for k in ("rec1", "rec5", "rec10", "mrr", "mrp")]),
                loss_f32=r32["loss"], state_f32=r32["state"], ranks_f32=r32["ranks"],
                metrics_f32=np.asarray([r32[k] for k in ("rec1", "rec5", "rec10", "mrr", "mrp")]))
+    if has_gap:
+        out.update(gap_bandwidth=168.0, **{f"x_gap_{s}": x_gap[s] for s in range(S)})
+    if warm_start:
+        out["mask_warmstart"] = mask_warm
+    out["l2_normalize"] = int(l2_normalize)
     if store_weights:
         for k, v in w.items():
             out["w|" + k.replace("/", "|")] = v
@@ -165,10 +179,14 @@ def build_all():
     cases = []
     cases.append(hier_case(tf, a, ref_loss, ref_hier, name="hier_default_arch", N=61, B=3, S=3, Lmax=6,
                            hidden_dim=128, num_layer=2, tcn_channel=(128, 128), kernel_size=5, seed=11,
-                           store_weights=False))
+                           store_weights=True))
     cases.append(hier_case(tf, a, ref_loss, ref_hier, name="hier_downsample_3lvl", N=40, B=4, S=4, Lmax=9,
                            hidden_dim=16, num_layer=2, tcn_channel=(32, 32, 48), kernel_size=3, seed=23,
                            store_weights=True))
+    # optional variants of SURVEY 8(f-4): gap decay, l2-normalised head, warm-start loss mask
+    cases.append(hier_case(tf, a, ref_loss, ref_hier, name="hier_gap_l2norm_warmstart", N=53, B=5, S=3, Lmax=7,
+                           hidden_dim=128, num_layer=2, tcn_channel=(128, 128), kernel_size=5, seed=37,
+                           store_weights=True, has_gap=True, l2_normalize=True, warm_start=True))
     cases.append(loss_case(tf, a, ref_loss))
     return cases
 
@@ -182,6 +200,7 @@ def main():
         path = os.path.join(GOLD, name + ".npz")
         if opt.check:
             old = np.load(path)
+            assert set(old.files) == set(out), (name, set(old.files) ^ set(out))
             for k, v in out.items():
                 if np.asarray(v).dtype.kind in "fc":
                     np.testing.assert_allclose(old[k], v, rtol=1e-12, atol=0, err_msg=f"{name}:{k}")

@@ -27,6 +27,18 @@ def load_hier_golden(name):
     return z, x, y, m, w
 
 
+def golden_variant_kwargs(z):
+    """oracle kwargs of the optional variants a fixture was generated with (gap decay, l2-normalised head, warm-start mask)"""
+    kw = {}
+    if "x_gap_0" in z.files:
+        kw.update(x_gap=[z[f"x_gap_{s}"] for s in range(int(z["S"]))], gap_bandwidth=float(z["gap_bandwidth"]))
+    if "l2_normalize" in z.files and int(z["l2_normalize"]):
+        kw["l2_norm"] = True
+    if "mask_warmstart" in z.files:
+        kw["mask_warmstart"] = z["mask_warmstart"]
+    return kw
+
+
 def small_case(B=5, S=3, L=7, N=97, seed=0, lengths="ragged", kernel_scale=2.0, tcn_channel=(128, 128),
                kernel_size=5, mask_keep=0.7):
     from hiertcn_b200.data_loader import synthetic_batch

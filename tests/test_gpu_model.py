@@ -3,7 +3,7 @@ sess.run fetch list) against the golden fixtures and the CPU oracle."""
 import numpy as np
 import pytest
 
-from helpers import load_hier_golden, small_case
+from helpers import golden_variant_kwargs, load_hier_golden, small_case
 from oracle import hiertcn_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -82,6 +82,43 @@ def test_step_matches_golden_downsample_narrow_widths(precision, tol):
     # the carried state round-trips through the host in the TF shape [B, G*H]
     out2 = model.step(x, y, m, out["state"])
     assert np.isfinite(out2["loss"])
+
+
+@pytest.mark.parametrize("precision,tol", [("f32", 1e-4), ("bf16", 2e-2)])
+def test_step_matches_golden_gap_decay_l2norm_warmstart(precision, tol):
+    """fixture produced by the reference's own python with has_gap (model_hier.py:40-47), l2_normalize (model_tcn.py:42-43)
+    and a warm-start loss mask (model.py:102-103)"""
+    from hiertcn_b200.args import make_args
+    from hiertcn_b200.model_hier import HierTCN
+    z, x, y, m, w = load_hier_golden("hier_gap_l2norm_warmstart")
+    kw = golden_variant_kwargs(z)
+    N = int(z["N"])
+    a = make_args(["--item_num", str(N), "--has_gap", "--l2_normalize", "--gap_bandwidth", str(kw["gap_bandwidth"])])
+    model = HierTCN(a, w, precision=precision).build()
+    out = model.step(x, y, m, z["state0"], per_position=True, topk=10, mask_warmstart=kw["mask_warmstart"], x_gap=kw["x_gap"])
+    assert abs(out["loss"] - z["loss_f64"]) <= tol * abs(z["loss_f64"])
+    np.testing.assert_allclose(out["state"], z["state_f64"], rtol=max(tol, 1e-4), atol=max(tol, 1e-5))
+    np.testing.assert_allclose(out["loss_bt"], z["loss_bt_f64"], rtol=tol, atol=max(tol, 1e-5) * 0.1)
+    if precision == "f32":
+        np.testing.assert_array_equal(out["ranks"], z["ranks_f64"])
+        got = np.asarray([out[k] for k in ("recall1", "recall5", "recall10", "mrr", "mrp")])
+        np.testing.assert_allclose(got, z["metrics_f64"], rtol=1e-4, atol=1e-6)
+        # the materialised logits are the NORMALISED ones; the fixture's are additionally zeroed by the warm-start mask
+        scores, _ = model.forward(x, y, m, z["state0"], x_gap=kw["x_gap"])
+        pred = scores.materialize()
+        y_id = np.concatenate(y, 1)
+        keep = (y_id > 0) & (kw["mask_warmstart"] > 0)
+        np.testing.assert_allclose(pred[keep], z["pred_f64"][keep], rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(np.linalg.norm(pred[y_id > 0], axis=-1), 1.0, rtol=1e-5)
+        # top-k: normalised values in the reference's order
+        ref = O.forward_loss_metrics(x, y, m, z["state0"], w, 2, "f64", **kw)
+        rows = out["row_of"].reshape(y_id.shape)
+        zv = ref["pred"][keep]
+        v_ref, i_ref = O.top_k(zv, 10)
+        np.testing.assert_allclose(out["topk_val"][rows[keep]], v_ref, rtol=1e-4, atol=1e-6)
+        assert np.mean(out["topk_idx"][rows[keep]] == i_ref) > 0.99
+    else:
+        assert abs(out["mrr"] - z["metrics_f64"][3]) < 5e-2
 
 
 def test_materialized_logits_match_reference_pred():

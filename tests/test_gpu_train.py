@@ -359,13 +359,13 @@ def test_fused_conv_forward_saves_match_fp32_levels(B, S, L, K, levels):
     h32 = torch.zeros((levels + 1, R, 128), device="cuda")
     a32 = torch.zeros((levels, R, 128), device="cuda")
     o32 = torch.zeros((Q, 128), device="cuda")
-    cabi.call("htcn_tcn_forward_train", xe_f.data_ptr(), w_in.data_ptr(), sb.data_ptr(), wp, bp, levels, K, slot_p, B, T, S,
+    cabi.call("htcn_tcn_forward_train", xe_f.data_ptr(), w_in.data_ptr(), sb.data_ptr(), wp, bp, None, None, levels, K, slot_p, B, T, S,
               row_d.data_ptr(), h32.data_ptr(), a32.data_ptr(), o32.data_ptr(), st)
     h16 = torch.full((levels + 1, R, 128), float("nan"), dtype=torch.bfloat16, device="cuda")
     a16 = torch.full((levels, R, 128), float("nan"), dtype=torch.bfloat16, device="cuda")
     o16 = torch.full((Q, 128), float("nan"), dtype=torch.bfloat16, device="cuda")
-    scratch = torch.empty((1 + levels * K) * 8192 + 4096, device="cuda")
-    cabi.call("htcn_tcn_forward_train_bf16", xe_b.data_ptr(), w_in.data_ptr(), sb.data_ptr(), wp, bp, levels, K, slot_p, B,
+    scratch = torch.empty(cabi.tcn_scratch_floats(levels, K), device="cuda")
+    cabi.call("htcn_tcn_forward_train_bf16", xe_b.data_ptr(), w_in.data_ptr(), sb.data_ptr(), wp, bp, None, None, levels, K, slot_p, B,
               T, S, row_d.data_ptr(), h16.data_ptr(), a16.data_ptr(), o16.data_ptr(), scratch.data_ptr(), st)
     torch.cuda.synchronize()
     for name, got, ref in (("h", h16, h32), ("a", a16, a32), ("hout", o16, o32)):

@@ -4,14 +4,17 @@ import numpy as np
 import pytest
 
 from oracle import hiertcn_oracle as O
-from helpers import GOLDEN, load_hier_golden, small_case
+from helpers import GOLDEN, golden_variant_kwargs, load_hier_golden, small_case
 
 
-@pytest.mark.parametrize("name", ["hier_default_arch", "hier_downsample_3lvl"])
+ALL_GOLDEN = ["hier_default_arch", "hier_downsample_3lvl", "hier_gap_l2norm_warmstart"]
+
+
+@pytest.mark.parametrize("name", ALL_GOLDEN)
 def test_literal_oracle_matches_reference_graph(name):
     z, x, y, m, w = load_hier_golden(name)
     G = int(z["num_layer"])
-    out = O.forward_loss_metrics(x, y, m, z["state0"], w, G, "f64", literal=True)
+    out = O.forward_loss_metrics(x, y, m, z["state0"], w, G, "f64", literal=True, **golden_variant_kwargs(z))
     np.testing.assert_allclose(out["pred"], z["pred_f64"], rtol=2e-6, atol=2e-6)   # fixture stored as f32
     np.testing.assert_allclose(out["state"], z["state_f64"], rtol=1e-12, atol=1e-13)
     np.testing.assert_allclose(out["loss"], z["loss_f64"], rtol=1e-12)
@@ -23,23 +26,23 @@ def test_literal_oracle_matches_reference_graph(name):
     np.testing.assert_allclose(got, z["metrics_f64"], rtol=1e-6)
 
 
-@pytest.mark.parametrize("name", ["hier_default_arch", "hier_downsample_3lvl"])
+@pytest.mark.parametrize("name", ALL_GOLDEN)
 def test_restructured_oracle_matches_reference_graph(name):
     """gather instead of one-hot matmul, hoisted GRU, split in-projection == the literal graph."""
     z, x, y, m, w = load_hier_golden(name)
     G = int(z["num_layer"])
-    out = O.forward_loss_metrics(x, y, m, z["state0"], w, G, "f64", literal=False)
+    out = O.forward_loss_metrics(x, y, m, z["state0"], w, G, "f64", literal=False, **golden_variant_kwargs(z))
     np.testing.assert_allclose(out["pred"], z["pred_f64"], rtol=2e-6, atol=2e-6)
     np.testing.assert_allclose(out["state"], z["state_f64"], rtol=1e-11, atol=1e-12)
     np.testing.assert_allclose(out["loss"], z["loss_f64"], rtol=1e-11)
     np.testing.assert_array_equal(out["ranks"], z["ranks_f64"])
 
 
-@pytest.mark.parametrize("name", ["hier_default_arch", "hier_downsample_3lvl"])
+@pytest.mark.parametrize("name", ALL_GOLDEN)
 def test_f32_restructured_within_1e4(name):
     """fp32 tier tolerance of the north star (1e-4 relative) holds for the fp32 oracle itself."""
     z, x, y, m, w = load_hier_golden(name)
-    out = O.forward_loss_metrics(x, y, m, z["state0"], w, int(z["num_layer"]), "f32")
+    out = O.forward_loss_metrics(x, y, m, z["state0"], w, int(z["num_layer"]), "f32", **golden_variant_kwargs(z))
     assert abs(out["loss"] - z["loss_f64"]) <= 1e-4 * abs(z["loss_f64"])
     np.testing.assert_allclose(out["state"], z["state_f64"], rtol=1e-4, atol=1e-5)
     np.testing.assert_allclose(out["loss"], z["loss_f32"], rtol=1e-5)
