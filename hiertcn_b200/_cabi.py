@@ -110,11 +110,8 @@ LAUNCHES_PER_CALL = {"htcn_gather_meanpool": 2, "htcn_gru_sessions": 1, "htcn_tc
                      "htcn_prepare_wout": 1, "htcn_score_ce_rank_topk": 2, "htcn_score_logits": 1,
                      "htcn_target_logit": 1, "htcn_score_finish": 1, "htcn_topk_merge": 1, "htcn_score_topk": 5, "htcn_score_ce_repair": 1,
                      "htcn_score_ce_repair_shard": 1, "htcn_score_ce_rank_topk_fused": 6,
-                     "htcn_catalog_gram": [_p, _i, _p, _i, _p, _p, _p],
-    "htcn_logit_rownorm": [_p, _i, _i, _p, _f, _p, _p],
-    "htcn_score_ce_rank_l2norm": [_p, _i, _i, _p, _p, _i, _i, _p, _p, _p, _i, _p, _p, _p, _p, _p],
-    "htcn_scale_rows": [_p, _p, C.c_int64, _i, _p],
-    "htcn_loss_metrics_reduce": 2, "htcn_sampled_rank_loss": 1, "htcn_calc_score": 1,
+                     "htcn_catalog_gram": 2, "htcn_logit_rownorm": 1, "htcn_score_ce_rank_l2norm": 2, "htcn_scale_rows": 1,
+                     "htcn_loss_metrics_reduce": 2, "htcn_sampled_rank_loss": 1, "htcn_calc_score": 1,
                      # training step (the per-call counts of the multi-launch entry points are added by the caller)
                      "htcn_loss_row_weights": 1, "htcn_score_ce_backward": 1, "htcn_gru_sessions_train": 1,
                      "htcn_gather_backward": 2, "htcn_adam_step": 1, "htcn_refresh_wout": 1,

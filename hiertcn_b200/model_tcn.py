@@ -33,6 +33,7 @@ class TCN(HierTCN):
         self.K = int(args.kernel_size)
         self.n_levels = len(args.tcn_channel)
         self.G = 0
+        self.l2_normalize = bool(getattr(args, "l2_normalize", False))      # model_tcn.py:42-43
         self.host_weights, self.scope, self.device = weights, scope, device
         self.built = False
         self._init_runtime_state()

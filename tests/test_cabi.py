@@ -78,3 +78,11 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", txt, flags=re.M), f
+
+
+def test_launch_table_is_consistent_with_the_signatures():
+    """every entry of the per-call launch table names a bound function and is an int (bench.py's gpu_launches claim)"""
+    from hiertcn_b200 import _cabi as cabi
+    for name, n in cabi.LAUNCHES_PER_CALL.items():
+        assert name in cabi.SIGNATURES, name
+        assert isinstance(n, int) and n >= 0, (name, n)
