@@ -20,7 +20,7 @@ WT_PITCH_BF16 = 144
 
 def tcn_scratch_floats(n_levels, K):
     """HTCN_TCN_SCRATCH_BYTES / 4: bf16 weight tiles (K taps + a possible down-sample kernel per level) + tables"""
-    return ((1 + n_levels * (K + 1)) * 128 * 128 * 2 + 640 + 2 * 8 * 512 + 256 + 3) // 4
+    return ((1 + n_levels * (K + 1)) * 128 * 128 * 2 + 640 + 2 * 8 * 512 + 256 + 296 * 2 * n_levels * 8192 + 3) // 4
 
 
 def gru_scratch_bytes(B):

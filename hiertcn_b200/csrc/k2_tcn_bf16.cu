@@ -7,8 +7,11 @@
 // out WITH their causal zero padding as physical rows:
 //   short sequences (L + P <= 128, P = (K-1)*d_max): floor(128/(L+P)) sequences per tile, each preceded by P
 //     zero rows -- the left pad of customized_tcn_cell.py:46-48 -- which also isolates neighbours;
-//   long sequences (config 3, L = 256): one sequence chunk per tile with the receptive-field halo
-//     RF-1 = (K-1)(2^n - 1) rows recomputed in front of the 128-(RF-1) new output positions.
+//   long sequences (config 3, L = 256): a CTA STREAMS a sequence in chunks of 128 new positions.  What chunk c+1 needs
+//     of chunk c is, per level, the last (K-1)*d rows of that level's INPUT; the owner threads of the tile's last 32
+//     rows park them in a per-CTA global scratch (L2-resident, double-buffered by chunk parity) and cp.async them back
+//     into the 32 spare rows in front of the tile while the epilogue math runs.  No receptive-field halo is recomputed
+//     (the first version recomputed RF-1 = 60 of every 128 rows at config 3: 47 % of its MMAs).
 // The activation tile lives in shared memory in the NO-SWIZZLE K-major UMMA layout with 8-row core matrices made
 // contiguous (SBO = 128 B): row r / 16-byte channel chunk c sits at c*ROWS*16 + r*16, i.e. rows are uniformly
 // 16 B apart, so conv tap k of a level with dilation d is the SAME buffer addressed through a descriptor whose
@@ -38,18 +41,30 @@ constexpr int kK2ProducerWarp = kK2EpiWarps, kK2MmaWarp = kK2EpiWarps + 1;
 
 struct K2Slot {          // per session slot: tiling of its B sequences
   int off, L;            // first column in [B,T], length
-  int tile0;             // first global tile index of this slot
-  int seq_per_tile;      // > 0: short mode;  0: long mode
-  int tiles_per_seq;     // long mode
+  int unit0;             // first global work-unit index of this slot
+  int seq_per_tile;      // > 0: short mode (unit = one tile of seq_per_tile sequences);  0: long mode (unit = one sequence)
+  int chunks;            // tiles per unit: 1 (short), ceil(L / 128) (long)
 };
 struct K2Geom {
-  int n_slots, n_tiles, B, T, K, n_levels;
+  int n_slots, n_units, B, T, K, n_levels;
   unsigned ds_mask;      // bit l: level l has a 1x1 down-sample residual (customized_tcn_cell.py:102-106): one more weight
                          // tile after the level's taps, accumulated into TMEM columns 128..255
   int P;                 // zero rows in front of each short sequence = max shift of the deepest level
-  int rf1;               // receptive field - 1 (long mode halo)
   K2Slot slot[HTCN_MAX_SLOTS];
 };
+constexpr int kHistBytes = kMaxSpare * kDim * 2;      // one level's parked rows: [16 channel chunks][32 rows][16 B] = 8 KB
+
+__device__ __forceinline__ int unit_slot(const K2Geom& g, int unit) {
+  int s = 0;
+  while (s + 1 < g.n_slots && g.slot[s + 1].unit0 <= unit) ++s;
+  return s;
+}
+// tiles CTA `cta` of `n_cta` runs: the chunks of units cta, cta + n_cta, ...
+__device__ __forceinline__ int cta_tile_count(const K2Geom& g, int cta, int n_cta) {
+  int n = 0;
+  for (int u = cta; u < g.n_units; u += n_cta) n += g.slot[unit_slot(g, u)].chunks;
+  return n;
+}
 
 struct alignas(1024) K2Smem {
   uint8_t w[kWStages][kWStageBytes];     // 64 KB
@@ -70,34 +85,38 @@ __device__ __forceinline__ uint64_t make_desc_act(uint32_t smem_addr) {
   return d;                                     // layout type 0 = no swizzle
 }
 
-__device__ __forceinline__ void tile_geometry(const K2Geom& g, int tile, int r, const int* out_row, int& src,
+// row r of chunk `chunk` of work unit `unit` (unit >= n_units: a dummy tile, every row is padding)
+__device__ __forceinline__ void tile_geometry(const K2Geom& g, int unit, int chunk, int r, const int* out_row, int& src,
                                               int& dst, int& sb, bool& own) {
-  int s = 0;
-  while (s + 1 < g.n_slots && g.slot[s + 1].tile0 <= tile) ++s;
+  src = -1; dst = -1; sb = 0; own = false;
+  if (unit >= g.n_units) return;
+  const int s = unit_slot(g, unit);
   const K2Slot& sl = g.slot[s];
-  const int lt = tile - sl.tile0;
+  const int lu = unit - sl.unit0;
   int b, t;
   bool is_out;
   if (sl.seq_per_tile > 0) {
     const int stride = sl.L + g.P;
     const int seg = r / stride;
     t = r % stride - g.P;
-    b = lt * sl.seq_per_tile + seg;
+    b = lu * sl.seq_per_tile + seg;
     is_out = seg < sl.seq_per_tile;
   } else {
-    const int step = kTR - g.rf1;
-    b = lt / sl.tiles_per_seq;
-    const int t0 = (lt % sl.tiles_per_seq) * step;
-    t = t0 - g.rf1 + r;
-    is_out = t >= t0;
+    b = lu;
+    t = chunk * kTR + r;
+    is_out = true;
   }
   const bool data = b < g.B && t >= 0 && t < sl.L;
   src = data ? b * g.T + sl.off + t : -1;
   sb = s * g.B + (b < g.B ? b : 0);
-  dst = -1;
-  own = data && is_out;            // this tile produces the row's final values at every level (halo rows are recomputed)
+  own = data && is_out;            // this tile produces the row's values at every level
   if (own) dst = out_row ? out_row[src] : src;
 }
+
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // kPair: the CTAs run as clusters of 2 that walk the SAME weight sequence in lock step; each CTA fetches one of the two
 // 64-column chunks of a weight tile and TMA-multicasts it into both CTAs' rings, so every weight byte crosses L2 -> SM once
@@ -110,14 +129,16 @@ k2_tcn_bf16(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfl
             const float* __restrict__ ds_bias_all /*[n_levels][128], read only for the levels of g.ds_mask*/,
             const int* __restrict__ out_row, __nv_bfloat16* __restrict__ hout,
             __nv_bfloat16* __restrict__ h_save /* [(n_levels+1)][B*T][128] every layer's output, or NULL */,
-            __nv_bfloat16* __restrict__ a_save /* [n_levels][B*T][128] relu(conv + b) before the residual, or NULL */) {
+            __nv_bfloat16* __restrict__ a_save /* [n_levels][B*T][128] relu(conv + b) before the residual, or NULL */,
+            uint8_t* __restrict__ hist /* [gridDim.x][2][n_levels][kHistBytes] parked level inputs of streamed sequences */) {
   extern __shared__ uint8_t smem_raw[];
   auto& sm = *reinterpret_cast<K2Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_layers = g.n_levels + 1;                       // layer 0 = in-projection
-  // kPair: both CTAs of a pair run the tile count of its first CTA; a tile index >= n_tiles is a dummy tile (all rows zero)
-  const int first_cta = kPair ? ((int)blockIdx.x & ~1) : (int)blockIdx.x;
-  const int my_tiles = (g.n_tiles - first_cta + (int)gridDim.x - 1) / (int)gridDim.x;
+  // kPair: both CTAs of a pair walk the same weight sequence in lock step, so both run the larger of their two tile
+  // counts; the surplus tiles of the other one are dummy tiles (all rows zero)
+  int my_tiles = cta_tile_count(g, (int)blockIdx.x, (int)gridDim.x);
+  if (kPair) my_tiles = max(my_tiles, cta_tile_count(g, (int)blockIdx.x ^ 1, (int)gridDim.x));
   const uint32_t crank = kPair ? cluster_ctarank() : 0u;
 
   if (tid == 0) {
@@ -224,11 +245,17 @@ k2_tcn_bf16(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfl
     const int ch = tid >> 7;                                    // channel half: 64*ch .. 64*ch+63
     uint8_t* my_act = sm.act + (kMaxSpare + r) * 16;            // + c * kRows * 16 for channel chunk c
     long long n_acc = 0;
+    int unit = blockIdx.x, chunk = 0, unit_chunks = unit < g.n_units ? g.slot[unit_slot(g, unit)].chunks : 1;
+    // streaming of long sequences: the threads of the tile's last kMaxSpare rows own the hand-over to the next chunk
+    const bool hist_owner = r >= kTR - kMaxSpare;
+    const int hj = r - (kTR - kMaxSpare);                       // spare row / parked row of this thread
+    uint8_t* my_hist = hist + (size_t)blockIdx.x * 2 * g.n_levels * kHistBytes;
+    bool spare_dirty = false;                                   // the spare rows hold parked data (not the zero pad)
     for (int it = 0; it < my_tiles; ++it) {
-      const int tile = blockIdx.x + it * gridDim.x;
       int src, dst, sb;
       bool own;
-      tile_geometry(g, tile, r, out_row, src, dst, sb, own);
+      tile_geometry(g, unit, chunk, r, out_row, src, dst, sb, own);
+      const bool streaming = unit_chunks > 1;
       const long long RT = (long long)g.B * g.T;
       // ---- stage the input rows (bf16 Xe) into the operand layout; zero rows stay zero
       {
@@ -243,6 +270,23 @@ k2_tcn_bf16(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfl
         mbar_wait(&sm.acc_ready, (uint32_t)(n_acc & 1));
         tc_fence_after_sync();
         const bool last = layer == n_layers - 1;
+        // The MMAs that read the spare rows have retired: refill them for the NEXT layer (conv level `layer`), whose
+        // taps reach back up to kMaxSpare rows -- with the rows chunk-1 parked for that level, or with the causal zero pad.
+        uint8_t* park = my_hist + ((size_t)(chunk & 1) * g.n_levels + layer) * kHistBytes;
+        if (!last && hist_owner) {
+          const uint8_t* prev = my_hist + ((size_t)((chunk & 1) ^ 1) * g.n_levels + layer) * kHistBytes;
+          if (streaming && chunk > 0) {
+#pragma unroll
+            for (int c = ch * 8; c < ch * 8 + 8; ++c)
+              cp_async_16(sm.act + c * (kRows * 16) + hj * 16, prev + (c * kMaxSpare + hj) * 16);
+            spare_dirty = true;
+          } else if (spare_dirty) {                              // back to the causal zero pad
+#pragma unroll
+            for (int c = ch * 8; c < ch * 8 + 8; ++c)
+              *reinterpret_cast<uint4*>(sm.act + c * (kRows * 16) + hj * 16) = make_uint4(0, 0, 0, 0);
+            spare_dirty = false;
+          }
+        }
         const float* bias_l = layer > 0 ? sm.bias[layer - 1] : nullptr;
         const bool ds = layer > 0 && ((g.ds_mask >> (layer - 1)) & 1u);
         const float* ds_bias_l = ds ? ds_bias_all + (layer - 1) * kDim : nullptr;
@@ -304,15 +348,25 @@ k2_tcn_bf16(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfl
                                       pack_bf16x2(o[6], o[7]));
             if (src < 0) packed = make_uint4(0, 0, 0, 0);        // causal pad rows stay zero at every level
             if (h_save && own) reinterpret_cast<uint4*>(h_save + ((long long)layer * RT + src) * kDim)[c] = packed;
-            if (!last) *slot = packed;
-            else if (dst >= 0) reinterpret_cast<uint4*>(hout + (long long)dst * kDim)[c] = packed;
+            if (!last) {
+              *slot = packed;
+              // park this row of the next level's input for the sequence's next chunk (read back by this same thread)
+              if (streaming && hist_owner && chunk + 1 < unit_chunks)
+                *reinterpret_cast<uint4*>(park + (c * kMaxSpare + hj) * 16) = packed;
+            } else if (dst >= 0) reinterpret_cast<uint4*>(hout + (long long)dst * kDim)[c] = packed;
           }
         }
         tc_fence_before_sync();
         if (!last) {
+          if (hist_owner) cp_async_wait_all();                   // the parked rows have landed in the spare rows
           fence_proxy_async_smem();
           mbar_arrive(&sm.act_ready);
         }
+      }
+      if (++chunk == unit_chunks) {
+        unit += gridDim.x;
+        chunk = 0;
+        unit_chunks = unit < g.n_units ? g.slot[unit_slot(g, unit)].chunks : 1;
       }
     }
   }
@@ -363,28 +417,23 @@ int32_t tcn_forward_bf16(const void* xe, int xe_dtype, const float* w_in_x, cons
   }
   K2Geom g{};
   g.n_slots = slots.n; g.B = B; g.T = T; g.K = K; g.n_levels = n_levels; g.P = P;
-  g.rf1 = (K - 1) * ((1 << n_levels) - 1);
-  if (g.rf1 >= kTR - 8) {
-    set_error("tcn_forward(bf16): receptive field %d does not leave room in a 128-row tile", g.rf1 + 1);
-    return HTCN_ERR_UNSUPPORTED;
-  }
-  int tiles = 0;
+  int units = 0;
   for (int s = 0; s < slots.n; ++s) {
     K2Slot& sl = g.slot[s];
     sl.off = slots.off[s];
     sl.L = slots.off[s + 1] - slots.off[s];
-    sl.tile0 = tiles;
-    if (sl.L + P <= kTR) {
+    sl.unit0 = units;
+    if (sl.L + P <= kTR) {               // short: several zero-padded sequences per tile
       sl.seq_per_tile = kTR / (sl.L + P);
-      sl.tiles_per_seq = 0;
-      tiles += (B + sl.seq_per_tile - 1) / sl.seq_per_tile;
-    } else {
+      sl.chunks = 1;
+      units += (B + sl.seq_per_tile - 1) / sl.seq_per_tile;
+    } else {                             // long: one sequence per unit, streamed in chunks of 128 positions
       sl.seq_per_tile = 0;
-      sl.tiles_per_seq = (sl.L + (kTR - g.rf1) - 1) / (kTR - g.rf1);
-      tiles += B * sl.tiles_per_seq;
+      sl.chunks = (sl.L + kTR - 1) / kTR;
+      units += B;
     }
   }
-  g.n_tiles = tiles;
+  g.n_units = units;
   // scratch layout: [bf16 weight tiles (HTCN_TCN_SCRATCH_BYTES reserves K+1 per level)][tile source pointers][conv biases]
   // [down-sample biases]
   const float* tile_src[kK2MaxWeightTiles];
@@ -403,6 +452,7 @@ int32_t tcn_forward_bf16(const void* xe, int xe_dtype, const float* w_in_x, cons
   const float** ptrs_dev = reinterpret_cast<const float**>(sc + w_bytes);
   float* bias_dev = reinterpret_cast<float*>(sc + w_bytes + kK2PtrTableBytes);
   float* ds_bias_dev = bias_dev + HTCN_MAX_LEVELS * kDim;
+  uint8_t* hist_dev = reinterpret_cast<uint8_t*>(ds_bias_dev + HTCN_MAX_LEVELS * kDim) + 256;   // per-CTA parked rows
   // (pageable host source: the runtime stages the copy before returning, the stack array may die afterwards)
   HTCN_CUDA(cudaMemcpyAsync(ptrs_dev, tile_src, sizeof(float*) * n_wt, cudaMemcpyHostToDevice, st));
   for (int l = 0; l < n_levels; ++l) {
@@ -422,11 +472,11 @@ int32_t tcn_forward_bf16(const void* xe, int xe_dtype, const float* w_in_x, cons
   // halving the L2 -> SM weight traffic buys nothing, the kernel is bound by the latency of its 2-deep weight ring and of
   // the dependent layer chain, not by L2 bandwidth; independent CTAs stay the default.
   const char* mc = getenv("HTCN_K2_MULTICAST");
-  if (mc && atoi(mc) != 0 && tiles >= 2) {
+  if (mc && atoi(mc) != 0 && units >= 2) {
     auto kern = k2_tcn_bf16<true>;
     HTCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg{};
-    const int grid = tiles < 2 * 148 ? ((tiles + 1) & ~1) : 2 * 148;
+    const int grid = units < 2 * 148 ? ((units + 1) & ~1) : 2 * 148;
     cfg.gridDim = dim3((unsigned)grid, 1, 1);
     cfg.blockDim = dim3(kK2Threads, 1, 1);
     cfg.dynamicSmemBytes = smem;
@@ -440,14 +490,14 @@ int32_t tcn_forward_bf16(const void* xe, int xe_dtype, const float* w_in_x, cons
     cfg.numAttrs = 1;
     HTCN_CUDA(cudaLaunchKernelEx(&cfg, kern, tw, g, (const __nv_bfloat16*)xe, sbias, (const float*)bias_dev,
                                  (const float*)ds_bias_dev, out_row,
-                                 (__nv_bfloat16*)hout, (__nv_bfloat16*)h_save, (__nv_bfloat16*)a_save));
+                                 (__nv_bfloat16*)hout, (__nv_bfloat16*)h_save, (__nv_bfloat16*)a_save, hist_dev));
     return HTCN_OK;
   }
   auto kern = k2_tcn_bf16<false>;
   HTCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = tiles < 2 * 148 ? tiles : 2 * 148;
+  const int grid = units < 2 * 148 ? units : 2 * 148;
   kern<<<grid, kK2Threads, smem, st>>>(tw, g, (const __nv_bfloat16*)xe, sbias, bias_dev, ds_bias_dev, out_row,
-                                       (__nv_bfloat16*)hout, (__nv_bfloat16*)h_save, (__nv_bfloat16*)a_save);
+                                       (__nv_bfloat16*)hout, (__nv_bfloat16*)h_save, (__nv_bfloat16*)a_save, hist_dev);
   HTCN_LAUNCH_CHECK("k2_tcn_bf16");
   return HTCN_OK;
 }

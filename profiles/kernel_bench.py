@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Per-kernel roofline measurements (device-resident, CUDA events, L2 flushed between iterations).
 
-    python profiles/kernel_bench.py [--out profiles/r1_kernels.jsonl]
+    python profiles/kernel_bench.py [--out profiles/r2_kernels.jsonl]
 
 One JSON line per kernel with achieved GB/s or TFLOP/s against MEASURED_PEAKS.json:
   K1 gather+meanpool   cfg2 shape, uniform ids over a 1M x 128 fp32 table (512 MB >> L2): HBM-bound
@@ -60,7 +60,7 @@ def line(out, kernel, ms, bound, work, peak_key, note):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r1_kernels.jsonl"))
+    ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r2_kernels.jsonl"))
     ap.add_argument("--only", default="")
     opt = ap.parse_args()
     out = open(opt.out, "w")

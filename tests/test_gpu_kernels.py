@@ -670,8 +670,11 @@ def test_k2_downsample_residual_and_narrow_levels(lib, channels, K, tier):
     assert (got[..., C:] == 0).all(), "padded channels must stay exactly zero"
 
 
-@pytest.mark.parametrize("B,S,L,K,levels", [(7, 3, 9, 5, 2), (3, 1, 300, 5, 4), (150, 10, 20, 5, 2), (4, 2, 1, 3, 3), (5, 1, 200, 5, 2)])
+@pytest.mark.parametrize("B,S,L,K,levels", [(7, 3, 9, 5, 2), (3, 1, 300, 5, 4), (150, 10, 20, 5, 2), (4, 2, 1, 3, 3), (5, 1, 200, 5, 2),
+                                            (330, 1, 260, 5, 4), (40, 2, 150, 3, 3)])
 def test_k2_tcn_bf16_tcgen05(lib, B, S, L, K, levels):
+    """short sequences (several zero-padded sequences per 128-row tile) and long ones (streamed in chunks of 128 positions,
+    the previous chunk's last rows handed over per level; 330 sequences = more work units than CTAs)"""
     x, y, m, s0, w = small_case(B=B, S=S, L=L, N=301, seed=3, tcn_channel=(128,) * levels, kernel_size=K,
                                 lengths="ragged" if L < 100 else "dense", kernel_scale=1.0)
     pk = pack(x, y, m)
