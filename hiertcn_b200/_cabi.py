@@ -58,9 +58,9 @@ SIGNATURES = {
     "htcn_score_ce_backward": [_p, _i, _i, _p, _p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p],
     "htcn_score_ce_backward_bf16": [_p, _p, C.c_int64, _i, _p, _p, C.c_int64, _p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p],
     "htcn_cast_transpose_bf16": [_p, _i, C.c_int64, _p, _p, C.c_int64, _p],
-    "htcn_tcn_forward_train_bf16": [_p, _p, _p, _pp, _pp, _pp, _pp, _i, _i, _ip, _i, _i, _i, _p, _p, _p, _p, _p, _p],
-    "htcn_tcn_forward_train": [_p, _p, _p, _pp, _pp, _pp, _pp, _i, _i, _ip, _i, _i, _i, _p, _p, _p, _p, _p],
-    "htcn_tcn_backward": [_p, _p, _p, _i, _p, _pp, _pp, _i, _i, _ip, _i, _i, _i, _p, _p, _p, _pp, _pp, _pp, _pp, _p, _p, _p, _p],
+    "htcn_tcn_forward_train_bf16": [_p, _p, _p, _pp, _pp, _pp, _pp, _i, _i, _ip, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p],
+    "htcn_tcn_forward_train": [_p, _p, _p, _pp, _pp, _pp, _pp, _i, _i, _ip, _i, _i, _i, _p, _p, _p, _p, _p, _p],
+    "htcn_tcn_backward": [_p, _p, _p, _i, _p, _pp, _pp, _i, _i, _ip, _i, _i, _i, _p, _p, _p, _p, _pp, _pp, _pp, _pp, _p, _p, _p, _p],
     "htcn_gru_sessions_train": [_p, _p, _p, _pp, _pp, _pp, _pp, _i, _p, _i, _i, _p, _p, _p, _p, _p],
     "htcn_gru_backward": [_p, _p, _p, _p, _pp, _pp, _i, _p, _i, _i, _p, _p, _pp, _pp, _pp, _pp, _p, _p, _p],
     "htcn_gather_backward": [_p, _p, _p, _p, _ip, _i, _i, _i, _i, _p, _p, _p],

@@ -16,9 +16,12 @@ namespace htcn {
 
 namespace {
 
+// drop (or NULL): [S][drop_stride] dropout scales of this level (forward: a_dropped = a * drop[slot, c]); T / slots locate
+// the slot of a row
 template <bool kBf16>
 __global__ void relu_bwd_kernel(long long n4, float4* __restrict__ dcur, const void* __restrict__ h_next,
-                                const void* __restrict__ a_l, float4* __restrict__ dp) {
+                                const void* __restrict__ a_l, float4* __restrict__ dp, const float* __restrict__ drop,
+                                int drop_stride, int T, SlotTable slots) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   float4 d = dcur[i];
@@ -35,6 +38,13 @@ __global__ void relu_bwd_kernel(long long n4, float4* __restrict__ dcur, const v
   dcur[i] = d;
   float4 p;
   p.x = a.x > 0.f ? d.x : 0.f; p.y = a.y > 0.f ? d.y : 0.f; p.z = a.z > 0.f ? d.z : 0.f; p.w = a.w > 0.f ? d.w : 0.f;
+  if (drop) {
+    const int pos = (int)((i >> 5) % T);
+    int s = 0;
+    while (s + 1 < slots.n && slots.off[s + 1] <= pos) ++s;
+    const float4 m = __ldg(reinterpret_cast<const float4*>(drop + (long long)s * drop_stride) + (i & 31));
+    p.x *= m.x; p.y *= m.y; p.z *= m.z; p.w *= m.w;
+  }
   dp[i] = p;
 }
 
@@ -69,8 +79,8 @@ extern "C" int32_t htcn_tcn_forward_train(const float* xe, const float* w_in_x, 
                                           const float* const* conv_w_host, const float* const* conv_b_host,
                                           const float* const* ds_w_host, const float* const* ds_b_host,
                                           int32_t n_levels, int32_t kernel_size, const int32_t* slot_off_host, int32_t B,
-                                          int32_t T, int32_t S, const int32_t* out_row, float* h_save, float* a_save,
-                                          float* hout, void* stream) {
+                                          int32_t T, int32_t S, const int32_t* out_row, const float* dropout_scale,
+                                          float* h_save, float* a_save, float* hout, void* stream) {
   using namespace htcn;
   HTCN_REQUIRE(xe && w_in_x && h_save && hout && slot_off_host && out_row, "tcn_forward_train: NULL pointer");
   HTCN_REQUIRE(B > 0 && T > 0 && S > 0 && S <= HTCN_MAX_SLOTS, "tcn_forward_train: B=%d T=%d S=%d", B, T, S);
@@ -96,11 +106,12 @@ extern "C" int32_t htcn_tcn_forward_train(const float* xe, const float* w_in_x, 
       // res = h_l Wds + bds, parked in a_save[l]: the conv launch below reads resid[r,c] and then writes aux[r,c] from the
       // same thread, so the two may share the buffer
       a.w = ds_w_host[l]; a.bias = ds_b_host ? ds_b_host[l] : nullptr; a.K = 1; a.dil = 1; a.conv_epilogue = 0;
-      a.out = a_save + (long long)l * R * kDim; a.aux = nullptr;
+      a.out = a_save + (long long)l * R * kDim; a.aux = nullptr; a.drop = nullptr;
       rc = k2_level_launch(a, slots, st);
       if (rc) return rc;
     }
     a.w = conv_w_host[l]; a.bias = conv_b_host[l]; a.K = kernel_size; a.dil = 1 << l;
+    a.drop = dropout_scale ? dropout_scale + l * kDim : nullptr; a.drop_stride = n_levels * kDim;
     a.conv_epilogue = ds ? 3 : 1;
     a.resid = ds ? a_save + (long long)l * R * kDim : nullptr;
     a.out = h_save + (long long)(l + 1) * R * kDim;
@@ -119,7 +130,8 @@ extern "C" int32_t htcn_tcn_forward_train_bf16(const void* xe, const float* w_in
                                                const float* const* conv_w_host, const float* const* conv_b_host,
                                                const float* const* ds_w_host, const float* const* ds_b_host,
                                                int32_t n_levels, int32_t kernel_size, const int32_t* slot_off_host,
-                                               int32_t B, int32_t T, int32_t S, const int32_t* out_row, void* h_save,
+                                               int32_t B, int32_t T, int32_t S, const int32_t* out_row,
+                                               const float* dropout_scale, void* h_save,
                                                void* a_save, void* hout, float* scratch, void* stream) {
   using namespace htcn;
   HTCN_REQUIRE(xe && w_in_x && h_save && hout && slot_off_host && out_row && scratch, "tcn_forward_train_bf16: NULL pointer");
@@ -132,14 +144,14 @@ extern "C" int32_t htcn_tcn_forward_train_bf16(const void* xe, const float* w_in
   for (int i = 0; i <= S; ++i) slots.off[i] = slot_off_host[i];
   HTCN_REQUIRE(slots.off[0] == 0 && slots.off[S] == T, "tcn_forward_train_bf16: slot_off does not span T");
   return tcn_forward_bf16(xe, HTCN_BF16, w_in_x, sbias, conv_w_host, conv_b_host, ds_w_host, ds_b_host, n_levels, kernel_size, slots, B, T, out_row,
-                          hout, HTCN_BF16, scratch, as_stream(stream), h_save, a_save);
+                          hout, HTCN_BF16, scratch, as_stream(stream), h_save, a_save, dropout_scale);
 }
 
 extern "C" int32_t htcn_tcn_backward(const float* d_hout, const int32_t* out_row, const void* xe, int32_t save_dtype,
                                      const float* w_in_x, const float* const* conv_w_host,
                                      const float* const* ds_w_host, int32_t n_levels,
                                      int32_t kernel_size, const int32_t* slot_off_host, int32_t B, int32_t T, int32_t S,
-                                     const void* h_save, const void* a_save, float* scratch,
+                                     const float* dropout_scale, const void* h_save, const void* a_save, float* scratch,
                                      float* const* d_conv_w_host, float* const* d_conv_b_host,
                                      float* const* d_ds_w_host, float* const* d_ds_b_host, float* d_w_in_x,
                                      float* d_sbias, float* d_xe, void* stream) {
@@ -171,9 +183,11 @@ extern "C" int32_t htcn_tcn_backward(const float* d_hout, const int32_t* out_row
     const uint8_t* h_n = reinterpret_cast<const uint8_t*>(h_save) + (size_t)(l + 1) * R * kDim * esz;
     const uint8_t* a_l = reinterpret_cast<const uint8_t*>(a_save) + (size_t)l * R * kDim * esz;
     if (bf)
-      relu_bwd_kernel<true><<<eb, 256, 0, st>>>(R * 32, reinterpret_cast<float4*>(dcur), h_n, a_l, reinterpret_cast<float4*>(dp));
+      relu_bwd_kernel<true><<<eb, 256, 0, st>>>(R * 32, reinterpret_cast<float4*>(dcur), h_n, a_l, reinterpret_cast<float4*>(dp),
+                                                dropout_scale ? dropout_scale + l * kDim : nullptr, n_levels * kDim, T, slots);
     else
-      relu_bwd_kernel<false><<<eb, 256, 0, st>>>(R * 32, reinterpret_cast<float4*>(dcur), h_n, a_l, reinterpret_cast<float4*>(dp));
+      relu_bwd_kernel<false><<<eb, 256, 0, st>>>(R * 32, reinterpret_cast<float4*>(dcur), h_n, a_l, reinterpret_cast<float4*>(dp),
+                                                 dropout_scale ? dropout_scale + l * kDim : nullptr, n_levels * kDim, T, slots);
     HTCN_LAUNCH_CHECK("relu_bwd_kernel");
     const int dil = 1 << l;
     for (int tap = 0; tap < kernel_size; ++tap) {

@@ -87,10 +87,11 @@ __device__ __forceinline__ uint64_t make_desc_act(uint32_t smem_addr) {
 
 // row r of chunk `chunk` of work unit `unit` (unit >= n_units: a dummy tile, every row is padding)
 __device__ __forceinline__ void tile_geometry(const K2Geom& g, int unit, int chunk, int r, const int* out_row, int& src,
-                                              int& dst, int& sb, bool& own) {
-  src = -1; dst = -1; sb = 0; own = false;
+                                              int& dst, int& sb, bool& own, int& slot) {
+  src = -1; dst = -1; sb = 0; own = false; slot = 0;
   if (unit >= g.n_units) return;
   const int s = unit_slot(g, unit);
+  slot = s;
   const K2Slot& sl = g.slot[s];
   const int lu = unit - sl.unit0;
   int b, t;
@@ -130,7 +131,8 @@ k2_tcn_bf16(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfl
             const int* __restrict__ out_row, __nv_bfloat16* __restrict__ hout,
             __nv_bfloat16* __restrict__ h_save /* [(n_levels+1)][B*T][128] every layer's output, or NULL */,
             __nv_bfloat16* __restrict__ a_save /* [n_levels][B*T][128] relu(conv + b) before the residual, or NULL */,
-            uint8_t* __restrict__ hist /* [gridDim.x][2][n_levels][kHistBytes] parked level inputs of streamed sequences */) {
+            uint8_t* __restrict__ hist /* [gridDim.x][2][n_levels][kHistBytes] parked level inputs of streamed sequences */,
+            const float* __restrict__ drop /* [S][n_levels][128] training dropout scales (customized_tcn_cell.py:100,119) or NULL */) {
   extern __shared__ uint8_t smem_raw[];
   auto& sm = *reinterpret_cast<K2Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -252,9 +254,9 @@ k2_tcn_bf16(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfl
     uint8_t* my_hist = hist + (size_t)blockIdx.x * 2 * g.n_levels * kHistBytes;
     bool spare_dirty = false;                                   // the spare rows hold parked data (not the zero pad)
     for (int it = 0; it < my_tiles; ++it) {
-      int src, dst, sb;
+      int src, dst, sb, slot_idx;
       bool own;
-      tile_geometry(g, unit, chunk, r, out_row, src, dst, sb, own);
+      tile_geometry(g, unit, chunk, r, out_row, src, dst, sb, own, slot_idx);
       const bool streaming = unit_chunks > 1;
       const long long RT = (long long)g.B * g.T;
       // ---- stage the input rows (bf16 Xe) into the operand layout; zero rows stay zero
@@ -290,6 +292,7 @@ k2_tcn_bf16(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfl
         const float* bias_l = layer > 0 ? sm.bias[layer - 1] : nullptr;
         const bool ds = layer > 0 && ((g.ds_mask >> (layer - 1)) & 1u);
         const float* ds_bias_l = ds ? ds_bias_all + (layer - 1) * kDim : nullptr;
+        const float* drop_l = (drop && layer > 0) ? drop + ((long long)slot_idx * g.n_levels + (layer - 1)) * kDim : nullptr;
         const float* sb_row = (layer == 0 && sbias && src >= 0) ? sbias + (long long)sb * kDim : nullptr;
 #pragma unroll 1
         for (int cc = ch * 2; cc < ch * 2 + 2; ++cc) {           // 2 x 32 channels
@@ -335,8 +338,9 @@ k2_tcn_bf16(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfl
               }
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
-                const float a = fmaxf(__uint_as_float(v[q * 8 + e]) + bias_l[c * 8 + e], 0.f);   // relu(conv + b)
-                av[e] = a;
+                float a = fmaxf(__uint_as_float(v[q * 8 + e]) + bias_l[c * 8 + e], 0.f);         // relu(conv + b)
+                av[e] = a;                                                                       // saved before dropout
+                if (drop_l) a *= __ldg(drop_l + c * 8 + e);                                      // training only
                 o[e] = fmaxf(a + rs[e], 0.f);                                                    // relu(a + residual)
               }
               if (a_save && own)
@@ -399,7 +403,7 @@ int32_t tcn_forward_bf16(const void* xe, int xe_dtype, const float* w_in_x, cons
                          const float* const* conv_w, const float* const* conv_b, const float* const* ds_w,
                          const float* const* ds_b, int n_levels, int K,
                          const SlotTable& slots, int B, int T, const int* out_row, void* hout, int hout_dtype,
-                         float* scratch, cudaStream_t st, void* h_save, void* a_save) {
+                         float* scratch, cudaStream_t st, void* h_save, void* a_save, const float* drop) {
   if (xe_dtype != HTCN_BF16 || hout_dtype != HTCN_BF16) {
     set_error("tcn_forward(bf16): xe and hout must be bf16");
     return HTCN_ERR_INVALID;
@@ -490,14 +494,14 @@ int32_t tcn_forward_bf16(const void* xe, int xe_dtype, const float* w_in_x, cons
     cfg.numAttrs = 1;
     HTCN_CUDA(cudaLaunchKernelEx(&cfg, kern, tw, g, (const __nv_bfloat16*)xe, sbias, (const float*)bias_dev,
                                  (const float*)ds_bias_dev, out_row,
-                                 (__nv_bfloat16*)hout, (__nv_bfloat16*)h_save, (__nv_bfloat16*)a_save, hist_dev));
+                                 (__nv_bfloat16*)hout, (__nv_bfloat16*)h_save, (__nv_bfloat16*)a_save, hist_dev, drop));
     return HTCN_OK;
   }
   auto kern = k2_tcn_bf16<false>;
   HTCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = units < 2 * 148 ? units : 2 * 148;
   kern<<<grid, kK2Threads, smem, st>>>(tw, g, (const __nv_bfloat16*)xe, sbias, bias_dev, ds_bias_dev, out_row,
-                                       (__nv_bfloat16*)hout, (__nv_bfloat16*)h_save, (__nv_bfloat16*)a_save, hist_dev);
+                                       (__nv_bfloat16*)hout, (__nv_bfloat16*)h_save, (__nv_bfloat16*)a_save, hist_dev, drop);
   HTCN_LAUNCH_CHECK("k2_tcn_bf16");
   return HTCN_OK;
 }

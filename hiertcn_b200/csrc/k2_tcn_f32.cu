@@ -123,11 +123,13 @@ k2_level_f32(LevelArgs a, SlotTable slots) {
       dst = d;
     }
     const float* sb = nullptr;
-    if (a.sbias) {
+    const float* dr = nullptr;
+    if (a.sbias || a.drop) {
       const int b = (int)(r / a.T), p = (int)(r % a.T);
       int s = 0;
       while (s + 1 < slots.n && slots.off[s + 1] <= p) ++s;
-      sb = a.sbias + ((long long)s * a.B + b) * kDim;
+      if (a.sbias) sb = a.sbias + ((long long)s * a.B + b) * kDim;
+      if (a.drop) dr = a.drop + (long long)s * a.drop_stride;
     }
 #pragma unroll
     for (int jh = 0; jh < 2; ++jh) {
@@ -140,7 +142,8 @@ k2_level_f32(LevelArgs a, SlotTable slots) {
         if (sb) v += __ldg(sb + c + j);
         if (a.conv_epilogue == 1 || a.conv_epilogue == 3) {
           v = fmaxf(v, 0.f);
-          ax[j] = v;
+          ax[j] = v;                                   // saved BEFORE the dropout scale (the backward re-applies it)
+          if (dr) v *= __ldg(dr + c + j);
           const float res = a.conv_epilogue == 1 ? load_act(a.in, a.in_bf16, r * kDim + c + j) : a.resid[r * kDim + c + j];
           v = fmaxf(v + res, 0.f);
         } else if (a.conv_epilogue == 2) {

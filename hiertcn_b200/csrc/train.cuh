@@ -22,6 +22,8 @@ struct LevelArgs {
   int in_bf16, out_bf16;
   float* aux;                 // [R,128] relu(conv + bias) before the residual add, saved for the backward, or NULL
   const float* resid;         // [R,128] added in epilogues 2 and 3 (may alias out in 2)
+  const float* drop;          // training dropout (customized_tcn_cell.py:100,119: noise_shape [1,1,C], one channel mask per
+  int drop_stride;            //   slot and level): relu(conv + b) is multiplied by drop[slot(r) * drop_stride + c]; NULL = off
   int anti;                   // 1: taps read r + shift, zero beyond the END of r's sequence (transposed convolution)
   int w_nt;                   // 1: every W[tap] is applied transposed
 };
@@ -35,7 +37,8 @@ int32_t tcn_forward_bf16(const void* xe, int xe_dtype, const float* w_in_x, cons
                          const float* const* conv_w, const float* const* conv_b, const float* const* ds_w,
                          const float* const* ds_b, int n_levels, int K,
                          const SlotTable& slots, int B, int T, const int* out_row, void* hout, int hout_dtype,
-                         float* scratch, cudaStream_t st, void* h_save = nullptr, void* a_save = nullptr);
+                         float* scratch, cudaStream_t st, void* h_save = nullptr, void* a_save = nullptr,
+                         const float* drop = nullptr /* [S][n_levels][128] dropout scales (training) */);
 
 // C[M,N] (+)= A[M,K] * op(B).  trans_b = 0: B is [K,N] with leading dimension ldb; trans_b = 1: B is [N,K].
 // N % 128 == 0, K % 16 == 0, all leading dimensions multiples of 4 floats, 16-byte aligned bases.

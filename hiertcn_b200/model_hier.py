@@ -102,8 +102,7 @@ class HierTCN:
         if getattr(args, "has_gap", False) and getattr(args, "train_gap", False):
             raise NotImplementedError("train_gap (learned gap bandwidth, model_hier.py:42-45); the fixed-bandwidth decay is built")
         self.l2_normalize = bool(getattr(args, "l2_normalize", False))     # model_tcn.py:42-43
-        if float(args.dropout) != 0.0:
-            raise NotImplementedError("dropout > 0 (reference default 0.0, args.py:64)")
+        # args.dropout > 0 acts in HierTCNTrainer only (tf.layers.Dropout is the identity when training=False)
         self.N = int(args.item_num)
         self.G = int(args.num_layer)
         self.K = int(args.kernel_size)

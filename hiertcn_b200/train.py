@@ -118,8 +118,28 @@ class HierTCNTrainer:
         return flat[o:o + int(np.prod(shape))].view(*shape)
 
     # ------------------------------------------------------------------ forward + backward
+    def dropout_scales(self, S, masks=None):
+        """[S, n_levels, 128] device array of dropout scales for one training step, or None when args.dropout == 0.
+        The reference's TemporalBlock applies tf.layers.Dropout(rate, noise_shape=[1,1,C]) to relu(conv) before the residual
+        add (customized_tcn_cell.py:100,119): one Bernoulli(1-rate) channel mask per dropout op -- the unrolled graph has
+        one op per (session slot, level) --, shared over batch and time, scaled by 1/(1-rate).  ``masks``: explicit
+        [S, n_levels, C] 0/1 keep-masks (tests); otherwise drawn from a numpy generator seeded by (seed, step)."""
+        rate = float(self.m.args.dropout)
+        if rate <= 0.0 and masks is None:
+            return None
+        torch = _torch()
+        L = self.m.n_levels
+        if masks is None:
+            rng = np.random.default_rng([int(self.m.seed), self.t])
+            masks = rng.random((S, L, D)) >= rate
+        keep = 1.0 - rate
+        sc = np.zeros((S, L, D), np.float32)
+        mk = np.asarray(masks, np.float32)
+        sc[:, :, :mk.shape[2]] = mk / np.float32(keep)
+        return torch.from_numpy(sc).to(self.m.device)
+
     def forward_backward(self, x_list=None, y_list=None, mask_list=None, state=None, staged=None, metrics=False,
-                         mask_warmstart=None, x_gap=None):
+                         mask_warmstart=None, x_gap=None, dropout_masks=None):
         """Accumulates the gradients of sum_b(sum_t loss/(n_b+1e-6)) into ``self.grads`` (the 1/user_count is applied by
         the optimiser).  Returns dict(scalars [8] device: loss, ..., user_count, n_valid; state [B,G*H] device)."""
         torch = _torch()
@@ -156,16 +176,17 @@ class HierTCNTrainer:
         h_save = buf("tr_h_save_bf16" if fused else "tr_h_save", (L + 1, R, D), sdt)
         a_save = buf("tr_a_save_bf16" if fused else "tr_a_save", (max(L, 1), R, D), sdt)
         hout = buf("tr_hout_bf16" if fused else "tr_hout", (max(Q, 1), D), sdt)
+        drop = self.dropout_scales(S, dropout_masks)             # None unless args.dropout > 0 (training only)
         if fused:
             k2f_scratch = buf("k2_scratch_bf16", (cabi.tcn_scratch_floats(L, K),), f32)
             cabi.call("htcn_tcn_forward_train_bf16", xe.data_ptr(), m.w_in_x.data_ptr(), sbias.data_ptr(), m._conv_w_pp[0],
-                      m._conv_b_pp[0], m._ds_w_pp[0], m._ds_b_pp[0], L, K, slot_p, B, T, S, d["row_of"].data_ptr(), h_save.data_ptr(), a_save.data_ptr(),
-                      hout.data_ptr(), k2f_scratch.data_ptr(), st)
+                      m._conv_b_pp[0], m._ds_w_pp[0], m._ds_b_pp[0], L, K, slot_p, B, T, S, d["row_of"].data_ptr(), P(drop),
+                      h_save.data_ptr(), a_save.data_ptr(), hout.data_ptr(), k2f_scratch.data_ptr(), st)
             cabi.note_launches(2)
         else:
             cabi.call("htcn_tcn_forward_train", xe.data_ptr(), m.w_in_x.data_ptr(), sbias.data_ptr(), m._conv_w_pp[0],
-                      m._conv_b_pp[0], m._ds_w_pp[0], m._ds_b_pp[0], L, K, slot_p, B, T, S, d["row_of"].data_ptr(), h_save.data_ptr(), a_save.data_ptr(),
-                      hout.data_ptr(), st)
+                      m._conv_b_pp[0], m._ds_w_pp[0], m._ds_b_pp[0], L, K, slot_p, B, T, S, d["row_of"].data_ptr(), P(drop),
+                      h_save.data_ptr(), a_save.data_ptr(), hout.data_ptr(), st)
             cabi.note_launches(L + 2)
         scalars = torch.zeros(8, dtype=f32, device=m.device)
         if Q == 0:
@@ -218,7 +239,7 @@ class HierTCNTrainer:
         d_xe = buf("tr_d_xe", (R, D), f32)
         k2_scratch = buf("tr_k2_scratch", (3 if m.has_ds else 2, R, D), f32)
         cabi.call("htcn_tcn_backward", d_hout.data_ptr(), d["row_of"].data_ptr(), xe.data_ptr(), sdt_c, m.w_in_x.data_ptr(),
-                  m._conv_w_pp[0], m._ds_w_pp[0], L, K, slot_p, B, T, S, h_save.data_ptr(), a_save.data_ptr(),
+                  m._conv_w_pp[0], m._ds_w_pp[0], L, K, slot_p, B, T, S, P(drop), h_save.data_ptr(), a_save.data_ptr(),
                   k2_scratch.data_ptr(), self._d_conv_w[0], self._d_conv_b[0], self._d_ds_w[0], self._d_ds_b[0],
                   self.g["w_in_x"].data_ptr(), d_sbias.data_ptr(), d_xe.data_ptr(), st)
         cabi.note_launches(1 + L * (K + 3) + 3)
@@ -263,10 +284,11 @@ class HierTCNTrainer:
         return scalars
 
     def train_step(self, x_list, y_list, mask_list, state=None, lr=None, metrics=False, state_on_device=False,
-                   mask_warmstart=None, x_gap=None):
+                   mask_warmstart=None, x_gap=None, dropout_masks=None):
         """One optimisation step on one batch.  Returns dict(loss, user_count, n_valid, state [+ metrics]); ``state`` is
         the carried user state for the next batch (numpy, or the device tensor with ``state_on_device``)."""
-        r = self.forward_backward(x_list, y_list, mask_list, state, metrics=metrics, mask_warmstart=mask_warmstart, x_gap=x_gap)
+        r = self.forward_backward(x_list, y_list, mask_list, state, metrics=metrics, mask_warmstart=mask_warmstart, x_gap=x_gap,
+                                  dropout_masks=dropout_masks)
         sc = self.apply_gradients(r["scalars"], lr).cpu().numpy()
         out = dict(loss=float(sc[0]), user_count=float(sc[6]), n_valid=float(sc[7]))
         if metrics:

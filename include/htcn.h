@@ -347,12 +347,17 @@ int32_t htcn_cast_transpose_bf16(const void* src, int32_t src_dtype, int64_t R, 
 
 /* K2 forward that keeps what the backward needs: h_save [(n_levels+1), B*T, 128] (the in-projection output and
  * every level's output) and a_save [n_levels, B*T, 128] (relu(conv+bias) before the residual add);
- * hout [Q,128] f32 = rows of the last level compacted through out_row [B*T] (-1 = not scored). */
+ * hout [Q,128] f32 = rows of the last level compacted through out_row [B*T] (-1 = not scored).
+ * dropout_scale [S, n_levels, 128] f32 or NULL: training dropout of customized_tcn_cell.py:100,119 -- tf.layers.Dropout with
+ * noise_shape [1,1,C], i.e. ONE channel mask per dropout op, shared over batch and time; the graph has one op per session
+ * slot and level.  Entries are 0 or 1/(1-rate) (drawn by the caller); relu(conv+b) is multiplied by them before the
+ * residual add; a_save keeps the value before the scale.  The same array goes to htcn_tcn_backward. */
 int32_t htcn_tcn_forward_train(const float* xe, const float* w_in_x, const float* sbias,
                                const float* const* conv_w_host, const float* const* conv_b_host,
                                const float* const* ds_w_host, const float* const* ds_b_host, int32_t n_levels,
                                int32_t kernel_size, const int32_t* slot_off_host, int32_t B, int32_t T, int32_t S,
-                               const int32_t* out_row, float* h_save, float* a_save, float* hout, void* stream);
+                               const int32_t* out_row, const float* dropout_scale, float* h_save, float* a_save, float* hout,
+                               void* stream);
 
 /* The same on the tensor cores: the fused tcgen05 conv stack (htcn_tcn_forward, HTCN_BF16) with every layer's output
  * (h_save [(n_levels+1), B*T, 128]) and every level's pre-residual activation (a_save [n_levels, B*T, 128]) written out
@@ -361,8 +366,8 @@ int32_t htcn_tcn_forward_train_bf16(const void* xe, const float* w_in_x, const f
                                     const float* const* conv_w_host, const float* const* conv_b_host,
                                     const float* const* ds_w_host, const float* const* ds_b_host, int32_t n_levels,
                                     int32_t kernel_size, const int32_t* slot_off_host, int32_t B, int32_t T, int32_t S,
-                                    const int32_t* out_row, void* h_save, void* a_save, void* hout, float* scratch,
-                                    void* stream);
+                                    const int32_t* out_row, const float* dropout_scale, void* h_save, void* a_save,
+                                    void* hout, float* scratch, void* stream);
 
 /* Backward of the conv stack + in-projection (customized_tcn_cell.py:109-127, model_tcn.py:35).
  * xe, h_save, a_save are of save_dtype (HTCN_F32 from htcn_tcn_forward_train, HTCN_BF16 from ..._train_bf16); the
@@ -372,8 +377,8 @@ int32_t htcn_tcn_forward_train_bf16(const void* xe, const float* w_in_x, const f
 int32_t htcn_tcn_backward(const float* d_hout, const int32_t* out_row, const void* xe, int32_t save_dtype,
                           const float* w_in_x, const float* const* conv_w_host, const float* const* ds_w_host,
                           int32_t n_levels, int32_t kernel_size,
-                          const int32_t* slot_off_host, int32_t B, int32_t T, int32_t S, const void* h_save,
-                          const void* a_save, float* scratch, float* const* d_conv_w_host,
+                          const int32_t* slot_off_host, int32_t B, int32_t T, int32_t S, const float* dropout_scale,
+                          const void* h_save, const void* a_save, float* scratch, float* const* d_conv_w_host,
                           float* const* d_conv_b_host, float* const* d_ds_w_host, float* const* d_ds_b_host,
                           float* d_w_in_x, float* d_sbias, float* d_xe, void* stream);
 

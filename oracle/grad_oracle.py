@@ -40,8 +40,10 @@ def _gru(p, x, state, G, H):
     return torch.cat(new, 1)
 
 
-def _tcn(p, h, n_levels, K):
-    """customized_tcn_cell.py:46-49,109-127,157-161: one conv per block, relu inside and after the residual"""
+def _tcn(p, h, n_levels, K, drop=None):
+    """customized_tcn_cell.py:46-49,109-127,157-161: one conv per block, relu inside and after the residual.
+    ``drop`` [n_levels, C]: dropout scales (0 or 1/keep) of this slot's TemporalBlocks -- tf.layers.Dropout with
+    noise_shape [1,1,C] on relu(conv) before the residual add (customized_tcn_cell.py:100,119)"""
     for lvl in range(n_levels):
         pre = f"hier/tcn/temporal_conv_net/tblock_{lvl}/conv1/"
         d = 2 ** lvl
@@ -49,11 +51,14 @@ def _tcn(p, h, n_levels, K):
         a = F.conv1d(xp, p[pre + "kernel"].permute(2, 1, 0), p[pre + "bias"], dilation=d).transpose(1, 2)
         ds = f"hier/tcn/temporal_conv_net/tblock_{lvl}/dense/"
         res = h @ p[ds + "kernel"] + p[ds + "bias"] if (ds + "kernel") in p else h      # customized_tcn_cell.py:102-106,123-124
-        h = torch.relu(torch.relu(a) + res)
+        a = torch.relu(a)
+        if drop is not None:
+            a = a * torch.as_tensor(np.asarray(drop[lvl])[:a.shape[-1]], dtype=a.dtype)
+        h = torch.relu(a + res)
     return h
 
 
-def loss_fp64(p, x_list, y_list, mask_list, state, num_layer=2, literal=False):
+def loss_fp64(p, x_list, y_list, mask_list, state, num_layer=2, literal=False, dropout_scales=None):
     """Scalar training loss (model.py:105-117) as a torch expression of the parameter dict ``p``."""
     dt = p["hier/emb/kernel"].dtype
     E, be = p["hier/emb/kernel"], p["hier/emb/bias"]
@@ -76,7 +81,7 @@ def loss_fp64(p, x_list, y_list, mask_list, state, num_layer=2, literal=False):
             ys = (E[y] * (y > 0).unsqueeze(-1)).sum(1) / (y > 0).sum(1, keepdim=True) + be
         feat = state.unsqueeze(1).expand(-1, xe.shape[1], -1)
         h0 = torch.cat([xe, feat], -1) @ p["hier/tcn/emb/kernel"]               # model_hier.py:54-55, model_tcn.py:35
-        houts.append(_tcn(p, h0, n_levels, K))
+        houts.append(_tcn(p, h0, n_levels, K, None if dropout_scales is None else dropout_scales[s]))
         state = _gru(p, ys, state, num_layer, H) * torch.tensor(np.asarray(mask_list[s]), dtype=dt).reshape(-1, 1)
     hout = torch.cat(houts, 1)
     y_id = torch.from_numpy(np.concatenate([np.asarray(v) for v in y_list], 1).astype(np.int64))
@@ -90,10 +95,10 @@ def loss_fp64(p, x_list, y_list, mask_list, state, num_layer=2, literal=False):
     return ((loss_bt.sum(1) / (act + 1e-6)).sum() / uc), state                   # model.py:111-117
 
 
-def loss_and_grads(w, x_list, y_list, mask_list, state, num_layer=2, literal=False):
+def loss_and_grads(w, x_list, y_list, mask_list, state, num_layer=2, literal=False, dropout_scales=None):
     """-> (loss float, dict name -> fp64 numpy gradient, new state)"""
     p = _params(w)
-    loss, st = loss_fp64(p, x_list, y_list, mask_list, state, num_layer, literal)
+    loss, st = loss_fp64(p, x_list, y_list, mask_list, state, num_layer, literal, dropout_scales)
     loss.backward()
     g = {k: (v.grad.numpy() if v.grad is not None else np.zeros(v.shape)) for k, v in p.items()}
     return float(loss.detach()), g, st.detach().numpy()

@@ -123,7 +123,7 @@ def main():
         sc3 = torch.empty((cabi.tcn_scratch_floats(4, 5),), dtype=f32, device="cuda")
         sp3, k3keep = cabi.int_array([0, L3])
         ms = timed(lambda: cabi.call("htcn_tcn_forward", xe3.data_ptr(), cabi.HTCN_BF16, cabi.HTCN_BF16, m3.w_in_x.data_ptr(), None,
-                                     m3._conv_w_pp[0], m3._conv_b_pp[0], 4, 5, sp3, B3, L3, 1, None, h3.data_ptr(), cabi.HTCN_BF16,
+                                     m3._conv_w_pp[0], m3._conv_b_pp[0], None, None, 4, 5, sp3, B3, L3, 1, None, h3.data_ptr(), cabi.HTCN_BF16,
                                      sc3.data_ptr(), st))
         line(out, "K2 conv stack bf16 tcgen05 (cfg3: 4096 x 256, 4 levels)", ms, "tensor", B3 * (167.8e6 + 2 * L3 * 128 * 128), "bf16_tflops",
              "BASELINE config 3; useful FLOPs only (the 60-row receptive-field halo recomputed per 128-row tile is not counted)")

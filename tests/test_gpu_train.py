@@ -360,13 +360,13 @@ def test_fused_conv_forward_saves_match_fp32_levels(B, S, L, K, levels):
     a32 = torch.zeros((levels, R, 128), device="cuda")
     o32 = torch.zeros((Q, 128), device="cuda")
     cabi.call("htcn_tcn_forward_train", xe_f.data_ptr(), w_in.data_ptr(), sb.data_ptr(), wp, bp, None, None, levels, K, slot_p, B, T, S,
-              row_d.data_ptr(), h32.data_ptr(), a32.data_ptr(), o32.data_ptr(), st)
+              row_d.data_ptr(), None, h32.data_ptr(), a32.data_ptr(), o32.data_ptr(), st)
     h16 = torch.full((levels + 1, R, 128), float("nan"), dtype=torch.bfloat16, device="cuda")
     a16 = torch.full((levels, R, 128), float("nan"), dtype=torch.bfloat16, device="cuda")
     o16 = torch.full((Q, 128), float("nan"), dtype=torch.bfloat16, device="cuda")
     scratch = torch.empty(cabi.tcn_scratch_floats(levels, K), device="cuda")
     cabi.call("htcn_tcn_forward_train_bf16", xe_b.data_ptr(), w_in.data_ptr(), sb.data_ptr(), wp, bp, None, None, levels, K, slot_p, B,
-              T, S, row_d.data_ptr(), h16.data_ptr(), a16.data_ptr(), o16.data_ptr(), scratch.data_ptr(), st)
+              T, S, row_d.data_ptr(), None, h16.data_ptr(), a16.data_ptr(), o16.data_ptr(), scratch.data_ptr(), st)
     torch.cuda.synchronize()
     for name, got, ref in (("h", h16, h32), ("a", a16, a32), ("hout", o16, o32)):
         g, r = got.float().cpu().numpy(), ref.cpu().numpy()
@@ -416,3 +416,42 @@ def test_gradients_downsample_levels_and_narrow_widths(precision, tol):
             assert sd[k].shape == ref_w[k].shape
             diff = np.abs(sd[k] - ref_w[k])        # the first Adam step moves every coordinate by ~lr * sign(g)
             assert np.mean(diff) <= 0.02 * 1e-2 and np.mean(diff > 0.25 * 1e-2) < 0.01, k
+
+
+@pytest.mark.parametrize("precision,tol", [("f32", 2e-4), ("bf16", 3e-2)])
+def test_training_dropout_channel_masks(precision, tol):
+    """args.dropout > 0 (customized_tcn_cell.py:100,119): one channel mask per (slot, level) shared over batch and time, scaled
+    by 1/keep, on relu(conv) before the residual add; explicit masks so the autograd oracle sees the same draw"""
+    from hiertcn_b200.args import make_args
+    from hiertcn_b200.model_hier import HierTCN
+    from hiertcn_b200.train import HierTCNTrainer
+    x, y, m, s0, w = small_case(B=7, S=3, L=8, N=181, seed=12)
+    rate = 0.3
+    masks = np.random.default_rng(5).random((3, 2, 128)) >= rate
+    scales = masks.astype(np.float64) / (1.0 - rate)
+    ref_loss, ref_g, _ = GO.loss_and_grads(w, x, y, m, s0, dropout_scales=scales)
+    base_loss, _, _ = GO.loss_and_grads(w, x, y, m, s0)
+    assert abs(ref_loss - base_loss) > 1e-3 * abs(base_loss)                  # the masks do change the function
+    a = make_args(["--item_num", "181", "--dropout", str(rate)])
+    model = HierTCN(a, w, precision=precision).build()
+    ev = model.step(x, y, m, s0)["loss"]                                       # inference: dropout is the identity
+    assert abs(ev - base_loss) <= max(tol, 1e-4) * abs(base_loss)
+    tr = HierTCNTrainer(model, learning_rate=1e-2)
+    r = tr.forward_backward(x, y, m, s0, dropout_masks=masks)
+    sc = r["scalars"].cpu().numpy()
+    assert abs(sc[0] - ref_loss) <= max(tol, 1e-4) * abs(ref_loss)
+    got = tr.named_gradients(sc[6])
+    for k in ref_g:
+        if precision == "f32":
+            assert np.abs(got[k] - ref_g[k]).max() <= tol * np.abs(ref_g[k]).max() + 1e-9, k
+        else:
+            assert np.linalg.norm(got[k] - ref_g[k]) <= tol * np.linalg.norm(ref_g[k]) + 1e-9, k
+    # without explicit masks the trainer draws its own (seeded by the step): a different loss than the mask-free one
+    r2 = tr.forward_backward(x, y, m, s0)
+    assert abs(float(r2["scalars"][0]) - base_loss) > 1e-4 * abs(base_loss)
+    tr.grads.zero_()
+    if precision == "bf16":        # fused tcgen05 conv stack with dropout: same loss to the tier's tolerance
+        tr.k2_tcgen05 = True
+        r3 = tr.forward_backward(x, y, m, s0, dropout_masks=masks)
+        assert abs(float(r3["scalars"][0]) - ref_loss) <= 3e-2 * abs(ref_loss)
+        tr.grads.zero_()
