@@ -123,7 +123,10 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // 64-column chunks of a weight tile and TMA-multicasts it into both CTAs' rings, so every weight byte crosses L2 -> SM once
 // per CTA pair instead of once per CTA (the kernel sat at the L2 read ceiling: 352 KB of weights per 128-row tile).
 // A ring stage is refilled only when BOTH CTAs' MMAs have released it (tcgen05.commit multicast onto both w_empty barriers).
-template <bool kPair>
+// kStream: some slot is longer than a tile (chunked streaming with the per-level hand-over); kAux: anything beyond the plain
+// inference stack -- down-sample levels, training dropout, saved activations.  Compile-time switches: the plain short-sequence
+// kernel (the hier hot path) keeps its register budget (the all-in-one version spilled 264 B per thread and ran 22 % slower).
+template <bool kPair, bool kStream, bool kAux>
 __global__ void __launch_bounds__(kK2Threads, 2)
 k2_tcn_bf16(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfloat16* __restrict__ xe,
             const float* __restrict__ sbias, const float* __restrict__ bias_all /*[n_levels][128]*/,
@@ -156,7 +159,7 @@ k2_tcn_bf16(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfl
   for (int i = tid; i < g.n_levels * kDim; i += kK2Threads) sm.bias[i / kDim][i % kDim] = bias_all[i];
   for (int i = tid; i < kActBytes / 16; i += kK2Threads) reinterpret_cast<uint4*>(sm.act)[i] = make_uint4(0, 0, 0, 0);
   if (warp == kK2MmaWarp) {
-    if (g.ds_mask) tmem_alloc<256>(&sm.tmem_base);            // second accumulator: the down-sample residual
+    if (kAux && g.ds_mask) tmem_alloc<256>(&sm.tmem_base);    // second accumulator: the down-sample residual
     else tmem_alloc<128>(&sm.tmem_base);
   }
   tc_fence_before_sync();
@@ -168,7 +171,7 @@ k2_tcn_bf16(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfl
   if (warp == kK2ProducerWarp) {
     // ===================== weight producer: [W_in, L0 taps, L1 taps, ...] per tile, 2-stage ring =====================
     if (lane == 0) {
-      const int per_tile = 1 + g.n_levels * g.K + __popc(g.ds_mask);
+      const int per_tile = 1 + g.n_levels * g.K + (kAux ? __popc(g.ds_mask) : 0);
       long long n = 0;
       for (int it = 0; it < my_tiles; ++it) {
         for (int j = 0; j < per_tile; ++j, ++n) {
@@ -217,7 +220,7 @@ k2_tcn_bf16(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfl
               else umma_commit(&sm.w_empty[s]);
             }
           }
-          if (layer > 0 && ((g.ds_mask >> (layer - 1)) & 1u)) {  // res = in @ W_ds: unshifted rows, second accumulator
+          if (kAux && layer > 0 && ((g.ds_mask >> (layer - 1)) & 1u)) {  // res = in @ W_ds: unshifted rows, second accumulator
             const int s = (int)(n % kWStages);
             mbar_wait(&sm.w_full[s], (uint32_t)((n / kWStages) & 1));
             tc_fence_after_sync();
@@ -249,7 +252,7 @@ k2_tcn_bf16(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfl
     long long n_acc = 0;
     int unit = blockIdx.x, chunk = 0, unit_chunks = unit < g.n_units ? g.slot[unit_slot(g, unit)].chunks : 1;
     // streaming of long sequences: the threads of the tile's last kMaxSpare rows own the hand-over to the next chunk
-    const bool hist_owner = r >= kTR - kMaxSpare;
+    const bool hist_owner = kStream && r >= kTR - kMaxSpare;
     const int hj = r - (kTR - kMaxSpare);                       // spare row / parked row of this thread
     uint8_t* my_hist = hist + (size_t)blockIdx.x * 2 * g.n_levels * kHistBytes;
     bool spare_dirty = false;                                   // the spare rows hold parked data (not the zero pad)
@@ -257,7 +260,7 @@ k2_tcn_bf16(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfl
       int src, dst, sb, slot_idx;
       bool own;
       tile_geometry(g, unit, chunk, r, out_row, src, dst, sb, own, slot_idx);
-      const bool streaming = unit_chunks > 1;
+      const bool streaming = kStream && unit_chunks > 1;
       const long long RT = (long long)g.B * g.T;
       // ---- stage the input rows (bf16 Xe) into the operand layout; zero rows stay zero
       {
@@ -275,7 +278,7 @@ k2_tcn_bf16(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfl
         // The MMAs that read the spare rows have retired: refill them for the NEXT layer (conv level `layer`), whose
         // taps reach back up to kMaxSpare rows -- with the rows chunk-1 parked for that level, or with the causal zero pad.
         uint8_t* park = my_hist + ((size_t)(chunk & 1) * g.n_levels + layer) * kHistBytes;
-        if (!last && hist_owner) {
+        if (kStream && !last && hist_owner) {
           const uint8_t* prev = my_hist + ((size_t)((chunk & 1) ^ 1) * g.n_levels + layer) * kHistBytes;
           if (streaming && chunk > 0) {
 #pragma unroll
@@ -290,9 +293,9 @@ k2_tcn_bf16(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfl
           }
         }
         const float* bias_l = layer > 0 ? sm.bias[layer - 1] : nullptr;
-        const bool ds = layer > 0 && ((g.ds_mask >> (layer - 1)) & 1u);
+        const bool ds = kAux && layer > 0 && ((g.ds_mask >> (layer - 1)) & 1u);
         const float* ds_bias_l = ds ? ds_bias_all + (layer - 1) * kDim : nullptr;
-        const float* drop_l = (drop && layer > 0) ? drop + ((long long)slot_idx * g.n_levels + (layer - 1)) * kDim : nullptr;
+        const float* drop_l = (kAux && drop && layer > 0) ? drop + ((long long)slot_idx * g.n_levels + (layer - 1)) * kDim : nullptr;
         const float* sb_row = (layer == 0 && sbias && src >= 0) ? sbias + (long long)sb * kDim : nullptr;
 #pragma unroll 1
         for (int cc = ch * 2; cc < ch * 2 + 2; ++cc) {           // 2 x 32 channels
@@ -343,7 +346,7 @@ k2_tcn_bf16(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfl
                 if (drop_l) a *= __ldg(drop_l + c * 8 + e);                                      // training only
                 o[e] = fmaxf(a + rs[e], 0.f);                                                    // relu(a + residual)
               }
-              if (a_save && own)
+              if (kAux && a_save && own)
                 reinterpret_cast<uint4*>(a_save + ((long long)(layer - 1) * RT + src) * kDim)[c] =
                     make_uint4(pack_bf16x2(av[0], av[1]), pack_bf16x2(av[2], av[3]), pack_bf16x2(av[4], av[5]),
                                pack_bf16x2(av[6], av[7]));
@@ -351,18 +354,18 @@ k2_tcn_bf16(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfl
             uint4 packed = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
                                       pack_bf16x2(o[6], o[7]));
             if (src < 0) packed = make_uint4(0, 0, 0, 0);        // causal pad rows stay zero at every level
-            if (h_save && own) reinterpret_cast<uint4*>(h_save + ((long long)layer * RT + src) * kDim)[c] = packed;
+            if (kAux && h_save && own) reinterpret_cast<uint4*>(h_save + ((long long)layer * RT + src) * kDim)[c] = packed;
             if (!last) {
               *slot = packed;
               // park this row of the next level's input for the sequence's next chunk (read back by this same thread)
-              if (streaming && hist_owner && chunk + 1 < unit_chunks)
+              if (kStream && streaming && hist_owner && chunk + 1 < unit_chunks)
                 *reinterpret_cast<uint4*>(park + (c * kMaxSpare + hj) * 16) = packed;
             } else if (dst >= 0) reinterpret_cast<uint4*>(hout + (long long)dst * kDim)[c] = packed;
           }
         }
         tc_fence_before_sync();
         if (!last) {
-          if (hist_owner) cp_async_wait_all();                   // the parked rows have landed in the spare rows
+          if (kStream && hist_owner) cp_async_wait_all();        // the parked rows have landed in the spare rows
           fence_proxy_async_smem();
           mbar_arrive(&sm.act_ready);
         }
@@ -379,7 +382,7 @@ k2_tcn_bf16(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfl
   else __syncthreads();
   if (warp == kK2MmaWarp) {
     tc_fence_after_sync();
-    if (g.ds_mask) tmem_dealloc<256>(tmem);
+    if (kAux && g.ds_mask) tmem_dealloc<256>(tmem);
     else tmem_dealloc<128>(tmem);
   }
 }
@@ -476,34 +479,45 @@ int32_t tcn_forward_bf16(const void* xe, int xe_dtype, const float* w_in_x, cons
   // halving the L2 -> SM weight traffic buys nothing, the kernel is bound by the latency of its 2-deep weight ring and of
   // the dependent layer chain, not by L2 bandwidth; independent CTAs stay the default.
   const char* mc = getenv("HTCN_K2_MULTICAST");
-  if (mc && atoi(mc) != 0 && units >= 2) {
-    auto kern = k2_tcn_bf16<true>;
-    HTCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cudaLaunchConfig_t cfg{};
-    const int grid = units < 2 * 148 ? ((units + 1) & ~1) : 2 * 148;
-    cfg.gridDim = dim3((unsigned)grid, 1, 1);
-    cfg.blockDim = dim3(kK2Threads, 1, 1);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    HTCN_CUDA(cudaLaunchKernelEx(&cfg, kern, tw, g, (const __nv_bfloat16*)xe, sbias, (const float*)bias_dev,
-                                 (const float*)ds_bias_dev, out_row,
-                                 (__nv_bfloat16*)hout, (__nv_bfloat16*)h_save, (__nv_bfloat16*)a_save, hist_dev, drop));
-    return HTCN_OK;
+  const bool pair = mc && atoi(mc) != 0 && units >= 2;
+  bool stream = false;
+  for (int s = 0; s < slots.n; ++s) stream |= g.slot[s].chunks > 1;
+  const bool aux = g.ds_mask != 0 || drop || h_save || a_save;
+  const int grid = pair ? (units < 2 * 148 ? ((units + 1) & ~1) : 2 * 148) : (units < 2 * 148 ? units : 2 * 148);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  cfg.blockDim = dim3(kK2Threads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = pair ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+#define HTCN_K2_LAUNCH(PAIR, STREAM, AUX)                                                                               \
+  do {                                                                                                                  \
+    auto kern = k2_tcn_bf16<PAIR, STREAM, AUX>;                                                                         \
+    HTCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                      \
+    HTCN_CUDA(cudaLaunchKernelEx(&cfg, kern, tw, g, (const __nv_bfloat16*)xe, sbias, (const float*)bias_dev,            \
+                                 (const float*)ds_bias_dev, out_row, (__nv_bfloat16*)hout, (__nv_bfloat16*)h_save,      \
+                                 (__nv_bfloat16*)a_save, hist_dev, drop));                                              \
+    return HTCN_OK;                                                                                                     \
+  } while (0)
+  if (pair) {                      // multicast ablation: plain inference stacks only
+    if (aux) {
+      set_error("tcn_forward(bf16): HTCN_K2_MULTICAST supports the plain inference stack only");
+      return HTCN_ERR_UNSUPPORTED;
+    }
+    if (stream) HTCN_K2_LAUNCH(true, true, false);
+    HTCN_K2_LAUNCH(true, false, false);
   }
-  auto kern = k2_tcn_bf16<false>;
-  HTCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = units < 2 * 148 ? units : 2 * 148;
-  kern<<<grid, kK2Threads, smem, st>>>(tw, g, (const __nv_bfloat16*)xe, sbias, bias_dev, ds_bias_dev, out_row,
-                                       (__nv_bfloat16*)hout, (__nv_bfloat16*)h_save, (__nv_bfloat16*)a_save, hist_dev, drop);
-  HTCN_LAUNCH_CHECK("k2_tcn_bf16");
-  return HTCN_OK;
+  if (stream && aux) HTCN_K2_LAUNCH(false, true, true);
+  if (stream) HTCN_K2_LAUNCH(false, true, false);
+  if (aux) HTCN_K2_LAUNCH(false, false, true);
+  HTCN_K2_LAUNCH(false, false, false);
+#undef HTCN_K2_LAUNCH
 }
 
 }  // namespace htcn
