@@ -75,7 +75,7 @@ def load_peaks():
 def load_traffic(opt, wl):
     """dram bytes per launch of the dominant kernel from the committed ncu capture (only valid for the default
     cfg2 / bf16 configuration it was taken on); None otherwise"""
-    p = os.path.join(ROOT, "profiles", "r1_k4_traffic.json")
+    p = os.path.join(ROOT, "profiles", "r2_k4_traffic.json")
     if opt.workload != "cfg2" or opt.batch or opt.precision != "bf16" or opt.n_split or not os.path.exists(p):
         return None
     d = json.load(open(p))

@@ -139,9 +139,12 @@ class HierTCNTrainer:
         return torch.from_numpy(sc).to(self.m.device)
 
     def forward_backward(self, x_list=None, y_list=None, mask_list=None, state=None, staged=None, metrics=False,
-                         mask_warmstart=None, x_gap=None, dropout_masks=None):
+                         mask_warmstart=None, x_gap=None, dropout_masks=None, neg_ids=None, loss_kind=None):
         """Accumulates the gradients of sum_b(sum_t loss/(n_b+1e-6)) into ``self.grads`` (the 1/user_count is applied by
-        the optimiser).  Returns dict(scalars [8] device: loss, ..., user_count, n_valid; state [B,G*H] device)."""
+        the optimiser).  Returns dict(scalars [8] device: loss, ..., user_count, n_valid; state [B,G*H] device).
+        ``neg_ids [Q,k]`` (k <= 32; host or device): train on the sampled ranking loss of reference loss.py:22-71
+        (``loss_kind`` or args.loss: nce / hinge_sigmoid / hinge_logsigmoid / hinge_linear / bpr) against the rows of the
+        output table instead of the full-softmax cross-entropy -- no catalog sweep, gradients reach only the gathered rows."""
         torch = _torch()
         m = self.m
         d = staged if staged is not None else m.stage(x_list, y_list, mask_list, state, None, mask_warmstart, x_gap)
@@ -191,6 +194,29 @@ class HierTCNTrainer:
         scalars = torch.zeros(8, dtype=f32, device=m.device)
         if Q == 0:
             return dict(scalars=scalars, state=state_out)
+        if neg_ids is not None:
+            # ---- sampled ranking loss (loss.py:22-71): 1 + k gathered rows of W_out^T per scored position
+            a = m.args
+            kind = loss_kind or (a.loss if a.loss in cabi.LOSS_KINDS else "hinge_logsigmoid")
+            neg = neg_ids if hasattr(neg_ids, "data_ptr") else torch.from_numpy(np.ascontiguousarray(neg_ids, np.int32)).to(m.device)
+            k = int(neg.shape[1])
+            assert int(neg.shape[0]) == Q, "neg_ids must have one row per scored position"
+            h_prec = cabi.HTCN_BF16 if fused else cabi.HTCN_F32
+            loss_row = buf("loss_row", (Q,), f32)
+            cabi.call("htcn_sampled_rank_loss", hout.data_ptr(), h_prec, Q, self.p["wt"].data_ptr(), d["y_rows"].data_ptr(),
+                      neg.data_ptr(), k, cabi.LOSS_KINDS[kind], float(a.hinge_delta), float(a.nce_weight),
+                      int(a.num_neg_sample), loss_row.data_ptr(), st)
+            cabi.call("htcn_loss_metrics_reduce", loss_row.data_ptr(), None, d["row_of"].data_ptr(), y_loss.data_ptr(),
+                      B, T, N, None, None, None, buf("user_part", (B, 8), f32).data_ptr(), scalars.data_ptr(), st)
+            g_row = buf("tr_g_row", (Q,), f32)
+            cabi.call("htcn_loss_row_weights", y_loss.data_ptr(), d["row_of"].data_ptr(), B, T, g_row.data_ptr(), st)
+            d_hout = buf("tr_d_hout", (Q, D), f32)
+            cabi.call("htcn_sampled_rank_loss_backward", hout.data_ptr(), h_prec, Q, self.p["wt"].data_ptr(),
+                      d["y_rows"].data_ptr(), neg.data_ptr(), k, cabi.LOSS_KINDS[kind], float(a.hinge_delta),
+                      float(a.nce_weight), int(a.num_neg_sample), g_row.data_ptr(), d_hout.data_ptr(),
+                      self.g["wt"].data_ptr(), st)
+            return self._backward_below_head(d, d_hout, xe, sdt_c, yp, state_pre, gates, h_save, a_save, drop, scalars,
+                                             state_out, slot_p, slot_keep)
         # ---- loss (one streaming sweep: log-sum-exp per row, optionally the rank metrics)
         ns = m.n_split_for(Q, N)
         zy = buf("zy", (Q,), f32)
@@ -235,6 +261,21 @@ class HierTCNTrainer:
             cabi.call("htcn_score_ce_backward", hout.data_ptr(), cabi.HTCN_F32, Q, m.wt.data_ptr(), m.b_out.data_ptr(), N, 0,
                       d["y_rows"].data_ptr(), loss_row.data_ptr(), zy.data_ptr(), g_row.data_ptr(), d_hout.data_ptr(),
                       self.g["wt"].data_ptr(), self.g["b_out"].data_ptr(), st)
+        return self._backward_below_head(d, d_hout, xe, sdt_c, yp, state_pre, gates, h_save, a_save, drop, scalars, state_out,
+                                         slot_p, slot_keep)
+
+    def _backward_below_head(self, d, d_hout, xe, sdt_c, yp, state_pre, gates, h_save, a_save, drop, scalars, state_out,
+                             slot_p, slot_keep):
+        """conv stack, GRU (BPTT over the S steps) and embedding backward, given dL/dHout"""
+        torch = _torch()
+        m = self.m
+        B, T, S = d["B"], d["T"], d["S"]
+        G, L, K, N = m.G, m.n_levels, m.K, m.N
+        R = B * T
+        st = m.stream_ptr()
+        f32 = torch.float32
+        P = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
+        buf = m._buf
         d_sbias = buf("tr_d_sbias", (S, B, D), f32)
         d_xe = buf("tr_d_xe", (R, D), f32)
         k2_scratch = buf("tr_k2_scratch", (3 if m.has_ds else 2, R, D), f32)
@@ -284,11 +325,11 @@ class HierTCNTrainer:
         return scalars
 
     def train_step(self, x_list, y_list, mask_list, state=None, lr=None, metrics=False, state_on_device=False,
-                   mask_warmstart=None, x_gap=None, dropout_masks=None):
+                   mask_warmstart=None, x_gap=None, dropout_masks=None, neg_ids=None, loss_kind=None):
         """One optimisation step on one batch.  Returns dict(loss, user_count, n_valid, state [+ metrics]); ``state`` is
         the carried user state for the next batch (numpy, or the device tensor with ``state_on_device``)."""
         r = self.forward_backward(x_list, y_list, mask_list, state, metrics=metrics, mask_warmstart=mask_warmstart, x_gap=x_gap,
-                                  dropout_masks=dropout_masks)
+                                  dropout_masks=dropout_masks, neg_ids=neg_ids, loss_kind=loss_kind)
         sc = self.apply_gradients(r["scalars"], lr).cpu().numpy()
         out = dict(loss=float(sc[0]), user_count=float(sc[6]), n_valid=float(sc[7]))
         if metrics:

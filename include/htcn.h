@@ -296,6 +296,15 @@ int32_t htcn_sampled_rank_loss(const void* pred, int32_t precision, int32_t Q, c
                                int32_t loss_kind, float hinge_delta, float nce_weight,
                                int32_t num_neg_sample, float* loss_row, void* stream);
 
+/* Backward of htcn_sampled_rank_loss: g_row [Q] = dL/dloss_row.  d_pred [Q,128] f32 is overwritten (rows with pos_id == 0
+ * get zeros), d_table [N,128] f32 (the gradient of the positive / negative rows of `table`) is accumulated with atomics;
+ * the null item 0 owns no row.  Hinge kinds use the relu gradient where the hinge is strictly positive (TF's ReluGrad).
+ * k <= 32. */
+int32_t htcn_sampled_rank_loss_backward(const void* pred, int32_t precision, int32_t Q, const float* table,
+                                        const int32_t* pos_id, const int32_t* neg_id, int32_t k, int32_t loss_kind,
+                                        float hinge_delta, float nce_weight, int32_t num_neg_sample, const float* g_row,
+                                        float* d_pred, float* d_table, void* stream);
+
 /* calc_score (reference loss.py:76-105): score[q,j] of k candidate rows table[cand_id[q,j]] for every query;
  * rank_metric 0 = 'l2' (-||pred - y'||^2), 1 = 'inner_prod' (<pred, y'>); pred is not normalised (as in the
  * reference).  cand_id [Q,k] int32 (0 -> zero row), score [Q,k] f32. */

@@ -58,7 +58,32 @@ def _tcn(p, h, n_levels, K, drop=None):
     return h
 
 
-def loss_fp64(p, x_list, y_list, mask_list, state, num_layer=2, literal=False, dropout_scales=None):
+def _sampled_rows(hout, table, y_id, neg_bt, kind, delta=0.1, nce_weight=1.0, num_neg=20):
+    """reference loss.py:22-71 with pred = the user embedding, y = the target's row of ``table`` and y_impression = the rows
+    of the sampled negatives (id 0 -> zero row).  hout [B,T,d], y_id [B,T], neg_bt [B,T,k] -> loss [B,T]"""
+    mask0 = lambda ids: (ids > 0).unsqueeze(-1).to(hout.dtype)  # noqa: E731
+    y = table[y_id] * mask0(y_id)
+    yi = table[neg_bt] * mask0(neg_bt)
+    ss = (hout * hout).sum(-1, keepdim=True)
+    ph = hout * torch.rsqrt(torch.clamp(ss, min=1e-12))                         # tf.nn.l2_normalize
+    inner = (ph * y).sum(-1)
+    ip = torch.einsum("btd,btkd->btk", ph, yi)
+    ls = F.logsigmoid
+    if kind == "nce":
+        return -ls(inner) - ls(-ip).sum(2) / num_neg * nce_weight
+    if kind == "hinge_sigmoid":
+        return torch.relu(torch.sigmoid(ip) - torch.sigmoid(inner).unsqueeze(-1) + delta).mean(2)
+    if kind == "hinge_logsigmoid":
+        return torch.relu(ls(ip) - ls(inner).unsqueeze(-1) + delta).mean(2)
+    if kind == "hinge_linear":
+        return torch.relu(ip - inner.unsqueeze(-1) + delta).mean(2)
+    if kind == "bpr":
+        return -ls(torch.sigmoid(inner).unsqueeze(-1) - torch.sigmoid(ip)).mean(2)
+    raise NotImplementedError(kind)
+
+
+def loss_fp64(p, x_list, y_list, mask_list, state, num_layer=2, literal=False, dropout_scales=None, neg_ids=None,
+              loss_kind="hinge_logsigmoid", hinge_delta=0.1, nce_weight=1.0, num_neg_sample=20):
     """Scalar training loss (model.py:105-117) as a torch expression of the parameter dict ``p``."""
     dt = p["hier/emb/kernel"].dtype
     E, be = p["hier/emb/kernel"], p["hier/emb/bias"]
@@ -86,6 +111,15 @@ def loss_fp64(p, x_list, y_list, mask_list, state, num_layer=2, literal=False, d
     hout = torch.cat(houts, 1)
     y_id = torch.from_numpy(np.concatenate([np.asarray(v) for v in y_list], 1).astype(np.int64))
     mask = (y_id > 0).to(dt)
+    if neg_ids is not None:          # sampled ranking loss against the rows of the output table (loss.py:22-71)
+        neg = np.asarray(neg_ids)
+        neg_bt = np.zeros(tuple(y_id.shape) + (neg.shape[1],), np.int64)
+        neg_bt[y_id.numpy() > 0] = neg                                          # rows of neg_ids follow the scored positions
+        loss_bt = _sampled_rows(hout, p["hier/tcn/dense/kernel"].t(), y_id, torch.from_numpy(neg_bt), loss_kind, hinge_delta,
+                                nce_weight, num_neg_sample) * mask
+        act = mask.sum(1)
+        uc = torch.sign(act).sum()
+        return ((loss_bt.sum(1) / (act + 1e-6)).sum() / uc), state
     z = (hout @ p["hier/tcn/dense/kernel"] + p["hier/tcn/dense/bias"]) * mask.unsqueeze(-1)     # model.py:105
     lse = torch.logsumexp(z, -1)
     zy = z.gather(2, y_id.unsqueeze(-1)).squeeze(-1)
@@ -95,10 +129,11 @@ def loss_fp64(p, x_list, y_list, mask_list, state, num_layer=2, literal=False, d
     return ((loss_bt.sum(1) / (act + 1e-6)).sum() / uc), state                   # model.py:111-117
 
 
-def loss_and_grads(w, x_list, y_list, mask_list, state, num_layer=2, literal=False, dropout_scales=None):
-    """-> (loss float, dict name -> fp64 numpy gradient, new state)"""
+def loss_and_grads(w, x_list, y_list, mask_list, state, num_layer=2, literal=False, dropout_scales=None, **sampled):
+    """-> (loss float, dict name -> fp64 numpy gradient, new state).  ``sampled``: neg_ids / loss_kind / hinge_delta /
+    nce_weight / num_neg_sample of the sampled ranking losses"""
     p = _params(w)
-    loss, st = loss_fp64(p, x_list, y_list, mask_list, state, num_layer, literal, dropout_scales)
+    loss, st = loss_fp64(p, x_list, y_list, mask_list, state, num_layer, literal, dropout_scales, **sampled)
     loss.backward()
     g = {k: (v.grad.numpy() if v.grad is not None else np.zeros(v.shape)) for k, v in p.items()}
     return float(loss.detach()), g, st.detach().numpy()

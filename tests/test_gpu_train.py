@@ -455,3 +455,34 @@ def test_training_dropout_channel_masks(precision, tol):
         r3 = tr.forward_backward(x, y, m, s0, dropout_masks=masks)
         assert abs(float(r3["scalars"][0]) - ref_loss) <= 3e-2 * abs(ref_loss)
         tr.grads.zero_()
+
+
+@pytest.mark.parametrize("kind", ["nce", "hinge_sigmoid", "hinge_logsigmoid", "hinge_linear", "bpr"])
+def test_training_on_the_sampled_ranking_losses(kind):
+    """backward of reference loss.py:22-71 (htcn_sampled_rank_loss_backward) through the whole stack vs the fp64 autograd
+    oracle: gradients of the gathered table rows, of the user embeddings' producers, and none for the output bias"""
+    x, y, m, s0, w = small_case(B=6, S=3, L=7, N=211, seed=9, kernel_scale=1.0)
+    y_id = np.concatenate(y, 1)
+    Q = int((y_id > 0).sum())
+    neg = np.random.default_rng(2).integers(0, 211, size=(Q, 20)).astype(np.int32)     # includes the null id 0
+    ref_loss, ref_g, _ = GO.loss_and_grads(w, x, y, m, s0, neg_ids=neg, loss_kind=kind)
+    tr = make_trainer(w, 211)
+    r = tr.forward_backward(x, y, m, s0, neg_ids=neg, loss_kind=kind)
+    sc = r["scalars"].cpu().numpy()
+    assert abs(sc[0] - ref_loss) <= 1e-4 * abs(ref_loss)
+    got = tr.named_gradients(sc[6])
+    # a hinge sitting within fp32 rounding of its kink may fall on the other side: bound the error in norm
+    for k_ in ref_g:
+        ref = ref_g[k_]
+        if np.abs(ref).max() == 0:
+            assert np.abs(got[k_]).max() == 0, k_
+            continue
+        assert np.linalg.norm(got[k_] - ref) <= 2e-3 * np.linalg.norm(ref) + 1e-9, (k_, np.linalg.norm(got[k_] - ref) / np.linalg.norm(ref))
+    assert np.abs(got["hier/tcn/dense/bias"]).max() == 0
+    assert np.all(got["hier/tcn/dense/kernel"][:, 0] == 0)          # the null id owns no row gradient
+    # one optimisation step lowers this batch's sampled loss
+    tr2 = make_trainer(w, 211)
+    l0 = tr2.train_step(x, y, m, s0, neg_ids=neg, loss_kind=kind)["loss"]
+    for _ in range(3):
+        l1 = tr2.train_step(x, y, m, s0, neg_ids=neg, loss_kind=kind)["loss"]
+    assert l1 < l0

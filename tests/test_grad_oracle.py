@@ -74,3 +74,24 @@ def test_training_reduces_loss():
     batches = [(x, y, m)] * 4
     losses, w2, _ = GO.train_steps(w, batches, s0, lr=1e-2)
     assert losses[-1] < losses[0]
+
+
+def test_sampled_loss_rows_of_the_autograd_restatement_match_the_numpy_oracle():
+    """oracle/grad_oracle._sampled_rows (torch, differentiable) == oracle.calc_loss_sampled (numpy), which is pinned against the
+    reference's own loss.py through tests/golden/loss_vectors.npz"""
+    import torch
+    from oracle import grad_oracle as GO
+    from oracle import hiertcn_oracle as O
+    rng = np.random.default_rng(3)
+    B, T, k, N, d = 3, 4, 6, 40, 16
+    table = rng.normal(size=(N, d))
+    hout = rng.normal(size=(B, T, d))
+    y_id = rng.integers(1, N, size=(B, T))
+    neg = rng.integers(0, N, size=(B, T, k))
+    tz = table.copy()
+    tz[0] = 0.0                                                # id 0 -> zero row
+    for kind in ("nce", "hinge_sigmoid", "hinge_logsigmoid", "hinge_linear", "bpr"):
+        got = GO._sampled_rows(torch.tensor(hout), torch.tensor(table), torch.tensor(y_id), torch.tensor(neg), kind,
+                               0.1, 1.0, 20).numpy()
+        ref = O.calc_loss_sampled(hout, tz[y_id], tz[neg], kind, 20, 1.0, 0.1)
+        np.testing.assert_allclose(got, ref, rtol=1e-10, atol=1e-12)
