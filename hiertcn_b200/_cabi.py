@@ -11,7 +11,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libhtcn.so")
 
-HTCN_F32, HTCN_BF16 = 0, 1
+HTCN_F32, HTCN_BF16, HTCN_F32_W256 = 0, 1, 2
 SCORE_CE, SCORE_RANK, SCORE_TOPK = 1, 2, 4
 LOSS_KINDS = {"nce": 0, "hinge_sigmoid": 1, "hinge_logsigmoid": 2, "hinge_linear": 3, "bpr": 4}
 MAX_TOPK = 128
@@ -36,6 +36,7 @@ SIGNATURES = {
     "htcn_gather_meanpool": [_p, _i, _p, _i, _p, _p, _ip, _i, _i, _i, _p, _i, _p, _p],
     "htcn_gru_sessions": [_p, _p, _p, _pp, _pp, _pp, _pp, _i, _p, _i, _i, _i, _p, _p, _p, _p, _p],
     "htcn_tcn_forward": [_p, _i, _i, _p, _p, _pp, _pp, _pp, _pp, _i, _i, _ip, _i, _i, _i, _p, _p, _i, _p, _p],
+    "htcn_tcn_forward_wide": [_p, _i, _p, _p, _pp, _pp, _pp, _pp, _ip, _i, _i, _ip, _i, _i, _i, _p, _p, C.c_int64, _p, _p],
     "htcn_prepare_wout": [_p, _p, _i, _p, _i, _p],
     "htcn_score_ce_rank_topk": [_p, _i, _i, _p, _p, _i, _i, _p, _p, _i, _u, _i, _i, _p, _p, _p, _p, _p, _p],
     "htcn_score_logits": [_p, _i, _i, _p, _i, _p, _i, _p, _p],

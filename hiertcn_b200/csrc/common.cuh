@@ -36,6 +36,8 @@ struct ScoreArgs {
   float* topk_val; int* topk_idx;                    // [n_split,Q,k]
   int Q, n_items, n0, k, n_split;
   unsigned flags;
+  int planes;                // fp32 tier only, 0/1 = plain; 2: hout is [2][Q][128] (block-planar), wt rows are 256 floats
+                             // (HTCN_F32_W256: a 256-channel last level, args.py:310-311)
   const float* row_scale;    // [Q] or NULL: the CE sum runs on row_scale[q] * z (l2-normalised head, model_tcn.py:42-43);
                              // part_max then holds the SCALED reference point; ranks always compare the raw logits
 };

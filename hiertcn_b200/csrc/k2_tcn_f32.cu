@@ -29,6 +29,15 @@ k2_level_f32(LevelArgs a, SlotTable slots) {
   __shared__ int t_left[kTM];                      // rows remaining after it in the sequence (anti-causal taps)
   const int tid = threadIdx.x;
   const long long r0 = (long long)blockIdx.x * kTM;
+  // wide levels (129..256 channels = two 128-wide planes, fp32 tier only): this CTA computes output plane po
+  const int po = blockIdx.y;
+  const int n_in = a.in_planes > 1 ? a.in_planes : 1;
+  if (po > 0 || n_in > 1) {
+    a.w += (long long)po * n_in * a.K * kDim * kDim;
+    if (a.bias) a.bias += po * kDim;
+    a.out = reinterpret_cast<float*>(a.out) + po * a.out_plane_stride;          // wide paths are fp32 in / out
+    if (a.resid) a.resid += po * a.resid_plane_stride;
+  }
 
   if (tid < kTM) {
     const long long r = r0 + tid;
@@ -54,9 +63,9 @@ k2_level_f32(LevelArgs a, SlotTable slots) {
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 
   const int lrow = tid & 127, lhalf = tid >> 7;   // loader mapping: row, 8-wide k half
-  for (int tap = 0; tap < a.K; ++tap) {
-    const int shift = (a.K - 1 - tap) * a.dil;
-    const long long src = a.anti ? (r0 + lrow + shift) : (r0 + lrow - shift);
+  for (int tap = 0; tap < n_in * a.K; ++tap) {
+    const int shift = (a.K - 1 - tap % a.K) * a.dil;
+    const long long src = (a.anti ? (r0 + lrow + shift) : (r0 + lrow - shift)) + (tap / a.K) * (a.in_plane_stride / kDim);
     const bool ok = (r0 + lrow < a.R) && (a.anti ? (shift <= t_left[lrow]) : (t_in_seq[lrow] - shift >= 0));
     for (int c0 = 0; c0 < kDim; c0 += kTK) {
       // A chunk: in[src][c0 + lhalf*8 .. +8] -> As[kk][lrow]
@@ -144,7 +153,8 @@ k2_level_f32(LevelArgs a, SlotTable slots) {
           v = fmaxf(v, 0.f);
           ax[j] = v;                                   // saved BEFORE the dropout scale (the backward re-applies it)
           if (dr) v *= __ldg(dr + c + j);
-          const float res = a.conv_epilogue == 1 ? load_act(a.in, a.in_bf16, r * kDim + c + j) : a.resid[r * kDim + c + j];
+          const float res = a.conv_epilogue == 1 ? load_act(a.in, a.in_bf16, po * a.in_plane_stride + r * kDim + c + j)
+                                                 : a.resid[r * kDim + c + j];
           v = fmaxf(v + res, 0.f);
         } else if (a.conv_epilogue == 2) {
           v += a.resid[r * kDim + c + j];
@@ -166,6 +176,57 @@ k2_level_f32(LevelArgs a, SlotTable slots) {
 int32_t k2_level_launch(const LevelArgs& a, const SlotTable& slots, cudaStream_t st) {
   k2_level_f32<<<ceil_div(a.R, kTM), kK2Threads, 0, st>>>(a, slots);
   HTCN_LAUNCH_CHECK("k2_level_f32");
+  return HTCN_OK;
+}
+
+// fp32 conv stack whose levels may be up to 256 channels wide (two 128-wide planes): activations are block-planar
+// [P][R][128]; a level with P_in input planes runs as P_in*K taps, one CTA column per output plane (weights pre-arranged as
+// [P_out, P_in*K, 128, 128] by hiertcn_b200.weights.to_device_layout).  hout: [P_last][n_out_rows][128] fp32.
+int32_t tcn_forward_f32_wide(const void* xe, int xe_dtype, const float* w_in_x, const float* sbias,
+                             const float* const* conv_w, const float* const* conv_b, const float* const* ds_w,
+                             const float* const* ds_b, const int* planes, int n_levels, int K, const SlotTable& slots, int B,
+                             int T, const int* out_row, float* hout, long long hout_plane_rows, float* scratch,
+                             cudaStream_t st) {
+  const long long R = (long long)B * T;
+  const int grid = ceil_div(R, kTM);
+  const long long plane = R * kDim;
+  float* buf[2] = {scratch, scratch + 2 * plane};          // two planes each
+  float* res_buf = scratch + 4 * plane;
+  LevelArgs a{};
+  a.R = R; a.T = T; a.B = B;
+  a.in = xe; a.in_bf16 = (xe_dtype == HTCN_BF16);
+  a.w = w_in_x; a.sbias = sbias; a.K = 1; a.dil = 1; a.conv_epilogue = 0;
+  a.out = buf[0];
+  k2_level_f32<<<grid, kK2Threads, 0, st>>>(a, slots);      // in-projection: always 128 wide
+  HTCN_LAUNCH_CHECK("k2_level_f32(in-proj)");
+  int p_in = 1;
+  for (int l = 0; l < n_levels; ++l) {
+    const bool last = (l == n_levels - 1);
+    const int p_out = planes[l];
+    const bool ds = ds_w && ds_w[l];
+    if (!ds && p_in != p_out) {
+      set_error("tcn_forward_wide: level %d changes the plane count without a down-sample kernel", l);
+      return HTCN_ERR_INVALID;
+    }
+    a = LevelArgs{};
+    a.R = R; a.T = T; a.B = B;
+    a.in = buf[l & 1]; a.in_planes = p_in; a.in_plane_stride = plane;
+    if (ds) {
+      a.w = ds_w[l]; a.bias = ds_b ? ds_b[l] : nullptr; a.K = 1; a.dil = 1; a.conv_epilogue = 0;
+      a.out = res_buf; a.out_plane_stride = plane;
+      k2_level_f32<<<dim3(grid, p_out), kK2Threads, 0, st>>>(a, slots);
+      HTCN_LAUNCH_CHECK("k2_level_f32(down-sample)");
+    }
+    a.w = conv_w[l]; a.bias = conv_b[l]; a.K = K; a.dil = 1 << l; a.conv_epilogue = ds ? 3 : 1;
+    a.resid = ds ? res_buf : nullptr;
+    a.resid_plane_stride = plane;
+    a.out = last ? hout : buf[(l + 1) & 1];
+    a.out_plane_stride = last ? hout_plane_rows * kDim : plane;
+    a.out_row = last ? out_row : nullptr;
+    k2_level_f32<<<dim3(grid, p_out), kK2Threads, 0, st>>>(a, slots);
+    HTCN_LAUNCH_CHECK("k2_level_f32(conv)");
+    p_in = p_out;
+  }
   return HTCN_OK;
 }
 
@@ -243,4 +304,29 @@ extern "C" int32_t htcn_tcn_forward(const void* xe, int32_t xe_dtype, int32_t pr
                             T, out_row, hout, hout_dtype, scratch, as_stream(stream));
   set_error("tcn_forward: precision %d", precision);
   return HTCN_ERR_INVALID;
+}
+
+
+extern "C" int32_t htcn_tcn_forward_wide(const void* xe, int32_t xe_dtype, const float* w_in_x, const float* sbias,
+                                         const float* const* conv_w_host, const float* const* conv_b_host,
+                                         const float* const* ds_w_host, const float* const* ds_b_host,
+                                         const int32_t* level_planes_host, int32_t n_levels, int32_t kernel_size,
+                                         const int32_t* slot_off_host, int32_t B, int32_t T, int32_t S,
+                                         const int32_t* out_row, float* hout, int64_t hout_plane_rows, float* scratch,
+                                         void* stream) {
+  using namespace htcn;
+  HTCN_REQUIRE(xe && w_in_x && hout && slot_off_host && scratch && level_planes_host, "tcn_forward_wide: NULL pointer");
+  HTCN_REQUIRE(B > 0 && T > 0 && S > 0 && S <= HTCN_MAX_SLOTS, "tcn_forward_wide: B=%d T=%d S=%d", B, T, S);
+  HTCN_REQUIRE(n_levels >= 1 && n_levels <= HTCN_MAX_LEVELS && conv_w_host && conv_b_host, "tcn_forward_wide: n_levels=%d", n_levels);
+  HTCN_REQUIRE(kernel_size >= 1 && kernel_size <= 8, "tcn_forward_wide: kernel_size=%d", kernel_size);
+  HTCN_REQUIRE(xe_dtype == HTCN_F32 || xe_dtype == HTCN_BF16, "tcn_forward_wide: xe dtype");
+  for (int l = 0; l < n_levels; ++l)
+    HTCN_REQUIRE(level_planes_host[l] == 1 || level_planes_host[l] == 2, "tcn_forward_wide: level %d has %d planes", l, level_planes_host[l]);
+  HTCN_REQUIRE(hout_plane_rows > 0, "tcn_forward_wide: hout_plane_rows");
+  SlotTable slots;
+  slots.n = S;
+  for (int i = 0; i <= S; ++i) slots.off[i] = slot_off_host[i];
+  HTCN_REQUIRE(slots.off[0] == 0 && slots.off[S] == T, "tcn_forward_wide: slot_off does not span T");
+  return tcn_forward_f32_wide(xe, xe_dtype, w_in_x, sbias, conv_w_host, conv_b_host, ds_w_host, ds_b_host, level_planes_host,
+                              n_levels, kernel_size, slots, B, T, out_row, hout, hout_plane_rows, scratch, as_stream(stream));
 }

@@ -7,7 +7,9 @@ namespace htcn {
 
 int32_t score_f32(const ScoreArgs& a, cudaStream_t st);
 int32_t target_logit_f32(const float* hout, const float* wt, const float* b_out, const int* y_id, int Q,
-                         int n_items, int n0, float* zy, cudaStream_t st);
+                         int n_items, int n0, float* zy, cudaStream_t st, int planes = 1);
+static inline bool is_f32(int precision) { return precision == HTCN_F32 || precision == HTCN_F32_W256; }
+static inline int planes_of(int precision) { return precision == HTCN_F32_W256 ? 2 : 1; }
 // bf16 tier (k4_score_bf16.cu)
 int32_t score_bf16(const ScoreArgs& a, cudaStream_t st);
 int32_t target_logit_bf16(const void* hout, const void* wt, const float* b_out, const int* y_id, int Q,
@@ -27,9 +29,9 @@ static int topk_heap_splits(int precision, int n_items, int n_split) {
 // ---- W_out [128, N] f32 -> W_out^T [N, 128] f32 | [N, 144] bf16 augmented (32x32 smem transpose) ----
 template <bool kBf16>
 __global__ void prepare_wout_kernel(const float* __restrict__ w, const float* __restrict__ b, int N,
-                                    void* __restrict__ out) {
+                                    void* __restrict__ out, int f32_pitch = kDim) {
   __shared__ float tile[32][33];
-  constexpr int pitch = kBf16 ? kWtPitchBf16 : kDim;
+  const int pitch = kBf16 ? kWtPitchBf16 : f32_pitch;     // f32: 128, or 256 for HTCN_F32_W256 (grid.y = pitch / 32)
   const int n0 = blockIdx.x * 32;
   const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
   if (blockIdx.y == kDim / 32) {                  // bf16 only: the bias columns 128..143 of 32 items
@@ -62,18 +64,19 @@ __global__ void prepare_wout_kernel(const float* __restrict__ w, const float* __
 // ---- full logits for small catalogs (the tensor the reference materialises) ---------------------
 __global__ void score_logits_kernel(const void* __restrict__ hout, int h_bf16, int Q, const void* __restrict__ wt,
                                     int w_bf16, const float* __restrict__ b_out, int n_items,
-                                    float* __restrict__ logits) {
+                                    float* __restrict__ logits, int planes) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)Q * n_items) return;
   const int q = (int)(i / n_items), j = (int)(i % n_items);
   const __nv_bfloat16* wb = reinterpret_cast<const __nv_bfloat16*>(wt) + (long long)j * kWtPitchBf16;
   float acc = 0.f;
-  for (int k = 0; k < kDim; ++k) {
-    const float a = h_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(hout)[(long long)q * kDim + k])
-                           : reinterpret_cast<const float*>(hout)[(long long)q * kDim + k];
-    const float b = w_bf16 ? __bfloat162float(wb[k]) : reinterpret_cast<const float*>(wt)[(long long)j * kDim + k];
-    acc = fmaf(a, b, acc);
-  }
+  for (int p = 0; p < planes; ++p)            // planes > 1: fp32 only, hout block-planar [P][Q][128], wt rows P*128 floats
+    for (int k = 0; k < kDim; ++k) {
+      const float a = h_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(hout)[(long long)q * kDim + k])
+                             : reinterpret_cast<const float*>(hout)[((long long)p * Q + q) * kDim + k];
+      const float b = w_bf16 ? __bfloat162float(wb[k]) : reinterpret_cast<const float*>(wt)[((long long)j * planes + p) * kDim + k];
+      acc = fmaf(a, b, acc);
+    }
   // bf16 tier: the bias is the (hi, lo) pair stored in the augmented columns, as the tensor-core sweep sees it
   const float bias = w_bf16 ? (__bfloat162float(wb[kDim]) + __bfloat162float(wb[kDim + 1])) : b_out[j];
   logits[i] = acc + bias;
@@ -354,9 +357,10 @@ extern "C" int32_t htcn_prepare_wout(const float* w_out, const float* b_out, int
     HTCN_REQUIRE(b_out, "prepare_wout: the bf16 layout folds the bias in, b_out is required");
     dim3 grid(ceil_div(N, 32), kDim / 32 + 1);
     prepare_wout_kernel<true><<<grid, block, 0, as_stream(stream)>>>(w_out, b_out, N, w_out_t);
-  } else if (dtype == HTCN_F32) {
-    dim3 grid(ceil_div(N, 32), kDim / 32);
-    prepare_wout_kernel<false><<<grid, block, 0, as_stream(stream)>>>(w_out, b_out, N, w_out_t);
+  } else if (is_f32(dtype)) {
+    const int pitch = planes_of(dtype) * kDim;
+    dim3 grid(ceil_div(N, 32), pitch / 32);
+    prepare_wout_kernel<false><<<grid, block, 0, as_stream(stream)>>>(w_out, b_out, N, w_out_t, pitch);
   } else {
     HTCN_REQUIRE(false, "prepare_wout: dtype %d", dtype);
   }
@@ -370,8 +374,10 @@ extern "C" int32_t htcn_score_logits(const void* hout, int32_t hout_dtype, int32
   HTCN_REQUIRE(hout && w_out_t && logits && Q > 0 && n_items > 0, "score_logits: bad args");
   HTCN_REQUIRE(b_out || w_dtype == HTCN_BF16, "score_logits: b_out is NULL");
   const long long n = (long long)Q * n_items;
+  HTCN_REQUIRE(hout_dtype != HTCN_F32_W256 || w_dtype != HTCN_BF16, "score_logits: 256-wide embeddings are fp32 only");
   score_logits_kernel<<<ceil_div(n, 256), 256, 0, as_stream(stream)>>>(hout, hout_dtype == HTCN_BF16, Q, w_out_t,
-                                                                      w_dtype == HTCN_BF16, b_out, n_items, logits);
+                                                                      w_dtype == HTCN_BF16, b_out, n_items, logits,
+                                                                      planes_of(hout_dtype));
   HTCN_LAUNCH_CHECK("score_logits");
   return HTCN_OK;
 }
@@ -381,9 +387,9 @@ extern "C" int32_t htcn_target_logit(const void* hout, int32_t precision, int32_
                                      float* target_logit, void* stream) {
   HTCN_REQUIRE(hout && w_out_t && y_id && target_logit && Q > 0 && n_items > 0, "target_logit: bad args");
   HTCN_REQUIRE(b_out || precision == HTCN_BF16, "target_logit: b_out is NULL");
-  if (precision == HTCN_F32)
+  if (is_f32(precision))
     return target_logit_f32((const float*)hout, (const float*)w_out_t, b_out, y_id, Q, n_items, n0, target_logit,
-                            as_stream(stream));
+                            as_stream(stream), planes_of(precision));
   if (precision == HTCN_BF16)
     return target_logit_bf16(hout, w_out_t, b_out, y_id, Q, n_items, n0, target_logit, as_stream(stream));
   HTCN_REQUIRE(false, "target_logit: precision %d", precision);
@@ -412,7 +418,8 @@ extern "C" int32_t htcn_score_ce_rank_topk(const void* hout, int32_t precision, 
   }
   ScoreArgs a{hout, w_out_t, b_out, y_id, target_logit, part_max, part_sum, part_cnt, topk_val, topk_idx,
               Q, n_items, n0, k, n_split, flags};
-  if (precision == HTCN_F32) {
+  if (is_f32(precision)) {
+    a.planes = planes_of(precision);
     return score_f32(a, st);
   }
   if (precision == HTCN_BF16) return score_bf16(a, st);
@@ -430,7 +437,7 @@ extern "C" int32_t htcn_score_topk(const void* hout, int32_t precision, int32_t 
                                    void* stream) {
   HTCN_REQUIRE(hout && w_out_t && workspace && out_val && out_idx && Q > 0 && n_items > 0, "score_topk: bad args");
   HTCN_REQUIRE(k >= 1 && k <= HTCN_MAX_TOPK, "score_topk: k=%d out of [1,%d]", k, HTCN_MAX_TOPK);
-  HTCN_REQUIRE(precision == HTCN_F32 || precision == HTCN_BF16, "score_topk: precision %d", precision);
+  HTCN_REQUIRE(is_f32(precision) || precision == HTCN_BF16, "score_topk: precision %d", precision);
   HTCN_REQUIRE(workspace_bytes >= htcn_topk_workspace_bytes(precision, Q, n_items, k, n_split),
                "score_topk: workspace too small (%lld bytes)", (long long)workspace_bytes);
   cudaStream_t st = as_stream(stream);
@@ -490,7 +497,7 @@ extern "C" int32_t htcn_score_ce_repair(const void* hout, int32_t precision, int
                                         int32_t n_items, const float* target_logit, float* loss_row, int32_t* repaired,
                                         void* stream) {
   HTCN_REQUIRE(hout && w_out_t && target_logit && loss_row && Q > 0 && n_items > 0, "score_ce_repair: bad args");
-  if (precision == HTCN_F32) return HTCN_OK;           // the fp32 sweep keeps a running max: nothing to repair
+  if (is_f32(precision)) return HTCN_OK;               // the fp32 sweep keeps a running max: nothing to repair
   HTCN_REQUIRE(precision == HTCN_BF16, "score_ce_repair: precision %d", precision);
   const int chunks = ceil_div(Q, 256);
   const int grid = chunks < 148 * 8 ? chunks : 148 * 8;
@@ -506,7 +513,7 @@ extern "C" int32_t htcn_score_ce_repair_shard(const void* hout, int32_t precisio
                                               int32_t* repaired, void* stream) {
   HTCN_REQUIRE(hout && w_out_t && part_max && part_sum && Q > 0 && n_items > 0 && n_split >= 1,
                "score_ce_repair_shard: bad args");
-  if (precision == HTCN_F32) return HTCN_OK;           // the fp32 sweep keeps a running max per split
+  if (is_f32(precision)) return HTCN_OK;               // the fp32 sweep keeps a running max per split
   HTCN_REQUIRE(precision == HTCN_BF16, "score_ce_repair_shard: precision %d", precision);
   const int chunks = ceil_div(Q, 256);
   const int grid = chunks < 148 * 8 ? chunks : 148 * 8;

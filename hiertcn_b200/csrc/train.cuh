@@ -24,6 +24,10 @@ struct LevelArgs {
   const float* resid;         // [R,128] added in epilogues 2 and 3 (may alias out in 2)
   const float* drop;          // training dropout (customized_tcn_cell.py:100,119: noise_shape [1,1,C], one channel mask per
   int drop_stride;            //   slot and level): relu(conv + b) is multiplied by drop[slot(r) * drop_stride + c]; NULL = off
+  int in_planes;              // 0/1: plain.  P > 1: the input is P 128-wide planes ([P][R][128], in_plane_stride floats apart),
+  long long in_plane_stride;  //   run as P*K taps: tap = pi*K + kt reads plane pi shifted by (K-1-kt)*dil, w = [.., P*K, 128, 128]
+  long long out_plane_stride; // grid.y = output plane po: w += po*P*K*128*128, bias += po*128, out / resid / identity residual plane po
+  long long resid_plane_stride;
   int anti;                   // 1: taps read r + shift, zero beyond the END of r's sequence (transposed convolution)
   int w_nt;                   // 1: every W[tap] is applied transposed
 };

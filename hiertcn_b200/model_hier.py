@@ -68,7 +68,7 @@ class CatalogScores:
         out = np.zeros((self.B * self.T, m.N), dtype=np.float32)
         if self.Q:
             lg = torch.empty((self.Q, m.N), dtype=torch.float32, device=m.device)
-            cabi.call("htcn_score_logits", self.hout.data_ptr(), m.act_dtype, self.Q, m.wt.data_ptr(), m.act_dtype,
+            cabi.call("htcn_score_logits", self.hout.data_ptr(), m.k4_dtype, self.Q, m.wt.data_ptr(), m.act_dtype,
                       m.b_out.data_ptr(), m.N, lg.data_ptr(), m.stream_ptr())
             if m.l2_normalize:          # model_tcn.py:42-43
                 cabi.call("htcn_scale_rows", lg.data_ptr(), m.row_scale(self).data_ptr(), self.Q, m.N, m.stream_ptr())
@@ -93,9 +93,13 @@ class HierTCN:
             raise NotImplementedError("only model_type='hier' with model_low_type='tcn' is the hot path")
         # widths below 128 run zero-padded to 128 (hiertcn_b200.weights.to_device_layout); levels that change the width get
         # the 1x1 down-sample residual of customized_tcn_cell.py:102-106
-        if max(list(args.tcn_channel) + [int(args.hidden_dim), int(getattr(args, "emb_dim", 128))]) > 128:
-            raise NotImplementedError("widths above 128 (tcn_channel / hidden_dim / emb_dim): the sm_100a kernels run "
+        if max(int(args.hidden_dim), int(getattr(args, "emb_dim", 128))) > 128 or max(args.tcn_channel) > 256:
+            raise NotImplementedError("hidden_dim / emb_dim above 128 or tcn_channel above 256: the sm_100a kernels run "
                                       "128-wide blocks")
+        if max(args.tcn_channel) > 128 and self.precision != "f32":
+            # 129..256-channel levels (the single-level default of args.py:310-311) run as two 128-wide planes on the fp32
+            # kernels; the tcgen05 tier is built for levels up to 128 channels
+            raise NotImplementedError("tcn_channel above 128 needs precision='f32' (two-plane fp32 kernels)")
         for flag in ("has_batchnorm", "has_layernorm", "has_impression"):
             if getattr(args, flag, False):
                 raise NotImplementedError("%s is outside the hot path (SURVEY.md A.8)" % flag)
@@ -159,20 +163,33 @@ class HierTCN:
         self.b_out = up(lay["b_out"])
         self._w_out_host = lay["w_out"]                 # fp32 master of the output table (hiertcn_b200.train, bf16 tier)
         w_out = up(lay["w_out"])                        # [128, N] TF layout (rows beyond the last level's width are zero)
-        self.act_dtype = cabi.HTCN_BF16 if self.precision == "bf16" else cabi.HTCN_F32
-        tdt = torch.bfloat16 if self.precision == "bf16" else torch.float32
-        self.act_torch_dtype = tdt
-        self.n_out = int(w_out.shape[1])               # == N, or this rank's catalog shard (hiertcn_b200.dist)
-        pitch = cabi.WT_PITCH_BF16 if self.precision == "bf16" else D     # bf16 rows carry the bias (b_hi, b_lo)
-        self.wt = torch.empty((self.n_out, pitch), dtype=tdt, device=dev)  # W_out^T, K-major rows
-        cabi.call("htcn_prepare_wout", w_out.data_ptr(), self.b_out.data_ptr(), self.n_out, self.wt.data_ptr(),
-                  self.act_dtype, self.stream_ptr())
+        self._finish_build_head(w_out, meta)
         self.wt_f32 = self.wt if self.precision == "f32" else None
         torch.cuda.synchronize(dev)
         del w_out
         self.refresh_pointer_tables()
         self.built = True
         return self
+
+    def _finish_build_head(self, w_out, meta):
+        """dtypes + the scoring table W_out^T; ``wide``: some level has 129..256 channels (two 128-wide planes, fp32 kernels)"""
+        torch = _torch()
+        dev = self.device
+        self.act_dtype = cabi.HTCN_BF16 if self.precision == "bf16" else cabi.HTCN_F32
+        tdt = torch.bfloat16 if self.precision == "bf16" else torch.float32
+        self.act_torch_dtype = tdt
+        self.wide = bool(meta["wide"])
+        self.level_planes = list(meta["planes"])
+        self.head_planes = self.level_planes[-1] if self.level_planes else 1
+        if self.wide and self.precision != "f32":
+            raise NotImplementedError("tcn_channel above 128 needs precision='f32'")
+        # precision / dtype code of the K4 calls: 256-wide user embeddings are block-planar [2][Q][128]
+        self.k4_dtype = cabi.HTCN_F32_W256 if self.head_planes == 2 else self.act_dtype
+        self.n_out = int(w_out.shape[1])               # == N, or this rank's catalog shard (hiertcn_b200.dist)
+        pitch = cabi.WT_PITCH_BF16 if self.precision == "bf16" else D * self.head_planes   # bf16 rows carry the bias
+        self.wt = torch.empty((self.n_out, pitch), dtype=tdt, device=dev)  # W_out^T, K-major rows
+        cabi.call("htcn_prepare_wout", w_out.data_ptr(), self.b_out.data_ptr(), self.n_out, self.wt.data_ptr(),
+                  self.k4_dtype, self.stream_ptr())
 
     def refresh_pointer_tables(self):
         """host arrays of device pointers the C ABI takes (rebuilt when the trainer re-homes the parameters)"""
@@ -330,8 +347,17 @@ class HierTCN:
                   self._gru_pp[0][0], self._gru_pp[1][0], self._gru_pp[2][0], self._gru_pp[3][0], self.G,
                   self.w_in_state.data_ptr(), B, S, cabi.HTCN_BF16 if k3_bf16 else cabi.HTCN_F32,
                   k3_scratch.data_ptr() if k3_bf16 else None, None, sbias.data_ptr(), state_out.data_ptr(), st)
-        hout = self._buf("hout", (max(Q, 1), D), self.act_torch_dtype)
+        hout = self._buf("hout", (self.head_planes * max(Q, 1), D), self.act_torch_dtype)   # wide head: planes [P][Q][128]
         k2_precision = self._k2_precision()
+        if self.wide:
+            scratch = self._buf("k2_scratch", (6 * B * T, D), f32)
+            planes_p, planes_keep = cabi.int_array(self.level_planes)
+            cabi.call("htcn_tcn_forward_wide", xe.data_ptr(), self.act_dtype, self.w_in_x.data_ptr(), sbias.data_ptr(),
+                      self._conv_w_pp[0], self._conv_b_pp[0], self._ds_w_pp[0], self._ds_b_pp[0], planes_p, self.n_levels,
+                      self.K, slot_p, B, T, S, d["row_of"].data_ptr(), hout.data_ptr(), max(Q, 1), scratch.data_ptr(), st)
+            cabi.note_launches(self.n_levels + 1 + sum(t is not None for t in self.ds_w))
+            del slot_keep, planes_keep
+            return CatalogScores(self, hout, Q, d["row_of"], d["y_rows"], d.get("y_loss", d["y_id"]), B, T), state_out
         if k2_precision == cabi.HTCN_F32:
             scratch = self._buf("k2_scratch", ((3 if self.has_ds else 2) * B * T, D), f32)
         else:       # bf16 weight tiles + pointer table + biases of the fused tcgen05 conv stack
@@ -394,7 +420,7 @@ class HierTCN:
         P = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
         need_t = ce or rank
         if need_t:      # target logits first (own launch so the sweep can be timed on its own)
-            cabi.call("htcn_target_logit", scores.hout.data_ptr(), self.act_dtype, Q, self.wt.data_ptr(),
+            cabi.call("htcn_target_logit", scores.hout.data_ptr(), self.k4_dtype, Q, self.wt.data_ptr(),
                       self.b_out.data_ptr(), self.N, 0, scores.y_rows.data_ptr(), zy.data_ptr(), st)
         ev = getattr(self, "sweep_events", None)
         if ev is not None:
@@ -402,6 +428,8 @@ class HierTCN:
             e0.record(torch.cuda.current_stream(self.device))
         fused = bool(topk) and ce and rank and not self.l2_normalize    # loss + rank + top-k: two catalog sweeps instead of three
         zy_fin = zy
+        if self.l2_normalize and self.head_planes > 1:
+            raise NotImplementedError("l2_normalize with a 256-channel last level")
         if self.l2_normalize and flags:
             # l2-normalised head (model_tcn.py:42-43): CE on row_scale * z with row_scale = 1/||z|| from the catalog's Gram
             # matrix; ranks are invariant under the positive scale
@@ -414,18 +442,18 @@ class HierTCN:
                       self.b_out.data_ptr(), self.N, 0, scores.y_rows.data_ptr(), zy.data_ptr(), rs.data_ptr(), ns,
                       pm.data_ptr(), ps.data_ptr(), pc.data_ptr(), zy_fin.data_ptr(), st)
         elif fused:
-            nbytes = int(cabi.load().htcn_topk_workspace_bytes(self.act_dtype, Q, self.N, topk, ns))
+            nbytes = int(cabi.load().htcn_topk_workspace_bytes(self.k4_dtype, Q, self.N, topk, ns))
             ws = self._buf("topk_ws", (nbytes,), torch.uint8)
             ov = torch.empty((Q, topk), dtype=f32, device=self.device)
             oi = torch.empty((Q, topk), dtype=i32, device=self.device)
             ovf = torch.zeros(1, dtype=i32, device=self.device)
-            cabi.call("htcn_score_ce_rank_topk_fused", scores.hout.data_ptr(), self.act_dtype, Q, self.wt.data_ptr(),
+            cabi.call("htcn_score_ce_rank_topk_fused", scores.hout.data_ptr(), self.k4_dtype, Q, self.wt.data_ptr(),
                       self.b_out.data_ptr(), self.N, 0, scores.y_rows.data_ptr(), zy.data_ptr(), topk, ns, ws.data_ptr(),
                       nbytes, P(pm), P(ps), P(pc), ov.data_ptr(), oi.data_ptr(), ovf.data_ptr(), st)
             out.update(topk_val=ov, topk_idx=oi)
             self._topk_overflow = ovf
         elif flags:
-            cabi.call("htcn_score_ce_rank_topk", scores.hout.data_ptr(), self.act_dtype, Q, self.wt.data_ptr(),
+            cabi.call("htcn_score_ce_rank_topk", scores.hout.data_ptr(), self.k4_dtype, Q, self.wt.data_ptr(),
                       self.b_out.data_ptr(), self.N, 0, scores.y_rows.data_ptr(), zy.data_ptr(), 1,
                       flags, 0, ns, P(pm), P(ps), P(pc), None, None, st)
             cabi.note_launches(-1)      # have_target=1: the sweep call launched one kernel, not two
@@ -439,7 +467,7 @@ class HierTCN:
                       scores.y_rows.data_ptr(), zy_fin.data_ptr(), P(loss_row), P(rank_row), st)
             if ce and self.precision == "bf16" and self.n_out == self.N and not self.l2_normalize:
                 # rows whose target is > 88 nats below the best logit overflow the target-referenced partial sum: redo them
-                cabi.call("htcn_score_ce_repair", scores.hout.data_ptr(), self.act_dtype, Q, self.wt.data_ptr(), self.N,
+                cabi.call("htcn_score_ce_repair", scores.hout.data_ptr(), self.k4_dtype, Q, self.wt.data_ptr(), self.N,
                           zy.data_ptr(), loss_row.data_ptr(), None, st)
             out.update(loss_row=loss_row, rank_row=rank_row, target_logit=zy_fin)
         if fused and int(self._topk_overflow.item()):          # pathological ties overflowed a candidate list
@@ -483,17 +511,17 @@ class HierTCN:
         f32, i32 = torch.float32, torch.int32
         tiles_q = max(1, math.ceil(Q / 128))
         ns = int(max(1, min(math.ceil(2 * 148 / tiles_q), 32, max(1, self.n_out // 256))))
-        nbytes = int(cabi.load().htcn_topk_workspace_bytes(self.act_dtype, Q, self.n_out, k, ns))
+        nbytes = int(cabi.load().htcn_topk_workspace_bytes(self.k4_dtype, Q, self.n_out, k, ns))
         ws = self._buf("topk_ws", (nbytes,), torch.uint8)
         ov = torch.empty((Q, k), dtype=f32, device=self.device)
         oi = torch.empty((Q, k), dtype=i32, device=self.device)
         ovf = torch.zeros(1, dtype=i32, device=self.device)
-        cabi.call("htcn_score_topk", hout.data_ptr(), self.act_dtype, Q, self.wt.data_ptr(), self.b_out.data_ptr(), self.n_out,
+        cabi.call("htcn_score_topk", hout.data_ptr(), self.k4_dtype, Q, self.wt.data_ptr(), self.b_out.data_ptr(), self.n_out,
                   n0, k, ns, ws.data_ptr(), nbytes, ov.data_ptr(), oi.data_ptr(), ovf.data_ptr(), self.stream_ptr())
         if int(ovf.item()):                                   # pathological ties: exact heap path
             tv = torch.empty((ns, Q, k), dtype=f32, device=self.device)
             ti = torch.empty((ns, Q, k), dtype=i32, device=self.device)
-            cabi.call("htcn_score_ce_rank_topk", hout.data_ptr(), self.act_dtype, Q, self.wt.data_ptr(), self.b_out.data_ptr(),
+            cabi.call("htcn_score_ce_rank_topk", hout.data_ptr(), self.k4_dtype, Q, self.wt.data_ptr(), self.b_out.data_ptr(),
                       self.n_out, n0, None, None, 1, cabi.SCORE_TOPK, k, ns, None, None, None, tv.data_ptr(), ti.data_ptr(),
                       self.stream_ptr())
             cabi.call("htcn_topk_merge", tv.data_ptr(), ti.data_ptr(), ns, Q, k, ov.data_ptr(), oi.data_ptr(), self.stream_ptr())
@@ -540,6 +568,8 @@ class HierTCN:
         scores.check_fresh()
         if self.n_out != self.N:
             raise cabi.HtcnError("sampled_loss gathers rows of the whole output table; this model holds a catalog shard")
+        if self.head_planes > 1:
+            raise NotImplementedError("sampled ranking losses with a 256-channel last level")
         a = self.args
         kind = kind or (a.loss if a.loss in cabi.LOSS_KINDS else "hinge_logsigmoid")
         if kind not in cabi.LOSS_KINDS:

@@ -5,9 +5,10 @@ BASELINE config 3: low-level TCN only, long sequences, dilations 1-2-4-8).
 
 on the same kernels as the hierarchical path: K1 gathers the rows of ``tcn/emb/kernel`` (id 0 -> zeros), K2 runs the
 conv stack (its in-projection is fed the identity, because here the 'emb' dense IS the gather), K4 scores the
-catalog.  Levels up to 128 channels (narrower ones run zero-padded, width changes get the 1x1 down-sample residual of
-customized_tcn_cell.py:102-106); the reference's default single-level stack ends with two 256-channel levels
-(args.py:310-311), which the 128-wide kernels do not run -- config 3 uses [128]*4.
+catalog.  Levels narrower than 128 channels run zero-padded, width changes get the 1x1 down-sample residual of
+customized_tcn_cell.py:102-106; levels of 129..256 channels -- the reference's default single-level stack is
+[128,128,128,128,256,256] (args.py:310-311) -- run as two 128-wide planes on the fp32 kernels (precision='f32' only; the
+tcgen05 tier is built for levels up to 128 channels, config 3 uses [128]*4).
 """
 from __future__ import annotations
 
@@ -27,8 +28,11 @@ class TCN(HierTCN):
     def __init__(self, args, weights, device=None, precision=None, scope="tcn"):
         self.args = args
         self.precision = precision or getattr(args, "precision", "bf16")
-        if max(args.tcn_channel) > 128:
-            raise NotImplementedError("tcn_channel above 128: the sm_100a kernels run 128-wide blocks")
+        if max(args.tcn_channel) > 256:
+            raise NotImplementedError("tcn_channel above 256")
+        if max(args.tcn_channel) > 128 and self.precision != "f32":
+            raise NotImplementedError("tcn_channel above 128 (the reference's single-level default ends with two 256-channel "
+                                      "levels, args.py:310-311) needs precision='f32': two-plane fp32 kernels")
         self.N = int(args.item_num)
         self.K = int(args.kernel_size)
         self.n_levels = len(args.tcn_channel)
@@ -58,13 +62,7 @@ class TCN(HierTCN):
         self.ds_b = [up(lay[f"ds_b{l}"]) if meta["ds"][l] else None for l in range(self.n_levels)]
         self.b_out = up(lay["b_out"])
         w_out = up(lay["w_out"])
-        self.act_dtype = cabi.HTCN_BF16 if self.precision == "bf16" else cabi.HTCN_F32
-        self.act_torch_dtype = torch.bfloat16 if self.precision == "bf16" else torch.float32
-        self.n_out = int(w_out.shape[1])
-        pitch = cabi.WT_PITCH_BF16 if self.precision == "bf16" else D
-        self.wt = torch.empty((self.n_out, pitch), dtype=self.act_torch_dtype, device=self.device)
-        cabi.call("htcn_prepare_wout", w_out.data_ptr(), self.b_out.data_ptr(), self.n_out, self.wt.data_ptr(),
-                  self.act_dtype, self.stream_ptr())
+        self._finish_build_head(w_out, meta)
         self.wt_f32 = self.wt if self.precision == "f32" else None
         torch.cuda.synchronize(self.device)
         self.refresh_pointer_tables()
@@ -91,8 +89,15 @@ class TCN(HierTCN):
         xe = self._buf("xe", (B * L, D), self.act_torch_dtype)
         cabi.call("htcn_gather_meanpool", self.E.data_ptr(), D, None, self.N, x_d.data_ptr(), None, slot_p, B, L, 1,
                   xe.data_ptr(), self.act_dtype, None, st)
-        hout = self._buf("hout", (max(Q, 1), D), self.act_torch_dtype)
+        hout = self._buf("hout", (self.head_planes * max(Q, 1), D), self.act_torch_dtype)
         prec = self._k2_precision()
+        if self.wide:
+            scratch = self._buf("k2_scratch", (6 * B * L, D), torch.float32)
+            planes_p, planes_keep = cabi.int_array(self.level_planes)
+            cabi.call("htcn_tcn_forward_wide", xe.data_ptr(), self.act_dtype, self.w_in_x.data_ptr(), None, self._conv_w_pp[0],
+                      self._conv_b_pp[0], self._ds_w_pp[0], self._ds_b_pp[0], planes_p, self.n_levels, self.K, slot_p, B, L, 1,
+                      row_d.data_ptr(), hout.data_ptr(), max(Q, 1), scratch.data_ptr(), st)
+            return CatalogScores(self, hout, Q, row_d, yrows_d, y_d, B, L)
         if prec == cabi.HTCN_F32:
             scratch = self._buf("k2_scratch", ((3 if self.has_ds else 2) * B * L, D), torch.float32)
         else:

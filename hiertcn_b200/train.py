@@ -36,6 +36,8 @@ class HierTCNTrainer:
         self.bf16 = model.precision == "bf16"
         if model.n_out != model.N:
             raise NotImplementedError("training with a catalog-sharded output table")
+        if getattr(model, "wide", False):
+            raise NotImplementedError("training with tcn_channel above 128 (the two-plane fp32 kernels are forward only)")
         if model.l2_normalize:
             raise NotImplementedError("training through the l2-normalised head (model_tcn.py:42-43): evaluation only")
         self.m, self.dist, self.world = model, dist, int(world)

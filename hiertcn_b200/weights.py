@@ -171,9 +171,16 @@ def layout_meta(w, scope="hier"):
         m["H"] = int(w["hier/multi_rnn_cell/cell_0/gru_cell/candidate/kernel"].shape[1]) if G else PAD
     else:
         m["ed"], m["G"], m["H"] = PAD, 0, PAD
-    for name, v in (("emb_dim", m["ed"]), ("hidden_dim", m["H"])) + tuple(("tcn_channel", c) for c in chans):
+    for name, v in (("emb_dim", m["ed"]), ("hidden_dim", m["H"])):
         if v > PAD:
             raise NotImplementedError("%s = %d: widths above 128 are not built (the kernels run 128-wide blocks)" % (name, v))
+    for c in chans:
+        if c > 2 * PAD:
+            raise NotImplementedError("tcn_channel = %d: at most 256 (two 128-wide planes, fp32 tier)" % c)
+    # 128-wide planes per level output (1, or 2 for the 129..256-channel levels of args.py:310-311); the in-projection
+    # always produces 128 channels (model_tcn.py:35)
+    m["planes"] = [-(-c // PAD) for c in chans]
+    m["wide"] = any(p > 1 for p in m["planes"])
     return m
 
 
@@ -199,14 +206,22 @@ def to_device_layout(w, scope="hier"):
         d["E"] = np.ascontiguousarray(w[tcn + "/emb/kernel"], np.float32)    # the 'emb' dense applied to a one-hot = a gather
         d["b_emb"] = np.zeros(PAD, np.float32)
         d["w_in_x"] = np.eye(PAD, dtype=np.float32)
+    pin = 1
     for l, c in enumerate(m["channels"]):
         p = f"{tcn}/temporal_conv_net/tblock_{l}"
         k = w[p + "/conv1/kernel"]
-        kw = np.zeros((k.shape[0], PAD, PAD), np.float32)
-        kw[:, :k.shape[1], :k.shape[2]] = k
-        d[f"conv_w{l}"], d[f"conv_b{l}"] = kw, _pad1(w[p + "/conv1/bias"], PAD)
+        pout = m["planes"][l]
+        if pin == 1 and pout == 1:
+            kw = np.zeros((k.shape[0], PAD, PAD), np.float32)
+            kw[:, :k.shape[1], :k.shape[2]] = k
+        else:
+            kw = _plane_blocks(k, pin, pout)           # [pout, pin*K, 128, 128]
+        d[f"conv_w{l}"], d[f"conv_b{l}"] = kw, _pad1(w[p + "/conv1/bias"], pout * PAD)
         if m["ds"][l]:
-            d[f"ds_w{l}"], d[f"ds_b{l}"] = _pad2(w[p + "/dense/kernel"], PAD, PAD), _pad1(w[p + "/dense/bias"], PAD)
+            dk = w[p + "/dense/kernel"]
+            d[f"ds_w{l}"] = _pad2(dk, PAD, PAD) if pin == 1 and pout == 1 else _plane_blocks(dk[None], pin, pout)
+            d[f"ds_b{l}"] = _pad1(w[p + "/dense/bias"], pout * PAD)
+        pin = pout
     for g in range(G):
         p = f"hier/multi_rnn_cell/cell_{g}/gru_cell"
         inp = ed if g == 0 else H
@@ -220,9 +235,30 @@ def to_device_layout(w, scope="hier"):
         d[f"gate_w{g}"], d[f"gate_b{g}"], d[f"cand_w{g}"], d[f"cand_b{g}"] = GW, GB, CW, _pad1(cb, PAD)
     if tcn + "/dense/kernel" in w:
         wo = w[tcn + "/dense/kernel"]
-        d["w_out"] = _pad2(wo, PAD, wo.shape[1])
+        d["w_out"] = _pad2(wo, pin * PAD, wo.shape[1])
         d["b_out"] = np.ascontiguousarray(w[tcn + "/dense/bias"], np.float32)
     return d, m
+
+
+def _plane_blocks(k, pin, pout):
+    """TF conv kernel [K, Cin, Cout] -> [pout, pin*K, 128, 128]: block (po, pi*K + tap) = k[tap, pi*128.., po*128..]
+    zero-padded -- a level whose input has `pin` planes is run as pin*K taps over 128-wide planes"""
+    K = k.shape[0]
+    out = np.zeros((pout, pin * K, PAD, PAD), np.float32)
+    for po in range(pout):
+        for pi in range(pin):
+            blk = k[:, pi * PAD:(pi + 1) * PAD, po * PAD:(po + 1) * PAD]
+            out[po, pi * K:(pi + 1) * K, :blk.shape[1], :blk.shape[2]] = blk
+    return out
+
+
+def _unplane_blocks(b, K, cin, cout):
+    pout, pin = b.shape[0], b.shape[1] // K
+    k = np.zeros((K, pin * PAD, pout * PAD), np.float32)
+    for po in range(pout):
+        for pi in range(pin):
+            k[:, pi * PAD:(pi + 1) * PAD, po * PAD:(po + 1) * PAD] = b[po, pi * K:(pi + 1) * K]
+    return k[:, :cin, :cout]
 
 
 def from_device_layout(d, m):
@@ -239,9 +275,13 @@ def from_device_layout(d, m):
     cin = PAD
     for l, c in enumerate(m["channels"]):
         p = f"{tcn}/temporal_conv_net/tblock_{l}"
-        w[p + "/conv1/kernel"], w[p + "/conv1/bias"] = d[f"conv_w{l}"][:, :cin, :c], d[f"conv_b{l}"][:c]
+        cw = d[f"conv_w{l}"]
+        w[p + "/conv1/kernel"] = cw[:, :cin, :c] if cw.ndim == 3 else _unplane_blocks(cw, m["K"], cin, c)
+        w[p + "/conv1/bias"] = d[f"conv_b{l}"][:c]
         if m["ds"][l]:
-            w[p + "/dense/kernel"], w[p + "/dense/bias"] = d[f"ds_w{l}"][:cin, :c], d[f"ds_b{l}"][:c]
+            dw = d[f"ds_w{l}"]
+            w[p + "/dense/kernel"] = dw[:cin, :c] if dw.ndim == 2 else _unplane_blocks(dw, 1, cin, c)[0]
+            w[p + "/dense/bias"] = d[f"ds_b{l}"][:c]
         cin = c
     if "w_out" in d or "wt" in d:
         wo = d["w_out"] if "w_out" in d else np.ascontiguousarray(d["wt"].T)

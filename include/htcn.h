@@ -44,7 +44,11 @@ typedef enum {
   HTCN_ERR_UNSUPPORTED = -3   /* valid request this build does not implement          */
 } htcn_status;
 
-typedef enum { HTCN_F32 = 0, HTCN_BF16 = 1 } htcn_dtype;
+/* HTCN_F32_W256: fp32 tier with 256-wide user embeddings (the last TCN level has 129..256 channels, e.g. the reference's
+ * single-level default [128,128,128,128,256,256], args.py:310-311): hout is block-planar [2][Q][128], w_out_t rows are 256
+ * floats.  Accepted as `precision` / dtype by htcn_prepare_wout, htcn_target_logit, htcn_score_ce_rank_topk (k <= 64 with
+ * HTCN_SCORE_TOPK), htcn_score_logits (hout_dtype; w_dtype must be HTCN_F32), htcn_score_topk, htcn_score_ce_rank_topk_fused. */
+typedef enum { HTCN_F32 = 0, HTCN_BF16 = 1, HTCN_F32_W256 = 2 } htcn_dtype;
 
 /* flags of htcn_score_ce_rank_topk */
 #define HTCN_SCORE_CE   1u    /* softmax cross-entropy partials            (loss.py:20-21)   */
@@ -140,6 +144,20 @@ int32_t htcn_tcn_forward(const void* xe, int32_t xe_dtype, int32_t precision,
                          int32_t B, int32_t T, int32_t S,
                          const int32_t* out_row, void* hout, int32_t hout_dtype, float* scratch,
                          void* stream);
+
+/* The fp32 conv stack with levels up to 256 channels wide (customized_tcn_cell.py:109-127 with n_outputs in 129..256):
+ * activations are block-planar [P][B*T][128]; level_planes_host[l] in {1, 2} = 128-wide planes of level l's output (the
+ * in-projection always produces one); conv_w_host[l] -> [P_out, P_in*K, 128, 128] f32 (block (po, pi*K + tap) =
+ * W[tap][pi*128.., po*128..] zero-padded), conv_b_host[l] -> [P_out*128]; ds_w_host[l] -> [P_out, P_in, 128, 128],
+ * ds_b_host[l] -> [P_out*128] (required where the plane count changes) -- the layouts hiertcn_b200.weights.to_device_layout
+ * produces.  hout: [P_last][hout_plane_rows][128] f32 (compacted through out_row).  scratch: 6*B*T*128 floats.
+ * fp32 tier only; the tcgen05 tier runs levels up to 128 channels. */
+int32_t htcn_tcn_forward_wide(const void* xe, int32_t xe_dtype, const float* w_in_x, const float* sbias,
+                              const float* const* conv_w_host, const float* const* conv_b_host,
+                              const float* const* ds_w_host, const float* const* ds_b_host,
+                              const int32_t* level_planes_host, int32_t n_levels, int32_t kernel_size,
+                              const int32_t* slot_off_host, int32_t B, int32_t T, int32_t S, const int32_t* out_row,
+                              float* hout, int64_t hout_plane_rows, float* scratch, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * weight preparation for K4 (one-time, at load): w_out [128,N] f32 + b_out [N] f32 (the TF layout of

@@ -302,6 +302,61 @@ def test_single_level_model_tcn(B, L, levels, precision):
         assert (np.abs(r["ranks"].cpu().numpy() - met[6]) <= amb).all()
 
 
+@pytest.mark.parametrize("channels,K,L", [((128, 128, 128, 128, 256, 256), 5, 150), ((200, 256, 96), 3, 33), ((128, 256, 128), 5, 40)])
+def test_single_level_tcn_with_256_channel_levels(channels, K, L):
+    """the reference's single-level default stack [128,128,128,128,256,256] (args.py:310-311; dilations up to 32) and other
+    stacks with 129..256-channel levels: two 128-wide planes on the fp32 kernels (down-sample residual where the width
+    changes, K = 256 contraction in the scoring head), against the fp64 oracle -- logits, CE, ranks, top-k"""
+    from hiertcn_b200.args import make_args
+    from hiertcn_b200.model_tcn import TCN
+    from hiertcn_b200.weights import init_weights, tcn_weight_shapes
+    N, B = 301, 4
+    w = init_weights(tcn_weight_shapes(N, channels, K, output_dim=N), seed=5, kernel_scale=1.5, bias_noise=0.1)
+    rng = np.random.default_rng(L)
+    x = rng.integers(1, N, size=(B, L))
+    x[:, 0] = 0
+    n = rng.integers(1, L + 1, size=B)
+    y = np.where(np.arange(L)[None, :] < n[:, None], rng.integers(1, N, size=(B, L)), 0)
+    a = make_args(["--item_num", str(N), "--tcn_channel", ",".join(str(c) for c in channels), "--kernel_size", str(K)])
+    with pytest.raises(NotImplementedError):
+        TCN(a, w, precision="bf16")
+    model = TCN(a, w, precision="f32").build()
+    scores = model.forward(x, y)
+    pred64 = O.model_tcn(O.one_hot_signed(x, N, np.float64), {k: v.astype(np.float64) for k, v in w.items()}, "tcn", "f64")
+    loss, loss_bt, mask_y, act, uc, pred_m = O.hier_loss(pred64, y)
+    met = O.calc_metric_fast(pred_m, mask_y, act, uc, y)
+    scale = np.abs(pred_m).max()
+    np.testing.assert_allclose(scores.materialize(), pred_m, rtol=1e-4, atol=1e-4 * scale)
+    r = model.loss(scores, metrics=True, per_position=True)
+    sc = r["scalars"].cpu().numpy()
+    assert abs(sc[0] - loss) <= 1e-4 * abs(loss)
+    np.testing.assert_allclose(r["loss_bt"].cpu().numpy(), loss_bt, rtol=1e-4, atol=1e-4)
+    amb = O.rank_ambiguity(pred_m, y, 2e-5) * (y > 0)
+    assert (np.abs(r["ranks"].cpu().numpy() - met[6]) <= amb).all()
+    tk = model.score(scores, ce=False, rank=False, topk=20)
+    zv = pred64.reshape(-1, N)[y.reshape(-1) > 0]
+    v_ref, i_ref = O.top_k(zv, 20)
+    np.testing.assert_allclose(tk["topk_val"].cpu().numpy(), v_ref, rtol=1e-4, atol=1e-4 * scale)
+    assert np.mean(tk["topk_idx"].cpu().numpy() == i_ref) > 0.98
+
+
+def test_hier_with_a_256_channel_level():
+    """model_hier with tcn_channel = [128, 256] (fp32 tier): conditioned TCN + GRU + 256-wide scoring head vs the oracle"""
+    from hiertcn_b200.args import make_args
+    from hiertcn_b200.model_hier import HierTCN
+    x, y, m, s0, w = small_case(B=6, S=3, L=9, N=211, seed=31, tcn_channel=(128, 256), kernel_size=5)
+    ref = O.forward_loss_metrics(x, y, m, s0, w, 2, "f64")
+    a = make_args(["--item_num", "211", "--tcn_channel", "128,256"])
+    model = HierTCN(a, w, precision="f32").build()
+    out = model.step(x, y, m, s0, per_position=True, topk=10)
+    assert abs(out["loss"] - ref["loss"]) <= 1e-4 * abs(ref["loss"])
+    np.testing.assert_allclose(out["state"], ref["state"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(out["loss_bt"], ref["loss_bt"], rtol=1e-4, atol=2e-5)
+    y_id = np.concatenate(y, 1).astype(np.int64)
+    amb = O.rank_ambiguity(ref["pred"], y_id, 2e-5) * (y_id > 0)
+    assert (np.abs(out["ranks"] - ref["ranks"]) <= amb).all()
+
+
 @pytest.mark.parametrize("precision", ["f32", "bf16"])
 def test_device_batcher_equals_host_loader(precision):
     """batches assembled in HBM (htcn_assemble_batch, fixed slot width) == the queue loader's host batches: same loss,
