@@ -433,6 +433,43 @@ def debug_logits_bf16(lib, hd, wt, bd):
     return out
 
 
+@pytest.mark.parametrize("Q,N,n_split", [(130, 2000, 3), (5, 77, 1)])
+def test_k4_f32_256_wide_embeddings(lib, Q, N, n_split):
+    """HTCN_F32_W256: user embeddings of a 256-channel last level (block-planar [2][Q][128]), table rows of 256 floats;
+    logits / CE / strict rank / top-k vs numpy float64"""
+    rng = np.random.default_rng(Q + N)
+    h = rng.normal(size=(Q, 256)).astype(np.float32)
+    w_out = (rng.normal(size=(256, N)) * 0.2).astype(np.float32)
+    b_out = (rng.normal(size=N) * 0.2).astype(np.float32)
+    y = rng.integers(1, N, size=Q).astype(np.int32)
+    k = 32
+    W = lib.HTCN_F32_W256
+    wt = torch.empty((N, 256), dtype=torch.float32, device="cuda")
+    w_out_d, bd, yd = dev(w_out), dev(b_out), dev(y)
+    lib.call("htcn_prepare_wout", P(w_out_d), P(bd), N, P(wt), W, None)
+    np.testing.assert_array_equal(wt.cpu().numpy(), w_out.T)
+    hp = dev(np.ascontiguousarray(np.stack([h[:, :128], h[:, 128:]])))          # planes
+    z = h.astype(np.float64) @ w_out.astype(np.float64) + b_out
+    lg = torch.empty((Q, N), dtype=torch.float32, device="cuda")
+    lib.call("htcn_score_logits", P(hp), W, Q, P(wt), lib.HTCN_F32, P(bd), N, P(lg), None)
+    np.testing.assert_allclose(lg.cpu().numpy(), z, rtol=1e-4, atol=1e-4)
+    zy, pm, ps, pc, tv, ti = run_score(lib, hp.view(2 * Q, 128)[:Q], wt, bd, yd, lib.SCORE_CE | lib.SCORE_RANK | lib.SCORE_TOPK, k,
+                                       n_split, precision=W)
+    np.testing.assert_allclose(zy.cpu().numpy(), z[np.arange(Q), y], rtol=1e-4, atol=1e-4)
+    loss_row = torch.empty(Q, dtype=torch.float32, device="cuda")
+    rank_row = torch.empty(Q, dtype=torch.float32, device="cuda")
+    lib.call("htcn_score_finish", P(pm), P(ps), P(pc), n_split, Q, P(yd), P(zy), P(loss_row), P(rank_row), None)
+    ref_loss = O.softmax_cross_entropy_with_logits(y, z)
+    np.testing.assert_allclose(loss_row.cpu().numpy(), ref_loss, rtol=1e-4, atol=1e-4)
+    z_gpu = lg.cpu().numpy()
+    np.testing.assert_array_equal(rank_row.cpu().numpy(), (z_gpu > zy.cpu().numpy()[:, None]).sum(1))      # self-consistent
+    ov = torch.empty((Q, k), dtype=torch.float32, device="cuda")
+    oi = torch.empty((Q, k), dtype=torch.int32, device="cuda")
+    lib.call("htcn_topk_merge", P(tv), P(ti), n_split, Q, k, P(ov), P(oi), None)
+    v_ref, i_ref = O.top_k(z_gpu, min(k, N))
+    np.testing.assert_array_equal(oi.cpu().numpy()[:, :min(k, N)], i_ref)
+
+
 # epilogue variants of the fused CE+rank sweep (HTCN_K4_EPI): the default (= "4") is the packed f32x2 epilogue with 1/4 of
 # the exponentials on the FMA pipe (degree-3 polynomial, 1e-4 per term) and the STRICT FSET compare (rank == #{z > z_y} on
 # the swept logits, bit for bit); "304" = the opt-in sign-bit rank count (3.7% faster, may miss a logit one ulp above the

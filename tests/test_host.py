@@ -141,3 +141,22 @@ def test_device_layout_padding_is_exact_and_round_trips():
     assert np.array_equal(pad["pred"], ref["pred"]) and np.array_equal(unpad_state(pad["state"], meta), ref["state"])
     full = pad["state"].reshape(len(ref["state"]), 2, 128)
     assert (full[:, :, 16:] == 0).all(), "padded GRU units must stay exactly zero"
+
+
+def test_device_layout_two_plane_levels_round_trip():
+    """129..256-channel levels (the reference's single-level default [128,128,128,128,256,256], args.py:310-311) are laid
+    out as 128-wide planes: conv kernels as [P_out, P_in*K, 128, 128] blocks; the layout round-trips the TF shapes"""
+    from hiertcn_b200.args import make_args
+    from hiertcn_b200.weights import from_device_layout, init_weights, tcn_weight_shapes, to_device_layout
+    a = make_args(["--model_type", "tcn"])
+    assert list(a.tcn_channel) == [128, 128, 128, 128, 256, 256]
+    w = init_weights(tcn_weight_shapes(300, tuple(a.tcn_channel), 5, 300, "tcn"), seed=1, bias_noise=0.1)
+    lay, meta = to_device_layout(w, "tcn")
+    assert meta["planes"] == [1, 1, 1, 1, 2, 2] and meta["wide"] and meta["ds"] == [False] * 4 + [True, False]
+    assert lay["conv_w4"].shape == (2, 5, 128, 128) and lay["conv_w5"].shape == (2, 10, 128, 128)
+    assert lay["ds_w4"].shape == (2, 1, 128, 128) and lay["w_out"].shape == (256, 300)
+    # block (po, pi*K + tap) = W[tap][pi*128.., po*128..]
+    k5 = w["tcn/temporal_conv_net/tblock_5/conv1/kernel"]
+    assert np.array_equal(lay["conv_w5"][1, 5 + 2], k5[2, 128:256, 128:256])
+    back = from_device_layout(lay, meta)
+    assert set(back) == set(w) and all(np.array_equal(back[k], w[k]) for k in w)
