@@ -62,7 +62,7 @@ SIGNATURES = {
     "htcn_cast_transpose_bf16": [_p, _i, C.c_int64, _p, _p, C.c_int64, _p],
     "htcn_tcn_forward_train_bf16": [_p, _p, _p, _pp, _pp, _pp, _pp, _i, _i, _ip, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p],
     "htcn_tcn_forward_train": [_p, _p, _p, _pp, _pp, _pp, _pp, _i, _i, _ip, _i, _i, _i, _p, _p, _p, _p, _p, _p],
-    "htcn_tcn_backward": [_p, _p, _p, _i, _p, _pp, _pp, _i, _i, _ip, _i, _i, _i, _p, _p, _p, _p, _pp, _pp, _pp, _pp, _p, _p, _p, _p],
+    "htcn_tcn_backward": [_p, _p, _p, _i, _p, _pp, _pp, _i, _i, _ip, _i, _i, _i, _p, _p, _p, _p, _p, _pp, _pp, _pp, _pp, _p, _p, _p, _p],
     "htcn_gru_sessions_train": [_p, _p, _p, _pp, _pp, _pp, _pp, _i, _p, _i, _i, _p, _p, _p, _p, _p],
     "htcn_gru_backward": [_p, _p, _p, _p, _pp, _pp, _i, _p, _i, _i, _p, _p, _pp, _pp, _pp, _pp, _p, _p, _p],
     "htcn_gather_backward": [_p, _p, _p, _p, _ip, _i, _i, _i, _i, _p, _p, _p],
@@ -75,7 +75,8 @@ PLAIN = {"htcn_abi_version": (C.c_int32, []), "htcn_last_error": (C.c_char_p, []
          "htcn_topk_workspace_bytes": (C.c_int64, [_i, _i, _i, _i, _i]),
          "htcn_gru_backward_scratch_floats": (C.c_int64, [_i, _i, _i]),
          "htcn_batcher_scratch_ints": (C.c_int64, [_i, _i]),
-         "htcn_catalog_gram_scratch_floats": (C.c_int64, [])}
+         "htcn_catalog_gram_scratch_floats": (C.c_int64, []),
+         "htcn_tcn_backward_tc_scratch_bytes": (C.c_int64, [_i, _i, _i, _i, _i])}
 
 
 class HtcnError(RuntimeError):

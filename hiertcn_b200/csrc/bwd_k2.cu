@@ -152,7 +152,7 @@ extern "C" int32_t htcn_tcn_backward(const float* d_hout, const int32_t* out_row
                                      const float* const* ds_w_host, int32_t n_levels,
                                      int32_t kernel_size, const int32_t* slot_off_host, int32_t B, int32_t T, int32_t S,
                                      const float* dropout_scale, const void* h_save, const void* a_save, float* scratch,
-                                     float* const* d_conv_w_host, float* const* d_conv_b_host,
+                                     void* tc_scratch, float* const* d_conv_w_host, float* const* d_conv_b_host,
                                      float* const* d_ds_w_host, float* const* d_ds_b_host, float* d_w_in_x,
                                      float* d_sbias, float* d_xe, void* stream) {
   using namespace htcn;
@@ -173,6 +173,12 @@ extern "C" int32_t htcn_tcn_backward(const float* d_hout, const int32_t* out_row
   const long long R = (long long)B * T;
   float* dcur = scratch;                    // [R,128] gradient flowing down the stack
   float* dp = scratch + R * kDim;           // [R,128] gradient at the conv pre-activation
+  // tc_scratch != NULL: the weight gradients run on the tensor cores from zero-padded transposed bf16 copies of the
+  // activations (bwd_wgrad_bf16.cu) instead of the fp32 split-K products
+  const int P = n_levels > 0 ? (kernel_size - 1) * (1 << (n_levels - 1)) : 0;
+  const PadGeom pg = make_pad_geom(slots, B, T, P);
+  __nv_bfloat16* aT = reinterpret_cast<__nv_bfloat16*>(tc_scratch);
+  __nv_bfloat16* bT = aT ? aT + 128 * pg.Kp : nullptr;
   const int eb = ceil_div(R * 32, 256);
   rows_compact_kernel<<<eb, 256, 0, st>>>(R, out_row, reinterpret_cast<const float4*>(d_hout),
                                           reinterpret_cast<float4*>(dcur), 0);
@@ -190,17 +196,35 @@ extern "C" int32_t htcn_tcn_backward(const float* d_hout, const int32_t* out_row
                                                  dropout_scale ? dropout_scale + l * kDim : nullptr, n_levels * kDim, T, slots);
     HTCN_LAUNCH_CHECK("relu_bwd_kernel");
     const int dil = 1 << l;
-    for (int tap = 0; tap < kernel_size; ++tap) {
-      rc = sgemm_tn_atomic(R, h_l, kDim, dp, kDim, d_conv_w_host[l] + (long long)tap * kDim * kDim, kDim,
-                           (kernel_size - 1 - tap) * dil, T, &slots, st, bf);
+    if (aT) {
+      rc = pad_transpose_bf16(h_l, bf, pg, aT, st);
       if (rc) return rc;
+      rc = pad_transpose_bf16(dp, false, pg, bT, st);
+      if (rc) return rc;
+      int shifts[8];
+      for (int tap = 0; tap < kernel_size; ++tap) shifts[tap] = (kernel_size - 1 - tap) * dil;
+      rc = wgrad_bf16(aT, bT, pg.Kp, shifts, kernel_size, d_conv_w_host[l], st);
+      if (rc) return rc;
+    } else {
+      for (int tap = 0; tap < kernel_size; ++tap) {
+        rc = sgemm_tn_atomic(R, h_l, kDim, dp, kDim, d_conv_w_host[l] + (long long)tap * kDim * kDim, kDim,
+                             (kernel_size - 1 - tap) * dil, T, &slots, st, bf);
+        if (rc) return rc;
+      }
     }
     rc = colsum_atomic(R, dp, kDim, kDim, d_conv_b_host[l], st);
     if (rc) return rc;
     const float* resid = dcur;                  // identity residual: dL/dh_l = ds + ...
     if (ds_w_host && ds_w_host[l]) {            // down-sample residual: dWds += h_l^T ds, dbds += colsum(ds), ds Wds^T + ...
       HTCN_REQUIRE(d_ds_w_host && d_ds_w_host[l] && d_ds_b_host && d_ds_b_host[l], "tcn_backward: down-sample gradient pointers NULL");
-      rc = sgemm_tn_atomic(R, h_l, kDim, dcur, kDim, d_ds_w_host[l], kDim, 0, T, nullptr, st, bf);
+      if (aT) {                                  // aT still holds h_l^T
+        const int zero = 0;
+        rc = pad_transpose_bf16(dcur, false, pg, bT, st);
+        if (rc) return rc;
+        rc = wgrad_bf16(aT, bT, pg.Kp, &zero, 1, d_ds_w_host[l], st);
+      } else {
+        rc = sgemm_tn_atomic(R, h_l, kDim, dcur, kDim, d_ds_w_host[l], kDim, 0, T, nullptr, st, bf);
+      }
       if (rc) return rc;
       rc = colsum_atomic(R, dcur, kDim, kDim, d_ds_b_host[l], st);
       if (rc) return rc;
@@ -216,9 +240,25 @@ extern "C" int32_t htcn_tcn_backward(const float* d_hout, const int32_t* out_row
     rc = k2_level_launch(a, slots, st);
     if (rc) return rc;
   }
-  rc = sgemm_tn_atomic(R, xe, kDim, dcur, kDim, d_w_in_x, kDim, 0, T, nullptr, st, bf);
+  if (aT) {
+    const int zero = 0;
+    rc = pad_transpose_bf16(xe, bf, pg, aT, st);
+    if (rc) return rc;
+    rc = pad_transpose_bf16(dcur, false, pg, bT, st);
+    if (rc) return rc;
+    rc = wgrad_bf16(aT, bT, pg.Kp, &zero, 1, d_w_in_x, st);
+  } else {
+    rc = sgemm_tn_atomic(R, xe, kDim, dcur, kDim, d_w_in_x, kDim, 0, T, nullptr, st, bf);
+  }
   if (rc) return rc;
   slot_sum_kernel<<<dim3(B, S), kDim, 0, st>>>(dcur, B, T, slots, d_sbias);
   HTCN_LAUNCH_CHECK("slot_sum_kernel");
   return sgemm(true, R, kDim, kDim, dcur, kDim, w_in_x, kDim, d_xe, kDim, false, st);
+}
+
+
+extern "C" int64_t htcn_tcn_backward_tc_scratch_bytes(int32_t B, int32_t T, int32_t S, int32_t n_levels, int32_t kernel_size) {
+  const long long P = n_levels > 0 ? (long long)(kernel_size - 1) * (1 << (n_levels - 1)) : 0;
+  const long long Kp = ((long long)B * (T + (long long)S * P) + 63) / 64 * 64;
+  return 2 * 128 * Kp * 2;
 }

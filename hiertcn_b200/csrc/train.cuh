@@ -57,6 +57,19 @@ int32_t sgemm(bool trans_b, long long M, int N, int K, const float* A, int lda, 
 int32_t sgemm_tn_atomic(long long R, const void* A, int lda, const float* D, int ldd, float* C, int ldc, int shift,
                         int T, const SlotTable* slots, cudaStream_t st, bool a_bf16 = false);
 
+// ---- tensor-core weight gradients (bwd_wgrad_bf16.cu) ----
+// zero-padded, transposed bf16 copy of a [B*T,128] activation: [128][Kp], every sequence preceded by P zero columns
+struct PadGeom {
+  int n_slots, B, T, P;
+  int off[HTCN_MAX_SLOTS + 1];
+  long long base[HTCN_MAX_SLOTS + 1];    // first column of slot s
+  long long Kp;                          // columns, multiple of 64
+};
+PadGeom make_pad_geom(const SlotTable& slots, int B, int T, int P);
+int32_t pad_transpose_bf16(const void* src, bool src_bf16, const PadGeom& g, void* dst, cudaStream_t st);
+// dW[t][cin][cout] += sum_col aT[cin][col - shifts[t]] * bT[cout][col]; aT, bT bf16 [128][Kp]; dW fp32, atomics
+int32_t wgrad_bf16(const void* aT, const void* bT, long long Kp, const int* shifts, int n_taps, float* dW, cudaStream_t st);
+
 // out[f] += sum_r D[r, f]  (f < cols, cols <= 256)
 int32_t colsum_atomic(long long R, const float* D, int ldd, int cols, float* out, cudaStream_t st);
 

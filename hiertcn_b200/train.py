@@ -281,9 +281,14 @@ class HierTCNTrainer:
         d_sbias = buf("tr_d_sbias", (S, B, D), f32)
         d_xe = buf("tr_d_xe", (R, D), f32)
         k2_scratch = buf("tr_k2_scratch", (3 if m.has_ds else 2, R, D), f32)
+        # bf16 tier: weight gradients of the conv stack on the tensor cores (set self.wgrad_tcgen05 = False for the fp32
+        # split-K products); the relu gates stay those of the fp32 forward, only the products round their operands to bf16
+        tc = None
+        if self.bf16 and getattr(self, "wgrad_tcgen05", True):
+            tc = buf("tr_k2_tc_scratch", (int(cabi.load().htcn_tcn_backward_tc_scratch_bytes(B, T, S, L, K)),), torch.uint8)
         cabi.call("htcn_tcn_backward", d_hout.data_ptr(), d["row_of"].data_ptr(), xe.data_ptr(), sdt_c, m.w_in_x.data_ptr(),
                   m._conv_w_pp[0], m._ds_w_pp[0], L, K, slot_p, B, T, S, P(drop), h_save.data_ptr(), a_save.data_ptr(),
-                  k2_scratch.data_ptr(), self._d_conv_w[0], self._d_conv_b[0], self._d_ds_w[0], self._d_ds_b[0],
+                  k2_scratch.data_ptr(), P(tc), self._d_conv_w[0], self._d_conv_b[0], self._d_ds_w[0], self._d_ds_b[0],
                   self.g["w_in_x"].data_ptr(), d_sbias.data_ptr(), d_xe.data_ptr(), st)
         cabi.note_launches(1 + L * (K + 3) + 3)
         d_yp = buf("tr_d_yp", (S, B, D), f32)

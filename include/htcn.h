@@ -400,12 +400,17 @@ int32_t htcn_tcn_forward_train_bf16(const void* xe, const float* w_in_x, const f
  * xe, h_save, a_save are of save_dtype (HTCN_F32 from htcn_tcn_forward_train, HTCN_BF16 from ..._train_bf16); the
  * gradients are fp32.  scratch: 2*B*T*128 floats (3*B*T*128 with a down-sample level).  d_conv_w[l] [K,128,128],
  * d_conv_b[l] [128], d_ds_w[l] [128,128], d_ds_b[l] [128] (levels with ds_w_host[l] != NULL), d_w_in_x [128,128]
- * accumulated; d_sbias [S,B,128] and d_xe [B*T,128] overwritten. */
+ * accumulated; d_sbias [S,B,128] and d_xe [B*T,128] overwritten.
+ * tc_scratch (device, htcn_tcn_backward_tc_scratch_bytes(...) bytes) or NULL: when given, the weight gradients
+ * dW[tap] = h[shifted]^T dp run on the tensor cores (tcgen05, bf16 operands, fp32 accumulation) from zero-padded
+ * transposed bf16 copies of the activations written into it; NULL = fp32 split-K products (the 1e-4 tier). */
+int64_t htcn_tcn_backward_tc_scratch_bytes(int32_t B, int32_t T, int32_t S, int32_t n_levels, int32_t kernel_size);
 int32_t htcn_tcn_backward(const float* d_hout, const int32_t* out_row, const void* xe, int32_t save_dtype,
                           const float* w_in_x, const float* const* conv_w_host, const float* const* ds_w_host,
                           int32_t n_levels, int32_t kernel_size,
                           const int32_t* slot_off_host, int32_t B, int32_t T, int32_t S, const float* dropout_scale,
-                          const void* h_save, const void* a_save, float* scratch, float* const* d_conv_w_host,
+                          const void* h_save, const void* a_save, float* scratch, void* tc_scratch,
+                          float* const* d_conv_w_host,
                           float* const* d_conv_b_host, float* const* d_ds_w_host, float* const* d_ds_b_host,
                           float* d_w_in_x, float* d_sbias, float* d_xe, void* stream);
 
