@@ -177,8 +177,10 @@ extern "C" int32_t htcn_tcn_backward(const float* d_hout, const int32_t* out_row
   // activations (bwd_wgrad_bf16.cu) instead of the fp32 split-K products
   const int P = n_levels > 0 ? (kernel_size - 1) * (1 << (n_levels - 1)) : 0;
   const PadGeom pg = make_pad_geom(slots, B, T, P);
-  __nv_bfloat16* aT = reinterpret_cast<__nv_bfloat16*>(tc_scratch);
-  __nv_bfloat16* bT = aT ? aT + 128 * pg.Kp : nullptr;
+  __nv_bfloat16* bT = reinterpret_cast<__nv_bfloat16*>(tc_scratch);     // dp^T; then one pre-shifted h^T per tap
+  __nv_bfloat16* aT = bT ? bT + 128 * pg.Kp : nullptr;
+  const long long a_stride = 128 * pg.Kp;
+  const int zero = 0;
   const int eb = ceil_div(R * 32, 256);
   rows_compact_kernel<<<eb, 256, 0, st>>>(R, out_row, reinterpret_cast<const float4*>(d_hout),
                                           reinterpret_cast<float4*>(dcur), 0);
@@ -197,13 +199,13 @@ extern "C" int32_t htcn_tcn_backward(const float* d_hout, const int32_t* out_row
     HTCN_LAUNCH_CHECK("relu_bwd_kernel");
     const int dil = 1 << l;
     if (aT) {
-      rc = pad_transpose_bf16(h_l, bf, pg, aT, st);
-      if (rc) return rc;
-      rc = pad_transpose_bf16(dp, false, pg, bT, st);
-      if (rc) return rc;
       int shifts[8];
       for (int tap = 0; tap < kernel_size; ++tap) shifts[tap] = (kernel_size - 1 - tap) * dil;
-      rc = wgrad_bf16(aT, bT, pg.Kp, shifts, kernel_size, d_conv_w_host[l], st);
+      rc = pad_transpose_bf16(h_l, bf, pg, shifts, kernel_size, aT, a_stride, st);
+      if (rc) return rc;
+      rc = pad_transpose_bf16(dp, false, pg, &zero, 1, bT, 0, st);
+      if (rc) return rc;
+      rc = wgrad_bf16(aT, a_stride, bT, pg.Kp, kernel_size, d_conv_w_host[l], st);
       if (rc) return rc;
     } else {
       for (int tap = 0; tap < kernel_size; ++tap) {
@@ -217,11 +219,10 @@ extern "C" int32_t htcn_tcn_backward(const float* d_hout, const int32_t* out_row
     const float* resid = dcur;                  // identity residual: dL/dh_l = ds + ...
     if (ds_w_host && ds_w_host[l]) {            // down-sample residual: dWds += h_l^T ds, dbds += colsum(ds), ds Wds^T + ...
       HTCN_REQUIRE(d_ds_w_host && d_ds_w_host[l] && d_ds_b_host && d_ds_b_host[l], "tcn_backward: down-sample gradient pointers NULL");
-      if (aT) {                                  // aT still holds h_l^T
-        const int zero = 0;
-        rc = pad_transpose_bf16(dcur, false, pg, bT, st);
+      if (aT) {                                  // the last tap's copy of h_l^T is the unshifted one
+        rc = pad_transpose_bf16(dcur, false, pg, &zero, 1, bT, 0, st);
         if (rc) return rc;
-        rc = wgrad_bf16(aT, bT, pg.Kp, &zero, 1, d_ds_w_host[l], st);
+        rc = wgrad_bf16(aT + (kernel_size - 1) * a_stride, a_stride, bT, pg.Kp, 1, d_ds_w_host[l], st);
       } else {
         rc = sgemm_tn_atomic(R, h_l, kDim, dcur, kDim, d_ds_w_host[l], kDim, 0, T, nullptr, st, bf);
       }
@@ -241,12 +242,11 @@ extern "C" int32_t htcn_tcn_backward(const float* d_hout, const int32_t* out_row
     if (rc) return rc;
   }
   if (aT) {
-    const int zero = 0;
-    rc = pad_transpose_bf16(xe, bf, pg, aT, st);
+    rc = pad_transpose_bf16(xe, bf, pg, &zero, 1, aT, a_stride, st);
     if (rc) return rc;
-    rc = pad_transpose_bf16(dcur, false, pg, bT, st);
+    rc = pad_transpose_bf16(dcur, false, pg, &zero, 1, bT, 0, st);
     if (rc) return rc;
-    rc = wgrad_bf16(aT, bT, pg.Kp, &zero, 1, d_w_in_x, st);
+    rc = wgrad_bf16(aT, a_stride, bT, pg.Kp, 1, d_w_in_x, st);
   } else {
     rc = sgemm_tn_atomic(R, xe, kDim, dcur, kDim, d_w_in_x, kDim, 0, T, nullptr, st, bf);
   }
@@ -260,5 +260,5 @@ extern "C" int32_t htcn_tcn_backward(const float* d_hout, const int32_t* out_row
 extern "C" int64_t htcn_tcn_backward_tc_scratch_bytes(int32_t B, int32_t T, int32_t S, int32_t n_levels, int32_t kernel_size) {
   const long long P = n_levels > 0 ? (long long)(kernel_size - 1) * (1 << (n_levels - 1)) : 0;
   const long long Kp = ((long long)B * (T + (long long)S * P) + 63) / 64 * 64;
-  return 2 * 128 * Kp * 2;
+  return (1 + (long long)(kernel_size > 1 ? kernel_size : 1)) * 128 * Kp * 2;     // dp^T + one pre-shifted h^T per tap
 }

@@ -6,9 +6,11 @@
 // that the fp32 split-K kernel (sgemm_tn_atomic) runs at FFMA speed -- 8.3 ms of the 49 ms step.  Here both operands are
 // first written TRANSPOSED and ZERO-PADDED as bf16 [128][Kp] (pad_transpose_bf16: every sequence is preceded by P = the
 // largest shift zero columns, so a shifted read can never reach the previous sequence -- the same physical-padding idea as
-// the forward conv kernel), which makes every tap a plain K-major x K-major tcgen05 GEMM whose A tile is the TMA box at
-// column k0 - shift (negative coordinates are zero-filled).  One CTA accumulates up to 3 taps (3 x 128 TMEM columns) over
-// its share of the columns and adds its partial to dW with float4 atomics.
+// the forward conv kernel).  The tap shift runs along the CONTRACTION (innermost, contiguous) dimension, and a TMA box must
+// start 16-byte aligned there (a box at column k0 - shift faults as an illegal instruction for odd shifts), so the A
+// operand is written once PER TAP, already shifted (pad_transpose reads a 64-column tile plus the largest shift once and
+// writes every tap's copy).  Every tap is then a plain K-major x K-major tcgen05 GEMM.  One CTA accumulates up to 3 taps
+// (3 x 128 TMEM columns) over its share of the columns and adds its partial to dW with float4 atomics.
 #include "train.cuh"
 #include "sm100.cuh"
 
@@ -31,11 +33,11 @@ struct alignas(1024) WgSmem {
 
 struct WgTaps {
   int n;
-  int shift[kWgMaxTaps];
 };
 
 __global__ void __launch_bounds__(kWgThreads, 1)
-wgrad_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int n_steps,
+wgrad_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant__ CUtensorMap tmap_a1,
+                  const __grid_constant__ CUtensorMap tmap_a2, const __grid_constant__ CUtensorMap tmap_b, int n_steps,
                   WgTaps taps, float* __restrict__ dW /* [taps.n][128][128], accumulated */) {
   extern __shared__ uint8_t smem_raw[];
   auto& sm = *reinterpret_cast<WgSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -43,7 +45,7 @@ wgrad_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const int s0 = (int)((long long)n_steps * blockIdx.x / gridDim.x);
   const int s1 = (int)((long long)n_steps * (blockIdx.x + 1) / gridDim.x);
   if (threadIdx.x == 0) {
-    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_a0);
     prefetch_tmap(&tmap_b);
     for (int s = 0; s < kWgStages; ++s) {
       mbar_init(&sm.full[s], 1);
@@ -66,7 +68,9 @@ wgrad_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         mbar_arrive_expect_tx(&sm.full[s], (uint32_t)((1 + taps.n) * kWgTile));
         const int k0 = i * 64;
         tma_load_2d(sm.b[s], &tmap_b, k0, 0, &sm.full[s]);
-        for (int t = 0; t < taps.n; ++t) tma_load_2d(sm.a[s][t], &tmap_a, k0 - taps.shift[t], 0, &sm.full[s]);
+        tma_load_2d(sm.a[s][0], &tmap_a0, k0, 0, &sm.full[s]);
+        if (taps.n > 1) tma_load_2d(sm.a[s][1], &tmap_a1, k0, 0, &sm.full[s]);
+        if (taps.n > 2) tma_load_2d(sm.a[s][2], &tmap_a2, k0, 0, &sm.full[s]);
       }
     }
   } else if (warp == 1) {
@@ -115,32 +119,48 @@ wgrad_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   }
 }
 
-// src [R,128] (f32 or bf16) -> dst [128][Kp] bf16: dst[c][col(r)] = src[r][c], zero in the pad columns.  Column layout
-// (slot-major): slot s starts at base[s]; user b's sequence occupies W_s = L_s + P columns, P zero columns first.
+// src [R,128] (f32 or bf16) -> n_shift copies dst_i [128][Kp] bf16 (dst_stride elements apart):
+//     dst_i[c][col] = src[row(col - shift_i)][c]   where col - shift_i falls on a position of the SAME sequence, else 0.
+// Column layout (slot-major): slot s starts at base[s]; user b's sequence occupies W_s = L_s + P columns, P zero columns
+// first (P >= every shift).  A block reads the 64 + max_shift source columns of its tile once.
+struct PadShifts {
+  int n, max_shift;
+  int shift[8];
+};
+constexpr int kPadHalo = 32;
+
 template <bool kBf16>
 __global__ void __launch_bounds__(256)
-pad_transpose_bf16_kernel(const void* __restrict__ src, PadGeom g, __nv_bfloat16* __restrict__ dst) {
-  __shared__ float tile[64][129];
-  __shared__ long long srow[64];
+pad_transpose_bf16_kernel(const void* __restrict__ src, PadGeom g, PadShifts sh, __nv_bfloat16* __restrict__ dst,
+                          long long dst_stride) {
+  extern __shared__ float pt_smem[];
+  float (*tile)[129] = reinterpret_cast<float (*)[129]>(pt_smem);           // [64 + kPadHalo][129]: tile row j = column col0 - kPadHalo + j
+  __shared__ long long srow[64 + kPadHalo];
+  __shared__ int sstart[64 + kPadHalo];                                     // first column of the sequence window the column lies in
   const int tid = threadIdx.x;
   const long long col0 = (long long)blockIdx.x * 64;
-  if (tid < 64) {
-    const long long col = col0 + tid;
+  if (tid < 64 + kPadHalo) {
+    const long long col = col0 - kPadHalo + tid;
     long long r = -1;
-    if (col < g.base[g.n_slots]) {
+    int wstart = 0x7fffffff;                                                // no window: every source is refused
+    if (col >= 0 && col < g.base[g.n_slots]) {
       int s = 0;
       while (s + 1 < g.n_slots && g.base[s + 1] <= col) ++s;
       const int W = g.off[s + 1] - g.off[s] + g.P;
       const long long rel = col - g.base[s];
       const int b = (int)(rel / W), t = (int)(rel % W) - g.P;
       if (t >= 0) r = (long long)b * g.T + g.off[s] + t;
+      wstart = (int)(col - rel % W - (col0 - kPadHalo));                   // tile-row index of the window's first column
     }
     srow[tid] = r;
+    sstart[tid] = wstart;
   }
   __syncthreads();
-  for (int i = tid; i < 64 * 32; i += 256) {
-    const int c = i >> 5, q = i & 31;
-    const long long r = srow[c];
+  const int j_lo = kPadHalo - sh.max_shift;
+  for (int i = tid; i < (64 + kPadHalo) * 32; i += 256) {
+    const int j = i >> 5, q = i & 31;
+    if (j < j_lo) continue;
+    const long long r = srow[j];
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (r >= 0) {
       if (kBf16) {
@@ -150,14 +170,24 @@ pad_transpose_bf16_kernel(const void* __restrict__ src, PadGeom g, __nv_bfloat16
         v = reinterpret_cast<const float4*>(src)[r * 32 + q];
       }
     }
-    tile[c][q * 4 + 0] = v.x; tile[c][q * 4 + 1] = v.y; tile[c][q * 4 + 2] = v.z; tile[c][q * 4 + 3] = v.w;
+    tile[j][q * 4 + 0] = v.x; tile[j][q * 4 + 1] = v.y; tile[j][q * 4 + 2] = v.z; tile[j][q * 4 + 3] = v.w;
   }
   __syncthreads();
-  for (int i = tid; i < 128 * 8; i += 256) {
-    const int ch = i >> 3, seg = i & 7;
-    const uint4 o = make_uint4(pack_bf16x2(tile[seg * 8 + 0][ch], tile[seg * 8 + 1][ch]), pack_bf16x2(tile[seg * 8 + 2][ch], tile[seg * 8 + 3][ch]),
-                               pack_bf16x2(tile[seg * 8 + 4][ch], tile[seg * 8 + 5][ch]), pack_bf16x2(tile[seg * 8 + 6][ch], tile[seg * 8 + 7][ch]));
-    *reinterpret_cast<uint4*>(dst + (long long)ch * g.Kp + col0 + seg * 8) = o;
+  for (int si = 0; si < sh.n; ++si) {
+    const int s_ = sh.shift[si];
+    for (int i = tid; i < 128 * 8; i += 256) {
+      const int ch = i >> 3, seg = i & 7;
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int jd = kPadHalo + seg * 8 + e;            // destination column, as a tile row
+        const int js = jd - s_;                           // source column
+        // same sequence window: the source must not lie before the window of the destination column
+        v[e] = js >= sstart[jd] ? tile[js][ch] : 0.f;      // (the window may start left of the tile: negative)
+      }
+      *reinterpret_cast<uint4*>(dst + si * dst_stride + (long long)ch * g.Kp + col0 + seg * 8) =
+          make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    }
   }
 }
 
@@ -176,20 +206,36 @@ PadGeom make_pad_geom(const SlotTable& slots, int B, int T, int P) {
   return g;
 }
 
-int32_t pad_transpose_bf16(const void* src, bool src_bf16, const PadGeom& g, void* dst, cudaStream_t st) {
+int32_t pad_transpose_bf16(const void* src, bool src_bf16, const PadGeom& g, const int* shifts, int n_shifts, void* dst,
+                           long long dst_stride, cudaStream_t st) {
+  PadShifts sh{};
+  sh.n = n_shifts;
+  for (int i = 0; i < n_shifts; ++i) {
+    sh.shift[i] = shifts[i];
+    if (shifts[i] > sh.max_shift) sh.max_shift = shifts[i];
+  }
+  if (n_shifts < 1 || n_shifts > 8 || sh.max_shift > kPadHalo || sh.max_shift > g.P) {
+    set_error("pad_transpose: %d shifts, largest %d (halo %d, pad %d)", n_shifts, sh.max_shift, kPadHalo, g.P);
+    return HTCN_ERR_INVALID;
+  }
   const int grid = (int)(g.Kp / 64);
-  if (src_bf16) pad_transpose_bf16_kernel<true><<<grid, 256, 0, st>>>(src, g, reinterpret_cast<__nv_bfloat16*>(dst));
-  else pad_transpose_bf16_kernel<false><<<grid, 256, 0, st>>>(src, g, reinterpret_cast<__nv_bfloat16*>(dst));
+  const size_t smem = sizeof(float) * (64 + kPadHalo) * 129;
+  if (src_bf16) {
+    HTCN_CUDA(cudaFuncSetAttribute(pad_transpose_bf16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pad_transpose_bf16_kernel<true><<<grid, 256, smem, st>>>(src, g, sh, reinterpret_cast<__nv_bfloat16*>(dst), dst_stride);
+  } else {
+    HTCN_CUDA(cudaFuncSetAttribute(pad_transpose_bf16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pad_transpose_bf16_kernel<false><<<grid, 256, smem, st>>>(src, g, sh, reinterpret_cast<__nv_bfloat16*>(dst), dst_stride);
+  }
   HTCN_LAUNCH_CHECK("pad_transpose_bf16_kernel");
   return HTCN_OK;
 }
 
-// dW[t][cin][cout] += sum_col aT[cin][col - shift[t]] * bT[cout][col]     (aT, bT: bf16 [128][Kp] from pad_transpose_bf16)
-int32_t wgrad_bf16(const void* aT, const void* bT, long long Kp, const int* shifts, int n_taps, float* dW, cudaStream_t st) {
-  CUtensorMap ta, tb;
-  int32_t rc = make_tmap_bf16(&ta, aT, 128, (uint32_t)Kp, (uint32_t)Kp, 64, 128, 128);
-  if (rc) return rc;
-  rc = make_tmap_bf16(&tb, bT, 128, (uint32_t)Kp, (uint32_t)Kp, 64, 128, 128);
+// dW[t][cin][cout] += sum_col aT_t[cin][col] * bT[cout][col]   (aT_t = aT + t * a_stride: tap t's pre-shifted copy; bf16
+// [128][Kp] from pad_transpose_bf16)
+int32_t wgrad_bf16(const void* aT, long long a_stride, const void* bT, long long Kp, int n_taps, float* dW, cudaStream_t st) {
+  CUtensorMap tb;
+  int32_t rc = make_tmap_bf16(&tb, bT, 128, (uint32_t)Kp, (uint32_t)Kp, 64, 128, 128);
   if (rc) return rc;
   const size_t smem = sizeof(WgSmem) + 1024;
   HTCN_CUDA(cudaFuncSetAttribute(wgrad_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -198,11 +244,33 @@ int32_t wgrad_bf16(const void* aT, const void* bT, long long Kp, const int* shif
   for (int t0 = 0; t0 < n_taps; t0 += kWgMaxTaps) {
     WgTaps taps{};
     taps.n = n_taps - t0 < kWgMaxTaps ? n_taps - t0 : kWgMaxTaps;
-    for (int t = 0; t < taps.n; ++t) taps.shift[t] = shifts[t0 + t];
-    wgrad_bf16_kernel<<<grid, kWgThreads, smem, st>>>(ta, tb, n_steps, taps, dW + (long long)t0 * 128 * 128);
+    CUtensorMap ta[kWgMaxTaps];
+    for (int t = 0; t < kWgMaxTaps; ++t) {
+      const int tt = t < taps.n ? t0 + t : t0;
+      rc = make_tmap_bf16(&ta[t], reinterpret_cast<const __nv_bfloat16*>(aT) + tt * a_stride, 128, (uint32_t)Kp, (uint32_t)Kp, 64, 128, 128);
+      if (rc) return rc;
+    }
+    wgrad_bf16_kernel<<<grid, kWgThreads, smem, st>>>(ta[0], ta[1], ta[2], tb, n_steps, taps, dW + (long long)t0 * 128 * 128);
     HTCN_LAUNCH_CHECK("wgrad_bf16_kernel");
   }
   return HTCN_OK;
 }
 
 }  // namespace htcn
+
+// test hooks (not part of include/htcn.h): the two stages of the tensor-core weight gradient on their own
+extern "C" int32_t htcn_debug_pad_transpose(const void* src, int32_t src_bf16, const int32_t* slot_off_host, int32_t B, int32_t T,
+                                            int32_t S, int32_t P, const int32_t* shifts_host, int32_t n_shifts, void* dst,
+                                            int64_t* kp_out, void* stream) {
+  using namespace htcn;
+  SlotTable slots;
+  slots.n = S;
+  for (int i = 0; i <= S; ++i) slots.off[i] = slot_off_host[i];
+  const PadGeom g = make_pad_geom(slots, B, T, P);
+  if (kp_out) *kp_out = g.Kp;
+  if (!dst) return HTCN_OK;
+  return pad_transpose_bf16(src, src_bf16 != 0, g, shifts_host, n_shifts, dst, 128 * g.Kp, as_stream(stream));
+}
+extern "C" int32_t htcn_debug_wgrad(const void* aT, const void* bT, int64_t Kp, int32_t n_taps, float* dW, void* stream) {
+  return htcn::wgrad_bf16(aT, 128 * Kp, bT, Kp, n_taps, dW, htcn::as_stream(stream));
+}

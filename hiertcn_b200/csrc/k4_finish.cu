@@ -34,7 +34,7 @@ __global__ void prepare_wout_kernel(const float* __restrict__ w, const float* __
   const int pitch = kBf16 ? kWtPitchBf16 : f32_pitch;     // f32: 128, or 256 for HTCN_F32_W256 (grid.y = pitch / 32)
   const int n0 = blockIdx.x * 32;
   const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
-  if (blockIdx.y == kDim / 32) {                  // bf16 only: the bias columns 128..143 of 32 items
+  if (kBf16 && blockIdx.y == kDim / 32) {         // bf16 only: the bias columns 128..143 of 32 items
     if (ty == 0 && n0 + tx < N) {
       __nv_bfloat16* row = reinterpret_cast<__nv_bfloat16*>(out) + (long long)(n0 + tx) * pitch + kDim;
       const float bv = b[n0 + tx];

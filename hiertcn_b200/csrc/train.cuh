@@ -66,9 +66,12 @@ struct PadGeom {
   long long Kp;                          // columns, multiple of 64
 };
 PadGeom make_pad_geom(const SlotTable& slots, int B, int T, int P);
-int32_t pad_transpose_bf16(const void* src, bool src_bf16, const PadGeom& g, void* dst, cudaStream_t st);
-// dW[t][cin][cout] += sum_col aT[cin][col - shifts[t]] * bT[cout][col]; aT, bT bf16 [128][Kp]; dW fp32, atomics
-int32_t wgrad_bf16(const void* aT, const void* bT, long long Kp, const int* shifts, int n_taps, float* dW, cudaStream_t st);
+// n_shifts copies, copy i shifted by shifts[i] columns inside every sequence (zero before its start), dst_stride elements apart
+int32_t pad_transpose_bf16(const void* src, bool src_bf16, const PadGeom& g, const int* shifts, int n_shifts, void* dst,
+                           long long dst_stride, cudaStream_t st);
+// dW[t][cin][cout] += sum_col aT_t[cin][col] * bT[cout][col]; aT_t = aT + t * a_stride (tap t's pre-shifted copy), bT: bf16
+// [128][Kp]; dW fp32, atomics
+int32_t wgrad_bf16(const void* aT, long long a_stride, const void* bT, long long Kp, int n_taps, float* dW, cudaStream_t st);
 
 // out[f] += sum_r D[r, f]  (f < cols, cols <= 256)
 int32_t colsum_atomic(long long R, const float* D, int ldd, int cols, float* out, cudaStream_t st);

@@ -486,3 +486,66 @@ def test_training_on_the_sampled_ranking_losses(kind):
     for _ in range(3):
         l1 = tr2.train_step(x, y, m, s0, neg_ids=neg, loss_kind=kind)["loss"]
     assert l1 < l0
+
+
+@pytest.mark.parametrize("B,S,L,K,dil", [(5, 3, 7, 5, 2), (40, 10, 20, 5, 1), (3, 1, 300, 3, 8)])
+def test_tensor_core_weight_gradient_gemm(B, S, L, K, dil):
+    """bwd_wgrad_bf16.cu on its own: pad-transpose + tcgen05 TN GEMM == sum_r h[r - shift]^T dp[r] with the causal
+    zeroing at sequence starts, on bf16-rounded operands (fp32 accumulation)"""
+    import ctypes as C
+    from hiertcn_b200 import _cabi as cabi
+    from oracle import hiertcn_oracle as O
+    lib = cabi.load()
+    rng = np.random.default_rng(B + L)
+    T = S * L
+    R = B * T
+    h = O.bf16_round(rng.normal(size=(R, 128)).astype(np.float32))
+    dp = O.bf16_round((rng.normal(size=(R, 128)) * (rng.random((R, 128)) < 0.5)).astype(np.float32))
+    slot_p, keep = cabi.int_array(np.arange(S + 1) * L)
+    P_ = (K - 1) * dil
+    kp = C.c_int64(0)
+    st = torch.cuda.current_stream().cuda_stream
+    fn = lib.htcn_debug_pad_transpose
+    fn.restype = C.c_int32
+    fn.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32),
+                   C.c_int32, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]
+    shifts = [(K - 1 - tap) * dil for tap in range(K)]
+    sh_p, keep2 = cabi.int_array(shifts)
+    zero_p, keep3 = cabi.int_array([0])
+    assert fn(None, 0, slot_p, B, T, S, P_, sh_p, K, None, C.byref(kp), st) == 0
+    Kp = kp.value
+    assert Kp % 64 == 0 and Kp >= B * S * (L + P_)
+    h_d, dp_d = dev(h), dev(dp).to(torch.bfloat16)
+    aT = torch.full((K, 128, Kp), float("nan"), dtype=torch.bfloat16, device="cuda")      # one pre-shifted copy per tap
+    bT = torch.full((128, Kp), float("nan"), dtype=torch.bfloat16, device="cuda")
+    assert fn(h_d.data_ptr(), 0, slot_p, B, T, S, P_, sh_p, K, aT.data_ptr(), None, st) == 0      # fp32 source
+    assert fn(dp_d.data_ptr(), 1, slot_p, B, T, S, P_, zero_p, 1, bT.data_ptr(), None, st) == 0   # bf16 source
+    torch.cuda.synchronize()
+    a_np = aT.float().cpu().numpy()
+    assert np.isfinite(a_np).all(), "every column must be written"
+    # layout: slot-major, each sequence preceded by P zero columns; copy `tap` is shifted right by its shift inside the sequence
+    for tap, sh in enumerate(shifts):
+        ref = np.zeros((128, Kp), np.float32)
+        col = 0
+        for s in range(S):
+            for b in range(B):
+                col += P_
+                rows = b * T + s * L + np.arange(L - sh)
+                ref[:, col + sh:col + L] = h[rows].T
+                col += L
+        np.testing.assert_array_equal(a_np[tap], ref)
+    gw = lib.htcn_debug_wgrad
+    gw.restype = C.c_int32
+    gw.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]
+    dW = torch.ones((K, 128, 128), dtype=torch.float32, device="cuda")           # accumulated into
+    rc = gw(aT.data_ptr(), bT.data_ptr(), Kp, K, dW.data_ptr(), st)
+    assert rc == 0, lib.htcn_last_error().decode()
+    torch.cuda.synchronize()
+    got = dW.cpu().numpy() - 1.0
+    t_in = np.tile(np.arange(L), B * S)                  # position of every flat row inside its sequence
+    for tap, sh in enumerate(shifts):
+        src = np.arange(R) - sh
+        ok = t_in - sh >= 0
+        hs = np.where(ok[:, None], h[np.clip(src, 0, R - 1)], 0.0)
+        want = hs.astype(np.float64).T @ dp.astype(np.float64)
+        np.testing.assert_allclose(got[tap], want, rtol=2e-4, atol=2e-4 * np.abs(want).max())
