@@ -16,6 +16,7 @@ SCORE_CE, SCORE_RANK, SCORE_TOPK = 1, 2, 4
 LOSS_KINDS = {"nce": 0, "hinge_sigmoid": 1, "hinge_logsigmoid": 2, "hinge_linear": 3, "bpr": 4}
 MAX_TOPK = 128
 WT_PITCH_BF16 = 144
+K2TC_SCRATCH_BYTES = 8 * 2 * 128 * 128 * 2          # HTCN_K2TC_SCRATCH_BYTES
 
 
 def tcn_scratch_floats(n_levels, K):
@@ -61,7 +62,7 @@ SIGNATURES = {
     "htcn_score_ce_backward_bf16": [_p, _p, C.c_int64, _i, _p, _p, C.c_int64, _p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p],
     "htcn_cast_transpose_bf16": [_p, _i, C.c_int64, _p, _p, C.c_int64, _p],
     "htcn_tcn_forward_train_bf16": [_p, _p, _p, _pp, _pp, _pp, _pp, _i, _i, _ip, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p],
-    "htcn_tcn_forward_train": [_p, _p, _p, _pp, _pp, _pp, _pp, _i, _i, _ip, _i, _i, _i, _p, _p, _p, _p, _p, _p],
+    "htcn_tcn_forward_train": [_p, _p, _p, _pp, _pp, _pp, _pp, _i, _i, _ip, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p],
     "htcn_tcn_backward": [_p, _p, _p, _i, _p, _pp, _pp, _i, _i, _ip, _i, _i, _i, _p, _p, _p, _p, _p, _pp, _pp, _pp, _pp, _p, _p, _p, _p],
     "htcn_gru_sessions_train": [_p, _p, _p, _pp, _pp, _pp, _pp, _i, _p, _i, _i, _p, _p, _p, _p, _p],
     "htcn_gru_backward": [_p, _p, _p, _p, _pp, _pp, _i, _p, _i, _i, _p, _p, _pp, _pp, _pp, _pp, _p, _p, _p],

@@ -80,7 +80,7 @@ extern "C" int32_t htcn_tcn_forward_train(const float* xe, const float* w_in_x, 
                                           const float* const* ds_w_host, const float* const* ds_b_host,
                                           int32_t n_levels, int32_t kernel_size, const int32_t* slot_off_host, int32_t B,
                                           int32_t T, int32_t S, const int32_t* out_row, const float* dropout_scale,
-                                          float* h_save, float* a_save, float* hout, void* stream) {
+                                          float* h_save, float* a_save, float* hout, void* tc_scratch, void* stream) {
   using namespace htcn;
   HTCN_REQUIRE(xe && w_in_x && h_save && hout && slot_off_host && out_row, "tcn_forward_train: NULL pointer");
   HTCN_REQUIRE(B > 0 && T > 0 && S > 0 && S <= HTCN_MAX_SLOTS, "tcn_forward_train: B=%d T=%d S=%d", B, T, S);
@@ -95,6 +95,8 @@ extern "C" int32_t htcn_tcn_forward_train(const float* xe, const float* w_in_x, 
   const long long R = (long long)B * T;
   LevelArgs a{};
   a.R = R; a.T = T; a.B = B;
+  // tc_scratch: every level on the tensor cores with fp32-grade split products (k2_level_tc.cu); NULL: the FFMA kernel
+  a.tc_ws = tc_scratch; a.tc_split = 1;
   a.in = xe; a.w = w_in_x; a.sbias = sbias; a.K = 1; a.dil = 1; a.conv_epilogue = 0; a.out = h_save;
   int32_t rc = k2_level_launch(a, slots, st);
   if (rc) return rc;
@@ -177,7 +179,8 @@ extern "C" int32_t htcn_tcn_backward(const float* d_hout, const int32_t* out_row
   // activations (bwd_wgrad_bf16.cu) instead of the fp32 split-K products
   const int P = n_levels > 0 ? (kernel_size - 1) * (1 << (n_levels - 1)) : 0;
   const PadGeom pg = make_pad_geom(slots, B, T, P);
-  __nv_bfloat16* bT = reinterpret_cast<__nv_bfloat16*>(tc_scratch);     // dp^T; then one pre-shifted h^T per tap
+  // layout: [bf16 weight tiles of the level being run (k2_level_tc.cu)][dp^T][one pre-shifted h^T per tap]
+  __nv_bfloat16* bT = tc_scratch ? reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(tc_scratch) + HTCN_K2TC_WS_BYTES) : nullptr;
   __nv_bfloat16* aT = bT ? bT + 128 * pg.Kp : nullptr;
   const long long a_stride = 128 * pg.Kp;
   const int zero = 0;
@@ -230,12 +233,16 @@ extern "C" int32_t htcn_tcn_backward(const float* d_hout, const int32_t* out_row
       rc = colsum_atomic(R, dcur, kDim, kDim, d_ds_b_host[l], st);
       if (rc) return rc;
       float* dres = scratch + 2 * R * kDim;     // third scratch plane
-      rc = sgemm(true, R, kDim, kDim, dcur, kDim, ds_w_host[l], kDim, dres, kDim, false, st);
+      LevelArgs d{};                            // dres = ds Wds^T
+      d.R = R; d.T = T; d.B = B; d.tc_ws = tc_scratch;
+      d.in = dcur; d.w = ds_w_host[l]; d.K = 1; d.dil = 1; d.conv_epilogue = 0; d.out = dres; d.anti = 1; d.w_nt = 1;
+      if (tc_scratch && k2_level_tc_supported(d, slots)) rc = k2_level_tc_launch(d, slots, st);
+      else rc = sgemm(true, R, kDim, kDim, dcur, kDim, ds_w_host[l], kDim, dres, kDim, false, st);
       if (rc) return rc;
       resid = dres;
     }
     LevelArgs a{};
-    a.R = R; a.T = T; a.B = B;
+    a.R = R; a.T = T; a.B = B; a.tc_ws = tc_scratch;      // plain bf16 products: the gates are the saved forward's
     a.in = dp; a.w = conv_w_host[l]; a.K = kernel_size; a.dil = dil; a.conv_epilogue = 2; a.resid = resid; a.out = dcur;
     a.anti = 1; a.w_nt = 1;
     rc = k2_level_launch(a, slots, st);
@@ -253,6 +260,10 @@ extern "C" int32_t htcn_tcn_backward(const float* d_hout, const int32_t* out_row
   if (rc) return rc;
   slot_sum_kernel<<<dim3(B, S), kDim, 0, st>>>(dcur, B, T, slots, d_sbias);
   HTCN_LAUNCH_CHECK("slot_sum_kernel");
+  LevelArgs d{};                                // dXe = dh_0 W_in_x^T
+  d.R = R; d.T = T; d.B = B; d.tc_ws = tc_scratch;
+  d.in = dcur; d.w = w_in_x; d.K = 1; d.dil = 1; d.conv_epilogue = 0; d.out = d_xe; d.anti = 1; d.w_nt = 1;
+  if (tc_scratch && k2_level_tc_supported(d, slots)) return k2_level_tc_launch(d, slots, st);
   return sgemm(true, R, kDim, kDim, dcur, kDim, w_in_x, kDim, d_xe, kDim, false, st);
 }
 
@@ -260,5 +271,6 @@ extern "C" int32_t htcn_tcn_backward(const float* d_hout, const int32_t* out_row
 extern "C" int64_t htcn_tcn_backward_tc_scratch_bytes(int32_t B, int32_t T, int32_t S, int32_t n_levels, int32_t kernel_size) {
   const long long P = n_levels > 0 ? (long long)(kernel_size - 1) * (1 << (n_levels - 1)) : 0;
   const long long Kp = ((long long)B * (T + (long long)S * P) + 63) / 64 * 64;
-  return (1 + (long long)(kernel_size > 1 ? kernel_size : 1)) * 128 * Kp * 2;     // dp^T + one pre-shifted h^T per tap
+  // level weight tiles + dp^T + one pre-shifted h^T per tap
+  return htcn::HTCN_K2TC_WS_BYTES + (1 + (long long)(kernel_size > 1 ? kernel_size : 1)) * 128 * Kp * 2;
 }

@@ -174,6 +174,7 @@ k2_level_f32(LevelArgs a, SlotTable slots) {
 }
 
 int32_t k2_level_launch(const LevelArgs& a, const SlotTable& slots, cudaStream_t st) {
+  if (a.tc_ws && k2_level_tc_supported(a, slots)) return k2_level_tc_launch(a, slots, st);
   k2_level_f32<<<ceil_div(a.R, kTM), kK2Threads, 0, st>>>(a, slots);
   HTCN_LAUNCH_CHECK("k2_level_f32");
   return HTCN_OK;

@@ -30,8 +30,15 @@ struct LevelArgs {
   long long resid_plane_stride;
   int anti;                   // 1: taps read r + shift, zero beyond the END of r's sequence (transposed convolution)
   int w_nt;                   // 1: every W[tap] is applied transposed
+  void* tc_ws;                // non-NULL: run the level on the tensor cores (k2_level_tc.cu) when its shape allows; device
+                              //   workspace of HTCN_K2TC_WS_BYTES for the level's bf16 weight tiles
+  int tc_split;               // tensor-core path: 1 = fp32-grade products (bf16 hi/lo split, 3 MMAs), 0 = plain bf16
 };
+constexpr long long HTCN_K2TC_WS_BYTES = 8LL * 2 * 128 * 128 * 2;      // K <= 8 taps x (hi, lo) x 32 KB
+// dispatches to k2_level_tc_launch when a.tc_ws is set and k2_level_tc_supported(a), else the FFMA kernel
 int32_t k2_level_launch(const LevelArgs& a, const SlotTable& slots, cudaStream_t st);
+bool k2_level_tc_supported(const LevelArgs& a, const SlotTable& slots);
+int32_t k2_level_tc_launch(const LevelArgs& a, const SlotTable& slots, cudaStream_t st);
 
 // fused tcgen05 conv stack (k2_tcn_bf16.cu); h_save / a_save (bf16, optional) keep every layer's output and every
 // level's pre-residual activation for the backward

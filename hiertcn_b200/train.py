@@ -189,10 +189,14 @@ class HierTCNTrainer:
                       h_save.data_ptr(), a_save.data_ptr(), hout.data_ptr(), k2f_scratch.data_ptr(), st)
             cabi.note_launches(2)
         else:
+            # bf16 tier: the levels run on the tensor cores with fp32-grade split products (``self.k2_split_tc = False``: FFMA)
+            tcf = None
+            if self.bf16 and getattr(self, "k2_split_tc", True):
+                tcf = buf("tr_k2_tcf_scratch", (cabi.K2TC_SCRATCH_BYTES,), torch.uint8)
             cabi.call("htcn_tcn_forward_train", xe.data_ptr(), m.w_in_x.data_ptr(), sbias.data_ptr(), m._conv_w_pp[0],
                       m._conv_b_pp[0], m._ds_w_pp[0], m._ds_b_pp[0], L, K, slot_p, B, T, S, d["row_of"].data_ptr(), P(drop),
-                      h_save.data_ptr(), a_save.data_ptr(), hout.data_ptr(), st)
-            cabi.note_launches(L + 2)
+                      h_save.data_ptr(), a_save.data_ptr(), hout.data_ptr(), P(tcf), st)
+            cabi.note_launches(L + 2 + (L + 1 if tcf is not None else 0))
         scalars = torch.zeros(8, dtype=f32, device=m.device)
         if Q == 0:
             return dict(scalars=scalars, state=state_out)

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define HTCN_ABI_VERSION 3
+#define HTCN_ABI_VERSION 4
 #define HTCN_DIM 128          /* D = C = H */
 #define HTCN_MAX_SLOTS 64     /* S (args.max_session_num, default 10) */
 #define HTCN_MAX_LEVELS 8     /* TCN levels (len(args.tcn_channel)) */
@@ -378,13 +378,18 @@ int32_t htcn_cast_transpose_bf16(const void* src, int32_t src_dtype, int64_t R, 
  * dropout_scale [S, n_levels, 128] f32 or NULL: training dropout of customized_tcn_cell.py:100,119 -- tf.layers.Dropout with
  * noise_shape [1,1,C], i.e. ONE channel mask per dropout op, shared over batch and time; the graph has one op per session
  * slot and level.  Entries are 0 or 1/(1-rate) (drawn by the caller); relu(conv+b) is multiplied by them before the
- * residual add; a_save keeps the value before the scale.  The same array goes to htcn_tcn_backward. */
+ * residual add; a_save keeps the value before the scale.  The same array goes to htcn_tcn_backward.
+ * tc_scratch (device, HTCN_K2TC_SCRATCH_BYTES) or NULL: when given, every level runs on the tensor cores with fp32-grade
+ * products -- activations and weights split into two bf16 each, x w ~= x_hi w_hi + x_lo w_hi + x_hi w_lo (three tcgen05
+ * MMAs, fp32 accumulation, ~1e-5 relative), so the saved activations and ReLU gates are those of the fp32 stack; levels the
+ * tensor-core kernel does not take (a slot longer than 128 - (K-1)*d positions) and NULL run the FFMA kernel. */
+#define HTCN_K2TC_SCRATCH_BYTES (8 * 2 * 128 * 128 * 2)
 int32_t htcn_tcn_forward_train(const float* xe, const float* w_in_x, const float* sbias,
                                const float* const* conv_w_host, const float* const* conv_b_host,
                                const float* const* ds_w_host, const float* const* ds_b_host, int32_t n_levels,
                                int32_t kernel_size, const int32_t* slot_off_host, int32_t B, int32_t T, int32_t S,
                                const int32_t* out_row, const float* dropout_scale, float* h_save, float* a_save, float* hout,
-                               void* stream);
+                               void* tc_scratch, void* stream);
 
 /* The same on the tensor cores: the fused tcgen05 conv stack (htcn_tcn_forward, HTCN_BF16) with every layer's output
  * (h_save [(n_levels+1), B*T, 128]) and every level's pre-residual activation (a_save [n_levels, B*T, 128]) written out
@@ -403,7 +408,9 @@ int32_t htcn_tcn_forward_train_bf16(const void* xe, const float* w_in_x, const f
  * accumulated; d_sbias [S,B,128] and d_xe [B*T,128] overwritten.
  * tc_scratch (device, htcn_tcn_backward_tc_scratch_bytes(...) bytes) or NULL: when given, the weight gradients
  * dW[tap] = h[shifted]^T dp run on the tensor cores (tcgen05, bf16 operands, fp32 accumulation) from zero-padded
- * transposed bf16 copies of the activations written into it; NULL = fp32 split-K products (the 1e-4 tier). */
+ * transposed bf16 copies of the activations written into it, and the data gradients (transposed convolutions, dXe) as
+ * plain bf16 tcgen05 products (k2_level_tc.cu; the ReLU gates are the saved forward's); NULL = fp32 split-K products and
+ * FFMA levels (the 1e-4 tier). */
 int64_t htcn_tcn_backward_tc_scratch_bytes(int32_t B, int32_t T, int32_t S, int32_t n_levels, int32_t kernel_size);
 int32_t htcn_tcn_backward(const float* d_hout, const int32_t* out_row, const void* xe, int32_t save_dtype,
                           const float* w_in_x, const float* const* conv_w_host, const float* const* ds_w_host,

@@ -360,7 +360,21 @@ def test_fused_conv_forward_saves_match_fp32_levels(B, S, L, K, levels):
     a32 = torch.zeros((levels, R, 128), device="cuda")
     o32 = torch.zeros((Q, 128), device="cuda")
     cabi.call("htcn_tcn_forward_train", xe_f.data_ptr(), w_in.data_ptr(), sb.data_ptr(), wp, bp, None, None, levels, K, slot_p, B, T, S,
-              row_d.data_ptr(), None, h32.data_ptr(), a32.data_ptr(), o32.data_ptr(), st)
+              row_d.data_ptr(), None, h32.data_ptr(), a32.data_ptr(), o32.data_ptr(), None, st)
+    # the same levels on the tensor cores with split-bf16 products (k2_level_tc.cu): fp32 grade
+    hs = torch.full((levels + 1, R, 128), float("nan"), device="cuda")
+    as_ = torch.full((levels, R, 128), float("nan"), device="cuda")
+    os_ = torch.full((Q, 128), float("nan"), device="cuda")
+    tc_ws = torch.empty(cabi.K2TC_SCRATCH_BYTES, dtype=torch.uint8, device="cuda")
+    cabi.call("htcn_tcn_forward_train", xe_f.data_ptr(), w_in.data_ptr(), sb.data_ptr(), wp, bp, None, None, levels, K, slot_p, B, T, S,
+              row_d.data_ptr(), None, hs.data_ptr(), as_.data_ptr(), os_.data_ptr(), tc_ws.data_ptr(), st)
+    torch.cuda.synchronize()
+    for name, got, ref in (("h", hs, h32), ("a", as_, a32), ("hout", os_, o32)):
+        g, r = got.cpu().numpy(), ref.cpu().numpy()
+        assert np.isfinite(g).all(), name + ": rows not written (split tensor-core levels)"
+        assert np.abs(g - r).max() <= 1e-4 * np.abs(r).max(), (name, float(np.abs(g - r).max()), float(np.abs(r).max()))
+        gates_differ = np.mean((g > 0) != (r > 0))
+        assert gates_differ <= max(5e-5, 3.0 / g.size), (name, gates_differ)
     h16 = torch.full((levels + 1, R, 128), float("nan"), dtype=torch.bfloat16, device="cuda")
     a16 = torch.full((levels, R, 128), float("nan"), dtype=torch.bfloat16, device="cuda")
     o16 = torch.full((Q, 128), float("nan"), dtype=torch.bfloat16, device="cuda")
