@@ -60,6 +60,7 @@ SIGNATURES = {
     "htcn_loss_row_weights": [_p, _p, _i, _i, _p, _p],
     "htcn_score_ce_backward": [_p, _i, _i, _p, _p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p],
     "htcn_score_ce_backward_bf16": [_p, _p, C.c_int64, _i, _p, _p, C.c_int64, _p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p],
+    "htcn_score_ce_fwd_bwd_bf16": [_p, _p, C.c_int64, _i, _p, _p, C.c_int64, _p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p],
     "htcn_cast_transpose_bf16": [_p, _i, C.c_int64, _p, _p, C.c_int64, _p],
     "htcn_tcn_forward_train_bf16": [_p, _p, _p, _pp, _pp, _pp, _pp, _i, _i, _ip, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p],
     "htcn_tcn_forward_train": [_p, _p, _p, _pp, _pp, _pp, _pp, _i, _i, _ip, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p],
@@ -120,7 +121,7 @@ LAUNCHES_PER_CALL = {"htcn_gather_meanpool": 2, "htcn_gru_sessions": 1, "htcn_tc
                      # training step (the per-call counts of the multi-launch entry points are added by the caller)
                      "htcn_loss_row_weights": 1, "htcn_score_ce_backward": 1, "htcn_gru_sessions_train": 1,
                      "htcn_gather_backward": 2, "htcn_adam_step": 1, "htcn_refresh_wout": 1,
-                     "htcn_score_ce_backward_bf16": 3, "htcn_cast_transpose_bf16": 1, "htcn_assemble_batch": 4}
+                     "htcn_score_ce_backward_bf16": 3, "htcn_score_ce_fwd_bwd_bf16": 6, "htcn_cast_transpose_bf16": 1, "htcn_assemble_batch": 4}
 launch_count = 0
 
 
@@ -139,7 +140,7 @@ def call(name: str, *args):
 
 
 def ce_bwd_bf16_ws_floats(Q, N):
-    return 3 * (-(-Q // 64) * 64) + (-(-N // 64) * 64)            # HTCN_CE_BWD_BF16_WS_FLOATS
+    return 4 * (-(-Q // 64) * 64) + (-(-N // 64) * 64)            # HTCN_CE_BWD_BF16_WS_FLOATS
 
 
 def ptr_array(ptrs):

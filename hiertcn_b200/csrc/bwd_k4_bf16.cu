@@ -63,12 +63,18 @@ struct BwdArgs {
   const int* yq;
   float* out;               // pass A: d_hout [Q,128]; pass B: d_wt [n_items,128]   (atomic accumulation)
   float* d_b;               // pass B: [n_items] or NULL
+  float* lsum;              // pass F: [Q] sum_j exp(z_j - z_y), atomic accumulation (lseL then holds z_y * log2e)
   int Q, n_items, n0;
   int n_stream;             // rows of the streamed operand (pass A: n_items, pass B: Q)
   int n_split;
 };
 
-template <bool kPassB>
+// kMode 0: pass A, 1: pass B, 2: pass F = forward + pass A in one sweep.  With the TARGET logit as the reference point
+// (the forward sweep's convention: loss = log sum_j exp(z_j - z_y), k4_score_bf16.cu) the softmax numerator needs no
+// running maximum, so O = sum_j exp(z_j - z_y) w_j and l = sum_j exp(z_j - z_y) accumulate without rescaling and
+//     loss_q = log l_q,     dHout[q] = g_q (O_q / l_q - w_{y_q})
+// come out of ONE catalog sweep (ce_fused_finish_kernel): the separate forward sweep that only produced lse is gone.
+template <int kMode>
 __global__ void __launch_bounds__(kThreads, 1)
 k4_ce_backward_bf16(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_y,
                     const __grid_constant__ CUtensorMap tmap_v, BwdArgs a) {
@@ -81,6 +87,8 @@ k4_ce_backward_bf16(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   const int t_end = (int)((long long)tiles_all * (blockIdx.y + 1) / a.n_split);
   const int n_iter = t_end - t_begin;
   if (n_iter <= 0) return;
+  constexpr bool kPassB = kMode == 1;
+  constexpr bool kPassF = kMode == 2;
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmap_x);
@@ -194,7 +202,7 @@ k4_ce_backward_bf16(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       laneL = a.bL[mrow];
       laneI = a.n0 + mrow;
     }
-    float db_acc = 0.f;
+    float db_acc = 0.f;           // pass B: db_j; pass F: l_q (this warp's 32 of every 64 columns)
     const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
     // colA / colB / colI are consecutive [kStages][kBN] arrays: shared-window address of this warp's first column
     const uint32_t col_base = smem_u32(&sm.colA[0][0]) + cg * kColsPerWarp * 4;
@@ -229,7 +237,10 @@ k4_ce_backward_bf16(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float z = __uint_as_float(r[u + e]);
-          if (!kPassB) {
+          if (kPassF) {
+            pv[e] = ex2_approx(fmaf(z, kLog2e, av[e] - laneL));      // exp(z_j - z_y); the padding columns carry b = -inf
+            db_acc += pv[e];
+          } else if (!kPassB) {
             pv[e] = ex2_approx(fmaf(z, kLog2e, av[e] - laneL)) - ((u + e == tgt) ? 1.f : 0.f);
           } else {
             pv[e] = bv[e] * (ex2_approx(fmaf(z, kLog2e, laneL - av[e])) - ((iv[e] == laneI) ? 1.f : 0.f));
@@ -250,7 +261,7 @@ k4_ce_backward_bf16(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     mbar_wait(&sm.o_full, 0);
     tc_fence_after_sync();
     const bool row_ok = kPassB ? (mrow < a.n_items) : (mrow < a.Q);
-    const float scale = kPassB ? 1.f : lane_g;
+    const float scale = (kPassB || kPassF) ? 1.f : lane_g;
 #pragma unroll
     for (int c = 0; c < 64; c += 32) {                               // 128 output columns / 2 column groups
       uint32_t r[32];
@@ -266,6 +277,7 @@ k4_ce_backward_bf16(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       }
     }
     if (kPassB && a.d_b && row_ok) atomicAdd(a.d_b + mrow, db_acc);
+    if (kPassF && row_ok) atomicAdd(a.lsum + mrow, db_acc);
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -287,6 +299,94 @@ __global__ void k4_bwd_prep_kernel(const float* __restrict__ b_out, int n_items,
     gq[i] = ok ? g_row[i] : 0.f;
     yq[i] = ok ? y_id[i] : -2;
   }
+}
+
+// pass F bookkeeping: bL as above; zyL [ceil64(Q)] = z_y * log2e (0 padding); yq (-2 padding)
+__global__ void k4_fused_prep_kernel(const float* __restrict__ b_out, int n_items, int n64, const float* __restrict__ zy,
+                                     const int* __restrict__ y_id, int Q, int q64, float* __restrict__ bL,
+                                     float* __restrict__ zyL, int* __restrict__ yq, float* __restrict__ lsum) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n64) bL[i] = (i < n_items) ? b_out[i] * kLog2e : -INFINITY;
+  if (i < q64) {
+    const bool ok = i < Q;
+    zyL[i] = ok ? zy[i] * kLog2e : 0.f;
+    yq[i] = ok ? y_id[i] : -2;
+    lsum[i] = 0.f;
+  }
+}
+
+// After pass F: d_hout holds O_q = sum_j exp(z_j - z_y) w_j and lsum l_q = sum_j exp(z_j - z_y).  One warp per row:
+//     loss_q = log l_q,    dHout[q] = g_q (O_q / l_q - w_{y_q})
+// A row whose sum left the fp32 range (some logit more than ~69 nats above the target's) is redone here exactly, with a
+// running maximum, on the same bf16 operands (lane per item for the logits, lane per 4 channels for the weighted sum).
+constexpr int kFinishWarps = 8;
+__global__ void __launch_bounds__(32 * kFinishWarps)
+ce_fused_finish_kernel(int Q, const float* __restrict__ lsum, const float* __restrict__ zy, const float* __restrict__ g_row,
+                       const int* __restrict__ y_id, const __nv_bfloat16* __restrict__ hout,
+                       const __nv_bfloat16* __restrict__ w_out_t, const float* __restrict__ b_out, int n_items, int n0,
+                       float* __restrict__ d_hout, float* __restrict__ loss_row) {
+  __shared__ float hs[kFinishWarps][kDim];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const long long q = (long long)blockIdx.x * kFinishWarps + wib;
+  if (q >= Q) return;
+  const float l = lsum[q];
+  float4 o = reinterpret_cast<const float4*>(d_hout + q * kDim)[lane];
+  float loss;
+  if (l < 1.2676506e30f && l > 0.f) {                         // 2^100: the sums are in range
+    loss = __logf(l);
+    const float inv = 1.f / l;
+    o.x *= inv; o.y *= inv; o.z *= inv; o.w *= inv;
+  } else {
+    const uint2 hq = reinterpret_cast<const uint2*>(hout + q * kDim)[lane];
+    hs[wib][4 * lane + 0] = bf16_lo(hq.x); hs[wib][4 * lane + 1] = bf16_hi(hq.x);
+    hs[wib][4 * lane + 2] = bf16_lo(hq.y); hs[wib][4 * lane + 3] = bf16_hi(hq.y);
+    __syncwarp();
+    auto logit = [&](int j) {
+      const uint4* wr = reinterpret_cast<const uint4*>(w_out_t + (long long)j * kWtPitchBf16);
+      float z = b_out[j];
+#pragma unroll 4
+      for (int c = 0; c < 16; ++c) {
+        const uint4 w8 = __ldg(wr + c);
+        const float* h = &hs[wib][c * 8];
+        z = fmaf(h[0], bf16_lo(w8.x), z); z = fmaf(h[1], bf16_hi(w8.x), z); z = fmaf(h[2], bf16_lo(w8.y), z);
+        z = fmaf(h[3], bf16_hi(w8.y), z); z = fmaf(h[4], bf16_lo(w8.z), z); z = fmaf(h[5], bf16_hi(w8.z), z);
+        z = fmaf(h[6], bf16_lo(w8.w), z); z = fmaf(h[7], bf16_hi(w8.w), z);
+      }
+      return z;
+    };
+    float m = -INFINITY;
+    for (int j = lane; j < n_items; j += 32) m = fmaxf(m, logit(j));
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+    float ls = 0.f;
+    o = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j0 = 0; j0 < n_items; j0 += 32) {
+      const int j = j0 + lane;
+      const float p = j < n_items ? expf(logit(j) - m) : 0.f;
+      ls += p;
+      const int cnt = n_items - j0 < 32 ? n_items - j0 : 32;
+      for (int i = 0; i < cnt; ++i) {
+        const float pj = __shfl_sync(0xffffffffu, p, i);
+        const uint2 w4 = __ldg(reinterpret_cast<const uint2*>(w_out_t + (long long)(j0 + i) * kWtPitchBf16) + lane);
+        o.x = fmaf(pj, bf16_lo(w4.x), o.x); o.y = fmaf(pj, bf16_hi(w4.x), o.y);
+        o.z = fmaf(pj, bf16_lo(w4.y), o.z); o.w = fmaf(pj, bf16_hi(w4.y), o.w);
+      }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) ls += __shfl_xor_sync(0xffffffffu, ls, d);
+    loss = m + logf(ls) - zy[q];
+    const float inv = 1.f / ls;
+    o.x *= inv; o.y *= inv; o.z *= inv; o.w *= inv;
+  }
+  const int y = y_id[q] - n0;
+  float4 wy = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (y >= 0 && y < n_items) {
+    const uint2 w4 = __ldg(reinterpret_cast<const uint2*>(w_out_t + (long long)y * kWtPitchBf16) + lane);
+    wy = make_float4(bf16_lo(w4.x), bf16_hi(w4.x), bf16_lo(w4.y), bf16_hi(w4.y));
+  }
+  const float g = g_row[q];
+  reinterpret_cast<float4*>(d_hout + q * kDim)[lane] = make_float4(g * (o.x - wy.x), g * (o.y - wy.y), g * (o.z - wy.z), g * (o.w - wy.w));
+  if (lane == 0) loss_row[q] = loss;
 }
 
 // src [R,128] f32 -> rows [R,128] bf16 (optional) and its transpose [128, r_pad] bf16 (optional), 32x32 smem tiles
@@ -313,7 +413,7 @@ __global__ void cast_transpose_bf16_kernel(const void* __restrict__ src, int src
   }
 }
 
-template <bool kPassB>
+template <int kMode>
 int32_t launch_bwd(const void* x, uint64_t x_rows, uint32_t x_pitch, const void* y, uint64_t y_rows, uint32_t y_pitch,
                    const void* v, uint64_t v_cols, uint64_t v_pitch, BwdArgs a, cudaStream_t st) {
   CUtensorMap tx, ty, tv;
@@ -331,7 +431,7 @@ int32_t launch_bwd(const void* x, uint64_t x_rows, uint32_t x_pitch, const void*
   if (ns < 1) ns = 1;
   a.n_split = ns;
   const size_t smem = sizeof(BwdSmem) + 1024;
-  auto kern = k4_ce_backward_bf16<kPassB>;
+  auto kern = k4_ce_backward_bf16<kMode>;
   HTCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<dim3(m_tiles, ns), kThreads, smem, st>>>(tx, ty, tv, a);
   HTCN_LAUNCH_CHECK("k4_ce_backward_bf16");
@@ -378,13 +478,54 @@ extern "C" int32_t htcn_score_ce_backward_bf16(const void* hout, const void* hou
   k4_bwd_prep_kernel<<<ceil_div(q64 > n64 ? q64 : n64, 256), 256, 0, st>>>(b_out, n_items, n64, loss_row, target_logit, g_row,
                                                                           y_id, Q, q64, bL, lseL, gq, yq);
   HTCN_LAUNCH_CHECK("k4_bwd_prep_kernel");
-  BwdArgs a{bL, lseL, gq, yq, d_hout, nullptr, Q, n_items, n0, n_items, 1};
-  int32_t rc = launch_bwd<false>(hout, (uint64_t)Q, kDim, w_out_t, (uint64_t)n_items, kWtPitchBf16, w_out, (uint64_t)n_items,
+  BwdArgs a{bL, lseL, gq, yq, d_hout, nullptr, nullptr, Q, n_items, n0, n_items, 1};
+  int32_t rc = launch_bwd<0>(hout, (uint64_t)Q, kDim, w_out_t, (uint64_t)n_items, kWtPitchBf16, w_out, (uint64_t)n_items,
                                  (uint64_t)n_pad, a, st);
   if (rc) return rc;
   a.out = d_w_out_t;
   a.d_b = d_b_out;
   a.n_stream = Q;
-  return launch_bwd<true>(w_out_t, (uint64_t)n_items, kWtPitchBf16, hout, (uint64_t)Q, kDim, hout_t, (uint64_t)Q,
+  return launch_bwd<1>(w_out_t, (uint64_t)n_items, kWtPitchBf16, hout, (uint64_t)Q, kDim, hout_t, (uint64_t)Q,
                           (uint64_t)q_pad, a, st);
+}
+
+
+// Forward + backward of the full-catalog softmax-CE head in TWO catalog sweeps (pass F: loss and dHout; pass B: dW^T, db)
+extern "C" int32_t htcn_score_ce_fwd_bwd_bf16(const void* hout, const void* hout_t, int64_t q_pad, int32_t Q,
+                                              const void* w_out_t, const void* w_out, int64_t n_pad, const float* b_out,
+                                              int32_t n_items, int32_t n0, const int32_t* y_id, const float* target_logit,
+                                              const float* g_row, float* workspace, float* loss_row, float* d_hout,
+                                              float* d_w_out_t, float* d_b_out, void* stream) {
+  HTCN_REQUIRE(hout && hout_t && w_out_t && w_out && b_out && y_id && loss_row && target_logit && g_row && workspace &&
+                   d_hout && d_w_out_t,
+               "score_ce_fwd_bwd_bf16: NULL pointer");
+  HTCN_REQUIRE(Q >= 0 && n_items > 0 && q_pad >= Q && q_pad % 8 == 0 && n_pad >= n_items && n_pad % 8 == 0,
+               "score_ce_fwd_bwd_bf16: Q=%d q_pad=%lld n_items=%d n_pad=%lld", Q, (long long)q_pad, n_items, (long long)n_pad);
+  if (Q == 0) return HTCN_OK;
+  cudaStream_t st = as_stream(stream);
+  HTCN_CUDA(cudaMemsetAsync(d_hout, 0, sizeof(float) * (size_t)Q * kDim, st));
+  const int q64 = ceil_div(Q, kBN) * kBN, n64 = ceil_div(n_items, kBN) * kBN;
+  float* bL = workspace;                 // HTCN_CE_BWD_BF16_WS_FLOATS(Q, n_items)
+  float* lseL = bL + n64;
+  float* gq = lseL + q64;
+  int* yq = reinterpret_cast<int*>(gq + q64);
+  float* lsum = reinterpret_cast<float*>(yq + q64);
+  const int pb = ceil_div(q64 > n64 ? q64 : n64, 256);
+  k4_fused_prep_kernel<<<pb, 256, 0, st>>>(b_out, n_items, n64, target_logit, y_id, Q, q64, bL, lseL, yq, lsum);
+  HTCN_LAUNCH_CHECK("k4_fused_prep_kernel");
+  BwdArgs a{bL, lseL, gq, yq, d_hout, nullptr, lsum, Q, n_items, n0, n_items, 1};
+  int32_t rc = launch_bwd<2>(hout, (uint64_t)Q, kDim, w_out_t, (uint64_t)n_items, kWtPitchBf16, w_out, (uint64_t)n_items,
+                             (uint64_t)n_pad, a, st);
+  if (rc) return rc;
+  ce_fused_finish_kernel<<<ceil_div(Q, kFinishWarps), 32 * kFinishWarps, 0, st>>>(
+      Q, lsum, target_logit, g_row, y_id, reinterpret_cast<const __nv_bfloat16*>(hout),
+      reinterpret_cast<const __nv_bfloat16*>(w_out_t), b_out, n_items, n0, d_hout, loss_row);
+  HTCN_LAUNCH_CHECK("ce_fused_finish_kernel");
+  k4_bwd_prep_kernel<<<pb, 256, 0, st>>>(b_out, n_items, n64, loss_row, target_logit, g_row, y_id, Q, q64, bL, lseL, gq, yq);
+  HTCN_LAUNCH_CHECK("k4_bwd_prep_kernel");
+  a.out = d_w_out_t;
+  a.d_b = d_b_out;
+  a.n_stream = Q;
+  return launch_bwd<1>(w_out_t, (uint64_t)n_items, kWtPitchBf16, hout, (uint64_t)Q, kDim, hout_t, (uint64_t)Q,
+                       (uint64_t)q_pad, a, st);
 }

@@ -240,11 +240,24 @@ class HierTCNTrainer:
             prec = cabi.HTCN_BF16
         cabi.call("htcn_target_logit", hq.data_ptr(), prec, Q, m.wt.data_ptr(), m.b_out.data_ptr(), N, 0,
                   d["y_rows"].data_ptr(), zy.data_ptr(), st)
+        loss_row = buf("loss_row", (Q,), f32)
+        g_row = buf("tr_g_row", (Q,), f32)
+        cabi.call("htcn_loss_row_weights", y_loss.data_ptr(), d["row_of"].data_ptr(), B, T, g_row.data_ptr(), st)
+        d_hout = buf("tr_d_hout", (Q, D), f32)
+        if self.bf16 and not metrics and getattr(self, "k4_fused_fwd_bwd", True):
+            # loss + dHout in ONE catalog sweep (target-referenced sums need no running maximum), dW^T / db in a second
+            cabi.call("htcn_score_ce_fwd_bwd_bf16", hq.data_ptr(), hq_t.data_ptr(), q_pad, Q, m.wt.data_ptr(),
+                      self.w_out_bf16.data_ptr(), self.n_pad, m.b_out.data_ptr(), N, 0, d["y_rows"].data_ptr(), zy.data_ptr(),
+                      g_row.data_ptr(), buf("tr_k4_ws", (cabi.ce_bwd_bf16_ws_floats(Q, N),), f32).data_ptr(),
+                      loss_row.data_ptr(), d_hout.data_ptr(), self.g["wt"].data_ptr(), self.g["b_out"].data_ptr(), st)
+            cabi.call("htcn_loss_metrics_reduce", loss_row.data_ptr(), None, d["row_of"].data_ptr(), y_loss.data_ptr(),
+                      B, T, N, None, None, None, buf("user_part", (B, 8), f32).data_ptr(), scalars.data_ptr(), st)
+            return self._backward_below_head(d, d_hout, xe, sdt_c, yp, state_pre, gates, h_save, a_save, drop, scalars,
+                                             state_out, slot_p, slot_keep)
         cabi.call("htcn_score_ce_rank_topk", hq.data_ptr(), prec, Q, m.wt.data_ptr(), m.b_out.data_ptr(), N, 0,
                   d["y_rows"].data_ptr(), zy.data_ptr(), 1, cabi.SCORE_CE | (cabi.SCORE_RANK if metrics else 0), 0, ns,
                   pm.data_ptr(), ps.data_ptr(), P(pc), None, None, st)
         cabi.note_launches(-1)
-        loss_row = buf("loss_row", (Q,), f32)
         rank_row = buf("rank_row", (Q,), f32) if metrics else None
         cabi.call("htcn_score_finish", pm.data_ptr(), ps.data_ptr(), P(pc), ns, Q, d["y_rows"].data_ptr(), zy.data_ptr(),
                   loss_row.data_ptr(), P(rank_row), st)
@@ -254,9 +267,6 @@ class HierTCNTrainer:
         cabi.call("htcn_loss_metrics_reduce", loss_row.data_ptr(), P(rank_row), d["row_of"].data_ptr(), y_loss.data_ptr(),
                   B, T, N, None, None, None, buf("user_part", (B, 8), f32).data_ptr(), scalars.data_ptr(), st)
         # ---- backward
-        g_row = buf("tr_g_row", (Q,), f32)
-        cabi.call("htcn_loss_row_weights", y_loss.data_ptr(), d["row_of"].data_ptr(), B, T, g_row.data_ptr(), st)
-        d_hout = buf("tr_d_hout", (Q, D), f32)
         if self.bf16:
             cabi.call("htcn_score_ce_backward_bf16", hq.data_ptr(), hq_t.data_ptr(), q_pad, Q, m.wt.data_ptr(),
                       self.w_out_bf16.data_ptr(), self.n_pad, m.b_out.data_ptr(), N, 0, d["y_rows"].data_ptr(),

@@ -360,12 +360,25 @@ int32_t htcn_score_ce_backward(const void* hout, int32_t hout_dtype, int32_t Q, 
  * htcn_refresh_wout):  hout [Q,128], hout_t [128,q_pad] (its transpose), w_out_t [n_items,144] (scoring layout),
  * w_out [128,n_pad] (TF layout).  q_pad, n_pad: row pitches, multiples of 8.  workspace:
  * HTCN_CE_BWD_BF16_WS_FLOATS(Q, n_items) floats.  Outputs as htcn_score_ce_backward. */
-#define HTCN_CE_BWD_BF16_WS_FLOATS(Q, N) (3 * ((((int64_t)(Q)) + 63) / 64 * 64) + ((((int64_t)(N)) + 63) / 64 * 64))
+#define HTCN_CE_BWD_BF16_WS_FLOATS(Q, N) (4 * ((((int64_t)(Q)) + 63) / 64 * 64) + ((((int64_t)(N)) + 63) / 64 * 64))
 int32_t htcn_score_ce_backward_bf16(const void* hout, const void* hout_t, int64_t q_pad, int32_t Q,
                                     const void* w_out_t, const void* w_out, int64_t n_pad, const float* b_out,
                                     int32_t n_items, int32_t n0, const int32_t* y_id, const float* loss_row,
                                     const float* target_logit, const float* g_row, float* workspace, float* d_hout,
                                     float* d_w_out_t, float* d_b_out, void* stream);
+
+/* Loss AND gradients of the head in two catalog sweeps instead of three (training without the rank metrics): with the
+ * target logit as the reference point of the softmax sum (the forward sweep's convention) O_q = sum_j exp(z_j - z_y) w_j
+ * and l_q = sum_j exp(z_j - z_y) need no running maximum, so ONE sweep shaped like htcn_score_ce_backward_bf16's pass A
+ * yields loss_row[q] = log l_q (written here, [Q] f32) and d_hout[q] = g_q (O_q / l_q - w_y); the second sweep is pass B
+ * (d_w_out_t, d_b_out).  A row whose sum leaves the fp32 range (a logit ~69 nats above the target's) is redone exactly
+ * with a running maximum.  Same operands and workspace as htcn_score_ce_backward_bf16; replaces
+ * htcn_score_ce_rank_topk(HTCN_SCORE_CE) + htcn_score_finish + htcn_score_ce_repair + htcn_score_ce_backward_bf16. */
+int32_t htcn_score_ce_fwd_bwd_bf16(const void* hout, const void* hout_t, int64_t q_pad, int32_t Q,
+                                   const void* w_out_t, const void* w_out, int64_t n_pad, const float* b_out,
+                                   int32_t n_items, int32_t n0, const int32_t* y_id, const float* target_logit,
+                                   const float* g_row, float* workspace, float* loss_row, float* d_hout,
+                                   float* d_w_out_t, float* d_b_out, void* stream);
 
 /* src [R,128] (f32 or bf16) -> dst_rows [R,128] bf16 (or NULL) and dst_t [128,r_pad] bf16 = its transpose (or NULL;
  * columns R..r_pad-1 are zero).  r_pad % 8 == 0. */

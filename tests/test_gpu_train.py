@@ -563,3 +563,62 @@ def test_tensor_core_weight_gradient_gemm(B, S, L, K, dil):
         hs = np.where(ok[:, None], h[np.clip(src, 0, R - 1)], 0.0)
         want = hs.astype(np.float64).T @ dp.astype(np.float64)
         np.testing.assert_allclose(got[tap], want, rtol=2e-4, atol=2e-4 * np.abs(want).max())
+
+
+@pytest.mark.parametrize("Q,N,hot", [(200, 300, 0), (128, 64, 0), (1, 1000, 0), (333, 20778, 0), (1500, 257, 3), (700, 5000, 2)])
+def test_score_ce_fwd_bwd_bf16_two_sweeps(Q, N, hot):
+    """loss + dHout from ONE target-referenced sweep, dW^T / db from the second: against fp64 numpy on the same bf16-rounded
+    operands.  `hot` rows carry a logit > 69 nats above the target's (the sum leaves the fp32 range): the finish kernel
+    redoes them exactly with a running maximum."""
+    from hiertcn_b200 import _cabi as cabi
+    rng = np.random.default_rng(Q * 11 + N)
+    h = bf16r(rng.normal(0, 1, (Q, 128)))
+    wt = bf16r(rng.normal(0, 0.2, (N, 128)))
+    b = rng.normal(0, 0.5, N).astype(np.float32)
+    y = rng.integers(1, N, Q).astype(np.int32)
+    for i in range(hot):                                        # one dominant item for row i (not its target)
+        j = (int(y[i]) + 1 + i) % N
+        b[j] = 0.0
+        wt[j] = bf16r(h[i] * (150.0 + 40 * i) / float(h[i] @ h[i]))
+    g = rng.uniform(0.1, 1.0, Q).astype(np.float32)
+    z = h.astype(np.float64) @ wt.astype(np.float64).T + b
+    mx = z.max(1, keepdims=True)
+    lse = (mx + np.log(np.exp(z - mx).sum(1, keepdims=True)))[:, 0]
+    zy = z[np.arange(Q), y]
+    if hot:
+        assert (z.max(1) - zy)[:hot].min() > 100
+    p = np.exp(z - lse[:, None])
+    p[np.arange(Q), y] -= 1.0
+    p *= g[:, None]
+    ref_dh, ref_dw, ref_db = p @ wt, p.T @ h, p.sum(0)
+    st = torch.cuda.current_stream().cuda_stream
+    q_pad, n_pad = -(-Q // 8) * 8, -(-N // 8) * 8
+    h_d, wt_d, b_d = dev(h), dev(wt), dev(b)
+    hq = torch.empty((Q, 128), dtype=torch.bfloat16, device="cuda")
+    hq_t = torch.empty((128, q_pad), dtype=torch.bfloat16, device="cuda")
+    w_aug = torch.empty((N, 144), dtype=torch.bfloat16, device="cuda")
+    w_tf = torch.empty((128, n_pad), dtype=torch.bfloat16, device="cuda")
+    cabi.call("htcn_cast_transpose_bf16", h_d.data_ptr(), cabi.HTCN_F32, Q, hq.data_ptr(), hq_t.data_ptr(), q_pad, st)
+    cabi.call("htcn_cast_transpose_bf16", wt_d.data_ptr(), cabi.HTCN_F32, N, None, w_tf.data_ptr(), n_pad, st)
+    cabi.call("htcn_refresh_wout", wt_d.data_ptr(), b_d.data_ptr(), N, w_aug.data_ptr(), cabi.HTCN_BF16, st)
+    y_d, g_d = dev(y), dev(g)
+    zy_d = torch.empty(Q, device="cuda")
+    cabi.call("htcn_target_logit", hq.data_ptr(), cabi.HTCN_BF16, Q, w_aug.data_ptr(), b_d.data_ptr(), N, 0, y_d.data_ptr(),
+              zy_d.data_ptr(), st)
+    loss = torch.full((Q,), float("nan"), device="cuda")
+    dh = torch.full((Q, 128), 7.0, device="cuda")
+    dw = torch.ones((N, 128), device="cuda")
+    db = torch.ones(N, device="cuda")
+    cabi.call("htcn_score_ce_fwd_bwd_bf16", hq.data_ptr(), hq_t.data_ptr(), q_pad, Q, w_aug.data_ptr(), w_tf.data_ptr(), n_pad,
+              b_d.data_ptr(), N, 0, y_d.data_ptr(), zy_d.data_ptr(), g_d.data_ptr(),
+              torch.empty(cabi.ce_bwd_bf16_ws_floats(Q, N), device="cuda").data_ptr(), loss.data_ptr(), dh.data_ptr(),
+              dw.data_ptr(), db.data_ptr(), st)
+    torch.cuda.synchronize()
+    got_loss = loss.cpu().numpy()
+    ref_loss = lse - zy
+    assert np.isfinite(got_loss).all()
+    assert np.abs(got_loss - ref_loss).max() <= 2e-3 * np.abs(ref_loss).max() + 2e-3, np.abs(got_loss - ref_loss).max()
+    for got, ref in ((dh.cpu().numpy(), ref_dh), (dw.cpu().numpy() - 1.0, ref_dw), (db.cpu().numpy() - 1.0, ref_db)):
+        assert np.isfinite(got).all()
+        assert np.abs(got - ref).max() <= 1e-2 * np.abs(ref).max() + 1e-6, (np.abs(got - ref).max(), np.abs(ref).max())
+        assert np.linalg.norm(got - ref) <= 5e-3 * np.linalg.norm(ref) + 1e-6
