@@ -312,7 +312,7 @@ class HierTCNTrainer:
                   m._gru_pp[0][0], m._gru_pp[2][0], G, m.w_in_state.data_ptr(), B, S, d_sbias.data_ptr(),
                   k3_scratch.data_ptr(), self._d_gru[0][0], self._d_gru[1][0], self._d_gru[2][0], self._d_gru[3][0],
                   self.g["w_in_state"].data_ptr(), d_yp.data_ptr(), st)
-        cabi.note_launches(G * (S + 1) + 4 * S * G + 9 * G)
+        cabi.note_launches(2 + G + 9 * G)          # setup, G sbias products, ONE recurrence kernel, 9 deferred products per layer
         cabi.call("htcn_gather_backward", d_xe.data_ptr(), d_yp.data_ptr(), d["x_id"].data_ptr(), d["y_id"].data_ptr(),
                   slot_p, B, T, S, N, self.g["E"].data_ptr(), self.g["b_emb"].data_ptr(), st)
         del slot_keep
