@@ -20,12 +20,13 @@ namespace htcn {
 namespace {
 
 // ---- the recurrence as ONE persistent kernel -----------------------------------------------------------------------
-// Users are independent, so a CTA owns kBpMB of them and walks all S x G cell calls (last step first, top layer first)
+// Users are independent, so a CTA owns kBpMB = 32 of them and walks all S x G cell calls (last step first, top layer first)
 // with the running gradients [dx | dh] of both layers in shared memory; the two skinny products of a cell call
 // ([32 x 128] Wc^T and [32 x 256] Wg^T) are FFMA register tiles fed by double-buffered 16-deep weight slices out of L2.
 // Replaces 4 launches per cell call (80 per step at S = 10, G = 2).  What the deferred weight-gradient GEMMs need (dcpre,
 // [drpre | dupre]) is written out as before.
-constexpr int kBpMB = 32;            // users per CTA
+constexpr int kBpMB = 32;            // users per CTA (16 with two CTAs per SM measured slower: 1.31 vs 1.21 ms)
+constexpr int kBpTU = kBpMB / 4;     // users per thread tile
 constexpr int kBpThreads = 256;
 constexpr int kBpKT = 16;            // contraction slice
 struct BpttSmem {
@@ -51,7 +52,7 @@ struct BpttArgs {
 
 // acc[i][j] += sum_k A[b0 + i][k] W[n4 + j][k],  k < K;  A in shared memory (row stride lda), W [256][K] in global memory
 template <int K>
-__device__ __forceinline__ void bp_gemm(const float* A, int lda, const float* __restrict__ W, float (&acc)[8][4], BpttSmem& sm,
+__device__ __forceinline__ void bp_gemm(const float* A, int lda, const float* __restrict__ W, float (&acc)[kBpTU][4], BpttSmem& sm,
                                         int tid, int b0, int n4) {
   float4 pre[4];
   const float4* wrow = reinterpret_cast<const float4*>(W + (long long)tid * K);
@@ -70,14 +71,14 @@ __device__ __forceinline__ void bp_gemm(const float* A, int lda, const float* __
     }
 #pragma unroll
     for (int kk = 0; kk < kBpKT; kk += 4) {
-      float4 a[8];
+      float4 a[kBpTU];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) a[i] = *reinterpret_cast<const float4*>(A + (b0 + i) * lda + k0 + kk);
+      for (int i = 0; i < kBpTU; ++i) a[i] = *reinterpret_cast<const float4*>(A + (b0 + i) * lda + k0 + kk);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float4 w = *reinterpret_cast<const float4*>(&wt[kk + j][n4]);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < kBpTU; ++i) {
           const float av = j == 0 ? a[i].x : j == 1 ? a[i].y : j == 2 ? a[i].z : a[i].w;
           acc[i][0] = fmaf(av, w.x, acc[i][0]); acc[i][1] = fmaf(av, w.y, acc[i][1]);
           acc[i][2] = fmaf(av, w.z, acc[i][2]); acc[i][3] = fmaf(av, w.w, acc[i][3]);
@@ -92,7 +93,7 @@ __global__ void __launch_bounds__(kBpThreads, 1) gru_bptt_kernel(BpttArgs a) {
   BpttSmem& sm = *reinterpret_cast<BpttSmem*>(bp_smem);
   const int tid = threadIdx.x;
   const int u0 = blockIdx.x * kBpMB;
-  const int n4 = 4 * (tid & 63), b0 = 8 * (tid >> 6);
+  const int n4 = 4 * (tid & 63), b0 = kBpTU * (tid >> 6);
   const long long BD = (long long)a.B * kDim;
   constexpr int G = 2;
   for (int s = a.S - 1; s >= 0; --s) {
@@ -100,67 +101,94 @@ __global__ void __launch_bounds__(kBpThreads, 1) gru_bptt_kernel(BpttArgs a) {
       const float* gr = a.gates + ((long long)(s * G + g) * 3 + 0) * BD;
       const float* gu = gr + BD;
       const float* gc = gu + BD;
-      // ---- A: gate gradients of this cell call
-      for (int idx = tid; idx < kBpMB * kDim; idx += kBpThreads) {
-        const int b = idx >> 7, c = idx & 127, ub = u0 + b;
-        float dcp = 0.f, dup = 0.f, cr = 0.f;
+      // ---- A: gate gradients of this cell call (float4 per thread and iteration, loads of all iterations in flight)
+#pragma unroll
+      for (int it4 = 0; it4 < kBpMB * 32 / kBpThreads; ++it4) {
+        const int idx = tid + it4 * kBpThreads;
+        const int b = idx >> 5, c = (idx & 31) * 4, ub = u0 + b;
+        float4 dcp = make_float4(0.f, 0.f, 0.f, 0.f), dup = dcp, cr = dcp;
         if (ub < a.B) {
-          float dhn = (s + 1 < a.S) ? sm.outs[g][b][128 + c] * a.mask[(long long)s * a.B + ub] : 0.f;
-          if (g + 1 < G) dhn += sm.outs[g + 1][b][c];
           const long long gi = (long long)ub * kDim + c, row = (long long)s * a.B + ub;
-          const float u = gu[gi], cc = gc[gi], h = a.state_pre[row * 256 + g * kDim + c];
-          const float du = dhn * (h - cc), dc = dhn * (1.f - u);
-          dcp = dc * (1.f - cc * cc);
-          dup = du * u * (1.f - u);
-          cr = dhn * u;
-          a.DC[g][row * kDim + c] = dcp;
-          a.DG[g][row * 256 + 128 + c] = dup;
+          const float4 u = *reinterpret_cast<const float4*>(gu + gi), cc = *reinterpret_cast<const float4*>(gc + gi);
+          const float4 h = *reinterpret_cast<const float4*>(a.state_pre + row * 256 + g * kDim + c);
+          float4 dhn = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (s + 1 < a.S) {
+            const float mk = a.mask[(long long)s * a.B + ub];
+            const float4 o = *reinterpret_cast<const float4*>(&sm.outs[g][b][128 + c]);
+            dhn = make_float4(o.x * mk, o.y * mk, o.z * mk, o.w * mk);
+          }
+          if (g + 1 < G) {
+            const float4 o = *reinterpret_cast<const float4*>(&sm.outs[g + 1][b][c]);
+            dhn.x += o.x; dhn.y += o.y; dhn.z += o.z; dhn.w += o.w;
+          }
+#define HTCN_BP_A(f)                                        \
+          {                                                 \
+            const float du = dhn.f * (h.f - cc.f), dc = dhn.f * (1.f - u.f); \
+            dcp.f = dc * (1.f - cc.f * cc.f);               \
+            dup.f = du * u.f * (1.f - u.f);                 \
+            cr.f = dhn.f * u.f;                             \
+          }
+          HTCN_BP_A(x) HTCN_BP_A(y) HTCN_BP_A(z) HTCN_BP_A(w)
+#undef HTCN_BP_A
+          *reinterpret_cast<float4*>(a.DC[g] + row * kDim + c) = dcp;
+          *reinterpret_cast<float4*>(a.DG[g] + row * 256 + 128 + c) = dup;
         }
-        sm.dc[b][c] = dcp;
-        sm.dg[b][128 + c] = dup;
-        sm.carry[b][c] = cr;
+        *reinterpret_cast<float4*>(&sm.dc[b][c]) = dcp;
+        *reinterpret_cast<float4*>(&sm.dg[b][128 + c]) = dup;
+        *reinterpret_cast<float4*>(&sm.carry[b][c]) = cr;
       }
       __syncthreads();
       // ---- [dx_c | drh] = dcpre Wc^T
-      float acc[8][4];
+      float acc[kBpTU][4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < kBpTU; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
       bp_gemm<128>(&sm.dc[0][0], 128, a.wc[g], acc, sm, tid, b0, n4);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(&sm.tmp[b0 + i][n4]) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+      for (int i = 0; i < kBpTU; ++i) *reinterpret_cast<float4*>(&sm.tmp[b0 + i][n4]) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
       __syncthreads();
       // ---- B: drpre, and the start of this cell call's [dx | dh]
-      for (int idx = tid; idx < kBpMB * kDim; idx += kBpThreads) {
-        const int b = idx >> 7, c = idx & 127, ub = u0 + b;
-        float drp = 0.f, dh = 0.f;
+#pragma unroll
+      for (int it4 = 0; it4 < kBpMB * 32 / kBpThreads; ++it4) {
+        const int idx = tid + it4 * kBpThreads;
+        const int b = idx >> 5, c = (idx & 31) * 4, ub = u0 + b;
+        float4 drp = make_float4(0.f, 0.f, 0.f, 0.f), dh = drp;
         if (ub < a.B) {
           const long long gi = (long long)ub * kDim + c, row = (long long)s * a.B + ub;
-          const float drh = sm.tmp[b][128 + c], rr = gr[gi], hh = a.state_pre[row * 256 + g * kDim + c];
-          drp = drh * hh * rr * (1.f - rr);
-          dh = sm.carry[b][c] + drh * rr + a.sbc[g][row * kDim + c];
-          a.DG[g][row * 256 + c] = drp;
+          const float4 rr = *reinterpret_cast<const float4*>(gr + gi);
+          const float4 hh = *reinterpret_cast<const float4*>(a.state_pre + row * 256 + g * kDim + c);
+          const float4 sb = *reinterpret_cast<const float4*>(a.sbc[g] + row * kDim + c);
+          const float4 drh = *reinterpret_cast<const float4*>(&sm.tmp[b][128 + c]);
+          const float4 cr = *reinterpret_cast<const float4*>(&sm.carry[b][c]);
+          drp = make_float4(drh.x * hh.x * rr.x * (1.f - rr.x), drh.y * hh.y * rr.y * (1.f - rr.y),
+                            drh.z * hh.z * rr.z * (1.f - rr.z), drh.w * hh.w * rr.w * (1.f - rr.w));
+          dh = make_float4(cr.x + drh.x * rr.x + sb.x, cr.y + drh.y * rr.y + sb.y, cr.z + drh.z * rr.z + sb.z,
+                           cr.w + drh.w * rr.w + sb.w);
+          *reinterpret_cast<float4*>(a.DG[g] + row * 256 + c) = drp;
         }
-        sm.dg[b][c] = drp;
-        sm.outs[g][b][c] = sm.tmp[b][c];
-        sm.outs[g][b][128 + c] = dh;
+        *reinterpret_cast<float4*>(&sm.dg[b][c]) = drp;
+        *reinterpret_cast<float4*>(&sm.outs[g][b][c]) = *reinterpret_cast<const float4*>(&sm.tmp[b][c]);
+        *reinterpret_cast<float4*>(&sm.outs[g][b][128 + c]) = dh;
       }
       __syncthreads();
       // ---- [dx | dh] += [drpre | dupre] Wg^T
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < kBpTU; ++i) {
         const float4 o = *reinterpret_cast<const float4*>(&sm.outs[g][b0 + i][n4]);
         acc[i][0] = o.x; acc[i][1] = o.y; acc[i][2] = o.z; acc[i][3] = o.w;
       }
       bp_gemm<256>(&sm.dg[0][0], 256, a.wg[g], acc, sm, tid, b0, n4);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(&sm.outs[g][b0 + i][n4]) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+      for (int i = 0; i < kBpTU; ++i) *reinterpret_cast<float4*>(&sm.outs[g][b0 + i][n4]) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
       __syncthreads();
       if (g == 0) {                                              // dL/dyp[s] = dx of layer 0
-        for (int idx = tid; idx < kBpMB * kDim; idx += kBpThreads) {
-          const int b = idx >> 7, c = idx & 127, ub = u0 + b;
-          if (ub < a.B) a.d_yp[((long long)s * a.B + ub) * kDim + c] = sm.outs[0][b][c];
+#pragma unroll
+        for (int it4 = 0; it4 < kBpMB * 32 / kBpThreads; ++it4) {
+          const int idx = tid + it4 * kBpThreads;
+          const int b = idx >> 5, c = (idx & 31) * 4, ub = u0 + b;
+          if (ub < a.B)
+            *reinterpret_cast<float4*>(a.d_yp + ((long long)s * a.B + ub) * kDim + c) = *reinterpret_cast<const float4*>(&sm.outs[0][b][c]);
         }
       }
     }

@@ -425,7 +425,18 @@ int32_t launch_bwd(const void* x, uint64_t x_rows, uint32_t x_pitch, const void*
   if (rc) return rc;
   const int m_tiles = ceil_div((long long)x_rows, kHalves * kBM);
   const int s_tiles = ceil_div(a.n_stream, kBN);
-  int ns = ceil_div(4 * 148, m_tiles);                  // about four waves of CTAs
+  // about four waves of CTAs (1 CTA per SM); among the split counts around that, the one whose last wave is fullest
+  // (config 5's pass B: 82 item tiles x 8 splits = 4.43 waves ran as 5; 9 splits = 4.99)
+  int ns = 1;
+  if (m_tiles < 4 * 148) {
+    const int lo = ceil_div(3 * 148, m_tiles), hi = ceil_div(6 * 148, m_tiles);
+    double best = -1.0;
+    for (int c = lo; c <= hi; ++c) {
+      const long long ctas = (long long)m_tiles * c;
+      const double eff = (double)ctas / (double)(ceil_div(ctas, 148) * 148);
+      if (eff > best + 1e-9) { best = eff; ns = c; }
+    }
+  }
   if (ns > s_tiles) ns = s_tiles;
   if (ns > 65535) ns = 65535;
   if (ns < 1) ns = 1;

@@ -45,12 +45,16 @@ struct LvGeom {
   LvSlot slot[HTCN_MAX_SLOTS];
 };
 
+// kSplit runs one CTA per SM with TWO tile buffers (and two TMEM accumulators): the worker warps stage tile i+1 and drain
+// tile i-1 while the tensor pipe works on tile i (120 MMAs, ~4 us: as long as the tile's HBM traffic).  The plain variant
+// (40 MMAs per tile, worker-bound) keeps one buffer and two CTAs per SM instead.
 template <bool kSplit>
 struct alignas(1024) LvSmem {
+  static constexpr int kBufs = kSplit ? 2 : 1;
   uint8_t w[kLvStages][kLvWStage];                 // 64 KB
-  uint8_t act[kSplit ? 2 : 1][kLvActBytes];        // hi (, lo) planes
+  uint8_t act[kBufs][kSplit ? 2 : 1][kLvActBytes]; // [tile buffer][hi (, lo) plane]
   float bias[kDim];
-  uint64_t w_full[kLvStages], w_empty[kLvStages], acc_ready, act_ready;
+  uint64_t w_full[kLvStages], w_empty[kLvStages], acc_ready[2], act_ready[2];
   uint32_t tmem_base;
 };
 
@@ -99,13 +103,16 @@ k2_level_tc(const __grid_constant__ CUtensorMap tmap_w, LvGeom g, LevelArgs a) {
       mbar_init(&sm.w_full[s], 1);
       mbar_init(&sm.w_empty[s], 1);
     }
-    mbar_init(&sm.acc_ready, 1);
-    mbar_init(&sm.act_ready, 32 * kLvWorkWarps);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&sm.acc_ready[b], 1);
+      mbar_init(&sm.act_ready[b], 32 * kLvWorkWarps);
+    }
     fence_barrier_init();
   }
   for (int i = tid; i < kDim; i += kLvThreads) sm.bias[i] = a.bias ? a.bias[i] : 0.f;
   for (int i = tid; i < (int)sizeof(sm.act) / 16; i += kLvThreads) reinterpret_cast<uint4*>(sm.act)[i] = make_uint4(0, 0, 0, 0);
-  if (warp == kLvMmaWarp) tmem_alloc<128>(&sm.tmem_base);
+  constexpr int kBufs = LvSmem<kSplit>::kBufs;
+  if (warp == kLvMmaWarp) tmem_alloc<128 * kBufs>(&sm.tmem_base);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -129,11 +136,13 @@ k2_level_tc(const __grid_constant__ CUtensorMap tmap_w, LvGeom g, LevelArgs a) {
     // ===================== MMA issuer (warp-uniform control flow, one elected lane issues) =====================
     const bool leader = elect_one();
     constexpr uint32_t idesc = make_idesc_bf16(kLvRows, 128);
-    const uint32_t act_hi = smem_u32(sm.act[0]);
-    const uint32_t act_lo = smem_u32(sm.act[kSplit ? 1 : 0]);
     long long n = 0;
     for (int it = 0; it < my_tiles; ++it) {
-      mbar_wait(&sm.act_ready, (uint32_t)(it & 1));
+      const int tb = it % kBufs;
+      const uint32_t act_hi = smem_u32(sm.act[tb][0]);
+      const uint32_t act_lo = smem_u32(sm.act[tb][kSplit ? 1 : 0]);
+      const uint32_t tacc = tmem + tb * 128;
+      mbar_wait(&sm.act_ready[tb], (uint32_t)((it / kBufs) & 1));
       tc_fence_after_sync();
       for (int tap = 0; tap < a.K; ++tap) {
         const int shift = (a.K - 1 - tap) * a.dil;
@@ -149,53 +158,61 @@ k2_level_tc(const __grid_constant__ CUtensorMap tmap_w, LvGeom g, LevelArgs a) {
             const uint32_t koff = (uint32_t)(2 * k) * (kLvBufRows * 16);
             const uint64_t da = lv_desc_act(act_hi + row0 + koff);
             const uint64_t db = make_desc_k_sw128(w_base + (k >> 2) * (kLvWStage / 2) + (k & 3) * 32);
-            if (leader) umma_bf16(tmem, da, db, idesc, (tap | k | part) != 0);        // x_hi w_hi, or x_hi w_lo
+            if (leader) umma_bf16(tacc, da, db, idesc, (tap | k | part) != 0);        // x_hi w_hi, or x_hi w_lo
             if (kSplit && part == 0) {
               const uint64_t dl = lv_desc_act(act_lo + row0 + koff);
-              if (leader) umma_bf16(tmem, dl, db, idesc, true);                       // x_lo w_hi
+              if (leader) umma_bf16(tacc, dl, db, idesc, true);                       // x_lo w_hi
             }
           }
           if (leader) umma_commit(&sm.w_empty[s]);
         }
       }
-      if (leader) umma_commit(&sm.acc_ready);
+      if (leader) umma_commit(&sm.acc_ready[tb]);
     }
   } else {
     // ===================== stage rows + epilogue: thread = 64 channels of one tile row =====================
     const int r = tid & 127;                                   // TMEM lane r
     const int ch = tid >> 7;                                   // channel half
     const int buf_row = (anti ? 0 : kLvSpare) + r;
-    uint8_t* my_hi = sm.act[0] + buf_row * 16;                 // + c * kLvBufRows * 16 for channel chunk c
-    uint8_t* my_lo = sm.act[kSplit ? 1 : 0] + buf_row * 16;
     const int epi = a.conv_epilogue;
-    int unit = blockIdx.x;
-    int src, sb, slot;
-    lv_row(g, unit, r, anti, src, sb, slot);
-    for (int it = 0; it < my_tiles; ++it) {
-      // ---- stage this tile's input rows
-      {
-        const float4* p = src >= 0 ? reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.in) + (long long)src * kDim + ch * 64)
-                                   : nullptr;
-        float4 x[16];
+    // stage the input rows of the tile whose row of this thread is `src_` into tile buffer tb
+    auto stage = [&](int tb, int src_) {
+      uint8_t* my_hi = sm.act[tb][0] + buf_row * 16;           // + c * kLvBufRows * 16 for channel chunk c
+      uint8_t* my_lo = sm.act[tb][kSplit ? 1 : 0] + buf_row * 16;
+      const float4* p = src_ >= 0 ? reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.in) + (long long)src_ * kDim + ch * 64)
+                                  : nullptr;
+      float4 x[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) x[i] = p ? __ldg(p + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 0; i < 16; ++i) x[i] = p ? __ldg(p + i) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float v[8] = {x[2 * c].x, x[2 * c].y, x[2 * c].z, x[2 * c].w, x[2 * c + 1].x, x[2 * c + 1].y, x[2 * c + 1].z, x[2 * c + 1].w};
-          const int off = (ch * 8 + c) * (kLvBufRows * 16);
-          if (kSplit) {
-            float h[8], l[8];
+      for (int c = 0; c < 8; ++c) {
+        const float v[8] = {x[2 * c].x, x[2 * c].y, x[2 * c].z, x[2 * c].w, x[2 * c + 1].x, x[2 * c + 1].y, x[2 * c + 1].z, x[2 * c + 1].w};
+        const int off = (ch * 8 + c) * (kLvBufRows * 16);
+        if (kSplit) {
+          float h[8], l[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) split_bf16(v[e], h[e], l[e]);
-            *reinterpret_cast<uint4*>(my_hi + off) = make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
-            *reinterpret_cast<uint4*>(my_lo + off) = make_uint4(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]), pack_bf16x2(l[4], l[5]), pack_bf16x2(l[6], l[7]));
-          } else {
-            *reinterpret_cast<uint4*>(my_hi + off) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-          }
+          for (int e = 0; e < 8; ++e) split_bf16(v[e], h[e], l[e]);
+          *reinterpret_cast<uint4*>(my_hi + off) = make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
+          *reinterpret_cast<uint4*>(my_lo + off) = make_uint4(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]), pack_bf16x2(l[4], l[5]), pack_bf16x2(l[6], l[7]));
+        } else {
+          *reinterpret_cast<uint4*>(my_hi + off) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
         }
       }
       fence_proxy_async_smem();
-      mbar_arrive(&sm.act_ready);
+      mbar_arrive(&sm.act_ready[tb]);
+    };
+    int unit = blockIdx.x;
+    int src, sb, slot;
+    lv_row(g, unit, r, anti, src, sb, slot);
+    int nsrc = -1, nsb = 0, nslot = 0;                         // the next tile's row of this thread
+    stage(0, src);
+    for (int it = 0; it < my_tiles; ++it) {
+      const int tb = it % kBufs;
+      const uint32_t tacc = tmem + tb * 128;
+      if (it + 1 < my_tiles) lv_row(g, unit + (int)gridDim.x, r, anti, nsrc, nsb, nslot);
+      // two buffers: tile it+1 is staged BEFORE tile it is drained (its buffer and accumulator were released by the drain of
+      // tile it-1), so the tensor pipe never waits for the workers
+      if (kBufs == 2 && it + 1 < my_tiles) stage((it + 1) % kBufs, nsrc);
       // ---- epilogue
       const float* res_row = nullptr;                           // row added to the result (fp32)
       if (src >= 0) {
@@ -206,7 +223,7 @@ k2_level_tc(const __grid_constant__ CUtensorMap tmap_w, LvGeom g, LevelArgs a) {
       const float* drop_row = (a.drop && (epi == 1 || epi == 3)) ? a.drop + (long long)slot * a.drop_stride : nullptr;
       float* out_row = src >= 0 ? reinterpret_cast<float*>(a.out) + (long long)src * kDim : nullptr;
       float* aux_row = (src >= 0 && a.aux && (epi == 1 || epi == 3)) ? a.aux + (long long)src * kDim : nullptr;
-      mbar_wait(&sm.acc_ready, (uint32_t)(it & 1));
+      mbar_wait(&sm.acc_ready[tb], (uint32_t)((it / kBufs) & 1));
       tc_fence_after_sync();
 #pragma unroll 1
       for (int cc = ch * 2; cc < ch * 2 + 2; ++cc) {            // 2 x 32 channels
@@ -219,7 +236,7 @@ k2_level_tc(const __grid_constant__ CUtensorMap tmap_w, LvGeom g, LevelArgs a) {
           for (int i = 0; i < 8; ++i) rs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         uint32_t v[32];
-        tmem_ld_32x32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + cc * 32, v);
+        tmem_ld_32x32(tacc + ((uint32_t)((warp & 3) * 32) << 16) + cc * 32, v);
         tmem_ld_wait(v);
         if (out_row) {
 #pragma unroll
@@ -247,14 +264,15 @@ k2_level_tc(const __grid_constant__ CUtensorMap tmap_w, LvGeom g, LevelArgs a) {
       }
       tc_fence_before_sync();
       unit += gridDim.x;
-      if (it + 1 < my_tiles) lv_row(g, unit, r, anti, src, sb, slot);
+      src = nsrc; sb = nsb; slot = nslot;
+      if (kBufs == 1 && it + 1 < my_tiles) stage(0, src);
     }
   }
   tc_fence_before_sync();
   __syncthreads();
   if (warp == kLvMmaWarp) {
     tc_fence_after_sync();
-    tmem_dealloc<128>(tmem);
+    tmem_dealloc<128 * kBufs>(tmem);
   }
 }
 
