@@ -40,6 +40,7 @@ SIGNATURES = {
     "htcn_tcn_forward_wide": [_p, _i, _p, _p, _pp, _pp, _pp, _pp, _ip, _i, _i, _ip, _i, _i, _i, _p, _p, C.c_int64, _p, _p],
     "htcn_prepare_wout": [_p, _p, _i, _p, _i, _p],
     "htcn_score_ce_rank_topk": [_p, _i, _i, _p, _p, _i, _i, _p, _p, _i, _u, _i, _i, _p, _p, _p, _p, _p, _p],
+    "htcn_score_ce_rank_folded": [_p, _i, _p, _i, _i, _p, _p, _u, _i, _p, _p, _p, _p, _p],
     "htcn_score_logits": [_p, _i, _i, _p, _i, _p, _i, _p, _p],
     "htcn_target_logit": [_p, _i, _i, _p, _p, _i, _i, _p, _p, _p],
     "htcn_score_finish": [_p, _p, _p, _i, _i, _p, _p, _p, _p, _p],
@@ -112,7 +113,7 @@ def load(path: str | None = None):
 # kernels launched per successful call (bench.py's gpu_launches claim); htcn_tcn_forward launches
 # n_levels + 1 (counted by the caller through note_launches)
 LAUNCHES_PER_CALL = {"htcn_gather_meanpool": 2, "htcn_gru_sessions": 1, "htcn_tcn_forward": 0,
-                     "htcn_prepare_wout": 1, "htcn_score_ce_rank_topk": 2, "htcn_score_logits": 1,
+                     "htcn_prepare_wout": 1, "htcn_score_ce_rank_topk": 2, "htcn_score_ce_rank_folded": 3, "htcn_score_logits": 1,
                      "htcn_target_logit": 1, "htcn_score_finish": 1, "htcn_topk_merge": 1, "htcn_score_topk": 5, "htcn_score_ce_repair": 1,
                      "htcn_score_ce_repair_shard": 1, "htcn_score_ce_rank_topk_fused": 6,
                      "htcn_catalog_gram": 2, "htcn_logit_rownorm": 1, "htcn_score_ce_rank_l2norm": 2, "htcn_scale_rows": 1,
@@ -137,6 +138,10 @@ def call(name: str, *args):
     launch_count += LAUNCHES_PER_CALL.get(name, 0)
     if rc != 0:
         raise HtcnError("%s failed (%d): %s" % (name, rc, lib.htcn_last_error().decode()))
+
+
+def score_fold_ws_bytes(Q):
+    return (Q * 128 * 2 + 255) // 256 * 256 + Q * 4               # HTCN_SCORE_FOLD_WS_BYTES
 
 
 def ce_bwd_bf16_ws_floats(Q, N):

@@ -92,10 +92,14 @@ __global__ void refresh_wout_bf16_kernel(const float* __restrict__ wt, const flo
   if (c < kDim) {
     const float2 w = *reinterpret_cast<const float2*>(wt + n * kDim + c);
     lo = w.x; hi = w.y;
-  } else if (c == kDim) {
+  } else if (c == kDim || c == kDim + 2) {        // [b_hi, b_lo | b_hi, b_lo, 1, 1, 1 | 0...]: see prepare_wout_kernel
     const float bv = b[n];
     lo = __bfloat162float(__float2bfloat16_rn(bv));
     hi = bv - lo;
+  } else if (c == kDim + 4) {
+    lo = hi = 1.f;
+  } else if (c == kDim + 6) {
+    lo = 1.f;
   }
   *reinterpret_cast<uint32_t*>(out + n * kWtPitchBf16 + c) = pack_bf16x2(lo, hi);
 }

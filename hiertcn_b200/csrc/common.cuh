@@ -40,6 +40,8 @@ struct ScoreArgs {
                              // (HTCN_F32_W256: a 256-channel last level, args.py:310-311)
   const float* row_scale;    // [Q] or NULL: the CE sum runs on row_scale[q] * z (l2-normalised head, model_tcn.py:42-43);
                              // part_max then holds the SCALED reference point; ranks always compare the raw logits
+  const int* fold_self;      // bf16 folded CE + rank sweep only (k4_score_bf16.cu, kFold): [Q] sign bit of the target column's
+                             // own accumulator (taken out of the count by split 0); hout then holds the NEGATED embeddings
 };
 
 #define HTCN_REQUIRE(cond, ...)            \

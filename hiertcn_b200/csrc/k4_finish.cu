@@ -12,6 +12,7 @@ static inline bool is_f32(int precision) { return precision == HTCN_F32 || preci
 static inline int planes_of(int precision) { return precision == HTCN_F32_W256 ? 2 : 1; }
 // bf16 tier (k4_score_bf16.cu)
 int32_t score_bf16(const ScoreArgs& a, cudaStream_t st);
+int32_t score_ce_rank_folded_bf16(const ScoreArgs& a, void* workspace, cudaStream_t st);
 int32_t target_logit_bf16(const void* hout, const void* wt, const float* b_out, const int* y_id, int Q,
                           int n_items, int n0, float* zy, cudaStream_t st);
 long long topk_workspace_bytes_bf16(int Q, int n_items, int k, int n_split);
@@ -39,9 +40,12 @@ __global__ void prepare_wout_kernel(const float* __restrict__ w, const float* __
       __nv_bfloat16* row = reinterpret_cast<__nv_bfloat16*>(out) + (long long)(n0 + tx) * pitch + kDim;
       const float bv = b[n0 + tx];
       const __nv_bfloat16 hi = __float2bfloat16_rn(bv);
-      row[0] = hi;
-      row[1] = __float2bfloat16_rn(bv - __bfloat162float(hi));
-      for (int i = 2; i < pitch - kDim; ++i) row[i] = __float2bfloat16_rn(0.f);
+      const __nv_bfloat16 lo = __float2bfloat16_rn(bv - __bfloat162float(hi));
+      // [b_hi, b_lo | b_hi, b_lo, 1, 1, 1 | 0 x 9]: the sweeps multiply the first pair by A's constant [1, 1]; the folded
+      // CE + rank sweep (kFold, k4_score_bf16.cu) uses all seven: (c_hi + c_lo)(b_hi + b_lo) + t1 + t2 + t3
+      row[0] = hi; row[1] = lo; row[2] = hi; row[3] = lo;
+      row[4] = row[5] = row[6] = __float2bfloat16_rn(1.f);
+      for (int i = 7; i < pitch - kDim; ++i) row[i] = __float2bfloat16_rn(0.f);
     }
     return;
   }
@@ -424,6 +428,23 @@ extern "C" int32_t htcn_score_ce_rank_topk(const void* hout, int32_t precision, 
   }
   if (precision == HTCN_BF16) return score_bf16(a, st);
   HTCN_REQUIRE(false, "score: precision %d", precision);
+}
+
+// CE (+ rank) sweep of the bf16 tier with the exponent folded into the tensor-core product (k4_score_bf16.cu, kFoldFlag)
+extern "C" int32_t htcn_score_ce_rank_folded(const void* hout, int32_t Q, const void* w_out_t, int32_t n_items, int32_t n0,
+                                             const int32_t* y_id, const float* target_logit, uint32_t flags,
+                                             int32_t n_split, float* part_max, float* part_sum, int32_t* part_cnt,
+                                             void* workspace, void* stream) {
+  HTCN_REQUIRE(hout && w_out_t && y_id && target_logit && part_max && part_sum && workspace && Q > 0 && n_items > 0 &&
+                   n_split >= 1,
+               "score_folded: bad args");
+  HTCN_REQUIRE(flags == HTCN_SCORE_CE || flags == (HTCN_SCORE_CE | HTCN_SCORE_RANK), "score_folded: flags 0x%x", flags);
+  HTCN_REQUIRE(!(flags & HTCN_SCORE_RANK) || part_cnt, "score_folded: RANK partial buffer NULL");
+  const int n_tiles = (n_items + 63) / 64;
+  HTCN_REQUIRE(n_split <= n_tiles, "score_folded: n_split=%d exceeds the number of 64-item tiles (%d)", n_split, n_tiles);
+  ScoreArgs a{hout, w_out_t, nullptr, y_id, target_logit, part_max, part_sum, part_cnt, nullptr, nullptr,
+              Q, n_items, n0, 0, n_split, flags};
+  return score_ce_rank_folded_bf16(a, workspace, as_stream(stream));
 }
 
 extern "C" int64_t htcn_topk_workspace_bytes(int32_t precision, int32_t Q, int32_t n_items, int32_t k, int32_t n_split) {

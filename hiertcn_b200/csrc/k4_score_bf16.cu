@@ -84,11 +84,26 @@ enum : unsigned { kTwoSlices = 32768u };          // A/B variant: 8 epilogue war
 // kRowScale: the exponent multiplier is row_scale[q] * log2e instead of the constant log2e (l2-normalised head,
 // model_tcn.py:42-43); a compile-time variant so the default sweep keeps its immediate operands
 enum : unsigned { kRowScale = 65536u };
+// kFold (round 2, the default CE + rank sweep): the difference to the target logit comes out of the TENSOR CORE.  A holds
+// the NEGATED user embeddings (an exact copy, htcn_score_ce_rank_folded writes it), the 16-wide constant K chunk of row q is
+// [-1, -1, 0, 0, t1, t2, t3, 0...] with t1 + t2 + t3 = z_y EXACTLY (three bf16 pieces of the fp32 target logit) against the
+// table's [b_hi, b_lo, b_hi, b_lo, 1, 1, 1, 0...], so the accumulator IS  d_j = z_y - z_j  in the sweep's own arithmetic
+// (negation is exact at every step of the accumulation, so -d_j + z_y differs from the plain swept logit by at most the one
+// rounding of the last addition):
+//     rank  += sign bit of d_j                     (z_j above the target <=> d_j < 0): one LEA.HI, no FSET + FADD2/2
+//     CE    += 2^(-log2e d_j) = e^(z_j - z_y)      MUFU lanes: one FMUL2 per pair (was FFMA2); polynomial lanes fold the
+//                                                  scale into their range reduction (no extra instruction)
+// The target's own column gives d_y = the rounding residue of z_y (either sign); k4_target_bf16<true> evaluates that
+// residue with the same product and the sweep takes its sign bit out of the count again: the rank is exactly
+// #{j != y : d_j < 0} on the swept accumulators (tests: bit-equal to the dumped accumulators, and equal to the strict count
+// on the plain logits up to exact floating-point ties).
+enum : unsigned { kFoldFlag = 131072u };
 template <unsigned kFlags>
 constexpr int cg2_slices() { return (kFlags & kTwoSlices) ? 2 : kSlicesScore; }
 constexpr unsigned packed_flags(int poly_pairs, bool deg2 = false, bool sign_rank = false) {
   return kModePacked | ((unsigned)poly_pairs << kPolyPairsShift) | (deg2 ? kPolyDeg2 : 0u) | (sign_rank ? kSignRank : 0u);
 }
+constexpr unsigned folded_flags(int poly_pairs) { return packed_flags(poly_pairs, false, true) | kFoldFlag; }
 
 template <bool kDeg2, bool kNegated = false>
 __device__ __forceinline__ float2 ex2_poly2(float2 t) {          // kNegated: the argument is -t
@@ -118,6 +133,26 @@ __device__ __forceinline__ float2 ex2_poly2(float2 t) {          // kNegated: th
                      __int_as_float(__float_as_int(p.y) + (__float_as_int(r.y) << 23)));
 }
 
+// 2^(c x) with the scale folded into the range reduction: r = c x + magic, -n = magic - r, f = c x - n  (three FFMA2, the
+// same count as ex2_poly2 needs for an already scaled argument)
+template <bool kDeg2>
+__device__ __forceinline__ float2 ex2_poly2_scaled(float2 x, float c) {
+  const float2 magic = make_float2(12582912.0f, 12582912.0f), m1 = make_float2(-1.0f, -1.0f), cc = make_float2(c, c);
+  const float2 r = ffma2(x, cc, magic);
+  const float2 nn = ffma2(r, m1, magic);
+  const float2 f = ffma2(x, cc, nn);
+  float2 p;
+  if (kDeg2) {
+    p = ffma2(f, make_float2(0.23986403f, 0.23986403f), make_float2(0.70294179f, 0.70294179f));
+  } else {
+    p = ffma2(f, make_float2(0.05500892922282219f, 0.05500892922282219f), make_float2(0.24221095442771912f, 0.24221095442771912f));
+    p = ffma2(p, f, make_float2(0.6932829022407532f, 0.6932829022407532f));
+  }
+  p = ffma2(p, f, make_float2(1.0f, 1.0f));
+  return make_float2(__int_as_float(__float_as_int(p.x) + (__float_as_int(r.x) << 23)),
+                     __int_as_float(__float_as_int(p.y) + (__float_as_int(r.y) << 23)));
+}
+
 // one full 32-column chunk of a row: sum2 += 2^((z - zy) log2e), cf2 += [z > zy]
 __device__ __forceinline__ void add_sign_bit(uint32_t& acc, float x) {      // acc += (x < 0 or x == -0)
   asm("{ .reg .u32 t;\n\tshr.u32 t, %1, 31;\n\tadd.u32 %0, %0, t; }" : "+r"(acc) : "r"(__float_as_uint(x)));
@@ -126,7 +161,7 @@ constexpr float kPolyRange = 125.0f;             // |t| the exponent-field arith
 // `zyl` = z_y * log2e: rounded to nearest (strict-compare variants) or UP (kSign)
 // kGMax: also keep the running maximum of the logits (pass 1 of the two-pass top-k fused into the loss sweep): one FMNMX3
 // per logit pair.
-template <bool kCE, bool kRank, int kPolyPairs, bool kDeg2, bool kSign, bool kGMax = false>
+template <bool kCE, bool kRank, int kPolyPairs, bool kDeg2, bool kSign, bool kGMax = false, bool kFold = false>
 __device__ __forceinline__ void ce_rank_chunk_packed(const uint32_t (&r)[32], float zy, float zyl, float2 (&sum2)[2],
                                                      float2 (&cf2)[2], float& amax, uint32_t (&cnt2)[2], float (&gm2)[2],
                                                      const float cl = kLog2e /* exponent multiplier (kRowScale: per row) */) {
@@ -135,7 +170,24 @@ __device__ __forceinline__ void ce_rank_chunk_packed(const uint32_t (&r)[32], fl
     const float2 z = make_float2(__uint_as_float(r[2 * p]), __uint_as_float(r[2 * p + 1]));
     if (kGMax) gm2[p & 1] = fmaxf(fmaxf(gm2[p & 1], z.x), z.y);                              // one FMNMX3
     const bool poly = ((p + 1) * kPolyPairs) / 16 != (p * kPolyPairs) / 16;
-    if (kSign) {
+    if (kSign && kFold) {
+      // z = d = z_y - z_j (natural units): the exponent is -cl * d
+      if (kCE) {
+        float2 e;
+        if (poly) {
+          amax = fmaxf(fmaxf(amax, fabsf(z.x)), fabsf(z.y));                                // one FMNMX3 (range: kPolyRange / cl)
+          e = ex2_poly2_scaled<kDeg2>(z, -cl);
+        } else {
+          const float2 tn = fmul2(z, make_float2(cl, cl));
+          e = make_float2(ex2_approx(-tn.x), ex2_approx(-tn.y));
+        }
+        sum2[p & 1] = fadd2(sum2[p & 1], e);
+      }
+      if (kRank) {
+        add_sign_bit(cnt2[p & 1], z.x);
+        add_sign_bit(cnt2[(p & 1) ^ 1], z.y);
+      }
+    } else if (kSign) {
       const float2 tn = ffma2(z, make_float2(-cl, -cl), make_float2(zyl, zyl));     // -(t): sign bit set <=> z above z_y
       if (kCE) {
         if (poly) amax = fmaxf(fmaxf(amax, fabsf(tn.x)), fabsf(tn.y));                      // one FMNMX3
@@ -174,6 +226,20 @@ struct alignas(1024) ScoreSmem {
 __device__ __forceinline__ void write_a_bias_row(uint8_t* a_bias, int r) {
   const int sw = (r >> 2) & 1;
   *reinterpret_cast<uint4*>(a_bias + r * 32 + ((0 ^ sw) << 4)) = make_uint4(0x3F803F80u, 0u, 0u, 0u);
+  *reinterpret_cast<uint4*>(a_bias + r * 32 + ((1 ^ sw) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+}
+
+// folded sweep: row r = bf16 [-1, -1, 0, 0, t1, t2, t3, 0 x9], t1 + t2 + t3 = T exactly (three round-to-nearest bf16 pieces of
+// a 24-bit significand)
+__device__ __forceinline__ uint32_t bf16_bits(float x) { return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(x)); }
+__device__ __forceinline__ void write_a_fold_row(uint8_t* a_bias, int r, float T) {
+  const float t1 = __bfloat162float(__float2bfloat16_rn(T));
+  const float r1 = T - t1;
+  const float t2 = __bfloat162float(__float2bfloat16_rn(r1));
+  const float t3 = r1 - t2;
+  const int sw = (r >> 2) & 1;
+  *reinterpret_cast<uint4*>(a_bias + r * 32 + ((0 ^ sw) << 4)) =
+      make_uint4(0xBF80BF80u, 0u, bf16_bits(t1) | (bf16_bits(t2) << 16), bf16_bits(t3));
   *reinterpret_cast<uint4*>(a_bias + r * 32 + ((1 ^ sw) << 4)) = make_uint4(0u, 0u, 0u, 0u);
 }
 
@@ -474,6 +540,8 @@ k4_score_bf16_cg2(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   constexpr int kPolyEvery = (kFlags & kModePoly4) ? 4 : (kFlags & kModePoly8) ? 8 : 0x40000000;
   constexpr bool kPacked = (kFlags & kModePacked) && !kDump;
   constexpr bool kSign = kPacked && (kFlags & kSignRank);
+  constexpr bool kFold = (kFlags & kFoldFlag) != 0;              // accumulator = negated exponent (see kFoldFlag); dump: as is
+  static_assert(!kFold || (kFlags & kSignRank) || (kFlags & kModeDump), "kFold rides on the sign-bit epilogue");
   constexpr int kPolyPairs = (kFlags >> kPolyPairsShift) & 15;
   constexpr int BN = 256, kSlices = cg2_slices<kFlags>(), kEpiWarps = 4 * kSlices, kColsPerWarp = BN / kSlices;
   constexpr uint32_t kHalfStageBytes = 2 * 128 * 128 + 128 * 32;
@@ -503,7 +571,11 @@ k4_score_bf16_cg2(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
     fence_barrier_init();
   }
-  if (threadIdx.x >= 64 && threadIdx.x < 64 + kBM) write_a_bias_row(sm.a_bias, threadIdx.x - 64);
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + kBM) {
+    const int r = threadIdx.x - 64;
+    if (kFold) write_a_fold_row(sm.a_bias, r, q0 + r < a.Q ? a.zy[q0 + r] : 0.f);
+    else write_a_bias_row(sm.a_bias, r);
+  }
   fence_proxy_async_smem();
   if (warp == 1) tmem_alloc_cg2<512>(&sm.tmem_base);
   tc_fence_before_sync();
@@ -612,9 +684,9 @@ k4_score_bf16_cg2(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             if (lane == 0) mbar_arrive_cluster(&sm.t_empty[buf], 0);   // the leader's barrier
           }
           if (kFlags & kRowScale)
-            ce_rank_chunk_packed<kCE, kRank, kPolyPairs, (kFlags & kPolyDeg2) != 0, kSign, kGMax>(r, zy, zyl, sum2, cf2, amax, cnt2, gm2, cl);
+            ce_rank_chunk_packed<kCE, kRank, kPolyPairs, (kFlags & kPolyDeg2) != 0, kSign, kGMax, (kFlags & kFoldFlag) != 0>(r, zy, zyl, sum2, cf2, amax, cnt2, gm2, cl);
           else
-            ce_rank_chunk_packed<kCE, kRank, kPolyPairs, (kFlags & kPolyDeg2) != 0, kSign, kGMax>(r, zy, zyl, sum2, cf2, amax, cnt2, gm2);
+            ce_rank_chunk_packed<kCE, kRank, kPolyPairs, (kFlags & kPolyDeg2) != 0, kSign, kGMax, (kFlags & kFoldFlag) != 0>(r, zy, zyl, sum2, cf2, amax, cnt2, gm2);
         }
         if (kRank && (i & 4095) == 4095) {
           cnt += (int)((cf2[0].x + cf2[0].y) + (cf2[1].x + cf2[1].y));
@@ -637,9 +709,9 @@ k4_score_bf16_cg2(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         }
         if (kPacked && c + 32 <= lim) {
           if (kFlags & kRowScale)
-            ce_rank_chunk_packed<kCE, kRank, kPolyPairs, (kFlags & kPolyDeg2) != 0, kSign, kGMax>(r, zy, zyl, sum2, cf2, amax, cnt2, gm2, cl);
+            ce_rank_chunk_packed<kCE, kRank, kPolyPairs, (kFlags & kPolyDeg2) != 0, kSign, kGMax, (kFlags & kFoldFlag) != 0>(r, zy, zyl, sum2, cf2, amax, cnt2, gm2, cl);
           else
-            ce_rank_chunk_packed<kCE, kRank, kPolyPairs, (kFlags & kPolyDeg2) != 0, kSign, kGMax>(r, zy, zyl, sum2, cf2, amax, cnt2, gm2);
+            ce_rank_chunk_packed<kCE, kRank, kPolyPairs, (kFlags & kPolyDeg2) != 0, kSign, kGMax, (kFlags & kFoldFlag) != 0>(r, zy, zyl, sum2, cf2, amax, cnt2, gm2);
         } else if ((kGMax || kFilter) && !(kCE || kRank || kDump) && c + 32 <= lim) {
           // stand-alone passes of the two-pass top-k: one FMNMX per logit
           float m0 = __uint_as_float(r[0]), m1 = __uint_as_float(r[1]), m2 = __uint_as_float(r[2]), m3 = __uint_as_float(r[3]);
@@ -665,10 +737,10 @@ k4_score_bf16_cg2(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
               if (row_ok) dump[(long long)(q0 + row) * a.n_items + jbase + c + u] = z;
             }
             if (kCE) {
-              const float t = fmaf(z, cl, -zyl);
+              const float t = kFold ? -cl * z : fmaf(z, cl, -zyl);
               sum4[u & 3] += ((u % kPolyEvery) == kPolyEvery - 1) ? ex2_poly(t) : ex2_approx(t);
             }
-            if (kRank) cf[u & 3] += set_gt_f(z, zy);
+            if (kRank) cf[u & 3] += kFold ? (float)(__float_as_uint(z) >> 31) : set_gt_f(z, zy);
             if (kGMax) gm2[u & 1] = fmaxf(gm2[u & 1], z);
           }
         } else if (c < lim) {
@@ -682,8 +754,8 @@ k4_score_bf16_cg2(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
               if (kDump) {
                 if (row_ok) dump[(long long)(q0 + row) * a.n_items + jbase + c + u] = z;
               }
-              if (kCE) sum4[0] += ex2_approx(fmaf(z, cl, -zyl));
-              if (kRank) cf[0] += set_gt_f(z, zy);
+              if (kCE) sum4[0] += ex2_approx(kFold ? -cl * z : fmaf(z, cl, -zyl));
+              if (kRank) cf[0] += kFold ? (float)(__float_as_uint(z) >> 31) : set_gt_f(z, zy);
               if (kGMax) gm2[0] = fmaxf(gm2[0], z);
               if (kFilter && z >= row_thr) append(z, a.n0 + jbase + c + u);
             }
@@ -702,7 +774,7 @@ k4_score_bf16_cg2(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
     float sum = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
     if (kPacked) sum += (sum2[0].x + sum2[0].y) + (sum2[1].x + sum2[1].y);
-    if (kPacked && !(amax < kPolyRange)) sum = INFINITY;         // a polynomial lane left its range: the row is redone exactly
+    if (kPacked && !(amax < (kFold ? kPolyRange / kLog2e : kPolyRange))) sum = INFINITY;   // a polynomial lane left its range: the row is redone exactly
     if (kPacked && kRank) cnt += (int)((cf2[0].x + cf2[0].y) + (cf2[1].x + cf2[1].y));   // counts of the fast-path tiles
     if (kSign) cnt += (int)(cnt2[0] + cnt2[1]);
     if (half > 0) {
@@ -722,6 +794,7 @@ k4_score_bf16_cg2(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           a.part_max[o] = (kFlags & kRowScale) ? zy * a.row_scale[q0 + row] : zy;
           a.part_sum[o] = sum;
         }
+        if (kFold && kRank && split == 0) cnt -= a.fold_self[q0 + row];      // the target column's own sign bit
         if (kRank) a.part_cnt[o] = cnt;
       }
     }
@@ -756,9 +829,13 @@ __device__ __forceinline__ void store_row_sw128(uint8_t (*dst)[kChunkBytesA], in
   }
 }
 
+// kFoldT: `hout` is the negated copy and the constant chunk carries z_y (`zy`, an INPUT here): the diagonal is the folded
+// sweep's accumulator d_y of the target column itself, the rounding residue of z_y; its sign bit goes to `self_neg`
+template <bool kFoldT>
 __global__ void __launch_bounds__(128, 1)
 k4_target_bf16(const __nv_bfloat16* __restrict__ hout, const __nv_bfloat16* __restrict__ wt /*[n,144]*/,
-               const int* __restrict__ y_id, int Q, int n_items, int n0, float* __restrict__ zy) {
+               const int* __restrict__ y_id, int Q, int n_items, int n0, float* __restrict__ zy,
+               int* __restrict__ self_neg = nullptr) {
   extern __shared__ uint8_t smem_raw[];
   auto& sm = *reinterpret_cast<TargetSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int r = threadIdx.x, warp = r >> 5, lane = r & 31;
@@ -771,7 +848,8 @@ k4_target_bf16(const __nv_bfloat16* __restrict__ hout, const __nv_bfloat16* __re
   const uint4* wrow = y >= 0 ? reinterpret_cast<const uint4*>(wt + (long long)y * kWtPitchBf16) : nullptr;
   store_row_sw128(sm.a, r, q < Q ? reinterpret_cast<const uint4*>(hout + (long long)q * kDim) : nullptr);
   store_row_sw128(sm.b, r, wrow);
-  write_a_bias_row(sm.a_bias, r);
+  if (kFoldT) write_a_fold_row(sm.a_bias, r, q < Q ? zy[q] : 0.f);
+  else write_a_bias_row(sm.a_bias, r);
   {
     const int sw = (r >> 2) & 1;                                // chunks 16,17 of the augmented row: [b_hi, b_lo, 0...]
     *reinterpret_cast<uint4*>(sm.b_bias + r * 32 + ((0 ^ sw) << 4)) = wrow ? __ldg(wrow + 16) : make_uint4(0, 0, 0, 0);
@@ -801,7 +879,11 @@ k4_target_bf16(const __nv_bfloat16* __restrict__ hout, const __nv_bfloat16* __re
 #pragma unroll
   for (int u = 0; u < 32; ++u)
     if (u == lane) d = __uint_as_float(v[u]);
-  if (y >= 0) zy[q] = d;
+  if (kFoldT) {
+    if (q < Q) self_neg[q] = y >= 0 ? (int)(__float_as_uint(d) >> 31) : 0;
+  } else if (y >= 0) {
+    zy[q] = d;
+  }
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 0) {
@@ -991,8 +1073,8 @@ int32_t target_logit_bf16(const void* hout, const void* wt, const float* b_out, 
                           int n0, float* zy, cudaStream_t st) {
   (void)b_out;                                   // the bias lives in the augmented columns of wt
   const size_t smem = sizeof(TargetSmem) + 1024;
-  HTCN_CUDA(cudaFuncSetAttribute(k4_target_bf16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k4_target_bf16<<<ceil_div(Q, kBM), 128, smem, st>>>((const __nv_bfloat16*)hout, (const __nv_bfloat16*)wt, y_id, Q,
+  HTCN_CUDA(cudaFuncSetAttribute(k4_target_bf16<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k4_target_bf16<false><<<ceil_div(Q, kBM), 128, smem, st>>>((const __nv_bfloat16*)hout, (const __nv_bfloat16*)wt, y_id, Q,
                                                      n_items, n0, zy);
   HTCN_LAUNCH_CHECK("k4_target_bf16");
   return HTCN_OK;
@@ -1158,6 +1240,65 @@ int32_t score_topk_bf16(const void* hout, int Q, const void* wt, int n_items, in
   return HTCN_OK;
 }
 
+// hs = -h (sign bits flipped: exact)
+__global__ void fold_negate_rows_kernel(const uint4* __restrict__ h, long long n8, uint4* __restrict__ hs) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const uint4 v = h[i];
+  hs[i] = make_uint4(v.x ^ 0x80008000u, v.y ^ 0x80008000u, v.z ^ 0x80008000u, v.w ^ 0x80008000u);
+}
+
+// workspace: [hs: Q x 128 bf16][self_neg: Q ints]  (HTCN_SCORE_FOLD_WS_BYTES)
+static int32_t fold_prepare(const ScoreArgs& a, void* workspace, ScoreArgs& f, cudaStream_t st) {
+  __nv_bfloat16* hs = reinterpret_cast<__nv_bfloat16*>(workspace);
+  int* self_neg = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(workspace) + (((size_t)a.Q * kDim * 2 + 255) & ~(size_t)255));
+  const long long n8 = (long long)a.Q * kDim / 8;
+  fold_negate_rows_kernel<<<ceil_div(n8, 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(a.hout), n8, reinterpret_cast<uint4*>(hs));
+  HTCN_LAUNCH_CHECK("fold_negate_rows_kernel");
+  const size_t smem = sizeof(TargetSmem) + 1024;
+  HTCN_CUDA(cudaFuncSetAttribute(k4_target_bf16<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k4_target_bf16<true><<<ceil_div(a.Q, kBM), 128, smem, st>>>(hs, (const __nv_bfloat16*)a.wt, a.y_id, a.Q, a.n_items, a.n0,
+                                                             const_cast<float*>(a.zy), self_neg);
+  HTCN_LAUNCH_CHECK("k4_target_bf16<fold>");
+  f = a;
+  f.hout = hs;
+  f.fold_self = self_neg;
+  return HTCN_OK;
+}
+
+// CE + rank sweep with the difference to the target folded into the MMA (kFoldFlag).  a.hout: the plain bf16 user embeddings;
+// a.zy: the plain target logits (they ride in the constant K chunk); a.y_id required.
+int32_t score_ce_rank_folded_bf16(const ScoreArgs& a, void* workspace, cudaStream_t st) {
+  ScoreArgs f;
+  int32_t rc = fold_prepare(a, workspace, f, st);
+  if (rc) return rc;
+  constexpr unsigned kCR = HTCN_SCORE_CE | HTCN_SCORE_RANK;
+  if (a.flags == kCR) {
+    const char* e = getenv("HTCN_K4_FOLD_POLY");       // A/B runs: polynomial logit pairs per 16 (default 4)
+    switch (e ? atoi(e) : 4) {
+      case 2: return launch_score_cg2<kCR | folded_flags(2)>(f, nullptr, st);
+      case 3: return launch_score_cg2<kCR | folded_flags(3)>(f, nullptr, st);
+      case 5: return launch_score_cg2<kCR | folded_flags(5)>(f, nullptr, st);
+      case 6: return launch_score_cg2<kCR | folded_flags(6)>(f, nullptr, st);
+      case 8: return launch_score_cg2<kCR | folded_flags(8)>(f, nullptr, st);
+      default: return launch_score_cg2<kCR | folded_flags(4)>(f, nullptr, st);
+    }
+  }
+  if (a.flags == HTCN_SCORE_CE) return launch_score_cg2<HTCN_SCORE_CE | folded_flags(4)>(f, nullptr, st);
+  set_error("score_folded(bf16): flags 0x%x (CE or CE | RANK)", a.flags);
+  return HTCN_ERR_INVALID;
+}
+
+// test hook: the accumulators d[q, j] = z_y - z_j the folded sweep sees
+int32_t dump_folded_bf16(const ScoreArgs& a, void* workspace, float* tn, cudaStream_t st) {
+  ScoreArgs f;
+  int32_t rc = fold_prepare(a, workspace, f, st);
+  if (rc) return rc;
+  f.n_split = 1;
+  f.flags = kModeDump;
+  return launch_score_cg2<kModeDump | kFoldFlag>(f, tn, st);
+}
+
 int32_t dump_logits_bf16(const void* hout, int Q, const void* wt, int n_items, float* logits, cudaStream_t st) {
   ScoreArgs a{};
   a.hout = hout; a.wt = wt; a.Q = Q; a.n_items = n_items; a.n_split = 1; a.flags = kModeDump;
@@ -1174,4 +1315,15 @@ extern "C" int32_t htcn_debug_logits_bf16(const void* hout, int32_t Q, const voi
   (void)b_out;
   HTCN_REQUIRE(hout && w_out_t && logits && Q > 0 && n_items > 0, "debug_logits_bf16: bad args");
   return dump_logits_bf16(hout, Q, w_out_t, n_items, logits, as_stream(stream));
+}
+
+// test hook: the accumulators of the folded sweep, d[q, j] = z_y - z_j as the tensor core forms them
+extern "C" int32_t htcn_debug_folded_bf16(const void* hout, int32_t Q, const void* w_out_t, int32_t n_items, int32_t n0,
+                                          const int32_t* y_id, const float* target_logit, void* workspace, float* tn,
+                                          void* stream) {
+  using namespace htcn;
+  HTCN_REQUIRE(hout && w_out_t && y_id && target_logit && workspace && tn && Q > 0 && n_items > 0, "debug_folded_bf16: bad args");
+  ScoreArgs a{};
+  a.hout = hout; a.wt = w_out_t; a.y_id = y_id; a.zy = target_logit; a.Q = Q; a.n_items = n_items; a.n0 = n0; a.n_split = 1;
+  return dump_folded_bf16(a, workspace, tn, as_stream(stream));
 }

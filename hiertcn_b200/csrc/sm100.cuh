@@ -358,6 +358,16 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
       : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
   return d;
 }
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  float2 d;
+  asm("{ .reg .b64 a, b, d;\n\t"
+      "mov.b64 a, {%2, %3}; mov.b64 b, {%4, %5};\n\t"
+      "mul.rn.f32x2 d, a, b;\n\t"
+      "mov.b64 {%0, %1}, d; }"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
 __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
   float2 d;
   asm("{ .reg .b64 a, b, d;\n\t"

@@ -106,6 +106,10 @@ class HierTCN:
         if getattr(args, "has_gap", False) and getattr(args, "train_gap", False):
             raise NotImplementedError("train_gap (learned gap bandwidth, model_hier.py:42-45); the fixed-bandwidth decay is built")
         self.l2_normalize = bool(getattr(args, "l2_normalize", False))     # model_tcn.py:42-43
+        # bf16 tier: the CE (+ rank) sweep with the softmax exponent folded into the tensor-core product
+        # (htcn_score_ce_rank_folded).  HTCN_K4_FOLD=0 (or an explicit HTCN_K4_EPI / HTCN_K4_CTA_GROUP=1) selects the older
+        # epilogues of htcn_score_ce_rank_topk for A/B runs.
+        self.k4_fold_enabled = True
         # args.dropout > 0 acts in HierTCNTrainer only (tf.layers.Dropout is the identity when training=False)
         self.N = int(args.item_num)
         self.G = int(args.num_layer)
@@ -391,6 +395,12 @@ class HierTCN:
         want = max(math.ceil(2 * 148 / tiles_q), 4)
         return int(max(1, min(want, 32, max(1, n_items // 256))))
 
+    @property
+    def k4_fold(self):
+        import os
+        return (getattr(self, "k4_fold_enabled", True) and os.environ.get("HTCN_K4_FOLD", "1") != "0" and "HTCN_K4_EPI" not in os.environ
+                and os.environ.get("HTCN_K4_CTA_GROUP", "2") == "2")
+
     def score(self, scores: CatalogScores, ce=True, rank=True, topk=0):
         """One streaming sweep over the catalog.  Returns dict of device tensors:
         loss_row [Q], rank_row [Q] and, with topk, topk_val / topk_idx [Q,k]."""
@@ -452,6 +462,11 @@ class HierTCN:
                       nbytes, P(pm), P(ps), P(pc), ov.data_ptr(), oi.data_ptr(), ovf.data_ptr(), st)
             out.update(topk_val=ov, topk_idx=oi)
             self._topk_overflow = ovf
+        elif ce and self.precision == "bf16" and self.k4_fold:      # (read per call: the sweep scripts switch variants)
+            # the default loss sweep of the bf16 tier: exponent and rank compare folded into the tensor-core product
+            ws = self._buf("fold_ws", (cabi.score_fold_ws_bytes(Q),), torch.uint8)
+            cabi.call("htcn_score_ce_rank_folded", scores.hout.data_ptr(), Q, self.wt.data_ptr(), self.N, 0,
+                      scores.y_rows.data_ptr(), zy.data_ptr(), flags, ns, P(pm), P(ps), P(pc), ws.data_ptr(), st)
         elif flags:
             cabi.call("htcn_score_ce_rank_topk", scores.hout.data_ptr(), self.k4_dtype, Q, self.wt.data_ptr(),
                       self.b_out.data_ptr(), self.N, 0, scores.y_rows.data_ptr(), zy.data_ptr(), 1,

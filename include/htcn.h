@@ -207,6 +207,20 @@ int32_t htcn_target_logit(const void* hout, int32_t precision, int32_t Q,
                           const void* w_out_t, const float* b_out, int32_t n_items, int32_t n0,
                           const int32_t* y_id, float* target_logit, void* stream);
 
+/* bf16 tier, CE (+ RANK) over a replicated or sharded catalog with the difference to the target logit FOLDED INTO THE
+ * TENSOR-CORE PRODUCT (the default loss sweep of HierTCN.score).  The call writes the negated embeddings (an exact copy) into
+ * the workspace and gives row q the constant K chunk [-1, -1, 0, 0, t1, t2, t3] (t1 + t2 + t3 = target_logit[q] exactly)
+ * against the table's [b_hi, b_lo, b_hi, b_lo, 1, 1, 1] columns 128..134, so the accumulator is d_j = z_y - z_j in the
+ * sweep's own arithmetic: the rank adds the sign bit of d_j (one instruction per logit), the CE sum 2^(-log2e d_j).  The
+ * target's own column holds the rounding residue of z_y; its sign bit (evaluated by the same product) is taken out of the
+ * count, which is therefore exactly #{j != y : d_j < 0} on the swept accumulators -- the strict count of loss.py:179 up to
+ * exact floating-point ties.  flags: HTCN_SCORE_CE or HTCN_SCORE_CE | HTCN_SCORE_RANK; partials as htcn_score_ce_rank_topk
+ * (part_max = target_logit, the reference point); workspace: HTCN_SCORE_FOLD_WS_BYTES(Q). */
+#define HTCN_SCORE_FOLD_WS_BYTES(Q) (((((int64_t)(Q)) * 128 * 2 + 255) / 256 * 256) + ((int64_t)(Q)) * 4)
+int32_t htcn_score_ce_rank_folded(const void* hout, int32_t Q, const void* w_out_t, int32_t n_items, int32_t n0,
+                                  const int32_t* y_id, const float* target_logit, uint32_t flags, int32_t n_split,
+                                  float* part_max, float* part_sum, int32_t* part_cnt, void* workspace, void* stream);
+
 /* merge CE / rank partials of n_part (= splits x shards) parts:
  *   loss_row[q] = log sum_j exp(z_j) - target_logit[q]   (0 where y_id == 0);  rank_row[q] = sum cnt */
 int32_t htcn_score_finish(const float* part_max, const float* part_sum, const int32_t* part_cnt,

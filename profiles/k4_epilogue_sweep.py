@@ -60,7 +60,11 @@ def main():
     Q = scores.Q
     flops = 2.0 * Q * 128 * N
     for v in [int(s) for s in opt.variants.split(",")]:
-        os.environ["HTCN_K4_EPI"] = str(v)
+        if v >= 2000:                        # 2000 + n: the folded sweep (the default) with n polynomial pairs per 16
+            os.environ.pop("HTCN_K4_EPI", None)
+            os.environ["HTCN_K4_FOLD_POLY"] = str(v - 2000)
+        else:
+            os.environ["HTCN_K4_EPI"] = str(v)
         model.sweep_events = []
         clk = Clocks()
         res = None

@@ -495,7 +495,9 @@ def test_k4_bf16_tcgen05(lib, Q, N, n_split, epi, tol, monkeypatch):
     assert np.array_equal(wt_h[:, :128], O.bf16_round(w_out.T))
     b_hi = O.bf16_round(b_out)                                   # bias folded into the GEMM as (hi, lo) bf16 columns
     assert np.array_equal(wt_h[:, 128], b_hi) and np.array_equal(wt_h[:, 129], O.bf16_round(b_out - b_hi))
-    assert (wt_h[:, 130:] == 0).all()
+    # columns 130..134 serve the folded sweep (b_hi, b_lo again and three ones); every other kernel multiplies them by zero
+    assert np.array_equal(wt_h[:, 130], b_hi) and np.array_equal(wt_h[:, 131], wt_h[:, 129])
+    assert (wt_h[:, 132:135] == 1).all() and (wt_h[:, 135:] == 0).all()
     # 1. the logits the tensor-core sweep sees == bf16 operands, fp32 accumulate
     z_gpu = debug_logits_bf16(lib, hd, wt, bd).cpu().numpy()
     z64 = hout.astype(np.float64) @ O.bf16_round(w_out).astype(np.float64) + b_out
@@ -541,6 +543,84 @@ def test_k4_bf16_tcgen05(lib, Q, N, n_split, epi, tol, monkeypatch):
     v_ref, i_ref = O.top_k(z_gpu, k)
     np.testing.assert_array_equal(oi.cpu().numpy(), i_ref)
     np.testing.assert_array_equal(ov.cpu().numpy(), v_ref)
+
+
+def debug_folded_bf16(lib, hd, wt, yd, zy, n0=0):
+    import ctypes as C
+    L = lib.load()
+    fn = L.htcn_debug_folded_bf16
+    fn.restype = C.c_int32
+    fn.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                   C.c_void_p]
+    Q, N = hd.shape[0], wt.shape[0]
+    out = torch.full((Q, N), float("nan"), dtype=torch.float32, device="cuda")
+    ws = torch.empty(lib.score_fold_ws_bytes(Q), dtype=torch.uint8, device="cuda")
+    rc = fn(P(hd), Q, P(wt), N, n0, P(yd), P(zy), P(ws), P(out), None)
+    assert rc == 0, L.htcn_last_error()
+    torch.cuda.synchronize()
+    return out
+
+
+@pytest.mark.parametrize("Q,N,n_split", [(128, 256, 1), (200, 1000, 1), (130, 20778, 7), (5, 77, 1), (300, 4099, 3), (257, 512, 2)])
+def test_k4_bf16_folded_sweep(lib, Q, N, n_split):
+    """htcn_score_ce_rank_folded (the default loss sweep of the bf16 tier): the accumulator of the tensor-core product is
+    d_j = z_y - z_j.  (1) the dumped accumulators are the plain swept logits subtracted from the target logit, to one
+    rounding; (2) the CE sum is sum_j e^(-d_j) and the rank is EXACTLY #{j != y : d_j < 0} on those accumulators; (3) the rank
+    equals the strict count on the plain logits up to exact floating-point ties."""
+    rng = np.random.default_rng(Q * 3 + N)
+    hout = O.bf16_round(rng.normal(size=(Q, 128)).astype(np.float32))
+    w_out = (rng.normal(size=(128, N)) * 0.3).astype(np.float32)
+    b_out = (rng.normal(size=N) * 0.2).astype(np.float32)
+    y = rng.integers(1, N, size=Q).astype(np.int32)
+    if N >= 1000:                                               # exact ties with the target: duplicates of the target's item
+        for q in range(0, Q, 9):
+            j = (int(y[q]) + 17) % N
+            if j != 0:
+                w_out[:, j] = w_out[:, y[q]]
+                b_out[j] = b_out[y[q]]
+    w_out_d = dev(w_out)
+    wt = torch.empty((N, lib.WT_PITCH_BF16), dtype=torch.bfloat16, device="cuda")
+    hd, bd, yd = dev(hout).to(torch.bfloat16), dev(b_out), dev(y)
+    lib.call("htcn_prepare_wout", P(w_out_d), P(bd), N, P(wt), lib.HTCN_BF16, None)
+    z_gpu = debug_logits_bf16(lib, hd, wt, bd).cpu().numpy()
+    zy = torch.empty(Q, dtype=torch.float32, device="cuda")
+    lib.call("htcn_target_logit", P(hd), lib.HTCN_BF16, Q, P(wt), P(bd), N, 0, P(yd), P(zy), None)
+    zy_h = zy.cpu().numpy()
+    # (1) accumulators: z_y - z_j, one rounding away from the difference of the plain swept logits
+    d = debug_folded_bf16(lib, hd, wt, yd, zy).cpu().numpy()
+    want = zy_h[:, None].astype(np.float64) - z_gpu.astype(np.float64)
+    ulp = np.spacing(np.maximum(np.abs(z_gpu), np.abs(zy_h)[:, None]).astype(np.float32)).astype(np.float64)
+    assert (np.abs(d - want) <= 3 * ulp).all(), float((np.abs(d - want) / ulp).max())
+    assert np.abs(d[np.arange(Q), y]).max() <= 1e-5             # the target's own column: the rounding residue of z_y
+    # (2)
+    pm = torch.empty((n_split, Q), dtype=torch.float32, device="cuda")
+    ps = torch.empty((n_split, Q), dtype=torch.float32, device="cuda")
+    pc = torch.empty((n_split, Q), dtype=torch.int32, device="cuda")
+    ws = torch.empty(lib.score_fold_ws_bytes(Q), dtype=torch.uint8, device="cuda")
+    lib.call("htcn_score_ce_rank_folded", P(hd), Q, P(wt), N, 0, P(yd), P(zy), lib.SCORE_CE | lib.SCORE_RANK, n_split,
+             P(pm), P(ps), P(pc), P(ws), None)
+    loss_row = torch.empty(Q, dtype=torch.float32, device="cuda")
+    rank_row = torch.empty(Q, dtype=torch.float32, device="cuda")
+    lib.call("htcn_score_finish", P(pm), P(ps), P(pc), n_split, Q, P(yd), P(zy), P(loss_row), P(rank_row), None)
+    got_loss, got_rank = loss_row.cpu().numpy(), rank_row.cpu().numpy()
+    neg = np.signbit(d)
+    neg[np.arange(Q), y] = False
+    np.testing.assert_array_equal(got_rank, neg.sum(1))          # bit-exact on the swept accumulators
+    loss_from_d = np.log(np.exp(-d.astype(np.float64)).sum(1))
+    np.testing.assert_allclose(got_loss, loss_from_d, rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(got_loss, O.softmax_cross_entropy_with_logits(y, z_gpu.astype(np.float64)), rtol=1e-4, atol=1e-5)
+    # (3) the strict count on the plain logits; only a logit within one rounding of the target can differ
+    strict = (z_gpu > zy_h[:, None]).sum(1)
+    close = (np.abs(want) <= 3 * ulp).sum(1) - 1
+    assert (np.abs(got_rank - strict) <= close).all(), (got_rank - strict, close)
+    ties = (z_gpu == zy_h[:, None]).sum(1) - 1
+    assert ties.max() >= (1 if N >= 1000 else 0)
+    # CE only
+    ps2 = torch.empty((n_split, Q), dtype=torch.float32, device="cuda")
+    lib.call("htcn_score_ce_rank_folded", P(hd), Q, P(wt), N, 0, P(yd), P(zy), lib.SCORE_CE, n_split, P(pm), P(ps2), None,
+             P(ws), None)
+    torch.cuda.synchronize()
+    assert torch.equal(ps2, ps)
 
 
 def test_k4_bf16_ce_overflow_rows_are_repaired(lib):
