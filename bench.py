@@ -718,7 +718,7 @@ def main():
     sweep_ms = float(np.mean([s[0] for s in sweep]))
     achieved = sweep[0][1] / (sweep_ms * 1e-3) / 1e12
     peak = peaks["tf_sust"]
-    roofline = {"kernel": "k4_score_bf16_cg2<CE|RANK, packed f32x2 epilogue>" if opt.precision == "bf16" else "k4_score_f32",
+    roofline = {"kernel": "k4_score_bf16_cg2<CE|RANK, target folded into the MMA, packed f32x2 epilogue>" if opt.precision == "bf16" else "k4_score_f32",
                 "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "peak_source": peaks["src"] + " (sustained cuBLAS bf16: the kernel is timed inside a long step)",
                 "traffic": load_traffic(opt, wl), "ms_per_launch": sweep_ms, "share_of_step": sweep_ms / ms_per_step,
