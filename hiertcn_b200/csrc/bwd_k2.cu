@@ -175,14 +175,13 @@ extern "C" int32_t htcn_tcn_backward(const float* d_hout, const int32_t* out_row
   const long long R = (long long)B * T;
   float* dcur = scratch;                    // [R,128] gradient flowing down the stack
   float* dp = scratch + R * kDim;           // [R,128] gradient at the conv pre-activation
-  // tc_scratch != NULL: the weight gradients run on the tensor cores from zero-padded transposed bf16 copies of the
-  // activations (bwd_wgrad_bf16.cu) instead of the fp32 split-K products
+  // tc_scratch != NULL: the weight gradients run on the tensor cores from zero-padded bf16 copies of the activations
+  // (bwd_wgrad_bf16.cu, MN-major operands) instead of the fp32 split-K products
   const int P = n_levels > 0 ? (kernel_size - 1) * (1 << (n_levels - 1)) : 0;
   const PadGeom pg = make_pad_geom(slots, B, T, P);
-  // layout: [bf16 weight tiles of the level being run (k2_level_tc.cu)][dp^T][one pre-shifted h^T per tap]
+  // layout: [bf16 weight tiles of the level being run (k2_level_tc.cu)][dp, zero-padded rows][h_l, zero-padded rows]
   __nv_bfloat16* bT = tc_scratch ? reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(tc_scratch) + HTCN_K2TC_WS_BYTES) : nullptr;
   __nv_bfloat16* aT = bT ? bT + 128 * pg.Kp : nullptr;
-  const long long a_stride = 128 * pg.Kp;
   const int zero = 0;
   const int eb = ceil_div(R * 32, 256);
   rows_compact_kernel<<<eb, 256, 0, st>>>(R, out_row, reinterpret_cast<const float4*>(d_hout),
@@ -202,13 +201,13 @@ extern "C" int32_t htcn_tcn_backward(const float* d_hout, const int32_t* out_row
     HTCN_LAUNCH_CHECK("relu_bwd_kernel");
     const int dil = 1 << l;
     if (aT) {
-      int shifts[8];
+      int shifts[8];                            // MN-major operands: one padded copy each, the tap shift is a TMA row offset
       for (int tap = 0; tap < kernel_size; ++tap) shifts[tap] = (kernel_size - 1 - tap) * dil;
-      rc = pad_transpose_bf16(h_l, bf, pg, shifts, kernel_size, aT, a_stride, st);
+      rc = pad_rows_bf16(h_l, bf, pg, aT, st);
       if (rc) return rc;
-      rc = pad_transpose_bf16(dp, false, pg, &zero, 1, bT, 0, st);
+      rc = pad_rows_bf16(dp, false, pg, bT, st);
       if (rc) return rc;
-      rc = wgrad_bf16(aT, a_stride, bT, pg.Kp, kernel_size, d_conv_w_host[l], st);
+      rc = wgrad_mn_bf16(aT, bT, pg.Kp, shifts, kernel_size, d_conv_w_host[l], st);
       if (rc) return rc;
     } else {
       for (int tap = 0; tap < kernel_size; ++tap) {
@@ -222,10 +221,10 @@ extern "C" int32_t htcn_tcn_backward(const float* d_hout, const int32_t* out_row
     const float* resid = dcur;                  // identity residual: dL/dh_l = ds + ...
     if (ds_w_host && ds_w_host[l]) {            // down-sample residual: dWds += h_l^T ds, dbds += colsum(ds), ds Wds^T + ...
       HTCN_REQUIRE(d_ds_w_host && d_ds_w_host[l] && d_ds_b_host && d_ds_b_host[l], "tcn_backward: down-sample gradient pointers NULL");
-      if (aT) {                                  // the last tap's copy of h_l^T is the unshifted one
-        rc = pad_transpose_bf16(dcur, false, pg, &zero, 1, bT, 0, st);
+      if (aT) {                                  // aT still holds the padded h_l
+        rc = pad_rows_bf16(dcur, false, pg, bT, st);
         if (rc) return rc;
-        rc = wgrad_bf16(aT + (kernel_size - 1) * a_stride, a_stride, bT, pg.Kp, 1, d_ds_w_host[l], st);
+        rc = wgrad_mn_bf16(aT, bT, pg.Kp, &zero, 1, d_ds_w_host[l], st);
       } else {
         rc = sgemm_tn_atomic(R, h_l, kDim, dcur, kDim, d_ds_w_host[l], kDim, 0, T, nullptr, st, bf);
       }
@@ -249,11 +248,11 @@ extern "C" int32_t htcn_tcn_backward(const float* d_hout, const int32_t* out_row
     if (rc) return rc;
   }
   if (aT) {
-    rc = pad_transpose_bf16(xe, bf, pg, &zero, 1, aT, a_stride, st);
+    rc = pad_rows_bf16(xe, bf, pg, aT, st);
     if (rc) return rc;
-    rc = pad_transpose_bf16(dcur, false, pg, &zero, 1, bT, 0, st);
+    rc = pad_rows_bf16(dcur, false, pg, bT, st);
     if (rc) return rc;
-    rc = wgrad_bf16(aT, a_stride, bT, pg.Kp, 1, d_w_in_x, st);
+    rc = wgrad_mn_bf16(aT, bT, pg.Kp, &zero, 1, d_w_in_x, st);
   } else {
     rc = sgemm_tn_atomic(R, xe, kDim, dcur, kDim, d_w_in_x, kDim, 0, T, nullptr, st, bf);
   }
@@ -271,6 +270,6 @@ extern "C" int32_t htcn_tcn_backward(const float* d_hout, const int32_t* out_row
 extern "C" int64_t htcn_tcn_backward_tc_scratch_bytes(int32_t B, int32_t T, int32_t S, int32_t n_levels, int32_t kernel_size) {
   const long long P = n_levels > 0 ? (long long)(kernel_size - 1) * (1 << (n_levels - 1)) : 0;
   const long long Kp = ((long long)B * (T + (long long)S * P) + 63) / 64 * 64;
-  // level weight tiles + dp^T + one pre-shifted h^T per tap
-  return htcn::HTCN_K2TC_WS_BYTES + (1 + (long long)(kernel_size > 1 ? kernel_size : 1)) * 128 * Kp * 2;
+  (void)kernel_size;                          // level weight tiles + zero-padded bf16 copies of dp and of h_l
+  return htcn::HTCN_K2TC_WS_BYTES + 2 * 128 * Kp * 2;
 }

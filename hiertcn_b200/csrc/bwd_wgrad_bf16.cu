@@ -119,6 +119,146 @@ wgrad_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
   }
 }
 
+// ---- the same product with MN-MAJOR operands: no transposes -------------------------------------------------------------
+// dW[t][cin][cout] += sum_r hP[r - shift_t][cin] dpP[r][cout] over zero-padded ROW-major bf16 copies hP, dpP [Kp][128] (every
+// sequence preceded by P zero rows).  Both operands are fed to tcgen05 as MN-major tiles: a TMA box of 64 rows x 64 channels
+// with the 128-byte swizzle IS the canonical MN-major SWIZZLE_128B atom (rows = contraction index, 128-byte rows of 64
+// channels, 8-row groups 1024 B apart = SBO; the second 64-channel block LBO = 8192 B further), so the tap shift is the box's
+// ROW coordinate -- any integer, negative rows are zero-filled -- and ONE padded copy of the activation serves every tap
+// (the K-major version above needs one pre-shifted transposed copy per tap: a box must start 16-byte aligned along the
+// contiguous dimension).
+__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(8192 >> 4) << 16;      // leading byte offset: next 64-element block along M / N
+  d |= (uint64_t)(1024 >> 4) << 32;      // stride byte offset: next 8-row group along K
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;                // SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor, bf16 x bf16 -> fp32, BOTH operands MN-major (bits 15, 16)
+__host__ __device__ constexpr uint32_t make_idesc_bf16_mn(int M, int N) {
+  return make_idesc_bf16(M, N) | (1u << 15) | (1u << 16);
+}
+
+struct WgShifts {
+  int n;
+  int shift[kWgMaxTaps];
+};
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+wgrad_mn_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int n_steps,
+                     WgShifts taps, float* __restrict__ dW /* [taps.n][128][128], accumulated */) {
+  extern __shared__ uint8_t smem_raw[];
+  auto& sm = *reinterpret_cast<WgSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int s0 = (int)((long long)n_steps * blockIdx.x / gridDim.x);
+  const int s1 = (int)((long long)n_steps * (blockIdx.x + 1) / gridDim.x);
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+    for (int s = 0; s < kWgStages; ++s) {
+      mbar_init(&sm.full[s], 1);
+      mbar_init(&sm.empty[s], 1);
+    }
+    mbar_init(&sm.done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(&sm.tmem_base);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = __shfl_sync(0xffffffffu, sm.tmem_base, 0);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = s0; i < s1; ++i) {
+        const int n = i - s0, s = n % kWgStages;
+        mbar_wait_relaxed(&sm.empty[s], (uint32_t)(((n / kWgStages) & 1) ^ 1));
+        mbar_arrive_expect_tx(&sm.full[s], (uint32_t)((1 + taps.n) * kWgTile));
+        const int k0 = i * 64;                                   // 64 rows of the contraction per stage
+        tma_load_2d(sm.b[s], &tmap_b, 0, k0, &sm.full[s]);
+        tma_load_2d(sm.b[s] + kWgTile / 2, &tmap_b, 64, k0, &sm.full[s]);
+        for (int t = 0; t < taps.n; ++t) {
+          tma_load_2d(sm.a[s][t], &tmap_a, 0, k0 - taps.shift[t], &sm.full[s]);
+          tma_load_2d(sm.a[s][t] + kWgTile / 2, &tmap_a, 64, k0 - taps.shift[t], &sm.full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const bool leader = elect_one();
+    constexpr uint32_t idesc = make_idesc_bf16_mn(128, 128);
+    for (int i = s0; i < s1; ++i) {
+      const int n = i - s0, s = n % kWgStages;
+      mbar_wait(&sm.full[s], (uint32_t)((n / kWgStages) & 1));
+      tc_fence_after_sync();
+      for (int t = 0; t < taps.n; ++t) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {                            // 16 rows of the contraction = two 8-row groups = 2048 B
+          const uint64_t da = make_desc_mn_sw128(smem_u32(sm.a[s][t]) + k * 2048);
+          const uint64_t db = make_desc_mn_sw128(smem_u32(sm.b[s]) + k * 2048);
+          if (leader) umma_bf16(tmem + t * 128, da, db, idesc, (n | k) != 0);
+        }
+      }
+      if (leader) umma_commit(&sm.empty[s]);
+    }
+    if (leader) umma_commit(&sm.done);
+  } else if (s1 > s0) {
+    mbar_wait(&sm.done, 0);
+    tc_fence_after_sync();
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    for (int t = 0; t < taps.n; ++t) {
+      float* dst = dW + ((long long)t * 128 + row) * 128;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem + ((uint32_t)(quarter * 32) << 16) + t * 128 + c * 32, v);
+        tmem_ld_wait(v);
+#pragma unroll
+        for (int u = 0; u < 32; u += 4)
+          atomicAdd(reinterpret_cast<float4*>(dst + c * 32 + u),
+                    make_float4(__uint_as_float(v[u]), __uint_as_float(v[u + 1]), __uint_as_float(v[u + 2]), __uint_as_float(v[u + 3])));
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc<512>(tmem);
+  }
+}
+
+// src [R,128] (f32 or bf16) -> dst [Kp][128] bf16, row-major: row(col) as in PadGeom (slot-major, every sequence preceded by
+// P zero rows); one warp per destination row
+template <bool kBf16>
+__global__ void __launch_bounds__(256)
+pad_rows_bf16_kernel(const void* __restrict__ src, PadGeom g, __nv_bfloat16* __restrict__ dst) {
+  const long long col = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (col >= g.Kp) return;
+  long long r = -1;
+  if (col < g.base[g.n_slots]) {
+    int s = 0;
+    while (s + 1 < g.n_slots && g.base[s + 1] <= col) ++s;
+    const int W = g.off[s + 1] - g.off[s] + g.P;
+    const long long rel = col - g.base[s];
+    const int b = (int)(rel / W), t = (int)(rel % W) - g.P;
+    if (t >= 0) r = (long long)b * g.T + g.off[s] + t;
+  }
+  uint2 o = make_uint2(0u, 0u);
+  if (r >= 0) {
+    if (kBf16) {
+      o = reinterpret_cast<const uint2*>(src)[r * 32 + lane];
+    } else {
+      const float4 v = reinterpret_cast<const float4*>(src)[r * 32 + lane];
+      o = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    }
+  }
+  reinterpret_cast<uint2*>(dst)[col * 32 + lane] = o;
+}
+
 // src [R,128] (f32 or bf16) -> n_shift copies dst_i [128][Kp] bf16 (dst_stride elements apart):
 //     dst_i[c][col] = src[row(col - shift_i)][c]   where col - shift_i falls on a position of the SAME sequence, else 0.
 // Column layout (slot-major): slot s starts at base[s]; user b's sequence occupies W_s = L_s + P columns, P zero columns
@@ -256,6 +396,36 @@ int32_t wgrad_bf16(const void* aT, long long a_stride, const void* bT, long long
   return HTCN_OK;
 }
 
+
+int32_t pad_rows_bf16(const void* src, bool src_bf16, const PadGeom& g, void* dst, cudaStream_t st) {
+  const int grid = (int)((g.Kp + 7) / 8);
+  if (src_bf16) pad_rows_bf16_kernel<true><<<grid, 256, 0, st>>>(src, g, reinterpret_cast<__nv_bfloat16*>(dst));
+  else pad_rows_bf16_kernel<false><<<grid, 256, 0, st>>>(src, g, reinterpret_cast<__nv_bfloat16*>(dst));
+  HTCN_LAUNCH_CHECK("pad_rows_bf16_kernel");
+  return HTCN_OK;
+}
+
+// dW[t][cin][cout] += sum_r aP[r - shifts[t]][cin] * bP[r][cout]   (aP, bP: bf16 [Kp][128] from pad_rows_bf16)
+int32_t wgrad_mn_bf16(const void* aP, const void* bP, long long Kp, const int* shifts, int n_taps, float* dW, cudaStream_t st) {
+  CUtensorMap ta, tb;
+  int32_t rc = make_tmap_bf16(&ta, aP, (uint64_t)Kp, 128, 128, 64, 64, 128);
+  if (rc) return rc;
+  rc = make_tmap_bf16(&tb, bP, (uint64_t)Kp, 128, 128, 64, 64, 128);
+  if (rc) return rc;
+  const size_t smem = sizeof(WgSmem) + 1024;
+  HTCN_CUDA(cudaFuncSetAttribute(wgrad_mn_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int n_steps = (int)(Kp / 64);
+  const int grid = n_steps < 148 ? n_steps : 148;
+  for (int t0 = 0; t0 < n_taps; t0 += kWgMaxTaps) {
+    WgShifts taps{};
+    taps.n = n_taps - t0 < kWgMaxTaps ? n_taps - t0 : kWgMaxTaps;
+    for (int t = 0; t < taps.n; ++t) taps.shift[t] = shifts[t0 + t];
+    wgrad_mn_bf16_kernel<<<grid, kWgThreads, smem, st>>>(ta, tb, n_steps, taps, dW + (long long)t0 * 128 * 128);
+    HTCN_LAUNCH_CHECK("wgrad_mn_bf16_kernel");
+  }
+  return HTCN_OK;
+}
+
 }  // namespace htcn
 
 // test hooks (not part of include/htcn.h): the two stages of the tensor-core weight gradient on their own
@@ -273,4 +443,18 @@ extern "C" int32_t htcn_debug_pad_transpose(const void* src, int32_t src_bf16, c
 }
 extern "C" int32_t htcn_debug_wgrad(const void* aT, const void* bT, int64_t Kp, int32_t n_taps, float* dW, void* stream) {
   return htcn::wgrad_bf16(aT, 128 * Kp, bT, Kp, n_taps, dW, htcn::as_stream(stream));
+}
+
+extern "C" int32_t htcn_debug_pad_rows(const void* src, int32_t src_bf16, const int32_t* slot_off_host, int32_t B, int32_t T,
+                                       int32_t S, int32_t P, void* dst, void* stream) {
+  using namespace htcn;
+  SlotTable slots;
+  slots.n = S;
+  for (int i = 0; i <= S; ++i) slots.off[i] = slot_off_host[i];
+  const PadGeom g = make_pad_geom(slots, B, T, P);
+  return pad_rows_bf16(src, src_bf16 != 0, g, dst, as_stream(stream));
+}
+extern "C" int32_t htcn_debug_wgrad_mn(const void* aP, const void* bP, int64_t Kp, const int32_t* shifts_host, int32_t n_taps,
+                                       float* dW, void* stream) {
+  return htcn::wgrad_mn_bf16(aP, bP, Kp, shifts_host, n_taps, dW, htcn::as_stream(stream));
 }

@@ -80,6 +80,11 @@ int32_t pad_transpose_bf16(const void* src, bool src_bf16, const PadGeom& g, con
 // [128][Kp]; dW fp32, atomics
 int32_t wgrad_bf16(const void* aT, long long a_stride, const void* bT, long long Kp, int n_taps, float* dW, cudaStream_t st);
 
+// the same with MN-major operands (no transposes): row-major zero-padded bf16 copies [Kp][128]; the tap shift is a TMA row
+// coordinate, one copy serves every tap:  dW[t][cin][cout] += sum_r aP[r - shifts[t]][cin] * bP[r][cout]
+int32_t pad_rows_bf16(const void* src, bool src_bf16, const PadGeom& g, void* dst, cudaStream_t st);
+int32_t wgrad_mn_bf16(const void* aP, const void* bP, long long Kp, const int* shifts, int n_taps, float* dW, cudaStream_t st);
+
 // out[f] += sum_r D[r, f]  (f < cols, cols <= 256)
 int32_t colsum_atomic(long long R, const float* D, int ldd, int cols, float* out, cudaStream_t st);
 

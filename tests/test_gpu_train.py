@@ -622,3 +622,63 @@ def test_score_ce_fwd_bwd_bf16_two_sweeps(Q, N, hot):
         assert np.isfinite(got).all()
         assert np.abs(got - ref).max() <= 1e-2 * np.abs(ref).max() + 1e-6, (np.abs(got - ref).max(), np.abs(ref).max())
         assert np.linalg.norm(got - ref) <= 5e-3 * np.linalg.norm(ref) + 1e-6
+
+
+@pytest.mark.parametrize("B,S,L,K,dil", [(5, 3, 7, 5, 2), (40, 10, 20, 5, 1), (3, 1, 300, 3, 8), (64, 10, 20, 1, 1)])
+def test_tensor_core_weight_gradient_mn_major(B, S, L, K, dil):
+    """bwd_wgrad_bf16.cu, MN-major variant: ONE row-major zero-padded bf16 copy per tensor, the tap shift as the TMA row
+    coordinate == sum_r h[r - shift]^T dp[r] with the causal zeroing at sequence starts (bf16 operands, fp32 accumulation)"""
+    import ctypes as C
+    from hiertcn_b200 import _cabi as cabi
+    from oracle import hiertcn_oracle as O
+    lib = cabi.load()
+    rng = np.random.default_rng(B * 3 + L)
+    T = S * L
+    R = B * T
+    h = O.bf16_round(rng.normal(size=(R, 128)).astype(np.float32))
+    dp = O.bf16_round((rng.normal(size=(R, 128)) * (rng.random((R, 128)) < 0.5)).astype(np.float32))
+    slot_p, keep = cabi.int_array(np.arange(S + 1) * L)
+    P_ = (K - 1) * dil
+    kp = C.c_int64(0)
+    st = torch.cuda.current_stream().cuda_stream
+    geom = lib.htcn_debug_pad_transpose
+    geom.restype = C.c_int32
+    geom.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32),
+                     C.c_int32, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]
+    zero_p, keep3 = cabi.int_array([0])
+    assert geom(None, 0, slot_p, B, T, S, P_, zero_p, 1, None, C.byref(kp), st) == 0
+    Kp = kp.value
+    pr = lib.htcn_debug_pad_rows
+    pr.restype = C.c_int32
+    pr.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    h_d, dp_d = dev(h), dev(dp).to(torch.bfloat16)
+    aP = torch.full((Kp, 128), float("nan"), dtype=torch.bfloat16, device="cuda")
+    bP = torch.full((Kp, 128), float("nan"), dtype=torch.bfloat16, device="cuda")
+    assert pr(h_d.data_ptr(), 0, slot_p, B, T, S, P_, aP.data_ptr(), st) == 0       # fp32 source
+    assert pr(dp_d.data_ptr(), 1, slot_p, B, T, S, P_, bP.data_ptr(), st) == 0      # bf16 source
+    torch.cuda.synchronize()
+    ref = np.zeros((Kp, 128), np.float32)
+    row = 0
+    for s in range(S):
+        for b in range(B):
+            row += P_
+            ref[row:row + L] = h[b * T + s * L + np.arange(L)]
+            row += L
+    np.testing.assert_array_equal(aP.float().cpu().numpy(), ref)
+    shifts = [(K - 1 - tap) * dil for tap in range(K)]
+    sh_p, keep2 = cabi.int_array(shifts)
+    gw = lib.htcn_debug_wgrad_mn
+    gw.restype = C.c_int32
+    gw.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int32), C.c_int32, C.c_void_p, C.c_void_p]
+    dW = torch.ones((K, 128, 128), dtype=torch.float32, device="cuda")
+    rc = gw(aP.data_ptr(), bP.data_ptr(), Kp, sh_p, K, dW.data_ptr(), st)
+    assert rc == 0, lib.htcn_last_error().decode()
+    torch.cuda.synchronize()
+    got = dW.cpu().numpy() - 1.0
+    t_in = np.tile(np.arange(L), B * S)
+    for tap, sh in enumerate(shifts):
+        src = np.arange(R) - sh
+        ok = t_in >= sh
+        hs = np.where(ok[:, None], h[np.clip(src, 0, R - 1)], 0.0)
+        want = hs.astype(np.float64).T @ dp.astype(np.float64)
+        assert np.abs(got[tap] - want).max() <= 1e-4 * np.abs(want).max() + 1e-6, (tap, np.abs(got[tap] - want).max(), np.abs(want).max())
