@@ -235,28 +235,39 @@ wgrad_mn_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
 template <bool kBf16>
 __global__ void __launch_bounds__(256)
 pad_rows_bf16_kernel(const void* __restrict__ src, PadGeom g, __nv_bfloat16* __restrict__ dst) {
-  const long long col = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  constexpr int kRowsPerWarp = 8;                                  // 8 loads in flight per lane
   const int lane = threadIdx.x & 31;
-  if (col >= g.Kp) return;
-  long long r = -1;
-  if (col < g.base[g.n_slots]) {
-    int s = 0;
-    while (s + 1 < g.n_slots && g.base[s + 1] <= col) ++s;
-    const int W = g.off[s + 1] - g.off[s] + g.P;
-    const long long rel = col - g.base[s];
-    const int b = (int)(rel / W), t = (int)(rel % W) - g.P;
-    if (t >= 0) r = (long long)b * g.T + g.off[s] + t;
-  }
-  uint2 o = make_uint2(0u, 0u);
-  if (r >= 0) {
-    if (kBf16) {
-      o = reinterpret_cast<const uint2*>(src)[r * 32 + lane];
-    } else {
-      const float4 v = reinterpret_cast<const float4*>(src)[r * 32 + lane];
-      o = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  const long long col0 = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * kRowsPerWarp;
+  if (col0 >= g.Kp) return;
+  long long my_r = -1;                                             // lane i < 8 resolves destination row col0 + i
+  {
+    const long long col = col0 + lane;
+    if (lane < kRowsPerWarp && col < g.base[g.n_slots]) {
+      int s = 0;
+      while (s + 1 < g.n_slots && g.base[s + 1] <= col) ++s;
+      const int W = g.off[s + 1] - g.off[s] + g.P;
+      const long long rel = col - g.base[s];
+      const int b = (int)(rel / W), t = (int)(rel % W) - g.P;
+      if (t >= 0) my_r = (long long)b * g.T + g.off[s] + t;
     }
   }
-  reinterpret_cast<uint2*>(dst)[col * 32 + lane] = o;
+  uint2 o[kRowsPerWarp];
+#pragma unroll
+  for (int i = 0; i < kRowsPerWarp; ++i) {
+    const long long r = __shfl_sync(0xffffffffu, my_r, i);
+    o[i] = make_uint2(0u, 0u);
+    if (r >= 0) {
+      if (kBf16) {
+        o[i] = reinterpret_cast<const uint2*>(src)[r * 32 + lane];
+      } else {
+        const float4 v = ldg_nc_f4(reinterpret_cast<const float4*>(src) + r * 32 + lane);
+        o[i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kRowsPerWarp; ++i)
+    if (col0 + i < g.Kp) reinterpret_cast<uint2*>(dst)[(col0 + i) * 32 + lane] = o[i];
 }
 
 // src [R,128] (f32 or bf16) -> n_shift copies dst_i [128][Kp] bf16 (dst_stride elements apart):
@@ -398,7 +409,7 @@ int32_t wgrad_bf16(const void* aT, long long a_stride, const void* bT, long long
 
 
 int32_t pad_rows_bf16(const void* src, bool src_bf16, const PadGeom& g, void* dst, cudaStream_t st) {
-  const int grid = (int)((g.Kp + 7) / 8);
+  const int grid = (int)((g.Kp + 63) / 64);
   if (src_bf16) pad_rows_bf16_kernel<true><<<grid, 256, 0, st>>>(src, g, reinterpret_cast<__nv_bfloat16*>(dst));
   else pad_rows_bf16_kernel<false><<<grid, 256, 0, st>>>(src, g, reinterpret_cast<__nv_bfloat16*>(dst));
   HTCN_LAUNCH_CHECK("pad_rows_bf16_kernel");
