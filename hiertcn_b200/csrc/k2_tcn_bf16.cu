@@ -387,6 +387,299 @@ k2_tcn_bf16(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfl
   }
 }
 
+
+// ---- two tile chains per CTA (the default) ---------------------------------------------------------------------------
+// The kernel above keeps ONE tile per CTA and two CTAs per SM; a tile's layer is a strictly serial MMA phase (5 taps through
+// a 2-deep weight ring: the refill latency of the ring, ~2000 clk per tap, not the 512 clk of its MMAs) followed by an
+// epilogue phase, so each CTA keeps the tensor pipe busy ~20 % of the time (ncu: 39-41 % with two CTAs).  Here ONE CTA per SM
+// runs two independent tile chains (two operand tiles, two TMEM accumulators, two groups of 8 worker warps) served by one
+// MMA warp that alternates between them layer by layer, and the weight ring is FOUR stages deep (128 KB): while chain A's
+// epilogue runs, the tensor pipe works on chain B, and a layer's taps are already in shared memory when its turn comes.
+// Chain c of CTA b behaves like "virtual CTA" 2b + c of the single-chain kernel (units, streaming hand-over scratch).
+constexpr int kDualWStages = 4;
+constexpr int kK2DualThreads = 32 * (2 * kK2EpiWarps + 2);       // warps 0-7 chain 0, 8-15 chain 1, 16 TMA producer, 17 MMA
+constexpr int kK2DualProducerWarp = 2 * kK2EpiWarps, kK2DualMmaWarp = 2 * kK2EpiWarps + 1;
+struct alignas(1024) K2SmemDual {
+  uint8_t w[kDualWStages][kWStageBytes];   // 128 KB
+  uint8_t act[2][kActBytes];               // 80 KB
+  float bias[HTCN_MAX_LEVELS][kDim];
+  uint64_t w_full[kDualWStages], w_empty[kDualWStages], acc_ready[2], act_ready[2];
+  uint32_t tmem_base;
+};
+
+// weight tiles of one layer in the order the kernel consumes them: layer 0 = the in-projection, layer l >= 1 = the K taps of
+// level l-1 followed by its down-sample kernel if it has one
+__device__ __forceinline__ void k2_layer_tiles(const K2Geom& g, int layer, int& first, int& taps, bool& ds) {
+  if (layer == 0) {
+    first = 0; taps = 1; ds = false;
+    return;
+  }
+  const int l = layer - 1;
+  first = 1 + l * g.K + __popc(g.ds_mask & ((1u << l) - 1u));
+  taps = g.K;
+  ds = (g.ds_mask >> l) & 1u;
+}
+
+template <bool kStream, bool kAux>
+__global__ void __launch_bounds__(kK2DualThreads, 1)
+k2_tcn_bf16_dual(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfloat16* __restrict__ xe,
+                 const float* __restrict__ sbias, const float* __restrict__ bias_all, const float* __restrict__ ds_bias_all,
+                 const int* __restrict__ out_row, __nv_bfloat16* __restrict__ hout, __nv_bfloat16* __restrict__ h_save,
+                 __nv_bfloat16* __restrict__ a_save, uint8_t* __restrict__ hist, const float* __restrict__ drop) {
+  extern __shared__ uint8_t smem_raw[];
+  auto& sm = *reinterpret_cast<K2SmemDual*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_layers = g.n_levels + 1;                       // layer 0 = in-projection
+  const int n_vc = 2 * (int)gridDim.x;                       // virtual CTAs = tile chains
+  const int tiles0 = cta_tile_count(g, 2 * (int)blockIdx.x, n_vc), tiles1 = cta_tile_count(g, 2 * (int)blockIdx.x + 1, n_vc);
+  const int steps0 = tiles0 * n_layers, steps1 = tiles1 * n_layers;      // layers each chain runs
+  const int n_rounds = steps0 > steps1 ? steps0 : steps1;
+  const bool two_acc = kAux && g.ds_mask != 0;               // second accumulator per chain: the down-sample residual
+
+  if (tid == 0) {
+    prefetch_tmap(&tmap_w);
+    for (int s = 0; s < kDualWStages; ++s) {
+      mbar_init(&sm.w_full[s], 1);
+      mbar_init(&sm.w_empty[s], 1);
+    }
+    for (int c = 0; c < 2; ++c) {
+      mbar_init(&sm.acc_ready[c], 1);
+      mbar_init(&sm.act_ready[c], 32 * kK2EpiWarps);
+    }
+    fence_barrier_init();
+  }
+  for (int i = tid; i < g.n_levels * kDim; i += kK2DualThreads) sm.bias[i / kDim][i % kDim] = bias_all[i];
+  for (int i = tid; i < 2 * kActBytes / 16; i += kK2DualThreads) reinterpret_cast<uint4*>(sm.act)[i] = make_uint4(0, 0, 0, 0);
+  if (warp == kK2DualMmaWarp) {
+    if (two_acc) tmem_alloc<512>(&sm.tmem_base);
+    else tmem_alloc<256>(&sm.tmem_base);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = __shfl_sync(0xffffffffu, sm.tmem_base, 0);
+  const uint32_t acc_cols = two_acc ? 256u : 128u;           // TMEM columns per chain
+
+  if (warp == kK2DualProducerWarp) {
+    // ===================== weight producer: the tiles of (chain 0, layer i), (chain 1, layer i), ... =====================
+    if (lane == 0) {
+      long long n = 0;
+      for (int i = 0; i < n_rounds; ++i) {
+        int first, taps;
+        bool ds;
+        k2_layer_tiles(g, i % n_layers, first, taps, ds);
+        const int cnt = taps + ((kAux && ds) ? 1 : 0);
+        for (int cn = 0; cn < 2; ++cn) {
+          if (i >= (cn ? steps1 : steps0)) continue;
+          for (int j = first; j < first + cnt; ++j, ++n) {
+            const int s = (int)(n % kDualWStages);
+            mbar_wait_relaxed(&sm.w_empty[s], (uint32_t)(((n / kDualWStages) & 1) ^ 1));
+            mbar_arrive_expect_tx(&sm.w_full[s], kWStageBytes);
+            tma_load_2d(sm.w[s], &tmap_w, 0, j * 128, &sm.w_full[s]);
+            tma_load_2d(sm.w[s] + kWStageBytes / 2, &tmap_w, 64, j * 128, &sm.w_full[s]);
+          }
+        }
+      }
+    }
+  } else if (warp == kK2DualMmaWarp) {
+    // ===================== MMA issuer: alternates between the chains layer by layer =====================
+    const bool leader = elect_one();
+    constexpr uint32_t idesc = make_idesc_bf16(kTR, 128);
+    long long n = 0;
+    for (int i = 0; i < n_rounds; ++i) {
+      const int layer = i % n_layers;
+      int first, taps;
+      bool ds;
+      k2_layer_tiles(g, layer, first, taps, ds);
+      const int dil = layer == 0 ? 1 : (1 << (layer - 1));
+      for (int cn = 0; cn < 2; ++cn) {
+        if (i >= (cn ? steps1 : steps0)) continue;
+        const uint32_t act0 = smem_u32(sm.act[cn]);
+        const uint32_t tacc = tmem + (uint32_t)cn * acc_cols;
+        mbar_wait(&sm.act_ready[cn], (uint32_t)(i & 1));         // operand tile written + fenced by the chain's worker warps
+        tc_fence_after_sync();
+        for (int tap = 0; tap < taps; ++tap, ++n) {
+          const int s = (int)(n % kDualWStages);
+          mbar_wait(&sm.w_full[s], (uint32_t)((n / kDualWStages) & 1));
+          tc_fence_after_sync();
+          const int shift = (taps - 1 - tap) * dil;              // rows back in time (customized_tcn_cell.py:46-49)
+          const uint32_t a_base = act0 + (uint32_t)(kMaxSpare - shift) * 16;
+          const uint32_t w_base = smem_u32(sm.w[s]);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const uint64_t da = make_desc_act(a_base + (uint32_t)(2 * k) * (kRows * 16));
+            const uint64_t db = make_desc_k_sw128(w_base + (k >> 2) * (kWStageBytes / 2) + (k & 3) * 32);
+            if (leader) umma_bf16(tacc, da, db, idesc, (tap | k) != 0);
+          }
+          if (leader) umma_commit(&sm.w_empty[s]);
+        }
+        if (kAux && ds) {                                        // res = in @ W_ds: unshifted rows, second accumulator
+          const int s = (int)(n % kDualWStages);
+          mbar_wait(&sm.w_full[s], (uint32_t)((n / kDualWStages) & 1));
+          tc_fence_after_sync();
+          const uint32_t a_base = act0 + (uint32_t)kMaxSpare * 16;
+          const uint32_t w_base = smem_u32(sm.w[s]);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const uint64_t da = make_desc_act(a_base + (uint32_t)(2 * k) * (kRows * 16));
+            const uint64_t db = make_desc_k_sw128(w_base + (k >> 2) * (kWStageBytes / 2) + (k & 3) * 32);
+            if (leader) umma_bf16(tacc + 128, da, db, idesc, k != 0);
+          }
+          if (leader) umma_commit(&sm.w_empty[s]);
+          ++n;
+        }
+        if (leader) umma_commit(&sm.acc_ready[cn]);
+      }
+    }
+  } else {
+    const int cn = warp >> 3;                                   // tile chain of this worker warp
+    const int vc = 2 * (int)blockIdx.x + cn;                    // its virtual CTA
+    const int tiles_g = cn ? tiles1 : tiles0;
+    const uint32_t tmem_c = tmem + (uint32_t)cn * acc_cols;
+    // ===================== loader + epilogue: thread = 64 channels (half ch) of one tile row =====================
+    // (with 4 epilogue warps -- one per scheduler -- the dependent FADD/FMNMX chains of the epilogue issued at ~4.5 clk per
+    // instruction and the MMA warp spent 2/3 of its time waiting for act_ready: ncu source view, profiles/r1_k2_ncu.txt)
+    const int tg = tid - 256 * cn;                                 // thread index inside the chain's worker group
+    const int r = tg & 127;                                    // TMEM lane r (warp w may touch lanes 32(w%4)..+31)
+    const int ch = tg >> 7;                                     // channel half: 64*ch .. 64*ch+63
+    uint8_t* my_act = sm.act[cn] + (kMaxSpare + r) * 16;            // + c * kRows * 16 for channel chunk c
+    long long n_acc = 0;
+    int unit = vc, chunk = 0, unit_chunks = unit < g.n_units ? g.slot[unit_slot(g, unit)].chunks : 1;
+    // streaming of long sequences: the threads of the tile's last kMaxSpare rows own the hand-over to the next chunk
+    const bool hist_owner = kStream && r >= kTR - kMaxSpare;
+    const int hj = r - (kTR - kMaxSpare);                       // spare row / parked row of this thread
+    uint8_t* my_hist = hist + (size_t)vc * 2 * g.n_levels * kHistBytes;
+    bool spare_dirty = false;                                   // the spare rows hold parked data (not the zero pad)
+    for (int it = 0; it < tiles_g; ++it) {
+      int src, dst, sb, slot_idx;
+      bool own;
+      tile_geometry(g, unit, chunk, r, out_row, src, dst, sb, own, slot_idx);
+      const bool streaming = kStream && unit_chunks > 1;
+      const long long RT = (long long)g.B * g.T;
+      // ---- stage the input rows (bf16 Xe) into the operand layout; zero rows stay zero
+      {
+        const uint4* p = src >= 0 ? reinterpret_cast<const uint4*>(xe + (long long)src * kDim) : nullptr;
+#pragma unroll
+        for (int c = ch * 8; c < ch * 8 + 8; ++c)
+          *reinterpret_cast<uint4*>(my_act + c * (kRows * 16)) = p ? __ldg(p + c) : make_uint4(0, 0, 0, 0);
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&sm.act_ready[cn]);
+      for (int layer = 0; layer < n_layers; ++layer, ++n_acc) {
+        mbar_wait(&sm.acc_ready[cn], (uint32_t)(n_acc & 1));
+        tc_fence_after_sync();
+        const bool last = layer == n_layers - 1;
+        // The MMAs that read the spare rows have retired: refill them for the NEXT layer (conv level `layer`), whose
+        // taps reach back up to kMaxSpare rows -- with the rows chunk-1 parked for that level, or with the causal zero pad.
+        uint8_t* park = my_hist + ((size_t)(chunk & 1) * g.n_levels + layer) * kHistBytes;
+        if (kStream && !last && hist_owner) {
+          const uint8_t* prev = my_hist + ((size_t)((chunk & 1) ^ 1) * g.n_levels + layer) * kHistBytes;
+          if (streaming && chunk > 0) {
+#pragma unroll
+            for (int c = ch * 8; c < ch * 8 + 8; ++c)
+              cp_async_16(sm.act[cn] + c * (kRows * 16) + hj * 16, prev + (c * kMaxSpare + hj) * 16);
+            spare_dirty = true;
+          } else if (spare_dirty) {                              // back to the causal zero pad
+#pragma unroll
+            for (int c = ch * 8; c < ch * 8 + 8; ++c)
+              *reinterpret_cast<uint4*>(sm.act[cn] + c * (kRows * 16) + hj * 16) = make_uint4(0, 0, 0, 0);
+            spare_dirty = false;
+          }
+        }
+        const float* bias_l = layer > 0 ? sm.bias[layer - 1] : nullptr;
+        const bool ds = kAux && layer > 0 && ((g.ds_mask >> (layer - 1)) & 1u);
+        const float* ds_bias_l = ds ? ds_bias_all + (layer - 1) * kDim : nullptr;
+        const float* drop_l = (kAux && drop && layer > 0) ? drop + ((long long)slot_idx * g.n_levels + (layer - 1)) * kDim : nullptr;
+        const float* sb_row = (layer == 0 && sbias && src >= 0) ? sbias + (long long)sb * kDim : nullptr;
+#pragma unroll 1
+        for (int cc = ch * 2; cc < ch * 2 + 2; ++cc) {           // 2 x 32 channels
+          // the per-(slot, user) bias of the in-projection: all 8 loads of this 32-channel group in flight BEFORE the TMEM
+          // read (inside the q loop each 16-byte group exposed a full L2 latency: 22 % of the epilogue warps' samples)
+          float4 sbv[8];
+          if (sb_row) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) sbv[i] = __ldg(reinterpret_cast<const float4*>(sb_row + cc * 32) + i);
+          }
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_c + ((uint32_t)((warp & 3) * 32) << 16) + cc * 32, v);
+          tmem_ld_wait(v);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {                          // 4 x 8 channels = one 16-byte chunk each
+            const int c = cc * 4 + q;
+            uint4* slot = reinterpret_cast<uint4*>(my_act + c * (kRows * 16));
+            float o[8], av[8];
+            if (layer == 0) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(v[q * 8 + e]);
+              if (sb_row) {
+                const float4 s0 = sbv[2 * q], s1 = sbv[2 * q + 1];
+                o[0] += s0.x; o[1] += s0.y; o[2] += s0.z; o[3] += s0.w;
+                o[4] += s1.x; o[5] += s1.y; o[6] += s1.z; o[7] += s1.w;
+              }
+            } else {
+              float rs[8];
+              if (ds) {                                          // residual = in @ W_ds + b_ds from the second accumulator
+                uint32_t v2[8];
+                tmem_ld_32x8(tmem_c + ((uint32_t)((warp & 3) * 32) << 16) + 128 + c * 8, v2);
+                tmem_ld_wait(v2);
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(ds_bias_l + c * 8));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(ds_bias_l + c * 8) + 1);
+                rs[0] = __uint_as_float(v2[0]) + b0.x; rs[1] = __uint_as_float(v2[1]) + b0.y;
+                rs[2] = __uint_as_float(v2[2]) + b0.z; rs[3] = __uint_as_float(v2[3]) + b0.w;
+                rs[4] = __uint_as_float(v2[4]) + b1.x; rs[5] = __uint_as_float(v2[5]) + b1.y;
+                rs[6] = __uint_as_float(v2[6]) + b1.z; rs[7] = __uint_as_float(v2[7]) + b1.w;
+              } else {
+                const uint4 res = *slot;                         // this row's input to the level (bf16 x 8)
+                rs[0] = bf16_lo(res.x); rs[1] = bf16_hi(res.x); rs[2] = bf16_lo(res.y); rs[3] = bf16_hi(res.y);
+                rs[4] = bf16_lo(res.z); rs[5] = bf16_hi(res.z); rs[6] = bf16_lo(res.w); rs[7] = bf16_hi(res.w);
+              }
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                float a = fmaxf(__uint_as_float(v[q * 8 + e]) + bias_l[c * 8 + e], 0.f);         // relu(conv + b)
+                av[e] = a;                                                                       // saved before dropout
+                if (drop_l) a *= __ldg(drop_l + c * 8 + e);                                      // training only
+                o[e] = fmaxf(a + rs[e], 0.f);                                                    // relu(a + residual)
+              }
+              if (kAux && a_save && own)
+                reinterpret_cast<uint4*>(a_save + ((long long)(layer - 1) * RT + src) * kDim)[c] =
+                    make_uint4(pack_bf16x2(av[0], av[1]), pack_bf16x2(av[2], av[3]), pack_bf16x2(av[4], av[5]),
+                               pack_bf16x2(av[6], av[7]));
+            }
+            uint4 packed = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
+                                      pack_bf16x2(o[6], o[7]));
+            if (src < 0) packed = make_uint4(0, 0, 0, 0);        // causal pad rows stay zero at every level
+            if (kAux && h_save && own) reinterpret_cast<uint4*>(h_save + ((long long)layer * RT + src) * kDim)[c] = packed;
+            if (!last) {
+              *slot = packed;
+              // park this row of the next level's input for the sequence's next chunk (read back by this same thread)
+              if (kStream && streaming && hist_owner && chunk + 1 < unit_chunks)
+                *reinterpret_cast<uint4*>(park + (c * kMaxSpare + hj) * 16) = packed;
+            } else if (dst >= 0) reinterpret_cast<uint4*>(hout + (long long)dst * kDim)[c] = packed;
+          }
+        }
+        tc_fence_before_sync();
+        if (!last) {
+          if (kStream && hist_owner) cp_async_wait_all();        // the parked rows have landed in the spare rows
+          fence_proxy_async_smem();
+          mbar_arrive(&sm.act_ready[cn]);
+        }
+      }
+      if (++chunk == unit_chunks) {
+        unit += n_vc;
+        chunk = 0;
+        unit_chunks = unit < g.n_units ? g.slot[unit_slot(g, unit)].chunks : 1;
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == kK2DualMmaWarp) {
+    tc_fence_after_sync();
+    if (two_acc) tmem_dealloc<512>(tmem);
+    else tmem_dealloc<256>(tmem);
+  }
+}
+
 // weights f32 [tap][cin][cout] (TF layout, customized_convolution_layer.py:137) -> bf16 [tap][cout][cin]
 // tile_src[j]: the [128 cin][128 cout] fp32 source of weight tile j, in the order the kernel consumes them:
 // in-projection, then per level its K taps and, if it has one, the down-sample Dense kernel
@@ -483,6 +776,32 @@ int32_t tcn_forward_bf16(const void* xe, int xe_dtype, const float* w_in_x, cons
   bool stream = false;
   for (int s = 0; s < slots.n; ++s) stream |= g.slot[s].chunks > 1;
   const bool aux = g.ds_mask != 0 || drop || h_save || a_save;
+  // one CTA per SM running two tile chains over a 4-deep weight ring (k2_tcn_bf16_dual) for streamed long sequences, the
+  // single-chain kernel (two CTAs per SM, 2-deep ring) otherwise -- measured: config 3 (4096 x 256, 4 levels) 0.817 vs
+  // 0.856 ms, config 2 (40960 x 20, 2 levels) 0.638 vs 0.612 ms: both variants stream 352 KB of weights per tile out of L2
+  // (~53 % of the chip's L2 throughput) and serialise a tile's MMA and epilogue phases, the deeper ring only helps the longer
+  // layer chains.  HTCN_K2_DUAL=1 / 0 forces one or the other.
+  const char* dual_env = getenv("HTCN_K2_DUAL");
+  const bool dual = dual_env ? atoi(dual_env) != 0 : stream;
+  if (!pair && dual) {
+    const size_t smem_d = sizeof(K2SmemDual) + 1024;
+    const int grid_d = (units + 1) / 2 < 148 ? (units + 1) / 2 : 148;
+#define HTCN_K2_LAUNCH_DUAL(STREAM, AUX)                                                                                 \
+  do {                                                                                                                  \
+    auto kern = k2_tcn_bf16_dual<STREAM, AUX>;                                                                          \
+    HTCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d));                    \
+    kern<<<grid_d, kK2DualThreads, smem_d, st>>>(tw, g, (const __nv_bfloat16*)xe, sbias, (const float*)bias_dev,         \
+                                                 (const float*)ds_bias_dev, out_row, (__nv_bfloat16*)hout,              \
+                                                 (__nv_bfloat16*)h_save, (__nv_bfloat16*)a_save, hist_dev, drop);       \
+    HTCN_LAUNCH_CHECK("k2_tcn_bf16_dual");                                                                              \
+    return HTCN_OK;                                                                                                     \
+  } while (0)
+    if (stream && aux) HTCN_K2_LAUNCH_DUAL(true, true);
+    if (stream) HTCN_K2_LAUNCH_DUAL(true, false);
+    if (aux) HTCN_K2_LAUNCH_DUAL(false, true);
+    HTCN_K2_LAUNCH_DUAL(false, false);
+#undef HTCN_K2_LAUNCH_DUAL
+  }
   const int grid = pair ? (units < 2 * 148 ? ((units + 1) & ~1) : 2 * 148) : (units < 2 * 148 ? units : 2 * 148);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid, 1, 1);

@@ -823,6 +823,15 @@ def test_k2_tcn_bf16_tcgen05(lib, B, S, L, K, levels):
     finally:
         del os.environ["HTCN_K2_MULTICAST"]
     np.testing.assert_array_equal(got_mc, got)
+    # the two-chain kernel (one CTA per SM, two tiles in flight, 4-deep weight ring: the default for streamed sequences) and
+    # the single-chain kernel give the same bits
+    for dual in ("0", "1"):
+        os.environ["HTCN_K2_DUAL"] = dual
+        try:
+            got_d = run_k2_bf16(lib, xe, w, sbias, pk["slot_off"], B, T, S, K, levels).float().cpu().numpy().reshape(B, T, 128)
+        finally:
+            del os.environ["HTCN_K2_DUAL"]
+        np.testing.assert_array_equal(got_d, got)
 
 
 def test_k2_bf16_causality_and_isolation(lib):
