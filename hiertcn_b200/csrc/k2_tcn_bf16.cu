@@ -248,7 +248,7 @@ k2_tcn_bf16(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfl
     // instruction and the MMA warp spent 2/3 of its time waiting for act_ready: ncu source view, profiles/r1_k2_ncu.txt)
     const int r = tid & 127;                                    // TMEM lane r (warp w may touch lanes 32(w%4)..+31)
     const int ch = tid >> 7;                                    // channel half: 64*ch .. 64*ch+63
-    uint8_t* my_act = sm.act + (kMaxSpare + r) * 16;            // + c * kRows * 16 for channel chunk c
+    const uint32_t my_act = smem_u32(sm.act) + (kMaxSpare + r) * 16;      // + c * kRows * 16 for channel chunk c (shared window)
     long long n_acc = 0;
     int unit = blockIdx.x, chunk = 0, unit_chunks = unit < g.n_units ? g.slot[unit_slot(g, unit)].chunks : 1;
     // streaming of long sequences: the threads of the tile's last kMaxSpare rows own the hand-over to the next chunk
@@ -267,7 +267,7 @@ k2_tcn_bf16(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfl
         const uint4* p = src >= 0 ? reinterpret_cast<const uint4*>(xe + (long long)src * kDim) : nullptr;
 #pragma unroll
         for (int c = ch * 8; c < ch * 8 + 8; ++c)
-          *reinterpret_cast<uint4*>(my_act + c * (kRows * 16)) = p ? __ldg(p + c) : make_uint4(0, 0, 0, 0);
+          sts_u4(my_act + c * (kRows * 16), p ? __ldg(p + c) : make_uint4(0, 0, 0, 0));
       }
       fence_proxy_async_smem();
       mbar_arrive(&sm.act_ready);
@@ -288,11 +288,11 @@ k2_tcn_bf16(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfl
           } else if (spare_dirty) {                              // back to the causal zero pad
 #pragma unroll
             for (int c = ch * 8; c < ch * 8 + 8; ++c)
-              *reinterpret_cast<uint4*>(sm.act + c * (kRows * 16) + hj * 16) = make_uint4(0, 0, 0, 0);
+              sts_u4(smem_u32(sm.act) + c * (kRows * 16) + hj * 16, make_uint4(0, 0, 0, 0));
             spare_dirty = false;
           }
         }
-        const float* bias_l = layer > 0 ? sm.bias[layer - 1] : nullptr;
+        const uint32_t bias_s = smem_u32(sm.bias[layer > 0 ? layer - 1 : 0]);      // shared-window address of the level's bias
         const bool ds = kAux && layer > 0 && ((g.ds_mask >> (layer - 1)) & 1u);
         const float* ds_bias_l = ds ? ds_bias_all + (layer - 1) * kDim : nullptr;
         const float* drop_l = (kAux && drop && layer > 0) ? drop + ((long long)slot_idx * g.n_levels + (layer - 1)) * kDim : nullptr;
@@ -312,7 +312,7 @@ k2_tcn_bf16(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfl
 #pragma unroll
           for (int q = 0; q < 4; ++q) {                          // 4 x 8 channels = one 16-byte chunk each
             const int c = cc * 4 + q;
-            uint4* slot = reinterpret_cast<uint4*>(my_act + c * (kRows * 16));
+            const uint32_t slot = my_act + c * (kRows * 16);
             float o[8], av[8];
             if (layer == 0) {
 #pragma unroll
@@ -335,13 +335,15 @@ k2_tcn_bf16(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfl
                 rs[4] = __uint_as_float(v2[4]) + b1.x; rs[5] = __uint_as_float(v2[5]) + b1.y;
                 rs[6] = __uint_as_float(v2[6]) + b1.z; rs[7] = __uint_as_float(v2[7]) + b1.w;
               } else {
-                const uint4 res = *slot;                         // this row's input to the level (bf16 x 8)
+                const uint4 res = lds_u4(slot);                  // this row's input to the level (bf16 x 8)
                 rs[0] = bf16_lo(res.x); rs[1] = bf16_hi(res.x); rs[2] = bf16_lo(res.y); rs[3] = bf16_hi(res.y);
                 rs[4] = bf16_lo(res.z); rs[5] = bf16_hi(res.z); rs[6] = bf16_lo(res.w); rs[7] = bf16_hi(res.w);
               }
+              const float4 bv0 = lds_f4(bias_s + c * 32), bv1 = lds_f4(bias_s + c * 32 + 16);
+              const float bl[8] = {bv0.x, bv0.y, bv0.z, bv0.w, bv1.x, bv1.y, bv1.z, bv1.w};
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
-                float a = fmaxf(__uint_as_float(v[q * 8 + e]) + bias_l[c * 8 + e], 0.f);         // relu(conv + b)
+                float a = fmaxf(__uint_as_float(v[q * 8 + e]) + bl[e], 0.f);                     // relu(conv + b)
                 av[e] = a;                                                                       // saved before dropout
                 if (drop_l) a *= __ldg(drop_l + c * 8 + e);                                      // training only
                 o[e] = fmaxf(a + rs[e], 0.f);                                                    // relu(a + residual)
@@ -356,7 +358,7 @@ k2_tcn_bf16(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfl
             if (src < 0) packed = make_uint4(0, 0, 0, 0);        // causal pad rows stay zero at every level
             if (kAux && h_save && own) reinterpret_cast<uint4*>(h_save + ((long long)layer * RT + src) * kDim)[c] = packed;
             if (!last) {
-              *slot = packed;
+              sts_u4(slot, packed);
               // park this row of the next level's input for the sequence's next chunk (read back by this same thread)
               if (kStream && streaming && hist_owner && chunk + 1 < unit_chunks)
                 *reinterpret_cast<uint4*>(park + (c * kMaxSpare + hj) * 16) = packed;
@@ -542,7 +544,7 @@ k2_tcn_bf16_dual(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __n
     const int tg = tid - 256 * cn;                                 // thread index inside the chain's worker group
     const int r = tg & 127;                                    // TMEM lane r (warp w may touch lanes 32(w%4)..+31)
     const int ch = tg >> 7;                                     // channel half: 64*ch .. 64*ch+63
-    uint8_t* my_act = sm.act[cn] + (kMaxSpare + r) * 16;            // + c * kRows * 16 for channel chunk c
+    const uint32_t my_act = smem_u32(sm.act[cn]) + (kMaxSpare + r) * 16;  // + c * kRows * 16 for channel chunk c (shared window)
     long long n_acc = 0;
     int unit = vc, chunk = 0, unit_chunks = unit < g.n_units ? g.slot[unit_slot(g, unit)].chunks : 1;
     // streaming of long sequences: the threads of the tile's last kMaxSpare rows own the hand-over to the next chunk
@@ -561,7 +563,7 @@ k2_tcn_bf16_dual(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __n
         const uint4* p = src >= 0 ? reinterpret_cast<const uint4*>(xe + (long long)src * kDim) : nullptr;
 #pragma unroll
         for (int c = ch * 8; c < ch * 8 + 8; ++c)
-          *reinterpret_cast<uint4*>(my_act + c * (kRows * 16)) = p ? __ldg(p + c) : make_uint4(0, 0, 0, 0);
+          sts_u4(my_act + c * (kRows * 16), p ? __ldg(p + c) : make_uint4(0, 0, 0, 0));
       }
       fence_proxy_async_smem();
       mbar_arrive(&sm.act_ready[cn]);
@@ -582,11 +584,11 @@ k2_tcn_bf16_dual(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __n
           } else if (spare_dirty) {                              // back to the causal zero pad
 #pragma unroll
             for (int c = ch * 8; c < ch * 8 + 8; ++c)
-              *reinterpret_cast<uint4*>(sm.act[cn] + c * (kRows * 16) + hj * 16) = make_uint4(0, 0, 0, 0);
+              sts_u4(smem_u32(sm.act[cn]) + c * (kRows * 16) + hj * 16, make_uint4(0, 0, 0, 0));
             spare_dirty = false;
           }
         }
-        const float* bias_l = layer > 0 ? sm.bias[layer - 1] : nullptr;
+        const uint32_t bias_s = smem_u32(sm.bias[layer > 0 ? layer - 1 : 0]);      // shared-window address of the level's bias
         const bool ds = kAux && layer > 0 && ((g.ds_mask >> (layer - 1)) & 1u);
         const float* ds_bias_l = ds ? ds_bias_all + (layer - 1) * kDim : nullptr;
         const float* drop_l = (kAux && drop && layer > 0) ? drop + ((long long)slot_idx * g.n_levels + (layer - 1)) * kDim : nullptr;
@@ -606,7 +608,7 @@ k2_tcn_bf16_dual(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __n
 #pragma unroll
           for (int q = 0; q < 4; ++q) {                          // 4 x 8 channels = one 16-byte chunk each
             const int c = cc * 4 + q;
-            uint4* slot = reinterpret_cast<uint4*>(my_act + c * (kRows * 16));
+            const uint32_t slot = my_act + c * (kRows * 16);
             float o[8], av[8];
             if (layer == 0) {
 #pragma unroll
@@ -629,13 +631,15 @@ k2_tcn_bf16_dual(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __n
                 rs[4] = __uint_as_float(v2[4]) + b1.x; rs[5] = __uint_as_float(v2[5]) + b1.y;
                 rs[6] = __uint_as_float(v2[6]) + b1.z; rs[7] = __uint_as_float(v2[7]) + b1.w;
               } else {
-                const uint4 res = *slot;                         // this row's input to the level (bf16 x 8)
+                const uint4 res = lds_u4(slot);                  // this row's input to the level (bf16 x 8)
                 rs[0] = bf16_lo(res.x); rs[1] = bf16_hi(res.x); rs[2] = bf16_lo(res.y); rs[3] = bf16_hi(res.y);
                 rs[4] = bf16_lo(res.z); rs[5] = bf16_hi(res.z); rs[6] = bf16_lo(res.w); rs[7] = bf16_hi(res.w);
               }
+              const float4 bv0 = lds_f4(bias_s + c * 32), bv1 = lds_f4(bias_s + c * 32 + 16);
+              const float bl[8] = {bv0.x, bv0.y, bv0.z, bv0.w, bv1.x, bv1.y, bv1.z, bv1.w};
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
-                float a = fmaxf(__uint_as_float(v[q * 8 + e]) + bias_l[c * 8 + e], 0.f);         // relu(conv + b)
+                float a = fmaxf(__uint_as_float(v[q * 8 + e]) + bl[e], 0.f);                     // relu(conv + b)
                 av[e] = a;                                                                       // saved before dropout
                 if (drop_l) a *= __ldg(drop_l + c * 8 + e);                                      // training only
                 o[e] = fmaxf(a + rs[e], 0.f);                                                    // relu(a + residual)
@@ -650,7 +654,7 @@ k2_tcn_bf16_dual(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __n
             if (src < 0) packed = make_uint4(0, 0, 0, 0);        // causal pad rows stay zero at every level
             if (kAux && h_save && own) reinterpret_cast<uint4*>(h_save + ((long long)layer * RT + src) * kDim)[c] = packed;
             if (!last) {
-              *slot = packed;
+              sts_u4(slot, packed);
               // park this row of the next level's input for the sequence's next chunk (read back by this same thread)
               if (kStream && streaming && hist_owner && chunk + 1 < unit_chunks)
                 *reinterpret_cast<uint4*>(park + (c * kMaxSpare + hj) * 16) = packed;

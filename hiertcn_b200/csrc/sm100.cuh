@@ -330,6 +330,16 @@ __device__ __forceinline__ float4 lds_f4(uint32_t saddr) {     // 128-bit shared
   asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
   return v;
 }
+// 128-bit shared-memory accesses through a 32-bit shared-window address: a pointer derived from a reference to the dynamic
+// shared struct compiles to GENERIC LD.E / ST.E, which the epilogues of the conv stack paid for (ncu source view)
+__device__ __forceinline__ uint4 lds_u4(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void sts_u4(uint32_t saddr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 __device__ __forceinline__ float set_gt_f(float a, float b) {  // 1.0f if a > b else 0.0f (one FSET.BF)
   float d;
   asm("set.gt.f32.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));

@@ -955,3 +955,45 @@ def test_score_topk_overflow_is_reported_and_model_falls_back(lib):
     out = model.topk(hq, Q, k)
     assert (out["topk_idx"].cpu().numpy() == np.arange(k)[None, :]).all()
     assert (out["topk_val"] == 0.25).all()
+
+
+def test_k4_bf16_folded_sweep_over_catalog_shards(lib):
+    """the folded sweep on three catalog shards (n0 offsets; a row's target lives in exactly one of them, whose split 0
+    takes the target column's own sign bit out of the count) merges to the ranks of the whole-catalog sweep, bit for bit"""
+    rng = np.random.default_rng(11)
+    Q, N = 260, 6000
+    hout = O.bf16_round(rng.normal(size=(Q, 128)).astype(np.float32))
+    w_out = (rng.normal(size=(128, N)) * 0.3).astype(np.float32)
+    b_out = (rng.normal(size=N) * 0.2).astype(np.float32)
+    y = rng.integers(1, N, size=Q).astype(np.int32)
+    wt = torch.empty((N, lib.WT_PITCH_BF16), dtype=torch.bfloat16, device="cuda")
+    hd, bd, yd, w_out_d = dev(hout).to(torch.bfloat16), dev(b_out), dev(y), dev(w_out)
+    lib.call("htcn_prepare_wout", P(w_out_d), P(bd), N, P(wt), lib.HTCN_BF16, None)
+    zy = torch.zeros(Q, dtype=torch.float32, device="cuda")
+    lib.call("htcn_target_logit", P(hd), lib.HTCN_BF16, Q, P(wt), P(bd), N, 0, P(yd), P(zy), None)
+    ws = torch.empty(lib.score_fold_ws_bytes(Q), dtype=torch.uint8, device="cuda")
+
+    def fold(n0, n1, ns):
+        pm = torch.empty((ns, Q), dtype=torch.float32, device="cuda")
+        ps = torch.empty((ns, Q), dtype=torch.float32, device="cuda")
+        pc = torch.empty((ns, Q), dtype=torch.int32, device="cuda")
+        lib.call("htcn_score_ce_rank_folded", P(hd), Q, wt[n0:n1].data_ptr(), n1 - n0, n0, P(yd), P(zy),
+                 lib.SCORE_CE | lib.SCORE_RANK, ns, P(pm), P(ps), P(pc), P(ws), None)
+        torch.cuda.synchronize()
+        return pm, ps, pc
+
+    def finish(parts):
+        pm = torch.cat([p[0] for p in parts]); ps = torch.cat([p[1] for p in parts]); pc = torch.cat([p[2] for p in parts])
+        lr = torch.empty(Q, dtype=torch.float32, device="cuda"); rr = torch.empty(Q, dtype=torch.float32, device="cuda")
+        lib.call("htcn_score_finish", P(pm), P(ps), P(pc), pm.shape[0], Q, P(yd), P(zy), P(lr), P(rr), None)
+        torch.cuda.synchronize()
+        return lr.cpu().numpy(), rr.cpu().numpy()
+
+    l1, r1 = finish([fold(0, N, 2)])
+    bounds = [0, 1792, 4352, N]
+    l3, r3 = finish([fold(bounds[s], bounds[s + 1], 1 + s) for s in range(3)])
+    np.testing.assert_array_equal(r1, r3)
+    np.testing.assert_allclose(l1, l3, rtol=2e-6, atol=2e-6)
+    z = debug_logits_bf16(lib, hd, wt, bd).cpu().numpy()
+    strict = (z > zy.cpu().numpy()[:, None]).sum(1)
+    assert np.abs(r1 - strict).max() <= 1                        # only a logit within one rounding of the target can differ
