@@ -20,6 +20,10 @@
 #include "common.cuh"
 #include "sm100.cuh"
 
+#ifndef HTCN_K3_DEFAULT_MODE
+#define HTCN_K3_DEFAULT_MODE 1
+#endif
+
 namespace htcn {
 using namespace sm100;
 
@@ -359,17 +363,15 @@ int32_t gru_sessions_bf16_cluster(const float* yp, const float* mask, const floa
                                   const float* w_in_state, int B, int S, float* state_pre, float* sbias, float* state_out,
                                   float* scratch, cudaStream_t st);
 
-int32_t gru_sessions_bf16(const float* yp, const float* mask, const float* state_in, const float* const* gate_w,
-                          const float* const* gate_b, const float* const* cand_w, const float* const* cand_b,
-                          const float* w_in_state, int B, int S, float* state_pre, float* sbias, float* state_out,
-                          float* scratch, cudaStream_t st) {
-  // default: the 4-CTA cluster kernel with shared-memory-resident weights (k3_gru_cluster.cu; HTCN_K3_CLUSTER=1 / 2 pick
-  // its DSMEM publication scheme); HTCN_K3_CLUSTER=0 selects this file's single-CTA kernel that streams the weights from L2
-  const char* cl = getenv("HTCN_K3_CLUSTER");
-  if (!cl || atoi(cl) != 0)
-    return gru_sessions_bf16_cluster(yp, mask, state_in, gate_w, gate_b, cand_w, cand_b, w_in_state, B, S, state_pre, sbias,
-                                     state_out, scratch, st);
-  // scratch layout: [14 bf16 weight tiles][4 device pointers][768 bias floats]
+int32_t gru_sessions_bf16_t(const float* yp, const float* mask, const float* state_in, const float* const* gate_w,
+                            const float* const* gate_b, const float* const* cand_w, const float* const* cand_b,
+                            const float* w_in_state, int B, int S, float* state_pre, float* sbias, float* state_out,
+                            float* scratch, int variant, cudaStream_t st);
+
+// scratch layout of the kernels that stream [n][k] weight tiles: [14 bf16 weight tiles][4 device pointers][768 bias floats]
+int32_t k3_prepare_stream_weights(const float* const* gate_w, const float* const* gate_b, const float* const* cand_w,
+                                  const float* const* cand_b, const float* w_in_state, float* scratch, cudaStream_t st,
+                                  __nv_bfloat16** w_out, float** bias_out) {
   uint8_t* sc = reinterpret_cast<uint8_t*>(scratch);
   __nv_bfloat16* w_bf16 = reinterpret_cast<__nv_bfloat16*>(sc);
   const size_t w_bytes = (size_t)14 * 128 * 128 * 2;
@@ -383,8 +385,33 @@ int32_t gru_sessions_bf16(const float* yp, const float* mask, const float* state
   }
   k3_prepare_weights<<<14, 256, 0, st>>>(w_in_state, ptrs_dev, w_bf16);
   HTCN_LAUNCH_CHECK("k3_prepare_weights");
+  *w_out = w_bf16;
+  *bias_out = bias_dev;
+  return HTCN_OK;
+}
+
+int32_t gru_sessions_bf16(const float* yp, const float* mask, const float* state_in, const float* const* gate_w,
+                          const float* const* gate_b, const float* const* cand_w, const float* const* cand_b,
+                          const float* w_in_state, int B, int S, float* state_pre, float* sbias, float* state_out,
+                          float* scratch, cudaStream_t st) {
+  // HTCN_K3_CLUSTER picks the kernel: 0 = this file's single-CTA kernel (128 users on the MMA M axis, weights streamed
+  // from L2); 1 / 2 = the 4-CTA cluster kernel with shared-memory-resident weight slices (k3_gru_cluster.cu; plain DSMEM
+  // stores or st.async); 3, 4, 5 = the users-on-N kernel (k3_gru_t.cu: hidden units on the MMA M axis, 32 / 64 users per
+  // CTA on N, no exchange between CTAs) in its three shared-memory budgets
+  const char* cl = getenv("HTCN_K3_CLUSTER");
+  const int mode = cl ? atoi(cl) : HTCN_K3_DEFAULT_MODE;
+  if (mode >= 3)
+    return gru_sessions_bf16_t(yp, mask, state_in, gate_w, gate_b, cand_w, cand_b, w_in_state, B, S, state_pre, sbias,
+                               state_out, scratch, mode - 3, st);
+  if (mode != 0)
+    return gru_sessions_bf16_cluster(yp, mask, state_in, gate_w, gate_b, cand_w, cand_b, w_in_state, B, S, state_pre, sbias,
+                                     state_out, scratch, st);
+  __nv_bfloat16* w_bf16;
+  float* bias_dev;
+  int32_t rc = k3_prepare_stream_weights(gate_w, gate_b, cand_w, cand_b, w_in_state, scratch, st, &w_bf16, &bias_dev);
+  if (rc) return rc;
   CUtensorMap tw;
-  int32_t rc = make_tmap_bf16(&tw, w_bf16, (uint64_t)14 * 128, kDim, kDim, 64, 128, 128);
+  rc = make_tmap_bf16(&tw, w_bf16, (uint64_t)14 * 128, kDim, kDim, 64, 128, 128);
   if (rc) return rc;
   const size_t smem = sizeof(K3Smem) + 1024;
   HTCN_CUDA(cudaFuncSetAttribute(k3_gru_bf16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -1,0 +1,362 @@
+// K3 (bf16 tier), users-on-N variant: GRU over sessions with NO exchange between CTAs.
+//
+// The other two tensor-core GRU kernels put the users on the MMA M axis (M = 128 users per CTA or per 4-CTA cluster), so a
+// batch of 4096 users either runs on 32 SMs (k3_gru_bf16.cu) or has to split the hidden columns over a cluster and exchange
+// every h' slice through distributed shared memory (k3_gru_cluster.cu: 40 dependent phases of ~3.4 us, most of it the
+// exchange).  Here the roles of the operands are swapped:
+//   D[hidden unit, user] = W^T[hidden unit, k] * act[user, k]^T
+// A = a 128-row weight tile (K-major, 128-byte swizzle, the [n][k] tiles of k3_prepare_weights), B = the activations of
+// the CTA's own kNU = 32 users (N = 32; no-swizzle K-major, 16-byte K chunks), the accumulator is TMEM lane = hidden unit,
+// column = user.  A CTA owns ALL 128 hidden units of its 32 users, so 128 CTAs work on 4096 users and no h' ever leaves the
+// SM: the fp32 state of (unit j, 16 users) lives in the registers of one epilogue thread, which writes the bf16 copies the
+// next product reads straight into its own CTA's operand slots.
+//
+// The price is the weights: all five matrices of a step (448 KB bf16) cannot be resident.  The layer-0 gate kernel (128 KB)
+// stays in shared memory for the whole call; the other 20 sub-tiles of 16 KB stream from L2 through a TMA ring every step
+// -- they do not depend on the recurrence, so the producer warp runs ahead of it.
+//
+// Operand slots (bf16 [32 users][128 k] each): X | H0 | T0 | H1 | T1.   Step s (customed_gru_cell.py:309-337 per layer,
+// :1050-1073 stacking; model_hier.py:54-55,91,93):
+//   G0 : [r|u] = sigmoid([X | H0] Wg0 + bg0)           E: T0 <- r * h0
+//   SB : sbias[s] = [H0 | H1] @ W_in[D:]               (off the critical path: drained while C0 runs)
+//   C0 : c = tanh([X | T0] Wc0 + bc0)                  E: h0' = u*h0 + (1-u)*c ; T0 <- h0' ; h0 <- m*h0' ; H0 <- h0
+//   G1 : [r|u] = sigmoid([T0 | H1] Wg1 + bg1)          E: T1 <- r * h1
+//   C1 : c = tanh([T0 | T1] Wc1 + bc1)                 E: h1 <- m*h1' ; H1 <- h1 ; (X <- x_{s+1} was staged under G1)
+// The r and u halves of a gate product are committed separately: the epilogue forms r*h while the u MMAs still run.
+#include <cstdlib>
+
+#include "common.cuh"
+#include "sm100.cuh"
+
+namespace htcn {
+using namespace sm100;
+
+int32_t k3_prepare_stream_weights(const float* const* gate_w, const float* const* gate_b, const float* const* cand_w,
+                                  const float* const* cand_b, const float* w_in_state, float* scratch, cudaStream_t st,
+                                  __nv_bfloat16** w_out, float** bias_out);
+
+namespace k3t {
+constexpr int kSub = 128 * 64 * 2;                // one weight sub-tile: 128 hidden units x 64 k, bf16, 128-byte swizzle = 16 KB
+constexpr int kSubPerStep = 28;                   // G0r 4 | G0u 4 | SB 4 | C0 4 | G1r 4 | G1u 4 | C1 4
+constexpr int kUsersPerThread = 16;
+enum Slot { kX = 0, kH0 = 1, kT0 = 2, kH1 = 3, kT1 = 4, kSlots = 5 };
+enum Product { kG0r = 0, kG0u, kSB, kC0, kG1r, kG1u, kC1 };
+
+template <int kNU, int kRes, int kStages>
+struct Cfg {
+  static constexpr int kEpiWarps = 4 * (kNU / kUsersPerThread);     // 4 TMEM lane quarters x user groups of 16
+  static constexpr int kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
+  static constexpr int kThreads = 32 * (kEpiWarps + 2);
+  // K chunks (8 k = 16 B per user row) are kNU*16 + 16 bytes apart: the 32 lanes of a warp store 2 bytes each into 4
+  // consecutive chunks of one user row, the 16 bytes of padding put those on different banks
+  static constexpr int kChunkStride = kNU * 16 + 16;
+  static constexpr int kSlotBytes = 16 * kChunkStride;
+  static constexpr uint32_t kColR = 0, kColU = kNU, kColC = 2 * kNU, kColSb = 3 * kNU, kTmemCols = 4 * kNU;
+  struct alignas(1024) Smem {
+    uint8_t res[kRes > 0 ? kRes : 1][kSub];
+    uint8_t ring[kStages][kSub];
+    alignas(16) uint8_t act[kSlots][kSlotBytes];
+    uint64_t w_full[kStages], w_empty[kStages], res_full, act_ready, acc_r, acc_u, acc_c, acc_sb;
+    uint32_t tmem_base;
+  };
+};
+
+__device__ __forceinline__ uint64_t make_desc_nosw(uint32_t smem_addr, uint32_t lbo) {   // 8-row groups 128 B apart
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(lbo >> 4) << 16;
+  d |= (uint64_t)(128 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(tanh_fast(0.5f * x), 0.5f, 0.5f); }
+__device__ __forceinline__ void sts_bf16(uint32_t saddr, float v) {
+  const unsigned short b = __bfloat16_as_ushort(__float2bfloat16_rn(v));
+  asm volatile("st.shared.b16 [%0], %1;" ::"r"(saddr), "h"(b) : "memory");
+}
+// first weight tile (of the 14 [128 n][128 k] tiles k3_prepare_weights writes) of a product
+__host__ __device__ constexpr int tile_of(int product) {
+  return product == kSB ? 0 : product == kG0r ? 2 : product == kG0u ? 4 : product == kC0 ? 6 : product == kG1r ? 8
+         : product == kG1u ? 10 : 12;
+}
+}  // namespace k3t
+
+template <int kNU, int kRes, int kStages>
+__global__ void __launch_bounds__(k3t::Cfg<kNU, kRes, kStages>::kThreads, 1)
+k3_gru_bf16_t(const __grid_constant__ CUtensorMap tmap_w, const float* __restrict__ yp, const float* __restrict__ mask,
+              const float* __restrict__ state_in, const float* __restrict__ bias_all /* [bg0 256][bc0 128][bg1 256][bc1 128] */,
+              int B, int S, int do_sbias, float* __restrict__ state_pre, float* __restrict__ sbias,
+              float* __restrict__ state_out) {
+  using namespace k3t;
+  using C = Cfg<kNU, kRes, kStages>;
+  using Smem = typename C::Smem;
+  extern __shared__ uint8_t smem_raw[];
+  auto& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    prefetch_tmap(&tmap_w);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&sm.w_full[s], 1);
+      mbar_init(&sm.w_empty[s], 1);
+    }
+    mbar_init(&sm.res_full, 1);
+    mbar_init(&sm.act_ready, C::kEpiWarps);                       // one arrive per epilogue warp
+    mbar_init(&sm.acc_r, 1);
+    mbar_init(&sm.acc_u, 1);
+    mbar_init(&sm.acc_c, 1);
+    mbar_init(&sm.acc_sb, 1);
+    fence_barrier_init();
+  }
+  if (warp == C::kMmaWarp) tmem_alloc<C::kTmemCols>(&sm.tmem_base);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = __shfl_sync(0xffffffffu, sm.tmem_base, 0);
+
+  if (warp == C::kProducerWarp) {
+    // ===================== weight producer: resident sub-tiles once, the rest of every step through the ring ==========
+    if (lane == 0) {
+      if (kRes > 0) {
+        mbar_arrive_expect_tx(&sm.res_full, kRes * kSub);
+        for (int i = 0; i < kRes; ++i)
+          tma_load_2d(sm.res[i], &tmap_w, (i & 1) * 64, (tile_of(i >> 2) + ((i >> 1) & 1)) * 128, &sm.res_full);
+      }
+      long long n = 0;
+      for (int s = 0; s < S; ++s) {
+        for (int i = kRes; i < kSubPerStep; ++i) {
+          const int p = i >> 2, kt = i & 3;
+          if (p == kSB && !do_sbias) continue;
+          const int st = (int)(n % kStages);
+          mbar_wait_relaxed(&sm.w_empty[st], (uint32_t)(((n / kStages) & 1) ^ 1));
+          mbar_arrive_expect_tx(&sm.w_full[st], kSub);
+          tma_load_2d(sm.ring[st], &tmap_w, (kt & 1) * 64, (tile_of(p) + (kt >> 1)) * 128, &sm.w_full[st]);
+          ++n;
+        }
+      }
+    }
+  } else if (warp == C::kMmaWarp) {
+    // ===================== MMA issuer (warp-uniform control flow, one elected lane issues) =====================
+    const bool leader = elect_one();
+    constexpr uint32_t idesc = make_idesc_bf16(128, kNU);
+    const uint32_t act0 = smem_u32(sm.act);
+    long long n = 0, n_act = 0;
+    // one product = 4 sub-tiles (K = 256 = two operand slots) into the kNU accumulator columns at d_col
+    auto product = [&](int p, uint32_t d_col, int slot_a, int slot_b) {
+#pragma unroll
+      for (int kt = 0; kt < 4; ++kt) {
+        const int i = p * 4 + kt;
+        uint32_t w_base;
+        int st = 0;
+        if (i < kRes) {
+          w_base = smem_u32(sm.res[i < kRes ? i : 0]);
+        } else {
+          st = (int)(n % kStages);
+          mbar_wait(&sm.w_full[st], (uint32_t)((n / kStages) & 1));
+          tc_fence_after_sync();
+          w_base = smem_u32(sm.ring[st]);
+        }
+        const uint32_t slot = act0 + (uint32_t)((kt >> 1) ? slot_b : slot_a) * C::kSlotBytes;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const uint64_t da = make_desc_k_sw128(w_base + kk * 32);
+          const uint64_t db = make_desc_nosw(slot + (uint32_t)((kt & 1) * 8 + kk * 2) * C::kChunkStride, C::kChunkStride);
+          if (leader) umma_bf16(tmem + d_col, da, db, idesc, !(kt == 0 && kk == 0));
+        }
+        if (i >= kRes) {
+          if (leader) umma_commit(&sm.w_empty[st]);
+          ++n;
+        }
+      }
+    };
+    auto wait_operand = [&]() {
+      mbar_wait(&sm.act_ready, (uint32_t)(n_act & 1));
+      tc_fence_after_sync();
+      ++n_act;
+    };
+    if (kRes > 0) {
+      mbar_wait(&sm.res_full, 0);
+      tc_fence_after_sync();
+    }
+    for (int s = 0; s < S; ++s) {
+      wait_operand();                                             // X, H0, H1 of this step
+      product(kG0r, C::kColR, kX, kH0);
+      if (leader) umma_commit(&sm.acc_r);
+      product(kG0u, C::kColU, kX, kH0);
+      if (leader) umma_commit(&sm.acc_u);
+      if (do_sbias) {
+        product(kSB, C::kColSb, kH0, kH1);
+        if (leader) umma_commit(&sm.acc_sb);
+      }
+      wait_operand();                                             // T0 = r * h0
+      product(kC0, C::kColC, kX, kT0);
+      if (leader) umma_commit(&sm.acc_c);
+      wait_operand();                                             // T0 = h0' (unmasked), H0 = m * h0'
+      product(kG1r, C::kColR, kT0, kH1);
+      if (leader) umma_commit(&sm.acc_r);
+      product(kG1u, C::kColU, kT0, kH1);
+      if (leader) umma_commit(&sm.acc_u);
+      wait_operand();                                             // T1 = r * h1
+      product(kC1, C::kColC, kT0, kT1);
+      if (leader) umma_commit(&sm.acc_c);
+    }
+  } else {
+    // ===================== epilogue: thread = hidden unit j of 16 users =====================
+    const int quarter = warp & 3, ug = warp >> 2;
+    const int j = quarter * 32 + lane;                            // hidden unit = TMEM lane
+    const int u0 = ug * kUsersPerThread;                          // first user (row of the operand slots) of this thread
+    const long long b0 = (long long)blockIdx.x * kNU + u0;
+    const int n_ok = (int)max(0LL, min((long long)kUsersPerThread, (long long)B - b0));
+    const uint32_t t_lane = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)u0;
+    // shared address of (user u0, k = j) in slot 0; users are 16 B apart, slots kSlotBytes apart
+    const uint32_t a0 = smem_u32(sm.act) + (uint32_t)(j >> 3) * C::kChunkStride + (uint32_t)u0 * 16 + (uint32_t)(j & 7) * 2;
+    float bgr[2], bgu[2], bcc[2];
+#pragma unroll
+    for (int l = 0; l < 2; ++l) {
+      bgr[l] = __ldg(bias_all + l * 384 + j);
+      bgu[l] = __ldg(bias_all + l * 384 + 128 + j);
+      bcc[l] = __ldg(bias_all + l * 384 + 256 + j);
+    }
+    float h[2][kUsersPerThread], xn[kUsersPerThread], m[kUsersPerThread], u[kUsersPerThread];
+    uint32_t par_r = 0, par_u = 0, par_c = 0, par_sb = 0;
+    auto put = [&](int slot, int i, float v) { sts_bf16(a0 + (uint32_t)slot * C::kSlotBytes + (uint32_t)i * 16, v); };
+    // every lane orders its own operand stores before the async proxy, then ONE lane per warp arrives (256 arrives on one
+    // mbarrier serialise)
+    auto publish = [&]() {
+      tc_fence_before_sync();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.act_ready);
+    };
+    auto wait_acc = [&](uint64_t* bar, uint32_t& par) {
+      mbar_wait(bar, par);
+      par ^= 1;
+      tc_fence_after_sync();
+    };
+    auto ld_acc = [&](uint32_t col, float (&v)[kUsersPerThread]) {
+      uint32_t r[16];
+      tmem_ld_32x16(t_lane + col, r);
+      tmem_ld_wait(r);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+    };
+    // prologue: state and the first input -> registers and operand slots
+#pragma unroll
+    for (int i = 0; i < kUsersPerThread; ++i) {
+      const bool ok = i < n_ok;
+      h[0][i] = ok ? __ldg(state_in + (b0 + i) * 256 + j) : 0.f;
+      h[1][i] = ok ? __ldg(state_in + (b0 + i) * 256 + 128 + j) : 0.f;
+      xn[i] = ok ? __ldg(yp + (b0 + i) * kDim + j) : 0.f;
+      put(kH0, i, h[0][i]);
+      put(kH1, i, h[1][i]);
+      put(kX, i, xn[i]);
+    }
+    publish();
+    for (int s = 0; s < S; ++s) {
+      // ---- under G0: emit the state before the step, fetch the mask and the next input
+      if (state_pre) {
+#pragma unroll
+        for (int i = 0; i < kUsersPerThread; ++i)
+          if (i < n_ok) {
+            float* o = state_pre + ((long long)s * B + b0 + i) * 256 + j;
+            o[0] = h[0][i];
+            o[128] = h[1][i];
+          }
+      }
+#pragma unroll
+      for (int i = 0; i < kUsersPerThread; ++i) {
+        const bool ok = i < n_ok;
+        m[i] = ok ? __ldg(mask + (long long)s * B + b0 + i) : 0.f;
+        xn[i] = (ok && s + 1 < S) ? __ldg(yp + ((long long)(s + 1) * B + b0 + i) * kDim + j) : 0.f;
+      }
+#pragma unroll
+      for (int l = 0; l < 2; ++l) {
+        const int slot_t = l == 0 ? kT0 : kT1, slot_h = l == 0 ? kH0 : kH1;
+        float v[kUsersPerThread];
+        wait_acc(&sm.acc_r, par_r);                                // ---- E_g: T <- r * h
+        ld_acc(C::kColR, v);
+#pragma unroll
+        for (int i = 0; i < kUsersPerThread; ++i) put(slot_t, i, sigmoid_fast(v[i] + bgr[l]) * h[l][i]);
+        publish();
+        wait_acc(&sm.acc_u, par_u);                                // under the candidate product: u, and the sbias rows
+        ld_acc(C::kColU, v);
+#pragma unroll
+        for (int i = 0; i < kUsersPerThread; ++i) u[i] = sigmoid_fast(v[i] + bgu[l]);
+        if (l == 0 && do_sbias) {
+          wait_acc(&sm.acc_sb, par_sb);
+          ld_acc(C::kColSb, v);
+#pragma unroll
+          for (int i = 0; i < kUsersPerThread; ++i)
+            if (i < n_ok) sbias[((long long)s * B + b0 + i) * kDim + j] = v[i];
+        }
+        wait_acc(&sm.acc_c, par_c);                                // ---- E_c: h' = u*h + (1-u)*c
+        ld_acc(C::kColC, v);
+#pragma unroll
+        for (int i = 0; i < kUsersPerThread; ++i) {
+          const float c = tanh_fast(v[i] + bcc[l]);
+          const float o = fmaf(u[i], h[l][i] - c, c);              // UNMASKED: the input of the layer above
+          h[l][i] = m[i] * o;                                      // state *= mask (model_hier.py:93)
+          if (l == 0) put(kT0, i, o);
+          put(slot_h, i, h[l][i]);
+        }
+        if (l == 0 || s + 1 < S) publish();
+        if (l == 0) {                                              // under G1: stage the next step's input (X is free since C0)
+#pragma unroll
+          for (int i = 0; i < kUsersPerThread; ++i) put(kX, i, xn[i]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < kUsersPerThread; ++i)
+      if (i < n_ok) {
+        float* o = state_out + (b0 + i) * 256 + j;
+        o[0] = h[0][i];
+        o[128] = h[1][i];
+      }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == C::kMmaWarp) {
+    tc_fence_after_sync();
+    tmem_dealloc<C::kTmemCols>(tmem);
+  }
+}
+
+template <int kNU, int kRes, int kStages>
+static int32_t launch_t(const CUtensorMap& tw, const float* yp, const float* mask, const float* state_in, const float* bias_dev,
+                        int B, int S, float* state_pre, float* sbias, float* state_out, cudaStream_t st) {
+  using C = k3t::Cfg<kNU, kRes, kStages>;
+  const size_t smem = sizeof(typename C::Smem) + 1024;
+  static_assert(sizeof(typename C::Smem) + 1024 <= 232448, "shared-memory budget of one CTA");
+  auto kern = k3_gru_bf16_t<kNU, kRes, kStages>;
+  HTCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<ceil_div(B, kNU), C::kThreads, smem, st>>>(tw, yp, mask, state_in, bias_dev, B, S, sbias != nullptr, state_pre, sbias,
+                                                   state_out);
+  HTCN_LAUNCH_CHECK("k3_gru_bf16_t");
+  return HTCN_OK;
+}
+
+// variant 0: 32 users per CTA, layer-0 gates resident (128 KB), 3-stage ring; 1: 32 users, r half resident, 7 stages;
+// 2: 64 users per CTA, r half resident, 4 stages
+int32_t gru_sessions_bf16_t(const float* yp, const float* mask, const float* state_in, const float* const* gate_w,
+                            const float* const* gate_b, const float* const* cand_w, const float* const* cand_b,
+                            const float* w_in_state, int B, int S, float* state_pre, float* sbias, float* state_out,
+                            float* scratch, int variant, cudaStream_t st) {
+  __nv_bfloat16* w_bf16;
+  float* bias_dev;
+  int32_t rc = k3_prepare_stream_weights(gate_w, gate_b, cand_w, cand_b, w_in_state, scratch, st, &w_bf16, &bias_dev);
+  if (rc) return rc;
+  CUtensorMap tw;
+  rc = make_tmap_bf16(&tw, w_bf16, (uint64_t)14 * 128, kDim, kDim, 64, 128, 128);
+  if (rc) return rc;
+  if (variant == 1) return launch_t<32, 4, 7>(tw, yp, mask, state_in, bias_dev, B, S, state_pre, sbias, state_out, st);
+  if (variant == 2) return launch_t<64, 4, 4>(tw, yp, mask, state_in, bias_dev, B, S, state_pre, sbias, state_out, st);
+  return launch_t<32, 8, 3>(tw, yp, mask, state_in, bias_dev, B, S, state_pre, sbias, state_out, st);
+}
+
+}  // namespace htcn
