@@ -25,7 +25,7 @@ def tcn_scratch_floats(n_levels, K):
 
 
 def gru_scratch_bytes(B):
-    return 14 * 128 * 128 * 2 + 4096          # HTCN_GRU_SCRATCH_BYTES: independent of B (the fp32 state lives in TMEM)
+    return 14 * 128 * 128 * 2 + 4096          # HTCN_GRU_SCRATCH_BYTES: independent of B (the fp32 state lives on chip)
 
 _p, _i, _u, _f = C.c_void_p, C.c_int32, C.c_uint32, C.c_float
 _pp = C.POINTER(C.c_void_p)        # host array of device pointers

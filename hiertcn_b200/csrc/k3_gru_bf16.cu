@@ -21,7 +21,7 @@
 #include "sm100.cuh"
 
 #ifndef HTCN_K3_DEFAULT_MODE
-#define HTCN_K3_DEFAULT_MODE 1
+#define HTCN_K3_DEFAULT_MODE 3
 #endif
 
 namespace htcn {
@@ -368,6 +368,11 @@ int32_t gru_sessions_bf16_t(const float* yp, const float* mask, const float* sta
                             const float* w_in_state, int B, int S, float* state_pre, float* sbias, float* state_out,
                             float* scratch, int variant, cudaStream_t st);
 
+int32_t gru_sessions_bf16_w(const float* yp, const float* mask, const float* state_in, const float* const* gate_w,
+                            const float* const* gate_b, const float* const* cand_w, const float* const* cand_b,
+                            const float* w_in_state, int B, int S, float* state_pre, float* sbias, float* state_out,
+                            float* scratch, int variant, cudaStream_t st);
+
 // scratch layout of the kernels that stream [n][k] weight tiles: [14 bf16 weight tiles][4 device pointers][768 bias floats]
 int32_t k3_prepare_stream_weights(const float* const* gate_w, const float* const* gate_b, const float* const* cand_w,
                                   const float* const* cand_b, const float* w_in_state, float* scratch, cudaStream_t st,
@@ -390,16 +395,78 @@ int32_t k3_prepare_stream_weights(const float* const* gate_w, const float* const
   return HTCN_OK;
 }
 
+// Weight preparation of the users-on-N kernels (k3_gru_t.cu, k3_gru_w.cu): ONE launch writes the 14 bf16 tiles and the bias
+// block (the pointers travel as kernel arguments: no memcpy nodes -- the five cudaMemcpyAsync of k3_prepare_stream_weights cost
+// more than the kernel they feed).   scratch layout: [14 bf16 tiles][768 bias floats]
+struct K3RepArgs {
+  const float* w[5];     // W_in[D:], gates 0, candidate 0, gates 1, candidate 1
+  const float* b[4];     // gates 0, candidate 0, gates 1, candidate 1
+};
+__global__ void k3_prepare_weights_rep(K3RepArgs a, __nv_bfloat16* __restrict__ out, float* __restrict__ bias_out) {
+  const int j = blockIdx.x;
+  const float* src;
+  int ld, n0, k0;
+  if (j < 2) { src = a.w[0]; ld = 128; n0 = 0; k0 = j * 128; }
+  else {
+    const int l = (j - 2) / 6, t = (j - 2) % 6;
+    if (t < 4) { src = a.w[1 + 2 * l]; ld = 256; n0 = (t >> 1) * 128; k0 = (t & 1) * 128; }
+    else { src = a.w[2 + 2 * l]; ld = 128; n0 = 0; k0 = (t - 4) * 128; }
+  }
+  // written as the SHARED-MEMORY IMAGE of the two 16 KB sub-tiles (k halves of 64) of the tile: rows of 128 B with the 128-byte
+  // swizzle already applied (16-byte chunk index ^= row % 8), so a kernel fetches a sub-tile with ONE 1-D bulk copy
+  // (cp.async.bulk, no tensor map, no per-row address generation) and reads it with the SWIZZLE_128B UMMA descriptor
+  __nv_bfloat16* dst = out + (long long)j * 128 * 128;
+  // thread = (n, 8 consecutive k): coalesced reads along n, one 16-byte store
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < 128 * 16; i += blockDim.x * gridDim.y) {
+    const int n = i & 127, kc = i >> 7;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = src ? __ldg(src + (long long)(k0 + kc * 8 + e) * ld + n0 + n) : 0.f;
+    const int hf = kc >> 3, c = (kc & 7) ^ (n & 7);
+    *reinterpret_cast<uint4*>(dst + hf * (128 * 64) + n * 64 + c * 8) =
+        make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  }
+  if (j == 0 && blockIdx.y == 0)
+    for (int i = threadIdx.x; i < 768; i += blockDim.x) {
+      const int l = i / 384, q = i % 384;
+      bias_out[i] = q < 256 ? a.b[2 * l][q] : a.b[2 * l + 1][q - 256];
+    }
+}
+
+int32_t k3_prepare_rep(const float* const* gate_w, const float* const* gate_b, const float* const* cand_w,
+                       const float* const* cand_b, const float* w_in_state, float* scratch, cudaStream_t st,
+                       const uint8_t** w_out, float** bias_out) {
+  K3RepArgs a;
+  a.w[0] = w_in_state;
+  for (int l = 0; l < 2; ++l) {
+    a.w[1 + 2 * l] = gate_w[l];
+    a.w[2 + 2 * l] = cand_w[l];
+    a.b[2 * l] = gate_b[l];
+    a.b[2 * l + 1] = cand_b[l];
+  }
+  __nv_bfloat16* w_bf16 = reinterpret_cast<__nv_bfloat16*>(scratch);
+  float* bias_dev = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(scratch) + (size_t)14 * 128 * 128 * 2);
+  k3_prepare_weights_rep<<<dim3(14, 8), 256, 0, st>>>(a, w_bf16, bias_dev);
+  HTCN_LAUNCH_CHECK("k3_prepare_weights_rep");
+  *w_out = reinterpret_cast<const uint8_t*>(w_bf16);
+  *bias_out = bias_dev;
+  return HTCN_OK;
+}
+
 int32_t gru_sessions_bf16(const float* yp, const float* mask, const float* state_in, const float* const* gate_w,
                           const float* const* gate_b, const float* const* cand_w, const float* const* cand_b,
                           const float* w_in_state, int B, int S, float* state_pre, float* sbias, float* state_out,
                           float* scratch, cudaStream_t st) {
   // HTCN_K3_CLUSTER picks the kernel: 0 = this file's single-CTA kernel (128 users on the MMA M axis, weights streamed
   // from L2); 1 / 2 = the 4-CTA cluster kernel with shared-memory-resident weight slices (k3_gru_cluster.cu; plain DSMEM
-  // stores or st.async); 3, 4, 5 = the users-on-N kernel (k3_gru_t.cu: hidden units on the MMA M axis, 32 / 64 users per
-  // CTA on N, no exchange between CTAs) in its three shared-memory budgets
+  // stores or st.async); 3 (default), 4 = the users-on-N kernel (k3_gru_t.cu: hidden units on the MMA M axis, 32 users per
+  // CTA on N, no exchange between CTAs) in its two shared-memory budgets; 6, 7 = its wavefront form (k3_gru_w.cu: layer 0
+  // of step t+1 beside layer 1 of step t)
   const char* cl = getenv("HTCN_K3_CLUSTER");
   const int mode = cl ? atoi(cl) : HTCN_K3_DEFAULT_MODE;
+  if (mode >= 6)
+    return gru_sessions_bf16_w(yp, mask, state_in, gate_w, gate_b, cand_w, cand_b, w_in_state, B, S, state_pre, sbias,
+                               state_out, scratch, mode - 6, st);
   if (mode >= 3)
     return gru_sessions_bf16_t(yp, mask, state_in, gate_w, gate_b, cand_w, cand_b, w_in_state, B, S, state_pre, sbias,
                                state_out, scratch, mode - 3, st);

@@ -31,9 +31,9 @@
 namespace htcn {
 using namespace sm100;
 
-int32_t k3_prepare_stream_weights(const float* const* gate_w, const float* const* gate_b, const float* const* cand_w,
-                                  const float* const* cand_b, const float* w_in_state, float* scratch, cudaStream_t st,
-                                  __nv_bfloat16** w_out, float** bias_out);
+int32_t k3_prepare_rep(const float* const* gate_w, const float* const* gate_b, const float* const* cand_w,
+                       const float* const* cand_b, const float* w_in_state, float* scratch, cudaStream_t st,
+                       const uint8_t** w_out, float** bias_out);
 
 namespace k3t {
 constexpr int kSub = 128 * 64 * 2;                // one weight sub-tile: 128 hidden units x 64 k, bf16, 128-byte swizzle = 16 KB
@@ -88,7 +88,7 @@ __host__ __device__ constexpr int tile_of(int product) {
 
 template <int kNU, int kRes, int kStages>
 __global__ void __launch_bounds__(k3t::Cfg<kNU, kRes, kStages>::kThreads, 1)
-k3_gru_bf16_t(const __grid_constant__ CUtensorMap tmap_w, const float* __restrict__ yp, const float* __restrict__ mask,
+k3_gru_bf16_t(const uint8_t* __restrict__ w_img, const float* __restrict__ yp, const float* __restrict__ mask,
               const float* __restrict__ state_in, const float* __restrict__ bias_all /* [bg0 256][bc0 128][bg1 256][bc1 128] */,
               int B, int S, int do_sbias, float* __restrict__ state_pre, float* __restrict__ sbias,
               float* __restrict__ state_out) {
@@ -100,7 +100,6 @@ k3_gru_bf16_t(const __grid_constant__ CUtensorMap tmap_w, const float* __restric
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
-    prefetch_tmap(&tmap_w);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&sm.w_full[s], 1);
       mbar_init(&sm.w_empty[s], 1);
@@ -125,7 +124,7 @@ k3_gru_bf16_t(const __grid_constant__ CUtensorMap tmap_w, const float* __restric
       if (kRes > 0) {
         mbar_arrive_expect_tx(&sm.res_full, kRes * kSub);
         for (int i = 0; i < kRes; ++i)
-          tma_load_2d(sm.res[i], &tmap_w, (i & 1) * 64, (tile_of(i >> 2) + ((i >> 1) & 1)) * 128, &sm.res_full);
+          bulk_load_1d(sm.res[i], w_img + (size_t)((tile_of(i >> 2) + ((i >> 1) & 1)) * 2 + (i & 1)) * kSub, kSub, &sm.res_full);
       }
       long long n = 0;
       for (int s = 0; s < S; ++s) {
@@ -135,7 +134,7 @@ k3_gru_bf16_t(const __grid_constant__ CUtensorMap tmap_w, const float* __restric
           const int st = (int)(n % kStages);
           mbar_wait_relaxed(&sm.w_empty[st], (uint32_t)(((n / kStages) & 1) ^ 1));
           mbar_arrive_expect_tx(&sm.w_full[st], kSub);
-          tma_load_2d(sm.ring[st], &tmap_w, (kt & 1) * 64, (tile_of(p) + (kt >> 1)) * 128, &sm.w_full[st]);
+          bulk_load_1d(sm.ring[st], w_img + (size_t)((tile_of(p) + (kt >> 1)) * 2 + (kt & 1)) * kSub, kSub, &sm.w_full[st]);
           ++n;
         }
       }
@@ -258,22 +257,6 @@ k3_gru_bf16_t(const __grid_constant__ CUtensorMap tmap_w, const float* __restric
     }
     publish();
     for (int s = 0; s < S; ++s) {
-      // ---- under G0: emit the state before the step, fetch the mask and the next input
-      if (state_pre) {
-#pragma unroll
-        for (int i = 0; i < kUsersPerThread; ++i)
-          if (i < n_ok) {
-            float* o = state_pre + ((long long)s * B + b0 + i) * 256 + j;
-            o[0] = h[0][i];
-            o[128] = h[1][i];
-          }
-      }
-#pragma unroll
-      for (int i = 0; i < kUsersPerThread; ++i) {
-        const bool ok = i < n_ok;
-        m[i] = ok ? __ldg(mask + (long long)s * B + b0 + i) : 0.f;
-        xn[i] = (ok && s + 1 < S) ? __ldg(yp + ((long long)(s + 1) * B + b0 + i) * kDim + j) : 0.f;
-      }
 #pragma unroll
       for (int l = 0; l < 2; ++l) {
         const int slot_t = l == 0 ? kT0 : kT1, slot_h = l == 0 ? kH0 : kH1;
@@ -283,6 +266,26 @@ k3_gru_bf16_t(const __grid_constant__ CUtensorMap tmap_w, const float* __restric
 #pragma unroll
         for (int i = 0; i < kUsersPerThread; ++i) put(slot_t, i, sigmoid_fast(v[i] + bgr[l]) * h[l][i]);
         publish();
+        if (l == 0) {
+          // ---- under the candidate product: emit the state before the step, fetch the mask and the next input.  NOT at the top
+          // of the step: a fence.proxy.async (every publish) waits for the thread's outstanding global loads, and these take
+          // ~1500 clk from HBM -- placed before the first publish they sat on the critical path of every step
+          if (state_pre) {
+#pragma unroll
+            for (int i = 0; i < kUsersPerThread; ++i)
+              if (i < n_ok) {
+                float* o = state_pre + ((long long)s * B + b0 + i) * 256 + j;
+                o[0] = h[0][i];
+                o[128] = h[1][i];
+              }
+          }
+#pragma unroll
+          for (int i = 0; i < kUsersPerThread; ++i) {
+            const bool ok = i < n_ok;
+            m[i] = ok ? __ldg(mask + (long long)s * B + b0 + i) : 0.f;
+            xn[i] = (ok && s + 1 < S) ? __ldg(yp + ((long long)(s + 1) * B + b0 + i) * kDim + j) : 0.f;
+          }
+        }
         wait_acc(&sm.acc_u, par_u);                                // under the candidate product: u, and the sbias rows
         ld_acc(C::kColU, v);
 #pragma unroll
@@ -328,34 +331,30 @@ k3_gru_bf16_t(const __grid_constant__ CUtensorMap tmap_w, const float* __restric
 }
 
 template <int kNU, int kRes, int kStages>
-static int32_t launch_t(const CUtensorMap& tw, const float* yp, const float* mask, const float* state_in, const float* bias_dev,
+static int32_t launch_t(const uint8_t* tw, const float* yp, const float* mask, const float* state_in, const float* bias_dev,
                         int B, int S, float* state_pre, float* sbias, float* state_out, cudaStream_t st) {
   using C = k3t::Cfg<kNU, kRes, kStages>;
   const size_t smem = sizeof(typename C::Smem) + 1024;
   static_assert(sizeof(typename C::Smem) + 1024 <= 232448, "shared-memory budget of one CTA");
   auto kern = k3_gru_bf16_t<kNU, kRes, kStages>;
   HTCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<ceil_div(B, kNU), C::kThreads, smem, st>>>(tw, yp, mask, state_in, bias_dev, B, S, sbias != nullptr, state_pre, sbias,
-                                                   state_out);
+  kern<<<ceil_div(B, kNU), C::kThreads, smem, st>>>(tw, yp, mask, state_in, bias_dev, B, S, sbias != nullptr, state_pre,
+                                                   sbias, state_out);
   HTCN_LAUNCH_CHECK("k3_gru_bf16_t");
   return HTCN_OK;
 }
 
-// variant 0: 32 users per CTA, layer-0 gates resident (128 KB), 3-stage ring; 1: 32 users, r half resident, 7 stages;
-// 2: 64 users per CTA, r half resident, 4 stages
+// variant 0: layer-0 gates resident (128 KB), 3-stage ring; 1: only their r half resident, 7-stage ring.  (64 users per CTA
+// -- kNU = 64, 16 epilogue warps -- was tried: 108 us against 84, the per-SM weight stream is the same and 576 threads spill)
 int32_t gru_sessions_bf16_t(const float* yp, const float* mask, const float* state_in, const float* const* gate_w,
                             const float* const* gate_b, const float* const* cand_w, const float* const* cand_b,
                             const float* w_in_state, int B, int S, float* state_pre, float* sbias, float* state_out,
                             float* scratch, int variant, cudaStream_t st) {
-  __nv_bfloat16* w_bf16;
   float* bias_dev;
-  int32_t rc = k3_prepare_stream_weights(gate_w, gate_b, cand_w, cand_b, w_in_state, scratch, st, &w_bf16, &bias_dev);
-  if (rc) return rc;
-  CUtensorMap tw;
-  rc = make_tmap_bf16(&tw, w_bf16, (uint64_t)14 * 128, kDim, kDim, 64, 128, 128);
+  const uint8_t* tw;
+  int32_t rc = k3_prepare_rep(gate_w, gate_b, cand_w, cand_b, w_in_state, scratch, st, &tw, &bias_dev);
   if (rc) return rc;
   if (variant == 1) return launch_t<32, 4, 7>(tw, yp, mask, state_in, bias_dev, B, S, state_pre, sbias, state_out, st);
-  if (variant == 2) return launch_t<64, 4, 4>(tw, yp, mask, state_in, bias_dev, B, S, state_pre, sbias, state_out, st);
   return launch_t<32, 8, 3>(tw, yp, mask, state_in, bias_dev, B, S, state_pre, sbias, state_out, st);
 }
 

@@ -100,7 +100,7 @@ int32_t htcn_gather_meanpool(const float* emb_table, int32_t emb_pitch, const fl
  *            HTCN_BF16 = tcgen05 tensor cores, bf16 operands / fp32 accumulate and fp32 state (num_layer == 2 only);
  *                        needs scratch >= HTCN_GRU_SCRATCH_BYTES(B) device bytes (bf16 weight tiles), else may be NULL.
  * ------------------------------------------------------------------------------------------- */
-#define HTCN_GRU_SCRATCH_BYTES(B) (14 * 128 * 128 * 2 + 4096)   /* independent of B: the fp32 state lives in TMEM */
+#define HTCN_GRU_SCRATCH_BYTES(B) (14 * 128 * 128 * 2 + 4096)   /* independent of B: the fp32 state lives on chip */
 int32_t htcn_gru_sessions(const float* yp, const float* mask, const float* state_in,
                           const float* const* gate_w_host, const float* const* gate_b_host,
                           const float* const* cand_w_host, const float* const* cand_b_host,

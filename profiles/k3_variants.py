@@ -5,8 +5,8 @@ whole-call time (CUDA events, L2 flushed), agreement with the streaming kernel, 
     python profiles/k3_variants.py [--out profiles/r2_k3_variants.jsonl] [--modes 0,1,3,4,5]
 
 HTCN_K3_CLUSTER: 0 = users on M, weights streamed (k3_gru_bf16.cu); 1 / 2 = 4-CTA cluster, resident weight slices, DSMEM
-exchange (k3_gru_cluster.cu); 3 / 4 / 5 = users on N, no exchange (k3_gru_t.cu: 32 users + 128 KB resident, 32 users + 64 KB
-resident + deep ring, 64 users per CTA)."""
+exchange (k3_gru_cluster.cu); 3 (default) / 4 = users on N, no exchange (k3_gru_t.cu: 128 KB of weights resident + 3-stage
+ring, 64 KB resident + 7-stage ring); 6 / 7 = its wavefront form (k3_gru_w.cu)."""
 import argparse
 import json
 import os
@@ -23,7 +23,7 @@ from hiertcn_b200 import _cabi as cabi  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r2_k3_variants.jsonl"))
-    ap.add_argument("--modes", default="0,1,2,3,4,5")
+    ap.add_argument("--modes", default="0,1,2,3,4,6,7")
     ap.add_argument("--B", type=int, default=4096)
     ap.add_argument("--S", type=int, default=10)
     ap.add_argument("--iters", type=int, default=20)
