@@ -364,6 +364,7 @@ def sharded_leg(opt, rank, world, local, items=8 * 1024 * 1024, queries=4096, k=
     import torch.distributed as dist
     from hiertcn_b200 import _cabi as cabi
     from hiertcn_b200.dist import CatalogTable, CudaScoreOps, ShardedCatalogScorer, shard_bounds
+    from hiertcn_b200.peer import PeerShardedCatalogScorer
     dev = torch.device("cuda", local)
     cabi.load()
 
@@ -391,8 +392,31 @@ def sharded_leg(opt, rank, world, local, items=8 * 1024 * 1024, queries=4096, k=
     hp = torch.randn((Qp, 128), device=dev, generator=gq).to(torch.bfloat16)
     yp = torch.randint(1, parity_items, (Qp,), device=dev, generator=gq, dtype=torch.int32)
     b = shard_bounds(parity_items, world)
+    # the exchanges run as our own peer-memory kernels (hiertcn_b200.peer); the NCCL-collective path is timed beside them.
+    # A peer-buffer setup failure (no CUDA IPC between the ranks) raises on every rank alike: fall back and say so.
+    exchange = "nccl collectives"
     sc = ShardedCatalogScorer(CudaScoreOps(full.rows(b[rank], b[rank + 1])), dist, rank, world, parity_items, n_split=3)
-    got = sc.score(hp, yp, k=k)
+    psc = None
+    if world > 1 and not os.environ.get("HTCN_SHARDED_NCCL"):
+        why = ""
+        try:
+            psc = PeerShardedCatalogScorer(sc.ops, dist, rank, world, parity_items, n_split=3)
+            got = psc.score(hp, yp, k=k)
+            torch.cuda.synchronize(dev)
+            psc.check()
+        except RuntimeError as e:
+            why = str(e)[:120]
+        fine = torch.tensor([0 if why else 1], device=dev)
+        dist.all_reduce(fine, op=dist.ReduceOp.MIN)                  # one rank's failure sends every rank to the collectives
+        if int(fine.item()):
+            exchange = "peer-memory kernels (htcn_peer_exchange / htcn_peer_bcast_owned over NVLink, CUDA IPC)"
+        else:
+            exchange = "nccl collectives (peer path unavailable: %s)" % (why or "failed on another rank")
+            if psc is not None:
+                psc.close()
+            psc = None
+    if psc is None:
+        got = sc.score(hp, yp, k=k)
     ops = CudaScoreOps(full)
     zy = torch.zeros(Qp, dtype=torch.float32, device=dev)
     ops.target_logit(hp, yp, 0, parity_items, zy)
@@ -406,7 +430,9 @@ def sharded_leg(opt, rank, world, local, items=8 * 1024 * 1024, queries=4096, k=
     ok = torch.tensor([int(all(checks.values()))] + [int(v) for v in checks.values()], device=dev)
     if world > 1:
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-    del full, ops, part, ref, got, sc
+    if psc is not None:
+        psc.close()
+    del full, ops, part, ref, got, sc, psc
     torch.cuda.empty_cache()
     # ---- timing: 8M items, this rank's shard only
     b = shard_bounds(items, world)
@@ -415,39 +441,64 @@ def sharded_leg(opt, rank, world, local, items=8 * 1024 * 1024, queries=4096, k=
     h = torch.randn((Ql, 128), device=dev, generator=gq).to(torch.bfloat16)
     y = torch.randint(1, items, (Ql,), device=dev, generator=gq, dtype=torch.int32)
     ns = n_split_for(queries)
-    sc = ShardedCatalogScorer(CudaScoreOps(shard), dist, rank, world, items, n_split=ns)
-    for _ in range(3):
-        out = sc.score(h, y, k=k)
-    torch.cuda.synchronize(dev)
-    if world > 1:
-        dist.barrier()
-    steps = max(3, opt.steps)
-    sc.phases = []
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        out = sc.score(h, y, k=k)
-    e1.record()
-    torch.cuda.synchronize(dev)
-    phases = sc.phase_ms()
     names = ["allgather_queries", "target_logit", "allreduce_target", "sweep", "alltoall_partials", "merge"]
-    t = torch.tensor([e0.elapsed_time(e1) / steps] + [phases.get(n, 0.0) / steps for n in names], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    steps = max(3, opt.steps)
+
+    def timed(sc):
+        for _ in range(3):
+            out = sc.score(h, y, k=k)
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        sc.phases = []
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = sc.score(h, y, k=k)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        phases = sc.phase_ms()
+        sc.phases = None
+        t = torch.tensor([e0.elapsed_time(e1) / steps] + [phases.get(n, 0.0) / steps for n in names], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t, out
+
+    shard_ops = CudaScoreOps(shard)
+    t_nccl = None
+    if exchange.startswith("peer"):
+        psc = PeerShardedCatalogScorer(shard_ops, dist, rank, world, items, n_split=ns)
+        t, out = timed(psc)
+        psc.check()
+        t_nccl, out_nccl = timed(ShardedCatalogScorer(shard_ops, dist, rank, world, items, n_split=ns))
+        same = torch.tensor([int(all(torch.equal(out[n], out_nccl[n]) for n in out_nccl))], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        peer_equals_nccl = bool(same.item())
+    else:
+        t, out = timed(ShardedCatalogScorer(shard_ops, dist, rank, world, items, n_split=ns))
+        peer_equals_nccl = None
     v, i = out["topk_val"], out["topk_idx"]
     sane = bool((v[:, :-1] >= v[:, 1:]).all() and (i >= 0).all() and (i < items).all() and torch.isfinite(out["loss_row"]).all())
+    if exchange.startswith("peer"):
+        psc.close()
     if rank != 0:
         return None
     ms = float(t[0].item())
     ph = {n: float(t[1 + j].item()) for j, n in enumerate(names)}
     coll = {n: ph[n] for n in ("allgather_queries", "allreduce_target", "alltoall_partials")}
-    return {"workload": "CE + rank + top-%d of %d queries over %d items, catalog sharded %d ways (bf16 tier)" % (k, queries, items, world),
-            "ms_per_call": ms, "queries_per_s": queries / (ms * 1e-3), "n_split": ns,
-            "useful_tflops_per_gpu": 2.0 * queries * 128 * (items / world) / (ms * 1e-3) / 1e12,
-            "phase_ms": ph, "collective_ms": sum(coll.values()), "limiting_collective": max(coll, key=coll.get) if world > 1 else None,
-            "sorted_in_range_finite": sane, "sharded_parity": bool(ok[0].item()),
-            "parity_checks": {n: bool(ok[1 + j].item()) for j, n in enumerate(checks)},
-            "parity_config": "%d queries per rank x %d items: sharded %d ways vs whole catalog on one GPU" % (Qp, parity_items, world)}
+    rec = {"workload": "CE + rank + top-%d of %d queries over %d items, catalog sharded %d ways (bf16 tier)" % (k, queries, items, world),
+           "exchange": exchange,
+           "ms_per_call": ms, "queries_per_s": queries / (ms * 1e-3), "n_split": ns,
+           "useful_tflops_per_gpu": 2.0 * queries * 128 * (items / world) / (ms * 1e-3) / 1e12,
+           "phase_ms": ph, "collective_ms": sum(coll.values()), "limiting_collective": max(coll, key=coll.get) if world > 1 else None,
+           "sorted_in_range_finite": sane, "sharded_parity": bool(ok[0].item()),
+           "parity_checks": {n: bool(ok[1 + j].item()) for j, n in enumerate(checks)},
+           "parity_config": "%d queries per rank x %d items: sharded %d ways vs whole catalog on one GPU" % (Qp, parity_items, world)}
+    if t_nccl is not None:
+        phn = {n: float(t_nccl[1 + j].item()) for j, n in enumerate(names)}
+        rec["nccl_path"] = {"ms_per_call": float(t_nccl[0].item()), "phase_ms": phn,
+                            "collective_ms": sum(phn[n] for n in coll), "same_results_as_peer_path": peer_equals_nccl}
+    return rec
 
 
 def kernels_leg(model, staged, neg_dev, peaks, wl):

@@ -30,6 +30,7 @@ def gru_scratch_bytes(B):
 _p, _i, _u, _f = C.c_void_p, C.c_int32, C.c_uint32, C.c_float
 _pp = C.POINTER(C.c_void_p)        # host array of device pointers
 _ip = C.POINTER(C.c_int32)         # host int array
+_lp = C.POINTER(C.c_int64)         # host int64 array
 
 # name -> argtypes; every function returns int32 status unless noted.  Keep in sync with include/htcn.h
 # (tests/test_cabi.py parses the header and compares).
@@ -72,6 +73,14 @@ SIGNATURES = {
     "htcn_adam_step": [_p, _p, _p, _p, C.c_int64, _f, _f, _f, _f, _p, _i, _p],
     "htcn_refresh_wout": [_p, _p, _i, _p, _i, _p],
     "htcn_assemble_batch": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p],
+    # peer-memory exchanges of the catalog-sharded path
+    "htcn_peer_alloc": [C.c_int64, _pp],
+    "htcn_peer_free": [_p],
+    "htcn_peer_export": [_p, _p],
+    "htcn_peer_import": [_p, _pp],
+    "htcn_peer_unimport": [_p],
+    "htcn_peer_exchange": [_pp, _pp, _lp, _ip, _lp, _lp, _i, _i, _i, _pp, _p, _p, _p, _u, _p],
+    "htcn_peer_bcast_owned": [_p, _p, _i, _i, _i, _pp, _i, _pp, _p, _p, _p, _u, _p],
 }
 PLAIN = {"htcn_abi_version": (C.c_int32, []), "htcn_last_error": (C.c_char_p, []),
          "htcn_device_ok": (C.c_int32, []),
@@ -122,7 +131,8 @@ LAUNCHES_PER_CALL = {"htcn_gather_meanpool": 2, "htcn_gru_sessions": 1, "htcn_tc
                      # training step (the per-call counts of the multi-launch entry points are added by the caller)
                      "htcn_loss_row_weights": 1, "htcn_score_ce_backward": 1, "htcn_gru_sessions_train": 1,
                      "htcn_gather_backward": 2, "htcn_adam_step": 1, "htcn_refresh_wout": 1,
-                     "htcn_score_ce_backward_bf16": 3, "htcn_score_ce_fwd_bwd_bf16": 6, "htcn_cast_transpose_bf16": 1, "htcn_assemble_batch": 4}
+                     "htcn_score_ce_backward_bf16": 3, "htcn_score_ce_fwd_bwd_bf16": 6, "htcn_cast_transpose_bf16": 1, "htcn_assemble_batch": 4,
+                     "htcn_peer_exchange": 1, "htcn_peer_bcast_owned": 1}
 launch_count = 0
 
 
@@ -152,6 +162,11 @@ def ptr_array(ptrs):
     """host array of device pointers"""
     arr = (C.c_void_p * len(ptrs))(*[C.c_void_p(int(p)) for p in ptrs])
     return C.cast(arr, _pp), arr       # keep `arr` alive while the call runs
+
+
+def long_array(vals):
+    arr = (C.c_int64 * len(vals))(*[int(v) for v in vals])
+    return C.cast(arr, _lp), arr
 
 
 def int_array(vals):

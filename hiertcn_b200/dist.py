@@ -169,30 +169,41 @@ class CudaScoreOps:
                        m.b_out.data_ptr() if m.b_out is not None else None, n1 - n0, n0, y_all.data_ptr(), zy.data_ptr(),
                        m.stream_ptr())
 
-    def sweep(self, h_all, y_all, zy, n0, n1, k, n_split, ce, rank):
+    def sweep(self, h_all, y_all, zy, n0, n1, k, n_split, ce, rank, out=None, sync_overflow=True):
+        """CE / rank partials [n_split, Q] and the shard's sorted top-k list [1, Q, k].  ``out``: caller-owned result tensors
+        (pm, ps, pc, tv, ti, ovf) to write into instead of fresh ones.  The two-pass top-k reports rows whose candidate list
+        overflowed (mass ties at the threshold) in ``ovf``: with ``sync_overflow`` the flag is read here (a host sync) and the
+        always-exact heap sweep redoes the list; without, ``out["ovf"]`` is left for the caller to check after its own sync."""
         torch, cabi, m = self.torch, self.cabi, self.m
         Q = h_all.shape[0]
         f32, i32 = torch.float32, torch.int32
         P = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
-        out = dict(pm=None, ps=None, pc=None, tv=None, ti=None)
+        given = out or {}
+        out = dict(pm=None, ps=None, pc=None, tv=None, ti=None, ovf=None)
+        new = lambda name, shape, dt: given[name] if given.get(name) is not None else torch.empty(shape, dtype=dt, device=m.device)  # noqa: E731
         flags = (cabi.SCORE_CE if ce else 0) | (cabi.SCORE_RANK if rank else 0)
         fused = bool(k) and ce and rank and getattr(self, "fuse_topk", True)
         if flags:
-            out["pm"] = torch.empty((n_split, Q), dtype=f32, device=m.device) if ce else None
-            out["ps"] = torch.empty((n_split, Q), dtype=f32, device=m.device) if ce else None
-            out["pc"] = torch.empty((n_split, Q), dtype=i32, device=m.device) if rank else None
+            out["pm"] = new("pm", (n_split, Q), f32) if ce else None
+            out["ps"] = new("ps", (n_split, Q), f32) if ce else None
+            out["pc"] = new("pc", (n_split, Q), i32) if rank else None
+        if k:
+            out["tv"] = new("tv", (1, Q, k), f32)
+            out["ti"] = new("ti", (1, Q, k), i32)
+            if given.get("ovf") is not None:
+                out["ovf"] = given["ovf"]
+                out["ovf"].zero_()
+            else:
+                out["ovf"] = torch.zeros(1, dtype=i32, device=m.device)
         if fused:
             # loss + rank + top-k in two sweeps of the shard: the CE / rank sweep records the group maxima pass 1 of the
             # two-pass top-k would need a sweep of its own for
             nb = int(cabi.load().htcn_topk_workspace_bytes(m.act_dtype, Q, n1 - n0, k, n_split))
             ws = torch.empty(nb, dtype=torch.uint8, device=m.device)
-            out["tv"] = torch.empty((1, Q, k), dtype=f32, device=m.device)
-            out["ti"] = torch.empty((1, Q, k), dtype=i32, device=m.device)
-            ovf = torch.zeros(1, dtype=i32, device=m.device)
             cabi.call("htcn_score_ce_rank_topk_fused", h_all.data_ptr(), m.act_dtype, Q, m.wt.data_ptr(), P(m.b_out), n1 - n0,
                       n0, y_all.data_ptr(), zy.data_ptr(), k, n_split, ws.data_ptr(), nb, P(out["pm"]), P(out["ps"]),
-                      P(out["pc"]), out["tv"].data_ptr(), out["ti"].data_ptr(), ovf.data_ptr(), m.stream_ptr())
-            if int(ovf.item()):              # mass ties overflowed a candidate list: the always-exact heap sweep
+                      P(out["pc"]), out["tv"].data_ptr(), out["ti"].data_ptr(), out["ovf"].data_ptr(), m.stream_ptr())
+            if sync_overflow and int(out["ovf"].item()):     # mass ties overflowed a candidate list: the always-exact heap sweep
                 self._heap_topk(h_all, n0, n1, k, n_split, out)
             return out
         if flags:
@@ -204,12 +215,9 @@ class CudaScoreOps:
             # otherwise); one sorted list per row = one "part" for the cross-shard merge
             nb = int(cabi.load().htcn_topk_workspace_bytes(m.act_dtype, Q, n1 - n0, k, n_split))
             ws = torch.empty(nb, dtype=torch.uint8, device=m.device)
-            out["tv"] = torch.empty((1, Q, k), dtype=f32, device=m.device)
-            out["ti"] = torch.empty((1, Q, k), dtype=i32, device=m.device)
-            ovf = torch.zeros(1, dtype=i32, device=m.device)
             cabi.call("htcn_score_topk", h_all.data_ptr(), m.act_dtype, Q, m.wt.data_ptr(), P(m.b_out), n1 - n0, n0, k,
-                      n_split, ws.data_ptr(), nb, out["tv"].data_ptr(), out["ti"].data_ptr(), ovf.data_ptr(), m.stream_ptr())
-            if int(ovf.item()):
+                      n_split, ws.data_ptr(), nb, out["tv"].data_ptr(), out["ti"].data_ptr(), out["ovf"].data_ptr(), m.stream_ptr())
+            if sync_overflow and int(out["ovf"].item()):
                 self._heap_topk(h_all, n0, n1, k, n_split, out)
         return out
 

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define HTCN_ABI_VERSION 4
+#define HTCN_ABI_VERSION 5
 #define HTCN_DIM 128          /* D = C = H */
 #define HTCN_MAX_SLOTS 64     /* S (args.max_session_num, default 10) */
 #define HTCN_MAX_LEVELS 8     /* TCN levels (len(args.tcn_channel)) */
@@ -499,6 +499,36 @@ int32_t htcn_assemble_batch(const int32_t* items, const int32_t* sess_off, const
                             const uint8_t* sched_last, int32_t sched_pitch, int32_t first_session, int32_t B, int32_t S,
                             int32_t L, int32_t* x_id, int32_t* y_id, float* mask, int32_t* row_of, int32_t* y_rows,
                             int32_t* n_valid, int32_t* scratch, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Peer-memory exchanges of the catalog-sharded scoring path (BASELINE config 4; the reference has no distributed code).
+ * One process per GPU; every rank allocates one buffer with the SAME layout (htcn_peer_alloc), publishes its CUDA IPC handle
+ * (htcn_peer_export, HTCN_PEER_HANDLE_BYTES bytes -- exchange them with any host-side all-gather) and maps the other
+ * ranks' buffers (htcn_peer_import).  An exchange is then ONE kernel: it stores rows straight into the peers' buffers over
+ * NVLink, raises flag[kind][my rank] = epoch in every peer's buffer (system-scope release) and waits until every peer has
+ * raised its flag here.  epoch must grow by one per call on every rank; *err (device int) is set to 1 if a peer did not
+ * arrive within ~1.5 s.  done: HTCN_MAX_PEERS device uint32 counters, zero-initialised, private to the rank.
+ *   htcn_peer_exchange   : n_peers * n_seg 2-D segments (index p * n_seg + s; n_rows rows of row_bytes, every size,
+ *                          pitch and address a multiple of 16) -- the all-gather of the query rows and the all-to-all of
+ *                          the per-shard partials (max, sum, count, top-k values, top-k indices);
+ *   htcn_peer_bcast_owned: dst[p][q] = src[q] for the rows whose target id this shard owns (n0 <= y_id[q] < n1) --
+ *                          completes the target-logit vector on every rank (the all-reduce of the NCCL path).
+ * ------------------------------------------------------------------------------------------- */
+#define HTCN_MAX_PEERS 8
+#define HTCN_PEER_MAX_SEGS 6
+#define HTCN_PEER_HANDLE_BYTES 64
+int32_t htcn_peer_alloc(int64_t bytes, void** ptr);
+int32_t htcn_peer_free(void* ptr);
+int32_t htcn_peer_export(const void* ptr, uint8_t* handle);
+int32_t htcn_peer_import(const uint8_t* handle, void** ptr);
+int32_t htcn_peer_unimport(void* ptr);
+int32_t htcn_peer_exchange(const void* const* src, void* const* dst, const int64_t* row_bytes, const int32_t* n_rows,
+                           const int64_t* src_pitch, const int64_t* dst_pitch, int32_t n_seg, int32_t n_peers,
+                           int32_t rank, void* const* flag_remote, void* flag_local, void* done, void* err,
+                           uint32_t epoch, void* stream);
+int32_t htcn_peer_bcast_owned(const float* src, const int32_t* y_id, int32_t Q, int32_t n0, int32_t n1,
+                              void* const* dst, int32_t n_peers, void* const* flag_remote, void* flag_local,
+                              void* done, void* err, uint32_t epoch, void* stream);
 
 #ifdef __cplusplus
 }

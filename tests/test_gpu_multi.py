@@ -76,6 +76,62 @@ def test_sharded_catalog_scoring_nccl(precision):
     assert all(ret.get(r) for r in range(2)), dict(ret)
 
 
+def _peer_worker(rank, world, port, precision, ret):
+    """the peer-memory exchange kernels (hiertcn_b200.peer) against the NCCL collectives: same inputs, same shard kernels,
+    every output bit for bit, over several calls (the epoch flags) and with k = 0"""
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from hiertcn_b200.args import make_args
+        from hiertcn_b200.dist import CudaScoreOps, ShardedCatalogScorer, make_sharded_model
+        from hiertcn_b200.peer import PeerShardedCatalogScorer
+        from hiertcn_b200.weights import hier_weight_shapes, init_weights
+        N, Ql, k = 50_000, 300, 100
+        w = init_weights(hier_weight_shapes(N), seed=3, kernel_scale=2.0, bias_noise=0.2)
+        a = make_args(["--item_num", str(N)])
+        dt = torch.bfloat16 if precision == "bf16" else torch.float32
+        m_sh, n0, n1 = make_sharded_model(a, w, rank, world, precision)
+        ops = CudaScoreOps(m_sh)
+        nccl = ShardedCatalogScorer(ops, dist, rank, world, N, n_split=3)
+        peer = PeerShardedCatalogScorer(ops, dist, rank, world, N, n_split=3)
+        ok = True
+        for it, kk in enumerate((k, k, 0, k)):
+            g = torch.Generator(device="cuda").manual_seed(100 * it + rank)
+            h = torch.randn((Ql, 128), device="cuda", generator=g).to(dt)
+            y = torch.randint(1, N, (Ql,), device="cuda", generator=g, dtype=torch.int32)
+            want = nccl.score(h, y, k=kk)
+            got = peer.score(h, y, k=kk)
+            torch.cuda.synchronize()
+            peer.check()
+            assert set(got) == set(want), (sorted(got), sorted(want))
+            for name in want:
+                ok &= bool(torch.equal(got[name], want[name]))
+        assert peer.buf is not None                      # the peer path ran (no silent fall-back to the collectives)
+        peer.close()
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("precision", ["bf16", "f32"])
+def test_sharded_catalog_scoring_peer_memory(precision):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    port = _free_port()
+    procs = [ctx.Process(target=_peer_worker, args=(r, 2, port, precision, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    assert all(ret.get(r) for r in range(2)), dict(ret)
+
+
 def _train_worker(rank, world, port, ret):
     """data-parallel training: each rank owns half of the users; after 3 Adam steps every rank must hold the weights a
     single process gets from the whole batch (gradients and the user count are all-reduced, hiertcn_b200.train)."""
