@@ -346,8 +346,11 @@ def train_leg(opt, wl, rank, world, local, sample_clocks=False):
             "gpu_launches": int(launches),
             "dp_parity": dp_parity,
             "allreduce": {"ms_per_step": allreduce_ms, "share_of_step": allreduce_ms / ms_per_step, "bytes": int(tr.n_flat) * 4,
-                          "overlap": "none: one NCCL all-reduce of the flat gradient buffer between backward and Adam "
-                                     "(device time between two events on the compute stream, max over ranks)"},
+                          "path": ("one peer-memory kernel: reduce-scatter + all-gather of the flat gradient over NVLink, the scalar "
+                                   "all-reduce and the Adam update fused (htcn_peer_allreduce_adam); ms_per_step covers all of it")
+                                  if tr.peer is not None else
+                                  "NCCL all-reduce of the flat gradient buffer + of the 8 scalars between backward and Adam (Adam not included)",
+                          "overlap": "none (device time between two events on the compute stream, max over ranks)"},
             "roofline": {"kernel": "whole step, catalog products only", "bound": "tensor", "achieved": flops / (ms_per_step * 1e-3) / 1e12 / world,
                          "peak": peaks["tf_sust"], "unit": "TFLOP/s", "frac": flops / (ms_per_step * 1e-3) / 1e12 / world / peaks["tf_sust"],
                          "peak_source": peaks["src"], "traffic": None},
@@ -716,7 +719,17 @@ def main():
     # ---------------- extra legs (see module docstring) ----------------
     legs = {}
     if not opt.no_legs:
-        kern = kernels_leg(model, staged, neg_dev, peaks, wl) if rank == 0 else None
+        # a leg that fails (on every rank alike: a shape that does not divide, an allocation) is reported in its place and
+        # must not take the headline line with it
+        def guarded(name, fn):
+            try:
+                return fn()
+            except Exception as e:      # noqa: BLE001
+                import traceback
+                traceback.print_exc()
+                return {"error": "%s leg failed: %s" % (name, repr(e)[:300])} if rank == 0 else None
+
+        kern = guarded("kernels", lambda: kernels_leg(model, staged, neg_dev, peaks, wl)) if rank == 0 else None
         # strong scaling of configs[1]: the global batch of wl["B"] users split over the ranks
         if world > 1 and wl["B"] % world == 0:
             Bs = wl["B"] // world
@@ -752,12 +765,14 @@ def main():
                               "ms_per_step": ms_per_step, "value": value, "unit": UNIT, "scaling": "strong"}
         if kern is not None:
             legs["kernels"] = kern
-        sh = sharded_leg(opt, rank, world, local)
+        sh = guarded("sharded", lambda: sharded_leg(opt, rank, world, local))
         if sh is not None:
             legs["sharded"] = sh
         torch.cuda.empty_cache()
-        tl = train_leg(opt, dict(WORKLOADS["cfg5"]), rank, world, local)
-        if tl is not None:
+        tl = guarded("train", lambda: train_leg(opt, dict(WORKLOADS["cfg5"]), rank, world, local))
+        if tl is not None and "error" in tl:
+            legs["train"] = tl
+        elif tl is not None:
             legs["train"] = {k: tl[k] for k in ("metric", "value", "unit", "ms_per_step", "scaling", "config", "loss", "e2e",
                                                 "gpu_launches", "allreduce", "dp_parity", "roofline")}
 

@@ -81,6 +81,7 @@ SIGNATURES = {
     "htcn_peer_unimport": [_p],
     "htcn_peer_exchange": [_pp, _pp, _lp, _ip, _lp, _lp, _i, _i, _i, _pp, _p, _p, _p, _u, _p],
     "htcn_peer_bcast_owned": [_p, _p, _i, _i, _i, _pp, _i, _pp, _p, _p, _p, _u, _p],
+    "htcn_peer_allreduce_adam": [_pp, _pp, _pp, _i, _i, _p, _p, _p, C.c_int64, _f, _f, _f, _f, _p, _pp, _pp, _p, _p, _p, _p, _u, _p],
 }
 PLAIN = {"htcn_abi_version": (C.c_int32, []), "htcn_last_error": (C.c_char_p, []),
          "htcn_device_ok": (C.c_int32, []),
@@ -132,7 +133,7 @@ LAUNCHES_PER_CALL = {"htcn_gather_meanpool": 2, "htcn_gru_sessions": 1, "htcn_tc
                      "htcn_loss_row_weights": 1, "htcn_score_ce_backward": 1, "htcn_gru_sessions_train": 1,
                      "htcn_gather_backward": 2, "htcn_adam_step": 1, "htcn_refresh_wout": 1,
                      "htcn_score_ce_backward_bf16": 3, "htcn_score_ce_fwd_bwd_bf16": 6, "htcn_cast_transpose_bf16": 1, "htcn_assemble_batch": 4,
-                     "htcn_peer_exchange": 1, "htcn_peer_bcast_owned": 1}
+                     "htcn_peer_exchange": 1, "htcn_peer_bcast_owned": 1, "htcn_peer_allreduce_adam": 1}
 launch_count = 0
 
 

@@ -112,6 +112,120 @@ __global__ void __launch_bounds__(kPeerThreads) peer_bcast_owned_kernel(const Pe
   publish_and_wait(a.flag_remote, a.flag_local, a.done, a.err, 0, a.n_peers - 1, gridDim.x, blockIdx.x == 0, a.epoch);
 }
 
+// ---- data-parallel training: gradient all-reduce + scalar all-reduce + Adam in ONE kernel over peer memory --------------
+struct PeerAdamArgs {
+  const float4* grads[HTCN_MAX_PEERS];     // every rank's flat gradient buffer (mine included)
+  float4* reduced[HTCN_MAX_PEERS];         // every rank's reduced-gradient buffer
+  const float* scalars[HTCN_MAX_PEERS];    // every rank's {loss, r@1, r@5, r@10, mrr, mrp, user_count, n_valid}
+  uint32_t* flag_in_remote[HTCN_MAX_PEERS];
+  uint32_t* flag_mid_remote[HTCN_MAX_PEERS];
+  uint32_t* flag_in_local;
+  uint32_t* flag_mid_local;
+  uint32_t* done;
+  int* err;
+  float4* p; float4* g; float4* m; float4* v;
+  float* scalars_out;                      // [8] global means / counts (what allreduce_scalars returns)
+  long long n4;
+  int n_peers, rank;
+  uint32_t epoch;
+  float lr_t, b1, b2, eps;
+};
+
+__device__ __forceinline__ void wait_flags(const uint32_t* flag_local, int n_peers, uint32_t epoch, int* err) {
+  for (int p = 0; p < n_peers; ++p) {
+    const long long t0 = clock64();
+    while ((int32_t)(ld_acquire_sys(flag_local + p) - epoch) < 0) {
+      if (clock64() - t0 > kSpinLimit) {
+        atomicExch(err, 1);
+        break;
+      }
+      __nanosleep(100);
+    }
+  }
+}
+
+// Persistent grid (every block co-resident).  Phase A: rank r sums slice r of the flat gradient over all ranks (peer loads,
+// fixed rank order: every replica receives the SAME bits) and stores the sums into every rank's `reduced` buffer -- a
+// reduce-scatter and an all-gather without a staging copy.  Phase B: the ordinary TF-Adam update (bwd_k1_adam.cu) on the
+// reduced gradient, and the rank's own gradient buffer is cleared for the next step.
+__global__ void __launch_bounds__(kPeerThreads) peer_allreduce_adam_kernel(const PeerAdamArgs a) {
+  __shared__ float s_div;
+  const int W = a.n_peers;
+  if (threadIdx.x == 0) {
+    if (blockIdx.x == 0) {                 // my gradients and scalars are complete (stream order): tell everybody
+      __threadfence_system();
+      for (int p = 0; p < W; ++p) st_release_sys(a.flag_in_remote[p], a.epoch);
+    }
+    wait_flags(a.flag_in_local, W, a.epoch, a.err);
+    float total = 0.f;                     // global user count = the divisor of the summed gradient (model.py:116-117)
+    for (int p = 0; p < W; ++p) total += a.scalars[p][6];
+    s_div = total;
+    if (blockIdx.x == 0) {
+      for (int j = 0; j < 6; ++j) {
+        float acc = 0.f;
+        for (int p = 0; p < W; ++p) {
+          const float c = a.scalars[p][6];
+          if (c > 0.f) acc += a.scalars[p][j] * c;        // a rank without a scored user reports NaN means: it contributes nothing
+        }
+        a.scalars_out[j] = acc / total;
+      }
+      float nv = 0.f;
+      for (int p = 0; p < W; ++p) nv += a.scalars[p][7];
+      a.scalars_out[6] = total;
+      a.scalars_out[7] = nv;
+    }
+  }
+  __syncthreads();
+  // ---- phase A: my slice
+  const long long per = (a.n4 + W - 1) / W, lo = per * a.rank, hi = lo + per < a.n4 ? lo + per : a.n4;
+  for (long long i = lo + (long long)blockIdx.x * kPeerThreads + threadIdx.x; i < hi; i += (long long)gridDim.x * kPeerThreads) {
+    float4 part[HTCN_MAX_PEERS];
+#pragma unroll
+    for (int p = 0; p < HTCN_MAX_PEERS; ++p)
+      if (p < W) part[p] = a.grads[p][i];
+    float4 s = part[0];
+#pragma unroll
+    for (int p = 1; p < HTCN_MAX_PEERS; ++p)
+      if (p < W) { s.x += part[p].x; s.y += part[p].y; s.z += part[p].z; s.w += part[p].w; }
+#pragma unroll
+    for (int p = 0; p < HTCN_MAX_PEERS; ++p)
+      if (p < W) a.reduced[p][i] = s;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(&a.done[0], 1u);
+    if (prev == gridDim.x - 1) {
+      a.done[0] = 0;
+      __threadfence_system();
+      for (int p = 0; p < W; ++p) st_release_sys(a.flag_mid_remote[p], a.epoch);
+    }
+    wait_flags(a.flag_mid_local, W, a.epoch, a.err);      // every slice of `reduced` has landed; nobody reads my gradients any more
+  }
+  __syncthreads();
+  // ---- phase B: Adam on the reduced gradient
+  const float div = s_div;
+  const float4* red = a.reduced[a.rank];
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long i = (long long)blockIdx.x * kPeerThreads + threadIdx.x; i < a.n4; i += (long long)gridDim.x * kPeerThreads) {
+    if (div > 0.f) {                      // no scored user anywhere: no loss, no update (see adam_kernel)
+      const float sc = 1.0f / div;
+      float4 gg = red[i], mm = a.m[i], vv = a.v[i], pp = a.p[i];
+#define HTCN_ADAM1(c)                                   \
+  {                                                     \
+    const float gr = gg.c * sc;                         \
+    mm.c = a.b1 * mm.c + (1.f - a.b1) * gr;             \
+    vv.c = a.b2 * vv.c + (1.f - a.b2) * gr * gr;        \
+    pp.c -= a.lr_t * mm.c / (sqrtf(vv.c) + a.eps);      \
+  }
+      HTCN_ADAM1(x) HTCN_ADAM1(y) HTCN_ADAM1(z) HTCN_ADAM1(w)
+#undef HTCN_ADAM1
+      a.p[i] = pp; a.m[i] = mm; a.v[i] = vv;
+    }
+    a.g[i] = zero;
+  }
+}
+
 }  // namespace htcn
 
 using namespace htcn;
@@ -211,5 +325,47 @@ extern "C" int32_t htcn_peer_bcast_owned(const float* src, const int32_t* y_id, 
   blocks = blocks > 16 ? 16 : blocks;
   peer_bcast_owned_kernel<<<blocks, kPeerThreads, 0, as_stream(stream)>>>(a, src, y_id, Q, n0, n1);
   HTCN_LAUNCH_CHECK("peer_bcast_owned_kernel");
+  return HTCN_OK;
+}
+
+extern "C" int32_t htcn_peer_allreduce_adam(void* const* grads, void* const* reduced, void* const* scalars, int32_t n_peers,
+                                            int32_t rank, float* param, float* m, float* v, int64_t n, float lr_t, float beta1,
+                                            float beta2, float eps, float* scalars_out, void* const* flag_in_remote,
+                                            void* const* flag_mid_remote, void* flag_in_local, void* flag_mid_local, void* done,
+                                            void* err, uint32_t epoch, void* stream) {
+  HTCN_REQUIRE(grads && reduced && scalars && param && m && v && scalars_out && flag_in_remote && flag_mid_remote &&
+                   flag_in_local && flag_mid_local && done && err && n > 0 && n % 4 == 0,
+               "peer_allreduce_adam: bad args (n=%lld must be a multiple of 4)", (long long)n);
+  HTCN_REQUIRE(n_peers >= 1 && n_peers <= HTCN_MAX_PEERS && rank >= 0 && rank < n_peers, "peer_allreduce_adam: n_peers=%d rank=%d",
+               n_peers, rank);
+  PeerAdamArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int p = 0; p < n_peers; ++p) {
+    a.grads[p] = static_cast<const float4*>(grads[p]);
+    a.reduced[p] = static_cast<float4*>(reduced[p]);
+    a.scalars[p] = static_cast<const float*>(scalars[p]);
+    a.flag_in_remote[p] = static_cast<uint32_t*>(flag_in_remote[p]);
+    a.flag_mid_remote[p] = static_cast<uint32_t*>(flag_mid_remote[p]);
+  }
+  a.flag_in_local = static_cast<uint32_t*>(flag_in_local);
+  a.flag_mid_local = static_cast<uint32_t*>(flag_mid_local);
+  a.done = static_cast<uint32_t*>(done);
+  a.err = static_cast<int*>(err);
+  a.p = reinterpret_cast<float4*>(param);
+  a.g = const_cast<float4*>(a.grads[rank]);
+  a.m = reinterpret_cast<float4*>(m);
+  a.v = reinterpret_cast<float4*>(v);
+  a.scalars_out = scalars_out;
+  a.n4 = n / 4;
+  a.n_peers = n_peers;
+  a.rank = rank;
+  a.epoch = epoch;
+  a.lr_t = lr_t; a.b1 = beta1; a.b2 = beta2; a.eps = eps;
+  // persistent: every block must be resident at once (the blocks meet at two flag waits); 2 blocks of 256 threads per SM
+  int dev = 0, sms = 0;
+  HTCN_CUDA(cudaGetDevice(&dev));
+  HTCN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  peer_allreduce_adam_kernel<<<2 * sms, kPeerThreads, 0, as_stream(stream)>>>(a);
+  HTCN_LAUNCH_CHECK("peer_allreduce_adam_kernel");
   return HTCN_OK;
 }

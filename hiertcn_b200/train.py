@@ -13,6 +13,7 @@ the embedding / output-table gradients are dense, and Adam's moment decay touche
 from __future__ import annotations
 
 import math
+import os
 
 import numpy as np
 
@@ -61,7 +62,31 @@ class HierTCNTrainer:
         self.n_flat = off
         f32 = torch.float32
         self.params = torch.zeros(off, dtype=f32, device=m.device)
-        self.grads = torch.zeros(off, dtype=f32, device=m.device)
+        self.peer = None
+        if dist is not None and self.world > 1 and not os.environ.get("HTCN_TRAIN_NCCL"):
+            # data parallel over NVLink peer memory: the gradient buffer lives in a symmetric allocation every rank maps, and
+            # all-reduce + Adam are one kernel (htcn_peer_allreduce_adam); a setup failure raises on every rank alike -> NCCL
+            from .peer import PeerBuffer, _align
+            try:
+                o_sc = 512
+                o_g = o_sc + 256
+                o_r = o_g + _align(off * 4)
+                self.peer = PeerBuffer(dist, dist.get_rank(), self.world, o_r + _align(off * 4), m.device)
+                self._peer_off = (o_sc, o_g, o_r)
+            except RuntimeError:
+                self.peer = None
+        if self.peer is not None:
+            b = self.peer
+            self.grads = b.view(self._peer_off[1], (off,), f32)
+            self._sym_scalars = b.view(self._peer_off[0], (8,), f32)
+            self._scalars_out = torch.zeros(8, dtype=f32, device=m.device)
+            W, r = self.world, b.rank
+            mk = lambda o: cabi.ptr_array([b.base[p] + o for p in range(W)])  # noqa: E731
+            self._peer_args = dict(grads=mk(self._peer_off[1]), reduced=mk(self._peer_off[2]), scalars=mk(self._peer_off[0]),
+                                   f_in=cabi.ptr_array([b.base[p] + (0 * 8 + r) * 4 for p in range(W)]),
+                                   f_mid=cabi.ptr_array([b.base[p] + (1 * 8 + r) * 4 for p in range(W)]))
+        else:
+            self.grads = torch.zeros(off, dtype=f32, device=m.device)
         self.adam_m = torch.zeros(off, dtype=f32, device=m.device)
         self.adam_v = torch.zeros(off, dtype=f32, device=m.device)
         wt_master = m.wt if not self.bf16 else torch.from_numpy(
@@ -325,6 +350,25 @@ class HierTCNTrainer:
 
     def apply_gradients(self, scalars, lr=None):
         """All-reduce (data parallel) and apply one Adam step; clears the gradient buffer."""
+        if self.peer is not None:
+            torch = _torch()
+            ev = getattr(self, "allreduce_events", None)
+            if ev is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(torch.cuda.current_stream(self.m.device))
+            self._sym_scalars.copy_(scalars)
+            self.t += 1
+            a, b = self._peer_args, self.peer
+            cabi.call("htcn_peer_allreduce_adam", a["grads"][0], a["reduced"][0], a["scalars"][0], self.world, b.rank,
+                      self.params.data_ptr(), self.adam_m.data_ptr(), self.adam_v.data_ptr(), self.n_flat, self.lr_t(lr),
+                      self.beta1, self.beta2, self.eps, self._scalars_out.data_ptr(), a["f_in"][0], a["f_mid"][0],
+                      b.own + 0 * 8 * 4, b.own + 1 * 8 * 4, b.own + 256, b.own + 256 + 64, self.t, self.m.stream_ptr())
+            if ev is not None:
+                e1.record(torch.cuda.current_stream(self.m.device))
+                ev.append((e0, e1))
+            if self.bf16:
+                self._refresh_bf16_tables()
+            return self._scalars_out.clone()
         if self.world > 1:
             ev = getattr(self, "allreduce_events", None)    # bench.py: [] -> (start, end) CUDA events of every exchange
             if ev is not None:
@@ -344,6 +388,19 @@ class HierTCNTrainer:
         if self.bf16:
             self._refresh_bf16_tables()
         return scalars
+
+    def check_peer(self):
+        """synchronises; raises if a flag wait of the fused all-reduce + Adam kernel ran into its spin limit"""
+        if self.peer is not None and int(self.peer.view(256 + 64, (1,), _torch().int32).item()):
+            raise RuntimeError("peer all-reduce: a rank did not arrive within the spin limit")
+
+    def close(self):
+        """unmap / free the symmetric gradient buffer (collective-free; call on every rank once training is over)"""
+        if self.peer is not None:
+            _torch().cuda.synchronize(self.m.device)
+            self.grads = self.grads.clone()
+            self.peer.close()
+            self.peer = None
 
     def train_step(self, x_list, y_list, mask_list, state=None, lr=None, metrics=False, state_on_device=False,
                    mask_warmstart=None, x_gap=None, dropout_masks=None, neg_ids=None, loss_kind=None):

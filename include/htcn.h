@@ -530,6 +530,19 @@ int32_t htcn_peer_bcast_owned(const float* src, const int32_t* y_id, int32_t Q, 
                               void* const* dst, int32_t n_peers, void* const* flag_remote, void* flag_local,
                               void* done, void* err, uint32_t epoch, void* stream);
 
+/* Data-parallel training step over peer memory (BASELINE config 5): gradient all-reduce, all-reduce of the loss / metric
+ * scalars and the TF-Adam update of htcn_adam_step in ONE kernel.  grads[p] / reduced[p] / scalars[p]: rank p's flat gradient
+ * buffer (n floats), reduced-gradient buffer (n floats) and scalars[8] = {loss, r@1, r@5, r@10, mrr, mrp, user_count,
+ * n_valid}, all inside the ranks' symmetric buffers.  Rank r sums slice r of the gradient over the ranks in rank order (every
+ * replica applies the same bits) and stores it into every rank's reduced buffer; after the second flag wait every rank
+ * updates ALL parameters with reduced / sum(user_count) and clears its own gradient buffer.  scalars_out [8]: the global
+ * means (weighted by user_count) and counts.  Two flag kinds (in, mid), epoch as above. */
+int32_t htcn_peer_allreduce_adam(void* const* grads, void* const* reduced, void* const* scalars, int32_t n_peers,
+                                 int32_t rank, float* param, float* m, float* v, int64_t n, float lr_t, float beta1,
+                                 float beta2, float eps, float* scalars_out, void* const* flag_in_remote,
+                                 void* const* flag_mid_remote, void* flag_in_local, void* flag_mid_local, void* done,
+                                 void* err, uint32_t epoch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -132,12 +132,17 @@ def test_sharded_catalog_scoring_peer_memory(precision):
     assert all(ret.get(r) for r in range(2)), dict(ret)
 
 
-def _train_worker(rank, world, port, ret):
+def _train_worker(rank, world, port, path, ret):
     """data-parallel training: each rank owns half of the users; after 3 Adam steps every rank must hold the weights a
-    single process gets from the whole batch (gradients and the user count are all-reduced, hiertcn_b200.train)."""
+    single process gets from the whole batch (gradients and the user count are all-reduced, hiertcn_b200.train) -- with the
+    exchange as one peer-memory kernel fused with Adam (htcn_peer_allreduce_adam) or as NCCL all-reduces + htcn_adam_step."""
     import sys
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    if path == "nccl":
+        os.environ["HTCN_TRAIN_NCCL"] = "1"
+    else:
+        os.environ.pop("HTCN_TRAIN_NCCL", None)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
@@ -153,6 +158,7 @@ def _train_worker(rank, world, port, ret):
         batches = [synthetic_batch(B, 3, 6, N, seed=40 + i, lengths="ragged", id_dist="uniform", mask_keep=0.7) for i in range(3)]
         lo, hi = rank * B // world, (rank + 1) * B // world
         tr = HierTCNTrainer(HierTCN(a, w, precision="f32").build(), learning_rate=1e-2, dist=dist, world=world)
+        assert (tr.peer is not None) == (path == "peer")           # no silent fall-back to the collectives
         ref = HierTCNTrainer(HierTCN(a, w, precision="f32").build(), learning_rate=1e-2)
         st_dp, st_ref, ok = s0[lo:hi], s0, True
         for x, y, m in batches:
@@ -166,19 +172,27 @@ def _train_worker(rank, world, port, ret):
         for k in wr:      # atomics reorder fp32 sums, and Adam turns a sign flip of a ~0 gradient into an lr-sized move
             d = np.abs(wd[k] - wr[k])
             ok &= float(np.mean(d)) <= 0.01 * budget and float(np.mean(d > 0.25 * budget)) < 0.005
+        # the replicas hold the same bits: every rank applied the same reduced gradient
+        cs = torch.stack([tr.params.double().sum(), tr.params.double().abs().sum()])
+        lo_, hi_ = cs.clone(), cs.clone()
+        dist.all_reduce(lo_, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
+        ok &= bool(torch.equal(lo_, hi_))
+        tr.check_peer()
         ret[rank] = bool(ok)
     finally:
         dist.destroy_process_group()
 
 
-def test_data_parallel_training_nccl():
+@pytest.mark.parametrize("path", ["peer", "nccl"])
+def test_data_parallel_training_nccl(path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     ret = ctx.Manager().dict()
     port = _free_port()
-    procs = [ctx.Process(target=_train_worker, args=(r, 2, port, ret)) for r in range(2)]
+    procs = [ctx.Process(target=_train_worker, args=(r, 2, port, path, ret)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:
