@@ -366,7 +366,7 @@ def sharded_leg(opt, rank, world, local, items=8 * 1024 * 1024, queries=4096, k=
     import torch
     import torch.distributed as dist
     from hiertcn_b200 import _cabi as cabi
-    from hiertcn_b200.dist import CatalogTable, CudaScoreOps, ShardedCatalogScorer, shard_bounds
+    from hiertcn_b200.dist import CatalogTable, CudaScoreOps, ShardedCatalogScorer, choose_n_split, shard_bounds
     from hiertcn_b200.peer import PeerShardedCatalogScorer
     dev = torch.device("cuda", local)
     cabi.load()
@@ -385,7 +385,7 @@ def sharded_leg(opt, rank, world, local, items=8 * 1024 * 1024, queries=4096, k=
         return wt
 
     def n_split_for(Q):
-        return int(max(1, min(max(-(-2 * 148 // max(1, -(-Q // 128))), 4), 32)))
+        return choose_n_split(Q, items // world, torch.cuda.get_device_properties(dev).multi_processor_count)
 
     Ql = queries // world
     # ---- parity: the same 1M-item table on every rank; sharded N ways vs scored whole on this rank

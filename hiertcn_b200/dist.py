@@ -32,6 +32,27 @@ def shard_bounds(n_items: int, world: int, align: int = 256):
     return b
 
 
+def choose_n_split(Q: int, n_items: int, sms: int = 148) -> int:
+    """Catalog split count of a K4 sweep over Q query rows: the grid is ceil(Q/128) row tiles x n_split, one CTA per SM, so
+    the sweep takes ceil(tiles * n_split / sms) waves of (catalog / n_split) items each.  Large Q (many waves anyway): 4
+    splits, so the CTAs of a wave share a quarter of the catalog in L2 (measured +4 % at config 2).  Small Q (config 4:
+    4096 queries = 32 row tiles): the split count that wastes the least of its last wave -- 10 splits are 320 CTAs = 2.16
+    waves, i.e. three waves of a tenth each (0.30 of a full sweep per SM), 9 splits are 288 CTAs = two nearly full waves
+    of a ninth (0.22): a quarter less time for the same work."""
+    tiles_q = max(1, -(-Q // 128))
+    tiles_q += tiles_q & 1                                   # CTA pairs (cta_group::2)
+    cap = int(max(1, min(32, n_items // 256)))
+    if tiles_q * 4 >= 8 * sms:
+        return min(4, cap)
+    best, best_cost = min(4, cap), None
+    for ns in range(min(4, cap), cap + 1):
+        waves = -(-tiles_q * ns // sms)
+        cost = waves / ns * (1.0 + 0.004 * ns)               # a little per-split overhead: partial rows, pipeline fill
+        if best_cost is None or cost < best_cost - 1e-12:
+            best, best_cost = ns, cost
+    return best
+
+
 def allreduce_scalars(scalars, dist, world):
     """Global loss/metrics from per-rank ``scalars[8]`` = {loss, r@1, r@5, r@10, mrr, mrp, user_count, n_valid}:
     the per-rank values are means over that rank's users (model.py:116-117), so weight by user_count."""

@@ -389,11 +389,10 @@ class HierTCN:
         forced = getattr(self, "force_n_split", 0)
         if forced:
             return int(max(1, min(forced, max(1, n_items // 256))))
-        tiles_q = max(1, math.ceil(Q / 128))
-        # enough CTAs for two waves; at least 4 catalog splits so that the CTAs of a wave (launched split-major)
-        # share a quarter of the catalog in L2 at a time (measured +4% on the cfg2 sweep)
-        want = max(math.ceil(2 * 148 / tiles_q), 4)
-        return int(max(1, min(want, 32, max(1, n_items // 256))))
+        from .dist import choose_n_split
+        if getattr(self, "_sms", None) is None:
+            self._sms = int(_torch().cuda.get_device_properties(self.device).multi_processor_count)
+        return choose_n_split(Q, n_items, self._sms)
 
     @property
     def k4_fold(self):
