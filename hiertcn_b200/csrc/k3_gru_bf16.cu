@@ -21,7 +21,7 @@
 #include "sm100.cuh"
 
 #ifndef HTCN_K3_DEFAULT_MODE
-#define HTCN_K3_DEFAULT_MODE 3
+#define HTCN_K3_DEFAULT_MODE 5
 #endif
 
 namespace htcn {
@@ -459,9 +459,10 @@ int32_t gru_sessions_bf16(const float* yp, const float* mask, const float* state
                           float* scratch, cudaStream_t st) {
   // HTCN_K3_CLUSTER picks the kernel: 0 = this file's single-CTA kernel (128 users on the MMA M axis, weights streamed
   // from L2); 1 / 2 = the 4-CTA cluster kernel with shared-memory-resident weight slices (k3_gru_cluster.cu; plain DSMEM
-  // stores or st.async); 3 (default), 4 = the users-on-N kernel (k3_gru_t.cu: hidden units on the MMA M axis, 32 users per
-  // CTA on N, no exchange between CTAs) in its two shared-memory budgets; 6, 7 = its wavefront form (k3_gru_w.cu: layer 0
-  // of step t+1 beside layer 1 of step t)
+  // stores or st.async); 3, 4 = the users-on-N kernel (k3_gru_t.cu: hidden units on the MMA M axis, 32 users per CTA on N,
+  // no exchange between CTAs) in its two shared-memory budgets; 5 (default) = the same with the three weight tiles the
+  // recurrence waits for held in TENSOR MEMORY as the MMA's A operand (68 us at B=4096, S=10 against 79); 6, 7 = the
+  // wavefront form (k3_gru_w.cu: layer 0 of step t+1 beside layer 1 of step t)
   const char* cl = getenv("HTCN_K3_CLUSTER");
   const int mode = cl ? atoi(cl) : HTCN_K3_DEFAULT_MODE;
   if (mode >= 6)

@@ -161,7 +161,7 @@ def test_k3_cluster_variants_agree(lib, B, S, with_sbias, monkeypatch):
     yp, st_in, wis = dev(yps.astype(np.float32)), dev(s0), dev(w_in[128:])
     scratch = torch.empty(lib.gru_scratch_bytes(B) // 4, dtype=torch.float32, device="cuda")
     res = {}
-    for mode in ("0", "1", "2", "3", "4", "6", "7"):
+    for mode in ("0", "1", "2", "3", "4", "5", "6", "7"):
         monkeypatch.setenv("HTCN_K3_CLUSTER", mode)
         spre = torch.full((S, B, 256), 7.0, dtype=torch.float32, device="cuda")
         sbias = torch.full((S, B, 128), 7.0, dtype=torch.float32, device="cuda")
@@ -171,12 +171,12 @@ def test_k3_cluster_variants_agree(lib, B, S, with_sbias, monkeypatch):
                  P(sout), None)
         torch.cuda.synchronize()
         res[mode] = (spre.cpu().numpy(), sout.cpu().numpy(), sbias.cpu().numpy())
-    for mode in ("1", "2", "3", "4", "6", "7"):
+    for mode in ("1", "2", "3", "4", "5", "6", "7"):
         for a, b in zip(res[mode][:2 + with_sbias], res["0"]):
             np.testing.assert_allclose(a, b, rtol=0, atol=1e-5, err_msg="HTCN_K3_CLUSTER=" + mode)
         if not with_sbias:
             assert (res[mode][2] == 7.0).all()                     # no sbias pointer: nothing written
-    for mode in ("2", "3", "6"):
+    for mode in ("2", "3", "5", "6"):
         for got, ref in ((res[mode][0], state_pre), (res[mode][1], state_out)):
             err = np.abs(got - ref)
             assert err.max() <= 2e-2 * max(1.0, np.abs(ref).max()), err.max()
