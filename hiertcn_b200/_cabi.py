@@ -21,7 +21,7 @@ K2TC_SCRATCH_BYTES = 8 * 2 * 128 * 128 * 2          # HTCN_K2TC_SCRATCH_BYTES
 
 def tcn_scratch_floats(n_levels, K):
     """HTCN_TCN_SCRATCH_BYTES / 4: bf16 weight tiles (K taps + a possible down-sample kernel per level) + tables"""
-    return ((1 + n_levels * (K + 1)) * 128 * 128 * 2 + 640 + 2 * 8 * 512 + 256 + 296 * 2 * n_levels * 8192 + 3) // 4
+    return ((1 + n_levels * (K + 1)) * 128 * 128 * 2 + 640 + 2 * 8 * 512 + 256 + 592 * 2 * n_levels * 8192 + 3) // 4
 
 
 def gru_scratch_bytes(B):

@@ -23,48 +23,10 @@
 // epilogue overlaps the other's MMAs.
 #include <cstdlib>
 
-#include "common.cuh"
-#include "sm100.cuh"
+#include "k2_tcn.cuh"
 
 namespace htcn {
 using namespace sm100;
-
-constexpr int kTR = 128;                 // rows per tile
-constexpr int kMaxSpare = 32;            // supports (K-1)*d_max <= 32 rows of negative shift
-constexpr int kRows = kTR + kMaxSpare;   // rows of the activation buffer (spare rows in front)
-constexpr int kActBytes = 16 * kRows * 16;          // 16 channel chunks x rows x 16 B = 40 KB
-constexpr int kWStageBytes = 2 * 128 * 128;         // one tap: [128 cout][128 cin] bf16, two 64-col swizzled chunks
-constexpr int kWStages = 2;                         // 2 x 32 KB: with the 40 KB tile two CTAs fit one SM
-constexpr int kK2EpiWarps = 8;           // 4 TMEM lane quarters x 2 channel halves: a thread owns 64 channels of one tile row
-constexpr int kK2Threads = 32 * (kK2EpiWarps + 2);   // warps 0-7 epilogue/loader, warp 8 TMA producer, warp 9 MMA issuer
-constexpr int kK2ProducerWarp = kK2EpiWarps, kK2MmaWarp = kK2EpiWarps + 1;
-
-struct K2Slot {          // per session slot: tiling of its B sequences
-  int off, L;            // first column in [B,T], length
-  int unit0;             // first global work-unit index of this slot
-  int seq_per_tile;      // > 0: short mode (unit = one tile of seq_per_tile sequences);  0: long mode (unit = one sequence)
-  int chunks;            // tiles per unit: 1 (short), ceil(L / 128) (long)
-};
-struct K2Geom {
-  int n_slots, n_units, B, T, K, n_levels;
-  unsigned ds_mask;      // bit l: level l has a 1x1 down-sample residual (customized_tcn_cell.py:102-106): one more weight
-                         // tile after the level's taps, accumulated into TMEM columns 128..255
-  int P;                 // zero rows in front of each short sequence = max shift of the deepest level
-  K2Slot slot[HTCN_MAX_SLOTS];
-};
-constexpr int kHistBytes = kMaxSpare * kDim * 2;      // one level's parked rows: [16 channel chunks][32 rows][16 B] = 8 KB
-
-__device__ __forceinline__ int unit_slot(const K2Geom& g, int unit) {
-  int s = 0;
-  while (s + 1 < g.n_slots && g.slot[s + 1].unit0 <= unit) ++s;
-  return s;
-}
-// tiles CTA `cta` of `n_cta` runs: the chunks of units cta, cta + n_cta, ...
-__device__ __forceinline__ int cta_tile_count(const K2Geom& g, int cta, int n_cta) {
-  int n = 0;
-  for (int u = cta; u < g.n_units; u += n_cta) n += g.slot[unit_slot(g, u)].chunks;
-  return n;
-}
 
 struct alignas(1024) K2Smem {
   uint8_t w[kWStages][kWStageBytes];     // 64 KB
@@ -74,50 +36,6 @@ struct alignas(1024) K2Smem {
   uint32_t tmem_base;
 };
 
-// no-swizzle K-major descriptor: core matrix = 8 rows x 16 B contiguous (SBO = 128 B), the two 16-byte K chunks of
-// one K=16 step are LBO = kRows*16 B apart
-__device__ __forceinline__ uint64_t make_desc_act(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-  d |= (uint64_t)((kRows * 16) >> 4) << 16;     // leading byte offset (K direction)
-  d |= (uint64_t)(128 >> 4) << 32;              // stride byte offset (8-row groups)
-  d |= (uint64_t)1 << 46;
-  return d;                                     // layout type 0 = no swizzle
-}
-
-// row r of chunk `chunk` of work unit `unit` (unit >= n_units: a dummy tile, every row is padding)
-__device__ __forceinline__ void tile_geometry(const K2Geom& g, int unit, int chunk, int r, const int* out_row, int& src,
-                                              int& dst, int& sb, bool& own, int& slot) {
-  src = -1; dst = -1; sb = 0; own = false; slot = 0;
-  if (unit >= g.n_units) return;
-  const int s = unit_slot(g, unit);
-  slot = s;
-  const K2Slot& sl = g.slot[s];
-  const int lu = unit - sl.unit0;
-  int b, t;
-  bool is_out;
-  if (sl.seq_per_tile > 0) {
-    const int stride = sl.L + g.P;
-    const int seg = r / stride;
-    t = r % stride - g.P;
-    b = lu * sl.seq_per_tile + seg;
-    is_out = seg < sl.seq_per_tile;
-  } else {
-    b = lu;
-    t = chunk * kTR + r;
-    is_out = true;
-  }
-  const bool data = b < g.B && t >= 0 && t < sl.L;
-  src = data ? b * g.T + sl.off + t : -1;
-  sb = s * g.B + (b < g.B ? b : 0);
-  own = data && is_out;            // this tile produces the row's values at every level
-  if (own) dst = out_row ? out_row[src] : src;
-}
-
-__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // kPair: the CTAs run as clusters of 2 that walk the SAME weight sequence in lock step; each CTA fetches one of the two
 // 64-column chunks of a weight tile and TMA-multicasts it into both CTAs' rings, so every weight byte crosses L2 -> SM once
@@ -409,18 +327,6 @@ struct alignas(1024) K2SmemDual {
   uint32_t tmem_base;
 };
 
-// weight tiles of one layer in the order the kernel consumes them: layer 0 = the in-projection, layer l >= 1 = the K taps of
-// level l-1 followed by its down-sample kernel if it has one
-__device__ __forceinline__ void k2_layer_tiles(const K2Geom& g, int layer, int& first, int& taps, bool& ds) {
-  if (layer == 0) {
-    first = 0; taps = 1; ds = false;
-    return;
-  }
-  const int l = layer - 1;
-  first = 1 + l * g.K + __popc(g.ds_mask & ((1u << l) - 1u));
-  taps = g.K;
-  ds = (g.ds_mask >> l) & 1u;
-}
 
 template <bool kStream, bool kAux>
 __global__ void __launch_bounds__(kK2DualThreads, 1)
@@ -786,6 +692,12 @@ int32_t tcn_forward_bf16(const void* xe, int xe_dtype, const float* w_in_x, cons
   // (~53 % of the chip's L2 throughput) and serialise a tile's MMA and epilogue phases, the deeper ring only helps the longer
   // layer chains.  HTCN_K2_DUAL=1 / 0 forces one or the other.
   const char* dual_env = getenv("HTCN_K2_DUAL");
+  // The default for the plain inference stack: four tile chains per CTA sharing every weight tile (k2_tcn_quad.cu).
+  // HTCN_K2_QUAD=0 (or any HTCN_K2_DUAL / HTCN_K2_MULTICAST choice) selects the kernels of this file.
+  const char* quad_env = getenv("HTCN_K2_QUAD");
+  if (!aux && !pair && !dual_env && (quad_env ? atoi(quad_env) != 0 : true))
+    return k2_launch_quad(tw, g, (const __nv_bfloat16*)xe, sbias, (const float*)bias_dev, out_row, (__nv_bfloat16*)hout, hist_dev,
+                          stream, st);
   const bool dual = dual_env ? atoi(dual_env) != 0 : stream;
   if (!pair && dual) {
     const size_t smem_d = sizeof(K2SmemDual) + 1024;

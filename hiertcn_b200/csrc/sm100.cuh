@@ -170,6 +170,23 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
       : "memory");
 }
+// The same with the descriptors given as (low, high) 32-bit halves.  The low word holds the 14-bit start address (>> 4) and
+// the leading byte offset, the high word only layout constants: an issuer that walks an operand adds `bytes >> 4` to the LOW
+// word (shared-memory addresses never carry out of the 14 bits) -- one 32-bit add per MMA instead of rebuilding the 64-bit
+// descriptor (shift, mask, two ORs per operand: the issuing warp of k2_tcn_quad.cu spent ~25 instructions per MMA on that
+// and could not keep the tensor pipe fed).
+__device__ __forceinline__ void umma_bf16_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                               uint32_t idesc, bool accumulate) {
+  const uint32_t acc = accumulate ? 1u : 0u;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc)
+      : "memory");
+}
 // D[tmem] (+)= A[tmem] * B[smem]^T : the A operand (M rows = TMEM lanes, K-major, two bf16 per 32-bit column) is read from
 // tensor memory -- no shared-memory traffic for A
 __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, bool accumulate) {
@@ -328,6 +345,12 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
 __device__ __forceinline__ float4 lds_f4(uint32_t saddr) {     // 128-bit shared load from a 32-bit shared address
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+// the same for data that does not change while the kernel runs (bias tables): not volatile, the compiler may move it ahead
+__device__ __forceinline__ float4 lds_f4_const(uint32_t saddr) {
+  float4 v;
+  asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
   return v;
 }
 // 128-bit shared-memory accesses through a 32-bit shared-window address: a pointer derived from a reference to the dynamic

@@ -132,10 +132,10 @@ int32_t htcn_gru_sessions(const float* yp, const float* mask, const float* state
  *   ping-pong; 3*B*T*128 when a level has a down-sample residual); bf16 tier HTCN_TCN_SCRATCH_BYTES(n_levels,
  *   kernel_size) bytes (bf16 weight tiles).
  * The bf16 tier requires xe and hout in bf16 and (K-1)*2^(n_levels-1) <= 32 rows of causal shift; sequences longer
- * than a 128-row tile are streamed chunk by chunk (the scratch also parks each level's last 32 input rows per CTA).
+ * than a 128-row tile are streamed chunk by chunk (the scratch also parks each level's last 32 input rows per tile chain, up to 592 chains).
  * ------------------------------------------------------------------------------------------- */
 #define HTCN_TCN_SCRATCH_BYTES(n_levels, K) \
-  ((1 + (n_levels) * ((K) + 1)) * 128 * 128 * 2 + 640 + 2 * 8 * 512 + 256 + 296 * 2 * (n_levels) * 8192)
+  ((1 + (n_levels) * ((K) + 1)) * 128 * 128 * 2 + 640 + 2 * 8 * 512 + 256 + 592 * 2 * (n_levels) * 8192)
 int32_t htcn_tcn_forward(const void* xe, int32_t xe_dtype, int32_t precision,
                          const float* w_in_x, const float* sbias,
                          const float* const* conv_w_host, const float* const* conv_b_host,

@@ -826,8 +826,17 @@ def test_k2_tcn_bf16_tcgen05(lib, B, S, L, K, levels):
     finally:
         del os.environ["HTCN_K2_MULTICAST"]
     np.testing.assert_array_equal(got_mc, got)
-    # the two-chain kernel (one CTA per SM, two tiles in flight, 4-deep weight ring: the default for streamed sequences) and
-    # the single-chain kernel give the same bits
+    # the four-chain kernel (k2_tcn_quad.cu, the default) with its chains in lock step on one weight fetch per round (1), as two
+    # pairs (2) or independent (4), and the kernels of k2_tcn_bf16.cu (0) give the same bits
+    for quad in ("0", "1", "2", "4"):
+        os.environ["HTCN_K2_QUAD"] = quad
+        try:
+            got_q = run_k2_bf16(lib, xe, w, sbias, pk["slot_off"], B, T, S, K, levels).float().cpu().numpy().reshape(B, T, 128)
+        finally:
+            del os.environ["HTCN_K2_QUAD"]
+        np.testing.assert_array_equal(got_q, got, err_msg="HTCN_K2_QUAD=" + quad)
+    # the two-chain kernel (one CTA per SM, two tiles in flight, 4-deep weight ring) and the single-chain kernel give the
+    # same bits
     for dual in ("0", "1"):
         os.environ["HTCN_K2_DUAL"] = dual
         try:
