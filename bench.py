@@ -362,7 +362,10 @@ def sharded_leg(opt, rank, world, local, items=8 * 1024 * 1024, queries=4096, k=
     """BASELINE configs[3]: CE + rank + top-k of `queries` query rows over `items` items, the catalog sharded over the
     ranks (rank r owns rows [n0_r, n1_r) of W_out^T in the bf16 scoring layout).  Device time per phase / collective (max
     over ranks), and an in-run parity check of the sharded path against the replicated single-GPU path on a catalog of
-    `parity_items` items: ranks, top-k indices and values bit for bit, loss rows to 2e-6."""
+    `parity_items` items: ranks, top-k indices and values bit for bit; loss rows to 1e-5 relative -- the CE partial sums are
+    fp32 sums of a million exponentials taken in a different order (world x 3 splits against 4): measured 2.3e-5 / 2.7e-5 /
+    3.2e-5 absolute at 2 / 4 / 8 shards on losses near 20 (profiles/r2_sharded_loss_order.txt); the maximum of this run is
+    reported as `loss_max_abs_diff`."""
     import torch
     import torch.distributed as dist
     from hiertcn_b200 import _cabi as cabi
@@ -429,10 +432,13 @@ def sharded_leg(opt, rank, world, local, items=8 * 1024 * 1024, queries=4096, k=
     torch.cuda.synchronize(dev)
     checks = dict(rank=torch.equal(got["rank_row"], ref["rank_row"]), topk_idx=torch.equal(got["topk_idx"], ref["topk_idx"]),
                   topk_val=torch.equal(got["topk_val"], ref["topk_val"]),
-                  loss=bool(torch.allclose(got["loss_row"], ref["loss_row"], rtol=2e-6, atol=2e-6)))
+                  loss=bool(torch.allclose(got["loss_row"], ref["loss_row"], rtol=1e-5, atol=1e-5)))
     ok = torch.tensor([int(all(checks.values()))] + [int(v) for v in checks.values()], device=dev)
+    loss_diff = (got["loss_row"] - ref["loss_row"]).abs().max().reshape(1)
     if world > 1:
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        dist.all_reduce(loss_diff, op=dist.ReduceOp.MAX)
+    loss_diff = float(loss_diff.item())
     if psc is not None:
         psc.close()
     del full, ops, part, ref, got, sc, psc
@@ -495,7 +501,7 @@ def sharded_leg(opt, rank, world, local, items=8 * 1024 * 1024, queries=4096, k=
            "useful_tflops_per_gpu": 2.0 * queries * 128 * (items / world) / (ms * 1e-3) / 1e12,
            "phase_ms": ph, "collective_ms": sum(coll.values()), "limiting_collective": max(coll, key=coll.get) if world > 1 else None,
            "sorted_in_range_finite": sane, "sharded_parity": bool(ok[0].item()),
-           "parity_checks": {n: bool(ok[1 + j].item()) for j, n in enumerate(checks)},
+           "parity_checks": {n: bool(ok[1 + j].item()) for j, n in enumerate(checks)}, "loss_max_abs_diff": loss_diff,
            "parity_config": "%d queries per rank x %d items: sharded %d ways vs whole catalog on one GPU" % (Qp, parity_items, world)}
     if t_nccl is not None:
         phn = {n: float(t_nccl[1 + j].item()) for j, n in enumerate(names)}

@@ -1,4 +1,4 @@
-"""1-GPU emulation of the bench's sharded parity check: CE partials of a 1M-item catalog swept as W shards x 3 splits
+"""python profiles/sharded_loss_order.py -- 1-GPU emulation of the bench's sharded parity check: CE partials of a 1M-item catalog swept as W shards x 3 splits
 against the whole catalog x 4 splits -- how far do the fp32 loss rows move with the summation order?"""
 import sys, torch
 sys.path.insert(0, ".")
