@@ -68,6 +68,7 @@ SIGNATURES = {
     "htcn_tcn_forward_train": [_p, _p, _p, _pp, _pp, _pp, _pp, _i, _i, _ip, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p],
     "htcn_tcn_backward": [_p, _p, _p, _i, _p, _pp, _pp, _i, _i, _ip, _i, _i, _i, _p, _p, _p, _p, _p, _pp, _pp, _pp, _pp, _p, _p, _p, _p],
     "htcn_gru_sessions_train": [_p, _p, _p, _pp, _pp, _pp, _pp, _i, _p, _i, _i, _p, _p, _p, _p, _p],
+    "htcn_gru_sessions_train_bf16": [_p, _p, _p, _pp, _pp, _pp, _pp, _i, _p, _i, _i, _p, _p, _p, _p, _p, _p],
     "htcn_gru_backward": [_p, _p, _p, _p, _pp, _pp, _i, _p, _i, _i, _p, _p, _pp, _pp, _pp, _pp, _p, _p, _p],
     "htcn_gather_backward": [_p, _p, _p, _p, _ip, _i, _i, _i, _i, _p, _p, _p],
     "htcn_adam_step": [_p, _p, _p, _p, C.c_int64, _f, _f, _f, _f, _p, _i, _p],
@@ -130,7 +131,7 @@ LAUNCHES_PER_CALL = {"htcn_gather_meanpool": 2, "htcn_gru_sessions": 1, "htcn_tc
                      "htcn_loss_metrics_reduce": 2, "htcn_sampled_rank_loss": 1, "htcn_calc_score": 1,
                      "htcn_sampled_rank_loss_backward": 1,
                      # training step (the per-call counts of the multi-launch entry points are added by the caller)
-                     "htcn_loss_row_weights": 1, "htcn_score_ce_backward": 1, "htcn_gru_sessions_train": 1,
+                     "htcn_loss_row_weights": 1, "htcn_score_ce_backward": 1, "htcn_gru_sessions_train": 1, "htcn_gru_sessions_train_bf16": 2,
                      "htcn_gather_backward": 2, "htcn_adam_step": 1, "htcn_refresh_wout": 1,
                      "htcn_score_ce_backward_bf16": 3, "htcn_score_ce_fwd_bwd_bf16": 6, "htcn_cast_transpose_bf16": 1, "htcn_assemble_batch": 4,
                      "htcn_peer_exchange": 1, "htcn_peer_bcast_owned": 1, "htcn_peer_allreduce_adam": 1}

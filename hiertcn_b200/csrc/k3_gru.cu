@@ -159,7 +159,7 @@ k3_gru_sessions(const float* __restrict__ yp, const float* __restrict__ mask, co
 int32_t gru_sessions_bf16(const float* yp, const float* mask, const float* state_in, const float* const* gate_w,
                           const float* const* gate_b, const float* const* cand_w, const float* const* cand_b,
                           const float* w_in_state, int B, int S, float* state_pre, float* sbias, float* state_out,
-                          float* scratch, cudaStream_t st);
+                          float* scratch, cudaStream_t st, float* gates_save = nullptr);
 
 }  // namespace htcn
 
@@ -189,7 +189,7 @@ static int32_t gru_sessions_impl(const float* yp, const float* mask, const float
     HTCN_REQUIRE(num_layer == 2, "gru_sessions(bf16): the tensor-core kernel is built for num_layer == 2 (got %d)", num_layer);
     HTCN_REQUIRE(scratch, "gru_sessions(bf16): scratch (HTCN_GRU_SCRATCH_BYTES(B)) is required");
     return gru_sessions_bf16(yp, mask, state_in, W.gate_w, W.gate_b, W.cand_w, W.cand_b, w_in_state, B, S, state_pre, sbias,
-                             state_out, scratch, as_stream(stream));
+                             state_out, scratch, as_stream(stream), gates_save);
   }
   const size_t smem = sizeof(float) * (size_t)(3 + num_layer) * kUB * kDim;
   HTCN_CUDA(cudaFuncSetAttribute(k3_gru_sessions, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -221,4 +221,18 @@ extern "C" int32_t htcn_gru_sessions_train(const float* yp, const float* mask, c
   HTCN_REQUIRE(state_pre && gates_save, "gru_sessions_train: state_pre and gates_save are required");
   return gru_sessions_impl(yp, mask, state_in, gate_w_host, gate_b_host, cand_w_host, cand_b_host, num_layer, w_in_state,
                            B, S, HTCN_F32, nullptr, state_pre, sbias, state_out, gates_save, stream);
+}
+
+// The same on the tensor cores (bf16 operands, fp32 state and accumulation: k3_gru_t.cu with the gate activations written
+// out).  num_layer == 2; scratch as htcn_gru_sessions' bf16 tier.
+extern "C" int32_t htcn_gru_sessions_train_bf16(const float* yp, const float* mask, const float* state_in,
+                                                const float* const* gate_w_host, const float* const* gate_b_host,
+                                                const float* const* cand_w_host, const float* const* cand_b_host,
+                                                int32_t num_layer, const float* w_in_state, int32_t B, int32_t S,
+                                                float* scratch, float* state_pre, float* sbias, float* state_out,
+                                                float* gates_save, void* stream) {
+  using namespace htcn;
+  HTCN_REQUIRE(state_pre && gates_save, "gru_sessions_train_bf16: state_pre and gates_save are required");
+  return gru_sessions_impl(yp, mask, state_in, gate_w_host, gate_b_host, cand_w_host, cand_b_host, num_layer, w_in_state,
+                           B, S, HTCN_BF16, scratch, state_pre, sbias, state_out, gates_save, stream);
 }

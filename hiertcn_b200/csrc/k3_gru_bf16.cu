@@ -366,7 +366,7 @@ int32_t gru_sessions_bf16_cluster(const float* yp, const float* mask, const floa
 int32_t gru_sessions_bf16_t(const float* yp, const float* mask, const float* state_in, const float* const* gate_w,
                             const float* const* gate_b, const float* const* cand_w, const float* const* cand_b,
                             const float* w_in_state, int B, int S, float* state_pre, float* sbias, float* state_out,
-                            float* scratch, int variant, cudaStream_t st);
+                            float* scratch, int variant, cudaStream_t st, float* gates_save = nullptr);
 
 int32_t gru_sessions_bf16_w(const float* yp, const float* mask, const float* state_in, const float* const* gate_w,
                             const float* const* gate_b, const float* const* cand_w, const float* const* cand_b,
@@ -456,7 +456,11 @@ int32_t k3_prepare_rep(const float* const* gate_w, const float* const* gate_b, c
 int32_t gru_sessions_bf16(const float* yp, const float* mask, const float* state_in, const float* const* gate_w,
                           const float* const* gate_b, const float* const* cand_w, const float* const* cand_b,
                           const float* w_in_state, int B, int S, float* state_pre, float* sbias, float* state_out,
-                          float* scratch, cudaStream_t st) {
+                          float* scratch, cudaStream_t st, float* gates_save) {
+  // training forward (gates_save != NULL): the users-on-N kernel with the gate activations written out
+  if (gates_save)
+    return gru_sessions_bf16_t(yp, mask, state_in, gate_w, gate_b, cand_w, cand_b, w_in_state, B, S, state_pre, sbias,
+                               state_out, scratch, 2, st, gates_save);
   // HTCN_K3_CLUSTER picks the kernel: 0 = this file's single-CTA kernel (128 users on the MMA M axis, weights streamed
   // from L2); 1 / 2 = the 4-CTA cluster kernel with shared-memory-resident weight slices (k3_gru_cluster.cu; plain DSMEM
   // stores or st.async); 3, 4 = the users-on-N kernel (k3_gru_t.cu: hidden units on the MMA M axis, 32 users per CTA on N,

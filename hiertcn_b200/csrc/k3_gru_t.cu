@@ -103,12 +103,13 @@ __host__ __device__ constexpr int res_first(int p, bool ts) { return ts ? (p == 
 __host__ __device__ constexpr int ts_index(int p) { return p == kG0r ? 0 : p == kC0 ? 1 : 2; }
 }  // namespace k3t
 
-template <int kNU, int kRes, int kStages, bool kTs>
+template <int kNU, int kRes, int kStages, bool kTs, bool kGates>
 __global__ void __launch_bounds__(k3t::Cfg<kNU, kRes, kStages, kTs>::kThreads, 1)
 k3_gru_bf16_t(const uint8_t* __restrict__ w_img, const float* __restrict__ yp, const float* __restrict__ mask,
               const float* __restrict__ state_in, const float* __restrict__ bias_all /* [bg0 256][bc0 128][bg1 256][bc1 128] */,
               int B, int S, int do_sbias, float* __restrict__ state_pre, float* __restrict__ sbias,
-              float* __restrict__ state_out) {
+              float* __restrict__ state_out,
+              float* __restrict__ gates_save /* kGates: [S][2][3][B][128] = r, u, c of every cell call (for htcn_gru_backward) */) {
   using namespace k3t;
   using C = Cfg<kNU, kRes, kStages, kTs>;
   using Smem = typename C::Smem;
@@ -350,9 +351,19 @@ k3_gru_bf16_t(const uint8_t* __restrict__ w_img, const float* __restrict__ yp, c
         ld_acc(C::kColR, v);
         if (warp == 0) K3T_TR(1, l * 10 + 2);
 #pragma unroll
-        for (int i = 0; i < kUsersPerThread; ++i) put(slot_t, i, sigmoid_fast(v[i] + bgr[l]) * h[l][i]);
+        for (int i = 0; i < kUsersPerThread; ++i) {
+          v[i] = sigmoid_fast(v[i] + bgr[l]);
+          put(slot_t, i, v[i] * h[l][i]);
+        }
         publish();
         if (warp == 0) K3T_TR(1, l * 10 + 3);
+        // training: the gate activations go out behind the publish, under the product the issuer has just been released for
+        float* gs = kGates ? gates_save + ((long long)(s * 2 + l) * 3 * B + b0) * kDim + j : nullptr;
+        if (kGates) {
+#pragma unroll
+          for (int i = 0; i < kUsersPerThread; ++i)
+            if (i < n_ok) gs[(long long)i * kDim] = v[i];                                  // r
+        }
         if (l == 0) {
           // ---- under the candidate product: emit the state before the step, fetch the mask and the next input.  NOT at the top
           // of the step: a fence.proxy.async (every publish) waits for the thread's outstanding global loads, and these take
@@ -404,6 +415,14 @@ k3_gru_bf16_t(const uint8_t* __restrict__ w_img, const float* __restrict__ yp, c
         }
         if (l == 0 || s + 1 < S) publish();
         if (warp == 0) K3T_TR(1, l * 10 + 8);
+        if (kGates) {
+#pragma unroll
+          for (int i = 0; i < kUsersPerThread; ++i)
+            if (i < n_ok) {
+              gs[((long long)B + i) * kDim] = u[i];                                        // u
+              gs[(2LL * B + i) * kDim] = c[i];                                             // c
+            }
+        }
         if (l == 0) {
           // under G1r: sbias[s] out (its product ran under this epilogue), THEN the new masked h0 -- the sbias product reads the
           // H0 slot -- and the next step's input (X is free since C0); all three are published by the next publish (E_g1)
@@ -445,30 +464,35 @@ k3_gru_bf16_t(const uint8_t* __restrict__ w_img, const float* __restrict__ yp, c
   }
 }
 
-template <int kNU, int kRes, int kStages, bool kTs>
+template <int kNU, int kRes, int kStages, bool kTs, bool kGates = false>
 static int32_t launch_t(const uint8_t* tw, const float* yp, const float* mask, const float* state_in, const float* bias_dev,
-                        int B, int S, float* state_pre, float* sbias, float* state_out, cudaStream_t st) {
+                        int B, int S, float* state_pre, float* sbias, float* state_out, cudaStream_t st,
+                        float* gates_save = nullptr) {
   using C = k3t::Cfg<kNU, kRes, kStages, kTs>;
   const size_t smem = sizeof(typename C::Smem) + 1024;
   static_assert(sizeof(typename C::Smem) + 1024 <= 232448, "shared-memory budget of one CTA");
-  auto kern = k3_gru_bf16_t<kNU, kRes, kStages, kTs>;
+  auto kern = k3_gru_bf16_t<kNU, kRes, kStages, kTs, kGates>;
   HTCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<ceil_div(B, kNU), C::kThreads, smem, st>>>(tw, yp, mask, state_in, bias_dev, B, S, sbias != nullptr, state_pre,
-                                                   sbias, state_out);
+                                                   sbias, state_out, gates_save);
   HTCN_LAUNCH_CHECK("k3_gru_bf16_t");
   return HTCN_OK;
 }
 
-// variant 0: layer-0 gates resident (128 KB), 3-stage ring; 1: only their r half resident, 7-stage ring.  (64 users per CTA
-// -- kNU = 64, 16 epilogue warps -- was tried: 108 us against 84, the per-SM weight stream is the same and 576 threads spill)
+// variant 0: layer-0 gates resident (128 KB), 3-stage ring; 1: only their r half resident, 7-stage ring; 2: three weight
+// tiles in tensor memory.  (64 users per CTA -- kNU = 64, 16 epilogue warps -- was tried: 108 us against 84, the per-SM
+// weight stream is the same and 576 threads spill.)  gates_save != NULL: the training forward (variant 2 + the gate
+// activations of every cell call written out for htcn_gru_backward).
 int32_t gru_sessions_bf16_t(const float* yp, const float* mask, const float* state_in, const float* const* gate_w,
                             const float* const* gate_b, const float* const* cand_w, const float* const* cand_b,
                             const float* w_in_state, int B, int S, float* state_pre, float* sbias, float* state_out,
-                            float* scratch, int variant, cudaStream_t st) {
+                            float* scratch, int variant, cudaStream_t st, float* gates_save) {
   float* bias_dev;
   const uint8_t* tw;
   int32_t rc = k3_prepare_rep(gate_w, gate_b, cand_w, cand_b, w_in_state, scratch, st, &tw, &bias_dev);
   if (rc) return rc;
+  if (gates_save)
+    return launch_t<32, 8, 3, true, true>(tw, yp, mask, state_in, bias_dev, B, S, state_pre, sbias, state_out, st, gates_save);
   if (variant == 2) return launch_t<32, 8, 3, true>(tw, yp, mask, state_in, bias_dev, B, S, state_pre, sbias, state_out, st);
   if (variant == 1) return launch_t<32, 4, 7, false>(tw, yp, mask, state_in, bias_dev, B, S, state_pre, sbias, state_out, st);
   return launch_t<32, 8, 3, false>(tw, yp, mask, state_in, bias_dev, B, S, state_pre, sbias, state_out, st);

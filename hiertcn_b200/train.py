@@ -200,9 +200,19 @@ class HierTCNTrainer:
         sbias = buf("tr_sbias", (S, B, D), f32)
         gates = buf("tr_gates", (S, G, 3, B, D), f32)
         state_out = torch.empty((B, G * D), dtype=f32, device=m.device)
-        cabi.call("htcn_gru_sessions_train", yp.data_ptr(), d["mask"].data_ptr(), d["state"].data_ptr(), m._gru_pp[0][0],
-                  m._gru_pp[1][0], m._gru_pp[2][0], m._gru_pp[3][0], G, m.w_in_state.data_ptr(), B, S,
-                  state_pre.data_ptr(), sbias.data_ptr(), state_out.data_ptr(), gates.data_ptr(), st)
+        if self.bf16 and G == 2 and getattr(self, "k3_tcgen05", bool(os.environ.get("HTCN_TRAIN_K3_BF16"))):
+            # opt-in (``self.k3_tcgen05 = True`` / HTCN_TRAIN_K3_BF16=1): the tensor-core GRU of the inference path with the gate
+            # activations written out -- 0.08 ms against 1.0 ms for the fp32 kernel at 4096 users x 10 sessions (cfg5 step 24.7 ->
+            # 24.2 ms), but bf16 recurrent operands move every gradient below the GRU by 2-4 % (norm-relative, cosine >= 0.999)
+            # where the fp32 kernel keeps them within 0.4 % of the fp64 oracle: not the default
+            k3_scratch = buf("k3_scratch_bf16", (cabi.gru_scratch_bytes(B) // 4,), f32)
+            cabi.call("htcn_gru_sessions_train_bf16", yp.data_ptr(), d["mask"].data_ptr(), d["state"].data_ptr(), m._gru_pp[0][0],
+                      m._gru_pp[1][0], m._gru_pp[2][0], m._gru_pp[3][0], G, m.w_in_state.data_ptr(), B, S,
+                      k3_scratch.data_ptr(), state_pre.data_ptr(), sbias.data_ptr(), state_out.data_ptr(), gates.data_ptr(), st)
+        else:
+            cabi.call("htcn_gru_sessions_train", yp.data_ptr(), d["mask"].data_ptr(), d["state"].data_ptr(), m._gru_pp[0][0],
+                      m._gru_pp[1][0], m._gru_pp[2][0], m._gru_pp[3][0], G, m.w_in_state.data_ptr(), B, S,
+                      state_pre.data_ptr(), sbias.data_ptr(), state_out.data_ptr(), gates.data_ptr(), st)
         h_save = buf("tr_h_save_bf16" if fused else "tr_h_save", (L + 1, R, D), sdt)
         a_save = buf("tr_a_save_bf16" if fused else "tr_a_save", (max(L, 1), R, D), sdt)
         hout = buf("tr_hout_bf16" if fused else "tr_hout", (max(Q, 1), D), sdt)

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define HTCN_ABI_VERSION 5
+#define HTCN_ABI_VERSION 6
 #define HTCN_DIM 128          /* D = C = H */
 #define HTCN_MAX_SLOTS 64     /* S (args.max_session_num, default 10) */
 #define HTCN_MAX_LEVELS 8     /* TCN levels (len(args.tcn_channel)) */
@@ -454,6 +454,15 @@ int32_t htcn_gru_sessions_train(const float* yp, const float* mask, const float*
                                 const float* const* cand_w_host, const float* const* cand_b_host, int32_t num_layer,
                                 const float* w_in_state, int32_t B, int32_t S, float* state_pre, float* sbias,
                                 float* state_out, float* gates_save, void* stream);
+
+/* The same on the tensor cores (bf16 operands, fp32 state and accumulation): the users-on-N tcgen05 kernel of
+ * htcn_gru_sessions' bf16 tier with r, u, c of every cell call written out (customed_gru_cell.py:309-337).  num_layer must
+ * be 2; scratch: HTCN_GRU_SCRATCH_BYTES(B) bytes. */
+int32_t htcn_gru_sessions_train_bf16(const float* yp, const float* mask, const float* state_in,
+                                     const float* const* gate_w_host, const float* const* gate_b_host,
+                                     const float* const* cand_w_host, const float* const* cand_b_host, int32_t num_layer,
+                                     const float* w_in_state, int32_t B, int32_t S, float* scratch, float* state_pre,
+                                     float* sbias, float* state_out, float* gates_save, void* stream);
 
 /* Back-propagation through the S session steps (model_hier.py:30-37,91,93), truncated at the batch boundary.
  * d_sbias [S,B,128] comes from htcn_tcn_backward.  scratch: htcn_gru_backward_scratch_floats(B,S,G) floats.

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol(built):
     assert len(decl) >= 14
     for name in decl:
         assert hasattr(lib, name), "libhtcn.so does not export %s" % name
-    assert lib.htcn_abi_version() == 5
+    assert lib.htcn_abi_version() == 6
 
 
 def test_ctypes_prototypes_match_header(built):

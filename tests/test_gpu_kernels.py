@@ -143,6 +143,48 @@ def test_k3_gru_sessions(lib, B, S):
     assert (sout.cpu().numpy()[last] == 0).all()
 
 
+@pytest.mark.parametrize("B,S", [(300, 4), (45, 10)])
+def test_k3_train_forward_bf16_saves_gates(lib, B, S):
+    """htcn_gru_sessions_train_bf16 (the users-on-N tcgen05 GRU with r, u, c of every cell call written out): states bit-equal
+    to the inference kernel, gate activations within the bf16 bar of the fp32 training kernel, and consistent with the states:
+    m * (u*h + (1-u)*c) of layer l at step s == the state before step s+1 (customed_gru_cell.py:309-337, model_hier.py:93)"""
+    x, y, m, s0, w = small_case(B=B, S=S, L=4, N=97, seed=7)
+    _, _, yps = O.gru_over_sessions(y, m, s0, w, 2, "f32")
+    w_in = w["hier/tcn/emb/kernel"]
+    gru = []
+    for g in range(2):
+        p = f"hier/multi_rnn_cell/cell_{g}/gru_cell"
+        gru.append([dev(w[p + "/gates/kernel"]), dev(w[p + "/gates/bias"]), dev(w[p + "/candidate/kernel"]),
+                    dev(w[p + "/candidate/bias"])])
+    pps = [lib.ptr_array([l[i].data_ptr() for l in gru]) for i in range(4)]
+    mask_np = np.stack([mm.reshape(-1) for mm in m]).astype(np.float32)
+    mask, yp, st_in, wis = dev(mask_np), dev(yps.astype(np.float32)), dev(s0), dev(w_in[128:])
+    scratch = torch.empty(lib.gru_scratch_bytes(B) // 4, dtype=torch.float32, device="cuda")
+    new = lambda *shape: torch.full(shape, 7.0, dtype=torch.float32, device="cuda")  # noqa: E731
+    spre, sbias, sout, gates = new(S, B, 256), new(S, B, 128), new(B, 256), new(S, 2, 3, B, 128)
+    lib.call("htcn_gru_sessions_train_bf16", P(yp), P(mask), P(st_in), pps[0][0], pps[1][0], pps[2][0], pps[3][0], 2, P(wis), B, S,
+             P(scratch), P(spre), P(sbias), P(sout), P(gates), None)
+    spre_i, sbias_i, sout_i = new(S, B, 256), new(S, B, 128), new(B, 256)
+    lib.call("htcn_gru_sessions", P(yp), P(mask), P(st_in), pps[0][0], pps[1][0], pps[2][0], pps[3][0], 2, P(wis), B, S,
+             lib.HTCN_BF16, P(scratch), P(spre_i), P(sbias_i), P(sout_i), None)
+    spre_f, sbias_f, sout_f, gates_f = new(S, B, 256), new(S, B, 128), new(B, 256), new(S, 2, 3, B, 128)
+    lib.call("htcn_gru_sessions_train", P(yp), P(mask), P(st_in), pps[0][0], pps[1][0], pps[2][0], pps[3][0], 2, P(wis), B, S,
+             P(spre_f), P(sbias_f), P(sout_f), P(gates_f), None)
+    torch.cuda.synchronize()
+    for a, b in ((spre, spre_i), (sbias, sbias_i), (sout, sout_i)):
+        assert torch.equal(a, b)
+    g, gf = gates.cpu().numpy(), gates_f.cpu().numpy()
+    assert np.abs(g - gf).max() <= 2e-2, np.abs(g - gf).max()
+    sp, so = spre.cpu().numpy(), sout.cpu().numpy()
+    for s in range(S):
+        nxt = sp[s + 1] if s + 1 < S else so
+        for l in range(2):
+            h = sp[s][:, 128 * l:128 * (l + 1)]
+            u, c = g[s, l, 1], g[s, l, 2]
+            want = mask_np[s][:, None] * (u * h + (1.0 - u) * c)
+            np.testing.assert_allclose(nxt[:, 128 * l:128 * (l + 1)], want, rtol=0, atol=2e-6)
+
+
 @pytest.mark.parametrize("B,S,with_sbias", [(300, 4, True), (129, 2, False), (17, 1, True)])
 def test_k3_cluster_variants_agree(lib, B, S, with_sbias, monkeypatch):
     """The bf16 GRU kernels -- weights streamed from L2 (HTCN_K3_CLUSTER=0), 4-CTA cluster with resident weights and plain
