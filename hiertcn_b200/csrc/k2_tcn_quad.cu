@@ -17,6 +17,8 @@
 // problems spread over the SMs first and only then stack chains on an SM.
 // The plain inference stack only (no down-sample level -- that needs a second accumulator per chain --, no training
 // dropout, no saved activations): those run on k2_tcn_bf16.cu's kernels.
+#include <cstdlib>
+
 #include "k2_tcn.cuh"
 
 namespace htcn {
@@ -70,12 +72,16 @@ __global__ void __launch_bounds__(kQThreads, 1)
 k2_tcn_bf16_quad(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfloat16* __restrict__ xe,
                  const float* __restrict__ sbias, const float* __restrict__ bias_all /*[n_levels][128]*/,
                  const int* __restrict__ out_row, __nv_bfloat16* __restrict__ hout,
-                 uint8_t* __restrict__ hist /* [4 * gridDim.x][2][n_levels][kHistBytes] parked level inputs of streamed sequences */) {
+                 uint8_t* __restrict__ hist /* [4 * gridDim.x][2][n_levels][kHistBytes] parked level inputs of streamed sequences */,
+                 int kLag /* rounds group g runs behind group g-1 */) {
   using C = QuadCfg<kSpare>;
   using Smem = typename C::Smem;
   static_assert(!kStream || kSpare == kMaxSpare, "streamed chunks hand over kMaxSpare rows");
   constexpr int kRowsQ = C::kRowsQ;
   constexpr int kPerGroup = kQChains / kGroups;             // chains that share one fetch of a layer's weights
+  // Group g runs kLag rounds behind group g-1, so in any round the groups are at DIFFERENT layers: the short in-projection
+  // round (1 tap) of one group sits beside conv rounds (K taps) of the others instead of all chains idling the tensor pipe
+  // through the same short round and the input staging of a new tile
   extern __shared__ uint8_t smem_raw[];
   auto& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -86,7 +92,8 @@ k2_tcn_bf16_quad(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __n
 #pragma unroll
   for (int c = 0; c < kQChains; ++c) {
     steps[c] = cta_tile_count(g, c * (int)gridDim.x + (int)blockIdx.x, n_vc) * n_layers;
-    n_rounds = steps[c] > n_rounds ? steps[c] : n_rounds;
+    const int end = steps[c] + (c / kPerGroup) * kLag;
+    n_rounds = end > n_rounds ? end : n_rounds;
   }
 
   if (tid == 0) {
@@ -116,15 +123,16 @@ k2_tcn_bf16_quad(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __n
     if (lane == 0) {
       uint32_t stage = 0, wphase = 0;
       for (int i = 0; i < n_rounds; ++i) {
-        int first, taps;
-        bool ds;
-        k2_layer_tiles(g, i % n_layers, first, taps, ds);
 #pragma unroll
         for (int grp = 0; grp < kGroups; ++grp) {
+          const int il = i - grp * kLag;                         // the group's own round
           bool active = false;
 #pragma unroll
-          for (int c = grp * kPerGroup; c < (grp + 1) * kPerGroup; ++c) active |= i < steps[c];
+          for (int c = grp * kPerGroup; c < (grp + 1) * kPerGroup; ++c) active |= il >= 0 && il < steps[c];
           if (!active) continue;
+          int first, taps;
+          bool ds;
+          k2_layer_tiles(g, il % n_layers, first, taps, ds);
           for (int j = first; j < first + taps; ++j) {
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
@@ -151,15 +159,16 @@ k2_tcn_bf16_quad(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __n
     const uint32_t b_lo0 = ((smem_u32(&sm.w[0][0]) & 0x3FFFF) >> 4) | (1u << 16);
     uint32_t stage = 0, wphase = 0;
     for (int i = 0; i < n_rounds; ++i) {
-      const int layer = i % n_layers;
-      const int taps = layer == 0 ? 1 : g.K;
-      const int dil = layer == 0 ? 1 : (1 << (layer - 1));
 #pragma unroll
       for (int grp = 0; grp < kGroups; ++grp) {
+        const int il = i - grp * kLag;                           // the group's own round
         bool active = false;
 #pragma unroll
-        for (int c = grp * kPerGroup; c < (grp + 1) * kPerGroup; ++c) active |= i < steps[c];
+        for (int c = grp * kPerGroup; c < (grp + 1) * kPerGroup; ++c) active |= il >= 0 && il < steps[c];
         if (!active) continue;
+        const int layer = il % n_layers;
+        const int taps = layer == 0 ? 1 : g.K;
+        const int dil = layer == 0 ? 1 : (1 << (layer - 1));
         for (int tap = 0; tap < taps; ++tap) {
           const uint32_t shift = (uint32_t)((taps - 1 - tap) * dil);   // rows back in time (customized_tcn_cell.py:46-49)
 #pragma unroll
@@ -169,9 +178,9 @@ k2_tcn_bf16_quad(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __n
             const uint32_t b_lo = b_lo0 + stage * (kQStageBytes >> 4);
 #pragma unroll
             for (int c = grp * kPerGroup; c < (grp + 1) * kPerGroup; ++c) {
-              if (i >= steps[c]) continue;
+              if (il >= steps[c]) continue;
               if (tap == 0 && half == 0) {
-                mbar_wait(&sm.act_ready[c], (uint32_t)(i & 1));  // the chain's operand tile is written + fenced
+                mbar_wait(&sm.act_ready[c], (uint32_t)(il & 1)); // the chain's operand tile is written + fenced
                 tc_fence_after_sync();
               }
               // tap = the same tile read `shift` rows (16 B each) further back; K chunk pair k = 2k * kRowsQ rows further on
@@ -404,7 +413,8 @@ static int32_t launch_quad_g(const CUtensorMap& tw, const K2Geom& g, const __nv_
   const int grid = g.n_units < 148 ? g.n_units : 148;
   auto kern = k2_tcn_bf16_quad<kSpare, kStream, kGroups>;
   HTCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<grid, kQThreads, smem, st>>>(tw, g, xe, sbias, bias_dev, out_row, hout, hist_dev);
+  const char* lag_env = getenv("HTCN_K2_LAG");
+  kern<<<grid, kQThreads, smem, st>>>(tw, g, xe, sbias, bias_dev, out_row, hout, hist_dev, lag_env ? atoi(lag_env) : 1);
   HTCN_LAUNCH_CHECK("k2_tcn_bf16_quad");
   return HTCN_OK;
 }
@@ -413,10 +423,12 @@ template <int kSpare, bool kStream>
 static int32_t launch_quad(const CUtensorMap& tw, const K2Geom& g, const __nv_bfloat16* xe, const float* sbias,
                            const float* bias_dev, const int* out_row, __nv_bfloat16* hout, uint8_t* hist_dev, cudaStream_t st) {
   // HTCN_K2_QUAD = number of chain groups: 1 = all four chains in lock step (every weight tile fetched once per round, but
-  // the MMA and epilogue phases of a round do not overlap), 2 (default) = two pairs half a round apart (each pair fetches its
-  // own copy of the layer's weights; one pair's epilogue runs under the other's MMAs), 4 = four independent chains
+  // the MMA and epilogue phases of a round do not overlap), 2 = two pairs (each pair fetches its own copy of the layer's
+  // weights), 4 = four independent chains; group g runs HTCN_K2_LAG (default 1) rounds behind group g-1.  Measured
+  // (profiles/r2_k2_quad_sweep.txt): short sequences (config 2) 0.476 (4 groups, no lag) -> 0.436 ms (4 groups, lag 1), pairs
+  // 0.467; streamed long sequences (config 3) within 2 % of each other -- pairs (half the weight traffic) are the default there.
   const char* e = getenv("HTCN_K2_QUAD");
-  const int groups = e ? atoi(e) : 4;
+  const int groups = e ? atoi(e) : (kStream ? 2 : 4);
   if (groups == 1) return launch_quad_g<kSpare, kStream, 1>(tw, g, xe, sbias, bias_dev, out_row, hout, hist_dev, st);
   if (groups == 4) return launch_quad_g<kSpare, kStream, 4>(tw, g, xe, sbias, bias_dev, out_row, hout, hist_dev, st);
   return launch_quad_g<kSpare, kStream, 2>(tw, g, xe, sbias, bias_dev, out_row, hout, hist_dev, st);
