@@ -26,8 +26,9 @@ using namespace sm100;
 
 constexpr int kQChains = 4;
 constexpr int kQEpiWarps = 4 * kQChains;                 // warp w: chain w >> 2, TMEM lane quarter w & 3
-constexpr int kQThreads = 32 * (kQEpiWarps + 2);         // + TMA producer warp + MMA issuer warp
-constexpr int kQProducerWarp = kQEpiWarps, kQMmaWarp = kQEpiWarps + 1;
+// + kIssuers TMA producer warps + kIssuers MMA issuer warps (issuer w drives the chain groups [w, w+1) * kGroups / kIssuers
+// through its own part of the weight ring)
+constexpr int q_threads(int issuers) { return 32 * (kQEpiWarps + 2 * issuers); }
 constexpr int kQStageBytes = 128 * 64 * 2;               // half a tap: [128 cout][64 cin] bf16, 128-byte swizzle
 
 // kSpare = rows in front of a tile that a shifted tap may read (>= (K-1)*d_max; 32 when long sequences are streamed: the
@@ -67,8 +68,8 @@ __device__ __forceinline__ uint32_t relu_bf16x2(uint32_t x) {
   return y;
 }
 
-template <int kSpare, bool kStream, int kGroups>
-__global__ void __launch_bounds__(kQThreads, 1)
+template <int kSpare, bool kStream, int kGroups, int kIssuers>
+__global__ void __launch_bounds__(q_threads(kIssuers), 1)
 k2_tcn_bf16_quad(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfloat16* __restrict__ xe,
                  const float* __restrict__ sbias, const float* __restrict__ bias_all /*[n_levels][128]*/,
                  const int* __restrict__ out_row, __nv_bfloat16* __restrict__ hout,
@@ -79,6 +80,11 @@ k2_tcn_bf16_quad(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __n
   static_assert(!kStream || kSpare == kMaxSpare, "streamed chunks hand over kMaxSpare rows");
   constexpr int kRowsQ = C::kRowsQ;
   constexpr int kPerGroup = kQChains / kGroups;             // chains that share one fetch of a layer's weights
+  constexpr int kQThreads = q_threads(kIssuers);
+  constexpr int kGroupsPerIssuer = kGroups / kIssuers;
+  static_assert(kGroups % kIssuers == 0 && C::kStages >= 2 * kIssuers, "issuer split");
+  // ring of issuer w: stages [ring0, ring0 + ring_n) -- the first issuer takes the odd stage
+  constexpr int kRing0N = kIssuers == 1 ? C::kStages : (C::kStages + 1) / 2;
   // Group g runs kLag rounds behind group g-1, so in any round the groups are at DIFFERENT layers: the short in-projection
   // round (1 tap) of one group sits beside conv rounds (K taps) of the others instead of all chains idling the tensor pipe
   // through the same short round and the input staging of a new tile
@@ -112,19 +118,22 @@ k2_tcn_bf16_quad(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __n
     for (int i = tid; i < g.n_levels * kDim; i += kQThreads) sm.bias[i / kDim][i % kDim] = bias_all[i];
   for (int i = tid; i < kQChains * C::kActQ / 16; i += kQThreads)
     reinterpret_cast<uint4*>(&sm.act[0][0])[i] = make_uint4(0, 0, 0, 0);
-  if (warp == kQMmaWarp) tmem_alloc<512>(&sm.tmem_base);
+  if (warp == kQEpiWarps + kIssuers) tmem_alloc<512>(&sm.tmem_base);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = __shfl_sync(0xffffffffu, sm.tmem_base, 0);
 
-  if (warp == kQProducerWarp) {
+  if (warp >= kQEpiWarps && warp < kQEpiWarps + kIssuers) {
     // ===================== weight producer: the half-taps of layer (i mod n_layers), once per round =====================
+    const int iw = warp - kQEpiWarps;
+    const uint32_t ring0 = iw == 0 ? 0u : (uint32_t)kRing0N, ring_n = iw == 0 ? (uint32_t)kRing0N : (uint32_t)(C::kStages - kRing0N);
     if (lane == 0) {
-      uint32_t stage = 0, wphase = 0;
+      uint32_t stage = ring0, wphase = 0;
       for (int i = 0; i < n_rounds; ++i) {
 #pragma unroll
         for (int grp = 0; grp < kGroups; ++grp) {
+          if (grp / kGroupsPerIssuer != iw) continue;
           const int il = i - grp * kLag;                         // the group's own round
           bool active = false;
 #pragma unroll
@@ -139,8 +148,8 @@ k2_tcn_bf16_quad(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __n
               mbar_wait_relaxed(&sm.w_empty[stage], wphase ^ 1);
               mbar_arrive_expect_tx(&sm.w_full[stage], kQStageBytes);
               tma_load_2d(sm.w[stage], &tmap_w, 64 * half, j * 128, &sm.w_full[stage]);
-              if (++stage == C::kStages) {
-                stage = 0;
+              if (++stage == ring0 + ring_n) {
+                stage = ring0;
                 wphase ^= 1;
               }
             }
@@ -148,19 +157,22 @@ k2_tcn_bf16_quad(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __n
         }
       }
     }
-  } else if (warp == kQMmaWarp) {
-    // ===================== MMA issuer: tap-major, chain-minor =====================
+  } else if (warp >= kQEpiWarps + kIssuers) {
+    // ===================== MMA issuer(s): tap-major, chain-minor =====================
     // (the whole warp runs the uniform waits and descriptor arithmetic, one elected lane issues: see k2_tcn_bf16.cu)
+    const int iw = warp - kQEpiWarps - kIssuers;
+    const uint32_t ring0 = iw == 0 ? 0u : (uint32_t)kRing0N, ring_n = iw == 0 ? (uint32_t)kRing0N : (uint32_t)(C::kStages - kRing0N);
     const bool leader = elect_one();
     constexpr uint32_t idesc = make_idesc_bf16(kTR, 128);
     // descriptor halves (make_desc_act / make_desc_k_sw128): the issuer only ever adds 16-byte units to the low words
     constexpr uint32_t kAHi = (128u >> 4) | (1u << 14), kBHi = (1024u >> 4) | (1u << 14) | (2u << 29);
     const uint32_t a_lo0 = (((smem_u32(&sm.act[0][0]) + kSpare * 16) & 0x3FFFF) >> 4) | ((uint32_t)kRowsQ << 16);
     const uint32_t b_lo0 = ((smem_u32(&sm.w[0][0]) & 0x3FFFF) >> 4) | (1u << 16);
-    uint32_t stage = 0, wphase = 0;
+    uint32_t stage = ring0, wphase = 0;
     for (int i = 0; i < n_rounds; ++i) {
 #pragma unroll
       for (int grp = 0; grp < kGroups; ++grp) {
+        if (grp / kGroupsPerIssuer != iw) continue;
         const int il = i - grp * kLag;                           // the group's own round
         bool active = false;
 #pragma unroll
@@ -193,8 +205,8 @@ k2_tcn_bf16_quad(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __n
               if (tap == taps - 1 && half == 1 && leader) umma_commit(&sm.acc_ready[c]);
             }
             if (leader) umma_commit(&sm.w_empty[stage]);
-            if (++stage == C::kStages) {
-              stage = 0;
+            if (++stage == ring0 + ring_n) {
+              stage = ring0;
               wphase ^= 1;
             }
           }
@@ -400,21 +412,21 @@ k2_tcn_bf16_quad(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __n
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == kQMmaWarp) {
+  if (warp == kQEpiWarps + kIssuers) {
     tc_fence_after_sync();
     tmem_dealloc<512>(tmem);
   }
 }
 
-template <int kSpare, bool kStream, int kGroups>
+template <int kSpare, bool kStream, int kGroups, int kIssuers>
 static int32_t launch_quad_g(const CUtensorMap& tw, const K2Geom& g, const __nv_bfloat16* xe, const float* sbias,
                            const float* bias_dev, const int* out_row, __nv_bfloat16* hout, uint8_t* hist_dev, cudaStream_t st) {
   const size_t smem = sizeof(typename QuadCfg<kSpare>::Smem) + 1024;
   const int grid = g.n_units < 148 ? g.n_units : 148;
-  auto kern = k2_tcn_bf16_quad<kSpare, kStream, kGroups>;
+  auto kern = k2_tcn_bf16_quad<kSpare, kStream, kGroups, kIssuers>;
   HTCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const char* lag_env = getenv("HTCN_K2_LAG");
-  kern<<<grid, kQThreads, smem, st>>>(tw, g, xe, sbias, bias_dev, out_row, hout, hist_dev, lag_env ? atoi(lag_env) : 1);
+  kern<<<grid, q_threads(kIssuers), smem, st>>>(tw, g, xe, sbias, bias_dev, out_row, hout, hist_dev, lag_env ? atoi(lag_env) : 1);
   HTCN_LAUNCH_CHECK("k2_tcn_bf16_quad");
   return HTCN_OK;
 }
@@ -429,9 +441,16 @@ static int32_t launch_quad(const CUtensorMap& tw, const K2Geom& g, const __nv_bf
   // 0.467; streamed long sequences (config 3) within 2 % of each other -- pairs (half the weight traffic) are the default there.
   const char* e = getenv("HTCN_K2_QUAD");
   const int groups = e ? atoi(e) : (kStream ? 2 : 4);
-  if (groups == 1) return launch_quad_g<kSpare, kStream, 1>(tw, g, xe, sbias, bias_dev, out_row, hout, hist_dev, st);
-  if (groups == 4) return launch_quad_g<kSpare, kStream, 4>(tw, g, xe, sbias, bias_dev, out_row, hout, hist_dev, st);
-  return launch_quad_g<kSpare, kStream, 2>(tw, g, xe, sbias, bias_dev, out_row, hout, hist_dev, st);
+  // HTCN_K2_ISSUERS = 2: a second MMA-issuing warp (and producer warp): the chains 0-1 and 2-3 get an issuer and a part of
+  // the weight ring each -- with four independent chains ONE issuer spends ~59 instructions per half-tap of one chain, about the
+  // 256 clk of its 4 MMAs
+  const char* ie = getenv("HTCN_K2_ISSUERS");
+  const int issuers = ie ? atoi(ie) : 1;
+  if (issuers == 2 && groups == 4) return launch_quad_g<kSpare, kStream, 4, 2>(tw, g, xe, sbias, bias_dev, out_row, hout, hist_dev, st);
+  if (issuers == 2 && groups == 2) return launch_quad_g<kSpare, kStream, 2, 2>(tw, g, xe, sbias, bias_dev, out_row, hout, hist_dev, st);
+  if (groups == 1) return launch_quad_g<kSpare, kStream, 1, 1>(tw, g, xe, sbias, bias_dev, out_row, hout, hist_dev, st);
+  if (groups == 4) return launch_quad_g<kSpare, kStream, 4, 1>(tw, g, xe, sbias, bias_dev, out_row, hout, hist_dev, st);
+  return launch_quad_g<kSpare, kStream, 2, 1>(tw, g, xe, sbias, bias_dev, out_row, hout, hist_dev, st);
 }
 
 int32_t k2_launch_quad(const CUtensorMap& tw, const K2Geom& g, const __nv_bfloat16* xe, const float* sbias, const float* bias_dev,
