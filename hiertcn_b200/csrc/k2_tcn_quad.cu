@@ -298,7 +298,11 @@ k2_tcn_bf16_quad(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __n
               const uint4 packed = make_uint4(pack_bf16x2(a0.x, a0.y), pack_bf16x2(a1.x, a1.y), pack_bf16x2(a2.x, a2.y), pack_bf16x2(a3.x, a3.y));
               const int c = c0 + q;
               if (!last) {
+#ifndef HTCN_K2Q_NOSMEM   /* timing experiment only (-DHTCN_K2Q_NOSMEM): the epilogue without its shared-memory traffic */
                 if (src >= 0) sts_u4(my_act + c * (kRowsQ * 16), packed);          // causal pad rows are never written: they stay zero
+#else
+                if (src == -12345) sts_u4(my_act + c * (kRowsQ * 16), packed);
+#endif
                 if (do_park) *reinterpret_cast<uint4*>(park + (c * kMaxSpare + hj) * 16) = src >= 0 ? packed : make_uint4(0, 0, 0, 0);
               } else if (dst >= 0) reinterpret_cast<uint4*>(hout + (long long)dst * kDim)[c] = packed;
             }
@@ -345,7 +349,11 @@ k2_tcn_bf16_quad(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __n
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
               const uint32_t slot = my_act + (c0 + q) * (kRowsQ * 16);
+#ifndef HTCN_K2Q_NOSMEM
               res[q] = lds_u4(slot);
+#else
+              res[q] = make_uint4(slot, slot, slot, slot);
+#endif
             }
           };
           auto piece = [&](const uint32_t (&v)[16], const uint4 (&res)[2], int c0) {    // channels 8*c0 .. 8*c0+15 of this row
@@ -374,7 +382,11 @@ k2_tcn_bf16_quad(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __n
               }
               const uint4 packed = make_uint4(pk[0], pk[1], pk[2], pk[3]);
               if (!last) {
+#ifndef HTCN_K2Q_NOSMEM   /* timing experiment only (-DHTCN_K2Q_NOSMEM): the epilogue without its shared-memory traffic */
                 if (src >= 0) sts_u4(my_act + c * (kRowsQ * 16), packed);          // causal pad rows are never written: they stay zero
+#else
+                if (src == -12345) sts_u4(my_act + c * (kRowsQ * 16), packed);
+#endif
                 if (do_park) *reinterpret_cast<uint4*>(park + (c * kMaxSpare + hj) * 16) = src >= 0 ? packed : make_uint4(0, 0, 0, 0);
               } else if (dst >= 0) reinterpret_cast<uint4*>(hout + (long long)dst * kDim)[c] = packed;
             }
