@@ -33,14 +33,18 @@ constexpr int kQStageBytes = 128 * 64 * 2;               // half a tap: [128 cou
 
 // kSpare = rows in front of a tile that a shifted tap may read (>= (K-1)*d_max; 32 when long sequences are streamed: the
 // parked rows of the previous chunk land there).  Fewer spare rows = a smaller operand tile = a deeper weight ring.
-template <int kSpare>
+template <int kSpare, bool kFullTap = false>
 struct QuadCfg {
   static constexpr int kRowsQ = kTR + kSpare;
   static constexpr int kActQ = 16 * kRowsQ * 16;          // 16 channel chunks x rows x 16 B
-  static constexpr int kStages = kSpare == 8 ? 5 : 4;
+  // ring stages: half-taps (16 KB, 4..5 of them) or -- kFullTap -- two whole taps (32 KB: half the waits / commits / stage
+  // bookkeeping per MMA for the issuer)
+  static constexpr int kHalves = kFullTap ? 2 : 1;
+  static constexpr int kStageB = kQStageBytes * kHalves;
+  static constexpr int kStages = kFullTap ? 2 : (kSpare == 8 ? 5 : 4);
   static constexpr bool kBiasSmem = kSpare < 32;          // with 4 x 40 KB tiles the level biases stay in global memory (L1)
   struct alignas(1024) Smem {
-    uint8_t w[kStages][kQStageBytes];
+    uint8_t w[kStages][kStageB];
     uint8_t act[kQChains][kActQ];
     float bias[kBiasSmem ? HTCN_MAX_LEVELS : 1][kDim];
     uint64_t w_full[kStages], w_empty[kStages], acc_ready[kQChains], act_ready[kQChains];
@@ -68,14 +72,14 @@ __device__ __forceinline__ uint32_t relu_bf16x2(uint32_t x) {
   return y;
 }
 
-template <int kSpare, bool kStream, int kGroups, int kIssuers>
+template <int kSpare, bool kStream, int kGroups, int kIssuers, bool kFullTap>
 __global__ void __launch_bounds__(q_threads(kIssuers), 1)
 k2_tcn_bf16_quad(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfloat16* __restrict__ xe,
                  const float* __restrict__ sbias, const float* __restrict__ bias_all /*[n_levels][128]*/,
                  const int* __restrict__ out_row, __nv_bfloat16* __restrict__ hout,
                  uint8_t* __restrict__ hist /* [4 * gridDim.x][2][n_levels][kHistBytes] parked level inputs of streamed sequences */,
                  int kLag /* rounds group g runs behind group g-1 */) {
-  using C = QuadCfg<kSpare>;
+  using C = QuadCfg<kSpare, kFullTap>;
   using Smem = typename C::Smem;
   static_assert(!kStream || kSpare == kMaxSpare, "streamed chunks hand over kMaxSpare rows");
   constexpr int kRowsQ = C::kRowsQ;
@@ -145,10 +149,12 @@ k2_tcn_bf16_quad(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __n
           for (int j = first; j < first + taps; ++j) {
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
-              mbar_wait_relaxed(&sm.w_empty[stage], wphase ^ 1);
-              mbar_arrive_expect_tx(&sm.w_full[stage], kQStageBytes);
-              tma_load_2d(sm.w[stage], &tmap_w, 64 * half, j * 128, &sm.w_full[stage]);
-              if (++stage == ring0 + ring_n) {
+              if (half % C::kHalves == 0) {
+                mbar_wait_relaxed(&sm.w_empty[stage], wphase ^ 1);
+                mbar_arrive_expect_tx(&sm.w_full[stage], C::kStageB);
+              }
+              tma_load_2d(sm.w[stage] + (half % C::kHalves) * kQStageBytes, &tmap_w, 64 * half, j * 128, &sm.w_full[stage]);
+              if (half % C::kHalves == C::kHalves - 1 && ++stage == ring0 + ring_n) {
                 stage = ring0;
                 wphase ^= 1;
               }
@@ -185,9 +191,11 @@ k2_tcn_bf16_quad(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __n
           const uint32_t shift = (uint32_t)((taps - 1 - tap) * dil);   // rows back in time (customized_tcn_cell.py:46-49)
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
-            mbar_wait(&sm.w_full[stage], wphase);
-            tc_fence_after_sync();
-            const uint32_t b_lo = b_lo0 + stage * (kQStageBytes >> 4);
+            if (half % C::kHalves == 0) {
+              mbar_wait(&sm.w_full[stage], wphase);
+              tc_fence_after_sync();
+            }
+            const uint32_t b_lo = b_lo0 + stage * (C::kStageB >> 4) + (half % C::kHalves) * (kQStageBytes >> 4);
 #pragma unroll
             for (int c = grp * kPerGroup; c < (grp + 1) * kPerGroup; ++c) {
               if (il >= steps[c]) continue;
@@ -204,10 +212,12 @@ k2_tcn_bf16_quad(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __n
                                  (tap | half | kk) != 0);
               if (tap == taps - 1 && half == 1 && leader) umma_commit(&sm.acc_ready[c]);
             }
-            if (leader) umma_commit(&sm.w_empty[stage]);
-            if (++stage == ring0 + ring_n) {
-              stage = ring0;
-              wphase ^= 1;
+            if (half % C::kHalves == C::kHalves - 1) {
+              if (leader) umma_commit(&sm.w_empty[stage]);
+              if (++stage == ring0 + ring_n) {
+                stage = ring0;
+                wphase ^= 1;
+              }
             }
           }
         }
@@ -430,12 +440,12 @@ k2_tcn_bf16_quad(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __n
   }
 }
 
-template <int kSpare, bool kStream, int kGroups, int kIssuers>
+template <int kSpare, bool kStream, int kGroups, int kIssuers, bool kFullTap = false>
 static int32_t launch_quad_g(const CUtensorMap& tw, const K2Geom& g, const __nv_bfloat16* xe, const float* sbias,
                            const float* bias_dev, const int* out_row, __nv_bfloat16* hout, uint8_t* hist_dev, cudaStream_t st) {
-  const size_t smem = sizeof(typename QuadCfg<kSpare>::Smem) + 1024;
+  const size_t smem = sizeof(typename QuadCfg<kSpare, kFullTap>::Smem) + 1024;
   const int grid = g.n_units < 148 ? g.n_units : 148;
-  auto kern = k2_tcn_bf16_quad<kSpare, kStream, kGroups, kIssuers>;
+  auto kern = k2_tcn_bf16_quad<kSpare, kStream, kGroups, kIssuers, kFullTap>;
   HTCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const char* lag_env = getenv("HTCN_K2_LAG");
   kern<<<grid, q_threads(kIssuers), smem, st>>>(tw, g, xe, sbias, bias_dev, out_row, hout, hist_dev, lag_env ? atoi(lag_env) : 1);
@@ -458,6 +468,13 @@ static int32_t launch_quad(const CUtensorMap& tw, const K2Geom& g, const __nv_bf
   // 256 clk of its 4 MMAs
   const char* ie = getenv("HTCN_K2_ISSUERS");
   const int issuers = ie ? atoi(ie) : 1;
+  // HTCN_K2_FULLTAP: chain pairs / lock step over two whole-tap stages instead of 4-5 half-tap stages (half the waits, commits
+  // and stage bookkeeping per MMA in the issuer): pairs 0.476 -> 0.457 ms at config 2, 0.730 -> 0.711 ms at config 3 -- the
+  // default for streamed sequences (where pairs are the default)
+  const char* fe = getenv("HTCN_K2_FULLTAP");
+  const bool fulltap = fe ? atoi(fe) != 0 : kStream;
+  if (fulltap && groups == 2) return launch_quad_g<kSpare, kStream, 2, 1, true>(tw, g, xe, sbias, bias_dev, out_row, hout, hist_dev, st);
+  if (fulltap && groups == 1) return launch_quad_g<kSpare, kStream, 1, 1, true>(tw, g, xe, sbias, bias_dev, out_row, hout, hist_dev, st);
   if (issuers == 2 && groups == 4) return launch_quad_g<kSpare, kStream, 4, 2>(tw, g, xe, sbias, bias_dev, out_row, hout, hist_dev, st);
   if (issuers == 2 && groups == 2) return launch_quad_g<kSpare, kStream, 2, 2>(tw, g, xe, sbias, bias_dev, out_row, hout, hist_dev, st);
   if (groups == 1) return launch_quad_g<kSpare, kStream, 1, 1>(tw, g, xe, sbias, bias_dev, out_row, hout, hist_dev, st);
