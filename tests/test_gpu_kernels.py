@@ -888,6 +888,47 @@ def test_k2_tcn_bf16_tcgen05(lib, B, S, L, K, levels):
         np.testing.assert_array_equal(got_d, got)
 
 
+def test_k2_bf16_variants_on_random_shapes(lib, monkeypatch):
+    """randomised shapes (1..330 sequences of 1..300 positions, 1..11 slots, kernel sizes 1..5, 1..4 levels, ragged / dense,
+    with and without output compaction and sbias): every form of the four-chain kernel -- lock step, pairs with half- and
+    whole-tap stages, independent chains without / with a long lag, two issuers -- gives the bits of k2_tcn_bf16.cu's kernels"""
+    rng = np.random.default_rng(2024)
+    variants = (("default", {}), ("q1", {"HTCN_K2_QUAD": "1"}), ("q2", {"HTCN_K2_QUAD": "2", "HTCN_K2_FULLTAP": "0"}),
+                ("q2ft", {"HTCN_K2_QUAD": "2", "HTCN_K2_FULLTAP": "1"}), ("q4lag0", {"HTCN_K2_QUAD": "4", "HTCN_K2_LAG": "0"}),
+                ("q4lag3", {"HTCN_K2_QUAD": "4", "HTCN_K2_LAG": "3"}), ("q4i2", {"HTCN_K2_QUAD": "4", "HTCN_K2_ISSUERS": "2"}))
+    for case in range(24):
+        K = int(rng.integers(1, 6))
+        max_lv = 0
+        while max_lv < 4 and (K - 1) * (1 << max_lv) <= 32:
+            max_lv += 1
+        levels = int(rng.integers(1, max_lv + 1)) if K > 1 else int(rng.integers(1, 4))
+        S = int(rng.integers(1, 12))
+        L = int(rng.choice([1, 2, 5, 20, 33, 100, 127, 128, 129, 200, 300]))
+        B = int(rng.choice([1, 2, 3, 7, 40, 150, 330])) if L < 100 else int(rng.choice([1, 2, 5, 40, 160]))
+        S = min(S, 2) if L >= 100 else S
+        x, y, m, s0, w = small_case(B=B, S=S, L=L, N=301, seed=case, tcn_channel=(128,) * levels, kernel_size=K,
+                                    lengths="ragged" if rng.random() < 0.5 else "dense", kernel_scale=1.0)
+        pk = pack(x, y, m)
+        T = pk["x_id"].shape[1]
+        xe = dev(O.emb_gather(pk["x_id"], w["hier/emb/kernel"])).to(torch.bfloat16)
+        sbias = torch.randn((S, B, 128), device="cuda") * 0.3 if rng.random() < 0.8 else None
+        valid = pk["y_id"].reshape(-1) > 0
+        ro, n_out = None, None
+        if rng.random() < 0.5 and valid.any():
+            ro, n_out = dev(np.where(valid, np.cumsum(valid) - 1, -1).astype(np.int32)), int(valid.sum())
+        monkeypatch.setenv("HTCN_K2_QUAD", "0")
+        want = run_k2_bf16(lib, xe, w, sbias, pk["slot_off"], B, T, S, K, levels, out_row=ro, n_out=n_out).float().cpu().numpy()
+        monkeypatch.delenv("HTCN_K2_QUAD")
+        assert np.isfinite(want).all()
+        for name, env in variants:
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            got = run_k2_bf16(lib, xe, w, sbias, pk["slot_off"], B, T, S, K, levels, out_row=ro, n_out=n_out).float().cpu().numpy()
+            for k in env:
+                monkeypatch.delenv(k)
+            np.testing.assert_array_equal(got, want, err_msg="%s B=%d S=%d L=%d K=%d levels=%d" % (name, B, S, L, K, levels))
+
+
 def test_k2_bf16_causality_and_isolation(lib):
     B, L, levels, K = 6, 20, 2, 5
     x, y, m, s0, w = small_case(B=B, S=1, L=L, N=50, seed=4, tcn_channel=(128,) * levels, kernel_size=K, lengths="dense")
