@@ -13,6 +13,8 @@
 //
 // The recurrence is one persistent kernel (gru_bptt_kernel: a CTA per 32 users walks all S x G cell calls); all the
 // weight-gradient products are deferred to the end, where they are GEMMs with S*B rows.
+#include <cstdlib>
+
 #include "train.cuh"
 
 namespace htcn {
@@ -25,10 +27,11 @@ namespace {
 // ([32 x 128] Wc^T and [32 x 256] Wg^T) are FFMA register tiles fed by double-buffered 16-deep weight slices out of L2.
 // Replaces 4 launches per cell call (80 per step at S = 10, G = 2).  What the deferred weight-gradient GEMMs need (dcpre,
 // [drpre | dupre]) is written out as before.
-constexpr int kBpMB = 32;            // users per CTA (16 with two CTAs per SM measured slower: 1.31 vs 1.21 ms)
-constexpr int kBpTU = kBpMB / 4;     // users per thread tile
+// kBpMB = users per CTA: 32 at large batches (16 with two CTAs per SM measured slower at 4096 users: 1.31 vs 1.21 ms), 8 when
+// the batch is small (512 users per GPU in 8-way data-parallel training: 16 CTAs would leave 132 SMs idle)
 constexpr int kBpThreads = 256;
 constexpr int kBpKT = 16;            // contraction slice
+template <int kBpMB>
 struct BpttSmem {
   float outs[2][kBpMB][256];         // [layer][user][dx | dh] of the step being processed / the one after it
   float tmp[kBpMB][256];             // [dx_c | drh]
@@ -51,8 +54,8 @@ struct BpttArgs {
 };
 
 // acc[i][j] += sum_k A[b0 + i][k] W[n4 + j][k],  k < K;  A in shared memory (row stride lda), W [256][K] in global memory
-template <int K>
-__device__ __forceinline__ void bp_gemm(const float* A, int lda, const float* __restrict__ W, float (&acc)[kBpTU][4], BpttSmem& sm,
+template <int K, int kBpTU, class Smem>
+__device__ __forceinline__ void bp_gemm(const float* A, int lda, const float* __restrict__ W, float (&acc)[kBpTU][4], Smem& sm,
                                         int tid, int b0, int n4) {
   float4 pre[4];
   const float4* wrow = reinterpret_cast<const float4*>(W + (long long)tid * K);
@@ -88,9 +91,11 @@ __device__ __forceinline__ void bp_gemm(const float* A, int lda, const float* __
   }
 }
 
+template <int kBpMB>
 __global__ void __launch_bounds__(kBpThreads, 1) gru_bptt_kernel(BpttArgs a) {
+  constexpr int kBpTU = kBpMB / 4;     // users per thread tile
   extern __shared__ __align__(16) uint8_t bp_smem[];
-  BpttSmem& sm = *reinterpret_cast<BpttSmem*>(bp_smem);
+  BpttSmem<kBpMB>& sm = *reinterpret_cast<BpttSmem<kBpMB>*>(bp_smem);
   const int tid = threadIdx.x;
   const int u0 = blockIdx.x * kBpMB;
   const int n4 = 4 * (tid & 63), b0 = kBpTU * (tid >> 6);
@@ -144,7 +149,7 @@ __global__ void __launch_bounds__(kBpThreads, 1) gru_bptt_kernel(BpttArgs a) {
       for (int i = 0; i < kBpTU; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-      bp_gemm<128>(&sm.dc[0][0], 128, a.wc[g], acc, sm, tid, b0, n4);
+      bp_gemm<128, kBpTU>(&sm.dc[0][0], 128, a.wc[g], acc, sm, tid, b0, n4);
 #pragma unroll
       for (int i = 0; i < kBpTU; ++i) *reinterpret_cast<float4*>(&sm.tmp[b0 + i][n4]) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
       __syncthreads();
@@ -178,7 +183,7 @@ __global__ void __launch_bounds__(kBpThreads, 1) gru_bptt_kernel(BpttArgs a) {
         const float4 o = *reinterpret_cast<const float4*>(&sm.outs[g][b0 + i][n4]);
         acc[i][0] = o.x; acc[i][1] = o.y; acc[i][2] = o.z; acc[i][3] = o.w;
       }
-      bp_gemm<256>(&sm.dg[0][0], 256, a.wg[g], acc, sm, tid, b0, n4);
+      bp_gemm<256, kBpTU>(&sm.dg[0][0], 256, a.wg[g], acc, sm, tid, b0, n4);
 #pragma unroll
       for (int i = 0; i < kBpTU; ++i) *reinterpret_cast<float4*>(&sm.outs[g][b0 + i][n4]) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
       __syncthreads();
@@ -267,8 +272,15 @@ extern "C" int32_t htcn_gru_backward(const float* yp, const float* mask, const f
     for (int g = 0; g < G; ++g) {
       ba.sbc[g] = SBC[g]; ba.wc[g] = cand_w_host[g]; ba.wg[g] = gate_w_host[g]; ba.DC[g] = DC[g]; ba.DG[g] = DG[g];
     }
-    HTCN_CUDA(cudaFuncSetAttribute(gru_bptt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BpttSmem)));
-    gru_bptt_kernel<<<ceil_div(B, kBpMB), kBpThreads, sizeof(BpttSmem), st>>>(ba);
+    const char* mbe = getenv("HTCN_BPTT_MB");                   // users per CTA: 8 or 32, default by batch size
+    const int mb = mbe ? atoi(mbe) : (B <= 1024 ? 8 : 32);
+    if (mb == 8) {
+      HTCN_CUDA(cudaFuncSetAttribute(gru_bptt_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BpttSmem<8>)));
+      gru_bptt_kernel<8><<<ceil_div(B, 8), kBpThreads, sizeof(BpttSmem<8>), st>>>(ba);
+    } else {
+      HTCN_CUDA(cudaFuncSetAttribute(gru_bptt_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BpttSmem<32>)));
+      gru_bptt_kernel<32><<<ceil_div(B, 32), kBpThreads, sizeof(BpttSmem<32>), st>>>(ba);
+    }
     HTCN_LAUNCH_CHECK("gru_bptt_kernel");
   }
 

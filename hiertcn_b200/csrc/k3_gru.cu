@@ -7,11 +7,12 @@
 // customed_gru_cell.py:309-337, layer stacking :1050-1073, linear :1187-1197.  Also emits the hoisted
 // state half of the TCN in-projection, sbias[s] = state_pre[s] @ W_in[D:, :] (model_hier.py:54-55 +
 // model_tcn.py:35), so K2 never sees the 256-wide state.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace htcn {
 
-constexpr int kUB = 32;        // users per CTA
 constexpr int kGruThreads = 256;
 
 struct GruWeights {
@@ -26,7 +27,7 @@ __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf
 
 // acc[u] += sum_k src[u][k] * w[k*ldw + col]   for u in [u0, u0+NU), k in [0,128)
 template <int NU>
-__device__ __forceinline__ void dot_block(float (&acc)[NU], const float* __restrict__ src /*[kUB][128] smem*/,
+__device__ __forceinline__ void dot_block(float (&acc)[NU], const float* __restrict__ src /*[users][128] smem*/,
                                           int u0, const float* __restrict__ w, int ldw, int col) {
 #pragma unroll 2
   for (int k = 0; k < kDim; k += 4) {
@@ -45,6 +46,9 @@ __device__ __forceinline__ void dot_block(float (&acc)[NU], const float* __restr
   }
 }
 
+// kUB = users per CTA: 32 for large batches; 8 when the batch is small (data-parallel training at 512 users per GPU: 16 CTAs
+// of 32 users leave 132 SMs idle for the whole recurrence -- 64 CTAs of 8 users run it 2.5x faster)
+template <int kUB>
 __global__ void __launch_bounds__(kGruThreads, 1)
 k3_gru_sessions(const float* __restrict__ yp, const float* __restrict__ mask, const float* __restrict__ state_in,
                 GruWeights W, const float* __restrict__ w_in_state, int B, int S,
@@ -191,10 +195,20 @@ static int32_t gru_sessions_impl(const float* yp, const float* mask, const float
     return gru_sessions_bf16(yp, mask, state_in, W.gate_w, W.gate_b, W.cand_w, W.cand_b, w_in_state, B, S, state_pre, sbias,
                              state_out, scratch, as_stream(stream), gates_save);
   }
-  const size_t smem = sizeof(float) * (size_t)(3 + num_layer) * kUB * kDim;
-  HTCN_CUDA(cudaFuncSetAttribute(k3_gru_sessions, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k3_gru_sessions<<<ceil_div(B, kUB), kGruThreads, smem, as_stream(stream)>>>(
-      yp, mask, state_in, W, w_in_state, B, S, state_pre, sbias, state_out, gates_save);
+  // users per CTA: HTCN_K3_F32_UB (8 / 16 / 32), default by batch size
+  const char* ube = getenv("HTCN_K3_F32_UB");
+  const int ub = ube ? atoi(ube) : (B <= 1024 ? 8 : B <= 2048 ? 16 : 32);
+#define HTCN_K3_F32_LAUNCH(UB)                                                                                         \
+  do {                                                                                                                \
+    const size_t smem = sizeof(float) * (size_t)(3 + num_layer) * UB * kDim;                                          \
+    HTCN_CUDA(cudaFuncSetAttribute(k3_gru_sessions<UB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+    k3_gru_sessions<UB><<<ceil_div(B, UB), kGruThreads, smem, as_stream(stream)>>>(                                   \
+        yp, mask, state_in, W, w_in_state, B, S, state_pre, sbias, state_out, gates_save);                            \
+  } while (0)
+  if (ub == 8) HTCN_K3_F32_LAUNCH(8);
+  else if (ub == 16) HTCN_K3_F32_LAUNCH(16);
+  else HTCN_K3_F32_LAUNCH(32);
+#undef HTCN_K3_F32_LAUNCH
   HTCN_LAUNCH_CHECK("k3_gru_sessions");
   return HTCN_OK;
 }
