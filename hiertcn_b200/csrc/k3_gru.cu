@@ -49,7 +49,7 @@ __device__ __forceinline__ void dot_block(float (&acc)[NU], const float* __restr
 // kUB = users per CTA: 32 for large batches; 8 when the batch is small (data-parallel training at 512 users per GPU: 16 CTAs
 // of 32 users leave 132 SMs idle for the whole recurrence -- 64 CTAs of 8 users run it 2.5x faster)
 template <int kUB>
-__global__ void __launch_bounds__(kGruThreads, 1)
+__global__ void __launch_bounds__(kGruThreads, kUB <= 16 ? 2 : 1)
 k3_gru_sessions(const float* __restrict__ yp, const float* __restrict__ mask, const float* __restrict__ state_in,
                 GruWeights W, const float* __restrict__ w_in_state, int B, int S,
                 float* __restrict__ state_pre, float* __restrict__ sbias, float* __restrict__ state_out,
