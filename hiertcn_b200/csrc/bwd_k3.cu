@@ -108,8 +108,9 @@ __global__ void __launch_bounds__(kBpThreads, 1) gru_bptt_kernel(BpttArgs a) {
       const float* gc = gu + BD;
       // ---- A: gate gradients of this cell call (float4 per thread and iteration, loads of all iterations in flight)
 #pragma unroll
-      for (int it4 = 0; it4 < kBpMB * 32 / kBpThreads; ++it4) {
+      for (int it4 = 0; it4 < (kBpMB * 32 + kBpThreads - 1) / kBpThreads; ++it4) {
         const int idx = tid + it4 * kBpThreads;
+        if (kBpMB * 32 < kBpThreads && idx >= kBpMB * 32) break;
         const int b = idx >> 5, c = (idx & 31) * 4, ub = u0 + b;
         float4 dcp = make_float4(0.f, 0.f, 0.f, 0.f), dup = dcp, cr = dcp;
         if (ub < a.B) {
@@ -155,8 +156,9 @@ __global__ void __launch_bounds__(kBpThreads, 1) gru_bptt_kernel(BpttArgs a) {
       __syncthreads();
       // ---- B: drpre, and the start of this cell call's [dx | dh]
 #pragma unroll
-      for (int it4 = 0; it4 < kBpMB * 32 / kBpThreads; ++it4) {
+      for (int it4 = 0; it4 < (kBpMB * 32 + kBpThreads - 1) / kBpThreads; ++it4) {
         const int idx = tid + it4 * kBpThreads;
+        if (kBpMB * 32 < kBpThreads && idx >= kBpMB * 32) break;
         const int b = idx >> 5, c = (idx & 31) * 4, ub = u0 + b;
         float4 drp = make_float4(0.f, 0.f, 0.f, 0.f), dh = drp;
         if (ub < a.B) {
@@ -189,8 +191,9 @@ __global__ void __launch_bounds__(kBpThreads, 1) gru_bptt_kernel(BpttArgs a) {
       __syncthreads();
       if (g == 0) {                                              // dL/dyp[s] = dx of layer 0
 #pragma unroll
-        for (int it4 = 0; it4 < kBpMB * 32 / kBpThreads; ++it4) {
+        for (int it4 = 0; it4 < (kBpMB * 32 + kBpThreads - 1) / kBpThreads; ++it4) {
           const int idx = tid + it4 * kBpThreads;
+          if (kBpMB * 32 < kBpThreads && idx >= kBpMB * 32) break;
           const int b = idx >> 5, c = (idx & 31) * 4, ub = u0 + b;
           if (ub < a.B)
             *reinterpret_cast<float4*>(a.d_yp + ((long long)s * a.B + ub) * kDim + c) = *reinterpret_cast<const float4*>(&sm.outs[0][b][c]);
@@ -274,7 +277,10 @@ extern "C" int32_t htcn_gru_backward(const float* yp, const float* mask, const f
     }
     const char* mbe = getenv("HTCN_BPTT_MB");                   // users per CTA: 8 or 32, default by batch size
     const int mb = mbe ? atoi(mbe) : (B <= 1024 ? 8 : 32);
-    if (mb == 8) {
+    if (mb == 4) {
+      HTCN_CUDA(cudaFuncSetAttribute(gru_bptt_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BpttSmem<4>)));
+      gru_bptt_kernel<4><<<ceil_div(B, 4), kBpThreads, sizeof(BpttSmem<4>), st>>>(ba);
+    } else if (mb == 8) {
       HTCN_CUDA(cudaFuncSetAttribute(gru_bptt_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BpttSmem<8>)));
       gru_bptt_kernel<8><<<ceil_div(B, 8), kBpThreads, sizeof(BpttSmem<8>), st>>>(ba);
     } else {

@@ -596,9 +596,28 @@ k2_tcn_bf16_dual(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __n
 constexpr int kK2MaxWeightTiles = 1 + HTCN_MAX_LEVELS * 9;
 constexpr int kK2PtrTableBytes = 640;            // >= kK2MaxWeightTiles pointers, keeps the bias arrays 16-byte aligned
 static_assert(kK2MaxWeightTiles * 8 <= kK2PtrTableBytes, "pointer table");
-__global__ void k2_prepare_weights(const float* const* __restrict__ tile_src, __nv_bfloat16* __restrict__ out) {
+// One launch prepares everything the stack kernels read from the scratch: the bf16 weight tiles and the level biases.  The
+// source pointers travel as a kernel argument (a pointer table in device memory cost a pageable host-to-device memcpy plus
+// one device-to-device memcpy per bias vector on every call: ~0.1 ms of launches around a 0.43 ms kernel).
+struct K2PrepArgs {
+  const float* tile[kK2MaxWeightTiles];          // [128 cin][128 cout] fp32 sources, consumption order
+  const float* bias[HTCN_MAX_LEVELS];            // conv biases
+  const float* ds_bias[HTCN_MAX_LEVELS];         // down-sample biases (NULL: zeros / not a down-sample level)
+  int n_tiles, n_levels;
+  unsigned ds_mask;
+};
+__global__ void k2_prepare_weights(const __grid_constant__ K2PrepArgs a, __nv_bfloat16* __restrict__ out, float* __restrict__ bias_dev,
+                                   float* __restrict__ ds_bias_dev) {
   const int j = blockIdx.x;
-  const float* src = tile_src[j];
+  if (j == a.n_tiles) {                            // the extra block: biases
+    for (int i = threadIdx.x; i < a.n_levels * kDim; i += blockDim.x) {
+      const int l = i / kDim, c = i % kDim;
+      bias_dev[i] = a.bias[l][c];
+      if ((a.ds_mask >> l) & 1u) ds_bias_dev[i] = a.ds_bias[l] ? a.ds_bias[l][c] : 0.f;
+    }
+    return;
+  }
+  const float* src = a.tile[j];
   for (int i = threadIdx.x; i < kDim * kDim; i += blockDim.x) {
     const int cout = i / kDim, cin = i % kDim;
     out[(long long)j * kDim * kDim + i] = __float2bfloat16_rn(src[cin * kDim + cout]);
@@ -646,33 +665,28 @@ int32_t tcn_forward_bf16(const void* xe, int xe_dtype, const float* w_in_x, cons
   g.n_units = units;
   // scratch layout: [bf16 weight tiles (HTCN_TCN_SCRATCH_BYTES reserves K+1 per level)][tile source pointers][conv biases]
   // [down-sample biases]
-  const float* tile_src[kK2MaxWeightTiles];
+  K2PrepArgs pa{};
   int n_wt = 0;
-  tile_src[n_wt++] = w_in_x;
+  pa.tile[n_wt++] = w_in_x;
   for (int l = 0; l < n_levels; ++l) {
-    for (int tap = 0; tap < K; ++tap) tile_src[n_wt++] = conv_w[l] + (long long)tap * kDim * kDim;
+    for (int tap = 0; tap < K; ++tap) pa.tile[n_wt++] = conv_w[l] + (long long)tap * kDim * kDim;
+    pa.bias[l] = conv_b[l];
     if (ds_w && ds_w[l]) {
       g.ds_mask |= 1u << l;
-      tile_src[n_wt++] = ds_w[l];
+      pa.tile[n_wt++] = ds_w[l];
+      pa.ds_bias[l] = (ds_b && ds_b[l]) ? ds_b[l] : nullptr;
     }
   }
+  pa.n_tiles = n_wt; pa.n_levels = n_levels; pa.ds_mask = g.ds_mask;
+  // scratch layout: [bf16 weight tiles (HTCN_TCN_SCRATCH_BYTES reserves K+1 per level)][(unused) pointer table][conv biases]
+  // [down-sample biases][parked rows of streamed sequences]
   uint8_t* sc = reinterpret_cast<uint8_t*>(scratch);
   __nv_bfloat16* w_bf16 = reinterpret_cast<__nv_bfloat16*>(sc);
   const size_t w_bytes = (size_t)(1 + n_levels * (K + 1)) * kDim * kDim * 2;
-  const float** ptrs_dev = reinterpret_cast<const float**>(sc + w_bytes);
   float* bias_dev = reinterpret_cast<float*>(sc + w_bytes + kK2PtrTableBytes);
   float* ds_bias_dev = bias_dev + HTCN_MAX_LEVELS * kDim;
-  uint8_t* hist_dev = reinterpret_cast<uint8_t*>(ds_bias_dev + HTCN_MAX_LEVELS * kDim) + 256;   // per-CTA parked rows
-  // (pageable host source: the runtime stages the copy before returning, the stack array may die afterwards)
-  HTCN_CUDA(cudaMemcpyAsync(ptrs_dev, tile_src, sizeof(float*) * n_wt, cudaMemcpyHostToDevice, st));
-  for (int l = 0; l < n_levels; ++l) {
-    HTCN_CUDA(cudaMemcpyAsync(bias_dev + l * kDim, conv_b[l], kDim * 4, cudaMemcpyDeviceToDevice, st));
-    if ((g.ds_mask >> l) & 1u) {
-      if (ds_b && ds_b[l]) HTCN_CUDA(cudaMemcpyAsync(ds_bias_dev + l * kDim, ds_b[l], kDim * 4, cudaMemcpyDeviceToDevice, st));
-      else HTCN_CUDA(cudaMemsetAsync(ds_bias_dev + l * kDim, 0, kDim * 4, st));
-    }
-  }
-  k2_prepare_weights<<<n_wt, 256, 0, st>>>(ptrs_dev, w_bf16);
+  uint8_t* hist_dev = reinterpret_cast<uint8_t*>(ds_bias_dev + HTCN_MAX_LEVELS * kDim) + 256;   // per-chain parked rows
+  k2_prepare_weights<<<n_wt + 1, 256, 0, st>>>(pa, w_bf16, bias_dev, ds_bias_dev);
   HTCN_LAUNCH_CHECK("k2_prepare_weights");
   CUtensorMap tw;
   int32_t rc = make_tmap_bf16(&tw, w_bf16, (uint64_t)n_wt * kDim, kDim, kDim, 64, 128, 128);

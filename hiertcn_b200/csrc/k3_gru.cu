@@ -205,7 +205,8 @@ static int32_t gru_sessions_impl(const float* yp, const float* mask, const float
     k3_gru_sessions<UB><<<ceil_div(B, UB), kGruThreads, smem, as_stream(stream)>>>(                                   \
         yp, mask, state_in, W, w_in_state, B, S, state_pre, sbias, state_out, gates_save);                            \
   } while (0)
-  if (ub == 8) HTCN_K3_F32_LAUNCH(8);
+  if (ub == 4) HTCN_K3_F32_LAUNCH(4);
+  else if (ub == 8) HTCN_K3_F32_LAUNCH(8);
   else if (ub == 16) HTCN_K3_F32_LAUNCH(16);
   else HTCN_K3_F32_LAUNCH(32);
 #undef HTCN_K3_F32_LAUNCH
