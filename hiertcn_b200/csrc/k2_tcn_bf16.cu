@@ -28,6 +28,21 @@
 namespace htcn {
 using namespace sm100;
 
+// the 8 MMAs (K = 128) of one weight tile on one operand tile: the descriptors' low words advance by 16-byte units (the
+// 64-bit rebuild per MMA -- shift, mask, two ORs per operand -- kept the issuing warp, not the tensor pipe, busy; see
+// k2_tcn_quad.cu)
+__device__ __forceinline__ void k2_issue_tile(bool leader, uint32_t tacc, uint32_t a_base, uint32_t w_base, uint32_t idesc,
+                                              bool accumulate_first) {
+  constexpr uint32_t kAHi = (128u >> 4) | (1u << 14), kBHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+  const uint32_t a_lo = ((a_base & 0x3FFFF) >> 4) | ((uint32_t)kRows << 16);
+  const uint32_t b_lo = ((w_base & 0x3FFFF) >> 4) | (1u << 16);
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    if (leader)
+      umma_bf16_lohi(tacc, a_lo + (uint32_t)(2 * k) * kRows, kAHi, b_lo + (uint32_t)(k >> 2) * ((kWStageBytes / 2) >> 4) + (k & 3) * 2,
+                     kBHi, idesc, accumulate_first || k != 0);
+}
+
 struct alignas(1024) K2Smem {
   uint8_t w[kWStages][kWStageBytes];     // 64 KB
   uint8_t act[kActBytes];                // 40 KB
@@ -127,12 +142,7 @@ k2_tcn_bf16(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfl
             const int shift = (taps - 1 - tap) * dil;            // rows back in time (customized_tcn_cell.py:46-49)
             const uint32_t a_base = act0 + (uint32_t)(kMaxSpare - shift) * 16;
             const uint32_t w_base = smem_u32(sm.w[s]);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const uint64_t da = make_desc_act(a_base + (uint32_t)(2 * k) * (kRows * 16));
-              const uint64_t db = make_desc_k_sw128(w_base + (k >> 2) * (kWStageBytes / 2) + (k & 3) * 32);
-              if (leader) umma_bf16(tmem, da, db, idesc, (tap | k) != 0);
-            }
+            k2_issue_tile(leader, tmem, a_base, w_base, idesc, tap != 0);
             if (leader) {
               if (kPair) umma_commit_mc(&sm.w_empty[s], 0b11);
               else umma_commit(&sm.w_empty[s]);
@@ -144,12 +154,7 @@ k2_tcn_bf16(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __nv_bfl
             tc_fence_after_sync();
             const uint32_t a_base = act0 + (uint32_t)kMaxSpare * 16;
             const uint32_t w_base = smem_u32(sm.w[s]);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const uint64_t da = make_desc_act(a_base + (uint32_t)(2 * k) * (kRows * 16));
-              const uint64_t db = make_desc_k_sw128(w_base + (k >> 2) * (kWStageBytes / 2) + (k & 3) * 32);
-              if (leader) umma_bf16(tmem + 128, da, db, idesc, k != 0);
-            }
+            k2_issue_tile(leader, tmem + 128, a_base, w_base, idesc, false);
             if (leader) {
               if (kPair) umma_commit_mc(&sm.w_empty[s], 0b11);
               else umma_commit(&sm.w_empty[s]);
@@ -413,12 +418,7 @@ k2_tcn_bf16_dual(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __n
           const int shift = (taps - 1 - tap) * dil;              // rows back in time (customized_tcn_cell.py:46-49)
           const uint32_t a_base = act0 + (uint32_t)(kMaxSpare - shift) * 16;
           const uint32_t w_base = smem_u32(sm.w[s]);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const uint64_t da = make_desc_act(a_base + (uint32_t)(2 * k) * (kRows * 16));
-            const uint64_t db = make_desc_k_sw128(w_base + (k >> 2) * (kWStageBytes / 2) + (k & 3) * 32);
-            if (leader) umma_bf16(tacc, da, db, idesc, (tap | k) != 0);
-          }
+          k2_issue_tile(leader, tacc, a_base, w_base, idesc, tap != 0);
           if (leader) umma_commit(&sm.w_empty[s]);
         }
         if (kAux && ds) {                                        // res = in @ W_ds: unshifted rows, second accumulator
@@ -427,12 +427,7 @@ k2_tcn_bf16_dual(const __grid_constant__ CUtensorMap tmap_w, K2Geom g, const __n
           tc_fence_after_sync();
           const uint32_t a_base = act0 + (uint32_t)kMaxSpare * 16;
           const uint32_t w_base = smem_u32(sm.w[s]);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const uint64_t da = make_desc_act(a_base + (uint32_t)(2 * k) * (kRows * 16));
-            const uint64_t db = make_desc_k_sw128(w_base + (k >> 2) * (kWStageBytes / 2) + (k & 3) * 32);
-            if (leader) umma_bf16(tacc + 128, da, db, idesc, k != 0);
-          }
+          k2_issue_tile(leader, tacc + 128, a_base, w_base, idesc, false);
           if (leader) umma_commit(&sm.w_empty[s]);
           ++n;
         }
@@ -712,7 +707,9 @@ int32_t tcn_forward_bf16(const void* xe, int xe_dtype, const float* w_in_x, cons
   if (!aux && !pair && !dual_env && (quad_env ? atoi(quad_env) != 0 : true))
     return k2_launch_quad(tw, g, (const __nv_bfloat16*)xe, sbias, (const float*)bias_dev, out_row, (__nv_bfloat16*)hout, hist_dev,
                           stream, st);
-  const bool dual = dual_env ? atoi(dual_env) != 0 : stream;
+  // (with the issuer's descriptors advanced by their low words the two-chain kernel wins at both shapes: 0.523 vs 0.558 ms at
+  // config 2, 0.718 vs 0.790 at config 3 -- it is the default for everything the four-chain kernel does not take)
+  const bool dual = dual_env ? atoi(dual_env) != 0 : true;
   if (!pair && dual) {
     const size_t smem_d = sizeof(K2SmemDual) + 1024;
     const int grid_d = (units + 1) / 2 < 148 ? (units + 1) / 2 : 148;
