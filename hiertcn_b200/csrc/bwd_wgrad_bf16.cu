@@ -193,12 +193,13 @@ wgrad_mn_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       mbar_wait(&sm.full[s], (uint32_t)((n / kWgStages) & 1));
       tc_fence_after_sync();
       for (int t = 0; t < taps.n; ++t) {
+        // descriptor low words (make_desc_mn_sw128) advanced by 16-byte units per K step instead of a 64-bit rebuild per MMA
+        constexpr uint32_t kHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+        const uint32_t a_lo = ((smem_u32(sm.a[s][t]) & 0x3FFFF) >> 4) | ((8192u >> 4) << 16);
+        const uint32_t b_lo = ((smem_u32(sm.b[s]) & 0x3FFFF) >> 4) | ((8192u >> 4) << 16);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {                            // 16 rows of the contraction = two 8-row groups = 2048 B
-          const uint64_t da = make_desc_mn_sw128(smem_u32(sm.a[s][t]) + k * 2048);
-          const uint64_t db = make_desc_mn_sw128(smem_u32(sm.b[s]) + k * 2048);
-          if (leader) umma_bf16(tmem + t * 128, da, db, idesc, (n | k) != 0);
-        }
+        for (int k = 0; k < 4; ++k)                              // 16 rows of the contraction = two 8-row groups = 2048 B
+          if (leader) umma_bf16_lohi(tmem + t * 128, a_lo + k * (2048 >> 4), kHi, b_lo + k * (2048 >> 4), kHi, idesc, (n | k) != 0);
       }
       if (leader) umma_commit(&sm.empty[s]);
     }

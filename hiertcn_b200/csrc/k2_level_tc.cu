@@ -153,15 +153,19 @@ k2_level_tc(const __grid_constant__ CUtensorMap tmap_w, LvGeom g, LevelArgs a) {
           mbar_wait(&sm.w_full[s], (uint32_t)((n / kLvStages) & 1));
           tc_fence_after_sync();
           const uint32_t w_base = smem_u32(sm.w[s]);
+          // descriptor low words (lv_desc_act / make_desc_k_sw128), advanced by 16-byte units per K step: rebuilding the
+          // 64-bit descriptors per MMA cost the issuing warp more than the MMAs take (see k2_tcn_quad.cu)
+          constexpr uint32_t kAHi = (128u >> 4) | (1u << 14), kBHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+          const uint32_t ah_lo = (((act_hi + row0) & 0x3FFFF) >> 4) | ((uint32_t)kLvBufRows << 16);
+          const uint32_t al_lo = (((act_lo + row0) & 0x3FFFF) >> 4) | ((uint32_t)kLvBufRows << 16);
+          const uint32_t b_lo = ((w_base & 0x3FFFF) >> 4) | (1u << 16);
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
-            const uint32_t koff = (uint32_t)(2 * k) * (kLvBufRows * 16);
-            const uint64_t da = lv_desc_act(act_hi + row0 + koff);
-            const uint64_t db = make_desc_k_sw128(w_base + (k >> 2) * (kLvWStage / 2) + (k & 3) * 32);
-            if (leader) umma_bf16(tacc, da, db, idesc, (tap | k | part) != 0);        // x_hi w_hi, or x_hi w_lo
+            const uint32_t koff = (uint32_t)(2 * k) * kLvBufRows;
+            const uint32_t bk = b_lo + (uint32_t)(k >> 2) * ((kLvWStage / 2) >> 4) + (k & 3) * 2;
+            if (leader) umma_bf16_lohi(tacc, ah_lo + koff, kAHi, bk, kBHi, idesc, (tap | k | part) != 0);   // x_hi w_hi, or x_hi w_lo
             if (kSplit && part == 0) {
-              const uint64_t dl = lv_desc_act(act_lo + row0 + koff);
-              if (leader) umma_bf16(tacc, dl, db, idesc, true);                       // x_lo w_hi
+              if (leader) umma_bf16_lohi(tacc, al_lo + koff, kAHi, bk, kBHi, idesc, true);                  // x_lo w_hi
             }
           }
           if (leader) umma_commit(&sm.w_empty[s]);
