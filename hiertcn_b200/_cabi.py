@@ -56,6 +56,7 @@ SIGNATURES = {
     "htcn_scale_rows": [_p, _p, C.c_int64, _i, _p],
     "htcn_loss_metrics_reduce": [_p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p],
     "htcn_sampled_rank_loss": [_p, _i, _i, _p, _p, _p, _i, _i, _f, _f, _i, _p, _p],
+    "htcn_sampled_rank_loss_wt": [_p, _i, _p, _p, _p, _i, _i, _f, _f, _i, _p, _p],
     "htcn_sampled_rank_loss_backward": [_p, _i, _i, _p, _p, _p, _i, _i, _f, _f, _i, _p, _p, _p, _p],
     "htcn_calc_score": [_p, _i, _i, _p, _p, _i, _i, _p, _p],
     # training step
@@ -128,7 +129,7 @@ LAUNCHES_PER_CALL = {"htcn_gather_meanpool": 2, "htcn_gru_sessions": 1, "htcn_tc
                      "htcn_target_logit": 1, "htcn_score_finish": 1, "htcn_topk_merge": 1, "htcn_score_topk": 5, "htcn_score_ce_repair": 1,
                      "htcn_score_ce_repair_shard": 1, "htcn_score_ce_rank_topk_fused": 6,
                      "htcn_catalog_gram": 2, "htcn_logit_rownorm": 1, "htcn_score_ce_rank_l2norm": 2, "htcn_scale_rows": 1,
-                     "htcn_loss_metrics_reduce": 2, "htcn_sampled_rank_loss": 1, "htcn_calc_score": 1,
+                     "htcn_loss_metrics_reduce": 2, "htcn_sampled_rank_loss": 1, "htcn_sampled_rank_loss_wt": 1, "htcn_calc_score": 1,
                      "htcn_sampled_rank_loss_backward": 1,
                      # training step (the per-call counts of the multi-launch entry points are added by the caller)
                      "htcn_loss_row_weights": 1, "htcn_score_ce_backward": 1, "htcn_gru_sessions_train": 1, "htcn_gru_sessions_train_bf16": 2,

@@ -16,7 +16,22 @@ __device__ __forceinline__ float log_sigmoid(float x) {   // stable log(sigmoid(
 }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
-template <bool kBf16>
+// one lane's 4 channels of row `id` of the gather table: fp32 [N,128] rows (512 B), or -- kTabBf16 -- the bf16 scoring table
+// [N,144] of htcn_prepare_wout (288 B rows, weights in columns 0..127): half the gathered bytes, the same values where the
+// fp32 table is the widened bf16 one (the bf16 tier)
+template <bool kTabBf16>
+__device__ __forceinline__ float4 sl_load_row(const float4* __restrict__ table, long long id, int lane) {
+  if (kTabBf16) {
+    uint2 u;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];"
+                 : "=r"(u.x), "=r"(u.y)
+                 : "l"(reinterpret_cast<const uint8_t*>(table) + id * (HTCN_WT_PITCH_BF16 * 2) + lane * 8));
+    return make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
+  }
+  return ldg_nc_f4(table + id * 32 + lane);
+}
+
+template <bool kBf16, bool kTabBf16 = false>
 __global__ void __launch_bounds__(256)
 sampled_loss_kernel(const void* __restrict__ pred, int Q, const float4* __restrict__ table,
                     const int* __restrict__ pos_id, const int* __restrict__ neg_id, int k, int kind,
@@ -39,7 +54,7 @@ sampled_loss_kernel(const void* __restrict__ pred, int Q, const float4* __restri
   const float ss = warp_sum(p.x * p.x + p.y * p.y + p.z * p.z + p.w * p.w);
   const float inv = rsqrtf(fmaxf(ss, 1e-12f));
   p.x *= inv; p.y *= inv; p.z *= inv; p.w *= inv;
-  const float4 yp = ldg_nc_f4(table + (long long)pos * 32 + lane);
+  const float4 yp = sl_load_row<kTabBf16>(table, pos, lane);
   const float inner = warp_sum(p.x * yp.x + p.y * yp.y + p.z * yp.z + p.w * yp.w);
   float acc = 0.f;
   for (int j0 = 0; j0 < k; j0 += 4) {
@@ -49,7 +64,7 @@ sampled_loss_kernel(const void* __restrict__ pred, int Q, const float4* __restri
     for (int i = 0; i < 4; ++i) {
       id[i] = (j0 + i < k) ? __ldg(neg_id + (long long)q * k + j0 + i) : -1;
       v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (id[i] > 0) v[i] = ldg_nc_f4(table + (long long)id[i] * 32 + lane);   // id 0 -> zero row
+      if (id[i] > 0) v[i] = sl_load_row<kTabBf16>(table, id[i], lane);   // id 0 -> zero row
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -221,6 +236,20 @@ extern "C" int32_t htcn_calc_score(const void* pred, int32_t precision, int32_t 
   else
     HTCN_REQUIRE(false, "calc_score: precision %d", precision);
   HTCN_LAUNCH_CHECK("calc_score_kernel");
+  return HTCN_OK;
+}
+
+// The same against the bf16 scoring table [N, HTCN_WT_PITCH_BF16] (htcn_prepare_wout, bf16 tier): pred must be bf16
+extern "C" int32_t htcn_sampled_rank_loss_wt(const void* pred, int32_t Q, const void* wt_bf16, const int32_t* pos_id,
+                                             const int32_t* neg_id, int32_t k, int32_t loss_kind, float hinge_delta,
+                                             float nce_weight, int32_t num_neg_sample, float* loss_row, void* stream) {
+  using namespace htcn;
+  HTCN_REQUIRE(pred && wt_bf16 && pos_id && neg_id && loss_row && Q > 0 && k > 0, "sampled_rank_loss_wt: bad args");
+  HTCN_REQUIRE(loss_kind >= HTCN_LOSS_NCE && loss_kind <= HTCN_LOSS_BPR, "sampled_rank_loss_wt: kind %d", loss_kind);
+  const int nce_div = num_neg_sample > 0 ? num_neg_sample : k;
+  sampled_loss_kernel<true, true><<<ceil_div(Q, 8), 256, 0, as_stream(stream)>>>(pred, Q, (const float4*)wt_bf16, pos_id, neg_id, k,
+                                                                                loss_kind, hinge_delta, nce_weight, nce_div, loss_row);
+  HTCN_LAUNCH_CHECK("sampled_loss_kernel");
   return HTCN_OK;
 }
 

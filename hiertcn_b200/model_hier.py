@@ -588,12 +588,19 @@ class HierTCN:
         kind = kind or (a.loss if a.loss in cabi.LOSS_KINDS else "hinge_logsigmoid")
         if kind not in cabi.LOSS_KINDS:
             raise ValueError("sampled loss kind %r" % kind)
-        if self.wt_f32 is None:                  # gather table is fp32 in both tiers
-            self.wt_f32 = self.wt[:, :D].float().contiguous()
         neg = neg_ids if hasattr(neg_ids, "data_ptr") else torch.from_numpy(np.ascontiguousarray(neg_ids, np.int32)).to(self.device)
         Q, k = neg.shape
         assert Q == scores.Q
         out = torch.empty(Q, dtype=torch.float32, device=self.device)
+        if self.precision == "bf16" and self.wt_f32 is None and self.act_dtype == cabi.HTCN_BF16:
+            # bf16 tier: gather straight from the bf16 scoring table (288 B rows instead of a widened fp32 copy's 512 B:
+            # the same values, half the bytes, no second table in HBM)
+            cabi.call("htcn_sampled_rank_loss_wt", scores.hout.data_ptr(), Q, self.wt.data_ptr(), scores.y_rows.data_ptr(),
+                      neg.data_ptr(), k, cabi.LOSS_KINDS[kind], float(a.hinge_delta), float(a.nce_weight),
+                      int(a.num_neg_sample), out.data_ptr(), self.stream_ptr())
+            return out
+        if self.wt_f32 is None:                  # fp32 gather table
+            self.wt_f32 = self.wt[:, :D].float().contiguous()
         cabi.call("htcn_sampled_rank_loss", scores.hout.data_ptr(), self.act_dtype, Q, self.wt_f32.data_ptr(),
                   scores.y_rows.data_ptr(), neg.data_ptr(), k, cabi.LOSS_KINDS[kind], float(a.hinge_delta),
                   float(a.nce_weight), int(a.num_neg_sample), out.data_ptr(), self.stream_ptr())

@@ -328,6 +328,12 @@ int32_t htcn_sampled_rank_loss(const void* pred, int32_t precision, int32_t Q, c
                                int32_t loss_kind, float hinge_delta, float nce_weight,
                                int32_t num_neg_sample, float* loss_row, void* stream);
 
+/* The same gathering from the bf16 scoring table wt [N,HTCN_WT_PITCH_BF16] of htcn_prepare_wout (bf16 tier: 288 B rows
+ * instead of 512 B; pred [Q,128] bf16).  Equal, bit for bit, to htcn_sampled_rank_loss on the widened table wt[:, :128]. */
+int32_t htcn_sampled_rank_loss_wt(const void* pred, int32_t Q, const void* wt_bf16, const int32_t* pos_id,
+                                  const int32_t* neg_id, int32_t k, int32_t loss_kind, float hinge_delta,
+                                  float nce_weight, int32_t num_neg_sample, float* loss_row, void* stream);
+
 /* Backward of htcn_sampled_rank_loss: g_row [Q] = dL/dloss_row.  d_pred [Q,128] f32 is overwritten (rows with pos_id == 0
  * get zeros), d_table [N,128] f32 (the gradient of the positive / negative rows of `table`) is accumulated with atomics;
  * the null item 0 owns no row.  Hinge kinds use the relu gradient where the hinge is strictly positive (TF's ReluGrad).

@@ -444,6 +444,33 @@ def test_loss_metrics_reduce(lib):
 
 
 @pytest.mark.parametrize("kind", ["nce", "hinge_sigmoid", "hinge_logsigmoid", "hinge_linear", "bpr"])
+def test_sampled_rank_loss_from_the_bf16_scoring_table(lib, kind):
+    """htcn_sampled_rank_loss_wt gathers the 1 + k rows from the bf16 scoring table [N,144] (288 B rows): bit for bit the loss
+    of htcn_sampled_rank_loss on the widened fp32 copy wt[:, :128] (loss.py:22-71), id 0 = the null item included"""
+    rng = np.random.default_rng(11)
+    Q, N, k = 333, 5000, 20
+    w_out = (rng.normal(size=(128, N)) * 0.3).astype(np.float32)
+    b_out = (rng.normal(size=N) * 0.2).astype(np.float32)
+    wt = torch.empty((N, lib.WT_PITCH_BF16), dtype=torch.bfloat16, device="cuda")
+    wd, bd = dev(w_out), dev(b_out)
+    lib.call("htcn_prepare_wout", P(wd), P(bd), N, P(wt), lib.HTCN_BF16, None)
+    wide = wt[:, :128].float().contiguous()
+    pred = dev(rng.normal(size=(Q, 128)).astype(np.float32)).to(torch.bfloat16)
+    pos = rng.integers(0, N, size=Q).astype(np.int32)
+    pos[::17] = 0
+    neg = rng.integers(0, N, size=(Q, k)).astype(np.int32)
+    pos_d, neg_d = dev(pos), dev(neg)
+    a = torch.full((Q,), 7.0, dtype=torch.float32, device="cuda")
+    b = torch.full((Q,), 9.0, dtype=torch.float32, device="cuda")
+    lib.call("htcn_sampled_rank_loss", P(pred), lib.HTCN_BF16, Q, P(wide), P(pos_d), P(neg_d), k, lib.LOSS_KINDS[kind], 0.3, 1.5, 25,
+             P(a), None)
+    lib.call("htcn_sampled_rank_loss_wt", P(pred), Q, P(wt), P(pos_d), P(neg_d), k, lib.LOSS_KINDS[kind], 0.3, 1.5, 25, P(b), None)
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)
+    assert (b[::17] == 0).all()
+
+
+@pytest.mark.parametrize("kind", ["nce", "hinge_sigmoid", "hinge_logsigmoid", "hinge_linear", "bpr"])
 def test_sampled_rank_loss(lib, kind):
     rng = np.random.default_rng(3)
     Q, N, k = 77, 900, 20
