@@ -555,9 +555,7 @@ def kernels_leg(model, staged, neg_dev, peaks, wl):
                                "rows read for x and y (%d B each, packed emb_dim) + ids + Xe/Yp written" % row_b),
         "k3_gru_sessions": (k3, "hbm", B * S * (128 + 2 * 256) * 4, "Yp in, state_pre/sbias out; latency-bound in practice"),
         "k2_tcn_forward": (k2, "tensor", Q * (model.n_levels * 2.0 * model.K * 128 * 128 + 2.0 * 128 * 128), "useful FLOPs of the scored positions"),
-        "sampled_rank_loss": (sl, "hbm", Q * (21 * (256 if model.precision == "bf16" else 512) + 128 * e + 21 * 4 + 4),
-                              "21 gathered rows of W_out^T per position (bf16 tier: 256 B of the bf16 scoring table's 288 B rows; "
-                              "fp32 tier: 512 B) + the query row"),
+        "sampled_rank_loss": (sl, "hbm", Q * (21 * 512 + 128 * e + 21 * 4 + 4), "21 gathered fp32 rows of W_out^T per position + the query row"),
     }
     for name, (fn, bound, work, note) in works.items():
         for _ in range(2):

@@ -57,17 +57,18 @@ sampled_loss_kernel(const void* __restrict__ pred, int Q, const float4* __restri
   const float4 yp = sl_load_row<kTabBf16>(table, pos, lane);
   const float inner = warp_sum(p.x * yp.x + p.y * yp.y + p.z * yp.z + p.w * yp.w);
   float acc = 0.f;
-  for (int j0 = 0; j0 < k; j0 += 4) {
-    float4 v[4];
-    int id[4];
+  constexpr int kFly = 4;                                     // rows in flight per warp (8 with the bf16 table measured slower: 3.07 vs 2.58 ms)
+  for (int j0 = 0; j0 < k; j0 += kFly) {
+    float4 v[kFly];
+    int id[kFly];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < kFly; ++i) {
       id[i] = (j0 + i < k) ? __ldg(neg_id + (long long)q * k + j0 + i) : -1;
       v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (id[i] > 0) v[i] = sl_load_row<kTabBf16>(table, id[i], lane);   // id 0 -> zero row
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < kFly; ++i) {
       if (id[i] < 0) continue;
       const float s = warp_sum(p.x * v[i].x + p.y * v[i].y + p.z * v[i].z + p.w * v[i].w);
       switch (kind) {

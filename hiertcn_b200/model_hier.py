@@ -20,6 +20,8 @@ so the S-step recurrence is hoisted out of the session loop):
 """
 from __future__ import annotations
 
+import os
+
 import math
 
 import numpy as np
@@ -592,9 +594,12 @@ class HierTCN:
         Q, k = neg.shape
         assert Q == scores.Q
         out = torch.empty(Q, dtype=torch.float32, device=self.device)
-        if self.precision == "bf16" and self.wt_f32 is None and self.act_dtype == cabi.HTCN_BF16:
-            # bf16 tier: gather straight from the bf16 scoring table (288 B rows instead of a widened fp32 copy's 512 B:
-            # the same values, half the bytes, no second table in HBM)
+        if (self.precision == "bf16" and self.wt_f32 is None and self.act_dtype == cabi.HTCN_BF16
+                and os.environ.get("HTCN_SAMPLED_BF16TAB")):
+            # opt-in (HTCN_SAMPLED_BF16TAB=1): gather straight from the bf16 scoring table (288 B rows) instead of a widened
+            # fp32 copy (512 B rows): the same values and no second 512 MB table in HBM -- but measured SLOWER at config 2
+            # (2.58 vs 2.35 ms: the gather is bound by requests in flight, not bytes, and the 288-byte pitch splits rows
+            # over one more 128-byte line), so the widened copy stays the default
             cabi.call("htcn_sampled_rank_loss_wt", scores.hout.data_ptr(), Q, self.wt.data_ptr(), scores.y_rows.data_ptr(),
                       neg.data_ptr(), k, cabi.LOSS_KINDS[kind], float(a.hinge_delta), float(a.nce_weight),
                       int(a.num_neg_sample), out.data_ptr(), self.stream_ptr())
