@@ -20,9 +20,8 @@ so the S-step recurrence is hoisted out of the session loop):
 """
 from __future__ import annotations
 
-import os
-
 import math
+import os
 
 import numpy as np
 
