@@ -557,17 +557,20 @@ def kernels_leg(model, staged, neg_dev, peaks, wl):
         "k2_tcn_forward": (k2, "tensor", Q * (model.n_levels * 2.0 * model.K * 128 * 128 + 2.0 * 128 * 128), "useful FLOPs of the scored positions"),
         "sampled_rank_loss": (sl, "hbm", Q * (21 * 512 + 128 * e + 21 * 4 + 4), "21 gathered fp32 rows of W_out^T per position + the query row"),
     }
+    reps = 10
     for name, (fn, bound, work, note) in works.items():
-        for _ in range(2):
-            fn()
+        # sub-millisecond kernels timed right after an idle gap run at ramping clocks: warm up first, no host sync between
+        # the warm-up and the timed calls
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize(model.device)
+        for _ in range(10):
+            fn()
         e0.record(torch.cuda.current_stream(model.device))
-        for _ in range(3):
+        for _ in range(reps):
             fn()
         e1.record(torch.cuda.current_stream(model.device))
         torch.cuda.synchronize(model.device)
-        ms = e0.elapsed_time(e1) / 3
+        ms = e0.elapsed_time(e1) / reps
         peak = peaks["hbm"] if bound == "hbm" else peaks["tf_burst"]
         ach = work / (ms * 1e-3) / (1e9 if bound == "hbm" else 1e12)
         out[name] = {"ms": ms, "bound": bound, "achieved": ach, "peak": peak, "unit": "GB/s" if bound == "hbm" else "TFLOP/s",
